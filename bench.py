@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 batched-replication executor.
+
+Metric (BASELINE.json): simulated events/sec (whole box) of the discrete_queue model, 1,048,576 replications x
+10,000 events per GPU, Philox seeds.  One "step" = Model::init + 10,000 executed scheduler actions of every
+replication of the batch (1.05e10 events per GPU).
+
+  python bench.py [--gpus N --steps K --warmup W]            # our arm (N>1: launched by torchrun, one rank per GPU)
+  python bench.py --impl reference [--gpus N ...]            # CPU arm: the oracle port of the reference engine on
+                                                             # all host cores, bounded sample of the same workload
+
+Prints ONE JSON line on rank 0.  See DESIGN.md "Measurement" for what every key means.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (builder kwargs, replications per GPU, events per replication)
+    "discrete_queue": ("discrete_queue", {}, 1048576, 10000),
+    "serial_line": ("serial_line", {"n_proc": 32}, 100000, 100000),
+    "haulage": ("haulage", {"n_src": 8, "per_queue": 8}, 262144, 10000),
+}
+
+
+def build_model(name):
+    from quokkasim_b200 import workloads
+
+    fn, kw, _, _ = WORKLOADS[name]
+    return getattr(workloads, fn)(**kw)
+
+
+# ----------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if f[5 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------------- CPU arm
+def oracle_model(model):
+    from oracle.lowering import lower_to_oracle  # bench.py's CPU legs are the one place the oracle is timed
+
+    return lower_to_oracle(model)[0]
+
+
+def time_oracle(om, n_reps, n_events, threads, log, base_seed=1234, rep0=0):
+    t = time.perf_counter()
+    total, _, status, _, _ = om.run_batch(base_seed, rep0, n_reps, n_events=n_events, log=log, threads=threads,
+                                          want_stats=False)
+    dt = time.perf_counter() - t
+    return total, dt, int((status != 0).sum())
+
+
+def cpu_baseline(model, n_events, log, target_s=12.0):
+    om = oracle_model(model)
+    threads = os.cpu_count() or 1
+    cal_reps = max(threads, 16)
+    total, dt, _ = time_oracle(om, cal_reps, n_events, threads, log)
+    rate = total / dt
+    reps = int(max(cal_reps, min(65536, target_s * rate / max(n_events, 1))))
+    reps = max(threads, reps // threads * threads)
+    total, dt, faulted = time_oracle(om, reps, n_events, threads, log)
+    return {"value": total / dt, "unit": "events/s", "cores": threads, "kind": "port",
+            "sample": "%d replications x %d events of the same model and Philox seeds (%.1f s), oracle/ C++ "
+                      "restatement of the reference CPU path, %d std::threads, logging %s"
+                      % (reps, n_events, dt, threads, "on" if log else "off"), "faulted": faulted}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path (oracle port; the Rust engine cannot be built here) on all host
+    threads, each step a bounded sample of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    model = build_model(args.workload)
+    _, _, reps_gpu, n_events = WORKLOADS[args.workload]
+    n_events = args.events or n_events
+    om = oracle_model(model)
+    threads = os.cpu_count() or 1
+    log = args.log != "off"
+    total, dt, _ = time_oracle(om, max(threads, 16), n_events, threads, log)
+    rate = total / dt
+    reps = int(max(threads, min(65536, args.ref_step_seconds * rate / n_events)))
+    reps = max(threads, reps // threads * threads)
+    for _ in range(args.warmup):
+        time_oracle(om, reps, n_events, threads, log)
+    t_sum, ev_sum = 0.0, 0
+    for _ in range(args.steps):
+        total, dt, _ = time_oracle(om, reps, n_events, threads, log)
+        t_sum += dt
+        ev_sum += total
+    value = ev_sum / t_sum
+    sample = ("each step = %d replications x %d events (bounded sample of the %d-replication workload), oracle port "
+              "of the reference CPU path on %d host threads" % (reps, n_events, reps_gpu * args.gpus, threads))
+    print(json.dumps({
+        "impl": "reference", "metric": "simulated events/sec", "value": value, "unit": "events/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_sum / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": workload_config(args, reps_gpu, n_events),
+        "cpu_baseline": {"value": value, "unit": "events/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def workload_config(args, reps_gpu, n_events):
+    return {"workload": "%s batched: %d replications per GPU x %d events, Philox4x32-10 seeds"
+                        % (args.workload, args.reps or reps_gpu, n_events),
+            "replications_per_gpu": args.reps or reps_gpu, "events_per_replication": n_events,
+            "logging": args.log, "log_ring_records": args.log_capacity if args.log != "off" else 0,
+            "l2": "state planes (>= 0.5 GB) and log rings are larger than the 126 MB L2; no flush needed"}
+
+
+# ----------------------------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from quokkasim_b200 import parallel
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; quokkasim_b200 has no CPU path (use --impl reference)")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    _, _, reps_gpu, n_events = WORKLOADS[args.workload]
+    reps_gpu = args.reps or reps_gpu
+    n_events = args.events or n_events
+    log_cap = args.log_capacity if args.log != "off" else 0
+    model = build_model(args.workload)
+    stream = torch.cuda.current_stream(device)
+
+    def new_sim(log_capacity):
+        return model.sim(None, reps_gpu, t0=0, base_seed=1234, rep_offset=rank * reps_gpu, log_capacity=log_capacity,
+                         threads_per_block=args.threads_per_block, stream=stream.cuda_stream)
+
+    sim = new_sim(log_cap)
+    sim._materialize()  # device state allocated; inputs (model tables, seeds) resident before the timed region
+    L, b = sim.L, sim._batch
+    state_bytes = sim.state_bytes()
+
+    def one_step():
+        L.qk_batch_init(b, 0)
+        L.qk_batch_step_events(b, n_events)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    for _ in range(args.warmup):
+        one_step()
+    barrier()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kernel_ms = []
+    ev0.record(stream)
+    for _ in range(args.steps):
+        one_step()
+        if args.per_launch_timing:
+            kernel_ms.append(sim.last_step_ms()[0])
+    ev1.record(stream)
+    barrier()
+    elapsed_ms = ev0.elapsed_time(ev1)
+    clk = clocks.stop() if rank == 0 else None
+    if not args.per_launch_timing:
+        kernel_ms.append(sim.last_step_ms()[0])  # the dominant kernel: last step launch, CUDA events on its stream
+    summ = sim.summary()
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=device)
+    ev_total = torch.tensor([summ["n_events"], summ["n_log_records"], summ["n_faulted"]], dtype=torch.int64,
+                            device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ev_total, op=dist.ReduceOp.SUM)
+    elapsed_ms = float(t.item())
+    events_per_step = int(ev_total[0].item())
+    records_per_step = int(ev_total[1].item())
+    value = events_per_step * args.steps / (elapsed_ms * 1e-3)
+
+    # ---- end to end through the public API with host buffers: build tables on the host, create the batch (H2D),
+    # init + step, reduce the summary statistics (NCCL when N>1), read them and a log sample back (D2H)
+    sim.close()
+    del sim
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    h2d = d2h = 0
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        s2 = new_sim(log_cap)
+        s2.step_events(n_events)
+        comp, n_ev, n_fault = parallel.allreduce_summary(s2, device)
+        sm2 = s2.summary()
+        d2h = s2.n_comp * (6 + 2 + 2 + 64) * 8 + 48
+        if log_cap:
+            for r in range(0, min(reps_gpu, args.e2e_log_reps)):
+                recs, _ = s2.read_log(r)
+                d2h += recs.nbytes + 4
+        h2d = s2.info()["table_bytes"] + 64  # model tables + batch config: the path's only host inputs
+        s2.close()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_value = events_per_step * e2e_steps / float(e2e_t.item())
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
+        # algorithmic bytes of one step launch on one GPU: B_alg = L + 2*S/K per event
+        ev_gpu = events_per_step / world
+        log_bytes = 32.0 * records_per_step / world if log_cap else 0.0
+        alg_bytes = log_bytes + 2.0 * state_bytes * reps_gpu
+        k_ms = sorted(kernel_ms)[len(kernel_ms) // 2]
+        achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+        out = {
+            "metric": "simulated events/sec", "value": value, "unit": "events/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": workload_config(args, reps_gpu, n_events),
+            "e2e": {"value": e2e_value, "unit": "events/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps},
+            "gpu_launches": 2 * args.steps,
+            "clocks": clk,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "kernel": "qk_step_kernel",
+                         "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                         "bytes_per_event": alg_bytes / ev_gpu, "state_bytes_per_replication": state_bytes,
+                         "events_per_residency_K": n_events},
+            "faulted_replications": int(ev_total[2].item()),
+            "per_gpu_events_per_s": value / world,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            out["cpu_baseline"] = cpu_baseline(model, n_events, log_cap != 0)
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="discrete_queue", choices=sorted(WORKLOADS))
+    ap.add_argument("--reps", type=int, default=0, help="replications per GPU (default: the workload's)")
+    ap.add_argument("--events", type=int, default=0, help="events per replication (default: the workload's)")
+    ap.add_argument("--log", default="ring", choices=["ring", "off"])
+    ap.add_argument("--log-capacity", type=int, default=64)
+    ap.add_argument("--threads-per-block", type=int, default=0)
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-log-reps", type=int, default=256)
+    ap.add_argument("--ref-step-seconds", type=float, default=6.0)
+    ap.add_argument("--per-launch-timing", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        sys.stderr.write("bench.py: note: the timing rules ask for >= 3 warm-up steps\n")
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

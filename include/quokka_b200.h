@@ -1,0 +1,269 @@
+/*
+ * quokka_b200.h -- C ABI of the B200 batched-replication executor for QuokkaSim models.
+ *
+ * This is the drop-in boundary for ONE hot path of jajetloh/quokkasim v0.2.2: advancing many
+ * independent replications of one stock-and-flow model in lockstep.  The reference has no FFI of
+ * its own; what its generated code binds is the NeXosim engine API.  Each entry point below names
+ * the reference call it replaces (paths relative to /root/reference/quokkasim/src unless noted):
+ *
+ *   qk_model_create / qk_model_add_component   <- ComponentModel::register_component ->
+ *                                                 SimInit::add_model         core.rs:1180-1196, 419-423
+ *   qk_model_set_dist                          <- with_process_time_distr / with_process_quantity_distr
+ *                                                 (quokkasim_derive_macros/src/lib.rs:73-78) with a
+ *                                                 Distribution built by DistributionFactory::create
+ *                                                                                      common.rs:73-148
+ *   qk_model_add_delay_mode                    <- with_delay_mode(DelayModeChange::Add) delays.rs:157-164
+ *   qk_model_connect                           <- connect_components!(&mut a,&mut b[,n]) core.rs:565-1178
+ *   qk_model_set_logged                        <- connect_logger!(&mut logger,&mut c)   core.rs:1303-1338
+ *   qk_model_schedule_env_state                <- create_scheduled_event!(SetEnvironmentState)
+ *                                                                                      core.rs:1393-1396
+ *   qk_batch_create + qk_batch_init            <- SimInit::init(t0) (one Simulation per replication)
+ *                                                 quokkasim_examples/src/bin/discrete_queue.rs:109
+ *   qk_batch_step_until / qk_batch_step_events <- Simulation::step_until / step   discrete_queue.rs:111
+ *   qk_batch_read_log                          <- Logger::get_buffer().into_reader()    core.rs:388-401
+ *   qk_batch_comp_stats / qk_batch_reduce_stats<- (no counterpart: the reference has no summaries;
+ *                                                 defined from the log records, DESIGN.md "Statistics")
+ *
+ * Conventions
+ *   - every function returns QK_OK (0) or a negative qk_status; qk_last_error() gives the
+ *     thread-local message of the last failure on the calling thread
+ *   - plain pointers and sizes only; host buffers are caller-owned and copied; the library owns
+ *     all device memory of a batch; *_destroy frees
+ *   - a qk_batch is single-owner (not thread-safe), like `&mut Simulation`
+ *   - there is NO CPU fallback: qk_batch_create fails with QK_ERR_NO_DEVICE without a CUDA device
+ *   - per-replication faults (the reference's panics, e.g. "Time until next event is zero!"
+ *     discrete.rs:541) never abort the batch; they freeze that replication and are reported in the
+ *     per-replication status array (qk_batch_read_status)
+ */
+#ifndef QUOKKA_B200_H
+#define QUOKKA_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QK_ABI_VERSION 1
+
+typedef enum {
+  QK_OK = 0,
+  QK_ERR_INVALID_ARG = -1,
+  QK_ERR_UNSUPPORTED_CONNECTION = -2, /* "No component connection defined from {} to {}" */
+  QK_ERR_PORT_IN_USE = -3,            /* second connection on a single-reply port */
+  QK_ERR_NO_DEVICE = -4,
+  QK_ERR_CUDA = -5,
+  QK_ERR_STATE = -6, /* call out of order (e.g. step before init) */
+  QK_ERR_CAPACITY = -7, /* model exceeds a compiled-in or shared-memory limit */
+  QK_ERR_BUFFER_TOO_SMALL = -8
+} qk_status;
+
+/* component kinds (ComponentModel variants, core.rs:505-557; the item/vector element type is not
+ * part of the kind: items are opaque 32-bit handles on the device) */
+typedef enum {
+  QK_DISCRETE_STOCK = 1,            /* DiscreteStock            discrete.rs:38-59   */
+  QK_DISCRETE_PROCESS = 2,          /* DiscreteProcess          discrete.rs:320-355 */
+  QK_DISCRETE_SOURCE = 3,           /* DiscreteSource           discrete.rs:689-723 */
+  QK_DISCRETE_SINK = 4,             /* DiscreteSink             discrete.rs:942-974 */
+  QK_DISCRETE_PARALLEL_PROCESS = 5, /* DiscreteParallelProcess  discrete.rs:1188-1224 */
+  QK_ENVIRONMENT = 6                /* BasicEnvironment         core.rs:218-226 */
+} qk_component_kind;
+
+/* DistributionConfig (common.rs:37-44) */
+typedef enum {
+  QK_DIST_CONSTANT = 0,    /* p0 = value */
+  QK_DIST_UNIFORM = 1,     /* p0 = min, p1 = max */
+  QK_DIST_TRIANGULAR = 2,  /* p0 = min, p1 = max, p2 = mode */
+  QK_DIST_NORMAL = 3,      /* p0 = mean, p1 = std */
+  QK_DIST_TRUNCNORMAL = 4, /* p0 = mean, p1 = std, p2 = min, p3 = max */
+  QK_DIST_EXPONENTIAL = 5  /* p0 = mean */
+} qk_dist_kind;
+
+typedef struct {
+  uint32_t kind;   /* qk_dist_kind */
+  uint32_t stream; /* the seed DistributionFactory::create would have given this instance
+                      (common.rs:76,83,97,120,133): instances with equal `stream` draw identical
+                      sequences, which reproduces the factory's seed sharing */
+  double p[4];
+} qk_dist_desc;
+
+typedef struct {
+  uint32_t kind;            /* qk_component_kind */
+  uint32_t low_capacity;    /* DiscreteStock.low_capacity (default 0)  discrete.rs:70 */
+  uint32_t max_capacity;    /* DiscreteStock.max_capacity (default 1)  discrete.rs:71 */
+  uint32_t n_initial_items; /* with_initial_resource(ItemDeque) length; handles are assigned by the library */
+  uint32_t capacity_hint;   /* 0 = derive. Stock: item-ring slots; ParallelProcess: in-flight slots */
+  uint32_t initial_env_state; /* BasicEnvironment::with_state: 0 Normal, 1 Stopped */
+} qk_component_desc;
+
+/* log records: one per `self.log(..)` call of a component (discrete.rs:235-251,566-582; core.rs:273-289) */
+typedef enum {
+  QK_LOG_PROCESS_START = 1,    /* payload = item handle */
+  QK_LOG_PROCESS_CONTINUE = 2, /* reason */
+  QK_LOG_PROCESS_FINISH = 3,   /* payload = item handle */
+  QK_LOG_PROCESS_NONSTART = 4, /* reason */
+  QK_LOG_PROCESS_STOPPED = 5,  /* reason */
+  QK_LOG_WITHDRAW_REQUEST = 6,
+  QK_LOG_DELAY_START = 7, /* payload = delay-mode index */
+  QK_LOG_DELAY_END = 8,
+  QK_LOG_STOCK_ADD = 16,          /* payload = item handle */
+  QK_LOG_STOCK_REMOVE = 17,       /* payload = item handle or QK_ITEM_NONE */
+  QK_LOG_STOCK_STATE_CHANGE = 18, /* reason = 0 Empty / 1 Normal / 2 Full; payload = occupied<<32 | empty */
+  QK_LOG_ENV_STATE = 24           /* reason = 0 Normal / 1 Stopped */
+} qk_log_kind;
+
+typedef enum {
+  QK_REASON_NONE = 0,
+  QK_REASON_UPSTREAM_EMPTY = 1,           /* "Upstream is empty" */
+  QK_REASON_UPSTREAM_NOT_CONNECTED = 2,   /* "Upstream is not connected" */
+  QK_REASON_DOWNSTREAM_FULL = 3,          /* "Downstream is full" */
+  QK_REASON_DOWNSTREAM_NOT_CONNECTED = 4, /* "Downstream is not connected" */
+  QK_REASON_UPSTREAM_NO_RESOURCE = 5,     /* "Upstream did not provide resource" */
+  QK_REASON_STOPPED_BY_ENV = 6,           /* "Stopped by environment" */
+  QK_REASON_RESUMED_BY_ENV = 7,           /* "Resumed by environment" */
+  QK_REASON_UPSTREAM_FULL = 8             /* "Upstream is full" (DiscreteParallelProcess, discrete.rs:1390) */
+} qk_reason;
+
+#define QK_SRC_INIT 0xFFFFu /* source_event_id "INIT_000000" (common.rs:14) */
+#define QK_SRC_SCH 0xFFFEu  /* source_event_id "SCH_000000"  (common.rs:18) */
+#define QK_ITEM_NONE 0xFFFFFFFFFFFFFFFFull
+/* item handle = (source ordinal << 26) | index; ordinal 63 = initial stock contents */
+#define QK_ITEM_SOURCE(h) ((uint32_t)(h) >> 26)
+#define QK_ITEM_INDEX(h) ((uint32_t)(h)&0x3FFFFFFu)
+
+typedef struct {
+  uint64_t time_ns;  /* absolute ns since MonotonicTime::EPOCH */
+  uint16_t comp;     /* component id (registration order) */
+  uint8_t kind;      /* qk_log_kind */
+  uint8_t reason;    /* qk_reason or state category */
+  uint32_t seq;      /* next_event_index at the time of the call: EventId = "{code}_{seq:06}" */
+  uint16_t src_comp; /* source_event_id component, or QK_SRC_INIT / QK_SRC_SCH */
+  uint16_t aux;      /* 0 (device-internal lane tag, cleared on read) */
+  uint32_t src_seq;
+  uint64_t payload;
+} qk_log_record; /* 32 bytes */
+
+/* per-replication fault codes */
+typedef enum {
+  QK_REP_OK = 0,
+  QK_REP_ZERO_DURATION = 1,  /* panic!("Time until next event is zero!") */
+  QK_REP_BAD_DURATION = 2,   /* Duration::from_secs_f64 panic (negative / NaN / overflow) */
+  QK_REP_TAPE_EXHAUSTED = 3, /* variate tape shorter than the number of sample() calls */
+  QK_REP_STOCK_OVERFLOW = 4, /* item ring full (stock capacity is advisory in the reference) */
+  QK_REP_EMIT_OVERFLOW = 5,  /* too many pending emit_change events on one stock */
+  QK_REP_PARALLEL_OVERFLOW = 6,
+  QK_REP_ITEM_INDEX_OVERFLOW = 7
+} qk_rep_status;
+
+/* per-component, per-replication summary (exact integers) */
+typedef struct {
+  uint64_t count;   /* process-like: ProcessFinish records ; stock: Add records */
+  uint64_t time_ns; /* process-like: busy ns (countdown actually consumed) ; stock: integral of occupancy, item*ns */
+  uint64_t aux;     /* process-like: ns spent in an active delay ; stock: maximum occupancy seen */
+  uint64_t level;   /* process-like: items in progress now ; stock: occupancy now */
+} qk_comp_stats;
+
+/* whole-batch reduction of qk_comp_stats over the replications of THIS batch (one GPU).
+ * sums are exact (128-bit as hi/lo); multi-GPU callers add the fields across ranks
+ * (NCCL sum over the u64 arrays, min/max on the extrema) -- see qk_batch_reduce_stats_device. */
+#define QK_HIST_BINS 32
+typedef struct {
+  uint64_t sum_count;
+  uint64_t sum_time_lo, sum_time_hi; /* 128-bit sum of time_ns = hi * 2^64 + lo */
+  uint64_t sum_level;
+  uint64_t min_count, max_count;
+  uint64_t min_time, max_time;
+  double sumsq_time; /* sum over replications of (time_ns * 1e-9)^2, fixed reduction order */
+  double sumsq_count;
+  uint64_t hist_time[QK_HIST_BINS]; /* replications binned on time_ns over [hist_lo_time, hist_hi_time] */
+  uint64_t hist_count[QK_HIST_BINS];
+  uint64_t hist_lo_time, hist_hi_time, hist_lo_count, hist_hi_count;
+} qk_comp_summary;
+
+typedef struct {
+  uint64_t n_reps;
+  uint64_t n_events;   /* executed scheduler actions, all replications */
+  uint64_t n_faulted;  /* replications with status != QK_REP_OK */
+  uint64_t n_log_records;
+  uint64_t min_now_ns, max_now_ns;
+} qk_batch_summary;
+
+typedef struct qk_model qk_model;
+typedef struct qk_batch qk_batch;
+
+/* ---- model description (host only) ---------------------------------------------------------- */
+int qk_abi_version(void);
+int qk_model_create(qk_model** out);
+void qk_model_destroy(qk_model*);
+/* registration order = component id = scheduler origin rank - 1 */
+int qk_model_add_component(qk_model*, const qk_component_desc*, uint32_t* out_id);
+/* which: 0 = process_time_distr, 1 = process_quantity_distr; out_dist_id identifies the instance for tapes */
+int qk_model_set_dist(qk_model*, uint32_t comp, uint32_t which, const qk_dist_desc*, uint32_t* out_dist_id);
+int qk_model_add_delay_mode(qk_model*, uint32_t comp, const qk_dist_desc* until_delay, const qk_dist_desc* until_fix,
+                            uint32_t* out_until_delay_id, uint32_t* out_until_fix_id);
+/* port_n = -1 for None */
+int qk_model_connect(qk_model*, uint32_t a, uint32_t b, int32_t port_n);
+int qk_model_set_logged(qk_model*, uint32_t comp, int enabled);
+int qk_model_schedule_env_state(qk_model*, uint64_t t_ns, uint32_t env, uint32_t state);
+int qk_model_n_components(const qk_model*, uint32_t* out);
+int qk_model_n_dists(const qk_model*, uint32_t* out);
+/* bytes of on-chip state one replication needs (for capacity planning / roofline arithmetic) */
+int qk_model_state_bytes(const qk_model*, int with_log, uint32_t* out_bytes);
+
+/* ---- batch of replications on one GPU -------------------------------------------------------- */
+typedef struct {
+  uint64_t n_reps;
+  uint64_t rep_offset;   /* global index of this batch's first replication (Philox counter words 0,1) */
+  uint64_t base_seed;    /* Philox key */
+  int32_t device;        /* CUDA device ordinal */
+  uint32_t log_capacity; /* records kept per replication (ring, power of two); 0 = logging off */
+  uint32_t threads_per_block; /* 0 = choose */
+  uint32_t flags;        /* reserved, 0 */
+  void* stream;          /* cudaStream_t to launch on, NULL = the library creates its own */
+} qk_batch_config;
+
+/* launch geometry and memory footprint chosen for a batch (for roofline arithmetic and capacity planning) */
+typedef struct {
+  uint32_t threads_per_block, grid_blocks, shared_bytes_per_block, table_bytes;
+  uint32_t slots64, slots32;         /* per-replication state: slots64 * 8 + slots32 * 4 bytes */
+  uint32_t state_bytes_per_rep;
+  uint32_t resident_blocks_per_sm;   /* occupancy of the step kernel as reported by the CUDA runtime */
+  uint64_t replications_padded;
+  uint64_t state_bytes_total, log_bytes_total;
+} qk_batch_info;
+
+int qk_batch_create(const qk_model*, const qk_batch_config*, qk_batch** out);
+int qk_batch_info_get(qk_batch*, qk_batch_info* out);
+void qk_batch_destroy(qk_batch*);
+/* pre-drawn variate tape for one distribution instance: values[rep * per_rep_len + i], host pointer, copied */
+int qk_batch_set_tape(qk_batch*, uint32_t dist_id, const double* values, uint64_t per_rep_len);
+/* Model::init of every component at t0 (registration order) */
+int qk_batch_init(qk_batch*, uint64_t t0_ns);
+int qk_batch_step_until(qk_batch*, uint64_t t_ns);
+int qk_batch_step_events(qk_batch*, uint64_t n_events);
+int qk_batch_synchronize(qk_batch*);
+
+/* ---- results ------------------------------------------------------------------------------------ */
+int qk_batch_summary_get(qk_batch*, qk_batch_summary* out);
+int qk_batch_read_status(qk_batch*, uint64_t rep0, uint64_t n, uint32_t* status, uint64_t* now_ns, uint64_t* n_events);
+int qk_batch_comp_stats(qk_batch*, uint64_t rep0, uint64_t n, uint32_t comp, qk_comp_stats* out);
+int qk_batch_reduce_stats(qk_batch*, qk_comp_summary* out, uint32_t n_comp);
+/* device-resident variant for multi-GPU: fills caller-provided DEVICE arrays so that the caller can
+ * all-reduce them (NCCL) without a host round trip. sums: [n_comp][6] u64 (count, time_lo, time_hi, level,
+ * n_events(comp 0 only), n_faulted(comp 0 only)); extrema: [n_comp][4] u64 (min_count, min_time, then
+ * ~max_count, ~max_time so that one MIN all-reduce serves both). */
+int qk_batch_reduce_stats_device(qk_batch*, uint64_t* d_sums, uint64_t* d_extrema, uint32_t n_comp);
+/* histograms over caller-supplied global ranges (after the extrema all-reduce): d_hist [n_comp][2][QK_HIST_BINS] */
+int qk_batch_histograms_device(qk_batch*, const uint64_t* d_extrema, uint64_t* d_hist, uint32_t n_comp);
+/* records of one replication, oldest first (at most log_capacity newest); *n_total = records ever written */
+int qk_batch_read_log(qk_batch*, uint64_t rep, qk_log_record* buf, uint64_t cap, uint64_t* n_out, uint64_t* n_total);
+/* discrete stock contents in FIFO order */
+int qk_batch_read_stock(qk_batch*, uint64_t rep, uint32_t comp, uint32_t* items, uint64_t cap, uint64_t* n_out);
+/* timing of the last step call measured with CUDA events on the batch's stream (ms) and kernels launched */
+int qk_batch_last_step_ms(qk_batch*, float* ms, uint32_t* n_launches);
+
+const char* qk_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QUOKKA_B200_H */

@@ -1,0 +1,36 @@
+"""Lower a model built with the mirrored builder API (quokkasim_b200.api objects) into oracle rows.
+
+TEST INFRASTRUCTURE (like everything under oracle/): duck-typed so that it does not import the product.
+Used by tests/, __graft_entry__.smoke() and bench.py's CPU legs only.
+"""
+from . import oracle as O
+
+
+def lower_to_oracle(model):
+    """Returns (OracleModel, {id(Distribution): [oracle distribution-instance ids]})."""
+    om = O.OracleModel()
+    dist_ids = {}
+    comps = [c.component for c in model.components]
+    index = {id(c): i for i, c in enumerate(comps)}
+    for c in comps:
+        if c.KIND == O.DISCRETE_STOCK:
+            i = om.add_component(c.KIND, c.low_capacity, c.max_capacity, len(c.resource))
+        else:
+            i = om.add_component(c.KIND)
+        assert i == index[id(c)]
+        if hasattr(c, "process_time_distr"):
+            for which, d in ((0, c.process_time_distr), (1, c.process_quantity_distr)):
+                did = om.set_dist(i, which, O.make_dist(d.kind, d.stream, d.params))
+                dist_ids.setdefault(id(d), []).append(did)
+            for dm in c.delay_modes:
+                ud, uf = dm.until_delay_distr, dm.until_fix_distr
+                _, a, b = om.add_delay_mode(i, O.make_dist(ud.kind, ud.stream, ud.params),
+                                            O.make_dist(uf.kind, uf.stream, uf.params))
+                dist_ids.setdefault(id(ud), []).append(a)
+                dist_ids.setdefault(id(uf), []).append(b)
+    conns = sorted((x for c in comps for x in c._conns), key=lambda x: x[0])
+    for _, a, b, n in conns:
+        om.connect(index[id(a)], index[id(b)], n)
+    for t, env, state in model.ext:
+        om.schedule_env(t, index[id(env.component)], state)
+    return om, dist_ids

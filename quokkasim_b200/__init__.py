@@ -1,0 +1,17 @@
+"""quokkasim_b200 -- B200-native batched-replication executor for QuokkaSim stock-and-flow models.
+
+Host-side mirror of the reference's model-builder API (api.py) over a C-ABI shared library
+(libquokka_b200.so, include/quokka_b200.h) whose hot path is hand-written sm_100a CUDA.
+There is no CPU execution path in this package.
+"""
+from .api import (  # noqa: F401
+    BasicEnvironment, BasicEnvironmentLogger, BasicEnvironmentState, BatchedSimInit, BatchedSimulation,
+    ComponentConnectionError, ComponentLogger, ComponentModel, ComponentModelAddress, DelayMode, DelayModeChange,
+    DiscreteParallelProcess, DiscreteProcess, DiscreteProcessLogger, DiscreteSink, DiscreteSource, DiscreteStock,
+    DiscreteStockLogger, Distribution, DistributionConfig, DistributionFactory, DistributionParametersError, Duration,
+    ItemDeque, Mailbox, MonotonicTime, ScheduledEvent, ScheduledEventConfig, Scheduler, StringItemFactory,
+    connect_components, connect_logger, create_scheduled_event, register_component,
+)
+from ._capi import QkError  # noqa: F401
+
+__version__ = "0.1.0"

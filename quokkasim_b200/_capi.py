@@ -1,0 +1,161 @@
+"""ctypes binding of include/quokka_b200.h (the C-ABI shared library with the sm_100a kernels).
+
+There is no CPU fallback: if libquokka_b200.so is missing this module raises at load time, and every
+batch call fails loudly when no CUDA device is present (QK_ERR_NO_DEVICE).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+DEFAULT_LIB = os.path.join(_HERE, "libquokka_b200.so")
+
+# qk_component_kind
+DISCRETE_STOCK, DISCRETE_PROCESS, DISCRETE_SOURCE, DISCRETE_SINK, DISCRETE_PARALLEL_PROCESS, ENVIRONMENT = 1, 2, 3, 4, 5, 6
+# qk_dist_kind
+DIST_CONSTANT, DIST_UNIFORM, DIST_TRIANGULAR, DIST_NORMAL, DIST_TRUNCNORMAL, DIST_EXPONENTIAL = 0, 1, 2, 3, 4, 5
+# qk_log_kind
+LOG_PROCESS_START, LOG_PROCESS_CONTINUE, LOG_PROCESS_FINISH, LOG_PROCESS_NONSTART = 1, 2, 3, 4
+LOG_PROCESS_STOPPED, LOG_WITHDRAW_REQUEST, LOG_DELAY_START, LOG_DELAY_END = 5, 6, 7, 8
+LOG_STOCK_ADD, LOG_STOCK_REMOVE, LOG_STOCK_STATE_CHANGE, LOG_ENV_STATE = 16, 17, 18, 24
+SRC_INIT, SRC_SCH = 0xFFFF, 0xFFFE
+ITEM_NONE = 0xFFFFFFFFFFFFFFFF
+HIST_BINS = 32
+TIME_NONE = 0xFFFFFFFFFFFFFFFF
+
+STATUS_NAMES = {
+    0: "QK_OK", -1: "QK_ERR_INVALID_ARG", -2: "QK_ERR_UNSUPPORTED_CONNECTION", -3: "QK_ERR_PORT_IN_USE",
+    -4: "QK_ERR_NO_DEVICE", -5: "QK_ERR_CUDA", -6: "QK_ERR_STATE", -7: "QK_ERR_CAPACITY",
+    -8: "QK_ERR_BUFFER_TOO_SMALL",
+}
+
+# every symbol include/quokka_b200.h declares (tests check the library exports all of them)
+EXPORTED_SYMBOLS = [
+    "qk_abi_version", "qk_model_create", "qk_model_destroy", "qk_model_add_component", "qk_model_set_dist",
+    "qk_model_add_delay_mode", "qk_model_connect", "qk_model_set_logged", "qk_model_schedule_env_state",
+    "qk_model_n_components", "qk_model_n_dists", "qk_model_state_bytes", "qk_batch_create", "qk_batch_destroy",
+    "qk_batch_info_get",
+    "qk_batch_set_tape", "qk_batch_init", "qk_batch_step_until", "qk_batch_step_events", "qk_batch_synchronize",
+    "qk_batch_summary_get", "qk_batch_read_status", "qk_batch_comp_stats", "qk_batch_reduce_stats",
+    "qk_batch_reduce_stats_device", "qk_batch_histograms_device", "qk_batch_read_log", "qk_batch_read_stock",
+    "qk_batch_last_step_ms", "qk_last_error",
+]
+
+
+class QkError(RuntimeError):
+    """A failed C-ABI call; .status is the qk_status, the message is qk_last_error()."""
+
+    def __init__(self, status, msg):
+        super().__init__("%s: %s" % (STATUS_NAMES.get(status, status), msg))
+        self.status = status
+        self.detail = msg
+
+
+class DistDesc(C.Structure):
+    _fields_ = [("kind", C.c_uint32), ("stream", C.c_uint32), ("p", C.c_double * 4)]
+
+
+class ComponentDesc(C.Structure):
+    _fields_ = [
+        ("kind", C.c_uint32), ("low_capacity", C.c_uint32), ("max_capacity", C.c_uint32),
+        ("n_initial_items", C.c_uint32), ("capacity_hint", C.c_uint32), ("initial_env_state", C.c_uint32),
+    ]
+
+
+class BatchConfig(C.Structure):
+    _fields_ = [
+        ("n_reps", C.c_uint64), ("rep_offset", C.c_uint64), ("base_seed", C.c_uint64), ("device", C.c_int32),
+        ("log_capacity", C.c_uint32), ("threads_per_block", C.c_uint32), ("flags", C.c_uint32), ("stream", C.c_void_p),
+    ]
+
+
+class BatchSummary(C.Structure):
+    _fields_ = [
+        ("n_reps", C.c_uint64), ("n_events", C.c_uint64), ("n_faulted", C.c_uint64), ("n_log_records", C.c_uint64),
+        ("min_now_ns", C.c_uint64), ("max_now_ns", C.c_uint64),
+    ]
+
+
+class BatchInfo(C.Structure):
+    _fields_ = [
+        ("threads_per_block", C.c_uint32), ("grid_blocks", C.c_uint32), ("shared_bytes_per_block", C.c_uint32),
+        ("table_bytes", C.c_uint32), ("slots64", C.c_uint32), ("slots32", C.c_uint32),
+        ("state_bytes_per_rep", C.c_uint32), ("resident_blocks_per_sm", C.c_uint32),
+        ("replications_padded", C.c_uint64), ("state_bytes_total", C.c_uint64), ("log_bytes_total", C.c_uint64),
+    ]
+
+
+LOG_DTYPE = np.dtype(
+    [("time_ns", "<u8"), ("comp", "<u2"), ("kind", "u1"), ("reason", "u1"), ("seq", "<u4"), ("src_comp", "<u2"),
+     ("aux", "<u2"), ("src_seq", "<u4"), ("payload", "<u8")]
+)
+COMP_STATS_DTYPE = np.dtype([("count", "<u8"), ("time_ns", "<u8"), ("aux", "<u8"), ("level", "<u8")])
+COMP_SUMMARY_DTYPE = np.dtype(
+    [("sum_count", "<u8"), ("sum_time_lo", "<u8"), ("sum_time_hi", "<u8"), ("sum_level", "<u8"),
+     ("min_count", "<u8"), ("max_count", "<u8"), ("min_time", "<u8"), ("max_time", "<u8"),
+     ("sumsq_time", "<f8"), ("sumsq_count", "<f8"), ("hist_time", "<u8", (HIST_BINS,)),
+     ("hist_count", "<u8", (HIST_BINS,)), ("hist_lo_time", "<u8"), ("hist_hi_time", "<u8"),
+     ("hist_lo_count", "<u8"), ("hist_hi_count", "<u8")]
+)
+assert LOG_DTYPE.itemsize == 32 and COMP_STATS_DTYPE.itemsize == 32
+
+_LIBS = {}
+
+
+def load_library(path=None):
+    """Load the C-ABI library (default: the in-tree libquokka_b200.so) and declare its signatures."""
+    path = os.path.abspath(path or DEFAULT_LIB)
+    if path in _LIBS:
+        return _LIBS[path]
+    if not os.path.exists(path):
+        raise ImportError(
+            "%s not found: build it with `python -m quokkasim_b200.build` (nvcc, sm_100a). "
+            "quokkasim_b200 has no CPU fallback." % path
+        )
+    L = C.CDLL(path)
+    vp, u32, u64, i32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int32
+    P = C.POINTER
+    sig = {
+        "qk_abi_version": (C.c_int, []),
+        "qk_model_create": (C.c_int, [P(vp)]),
+        "qk_model_destroy": (None, [vp]),
+        "qk_model_add_component": (C.c_int, [vp, P(ComponentDesc), P(u32)]),
+        "qk_model_set_dist": (C.c_int, [vp, u32, u32, P(DistDesc), P(u32)]),
+        "qk_model_add_delay_mode": (C.c_int, [vp, u32, P(DistDesc), P(DistDesc), P(u32), P(u32)]),
+        "qk_model_connect": (C.c_int, [vp, u32, u32, i32]),
+        "qk_model_set_logged": (C.c_int, [vp, u32, C.c_int]),
+        "qk_model_schedule_env_state": (C.c_int, [vp, u64, u32, u32]),
+        "qk_model_n_components": (C.c_int, [vp, P(u32)]),
+        "qk_model_n_dists": (C.c_int, [vp, P(u32)]),
+        "qk_model_state_bytes": (C.c_int, [vp, C.c_int, P(u32)]),
+        "qk_batch_create": (C.c_int, [vp, P(BatchConfig), P(vp)]),
+        "qk_batch_destroy": (None, [vp]),
+        "qk_batch_info_get": (C.c_int, [vp, P(BatchInfo)]),
+        "qk_batch_set_tape": (C.c_int, [vp, u32, vp, u64]),
+        "qk_batch_init": (C.c_int, [vp, u64]),
+        "qk_batch_step_until": (C.c_int, [vp, u64]),
+        "qk_batch_step_events": (C.c_int, [vp, u64]),
+        "qk_batch_synchronize": (C.c_int, [vp]),
+        "qk_batch_summary_get": (C.c_int, [vp, P(BatchSummary)]),
+        "qk_batch_read_status": (C.c_int, [vp, u64, u64, vp, vp, vp]),
+        "qk_batch_comp_stats": (C.c_int, [vp, u64, u64, u32, vp]),
+        "qk_batch_reduce_stats": (C.c_int, [vp, vp, u32]),
+        "qk_batch_reduce_stats_device": (C.c_int, [vp, vp, vp, u32]),
+        "qk_batch_histograms_device": (C.c_int, [vp, vp, vp, u32]),
+        "qk_batch_read_log": (C.c_int, [vp, u64, vp, u64, P(u64), P(u64)]),
+        "qk_batch_read_stock": (C.c_int, [vp, u64, u32, vp, u64, P(u64)]),
+        "qk_batch_last_step_ms": (C.c_int, [vp, P(C.c_float), P(u32)]),
+        "qk_last_error": (C.c_char_p, []),
+    }
+    for name, (res, args) in sig.items():
+        f = getattr(L, name)
+        f.restype = res
+        f.argtypes = args
+    _LIBS[path] = L
+    return L
+
+
+def check(L, rc):
+    if rc != 0:
+        raise QkError(rc, (L.qk_last_error() or b"").decode("utf-8", "replace"))

@@ -1,0 +1,670 @@
+/*
+ * qk_batch.cu -- batch lifecycle behind the C ABI: device memory, kernel launches, result read-back and the
+ * per-GPU summary reduction.  One qk_batch == the replications [rep_offset, rep_offset + n_reps) on ONE GPU;
+ * multi-GPU runs are one process (and one qk_batch) per GPU, the only cross-GPU step being an all-reduce of
+ * the small arrays filled by qk_batch_reduce_stats_device (done by the caller with NCCL).
+ *
+ * Replaces SimInit::init + Simulation::step_until for the batched path
+ * (/root/reference/quokkasim_examples/src/bin/discrete_queue.rs:109-111).
+ */
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "qk_kernels.cuh"
+#include "qk_model.h"
+
+#define CUDA_TRY(expr)                                                                    \
+  do {                                                                                    \
+    cudaError_t _e = (expr);                                                              \
+    if (_e != cudaSuccess) {                                                              \
+      qk_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return QK_ERR_CUDA;                                                                 \
+    }                                                                                     \
+  } while (0)
+
+struct qk_batch {
+  qk_batch_config cfg;
+  QkLowered low;
+  bool log;
+  uint32_t nt, grid, smem_bytes, table_bytes_padded;
+  uint64_t rep_pad;
+  uint64_t* g64;
+  uint32_t* g32;
+  uint8_t* d_tables;
+  uint4* d_log;
+  std::vector<double*> h_tapes; /* device pointers, host copy */
+  std::vector<uint64_t> h_tape_len;
+  const double** d_tapes;
+  uint64_t* d_tape_len;
+  bool any_tape;
+  cudaStream_t stream;
+  bool own_stream;
+  cudaEvent_t ev0, ev1;
+  bool initialised;
+  float last_ms;
+  uint32_t last_launches;
+  uint64_t total_launches;
+  /* reduction scratch */
+  uint64_t* d_sums;
+  uint64_t* d_ext;
+  uint64_t* d_hist;
+  double* d_sq_partial;
+  double* d_sq;
+  uint32_t red_blocks;
+};
+
+static uint32_t choose_nt(uint32_t per_rep_bytes, uint32_t table_bytes, uint32_t* threads_per_sm) {
+  uint32_t best_nt = 0, best_thr = 0;
+  for (uint32_t nt = 256; nt >= 32; nt -= 32) {
+    const uint64_t bytes = (uint64_t)table_bytes + (uint64_t)per_rep_bytes * nt;
+    if (bytes > 227u * 1024u) continue;
+    uint32_t bps = (uint32_t)((228u * 1024u) / (bytes + 1024u));
+    if (bps > 32) bps = 32;
+    uint32_t thr = bps * nt;
+    if (thr > 2048) thr = 2048;
+    if (thr > best_thr) {
+      best_thr = thr;
+      best_nt = nt;
+    }
+  }
+  if (threads_per_sm) *threads_per_sm = best_thr;
+  return best_nt;
+}
+
+static int launch_step(qk_batch* b, uint32_t do_init, uint64_t t0, uint64_t t_until, uint64_t budget) {
+  KParams P;
+  memset(&P, 0, sizeof(P));
+  P.g64 = b->g64;
+  P.g32 = b->g32;
+  P.tables = b->d_tables;
+  P.table_bytes = b->table_bytes_padded;
+  P.n64 = b->low.hdr.n64;
+  P.n32 = b->low.hdr.n32;
+  P.n_reps = b->cfg.n_reps;
+  P.rep_pad = b->rep_pad;
+  P.rep_offset = b->cfg.rep_offset;
+  P.seed = b->cfg.base_seed;
+  P.log = b->d_log;
+  P.log_cap = b->log ? b->cfg.log_capacity : 0;
+  P.tapes = b->any_tape ? b->d_tapes : nullptr;
+  P.tape_len = b->d_tape_len;
+  P.t0 = t0;
+  P.t_until = t_until;
+  P.event_budget = budget;
+  P.do_init = do_init;
+  CUDA_TRY(cudaEventRecord(b->ev0, b->stream));
+  if (b->log)
+    qk_step_kernel<true><<<b->grid, b->nt, b->smem_bytes, b->stream>>>(P);
+  else
+    qk_step_kernel<false><<<b->grid, b->nt, b->smem_bytes, b->stream>>>(P);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaEventRecord(b->ev1, b->stream));
+  b->last_launches = 1;
+  b->total_launches += 1;
+  return QK_OK;
+}
+
+/* ================================= per-GPU summary reduction ================================= */
+
+__global__ void qk_comp_stats_kernel(const uint8_t* tables, const uint64_t* g64, const uint32_t* g32,
+                                     uint64_t rep_pad, uint64_t rep0, uint64_t n, uint32_t comp, qk_comp_stats* out) {
+  const DevHeader* h = reinterpret_cast<const DevHeader*>(tables);
+  const DevComp* c = reinterpret_cast<const DevComp*>(tables + h->off_comps) + comp;
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) qk_comp_stats_dev(c, g64, g32, rep_pad, rep0 + i, &out[i]);
+}
+
+__device__ __forceinline__ uint64_t warp_sum_u64(uint64_t v) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+  return v;
+}
+__device__ __forceinline__ uint64_t warp_min_u64(uint64_t v) {
+  for (int o = 16; o > 0; o >>= 1) {
+    const uint64_t w = __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    v = w < v ? w : v;
+  }
+  return v;
+}
+__device__ __forceinline__ double warp_sum_f64(double v) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+  return v;
+}
+
+/* grid = (red_blocks, n_comp).  sums[c] = {count, time_lo32 sum, time_hi32 sum, level, n_events, n_faulted};
+ * ext[c] = {min_count, min_time, ~max_count, ~max_time}; sq_partial[c][block] = {sum t^2, sum count^2} */
+__global__ void __launch_bounds__(256) qk_reduce_kernel(const uint8_t* tables, const uint64_t* g64,
+                                                        const uint32_t* g32, uint64_t rep_pad, uint64_t n_reps,
+                                                        uint64_t* sums, uint64_t* ext, double* sq_partial) {
+  const DevHeader* h = reinterpret_cast<const DevHeader*>(tables);
+  const uint32_t comp = blockIdx.y;
+  const DevComp* c = reinterpret_cast<const DevComp*>(tables + h->off_comps) + comp;
+  uint64_t a[6] = {0, 0, 0, 0, 0, 0};
+  uint64_t mn[4] = {~0ull, ~0ull, ~0ull, ~0ull};
+  double sq[2] = {0.0, 0.0};
+  for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_reps; r += (uint64_t)gridDim.x * blockDim.x) {
+    qk_comp_stats s;
+    qk_comp_stats_dev(c, g64, g32, rep_pad, r, &s);
+    a[0] += s.count;
+    a[1] += s.time_ns & 0xFFFFFFFFull;
+    a[2] += s.time_ns >> 32;
+    a[3] += s.level;
+    if (comp == 0) {
+      a[4] += g64[(size_t)G64_NEVENTS * rep_pad + r];
+      a[5] += g32[(size_t)G32_STATUS * rep_pad + r] ? 1 : 0;
+    }
+    mn[0] = s.count < mn[0] ? s.count : mn[0];
+    mn[1] = s.time_ns < mn[1] ? s.time_ns : mn[1];
+    mn[2] = ~s.count < mn[2] ? ~s.count : mn[2];
+    mn[3] = ~s.time_ns < mn[3] ? ~s.time_ns : mn[3];
+    const double ts = (double)s.time_ns * 1e-9;
+    sq[0] += ts * ts;
+    sq[1] += (double)s.count * (double)s.count;
+  }
+  __shared__ uint64_t sh_a[8][6];
+  __shared__ uint64_t sh_m[8][4];
+  __shared__ double sh_q[8][2];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int k = 0; k < 6; ++k) {
+    const uint64_t v = warp_sum_u64(a[k]);
+    if (lane == 0) sh_a[wid][k] = v;
+  }
+  for (int k = 0; k < 4; ++k) {
+    const uint64_t v = warp_min_u64(mn[k]);
+    if (lane == 0) sh_m[wid][k] = v;
+  }
+  for (int k = 0; k < 2; ++k) {
+    const double v = warp_sum_f64(sq[k]);
+    if (lane == 0) sh_q[wid][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int nw = blockDim.x >> 5;
+    for (int k = 0; k < 6; ++k) {
+      uint64_t v = 0;
+      for (int w = 0; w < nw; ++w) v += sh_a[w][k];
+      atomicAdd((unsigned long long*)&sums[comp * 6 + k], (unsigned long long)v);
+    }
+    for (int k = 0; k < 4; ++k) {
+      uint64_t v = ~0ull;
+      for (int w = 0; w < nw; ++w) v = sh_m[w][k] < v ? sh_m[w][k] : v;
+      atomicMin((unsigned long long*)&ext[comp * 4 + k], (unsigned long long)v);
+    }
+    for (int k = 0; k < 2; ++k) {
+      double v = 0;
+      for (int w = 0; w < nw; ++w) v += sh_q[w][k];
+      sq_partial[((size_t)comp * gridDim.x + blockIdx.x) * 2 + k] = v;
+    }
+  }
+}
+
+/* fixed-order final sum of the per-block partials: deterministic fp64 result */
+__global__ void qk_reduce_sq_kernel(const double* sq_partial, uint32_t n_blocks, double* sq) {
+  const uint32_t comp = blockIdx.x;
+  if (threadIdx.x < 2) {
+    double v = 0;
+    for (uint32_t b = 0; b < n_blocks; ++b) v += sq_partial[((size_t)comp * n_blocks + b) * 2 + threadIdx.x];
+    sq[comp * 2 + threadIdx.x] = v;
+  }
+}
+
+/* hist[c][0][bin] over time_ns, hist[c][1][bin] over count; ranges from ext (min, ~max) */
+__global__ void __launch_bounds__(256) qk_hist_kernel(const uint8_t* tables, const uint64_t* g64, const uint32_t* g32,
+                                                      uint64_t rep_pad, uint64_t n_reps, const uint64_t* ext,
+                                                      uint64_t* hist) {
+  const DevHeader* h = reinterpret_cast<const DevHeader*>(tables);
+  const uint32_t comp = blockIdx.y;
+  const DevComp* c = reinterpret_cast<const DevComp*>(tables + h->off_comps) + comp;
+  __shared__ unsigned long long sh[2][QK_HIST_BINS];
+  if (threadIdx.x < 2 * QK_HIST_BINS) sh[threadIdx.x / QK_HIST_BINS][threadIdx.x % QK_HIST_BINS] = 0;
+  __syncthreads();
+  const uint64_t lo_c = ext[comp * 4 + 0], lo_t = ext[comp * 4 + 1];
+  const uint64_t hi_c = ~ext[comp * 4 + 2], hi_t = ~ext[comp * 4 + 3];
+  const uint64_t w_c = (hi_c - lo_c) / QK_HIST_BINS + 1, w_t = (hi_t - lo_t) / QK_HIST_BINS + 1;
+  for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_reps; r += (uint64_t)gridDim.x * blockDim.x) {
+    qk_comp_stats s;
+    qk_comp_stats_dev(c, g64, g32, rep_pad, r, &s);
+    if (s.time_ns >= lo_t && s.time_ns <= hi_t) atomicAdd(&sh[0][(s.time_ns - lo_t) / w_t], 1ull);
+    if (s.count >= lo_c && s.count <= hi_c) atomicAdd(&sh[1][(s.count - lo_c) / w_c], 1ull);
+  }
+  __syncthreads();
+  if (threadIdx.x < 2 * QK_HIST_BINS) {
+    const unsigned long long v = sh[threadIdx.x / QK_HIST_BINS][threadIdx.x % QK_HIST_BINS];
+    if (v) atomicAdd((unsigned long long*)&hist[(size_t)comp * 2 * QK_HIST_BINS + threadIdx.x], v);
+  }
+}
+
+__global__ void qk_batch_summary_kernel(const uint64_t* g64, const uint32_t* g32, uint64_t rep_pad, uint64_t n_reps,
+                                        uint64_t* out /* n_events, n_faulted, n_log, min_now, ~max_now */) {
+  uint64_t ev = 0, fa = 0, lg = 0, mn = ~0ull, mx = ~0ull;
+  for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_reps; r += (uint64_t)gridDim.x * blockDim.x) {
+    ev += g64[(size_t)G64_NEVENTS * rep_pad + r];
+    fa += g32[(size_t)G32_STATUS * rep_pad + r] ? 1 : 0;
+    lg += g32[(size_t)G32_LOGCNT * rep_pad + r];
+    const uint64_t now = g64[(size_t)G64_NOW * rep_pad + r];
+    mn = now < mn ? now : mn;
+    mx = ~now < mx ? ~now : mx;
+  }
+  ev = warp_sum_u64(ev);
+  fa = warp_sum_u64(fa);
+  lg = warp_sum_u64(lg);
+  mn = warp_min_u64(mn);
+  mx = warp_min_u64(mx);
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd((unsigned long long*)&out[0], (unsigned long long)ev);
+    atomicAdd((unsigned long long*)&out[1], (unsigned long long)fa);
+    atomicAdd((unsigned long long*)&out[2], (unsigned long long)lg);
+    atomicMin((unsigned long long*)&out[3], (unsigned long long)mn);
+    atomicMin((unsigned long long*)&out[4], (unsigned long long)mx);
+  }
+}
+
+/* ============================================ C ABI ============================================ */
+extern "C" {
+
+int qk_batch_create(const qk_model* m, const qk_batch_config* cfg, qk_batch** out) {
+  if (!m || !cfg || !out) {
+    qk_set_error("qk_batch_create: NULL argument");
+    return QK_ERR_INVALID_ARG;
+  }
+  if (cfg->n_reps == 0) {
+    qk_set_error("qk_batch_create: n_reps must be > 0");
+    return QK_ERR_INVALID_ARG;
+  }
+  if (cfg->log_capacity && (cfg->log_capacity & (cfg->log_capacity - 1))) {
+    qk_set_error("qk_batch_create: log_capacity must be a power of two");
+    return QK_ERR_INVALID_ARG;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    qk_set_error("qk_batch_create: no CUDA device (this library has no CPU fallback)");
+    return QK_ERR_NO_DEVICE;
+  }
+  if (cfg->device < 0 || cfg->device >= ndev) {
+    qk_set_error("qk_batch_create: device %d out of range (%d devices)", cfg->device, ndev);
+    return QK_ERR_INVALID_ARG;
+  }
+  CUDA_TRY(cudaSetDevice(cfg->device));
+  qk_batch* b = new qk_batch();
+  memset(&b->cfg, 0, sizeof(b->cfg));
+  b->cfg = *cfg;
+  b->log = cfg->log_capacity != 0;
+  b->g64 = nullptr;
+  b->g32 = nullptr;
+  b->d_tables = nullptr;
+  b->d_log = nullptr;
+  b->d_tapes = nullptr;
+  b->d_tape_len = nullptr;
+  b->any_tape = false;
+  b->stream = nullptr;
+  b->own_stream = false;
+  b->ev0 = b->ev1 = nullptr;
+  b->initialised = false;
+  b->last_ms = 0;
+  b->last_launches = 0;
+  b->total_launches = 0;
+  b->d_sums = b->d_ext = b->d_hist = nullptr;
+  b->d_sq_partial = b->d_sq = nullptr;
+  int rc = qk_lower(m, b->log, &b->low);
+  if (rc) {
+    delete b;
+    return rc;
+  }
+  const DevHeader& h = b->low.hdr;
+  b->table_bytes_padded = (h.total_bytes + 15u) & ~15u;
+  const uint32_t per_rep = h.n64 * 8 + h.n32 * 4;
+  uint32_t nt = cfg->threads_per_block;
+  if (nt == 0) nt = choose_nt(per_rep, b->table_bytes_padded, nullptr);
+  if (nt == 0 || nt > QK_MAX_NT || (nt & 31) ||
+      (uint64_t)b->table_bytes_padded + (uint64_t)per_rep * nt > 227u * 1024u) {
+    qk_set_error("qk_batch_create: model needs %u B of on-chip state per replication (+%u B tables); "
+                 "no block size fits the 227 KB of shared memory", per_rep, b->table_bytes_padded);
+    delete b;
+    return QK_ERR_CAPACITY;
+  }
+  b->nt = nt;
+  b->smem_bytes = b->table_bytes_padded + per_rep * nt;
+  b->grid = (uint32_t)((cfg->n_reps + nt - 1) / nt);
+  b->rep_pad = (uint64_t)b->grid * nt;
+  if (cfg->stream) {
+    b->stream = (cudaStream_t)cfg->stream;
+  } else {
+    CUDA_TRY(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+    b->own_stream = true;
+  }
+  CUDA_TRY(cudaEventCreate(&b->ev0));
+  CUDA_TRY(cudaEventCreate(&b->ev1));
+  CUDA_TRY(cudaMalloc(&b->g64, (size_t)h.n64 * b->rep_pad * 8));
+  CUDA_TRY(cudaMalloc(&b->g32, (size_t)h.n32 * b->rep_pad * 4));
+  CUDA_TRY(cudaMalloc(&b->d_tables, b->table_bytes_padded));
+  {
+    std::vector<uint8_t> padded(b->table_bytes_padded, 0);
+    memcpy(padded.data(), b->low.blob.data(), b->low.blob.size());
+    CUDA_TRY(cudaMemcpy(b->d_tables, padded.data(), padded.size(), cudaMemcpyHostToDevice));
+  }
+  if (b->log) CUDA_TRY(cudaMalloc(&b->d_log, (size_t)b->rep_pad * cfg->log_capacity * 32));
+  b->h_tapes.assign(h.n_dist, nullptr);
+  b->h_tape_len.assign(h.n_dist, 0);
+  CUDA_TRY(cudaMalloc(&b->d_tapes, sizeof(double*) * (h.n_dist ? h.n_dist : 1)));
+  CUDA_TRY(cudaMalloc(&b->d_tape_len, sizeof(uint64_t) * (h.n_dist ? h.n_dist : 1)));
+  CUDA_TRY(cudaMemset(b->d_tapes, 0, sizeof(double*) * (h.n_dist ? h.n_dist : 1)));
+  CUDA_TRY(cudaMemset(b->d_tape_len, 0, sizeof(uint64_t) * (h.n_dist ? h.n_dist : 1)));
+  CUDA_TRY(cudaFuncSetAttribute(qk_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  CUDA_TRY(cudaFuncSetAttribute(qk_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  b->red_blocks = 148 * 4;
+  CUDA_TRY(cudaMalloc(&b->d_sums, sizeof(uint64_t) * 6 * h.n_comp));
+  CUDA_TRY(cudaMalloc(&b->d_ext, sizeof(uint64_t) * 4 * h.n_comp));
+  CUDA_TRY(cudaMalloc(&b->d_hist, sizeof(uint64_t) * 2 * QK_HIST_BINS * h.n_comp));
+  CUDA_TRY(cudaMalloc(&b->d_sq_partial, sizeof(double) * 2 * b->red_blocks * h.n_comp));
+  CUDA_TRY(cudaMalloc(&b->d_sq, sizeof(double) * 2 * h.n_comp));
+  *out = b;
+  return QK_OK;
+}
+
+int qk_batch_info_get(qk_batch* b, qk_batch_info* out) {
+  if (!b || !out) return QK_ERR_INVALID_ARG;
+  CUDA_TRY(cudaSetDevice(b->cfg.device));
+  memset(out, 0, sizeof(*out));
+  out->threads_per_block = b->nt;
+  out->grid_blocks = b->grid;
+  out->shared_bytes_per_block = b->smem_bytes;
+  out->table_bytes = b->table_bytes_padded;
+  out->slots64 = b->low.hdr.n64;
+  out->slots32 = b->low.hdr.n32;
+  out->state_bytes_per_rep = b->low.hdr.n64 * 8 + b->low.hdr.n32 * 4;
+  int nb = 0;
+  if (b->log)
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, qk_step_kernel<true>, (int)b->nt, b->smem_bytes));
+  else
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, qk_step_kernel<false>, (int)b->nt, b->smem_bytes));
+  out->resident_blocks_per_sm = (uint32_t)nb;
+  out->replications_padded = b->rep_pad;
+  out->state_bytes_total = (uint64_t)out->state_bytes_per_rep * b->rep_pad;
+  out->log_bytes_total = b->log ? (uint64_t)b->rep_pad * b->cfg.log_capacity * 32 : 0;
+  return QK_OK;
+}
+
+void qk_batch_destroy(qk_batch* b) {
+  if (!b) return;
+  cudaSetDevice(b->cfg.device);
+  if (b->stream) cudaStreamSynchronize(b->stream);
+  cudaFree(b->g64);
+  cudaFree(b->g32);
+  cudaFree(b->d_tables);
+  cudaFree(b->d_log);
+  for (size_t i = 0; i < b->h_tapes.size(); ++i) cudaFree(b->h_tapes[i]);
+  cudaFree(b->d_tapes);
+  cudaFree(b->d_tape_len);
+  cudaFree(b->d_sums);
+  cudaFree(b->d_ext);
+  cudaFree(b->d_hist);
+  cudaFree(b->d_sq_partial);
+  cudaFree(b->d_sq);
+  if (b->ev0) cudaEventDestroy(b->ev0);
+  if (b->ev1) cudaEventDestroy(b->ev1);
+  if (b->own_stream) cudaStreamDestroy(b->stream);
+  delete b;
+}
+
+int qk_batch_set_tape(qk_batch* b, uint32_t dist_id, const double* values, uint64_t per_rep_len) {
+  if (!b || dist_id >= b->low.hdr.n_dist || (!values && per_rep_len)) {
+    qk_set_error("qk_batch_set_tape: invalid argument");
+    return QK_ERR_INVALID_ARG;
+  }
+  CUDA_TRY(cudaSetDevice(b->cfg.device));
+  if (b->h_tapes[dist_id]) {
+    CUDA_TRY(cudaFree(b->h_tapes[dist_id]));
+    b->h_tapes[dist_id] = nullptr;
+  }
+  const size_t n = (size_t)per_rep_len * b->cfg.n_reps;
+  double* d = nullptr;
+  CUDA_TRY(cudaMalloc(&d, (n ? n : 1) * sizeof(double)));
+  if (n) CUDA_TRY(cudaMemcpy(d, values, n * sizeof(double), cudaMemcpyHostToDevice));
+  b->h_tapes[dist_id] = d;
+  b->h_tape_len[dist_id] = per_rep_len;
+  b->any_tape = true;
+  CUDA_TRY(cudaMemcpy(b->d_tapes, b->h_tapes.data(), sizeof(double*) * b->h_tapes.size(), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(b->d_tape_len, b->h_tape_len.data(), sizeof(uint64_t) * b->h_tape_len.size(),
+                      cudaMemcpyHostToDevice));
+  return QK_OK;
+}
+
+int qk_batch_init(qk_batch* b, uint64_t t0_ns) {
+  if (!b) return QK_ERR_INVALID_ARG;
+  CUDA_TRY(cudaSetDevice(b->cfg.device));
+  int rc = launch_step(b, 1, t0_ns, QK_TIME_NONE, 0);
+  if (rc) return rc;
+  b->initialised = true;
+  return QK_OK;
+}
+
+int qk_batch_step_until(qk_batch* b, uint64_t t_ns) {
+  if (!b) return QK_ERR_INVALID_ARG;
+  if (!b->initialised) {
+    qk_set_error("qk_batch_step_until: call qk_batch_init first");
+    return QK_ERR_STATE;
+  }
+  if (t_ns == QK_TIME_NONE) return QK_ERR_INVALID_ARG;
+  CUDA_TRY(cudaSetDevice(b->cfg.device));
+  return launch_step(b, 0, 0, t_ns, ~0ull);
+}
+
+int qk_batch_step_events(qk_batch* b, uint64_t n_events) {
+  if (!b) return QK_ERR_INVALID_ARG;
+  if (!b->initialised) {
+    qk_set_error("qk_batch_step_events: call qk_batch_init first");
+    return QK_ERR_STATE;
+  }
+  CUDA_TRY(cudaSetDevice(b->cfg.device));
+  return launch_step(b, 0, 0, QK_TIME_NONE, n_events);
+}
+
+int qk_batch_synchronize(qk_batch* b) {
+  if (!b) return QK_ERR_INVALID_ARG;
+  CUDA_TRY(cudaSetDevice(b->cfg.device));
+  CUDA_TRY(cudaStreamSynchronize(b->stream));
+  return QK_OK;
+}
+
+int qk_batch_last_step_ms(qk_batch* b, float* ms, uint32_t* n_launches) {
+  if (!b) return QK_ERR_INVALID_ARG;
+  CUDA_TRY(cudaSetDevice(b->cfg.device));
+  CUDA_TRY(cudaEventSynchronize(b->ev1));
+  float t = 0;
+  CUDA_TRY(cudaEventElapsedTime(&t, b->ev0, b->ev1));
+  if (ms) *ms = t;
+  if (n_launches) *n_launches = b->last_launches;
+  return QK_OK;
+}
+
+int qk_batch_summary_get(qk_batch* b, qk_batch_summary* out) {
+  if (!b || !out) return QK_ERR_INVALID_ARG;
+  CUDA_TRY(cudaSetDevice(b->cfg.device));
+  uint64_t h[5] = {0, 0, 0, ~0ull, ~0ull};
+  uint64_t* d = nullptr;
+  CUDA_TRY(cudaMalloc(&d, sizeof(h)));
+  CUDA_TRY(cudaMemcpyAsync(d, h, sizeof(h), cudaMemcpyHostToDevice, b->stream));
+  qk_batch_summary_kernel<<<148, 256, 0, b->stream>>>(b->g64, b->g32, b->rep_pad, b->cfg.n_reps, d);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, b->stream));
+  CUDA_TRY(cudaStreamSynchronize(b->stream));
+  cudaFree(d);
+  out->n_reps = b->cfg.n_reps;
+  out->n_events = h[0];
+  out->n_faulted = h[1];
+  out->n_log_records = h[2];
+  out->min_now_ns = h[3];
+  out->max_now_ns = ~h[4];
+  return QK_OK;
+}
+
+static int check_range(qk_batch* b, uint64_t rep0, uint64_t n) {
+  if (!b || rep0 + n > b->cfg.n_reps || rep0 + n < rep0) {
+    qk_set_error("replication range [%llu, +%llu) out of bounds", (unsigned long long)rep0, (unsigned long long)n);
+    return QK_ERR_INVALID_ARG;
+  }
+  return QK_OK;
+}
+
+int qk_batch_read_status(qk_batch* b, uint64_t rep0, uint64_t n, uint32_t* status, uint64_t* now_ns,
+                         uint64_t* n_events) {
+  int rc = check_range(b, rep0, n);
+  if (rc) return rc;
+  CUDA_TRY(cudaSetDevice(b->cfg.device));
+  CUDA_TRY(cudaStreamSynchronize(b->stream));
+  if (status)
+    CUDA_TRY(cudaMemcpy(status, b->g32 + (size_t)G32_STATUS * b->rep_pad + rep0, n * 4, cudaMemcpyDeviceToHost));
+  if (now_ns)
+    CUDA_TRY(cudaMemcpy(now_ns, b->g64 + (size_t)G64_NOW * b->rep_pad + rep0, n * 8, cudaMemcpyDeviceToHost));
+  if (n_events)
+    CUDA_TRY(cudaMemcpy(n_events, b->g64 + (size_t)G64_NEVENTS * b->rep_pad + rep0, n * 8, cudaMemcpyDeviceToHost));
+  return QK_OK;
+}
+
+int qk_batch_comp_stats(qk_batch* b, uint64_t rep0, uint64_t n, uint32_t comp, qk_comp_stats* out) {
+  int rc = check_range(b, rep0, n);
+  if (rc) return rc;
+  if (comp >= b->low.hdr.n_comp || !out) return QK_ERR_INVALID_ARG;
+  if (n == 0) return QK_OK;
+  CUDA_TRY(cudaSetDevice(b->cfg.device));
+  qk_comp_stats* d = nullptr;
+  CUDA_TRY(cudaMalloc(&d, n * sizeof(qk_comp_stats)));
+  qk_comp_stats_kernel<<<(unsigned)((n + 255) / 256), 256, 0, b->stream>>>(b->d_tables, b->g64, b->g32, b->rep_pad,
+                                                                            rep0, n, comp, d);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpyAsync(out, d, n * sizeof(qk_comp_stats), cudaMemcpyDeviceToHost, b->stream));
+  CUDA_TRY(cudaStreamSynchronize(b->stream));
+  cudaFree(d);
+  return QK_OK;
+}
+
+int qk_batch_reduce_stats_device(qk_batch* b, uint64_t* d_sums, uint64_t* d_extrema, uint32_t n_comp) {
+  if (!b || !d_sums || !d_extrema || n_comp != b->low.hdr.n_comp) {
+    qk_set_error("qk_batch_reduce_stats_device: invalid argument (n_comp must equal the model's)");
+    return QK_ERR_INVALID_ARG;
+  }
+  CUDA_TRY(cudaSetDevice(b->cfg.device));
+  CUDA_TRY(cudaMemsetAsync(d_sums, 0, sizeof(uint64_t) * 6 * n_comp, b->stream));
+  CUDA_TRY(cudaMemsetAsync(d_extrema, 0xFF, sizeof(uint64_t) * 4 * n_comp, b->stream));
+  dim3 grid(b->red_blocks, n_comp);
+  qk_reduce_kernel<<<grid, 256, 0, b->stream>>>(b->d_tables, b->g64, b->g32, b->rep_pad, b->cfg.n_reps, d_sums,
+                                                d_extrema, b->d_sq_partial);
+  CUDA_TRY(cudaGetLastError());
+  qk_reduce_sq_kernel<<<n_comp, 32, 0, b->stream>>>(b->d_sq_partial, b->red_blocks, b->d_sq);
+  CUDA_TRY(cudaGetLastError());
+  return QK_OK;
+}
+
+int qk_batch_histograms_device(qk_batch* b, const uint64_t* d_extrema, uint64_t* d_hist, uint32_t n_comp) {
+  if (!b || !d_extrema || !d_hist || n_comp != b->low.hdr.n_comp) return QK_ERR_INVALID_ARG;
+  CUDA_TRY(cudaSetDevice(b->cfg.device));
+  CUDA_TRY(cudaMemsetAsync(d_hist, 0, sizeof(uint64_t) * 2 * QK_HIST_BINS * n_comp, b->stream));
+  dim3 grid(b->red_blocks, n_comp);
+  qk_hist_kernel<<<grid, 256, 0, b->stream>>>(b->d_tables, b->g64, b->g32, b->rep_pad, b->cfg.n_reps, d_extrema,
+                                              d_hist);
+  CUDA_TRY(cudaGetLastError());
+  return QK_OK;
+}
+
+int qk_batch_reduce_stats(qk_batch* b, qk_comp_summary* out, uint32_t n_comp) {
+  if (!b || !out || n_comp != b->low.hdr.n_comp) return QK_ERR_INVALID_ARG;
+  int rc = qk_batch_reduce_stats_device(b, b->d_sums, b->d_ext, n_comp);
+  if (rc) return rc;
+  rc = qk_batch_histograms_device(b, b->d_ext, b->d_hist, n_comp);
+  if (rc) return rc;
+  std::vector<uint64_t> sums(6 * n_comp), ext(4 * n_comp), hist(2 * QK_HIST_BINS * n_comp);
+  std::vector<double> sq(2 * n_comp);
+  CUDA_TRY(cudaMemcpyAsync(sums.data(), b->d_sums, sums.size() * 8, cudaMemcpyDeviceToHost, b->stream));
+  CUDA_TRY(cudaMemcpyAsync(ext.data(), b->d_ext, ext.size() * 8, cudaMemcpyDeviceToHost, b->stream));
+  CUDA_TRY(cudaMemcpyAsync(hist.data(), b->d_hist, hist.size() * 8, cudaMemcpyDeviceToHost, b->stream));
+  CUDA_TRY(cudaMemcpyAsync(sq.data(), b->d_sq, sq.size() * 8, cudaMemcpyDeviceToHost, b->stream));
+  CUDA_TRY(cudaStreamSynchronize(b->stream));
+  for (uint32_t c = 0; c < n_comp; ++c) {
+    qk_comp_summary& o = out[c];
+    memset(&o, 0, sizeof(o));
+    o.sum_count = sums[c * 6 + 0];
+    const uint64_t lo = sums[c * 6 + 1], hi = sums[c * 6 + 2];
+    /* the kernel sums the low and high 32-bit halves separately; recombine into a 128-bit total */
+    const uint64_t low64 = (hi << 32) + lo;
+    o.sum_time_lo = low64;
+    o.sum_time_hi = (hi >> 32) + (low64 < lo ? 1 : 0);
+    o.sum_level = sums[c * 6 + 3];
+    o.min_count = ext[c * 4 + 0];
+    o.min_time = ext[c * 4 + 1];
+    o.max_count = ~ext[c * 4 + 2];
+    o.max_time = ~ext[c * 4 + 3];
+    o.sumsq_time = sq[c * 2 + 0];
+    o.sumsq_count = sq[c * 2 + 1];
+    for (int k = 0; k < QK_HIST_BINS; ++k) {
+      o.hist_time[k] = hist[(size_t)c * 2 * QK_HIST_BINS + k];
+      o.hist_count[k] = hist[(size_t)c * 2 * QK_HIST_BINS + QK_HIST_BINS + k];
+    }
+    o.hist_lo_time = o.min_time;
+    o.hist_hi_time = o.max_time;
+    o.hist_lo_count = o.min_count;
+    o.hist_hi_count = o.max_count;
+  }
+  return QK_OK;
+}
+
+int qk_batch_read_log(qk_batch* b, uint64_t rep, qk_log_record* buf, uint64_t cap, uint64_t* n_out,
+                      uint64_t* n_total) {
+  int rc = check_range(b, rep, 1);
+  if (rc) return rc;
+  if (!b->log) {
+    qk_set_error("qk_batch_read_log: batch was created with log_capacity 0");
+    return QK_ERR_STATE;
+  }
+  CUDA_TRY(cudaSetDevice(b->cfg.device));
+  CUDA_TRY(cudaStreamSynchronize(b->stream));
+  uint32_t cnt = 0;
+  CUDA_TRY(cudaMemcpy(&cnt, b->g32 + (size_t)G32_LOGCNT * b->rep_pad + rep, 4, cudaMemcpyDeviceToHost));
+  const uint32_t lc = b->cfg.log_capacity;
+  const uint64_t kept = std::min<uint64_t>(cnt, lc);
+  if (n_total) *n_total = cnt;
+  if (n_out) *n_out = std::min<uint64_t>(kept, cap);
+  if (!buf || cap == 0) return QK_OK;
+  if (cap < kept) {
+    qk_set_error("qk_batch_read_log: buffer holds %llu records, %llu needed", (unsigned long long)cap,
+                 (unsigned long long)kept);
+    return QK_ERR_BUFFER_TOO_SMALL;
+  }
+  std::vector<qk_log_record> ring(lc);
+  CUDA_TRY(cudaMemcpy(ring.data(), reinterpret_cast<uint8_t*>(b->d_log) + (size_t)rep * lc * 32, (size_t)lc * 32,
+                      cudaMemcpyDeviceToHost));
+  const uint64_t first = cnt - kept; /* oldest record still in the ring */
+  for (uint64_t i = 0; i < kept; ++i) {
+    buf[i] = ring[(first + i) & (lc - 1)];
+    buf[i].aux = 0;
+  }
+  return QK_OK;
+}
+
+int qk_batch_read_stock(qk_batch* b, uint64_t rep, uint32_t comp, uint32_t* items, uint64_t cap, uint64_t* n_out) {
+  int rc = check_range(b, rep, 1);
+  if (rc) return rc;
+  if (comp >= b->low.hdr.n_comp || b->low.comps[comp].kind != QK_DISCRETE_STOCK) {
+    qk_set_error("qk_batch_read_stock: component %u is not a discrete stock", comp);
+    return QK_ERR_INVALID_ARG;
+  }
+  CUDA_TRY(cudaSetDevice(b->cfg.device));
+  CUDA_TRY(cudaStreamSynchronize(b->stream));
+  const DevComp& c = b->low.comps[comp];
+  uint32_t hc = 0;
+  CUDA_TRY(cudaMemcpy(&hc, b->g32 + (size_t)(c.o32 + S32_HC) * b->rep_pad + rep, 4, cudaMemcpyDeviceToHost));
+  const uint32_t head = hc & 0xFFFFu, cnt = hc >> 16;
+  if (n_out) *n_out = cnt;
+  if (!items) return QK_OK;
+  if (cap < cnt) return QK_ERR_BUFFER_TOO_SMALL;
+  std::vector<uint32_t> ring(c.ring_cap);
+  CUDA_TRY(cudaMemcpy2D(ring.data(), 4, b->g32 + (size_t)(c.o32 + S32_RING) * b->rep_pad + rep, b->rep_pad * 4, 4,
+                        c.ring_cap, cudaMemcpyDeviceToHost));
+  for (uint32_t i = 0; i < cnt; ++i) items[i] = ring[(head + i) % c.ring_cap];
+  return QK_OK;
+}
+
+} /* extern "C" */

@@ -1,0 +1,105 @@
+/*
+ * qk_internal.h -- lowered model tables and per-replication state layout shared by the host
+ * lowering (qk_model.cpp) and the sm_100a kernels (qk_kernels.cu).  Not part of the public ABI.
+ *
+ * Per-replication state is two planes of slots:
+ *     plane64: u64 slots   (times, countdowns, integrals)
+ *     plane32: u32 slots   (flags, counters, item rings)
+ * On chip a block of NT replications keeps them in shared memory replication-fastest
+ * (slot * NT + tid): whatever slot a lane touches, lane i hits bank i, so data-dependent
+ * component indices never cause bank conflicts.  In HBM the same planes are stored
+ * [slot][replication] so block load/store is fully coalesced.
+ */
+#ifndef QK_INTERNAL_H
+#define QK_INTERNAL_H
+#include <stdint.h>
+
+#include "../../include/quokka_b200.h"
+
+#define QK_TIME_NONE 0xFFFFFFFFFFFFFFFFull
+#define QK_MAX_DELAY_MODES 8
+#define QK_MAX_COMPONENTS 1024
+
+/* ---- global (per replication) slots ------------------------------------------------------------ */
+enum { G64_NOW = 0, G64_NEVENTS = 1, G64_FIRE0 = 2 }; /* fire[i] for i in [0, n_sched) follows */
+enum { G32_STATUS = 0, G32_EXT_CURSOR = 1, G32_LOGCNT = 2, G32_STALE0 = 3 }; /* stale mask words follow */
+
+/* ---- process-like slots, relative to DevComp.o64 / o32 ----------------------------------------- */
+enum { P64_LEFT = 0, P64_PREV = 1, P64_BUSY = 2, P64_BASE_COUNT = 3 }; /* optional: ttnpe, delayns, dm durations */
+enum { P32_FLAGS = 0, P32_ITEM = 1, P32_NFINISH = 2, P32_BASE_COUNT = 3 }; /* optional: next item index */
+/* flags */
+#define PF_HAS_ITEM 1u
+#define PF_ENV_STOPPED 2u
+#define PF_FIX_SHIFT 8 /* bits 8..15: delay mode k is in TimeUntilFix */
+/* LOG-only slots relative to olog64 / olog32 */
+enum { PL64_SCHED_SRC = 0, PL64_STALE_SRC = 1, PL64_COUNT = 2 };
+enum { L32_SEQ = 0 };
+
+/* ---- discrete stock slots ------------------------------------------------------------------------ */
+enum { S64_AREA = 0, S64_COUNT = 1 }; /* fire slot holds emit_t0 */
+enum { S32_HC = 0, S32_EMIT = 1, S32_NADD = 2, S32_MAXOCC = 3, S32_RING = 4 };
+/* S32_EMIT = n | split << 8 | head << 16 ; LOG: emit source seq ring at olog32 + 1 */
+
+/* ---- parallel process slots ---------------------------------------------------------------------- */
+enum { PP64_PREV = 0, PP64_BUSY = 1, PP64_BASE_COUNT = 2 }; /* then [delayns], dm durs, in-progress durations[cap] */
+enum { PP32_FLAGS = 0, PP32_NPROG = 1, PP32_COMPLETE = 2, PP32_NFINISH = 3, PP32_BASE_COUNT = 4 };
+/* then in-progress items[cap], complete ring[cap] */
+
+/* ---- environment --------------------------------------------------------------------------------- */
+enum { E32_STATE = 0, E32_COUNT = 1 };
+
+#define DC_LOGGED 1u
+
+typedef struct {
+  uint8_t kind;    /* qk_component_kind */
+  uint8_t n_dm;    /* delay modes */
+  uint8_t n_subs;  /* subscribers of state_emitter / emit_change */
+  uint8_t src_ord; /* source ordinal for item handles */
+  int16_t up, down, env;
+  uint16_t subs_off;
+  uint32_t low, max;
+  uint16_t o64, o32;
+  uint16_t olog64, olog32;
+  uint16_t fire_idx;  /* index into fire[] / stale mask, 0xFFFF if not schedulable */
+  uint16_t ring_cap;  /* stock: item ring slots ; parallel: in-flight slots */
+  uint16_t dist_time; /* distribution instance of process_time_distr */
+  uint16_t dm_off;    /* first DevDelayMode */
+  uint16_t o64_dm;    /* first delay-mode duration slot (absolute) */
+  uint16_t o64_ttnpe; /* absolute slot, 0xFFFF if none (only DiscreteSink keeps ttnpe across calls) */
+  uint16_t o64_delayns;
+  uint16_t o32_next_item; /* absolute slot (sources) */
+  uint16_t emit_depth;
+  uint16_t flags;
+} DevComp; /* 48 bytes */
+
+typedef struct {
+  uint32_t kind, stream;
+  double p[4];
+  uint32_t draw_slot; /* absolute plane32 slot of the draw counter */
+  uint32_t pad;
+} DevDist; /* 48 bytes */
+
+typedef struct {
+  uint16_t until_delay, until_fix; /* distribution instance ids */
+} DevDelayMode;
+
+typedef struct {
+  uint64_t t;
+  uint32_t type; /* 0 SetEnvironmentState */
+  uint32_t target;
+  uint32_t state;
+  uint32_t pad;
+} DevExt; /* 24 bytes */
+
+/* header of the table blob (all offsets in bytes from the blob start, 8-byte aligned) */
+typedef struct {
+  uint32_t n_comp, n_sched, n_dist, n_dm, n_subs, n_ext;
+  uint32_t n64, n32;         /* slots per replication (for the chosen LOG mode) */
+  uint32_t n_stale_words;
+  uint32_t ident_off;        /* index in subs[] of the identity list (subs[ident_off + c] == c) */
+  uint32_t off_comps, off_dists, off_dms, off_subs, off_sched, off_ext;
+  uint32_t total_bytes;
+  uint32_t log_enabled;
+} DevHeader;
+
+#endif

@@ -1,0 +1,769 @@
+/*
+ * qk_kernels.cuh -- the per-event state-update kernel of the batched-replication executor (sm_100a).
+ *
+ * One thread owns one replication ("thread group" of size 1): its scheduler queue, component state
+ * machines and stock rings live in shared memory, replication-fastest, for the whole launch, so HBM is
+ * touched only to load/store the state planes once per launch and to stream log records.
+ *
+ * What it replaces in the reference (paths relative to /root/reference/quokkasim/src):
+ *   - NeXosim's scheduler queue + executor behind Simulation::step_until / step
+ *     (call sites quokkasim_examples/src/bin/discrete_queue.rs:111; cx.schedule_event discrete.rs:194,219;
+ *     cx.schedule_keyed_event discrete.rs:549,556; action_key.cancel() discrete.rs:548): here every
+ *     component has ONE fire-time slot, the queue is "min over fire[]" (+ a stale bit mask for the
+ *     dropped-but-not-cancelled handles of SURVEY A.6 Q3), ordered by (time, registration rank).
+ *   - Process::update_state = pre -> impl -> post for DiscreteProcess / DiscreteSource / DiscreteSink /
+ *     DiscreteParallelProcess (core.rs:370-376; discrete.rs:404-564, 779-920, 1025-1167, 1280-1458)
+ *   - DiscreteStock add / remove / emit_change (core.rs:177-204; discrete.rs:161-233)
+ *   - DelayModes::update_state (delays.rs:86-142), BasicEnvironment::set_state (core.rs:256-265)
+ *   - Distribution::sample (common.rs:152-178) via Philox4x32-10 or a pre-drawn variate tape
+ *   - every `self.log(..)` (discrete.rs:235-251, 566-582) as a 32-byte binary record
+ *
+ * Control flow is arranged so that all lanes of a warp run the SAME code most of the time: an action
+ * (keyed event, stock emit_change, scheduled environment change) is expanded into a short list of
+ * update_state(p) calls, and the warp iterates "one update_state per lane per trip"; which component p is,
+ * is data, not control.
+ */
+#ifndef QK_KERNELS_CUH
+#define QK_KERNELS_CUH
+#include "qk_device.cuh"
+
+struct KParams {
+  uint64_t* g64; /* [n64][rep_pad] */
+  uint32_t* g32; /* [n32][rep_pad] */
+  const uint8_t* tables;
+  uint32_t table_bytes; /* multiple of 16 */
+  uint32_t n64, n32;
+  uint64_t n_reps, rep_pad, rep_offset, seed;
+  uint4* log;        /* [rep_pad][log_cap] records (2 x uint4 each) or NULL */
+  uint32_t log_cap;  /* power of two */
+  const double* const* tapes; /* [n_dist] device pointers or NULL entries */
+  const uint64_t* tape_len;   /* [n_dist] per-replication length */
+  uint64_t t0, t_until, event_budget;
+  uint32_t do_init;
+};
+
+struct Ctx {
+  uint64_t* s64; /* plane64 + tid */
+  uint32_t* s32; /* plane32 + tid */
+  uint32_t nt;
+  const DevHeader* hdr;
+  const DevComp* comps;
+  const DevDist* dists;
+  const DevDelayMode* dms;
+  const uint16_t* subs;
+  const uint16_t* sched;
+  const DevExt* ext;
+  uint64_t now;
+  uint32_t status;
+  uint4* log_base;
+  uint32_t log_mask;
+  uint32_t log_cnt;
+  uint32_t key0, key1, rep_lo, rep_hi;
+  uint64_t rep_local;
+  const double* const* tapes;
+  const uint64_t* tape_len;
+};
+
+#define S64(slot) cx.s64[(uint32_t)(slot) * cx.nt]
+#define S32(slot) cx.s32[(uint32_t)(slot) * cx.nt]
+#define SRC_INIT (((uint64_t)QK_SRC_INIT) << 32)
+#define SRC_SCH (((uint64_t)QK_SRC_SCH) << 32)
+
+/* ---- log(): allocate EventId "{code}_{seq:06}", emit one 32-byte record, return the new id ------------ */
+template <bool LOG>
+__device__ __forceinline__ uint64_t qk_log(Ctx& cx, const DevComp* c, uint32_t comp, uint64_t src, uint32_t kind,
+                                           uint32_t reason, uint64_t payload) {
+  if (!LOG) return 0;
+  const uint32_t seq = S32(c->olog32 + L32_SEQ);
+  S32(c->olog32 + L32_SEQ) = seq + 1;
+  if (c->flags & DC_LOGGED) {
+    uint4* r = cx.log_base + 2 * (size_t)(cx.log_cnt & cx.log_mask);
+    uint4 a, b;
+    a.x = (uint32_t)cx.now;
+    a.y = (uint32_t)(cx.now >> 32);
+    a.z = comp | (kind << 16) | (reason << 24);
+    a.w = seq;
+    b.x = (uint32_t)(src >> 32) & 0xFFFFu; /* src_comp | aux(0) << 16 */
+    b.y = (uint32_t)src;
+    b.z = (uint32_t)payload;
+    b.w = (uint32_t)(payload >> 32);
+    r[0] = a;
+    r[1] = b;
+    cx.log_cnt += 1;
+  }
+  return ((uint64_t)comp << 32) | seq;
+}
+
+/* ---- Distribution::sample (common.rs:152-178) + Duration::from_secs_f64 -------------------------------- */
+__device__ __forceinline__ double qk_sample(Ctx& cx, uint32_t dist_id) {
+  const DevDist* d = &cx.dists[dist_id];
+  if (d->kind == QK_DIST_CONSTANT) return d->p[0];
+  uint32_t draws = S32(d->draw_slot);
+  double v;
+  const double* tape = cx.tapes ? cx.tapes[dist_id] : nullptr;
+  if (tape) {
+    const uint64_t len = cx.tape_len[dist_id];
+    if (draws >= len) {
+      cx.status = QK_REP_TAPE_EXHAUSTED;
+      return 1.0;
+    }
+    v = tape[cx.rep_local * len + draws];
+    draws += 1;
+  } else {
+    double p[4] = {d->p[0], d->p[1], d->p[2], d->p[3]};
+    v = qk_sample_native(d->kind, p, d->stream, cx.key0, cx.key1, cx.rep_lo, cx.rep_hi, &draws);
+  }
+  S32(d->draw_slot) = draws;
+  return v;
+}
+
+/* sample + convert; on a fault sets cx.status and returns 1 (callers abandon the handler) */
+__device__ __forceinline__ uint64_t qk_sample_duration(Ctx& cx, uint32_t dist_id) {
+  const double secs = qk_sample(cx, dist_id);
+  if (cx.status) return 1;
+  uint64_t ns;
+  const uint32_t f = qk_from_secs_f64(secs, &ns);
+  if (f) {
+    cx.status = f;
+    return 1;
+  }
+  return ns;
+}
+
+/* ---- DiscreteStock (discrete.rs:158-252) ------------------------------------------------------------------ */
+__device__ __forceinline__ uint32_t qk_stock_cat(uint32_t cnt, uint32_t low, uint32_t max) {
+  /* get_state discrete.rs:161-171: Empty test first */
+  return cnt <= low ? 0u : (cnt >= max ? 2u : 1u);
+}
+
+/* cx.schedule_event(now + 1ns, Self::emit_change, ..) discrete.rs:193-194, 218-219 */
+template <bool LOG>
+__device__ __forceinline__ void qk_emit_push(Ctx& cx, const DevComp* c, uint32_t src_seq) {
+  const uint32_t fire = G64_FIRE0 + c->fire_idx;
+  uint32_t e = S32(c->o32 + S32_EMIT);
+  uint32_t n = e & 0xFFu, split = (e >> 8) & 0xFFu, head = (e >> 16) & 0xFFu;
+  const uint64_t T = cx.now + 1;
+  if (n == 0) {
+    S64(fire) = T;
+    split = 1;
+    head = 0;
+  } else if (S64(fire) == T) {
+    split += 1;
+  }
+  n += 1;
+  if (n > c->emit_depth) {
+    cx.status = QK_REP_EMIT_OVERFLOW;
+    return;
+  }
+  if (LOG) {
+    uint32_t pos = head + n - 1;
+    if (pos >= c->emit_depth) pos -= c->emit_depth;
+    S32(c->olog32 + 1 + pos) = src_seq;
+  }
+  S32(c->o32 + S32_EMIT) = n | (split << 8) | (head << 16);
+}
+
+template <bool LOG>
+__device__ __forceinline__ uint32_t qk_emit_pop(Ctx& cx, const DevComp* c) {
+  const uint32_t fire = G64_FIRE0 + c->fire_idx;
+  uint32_t e = S32(c->o32 + S32_EMIT);
+  uint32_t n = e & 0xFFu, split = (e >> 8) & 0xFFu, head = (e >> 16) & 0xFFu;
+  uint32_t src_seq = 0;
+  if (LOG) src_seq = S32(c->olog32 + 1 + head);
+  head += 1;
+  if (head >= c->emit_depth) head = 0;
+  n -= 1;
+  split -= 1;
+  if (n == 0) {
+    S64(fire) = QK_TIME_NONE;
+  } else if (split == 0) {
+    S64(fire) = S64(fire) + 1;
+    split = n;
+  }
+  S32(c->o32 + S32_EMIT) = n | (split << 8) | (head << 16);
+  return src_seq;
+}
+
+/* Stock::add = pre_add, add_impl, post_add (core.rs:177-183; discrete.rs:181-198). No capacity check. */
+template <bool LOG>
+__device__ __forceinline__ void qk_stock_add(Ctx& cx, uint32_t sidx, uint32_t item, uint64_t src) {
+  const DevComp* c = &cx.comps[sidx];
+  const uint32_t hc = S32(c->o32 + S32_HC);
+  uint32_t head = hc & 0xFFFFu, cnt = hc >> 16;
+  const uint32_t prev = qk_stock_cat(cnt, c->low, c->max);
+  if (cnt >= c->ring_cap) {
+    cx.status = QK_REP_STOCK_OVERFLOW;
+    return;
+  }
+  uint32_t pos = head + cnt;
+  if (pos >= c->ring_cap) pos -= c->ring_cap;
+  S32(c->o32 + S32_RING + pos) = item;
+  cnt += 1;
+  S32(c->o32 + S32_HC) = head | (cnt << 16);
+  S64(c->o64 + S64_AREA) -= cx.now; /* occupancy integral = sum(t_remove) - sum(t_add) + cnt * T */
+  S32(c->o32 + S32_NADD) += 1;
+  if (cnt > S32(c->o32 + S32_MAXOCC)) S32(c->o32 + S32_MAXOCC) = cnt;
+  const uint64_t id = qk_log<LOG>(cx, c, sidx, src, QK_LOG_STOCK_ADD, 0, item);
+  if (prev != qk_stock_cat(cnt, c->low, c->max)) qk_emit_push<LOG>(cx, c, (uint32_t)id);
+}
+
+/* Stock::remove (core.rs:197-204; discrete.rs:200-225); returns false for Remove(None) */
+template <bool LOG>
+__device__ __forceinline__ bool qk_stock_remove(Ctx& cx, uint32_t sidx, uint64_t src, uint32_t* item_out) {
+  const DevComp* c = &cx.comps[sidx];
+  const uint32_t hc = S32(c->o32 + S32_HC);
+  uint32_t head = hc & 0xFFFFu, cnt = hc >> 16;
+  const uint32_t prev = qk_stock_cat(cnt, c->low, c->max);
+  const bool some = cnt != 0;
+  uint32_t item = 0;
+  if (some) {
+    item = S32(c->o32 + S32_RING + head);
+    head += 1;
+    if (head >= c->ring_cap) head = 0;
+    cnt -= 1;
+    S32(c->o32 + S32_HC) = head | (cnt << 16);
+    S64(c->o64 + S64_AREA) += cx.now;
+  }
+  const uint64_t id = qk_log<LOG>(cx, c, sidx, src, QK_LOG_STOCK_REMOVE, 0, some ? (uint64_t)item : QK_ITEM_NONE);
+  if (prev != qk_stock_cat(cnt, c->low, c->max)) qk_emit_push<LOG>(cx, c, (uint32_t)id);
+  *item_out = item;
+  return some;
+}
+
+__device__ __forceinline__ uint32_t qk_stock_cat_of(Ctx& cx, int sidx) {
+  const DevComp* c = &cx.comps[sidx];
+  return qk_stock_cat(S32(c->o32 + S32_HC) >> 16, c->low, c->max);
+}
+
+/* ---- DelayModes::update_state (delays.rs:86-142) + DelayEnd/DelayStart logs (discrete.rs:441-451) ------- */
+template <bool LOG>
+__device__ __noinline__ void qk_tick_delays(Ctx& cx, const DevComp* c, uint32_t comp, uint32_t* flags_io,
+                                            uint64_t dt, uint64_t* src) {
+  uint32_t flags = *flags_io;
+  uint32_t mask = (flags >> PF_FIX_SHIFT) & 0xFFu;
+  int from = -1, to = -1;
+  if (mask) {
+    const int a = __ffs((int)mask) - 1; /* active_delay: first mode in TimeUntilFix, insertion order */
+    uint64_t dur = S64(c->o64_dm + a);
+    const uint64_t applied = dt < dur ? dt : dur;
+    S64(c->o64_delayns) += applied;
+    dur -= applied;
+    if (dur == 0) {
+      dur = qk_sample_duration(cx, cx.dms[c->dm_off + a].until_delay);
+      if (cx.status) return;
+      mask &= ~(1u << a);
+    }
+    S64(c->o64_dm + a) = dur;
+    from = a;
+  } else {
+    for (int k = 0; k < c->n_dm; ++k) {
+      const uint64_t dur = S64(c->o64_dm + k);
+      S64(c->o64_dm + k) = dur - (dt < dur ? dt : dur);
+    }
+  }
+  if (mask) {
+    to = __ffs((int)mask) - 1;
+  } else {
+    for (int k = 0; k < c->n_dm; ++k) {
+      if (S64(c->o64_dm + k) == 0) {
+        const uint64_t dur = qk_sample_duration(cx, cx.dms[c->dm_off + k].until_fix);
+        if (cx.status) return;
+        S64(c->o64_dm + k) = dur;
+        mask |= 1u << k;
+        to = k;
+        break;
+      }
+    }
+  }
+  flags = (flags & ~(0xFFu << PF_FIX_SHIFT)) | (mask << PF_FIX_SHIFT);
+  *flags_io = flags;
+  if (from != to) { /* DelayStateTransition::has_changed delays.rs:35-42 */
+    if (from >= 0) *src = qk_log<LOG>(cx, c, comp, *src, QK_LOG_DELAY_END, 0, (uint64_t)from);
+    if (to >= 0) *src = qk_log<LOG>(cx, c, comp, *src, QK_LOG_DELAY_START, 0, (uint64_t)to);
+  }
+}
+
+/* "Update cached environment state" (discrete.rs:455-471 and siblings) */
+template <bool LOG>
+__device__ __forceinline__ void qk_refresh_env(Ctx& cx, const DevComp* c, uint32_t comp, uint32_t* flags,
+                                               uint64_t* src) {
+  const bool new_stopped = c->env >= 0 ? (S32(cx.comps[c->env].o32 + E32_STATE) == 1u) : false;
+  const bool old_stopped = (*flags & PF_ENV_STOPPED) != 0;
+  if (!old_stopped && new_stopped) {
+    *src = qk_log<LOG>(cx, c, comp, *src, QK_LOG_PROCESS_STOPPED, QK_REASON_STOPPED_BY_ENV, 0);
+    *flags |= PF_ENV_STOPPED;
+  } else if (old_stopped && !new_stopped) {
+    *src = qk_log<LOG>(cx, c, comp, *src, QK_LOG_PROCESS_CONTINUE, QK_REASON_RESUMED_BY_ENV, 0);
+    *flags &= ~PF_ENV_STOPPED;
+  }
+}
+
+/* post_update_state (discrete.rs:535-564): keep the earlier of the pending keyed event and now+ttnpe.
+ * Cancelling == overwriting the single fire slot. */
+template <bool LOG>
+__device__ __forceinline__ void qk_post(Ctx& cx, const DevComp* c, uint64_t ttnpe, uint64_t src) {
+  if (ttnpe != QK_TIME_NONE) {
+    if (ttnpe == 0) {
+      cx.status = QK_REP_ZERO_DURATION; /* panic!("Time until next event is zero!") */
+      return;
+    }
+    const uint64_t next = cx.now + ttnpe;
+    const uint32_t fire = G64_FIRE0 + c->fire_idx;
+    if (next < S64(fire)) { /* NONE is the largest u64 */
+      S64(fire) = next;
+      if (LOG) S64(c->olog64 + PL64_SCHED_SRC) = src;
+    }
+  }
+}
+
+/* pre_update_state (discrete.rs:404-412): a handle whose time has come is forgotten, NOT cancelled; if its
+ * event has not fired yet it stays queued (Q3) -> move it to the stale mask (it fires at `now`, in rank order) */
+template <bool LOG>
+__device__ __forceinline__ void qk_pre(Ctx& cx, const DevComp* c) {
+  const uint32_t fire = G64_FIRE0 + c->fire_idx;
+  if (S64(fire) <= cx.now) {
+    S64(fire) = QK_TIME_NONE;
+    S32(G32_STALE0 + (c->fire_idx >> 5)) |= 1u << (c->fire_idx & 31);
+    if (LOG) S64(c->olog64 + PL64_STALE_SRC) = S64(c->olog64 + PL64_SCHED_SRC);
+  }
+}
+
+/* ---- DiscreteProcess / DiscreteSource / DiscreteSink update_state, one code path ----------------------------- */
+template <bool LOG>
+__device__ void qk_update_single(Ctx& cx, const DevComp* c, uint32_t comp, uint64_t src) {
+  const uint32_t kind = c->kind;
+  uint32_t flags = S32(c->o32 + P32_FLAGS);
+  uint64_t left = S64(c->o64 + P64_LEFT);
+  const uint64_t dt = cx.now - S64(c->o64 + P64_PREV);
+  uint64_t ttnpe = QK_TIME_NONE;
+  {
+    const bool is_in_delay = ((flags >> PF_FIX_SHIFT) & 0xFFu) != 0;
+    const bool has_item0 = (flags & PF_HAS_ITEM) != 0;
+    const bool is_in_process = has_item0 && !is_in_delay;
+    const bool is_env_blocked = (flags & PF_ENV_STOPPED) != 0;
+    if (!(is_in_delay || is_env_blocked) && has_item0) {
+      left -= (dt < left ? dt : left); /* saturating_sub */
+      if (left == 0) {
+        flags &= ~PF_HAS_ITEM;
+        const uint32_t item = S32(c->o32 + P32_ITEM);
+        src = qk_log<LOG>(cx, c, comp, src, QK_LOG_PROCESS_FINISH, 0, item);
+        S32(c->o32 + P32_NFINISH) += 1;
+        if (kind != QK_DISCRETE_SINK && c->down >= 0) { /* push_downstream: no downstream check at finish */
+          qk_stock_add<LOG>(cx, (uint32_t)c->down, item, src);
+          if (cx.status) return;
+        }
+      }
+    }
+    if (c->n_dm && !is_env_blocked && (is_in_delay || is_in_process)) {
+      qk_tick_delays<LOG>(cx, c, comp, &flags, dt, &src);
+      if (cx.status) return;
+    }
+  }
+  if (c->env >= 0 || (flags & PF_ENV_STOPPED)) qk_refresh_env<LOG>(cx, c, comp, &flags, &src);
+
+  const bool has_item = (flags & PF_HAS_ITEM) != 0;
+  const uint32_t fixmask = (flags >> PF_FIX_SHIFT) & 0xFFu;
+  const bool has_active_delay = fixmask != 0 || (flags & PF_ENV_STOPPED) != 0;
+  if (!has_item && !has_active_delay) {
+    /* match (&us_state, &ds_state) discrete.rs:480-516 / 854-872 / 1100-1125; 3 == not connected */
+    const bool need_us = kind != QK_DISCRETE_SOURCE, need_ds = kind != QK_DISCRETE_SINK;
+    const uint32_t us = need_us ? (c->up >= 0 ? qk_stock_cat_of(cx, c->up) : 3u) : 1u;
+    const uint32_t ds = need_ds ? (c->down >= 0 ? qk_stock_cat_of(cx, c->down) : 3u) : 1u;
+    const bool ok = (us == 1u || us == 2u) && (ds == 0u || ds == 1u);
+    if (ok) {
+      bool got = true;
+      uint32_t item;
+      if (need_us) {
+        src = qk_log<LOG>(cx, c, comp, src, QK_LOG_WITHDRAW_REQUEST, 0, 0);
+        got = qk_stock_remove<LOG>(cx, (uint32_t)c->up, src, &item);
+        if (cx.status) return;
+      }
+      if (got) {
+        const double secs = qk_sample(cx, c->dist_time);
+        if (cx.status) return;
+        if (!need_us) { /* ItemFactory::create_item discrete.rs:680-686 */
+          const uint32_t idx = S32(c->o32_next_item);
+          if (idx > 0x3FFFFFFu) {
+            cx.status = QK_REP_ITEM_INDEX_OVERFLOW;
+            return;
+          }
+          S32(c->o32_next_item) = idx + 1;
+          item = ((uint32_t)c->src_ord << 26) | idx;
+        }
+        uint64_t d;
+        const uint32_t f = qk_from_secs_f64(secs, &d);
+        if (f) {
+          cx.status = f;
+          return;
+        }
+        left = d;
+        flags |= PF_HAS_ITEM;
+        S32(c->o32 + P32_ITEM) = item;
+        S64(c->o64 + P64_BUSY) += d;
+        src = qk_log<LOG>(cx, c, comp, src, QK_LOG_PROCESS_START, 0, item);
+        ttnpe = d;
+      } else {
+        src = qk_log<LOG>(cx, c, comp, src, QK_LOG_PROCESS_NONSTART, QK_REASON_UPSTREAM_NO_RESOURCE, 0);
+      }
+    } else {
+      uint32_t reason;
+      if (need_us && us == 0u)
+        reason = QK_REASON_UPSTREAM_EMPTY;
+      else if (need_us && us == 3u)
+        reason = QK_REASON_UPSTREAM_NOT_CONNECTED;
+      else if (ds == 2u)
+        reason = QK_REASON_DOWNSTREAM_FULL;
+      else
+        reason = QK_REASON_DOWNSTREAM_NOT_CONNECTED;
+      src = qk_log<LOG>(cx, c, comp, src, QK_LOG_PROCESS_NONSTART, reason, 0);
+    }
+  } else if (kind == QK_DISCRETE_SINK) {
+    /* (Some, _) leaves ttnpe untouched (discrete.rs:1127-1129); (_, true) clears it (Q2, :1130-1132) */
+    ttnpe = has_item ? S64(c->o64_ttnpe) : QK_TIME_NONE;
+  } else if (has_item && (!has_active_delay || kind == QK_DISCRETE_SOURCE)) {
+    ttnpe = left; /* Process (Some,false) :518-520 ; Source (Some,_) :874-876 */
+  } else {
+    ttnpe = fixmask ? S64(c->o64_dm + (__ffs((int)fixmask) - 1)) : QK_TIME_NONE; /* (_, true) :521-523 */
+  }
+  if (kind == QK_DISCRETE_SINK) S64(c->o64_ttnpe) = ttnpe;
+  S32(c->o32 + P32_FLAGS) = flags;
+  S64(c->o64 + P64_LEFT) = left;
+  qk_post<LOG>(cx, c, ttnpe, src);
+  S64(c->o64 + P64_PREV) = cx.now;
+}
+
+/* ---- DiscreteParallelProcess::update_state_impl (discrete.rs:1280-1417) ---------------------------------------- */
+template <bool LOG>
+__device__ __noinline__ void qk_update_parallel(Ctx& cx, const DevComp* c, uint32_t comp, uint64_t src) {
+  uint32_t flags = S32(c->o32 + PP32_FLAGS);
+  const uint64_t dt = cx.now - S64(c->o64 + PP64_PREV);
+  const uint32_t cap = c->ring_cap;
+  const uint32_t dur0 = c->o64_dm + c->n_dm;
+  const uint32_t item0 = c->o32 + PP32_BASE_COUNT;
+  const uint32_t comp0 = item0 + cap;
+  uint32_t nprog = S32(c->o32 + PP32_NPROG);
+  uint32_t cq = S32(c->o32 + PP32_COMPLETE);
+  uint32_t chead = cq & 0xFFFFu, ccnt = cq >> 16;
+  {
+    const bool is_in_delay = ((flags >> PF_FIX_SHIFT) & 0xFFu) != 0;
+    const bool is_in_process = nprog > 0 && !is_in_delay;
+    const bool is_env_blocked = (flags & PF_ENV_STOPPED) != 0;
+    if (!(is_in_delay || is_env_blocked)) {
+      uint32_t w = 0;
+      for (uint32_t i = 0; i < nprog; ++i) { /* retain_mut :1298-1306 */
+        uint64_t d = S64(dur0 + i);
+        const uint32_t it = S32(item0 + i);
+        d -= (dt < d ? dt : d);
+        if (d == 0) {
+          if (ccnt >= cap) {
+            cx.status = QK_REP_PARALLEL_OVERFLOW;
+            return;
+          }
+          uint32_t pos = chead + ccnt;
+          if (pos >= cap) pos -= cap;
+          S32(comp0 + pos) = it;
+          ccnt += 1;
+        } else {
+          S64(dur0 + w) = d;
+          S32(item0 + w) = it;
+          w += 1;
+        }
+      }
+      nprog = w;
+      while (ccnt) { /* :1311-1327 -- the popped item is lost when downstream is Full */
+        const uint32_t it = S32(comp0 + chead);
+        chead += 1;
+        if (chead >= cap) chead = 0;
+        ccnt -= 1;
+        const uint32_t ds = c->down >= 0 ? qk_stock_cat_of(cx, c->down) : 3u;
+        if (ds == 0u || ds == 1u) {
+          src = qk_log<LOG>(cx, c, comp, src, QK_LOG_PROCESS_FINISH, 0, it);
+          S32(c->o32 + PP32_NFINISH) += 1;
+          qk_stock_add<LOG>(cx, (uint32_t)c->down, it, src);
+          if (cx.status) return;
+        } else {
+          src = qk_log<LOG>(cx, c, comp, src, QK_LOG_PROCESS_NONSTART,
+                            ds == 2u ? QK_REASON_DOWNSTREAM_FULL : QK_REASON_DOWNSTREAM_NOT_CONNECTED, 0);
+          break;
+        }
+      }
+    }
+    if (c->n_dm && !is_env_blocked && (is_in_delay || is_in_process)) {
+      qk_tick_delays<LOG>(cx, c, comp, &flags, dt, &src);
+      if (cx.status) return;
+    }
+  }
+  if (c->env >= 0 || (flags & PF_ENV_STOPPED)) qk_refresh_env<LOG>(cx, c, comp, &flags, &src);
+  uint64_t ttnpe = QK_TIME_NONE;
+  if (!(flags & PF_ENV_STOPPED)) {
+    for (;;) { /* :1373-1398 */
+      const uint32_t us = c->up >= 0 ? qk_stock_cat_of(cx, c->up) : 3u;
+      if (us == 0u || us == 1u) { /* Q4: withdraws while upstream is Empty|Normal */
+        src = qk_log<LOG>(cx, c, comp, src, QK_LOG_WITHDRAW_REQUEST, 0, 0);
+        uint32_t it;
+        const bool got = qk_stock_remove<LOG>(cx, (uint32_t)c->up, src, &it);
+        if (cx.status) return;
+        if (!got) break;
+        const uint64_t d = qk_sample_duration(cx, c->dist_time);
+        if (cx.status) return;
+        if (nprog >= cap) {
+          cx.status = QK_REP_PARALLEL_OVERFLOW;
+          return;
+        }
+        S64(dur0 + nprog) = d;
+        S32(item0 + nprog) = it;
+        nprog += 1;
+        S64(c->o64 + PP64_BUSY) += d;
+        src = qk_log<LOG>(cx, c, comp, src, QK_LOG_PROCESS_START, 0, it);
+      } else {
+        src = qk_log<LOG>(cx, c, comp, src, QK_LOG_PROCESS_NONSTART,
+                          us == 2u ? QK_REASON_UPSTREAM_FULL : QK_REASON_UPSTREAM_NOT_CONNECTED, 0);
+        break;
+      }
+    }
+    for (uint32_t i = 0; i < nprog; ++i) { /* :1400-1406 */
+      const uint64_t d = S64(dur0 + i);
+      if (d < ttnpe) ttnpe = d;
+    }
+  }
+  S32(c->o32 + PP32_FLAGS) = flags;
+  S32(c->o32 + PP32_NPROG) = nprog;
+  S32(c->o32 + PP32_COMPLETE) = chead | (ccnt << 16);
+  qk_post<LOG>(cx, c, ttnpe, src);
+  S64(c->o64 + PP64_PREV) = cx.now;
+}
+
+/* Process::update_state (core.rs:370-376) */
+template <bool LOG>
+__device__ __forceinline__ void qk_update_state(Ctx& cx, uint32_t comp, uint64_t src) {
+  const DevComp* c = &cx.comps[comp];
+  qk_pre<LOG>(cx, c);
+  if (c->kind == QK_DISCRETE_PARALLEL_PROCESS)
+    qk_update_parallel<LOG>(cx, c, comp, src);
+  else
+    qk_update_single<LOG>(cx, c, comp, src);
+}
+
+/* ============================================ the kernel ============================================ */
+#define QK_MAX_NT 256
+
+template <bool LOG>
+__global__ void __launch_bounds__(QK_MAX_NT) qk_step_kernel(const __grid_constant__ KParams P) {
+  QK_SMEM_DECL(smem);
+  const uint32_t tid = QK_TID, nt = QK_NT;
+
+  /* model tables -> shared memory (read with data-dependent component indices afterwards) */
+  {
+    const uint4* srcp = reinterpret_cast<const uint4*>(P.tables);
+    uint4* dstp = reinterpret_cast<uint4*>(smem);
+    for (uint32_t i = tid; i < P.table_bytes / 16; i += nt) dstp[i] = srcp[i];
+  }
+  __syncthreads();
+
+  Ctx cx;
+  cx.hdr = reinterpret_cast<const DevHeader*>(smem);
+  cx.comps = reinterpret_cast<const DevComp*>(smem + cx.hdr->off_comps);
+  cx.dists = reinterpret_cast<const DevDist*>(smem + cx.hdr->off_dists);
+  cx.dms = reinterpret_cast<const DevDelayMode*>(smem + cx.hdr->off_dms);
+  cx.subs = reinterpret_cast<const uint16_t*>(smem + cx.hdr->off_subs);
+  cx.sched = reinterpret_cast<const uint16_t*>(smem + cx.hdr->off_sched);
+  cx.ext = reinterpret_cast<const DevExt*>(smem + cx.hdr->off_ext);
+  cx.nt = nt;
+  uint64_t* plane64 = reinterpret_cast<uint64_t*>(smem + P.table_bytes);
+  uint32_t* plane32 = reinterpret_cast<uint32_t*>(smem + P.table_bytes + (size_t)P.n64 * nt * 8);
+  cx.s64 = plane64 + tid;
+  cx.s32 = plane32 + tid;
+  const uint64_t rep_local = (uint64_t)QK_BID * nt + tid;
+  const bool live = rep_local < P.n_reps;
+  const uint64_t rep_global = P.rep_offset + rep_local;
+  cx.rep_local = rep_local;
+  cx.key0 = (uint32_t)P.seed;
+  cx.key1 = (uint32_t)(P.seed >> 32);
+  cx.rep_lo = (uint32_t)rep_global;
+  cx.rep_hi = (uint32_t)(rep_global >> 32);
+  cx.tapes = P.tapes;
+  cx.tape_len = P.tape_len;
+  cx.log_mask = P.log_cap ? P.log_cap - 1 : 0;
+  cx.log_base = LOG ? P.log + 2 * (size_t)rep_local * P.log_cap : nullptr;
+  cx.status = 0;
+  const uint32_t n_comp = cx.hdr->n_comp, n_sched = cx.hdr->n_sched, n_ext = cx.hdr->n_ext;
+  const uint32_t n_stale_words = cx.hdr->n_stale_words;
+
+  if (P.do_init) {
+    /* fresh replication: zero state, no pending events, stocks hold their initial items */
+    for (uint32_t s = 0; s < P.n64; ++s) S64(s) = 0;
+    for (uint32_t s = 0; s < P.n32; ++s) S32(s) = 0;
+    for (uint32_t i = 0; i < n_sched; ++i) S64(G64_FIRE0 + i) = QK_TIME_NONE;
+    cx.now = P.t0;
+    cx.log_cnt = 0;
+    if (live) {
+      uint32_t initial_base = 0;
+      for (uint32_t i = 0; i < n_comp; ++i) {
+        const DevComp* c = &cx.comps[i];
+        if (c->o64_ttnpe != 0xFFFF) S64(c->o64_ttnpe) = QK_TIME_NONE;
+        /* DelayModes::modify(Add) samples until_delay when the mode is added (delays.rs:159-164) */
+        for (int k = 0; k < c->n_dm && !cx.status; ++k)
+          S64(c->o64_dm + k) = qk_sample_duration(cx, cx.dms[c->dm_off + k].until_delay);
+        if (c->kind == QK_DISCRETE_STOCK) {
+          /* with_initial_resource: the count rides in DevComp.dist_time (unused for stocks) */
+          const uint32_t n_init = c->dist_time;
+          for (uint32_t k = 0; k < n_init; ++k) S32(c->o32 + S32_RING + k) = (63u << 26) | (initial_base + k);
+          initial_base += n_init;
+          S32(c->o32 + S32_HC) = n_init << 16;
+          S32(c->o32 + S32_MAXOCC) = n_init;
+          S64(c->o64 + S64_AREA) = 0ull - (uint64_t)n_init * P.t0;
+        } else if (c->kind == QK_ENVIRONMENT) {
+          S32(c->o32 + E32_STATE) = c->low; /* initial state rides in `low` */
+        }
+      }
+      /* Model::init of every component in registration order (discrete.rs:392-398; core.rs:229-234) */
+      for (uint32_t i = 0; i < n_comp && !cx.status; ++i) {
+        const DevComp* c = &cx.comps[i];
+        if (c->kind == QK_ENVIRONMENT)
+          qk_log<LOG>(cx, c, i, SRC_INIT, QK_LOG_ENV_STATE, S32(c->o32 + E32_STATE), 0);
+        else if (c->kind != QK_DISCRETE_STOCK)
+          qk_update_state<LOG>(cx, i, SRC_INIT);
+      }
+    }
+    S64(G64_NEVENTS) = 0;
+  } else {
+    for (uint32_t s = 0; s < P.n64; ++s) S64(s) = P.g64[(size_t)s * P.rep_pad + rep_local];
+    for (uint32_t s = 0; s < P.n32; ++s) S32(s) = P.g32[(size_t)s * P.rep_pad + rep_local];
+    cx.now = S64(G64_NOW);
+    cx.status = S32(G32_STATUS);
+    cx.log_cnt = S32(G32_LOGCNT);
+  }
+
+  /* ---- event loop: one update_state per lane per trip ------------------------------------------------- */
+  uint64_t events_done = 0;
+  const uint64_t budget = live ? P.event_budget : 0;
+  uint32_t rem = 0, ptr = 0;
+  uint64_t src = 0;
+  uint32_t ext_cursor = S32(G32_EXT_CURSOR);
+  for (;;) {
+    if (rem == 0) {
+      if (cx.status || events_done >= budget) break;
+      /* pop the scheduler queue: min over (time, rank); rank 0 = externally scheduled events */
+      uint64_t best = ext_cursor < n_ext ? cx.ext[ext_cursor].t : QK_TIME_NONE;
+      int bi = -1;
+      for (uint32_t i = 0; i < n_sched; ++i) {
+        const uint64_t t = S64(G64_FIRE0 + i);
+        if (t < best) {
+          best = t;
+          bi = (int)i;
+        }
+      }
+      bool stale = false;
+      uint32_t stale_word = 0, stale_mask = 0;
+      for (uint32_t w = 0; w < n_stale_words; ++w) {
+        const uint32_t m = S32(G32_STALE0 + w);
+        if (m) {
+          const int is = (int)(w * 32) + __ffs((int)m) - 1;
+          if (best > cx.now || is < bi) { /* a stale handle fires at `now`, in rank order */
+            stale = true;
+            bi = is;
+            best = cx.now;
+            stale_word = w;
+            stale_mask = m & (m - 1);
+          }
+          break;
+        }
+      }
+      if (best == QK_TIME_NONE || best > P.t_until) break;
+      if (stale) S32(G32_STALE0 + stale_word) = stale_mask;
+      cx.now = best;
+      events_done += 1;
+      if (bi < 0) {
+        /* ScheduledEventConfig::SetEnvironmentState -> BasicEnvironment::set_state (core.rs:256-265, 1393-1396) */
+        const DevExt* e = &cx.ext[ext_cursor];
+        ext_cursor += 1;
+        const DevComp* c = &cx.comps[e->target];
+        if (S32(c->o32 + E32_STATE) != e->state) {
+          S32(c->o32 + E32_STATE) = e->state;
+          src = qk_log<LOG>(cx, c, e->target, SRC_SCH, QK_LOG_ENV_STATE, e->state, 0);
+          rem = c->n_subs;
+          ptr = c->subs_off;
+        }
+      } else {
+        const uint32_t comp = cx.sched[bi];
+        const DevComp* c = &cx.comps[comp];
+        if (c->kind == QK_DISCRETE_STOCK) {
+          /* emit_change (discrete.rs:227-233): log the state AT EMISSION TIME, then update_state on every
+           * subscriber in connection order */
+          const uint32_t src_seq = qk_emit_pop<LOG>(cx, c);
+          const uint32_t cnt = S32(c->o32 + S32_HC) >> 16;
+          const uint32_t empty = c->max > cnt ? c->max - cnt : 0;
+          src = qk_log<LOG>(cx, c, comp, ((uint64_t)comp << 32) | src_seq, QK_LOG_STOCK_STATE_CHANGE,
+                            qk_stock_cat(cnt, c->low, c->max), ((uint64_t)cnt << 32) | empty);
+          rem = c->n_subs;
+          ptr = c->subs_off;
+        } else {
+          /* keyed update_state(source_event_id) (discrete.rs:549,556) */
+          if (stale) {
+            if (LOG) src = S64(c->olog64 + PL64_STALE_SRC);
+          } else {
+            if (LOG) src = S64(c->olog64 + PL64_SCHED_SRC);
+            S64(G64_FIRE0 + bi) = QK_TIME_NONE;
+          }
+          rem = 1;
+          ptr = cx.hdr->ident_off + comp;
+        }
+      }
+      if (rem == 0) continue;
+    }
+    const uint32_t p = cx.subs[ptr];
+    ptr += 1;
+    rem -= 1;
+    qk_update_state<LOG>(cx, p, src);
+    if (cx.status) rem = 0;
+  }
+  /* step_until(t) leaves the clock at t */
+  if (!cx.status && live && P.t_until != QK_TIME_NONE && P.t_until > cx.now) cx.now = P.t_until;
+
+  S64(G64_NOW) = cx.now;
+  S64(G64_NEVENTS) += events_done;
+  S32(G32_STATUS) = cx.status;
+  S32(G32_EXT_CURSOR) = ext_cursor;
+  S32(G32_LOGCNT) = cx.log_cnt;
+  for (uint32_t s = 0; s < P.n64; ++s) P.g64[(size_t)s * P.rep_pad + rep_local] = S64(s);
+  for (uint32_t s = 0; s < P.n32; ++s) P.g32[(size_t)s * P.rep_pad + rep_local] = S32(s);
+}
+
+/* per-replication (count, time_ns, aux, level) of component c, from the HBM state planes */
+__device__ __forceinline__ void qk_comp_stats_dev(const DevComp* c, const uint64_t* g64, const uint32_t* g32,
+                                                  uint64_t rep_pad, uint64_t rep, qk_comp_stats* o) {
+#define G64(slot) g64[(size_t)(slot)*rep_pad + rep]
+#define G32(slot) g32[(size_t)(slot)*rep_pad + rep]
+  const uint64_t now = G64(G64_NOW);
+  if (c->kind == QK_DISCRETE_STOCK) {
+    const uint32_t cnt = G32(c->o32 + S32_HC) >> 16;
+    o->count = G32(c->o32 + S32_NADD);
+    o->time_ns = G64(c->o64 + S64_AREA) + (uint64_t)cnt * now;
+    o->aux = G32(c->o32 + S32_MAXOCC);
+    o->level = cnt;
+  } else if (c->kind == QK_DISCRETE_PARALLEL_PROCESS) {
+    const uint32_t nprog = G32(c->o32 + PP32_NPROG);
+    uint64_t busy = G64(c->o64 + PP64_BUSY);
+    for (uint32_t i = 0; i < nprog; ++i) busy -= G64(c->o64_dm + c->n_dm + i);
+    o->count = G32(c->o32 + PP32_NFINISH);
+    o->time_ns = busy;
+    o->aux = c->o64_delayns != 0xFFFF ? G64(c->o64_delayns) : 0;
+    o->level = nprog;
+  } else if (c->kind == QK_ENVIRONMENT) {
+    o->count = 0;
+    o->time_ns = 0;
+    o->aux = 0;
+    o->level = G32(c->o32 + E32_STATE);
+  } else {
+    const uint32_t flags = G32(c->o32 + P32_FLAGS);
+    const bool has = flags & PF_HAS_ITEM;
+    o->count = G32(c->o32 + P32_NFINISH);
+    o->time_ns = G64(c->o64 + P64_BUSY) - (has ? G64(c->o64 + P64_LEFT) : 0);
+    o->aux = c->o64_delayns != 0xFFFF ? G64(c->o64_delayns) : 0;
+    o->level = has ? 1 : 0;
+  }
+#undef G64
+#undef G32
+}
+
+#endif

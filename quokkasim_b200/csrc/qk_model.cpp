@@ -1,0 +1,472 @@
+/*
+ * qk_model.cpp -- model description tables behind the C ABI and their lowering to the device layout.
+ *
+ * Replaces, for the batched path, what the reference's generated enums do on the host:
+ * ComponentModel::register_component / connect_components / connect_logger and
+ * ScheduledEventConfig::schedule_event (core.rs:565-1401).  Instead of wiring NeXosim ports with
+ * closures, every call appends a row; qk_lower() turns the rows into the flat tables the kernels read.
+ */
+#include "qk_model.h"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+static thread_local char g_err[512] = "";
+
+void qk_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int qk_is_process_like(uint32_t k) {
+  return k == QK_DISCRETE_PROCESS || k == QK_DISCRETE_SOURCE || k == QK_DISCRETE_SINK ||
+         k == QK_DISCRETE_PARALLEL_PROCESS;
+}
+
+static const char* kind_name(uint32_t k) {
+  switch (k) {
+    case QK_DISCRETE_STOCK: return "StringStock";
+    case QK_DISCRETE_PROCESS: return "StringProcess";
+    case QK_DISCRETE_SOURCE: return "StringSource";
+    case QK_DISCRETE_SINK: return "StringSink";
+    case QK_DISCRETE_PARALLEL_PROCESS: return "StringParallelProcess";
+    case QK_ENVIRONMENT: return "BasicEnvironment";
+    default: return "?";
+  }
+}
+
+extern "C" {
+
+const char* qk_last_error(void) { return g_err; }
+int qk_abi_version(void) { return QK_ABI_VERSION; }
+
+int qk_model_create(qk_model** out) {
+  if (!out) {
+    qk_set_error("qk_model_create: out is NULL");
+    return QK_ERR_INVALID_ARG;
+  }
+  qk_model* m = new qk_model();
+  m->n_sources = 0;
+  m->n_initial_total = 0;
+  *out = m;
+  return QK_OK;
+}
+
+void qk_model_destroy(qk_model* m) { delete m; }
+
+int qk_model_add_component(qk_model* m, const qk_component_desc* d, uint32_t* out_id) {
+  if (!m || !d) {
+    qk_set_error("qk_model_add_component: NULL argument");
+    return QK_ERR_INVALID_ARG;
+  }
+  if (!(d->kind >= QK_DISCRETE_STOCK && d->kind <= QK_ENVIRONMENT)) {
+    qk_set_error("qk_model_add_component: unknown component kind %u", d->kind);
+    return QK_ERR_INVALID_ARG;
+  }
+  if (m->comps.size() >= QK_MAX_COMPONENTS) {
+    qk_set_error("qk_model_add_component: more than %d components", QK_MAX_COMPONENTS);
+    return QK_ERR_CAPACITY;
+  }
+  QkHostComp c;
+  c.d = *d;
+  c.up = c.down = c.env = -1;
+  c.dist_time = c.dist_qty = -1;
+  c.logged = false;
+  c.src_ord = -1;
+  c.initial_base = m->n_initial_total;
+  if (d->kind == QK_DISCRETE_STOCK) m->n_initial_total += d->n_initial_items;
+  if (d->kind == QK_DISCRETE_SOURCE) {
+    if (m->n_sources >= 63) {
+      qk_set_error("qk_model_add_component: at most 63 DiscreteSource components (item handle ordinal)");
+      return QK_ERR_CAPACITY;
+    }
+    c.src_ord = (int)m->n_sources++;
+  }
+  if (qk_is_process_like(d->kind)) {
+    /* Distribution::default() == Constant(1.) (common.rs:181-185) */
+    qk_dist_desc one;
+    memset(&one, 0, sizeof(one));
+    one.kind = QK_DIST_CONSTANT;
+    one.p[0] = 1.0;
+    c.dist_time = (int)m->dists.size();
+    m->dists.push_back(one);
+    c.dist_qty = (int)m->dists.size();
+    m->dists.push_back(one);
+  }
+  m->comps.push_back(c);
+  if (out_id) *out_id = (uint32_t)m->comps.size() - 1;
+  return QK_OK;
+}
+
+static int check_dist(const qk_dist_desc* d) {
+  if (!d) return 0;
+  switch (d->kind) {
+    case QK_DIST_CONSTANT:
+    case QK_DIST_UNIFORM:
+    case QK_DIST_NORMAL:
+    case QK_DIST_EXPONENTIAL:
+      return 1;
+    case QK_DIST_TRIANGULAR: /* rand_distr Triangular::new: max >= mode >= min, max > min */
+      return d->p[1] >= d->p[2] && d->p[2] >= d->p[0] && d->p[1] > d->p[0];
+    case QK_DIST_TRUNCNORMAL: /* common.rs:108-112 */
+      return d->p[2] < d->p[3];
+    default:
+      return 0;
+  }
+}
+
+int qk_model_set_dist(qk_model* m, uint32_t comp, uint32_t which, const qk_dist_desc* d, uint32_t* out_id) {
+  if (!m || comp >= m->comps.size() || !qk_is_process_like(m->comps[comp].d.kind) || which > 1) {
+    qk_set_error("qk_model_set_dist: component %u has no distribution slot %u", comp, which);
+    return QK_ERR_INVALID_ARG;
+  }
+  if (!check_dist(d)) {
+    qk_set_error("qk_model_set_dist: invalid distribution parameters");
+    return QK_ERR_INVALID_ARG;
+  }
+  int id = which == 0 ? m->comps[comp].dist_time : m->comps[comp].dist_qty;
+  m->dists[(size_t)id] = *d;
+  if (out_id) *out_id = (uint32_t)id;
+  return QK_OK;
+}
+
+int qk_model_add_delay_mode(qk_model* m, uint32_t comp, const qk_dist_desc* ud, const qk_dist_desc* uf,
+                            uint32_t* out_ud, uint32_t* out_uf) {
+  if (!m || comp >= m->comps.size() || !qk_is_process_like(m->comps[comp].d.kind)) {
+    qk_set_error("qk_model_add_delay_mode: component %u cannot carry delay modes", comp);
+    return QK_ERR_INVALID_ARG;
+  }
+  if (!check_dist(ud) || !check_dist(uf)) {
+    qk_set_error("qk_model_add_delay_mode: invalid distribution parameters");
+    return QK_ERR_INVALID_ARG;
+  }
+  if (m->comps[comp].dms.size() >= QK_MAX_DELAY_MODES) {
+    qk_set_error("qk_model_add_delay_mode: more than %d delay modes on one component", QK_MAX_DELAY_MODES);
+    return QK_ERR_CAPACITY;
+  }
+  DevDelayMode dm;
+  dm.until_delay = (uint16_t)m->dists.size();
+  m->dists.push_back(*ud);
+  dm.until_fix = (uint16_t)m->dists.size();
+  m->dists.push_back(*uf);
+  m->comps[comp].dms.push_back(dm);
+  if (out_ud) *out_ud = dm.until_delay;
+  if (out_uf) *out_uf = dm.until_fix;
+  return QK_OK;
+}
+
+/* connect_components (core.rs:565-1178).  Every supported (a,b) pair wires the same three
+ * connections as the reference arm it stands for; unsupported pairs return the reference's
+ * "No component connection defined" error (discrete_queue.rs:14-20). */
+int qk_model_connect(qk_model* m, uint32_t a, uint32_t b, int32_t port_n) {
+  if (!m || a >= m->comps.size() || b >= m->comps.size()) {
+    qk_set_error("qk_model_connect: component id out of range");
+    return QK_ERR_INVALID_ARG;
+  }
+  QkHostComp& A = m->comps[a];
+  QkHostComp& B = m->comps[b];
+  uint32_t ka = A.d.kind, kb = B.d.kind;
+  if (ka == QK_DISCRETE_STOCK &&
+      (kb == QK_DISCRETE_PROCESS || kb == QK_DISCRETE_SINK || kb == QK_DISCRETE_PARALLEL_PROCESS)) {
+    /* core.rs:886-891, 898-903, 916-921: state_emitter->update_state, req_upstream, withdraw_upstream */
+    if (B.up >= 0) {
+      qk_set_error("qk_model_connect: component %u already has an upstream stock (a second connection on "
+                   "req_upstream/withdraw_upstream is not supported)", b);
+      return QK_ERR_PORT_IN_USE;
+    }
+    A.subs.push_back((int)b);
+    B.up = (int)a;
+    return QK_OK;
+  }
+  if (kb == QK_DISCRETE_STOCK &&
+      (ka == QK_DISCRETE_PROCESS || ka == QK_DISCRETE_SOURCE || ka == QK_DISCRETE_PARALLEL_PROCESS)) {
+    /* core.rs:892-897, 904-915: state_emitter->update_state, req_downstream, push_downstream */
+    if (A.down >= 0) {
+      qk_set_error("qk_model_connect: component %u already has a downstream stock", a);
+      return QK_ERR_PORT_IN_USE;
+    }
+    B.subs.push_back((int)a);
+    A.down = (int)b;
+    return QK_OK;
+  }
+  if (ka == QK_ENVIRONMENT && qk_is_process_like(kb)) {
+    /* core.rs:1129-1148: emit_change->update_state, req_environment */
+    if (B.env >= 0) {
+      qk_set_error("qk_model_connect: component %u already has an environment", b);
+      return QK_ERR_PORT_IN_USE;
+    }
+    A.subs.push_back((int)b);
+    B.env = (int)a;
+    return QK_OK;
+  }
+  if (port_n >= 0)
+    qk_set_error("No component connection defined from %s to %s (n=Some(%d))", kind_name(ka), kind_name(kb), port_n);
+  else
+    qk_set_error("No component connection defined from %s to %s (n=None)", kind_name(ka), kind_name(kb));
+  return QK_ERR_UNSUPPORTED_CONNECTION;
+}
+
+int qk_model_set_logged(qk_model* m, uint32_t comp, int enabled) {
+  if (!m || comp >= m->comps.size()) {
+    qk_set_error("qk_model_set_logged: component id out of range");
+    return QK_ERR_INVALID_ARG;
+  }
+  m->comps[comp].logged = enabled != 0;
+  return QK_OK;
+}
+
+int qk_model_schedule_env_state(qk_model* m, uint64_t t_ns, uint32_t env, uint32_t state) {
+  if (!m || env >= m->comps.size() || m->comps[env].d.kind != QK_ENVIRONMENT || state > 1) {
+    /* core.rs:1397-1399 */
+    qk_set_error("schedule_event not implemented for types (SetEnvironmentState, %s)",
+                 (m && env < m->comps.size()) ? kind_name(m->comps[env].d.kind) : "?");
+    return QK_ERR_INVALID_ARG;
+  }
+  DevExt e;
+  memset(&e, 0, sizeof(e));
+  e.t = t_ns;
+  e.type = 0;
+  e.target = env;
+  e.state = state;
+  m->ext.push_back(e);
+  return QK_OK;
+}
+
+int qk_model_n_components(const qk_model* m, uint32_t* out) {
+  if (!m || !out) return QK_ERR_INVALID_ARG;
+  *out = (uint32_t)m->comps.size();
+  return QK_OK;
+}
+int qk_model_n_dists(const qk_model* m, uint32_t* out) {
+  if (!m || !out) return QK_ERR_INVALID_ARG;
+  *out = (uint32_t)m->dists.size();
+  return QK_OK;
+}
+int qk_model_state_bytes(const qk_model* m, int with_log, uint32_t* out) {
+  if (!m || !out) return QK_ERR_INVALID_ARG;
+  QkLowered l;
+  int rc = qk_lower(m, with_log != 0, &l);
+  if (rc) return rc;
+  *out = l.hdr.n64 * 8 + l.hdr.n32 * 4;
+  return QK_OK;
+}
+
+} /* extern "C" */
+
+/* ------------------------------------------------------------------------------------------------ */
+
+static uint32_t align8(uint32_t x) { return (x + 7u) & ~7u; }
+
+int qk_lower(const qk_model* m, bool log, QkLowered* out) {
+  const size_t nc = m->comps.size();
+  if (nc == 0) {
+    qk_set_error("qk_lower: model has no components");
+    return QK_ERR_INVALID_ARG;
+  }
+  std::vector<DevComp> dc(nc);
+  std::vector<DevDist> dd(m->dists.size());
+  std::vector<DevDelayMode> dms;
+  std::vector<uint16_t> subs;
+  std::vector<uint16_t> sched;
+
+  for (size_t i = 0; i < m->dists.size(); ++i) {
+    memset(&dd[i], 0, sizeof(DevDist));
+    dd[i].kind = m->dists[i].kind;
+    dd[i].stream = m->dists[i].stream;
+    for (int k = 0; k < 4; ++k) dd[i].p[k] = m->dists[i].p[k];
+    dd[i].draw_slot = 0xFFFFFFFFu;
+  }
+
+  /* schedulable components in rank order */
+  for (size_t i = 0; i < nc; ++i) {
+    memset(&dc[i], 0, sizeof(DevComp));
+    uint32_t k = m->comps[i].d.kind;
+    dc[i].fire_idx = 0xFFFF;
+    if (k == QK_DISCRETE_STOCK || qk_is_process_like(k)) {
+      dc[i].fire_idx = (uint16_t)sched.size();
+      sched.push_back((uint16_t)i);
+    }
+  }
+  uint32_t n_sched = (uint32_t)sched.size();
+  uint32_t n_stale_words = (n_sched + 31) / 32;
+  if (n_stale_words == 0) n_stale_words = 1;
+  uint32_t n64 = G64_FIRE0 + n_sched;
+  uint32_t n32 = G32_STALE0 + n_stale_words;
+
+  /* capacities that depend on neighbours */
+  std::vector<uint32_t> cap(nc, 0);
+  for (size_t i = 0; i < nc; ++i) { /* stock rings first */
+    const QkHostComp& c = m->comps[i];
+    if (c.d.kind != QK_DISCRETE_STOCK) continue;
+    uint32_t r;
+    if (c.d.capacity_hint) {
+      r = c.d.capacity_hint;
+    } else {
+      uint32_t base = std::max(c.d.max_capacity, c.d.n_initial_items);
+      if (base > 4096) {
+        qk_set_error("component %zu: max_capacity %u needs an explicit capacity_hint (item-ring slots)", i,
+                     c.d.max_capacity);
+        return QK_ERR_CAPACITY;
+      }
+      uint32_t producers = 0;
+      for (size_t j = 0; j < nc; ++j)
+        if (m->comps[j].down == (int)i && m->comps[j].d.kind != QK_DISCRETE_PARALLEL_PROCESS) producers++;
+      /* capacity is advisory (discrete.rs:181-186 has no check): each single-server producer that saw
+       * Empty/Normal when it started may still push when the stock is already at max */
+      r = base + producers;
+      if (r == 0) r = 1;
+    }
+    if (r < c.d.n_initial_items || r > 0xFFFF) {
+      qk_set_error("component %zu: item ring of %u slots is out of range", i, r);
+      return QK_ERR_CAPACITY;
+    }
+    cap[i] = r;
+  }
+  for (size_t i = 0; i < nc; ++i) {
+    const QkHostComp& c = m->comps[i];
+    if (c.d.kind != QK_DISCRETE_PARALLEL_PROCESS) continue;
+    uint32_t r = c.d.capacity_hint ? c.d.capacity_hint : (c.up >= 0 ? 2 * cap[(size_t)c.up] + 8 : 8);
+    if (r > 0xFFFF) return QK_ERR_CAPACITY;
+    cap[i] = r;
+  }
+
+  for (size_t i = 0; i < nc; ++i) {
+    const QkHostComp& c = m->comps[i];
+    DevComp& d = dc[i];
+    d.kind = (uint8_t)c.d.kind;
+    d.n_dm = (uint8_t)c.dms.size();
+    d.src_ord = (uint8_t)(c.src_ord >= 0 ? c.src_ord : 0);
+    d.up = (int16_t)c.up;
+    d.down = (int16_t)c.down;
+    d.env = (int16_t)c.env;
+    d.low = c.d.low_capacity;
+    d.max = c.d.max_capacity;
+    d.ring_cap = (uint16_t)cap[i];
+    d.dist_time = (uint16_t)(c.dist_time >= 0 ? c.dist_time : 0);
+    d.flags = c.logged ? DC_LOGGED : 0;
+    d.o64_ttnpe = 0xFFFF;
+    d.o64_delayns = 0xFFFF;
+    d.o32_next_item = 0xFFFF;
+    if (c.subs.size() > 255) {
+      qk_set_error("component %zu: more than 255 subscribers", i);
+      return QK_ERR_CAPACITY;
+    }
+    d.n_subs = (uint8_t)c.subs.size();
+    d.subs_off = (uint16_t)subs.size();
+    for (size_t k = 0; k < c.subs.size(); ++k) subs.push_back((uint16_t)c.subs[k]);
+    d.dm_off = (uint16_t)dms.size();
+    for (size_t k = 0; k < c.dms.size(); ++k) dms.push_back(c.dms[k]);
+
+    uint32_t kind = c.d.kind;
+    if (kind == QK_DISCRETE_PROCESS || kind == QK_DISCRETE_SOURCE || kind == QK_DISCRETE_SINK) {
+      d.o64 = (uint16_t)n64;
+      n64 += P64_BASE_COUNT;
+      if (kind == QK_DISCRETE_SINK) d.o64_ttnpe = (uint16_t)n64++;
+      if (d.n_dm) d.o64_delayns = (uint16_t)n64++;
+      d.o64_dm = (uint16_t)n64;
+      n64 += d.n_dm;
+      d.o32 = (uint16_t)n32;
+      n32 += P32_BASE_COUNT;
+      if (kind == QK_DISCRETE_SOURCE) d.o32_next_item = (uint16_t)n32++;
+    } else if (kind == QK_DISCRETE_PARALLEL_PROCESS) {
+      d.o64 = (uint16_t)n64;
+      n64 += PP64_BASE_COUNT;
+      if (d.n_dm) d.o64_delayns = (uint16_t)n64++;
+      d.o64_dm = (uint16_t)n64;
+      n64 += d.n_dm;
+      n64 += d.ring_cap; /* in-progress durations */
+      d.o32 = (uint16_t)n32;
+      n32 += PP32_BASE_COUNT + 2u * d.ring_cap;
+    } else if (kind == QK_DISCRETE_STOCK) {
+      d.o64 = (uint16_t)n64;
+      n64 += S64_COUNT;
+      d.o32 = (uint16_t)n32;
+      n32 += S32_RING + d.ring_cap;
+      uint32_t depth = 0;
+      for (size_t j = 0; j < nc; ++j) {
+        const QkHostComp& o = m->comps[j];
+        if (o.up == (int)i || o.down == (int)i)
+          depth += 2u * (o.d.kind == QK_DISCRETE_PARALLEL_PROCESS ? cap[j] : 1u);
+      }
+      if (depth < 2) depth = 2;
+      if (depth > 250) depth = 250;
+      d.emit_depth = (uint16_t)depth;
+      d.dist_time = (uint16_t)c.d.n_initial_items; /* table field reuse: initial item count */
+    } else { /* environment */
+      d.o32 = (uint16_t)n32;
+      n32 += E32_COUNT;
+      d.low = c.d.initial_env_state ? 1u : 0u; /* table field reuse: initial BasicEnvironmentState */
+    }
+    if (qk_is_process_like(kind)) {
+      if (m->dists[(size_t)c.dist_time].kind != QK_DIST_CONSTANT) dd[(size_t)c.dist_time].draw_slot = n32++;
+      for (size_t k = 0; k < c.dms.size(); ++k) {
+        if (m->dists[c.dms[k].until_delay].kind != QK_DIST_CONSTANT) dd[c.dms[k].until_delay].draw_slot = n32++;
+        if (m->dists[c.dms[k].until_fix].kind != QK_DIST_CONSTANT) dd[c.dms[k].until_fix].draw_slot = n32++;
+      }
+    }
+    if (log) {
+      d.olog32 = (uint16_t)n32;
+      n32 += 1; /* L32_SEQ */
+      if (kind == QK_DISCRETE_STOCK) n32 += d.emit_depth;
+      if (qk_is_process_like(kind)) {
+        d.olog64 = (uint16_t)n64;
+        n64 += PL64_COUNT;
+      }
+    }
+    if (n64 > 0xFFF0 || n32 > 0xFFF0) {
+      qk_set_error("model state exceeds 65520 slots per replication");
+      return QK_ERR_CAPACITY;
+    }
+  }
+  uint32_t ident_off = (uint32_t)subs.size();
+  for (size_t i = 0; i < nc; ++i) subs.push_back((uint16_t)i);
+
+  /* externally scheduled events: origin rank 0, FIFO among equal times (stable sort) */
+  std::vector<DevExt> ext = m->ext;
+  std::stable_sort(ext.begin(), ext.end(), [](const DevExt& a, const DevExt& b) { return a.t < b.t; });
+
+  DevHeader h;
+  memset(&h, 0, sizeof(h));
+  h.n_comp = (uint32_t)nc;
+  h.n_sched = n_sched;
+  h.n_dist = (uint32_t)dd.size();
+  h.n_dm = (uint32_t)dms.size();
+  h.n_subs = (uint32_t)subs.size();
+  h.n_ext = (uint32_t)ext.size();
+  h.n64 = n64;
+  h.n32 = n32;
+  h.n_stale_words = n_stale_words;
+  h.ident_off = ident_off;
+  h.log_enabled = log ? 1 : 0;
+  uint32_t off = align8((uint32_t)sizeof(DevHeader));
+  h.off_comps = off;
+  off = align8(off + (uint32_t)(nc * sizeof(DevComp)));
+  h.off_dists = off;
+  off = align8(off + (uint32_t)(dd.size() * sizeof(DevDist)));
+  h.off_ext = off;
+  off = align8(off + (uint32_t)(ext.size() * sizeof(DevExt)));
+  h.off_dms = off;
+  off = align8(off + (uint32_t)(dms.size() * sizeof(DevDelayMode)));
+  h.off_subs = off;
+  off = align8(off + (uint32_t)(subs.size() * sizeof(uint16_t)));
+  h.off_sched = off;
+  off = align8(off + (uint32_t)(sched.size() * sizeof(uint16_t)));
+  h.total_bytes = off;
+
+  out->blob.assign(off, 0);
+  memcpy(out->blob.data(), &h, sizeof(h));
+  memcpy(out->blob.data() + h.off_comps, dc.data(), nc * sizeof(DevComp));
+  if (!dd.empty()) memcpy(out->blob.data() + h.off_dists, dd.data(), dd.size() * sizeof(DevDist));
+  if (!ext.empty()) memcpy(out->blob.data() + h.off_ext, ext.data(), ext.size() * sizeof(DevExt));
+  if (!dms.empty()) memcpy(out->blob.data() + h.off_dms, dms.data(), dms.size() * sizeof(DevDelayMode));
+  memcpy(out->blob.data() + h.off_subs, subs.data(), subs.size() * sizeof(uint16_t));
+  if (!sched.empty()) memcpy(out->blob.data() + h.off_sched, sched.data(), sched.size() * sizeof(uint16_t));
+  out->hdr = h;
+  out->comps = dc;
+  out->dists = dd;
+  return QK_OK;
+}

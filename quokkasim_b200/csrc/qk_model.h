@@ -1,0 +1,40 @@
+/* qk_model.h -- host-side model description and lowering (internal). */
+#ifndef QK_MODEL_H
+#define QK_MODEL_H
+#include <string>
+#include <vector>
+
+#include "qk_internal.h"
+
+struct QkHostComp {
+  qk_component_desc d;
+  int up, down, env;
+  std::vector<int> subs;
+  int dist_time, dist_qty;
+  std::vector<DevDelayMode> dms;
+  bool logged;
+  int src_ord;
+  uint32_t initial_base;
+};
+
+struct qk_model {
+  std::vector<QkHostComp> comps;
+  std::vector<qk_dist_desc> dists;
+  std::vector<DevExt> ext;
+  uint32_t n_sources;
+  uint32_t n_initial_total;
+};
+
+struct QkLowered {
+  std::vector<uint8_t> blob; /* DevHeader + tables */
+  DevHeader hdr;
+  std::vector<DevComp> comps;
+  std::vector<DevDist> dists;
+};
+
+void qk_set_error(const char* fmt, ...);
+int qk_is_process_like(uint32_t kind);
+/* lowers the model for the given logging mode; returns QK_OK or an error */
+int qk_lower(const qk_model* m, bool log, QkLowered* out);
+
+#endif

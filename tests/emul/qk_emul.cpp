@@ -1,0 +1,254 @@
+/*
+ * qk_emul.cpp -- TEST INFRASTRUCTURE ONLY (see qk_host_emul.h).
+ *
+ * Implements the batch half of the C ABI (include/quokka_b200.h) on the CPU by compiling the REAL kernel
+ * source quokkasim_b200/csrc/qk_kernels.cuh with g++ and running it one replication per "block" (nt == 1).
+ * The model half (qk_model_*) is the product's own host code (qk_model.cpp), linked in unchanged.
+ * Used by `pytest -m "not gpu"` to check kernel logic against the oracle without a GPU.  Not shipped, not
+ * loaded by the quokkasim_b200 package.
+ */
+#define QK_HOST_EMUL 1
+#include <algorithm>
+#include <cstdlib>
+#include <vector>
+
+#include "qk_kernels.cuh"
+#include "qk_model.h"
+
+thread_local uint8_t* qk_emul_smem = nullptr;
+thread_local uint32_t qk_emul_bid = 0;
+
+struct qk_batch {
+  qk_batch_config cfg;
+  QkLowered low;
+  bool log;
+  uint32_t table_bytes_padded;
+  uint64_t rep_pad;
+  std::vector<uint64_t> g64;
+  std::vector<uint32_t> g32;
+  std::vector<uint8_t> tables;
+  std::vector<uint4> logbuf;
+  std::vector<std::vector<double> > tapes;
+  std::vector<const double*> tape_ptr;
+  std::vector<uint64_t> tape_len;
+  bool any_tape;
+  bool initialised;
+};
+
+static int run(qk_batch* b, uint32_t do_init, uint64_t t0, uint64_t t_until, uint64_t budget) {
+  KParams P;
+  memset(&P, 0, sizeof(P));
+  P.g64 = b->g64.data();
+  P.g32 = b->g32.data();
+  P.tables = b->tables.data();
+  P.table_bytes = b->table_bytes_padded;
+  P.n64 = b->low.hdr.n64;
+  P.n32 = b->low.hdr.n32;
+  P.n_reps = b->cfg.n_reps;
+  P.rep_pad = b->rep_pad;
+  P.rep_offset = b->cfg.rep_offset;
+  P.seed = b->cfg.base_seed;
+  P.log = b->log ? b->logbuf.data() : nullptr;
+  P.log_cap = b->log ? b->cfg.log_capacity : 0;
+  P.tapes = b->any_tape ? b->tape_ptr.data() : nullptr;
+  P.tape_len = b->tape_len.data();
+  P.t0 = t0;
+  P.t_until = t_until;
+  P.event_budget = budget;
+  P.do_init = do_init;
+  const size_t smem_bytes = b->table_bytes_padded + (size_t)P.n64 * 8 + (size_t)P.n32 * 4;
+  std::vector<uint64_t> smem((smem_bytes + 7) / 8 + 2);
+  qk_emul_smem = reinterpret_cast<uint8_t*>(smem.data());
+  for (uint64_t r = 0; r < b->rep_pad; ++r) {
+    qk_emul_bid = (uint32_t)r;
+    if (b->log)
+      qk_step_kernel<true>(P);
+    else
+      qk_step_kernel<false>(P);
+  }
+  qk_emul_smem = nullptr;
+  return QK_OK;
+}
+
+extern "C" {
+
+int qk_batch_create(const qk_model* m, const qk_batch_config* cfg, qk_batch** out) {
+  if (!m || !cfg || !out || cfg->n_reps == 0) return QK_ERR_INVALID_ARG;
+  if (cfg->log_capacity && (cfg->log_capacity & (cfg->log_capacity - 1))) return QK_ERR_INVALID_ARG;
+  qk_batch* b = new qk_batch();
+  b->cfg = *cfg;
+  b->log = cfg->log_capacity != 0;
+  int rc = qk_lower(m, b->log, &b->low);
+  if (rc) {
+    delete b;
+    return rc;
+  }
+  const DevHeader& h = b->low.hdr;
+  b->table_bytes_padded = (h.total_bytes + 15u) & ~15u;
+  b->rep_pad = cfg->n_reps;
+  b->g64.assign((size_t)h.n64 * b->rep_pad, 0);
+  b->g32.assign((size_t)h.n32 * b->rep_pad, 0);
+  b->tables.assign(b->table_bytes_padded, 0);
+  memcpy(b->tables.data(), b->low.blob.data(), b->low.blob.size());
+  if (b->log) b->logbuf.assign((size_t)b->rep_pad * cfg->log_capacity * 2, uint4{0, 0, 0, 0});
+  b->tapes.resize(h.n_dist);
+  b->tape_ptr.assign(h.n_dist ? h.n_dist : 1, nullptr);
+  b->tape_len.assign(h.n_dist ? h.n_dist : 1, 0);
+  b->any_tape = false;
+  b->initialised = false;
+  *out = b;
+  return QK_OK;
+}
+void qk_batch_destroy(qk_batch* b) { delete b; }
+
+int qk_batch_info_get(qk_batch* b, qk_batch_info* out) {
+  if (!b || !out) return QK_ERR_INVALID_ARG;
+  memset(out, 0, sizeof(*out));
+  out->threads_per_block = 1;
+  out->grid_blocks = (uint32_t)b->rep_pad;
+  out->table_bytes = b->table_bytes_padded;
+  out->slots64 = b->low.hdr.n64;
+  out->slots32 = b->low.hdr.n32;
+  out->state_bytes_per_rep = b->low.hdr.n64 * 8 + b->low.hdr.n32 * 4;
+  out->shared_bytes_per_block = out->table_bytes + out->state_bytes_per_rep;
+  out->replications_padded = b->rep_pad;
+  out->state_bytes_total = (uint64_t)out->state_bytes_per_rep * b->rep_pad;
+  out->log_bytes_total = b->log ? (uint64_t)b->rep_pad * b->cfg.log_capacity * 32 : 0;
+  return QK_OK;
+}
+
+int qk_batch_set_tape(qk_batch* b, uint32_t dist_id, const double* values, uint64_t per_rep_len) {
+  if (!b || dist_id >= b->low.hdr.n_dist) return QK_ERR_INVALID_ARG;
+  b->tapes[dist_id].assign(values, values + per_rep_len * b->cfg.n_reps);
+  if (b->tapes[dist_id].empty()) b->tapes[dist_id].push_back(0.0);
+  b->tape_ptr[dist_id] = b->tapes[dist_id].data();
+  b->tape_len[dist_id] = per_rep_len;
+  b->any_tape = true;
+  return QK_OK;
+}
+int qk_batch_init(qk_batch* b, uint64_t t0_ns) {
+  if (!b) return QK_ERR_INVALID_ARG;
+  b->initialised = true;
+  return run(b, 1, t0_ns, QK_TIME_NONE, 0);
+}
+int qk_batch_step_until(qk_batch* b, uint64_t t_ns) {
+  if (!b || !b->initialised) return QK_ERR_STATE;
+  return run(b, 0, 0, t_ns, ~0ull);
+}
+int qk_batch_step_events(qk_batch* b, uint64_t n) {
+  if (!b || !b->initialised) return QK_ERR_STATE;
+  return run(b, 0, 0, QK_TIME_NONE, n);
+}
+int qk_batch_synchronize(qk_batch*) { return QK_OK; }
+int qk_batch_last_step_ms(qk_batch*, float* ms, uint32_t* n) {
+  if (ms) *ms = 0;
+  if (n) *n = 1;
+  return QK_OK;
+}
+
+int qk_batch_summary_get(qk_batch* b, qk_batch_summary* out) {
+  if (!b || !out) return QK_ERR_INVALID_ARG;
+  memset(out, 0, sizeof(*out));
+  out->n_reps = b->cfg.n_reps;
+  out->min_now_ns = ~0ull;
+  for (uint64_t r = 0; r < b->cfg.n_reps; ++r) {
+    out->n_events += b->g64[(size_t)G64_NEVENTS * b->rep_pad + r];
+    out->n_faulted += b->g32[(size_t)G32_STATUS * b->rep_pad + r] ? 1 : 0;
+    out->n_log_records += b->g32[(size_t)G32_LOGCNT * b->rep_pad + r];
+    const uint64_t now = b->g64[(size_t)G64_NOW * b->rep_pad + r];
+    out->min_now_ns = std::min(out->min_now_ns, now);
+    out->max_now_ns = std::max(out->max_now_ns, now);
+  }
+  return QK_OK;
+}
+
+int qk_batch_read_status(qk_batch* b, uint64_t rep0, uint64_t n, uint32_t* status, uint64_t* now_ns,
+                         uint64_t* n_events) {
+  if (!b || rep0 + n > b->cfg.n_reps) return QK_ERR_INVALID_ARG;
+  for (uint64_t i = 0; i < n; ++i) {
+    if (status) status[i] = b->g32[(size_t)G32_STATUS * b->rep_pad + rep0 + i];
+    if (now_ns) now_ns[i] = b->g64[(size_t)G64_NOW * b->rep_pad + rep0 + i];
+    if (n_events) n_events[i] = b->g64[(size_t)G64_NEVENTS * b->rep_pad + rep0 + i];
+  }
+  return QK_OK;
+}
+
+int qk_batch_comp_stats(qk_batch* b, uint64_t rep0, uint64_t n, uint32_t comp, qk_comp_stats* out) {
+  if (!b || rep0 + n > b->cfg.n_reps || comp >= b->low.hdr.n_comp) return QK_ERR_INVALID_ARG;
+  for (uint64_t i = 0; i < n; ++i)
+    qk_comp_stats_dev(&b->low.comps[comp], b->g64.data(), b->g32.data(), b->rep_pad, rep0 + i, &out[i]);
+  return QK_OK;
+}
+
+int qk_batch_reduce_stats(qk_batch* b, qk_comp_summary* out, uint32_t n_comp) {
+  if (!b || !out || n_comp != b->low.hdr.n_comp) return QK_ERR_INVALID_ARG;
+  for (uint32_t c = 0; c < n_comp; ++c) {
+    qk_comp_summary& o = out[c];
+    memset(&o, 0, sizeof(o));
+    o.min_count = o.min_time = ~0ull;
+    unsigned __int128 tsum = 0;
+    std::vector<qk_comp_stats> st(b->cfg.n_reps);
+    qk_batch_comp_stats(b, 0, b->cfg.n_reps, c, st.data());
+    for (uint64_t r = 0; r < b->cfg.n_reps; ++r) {
+      o.sum_count += st[r].count;
+      tsum += st[r].time_ns;
+      o.sum_level += st[r].level;
+      o.min_count = std::min(o.min_count, st[r].count);
+      o.max_count = std::max(o.max_count, st[r].count);
+      o.min_time = std::min(o.min_time, st[r].time_ns);
+      o.max_time = std::max(o.max_time, st[r].time_ns);
+      const double ts = (double)st[r].time_ns * 1e-9;
+      o.sumsq_time += ts * ts;
+      o.sumsq_count += (double)st[r].count * (double)st[r].count;
+    }
+    o.sum_time_lo = (uint64_t)tsum;
+    o.sum_time_hi = (uint64_t)(tsum >> 64);
+    o.hist_lo_time = o.min_time;
+    o.hist_hi_time = o.max_time;
+    o.hist_lo_count = o.min_count;
+    o.hist_hi_count = o.max_count;
+    const uint64_t w_t = (o.max_time - o.min_time) / QK_HIST_BINS + 1, w_c = (o.max_count - o.min_count) / QK_HIST_BINS + 1;
+    for (uint64_t r = 0; r < b->cfg.n_reps; ++r) {
+      o.hist_time[(st[r].time_ns - o.min_time) / w_t] += 1;
+      o.hist_count[(st[r].count - o.min_count) / w_c] += 1;
+    }
+  }
+  return QK_OK;
+}
+int qk_batch_reduce_stats_device(qk_batch*, uint64_t*, uint64_t*, uint32_t) { return QK_ERR_NO_DEVICE; }
+int qk_batch_histograms_device(qk_batch*, const uint64_t*, uint64_t*, uint32_t) { return QK_ERR_NO_DEVICE; }
+
+int qk_batch_read_log(qk_batch* b, uint64_t rep, qk_log_record* buf, uint64_t cap, uint64_t* n_out,
+                      uint64_t* n_total) {
+  if (!b || rep >= b->cfg.n_reps || !b->log) return QK_ERR_INVALID_ARG;
+  const uint32_t cnt = b->g32[(size_t)G32_LOGCNT * b->rep_pad + rep];
+  const uint32_t lc = b->cfg.log_capacity;
+  const uint64_t kept = std::min<uint64_t>(cnt, lc);
+  if (n_total) *n_total = cnt;
+  if (n_out) *n_out = std::min<uint64_t>(kept, cap);
+  if (!buf || cap == 0) return QK_OK;
+  if (cap < kept) return QK_ERR_BUFFER_TOO_SMALL;
+  const qk_log_record* ring = reinterpret_cast<const qk_log_record*>(b->logbuf.data()) + (size_t)rep * lc;
+  const uint64_t first = cnt - kept;
+  for (uint64_t i = 0; i < kept; ++i) {
+    buf[i] = ring[(first + i) & (lc - 1)];
+    buf[i].aux = 0;
+  }
+  return QK_OK;
+}
+
+int qk_batch_read_stock(qk_batch* b, uint64_t rep, uint32_t comp, uint32_t* items, uint64_t cap, uint64_t* n_out) {
+  if (!b || rep >= b->cfg.n_reps || comp >= b->low.hdr.n_comp || b->low.comps[comp].kind != QK_DISCRETE_STOCK)
+    return QK_ERR_INVALID_ARG;
+  const DevComp& c = b->low.comps[comp];
+  const uint32_t hc = b->g32[(size_t)(c.o32 + S32_HC) * b->rep_pad + rep];
+  const uint32_t head = hc & 0xFFFFu, cnt = hc >> 16;
+  if (n_out) *n_out = cnt;
+  if (!items) return QK_OK;
+  if (cap < cnt) return QK_ERR_BUFFER_TOO_SMALL;
+  for (uint32_t i = 0; i < cnt; ++i)
+    items[i] = b->g32[(size_t)(c.o32 + S32_RING + (head + i) % c.ring_cap) * b->rep_pad + rep];
+  return QK_OK;
+}
+
+} /* extern "C" */

@@ -1,0 +1,56 @@
+/*
+ * qk_host_emul.h -- TEST INFRASTRUCTURE ONLY.
+ *
+ * Shims that let g++ compile quokkasim_b200/csrc/qk_kernels.cuh on the host, one "thread" per block
+ * (nt == 1), so the CPU-only test suite (-m "not gpu") can check the kernel LOGIC against the oracle
+ * without a GPU.  It is never part of libquokka_b200.so: the product build does not define QK_HOST_EMUL
+ * and does not have tests/emul on its include path.
+ */
+#ifndef QK_HOST_EMUL_H
+#define QK_HOST_EMUL_H
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+
+#define __device__
+#define __global__
+#define __forceinline__ inline
+#define __noinline__
+#define __launch_bounds__(x)
+#define __grid_constant__
+
+struct uint4 {
+  uint32_t x, y, z, w;
+};
+
+extern thread_local uint8_t* qk_emul_smem;
+extern thread_local uint32_t qk_emul_bid;
+#define QK_SMEM_DECL(name) uint8_t* name = qk_emul_smem
+#define QK_TID 0u
+#define QK_NT 1u
+#define QK_BID qk_emul_bid
+static inline void __syncthreads() {}
+
+static inline uint64_t __umul64hi(uint64_t a, uint64_t b) {
+  return (uint64_t)(((unsigned __int128)a * b) >> 64);
+}
+static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+static inline long long __double_as_longlong(double d) {
+  long long v;
+  std::memcpy(&v, &d, 8);
+  return v;
+}
+static inline double __longlong_as_double(long long v) {
+  double d;
+  std::memcpy(&d, &v, 8);
+  return d;
+}
+/* built with -ffp-contract=off: each of these is one IEEE round-to-nearest operation */
+static inline double __dmul_rn(double a, double b) { return a * b; }
+static inline double __dadd_rn(double a, double b) { return a + b; }
+static inline double __dsub_rn(double a, double b) { return a - b; }
+static inline double __ddiv_rn(double a, double b) { return a / b; }
+static inline double __dsqrt_rn(double a) { return std::sqrt(a); }
+static inline int __ffs(int v) { return __builtin_ffs(v); }
+
+#endif

@@ -1,0 +1,85 @@
+"""Shared test helpers: model zoo (the reference's example topologies), oracle lowering, parity comparison.
+
+The oracle (oracle/) is used here ONLY as the checker.
+"""
+import numpy as np
+
+import quokkasim_b200 as qk
+from oracle import oracle as O
+from quokkasim_b200 import _capi as capi
+
+
+from quokkasim_b200.workloads import (Model, assembly_line, car_workshop, discrete_queue, haulage,  # noqa: F401
+                                      serial_line)
+
+
+from oracle.lowering import lower_to_oracle  # noqa: F401,E402
+
+
+def make_tapes(model, n_reps, length, seed, lo=0.5, hi=9.5, dist_scale=None):
+    """Pre-drawn variate tapes: one (n_reps, length) array per random Distribution instance."""
+    rng = np.random.default_rng(seed)
+    tapes = {}
+    for d in model.random_dists:
+        a, b = lo, hi
+        if d.kind == capi.DIST_TRIANGULAR or d.kind == capi.DIST_UNIFORM:
+            a, b = d.params[0], d.params[1]
+        elif d.kind == capi.DIST_EXPONENTIAL:
+            a, b = 0.2 * d.params[0], 2.0 * d.params[0]
+        tapes[id(d)] = (d, rng.uniform(a, b, size=(n_reps, length)))
+    return tapes
+
+
+def run_oracle(model, om, dist_ids, rep, t0=0, base_seed=0, tapes=None, n_events=None, t_until=None, log=True):
+    s = O.OracleSim(om, base_seed=base_seed, rep=rep, t0_ns=t0, log=log)
+    if tapes:
+        for d, v in tapes.values():
+            for did in dist_ids[id(d)]:
+                s.set_tape(did, v[rep_local(rep, tapes)])
+    s.init()
+    if n_events is not None:
+        s.step_events(n_events)
+    if t_until is not None:
+        s.step_until(t_until)
+    return s
+
+
+def rep_local(rep, tapes):
+    return rep
+
+
+def assert_rep_parity(sim, osim, model, rep_local_idx, check_log=True):
+    """Bit-exact comparison of one replication: status, clock, event count, full log, stats, stock contents."""
+    st, now, ev = sim.status(rep_local_idx, 1)
+    assert int(st[0]) == osim.status, "status rep %d: %d vs oracle %d" % (rep_local_idx, st[0], osim.status)
+    assert int(ev[0]) == osim.n_events, "n_events rep %d: %d vs %d" % (rep_local_idx, ev[0], osim.n_events)
+    if osim.status == 0:
+        assert int(now[0]) == osim.now, "now rep %d: %d vs %d" % (rep_local_idx, now[0], osim.now)
+    if check_log:
+        glog, total = sim.read_log(rep_local_idx)
+        olog = osim.log()
+        assert total == len(olog), "log count rep %d: %d vs oracle %d" % (rep_local_idx, total, len(olog))
+        assert len(glog) == len(olog), "log ring too small for the test (%d kept of %d)" % (len(glog), total)
+        if glog.tobytes() != olog.tobytes():
+            for i in range(len(olog)):
+                if glog[i].tobytes() != olog[i].tobytes():
+                    raise AssertionError("rep %d record %d differs:\n  gpu    %r\n  oracle %r\n  prev   %r" % (
+                        rep_local_idx, i, glog[i], olog[i], olog[max(0, i - 3):i]))
+    if osim.status != 0:
+        return
+    for ci, cm in enumerate(model.components):
+        gs = sim.comp_stats(ci, rep_local_idx, 1)[0]
+        os_ = osim.comp_stats(ci)
+        if cm.variant == "StringStock":
+            items = osim.stock_items(ci)
+            assert int(gs["count"]) == int(os_["n_a"]), "stock %d n_add" % ci
+            assert int(gs["time_ns"]) == int(os_["t_a_ns"]), "stock %d area %d vs %d" % (ci, gs["time_ns"], os_["t_a_ns"])
+            assert int(gs["aux"]) == int(os_["t_b_ns"]), "stock %d max occupancy" % ci
+            assert int(gs["level"]) == len(items)
+            assert list(sim.read_stock(ci, rep_local_idx)) == items, "stock %d contents" % ci
+        elif cm.variant == "BasicEnvironment":
+            pass
+        else:
+            assert int(gs["count"]) == int(os_["n_b"]), "proc %d n_finish %d vs %d" % (ci, gs["count"], os_["n_b"])
+            assert int(gs["time_ns"]) == int(os_["t_a_ns"]), "proc %d busy %d vs %d" % (ci, gs["time_ns"], os_["t_a_ns"])
+            assert int(gs["aux"]) == int(os_["t_b_ns"]), "proc %d delay ns %d vs %d" % (ci, gs["aux"], os_["t_b_ns"])

@@ -1,0 +1,218 @@
+"""GPU parity tests: the CUDA path (through the C ABI of libquokka_b200.so) against the CPU oracle.
+
+Bit-exact on: per-replication status, clock, executed-action count, the complete record stream
+(time, component, kind, reason, seq, source id, payload), per-component statistics and stock contents.
+"""
+import numpy as np
+import pytest
+
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(lib, model, n_reps, n_events=None, t_until=None, tape_len=None, t0=0, seed=42, sample=None,
+           log_capacity=65536, rep_offset=0, threads_per_block=0):
+    om, dist_ids = H.lower_to_oracle(model)
+    tapes = H.make_tapes(model, n_reps, tape_len, seed=3) if tape_len else None
+    sim = model.sim(lib, n_reps, t0=t0, base_seed=seed, log_capacity=log_capacity, rep_offset=rep_offset,
+                    threads_per_block=threads_per_block)
+    if tapes:
+        for d, v in tapes.values():
+            sim.set_tape(d, v)
+    if n_events is not None:
+        sim.step_events(n_events)
+    if t_until is not None:
+        sim.step_until(t_until)
+    reps = range(n_reps) if sample is None else sample
+    for r in reps:
+        osim = H.run_oracle(model, om, dist_ids, rep_offset + r if not tapes else r, t0=t0, base_seed=seed,
+                            tapes=tapes, n_events=n_events, t_until=t_until)
+        H.assert_rep_parity(sim, osim, model, r)
+    s = sim.summary()
+    sim.close()
+    return s
+
+
+def test_discrete_queue_tape_events(gpu_lib):
+    """north_star parity clause: identical pre-drawn variate tape per replication -> identical trajectories."""
+    s = _check(gpu_lib, H.discrete_queue(), 256, n_events=2000, tape_len=800, log_capacity=8192)
+    assert s["n_events"] == 256 * 2000 and s["n_faulted"] == 0
+
+
+def test_discrete_queue_reference_horizon(gpu_lib):
+    """config C1: discrete_queue.rs exactly, step_until(200 s)."""
+    s = _check(gpu_lib, H.discrete_queue(), 64, t_until=200 * 10**9, tape_len=200, log_capacity=2048)
+    assert s["min_now_ns"] == s["max_now_ns"] == 200 * 10**9
+
+
+def test_discrete_queue_native_philox(gpu_lib):
+    """native Philox streams are specified operation by operation, so they are bit-exact too."""
+    _check(gpu_lib, H.discrete_queue(), 4096, n_events=3000, sample=list(range(0, 4096, 131)), log_capacity=16384)
+
+
+def test_rep_offset_is_the_philox_counter(gpu_lib):
+    """a shard [offset, offset+n) reproduces the same replications as the full batch (multi-GPU contract)."""
+    _check(gpu_lib, H.discrete_queue(), 96, n_events=1500, rep_offset=1000003, sample=[0, 1, 50, 95],
+           log_capacity=8192)
+
+
+def test_split_steps_equal_one_step(gpu_lib):
+    """state survives the HBM round trip between launches: 3 launches == 1 launch."""
+    m = H.discrete_queue()
+    a = m.sim(gpu_lib, 128, base_seed=5, log_capacity=8192)
+    a.step_events(700)
+    a.step_events(1)
+    a.step_events(799)
+    b = H.discrete_queue().sim(gpu_lib, 128, base_seed=5, log_capacity=8192)
+    b.step_events(1500)
+    for r in (0, 17, 127):
+        la, ta = a.read_log(r)
+        lb, tb = b.read_log(r)
+        assert ta == tb and la.tobytes() == lb.tobytes()
+    for ci in range(len(m.components)):
+        assert a.comp_stats(ci).tobytes() == b.comp_stats(ci).tobytes()
+    a.close()
+    b.close()
+
+
+def test_car_workshop_ties_and_shared_stocks(gpu_lib):
+    """car_workshop.rs: all-Constant times -> exact same-timestamp ties, shared stocks, stale keyed events (Q3)."""
+    m = H.car_workshop()
+    _check(gpu_lib, m, 32, t_until=m.t0 + 9 * 3600 * 10**9, t0=m.t0, log_capacity=4096)
+
+
+def test_assembly_line_parallel_process_and_environment(gpu_lib):
+    """assembly_line.rs: DiscreteParallelProcess + BasicEnvironment stop@1h / resume@2h, 3 days."""
+    m = H.assembly_line()
+    _check(gpu_lib, m, 64, t_until=m.t0 + 3 * 24 * 3600 * 10**9, t0=m.t0, sample=[0, 7, 63], log_capacity=16384)
+
+
+def test_assembly_line_tape(gpu_lib):
+    m = H.assembly_line()
+    _check(gpu_lib, m, 32, t_until=m.t0 + 2 * 24 * 3600 * 10**9, t0=m.t0, tape_len=1500, sample=[0, 31],
+           log_capacity=16384)
+
+
+def test_serial_line_breakdowns(gpu_lib):
+    """config C4 in miniature: DelayModes with Exponential until-delay / until-fix on every process."""
+    _check(gpu_lib, H.serial_line(n_proc=4), 256, n_events=20000, sample=[0, 100, 255], log_capacity=131072)
+
+
+def test_serial_line_32_processes(gpu_lib):
+    """config C4 topology (32 DiscreteProcess / 33 DiscreteStock), fewer events."""
+    _check(gpu_lib, H.serial_line(n_proc=32), 64, n_events=30000, sample=[0, 63], log_capacity=131072)
+
+
+def test_haulage_network(gpu_lib):
+    """config C5 in miniature: shared load/dump queues, several sources and sinks."""
+    _check(gpu_lib, H.haulage(n_src=3, per_queue=4), 128, n_events=20000, sample=[0, 64, 127], log_capacity=131072)
+
+
+def test_haulage_full_topology(gpu_lib):
+    """config C5 topology: 8 Sources, 64 Processes, 16 shared stocks, 8 Sinks."""
+    _check(gpu_lib, H.haulage(n_src=8, per_queue=8), 64, n_events=20000, sample=[0, 63], log_capacity=131072)
+
+
+def test_faults_freeze_one_replication_only(gpu_lib):
+    """tape value 0.0 -> Duration 0 -> "Time until next event is zero!" in that replication only."""
+    m = H.discrete_queue()
+    n = 64
+    tapes = H.make_tapes(m, n, 300, seed=9)
+    d0, v0 = list(tapes.values())[0]
+    v0[5, 3] = 0.0  # zero duration -> QK_REP_ZERO_DURATION
+    v0[9, 2] = -1.0  # negative -> QK_REP_BAD_DURATION
+    om, dist_ids = H.lower_to_oracle(m)
+    sim = m.sim(gpu_lib, n, log_capacity=4096)
+    for d, v in tapes.values():
+        sim.set_tape(d, v)
+    sim.step_events(600)
+    st, _, _ = sim.status()
+    assert st[5] == 1 and st[9] == 2 and (np.delete(st, [5, 9]) == 0).all()
+    for r in (4, 5, 9):
+        osim = H.run_oracle(m, om, dist_ids, r, tapes=tapes, n_events=600)
+        H.assert_rep_parity(sim, osim, m, r)
+    sim.close()
+
+
+def test_tape_exhaustion_is_reported(gpu_lib):
+    m = H.discrete_queue()
+    sim = m.sim(gpu_lib, 32, log_capacity=0)
+    for d, v in H.make_tapes(m, 32, 10, seed=1).values():
+        sim.set_tape(d, v)
+    sim.step_events(5000)
+    st, _, _ = sim.status()
+    assert (st == 3).all()
+    sim.close()
+
+
+def test_block_size_does_not_change_results(gpu_lib):
+    ref = None
+    for nt in (32, 64, 128, 256):
+        m = H.discrete_queue()
+        sim = m.sim(gpu_lib, 300, base_seed=11, threads_per_block=nt)
+        sim.step_events(4000)
+        blob = b"".join(sim.comp_stats(ci).tobytes() for ci in range(len(m.components)))
+        sim.close()
+        if ref is None:
+            ref = blob
+        assert blob == ref
+
+
+def test_reduce_stats_matches_per_replication_sums(gpu_lib):
+    """the on-device summary reduction (what multi-GPU runs all-reduce) equals numpy over per-rep stats."""
+    m = H.discrete_queue()
+    n = 5000
+    sim = m.sim(gpu_lib, n, base_seed=3)
+    sim.step_events(3000)
+    red = sim.reduce_stats()
+    for ci in range(len(m.components)):
+        st = sim.comp_stats(ci)
+        t = [int(x) for x in st["time_ns"]]
+        assert int(red[ci]["sum_count"]) == int(st["count"].sum())
+        assert (int(red[ci]["sum_time_hi"]) << 64) + int(red[ci]["sum_time_lo"]) == sum(t)
+        assert int(red[ci]["min_time"]) == min(t) and int(red[ci]["max_time"]) == max(t)
+        assert int(red[ci]["min_count"]) == int(st["count"].min()) and int(red[ci]["max_count"]) == int(st["count"].max())
+        assert int(red[ci]["hist_time"].sum()) == n and int(red[ci]["hist_count"].sum()) == n
+        lo, hi = int(red[ci]["hist_lo_time"]), int(red[ci]["hist_hi_time"])
+        w = (hi - lo) // 32 + 1
+        expect = np.bincount([(x - lo) // w for x in t], minlength=32)
+        assert (expect == red[ci]["hist_time"]).all()
+        ts = np.array(t, dtype=np.float64) * 1e-9
+        assert abs(red[ci]["sumsq_time"] - float((ts * ts).sum())) <= 1e-9 * max(1.0, float((ts * ts).sum()))
+    s = sim.summary()
+    assert s["n_events"] == n * 3000
+    sim.close()
+
+
+def test_invariants_at_scale(gpu_lib):
+    """size-independent properties at 262,144 replications x 2,000 events (no oracle): item conservation,
+    stock bounds, FIFO order of the items in every stock, monotone clocks."""
+    m = H.discrete_queue()
+    n = 262144
+    sim = m.sim(gpu_lib, n, base_seed=2024)
+    sim.step_events(2000)
+    st, now, ev = sim.status()
+    assert (st == 0).all() and (ev == 2000).all() and (now > 0).all()
+    stats = [sim.comp_stats(ci) for ci in range(len(m.components))]
+    src, q1, p1, q2, p2, q3, snk = stats
+    # items created = items in the system + items sunk
+    created = src["count"] + src["level"]
+    in_system = q1["level"] + p1["level"] + q2["level"] + p2["level"] + q3["level"] + snk["level"] + src["level"]
+    assert (created == in_system + snk["count"]).all()
+    # each stock: adds - removes == level, where removes == downstream starts
+    assert (q1["count"] - (p1["count"] + p1["level"]) == q1["level"]).all()
+    assert (q2["count"] - (p2["count"] + p2["level"]) == q2["level"]).all()
+    assert (q3["count"] - (snk["count"] + snk["level"]) == q3["level"]).all()
+    # single-producer stocks never exceed max_capacity (10); busy time never exceeds elapsed time
+    for q in (q1, q2, q3):
+        assert (q["aux"] <= 10).all()
+        assert (q["time_ns"] <= 10 * now).all()
+    for p in (src, p1, p2, snk):
+        assert (p["time_ns"] <= now).all()
+    for r in (0, n // 2, n - 1):
+        for ci in (1, 3, 5):
+            items = sim.read_stock(ci, r)
+            idx = [int(x) & 0x3FFFFFF for x in items]
+            assert idx == sorted(idx)
+    sim.close()
