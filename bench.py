@@ -164,6 +164,7 @@ def workload_config(args, reps_gpu, n_events):
                         % (args.workload, args.reps or reps_gpu, n_events),
             "replications_per_gpu": args.reps or reps_gpu, "events_per_replication": n_events,
             "logging": args.log, "log_ring_records": args.log_capacity if args.log != "off" else 0,
+            "state": args.state, "threads_per_block": args.threads_per_block,
             "l2": "state planes (>= 0.5 GB) and log rings are larger than the 126 MB L2; no flush needed"}
 
 
@@ -188,11 +189,14 @@ def run_ours(args):
     n_events = args.events or n_events
     log_cap = args.log_capacity if args.log != "off" else 0
     model = build_model(args.workload)
-    stream = torch.cuda.current_stream(device)
+    # a real (non-NULL) stream: the library launches on it, torch events and NCCL order against it
+    stream = torch.cuda.Stream(device)
+    torch.cuda.set_stream(stream)
 
     def new_sim(log_capacity):
         return model.sim(None, reps_gpu, t0=0, base_seed=1234, rep_offset=rank * reps_gpu, log_capacity=log_capacity,
-                         threads_per_block=args.threads_per_block, stream=stream.cuda_stream)
+                         threads_per_block=args.threads_per_block, stream=stream.cuda_stream,
+                         flags=1 if args.state == "hbm" else 0)
 
     sim = new_sim(log_cap)
     sim._materialize()  # device state allocated; inputs (model tables, seeds) resident before the timed region
@@ -316,6 +320,8 @@ def main():
     ap.add_argument("--log", default="ring", choices=["ring", "off"])
     ap.add_argument("--log-capacity", type=int, default=64)
     ap.add_argument("--threads-per-block", type=int, default=0)
+    ap.add_argument("--state", default="auto", choices=["auto", "hbm"],
+                    help="auto: state staged in shared memory when it fits; hbm: operate on the HBM planes in place")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--e2e-log-reps", type=int, default=256)
     ap.add_argument("--ref-step-seconds", type=float, default=6.0)

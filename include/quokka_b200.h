@@ -210,6 +210,11 @@ int qk_model_n_dists(const qk_model*, uint32_t* out);
 int qk_model_state_bytes(const qk_model*, int with_log, uint32_t* out_bytes);
 
 /* ---- batch of replications on one GPU -------------------------------------------------------- */
+/* State placement. Default: per-replication state is staged in shared memory for the whole launch; if the
+ * model is too large for even one warp per block, the batch falls back to operating directly on the HBM
+ * state planes (through L1/L2).  The two flags force one or the other. */
+#define QK_BATCH_STATE_IN_HBM 1u
+#define QK_BATCH_STATE_ON_CHIP 2u
 typedef struct {
   uint64_t n_reps;
   uint64_t rep_offset;   /* global index of this batch's first replication (Philox counter words 0,1) */
@@ -217,7 +222,7 @@ typedef struct {
   int32_t device;        /* CUDA device ordinal */
   uint32_t log_capacity; /* records kept per replication (ring, power of two); 0 = logging off */
   uint32_t threads_per_block; /* 0 = choose */
-  uint32_t flags;        /* reserved, 0 */
+  uint32_t flags;        /* QK_BATCH_* bits */
   void* stream;          /* cudaStream_t to launch on, NULL = the library creates its own */
 } qk_batch_config;
 
@@ -227,6 +232,8 @@ typedef struct {
   uint32_t slots64, slots32;         /* per-replication state: slots64 * 8 + slots32 * 4 bytes */
   uint32_t state_bytes_per_rep;
   uint32_t resident_blocks_per_sm;   /* occupancy of the step kernel as reported by the CUDA runtime */
+  uint32_t state_in_hbm;             /* 1 if the batch operates on the HBM planes in place */
+  uint32_t reserved;
   uint64_t replications_padded;
   uint64_t state_bytes_total, log_bytes_total;
 } qk_batch_info;

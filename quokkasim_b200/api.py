@@ -612,13 +612,13 @@ class BatchedSimInit:
         return register_component(self, component)
 
     def init(self, t0, n_replications=1, base_seed=0, device=0, rep_offset=0, log_capacity=0, threads_per_block=0,
-             stream=None, lib=None):
+             stream=None, lib=None, flags=0):
         """Returns (BatchedSimulation, Scheduler), like SimInit::init returns (Simulation, Scheduler).
 
         log_capacity: records kept per replication (power of two); 0 disables logging even if loggers are
         connected (statistics are always kept)."""
         sim = BatchedSimulation(self._components, int(t0), int(n_replications), int(base_seed), int(device),
-                                int(rep_offset), int(log_capacity), int(threads_per_block), stream, lib)
+                                int(rep_offset), int(log_capacity), int(threads_per_block), stream, lib, int(flags))
         return sim, Scheduler(sim)
 
 
@@ -629,7 +629,7 @@ class BatchedSimulation:
     after init() (as in assembly_line.rs:240-246) still land in the model tables."""
 
     def __init__(self, components, t0, n_reps, base_seed, device, rep_offset, log_capacity, threads_per_block, stream,
-                 lib):
+                 lib, flags=0):
         self.L = capi.load_library(lib)
         self.components = [c.component for c in components]
         self.variants = [c.variant for c in components]
@@ -641,6 +641,7 @@ class BatchedSimulation:
         self.log_capacity = log_capacity
         self.threads_per_block = threads_per_block
         self.stream = stream
+        self.flags = flags
         self._model = C.c_void_p()
         self._batch = C.c_void_p()
         self._ext = []
@@ -722,6 +723,7 @@ class BatchedSimulation:
         cfg.device = self.device
         cfg.log_capacity = self.log_capacity
         cfg.threads_per_block = self.threads_per_block
+        cfg.flags = self.flags
         cfg.stream = self.stream
         capi.check(L, L.qk_batch_create(self._model, C.byref(cfg), C.byref(self._batch)))
         for dist, v in self._tapes:

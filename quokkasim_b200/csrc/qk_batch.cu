@@ -30,6 +30,7 @@ struct qk_batch {
   qk_batch_config cfg;
   QkLowered low;
   bool log;
+  bool hbm; /* state operated on in place in HBM instead of staged in shared memory */
   uint32_t nt, grid, smem_bytes, table_bytes_padded;
   uint64_t rep_pad;
   uint64_t* g64;
@@ -97,10 +98,17 @@ static int launch_step(qk_batch* b, uint32_t do_init, uint64_t t0, uint64_t t_un
   P.event_budget = budget;
   P.do_init = do_init;
   CUDA_TRY(cudaEventRecord(b->ev0, b->stream));
-  if (b->log)
-    qk_step_kernel<true><<<b->grid, b->nt, b->smem_bytes, b->stream>>>(P);
-  else
-    qk_step_kernel<false><<<b->grid, b->nt, b->smem_bytes, b->stream>>>(P);
+  if (b->hbm) {
+    if (b->log)
+      qk_step_kernel<true, true><<<b->grid, b->nt, b->smem_bytes, b->stream>>>(P);
+    else
+      qk_step_kernel<false, true><<<b->grid, b->nt, b->smem_bytes, b->stream>>>(P);
+  } else {
+    if (b->log)
+      qk_step_kernel<true, false><<<b->grid, b->nt, b->smem_bytes, b->stream>>>(P);
+    else
+      qk_step_kernel<false, false><<<b->grid, b->nt, b->smem_bytes, b->stream>>>(P);
+  }
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaEventRecord(b->ev1, b->stream));
   b->last_launches = 1;
@@ -318,16 +326,33 @@ int qk_batch_create(const qk_model* m, const qk_batch_config* cfg, qk_batch** ou
   b->table_bytes_padded = (h.total_bytes + 15u) & ~15u;
   const uint32_t per_rep = h.n64 * 8 + h.n32 * 4;
   uint32_t nt = cfg->threads_per_block;
-  if (nt == 0) nt = choose_nt(per_rep, b->table_bytes_padded, nullptr);
-  if (nt == 0 || nt > QK_MAX_NT || (nt & 31) ||
-      (uint64_t)b->table_bytes_padded + (uint64_t)per_rep * nt > 227u * 1024u) {
-    qk_set_error("qk_batch_create: model needs %u B of on-chip state per replication (+%u B tables); "
-                 "no block size fits the 227 KB of shared memory", per_rep, b->table_bytes_padded);
-    delete b;
-    return QK_ERR_CAPACITY;
+  b->hbm = (cfg->flags & QK_BATCH_STATE_IN_HBM) != 0;
+  if (!b->hbm) {
+    if (nt == 0) nt = choose_nt(per_rep, b->table_bytes_padded, nullptr);
+    const bool fits = nt != 0 && nt <= QK_MAX_NT && !(nt & 31) &&
+                      (uint64_t)b->table_bytes_padded + (uint64_t)per_rep * nt <= 227u * 1024u;
+    if (!fits) {
+      if (cfg->flags & QK_BATCH_STATE_ON_CHIP) {
+        qk_set_error("qk_batch_create: model needs %u B of on-chip state per replication (+%u B tables); "
+                     "no block size fits the 227 KB of shared memory", per_rep, b->table_bytes_padded);
+        delete b;
+        return QK_ERR_CAPACITY;
+      }
+      b->hbm = true; /* too large for one warp per block on chip: operate on the HBM planes in place */
+      nt = cfg->threads_per_block;
+    }
+  }
+  if (b->hbm) {
+    if (nt == 0) nt = 128;
+    if (nt > QK_MAX_NT || (nt & 31) || b->table_bytes_padded > 200u * 1024u) {
+      qk_set_error("qk_batch_create: invalid threads_per_block %u or tables too large (%u B)", nt,
+                   b->table_bytes_padded);
+      delete b;
+      return QK_ERR_CAPACITY;
+    }
   }
   b->nt = nt;
-  b->smem_bytes = b->table_bytes_padded + per_rep * nt;
+  b->smem_bytes = b->table_bytes_padded + (b->hbm ? 0u : per_rep * nt);
   b->grid = (uint32_t)((cfg->n_reps + nt - 1) / nt);
   b->rep_pad = (uint64_t)b->grid * nt;
   if (cfg->stream) {
@@ -353,8 +378,10 @@ int qk_batch_create(const qk_model* m, const qk_batch_config* cfg, qk_batch** ou
   CUDA_TRY(cudaMalloc(&b->d_tape_len, sizeof(uint64_t) * (h.n_dist ? h.n_dist : 1)));
   CUDA_TRY(cudaMemset(b->d_tapes, 0, sizeof(double*) * (h.n_dist ? h.n_dist : 1)));
   CUDA_TRY(cudaMemset(b->d_tape_len, 0, sizeof(uint64_t) * (h.n_dist ? h.n_dist : 1)));
-  CUDA_TRY(cudaFuncSetAttribute(qk_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  CUDA_TRY(cudaFuncSetAttribute(qk_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  CUDA_TRY(cudaFuncSetAttribute(qk_step_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  CUDA_TRY(cudaFuncSetAttribute(qk_step_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  CUDA_TRY(cudaFuncSetAttribute(qk_step_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  CUDA_TRY(cudaFuncSetAttribute(qk_step_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   b->red_blocks = 148 * 4;
   CUDA_TRY(cudaMalloc(&b->d_sums, sizeof(uint64_t) * 6 * h.n_comp));
   CUDA_TRY(cudaMalloc(&b->d_ext, sizeof(uint64_t) * 4 * h.n_comp));
@@ -377,10 +404,18 @@ int qk_batch_info_get(qk_batch* b, qk_batch_info* out) {
   out->slots32 = b->low.hdr.n32;
   out->state_bytes_per_rep = b->low.hdr.n64 * 8 + b->low.hdr.n32 * 4;
   int nb = 0;
-  if (b->log)
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, qk_step_kernel<true>, (int)b->nt, b->smem_bytes));
-  else
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, qk_step_kernel<false>, (int)b->nt, b->smem_bytes));
+  if (b->hbm) {
+    if (b->log)
+      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, qk_step_kernel<true, true>, (int)b->nt, b->smem_bytes));
+    else
+      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, qk_step_kernel<false, true>, (int)b->nt, b->smem_bytes));
+  } else {
+    if (b->log)
+      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, qk_step_kernel<true, false>, (int)b->nt, b->smem_bytes));
+    else
+      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, qk_step_kernel<false, false>, (int)b->nt, b->smem_bytes));
+  }
+  out->state_in_hbm = b->hbm ? 1u : 0u;
   out->resident_blocks_per_sm = (uint32_t)nb;
   out->replications_padded = b->rep_pad;
   out->state_bytes_total = (uint64_t)out->state_bytes_per_rep * b->rep_pad;

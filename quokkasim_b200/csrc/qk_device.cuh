@@ -20,7 +20,8 @@
 #include "qk_host_emul.h"
 #else
 #include <cuda_runtime.h>
-#define QK_SMEM_DECL(name) extern __shared__ __align__(16) uint8_t name[]
+/* file-scope dynamic shared memory: every device function sees a pointer whose address space is known */
+extern __shared__ __align__(16) uint8_t qk_smem[];
 #define QK_TID threadIdx.x
 #define QK_NT blockDim.x
 #define QK_BID blockIdx.x
@@ -142,33 +143,40 @@ QK_DEV double qk_det_ln(double x) {
   return __dadd_rn(r, el);
 }
 
-/* one native variate of a non-constant distribution; *draws is the instance's draw counter */
-QK_DEV double qk_sample_native(uint32_t kind, const double* p, uint32_t stream, uint32_t key0, uint32_t key1,
-                               uint32_t rep_lo, uint32_t rep_hi, uint32_t* draws) {
+/* one native variate of a non-constant distribution; draws = the instance's draw counter (in and out).
+ * Everything by value and NOT inlined: one copy of the fp64 code in the kernel, no stack traffic. */
+struct QkVariate {
+  double value;
+  uint32_t draws;
+};
+__device__ __noinline__ QkVariate qk_sample_native(uint32_t kind, double p0, double p1, double p2, double p3,
+                                                   uint32_t stream, uint32_t key0, uint32_t key1, uint32_t rep_lo,
+                                                   uint32_t rep_hi, uint32_t draws) {
+  const double p[4] = {p0, p1, p2, p3};
   for (;;) {
     uint32_t x[4];
-    qk_philox4x32_10(rep_lo, rep_hi, stream, *draws, key0, key1, x);
-    *draws += 1;
+    qk_philox4x32_10(rep_lo, rep_hi, stream, draws, key0, key1, x);
+    draws += 1;
     const double u = qk_u01(x[0], x[1]);
     if (kind == QK_DIST_UNIFORM) {
       const double w = __dsub_rn(p[1], p[0]);
-      return __dadd_rn(p[0], __dmul_rn(u, w));
+      return QkVariate{__dadd_rn(p[0], __dmul_rn(u, w)), draws};
     } else if (kind == QK_DIST_TRIANGULAR) {
       const double mn = p[0], mx = p[1], mode = p[2];
       const double diff_mode_min = __dsub_rn(mode, mn);
       const double range = __dsub_rn(mx, mn);
       const double f_range = __dmul_rn(u, range);
       if (f_range < diff_mode_min) {
-        return __dadd_rn(mn, __dsqrt_rn(__dmul_rn(f_range, diff_mode_min)));
+        return QkVariate{__dadd_rn(mn, __dsqrt_rn(__dmul_rn(f_range, diff_mode_min))), draws};
       } else {
         const double a = __dsub_rn(range, f_range);
         const double b = __dsub_rn(mx, mode);
-        return __dsub_rn(mx, __dsqrt_rn(__dmul_rn(a, b)));
+        return QkVariate{__dsub_rn(mx, __dsqrt_rn(__dmul_rn(a, b))), draws};
       }
     } else if (kind == QK_DIST_EXPONENTIAL) {
       const double om = __dsub_rn(1.0, u);
       const double l = qk_det_ln(om);
-      return __dmul_rn(__dsub_rn(0.0, l), p[0]);
+      return QkVariate{__dmul_rn(__dsub_rn(0.0, l), p[0]), draws};
     } else { /* NORMAL / TRUNCNORMAL: Marsaglia polar on the two uniforms of one Philox block */
       const double u2 = qk_u01(x[2], x[3]);
       const double v1 = __dsub_rn(__dmul_rn(2.0, u), 1.0);
@@ -180,7 +188,7 @@ QK_DEV double qk_sample_native(uint32_t kind, const double* p, uint32_t stream, 
       const double f = __dsqrt_rn(q);
       const double xv = __dadd_rn(p[0], __dmul_rn(p[1], __dmul_rn(v1, f)));
       if (kind == QK_DIST_TRUNCNORMAL && !(xv >= p[2] && xv <= p[3])) continue; /* common.rs:166-173 */
-      return xv;
+      return QkVariate{xv, draws};
     }
   }
 }

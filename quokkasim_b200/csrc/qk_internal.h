@@ -97,6 +97,7 @@ typedef struct {
   uint32_t n64, n32;         /* slots per replication (for the chosen LOG mode) */
   uint32_t n_stale_words;
   uint32_t ident_off;        /* index in subs[] of the identity list (subs[ident_off + c] == c) */
+  uint32_t init_off, n_init; /* subs[init_off ..): components whose Model::init does something, registration order */
   uint32_t off_comps, off_dists, off_dms, off_subs, off_sched, off_ext;
   uint32_t total_bytes;
   uint32_t log_enabled;

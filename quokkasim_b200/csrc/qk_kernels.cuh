@@ -43,9 +43,10 @@ struct KParams {
 };
 
 struct Ctx {
-  uint64_t* s64; /* plane64 + tid */
-  uint32_t* s32; /* plane32 + tid */
-  uint32_t nt;
+  uint32_t base64, base32; /* on-chip: element offsets of this lane's slot 0 inside qk_smem */
+  uint64_t* g64;           /* HBM-resident state: plane pointers offset to this replication */
+  uint32_t* g32;
+  uint32_t stride;         /* on-chip: threads per block ; HBM: padded replication count */
   const DevHeader* hdr;
   const DevComp* comps;
   const DevDist* dists;
@@ -64,13 +65,27 @@ struct Ctx {
   const uint64_t* tape_len;
 };
 
-#define S64(slot) cx.s64[(uint32_t)(slot) * cx.nt]
-#define S32(slot) cx.s32[(uint32_t)(slot) * cx.nt]
+/* state accessors: the address space is a compile-time fact (shared via the file-scope qk_smem symbol, or
+ * global), so every access is an LDS/STS or LDG/STG -- never a generic load */
+template <bool HBM>
+__device__ __forceinline__ uint64_t* qk_p64(const Ctx& cx) {
+  if constexpr (HBM) return cx.g64; else return reinterpret_cast<uint64_t*>(qk_smem) + cx.base64;
+}
+template <bool HBM>
+__device__ __forceinline__ uint32_t* qk_p32(const Ctx& cx) {
+  if constexpr (HBM) return cx.g32; else return reinterpret_cast<uint32_t*>(qk_smem) + cx.base32;
+}
+template <bool HBM>
+__device__ __forceinline__ auto qk_ix(uint32_t slot, uint32_t stride) {
+  if constexpr (HBM) return (size_t)slot * stride; else return slot * stride;
+}
+#define S64(slot) (qk_p64<HBM>(cx)[qk_ix<HBM>((uint32_t)(slot), cx.stride)])
+#define S32(slot) (qk_p32<HBM>(cx)[qk_ix<HBM>((uint32_t)(slot), cx.stride)])
 #define SRC_INIT (((uint64_t)QK_SRC_INIT) << 32)
 #define SRC_SCH (((uint64_t)QK_SRC_SCH) << 32)
 
 /* ---- log(): allocate EventId "{code}_{seq:06}", emit one 32-byte record, return the new id ------------ */
-template <bool LOG>
+template <bool LOG, bool HBM>
 __device__ __forceinline__ uint64_t qk_log(Ctx& cx, const DevComp* c, uint32_t comp, uint64_t src, uint32_t kind,
                                            uint32_t reason, uint64_t payload) {
   if (!LOG) return 0;
@@ -95,6 +110,7 @@ __device__ __forceinline__ uint64_t qk_log(Ctx& cx, const DevComp* c, uint32_t c
 }
 
 /* ---- Distribution::sample (common.rs:152-178) + Duration::from_secs_f64 -------------------------------- */
+template <bool HBM>
 __device__ __forceinline__ double qk_sample(Ctx& cx, uint32_t dist_id) {
   const DevDist* d = &cx.dists[dist_id];
   if (d->kind == QK_DIST_CONSTANT) return d->p[0];
@@ -110,16 +126,19 @@ __device__ __forceinline__ double qk_sample(Ctx& cx, uint32_t dist_id) {
     v = tape[cx.rep_local * len + draws];
     draws += 1;
   } else {
-    double p[4] = {d->p[0], d->p[1], d->p[2], d->p[3]};
-    v = qk_sample_native(d->kind, p, d->stream, cx.key0, cx.key1, cx.rep_lo, cx.rep_hi, &draws);
+    const QkVariate r = qk_sample_native(d->kind, d->p[0], d->p[1], d->p[2], d->p[3], d->stream, cx.key0, cx.key1,
+                                         cx.rep_lo, cx.rep_hi, draws);
+    v = r.value;
+    draws = r.draws;
   }
   S32(d->draw_slot) = draws;
   return v;
 }
 
 /* sample + convert; on a fault sets cx.status and returns 1 (callers abandon the handler) */
+template <bool HBM>
 __device__ __forceinline__ uint64_t qk_sample_duration(Ctx& cx, uint32_t dist_id) {
-  const double secs = qk_sample(cx, dist_id);
+  const double secs = qk_sample<HBM>(cx, dist_id);
   if (cx.status) return 1;
   uint64_t ns;
   const uint32_t f = qk_from_secs_f64(secs, &ns);
@@ -137,7 +156,7 @@ __device__ __forceinline__ uint32_t qk_stock_cat(uint32_t cnt, uint32_t low, uin
 }
 
 /* cx.schedule_event(now + 1ns, Self::emit_change, ..) discrete.rs:193-194, 218-219 */
-template <bool LOG>
+template <bool LOG, bool HBM>
 __device__ __forceinline__ void qk_emit_push(Ctx& cx, const DevComp* c, uint32_t src_seq) {
   const uint32_t fire = G64_FIRE0 + c->fire_idx;
   uint32_t e = S32(c->o32 + S32_EMIT);
@@ -163,7 +182,7 @@ __device__ __forceinline__ void qk_emit_push(Ctx& cx, const DevComp* c, uint32_t
   S32(c->o32 + S32_EMIT) = n | (split << 8) | (head << 16);
 }
 
-template <bool LOG>
+template <bool LOG, bool HBM>
 __device__ __forceinline__ uint32_t qk_emit_pop(Ctx& cx, const DevComp* c) {
   const uint32_t fire = G64_FIRE0 + c->fire_idx;
   uint32_t e = S32(c->o32 + S32_EMIT);
@@ -185,7 +204,7 @@ __device__ __forceinline__ uint32_t qk_emit_pop(Ctx& cx, const DevComp* c) {
 }
 
 /* Stock::add = pre_add, add_impl, post_add (core.rs:177-183; discrete.rs:181-198). No capacity check. */
-template <bool LOG>
+template <bool LOG, bool HBM>
 __device__ __forceinline__ void qk_stock_add(Ctx& cx, uint32_t sidx, uint32_t item, uint64_t src) {
   const DevComp* c = &cx.comps[sidx];
   const uint32_t hc = S32(c->o32 + S32_HC);
@@ -203,12 +222,12 @@ __device__ __forceinline__ void qk_stock_add(Ctx& cx, uint32_t sidx, uint32_t it
   S64(c->o64 + S64_AREA) -= cx.now; /* occupancy integral = sum(t_remove) - sum(t_add) + cnt * T */
   S32(c->o32 + S32_NADD) += 1;
   if (cnt > S32(c->o32 + S32_MAXOCC)) S32(c->o32 + S32_MAXOCC) = cnt;
-  const uint64_t id = qk_log<LOG>(cx, c, sidx, src, QK_LOG_STOCK_ADD, 0, item);
-  if (prev != qk_stock_cat(cnt, c->low, c->max)) qk_emit_push<LOG>(cx, c, (uint32_t)id);
+  const uint64_t id = qk_log<LOG, HBM>(cx, c, sidx, src, QK_LOG_STOCK_ADD, 0, item);
+  if (prev != qk_stock_cat(cnt, c->low, c->max)) qk_emit_push<LOG, HBM>(cx, c, (uint32_t)id);
 }
 
 /* Stock::remove (core.rs:197-204; discrete.rs:200-225); returns false for Remove(None) */
-template <bool LOG>
+template <bool LOG, bool HBM>
 __device__ __forceinline__ bool qk_stock_remove(Ctx& cx, uint32_t sidx, uint64_t src, uint32_t* item_out) {
   const DevComp* c = &cx.comps[sidx];
   const uint32_t hc = S32(c->o32 + S32_HC);
@@ -224,20 +243,21 @@ __device__ __forceinline__ bool qk_stock_remove(Ctx& cx, uint32_t sidx, uint64_t
     S32(c->o32 + S32_HC) = head | (cnt << 16);
     S64(c->o64 + S64_AREA) += cx.now;
   }
-  const uint64_t id = qk_log<LOG>(cx, c, sidx, src, QK_LOG_STOCK_REMOVE, 0, some ? (uint64_t)item : QK_ITEM_NONE);
-  if (prev != qk_stock_cat(cnt, c->low, c->max)) qk_emit_push<LOG>(cx, c, (uint32_t)id);
+  const uint64_t id = qk_log<LOG, HBM>(cx, c, sidx, src, QK_LOG_STOCK_REMOVE, 0, some ? (uint64_t)item : QK_ITEM_NONE);
+  if (prev != qk_stock_cat(cnt, c->low, c->max)) qk_emit_push<LOG, HBM>(cx, c, (uint32_t)id);
   *item_out = item;
   return some;
 }
 
+template <bool HBM>
 __device__ __forceinline__ uint32_t qk_stock_cat_of(Ctx& cx, int sidx) {
   const DevComp* c = &cx.comps[sidx];
   return qk_stock_cat(S32(c->o32 + S32_HC) >> 16, c->low, c->max);
 }
 
 /* ---- DelayModes::update_state (delays.rs:86-142) + DelayEnd/DelayStart logs (discrete.rs:441-451) ------- */
-template <bool LOG>
-__device__ __noinline__ void qk_tick_delays(Ctx& cx, const DevComp* c, uint32_t comp, uint32_t* flags_io,
+template <bool LOG, bool HBM>
+__device__ __forceinline__ void qk_tick_delays(Ctx& cx, const DevComp* c, uint32_t comp, uint32_t* flags_io,
                                             uint64_t dt, uint64_t* src) {
   uint32_t flags = *flags_io;
   uint32_t mask = (flags >> PF_FIX_SHIFT) & 0xFFu;
@@ -249,7 +269,7 @@ __device__ __noinline__ void qk_tick_delays(Ctx& cx, const DevComp* c, uint32_t 
     S64(c->o64_delayns) += applied;
     dur -= applied;
     if (dur == 0) {
-      dur = qk_sample_duration(cx, cx.dms[c->dm_off + a].until_delay);
+      dur = qk_sample_duration<HBM>(cx, cx.dms[c->dm_off + a].until_delay);
       if (cx.status) return;
       mask &= ~(1u << a);
     }
@@ -266,7 +286,7 @@ __device__ __noinline__ void qk_tick_delays(Ctx& cx, const DevComp* c, uint32_t 
   } else {
     for (int k = 0; k < c->n_dm; ++k) {
       if (S64(c->o64_dm + k) == 0) {
-        const uint64_t dur = qk_sample_duration(cx, cx.dms[c->dm_off + k].until_fix);
+        const uint64_t dur = qk_sample_duration<HBM>(cx, cx.dms[c->dm_off + k].until_fix);
         if (cx.status) return;
         S64(c->o64_dm + k) = dur;
         mask |= 1u << k;
@@ -278,29 +298,29 @@ __device__ __noinline__ void qk_tick_delays(Ctx& cx, const DevComp* c, uint32_t 
   flags = (flags & ~(0xFFu << PF_FIX_SHIFT)) | (mask << PF_FIX_SHIFT);
   *flags_io = flags;
   if (from != to) { /* DelayStateTransition::has_changed delays.rs:35-42 */
-    if (from >= 0) *src = qk_log<LOG>(cx, c, comp, *src, QK_LOG_DELAY_END, 0, (uint64_t)from);
-    if (to >= 0) *src = qk_log<LOG>(cx, c, comp, *src, QK_LOG_DELAY_START, 0, (uint64_t)to);
+    if (from >= 0) *src = qk_log<LOG, HBM>(cx, c, comp, *src, QK_LOG_DELAY_END, 0, (uint64_t)from);
+    if (to >= 0) *src = qk_log<LOG, HBM>(cx, c, comp, *src, QK_LOG_DELAY_START, 0, (uint64_t)to);
   }
 }
 
 /* "Update cached environment state" (discrete.rs:455-471 and siblings) */
-template <bool LOG>
+template <bool LOG, bool HBM>
 __device__ __forceinline__ void qk_refresh_env(Ctx& cx, const DevComp* c, uint32_t comp, uint32_t* flags,
                                                uint64_t* src) {
   const bool new_stopped = c->env >= 0 ? (S32(cx.comps[c->env].o32 + E32_STATE) == 1u) : false;
   const bool old_stopped = (*flags & PF_ENV_STOPPED) != 0;
   if (!old_stopped && new_stopped) {
-    *src = qk_log<LOG>(cx, c, comp, *src, QK_LOG_PROCESS_STOPPED, QK_REASON_STOPPED_BY_ENV, 0);
+    *src = qk_log<LOG, HBM>(cx, c, comp, *src, QK_LOG_PROCESS_STOPPED, QK_REASON_STOPPED_BY_ENV, 0);
     *flags |= PF_ENV_STOPPED;
   } else if (old_stopped && !new_stopped) {
-    *src = qk_log<LOG>(cx, c, comp, *src, QK_LOG_PROCESS_CONTINUE, QK_REASON_RESUMED_BY_ENV, 0);
+    *src = qk_log<LOG, HBM>(cx, c, comp, *src, QK_LOG_PROCESS_CONTINUE, QK_REASON_RESUMED_BY_ENV, 0);
     *flags &= ~PF_ENV_STOPPED;
   }
 }
 
 /* post_update_state (discrete.rs:535-564): keep the earlier of the pending keyed event and now+ttnpe.
  * Cancelling == overwriting the single fire slot. */
-template <bool LOG>
+template <bool LOG, bool HBM>
 __device__ __forceinline__ void qk_post(Ctx& cx, const DevComp* c, uint64_t ttnpe, uint64_t src) {
   if (ttnpe != QK_TIME_NONE) {
     if (ttnpe == 0) {
@@ -318,7 +338,7 @@ __device__ __forceinline__ void qk_post(Ctx& cx, const DevComp* c, uint64_t ttnp
 
 /* pre_update_state (discrete.rs:404-412): a handle whose time has come is forgotten, NOT cancelled; if its
  * event has not fired yet it stays queued (Q3) -> move it to the stale mask (it fires at `now`, in rank order) */
-template <bool LOG>
+template <bool LOG, bool HBM>
 __device__ __forceinline__ void qk_pre(Ctx& cx, const DevComp* c) {
   const uint32_t fire = G64_FIRE0 + c->fire_idx;
   if (S64(fire) <= cx.now) {
@@ -329,8 +349,8 @@ __device__ __forceinline__ void qk_pre(Ctx& cx, const DevComp* c) {
 }
 
 /* ---- DiscreteProcess / DiscreteSource / DiscreteSink update_state, one code path ----------------------------- */
-template <bool LOG>
-__device__ void qk_update_single(Ctx& cx, const DevComp* c, uint32_t comp, uint64_t src) {
+template <bool LOG, bool HBM>
+__device__ __forceinline__ void qk_update_single(Ctx& cx, const DevComp* c, uint32_t comp, uint64_t src) {
   const uint32_t kind = c->kind;
   uint32_t flags = S32(c->o32 + P32_FLAGS);
   uint64_t left = S64(c->o64 + P64_LEFT);
@@ -346,20 +366,20 @@ __device__ void qk_update_single(Ctx& cx, const DevComp* c, uint32_t comp, uint6
       if (left == 0) {
         flags &= ~PF_HAS_ITEM;
         const uint32_t item = S32(c->o32 + P32_ITEM);
-        src = qk_log<LOG>(cx, c, comp, src, QK_LOG_PROCESS_FINISH, 0, item);
+        src = qk_log<LOG, HBM>(cx, c, comp, src, QK_LOG_PROCESS_FINISH, 0, item);
         S32(c->o32 + P32_NFINISH) += 1;
         if (kind != QK_DISCRETE_SINK && c->down >= 0) { /* push_downstream: no downstream check at finish */
-          qk_stock_add<LOG>(cx, (uint32_t)c->down, item, src);
+          qk_stock_add<LOG, HBM>(cx, (uint32_t)c->down, item, src);
           if (cx.status) return;
         }
       }
     }
     if (c->n_dm && !is_env_blocked && (is_in_delay || is_in_process)) {
-      qk_tick_delays<LOG>(cx, c, comp, &flags, dt, &src);
+      qk_tick_delays<LOG, HBM>(cx, c, comp, &flags, dt, &src);
       if (cx.status) return;
     }
   }
-  if (c->env >= 0 || (flags & PF_ENV_STOPPED)) qk_refresh_env<LOG>(cx, c, comp, &flags, &src);
+  if (c->env >= 0 || (flags & PF_ENV_STOPPED)) qk_refresh_env<LOG, HBM>(cx, c, comp, &flags, &src);
 
   const bool has_item = (flags & PF_HAS_ITEM) != 0;
   const uint32_t fixmask = (flags >> PF_FIX_SHIFT) & 0xFFu;
@@ -367,19 +387,19 @@ __device__ void qk_update_single(Ctx& cx, const DevComp* c, uint32_t comp, uint6
   if (!has_item && !has_active_delay) {
     /* match (&us_state, &ds_state) discrete.rs:480-516 / 854-872 / 1100-1125; 3 == not connected */
     const bool need_us = kind != QK_DISCRETE_SOURCE, need_ds = kind != QK_DISCRETE_SINK;
-    const uint32_t us = need_us ? (c->up >= 0 ? qk_stock_cat_of(cx, c->up) : 3u) : 1u;
-    const uint32_t ds = need_ds ? (c->down >= 0 ? qk_stock_cat_of(cx, c->down) : 3u) : 1u;
+    const uint32_t us = need_us ? (c->up >= 0 ? qk_stock_cat_of<HBM>(cx, c->up) : 3u) : 1u;
+    const uint32_t ds = need_ds ? (c->down >= 0 ? qk_stock_cat_of<HBM>(cx, c->down) : 3u) : 1u;
     const bool ok = (us == 1u || us == 2u) && (ds == 0u || ds == 1u);
     if (ok) {
       bool got = true;
       uint32_t item;
       if (need_us) {
-        src = qk_log<LOG>(cx, c, comp, src, QK_LOG_WITHDRAW_REQUEST, 0, 0);
-        got = qk_stock_remove<LOG>(cx, (uint32_t)c->up, src, &item);
+        src = qk_log<LOG, HBM>(cx, c, comp, src, QK_LOG_WITHDRAW_REQUEST, 0, 0);
+        got = qk_stock_remove<LOG, HBM>(cx, (uint32_t)c->up, src, &item);
         if (cx.status) return;
       }
       if (got) {
-        const double secs = qk_sample(cx, c->dist_time);
+        const double secs = qk_sample<HBM>(cx, c->dist_time);
         if (cx.status) return;
         if (!need_us) { /* ItemFactory::create_item discrete.rs:680-686 */
           const uint32_t idx = S32(c->o32_next_item);
@@ -400,10 +420,10 @@ __device__ void qk_update_single(Ctx& cx, const DevComp* c, uint32_t comp, uint6
         flags |= PF_HAS_ITEM;
         S32(c->o32 + P32_ITEM) = item;
         S64(c->o64 + P64_BUSY) += d;
-        src = qk_log<LOG>(cx, c, comp, src, QK_LOG_PROCESS_START, 0, item);
+        src = qk_log<LOG, HBM>(cx, c, comp, src, QK_LOG_PROCESS_START, 0, item);
         ttnpe = d;
       } else {
-        src = qk_log<LOG>(cx, c, comp, src, QK_LOG_PROCESS_NONSTART, QK_REASON_UPSTREAM_NO_RESOURCE, 0);
+        src = qk_log<LOG, HBM>(cx, c, comp, src, QK_LOG_PROCESS_NONSTART, QK_REASON_UPSTREAM_NO_RESOURCE, 0);
       }
     } else {
       uint32_t reason;
@@ -415,7 +435,7 @@ __device__ void qk_update_single(Ctx& cx, const DevComp* c, uint32_t comp, uint6
         reason = QK_REASON_DOWNSTREAM_FULL;
       else
         reason = QK_REASON_DOWNSTREAM_NOT_CONNECTED;
-      src = qk_log<LOG>(cx, c, comp, src, QK_LOG_PROCESS_NONSTART, reason, 0);
+      src = qk_log<LOG, HBM>(cx, c, comp, src, QK_LOG_PROCESS_NONSTART, reason, 0);
     }
   } else if (kind == QK_DISCRETE_SINK) {
     /* (Some, _) leaves ttnpe untouched (discrete.rs:1127-1129); (_, true) clears it (Q2, :1130-1132) */
@@ -428,13 +448,13 @@ __device__ void qk_update_single(Ctx& cx, const DevComp* c, uint32_t comp, uint6
   if (kind == QK_DISCRETE_SINK) S64(c->o64_ttnpe) = ttnpe;
   S32(c->o32 + P32_FLAGS) = flags;
   S64(c->o64 + P64_LEFT) = left;
-  qk_post<LOG>(cx, c, ttnpe, src);
+  qk_post<LOG, HBM>(cx, c, ttnpe, src);
   S64(c->o64 + P64_PREV) = cx.now;
 }
 
 /* ---- DiscreteParallelProcess::update_state_impl (discrete.rs:1280-1417) ---------------------------------------- */
-template <bool LOG>
-__device__ __noinline__ void qk_update_parallel(Ctx& cx, const DevComp* c, uint32_t comp, uint64_t src) {
+template <bool LOG, bool HBM>
+__device__ __forceinline__ void qk_update_parallel(Ctx& cx, const DevComp* c, uint32_t comp, uint64_t src) {
   uint32_t flags = S32(c->o32 + PP32_FLAGS);
   const uint64_t dt = cx.now - S64(c->o64 + PP64_PREV);
   const uint32_t cap = c->ring_cap;
@@ -475,36 +495,36 @@ __device__ __noinline__ void qk_update_parallel(Ctx& cx, const DevComp* c, uint3
         chead += 1;
         if (chead >= cap) chead = 0;
         ccnt -= 1;
-        const uint32_t ds = c->down >= 0 ? qk_stock_cat_of(cx, c->down) : 3u;
+        const uint32_t ds = c->down >= 0 ? qk_stock_cat_of<HBM>(cx, c->down) : 3u;
         if (ds == 0u || ds == 1u) {
-          src = qk_log<LOG>(cx, c, comp, src, QK_LOG_PROCESS_FINISH, 0, it);
+          src = qk_log<LOG, HBM>(cx, c, comp, src, QK_LOG_PROCESS_FINISH, 0, it);
           S32(c->o32 + PP32_NFINISH) += 1;
-          qk_stock_add<LOG>(cx, (uint32_t)c->down, it, src);
+          qk_stock_add<LOG, HBM>(cx, (uint32_t)c->down, it, src);
           if (cx.status) return;
         } else {
-          src = qk_log<LOG>(cx, c, comp, src, QK_LOG_PROCESS_NONSTART,
+          src = qk_log<LOG, HBM>(cx, c, comp, src, QK_LOG_PROCESS_NONSTART,
                             ds == 2u ? QK_REASON_DOWNSTREAM_FULL : QK_REASON_DOWNSTREAM_NOT_CONNECTED, 0);
           break;
         }
       }
     }
     if (c->n_dm && !is_env_blocked && (is_in_delay || is_in_process)) {
-      qk_tick_delays<LOG>(cx, c, comp, &flags, dt, &src);
+      qk_tick_delays<LOG, HBM>(cx, c, comp, &flags, dt, &src);
       if (cx.status) return;
     }
   }
-  if (c->env >= 0 || (flags & PF_ENV_STOPPED)) qk_refresh_env<LOG>(cx, c, comp, &flags, &src);
+  if (c->env >= 0 || (flags & PF_ENV_STOPPED)) qk_refresh_env<LOG, HBM>(cx, c, comp, &flags, &src);
   uint64_t ttnpe = QK_TIME_NONE;
   if (!(flags & PF_ENV_STOPPED)) {
     for (;;) { /* :1373-1398 */
-      const uint32_t us = c->up >= 0 ? qk_stock_cat_of(cx, c->up) : 3u;
+      const uint32_t us = c->up >= 0 ? qk_stock_cat_of<HBM>(cx, c->up) : 3u;
       if (us == 0u || us == 1u) { /* Q4: withdraws while upstream is Empty|Normal */
-        src = qk_log<LOG>(cx, c, comp, src, QK_LOG_WITHDRAW_REQUEST, 0, 0);
+        src = qk_log<LOG, HBM>(cx, c, comp, src, QK_LOG_WITHDRAW_REQUEST, 0, 0);
         uint32_t it;
-        const bool got = qk_stock_remove<LOG>(cx, (uint32_t)c->up, src, &it);
+        const bool got = qk_stock_remove<LOG, HBM>(cx, (uint32_t)c->up, src, &it);
         if (cx.status) return;
         if (!got) break;
-        const uint64_t d = qk_sample_duration(cx, c->dist_time);
+        const uint64_t d = qk_sample_duration<HBM>(cx, c->dist_time);
         if (cx.status) return;
         if (nprog >= cap) {
           cx.status = QK_REP_PARALLEL_OVERFLOW;
@@ -514,9 +534,9 @@ __device__ __noinline__ void qk_update_parallel(Ctx& cx, const DevComp* c, uint3
         S32(item0 + nprog) = it;
         nprog += 1;
         S64(c->o64 + PP64_BUSY) += d;
-        src = qk_log<LOG>(cx, c, comp, src, QK_LOG_PROCESS_START, 0, it);
+        src = qk_log<LOG, HBM>(cx, c, comp, src, QK_LOG_PROCESS_START, 0, it);
       } else {
-        src = qk_log<LOG>(cx, c, comp, src, QK_LOG_PROCESS_NONSTART,
+        src = qk_log<LOG, HBM>(cx, c, comp, src, QK_LOG_PROCESS_NONSTART,
                           us == 2u ? QK_REASON_UPSTREAM_FULL : QK_REASON_UPSTREAM_NOT_CONNECTED, 0);
         break;
       }
@@ -529,27 +549,31 @@ __device__ __noinline__ void qk_update_parallel(Ctx& cx, const DevComp* c, uint3
   S32(c->o32 + PP32_FLAGS) = flags;
   S32(c->o32 + PP32_NPROG) = nprog;
   S32(c->o32 + PP32_COMPLETE) = chead | (ccnt << 16);
-  qk_post<LOG>(cx, c, ttnpe, src);
+  qk_post<LOG, HBM>(cx, c, ttnpe, src);
   S64(c->o64 + PP64_PREV) = cx.now;
 }
 
 /* Process::update_state (core.rs:370-376) */
-template <bool LOG>
+template <bool LOG, bool HBM>
 __device__ __forceinline__ void qk_update_state(Ctx& cx, uint32_t comp, uint64_t src) {
   const DevComp* c = &cx.comps[comp];
-  qk_pre<LOG>(cx, c);
+  if (c->kind == QK_ENVIRONMENT) { /* only reached from the init list: BasicEnvironment::init logs its state */
+    qk_log<LOG, HBM>(cx, c, comp, src, QK_LOG_ENV_STATE, S32(c->o32 + E32_STATE), 0);
+    return;
+  }
+  qk_pre<LOG, HBM>(cx, c);
   if (c->kind == QK_DISCRETE_PARALLEL_PROCESS)
-    qk_update_parallel<LOG>(cx, c, comp, src);
+    qk_update_parallel<LOG, HBM>(cx, c, comp, src);
   else
-    qk_update_single<LOG>(cx, c, comp, src);
+    qk_update_single<LOG, HBM>(cx, c, comp, src);
 }
 
 /* ============================================ the kernel ============================================ */
 #define QK_MAX_NT 256
 
-template <bool LOG>
+template <bool LOG, bool HBM>
 __global__ void __launch_bounds__(QK_MAX_NT) qk_step_kernel(const __grid_constant__ KParams P) {
-  QK_SMEM_DECL(smem);
+  uint8_t* const smem = qk_smem;
   const uint32_t tid = QK_TID, nt = QK_NT;
 
   /* model tables -> shared memory (read with data-dependent component indices afterwards) */
@@ -568,12 +592,19 @@ __global__ void __launch_bounds__(QK_MAX_NT) qk_step_kernel(const __grid_constan
   cx.subs = reinterpret_cast<const uint16_t*>(smem + cx.hdr->off_subs);
   cx.sched = reinterpret_cast<const uint16_t*>(smem + cx.hdr->off_sched);
   cx.ext = reinterpret_cast<const DevExt*>(smem + cx.hdr->off_ext);
-  cx.nt = nt;
-  uint64_t* plane64 = reinterpret_cast<uint64_t*>(smem + P.table_bytes);
-  uint32_t* plane32 = reinterpret_cast<uint32_t*>(smem + P.table_bytes + (size_t)P.n64 * nt * 8);
-  cx.s64 = plane64 + tid;
-  cx.s32 = plane32 + tid;
   const uint64_t rep_local = (uint64_t)QK_BID * nt + tid;
+  if constexpr (HBM) {
+    cx.g64 = P.g64 + rep_local;
+    cx.g32 = P.g32 + rep_local;
+    cx.stride = (uint32_t)P.rep_pad;
+    cx.base64 = cx.base32 = 0;
+  } else {
+    cx.g64 = nullptr;
+    cx.g32 = nullptr;
+    cx.stride = nt;
+    cx.base64 = P.table_bytes / 8 + tid;
+    cx.base32 = (P.table_bytes + P.n64 * nt * 8) / 4 + tid;
+  }
   const bool live = rep_local < P.n_reps;
   const uint64_t rep_global = P.rep_offset + rep_local;
   cx.rep_local = rep_local;
@@ -603,7 +634,7 @@ __global__ void __launch_bounds__(QK_MAX_NT) qk_step_kernel(const __grid_constan
         if (c->o64_ttnpe != 0xFFFF) S64(c->o64_ttnpe) = QK_TIME_NONE;
         /* DelayModes::modify(Add) samples until_delay when the mode is added (delays.rs:159-164) */
         for (int k = 0; k < c->n_dm && !cx.status; ++k)
-          S64(c->o64_dm + k) = qk_sample_duration(cx, cx.dms[c->dm_off + k].until_delay);
+          S64(c->o64_dm + k) = qk_sample_duration<HBM>(cx, cx.dms[c->dm_off + k].until_delay);
         if (c->kind == QK_DISCRETE_STOCK) {
           /* with_initial_resource: the count rides in DevComp.dist_time (unused for stocks) */
           const uint32_t n_init = c->dist_time;
@@ -616,19 +647,13 @@ __global__ void __launch_bounds__(QK_MAX_NT) qk_step_kernel(const __grid_constan
           S32(c->o32 + E32_STATE) = c->low; /* initial state rides in `low` */
         }
       }
-      /* Model::init of every component in registration order (discrete.rs:392-398; core.rs:229-234) */
-      for (uint32_t i = 0; i < n_comp && !cx.status; ++i) {
-        const DevComp* c = &cx.comps[i];
-        if (c->kind == QK_ENVIRONMENT)
-          qk_log<LOG>(cx, c, i, SRC_INIT, QK_LOG_ENV_STATE, S32(c->o32 + E32_STATE), 0);
-        else if (c->kind != QK_DISCRETE_STOCK)
-          qk_update_state<LOG>(cx, i, SRC_INIT);
-      }
     }
     S64(G64_NEVENTS) = 0;
   } else {
-    for (uint32_t s = 0; s < P.n64; ++s) S64(s) = P.g64[(size_t)s * P.rep_pad + rep_local];
-    for (uint32_t s = 0; s < P.n32; ++s) S32(s) = P.g32[(size_t)s * P.rep_pad + rep_local];
+    if constexpr (!HBM) {
+      for (uint32_t s = 0; s < P.n64; ++s) S64(s) = P.g64[(size_t)s * P.rep_pad + rep_local];
+      for (uint32_t s = 0; s < P.n32; ++s) S32(s) = P.g32[(size_t)s * P.rep_pad + rep_local];
+    }
     cx.now = S64(G64_NOW);
     cx.status = S32(G32_STATUS);
     cx.log_cnt = S32(G32_LOGCNT);
@@ -637,8 +662,9 @@ __global__ void __launch_bounds__(QK_MAX_NT) qk_step_kernel(const __grid_constan
   /* ---- event loop: one update_state per lane per trip ------------------------------------------------- */
   uint64_t events_done = 0;
   const uint64_t budget = live ? P.event_budget : 0;
-  uint32_t rem = 0, ptr = 0;
-  uint64_t src = 0;
+  /* Model::init of every component in registration order is the first call list of the loop */
+  uint32_t rem = (P.do_init && live) ? cx.hdr->n_init : 0, ptr = cx.hdr->init_off;
+  uint64_t src = SRC_INIT;
   uint32_t ext_cursor = S32(G32_EXT_CURSOR);
   for (;;) {
     if (rem == 0) {
@@ -680,7 +706,7 @@ __global__ void __launch_bounds__(QK_MAX_NT) qk_step_kernel(const __grid_constan
         const DevComp* c = &cx.comps[e->target];
         if (S32(c->o32 + E32_STATE) != e->state) {
           S32(c->o32 + E32_STATE) = e->state;
-          src = qk_log<LOG>(cx, c, e->target, SRC_SCH, QK_LOG_ENV_STATE, e->state, 0);
+          src = qk_log<LOG, HBM>(cx, c, e->target, SRC_SCH, QK_LOG_ENV_STATE, e->state, 0);
           rem = c->n_subs;
           ptr = c->subs_off;
         }
@@ -690,10 +716,10 @@ __global__ void __launch_bounds__(QK_MAX_NT) qk_step_kernel(const __grid_constan
         if (c->kind == QK_DISCRETE_STOCK) {
           /* emit_change (discrete.rs:227-233): log the state AT EMISSION TIME, then update_state on every
            * subscriber in connection order */
-          const uint32_t src_seq = qk_emit_pop<LOG>(cx, c);
+          const uint32_t src_seq = qk_emit_pop<LOG, HBM>(cx, c);
           const uint32_t cnt = S32(c->o32 + S32_HC) >> 16;
           const uint32_t empty = c->max > cnt ? c->max - cnt : 0;
-          src = qk_log<LOG>(cx, c, comp, ((uint64_t)comp << 32) | src_seq, QK_LOG_STOCK_STATE_CHANGE,
+          src = qk_log<LOG, HBM>(cx, c, comp, ((uint64_t)comp << 32) | src_seq, QK_LOG_STOCK_STATE_CHANGE,
                             qk_stock_cat(cnt, c->low, c->max), ((uint64_t)cnt << 32) | empty);
           rem = c->n_subs;
           ptr = c->subs_off;
@@ -714,7 +740,7 @@ __global__ void __launch_bounds__(QK_MAX_NT) qk_step_kernel(const __grid_constan
     const uint32_t p = cx.subs[ptr];
     ptr += 1;
     rem -= 1;
-    qk_update_state<LOG>(cx, p, src);
+    qk_update_state<LOG, HBM>(cx, p, src);
     if (cx.status) rem = 0;
   }
   /* step_until(t) leaves the clock at t */
@@ -725,8 +751,10 @@ __global__ void __launch_bounds__(QK_MAX_NT) qk_step_kernel(const __grid_constan
   S32(G32_STATUS) = cx.status;
   S32(G32_EXT_CURSOR) = ext_cursor;
   S32(G32_LOGCNT) = cx.log_cnt;
-  for (uint32_t s = 0; s < P.n64; ++s) P.g64[(size_t)s * P.rep_pad + rep_local] = S64(s);
-  for (uint32_t s = 0; s < P.n32; ++s) P.g32[(size_t)s * P.rep_pad + rep_local] = S32(s);
+  if constexpr (!HBM) {
+    for (uint32_t s = 0; s < P.n64; ++s) P.g64[(size_t)s * P.rep_pad + rep_local] = S64(s);
+    for (uint32_t s = 0; s < P.n32; ++s) P.g32[(size_t)s * P.rep_pad + rep_local] = S32(s);
+  }
 }
 
 /* per-replication (count, time_ns, aux, level) of component c, from the HBM state planes */

@@ -424,6 +424,14 @@ int qk_lower(const qk_model* m, bool log, QkLowered* out) {
   }
   uint32_t ident_off = (uint32_t)subs.size();
   for (size_t i = 0; i < nc; ++i) subs.push_back((uint16_t)i);
+  /* Model::init list: every process-like component runs update_state(INIT_000000) (discrete.rs:392-398) and
+   * BasicEnvironment logs its state (core.rs:229-234); stocks use the default no-op init */
+  uint32_t init_off = (uint32_t)subs.size(), n_init = 0;
+  for (size_t i = 0; i < nc; ++i)
+    if (m->comps[i].d.kind != QK_DISCRETE_STOCK) {
+      subs.push_back((uint16_t)i);
+      n_init++;
+    }
 
   /* externally scheduled events: origin rank 0, FIFO among equal times (stable sort) */
   std::vector<DevExt> ext = m->ext;
@@ -441,6 +449,8 @@ int qk_lower(const qk_model* m, bool log, QkLowered* out) {
   h.n32 = n32;
   h.n_stale_words = n_stale_words;
   h.ident_off = ident_off;
+  h.init_off = init_off;
+  h.n_init = n_init;
   h.log_enabled = log ? 1 : 0;
   uint32_t off = align8((uint32_t)sizeof(DevHeader));
   h.off_comps = off;

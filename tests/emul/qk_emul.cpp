@@ -61,10 +61,12 @@ static int run(qk_batch* b, uint32_t do_init, uint64_t t0, uint64_t t_until, uin
   qk_emul_smem = reinterpret_cast<uint8_t*>(smem.data());
   for (uint64_t r = 0; r < b->rep_pad; ++r) {
     qk_emul_bid = (uint32_t)r;
-    if (b->log)
-      qk_step_kernel<true>(P);
-    else
-      qk_step_kernel<false>(P);
+    const bool hbm = (b->cfg.flags & QK_BATCH_STATE_IN_HBM) != 0;
+    if (b->log) {
+      if (hbm) qk_step_kernel<true, true>(P); else qk_step_kernel<true, false>(P);
+    } else {
+      if (hbm) qk_step_kernel<false, true>(P); else qk_step_kernel<false, false>(P);
+    }
   }
   qk_emul_smem = nullptr;
   return QK_OK;
@@ -114,6 +116,7 @@ int qk_batch_info_get(qk_batch* b, qk_batch_info* out) {
   out->replications_padded = b->rep_pad;
   out->state_bytes_total = (uint64_t)out->state_bytes_per_rep * b->rep_pad;
   out->log_bytes_total = b->log ? (uint64_t)b->rep_pad * b->cfg.log_capacity * 32 : 0;
+  out->state_in_hbm = (b->cfg.flags & QK_BATCH_STATE_IN_HBM) ? 1u : 0u;
   return QK_OK;
 }
 

@@ -25,7 +25,7 @@ struct uint4 {
 
 extern thread_local uint8_t* qk_emul_smem;
 extern thread_local uint32_t qk_emul_bid;
-#define QK_SMEM_DECL(name) uint8_t* name = qk_emul_smem
+#define qk_smem qk_emul_smem
 #define QK_TID 0u
 #define QK_NT 1u
 #define QK_BID qk_emul_bid
