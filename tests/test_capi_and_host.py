@@ -1,0 +1,152 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads and exports every symbol the header declares,
+the host-side builder mirror behaves like the reference's (names, defaults, error text), and the batch entry
+points fail loudly -- never fall back -- when there is no CUDA device."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+import quokkasim_b200 as qk
+from quokkasim_b200 import _capi as capi
+from conftest import has_gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_symbol_in_the_header():
+    hdr = open(os.path.join(ROOT, "include", "quokka_b200.h")).read()
+    declared = set(re.findall(r"\b(qk_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"qk_status", "qk_model", "qk_batch"}
+    L = capi.load_library()
+    for sym in sorted(declared):
+        assert hasattr(L, sym), "libquokka_b200.so does not export %s" % sym
+    assert declared == set(capi.EXPORTED_SYMBOLS), declared ^ set(capi.EXPORTED_SYMBOLS)
+    assert L.qk_abi_version() == 1
+
+
+def test_library_contains_sm_100a_code_only():
+    import subprocess
+
+    out = subprocess.run(["cuobjdump", "-lelf", capi.DEFAULT_LIB], stdout=subprocess.PIPE, text=True).stdout
+    assert "sm_100a" in out and "sm_90" not in out and "sm_80" not in out
+
+
+def test_model_table_calls_and_error_text():
+    L = capi.load_library()
+    m = C.c_void_p()
+    capi.check(L, L.qk_model_create(C.byref(m)))
+    ids = []
+    for kind in (capi.DISCRETE_SOURCE, capi.DISCRETE_STOCK, capi.DISCRETE_PROCESS, capi.DISCRETE_STOCK,
+                 capi.DISCRETE_SINK, capi.ENVIRONMENT):
+        d = capi.ComponentDesc()
+        d.kind = kind
+        d.max_capacity = 10
+        out = C.c_uint32()
+        capi.check(L, L.qk_model_add_component(m, C.byref(d), C.byref(out)))
+        ids.append(out.value)
+    assert ids == [0, 1, 2, 3, 4, 5]
+    src, q1, p, q2, snk, env = ids
+    for a, b in ((src, q1), (q1, p), (p, q2), (q2, snk), (env, p)):
+        capi.check(L, L.qk_model_connect(m, a, b, -1))
+    # unsupported pair: same message shape as the reference's Err (discrete_queue.rs:14-20)
+    rc = L.qk_model_connect(m, src, p, -1)
+    assert rc == -2
+    assert L.qk_last_error().decode() == "No component connection defined from StringSource to StringProcess (n=None)"
+    rc = L.qk_model_connect(m, q1, q2, 3)
+    assert rc == -2 and L.qk_last_error().decode().endswith("(n=Some(3))")
+    # second upstream on a single-reply port
+    assert L.qk_model_connect(m, q2, p, -1) == -3
+    # schedule_event arms that the reference does not implement (core.rs:1397-1399)
+    assert L.qk_model_schedule_env_state(m, 10, p, 1) == -1
+    assert b"schedule_event not implemented" in L.qk_last_error()
+    capi.check(L, L.qk_model_schedule_env_state(m, 10, env, 1))
+    bad = capi.DistDesc()
+    bad.kind = capi.DIST_TRIANGULAR
+    bad.p[0], bad.p[1], bad.p[2] = 5.0, 1.0, 3.0
+    assert L.qk_model_set_dist(m, p, 0, C.byref(bad), None) == -1
+    nb = C.c_uint32()
+    capi.check(L, L.qk_model_state_bytes(m, 0, C.byref(nb)))
+    small = nb.value
+    capi.check(L, L.qk_model_state_bytes(m, 1, C.byref(nb)))
+    assert 0 < small < nb.value < 4096
+    L.qk_model_destroy(m)
+
+
+@pytest.mark.skipif(has_gpu(), reason="checks the no-device behaviour")
+def test_no_cpu_fallback_without_a_device():
+    """the product path must fail loudly when it cannot run on a GPU"""
+    from quokkasim_b200 import workloads
+
+    sim = workloads.discrete_queue().sim(None, 4)
+    with pytest.raises(qk.QkError) as e:
+        sim.step_events(10)
+    assert e.value.status == -4 and "no CPU fallback" in str(e.value)
+
+
+def test_missing_library_is_a_loud_import_error(tmp_path):
+    with pytest.raises(ImportError):
+        capi.load_library(str(tmp_path / "libnope.so"))
+
+
+def test_builder_defaults_match_the_reference():
+    s = qk.DiscreteStock.new()
+    assert (s.element_name, s.element_type, s.low_capacity, s.max_capacity) == ("DiscreteStock", "DiscreteStock", 0, 1)
+    p = qk.DiscreteProcess.new()
+    assert p.process_time_distr.kind == capi.DIST_CONSTANT and p.process_time_distr.params[0] == 1.0
+    f = qk.StringItemFactory()
+    assert f.item_name(0) == "Item_0000" and f.item_name(12345) == "Item_12345"
+    assert qk.StringItemFactory("Car", 7, 3).item_name(1) == "Car_008"
+    assert str(qk.ComponentModel.StringStock(s, qk.Mailbox.new())) == "StringStock"
+
+
+def test_distribution_factory_seed_assignment_including_q6():
+    """common.rs:73-148: Uniform/Triangular/Constant arms bump next_seed, the Normal/TruncNormal/Exponential arms
+    return early and do not -> consecutive Exponentials share a stream."""
+    df = qk.DistributionFactory(base_seed=1234, next_seed=0)
+    a = df.create(qk.DistributionConfig.Triangular(1, 10, 6))
+    b = df.create(qk.DistributionConfig.Triangular(1, 10, 6))
+    c = df.create(qk.DistributionConfig.Constant(2.0))
+    e1 = df.create(qk.DistributionConfig.Exponential(5.0))
+    e2 = df.create(qk.DistributionConfig.Exponential(7.0))
+    n = df.create(qk.DistributionConfig.Normal(0.0, 1.0))
+    u = df.create(qk.DistributionConfig.Uniform(0.0, 1.0))
+    assert (a.stream, b.stream) == (0, 1)
+    assert c.kind == capi.DIST_CONSTANT
+    assert e1.stream == e2.stream == n.stream == u.stream == 3
+    assert df.next_seed == 4
+    assert qk.DistributionFactory.new(9).next_seed == 9
+    with pytest.raises(qk.DistributionParametersError):
+        df.create(qk.DistributionConfig.Triangular(5, 1, 3))
+    with pytest.raises(qk.DistributionParametersError):
+        df.create(qk.DistributionConfig.TruncNormal(0, 1, min=2, max=1))
+
+
+def test_connect_components_errors_like_the_reference():
+    src = qk.ComponentModel.StringSource(qk.DiscreteSource.new(), qk.Mailbox.new())
+    snk = qk.ComponentModel.StringSink(qk.DiscreteSink.new(), qk.Mailbox.new())
+    q = qk.ComponentModel.StringStock(qk.DiscreteStock.new(), qk.Mailbox.new())
+    with pytest.raises(qk.ComponentConnectionError) as e:
+        qk.connect_components(src, snk)
+    assert str(e.value) == "No component connection defined from StringSource to StringSink (n=None)"
+    with pytest.raises(qk.ComponentConnectionError):
+        qk.connect_components(q, src)  # a source has no upstream arm (core.rs:910-915 is Source -> Stock only)
+    qk.connect_components(src, q)
+    qk.connect_components(q, snk)
+    lg = qk.ComponentLogger.StringStockLogger(qk.DiscreteStockLogger.new("L"))
+    with pytest.raises(qk.ComponentConnectionError):
+        qk.connect_logger(lg, src)
+    qk.connect_logger(lg, q)
+
+
+def test_delay_mode_builder_follows_indexmap_semantics():
+    p = qk.DiscreteProcess.new()
+    d = qk.Distribution.Constant
+    p.with_delay_mode(qk.DelayModeChange.Add(qk.DelayMode("A", d(1), d(2))))
+    p.with_delay_mode(qk.DelayModeChange.Add(qk.DelayMode("B", d(3), d(4))))
+    p.with_delay_mode(qk.DelayModeChange.Add(qk.DelayMode("A", d(5), d(6))))  # same key keeps its position
+    assert [m.name for m in p.delay_modes] == ["A", "B"] and p.delay_modes[0].until_delay_distr.params[0] == 5
+    p.with_delay_mode(qk.DelayModeChange.Remove("A"))
+    assert [m.name for m in p.delay_modes] == ["B"]
+    p.with_delay_mode(qk.DelayModeChange.RemoveAll())
+    assert p.delay_modes == []
