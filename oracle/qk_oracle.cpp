@@ -96,8 +96,8 @@ int from_secs_f64(double secs, uint64_t* out_ns) {
   } else {
     return ORC_FAULT_BAD_DURATION; /* OverflowOrNan */
   }
-  /* our time base is u64 ns; a Duration above ~584 years cannot be scheduled */
-  if (s > 18446744073ull) return ORC_FAULT_BAD_DURATION;
+  /* the executor's time base is u64 ns: durations of 2^34 s (544 years) and more are a fault */
+  if (exp >= 34) return ORC_FAULT_BAD_DURATION;
   *out_ns = s * NANOS_PER_SEC + n;
   return 0;
 }

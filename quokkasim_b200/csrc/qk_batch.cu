@@ -26,7 +26,10 @@
     }                                                                                     \
   } while (0)
 
+typedef void (*StepKernel)(const KParams);
+
 struct qk_batch {
+  StepKernel kernel;
   qk_batch_config cfg;
   QkLowered low;
   bool log;
@@ -57,6 +60,27 @@ struct qk_batch {
   double* d_sq;
   uint32_t red_blocks;
 };
+
+/* one instantiation per (logging, state placement, block size): the block size is a template constant so that
+ * state-slot offsets become LDS/STS immediates */
+template <bool LOG>
+static StepKernel pick_kernel_log(bool hbm, uint32_t nt) {
+  if (hbm) return qk_step_kernel<LOG, 0>;
+  switch (nt) {
+    case 32: return qk_step_kernel<LOG, 32>;
+    case 64: return qk_step_kernel<LOG, 64>;
+    case 96: return qk_step_kernel<LOG, 96>;
+    case 128: return qk_step_kernel<LOG, 128>;
+    case 160: return qk_step_kernel<LOG, 160>;
+    case 192: return qk_step_kernel<LOG, 192>;
+    case 224: return qk_step_kernel<LOG, 224>;
+    case 256: return qk_step_kernel<LOG, 256>;
+    default: return qk_step_kernel<LOG, -1>;
+  }
+}
+static StepKernel pick_kernel(bool log, bool hbm, uint32_t nt) {
+  return log ? pick_kernel_log<true>(hbm, nt) : pick_kernel_log<false>(hbm, nt);
+}
 
 static uint32_t choose_nt(uint32_t per_rep_bytes, uint32_t table_bytes, uint32_t* threads_per_sm) {
   uint32_t best_nt = 0, best_thr = 0;
@@ -98,17 +122,7 @@ static int launch_step(qk_batch* b, uint32_t do_init, uint64_t t0, uint64_t t_un
   P.event_budget = budget;
   P.do_init = do_init;
   CUDA_TRY(cudaEventRecord(b->ev0, b->stream));
-  if (b->hbm) {
-    if (b->log)
-      qk_step_kernel<true, true><<<b->grid, b->nt, b->smem_bytes, b->stream>>>(P);
-    else
-      qk_step_kernel<false, true><<<b->grid, b->nt, b->smem_bytes, b->stream>>>(P);
-  } else {
-    if (b->log)
-      qk_step_kernel<true, false><<<b->grid, b->nt, b->smem_bytes, b->stream>>>(P);
-    else
-      qk_step_kernel<false, false><<<b->grid, b->nt, b->smem_bytes, b->stream>>>(P);
-  }
+  b->kernel<<<b->grid, b->nt, b->smem_bytes, b->stream>>>(P);
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaEventRecord(b->ev1, b->stream));
   b->last_launches = 1;
@@ -378,10 +392,8 @@ int qk_batch_create(const qk_model* m, const qk_batch_config* cfg, qk_batch** ou
   CUDA_TRY(cudaMalloc(&b->d_tape_len, sizeof(uint64_t) * (h.n_dist ? h.n_dist : 1)));
   CUDA_TRY(cudaMemset(b->d_tapes, 0, sizeof(double*) * (h.n_dist ? h.n_dist : 1)));
   CUDA_TRY(cudaMemset(b->d_tape_len, 0, sizeof(uint64_t) * (h.n_dist ? h.n_dist : 1)));
-  CUDA_TRY(cudaFuncSetAttribute(qk_step_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  CUDA_TRY(cudaFuncSetAttribute(qk_step_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  CUDA_TRY(cudaFuncSetAttribute(qk_step_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  CUDA_TRY(cudaFuncSetAttribute(qk_step_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  b->kernel = pick_kernel(b->log, b->hbm, b->nt);
+  CUDA_TRY(cudaFuncSetAttribute((const void*)b->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   b->red_blocks = 148 * 4;
   CUDA_TRY(cudaMalloc(&b->d_sums, sizeof(uint64_t) * 6 * h.n_comp));
   CUDA_TRY(cudaMalloc(&b->d_ext, sizeof(uint64_t) * 4 * h.n_comp));
@@ -404,17 +416,7 @@ int qk_batch_info_get(qk_batch* b, qk_batch_info* out) {
   out->slots32 = b->low.hdr.n32;
   out->state_bytes_per_rep = b->low.hdr.n64 * 8 + b->low.hdr.n32 * 4;
   int nb = 0;
-  if (b->hbm) {
-    if (b->log)
-      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, qk_step_kernel<true, true>, (int)b->nt, b->smem_bytes));
-    else
-      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, qk_step_kernel<false, true>, (int)b->nt, b->smem_bytes));
-  } else {
-    if (b->log)
-      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, qk_step_kernel<true, false>, (int)b->nt, b->smem_bytes));
-    else
-      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, qk_step_kernel<false, false>, (int)b->nt, b->smem_bytes));
-  }
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)b->kernel, (int)b->nt, b->smem_bytes));
   out->state_in_hbm = b->hbm ? 1u : 0u;
   out->resident_blocks_per_sm = (uint32_t)nb;
   out->replications_padded = b->rep_pad;

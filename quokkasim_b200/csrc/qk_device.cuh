@@ -25,9 +25,16 @@ extern __shared__ __align__(16) uint8_t qk_smem[];
 #define QK_TID threadIdx.x
 #define QK_NT blockDim.x
 #define QK_BID blockIdx.x
+#define QK_SYNCWARP() __syncwarp()
+#define QK_ANY_SYNC(p) __any_sync(0xFFFFFFFFu, (p))
+#define QK_BALLOT(p) __ballot_sync(0xFFFFFFFFu, (p))
+#define QK_POPC(x) __popc(x)
 #endif
 
 #define QK_DEV __device__ __forceinline__
+#ifndef QK_REFILL_LANES
+#define QK_REFILL_LANES 20 /* run the REFILL phase when this many lanes of the warp wait for a variate */
+#endif
 
 /* returns 0 and *ns, or a qk_rep_status fault code */
 QK_DEV uint32_t qk_from_secs_f64(double secs, uint64_t* ns) {

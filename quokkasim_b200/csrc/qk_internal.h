@@ -22,7 +22,13 @@
 
 /* ---- global (per replication) slots ------------------------------------------------------------ */
 enum { G64_NOW = 0, G64_NEVENTS = 1, G64_FIRE0 = 2 }; /* fire[i] for i in [0, n_sched) follows */
-enum { G32_STATUS = 0, G32_EXT_CURSOR = 1, G32_LOGCNT = 2, G32_STALE0 = 3 }; /* stale mask words follow */
+enum { G32_STATUS = 0, G32_EXT_CURSOR = 1, G32_LOGCNT = 2, G32_STALE0 = 3 }; /* stale mask words follow, then
+                                                                              the prefetch-pending mask words */
+
+/* pre-drawn process durations (deferred variate prefetch): a u64 slot per prefetchable distribution holds the
+ * NEXT duration in ns, already converted with Duration::from_secs_f64, or one of these codes */
+#define QK_DUR_EMPTY 0xFFFFFFFFFFFFFFFFull     /* consumed, waiting for the refill phase */
+#define QK_DUR_FAULT_BASE 0xFFFFFFFFFFFFFF00ull /* QK_DUR_FAULT_BASE + qk_rep_status: raise when consumed */
 
 /* ---- process-like slots, relative to DevComp.o64 / o32 ----------------------------------------- */
 enum { P64_LEFT = 0, P64_PREV = 1, P64_BUSY = 2, P64_BASE_COUNT = 3 }; /* optional: ttnpe, delayns, dm durations */
@@ -70,7 +76,11 @@ typedef struct {
   uint16_t o32_next_item; /* absolute slot (sources) */
   uint16_t emit_depth;
   uint16_t flags;
-} DevComp; /* 48 bytes */
+  uint16_t o64_nextdur; /* absolute slot of the pre-drawn next process duration, 0xFFFF if none */
+  uint16_t pf_idx;      /* bit index in the prefetch-pending mask */
+  uint32_t pad0;
+  uint64_t const_dur;   /* process_time_distr is Constant: its duration in ns (or a QK_DUR_FAULT code) */
+} DevComp; /* 64 bytes */
 
 typedef struct {
   uint32_t kind, stream;
@@ -98,6 +108,8 @@ typedef struct {
   uint32_t n_stale_words;
   uint32_t ident_off;        /* index in subs[] of the identity list (subs[ident_off + c] == c) */
   uint32_t init_off, n_init; /* subs[init_off ..): components whose Model::init does something, registration order */
+  uint32_t n_pf, n_pf_words, pf32; /* prefetchable distributions; pf32 = first pending-mask slot (plane32) */
+  uint32_t off_pf;           /* u16 pf_comp[n_pf]: prefetch index -> component */
   uint32_t off_comps, off_dists, off_dms, off_subs, off_sched, off_ext;
   uint32_t total_bytes;
   uint32_t log_enabled;

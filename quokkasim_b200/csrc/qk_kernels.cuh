@@ -60,6 +60,7 @@ struct Ctx {
   uint32_t log_mask;
   uint32_t log_cnt;
   uint32_t key0, key1, rep_lo, rep_hi;
+  uint32_t npend; /* consumed pre-drawn durations waiting for the REFILL phase */
   uint64_t rep_local;
   const double* const* tapes;
   const uint64_t* tape_len;
@@ -67,25 +68,34 @@ struct Ctx {
 
 /* state accessors: the address space is a compile-time fact (shared via the file-scope qk_smem symbol, or
  * global), so every access is an LDS/STS or LDG/STG -- never a generic load */
-template <bool HBM>
+template <int SM>
 __device__ __forceinline__ uint64_t* qk_p64(const Ctx& cx) {
-  if constexpr (HBM) return cx.g64; else return reinterpret_cast<uint64_t*>(qk_smem) + cx.base64;
+  if constexpr (SM == 0) return cx.g64; else return reinterpret_cast<uint64_t*>(qk_smem) + cx.base64;
 }
-template <bool HBM>
+template <int SM>
 __device__ __forceinline__ uint32_t* qk_p32(const Ctx& cx) {
-  if constexpr (HBM) return cx.g32; else return reinterpret_cast<uint32_t*>(qk_smem) + cx.base32;
+  if constexpr (SM == 0) return cx.g32; else return reinterpret_cast<uint32_t*>(qk_smem) + cx.base32;
 }
-template <bool HBM>
+/* SM is the state-placement mode of a kernel instantiation:
+ *   SM  > 0 : on chip, block size == SM known at compile time (slot offsets fold into LDS/STS immediates)
+ *   SM  < 0 : on chip, block size read at run time (host emulation / unusual sizes)
+ *   SM == 0 : state operated on in place in the HBM planes (models too large for shared memory) */
+template <int SM>
 __device__ __forceinline__ auto qk_ix(uint32_t slot, uint32_t stride) {
-  if constexpr (HBM) return (size_t)slot * stride; else return slot * stride;
+  if constexpr (SM == 0)
+    return (size_t)slot * stride;
+  else if constexpr (SM > 0)
+    return slot * (uint32_t)SM;
+  else
+    return slot * stride;
 }
-#define S64(slot) (qk_p64<HBM>(cx)[qk_ix<HBM>((uint32_t)(slot), cx.stride)])
-#define S32(slot) (qk_p32<HBM>(cx)[qk_ix<HBM>((uint32_t)(slot), cx.stride)])
+#define S64(slot) (qk_p64<SM>(cx)[qk_ix<SM>((uint32_t)(slot), cx.stride)])
+#define S32(slot) (qk_p32<SM>(cx)[qk_ix<SM>((uint32_t)(slot), cx.stride)])
 #define SRC_INIT (((uint64_t)QK_SRC_INIT) << 32)
 #define SRC_SCH (((uint64_t)QK_SRC_SCH) << 32)
 
 /* ---- log(): allocate EventId "{code}_{seq:06}", emit one 32-byte record, return the new id ------------ */
-template <bool LOG, bool HBM>
+template <bool LOG, int SM>
 __device__ __forceinline__ uint64_t qk_log(Ctx& cx, const DevComp* c, uint32_t comp, uint64_t src, uint32_t kind,
                                            uint32_t reason, uint64_t payload) {
   if (!LOG) return 0;
@@ -110,7 +120,7 @@ __device__ __forceinline__ uint64_t qk_log(Ctx& cx, const DevComp* c, uint32_t c
 }
 
 /* ---- Distribution::sample (common.rs:152-178) + Duration::from_secs_f64 -------------------------------- */
-template <bool HBM>
+template <int SM>
 __device__ __forceinline__ double qk_sample(Ctx& cx, uint32_t dist_id) {
   const DevDist* d = &cx.dists[dist_id];
   if (d->kind == QK_DIST_CONSTANT) return d->p[0];
@@ -136,9 +146,9 @@ __device__ __forceinline__ double qk_sample(Ctx& cx, uint32_t dist_id) {
 }
 
 /* sample + convert; on a fault sets cx.status and returns 1 (callers abandon the handler) */
-template <bool HBM>
+template <int SM>
 __device__ __forceinline__ uint64_t qk_sample_duration(Ctx& cx, uint32_t dist_id) {
-  const double secs = qk_sample<HBM>(cx, dist_id);
+  const double secs = qk_sample<SM>(cx, dist_id);
   if (cx.status) return 1;
   uint64_t ns;
   const uint32_t f = qk_from_secs_f64(secs, &ns);
@@ -149,6 +159,46 @@ __device__ __forceinline__ uint64_t qk_sample_duration(Ctx& cx, uint32_t dist_id
   return ns;
 }
 
+/* sample + convert for the prefetch slots: never raises, faults are encoded and raised when the value is consumed */
+template <int SM>
+__device__ __forceinline__ uint64_t qk_sample_duration_code(Ctx& cx, uint32_t dist_id) {
+  const uint32_t saved = cx.status;
+  cx.status = 0;
+  const uint64_t ns = qk_sample_duration<SM>(cx, dist_id);
+  const uint32_t f = cx.status;
+  cx.status = saved;
+  return f ? QK_DUR_FAULT_BASE + f : ns;
+}
+
+/* does the next update_state(comp) possibly start a process whose pre-drawn duration is still missing? */
+template <int SM>
+__device__ __forceinline__ bool qk_needs_refill_now(Ctx& cx, uint32_t comp) {
+  const DevComp* c = &cx.comps[comp];
+  if (c->o64_nextdur == 0xFFFF) return false;
+  if (S64(c->o64_nextdur) != QK_DUR_EMPTY) return false;
+  const uint32_t flags = S32(c->o32 + P32_FLAGS);
+  if (!(flags & PF_HAS_ITEM)) return true;
+  return S64(c->o64 + P64_LEFT) <= cx.now - S64(c->o64 + P64_PREV); /* finishes in this call, may restart */
+}
+
+/* REFILL: every lane with consumed slots draws their next durations (Distribution::sample, common.rs:152-178) */
+template <int SM>
+__device__ __forceinline__ void qk_refill(Ctx& cx) {
+  const uint32_t nw = cx.hdr->n_pf_words;
+  const uint16_t* pf_comp = reinterpret_cast<const uint16_t*>(reinterpret_cast<const uint8_t*>(cx.hdr) + cx.hdr->off_pf);
+  for (uint32_t w = 0; w < nw; ++w) {
+    uint32_t m = S32(cx.hdr->pf32 + w);
+    if (m) S32(cx.hdr->pf32 + w) = 0;
+    while (m) {
+      const uint32_t i = (uint32_t)__ffs((int)m) - 1;
+      m &= m - 1;
+      const DevComp* c = &cx.comps[pf_comp[w * 32 + i]];
+      S64(c->o64_nextdur) = qk_sample_duration_code<SM>(cx, c->dist_time);
+    }
+  }
+  cx.npend = 0;
+}
+
 /* ---- DiscreteStock (discrete.rs:158-252) ------------------------------------------------------------------ */
 __device__ __forceinline__ uint32_t qk_stock_cat(uint32_t cnt, uint32_t low, uint32_t max) {
   /* get_state discrete.rs:161-171: Empty test first */
@@ -156,7 +206,7 @@ __device__ __forceinline__ uint32_t qk_stock_cat(uint32_t cnt, uint32_t low, uin
 }
 
 /* cx.schedule_event(now + 1ns, Self::emit_change, ..) discrete.rs:193-194, 218-219 */
-template <bool LOG, bool HBM>
+template <bool LOG, int SM>
 __device__ __forceinline__ void qk_emit_push(Ctx& cx, const DevComp* c, uint32_t src_seq) {
   const uint32_t fire = G64_FIRE0 + c->fire_idx;
   uint32_t e = S32(c->o32 + S32_EMIT);
@@ -182,7 +232,7 @@ __device__ __forceinline__ void qk_emit_push(Ctx& cx, const DevComp* c, uint32_t
   S32(c->o32 + S32_EMIT) = n | (split << 8) | (head << 16);
 }
 
-template <bool LOG, bool HBM>
+template <bool LOG, int SM>
 __device__ __forceinline__ uint32_t qk_emit_pop(Ctx& cx, const DevComp* c) {
   const uint32_t fire = G64_FIRE0 + c->fire_idx;
   uint32_t e = S32(c->o32 + S32_EMIT);
@@ -204,7 +254,7 @@ __device__ __forceinline__ uint32_t qk_emit_pop(Ctx& cx, const DevComp* c) {
 }
 
 /* Stock::add = pre_add, add_impl, post_add (core.rs:177-183; discrete.rs:181-198). No capacity check. */
-template <bool LOG, bool HBM>
+template <bool LOG, int SM>
 __device__ __forceinline__ void qk_stock_add(Ctx& cx, uint32_t sidx, uint32_t item, uint64_t src) {
   const DevComp* c = &cx.comps[sidx];
   const uint32_t hc = S32(c->o32 + S32_HC);
@@ -222,12 +272,12 @@ __device__ __forceinline__ void qk_stock_add(Ctx& cx, uint32_t sidx, uint32_t it
   S64(c->o64 + S64_AREA) -= cx.now; /* occupancy integral = sum(t_remove) - sum(t_add) + cnt * T */
   S32(c->o32 + S32_NADD) += 1;
   if (cnt > S32(c->o32 + S32_MAXOCC)) S32(c->o32 + S32_MAXOCC) = cnt;
-  const uint64_t id = qk_log<LOG, HBM>(cx, c, sidx, src, QK_LOG_STOCK_ADD, 0, item);
-  if (prev != qk_stock_cat(cnt, c->low, c->max)) qk_emit_push<LOG, HBM>(cx, c, (uint32_t)id);
+  const uint64_t id = qk_log<LOG, SM>(cx, c, sidx, src, QK_LOG_STOCK_ADD, 0, item);
+  if (prev != qk_stock_cat(cnt, c->low, c->max)) qk_emit_push<LOG, SM>(cx, c, (uint32_t)id);
 }
 
 /* Stock::remove (core.rs:197-204; discrete.rs:200-225); returns false for Remove(None) */
-template <bool LOG, bool HBM>
+template <bool LOG, int SM>
 __device__ __forceinline__ bool qk_stock_remove(Ctx& cx, uint32_t sidx, uint64_t src, uint32_t* item_out) {
   const DevComp* c = &cx.comps[sidx];
   const uint32_t hc = S32(c->o32 + S32_HC);
@@ -243,20 +293,20 @@ __device__ __forceinline__ bool qk_stock_remove(Ctx& cx, uint32_t sidx, uint64_t
     S32(c->o32 + S32_HC) = head | (cnt << 16);
     S64(c->o64 + S64_AREA) += cx.now;
   }
-  const uint64_t id = qk_log<LOG, HBM>(cx, c, sidx, src, QK_LOG_STOCK_REMOVE, 0, some ? (uint64_t)item : QK_ITEM_NONE);
-  if (prev != qk_stock_cat(cnt, c->low, c->max)) qk_emit_push<LOG, HBM>(cx, c, (uint32_t)id);
+  const uint64_t id = qk_log<LOG, SM>(cx, c, sidx, src, QK_LOG_STOCK_REMOVE, 0, some ? (uint64_t)item : QK_ITEM_NONE);
+  if (prev != qk_stock_cat(cnt, c->low, c->max)) qk_emit_push<LOG, SM>(cx, c, (uint32_t)id);
   *item_out = item;
   return some;
 }
 
-template <bool HBM>
+template <int SM>
 __device__ __forceinline__ uint32_t qk_stock_cat_of(Ctx& cx, int sidx) {
   const DevComp* c = &cx.comps[sidx];
   return qk_stock_cat(S32(c->o32 + S32_HC) >> 16, c->low, c->max);
 }
 
 /* ---- DelayModes::update_state (delays.rs:86-142) + DelayEnd/DelayStart logs (discrete.rs:441-451) ------- */
-template <bool LOG, bool HBM>
+template <bool LOG, int SM>
 __device__ __forceinline__ void qk_tick_delays(Ctx& cx, const DevComp* c, uint32_t comp, uint32_t* flags_io,
                                             uint64_t dt, uint64_t* src) {
   uint32_t flags = *flags_io;
@@ -269,7 +319,7 @@ __device__ __forceinline__ void qk_tick_delays(Ctx& cx, const DevComp* c, uint32
     S64(c->o64_delayns) += applied;
     dur -= applied;
     if (dur == 0) {
-      dur = qk_sample_duration<HBM>(cx, cx.dms[c->dm_off + a].until_delay);
+      dur = qk_sample_duration<SM>(cx, cx.dms[c->dm_off + a].until_delay);
       if (cx.status) return;
       mask &= ~(1u << a);
     }
@@ -286,7 +336,7 @@ __device__ __forceinline__ void qk_tick_delays(Ctx& cx, const DevComp* c, uint32
   } else {
     for (int k = 0; k < c->n_dm; ++k) {
       if (S64(c->o64_dm + k) == 0) {
-        const uint64_t dur = qk_sample_duration<HBM>(cx, cx.dms[c->dm_off + k].until_fix);
+        const uint64_t dur = qk_sample_duration<SM>(cx, cx.dms[c->dm_off + k].until_fix);
         if (cx.status) return;
         S64(c->o64_dm + k) = dur;
         mask |= 1u << k;
@@ -298,29 +348,29 @@ __device__ __forceinline__ void qk_tick_delays(Ctx& cx, const DevComp* c, uint32
   flags = (flags & ~(0xFFu << PF_FIX_SHIFT)) | (mask << PF_FIX_SHIFT);
   *flags_io = flags;
   if (from != to) { /* DelayStateTransition::has_changed delays.rs:35-42 */
-    if (from >= 0) *src = qk_log<LOG, HBM>(cx, c, comp, *src, QK_LOG_DELAY_END, 0, (uint64_t)from);
-    if (to >= 0) *src = qk_log<LOG, HBM>(cx, c, comp, *src, QK_LOG_DELAY_START, 0, (uint64_t)to);
+    if (from >= 0) *src = qk_log<LOG, SM>(cx, c, comp, *src, QK_LOG_DELAY_END, 0, (uint64_t)from);
+    if (to >= 0) *src = qk_log<LOG, SM>(cx, c, comp, *src, QK_LOG_DELAY_START, 0, (uint64_t)to);
   }
 }
 
 /* "Update cached environment state" (discrete.rs:455-471 and siblings) */
-template <bool LOG, bool HBM>
+template <bool LOG, int SM>
 __device__ __forceinline__ void qk_refresh_env(Ctx& cx, const DevComp* c, uint32_t comp, uint32_t* flags,
                                                uint64_t* src) {
   const bool new_stopped = c->env >= 0 ? (S32(cx.comps[c->env].o32 + E32_STATE) == 1u) : false;
   const bool old_stopped = (*flags & PF_ENV_STOPPED) != 0;
   if (!old_stopped && new_stopped) {
-    *src = qk_log<LOG, HBM>(cx, c, comp, *src, QK_LOG_PROCESS_STOPPED, QK_REASON_STOPPED_BY_ENV, 0);
+    *src = qk_log<LOG, SM>(cx, c, comp, *src, QK_LOG_PROCESS_STOPPED, QK_REASON_STOPPED_BY_ENV, 0);
     *flags |= PF_ENV_STOPPED;
   } else if (old_stopped && !new_stopped) {
-    *src = qk_log<LOG, HBM>(cx, c, comp, *src, QK_LOG_PROCESS_CONTINUE, QK_REASON_RESUMED_BY_ENV, 0);
+    *src = qk_log<LOG, SM>(cx, c, comp, *src, QK_LOG_PROCESS_CONTINUE, QK_REASON_RESUMED_BY_ENV, 0);
     *flags &= ~PF_ENV_STOPPED;
   }
 }
 
 /* post_update_state (discrete.rs:535-564): keep the earlier of the pending keyed event and now+ttnpe.
  * Cancelling == overwriting the single fire slot. */
-template <bool LOG, bool HBM>
+template <bool LOG, int SM>
 __device__ __forceinline__ void qk_post(Ctx& cx, const DevComp* c, uint64_t ttnpe, uint64_t src) {
   if (ttnpe != QK_TIME_NONE) {
     if (ttnpe == 0) {
@@ -338,7 +388,7 @@ __device__ __forceinline__ void qk_post(Ctx& cx, const DevComp* c, uint64_t ttnp
 
 /* pre_update_state (discrete.rs:404-412): a handle whose time has come is forgotten, NOT cancelled; if its
  * event has not fired yet it stays queued (Q3) -> move it to the stale mask (it fires at `now`, in rank order) */
-template <bool LOG, bool HBM>
+template <bool LOG, int SM>
 __device__ __forceinline__ void qk_pre(Ctx& cx, const DevComp* c) {
   const uint32_t fire = G64_FIRE0 + c->fire_idx;
   if (S64(fire) <= cx.now) {
@@ -349,7 +399,7 @@ __device__ __forceinline__ void qk_pre(Ctx& cx, const DevComp* c) {
 }
 
 /* ---- DiscreteProcess / DiscreteSource / DiscreteSink update_state, one code path ----------------------------- */
-template <bool LOG, bool HBM>
+template <bool LOG, int SM>
 __device__ __forceinline__ void qk_update_single(Ctx& cx, const DevComp* c, uint32_t comp, uint64_t src) {
   const uint32_t kind = c->kind;
   uint32_t flags = S32(c->o32 + P32_FLAGS);
@@ -366,20 +416,20 @@ __device__ __forceinline__ void qk_update_single(Ctx& cx, const DevComp* c, uint
       if (left == 0) {
         flags &= ~PF_HAS_ITEM;
         const uint32_t item = S32(c->o32 + P32_ITEM);
-        src = qk_log<LOG, HBM>(cx, c, comp, src, QK_LOG_PROCESS_FINISH, 0, item);
+        src = qk_log<LOG, SM>(cx, c, comp, src, QK_LOG_PROCESS_FINISH, 0, item);
         S32(c->o32 + P32_NFINISH) += 1;
         if (kind != QK_DISCRETE_SINK && c->down >= 0) { /* push_downstream: no downstream check at finish */
-          qk_stock_add<LOG, HBM>(cx, (uint32_t)c->down, item, src);
+          qk_stock_add<LOG, SM>(cx, (uint32_t)c->down, item, src);
           if (cx.status) return;
         }
       }
     }
     if (c->n_dm && !is_env_blocked && (is_in_delay || is_in_process)) {
-      qk_tick_delays<LOG, HBM>(cx, c, comp, &flags, dt, &src);
+      qk_tick_delays<LOG, SM>(cx, c, comp, &flags, dt, &src);
       if (cx.status) return;
     }
   }
-  if (c->env >= 0 || (flags & PF_ENV_STOPPED)) qk_refresh_env<LOG, HBM>(cx, c, comp, &flags, &src);
+  if (c->env >= 0 || (flags & PF_ENV_STOPPED)) qk_refresh_env<LOG, SM>(cx, c, comp, &flags, &src);
 
   const bool has_item = (flags & PF_HAS_ITEM) != 0;
   const uint32_t fixmask = (flags >> PF_FIX_SHIFT) & 0xFFu;
@@ -387,20 +437,29 @@ __device__ __forceinline__ void qk_update_single(Ctx& cx, const DevComp* c, uint
   if (!has_item && !has_active_delay) {
     /* match (&us_state, &ds_state) discrete.rs:480-516 / 854-872 / 1100-1125; 3 == not connected */
     const bool need_us = kind != QK_DISCRETE_SOURCE, need_ds = kind != QK_DISCRETE_SINK;
-    const uint32_t us = need_us ? (c->up >= 0 ? qk_stock_cat_of<HBM>(cx, c->up) : 3u) : 1u;
-    const uint32_t ds = need_ds ? (c->down >= 0 ? qk_stock_cat_of<HBM>(cx, c->down) : 3u) : 1u;
+    const uint32_t us = need_us ? (c->up >= 0 ? qk_stock_cat_of<SM>(cx, c->up) : 3u) : 1u;
+    const uint32_t ds = need_ds ? (c->down >= 0 ? qk_stock_cat_of<SM>(cx, c->down) : 3u) : 1u;
     const bool ok = (us == 1u || us == 2u) && (ds == 0u || ds == 1u);
     if (ok) {
       bool got = true;
       uint32_t item;
       if (need_us) {
-        src = qk_log<LOG, HBM>(cx, c, comp, src, QK_LOG_WITHDRAW_REQUEST, 0, 0);
-        got = qk_stock_remove<LOG, HBM>(cx, (uint32_t)c->up, src, &item);
+        src = qk_log<LOG, SM>(cx, c, comp, src, QK_LOG_WITHDRAW_REQUEST, 0, 0);
+        got = qk_stock_remove<LOG, SM>(cx, (uint32_t)c->up, src, &item);
         if (cx.status) return;
       }
       if (got) {
-        const double secs = qk_sample<HBM>(cx, c->dist_time);
-        if (cx.status) return;
+        /* process_time_distr.sample() + Duration::from_secs_f64: Constant distributions were converted at
+         * lowering; random ones were drawn ahead of time by the REFILL phase of the event loop */
+        uint64_t d;
+        if (c->o64_nextdur != 0xFFFF) {
+          d = S64(c->o64_nextdur);
+          S64(c->o64_nextdur) = QK_DUR_EMPTY;
+          S32(cx.hdr->pf32 + (c->pf_idx >> 5)) |= 1u << (c->pf_idx & 31);
+          cx.npend += 1;
+        } else {
+          d = c->const_dur;
+        }
         if (!need_us) { /* ItemFactory::create_item discrete.rs:680-686 */
           const uint32_t idx = S32(c->o32_next_item);
           if (idx > 0x3FFFFFFu) {
@@ -410,20 +469,18 @@ __device__ __forceinline__ void qk_update_single(Ctx& cx, const DevComp* c, uint
           S32(c->o32_next_item) = idx + 1;
           item = ((uint32_t)c->src_ord << 26) | idx;
         }
-        uint64_t d;
-        const uint32_t f = qk_from_secs_f64(secs, &d);
-        if (f) {
-          cx.status = f;
+        if (d >= QK_DUR_FAULT_BASE) { /* from_secs_f64 panicked / tape exhausted / (EMPTY: refill logic bug) */
+          cx.status = d == QK_DUR_EMPTY ? 99u : (uint32_t)(d - QK_DUR_FAULT_BASE);
           return;
         }
         left = d;
         flags |= PF_HAS_ITEM;
         S32(c->o32 + P32_ITEM) = item;
         S64(c->o64 + P64_BUSY) += d;
-        src = qk_log<LOG, HBM>(cx, c, comp, src, QK_LOG_PROCESS_START, 0, item);
+        src = qk_log<LOG, SM>(cx, c, comp, src, QK_LOG_PROCESS_START, 0, item);
         ttnpe = d;
       } else {
-        src = qk_log<LOG, HBM>(cx, c, comp, src, QK_LOG_PROCESS_NONSTART, QK_REASON_UPSTREAM_NO_RESOURCE, 0);
+        src = qk_log<LOG, SM>(cx, c, comp, src, QK_LOG_PROCESS_NONSTART, QK_REASON_UPSTREAM_NO_RESOURCE, 0);
       }
     } else {
       uint32_t reason;
@@ -435,7 +492,7 @@ __device__ __forceinline__ void qk_update_single(Ctx& cx, const DevComp* c, uint
         reason = QK_REASON_DOWNSTREAM_FULL;
       else
         reason = QK_REASON_DOWNSTREAM_NOT_CONNECTED;
-      src = qk_log<LOG, HBM>(cx, c, comp, src, QK_LOG_PROCESS_NONSTART, reason, 0);
+      src = qk_log<LOG, SM>(cx, c, comp, src, QK_LOG_PROCESS_NONSTART, reason, 0);
     }
   } else if (kind == QK_DISCRETE_SINK) {
     /* (Some, _) leaves ttnpe untouched (discrete.rs:1127-1129); (_, true) clears it (Q2, :1130-1132) */
@@ -448,12 +505,12 @@ __device__ __forceinline__ void qk_update_single(Ctx& cx, const DevComp* c, uint
   if (kind == QK_DISCRETE_SINK) S64(c->o64_ttnpe) = ttnpe;
   S32(c->o32 + P32_FLAGS) = flags;
   S64(c->o64 + P64_LEFT) = left;
-  qk_post<LOG, HBM>(cx, c, ttnpe, src);
+  qk_post<LOG, SM>(cx, c, ttnpe, src);
   S64(c->o64 + P64_PREV) = cx.now;
 }
 
 /* ---- DiscreteParallelProcess::update_state_impl (discrete.rs:1280-1417) ---------------------------------------- */
-template <bool LOG, bool HBM>
+template <bool LOG, int SM>
 __device__ __forceinline__ void qk_update_parallel(Ctx& cx, const DevComp* c, uint32_t comp, uint64_t src) {
   uint32_t flags = S32(c->o32 + PP32_FLAGS);
   const uint64_t dt = cx.now - S64(c->o64 + PP64_PREV);
@@ -495,36 +552,36 @@ __device__ __forceinline__ void qk_update_parallel(Ctx& cx, const DevComp* c, ui
         chead += 1;
         if (chead >= cap) chead = 0;
         ccnt -= 1;
-        const uint32_t ds = c->down >= 0 ? qk_stock_cat_of<HBM>(cx, c->down) : 3u;
+        const uint32_t ds = c->down >= 0 ? qk_stock_cat_of<SM>(cx, c->down) : 3u;
         if (ds == 0u || ds == 1u) {
-          src = qk_log<LOG, HBM>(cx, c, comp, src, QK_LOG_PROCESS_FINISH, 0, it);
+          src = qk_log<LOG, SM>(cx, c, comp, src, QK_LOG_PROCESS_FINISH, 0, it);
           S32(c->o32 + PP32_NFINISH) += 1;
-          qk_stock_add<LOG, HBM>(cx, (uint32_t)c->down, it, src);
+          qk_stock_add<LOG, SM>(cx, (uint32_t)c->down, it, src);
           if (cx.status) return;
         } else {
-          src = qk_log<LOG, HBM>(cx, c, comp, src, QK_LOG_PROCESS_NONSTART,
+          src = qk_log<LOG, SM>(cx, c, comp, src, QK_LOG_PROCESS_NONSTART,
                             ds == 2u ? QK_REASON_DOWNSTREAM_FULL : QK_REASON_DOWNSTREAM_NOT_CONNECTED, 0);
           break;
         }
       }
     }
     if (c->n_dm && !is_env_blocked && (is_in_delay || is_in_process)) {
-      qk_tick_delays<LOG, HBM>(cx, c, comp, &flags, dt, &src);
+      qk_tick_delays<LOG, SM>(cx, c, comp, &flags, dt, &src);
       if (cx.status) return;
     }
   }
-  if (c->env >= 0 || (flags & PF_ENV_STOPPED)) qk_refresh_env<LOG, HBM>(cx, c, comp, &flags, &src);
+  if (c->env >= 0 || (flags & PF_ENV_STOPPED)) qk_refresh_env<LOG, SM>(cx, c, comp, &flags, &src);
   uint64_t ttnpe = QK_TIME_NONE;
   if (!(flags & PF_ENV_STOPPED)) {
     for (;;) { /* :1373-1398 */
-      const uint32_t us = c->up >= 0 ? qk_stock_cat_of<HBM>(cx, c->up) : 3u;
+      const uint32_t us = c->up >= 0 ? qk_stock_cat_of<SM>(cx, c->up) : 3u;
       if (us == 0u || us == 1u) { /* Q4: withdraws while upstream is Empty|Normal */
-        src = qk_log<LOG, HBM>(cx, c, comp, src, QK_LOG_WITHDRAW_REQUEST, 0, 0);
+        src = qk_log<LOG, SM>(cx, c, comp, src, QK_LOG_WITHDRAW_REQUEST, 0, 0);
         uint32_t it;
-        const bool got = qk_stock_remove<LOG, HBM>(cx, (uint32_t)c->up, src, &it);
+        const bool got = qk_stock_remove<LOG, SM>(cx, (uint32_t)c->up, src, &it);
         if (cx.status) return;
         if (!got) break;
-        const uint64_t d = qk_sample_duration<HBM>(cx, c->dist_time);
+        const uint64_t d = qk_sample_duration<SM>(cx, c->dist_time);
         if (cx.status) return;
         if (nprog >= cap) {
           cx.status = QK_REP_PARALLEL_OVERFLOW;
@@ -534,9 +591,9 @@ __device__ __forceinline__ void qk_update_parallel(Ctx& cx, const DevComp* c, ui
         S32(item0 + nprog) = it;
         nprog += 1;
         S64(c->o64 + PP64_BUSY) += d;
-        src = qk_log<LOG, HBM>(cx, c, comp, src, QK_LOG_PROCESS_START, 0, it);
+        src = qk_log<LOG, SM>(cx, c, comp, src, QK_LOG_PROCESS_START, 0, it);
       } else {
-        src = qk_log<LOG, HBM>(cx, c, comp, src, QK_LOG_PROCESS_NONSTART,
+        src = qk_log<LOG, SM>(cx, c, comp, src, QK_LOG_PROCESS_NONSTART,
                           us == 2u ? QK_REASON_UPSTREAM_FULL : QK_REASON_UPSTREAM_NOT_CONNECTED, 0);
         break;
       }
@@ -549,32 +606,32 @@ __device__ __forceinline__ void qk_update_parallel(Ctx& cx, const DevComp* c, ui
   S32(c->o32 + PP32_FLAGS) = flags;
   S32(c->o32 + PP32_NPROG) = nprog;
   S32(c->o32 + PP32_COMPLETE) = chead | (ccnt << 16);
-  qk_post<LOG, HBM>(cx, c, ttnpe, src);
+  qk_post<LOG, SM>(cx, c, ttnpe, src);
   S64(c->o64 + PP64_PREV) = cx.now;
 }
 
 /* Process::update_state (core.rs:370-376) */
-template <bool LOG, bool HBM>
+template <bool LOG, int SM>
 __device__ __forceinline__ void qk_update_state(Ctx& cx, uint32_t comp, uint64_t src) {
   const DevComp* c = &cx.comps[comp];
   if (c->kind == QK_ENVIRONMENT) { /* only reached from the init list: BasicEnvironment::init logs its state */
-    qk_log<LOG, HBM>(cx, c, comp, src, QK_LOG_ENV_STATE, S32(c->o32 + E32_STATE), 0);
+    qk_log<LOG, SM>(cx, c, comp, src, QK_LOG_ENV_STATE, S32(c->o32 + E32_STATE), 0);
     return;
   }
-  qk_pre<LOG, HBM>(cx, c);
+  qk_pre<LOG, SM>(cx, c);
   if (c->kind == QK_DISCRETE_PARALLEL_PROCESS)
-    qk_update_parallel<LOG, HBM>(cx, c, comp, src);
+    qk_update_parallel<LOG, SM>(cx, c, comp, src);
   else
-    qk_update_single<LOG, HBM>(cx, c, comp, src);
+    qk_update_single<LOG, SM>(cx, c, comp, src);
 }
 
 /* ============================================ the kernel ============================================ */
 #define QK_MAX_NT 256
 
-template <bool LOG, bool HBM>
-__global__ void __launch_bounds__(QK_MAX_NT) qk_step_kernel(const __grid_constant__ KParams P) {
+template <bool LOG, int SM>
+__global__ void __launch_bounds__(SM > 0 ? SM : QK_MAX_NT) qk_step_kernel(const __grid_constant__ KParams P) {
   uint8_t* const smem = qk_smem;
-  const uint32_t tid = QK_TID, nt = QK_NT;
+  const uint32_t tid = QK_TID, nt = SM > 0 ? (uint32_t)SM : QK_NT;
 
   /* model tables -> shared memory (read with data-dependent component indices afterwards) */
   {
@@ -593,7 +650,7 @@ __global__ void __launch_bounds__(QK_MAX_NT) qk_step_kernel(const __grid_constan
   cx.sched = reinterpret_cast<const uint16_t*>(smem + cx.hdr->off_sched);
   cx.ext = reinterpret_cast<const DevExt*>(smem + cx.hdr->off_ext);
   const uint64_t rep_local = (uint64_t)QK_BID * nt + tid;
-  if constexpr (HBM) {
+  if constexpr (SM == 0) {
     cx.g64 = P.g64 + rep_local;
     cx.g32 = P.g32 + rep_local;
     cx.stride = (uint32_t)P.rep_pad;
@@ -617,6 +674,7 @@ __global__ void __launch_bounds__(QK_MAX_NT) qk_step_kernel(const __grid_constan
   cx.log_mask = P.log_cap ? P.log_cap - 1 : 0;
   cx.log_base = LOG ? P.log + 2 * (size_t)rep_local * P.log_cap : nullptr;
   cx.status = 0;
+  cx.npend = 0;
   const uint32_t n_comp = cx.hdr->n_comp, n_sched = cx.hdr->n_sched, n_ext = cx.hdr->n_ext;
   const uint32_t n_stale_words = cx.hdr->n_stale_words;
 
@@ -632,9 +690,13 @@ __global__ void __launch_bounds__(QK_MAX_NT) qk_step_kernel(const __grid_constan
       for (uint32_t i = 0; i < n_comp; ++i) {
         const DevComp* c = &cx.comps[i];
         if (c->o64_ttnpe != 0xFFFF) S64(c->o64_ttnpe) = QK_TIME_NONE;
+        if (c->o64_nextdur != 0xFFFF) {
+          S64(c->o64_nextdur) = QK_DUR_EMPTY;
+          S32(cx.hdr->pf32 + (c->pf_idx >> 5)) |= 1u << (c->pf_idx & 31);
+        }
         /* DelayModes::modify(Add) samples until_delay when the mode is added (delays.rs:159-164) */
         for (int k = 0; k < c->n_dm && !cx.status; ++k)
-          S64(c->o64_dm + k) = qk_sample_duration<HBM>(cx, cx.dms[c->dm_off + k].until_delay);
+          S64(c->o64_dm + k) = qk_sample_duration<SM>(cx, cx.dms[c->dm_off + k].until_delay);
         if (c->kind == QK_DISCRETE_STOCK) {
           /* with_initial_resource: the count rides in DevComp.dist_time (unused for stocks) */
           const uint32_t n_init = c->dist_time;
@@ -650,7 +712,7 @@ __global__ void __launch_bounds__(QK_MAX_NT) qk_step_kernel(const __grid_constan
     }
     S64(G64_NEVENTS) = 0;
   } else {
-    if constexpr (!HBM) {
+    if constexpr (SM != 0) {
       for (uint32_t s = 0; s < P.n64; ++s) S64(s) = P.g64[(size_t)s * P.rep_pad + rep_local];
       for (uint32_t s = 0; s < P.n32; ++s) S32(s) = P.g32[(size_t)s * P.rep_pad + rep_local];
     }
@@ -659,6 +721,8 @@ __global__ void __launch_bounds__(QK_MAX_NT) qk_step_kernel(const __grid_constan
     cx.log_cnt = S32(G32_LOGCNT);
   }
 
+  for (uint32_t w = 0; w < cx.hdr->n_pf_words; ++w) cx.npend += (uint32_t)QK_POPC(S32(cx.hdr->pf32 + w));
+
   /* ---- event loop: one update_state per lane per trip ------------------------------------------------- */
   uint64_t events_done = 0;
   const uint64_t budget = live ? P.event_budget : 0;
@@ -666,9 +730,16 @@ __global__ void __launch_bounds__(QK_MAX_NT) qk_step_kernel(const __grid_constan
   uint32_t rem = (P.do_init && live) ? cx.hdr->n_init : 0, ptr = cx.hdr->init_off;
   uint64_t src = SRC_INIT;
   uint32_t ext_cursor = S32(G32_EXT_CURSOR);
+  /* The loop body is two straight-line phases -- SELECT (lanes whose call list is empty pop their scheduler queue)
+   * and UPDATE (every lane with a pending call runs one update_state) -- each entered and left by the whole warp,
+   * and the loop exit is a warp vote, so the warp is converged at the top of UPDATE on every trip. */
+  bool done = false;
   for (;;) {
-    if (rem == 0) {
-      if (cx.status || events_done >= budget) break;
+    QK_SYNCWARP();
+    if (rem == 0 && !done) {
+      done = cx.status != 0 || events_done >= budget;
+    }
+    if (rem == 0 && !done) {
       /* pop the scheduler queue: min over (time, rank); rank 0 = externally scheduled events */
       uint64_t best = ext_cursor < n_ext ? cx.ext[ext_cursor].t : QK_TIME_NONE;
       int bi = -1;
@@ -695,7 +766,9 @@ __global__ void __launch_bounds__(QK_MAX_NT) qk_step_kernel(const __grid_constan
           break;
         }
       }
-      if (best == QK_TIME_NONE || best > P.t_until) break;
+      if (best == QK_TIME_NONE || best > P.t_until) {
+        done = true; /* queue empty, or next action is beyond the step_until horizon */
+      } else {
       if (stale) S32(G32_STALE0 + stale_word) = stale_mask;
       cx.now = best;
       events_done += 1;
@@ -706,7 +779,7 @@ __global__ void __launch_bounds__(QK_MAX_NT) qk_step_kernel(const __grid_constan
         const DevComp* c = &cx.comps[e->target];
         if (S32(c->o32 + E32_STATE) != e->state) {
           S32(c->o32 + E32_STATE) = e->state;
-          src = qk_log<LOG, HBM>(cx, c, e->target, SRC_SCH, QK_LOG_ENV_STATE, e->state, 0);
+          src = qk_log<LOG, SM>(cx, c, e->target, SRC_SCH, QK_LOG_ENV_STATE, e->state, 0);
           rem = c->n_subs;
           ptr = c->subs_off;
         }
@@ -716,10 +789,10 @@ __global__ void __launch_bounds__(QK_MAX_NT) qk_step_kernel(const __grid_constan
         if (c->kind == QK_DISCRETE_STOCK) {
           /* emit_change (discrete.rs:227-233): log the state AT EMISSION TIME, then update_state on every
            * subscriber in connection order */
-          const uint32_t src_seq = qk_emit_pop<LOG, HBM>(cx, c);
+          const uint32_t src_seq = qk_emit_pop<LOG, SM>(cx, c);
           const uint32_t cnt = S32(c->o32 + S32_HC) >> 16;
           const uint32_t empty = c->max > cnt ? c->max - cnt : 0;
-          src = qk_log<LOG, HBM>(cx, c, comp, ((uint64_t)comp << 32) | src_seq, QK_LOG_STOCK_STATE_CHANGE,
+          src = qk_log<LOG, SM>(cx, c, comp, ((uint64_t)comp << 32) | src_seq, QK_LOG_STOCK_STATE_CHANGE,
                             qk_stock_cat(cnt, c->low, c->max), ((uint64_t)cnt << 32) | empty);
           rem = c->n_subs;
           ptr = c->subs_off;
@@ -735,13 +808,29 @@ __global__ void __launch_bounds__(QK_MAX_NT) qk_step_kernel(const __grid_constan
           ptr = cx.hdr->ident_off + comp;
         }
       }
-      if (rem == 0) continue;
+      } /* else: an action was popped */
     }
-    const uint32_t p = cx.subs[ptr];
-    ptr += 1;
-    rem -= 1;
-    qk_update_state<LOG, HBM>(cx, p, src);
-    if (cx.status) rem = 0;
+    QK_SYNCWARP();
+    if (!QK_ANY_SYNC(!done || rem != 0)) break; /* uniform exit: every lane of the warp has finished */
+    /* REFILL phase (deferred variate prefetch): the fp64 sampler is the most expensive code on the path, and only
+     * the few lanes that start a process need a variate on a given trip.  So starts consume a pre-drawn duration,
+     * and the sampler runs as its own phase -- for all lanes with consumed slots at once -- when enough lanes are
+     * waiting, or when some lane's next call could start a process whose slot is still empty. */
+    {
+      const bool must = rem != 0 && cx.npend != 0 && qk_needs_refill_now<SM>(cx, cx.subs[ptr]);
+      const uint32_t waiting = QK_BALLOT(cx.npend != 0);
+      if (QK_ANY_SYNC(must) || QK_POPC(waiting) >= QK_REFILL_LANES) {
+        if (cx.npend != 0) qk_refill<SM>(cx);
+      }
+    }
+    QK_SYNCWARP();
+    if (rem != 0) {
+      const uint32_t p = cx.subs[ptr];
+      ptr += 1;
+      rem -= 1;
+      qk_update_state<LOG, SM>(cx, p, src);
+      if (cx.status) rem = 0;
+    }
   }
   /* step_until(t) leaves the clock at t */
   if (!cx.status && live && P.t_until != QK_TIME_NONE && P.t_until > cx.now) cx.now = P.t_until;
@@ -751,7 +840,7 @@ __global__ void __launch_bounds__(QK_MAX_NT) qk_step_kernel(const __grid_constan
   S32(G32_STATUS) = cx.status;
   S32(G32_EXT_CURSOR) = ext_cursor;
   S32(G32_LOGCNT) = cx.log_cnt;
-  if constexpr (!HBM) {
+  if constexpr (SM != 0) {
     for (uint32_t s = 0; s < P.n64; ++s) P.g64[(size_t)s * P.rep_pad + rep_local] = S64(s);
     for (uint32_t s = 0; s < P.n32; ++s) P.g32[(size_t)s * P.rep_pad + rep_local] = S32(s);
   }

@@ -261,6 +261,26 @@ int qk_model_state_bytes(const qk_model* m, int with_log, uint32_t* out) {
 
 static uint32_t align8(uint32_t x) { return (x + 7u) & ~7u; }
 
+/* Duration::from_secs_f64 on the host, for Constant process times (resolved once at lowering):
+ * round-half-even of the exact binary value * 1e9; >= 2^34 s, negative and NaN are faults.
+ * Returns ns or QK_DUR_FAULT_BASE + qk_rep_status. */
+static uint64_t host_duration_code(double secs) {
+  if (!(secs >= 0.0)) return QK_DUR_FAULT_BASE + QK_REP_BAD_DURATION;
+  uint64_t bits;
+  memcpy(&bits, &secs, 8);
+  const int e = (int)((bits >> 52) & 0x7FF) - 1023;
+  const uint64_t mant = (bits & 0xFFFFFFFFFFFFFull) | 0x10000000000000ull;
+  if (e < -31) return 0;
+  if (e >= 34) return QK_DUR_FAULT_BASE + QK_REP_BAD_DURATION;
+  const unsigned __int128 prod = (unsigned __int128)mant * 1000000000ull;
+  const int sh = 52 - e; /* 19..83 */
+  unsigned __int128 q = prod >> sh;
+  const unsigned __int128 rem = prod & (((unsigned __int128)1 << sh) - 1);
+  const unsigned __int128 half = (unsigned __int128)1 << (sh - 1);
+  if (rem > half || (rem == half && (q & 1))) q += 1;
+  return (uint64_t)q;
+}
+
 int qk_lower(const qk_model* m, bool log, QkLowered* out) {
   const size_t nc = m->comps.size();
   if (nc == 0) {
@@ -294,8 +314,19 @@ int qk_lower(const qk_model* m, bool log, QkLowered* out) {
   uint32_t n_sched = (uint32_t)sched.size();
   uint32_t n_stale_words = (n_sched + 31) / 32;
   if (n_stale_words == 0) n_stale_words = 1;
+  /* prefetchable distributions: process_time_distr of single-server components when it is not Constant */
+  std::vector<uint16_t> pf_comp;
+  for (size_t i = 0; i < nc; ++i) {
+    uint32_t k = m->comps[i].d.kind;
+    if ((k == QK_DISCRETE_PROCESS || k == QK_DISCRETE_SOURCE || k == QK_DISCRETE_SINK) &&
+        m->dists[(size_t)m->comps[i].dist_time].kind != QK_DIST_CONSTANT)
+      pf_comp.push_back((uint16_t)i);
+  }
+  const uint32_t n_pf = (uint32_t)pf_comp.size();
+  const uint32_t n_pf_words = (n_pf + 31) / 32;
   uint32_t n64 = G64_FIRE0 + n_sched;
-  uint32_t n32 = G32_STALE0 + n_stale_words;
+  const uint32_t pf32 = G32_STALE0 + n_stale_words;
+  uint32_t n32 = pf32 + n_pf_words;
 
   /* capacities that depend on neighbours */
   std::vector<uint32_t> cap(nc, 0);
@@ -351,6 +382,10 @@ int qk_lower(const qk_model* m, bool log, QkLowered* out) {
     d.o64_ttnpe = 0xFFFF;
     d.o64_delayns = 0xFFFF;
     d.o32_next_item = 0xFFFF;
+    d.o64_nextdur = 0xFFFF;
+    d.pf_idx = 0xFFFF;
+    if (c.dist_time >= 0 && m->dists[(size_t)c.dist_time].kind == QK_DIST_CONSTANT)
+      d.const_dur = host_duration_code(m->dists[(size_t)c.dist_time].p[0]);
     if (c.subs.size() > 255) {
       qk_set_error("component %zu: more than 255 subscribers", i);
       return QK_ERR_CAPACITY;
@@ -372,6 +407,11 @@ int qk_lower(const qk_model* m, bool log, QkLowered* out) {
       d.o32 = (uint16_t)n32;
       n32 += P32_BASE_COUNT;
       if (kind == QK_DISCRETE_SOURCE) d.o32_next_item = (uint16_t)n32++;
+      for (uint32_t k = 0; k < n_pf; ++k)
+        if (pf_comp[k] == i) {
+          d.pf_idx = (uint16_t)k;
+          d.o64_nextdur = (uint16_t)n64++;
+        }
     } else if (kind == QK_DISCRETE_PARALLEL_PROCESS) {
       d.o64 = (uint16_t)n64;
       n64 += PP64_BASE_COUNT;
@@ -448,6 +488,9 @@ int qk_lower(const qk_model* m, bool log, QkLowered* out) {
   h.n64 = n64;
   h.n32 = n32;
   h.n_stale_words = n_stale_words;
+  h.n_pf = n_pf;
+  h.n_pf_words = n_pf_words;
+  h.pf32 = pf32;
   h.ident_off = ident_off;
   h.init_off = init_off;
   h.n_init = n_init;
@@ -465,6 +508,8 @@ int qk_lower(const qk_model* m, bool log, QkLowered* out) {
   off = align8(off + (uint32_t)(subs.size() * sizeof(uint16_t)));
   h.off_sched = off;
   off = align8(off + (uint32_t)(sched.size() * sizeof(uint16_t)));
+  h.off_pf = off;
+  off = align8(off + (uint32_t)(pf_comp.size() * sizeof(uint16_t)));
   h.total_bytes = off;
 
   out->blob.assign(off, 0);
@@ -475,6 +520,7 @@ int qk_lower(const qk_model* m, bool log, QkLowered* out) {
   if (!dms.empty()) memcpy(out->blob.data() + h.off_dms, dms.data(), dms.size() * sizeof(DevDelayMode));
   memcpy(out->blob.data() + h.off_subs, subs.data(), subs.size() * sizeof(uint16_t));
   if (!sched.empty()) memcpy(out->blob.data() + h.off_sched, sched.data(), sched.size() * sizeof(uint16_t));
+  if (!pf_comp.empty()) memcpy(out->blob.data() + h.off_pf, pf_comp.data(), pf_comp.size() * sizeof(uint16_t));
   out->hdr = h;
   out->comps = dc;
   out->dists = dd;

@@ -20,8 +20,8 @@ def _build_emul():
     srcs = [os.path.join(EMUL_DIR, f) for f in ("qk_emul.cpp", "qk_host_emul.h")]
     csrc = os.path.join(ROOT, "quokkasim_b200", "csrc")
     srcs += [os.path.join(csrc, f) for f in os.listdir(csrc)]
-    if not os.path.exists(EMUL_LIB) or any(os.path.getmtime(s) > os.path.getmtime(EMUL_LIB) for s in srcs):
-        subprocess.check_call(["make", "-C", EMUL_DIR, "-s", "-B"])
+    if not os.path.exists(EMUL_LIB) or not os.path.exists(EMUL_LIB.replace("emul.so", "emul_eager.so")) or any(os.path.getmtime(s) > os.path.getmtime(EMUL_LIB) for s in srcs):
+        subprocess.check_call(["make", "-C", EMUL_DIR, "-s", "-B", "libqk_emul.so", "libqk_emul_eager.so"])
     return EMUL_LIB
 
 
@@ -29,6 +29,12 @@ def _build_emul():
 def emul_lib():
     """Host build of the real kernel source (tests/emul): checks kernel LOGIC on CPU. Test-only."""
     return _build_emul()
+
+
+@pytest.fixture(scope="session")
+def emul_eager_lib(emul_lib):
+    """Same host build with the REFILL phase taken as soon as one lane waits (QK_REFILL_LANES=1)."""
+    return os.path.join(EMUL_DIR, "libqk_emul_eager.so")
 
 
 @pytest.fixture(scope="session")

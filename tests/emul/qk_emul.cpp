@@ -63,9 +63,9 @@ static int run(qk_batch* b, uint32_t do_init, uint64_t t0, uint64_t t_until, uin
     qk_emul_bid = (uint32_t)r;
     const bool hbm = (b->cfg.flags & QK_BATCH_STATE_IN_HBM) != 0;
     if (b->log) {
-      if (hbm) qk_step_kernel<true, true>(P); else qk_step_kernel<true, false>(P);
+      if (hbm) qk_step_kernel<true, 0>(P); else qk_step_kernel<true, -1>(P);
     } else {
-      if (hbm) qk_step_kernel<false, true>(P); else qk_step_kernel<false, false>(P);
+      if (hbm) qk_step_kernel<false, 0>(P); else qk_step_kernel<false, -1>(P);
     }
   }
   qk_emul_smem = nullptr;

@@ -29,6 +29,10 @@ extern thread_local uint32_t qk_emul_bid;
 #define QK_TID 0u
 #define QK_NT 1u
 #define QK_BID qk_emul_bid
+#define QK_SYNCWARP() ((void)0)
+#define QK_ANY_SYNC(p) (p)
+#define QK_BALLOT(p) ((p) ? 1u : 0u)
+#define QK_POPC(x) __builtin_popcount(x)
 static inline void __syncthreads() {}
 
 static inline uint64_t __umul64hi(uint64_t a, uint64_t b) {

@@ -47,6 +47,13 @@ def test_hbm_resident_state_path(emul_lib):
     _check(emul_lib, H.haulage(), 2, n_events=3000, log_capacity=16384, flags=1)
 
 
+def test_eager_refill_path(emul_eager_lib):
+    """deferred variate prefetch: results do not depend on WHEN the refill phase runs"""
+    _check(emul_eager_lib, H.discrete_queue(), 3, n_events=1200, log_capacity=8192)
+    _check(emul_eager_lib, H.serial_line(), 2, n_events=6000, tape_len=3000, log_capacity=32768)
+    _check(emul_eager_lib, H.haulage(), 2, n_events=4000, log_capacity=16384)
+
+
 def test_car_workshop(emul_lib):
     m = H.car_workshop()
     _check(emul_lib, m, 2, t_until=m.t0 + 9 * 3600 * 10**9, t0=m.t0, log_capacity=2048)
