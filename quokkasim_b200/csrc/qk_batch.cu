@@ -38,6 +38,8 @@ struct qk_batch {
   uint64_t rep_pad;
   uint64_t* g64;
   uint32_t* g32;
+  uint64_t* gs64; /* statistics planes */
+  uint32_t* gs32;
   uint8_t* d_tables;
   uint4* d_log;
   std::vector<double*> h_tapes; /* device pointers, host copy */
@@ -105,6 +107,8 @@ static int launch_step(qk_batch* b, uint32_t do_init, uint64_t t0, uint64_t t_un
   memset(&P, 0, sizeof(P));
   P.g64 = b->g64;
   P.g32 = b->g32;
+  P.gs64 = b->gs64;
+  P.gs32 = b->gs32;
   P.tables = b->d_tables;
   P.table_bytes = b->table_bytes_padded;
   P.n64 = b->low.hdr.n64;
@@ -133,11 +137,11 @@ static int launch_step(qk_batch* b, uint32_t do_init, uint64_t t0, uint64_t t_un
 /* ================================= per-GPU summary reduction ================================= */
 
 __global__ void qk_comp_stats_kernel(const uint8_t* tables, const uint64_t* g64, const uint32_t* g32,
-                                     uint64_t rep_pad, uint64_t rep0, uint64_t n, uint32_t comp, qk_comp_stats* out) {
+                                     const uint64_t* gs64, const uint32_t* gs32, uint64_t rep_pad, uint64_t rep0, uint64_t n, uint32_t comp, qk_comp_stats* out) {
   const DevHeader* h = reinterpret_cast<const DevHeader*>(tables);
   const DevComp* c = reinterpret_cast<const DevComp*>(tables + h->off_comps) + comp;
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) qk_comp_stats_dev(c, g64, g32, rep_pad, rep0 + i, &out[i]);
+  if (i < n) qk_comp_stats_dev(c, comp, g64, g32, gs64, gs32, rep_pad, rep0 + i, &out[i]);
 }
 
 __device__ __forceinline__ uint64_t warp_sum_u64(uint64_t v) {
@@ -159,7 +163,8 @@ __device__ __forceinline__ double warp_sum_f64(double v) {
 /* grid = (red_blocks, n_comp).  sums[c] = {count, time_lo32 sum, time_hi32 sum, level, n_events, n_faulted};
  * ext[c] = {min_count, min_time, ~max_count, ~max_time}; sq_partial[c][block] = {sum t^2, sum count^2} */
 __global__ void __launch_bounds__(256) qk_reduce_kernel(const uint8_t* tables, const uint64_t* g64,
-                                                        const uint32_t* g32, uint64_t rep_pad, uint64_t n_reps,
+                                                        const uint32_t* g32, const uint64_t* gs64,
+                                                        const uint32_t* gs32, uint64_t rep_pad, uint64_t n_reps,
                                                         uint64_t* sums, uint64_t* ext, double* sq_partial) {
   const DevHeader* h = reinterpret_cast<const DevHeader*>(tables);
   const uint32_t comp = blockIdx.y;
@@ -169,7 +174,7 @@ __global__ void __launch_bounds__(256) qk_reduce_kernel(const uint8_t* tables, c
   double sq[2] = {0.0, 0.0};
   for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_reps; r += (uint64_t)gridDim.x * blockDim.x) {
     qk_comp_stats s;
-    qk_comp_stats_dev(c, g64, g32, rep_pad, r, &s);
+    qk_comp_stats_dev(c, comp, g64, g32, gs64, gs32, rep_pad, r, &s);
     a[0] += s.count;
     a[1] += s.time_ns & 0xFFFFFFFFull;
     a[2] += s.time_ns >> 32;
@@ -235,7 +240,7 @@ __global__ void qk_reduce_sq_kernel(const double* sq_partial, uint32_t n_blocks,
 
 /* hist[c][0][bin] over time_ns, hist[c][1][bin] over count; ranges from ext (min, ~max) */
 __global__ void __launch_bounds__(256) qk_hist_kernel(const uint8_t* tables, const uint64_t* g64, const uint32_t* g32,
-                                                      uint64_t rep_pad, uint64_t n_reps, const uint64_t* ext,
+                                                      const uint64_t* gs64, const uint32_t* gs32, uint64_t rep_pad, uint64_t n_reps, const uint64_t* ext,
                                                       uint64_t* hist) {
   const DevHeader* h = reinterpret_cast<const DevHeader*>(tables);
   const uint32_t comp = blockIdx.y;
@@ -248,7 +253,7 @@ __global__ void __launch_bounds__(256) qk_hist_kernel(const uint8_t* tables, con
   const uint64_t w_c = (hi_c - lo_c) / QK_HIST_BINS + 1, w_t = (hi_t - lo_t) / QK_HIST_BINS + 1;
   for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_reps; r += (uint64_t)gridDim.x * blockDim.x) {
     qk_comp_stats s;
-    qk_comp_stats_dev(c, g64, g32, rep_pad, r, &s);
+    qk_comp_stats_dev(c, comp, g64, g32, gs64, gs32, rep_pad, r, &s);
     if (s.time_ns >= lo_t && s.time_ns <= hi_t) atomicAdd(&sh[0][(s.time_ns - lo_t) / w_t], 1ull);
     if (s.count >= lo_c && s.count <= hi_c) atomicAdd(&sh[1][(s.count - lo_c) / w_c], 1ull);
   }
@@ -317,6 +322,8 @@ int qk_batch_create(const qk_model* m, const qk_batch_config* cfg, qk_batch** ou
   b->log = cfg->log_capacity != 0;
   b->g64 = nullptr;
   b->g32 = nullptr;
+  b->gs64 = nullptr;
+  b->gs32 = nullptr;
   b->d_tables = nullptr;
   b->d_log = nullptr;
   b->d_tapes = nullptr;
@@ -379,6 +386,8 @@ int qk_batch_create(const qk_model* m, const qk_batch_config* cfg, qk_batch** ou
   CUDA_TRY(cudaEventCreate(&b->ev1));
   CUDA_TRY(cudaMalloc(&b->g64, (size_t)h.n64 * b->rep_pad * 8));
   CUDA_TRY(cudaMalloc(&b->g32, (size_t)h.n32 * b->rep_pad * 4));
+  CUDA_TRY(cudaMalloc(&b->gs64, (size_t)h.n_comp * ST_PER_COMP * b->rep_pad * 8));
+  CUDA_TRY(cudaMalloc(&b->gs32, (size_t)h.n_comp * ST_PER_COMP * b->rep_pad * 4));
   CUDA_TRY(cudaMalloc(&b->d_tables, b->table_bytes_padded));
   {
     std::vector<uint8_t> padded(b->table_bytes_padded, 0);
@@ -431,6 +440,8 @@ void qk_batch_destroy(qk_batch* b) {
   if (b->stream) cudaStreamSynchronize(b->stream);
   cudaFree(b->g64);
   cudaFree(b->g32);
+  cudaFree(b->gs64);
+  cudaFree(b->gs32);
   cudaFree(b->d_tables);
   cudaFree(b->d_log);
   for (size_t i = 0; i < b->h_tapes.size(); ++i) cudaFree(b->h_tapes[i]);
@@ -570,7 +581,7 @@ int qk_batch_comp_stats(qk_batch* b, uint64_t rep0, uint64_t n, uint32_t comp, q
   CUDA_TRY(cudaSetDevice(b->cfg.device));
   qk_comp_stats* d = nullptr;
   CUDA_TRY(cudaMalloc(&d, n * sizeof(qk_comp_stats)));
-  qk_comp_stats_kernel<<<(unsigned)((n + 255) / 256), 256, 0, b->stream>>>(b->d_tables, b->g64, b->g32, b->rep_pad,
+  qk_comp_stats_kernel<<<(unsigned)((n + 255) / 256), 256, 0, b->stream>>>(b->d_tables, b->g64, b->g32, b->gs64, b->gs32, b->rep_pad,
                                                                             rep0, n, comp, d);
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaMemcpyAsync(out, d, n * sizeof(qk_comp_stats), cudaMemcpyDeviceToHost, b->stream));
@@ -588,7 +599,7 @@ int qk_batch_reduce_stats_device(qk_batch* b, uint64_t* d_sums, uint64_t* d_extr
   CUDA_TRY(cudaMemsetAsync(d_sums, 0, sizeof(uint64_t) * 6 * n_comp, b->stream));
   CUDA_TRY(cudaMemsetAsync(d_extrema, 0xFF, sizeof(uint64_t) * 4 * n_comp, b->stream));
   dim3 grid(b->red_blocks, n_comp);
-  qk_reduce_kernel<<<grid, 256, 0, b->stream>>>(b->d_tables, b->g64, b->g32, b->rep_pad, b->cfg.n_reps, d_sums,
+  qk_reduce_kernel<<<grid, 256, 0, b->stream>>>(b->d_tables, b->g64, b->g32, b->gs64, b->gs32, b->rep_pad, b->cfg.n_reps, d_sums,
                                                 d_extrema, b->d_sq_partial);
   CUDA_TRY(cudaGetLastError());
   qk_reduce_sq_kernel<<<n_comp, 32, 0, b->stream>>>(b->d_sq_partial, b->red_blocks, b->d_sq);
@@ -601,7 +612,7 @@ int qk_batch_histograms_device(qk_batch* b, const uint64_t* d_extrema, uint64_t*
   CUDA_TRY(cudaSetDevice(b->cfg.device));
   CUDA_TRY(cudaMemsetAsync(d_hist, 0, sizeof(uint64_t) * 2 * QK_HIST_BINS * n_comp, b->stream));
   dim3 grid(b->red_blocks, n_comp);
-  qk_hist_kernel<<<grid, 256, 0, b->stream>>>(b->d_tables, b->g64, b->g32, b->rep_pad, b->cfg.n_reps, d_extrema,
+  qk_hist_kernel<<<grid, 256, 0, b->stream>>>(b->d_tables, b->g64, b->g32, b->gs64, b->gs32, b->rep_pad, b->cfg.n_reps, d_extrema,
                                               d_hist);
   CUDA_TRY(cudaGetLastError());
   return QK_OK;

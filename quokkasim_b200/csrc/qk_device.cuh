@@ -29,6 +29,9 @@ extern __shared__ __align__(16) uint8_t qk_smem[];
 #define QK_ANY_SYNC(p) __any_sync(0xFFFFFFFFu, (p))
 #define QK_BALLOT(p) __ballot_sync(0xFFFFFFFFu, (p))
 #define QK_POPC(x) __popc(x)
+__device__ __forceinline__ void qk_red_add64(uint64_t* p, uint64_t v) { atomicAdd((unsigned long long*)p, (unsigned long long)v); }
+__device__ __forceinline__ void qk_red_add32(uint32_t* p, uint32_t v) { atomicAdd(p, v); }
+__device__ __forceinline__ void qk_red_max32(uint32_t* p, uint32_t v) { atomicMax(p, v); }
 #endif
 
 #define QK_DEV __device__ __forceinline__

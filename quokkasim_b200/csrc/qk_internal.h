@@ -31,8 +31,8 @@ enum { G32_STATUS = 0, G32_EXT_CURSOR = 1, G32_LOGCNT = 2, G32_STALE0 = 3 }; /* 
 #define QK_DUR_FAULT_BASE 0xFFFFFFFFFFFFFF00ull /* QK_DUR_FAULT_BASE + qk_rep_status: raise when consumed */
 
 /* ---- process-like slots, relative to DevComp.o64 / o32 ----------------------------------------- */
-enum { P64_LEFT = 0, P64_PREV = 1, P64_BUSY = 2, P64_BASE_COUNT = 3 }; /* optional: ttnpe, delayns, dm durations */
-enum { P32_FLAGS = 0, P32_ITEM = 1, P32_NFINISH = 2, P32_BASE_COUNT = 3 }; /* optional: next item index */
+enum { P64_LEFT = 0, P64_PREV = 1, P64_BASE_COUNT = 2 }; /* optional: ttnpe, nextdur, dm durations */
+enum { P32_FLAGS = 0, P32_ITEM = 1, P32_BASE_COUNT = 2 }; /* optional: next item index */
 /* flags */
 #define PF_HAS_ITEM 1u
 #define PF_ENV_STOPPED 2u
@@ -42,14 +42,23 @@ enum { PL64_SCHED_SRC = 0, PL64_STALE_SRC = 1, PL64_COUNT = 2 };
 enum { L32_SEQ = 0 };
 
 /* ---- discrete stock slots ------------------------------------------------------------------------ */
-enum { S64_AREA = 0, S64_COUNT = 1 }; /* fire slot holds emit_t0 */
-enum { S32_HC = 0, S32_EMIT = 1, S32_NADD = 2, S32_MAXOCC = 3, S32_RING = 4 };
+enum { S64_COUNT = 0 }; /* the fire slot holds emit_t0; nothing else is 64-bit */
+enum { S32_HC = 0, S32_EMIT = 1, S32_RING = 2 };
 /* S32_EMIT = n | split << 8 | head << 16 ; LOG: emit source seq ring at olog32 + 1 */
 
 /* ---- parallel process slots ---------------------------------------------------------------------- */
-enum { PP64_PREV = 0, PP64_BUSY = 1, PP64_BASE_COUNT = 2 }; /* then [delayns], dm durs, in-progress durations[cap] */
-enum { PP32_FLAGS = 0, PP32_NPROG = 1, PP32_COMPLETE = 2, PP32_NFINISH = 3, PP32_BASE_COUNT = 4 };
+enum { PP64_PREV = 0, PP64_BASE_COUNT = 1 }; /* then dm durs, in-progress durations[cap] */
+enum { PP32_FLAGS = 0, PP32_NPROG = 1, PP32_COMPLETE = 2, PP32_BASE_COUNT = 3 };
 /* then in-progress items[cap], complete ring[cap] */
+
+/* ---- statistics planes ----------------------------------------------------------------------------
+ * Accumulators are NOT part of the on-chip state: they live only in HBM ([comp * 2 + k][replication]) and are
+ * updated with fire-and-forget RED atomics (the working set of the resident blocks stays in L2).
+ *   stat64[0]: process-like: sum of started durations (busy ns = this - remaining) ; stock: occupancy integral
+ *   stat64[1]: process-like: ns spent in an active delay
+ *   stat32[0]: process-like: ProcessFinish count ; stock: Add count
+ *   stat32[1]: stock: maximum occupancy */
+enum { ST64_TIME = 0, ST64_DELAY = 1, ST32_COUNT = 0, ST32_MAXOCC = 1, ST_PER_COMP = 2 };
 
 /* ---- environment --------------------------------------------------------------------------------- */
 enum { E32_STATE = 0, E32_COUNT = 1 };
@@ -72,15 +81,16 @@ typedef struct {
   uint16_t dm_off;    /* first DevDelayMode */
   uint16_t o64_dm;    /* first delay-mode duration slot (absolute) */
   uint16_t o64_ttnpe; /* absolute slot, 0xFFFF if none (only DiscreteSink keeps ttnpe across calls) */
-  uint16_t o64_delayns;
+  uint16_t pad1;
   uint16_t o32_next_item; /* absolute slot (sources) */
   uint16_t emit_depth;
   uint16_t flags;
   uint16_t o64_nextdur; /* absolute slot of the pre-drawn next process duration, 0xFFFF if none */
   uint16_t pf_idx;      /* bit index in the prefetch-pending mask */
-  uint32_t pad0;
-  uint64_t const_dur;   /* process_time_distr is Constant: its duration in ns (or a QK_DUR_FAULT code) */
-} DevComp; /* 64 bytes */
+  uint32_t const_dur_lo, const_dur_hi; /* process_time_distr is Constant: its duration in ns (or QK_DUR_FAULT code) */
+  uint32_t pad2;
+} DevComp; /* 68 bytes = 17 words: an odd word stride keeps per-lane table reads of different components off the
+              same shared-memory bank */
 
 typedef struct {
   uint32_t kind, stream;

@@ -30,6 +30,8 @@
 struct KParams {
   uint64_t* g64; /* [n64][rep_pad] */
   uint32_t* g32; /* [n32][rep_pad] */
+  uint64_t* gs64; /* statistics planes [n_comp * 2][rep_pad], HBM only */
+  uint32_t* gs32;
   const uint8_t* tables;
   uint32_t table_bytes; /* multiple of 16 */
   uint32_t n64, n32;
@@ -47,6 +49,9 @@ struct Ctx {
   uint64_t* g64;           /* HBM-resident state: plane pointers offset to this replication */
   uint32_t* g32;
   uint32_t stride;         /* on-chip: threads per block ; HBM: padded replication count */
+  uint64_t* gs64;          /* statistics planes, offset to this replication; row stride = rep_pad */
+  uint32_t* gs32;
+  uint64_t rep_pad;
   const DevHeader* hdr;
   const DevComp* comps;
   const DevDist* dists;
@@ -91,6 +96,10 @@ __device__ __forceinline__ auto qk_ix(uint32_t slot, uint32_t stride) {
 }
 #define S64(slot) (qk_p64<SM>(cx)[qk_ix<SM>((uint32_t)(slot), cx.stride)])
 #define S32(slot) (qk_p32<SM>(cx)[qk_ix<SM>((uint32_t)(slot), cx.stride)])
+/* statistics accumulators: fire-and-forget RED atomics on the HBM planes (see qk_internal.h) */
+#define QK_ST64_ADD(comp, k, v) qk_red_add64(&cx.gs64[(size_t)((comp)*ST_PER_COMP + (k)) * cx.rep_pad], (v))
+#define QK_ST32_ADD(comp, k, v) qk_red_add32(&cx.gs32[(size_t)((comp)*ST_PER_COMP + (k)) * cx.rep_pad], (v))
+#define QK_ST32_MAX(comp, k, v) qk_red_max32(&cx.gs32[(size_t)((comp)*ST_PER_COMP + (k)) * cx.rep_pad], (v))
 #define SRC_INIT (((uint64_t)QK_SRC_INIT) << 32)
 #define SRC_SCH (((uint64_t)QK_SRC_SCH) << 32)
 
@@ -269,9 +278,9 @@ __device__ __forceinline__ void qk_stock_add(Ctx& cx, uint32_t sidx, uint32_t it
   S32(c->o32 + S32_RING + pos) = item;
   cnt += 1;
   S32(c->o32 + S32_HC) = head | (cnt << 16);
-  S64(c->o64 + S64_AREA) -= cx.now; /* occupancy integral = sum(t_remove) - sum(t_add) + cnt * T */
-  S32(c->o32 + S32_NADD) += 1;
-  if (cnt > S32(c->o32 + S32_MAXOCC)) S32(c->o32 + S32_MAXOCC) = cnt;
+  QK_ST64_ADD(sidx, ST64_TIME, 0ull - cx.now); /* occupancy integral = sum(t_remove) - sum(t_add) + cnt * T */
+  QK_ST32_ADD(sidx, ST32_COUNT, 1u);
+  QK_ST32_MAX(sidx, ST32_MAXOCC, cnt);
   const uint64_t id = qk_log<LOG, SM>(cx, c, sidx, src, QK_LOG_STOCK_ADD, 0, item);
   if (prev != qk_stock_cat(cnt, c->low, c->max)) qk_emit_push<LOG, SM>(cx, c, (uint32_t)id);
 }
@@ -291,7 +300,7 @@ __device__ __forceinline__ bool qk_stock_remove(Ctx& cx, uint32_t sidx, uint64_t
     if (head >= c->ring_cap) head = 0;
     cnt -= 1;
     S32(c->o32 + S32_HC) = head | (cnt << 16);
-    S64(c->o64 + S64_AREA) += cx.now;
+    QK_ST64_ADD(sidx, ST64_TIME, cx.now);
   }
   const uint64_t id = qk_log<LOG, SM>(cx, c, sidx, src, QK_LOG_STOCK_REMOVE, 0, some ? (uint64_t)item : QK_ITEM_NONE);
   if (prev != qk_stock_cat(cnt, c->low, c->max)) qk_emit_push<LOG, SM>(cx, c, (uint32_t)id);
@@ -316,7 +325,7 @@ __device__ __forceinline__ void qk_tick_delays(Ctx& cx, const DevComp* c, uint32
     const int a = __ffs((int)mask) - 1; /* active_delay: first mode in TimeUntilFix, insertion order */
     uint64_t dur = S64(c->o64_dm + a);
     const uint64_t applied = dt < dur ? dt : dur;
-    S64(c->o64_delayns) += applied;
+    QK_ST64_ADD(comp, ST64_DELAY, applied);
     dur -= applied;
     if (dur == 0) {
       dur = qk_sample_duration<SM>(cx, cx.dms[c->dm_off + a].until_delay);
@@ -417,7 +426,7 @@ __device__ __forceinline__ void qk_update_single(Ctx& cx, const DevComp* c, uint
         flags &= ~PF_HAS_ITEM;
         const uint32_t item = S32(c->o32 + P32_ITEM);
         src = qk_log<LOG, SM>(cx, c, comp, src, QK_LOG_PROCESS_FINISH, 0, item);
-        S32(c->o32 + P32_NFINISH) += 1;
+        QK_ST32_ADD(comp, ST32_COUNT, 1u);
         if (kind != QK_DISCRETE_SINK && c->down >= 0) { /* push_downstream: no downstream check at finish */
           qk_stock_add<LOG, SM>(cx, (uint32_t)c->down, item, src);
           if (cx.status) return;
@@ -458,7 +467,7 @@ __device__ __forceinline__ void qk_update_single(Ctx& cx, const DevComp* c, uint
           S32(cx.hdr->pf32 + (c->pf_idx >> 5)) |= 1u << (c->pf_idx & 31);
           cx.npend += 1;
         } else {
-          d = c->const_dur;
+          d = ((uint64_t)c->const_dur_hi << 32) | c->const_dur_lo;
         }
         if (!need_us) { /* ItemFactory::create_item discrete.rs:680-686 */
           const uint32_t idx = S32(c->o32_next_item);
@@ -476,7 +485,7 @@ __device__ __forceinline__ void qk_update_single(Ctx& cx, const DevComp* c, uint
         left = d;
         flags |= PF_HAS_ITEM;
         S32(c->o32 + P32_ITEM) = item;
-        S64(c->o64 + P64_BUSY) += d;
+        QK_ST64_ADD(comp, ST64_TIME, d);
         src = qk_log<LOG, SM>(cx, c, comp, src, QK_LOG_PROCESS_START, 0, item);
         ttnpe = d;
       } else {
@@ -555,7 +564,7 @@ __device__ __forceinline__ void qk_update_parallel(Ctx& cx, const DevComp* c, ui
         const uint32_t ds = c->down >= 0 ? qk_stock_cat_of<SM>(cx, c->down) : 3u;
         if (ds == 0u || ds == 1u) {
           src = qk_log<LOG, SM>(cx, c, comp, src, QK_LOG_PROCESS_FINISH, 0, it);
-          S32(c->o32 + PP32_NFINISH) += 1;
+          QK_ST32_ADD(comp, ST32_COUNT, 1u);
           qk_stock_add<LOG, SM>(cx, (uint32_t)c->down, it, src);
           if (cx.status) return;
         } else {
@@ -590,7 +599,7 @@ __device__ __forceinline__ void qk_update_parallel(Ctx& cx, const DevComp* c, ui
         S64(dur0 + nprog) = d;
         S32(item0 + nprog) = it;
         nprog += 1;
-        S64(c->o64 + PP64_BUSY) += d;
+        QK_ST64_ADD(comp, ST64_TIME, d);
         src = qk_log<LOG, SM>(cx, c, comp, src, QK_LOG_PROCESS_START, 0, it);
       } else {
         src = qk_log<LOG, SM>(cx, c, comp, src, QK_LOG_PROCESS_NONSTART,
@@ -665,6 +674,9 @@ __global__ void __launch_bounds__(SM > 0 ? SM : QK_MAX_NT) qk_step_kernel(const 
   const bool live = rep_local < P.n_reps;
   const uint64_t rep_global = P.rep_offset + rep_local;
   cx.rep_local = rep_local;
+  cx.gs64 = P.gs64 + rep_local;
+  cx.gs32 = P.gs32 + rep_local;
+  cx.rep_pad = P.rep_pad;
   cx.key0 = (uint32_t)P.seed;
   cx.key1 = (uint32_t)(P.seed >> 32);
   cx.rep_lo = (uint32_t)rep_global;
@@ -685,6 +697,10 @@ __global__ void __launch_bounds__(SM > 0 ? SM : QK_MAX_NT) qk_step_kernel(const 
     for (uint32_t i = 0; i < n_sched; ++i) S64(G64_FIRE0 + i) = QK_TIME_NONE;
     cx.now = P.t0;
     cx.log_cnt = 0;
+    for (uint32_t s = 0; s < n_comp * ST_PER_COMP; ++s) {
+      cx.gs64[(size_t)s * P.rep_pad] = 0;
+      cx.gs32[(size_t)s * P.rep_pad] = 0;
+    }
     if (live) {
       uint32_t initial_base = 0;
       for (uint32_t i = 0; i < n_comp; ++i) {
@@ -703,8 +719,8 @@ __global__ void __launch_bounds__(SM > 0 ? SM : QK_MAX_NT) qk_step_kernel(const 
           for (uint32_t k = 0; k < n_init; ++k) S32(c->o32 + S32_RING + k) = (63u << 26) | (initial_base + k);
           initial_base += n_init;
           S32(c->o32 + S32_HC) = n_init << 16;
-          S32(c->o32 + S32_MAXOCC) = n_init;
-          S64(c->o64 + S64_AREA) = 0ull - (uint64_t)n_init * P.t0;
+          cx.gs32[(size_t)(i * ST_PER_COMP + ST32_MAXOCC) * P.rep_pad] = n_init;
+          cx.gs64[(size_t)(i * ST_PER_COMP + ST64_TIME) * P.rep_pad] = 0ull - (uint64_t)n_init * P.t0;
         } else if (c->kind == QK_ENVIRONMENT) {
           S32(c->o32 + E32_STATE) = c->low; /* initial state rides in `low` */
         }
@@ -847,24 +863,27 @@ __global__ void __launch_bounds__(SM > 0 ? SM : QK_MAX_NT) qk_step_kernel(const 
 }
 
 /* per-replication (count, time_ns, aux, level) of component c, from the HBM state planes */
-__device__ __forceinline__ void qk_comp_stats_dev(const DevComp* c, const uint64_t* g64, const uint32_t* g32,
+__device__ __forceinline__ void qk_comp_stats_dev(const DevComp* c, uint32_t comp, const uint64_t* g64,
+                                                  const uint32_t* g32, const uint64_t* gs64, const uint32_t* gs32,
                                                   uint64_t rep_pad, uint64_t rep, qk_comp_stats* o) {
 #define G64(slot) g64[(size_t)(slot)*rep_pad + rep]
 #define G32(slot) g32[(size_t)(slot)*rep_pad + rep]
+#define GS64(k) gs64[(size_t)(comp * ST_PER_COMP + (k)) * rep_pad + rep]
+#define GS32(k) gs32[(size_t)(comp * ST_PER_COMP + (k)) * rep_pad + rep]
   const uint64_t now = G64(G64_NOW);
   if (c->kind == QK_DISCRETE_STOCK) {
     const uint32_t cnt = G32(c->o32 + S32_HC) >> 16;
-    o->count = G32(c->o32 + S32_NADD);
-    o->time_ns = G64(c->o64 + S64_AREA) + (uint64_t)cnt * now;
-    o->aux = G32(c->o32 + S32_MAXOCC);
+    o->count = GS32(ST32_COUNT);
+    o->time_ns = GS64(ST64_TIME) + (uint64_t)cnt * now;
+    o->aux = GS32(ST32_MAXOCC);
     o->level = cnt;
   } else if (c->kind == QK_DISCRETE_PARALLEL_PROCESS) {
     const uint32_t nprog = G32(c->o32 + PP32_NPROG);
-    uint64_t busy = G64(c->o64 + PP64_BUSY);
+    uint64_t busy = GS64(ST64_TIME);
     for (uint32_t i = 0; i < nprog; ++i) busy -= G64(c->o64_dm + c->n_dm + i);
-    o->count = G32(c->o32 + PP32_NFINISH);
+    o->count = GS32(ST32_COUNT);
     o->time_ns = busy;
-    o->aux = c->o64_delayns != 0xFFFF ? G64(c->o64_delayns) : 0;
+    o->aux = GS64(ST64_DELAY);
     o->level = nprog;
   } else if (c->kind == QK_ENVIRONMENT) {
     o->count = 0;
@@ -874,13 +893,15 @@ __device__ __forceinline__ void qk_comp_stats_dev(const DevComp* c, const uint64
   } else {
     const uint32_t flags = G32(c->o32 + P32_FLAGS);
     const bool has = flags & PF_HAS_ITEM;
-    o->count = G32(c->o32 + P32_NFINISH);
-    o->time_ns = G64(c->o64 + P64_BUSY) - (has ? G64(c->o64 + P64_LEFT) : 0);
-    o->aux = c->o64_delayns != 0xFFFF ? G64(c->o64_delayns) : 0;
+    o->count = GS32(ST32_COUNT);
+    o->time_ns = GS64(ST64_TIME) - (has ? G64(c->o64 + P64_LEFT) : 0);
+    o->aux = GS64(ST64_DELAY);
     o->level = has ? 1 : 0;
   }
 #undef G64
 #undef G32
+#undef GS64
+#undef GS32
 }
 
 #endif

@@ -380,12 +380,15 @@ int qk_lower(const qk_model* m, bool log, QkLowered* out) {
     d.dist_time = (uint16_t)(c.dist_time >= 0 ? c.dist_time : 0);
     d.flags = c.logged ? DC_LOGGED : 0;
     d.o64_ttnpe = 0xFFFF;
-    d.o64_delayns = 0xFFFF;
     d.o32_next_item = 0xFFFF;
     d.o64_nextdur = 0xFFFF;
     d.pf_idx = 0xFFFF;
     if (c.dist_time >= 0 && m->dists[(size_t)c.dist_time].kind == QK_DIST_CONSTANT)
-      d.const_dur = host_duration_code(m->dists[(size_t)c.dist_time].p[0]);
+{
+      const uint64_t cd = host_duration_code(m->dists[(size_t)c.dist_time].p[0]);
+      d.const_dur_lo = (uint32_t)cd;
+      d.const_dur_hi = (uint32_t)(cd >> 32);
+    }
     if (c.subs.size() > 255) {
       qk_set_error("component %zu: more than 255 subscribers", i);
       return QK_ERR_CAPACITY;
@@ -401,7 +404,6 @@ int qk_lower(const qk_model* m, bool log, QkLowered* out) {
       d.o64 = (uint16_t)n64;
       n64 += P64_BASE_COUNT;
       if (kind == QK_DISCRETE_SINK) d.o64_ttnpe = (uint16_t)n64++;
-      if (d.n_dm) d.o64_delayns = (uint16_t)n64++;
       d.o64_dm = (uint16_t)n64;
       n64 += d.n_dm;
       d.o32 = (uint16_t)n32;
@@ -415,7 +417,6 @@ int qk_lower(const qk_model* m, bool log, QkLowered* out) {
     } else if (kind == QK_DISCRETE_PARALLEL_PROCESS) {
       d.o64 = (uint16_t)n64;
       n64 += PP64_BASE_COUNT;
-      if (d.n_dm) d.o64_delayns = (uint16_t)n64++;
       d.o64_dm = (uint16_t)n64;
       n64 += d.n_dm;
       n64 += d.ring_cap; /* in-progress durations */

@@ -26,6 +26,8 @@ struct qk_batch {
   uint64_t rep_pad;
   std::vector<uint64_t> g64;
   std::vector<uint32_t> g32;
+  std::vector<uint64_t> gs64;
+  std::vector<uint32_t> gs32;
   std::vector<uint8_t> tables;
   std::vector<uint4> logbuf;
   std::vector<std::vector<double> > tapes;
@@ -40,6 +42,8 @@ static int run(qk_batch* b, uint32_t do_init, uint64_t t0, uint64_t t_until, uin
   memset(&P, 0, sizeof(P));
   P.g64 = b->g64.data();
   P.g32 = b->g32.data();
+  P.gs64 = b->gs64.data();
+  P.gs32 = b->gs32.data();
   P.tables = b->tables.data();
   P.table_bytes = b->table_bytes_padded;
   P.n64 = b->low.hdr.n64;
@@ -90,6 +94,8 @@ int qk_batch_create(const qk_model* m, const qk_batch_config* cfg, qk_batch** ou
   b->rep_pad = cfg->n_reps;
   b->g64.assign((size_t)h.n64 * b->rep_pad, 0);
   b->g32.assign((size_t)h.n32 * b->rep_pad, 0);
+  b->gs64.assign((size_t)h.n_comp * ST_PER_COMP * b->rep_pad, 0);
+  b->gs32.assign((size_t)h.n_comp * ST_PER_COMP * b->rep_pad, 0);
   b->tables.assign(b->table_bytes_padded, 0);
   memcpy(b->tables.data(), b->low.blob.data(), b->low.blob.size());
   if (b->log) b->logbuf.assign((size_t)b->rep_pad * cfg->log_capacity * 2, uint4{0, 0, 0, 0});
@@ -179,7 +185,8 @@ int qk_batch_read_status(qk_batch* b, uint64_t rep0, uint64_t n, uint32_t* statu
 int qk_batch_comp_stats(qk_batch* b, uint64_t rep0, uint64_t n, uint32_t comp, qk_comp_stats* out) {
   if (!b || rep0 + n > b->cfg.n_reps || comp >= b->low.hdr.n_comp) return QK_ERR_INVALID_ARG;
   for (uint64_t i = 0; i < n; ++i)
-    qk_comp_stats_dev(&b->low.comps[comp], b->g64.data(), b->g32.data(), b->rep_pad, rep0 + i, &out[i]);
+    qk_comp_stats_dev(&b->low.comps[comp], comp, b->g64.data(), b->g32.data(), b->gs64.data(), b->gs32.data(),
+                      b->rep_pad, rep0 + i, &out[i]);
   return QK_OK;
 }
 

@@ -33,6 +33,9 @@ extern thread_local uint32_t qk_emul_bid;
 #define QK_ANY_SYNC(p) (p)
 #define QK_BALLOT(p) ((p) ? 1u : 0u)
 #define QK_POPC(x) __builtin_popcount(x)
+static inline void qk_red_add64(uint64_t* p, uint64_t v) { *p += v; }
+static inline void qk_red_add32(uint32_t* p, uint32_t v) { *p += v; }
+static inline void qk_red_max32(uint32_t* p, uint32_t v) { if (v > *p) *p = v; }
 static inline void __syncthreads() {}
 
 static inline uint64_t __umul64hi(uint64_t a, uint64_t b) {
