@@ -98,6 +98,20 @@ static uint32_t choose_nt(uint32_t per_rep_bytes, uint32_t table_bytes, uint32_t
       best_nt = nt;
     }
   }
+  /* among block sizes within 6% of the best residency prefer the smallest (>= 64): a block holds its shared memory
+   * until its slowest warp finishes, so small blocks recycle capacity sooner (measured: 64 beats 128..256) */
+  for (uint32_t nt = 64; nt < best_nt; nt += 32) {
+    const uint64_t bytes = (uint64_t)table_bytes + (uint64_t)per_rep_bytes * nt;
+    uint32_t bps = (uint32_t)((228u * 1024u) / (bytes + 1024u));
+    if (bps > 32) bps = 32;
+    uint32_t thr = bps * nt;
+    if (thr > 2048) thr = 2048;
+    if ((uint64_t)thr * 100 >= (uint64_t)best_thr * 94) {
+      best_nt = nt;
+      best_thr = thr;
+      break;
+    }
+  }
   if (threads_per_sm) *threads_per_sm = best_thr;
   return best_nt;
 }

@@ -637,8 +637,13 @@ __device__ __forceinline__ void qk_update_state(Ctx& cx, uint32_t comp, uint64_t
 /* ============================================ the kernel ============================================ */
 #define QK_MAX_NT 256
 
+constexpr int qk_lb_threads(int sm) { return sm > 0 ? sm : QK_MAX_NT; }
+constexpr int qk_lb_blocks(int sm) { return sm > 0 ? (512 / sm > 0 ? 512 / sm : 1) : 2; }
+/* shared memory admits roughly 512 resident threads per SM for the models this path targets, so ask ptxas for that
+ * occupancy explicitly (<= 128 registers); a bare __launch_bounds__(SM) made it cap some instantiations at 80
+ * registers and spill */
 template <bool LOG, int SM>
-__global__ void __launch_bounds__(SM > 0 ? SM : QK_MAX_NT) qk_step_kernel(const __grid_constant__ KParams P) {
+__global__ void __launch_bounds__(qk_lb_threads(SM), qk_lb_blocks(SM)) qk_step_kernel(const __grid_constant__ KParams P) {
   uint8_t* const smem = qk_smem;
   const uint32_t tid = QK_TID, nt = SM > 0 ? (uint32_t)SM : QK_NT;
 
