@@ -16,7 +16,7 @@
 #define __global__
 #define __forceinline__ inline
 #define __noinline__
-#define __launch_bounds__(x)
+#define __launch_bounds__(...)
 #define __grid_constant__
 
 struct uint4 {
