@@ -65,7 +65,14 @@ typedef enum {
   QK_DISCRETE_SOURCE = 3,           /* DiscreteSource           discrete.rs:689-723 */
   QK_DISCRETE_SINK = 4,             /* DiscreteSink             discrete.rs:942-974 */
   QK_DISCRETE_PARALLEL_PROCESS = 5, /* DiscreteParallelProcess  discrete.rs:1188-1224 */
-  QK_ENVIRONMENT = 6                /* BasicEnvironment         core.rs:218-226 */
+  QK_ENVIRONMENT = 6,               /* BasicEnvironment         core.rs:218-226 */
+  /* continuous components (components/vector.rs); resource f64 or Vector3, see qk_model_set_vector */
+  QK_VECTOR_STOCK = 16,    /* VectorStock    vector.rs:42-62   */
+  QK_VECTOR_PROCESS = 17,  /* VectorProcess  vector.rs:278-320 */
+  QK_VECTOR_SOURCE = 18,   /* VectorSource   vector.rs:1324-1358 */
+  QK_VECTOR_SINK = 19,     /* VectorSink     vector.rs:1578-1612 */
+  QK_VECTOR_COMBINER = 20, /* VectorCombiner vector.rs:726-765 */
+  QK_VECTOR_SPLITTER = 21  /* VectorSplitter vector.rs:1026-1065 */
 } qk_component_kind;
 
 /* DistributionConfig (common.rs:37-44) */
@@ -108,7 +115,21 @@ typedef enum {
   QK_LOG_STOCK_ADD = 16,          /* payload = item handle */
   QK_LOG_STOCK_REMOVE = 17,       /* payload = item handle or QK_ITEM_NONE */
   QK_LOG_STOCK_STATE_CHANGE = 18, /* reason = 0 Empty / 1 Normal / 2 Full; payload = occupied<<32 | empty */
-  QK_LOG_ENV_STATE = 24           /* reason = 0 Normal / 1 Stopped */
+  QK_LOG_ENV_STATE = 24,          /* reason = 0 Normal / 1 Stopped */
+  /* vector components: `payload` holds the bits of an fp64 scalar; each vector of the record follows as one
+   * QK_LOG_VEC_DATA continuation record (reason = index, seq = seq of the record it continues) whose three doubles
+   * overlay time_ns, (src_comp|aux|src_seq) and payload */
+  QK_LOG_VSTOCK_ADD = 32,          /* payload = balance after ; 1 vector = what was added */
+  QK_LOG_VSTOCK_REMOVE = 33,       /* payload = balance after ; 1 vector = what was removed */
+  QK_LOG_VSTOCK_STATE_CHANGE = 34, /* reason = state ; payload = occupied ; vector[0] = empty */
+  QK_LOG_VPROC_START = 40,         /* payload = quantity ; 1 vector */
+  QK_LOG_VPROC_SUCCESS = 41,       /* payload = quantity ; 1 vector */
+  QK_LOG_VPROC_FAILURE = 42,       /* reason */
+  QK_LOG_VPROC_COMBINE_START = 43, /* payload = quantity ; M vectors */
+  QK_LOG_VPROC_COMBINE_SUCCESS = 44,
+  QK_LOG_VPROC_SPLIT_START = 45,
+  QK_LOG_VPROC_SPLIT_SUCCESS = 46, /* payload = total ; N vectors */
+  QK_LOG_VEC_DATA = 63
 } qk_log_kind;
 
 typedef enum {
@@ -120,7 +141,11 @@ typedef enum {
   QK_REASON_UPSTREAM_NO_RESOURCE = 5,     /* "Upstream did not provide resource" */
   QK_REASON_STOPPED_BY_ENV = 6,           /* "Stopped by environment" */
   QK_REASON_RESUMED_BY_ENV = 7,           /* "Resumed by environment" */
-  QK_REASON_UPSTREAM_FULL = 8             /* "Upstream is full" (DiscreteParallelProcess, discrete.rs:1390) */
+  QK_REASON_UPSTREAM_FULL = 8,            /* "Upstream is full" (DiscreteParallelProcess, discrete.rs:1390) */
+  QK_REASON_AN_UPSTREAM_EMPTY = 9,        /* "At least one upstream is empty"   vector.rs:938 */
+  QK_REASON_NO_UPSTREAMS = 10,            /* "No upstreams are connected"       vector.rs:942 */
+  QK_REASON_A_DOWNSTREAM_FULL = 11,       /* "At least one downstream is full"  vector.rs:1231 */
+  QK_REASON_NO_DOWNSTREAMS = 12           /* "No downstreams are connected"     vector.rs:1235 */
 } qk_reason;
 
 #define QK_SRC_INIT 0xFFFFu /* source_event_id "INIT_000000" (common.rs:14) */
@@ -151,7 +176,8 @@ typedef enum {
   QK_REP_STOCK_OVERFLOW = 4, /* item ring full (stock capacity is advisory in the reference) */
   QK_REP_EMIT_OVERFLOW = 5,  /* too many pending emit_change events on one stock */
   QK_REP_PARALLEL_OVERFLOW = 6,
-  QK_REP_ITEM_INDEX_OVERFLOW = 7
+  QK_REP_ITEM_INDEX_OVERFLOW = 7,
+  QK_REP_SOURCE_VECTOR = 8 /* panic!("Source vector has total 0 or negative") vector.rs:1490 */
 } qk_rep_status;
 
 /* per-component, per-replication summary (exact integers) */
@@ -159,7 +185,9 @@ typedef struct {
   uint64_t count;   /* process-like: ProcessFinish records ; stock: Add records */
   uint64_t time_ns; /* process-like: busy ns (countdown actually consumed) ; stock: integral of occupancy, item*ns */
   uint64_t aux;     /* process-like: ns spent in an active delay ; stock: maximum occupancy seen */
-  uint64_t level;   /* process-like: items in progress now ; stock: occupancy now */
+  uint64_t level;   /* process-like: items in progress now ; stock: occupancy now (vector stock: state category) */
+  double fvalue;    /* vector stock: current total ; vector process-like: sum of success quantities ; else 0 */
+  double faux;      /* vector stock: integral of total dt (unit*s) ; vector process-like: in-flight total ; else 0 */
 } qk_comp_stats;
 
 /* whole-batch reduction of qk_comp_stats over the replications of THIS batch (one GPU).
@@ -203,6 +231,14 @@ int qk_model_add_delay_mode(qk_model*, uint32_t comp, const qk_dist_desc* until_
 /* port_n = -1 for None */
 int qk_model_connect(qk_model*, uint32_t a, uint32_t b, int32_t port_n);
 int qk_model_set_logged(qk_model*, uint32_t comp, int enabled);
+/* vector components. dim = 1 (f64) or 3 (Vector3). VectorStock: low/max capacity + initial resource (with_low_capacity,
+ * with_max_capacity, with_initial_resource); VectorSource: init = source_vector; other kinds: dim only */
+int qk_model_set_vector(qk_model*, uint32_t comp, uint32_t dim, double low_capacity, double max_capacity,
+                        const double* init);
+/* VectorCombiner<M> / VectorSplitter<N>: number of ports (1..5) and split_ratios (vector.rs:756, 1056) */
+int qk_model_set_ports(qk_model*, uint32_t comp, uint32_t n_ports, const double* split_ratios);
+/* create_scheduled_event!(SetLowCapacity(v)) on an F64Stock (core.rs:1382-1386): setter + add(0.) at t */
+int qk_model_schedule_low_capacity(qk_model*, uint64_t t_ns, uint32_t stock, double value);
 int qk_model_schedule_env_state(qk_model*, uint64_t t_ns, uint32_t env, uint32_t state);
 int qk_model_n_components(const qk_model*, uint32_t* out);
 int qk_model_n_dists(const qk_model*, uint32_t* out);
@@ -263,6 +299,8 @@ int qk_batch_reduce_stats_device(qk_batch*, uint64_t* d_sums, uint64_t* d_extrem
 int qk_batch_histograms_device(qk_batch*, const uint64_t* d_extrema, uint64_t* d_hist, uint32_t n_comp);
 /* records of one replication, oldest first (at most log_capacity newest); *n_total = records ever written */
 int qk_batch_read_log(qk_batch*, uint64_t rep, qk_log_record* buf, uint64_t cap, uint64_t* n_out, uint64_t* n_total);
+/* resource of a vector stock / in-flight vector of a vector process-like component (3 doubles) */
+int qk_batch_read_vector(qk_batch*, uint64_t rep, uint32_t comp, double* out3);
 /* discrete stock contents in FIFO order */
 int qk_batch_read_stock(qk_batch*, uint64_t rep, uint32_t comp, uint32_t* items, uint64_t cap, uint64_t* n_out);
 /* timing of the last step call measured with CUDA events on the batch's stream (ms) and kernels launched */

@@ -18,6 +18,11 @@ def lower_to_oracle(model):
         else:
             i = om.add_component(c.KIND)
         assert i == index[id(c)]
+        if hasattr(c, "vector_rows"):
+            dim, low, maxc, init = c.vector_rows()
+            om.set_vector(i, dim, low, maxc, init)
+            if getattr(c, "n_ports", None):
+                om.set_splits(i, list(c.split_ratios))
         if hasattr(c, "process_time_distr"):
             for which, d in ((0, c.process_time_distr), (1, c.process_quantity_distr)):
                 did = om.set_dist(i, which, O.make_dist(d.kind, d.stream, d.params))
@@ -33,4 +38,6 @@ def lower_to_oracle(model):
         om.connect(index[id(a)], index[id(b)], n)
     for t, env, state in model.ext:
         om.schedule_env(t, index[id(env.component)], state)
+    for t, stock, value in getattr(model, "ext_low", []):
+        om.schedule_low_capacity(t, index[id(stock.component)], value)
     return om, dist_ids

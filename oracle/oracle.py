@@ -31,7 +31,8 @@ LOG_DTYPE = np.dtype(
     ]
 )
 assert LOG_DTYPE.itemsize == 32
-STATS_DTYPE = np.dtype([("n_a", "<u8"), ("n_b", "<u8"), ("t_a_ns", "<u8"), ("t_b_ns", "<u8")])
+STATS_DTYPE = np.dtype([("n_a", "<u8"), ("n_b", "<u8"), ("t_a_ns", "<u8"), ("t_b_ns", "<u8"), ("fvalue", "<f8"),
+                        ("faux", "<f8")])
 
 
 class Dist(C.Structure):

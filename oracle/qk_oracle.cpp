@@ -16,6 +16,7 @@
 #include "qk_oracle.h"
 
 #include <algorithm>
+#include <array>
 #include <cmath>
 #include <cstring>
 #include <deque>
@@ -336,14 +337,21 @@ struct Comp {
   std::deque<uint32_t> items;
   /* environment */
   uint32_t env_state;
+  /* vector components (vector.rs): stock resource / process in-flight vector; combiner keeps M vectors */
+  double vres[3];
+  std::vector<std::array<double, 3> > parts;
+  double vlow; /* low_capacity is mutable at run time (SetLowCapacity, core.rs:1382-1386) */
+  bool ttnde_some;
+  uint64_t ttnde;
   /* stats */
   orc_comp_stats st;
   uint64_t area_last_t;
   Comp()
       : has_item(false), left(0), item(0), env_stopped(false), ttnpe_some(false), ttnpe(0), sched_some(false),
         sched_time(0), sched_key(0), next_event_index(0), previous_check_time(0), next_item_index(0), env_state(0),
-        area_last_t(0) {
+        vlow(0), ttnde_some(false), ttnde(0), area_last_t(0) {
     std::memset(&st, 0, sizeof(st));
+    vres[0] = vres[1] = vres[2] = 0;
   }
 };
 
@@ -358,6 +366,8 @@ struct Action {
   EvId src;
   uint64_t key; /* for keyed events */
   uint32_t ext_index;
+  int pay_cat;    /* VectorStock::emit_change carries the state computed when it was scheduled (vector.rs:130,158) */
+  double pay_occ;
 };
 struct ActionCmp {
   bool operator()(const Action& a, const Action& b) const {
@@ -382,6 +392,8 @@ struct orc_sim {
   std::priority_queue<Action, std::vector<Action>, ActionCmp> q;
   std::vector<uint8_t> cancelled; /* indexed by key */
   uint64_t next_seq;
+  int pay_cat_next = 0;
+  double pay_occ_next = 0;
   std::vector<orc_log_record> logs;
 
   /* ---- sampling -------------------------------------------------------------------------- */
@@ -435,6 +447,8 @@ struct orc_sim {
     a.src = src;
     a.key = key;
     a.ext_index = ext_index;
+    a.pay_cat = pay_cat_next;
+    a.pay_occ = pay_occ_next;
     q.push(a);
   }
   uint64_t schedule_keyed(uint64_t time, uint32_t comp, EvId src) {
@@ -937,6 +951,11 @@ struct orc_sim {
           c[i].dm[k].in_fix = false;
           c[i].dm[k].dur = dur_from(secs);
         }
+        if (d.kind == ORC_VECTOR_STOCK) {
+          for (int k = 0; k < 3; ++k) c[i].vres[k] = d.vinit[k];
+          c[i].vlow = d.vlow;
+          c[i].area_last_t = t0;
+        }
         if (d.kind == ORC_DISCRETE_STOCK) {
           for (uint32_t k = 0; k < d.n_initial; ++k) c[i].items.push_back((63u << 26) | (d.initial_base + k));
           c[i].area_last_t = t0;
@@ -947,8 +966,13 @@ struct orc_sim {
         const CompDef& d = m->comps[i];
         if (d.kind == ORC_ENVIRONMENT) {
           log((uint32_t)i, EV_INIT, ORC_LOG_ENV_STATE, (uint8_t)c[i].env_state, 0); /* core.rs:229-234 */
+        } else if (d.kind == ORC_VECTOR_COMBINER || d.kind == ORC_VECTOR_SPLITTER || d.kind == ORC_VECTOR_SOURCE ||
+                   d.kind == ORC_VECTOR_SINK) {
+          /* these init with EventId("{code}_{next_event_index:06}") instead of INIT_000000 (vector.rs:774,1111,1393,1619) */
+          EvId own = {(uint16_t)i, c[i].next_event_index};
+          update_state((uint32_t)i, own);
         } else if (is_process_like(d.kind)) {
-          update_state((uint32_t)i, EV_INIT); /* discrete.rs:392-398 */
+          update_state((uint32_t)i, EV_INIT); /* discrete.rs:392-398, vector.rs:355-361 */
         }
       }
       /* externally scheduled events: origin rank 0, FIFO (core.rs:1377-1401) */
@@ -979,7 +1003,7 @@ struct orc_sim {
             if (m->comps[a.target].kind == ORC_DISCRETE_STOCK)
               stock_emit_change(a.target, a.src);
             else
-              vstock_emit_change(a.target, a.src, a.key);
+              vstock_emit_change(a.target, a.src, a.pay_cat, a.pay_occ);
             break;
           case ACT_EXT:
             ext_fire(a);
@@ -999,19 +1023,19 @@ struct orc_sim {
     else
       ext_set_low_capacity(e);
   }
-  void vstock_emit_change(uint32_t, EvId, uint64_t);
+  void vstock_emit_change(uint32_t, EvId, int, double);
   void ext_set_low_capacity(const ExtEvent&);
+  void vstock_area(uint32_t);
 
   void finalize_stats() {
     for (size_t i = 0; i < c.size(); ++i)
       if (m->comps[i].kind == ORC_DISCRETE_STOCK) stock_area((uint32_t)i);
+      else if (m->comps[i].kind == ORC_VECTOR_STOCK) vstock_area((uint32_t)i);
   }
 };
 
 /* vector components are added in a later milestone; keep the link closed */
-void orc_sim::impl_vector(uint32_t, EvId*) {}
-void orc_sim::vstock_emit_change(uint32_t, EvId, uint64_t) {}
-void orc_sim::ext_set_low_capacity(const ExtEvent&) {}
+#include "qk_oracle_vector.inc"
 
 /* =========================================== C API ========================================== */
 extern "C" {
@@ -1092,6 +1116,10 @@ int orc_model_connect(orc_model* m, uint32_t a, uint32_t b, int32_t port_n) {
     B.env = (int)a;
     return 0;
   }
+  {
+    int rc = orc_connect_vector(m, a, b, port_n);
+    if (rc != -3) return rc;
+  }
   return -3; /* "No component connection defined from {} to {}" */
 }
 
@@ -1107,9 +1135,6 @@ int orc_model_schedule_env(orc_model* m, uint64_t t_ns, uint32_t env, uint32_t s
   return 0;
 }
 int orc_model_n_dists(const orc_model* m) { return (int)m->dists.size(); }
-int orc_model_set_vector(orc_model*, uint32_t, uint32_t, double, double, const double*) { return -1; }
-int orc_model_set_splits(orc_model*, uint32_t, uint32_t, const double*) { return -1; }
-int orc_model_schedule_low_capacity(orc_model*, uint64_t, uint32_t, double) { return -1; }
 
 orc_sim* orc_sim_new(const orc_model* m, uint64_t base_seed, uint64_t rep, uint64_t t0_ns, int log_enabled) {
   orc_sim* s = new orc_sim();
@@ -1173,7 +1198,6 @@ uint64_t orc_sim_stock_items(const orc_sim* s, uint32_t comp, uint32_t* buf, uin
   for (uint64_t i = 0; i < n; ++i) buf[i] = d[i];
   return d.size();
 }
-int orc_sim_vector_resource(const orc_sim*, uint32_t, double*) { return -1; }
 uint64_t orc_sim_draws(const orc_sim* s, uint32_t dist_id) {
   return dist_id < s->draws.size() ? s->draws[dist_id] : 0;
 }

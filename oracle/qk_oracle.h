@@ -74,7 +74,12 @@ enum {
   ORC_LOG_VSTOCK_REMOVE = 33,
   ORC_LOG_VSTOCK_STATE_CHANGE = 34,
   ORC_LOG_VPROC_START = 40,
-  ORC_LOG_VPROC_FINISH = 41,
+  ORC_LOG_VPROC_SUCCESS = 41,
+  ORC_LOG_VPROC_FAILURE = 42,
+  ORC_LOG_VPROC_COMBINE_START = 43,
+  ORC_LOG_VPROC_COMBINE_SUCCESS = 44,
+  ORC_LOG_VPROC_SPLIT_START = 45,
+  ORC_LOG_VPROC_SPLIT_SUCCESS = 46,
   ORC_LOG_VEC_DATA = 63 /* continuation record carrying 3 doubles */
 };
 
@@ -88,7 +93,11 @@ enum {
   ORC_REASON_UPSTREAM_NO_RESOURCE = 5,   /* "Upstream did not provide resource" */
   ORC_REASON_STOPPED_BY_ENV = 6,         /* "Stopped by environment" */
   ORC_REASON_RESUMED_BY_ENV = 7,         /* "Resumed by environment" */
-  ORC_REASON_UPSTREAM_FULL = 8           /* "Upstream is full" (ParallelProcess quirk Q4) */
+  ORC_REASON_UPSTREAM_FULL = 8,          /* "Upstream is full" (ParallelProcess quirk Q4) */
+  ORC_REASON_AN_UPSTREAM_EMPTY = 9,      /* "At least one upstream is empty" */
+  ORC_REASON_NO_UPSTREAMS = 10,          /* "No upstreams are connected" */
+  ORC_REASON_A_DOWNSTREAM_FULL = 11,     /* "At least one downstream is full" */
+  ORC_REASON_NO_DOWNSTREAMS = 12         /* "No downstreams are connected" */
 };
 
 /* per-replication status */
@@ -96,7 +105,8 @@ enum {
   ORC_OK = 0,
   ORC_FAULT_ZERO_DURATION = 1, /* panic!("Time until next event is zero!") discrete.rs:541 */
   ORC_FAULT_BAD_DURATION = 2,  /* Duration::from_secs_f64 panics: negative / NaN / overflow */
-  ORC_FAULT_TAPE_EXHAUSTED = 3
+  ORC_FAULT_TAPE_EXHAUSTED = 3,
+  ORC_FAULT_SOURCE_VECTOR = 8 /* panic!("Source vector has total 0 or negative") vector.rs:1490 */
 };
 
 #define ORC_SRC_INIT 0xFFFFu /* EventId::from_init()      common.rs:14 */
@@ -127,6 +137,8 @@ typedef struct {
   uint64_t n_b;    /* process-like: ProcessFinish count; stock: Remove count */
   uint64_t t_a_ns; /* process-like: busy ns ; stock: time-integral of occupancy (items*ns) */
   uint64_t t_b_ns; /* process-like: ns spent in an active delay ; stock: max occupancy */
+  double fvalue;   /* vector stock: current total ; vector process-like: sum of success quantities */
+  double faux;     /* vector stock: integral of total dt (unit*s) ; vector process-like: in-flight total */
 } orc_comp_stats;
 
 typedef struct orc_model orc_model;

@@ -13,5 +13,9 @@ from .api import (  # noqa: F401
     connect_components, connect_logger, create_scheduled_event, register_component,
 )
 from ._capi import QkError  # noqa: F401
+from .api import VectorProcessLogger, VectorStockLogger  # noqa: F401
+from .vector_api import (  # noqa: F401
+    Vector3, VectorCombiner, VectorProcess, VectorSink, VectorSource, VectorSplitter, VectorStock,
+)
 
 __version__ = "0.1.0"

@@ -13,12 +13,17 @@ DEFAULT_LIB = os.path.join(_HERE, "libquokka_b200.so")
 
 # qk_component_kind
 DISCRETE_STOCK, DISCRETE_PROCESS, DISCRETE_SOURCE, DISCRETE_SINK, DISCRETE_PARALLEL_PROCESS, ENVIRONMENT = 1, 2, 3, 4, 5, 6
+VECTOR_STOCK, VECTOR_PROCESS, VECTOR_SOURCE, VECTOR_SINK, VECTOR_COMBINER, VECTOR_SPLITTER = 16, 17, 18, 19, 20, 21
 # qk_dist_kind
 DIST_CONSTANT, DIST_UNIFORM, DIST_TRIANGULAR, DIST_NORMAL, DIST_TRUNCNORMAL, DIST_EXPONENTIAL = 0, 1, 2, 3, 4, 5
 # qk_log_kind
 LOG_PROCESS_START, LOG_PROCESS_CONTINUE, LOG_PROCESS_FINISH, LOG_PROCESS_NONSTART = 1, 2, 3, 4
 LOG_PROCESS_STOPPED, LOG_WITHDRAW_REQUEST, LOG_DELAY_START, LOG_DELAY_END = 5, 6, 7, 8
 LOG_STOCK_ADD, LOG_STOCK_REMOVE, LOG_STOCK_STATE_CHANGE, LOG_ENV_STATE = 16, 17, 18, 24
+LOG_VSTOCK_ADD, LOG_VSTOCK_REMOVE, LOG_VSTOCK_STATE_CHANGE = 32, 33, 34
+LOG_VPROC_START, LOG_VPROC_SUCCESS, LOG_VPROC_FAILURE = 40, 41, 42
+LOG_VPROC_COMBINE_START, LOG_VPROC_COMBINE_SUCCESS, LOG_VPROC_SPLIT_START, LOG_VPROC_SPLIT_SUCCESS = 43, 44, 45, 46
+LOG_VEC_DATA = 63
 SRC_INIT, SRC_SCH = 0xFFFF, 0xFFFE
 ITEM_NONE = 0xFFFFFFFFFFFFFFFF
 HIST_BINS = 32
@@ -34,6 +39,7 @@ STATUS_NAMES = {
 EXPORTED_SYMBOLS = [
     "qk_abi_version", "qk_model_create", "qk_model_destroy", "qk_model_add_component", "qk_model_set_dist",
     "qk_model_add_delay_mode", "qk_model_connect", "qk_model_set_logged", "qk_model_schedule_env_state",
+    "qk_model_set_vector", "qk_model_set_ports", "qk_model_schedule_low_capacity", "qk_batch_read_vector",
     "qk_model_n_components", "qk_model_n_dists", "qk_model_state_bytes", "qk_batch_create", "qk_batch_destroy",
     "qk_batch_info_get",
     "qk_batch_set_tape", "qk_batch_init", "qk_batch_step_until", "qk_batch_step_events", "qk_batch_synchronize",
@@ -91,7 +97,8 @@ LOG_DTYPE = np.dtype(
     [("time_ns", "<u8"), ("comp", "<u2"), ("kind", "u1"), ("reason", "u1"), ("seq", "<u4"), ("src_comp", "<u2"),
      ("aux", "<u2"), ("src_seq", "<u4"), ("payload", "<u8")]
 )
-COMP_STATS_DTYPE = np.dtype([("count", "<u8"), ("time_ns", "<u8"), ("aux", "<u8"), ("level", "<u8")])
+COMP_STATS_DTYPE = np.dtype([("count", "<u8"), ("time_ns", "<u8"), ("aux", "<u8"), ("level", "<u8"), ("fvalue", "<f8"),
+                             ("faux", "<f8")])
 COMP_SUMMARY_DTYPE = np.dtype(
     [("sum_count", "<u8"), ("sum_time_lo", "<u8"), ("sum_time_hi", "<u8"), ("sum_level", "<u8"),
      ("min_count", "<u8"), ("max_count", "<u8"), ("min_time", "<u8"), ("max_time", "<u8"),
@@ -99,7 +106,7 @@ COMP_SUMMARY_DTYPE = np.dtype(
      ("hist_count", "<u8", (HIST_BINS,)), ("hist_lo_time", "<u8"), ("hist_hi_time", "<u8"),
      ("hist_lo_count", "<u8"), ("hist_hi_count", "<u8")]
 )
-assert LOG_DTYPE.itemsize == 32 and COMP_STATS_DTYPE.itemsize == 32
+assert LOG_DTYPE.itemsize == 32 and COMP_STATS_DTYPE.itemsize == 48
 
 _LIBS = {}
 
@@ -127,6 +134,10 @@ def load_library(path=None):
         "qk_model_connect": (C.c_int, [vp, u32, u32, i32]),
         "qk_model_set_logged": (C.c_int, [vp, u32, C.c_int]),
         "qk_model_schedule_env_state": (C.c_int, [vp, u64, u32, u32]),
+        "qk_model_set_vector": (C.c_int, [vp, u32, u32, C.c_double, C.c_double, P(C.c_double)]),
+        "qk_model_set_ports": (C.c_int, [vp, u32, u32, P(C.c_double)]),
+        "qk_model_schedule_low_capacity": (C.c_int, [vp, u64, u32, C.c_double]),
+        "qk_batch_read_vector": (C.c_int, [vp, u64, u32, P(C.c_double)]),
         "qk_model_n_components": (C.c_int, [vp, P(u32)]),
         "qk_model_n_dists": (C.c_int, [vp, P(u32)]),
         "qk_model_state_bytes": (C.c_int, [vp, C.c_int, P(u32)]),

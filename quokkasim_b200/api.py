@@ -423,6 +423,8 @@ class ComponentModel:
         self.variant = variant
         self.component = component
         self.mailbox = mailbox
+        if variant in _VECTOR_VARIANTS:
+            _bind_vector_variant(variant, component)
 
     def __str__(self):  # #[derive(Display)] prints the variant name
         return self.variant
@@ -465,7 +467,8 @@ def connect_components(a, b, n=None):
     ok = (
         (va == "StringStock" and vb in _STOCK_TO_PROC)
         or (vb == "StringStock" and va in _PROC_TO_STOCK)
-        or (va == "BasicEnvironment" and vb in _ENV_TARGETS)
+        or (va == "BasicEnvironment" and (vb in _ENV_TARGETS or (vb in _VECTOR_VARIANTS and not vb.endswith("Stock"))))
+        or _vector_connection_ok(va, vb, n)
     )
     if not ok:
         raise ComponentConnectionError(
@@ -502,6 +505,20 @@ class BasicEnvironmentLogger(_Logger):
     ACCEPTS = ("BasicEnvironment",)
 
 
+class VectorStockLogger(_Logger):
+    """vector.rs:211-231"""
+
+    ACCEPTS = ("F64Stock", "Vector3Stock")
+
+
+class VectorProcessLogger(_Logger):
+    """vector.rs:543-562: one logger type for process, source, sink, combiner and splitter records"""
+
+    ACCEPTS = tuple("%s%s" % (p, k) for p in ("F64", "Vector3")
+                    for k in ["Process", "Source", "Sink"] + ["Combiner%d" % i for i in range(1, 6)]
+                    + ["Splitter%d" % i for i in range(1, 6)])
+
+
 class ComponentLogger:
     """The generated logger enum (core.rs:1216-1365)."""
 
@@ -509,6 +526,10 @@ class ComponentLogger:
         "StringStockLogger": DiscreteStockLogger,
         "StringProcessLogger": DiscreteProcessLogger,
         "BasicEnvironmentLogger": BasicEnvironmentLogger,
+        "F64StockLogger": VectorStockLogger,
+        "F64ProcessLogger": VectorProcessLogger,
+        "Vector3StockLogger": VectorStockLogger,
+        "Vector3ProcessLogger": VectorProcessLogger,
     }
 
     def __init__(self, variant, logger):
@@ -585,6 +606,9 @@ def create_scheduled_event(scheduler, time, event_config, component_addr, df=Non
     """create_scheduled_event!(&mut sched, &time, &cfg, &addr, &mut df) (core.rs:1377-1401, 1430-1434)."""
     if event_config.kind == "SetEnvironmentState" and component_addr.variant == "BasicEnvironment":
         scheduler._sim._schedule_env(int(time), component_addr.component, int(event_config.value))
+        return
+    if event_config.kind == "SetLowCapacity" and component_addr.variant == "F64Stock":  # core.rs:1382-1386
+        scheduler._sim._schedule_low(int(time), component_addr.component, float(event_config.value))
         return
     raise NotImplementedError(
         "schedule_event not implemented for types (%s, %s)" % (event_config, component_addr.variant)
@@ -668,11 +692,20 @@ class BatchedSimulation:
                 d.capacity_hint = c.capacity_hint
             elif isinstance(c, BasicEnvironment):
                 d.initial_env_state = c.state
-            else:
+            elif hasattr(c, "capacity_hint"):
                 d.capacity_hint = c.capacity_hint
             out = C.c_uint32()
             capi.check(L, L.qk_model_add_component(self._model, C.byref(d), C.byref(out)))
             assert out.value == c._id
+            if hasattr(c, "vector_rows"):
+                if c.dim is None:
+                    raise TypeError("vector component %r was never wrapped in a ComponentModel variant" % c.element_name)
+                dim, low, maxc, init = c.vector_rows()
+                arr = (C.c_double * 3)(*(list(init) + [0.0] * (3 - len(init))))
+                capi.check(L, L.qk_model_set_vector(self._model, c._id, dim, low, maxc, arr))
+                if getattr(c, "n_ports", None):
+                    ratios = (C.c_double * 5)(*(list(c.split_ratios) + [0.0] * (5 - len(c.split_ratios))))
+                    capi.check(L, L.qk_model_set_ports(self._model, c._id, c.n_ports, ratios))
             if isinstance(c, _ProcessLike):
                 for which, dist in ((0, c.process_time_distr), (1, c.process_quantity_distr)):
                     did = C.c_uint32()
@@ -693,13 +726,21 @@ class BatchedSimulation:
             if id(a) not in registered or id(b) not in registered:
                 raise ValueError("connect_components involves a component that was never registered")
             capi.check(L, L.qk_model_connect(self._model, a._id, b._id, n))
-        for t, env, state in self._ext:
-            capi.check(L, L.qk_model_schedule_env_state(self._model, t, env._id, state))
+        for kind, t, comp, value in self._ext:
+            if kind == "env":
+                capi.check(L, L.qk_model_schedule_env_state(self._model, t, comp._id, value))
+            else:
+                capi.check(L, L.qk_model_schedule_low_capacity(self._model, t, comp._id, value))
 
     def _schedule_env(self, t_ns, env, state):
         if self._batch:
             raise RuntimeError("scheduled events must be created before the first step of a BatchedSimulation")
-        self._ext.append((t_ns, env, state))
+        self._ext.append(("env", t_ns, env, state))
+
+    def _schedule_low(self, t_ns, stock, value):
+        if self._batch:
+            raise RuntimeError("scheduled events must be created before the first step of a BatchedSimulation")
+        self._ext.append(("low", t_ns, stock, value))
 
     def set_tape(self, distribution, values):
         """Pre-drawn variate tape for one Distribution instance: values[replication, i] is what its i-th
@@ -822,6 +863,13 @@ class BatchedSimulation:
                                                         C.byref(tot)))
         return buf, tot.value
 
+    def read_vector(self, component, replication):
+        """Resource of a vector stock / in-flight vector of a vector process-like component (3 doubles)."""
+        self._materialize()
+        out = (C.c_double * 3)()
+        capi.check(self.L, self.L.qk_batch_read_vector(self._batch, replication, self._cid(component), out))
+        return list(out)
+
     def read_stock(self, component, replication):
         self._materialize()
         n = C.c_uint64()
@@ -840,3 +888,19 @@ class BatchedSimulation:
     def histograms_device(self, d_extrema_ptr, d_hist_ptr):
         self._materialize()
         capi.check(self.L, self.L.qk_batch_histograms_device(self._batch, d_extrema_ptr, d_hist_ptr, self.n_comp))
+
+
+# --------------------------------------------------------------------------------------- vector family
+# (imported last: vector_api subclasses _Component / _ProcessLike defined above)
+from . import vector_api as _va  # noqa: E402
+
+_VECTOR_VARIANTS = _va.VECTOR_VARIANTS
+_bind_vector_variant = _va.bind_variant
+_vector_connection_ok = _va.connection_ok
+for _v, (_cls, _dim, _ports) in _VECTOR_VARIANTS.items():
+    ComponentModel._VARIANTS[_v] = _cls
+    setattr(ComponentModel, _v, _variant_ctor(_v))
+for _v in ("F64StockLogger", "F64ProcessLogger", "Vector3StockLogger", "Vector3ProcessLogger"):
+    setattr(ComponentLogger, _v, staticmethod(lambda logger, _v=_v: ComponentLogger(_v, logger)))
+Vector3, VectorStock, VectorProcess, VectorSource = _va.Vector3, _va.VectorStock, _va.VectorProcess, _va.VectorSource
+VectorSink, VectorCombiner, VectorSplitter = _va.VectorSink, _va.VectorCombiner, _va.VectorSplitter

@@ -155,7 +155,8 @@ __global__ void qk_comp_stats_kernel(const uint8_t* tables, const uint64_t* g64,
   const DevHeader* h = reinterpret_cast<const DevHeader*>(tables);
   const DevComp* c = reinterpret_cast<const DevComp*>(tables + h->off_comps) + comp;
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) qk_comp_stats_dev(c, comp, g64, g32, gs64, gs32, rep_pad, rep0 + i, &out[i]);
+  const DevVec* vecs = reinterpret_cast<const DevVec*>(tables + h->off_vecs);
+  if (i < n) qk_comp_stats_dev(c, vecs, comp, g64, g32, gs64, gs32, rep_pad, rep0 + i, &out[i]);
 }
 
 __device__ __forceinline__ uint64_t warp_sum_u64(uint64_t v) {
@@ -188,7 +189,7 @@ __global__ void __launch_bounds__(256) qk_reduce_kernel(const uint8_t* tables, c
   double sq[2] = {0.0, 0.0};
   for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_reps; r += (uint64_t)gridDim.x * blockDim.x) {
     qk_comp_stats s;
-    qk_comp_stats_dev(c, comp, g64, g32, gs64, gs32, rep_pad, r, &s);
+    qk_comp_stats_dev(c, reinterpret_cast<const DevVec*>(tables + h->off_vecs), comp, g64, g32, gs64, gs32, rep_pad, r, &s);
     a[0] += s.count;
     a[1] += s.time_ns & 0xFFFFFFFFull;
     a[2] += s.time_ns >> 32;
@@ -267,7 +268,7 @@ __global__ void __launch_bounds__(256) qk_hist_kernel(const uint8_t* tables, con
   const uint64_t w_c = (hi_c - lo_c) / QK_HIST_BINS + 1, w_t = (hi_t - lo_t) / QK_HIST_BINS + 1;
   for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_reps; r += (uint64_t)gridDim.x * blockDim.x) {
     qk_comp_stats s;
-    qk_comp_stats_dev(c, comp, g64, g32, gs64, gs32, rep_pad, r, &s);
+    qk_comp_stats_dev(c, reinterpret_cast<const DevVec*>(tables + h->off_vecs), comp, g64, g32, gs64, gs32, rep_pad, r, &s);
     if (s.time_ns >= lo_t && s.time_ns <= hi_t) atomicAdd(&sh[0][(s.time_ns - lo_t) / w_t], 1ull);
     if (s.count >= lo_c && s.count <= hi_c) atomicAdd(&sh[1][(s.count - lo_c) / w_c], 1ull);
   }
@@ -701,8 +702,24 @@ int qk_batch_read_log(qk_batch* b, uint64_t rep, qk_log_record* buf, uint64_t ca
   const uint64_t first = cnt - kept; /* oldest record still in the ring */
   for (uint64_t i = 0; i < kept; ++i) {
     buf[i] = ring[(first + i) & (lc - 1)];
-    buf[i].aux = 0;
+    if (buf[i].kind != QK_LOG_VEC_DATA) buf[i].aux = 0; /* continuation records carry fp64 bits there */
   }
+  return QK_OK;
+}
+
+int qk_batch_read_vector(qk_batch* b, uint64_t rep, uint32_t comp, double* out3) {
+  int rc = check_range(b, rep, 1);
+  if (rc) return rc;
+  if (comp >= b->low.hdr.n_comp || b->low.comps[comp].kind < QK_VECTOR_STOCK || !out3) {
+    qk_set_error("qk_batch_read_vector: component %u is not a vector component", comp);
+    return QK_ERR_INVALID_ARG;
+  }
+  CUDA_TRY(cudaSetDevice(b->cfg.device));
+  CUDA_TRY(cudaStreamSynchronize(b->stream));
+  const DevVec& v = b->low.vecs[b->low.comps[comp].vec_idx];
+  out3[0] = out3[1] = out3[2] = 0.0;
+  for (uint32_t k = 0; k < v.dim; ++k)
+    CUDA_TRY(cudaMemcpy(&out3[k], b->g64 + (size_t)(v.o64_res + k) * b->rep_pad + rep, 8, cudaMemcpyDeviceToHost));
   return QK_OK;
 }
 

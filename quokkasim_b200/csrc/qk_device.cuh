@@ -32,6 +32,8 @@ extern __shared__ __align__(16) uint8_t qk_smem[];
 __device__ __forceinline__ void qk_red_add64(uint64_t* p, uint64_t v) { atomicAdd((unsigned long long*)p, (unsigned long long)v); }
 __device__ __forceinline__ void qk_red_add32(uint32_t* p, uint32_t v) { atomicAdd(p, v); }
 __device__ __forceinline__ void qk_red_max32(uint32_t* p, uint32_t v) { atomicMax(p, v); }
+/* fp64 accumulator stored in a u64 plane: one thread owns the address, so the sum order is the program order */
+__device__ __forceinline__ void qk_red_addf64(uint64_t* p, double v) { atomicAdd(reinterpret_cast<double*>(p), v); }
 #endif
 
 #define QK_DEV __device__ __forceinline__

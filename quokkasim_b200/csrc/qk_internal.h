@@ -58,7 +58,9 @@ enum { PP32_FLAGS = 0, PP32_NPROG = 1, PP32_COMPLETE = 2, PP32_BASE_COUNT = 3 };
  *   stat64[1]: process-like: ns spent in an active delay
  *   stat32[0]: process-like: ProcessFinish count ; stock: Add count
  *   stat32[1]: stock: maximum occupancy */
-enum { ST64_TIME = 0, ST64_DELAY = 1, ST32_COUNT = 0, ST32_MAXOCC = 1, ST_PER_COMP = 2 };
+enum { ST64_TIME = 0, ST64_DELAY = 1, ST64_FQ = 2, ST32_COUNT = 0, ST32_MAXOCC = 1, ST_PER_COMP = 3 };
+/* vector components: stat64[ST64_TIME] of a VectorStock holds the fp64 integral of its total (unit*s);
+ * stat64[ST64_FQ] of a vector process-like component holds the fp64 sum of its success quantities */
 
 /* ---- environment --------------------------------------------------------------------------------- */
 enum { E32_STATE = 0, E32_COUNT = 1 };
@@ -81,7 +83,7 @@ typedef struct {
   uint16_t dm_off;    /* first DevDelayMode */
   uint16_t o64_dm;    /* first delay-mode duration slot (absolute) */
   uint16_t o64_ttnpe; /* absolute slot, 0xFFFF if none (only DiscreteSink keeps ttnpe across calls) */
-  uint16_t pad1;
+  uint16_t vec_idx; /* index into DevVec[] for vector components */
   uint16_t o32_next_item; /* absolute slot (sources) */
   uint16_t emit_depth;
   uint16_t flags;
@@ -105,11 +107,27 @@ typedef struct {
 
 typedef struct {
   uint64_t t;
-  uint32_t type; /* 0 SetEnvironmentState */
+  uint32_t type; /* 0 SetEnvironmentState, 1 SetLowCapacity (F64Stock) */
   uint32_t target;
   uint32_t state;
   uint32_t pad;
-} DevExt; /* 24 bytes */
+  double value;
+} DevExt; /* 32 bytes */
+
+/* extra description of a vector component (vector.rs); resource type f64 (dim 1) or Vector3 (dim 3) */
+typedef struct {
+  double vmax;      /* VectorStock.max_capacity */
+  double vinit[3];  /* VectorStock initial resource / VectorSource.source_vector */
+  double ratios[5]; /* VectorSplitter.split_ratios */
+  int16_t ups[5];   /* VectorCombiner upstream stocks by port */
+  int16_t downs[5]; /* VectorSplitter downstream stocks by port */
+  uint16_t dim, n_ports;
+  uint16_t dist_qty; /* process_quantity_distr */
+  uint16_t o64_res;  /* stock: resource[dim] ; process-like: in-flight vector[dim] (+1 quantity slot for combiners) */
+  uint16_t o64_low;  /* stock: run-time low_capacity (f64 bits) */
+  uint16_t o64_last; /* stock: time of the last level change (for the integral) */
+  double vlow;       /* VectorStock.low_capacity at t0 */
+} DevVec; /* 112 bytes */
 
 /* header of the table blob (all offsets in bytes from the blob start, 8-byte aligned) */
 typedef struct {
@@ -120,6 +138,7 @@ typedef struct {
   uint32_t init_off, n_init; /* subs[init_off ..): components whose Model::init does something, registration order */
   uint32_t n_pf, n_pf_words, pf32; /* prefetchable distributions; pf32 = first pending-mask slot (plane32) */
   uint32_t off_pf;           /* u16 pf_comp[n_pf]: prefetch index -> component */
+  uint32_t n_vec, off_vecs;  /* DevVec[] */
   uint32_t off_comps, off_dists, off_dms, off_subs, off_sched, off_ext;
   uint32_t total_bytes;
   uint32_t log_enabled;

@@ -59,6 +59,7 @@ struct Ctx {
   const uint16_t* subs;
   const uint16_t* sched;
   const DevExt* ext;
+  const DevVec* vecs;
   uint64_t now;
   uint32_t status;
   uint4* log_base;
@@ -619,12 +620,23 @@ __device__ __forceinline__ void qk_update_parallel(Ctx& cx, const DevComp* c, ui
   S64(c->o64 + PP64_PREV) = cx.now;
 }
 
+#include "qk_vector.cuh"
+
 /* Process::update_state (core.rs:370-376) */
 template <bool LOG, int SM>
 __device__ __forceinline__ void qk_update_state(Ctx& cx, uint32_t comp, uint64_t src) {
   const DevComp* c = &cx.comps[comp];
   if (c->kind == QK_ENVIRONMENT) { /* only reached from the init list: BasicEnvironment::init logs its state */
     qk_log<LOG, SM>(cx, c, comp, src, QK_LOG_ENV_STATE, S32(c->o32 + E32_STATE), 0);
+    return;
+  }
+  if (c->kind >= QK_VECTOR_PROCESS) {
+    /* Combiner / Splitter / VectorSource / VectorSink init with their own next id instead of INIT_000000
+     * (vector.rs:774,1111,1393,1619); SRC_INIT only ever arrives from the init list */
+    if (LOG && src == SRC_INIT && c->kind != QK_VECTOR_PROCESS)
+      src = ((uint64_t)comp << 32) | S32(c->olog32 + L32_SEQ);
+    qk_pre<LOG, SM>(cx, c);
+    qk_update_vector<LOG, SM>(cx, c, comp, src);
     return;
   }
   qk_pre<LOG, SM>(cx, c);
@@ -663,6 +675,7 @@ __global__ void __launch_bounds__(qk_lb_threads(SM), qk_lb_blocks(SM)) qk_step_k
   cx.subs = reinterpret_cast<const uint16_t*>(smem + cx.hdr->off_subs);
   cx.sched = reinterpret_cast<const uint16_t*>(smem + cx.hdr->off_sched);
   cx.ext = reinterpret_cast<const DevExt*>(smem + cx.hdr->off_ext);
+  cx.vecs = reinterpret_cast<const DevVec*>(smem + cx.hdr->off_vecs);
   const uint64_t rep_local = (uint64_t)QK_BID * nt + tid;
   if constexpr (SM == 0) {
     cx.g64 = P.g64 + rep_local;
@@ -728,6 +741,11 @@ __global__ void __launch_bounds__(qk_lb_threads(SM), qk_lb_blocks(SM)) qk_step_k
           cx.gs64[(size_t)(i * ST_PER_COMP + ST64_TIME) * P.rep_pad] = 0ull - (uint64_t)n_init * P.t0;
         } else if (c->kind == QK_ENVIRONMENT) {
           S32(c->o32 + E32_STATE) = c->low; /* initial state rides in `low` */
+        } else if (c->kind == QK_VECTOR_STOCK) {
+          const DevVec* v = &cx.vecs[c->vec_idx];
+          qk_vstore<SM>(cx, v->o64_res, v->dim, v->vinit);
+          S64(v->o64_low) = QK_D2U(v->vlow);
+          S64(v->o64_last) = P.t0;
         }
       }
     }
@@ -798,7 +816,12 @@ __global__ void __launch_bounds__(qk_lb_threads(SM), qk_lb_blocks(SM)) qk_step_k
         const DevExt* e = &cx.ext[ext_cursor];
         ext_cursor += 1;
         const DevComp* c = &cx.comps[e->target];
-        if (S32(c->o32 + E32_STATE) != e->state) {
+        if (e->type == 1) {
+          /* SetLowCapacity on an F64Stock: with_low_capacity_inplace, then add((0., SCH_000000)) (core.rs:1382-1386) */
+          S64(cx.vecs[c->vec_idx].o64_low) = QK_D2U(e->value);
+          const double zero[3] = {0.0, 0.0, 0.0};
+          qk_vstock_add<LOG, SM>(cx, e->target, zero, SRC_SCH);
+        } else if (S32(c->o32 + E32_STATE) != e->state) {
           S32(c->o32 + E32_STATE) = e->state;
           src = qk_log<LOG, SM>(cx, c, e->target, SRC_SCH, QK_LOG_ENV_STATE, e->state, 0);
           rem = c->n_subs;
@@ -815,6 +838,22 @@ __global__ void __launch_bounds__(qk_lb_threads(SM), qk_lb_blocks(SM)) qk_step_k
           const uint32_t empty = c->max > cnt ? c->max - cnt : 0;
           src = qk_log<LOG, SM>(cx, c, comp, ((uint64_t)comp << 32) | src_seq, QK_LOG_STOCK_STATE_CHANGE,
                             qk_stock_cat(cnt, c->low, c->max), ((uint64_t)cnt << 32) | empty);
+          rem = c->n_subs;
+          ptr = c->subs_off;
+        } else if (c->kind == QK_VECTOR_STOCK) {
+          /* VectorStock::emit_change (vector.rs:167-171) logs the state carried by the event */
+          uint32_t packed = 0;
+          uint64_t occ_bits = 0;
+          if (LOG) {
+            const uint32_t head = (S32(c->o32 + S32_EMIT) >> 16) & 0xFFu;
+            occ_bits = S64(c->olog64 + head);
+            packed = qk_emit_pop<LOG, SM>(cx, c);
+          } else {
+            qk_emit_pop<LOG, SM>(cx, c);
+          }
+          src = qk_log<LOG, SM>(cx, c, comp, ((uint64_t)comp << 32) | (packed & 0x3FFFFFFFu), QK_LOG_VSTOCK_STATE_CHANGE,
+                            packed >> 30, occ_bits);
+          qk_log_vec<LOG, SM>(cx, c, comp, src, 0, __dsub_rn(cx.vecs[c->vec_idx].vmax, QK_U2D(occ_bits)), 0.0, 0.0);
           rem = c->n_subs;
           ptr = c->subs_off;
         } else {
@@ -868,7 +907,7 @@ __global__ void __launch_bounds__(qk_lb_threads(SM), qk_lb_blocks(SM)) qk_step_k
 }
 
 /* per-replication (count, time_ns, aux, level) of component c, from the HBM state planes */
-__device__ __forceinline__ void qk_comp_stats_dev(const DevComp* c, uint32_t comp, const uint64_t* g64,
+__device__ __forceinline__ void qk_comp_stats_dev(const DevComp* c, const DevVec* vecs, uint32_t comp, const uint64_t* g64,
                                                   const uint32_t* g32, const uint64_t* gs64, const uint32_t* gs32,
                                                   uint64_t rep_pad, uint64_t rep, qk_comp_stats* o) {
 #define G64(slot) g64[(size_t)(slot)*rep_pad + rep]
@@ -876,7 +915,38 @@ __device__ __forceinline__ void qk_comp_stats_dev(const DevComp* c, uint32_t com
 #define GS64(k) gs64[(size_t)(comp * ST_PER_COMP + (k)) * rep_pad + rep]
 #define GS32(k) gs32[(size_t)(comp * ST_PER_COMP + (k)) * rep_pad + rep]
   const uint64_t now = G64(G64_NOW);
-  if (c->kind == QK_DISCRETE_STOCK) {
+  o->fvalue = 0.0;
+  o->faux = 0.0;
+  if (c->kind == QK_VECTOR_STOCK) {
+    const DevVec* v = &vecs[c->vec_idx];
+    double r[3] = {QK_U2D(G64(v->o64_res)), 0.0, 0.0};
+    if (v->dim == 3) {
+      r[1] = QK_U2D(G64(v->o64_res + 1));
+      r[2] = QK_U2D(G64(v->o64_res + 2));
+    }
+    const double total = qk_vtotal(r, v->dim);
+    o->count = GS32(ST32_COUNT);
+    o->time_ns = 0;
+    o->aux = 0;
+    o->level = qk_vcat(total, QK_U2D(G64(v->o64_low)), v->vmax);
+    o->fvalue = total;
+    o->faux = __dadd_rn(QK_U2D(GS64(ST64_TIME)), __dmul_rn(total, __dmul_rn((double)(now - G64(v->o64_last)), 1e-9)));
+  } else if (c->kind >= QK_VECTOR_PROCESS) {
+    const DevVec* v = &vecs[c->vec_idx];
+    const uint32_t flags = G32(c->o32 + P32_FLAGS);
+    const bool has = flags & PF_HAS_ITEM;
+    double r[3] = {QK_U2D(G64(v->o64_res)), 0.0, 0.0};
+    if (v->dim == 3) {
+      r[1] = QK_U2D(G64(v->o64_res + 1));
+      r[2] = QK_U2D(G64(v->o64_res + 2));
+    }
+    o->count = GS32(ST32_COUNT);
+    o->time_ns = GS64(ST64_TIME) - (has ? G64(c->o64 + P64_LEFT) : 0);
+    o->aux = GS64(ST64_DELAY);
+    o->level = has ? 1 : 0;
+    o->fvalue = QK_U2D(GS64(ST64_FQ));
+    o->faux = !has ? 0.0 : (c->kind == QK_VECTOR_COMBINER ? QK_U2D(G64(v->o64_res + v->dim)) : qk_vtotal(r, v->dim));
+  } else if (c->kind == QK_DISCRETE_STOCK) {
     const uint32_t cnt = G32(c->o32 + S32_HC) >> 16;
     o->count = GS32(ST32_COUNT);
     o->time_ns = GS64(ST64_TIME) + (uint64_t)cnt * now;

@@ -24,8 +24,9 @@ void qk_set_error(const char* fmt, ...) {
 
 int qk_is_process_like(uint32_t k) {
   return k == QK_DISCRETE_PROCESS || k == QK_DISCRETE_SOURCE || k == QK_DISCRETE_SINK ||
-         k == QK_DISCRETE_PARALLEL_PROCESS;
+         k == QK_DISCRETE_PARALLEL_PROCESS || (k >= QK_VECTOR_PROCESS && k <= QK_VECTOR_SPLITTER);
 }
+static int is_vector_kind(uint32_t k) { return k >= QK_VECTOR_STOCK && k <= QK_VECTOR_SPLITTER; }
 
 static const char* kind_name(uint32_t k) {
   switch (k) {
@@ -35,6 +36,12 @@ static const char* kind_name(uint32_t k) {
     case QK_DISCRETE_SINK: return "StringSink";
     case QK_DISCRETE_PARALLEL_PROCESS: return "StringParallelProcess";
     case QK_ENVIRONMENT: return "BasicEnvironment";
+    case QK_VECTOR_STOCK: return "VectorStock";
+    case QK_VECTOR_PROCESS: return "VectorProcess";
+    case QK_VECTOR_SOURCE: return "VectorSource";
+    case QK_VECTOR_SINK: return "VectorSink";
+    case QK_VECTOR_COMBINER: return "VectorCombiner";
+    case QK_VECTOR_SPLITTER: return "VectorSplitter";
     default: return "?";
   }
 }
@@ -63,7 +70,7 @@ int qk_model_add_component(qk_model* m, const qk_component_desc* d, uint32_t* ou
     qk_set_error("qk_model_add_component: NULL argument");
     return QK_ERR_INVALID_ARG;
   }
-  if (!(d->kind >= QK_DISCRETE_STOCK && d->kind <= QK_ENVIRONMENT)) {
+  if (!((d->kind >= QK_DISCRETE_STOCK && d->kind <= QK_ENVIRONMENT) || is_vector_kind(d->kind))) {
     qk_set_error("qk_model_add_component: unknown component kind %u", d->kind);
     return QK_ERR_INVALID_ARG;
   }
@@ -77,6 +84,14 @@ int qk_model_add_component(qk_model* m, const qk_component_desc* d, uint32_t* ou
   c.dist_time = c.dist_qty = -1;
   c.logged = false;
   c.src_ord = -1;
+  c.dim = is_vector_kind(d->kind) ? 1 : 0;
+  c.n_ports = (d->kind == QK_VECTOR_COMBINER || d->kind == QK_VECTOR_SPLITTER) ? 1 : 0;
+  c.vlow = c.vmax = 0.0; /* VectorStock defaults (vector.rs:70-71) */
+  for (int k = 0; k < 3; ++k) c.vinit[k] = 0.0;
+  for (int k = 0; k < 5; ++k) {
+    c.ratios[k] = 0.0;
+    c.ups[k] = c.downs[k] = -1;
+  }
   c.initial_base = m->n_initial_total;
   if (d->kind == QK_DISCRETE_STOCK) m->n_initial_total += d->n_initial_items;
   if (d->kind == QK_DISCRETE_SOURCE) {
@@ -203,6 +218,47 @@ int qk_model_connect(qk_model* m, uint32_t a, uint32_t b, int32_t port_n) {
     B.env = (int)a;
     return QK_OK;
   }
+  /* vector arms (core.rs:572-616 for f64, same shape for Vector3; combiner/splitter arms need Some(n)) */
+  if (ka == QK_VECTOR_STOCK && A.dim == B.dim) {
+    if (kb == QK_VECTOR_PROCESS || kb == QK_VECTOR_SINK || kb == QK_VECTOR_SPLITTER) {
+      if (B.up >= 0) {
+        qk_set_error("qk_model_connect: component %u already has an upstream stock", b);
+        return QK_ERR_PORT_IN_USE;
+      }
+      A.subs.push_back((int)b);
+      B.up = (int)a;
+      return QK_OK;
+    }
+    if (kb == QK_VECTOR_COMBINER && port_n >= 0 && (uint32_t)port_n < B.n_ports) {
+      if (B.ups[port_n] >= 0) {
+        qk_set_error("qk_model_connect: combiner %u upstream port %d is already connected", b, port_n);
+        return QK_ERR_PORT_IN_USE;
+      }
+      A.subs.push_back((int)b);
+      B.ups[port_n] = (int)a;
+      return QK_OK;
+    }
+  }
+  if (kb == QK_VECTOR_STOCK && A.dim == B.dim) {
+    if (ka == QK_VECTOR_PROCESS || ka == QK_VECTOR_SOURCE || ka == QK_VECTOR_COMBINER) {
+      if (A.down >= 0) {
+        qk_set_error("qk_model_connect: component %u already has a downstream stock", a);
+        return QK_ERR_PORT_IN_USE;
+      }
+      B.subs.push_back((int)a);
+      A.down = (int)b;
+      return QK_OK;
+    }
+    if (ka == QK_VECTOR_SPLITTER && port_n >= 0 && (uint32_t)port_n < A.n_ports) {
+      if (A.downs[port_n] >= 0) {
+        qk_set_error("qk_model_connect: splitter %u downstream port %d is already connected", a, port_n);
+        return QK_ERR_PORT_IN_USE;
+      }
+      B.subs.push_back((int)a);
+      A.downs[port_n] = (int)b;
+      return QK_OK;
+    }
+  }
   if (port_n >= 0)
     qk_set_error("No component connection defined from %s to %s (n=Some(%d))", kind_name(ka), kind_name(kb), port_n);
   else
@@ -232,6 +288,48 @@ int qk_model_schedule_env_state(qk_model* m, uint64_t t_ns, uint32_t env, uint32
   e.type = 0;
   e.target = env;
   e.state = state;
+  m->ext.push_back(e);
+  return QK_OK;
+}
+
+int qk_model_set_vector(qk_model* m, uint32_t comp, uint32_t dim, double low, double max, const double* init) {
+  if (!m || comp >= m->comps.size() || !is_vector_kind(m->comps[comp].d.kind) || !(dim == 1 || dim == 3)) {
+    qk_set_error("qk_model_set_vector: component %u is not a vector component or dim %u is not 1 or 3", comp, dim);
+    return QK_ERR_INVALID_ARG;
+  }
+  QkHostComp& c = m->comps[comp];
+  c.dim = dim;
+  c.vlow = low;
+  c.vmax = max;
+  for (uint32_t k = 0; k < 3; ++k) c.vinit[k] = (init && k < dim) ? init[k] : 0.0;
+  return QK_OK;
+}
+
+int qk_model_set_ports(qk_model* m, uint32_t comp, uint32_t n_ports, const double* ratios) {
+  if (!m || comp >= m->comps.size() || n_ports < 1 || n_ports > 5 ||
+      !(m->comps[comp].d.kind == QK_VECTOR_COMBINER || m->comps[comp].d.kind == QK_VECTOR_SPLITTER)) {
+    qk_set_error("qk_model_set_ports: component %u is not a combiner/splitter or n_ports %u not in 1..5", comp, n_ports);
+    return QK_ERR_INVALID_ARG;
+  }
+  QkHostComp& c = m->comps[comp];
+  c.n_ports = n_ports;
+  for (uint32_t k = 0; k < 5; ++k) c.ratios[k] = (ratios && k < n_ports) ? ratios[k] : 0.0;
+  return QK_OK;
+}
+
+int qk_model_schedule_low_capacity(qk_model* m, uint64_t t_ns, uint32_t stock, double value) {
+  if (!m || stock >= m->comps.size() || m->comps[stock].d.kind != QK_VECTOR_STOCK || m->comps[stock].dim != 1) {
+    /* core.rs:1397-1399: only (SetLowCapacity, F64Stock) has an arm */
+    qk_set_error("schedule_event not implemented for types (SetLowCapacity, %s)",
+                 (m && stock < m->comps.size()) ? kind_name(m->comps[stock].d.kind) : "?");
+    return QK_ERR_INVALID_ARG;
+  }
+  DevExt e;
+  memset(&e, 0, sizeof(e));
+  e.t = t_ns;
+  e.type = 1;
+  e.target = stock;
+  e.value = value;
   m->ext.push_back(e);
   return QK_OK;
 }
@@ -292,6 +390,7 @@ int qk_lower(const qk_model* m, bool log, QkLowered* out) {
   std::vector<DevDelayMode> dms;
   std::vector<uint16_t> subs;
   std::vector<uint16_t> sched;
+  std::vector<DevVec> vecs;
 
   for (size_t i = 0; i < m->dists.size(); ++i) {
     memset(&dd[i], 0, sizeof(DevDist));
@@ -306,7 +405,7 @@ int qk_lower(const qk_model* m, bool log, QkLowered* out) {
     memset(&dc[i], 0, sizeof(DevComp));
     uint32_t k = m->comps[i].d.kind;
     dc[i].fire_idx = 0xFFFF;
-    if (k == QK_DISCRETE_STOCK || qk_is_process_like(k)) {
+    if (k == QK_DISCRETE_STOCK || k == QK_VECTOR_STOCK || qk_is_process_like(k)) {
       dc[i].fire_idx = (uint16_t)sched.size();
       sched.push_back((uint16_t)i);
     }
@@ -437,6 +536,57 @@ int qk_lower(const qk_model* m, bool log, QkLowered* out) {
       if (depth > 250) depth = 250;
       d.emit_depth = (uint16_t)depth;
       d.dist_time = (uint16_t)c.d.n_initial_items; /* table field reuse: initial item count */
+    } else if (kind == QK_VECTOR_STOCK) {
+      DevVec v;
+      memset(&v, 0, sizeof(v));
+      v.dim = (uint16_t)c.dim;
+      v.vmax = c.vmax;
+      v.vlow = c.vlow;
+      for (int k = 0; k < 3; ++k) v.vinit[k] = c.vinit[k];
+      for (int k = 0; k < 5; ++k) v.ups[k] = v.downs[k] = -1;
+      d.o64 = (uint16_t)n64;
+      v.o64_res = (uint16_t)n64;
+      n64 += c.dim;
+      v.o64_low = (uint16_t)n64++;
+      v.o64_last = (uint16_t)n64++;
+      d.o32 = (uint16_t)n32;
+      n32 += S32_RING; /* S32_HC unused, S32_EMIT used */
+      uint32_t depth = 0;
+      for (size_t j = 0; j < nc; ++j) {
+        const QkHostComp& o = m->comps[j];
+        if (o.up == (int)i || o.down == (int)i) depth += 2;
+        for (int k = 0; k < 5; ++k)
+          if (o.ups[k] == (int)i || o.downs[k] == (int)i) depth += 2;
+      }
+      depth += 2 * (uint32_t)m->ext.size(); /* SetLowCapacity's add(0.) can flip the state too */
+      if (depth < 2) depth = 2;
+      if (depth > 250) depth = 250;
+      d.emit_depth = (uint16_t)depth;
+      d.vec_idx = (uint16_t)vecs.size();
+      vecs.push_back(v);
+    } else if (is_vector_kind(kind)) { /* vector process-like */
+      DevVec v;
+      memset(&v, 0, sizeof(v));
+      v.dim = (uint16_t)c.dim;
+      v.n_ports = (uint16_t)c.n_ports;
+      for (int k = 0; k < 3; ++k) v.vinit[k] = c.vinit[k];
+      for (int k = 0; k < 5; ++k) {
+        v.ratios[k] = c.ratios[k];
+        v.ups[k] = (int16_t)c.ups[k];
+        v.downs[k] = (int16_t)c.downs[k];
+      }
+      v.dist_qty = (uint16_t)c.dist_qty;
+      d.o64 = (uint16_t)n64;
+      n64 += P64_BASE_COUNT;
+      d.o64_dm = (uint16_t)n64;
+      n64 += d.n_dm;
+      v.o64_res = (uint16_t)n64;
+      n64 += c.dim + (kind == QK_VECTOR_COMBINER ? 1u : 0u);
+      d.o32 = (uint16_t)n32;
+      n32 += P32_BASE_COUNT;
+      if (m->dists[(size_t)c.dist_qty].kind != QK_DIST_CONSTANT) dd[(size_t)c.dist_qty].draw_slot = n32++;
+      d.vec_idx = (uint16_t)vecs.size();
+      vecs.push_back(v);
     } else { /* environment */
       d.o32 = (uint16_t)n32;
       n32 += E32_COUNT;
@@ -452,7 +602,11 @@ int qk_lower(const qk_model* m, bool log, QkLowered* out) {
     if (log) {
       d.olog32 = (uint16_t)n32;
       n32 += 1; /* L32_SEQ */
-      if (kind == QK_DISCRETE_STOCK) n32 += d.emit_depth;
+      if (kind == QK_DISCRETE_STOCK || kind == QK_VECTOR_STOCK) n32 += d.emit_depth;
+      if (kind == QK_VECTOR_STOCK) {
+        d.olog64 = (uint16_t)n64; /* occupied (f64) of each pending emit_change */
+        n64 += d.emit_depth;
+      }
       if (qk_is_process_like(kind)) {
         d.olog64 = (uint16_t)n64;
         n64 += PL64_COUNT;
@@ -469,7 +623,7 @@ int qk_lower(const qk_model* m, bool log, QkLowered* out) {
    * BasicEnvironment logs its state (core.rs:229-234); stocks use the default no-op init */
   uint32_t init_off = (uint32_t)subs.size(), n_init = 0;
   for (size_t i = 0; i < nc; ++i)
-    if (m->comps[i].d.kind != QK_DISCRETE_STOCK) {
+    if (m->comps[i].d.kind != QK_DISCRETE_STOCK && m->comps[i].d.kind != QK_VECTOR_STOCK) {
       subs.push_back((uint16_t)i);
       n_init++;
     }
@@ -511,6 +665,9 @@ int qk_lower(const qk_model* m, bool log, QkLowered* out) {
   off = align8(off + (uint32_t)(sched.size() * sizeof(uint16_t)));
   h.off_pf = off;
   off = align8(off + (uint32_t)(pf_comp.size() * sizeof(uint16_t)));
+  h.n_vec = (uint32_t)vecs.size();
+  h.off_vecs = off;
+  off = align8(off + (uint32_t)(vecs.size() * sizeof(DevVec)));
   h.total_bytes = off;
 
   out->blob.assign(off, 0);
@@ -522,7 +679,9 @@ int qk_lower(const qk_model* m, bool log, QkLowered* out) {
   memcpy(out->blob.data() + h.off_subs, subs.data(), subs.size() * sizeof(uint16_t));
   if (!sched.empty()) memcpy(out->blob.data() + h.off_sched, sched.data(), sched.size() * sizeof(uint16_t));
   if (!pf_comp.empty()) memcpy(out->blob.data() + h.off_pf, pf_comp.data(), pf_comp.size() * sizeof(uint16_t));
+  if (!vecs.empty()) memcpy(out->blob.data() + h.off_vecs, vecs.data(), vecs.size() * sizeof(DevVec));
   out->hdr = h;
+  out->vecs = vecs;
   out->comps = dc;
   out->dists = dd;
   return QK_OK;

@@ -15,6 +15,10 @@ struct QkHostComp {
   bool logged;
   int src_ord;
   uint32_t initial_base;
+  /* vector components */
+  uint32_t dim, n_ports;
+  double vlow, vmax, vinit[3], ratios[5];
+  int ups[5], downs[5];
 };
 
 struct qk_model {
@@ -30,6 +34,7 @@ struct QkLowered {
   DevHeader hdr;
   std::vector<DevComp> comps;
   std::vector<DevDist> dists;
+  std::vector<DevVec> vecs;
 };
 
 void qk_set_error(const char* fmt, ...);

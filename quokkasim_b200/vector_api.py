@@ -1,0 +1,196 @@
+"""Host-side mirror of the reference's continuous components (quokkasim/src/components/vector.rs) and the
+resource types they carry (core.rs:7-128).  Pure bookkeeping, like api.py: the objects only hold the fields that
+BatchedSimulation turns into C-ABI rows (qk_model_set_vector / qk_model_set_ports)."""
+from . import _capi as capi
+from .api import _Component, _ProcessLike
+
+
+class Vector3:
+    """core.rs:47-128"""
+
+    def __init__(self, values=(0.0, 0.0, 0.0)):
+        self.values = [float(x) for x in values]
+        assert len(self.values) == 3
+
+    @staticmethod
+    def default():
+        return Vector3()
+
+    def total(self):
+        return (self.values[0] + self.values[1]) + self.values[2]
+
+    def __repr__(self):
+        return "Vector3(%r)" % (self.values,)
+
+
+def _as_list(resource):
+    if isinstance(resource, Vector3):
+        return list(resource.values)
+    return [float(resource)]
+
+
+class VectorStock(_Component):
+    """vector.rs:42-77: low_capacity / max_capacity default to 0.0, resource to Default::default()"""
+
+    KIND = capi.VECTOR_STOCK
+    DEFAULT_NAME = "VectorStock"
+
+    def __init__(self):
+        super().__init__()
+        self.low_capacity = 0.0
+        self.max_capacity = 0.0
+        self.resource = None  # f64 0.0 or Vector3::default(), decided by the ComponentModel variant
+        self.dim = None
+
+    def with_low_capacity(self, v):
+        self.low_capacity = float(v)
+        return self
+
+    def with_max_capacity(self, v):
+        self.max_capacity = float(v)
+        return self
+
+    def with_low_capacity_inplace(self, v):
+        self.low_capacity = float(v)
+
+    def with_max_capacity_inplace(self, v):
+        self.max_capacity = float(v)
+
+    def with_initial_resource(self, resource):
+        self.resource = resource
+        return self
+
+    def vector_rows(self):
+        init = _as_list(self.resource) if self.resource is not None else [0.0] * self.dim
+        return self.dim, self.low_capacity, self.max_capacity, init
+
+
+class _VectorProcessLike(_ProcessLike):
+    def __init__(self):
+        super().__init__()
+        self.dim = None
+
+    def vector_rows(self):
+        return self.dim, 0.0, 0.0, [0.0] * self.dim
+
+
+class VectorProcess(_VectorProcessLike):
+    KIND = capi.VECTOR_PROCESS
+    DEFAULT_NAME = "VectorProcess"
+
+
+class VectorSource(_VectorProcessLike):
+    """vector.rs:1324-1400: creates `source_vector` scaled to the sampled quantity"""
+
+    KIND = capi.VECTOR_SOURCE
+    DEFAULT_NAME = "VectorSource"
+
+    def __init__(self):
+        super().__init__()
+        self.source_vector = None
+
+    def with_source_vector(self, v):
+        self.source_vector = v
+        return self
+
+    def with_source_vector_inplace(self, v):
+        self.source_vector = v
+
+    def vector_rows(self):
+        init = _as_list(self.source_vector) if self.source_vector is not None else [0.0] * self.dim
+        return self.dim, 0.0, 0.0, init
+
+
+class VectorSink(_VectorProcessLike):
+    KIND = capi.VECTOR_SINK
+    DEFAULT_NAME = "VectorSink"
+
+
+class VectorCombiner(_VectorProcessLike):
+    """vector.rs:726-820; `M` (number of upstream ports) is fixed by the ComponentModel variant (Combiner1..5)"""
+
+    KIND = capi.VECTOR_COMBINER
+    DEFAULT_NAME = "VectorCombiner"
+
+    def __init__(self):
+        super().__init__()
+        self.n_ports = None
+        self.split_ratios = None
+
+    def with_split_ratios(self, ratios):
+        self.split_ratios = [float(x) for x in ratios]  # unused by the reference, kept for parity
+        return self
+
+    def with_split_ratios_inplace(self, ratios):
+        self.split_ratios = [float(x) for x in ratios]
+
+
+class VectorSplitter(_VectorProcessLike):
+    """vector.rs:1026-1122; default split_ratios = [1/N; N]"""
+
+    KIND = capi.VECTOR_SPLITTER
+    DEFAULT_NAME = "VectorSplitter"
+
+    def __init__(self):
+        super().__init__()
+        self.n_ports = None
+        self.split_ratios = None
+
+    def with_split_ratios(self, ratios):
+        self.split_ratios = [float(x) for x in ratios]
+        return self
+
+    def with_split_ratios_inplace(self, ratios):
+        self.split_ratios = [float(x) for x in ratios]
+
+
+# ComponentModel variants of core.rs:505-533 -> (class, dim, ports)
+VECTOR_VARIANTS = {}
+for _prefix, _dim in (("F64", 1), ("Vector3", 3)):
+    VECTOR_VARIANTS[_prefix + "Stock"] = (VectorStock, _dim, None)
+    VECTOR_VARIANTS[_prefix + "Process"] = (VectorProcess, _dim, None)
+    VECTOR_VARIANTS[_prefix + "Source"] = (VectorSource, _dim, None)
+    VECTOR_VARIANTS[_prefix + "Sink"] = (VectorSink, _dim, None)
+    for _n in range(1, 6):
+        VECTOR_VARIANTS["%sCombiner%d" % (_prefix, _n)] = (VectorCombiner, _dim, _n)
+        VECTOR_VARIANTS["%sSplitter%d" % (_prefix, _n)] = (VectorSplitter, _dim, _n)
+
+
+def bind_variant(variant, component):
+    """What the enum variant's type parameters fix in Rust: resource type (f64 / Vector3) and port count."""
+    cls, dim, ports = VECTOR_VARIANTS[variant]
+    component.dim = dim
+    if ports is not None:
+        component.n_ports = ports
+        if component.split_ratios is None:
+            component.split_ratios = [1.0 / ports] * ports
+        if len(component.split_ratios) != ports:
+            raise TypeError("%s needs %d split ratios" % (variant, ports))
+    if isinstance(component, VectorStock) and component.resource is not None:
+        if len(_as_list(component.resource)) != dim:
+            raise TypeError("%s holds a %s resource" % (variant, "f64" if dim == 1 else "Vector3"))
+    if isinstance(component, VectorSource) and component.source_vector is not None:
+        if len(_as_list(component.source_vector)) != dim:
+            raise TypeError("%s creates a %s resource" % (variant, "f64" if dim == 1 else "Vector3"))
+
+
+def connection_ok(va, vb, n):
+    """The vector arms of connect_components (core.rs:572-883): same resource type on both sides; Stock -> CombinerM
+    and SplitterN -> Stock take Some(n)."""
+    for prefix in ("F64", "Vector3"):
+        if not (va.startswith(prefix) and vb.startswith(prefix)):
+            continue
+        a, b = va[len(prefix):], vb[len(prefix):]
+        if a == "Stock" and b in ("Process", "Sink"):
+            return True
+        if a == "Stock" and b.startswith("Splitter"):
+            return True
+        if a == "Stock" and b.startswith("Combiner"):
+            return n is not None and 0 <= n < int(b[-1])
+        if b == "Stock" and a in ("Process", "Source"):
+            return True
+        if b == "Stock" and a.startswith("Combiner"):
+            return True
+        if b == "Stock" and a.startswith("Splitter"):
+            return n is not None and 0 <= n < int(a[-1])
+    return False

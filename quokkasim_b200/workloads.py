@@ -10,6 +10,7 @@ class Model:
     def __init__(self):
         self.components = []
         self.ext = []  # (t_ns, env ComponentModel, state)
+        self.ext_low = []  # (t_ns, F64Stock ComponentModel, new low_capacity)
         self.random_dists = []  # Distribution objects that need tapes in tape mode
         self.by_name = {}
 
@@ -27,6 +28,8 @@ class Model:
                              lib=lib, flags=flags)
         for t, env, state in self.ext:
             qk.create_scheduled_event(sched, t, qk.ScheduledEventConfig.SetEnvironmentState(state), env.get_address())
+        for t, stock, value in self.ext_low:
+            qk.create_scheduled_event(sched, t, qk.ScheduledEventConfig.SetLowCapacity(value), stock.get_address())
         return sim
 
 
@@ -34,14 +37,21 @@ def _log_all(m):
     sl = qk.ComponentLogger.StringStockLogger(qk.DiscreteStockLogger.new("StockLogger"))
     pl = qk.ComponentLogger.StringProcessLogger(qk.DiscreteProcessLogger.new("ProcessLogger"))
     el = qk.ComponentLogger.BasicEnvironmentLogger(qk.BasicEnvironmentLogger.new("EnvLogger"))
+    vsl = {p: qk.ComponentLogger(p + "StockLogger", qk.VectorStockLogger.new(p + "StockLogger"))
+           for p in ("F64", "Vector3")}
+    vpl = {p: qk.ComponentLogger(p + "ProcessLogger", qk.VectorProcessLogger.new(p + "ProcessLogger"))
+           for p in ("F64", "Vector3")}
     for c in m.components:
-        if c.variant == "StringStock":
+        prefix = "F64" if c.variant.startswith("F64") else ("Vector3" if c.variant.startswith("Vector3") else None)
+        if prefix:
+            qk.connect_logger((vsl if c.variant.endswith("Stock") else vpl)[prefix], c)
+        elif c.variant == "StringStock":
             qk.connect_logger(sl, c)
         elif c.variant == "BasicEnvironment":
             qk.connect_logger(el, c)
         else:
             qk.connect_logger(pl, c)
-    m.loggers = (sl, pl, el)
+    m.loggers = (sl, pl, el, vsl, vpl)
 
 
 def discrete_queue(tri=(1.0, 10.0, 6.0), src_time=3.0, sink_time=1.0, cap=10):
@@ -248,3 +258,173 @@ def haulage(n_src=2, per_queue=3, cap=5):
     return m
 
 
+
+
+# ------------------------------------------------------------------------------------------- vector models
+def source_sink():
+    """quokkasim_examples/src/bin/source_sink.rs: Vector3 Source -> Stock -> Process -> Stock -> Sink, all Constant.
+    Registration order follows the example (stocks first)."""
+    m = Model()
+    c = qk.Distribution.Constant
+    source = qk.ComponentModel.Vector3Source(
+        qk.VectorSource.new().with_name("Source").with_process_quantity_distr(c(1.0)).with_process_time_distr(c(1.0))
+        .with_source_vector(qk.Vector3([1.0, 4.0, 5.0])), qk.Mailbox.new())
+    stock_1 = qk.ComponentModel.Vector3Stock(
+        qk.VectorStock.new().with_name("Stock 1").with_low_capacity(50.0).with_max_capacity(101.0)
+        .with_initial_resource(qk.Vector3([0.0, 0.0, 0.0])), qk.Mailbox.new())
+    process = qk.ComponentModel.Vector3Process(
+        qk.VectorProcess.new().with_name("Process").with_process_quantity_distr(c(1.0)).with_process_time_distr(c(1.0)),
+        qk.Mailbox.new())
+    stock_2 = qk.ComponentModel.Vector3Stock(
+        qk.VectorStock.new().with_name("Stock 2").with_low_capacity(50.0).with_max_capacity(101.0)
+        .with_initial_resource(qk.Vector3([0.0, 0.0, 0.0])), qk.Mailbox.new())
+    sink = qk.ComponentModel.Vector3Sink(
+        qk.VectorSink.new().with_name("Sink").with_process_quantity_distr(c(1.0)).with_process_time_distr(c(2.0)),
+        qk.Mailbox.new())
+    qk.connect_components(source, stock_1)
+    qk.connect_components(stock_1, process)
+    qk.connect_components(process, stock_2)
+    qk.connect_components(stock_2, sink)
+    for x in (stock_1, stock_2, source, process, sink):
+        m.reg(x)
+    _log_all(m)
+    return m
+
+
+def material_blending():
+    """quokkasim_examples/src/bin/material_blending.rs: 3 stockpiles, Combiner2 x2, Combiner1, Splitter2, stocks shared by
+    several processes, feedback loop through the stacker."""
+    m = Model()
+    c = qk.Distribution.Constant
+
+    def pile(name, code, low, maxc, init):
+        return qk.ComponentModel.Vector3Stock(
+            qk.VectorStock.new().with_name(name).with_code(code).with_low_capacity(low).with_max_capacity(maxc)
+            .with_initial_resource(qk.Vector3(init)), qk.Mailbox.new())
+
+    sp1 = pile("Stockpile 1", "SP1", 100.0, 10000.0, [8000.0, 2000.0, 0.0])
+    sp2 = pile("Stockpile 2", "SP2", 100.0, 10000.0, [0.0, 6000.0, 2000.0])
+    sp3 = pile("Stockpile 3", "SP3", 100.0, 10000.0, [5000.0, 5000.0, 0.0])
+    osp1 = pile("Output Stockpile 1", "OSP1", 100.0, 15000.0, [0.0, 0.0, 0.0])
+    osp2 = pile("Output Stockpile 2", "OSP2", 100.0, 15000.0, [0.0, 0.0, 0.0])
+    rc1 = qk.ComponentModel.Vector3Combiner2(
+        qk.VectorCombiner.new().with_name("Reclaimer 1").with_code("RC1").with_process_quantity_distr(c(100.0))
+        .with_process_time_distr(c(30.0)), qk.Mailbox.new())
+    rc2 = qk.ComponentModel.Vector3Combiner2(
+        qk.VectorCombiner.new().with_name("Reclaimer 2").with_code("RC2").with_process_quantity_distr(c(100.0))
+        .with_process_time_distr(c(30.0)), qk.Mailbox.new())
+    rc3 = qk.ComponentModel.Vector3Combiner1(
+        qk.VectorCombiner.new().with_name("Reclaimer 3").with_code("RC3").with_process_quantity_distr(c(100.0))
+        .with_process_time_distr(c(60.0)), qk.Mailbox.new())
+    stk = qk.ComponentModel.Vector3Splitter2(
+        qk.VectorSplitter.new().with_name("Stacker").with_code("STK").with_process_quantity_distr(c(600.0))
+        .with_process_time_distr(c(360.0)), qk.Mailbox.new())
+    qk.connect_components(sp1, rc1, 0)
+    qk.connect_components(sp2, rc1, 1)
+    qk.connect_components(rc1, osp1)
+    qk.connect_components(sp2, rc2, 0)
+    qk.connect_components(sp3, rc2, 1)
+    qk.connect_components(rc2, osp2)
+    qk.connect_components(sp1, rc3, 0)
+    qk.connect_components(rc3, osp1)
+    qk.connect_components(osp1, stk)
+    qk.connect_components(stk, sp2, 0)
+    qk.connect_components(stk, sp3, 1)
+    for x in (sp1, sp2, sp3, rc1, rc2, rc3, stk, osp1, osp2):
+        m.reg(x)
+    _log_all(m)
+    return m
+
+
+def scheduled_event_f64():
+    """quokkasim_examples/src/bin/scheduled_event.rs in spirit: F64 Stock -> Process -> Stock with
+    SetLowCapacity(10) on the first stock at 60 s."""
+    m = Model()
+    c = qk.Distribution.Constant
+    s1 = qk.ComponentModel.F64Stock(
+        qk.VectorStock.new().with_name("Stock1").with_code("S1").with_low_capacity(50.0).with_max_capacity(101.0)
+        .with_initial_resource(100.0), qk.Mailbox.new())
+    p = qk.ComponentModel.F64Process(
+        qk.VectorProcess.new().with_name("Process").with_code("P").with_process_quantity_distr(c(1.0))
+        .with_process_time_distr(c(1.0)), qk.Mailbox.new())
+    s2 = qk.ComponentModel.F64Stock(
+        qk.VectorStock.new().with_name("Stock2").with_code("S2").with_low_capacity(50.0).with_max_capacity(101.0)
+        .with_initial_resource(0.0), qk.Mailbox.new())
+    qk.connect_components(s1, p)
+    qk.connect_components(p, s2)
+    for x in (s1, p, s2):
+        m.reg(x)
+    m.ext_low.append((qk.Duration.from_secs(60), s1, 10.0))
+    _log_all(m)
+    return m
+
+
+def vector_flow(dim=3, random=True, breakdowns=True, env_events=True, sink_delay=False):
+    """BASELINE config C3: Source(qty U(0.5,1.5), time U(0.5,1.5), vector [1,4,5]) -> Stock(low 50, max 101) -> Process
+    -> Stock -> Sink, plus a Combiner2 / Splitter2 diamond as in material_blending.rs:128-141; optional breakdown
+    modes (transport.rs) and an environment stop/resume (delay_testing.rs)."""
+    m = Model()
+    df = qk.DistributionFactory(base_seed=555, next_seed=0)
+    P = "Vector3" if dim == 3 else "F64"
+    V = (lambda v: qk.Vector3(v)) if dim == 3 else (lambda v: float(sum(v)))
+
+    def dist(lo, hi):
+        if not random:
+            return qk.Distribution.Constant(0.5 * (lo + hi))
+        d = df.create(qk.DistributionConfig.Uniform(lo, hi))
+        m.random_dists.append(d)
+        return d
+
+    def cm(kind, comp):
+        return getattr(qk.ComponentModel, P + kind)(comp, qk.Mailbox.new())
+
+    def stock(name, low, maxc, init):
+        return cm("Stock", qk.VectorStock.new().with_name(name).with_code(name).with_low_capacity(low)
+                  .with_max_capacity(maxc).with_initial_resource(V(init)))
+
+    src = cm("Source", qk.VectorSource.new().with_name("Source").with_code("SRC").with_source_vector(V([1.0, 4.0, 5.0]))
+             .with_process_quantity_distr(dist(0.5, 1.5)).with_process_time_distr(dist(0.5, 1.5)))
+    s1 = stock("S1", 5.0, 101.0, [3.0, 3.0, 3.0])
+    proc = qk.VectorProcess.new().with_name("Process").with_code("PRC").with_process_quantity_distr(dist(0.8, 1.6)) \
+        .with_process_time_distr(dist(0.5, 1.5))
+    if breakdowns:
+        proc = proc.with_delay_mode(qk.DelayModeChange.Add(qk.DelayMode("Breakdown", dist(20.0, 40.0), dist(2.0, 6.0))))
+        proc = proc.with_delay_mode(qk.DelayModeChange.Add(qk.DelayMode("Service", dist(50.0, 70.0), dist(1.0, 3.0))))
+    p = cm("Process", proc)
+    s2 = stock("S2", 2.0, 60.0, [0.0, 0.0, 0.0])
+    s3 = stock("S3", 2.0, 60.0, [10.0, 0.0, 5.0])
+    comb = cm("Combiner2", qk.VectorCombiner.new().with_name("Combiner").with_code("CMB")
+              .with_process_quantity_distr(dist(0.3, 0.9)).with_process_time_distr(dist(1.0, 2.0)))
+    s4 = stock("S4", 1.0, 80.0, [0.0, 0.0, 0.0])
+    split = qk.VectorSplitter.new().with_name("Splitter").with_code("SPL").with_split_ratios([0.3, 0.7]) \
+        .with_process_quantity_distr(dist(0.5, 1.5)).with_process_time_distr(dist(0.7, 1.3))
+    spl = cm("Splitter2", split)
+    s5 = stock("S5", 0.5, 50.0, [0.0, 0.0, 0.0])
+    snk_c = qk.VectorSink.new().with_name("Sink").with_code("SNK").with_process_quantity_distr(dist(0.4, 1.2)) \
+        .with_process_time_distr(dist(0.5, 1.0))
+    if sink_delay:
+        snk_c = snk_c.with_delay_mode(qk.DelayModeChange.Add(qk.DelayMode("SinkDelay", dist(10.0, 20.0), dist(1.0, 2.0))))
+    snk = cm("Sink", snk_c)
+    qk.connect_components(src, s1)
+    qk.connect_components(s1, p)
+    qk.connect_components(p, s2)
+    qk.connect_components(s2, comb, 0)
+    qk.connect_components(s3, comb, 1)
+    qk.connect_components(comb, s4)
+    qk.connect_components(s4, spl)
+    qk.connect_components(spl, s3, 0)  # feedback into the combiner's second input
+    qk.connect_components(spl, s5, 1)
+    qk.connect_components(s5, snk)
+    comps = [src, s1, p, s2, s3, comb, s4, spl, s5, snk]
+    if env_events:
+        env = qk.ComponentModel.BasicEnvironment(qk.BasicEnvironment.new().with_name("Env").with_code("ENV"),
+                                                 qk.Mailbox.new())
+        for x in (src, p, comb, spl, snk):
+            qk.connect_components(env, x)
+        comps.append(env)
+        m.ext.append((qk.Duration.from_secs(40), env, qk.BasicEnvironmentState.Stopped))
+        m.ext.append((qk.Duration.from_secs(55), env, qk.BasicEnvironmentState.Normal))
+    for x in comps:
+        m.reg(x)
+    _log_all(m)
+    return m

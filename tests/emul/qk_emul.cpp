@@ -185,7 +185,7 @@ int qk_batch_read_status(qk_batch* b, uint64_t rep0, uint64_t n, uint32_t* statu
 int qk_batch_comp_stats(qk_batch* b, uint64_t rep0, uint64_t n, uint32_t comp, qk_comp_stats* out) {
   if (!b || rep0 + n > b->cfg.n_reps || comp >= b->low.hdr.n_comp) return QK_ERR_INVALID_ARG;
   for (uint64_t i = 0; i < n; ++i)
-    qk_comp_stats_dev(&b->low.comps[comp], comp, b->g64.data(), b->g32.data(), b->gs64.data(), b->gs32.data(),
+    qk_comp_stats_dev(&b->low.comps[comp], b->low.vecs.data(), comp, b->g64.data(), b->g32.data(), b->gs64.data(), b->gs32.data(),
                       b->rep_pad, rep0 + i, &out[i]);
   return QK_OK;
 }
@@ -242,8 +242,17 @@ int qk_batch_read_log(qk_batch* b, uint64_t rep, qk_log_record* buf, uint64_t ca
   const uint64_t first = cnt - kept;
   for (uint64_t i = 0; i < kept; ++i) {
     buf[i] = ring[(first + i) & (lc - 1)];
-    buf[i].aux = 0;
+    if (buf[i].kind != QK_LOG_VEC_DATA) buf[i].aux = 0; /* continuation records carry fp64 bits there */
   }
+  return QK_OK;
+}
+
+int qk_batch_read_vector(qk_batch* b, uint64_t rep, uint32_t comp, double* out3) {
+  if (!b || rep >= b->cfg.n_reps || comp >= b->low.hdr.n_comp || b->low.comps[comp].kind < QK_VECTOR_STOCK)
+    return QK_ERR_INVALID_ARG;
+  const DevVec& v = b->low.vecs[b->low.comps[comp].vec_idx];
+  out3[0] = out3[1] = out3[2] = 0.0;
+  for (uint32_t k = 0; k < v.dim; ++k) memcpy(&out3[k], &b->g64[(size_t)(v.o64_res + k) * b->rep_pad + rep], 8);
   return QK_OK;
 }
 

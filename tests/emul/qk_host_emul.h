@@ -36,6 +36,12 @@ extern thread_local uint32_t qk_emul_bid;
 static inline void qk_red_add64(uint64_t* p, uint64_t v) { *p += v; }
 static inline void qk_red_add32(uint32_t* p, uint32_t v) { *p += v; }
 static inline void qk_red_max32(uint32_t* p, uint32_t v) { if (v > *p) *p = v; }
+static inline void qk_red_addf64(uint64_t* p, double v) {
+  double d;
+  std::memcpy(&d, p, 8);
+  d += v;
+  std::memcpy(p, &d, 8);
+}
 static inline void __syncthreads() {}
 
 static inline uint64_t __umul64hi(uint64_t a, uint64_t b) {

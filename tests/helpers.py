@@ -10,7 +10,7 @@ from quokkasim_b200 import _capi as capi
 
 
 from quokkasim_b200.workloads import (Model, assembly_line, car_workshop, discrete_queue, haulage,  # noqa: F401
-                                      serial_line)
+                                      material_blending, scheduled_event_f64, serial_line, source_sink, vector_flow)
 
 
 from oracle.lowering import lower_to_oracle  # noqa: F401,E402
@@ -70,7 +70,25 @@ def assert_rep_parity(sim, osim, model, rep_local_idx, check_log=True):
     for ci, cm in enumerate(model.components):
         gs = sim.comp_stats(ci, rep_local_idx, 1)[0]
         os_ = osim.comp_stats(ci)
-        if cm.variant == "StringStock":
+        if cm.variant.startswith(("F64", "Vector3")):
+            # continuous components: fp64 values are compared BIT-exactly (same operation order, no FMA); the
+            # north_star tolerance would be 1e-9 relative
+            assert float(gs["fvalue"]).hex() == float(os_["fvalue"]).hex(), "comp %d fvalue %r vs %r" % (
+                ci, gs["fvalue"], os_["fvalue"])
+            assert float(gs["faux"]).hex() == float(os_["faux"]).hex(), "comp %d faux %r vs %r" % (
+                ci, gs["faux"], os_["faux"])
+            if cm.variant.endswith("Stock"):
+                assert int(gs["count"]) == int(os_["n_a"]), "vstock %d adds" % ci
+                got, want = sim.read_vector(ci, rep_local_idx), osim.vector_resource(ci)
+                assert [x.hex() for x in got] == [x.hex() for x in want], "vstock %d resource %r vs %r" % (ci, got, want)
+            else:
+                assert int(gs["count"]) == int(os_["n_b"]), "vproc %d successes" % ci
+                assert int(gs["time_ns"]) == int(os_["t_a_ns"]), "vproc %d busy" % ci
+                assert int(gs["aux"]) == int(os_["t_b_ns"]), "vproc %d delay ns" % ci
+                if "Combiner" not in cm.variant:
+                    got, want = sim.read_vector(ci, rep_local_idx), osim.vector_resource(ci)
+                    assert [x.hex() for x in got] == [x.hex() for x in want], "vproc %d in-flight" % ci
+        elif cm.variant == "StringStock":
             items = osim.stock_items(ci)
             assert int(gs["count"]) == int(os_["n_a"]), "stock %d n_add" % ci
             assert int(gs["time_ns"]) == int(os_["t_a_ns"]), "stock %d area %d vs %d" % (ci, gs["time_ns"], os_["t_a_ns"])

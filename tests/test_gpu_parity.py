@@ -216,3 +216,50 @@ def test_invariants_at_scale(gpu_lib):
             idx = [int(x) & 0x3FFFFFF for x in items]
             assert idx == sorted(idx)
     sim.close()
+
+
+# ------------------------------------------------------------------------------------- continuous components
+S = 10**9
+
+
+def test_vector_examples(gpu_lib):
+    """source_sink.rs, material_blending.rs, scheduled_event.rs (SetLowCapacity) -- fp64 stock levels bit-exact"""
+    _check(gpu_lib, H.source_sink(), 32, t_until=120 * S, sample=[0, 31], log_capacity=8192)
+    _check(gpu_lib, H.material_blending(), 32, t_until=3600 * S, sample=[0, 31], log_capacity=8192)
+    _check(gpu_lib, H.scheduled_event_f64(), 32, t_until=120 * S, sample=[0, 31], log_capacity=2048)
+
+
+@pytest.mark.parametrize("dim", [1, 3])
+def test_vector_flow_native(gpu_lib, dim):
+    """config C3 topology with native Philox streams, breakdowns and an environment stop/resume"""
+    _check(gpu_lib, H.vector_flow(dim), 512, n_events=6000, sample=[0, 129, 511], log_capacity=65536)
+
+
+def test_vector_flow_tape(gpu_lib):
+    _check(gpu_lib, H.vector_flow(3), 64, n_events=2500, tape_len=2500, sample=[0, 63], log_capacity=32768)
+
+
+def test_vector_flow_sink_delay(gpu_lib):
+    _check(gpu_lib, H.vector_flow(3, sink_delay=True), 64, n_events=4000, sample=[0, 63], log_capacity=32768)
+
+
+def test_vector_mass_balance_at_scale(gpu_lib):
+    """config C3 size (262,144 replications), no oracle: initial + sourced == stocks + in-flight + sunk within
+    1e-9 relative (BASELINE north_star tolerance for fp64 stock quantities)."""
+    m = H.vector_flow(3)
+    n = 262144
+    sim = m.sim(gpu_lib, n, base_seed=99)
+    sim.step_events(2000)
+    st, now, ev = sim.status()
+    assert (st == 0).all() and (ev == 2000).all()
+    names = [c.component.element_name for c in m.components]
+    stats = {nm: sim.comp_stats(i) for i, nm in enumerate(names)}
+    initial = 9.0 + 15.0  # S1 [3,3,3] + S3 [10,0,5]
+    stocks = sum(stats[k]["fvalue"] for k in ("S1", "S2", "S3", "S4", "S5"))
+    inflight = sum(stats[k]["faux"] for k in ("Process", "Combiner", "Splitter", "Sink"))
+    lhs = initial + stats["Source"]["fvalue"]
+    rhs = stocks + inflight + stats["Sink"]["fvalue"]
+    rel = np.abs(lhs - rhs) / np.maximum(1.0, np.abs(lhs))
+    assert rel.max() < 1e-9, rel.max()
+    assert (stats["Source"]["count"] > 0).all()
+    sim.close()

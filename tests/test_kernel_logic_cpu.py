@@ -167,3 +167,45 @@ def test_unconnected_ports(emul_lib):
     _log_all(m)
     s = _check(emul_lib, m, 1, t_until=50 * 10**9, log_capacity=256)
     assert s["n_log_records"] >= 5
+
+
+# ------------------------------------------------------------------------------------- continuous components
+S = 10**9
+
+
+def test_vector_source_sink_example(emul_lib):
+    """source_sink.rs: Vector3 Source -> Stock -> Process -> Stock -> Sink, all Constant, 120 s"""
+    _check(emul_lib, H.source_sink(), 2, t_until=120 * S, log_capacity=8192)
+
+
+def test_vector_material_blending_example(emul_lib):
+    """material_blending.rs: Combiner2 x2 + Combiner1 + Splitter2 on shared stockpiles, feedback loop, 1 h"""
+    _check(emul_lib, H.material_blending(), 2, t_until=3600 * S, log_capacity=8192)
+
+
+def test_vector_scheduled_low_capacity(emul_lib):
+    """scheduled_event.rs: SetLowCapacity on an F64Stock at 60 s (core.rs:1382-1386)"""
+    _check(emul_lib, H.scheduled_event_f64(), 2, t_until=120 * S, log_capacity=2048)
+
+
+@pytest.mark.parametrize("dim", [1, 3])
+def test_vector_flow_native(emul_lib, dim):
+    """config C3 topology: random quantities and times, two breakdown modes, environment stop/resume"""
+    _check(emul_lib, H.vector_flow(dim), 3, n_events=4000, log_capacity=32768)
+
+
+def test_vector_flow_tape(emul_lib):
+    _check(emul_lib, H.vector_flow(3), 3, n_events=2500, tape_len=2500, log_capacity=32768)
+
+
+def test_vector_flow_sink_delay_and_constant(emul_lib):
+    """VectorSink's own post rule (vector.rs:1780-1786) under a delay mode; all-Constant variant -> exact ties"""
+    _check(emul_lib, H.vector_flow(3, sink_delay=True), 2, n_events=3000, log_capacity=32768)
+    _check(emul_lib, H.vector_flow(3, random=False), 1, n_events=3000, log_capacity=32768)
+    _check(emul_lib, H.vector_flow(1, random=False, breakdowns=False, env_events=False), 1, n_events=2000,
+           log_capacity=32768)
+
+
+def test_vector_hbm_resident_and_eager(emul_lib, emul_eager_lib):
+    _check(emul_lib, H.vector_flow(3), 2, n_events=2000, log_capacity=32768, flags=1)
+    _check(emul_eager_lib, H.vector_flow(3), 2, n_events=2000, log_capacity=32768)
