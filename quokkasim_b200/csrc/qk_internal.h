@@ -94,6 +94,44 @@ typedef struct {
 } DevComp; /* 68 bytes = 17 words: an odd word stride keeps per-lane table reads of different components off the
               same shared-memory bank */
 
+/* ---- hot component rows --------------------------------------------------------------------------
+ * What the event loop reads of a component on every call, packed into three 16-byte quads so that one LDS.128 per
+ * quad brings it into registers (per-field LDS.U16 reads of DevComp cost one shared-memory wavefront each AND had to
+ * be repeated after every state store, because tables and state share one shared-memory array).  48-byte stride:
+ * quad index 3c mod 8 is a permutation for 8 consecutive components, so lanes that work on different components
+ * read different bank groups. */
+typedef struct {
+  uint8_t kind, n_dm, n_subs, src_ord;
+  uint16_t o32, o64;
+  uint16_t fire_idx, flags; /* DC_LOGGED */
+  uint16_t olog32, olog64;
+} DevHotA; /* every kind */
+typedef struct {
+  int16_t up, down;
+  int16_t env;
+  uint16_t dist_time;
+  uint16_t o64_dm, dm_off;
+  uint16_t o64_nextdur, pf_idx;
+} DevHotB; /* process-like */
+typedef struct {
+  uint32_t low, max;
+  uint16_t ring_cap, emit_depth;
+  uint16_t subs_off, o32;
+} DevHotSB; /* stocks and BasicEnvironment (which only uses subs_off / o32) */
+typedef struct {
+  uint16_t o64_ttnpe, o32_next_item;
+  uint32_t const_dur_lo, const_dur_hi;
+  uint16_t vec_idx, ring_cap;
+} DevHotC; /* process-like, second quad */
+typedef struct {
+  DevHotA a;
+  union {
+    DevHotB b;
+    DevHotSB sb;
+  };
+  DevHotC c;
+} DevHot; /* 48 bytes */
+
 typedef struct {
   uint32_t kind, stream;
   double p[4];
@@ -142,6 +180,8 @@ typedef struct {
   uint32_t off_comps, off_dists, off_dms, off_subs, off_sched, off_ext;
   uint32_t total_bytes;
   uint32_t log_enabled;
+  uint32_t off_hot; /* DevHot[n_comp], 16-byte aligned */
+  uint32_t pad[3];
 } DevHeader;
 
 #endif

@@ -60,6 +60,8 @@ struct Ctx {
   const uint16_t* sched;
   const DevExt* ext;
   const DevVec* vecs;
+  const DevHot* hot;
+  uint32_t pf32, n_pf_words; /* hoisted DevHeader fields (re-reading them after every state store is wasted LDS) */
   uint64_t now;
   uint32_t status;
   uint4* log_base;
@@ -104,14 +106,30 @@ __device__ __forceinline__ auto qk_ix(uint32_t slot, uint32_t stride) {
 #define SRC_INIT (((uint64_t)QK_SRC_INIT) << 32)
 #define SRC_SCH (((uint64_t)QK_SRC_SCH) << 32)
 
+/* one LDS.128 -> a 16-byte table quad in registers */
+template <class T>
+__device__ __forceinline__ T qk_ldq(const T* p) {
+  static_assert(sizeof(T) == 16, "table quads are 16 bytes");
+  union {
+    uint4 v;
+    T t;
+  } u;
+  u.v = *reinterpret_cast<const uint4*>(p);
+  return u.t;
+}
+#define QK_HOT_A(comp) qk_ldq(&cx.hot[comp].a)
+#define QK_HOT_B(comp) qk_ldq(&cx.hot[comp].b)
+#define QK_HOT_SB(comp) qk_ldq(&cx.hot[comp].sb)
+#define QK_HOT_C(comp) qk_ldq(&cx.hot[comp].c)
+
 /* ---- log(): allocate EventId "{code}_{seq:06}", emit one 32-byte record, return the new id ------------ */
 template <bool LOG, int SM>
-__device__ __forceinline__ uint64_t qk_log(Ctx& cx, const DevComp* c, uint32_t comp, uint64_t src, uint32_t kind,
+__device__ __forceinline__ uint64_t qk_log(Ctx& cx, const DevHotA& c, uint32_t comp, uint64_t src, uint32_t kind,
                                            uint32_t reason, uint64_t payload) {
   if (!LOG) return 0;
-  const uint32_t seq = S32(c->olog32 + L32_SEQ);
-  S32(c->olog32 + L32_SEQ) = seq + 1;
-  if (c->flags & DC_LOGGED) {
+  const uint32_t seq = S32(c.olog32 + L32_SEQ);
+  S32(c.olog32 + L32_SEQ) = seq + 1;
+  if (c.flags & DC_LOGGED) {
     uint4* r = cx.log_base + 2 * (size_t)(cx.log_cnt & cx.log_mask);
     uint4 a, b;
     a.x = (uint32_t)cx.now;
@@ -183,27 +201,28 @@ __device__ __forceinline__ uint64_t qk_sample_duration_code(Ctx& cx, uint32_t di
 /* does the next update_state(comp) possibly start a process whose pre-drawn duration is still missing? */
 template <int SM>
 __device__ __forceinline__ bool qk_needs_refill_now(Ctx& cx, uint32_t comp) {
-  const DevComp* c = &cx.comps[comp];
-  if (c->o64_nextdur == 0xFFFF) return false;
-  if (S64(c->o64_nextdur) != QK_DUR_EMPTY) return false;
-  const uint32_t flags = S32(c->o32 + P32_FLAGS);
+  const DevHotB b = QK_HOT_B(comp); /* stocks never appear in a call list */
+  if (b.o64_nextdur == 0xFFFF) return false;
+  if (S64(b.o64_nextdur) != QK_DUR_EMPTY) return false;
+  const DevHotA a = QK_HOT_A(comp);
+  const uint32_t flags = S32(a.o32 + P32_FLAGS);
   if (!(flags & PF_HAS_ITEM)) return true;
-  return S64(c->o64 + P64_LEFT) <= cx.now - S64(c->o64 + P64_PREV); /* finishes in this call, may restart */
+  return S64(a.o64 + P64_LEFT) <= cx.now - S64(a.o64 + P64_PREV); /* finishes in this call, may restart */
 }
 
 /* REFILL: every lane with consumed slots draws their next durations (Distribution::sample, common.rs:152-178) */
 template <int SM>
 __device__ __forceinline__ void qk_refill(Ctx& cx) {
-  const uint32_t nw = cx.hdr->n_pf_words;
+  const uint32_t nw = cx.n_pf_words;
   const uint16_t* pf_comp = reinterpret_cast<const uint16_t*>(reinterpret_cast<const uint8_t*>(cx.hdr) + cx.hdr->off_pf);
   for (uint32_t w = 0; w < nw; ++w) {
-    uint32_t m = S32(cx.hdr->pf32 + w);
-    if (m) S32(cx.hdr->pf32 + w) = 0;
+    uint32_t m = S32(cx.pf32 + w);
+    if (m) S32(cx.pf32 + w) = 0;
     while (m) {
       const uint32_t i = (uint32_t)__ffs((int)m) - 1;
       m &= m - 1;
-      const DevComp* c = &cx.comps[pf_comp[w * 32 + i]];
-      S64(c->o64_nextdur) = qk_sample_duration_code<SM>(cx, c->dist_time);
+      const DevHotB b = QK_HOT_B(pf_comp[w * 32 + i]);
+      S64(b.o64_nextdur) = qk_sample_duration_code<SM>(cx, b.dist_time);
     }
   }
   cx.npend = 0;
@@ -217,9 +236,9 @@ __device__ __forceinline__ uint32_t qk_stock_cat(uint32_t cnt, uint32_t low, uin
 
 /* cx.schedule_event(now + 1ns, Self::emit_change, ..) discrete.rs:193-194, 218-219 */
 template <bool LOG, int SM>
-__device__ __forceinline__ void qk_emit_push(Ctx& cx, const DevComp* c, uint32_t src_seq) {
-  const uint32_t fire = G64_FIRE0 + c->fire_idx;
-  uint32_t e = S32(c->o32 + S32_EMIT);
+__device__ __forceinline__ void qk_emit_push(Ctx& cx, const DevHotA& c, uint32_t emit_depth, uint32_t src_seq) {
+  const uint32_t fire = G64_FIRE0 + c.fire_idx;
+  uint32_t e = S32(c.o32 + S32_EMIT);
   uint32_t n = e & 0xFFu, split = (e >> 8) & 0xFFu, head = (e >> 16) & 0xFFu;
   const uint64_t T = cx.now + 1;
   if (n == 0) {
@@ -230,27 +249,27 @@ __device__ __forceinline__ void qk_emit_push(Ctx& cx, const DevComp* c, uint32_t
     split += 1;
   }
   n += 1;
-  if (n > c->emit_depth) {
+  if (n > emit_depth) {
     cx.status = QK_REP_EMIT_OVERFLOW;
     return;
   }
   if (LOG) {
     uint32_t pos = head + n - 1;
-    if (pos >= c->emit_depth) pos -= c->emit_depth;
-    S32(c->olog32 + 1 + pos) = src_seq;
+    if (pos >= emit_depth) pos -= emit_depth;
+    S32(c.olog32 + 1 + pos) = src_seq;
   }
-  S32(c->o32 + S32_EMIT) = n | (split << 8) | (head << 16);
+  S32(c.o32 + S32_EMIT) = n | (split << 8) | (head << 16);
 }
 
 template <bool LOG, int SM>
-__device__ __forceinline__ uint32_t qk_emit_pop(Ctx& cx, const DevComp* c) {
-  const uint32_t fire = G64_FIRE0 + c->fire_idx;
-  uint32_t e = S32(c->o32 + S32_EMIT);
+__device__ __forceinline__ uint32_t qk_emit_pop(Ctx& cx, const DevHotA& c, uint32_t emit_depth) {
+  const uint32_t fire = G64_FIRE0 + c.fire_idx;
+  uint32_t e = S32(c.o32 + S32_EMIT);
   uint32_t n = e & 0xFFu, split = (e >> 8) & 0xFFu, head = (e >> 16) & 0xFFu;
   uint32_t src_seq = 0;
-  if (LOG) src_seq = S32(c->olog32 + 1 + head);
+  if (LOG) src_seq = S32(c.olog32 + 1 + head);
   head += 1;
-  if (head >= c->emit_depth) head = 0;
+  if (head >= emit_depth) head = 0;
   n -= 1;
   split -= 1;
   if (n == 0) {
@@ -259,96 +278,100 @@ __device__ __forceinline__ uint32_t qk_emit_pop(Ctx& cx, const DevComp* c) {
     S64(fire) = S64(fire) + 1;
     split = n;
   }
-  S32(c->o32 + S32_EMIT) = n | (split << 8) | (head << 16);
+  S32(c.o32 + S32_EMIT) = n | (split << 8) | (head << 16);
   return src_seq;
 }
 
 /* Stock::add = pre_add, add_impl, post_add (core.rs:177-183; discrete.rs:181-198). No capacity check. */
 template <bool LOG, int SM>
 __device__ __forceinline__ void qk_stock_add(Ctx& cx, uint32_t sidx, uint32_t item, uint64_t src) {
-  const DevComp* c = &cx.comps[sidx];
-  const uint32_t hc = S32(c->o32 + S32_HC);
+  const DevHotA c = QK_HOT_A(sidx);
+  const DevHotSB sb = QK_HOT_SB(sidx);
+  const uint32_t hc = S32(c.o32 + S32_HC);
   uint32_t head = hc & 0xFFFFu, cnt = hc >> 16;
-  const uint32_t prev = qk_stock_cat(cnt, c->low, c->max);
-  if (cnt >= c->ring_cap) {
+  const uint32_t prev = qk_stock_cat(cnt, sb.low, sb.max);
+  if (cnt >= sb.ring_cap) {
     cx.status = QK_REP_STOCK_OVERFLOW;
     return;
   }
   uint32_t pos = head + cnt;
-  if (pos >= c->ring_cap) pos -= c->ring_cap;
-  S32(c->o32 + S32_RING + pos) = item;
+  if (pos >= sb.ring_cap) pos -= sb.ring_cap;
+  S32(c.o32 + S32_RING + pos) = item;
   cnt += 1;
-  S32(c->o32 + S32_HC) = head | (cnt << 16);
+  S32(c.o32 + S32_HC) = head | (cnt << 16);
   QK_ST64_ADD(sidx, ST64_TIME, 0ull - cx.now); /* occupancy integral = sum(t_remove) - sum(t_add) + cnt * T */
   QK_ST32_ADD(sidx, ST32_COUNT, 1u);
   QK_ST32_MAX(sidx, ST32_MAXOCC, cnt);
   const uint64_t id = qk_log<LOG, SM>(cx, c, sidx, src, QK_LOG_STOCK_ADD, 0, item);
-  if (prev != qk_stock_cat(cnt, c->low, c->max)) qk_emit_push<LOG, SM>(cx, c, (uint32_t)id);
+  if (prev != qk_stock_cat(cnt, sb.low, sb.max)) qk_emit_push<LOG, SM>(cx, c, sb.emit_depth, (uint32_t)id);
 }
 
 /* Stock::remove (core.rs:197-204; discrete.rs:200-225); returns false for Remove(None) */
 template <bool LOG, int SM>
 __device__ __forceinline__ bool qk_stock_remove(Ctx& cx, uint32_t sidx, uint64_t src, uint32_t* item_out) {
-  const DevComp* c = &cx.comps[sidx];
-  const uint32_t hc = S32(c->o32 + S32_HC);
+  const DevHotA c = QK_HOT_A(sidx);
+  const DevHotSB sb = QK_HOT_SB(sidx);
+  const uint32_t hc = S32(c.o32 + S32_HC);
   uint32_t head = hc & 0xFFFFu, cnt = hc >> 16;
-  const uint32_t prev = qk_stock_cat(cnt, c->low, c->max);
+  const uint32_t prev = qk_stock_cat(cnt, sb.low, sb.max);
   const bool some = cnt != 0;
   uint32_t item = 0;
   if (some) {
-    item = S32(c->o32 + S32_RING + head);
+    item = S32(c.o32 + S32_RING + head);
     head += 1;
-    if (head >= c->ring_cap) head = 0;
+    if (head >= sb.ring_cap) head = 0;
     cnt -= 1;
-    S32(c->o32 + S32_HC) = head | (cnt << 16);
+    S32(c.o32 + S32_HC) = head | (cnt << 16);
     QK_ST64_ADD(sidx, ST64_TIME, cx.now);
   }
   const uint64_t id = qk_log<LOG, SM>(cx, c, sidx, src, QK_LOG_STOCK_REMOVE, 0, some ? (uint64_t)item : QK_ITEM_NONE);
-  if (prev != qk_stock_cat(cnt, c->low, c->max)) qk_emit_push<LOG, SM>(cx, c, (uint32_t)id);
+  if (prev != qk_stock_cat(cnt, sb.low, sb.max)) qk_emit_push<LOG, SM>(cx, c, sb.emit_depth, (uint32_t)id);
   *item_out = item;
   return some;
 }
 
+/* state category of stock `sidx` (3 = not connected): one table quad + one state word */
 template <int SM>
 __device__ __forceinline__ uint32_t qk_stock_cat_of(Ctx& cx, int sidx) {
-  const DevComp* c = &cx.comps[sidx];
-  return qk_stock_cat(S32(c->o32 + S32_HC) >> 16, c->low, c->max);
+  if (sidx < 0) return 3u;
+  const DevHotSB sb = QK_HOT_SB(sidx);
+  return qk_stock_cat(S32(sb.o32 + S32_HC) >> 16, sb.low, sb.max);
 }
 
 /* ---- DelayModes::update_state (delays.rs:86-142) + DelayEnd/DelayStart logs (discrete.rs:441-451) ------- */
 template <bool LOG, int SM>
-__device__ __forceinline__ void qk_tick_delays(Ctx& cx, const DevComp* c, uint32_t comp, uint32_t* flags_io,
-                                            uint64_t dt, uint64_t* src) {
+__device__ __forceinline__ void qk_tick_delays(Ctx& cx, const DevHotA& c, const DevHotB& cb, uint32_t comp,
+                                               uint32_t* flags_io, uint64_t dt, uint64_t* src) {
   uint32_t flags = *flags_io;
   uint32_t mask = (flags >> PF_FIX_SHIFT) & 0xFFu;
   int from = -1, to = -1;
   if (mask) {
     const int a = __ffs((int)mask) - 1; /* active_delay: first mode in TimeUntilFix, insertion order */
-    uint64_t dur = S64(c->o64_dm + a);
+    uint64_t dur = S64(cb.o64_dm + a);
     const uint64_t applied = dt < dur ? dt : dur;
     QK_ST64_ADD(comp, ST64_DELAY, applied);
     dur -= applied;
     if (dur == 0) {
-      dur = qk_sample_duration<SM>(cx, cx.dms[c->dm_off + a].until_delay);
+      dur = qk_sample_duration<SM>(cx, cx.dms[cb.dm_off + a].until_delay);
       if (cx.status) return;
       mask &= ~(1u << a);
     }
-    S64(c->o64_dm + a) = dur;
+    S64(cb.o64_dm + a) = dur;
     from = a;
   } else {
-    for (int k = 0; k < c->n_dm; ++k) {
-      const uint64_t dur = S64(c->o64_dm + k);
-      S64(c->o64_dm + k) = dur - (dt < dur ? dt : dur);
+    for (int k = 0; k < c.n_dm; ++k) {
+      const uint64_t dur = S64(cb.o64_dm + k);
+      S64(cb.o64_dm + k) = dur - (dt < dur ? dt : dur);
     }
   }
   if (mask) {
     to = __ffs((int)mask) - 1;
   } else {
-    for (int k = 0; k < c->n_dm; ++k) {
-      if (S64(c->o64_dm + k) == 0) {
-        const uint64_t dur = qk_sample_duration<SM>(cx, cx.dms[c->dm_off + k].until_fix);
+    for (int k = 0; k < c.n_dm; ++k) {
+      if (S64(cb.o64_dm + k) == 0) {
+        const uint64_t dur = qk_sample_duration<SM>(cx, cx.dms[cb.dm_off + k].until_fix);
         if (cx.status) return;
-        S64(c->o64_dm + k) = dur;
+        S64(cb.o64_dm + k) = dur;
         mask |= 1u << k;
         to = k;
         break;
@@ -365,9 +388,9 @@ __device__ __forceinline__ void qk_tick_delays(Ctx& cx, const DevComp* c, uint32
 
 /* "Update cached environment state" (discrete.rs:455-471 and siblings) */
 template <bool LOG, int SM>
-__device__ __forceinline__ void qk_refresh_env(Ctx& cx, const DevComp* c, uint32_t comp, uint32_t* flags,
+__device__ __forceinline__ void qk_refresh_env(Ctx& cx, const DevHotA& c, int env, uint32_t comp, uint32_t* flags,
                                                uint64_t* src) {
-  const bool new_stopped = c->env >= 0 ? (S32(cx.comps[c->env].o32 + E32_STATE) == 1u) : false;
+  const bool new_stopped = env >= 0 ? (S32(QK_HOT_SB(env).o32 + E32_STATE) == 1u) : false;
   const bool old_stopped = (*flags & PF_ENV_STOPPED) != 0;
   if (!old_stopped && new_stopped) {
     *src = qk_log<LOG, SM>(cx, c, comp, *src, QK_LOG_PROCESS_STOPPED, QK_REASON_STOPPED_BY_ENV, 0);
@@ -381,17 +404,17 @@ __device__ __forceinline__ void qk_refresh_env(Ctx& cx, const DevComp* c, uint32
 /* post_update_state (discrete.rs:535-564): keep the earlier of the pending keyed event and now+ttnpe.
  * Cancelling == overwriting the single fire slot. */
 template <bool LOG, int SM>
-__device__ __forceinline__ void qk_post(Ctx& cx, const DevComp* c, uint64_t ttnpe, uint64_t src) {
+__device__ __forceinline__ void qk_post(Ctx& cx, const DevHotA& c, uint64_t ttnpe, uint64_t src) {
   if (ttnpe != QK_TIME_NONE) {
     if (ttnpe == 0) {
       cx.status = QK_REP_ZERO_DURATION; /* panic!("Time until next event is zero!") */
       return;
     }
     const uint64_t next = cx.now + ttnpe;
-    const uint32_t fire = G64_FIRE0 + c->fire_idx;
+    const uint32_t fire = G64_FIRE0 + c.fire_idx;
     if (next < S64(fire)) { /* NONE is the largest u64 */
       S64(fire) = next;
-      if (LOG) S64(c->olog64 + PL64_SCHED_SRC) = src;
+      if (LOG) S64(c.olog64 + PL64_SCHED_SRC) = src;
     }
   }
 }
@@ -399,22 +422,73 @@ __device__ __forceinline__ void qk_post(Ctx& cx, const DevComp* c, uint64_t ttnp
 /* pre_update_state (discrete.rs:404-412): a handle whose time has come is forgotten, NOT cancelled; if its
  * event has not fired yet it stays queued (Q3) -> move it to the stale mask (it fires at `now`, in rank order) */
 template <bool LOG, int SM>
-__device__ __forceinline__ void qk_pre(Ctx& cx, const DevComp* c) {
-  const uint32_t fire = G64_FIRE0 + c->fire_idx;
+__device__ __forceinline__ void qk_pre(Ctx& cx, const DevHotA& c) {
+  const uint32_t fire = G64_FIRE0 + c.fire_idx;
   if (S64(fire) <= cx.now) {
     S64(fire) = QK_TIME_NONE;
-    S32(G32_STALE0 + (c->fire_idx >> 5)) |= 1u << (c->fire_idx & 31);
-    if (LOG) S64(c->olog64 + PL64_STALE_SRC) = S64(c->olog64 + PL64_SCHED_SRC);
+    S32(G32_STALE0 + (c.fire_idx >> 5)) |= 1u << (c.fire_idx & 31);
+    if (LOG) S64(c.olog64 + PL64_STALE_SRC) = S64(c.olog64 + PL64_SCHED_SRC);
   }
+}
+
+/* ---- quick path ----------------------------------------------------------------------------------------------
+ * Most update_state calls change nothing but the countdown: a stock's emit_change is broadcast to every connected
+ * process, and a process that is busy (or idle and still blocked) only refreshes `previous_check_time`.  The event
+ * loop handles those calls while it walks a call list, so that the UPDATE phase -- the long, divergent handler --
+ * is only entered with calls that finish or start something.  Returns false (state untouched) when the call needs
+ * the full handler; otherwise it has done exactly what qk_update_single would have done. */
+template <bool LOG, int SM>
+__device__ __forceinline__ bool qk_try_quick(Ctx& cx, uint32_t comp, uint64_t src) {
+  const DevHotA c = QK_HOT_A(comp);
+  const uint32_t kind = c.kind;
+  if (kind < QK_DISCRETE_PROCESS || kind > QK_DISCRETE_SINK || c.n_dm != 0) return false;
+  const DevHotB cb = QK_HOT_B(comp);
+  const uint32_t flags = S32(c.o32 + P32_FLAGS);
+  if (cb.env >= 0 || (flags & PF_ENV_STOPPED)) return false;
+  const uint64_t fire = S64(G64_FIRE0 + c.fire_idx);
+  if (fire <= cx.now) return false; /* pre_update_state would drop the handle (Q3) */
+  if (flags & PF_HAS_ITEM) {
+    const uint64_t left = S64(c.o64 + P64_LEFT);
+    const uint64_t dt = cx.now - S64(c.o64 + P64_PREV);
+    if (left <= dt) return false; /* finishes */
+    const uint64_t rest = left - dt;
+    /* ttnpe: Process (Some,false) / Source (Some,_) = what is left ; Sink keeps its previous value */
+    const uint64_t ttnpe = kind == QK_DISCRETE_SINK ? S64(QK_HOT_C(comp).o64_ttnpe) : rest;
+    if (ttnpe != QK_TIME_NONE && (ttnpe == 0 || cx.now + ttnpe < fire)) return false; /* fault / reschedule */
+    S64(c.o64 + P64_LEFT) = rest;
+    S64(c.o64 + P64_PREV) = cx.now;
+    return true;
+  }
+  /* idle: quick only if it stays idle */
+  const bool need_us = kind != QK_DISCRETE_SOURCE, need_ds = kind != QK_DISCRETE_SINK;
+  const uint32_t us = need_us ? qk_stock_cat_of<SM>(cx, cb.up) : 1u;
+  const uint32_t ds = need_ds ? qk_stock_cat_of<SM>(cx, cb.down) : 1u;
+  if ((us == 1u || us == 2u) && (ds == 0u || ds == 1u)) return false; /* starts */
+  if (LOG) {
+    uint32_t reason;
+    if (need_us && us == 0u)
+      reason = QK_REASON_UPSTREAM_EMPTY;
+    else if (need_us && us == 3u)
+      reason = QK_REASON_UPSTREAM_NOT_CONNECTED;
+    else if (ds == 2u)
+      reason = QK_REASON_DOWNSTREAM_FULL;
+    else
+      reason = QK_REASON_DOWNSTREAM_NOT_CONNECTED;
+    qk_log<LOG, SM>(cx, c, comp, src, QK_LOG_PROCESS_NONSTART, reason, 0);
+  }
+  if (kind == QK_DISCRETE_SINK) S64(QK_HOT_C(comp).o64_ttnpe) = QK_TIME_NONE;
+  S64(c.o64 + P64_PREV) = cx.now;
+  return true;
 }
 
 /* ---- DiscreteProcess / DiscreteSource / DiscreteSink update_state, one code path ----------------------------- */
 template <bool LOG, int SM>
-__device__ __forceinline__ void qk_update_single(Ctx& cx, const DevComp* c, uint32_t comp, uint64_t src) {
-  const uint32_t kind = c->kind;
-  uint32_t flags = S32(c->o32 + P32_FLAGS);
-  uint64_t left = S64(c->o64 + P64_LEFT);
-  const uint64_t dt = cx.now - S64(c->o64 + P64_PREV);
+__device__ __forceinline__ void qk_update_single(Ctx& cx, const DevHotA& c, uint32_t comp, uint64_t src) {
+  const DevHotB cb = QK_HOT_B(comp);
+  const uint32_t kind = c.kind;
+  uint32_t flags = S32(c.o32 + P32_FLAGS);
+  uint64_t left = S64(c.o64 + P64_LEFT);
+  const uint64_t dt = cx.now - S64(c.o64 + P64_PREV);
   uint64_t ttnpe = QK_TIME_NONE;
   {
     const bool is_in_delay = ((flags >> PF_FIX_SHIFT) & 0xFFu) != 0;
@@ -425,21 +499,21 @@ __device__ __forceinline__ void qk_update_single(Ctx& cx, const DevComp* c, uint
       left -= (dt < left ? dt : left); /* saturating_sub */
       if (left == 0) {
         flags &= ~PF_HAS_ITEM;
-        const uint32_t item = S32(c->o32 + P32_ITEM);
+        const uint32_t item = S32(c.o32 + P32_ITEM);
         src = qk_log<LOG, SM>(cx, c, comp, src, QK_LOG_PROCESS_FINISH, 0, item);
         QK_ST32_ADD(comp, ST32_COUNT, 1u);
-        if (kind != QK_DISCRETE_SINK && c->down >= 0) { /* push_downstream: no downstream check at finish */
-          qk_stock_add<LOG, SM>(cx, (uint32_t)c->down, item, src);
+        if (kind != QK_DISCRETE_SINK && cb.down >= 0) { /* push_downstream: no downstream check at finish */
+          qk_stock_add<LOG, SM>(cx, (uint32_t)cb.down, item, src);
           if (cx.status) return;
         }
       }
     }
-    if (c->n_dm && !is_env_blocked && (is_in_delay || is_in_process)) {
-      qk_tick_delays<LOG, SM>(cx, c, comp, &flags, dt, &src);
+    if (c.n_dm && !is_env_blocked && (is_in_delay || is_in_process)) {
+      qk_tick_delays<LOG, SM>(cx, c, cb, comp, &flags, dt, &src);
       if (cx.status) return;
     }
   }
-  if (c->env >= 0 || (flags & PF_ENV_STOPPED)) qk_refresh_env<LOG, SM>(cx, c, comp, &flags, &src);
+  if (cb.env >= 0 || (flags & PF_ENV_STOPPED)) qk_refresh_env<LOG, SM>(cx, c, cb.env, comp, &flags, &src);
 
   const bool has_item = (flags & PF_HAS_ITEM) != 0;
   const uint32_t fixmask = (flags >> PF_FIX_SHIFT) & 0xFFu;
@@ -447,37 +521,38 @@ __device__ __forceinline__ void qk_update_single(Ctx& cx, const DevComp* c, uint
   if (!has_item && !has_active_delay) {
     /* match (&us_state, &ds_state) discrete.rs:480-516 / 854-872 / 1100-1125; 3 == not connected */
     const bool need_us = kind != QK_DISCRETE_SOURCE, need_ds = kind != QK_DISCRETE_SINK;
-    const uint32_t us = need_us ? (c->up >= 0 ? qk_stock_cat_of<SM>(cx, c->up) : 3u) : 1u;
-    const uint32_t ds = need_ds ? (c->down >= 0 ? qk_stock_cat_of<SM>(cx, c->down) : 3u) : 1u;
+    const uint32_t us = need_us ? qk_stock_cat_of<SM>(cx, cb.up) : 1u;
+    const uint32_t ds = need_ds ? qk_stock_cat_of<SM>(cx, cb.down) : 1u;
     const bool ok = (us == 1u || us == 2u) && (ds == 0u || ds == 1u);
     if (ok) {
       bool got = true;
       uint32_t item;
       if (need_us) {
         src = qk_log<LOG, SM>(cx, c, comp, src, QK_LOG_WITHDRAW_REQUEST, 0, 0);
-        got = qk_stock_remove<LOG, SM>(cx, (uint32_t)c->up, src, &item);
+        got = qk_stock_remove<LOG, SM>(cx, (uint32_t)cb.up, src, &item);
         if (cx.status) return;
       }
       if (got) {
         /* process_time_distr.sample() + Duration::from_secs_f64: Constant distributions were converted at
          * lowering; random ones were drawn ahead of time by the REFILL phase of the event loop */
+        const DevHotC cc = QK_HOT_C(comp);
         uint64_t d;
-        if (c->o64_nextdur != 0xFFFF) {
-          d = S64(c->o64_nextdur);
-          S64(c->o64_nextdur) = QK_DUR_EMPTY;
-          S32(cx.hdr->pf32 + (c->pf_idx >> 5)) |= 1u << (c->pf_idx & 31);
+        if (cb.o64_nextdur != 0xFFFF) {
+          d = S64(cb.o64_nextdur);
+          S64(cb.o64_nextdur) = QK_DUR_EMPTY;
+          S32(cx.pf32 + (cb.pf_idx >> 5)) |= 1u << (cb.pf_idx & 31);
           cx.npend += 1;
         } else {
-          d = ((uint64_t)c->const_dur_hi << 32) | c->const_dur_lo;
+          d = ((uint64_t)cc.const_dur_hi << 32) | cc.const_dur_lo;
         }
         if (!need_us) { /* ItemFactory::create_item discrete.rs:680-686 */
-          const uint32_t idx = S32(c->o32_next_item);
+          const uint32_t idx = S32(cc.o32_next_item);
           if (idx > 0x3FFFFFFu) {
             cx.status = QK_REP_ITEM_INDEX_OVERFLOW;
             return;
           }
-          S32(c->o32_next_item) = idx + 1;
-          item = ((uint32_t)c->src_ord << 26) | idx;
+          S32(cc.o32_next_item) = idx + 1;
+          item = ((uint32_t)c.src_ord << 26) | idx;
         }
         if (d >= QK_DUR_FAULT_BASE) { /* from_secs_f64 panicked / tape exhausted / (EMPTY: refill logic bug) */
           cx.status = d == QK_DUR_EMPTY ? 99u : (uint32_t)(d - QK_DUR_FAULT_BASE);
@@ -485,7 +560,7 @@ __device__ __forceinline__ void qk_update_single(Ctx& cx, const DevComp* c, uint
         }
         left = d;
         flags |= PF_HAS_ITEM;
-        S32(c->o32 + P32_ITEM) = item;
+        S32(c.o32 + P32_ITEM) = item;
         QK_ST64_ADD(comp, ST64_TIME, d);
         src = qk_log<LOG, SM>(cx, c, comp, src, QK_LOG_PROCESS_START, 0, item);
         ttnpe = d;
@@ -506,22 +581,24 @@ __device__ __forceinline__ void qk_update_single(Ctx& cx, const DevComp* c, uint
     }
   } else if (kind == QK_DISCRETE_SINK) {
     /* (Some, _) leaves ttnpe untouched (discrete.rs:1127-1129); (_, true) clears it (Q2, :1130-1132) */
-    ttnpe = has_item ? S64(c->o64_ttnpe) : QK_TIME_NONE;
+    ttnpe = has_item ? S64(QK_HOT_C(comp).o64_ttnpe) : QK_TIME_NONE;
   } else if (has_item && (!has_active_delay || kind == QK_DISCRETE_SOURCE)) {
     ttnpe = left; /* Process (Some,false) :518-520 ; Source (Some,_) :874-876 */
   } else {
-    ttnpe = fixmask ? S64(c->o64_dm + (__ffs((int)fixmask) - 1)) : QK_TIME_NONE; /* (_, true) :521-523 */
+    ttnpe = fixmask ? S64(cb.o64_dm + (__ffs((int)fixmask) - 1)) : QK_TIME_NONE; /* (_, true) :521-523 */
   }
-  if (kind == QK_DISCRETE_SINK) S64(c->o64_ttnpe) = ttnpe;
-  S32(c->o32 + P32_FLAGS) = flags;
-  S64(c->o64 + P64_LEFT) = left;
+  if (kind == QK_DISCRETE_SINK) S64(QK_HOT_C(comp).o64_ttnpe) = ttnpe;
+  S32(c.o32 + P32_FLAGS) = flags;
+  S64(c.o64 + P64_LEFT) = left;
   qk_post<LOG, SM>(cx, c, ttnpe, src);
-  S64(c->o64 + P64_PREV) = cx.now;
+  S64(c.o64 + P64_PREV) = cx.now;
 }
 
 /* ---- DiscreteParallelProcess::update_state_impl (discrete.rs:1280-1417) ---------------------------------------- */
 template <bool LOG, int SM>
 __device__ __forceinline__ void qk_update_parallel(Ctx& cx, const DevComp* c, uint32_t comp, uint64_t src) {
+  const DevHotA ha = QK_HOT_A(comp);
+  const DevHotB hb = QK_HOT_B(comp);
   uint32_t flags = S32(c->o32 + PP32_FLAGS);
   const uint64_t dt = cx.now - S64(c->o64 + PP64_PREV);
   const uint32_t cap = c->ring_cap;
@@ -564,29 +641,29 @@ __device__ __forceinline__ void qk_update_parallel(Ctx& cx, const DevComp* c, ui
         ccnt -= 1;
         const uint32_t ds = c->down >= 0 ? qk_stock_cat_of<SM>(cx, c->down) : 3u;
         if (ds == 0u || ds == 1u) {
-          src = qk_log<LOG, SM>(cx, c, comp, src, QK_LOG_PROCESS_FINISH, 0, it);
+          src = qk_log<LOG, SM>(cx, ha, comp, src, QK_LOG_PROCESS_FINISH, 0, it);
           QK_ST32_ADD(comp, ST32_COUNT, 1u);
           qk_stock_add<LOG, SM>(cx, (uint32_t)c->down, it, src);
           if (cx.status) return;
         } else {
-          src = qk_log<LOG, SM>(cx, c, comp, src, QK_LOG_PROCESS_NONSTART,
+          src = qk_log<LOG, SM>(cx, ha, comp, src, QK_LOG_PROCESS_NONSTART,
                             ds == 2u ? QK_REASON_DOWNSTREAM_FULL : QK_REASON_DOWNSTREAM_NOT_CONNECTED, 0);
           break;
         }
       }
     }
     if (c->n_dm && !is_env_blocked && (is_in_delay || is_in_process)) {
-      qk_tick_delays<LOG, SM>(cx, c, comp, &flags, dt, &src);
+      qk_tick_delays<LOG, SM>(cx, ha, hb, comp, &flags, dt, &src);
       if (cx.status) return;
     }
   }
-  if (c->env >= 0 || (flags & PF_ENV_STOPPED)) qk_refresh_env<LOG, SM>(cx, c, comp, &flags, &src);
+  if (c->env >= 0 || (flags & PF_ENV_STOPPED)) qk_refresh_env<LOG, SM>(cx, ha, c->env, comp, &flags, &src);
   uint64_t ttnpe = QK_TIME_NONE;
   if (!(flags & PF_ENV_STOPPED)) {
     for (;;) { /* :1373-1398 */
       const uint32_t us = c->up >= 0 ? qk_stock_cat_of<SM>(cx, c->up) : 3u;
       if (us == 0u || us == 1u) { /* Q4: withdraws while upstream is Empty|Normal */
-        src = qk_log<LOG, SM>(cx, c, comp, src, QK_LOG_WITHDRAW_REQUEST, 0, 0);
+        src = qk_log<LOG, SM>(cx, ha, comp, src, QK_LOG_WITHDRAW_REQUEST, 0, 0);
         uint32_t it;
         const bool got = qk_stock_remove<LOG, SM>(cx, (uint32_t)c->up, src, &it);
         if (cx.status) return;
@@ -601,9 +678,9 @@ __device__ __forceinline__ void qk_update_parallel(Ctx& cx, const DevComp* c, ui
         S32(item0 + nprog) = it;
         nprog += 1;
         QK_ST64_ADD(comp, ST64_TIME, d);
-        src = qk_log<LOG, SM>(cx, c, comp, src, QK_LOG_PROCESS_START, 0, it);
+        src = qk_log<LOG, SM>(cx, ha, comp, src, QK_LOG_PROCESS_START, 0, it);
       } else {
-        src = qk_log<LOG, SM>(cx, c, comp, src, QK_LOG_PROCESS_NONSTART,
+        src = qk_log<LOG, SM>(cx, ha, comp, src, QK_LOG_PROCESS_NONSTART,
                           us == 2u ? QK_REASON_UPSTREAM_FULL : QK_REASON_UPSTREAM_NOT_CONNECTED, 0);
         break;
       }
@@ -616,7 +693,7 @@ __device__ __forceinline__ void qk_update_parallel(Ctx& cx, const DevComp* c, ui
   S32(c->o32 + PP32_FLAGS) = flags;
   S32(c->o32 + PP32_NPROG) = nprog;
   S32(c->o32 + PP32_COMPLETE) = chead | (ccnt << 16);
-  qk_post<LOG, SM>(cx, c, ttnpe, src);
+  qk_post<LOG, SM>(cx, ha, ttnpe, src);
   S64(c->o64 + PP64_PREV) = cx.now;
 }
 
@@ -625,29 +702,35 @@ __device__ __forceinline__ void qk_update_parallel(Ctx& cx, const DevComp* c, ui
 /* Process::update_state (core.rs:370-376) */
 template <bool LOG, int SM>
 __device__ __forceinline__ void qk_update_state(Ctx& cx, uint32_t comp, uint64_t src) {
-  const DevComp* c = &cx.comps[comp];
-  if (c->kind == QK_ENVIRONMENT) { /* only reached from the init list: BasicEnvironment::init logs its state */
-    qk_log<LOG, SM>(cx, c, comp, src, QK_LOG_ENV_STATE, S32(c->o32 + E32_STATE), 0);
+  const DevHotA a = QK_HOT_A(comp);
+  if (a.kind >= QK_DISCRETE_PROCESS && a.kind <= QK_DISCRETE_SINK) {
+    qk_pre<LOG, SM>(cx, a);
+    qk_update_single<LOG, SM>(cx, a, comp, src);
     return;
   }
-  if (c->kind >= QK_VECTOR_PROCESS) {
+  const DevComp* c = &cx.comps[comp];
+  if (a.kind == QK_ENVIRONMENT) { /* only reached from the init list: BasicEnvironment::init logs its state */
+    qk_log<LOG, SM>(cx, a, comp, src, QK_LOG_ENV_STATE, S32(a.o32 + E32_STATE), 0);
+    return;
+  }
+  if (a.kind >= QK_VECTOR_PROCESS) {
     /* Combiner / Splitter / VectorSource / VectorSink init with their own next id instead of INIT_000000
      * (vector.rs:774,1111,1393,1619); SRC_INIT only ever arrives from the init list */
-    if (LOG && src == SRC_INIT && c->kind != QK_VECTOR_PROCESS)
-      src = ((uint64_t)comp << 32) | S32(c->olog32 + L32_SEQ);
-    qk_pre<LOG, SM>(cx, c);
+    if (LOG && src == SRC_INIT && a.kind != QK_VECTOR_PROCESS)
+      src = ((uint64_t)comp << 32) | S32(a.olog32 + L32_SEQ);
+    qk_pre<LOG, SM>(cx, a);
     qk_update_vector<LOG, SM>(cx, c, comp, src);
     return;
   }
-  qk_pre<LOG, SM>(cx, c);
-  if (c->kind == QK_DISCRETE_PARALLEL_PROCESS)
-    qk_update_parallel<LOG, SM>(cx, c, comp, src);
-  else
-    qk_update_single<LOG, SM>(cx, c, comp, src);
+  qk_pre<LOG, SM>(cx, a);
+  qk_update_parallel<LOG, SM>(cx, c, comp, src);
 }
 
 /* ============================================ the kernel ============================================ */
 #define QK_MAX_NT 256
+#ifndef QK_SCAN_ITERS
+#define QK_SCAN_ITERS 3 /* scheduler pops a lane may spend per trip looking for a call that needs the full handler */
+#endif
 
 constexpr int qk_lb_threads(int sm) { return sm > 0 ? sm : QK_MAX_NT; }
 constexpr int qk_lb_blocks(int sm) { return sm > 0 ? (512 / sm > 0 ? 512 / sm : 1) : 2; }
@@ -676,6 +759,9 @@ __global__ void __launch_bounds__(qk_lb_threads(SM), qk_lb_blocks(SM)) qk_step_k
   cx.sched = reinterpret_cast<const uint16_t*>(smem + cx.hdr->off_sched);
   cx.ext = reinterpret_cast<const DevExt*>(smem + cx.hdr->off_ext);
   cx.vecs = reinterpret_cast<const DevVec*>(smem + cx.hdr->off_vecs);
+  cx.hot = reinterpret_cast<const DevHot*>(smem + cx.hdr->off_hot);
+  cx.pf32 = cx.hdr->pf32;
+  cx.n_pf_words = cx.hdr->n_pf_words;
   const uint64_t rep_local = (uint64_t)QK_BID * nt + tid;
   if constexpr (SM == 0) {
     cx.g64 = P.g64 + rep_local;
@@ -726,7 +812,7 @@ __global__ void __launch_bounds__(qk_lb_threads(SM), qk_lb_blocks(SM)) qk_step_k
         if (c->o64_ttnpe != 0xFFFF) S64(c->o64_ttnpe) = QK_TIME_NONE;
         if (c->o64_nextdur != 0xFFFF) {
           S64(c->o64_nextdur) = QK_DUR_EMPTY;
-          S32(cx.hdr->pf32 + (c->pf_idx >> 5)) |= 1u << (c->pf_idx & 31);
+          S32(cx.pf32 + (c->pf_idx >> 5)) |= 1u << (c->pf_idx & 31);
         }
         /* DelayModes::modify(Add) samples until_delay when the mode is added (delays.rs:159-164) */
         for (int k = 0; k < c->n_dm && !cx.status; ++k)
@@ -760,115 +846,135 @@ __global__ void __launch_bounds__(qk_lb_threads(SM), qk_lb_blocks(SM)) qk_step_k
     cx.log_cnt = S32(G32_LOGCNT);
   }
 
-  for (uint32_t w = 0; w < cx.hdr->n_pf_words; ++w) cx.npend += (uint32_t)QK_POPC(S32(cx.hdr->pf32 + w));
+  for (uint32_t w = 0; w < cx.n_pf_words; ++w) cx.npend += (uint32_t)QK_POPC(S32(cx.pf32 + w));
 
-  /* ---- event loop: one update_state per lane per trip ------------------------------------------------- */
+  /* ---- event loop ----------------------------------------------------------------------------------------
+   * A lane's work is a stream of update_state(p) calls: an action popped from its scheduler queue expands into a
+   * call list ([p] for a keyed event, the subscriber list for an emit_change / environment change, the init list
+   * at t0).  Each trip of the loop has three warp-converged phases:
+   *   SCAN    every lane walks forward through its stream -- popping the next action when the list is empty and
+   *           disposing of the calls that only refresh a countdown (qk_try_quick) -- until it stands on a call that
+   *           needs the full handler (at most QK_SCAN_ITERS pops per trip, so no lane holds the warp for long);
+   *   REFILL  deferred variate prefetch (see below);
+   *   UPDATE  one full update_state per lane that has one. */
   uint64_t events_done = 0;
   const uint64_t budget = live ? P.event_budget : 0;
+  const uint64_t t_until = P.t_until;
   /* Model::init of every component in registration order is the first call list of the loop */
   uint32_t rem = (P.do_init && live) ? cx.hdr->n_init : 0, ptr = cx.hdr->init_off;
+  const uint32_t ident_off = cx.hdr->ident_off;
   uint64_t src = SRC_INIT;
   uint32_t ext_cursor = S32(G32_EXT_CURSOR);
-  /* The loop body is two straight-line phases -- SELECT (lanes whose call list is empty pop their scheduler queue)
-   * and UPDATE (every lane with a pending call runs one update_state) -- each entered and left by the whole warp,
-   * and the loop exit is a warp vote, so the warp is converged at the top of UPDATE on every trip. */
   bool done = false;
   for (;;) {
     QK_SYNCWARP();
-    if (rem == 0 && !done) {
-      done = cx.status != 0 || events_done >= budget;
-    }
-    if (rem == 0 && !done) {
-      /* pop the scheduler queue: min over (time, rank); rank 0 = externally scheduled events */
-      uint64_t best = ext_cursor < n_ext ? cx.ext[ext_cursor].t : QK_TIME_NONE;
-      int bi = -1;
-      for (uint32_t i = 0; i < n_sched; ++i) {
-        const uint64_t t = S64(G64_FIRE0 + i);
-        if (t < best) {
-          best = t;
-          bi = (int)i;
-        }
+#pragma unroll 1
+    for (int it = 0; it < QK_SCAN_ITERS; ++it) {
+      /* dispose of the quick calls at the head of the list */
+      while (rem != 0 && qk_try_quick<LOG, SM>(cx, cx.subs[ptr], src)) {
+        ptr += 1;
+        rem -= 1;
       }
-      bool stale = false;
-      uint32_t stale_word = 0, stale_mask = 0;
-      for (uint32_t w = 0; w < n_stale_words; ++w) {
-        const uint32_t m = S32(G32_STALE0 + w);
-        if (m) {
-          const int is = (int)(w * 32) + __ffs((int)m) - 1;
-          if (best > cx.now || is < bi) { /* a stale handle fires at `now`, in rank order */
-            stale = true;
-            bi = is;
-            best = cx.now;
-            stale_word = w;
-            stale_mask = m & (m - 1);
+      if (rem == 0 && !done) done = cx.status != 0 || events_done >= budget;
+      if (!QK_ANY_SYNC(rem == 0 && !done)) break; /* every lane stands on a full call or has finished */
+      if (rem == 0 && !done) {
+        /* pop the scheduler queue: min over (time, rank); rank 0 = externally scheduled events */
+        uint64_t best = ext_cursor < n_ext ? cx.ext[ext_cursor].t : QK_TIME_NONE;
+        int bi = -1;
+        for (uint32_t i = 0; i < n_sched; ++i) {
+          const uint64_t t = S64(G64_FIRE0 + i);
+          if (t < best) {
+            best = t;
+            bi = (int)i;
           }
-          break;
         }
-      }
-      if (best == QK_TIME_NONE || best > P.t_until) {
-        done = true; /* queue empty, or next action is beyond the step_until horizon */
-      } else {
-      if (stale) S32(G32_STALE0 + stale_word) = stale_mask;
-      cx.now = best;
-      events_done += 1;
-      if (bi < 0) {
-        /* ScheduledEventConfig::SetEnvironmentState -> BasicEnvironment::set_state (core.rs:256-265, 1393-1396) */
-        const DevExt* e = &cx.ext[ext_cursor];
-        ext_cursor += 1;
-        const DevComp* c = &cx.comps[e->target];
-        if (e->type == 1) {
-          /* SetLowCapacity on an F64Stock: with_low_capacity_inplace, then add((0., SCH_000000)) (core.rs:1382-1386) */
-          S64(cx.vecs[c->vec_idx].o64_low) = QK_D2U(e->value);
-          const double zero[3] = {0.0, 0.0, 0.0};
-          qk_vstock_add<LOG, SM>(cx, e->target, zero, SRC_SCH);
-        } else if (S32(c->o32 + E32_STATE) != e->state) {
-          S32(c->o32 + E32_STATE) = e->state;
-          src = qk_log<LOG, SM>(cx, c, e->target, SRC_SCH, QK_LOG_ENV_STATE, e->state, 0);
-          rem = c->n_subs;
-          ptr = c->subs_off;
-        }
-      } else {
-        const uint32_t comp = cx.sched[bi];
-        const DevComp* c = &cx.comps[comp];
-        if (c->kind == QK_DISCRETE_STOCK) {
-          /* emit_change (discrete.rs:227-233): log the state AT EMISSION TIME, then update_state on every
-           * subscriber in connection order */
-          const uint32_t src_seq = qk_emit_pop<LOG, SM>(cx, c);
-          const uint32_t cnt = S32(c->o32 + S32_HC) >> 16;
-          const uint32_t empty = c->max > cnt ? c->max - cnt : 0;
-          src = qk_log<LOG, SM>(cx, c, comp, ((uint64_t)comp << 32) | src_seq, QK_LOG_STOCK_STATE_CHANGE,
-                            qk_stock_cat(cnt, c->low, c->max), ((uint64_t)cnt << 32) | empty);
-          rem = c->n_subs;
-          ptr = c->subs_off;
-        } else if (c->kind == QK_VECTOR_STOCK) {
-          /* VectorStock::emit_change (vector.rs:167-171) logs the state carried by the event */
-          uint32_t packed = 0;
-          uint64_t occ_bits = 0;
-          if (LOG) {
-            const uint32_t head = (S32(c->o32 + S32_EMIT) >> 16) & 0xFFu;
-            occ_bits = S64(c->olog64 + head);
-            packed = qk_emit_pop<LOG, SM>(cx, c);
-          } else {
-            qk_emit_pop<LOG, SM>(cx, c);
+        bool stale = false;
+        uint32_t stale_word = 0, stale_mask = 0;
+        for (uint32_t w = 0; w < n_stale_words; ++w) {
+          const uint32_t m = S32(G32_STALE0 + w);
+          if (m) {
+            const int is = (int)(w * 32) + __ffs((int)m) - 1;
+            if (best > cx.now || is < bi) { /* a stale handle fires at `now`, in rank order */
+              stale = true;
+              bi = is;
+              best = cx.now;
+              stale_word = w;
+              stale_mask = m & (m - 1);
+            }
+            break;
           }
-          src = qk_log<LOG, SM>(cx, c, comp, ((uint64_t)comp << 32) | (packed & 0x3FFFFFFFu), QK_LOG_VSTOCK_STATE_CHANGE,
-                            packed >> 30, occ_bits);
-          qk_log_vec<LOG, SM>(cx, c, comp, src, 0, __dsub_rn(cx.vecs[c->vec_idx].vmax, QK_U2D(occ_bits)), 0.0, 0.0);
-          rem = c->n_subs;
-          ptr = c->subs_off;
+        }
+        if (best == QK_TIME_NONE || best > t_until) {
+          done = true; /* queue empty, or next action is beyond the step_until horizon */
         } else {
-          /* keyed update_state(source_event_id) (discrete.rs:549,556) */
-          if (stale) {
-            if (LOG) src = S64(c->olog64 + PL64_STALE_SRC);
+          if (stale) S32(G32_STALE0 + stale_word) = stale_mask;
+          cx.now = best;
+          events_done += 1;
+          if (bi < 0) {
+            /* ScheduledEventConfig::SetEnvironmentState -> BasicEnvironment::set_state (core.rs:256-265, 1393-1396) */
+            const DevExt* e = &cx.ext[ext_cursor];
+            ext_cursor += 1;
+            const uint32_t target = e->target;
+            const DevHotA a = QK_HOT_A(target);
+            if (e->type == 1) {
+              /* SetLowCapacity on an F64Stock: with_low_capacity_inplace, then add((0., SCH_000000)) (core.rs:1382-1386) */
+              S64(cx.vecs[cx.comps[target].vec_idx].o64_low) = QK_D2U(e->value);
+              const double zero[3] = {0.0, 0.0, 0.0};
+              qk_vstock_add<LOG, SM>(cx, target, zero, SRC_SCH);
+            } else if (S32(a.o32 + E32_STATE) != e->state) {
+              const uint32_t st = e->state;
+              S32(a.o32 + E32_STATE) = st;
+              src = qk_log<LOG, SM>(cx, a, target, SRC_SCH, QK_LOG_ENV_STATE, st, 0);
+              rem = a.n_subs;
+              ptr = QK_HOT_SB(target).subs_off;
+            }
           } else {
-            if (LOG) src = S64(c->olog64 + PL64_SCHED_SRC);
-            S64(G64_FIRE0 + bi) = QK_TIME_NONE;
+            const uint32_t comp = cx.sched[bi];
+            const DevHotA a = QK_HOT_A(comp);
+            if (a.kind == QK_DISCRETE_STOCK) {
+              /* emit_change (discrete.rs:227-233): log the state AT EMISSION TIME, then update_state on every
+               * subscriber in connection order */
+              const DevHotSB sb = QK_HOT_SB(comp);
+              const uint32_t src_seq = qk_emit_pop<LOG, SM>(cx, a, sb.emit_depth);
+              if (LOG) {
+                const uint32_t cnt = S32(a.o32 + S32_HC) >> 16;
+                const uint32_t empty = sb.max > cnt ? sb.max - cnt : 0;
+                src = qk_log<LOG, SM>(cx, a, comp, ((uint64_t)comp << 32) | src_seq, QK_LOG_STOCK_STATE_CHANGE,
+                                      qk_stock_cat(cnt, sb.low, sb.max), ((uint64_t)cnt << 32) | empty);
+              }
+              rem = a.n_subs;
+              ptr = sb.subs_off;
+            } else if (a.kind == QK_VECTOR_STOCK) {
+              /* VectorStock::emit_change (vector.rs:167-171) logs the state carried by the event */
+              const DevHotSB sb = QK_HOT_SB(comp);
+              const DevComp* c = &cx.comps[comp];
+              uint32_t packed = 0;
+              uint64_t occ_bits = 0;
+              if (LOG) {
+                const uint32_t head = (S32(a.o32 + S32_EMIT) >> 16) & 0xFFu;
+                occ_bits = S64(a.olog64 + head);
+              }
+              packed = qk_emit_pop<LOG, SM>(cx, a, sb.emit_depth);
+              src = qk_log<LOG, SM>(cx, a, comp, ((uint64_t)comp << 32) | (packed & 0x3FFFFFFFu),
+                                    QK_LOG_VSTOCK_STATE_CHANGE, packed >> 30, occ_bits);
+              qk_log_vec<LOG, SM>(cx, c, comp, src, 0, __dsub_rn(cx.vecs[c->vec_idx].vmax, QK_U2D(occ_bits)), 0.0, 0.0);
+              rem = a.n_subs;
+              ptr = sb.subs_off;
+            } else {
+              /* keyed update_state(source_event_id) (discrete.rs:549,556) */
+              if (stale) {
+                if (LOG) src = S64(a.olog64 + PL64_STALE_SRC);
+              } else {
+                if (LOG) src = S64(a.olog64 + PL64_SCHED_SRC);
+                S64(G64_FIRE0 + bi) = QK_TIME_NONE;
+              }
+              rem = 1;
+              ptr = ident_off + comp;
+            }
           }
-          rem = 1;
-          ptr = cx.hdr->ident_off + comp;
-        }
+        } /* an action was popped */
       }
-      } /* else: an action was popped */
+      QK_SYNCWARP();
     }
     QK_SYNCWARP();
     if (!QK_ANY_SYNC(!done || rem != 0)) break; /* uniform exit: every lane of the warp has finished */

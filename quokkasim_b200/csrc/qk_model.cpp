@@ -668,9 +668,53 @@ int qk_lower(const qk_model* m, bool log, QkLowered* out) {
   h.n_vec = (uint32_t)vecs.size();
   h.off_vecs = off;
   off = align8(off + (uint32_t)(vecs.size() * sizeof(DevVec)));
+  /* hot rows (see qk_internal.h) */
+  std::vector<DevHot> hot(nc);
+  for (size_t i = 0; i < nc; ++i) {
+    const DevComp& d = dc[i];
+    DevHot& q = hot[i];
+    memset(&q, 0, sizeof(q));
+    q.a.kind = d.kind;
+    q.a.n_dm = d.n_dm;
+    q.a.n_subs = d.n_subs;
+    q.a.src_ord = d.src_ord;
+    q.a.o32 = d.o32;
+    q.a.o64 = d.o64;
+    q.a.fire_idx = d.fire_idx;
+    q.a.flags = d.flags;
+    q.a.olog32 = d.olog32;
+    q.a.olog64 = d.olog64;
+    if (qk_is_process_like(d.kind)) {
+      q.b.up = d.up;
+      q.b.down = d.down;
+      q.b.env = d.env;
+      q.b.dist_time = d.dist_time;
+      q.b.o64_dm = d.o64_dm;
+      q.b.dm_off = d.dm_off;
+      q.b.o64_nextdur = d.o64_nextdur;
+      q.b.pf_idx = d.pf_idx;
+    } else {
+      q.sb.low = d.low;
+      q.sb.max = d.max;
+      q.sb.ring_cap = d.ring_cap;
+      q.sb.emit_depth = d.emit_depth;
+      q.sb.subs_off = d.subs_off;
+      q.sb.o32 = d.o32;
+    }
+    q.c.o64_ttnpe = d.o64_ttnpe;
+    q.c.o32_next_item = d.o32_next_item;
+    q.c.const_dur_lo = d.const_dur_lo;
+    q.c.const_dur_hi = d.const_dur_hi;
+    q.c.vec_idx = d.vec_idx;
+    q.c.ring_cap = d.ring_cap;
+  }
+  off = (off + 15u) & ~15u;
+  h.off_hot = off;
+  off = align8(off + (uint32_t)(nc * sizeof(DevHot)));
   h.total_bytes = off;
 
   out->blob.assign(off, 0);
+  memcpy(out->blob.data() + h.off_hot, hot.data(), nc * sizeof(DevHot));
   memcpy(out->blob.data(), &h, sizeof(h));
   memcpy(out->blob.data() + h.off_comps, dc.data(), nc * sizeof(DevComp));
   if (!dd.empty()) memcpy(out->blob.data() + h.off_dists, dd.data(), dd.size() * sizeof(DevDist));

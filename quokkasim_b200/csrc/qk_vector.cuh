@@ -132,6 +132,7 @@ __device__ __forceinline__ void qk_vstock_area(Ctx& cx, uint32_t sidx, const Dev
 template <bool LOG, int SM>
 __device__ __forceinline__ void qk_vstock_add(Ctx& cx, uint32_t sidx, const double* add, uint64_t src) {
   const DevComp* c = &cx.comps[sidx];
+  const DevHotA ha = QK_HOT_A(sidx);
   const DevVec* v = &cx.vecs[c->vec_idx];
   const uint32_t dim = v->dim;
   double r[3];
@@ -144,7 +145,7 @@ __device__ __forceinline__ void qk_vstock_add(Ctx& cx, uint32_t sidx, const doub
   qk_vstore<SM>(cx, v->o64_res, dim, r);
   QK_ST32_ADD(sidx, ST32_COUNT, 1u);
   const double after = qk_vtotal(r, dim);
-  const uint64_t id = qk_log<LOG, SM>(cx, c, sidx, src, QK_LOG_VSTOCK_ADD, 0, QK_D2U(after));
+  const uint64_t id = qk_log<LOG, SM>(cx, ha, sidx, src, QK_LOG_VSTOCK_ADD, 0, QK_D2U(after));
   qk_log_vec<LOG, SM>(cx, c, sidx, id, 0, add[0], add[1], add[2]);
   const uint32_t cur = qk_vcat(after, low, v->vmax);
   if (prev != cur) qk_vemit_push<LOG, SM>(cx, c, (uint32_t)id, cur, after);
@@ -154,6 +155,7 @@ __device__ __forceinline__ void qk_vstock_add(Ctx& cx, uint32_t sidx, const doub
 template <bool LOG, int SM>
 __device__ __forceinline__ void qk_vstock_remove(Ctx& cx, uint32_t sidx, double q, uint64_t src, double* out) {
   const DevComp* c = &cx.comps[sidx];
+  const DevHotA ha = QK_HOT_A(sidx);
   const DevVec* v = &cx.vecs[c->vec_idx];
   const uint32_t dim = v->dim;
   double r[3];
@@ -165,7 +167,7 @@ __device__ __forceinline__ void qk_vstock_remove(Ctx& cx, uint32_t sidx, double 
   qk_vremove(r, q, dim, out);
   qk_vstore<SM>(cx, v->o64_res, dim, r);
   const double after = qk_vtotal(r, dim);
-  const uint64_t id = qk_log<LOG, SM>(cx, c, sidx, src, QK_LOG_VSTOCK_REMOVE, 0, QK_D2U(after));
+  const uint64_t id = qk_log<LOG, SM>(cx, ha, sidx, src, QK_LOG_VSTOCK_REMOVE, 0, QK_D2U(after));
   qk_log_vec<LOG, SM>(cx, c, sidx, id, 0, out[0], out[1], out[2]);
   const uint32_t cur = qk_vcat(after, low, v->vmax);
   if (prev != cur) qk_vemit_push<LOG, SM>(cx, c, (uint32_t)id, cur, after);
@@ -186,6 +188,8 @@ __device__ __forceinline__ uint64_t qk_dm_next_event(Ctx& cx, const DevComp* c, 
 /* update_state_impl + post_update_state of the five vector process-like components */
 template <bool LOG, int SM>
 __device__ __forceinline__ void qk_update_vector(Ctx& cx, const DevComp* c, uint32_t comp, uint64_t src) {
+  const DevHotA ha = QK_HOT_A(comp);
+  const DevHotB hb = QK_HOT_B(comp);
   const DevVec* v = &cx.vecs[c->vec_idx];
   const uint32_t kind = c->kind, dim = v->dim;
   uint32_t flags = S32(c->o32 + P32_FLAGS);
@@ -207,7 +211,7 @@ __device__ __forceinline__ void qk_update_vector(Ctx& cx, const DevComp* c, uint
         if (kind == QK_VECTOR_COMBINER) {
           /* the running total and quantity were accumulated at CombineStart in the reference's order */
           const double quantity = QK_U2D(S64(v->o64_res + dim));
-          src = qk_log<LOG, SM>(cx, c, comp, src, QK_LOG_VPROC_COMBINE_SUCCESS, 0, QK_D2U(quantity));
+          src = qk_log<LOG, SM>(cx, ha, comp, src, QK_LOG_VPROC_COMBINE_SUCCESS, 0, QK_D2U(quantity));
           qk_log_vec<LOG, SM>(cx, c, comp, src, 0, r[0], r[1], r[2]);
           qk_red_addf64(&cx.gs64[(size_t)(comp * ST_PER_COMP + ST64_FQ) * cx.rep_pad], quantity);
           if (c->down >= 0) qk_vstock_add<LOG, SM>(cx, (uint32_t)c->down, r, src);
@@ -218,7 +222,7 @@ __device__ __forceinline__ void qk_update_vector(Ctx& cx, const DevComp* c, uint
             double clone[3] = {r[0], r[1], r[2]};
             qk_vremove(clone, __dmul_rn(total, v->ratios[i]), dim, parts[i]);
           }
-          src = qk_log<LOG, SM>(cx, c, comp, src, QK_LOG_VPROC_SPLIT_SUCCESS, 0, QK_D2U(total));
+          src = qk_log<LOG, SM>(cx, ha, comp, src, QK_LOG_VPROC_SPLIT_SUCCESS, 0, QK_D2U(total));
           for (uint32_t i = 0; i < v->n_ports; ++i) qk_log_vec<LOG, SM>(cx, c, comp, src, i, parts[i][0], parts[i][1], parts[i][2]);
           qk_red_addf64(&cx.gs64[(size_t)(comp * ST_PER_COMP + ST64_FQ) * cx.rep_pad], total);
           for (uint32_t i = 0; i < v->n_ports; ++i)
@@ -228,7 +232,7 @@ __device__ __forceinline__ void qk_update_vector(Ctx& cx, const DevComp* c, uint
             }
         } else {
           const double quantity = qk_vtotal(r, dim);
-          src = qk_log<LOG, SM>(cx, c, comp, src, QK_LOG_VPROC_SUCCESS, 0, QK_D2U(quantity));
+          src = qk_log<LOG, SM>(cx, ha, comp, src, QK_LOG_VPROC_SUCCESS, 0, QK_D2U(quantity));
           qk_log_vec<LOG, SM>(cx, c, comp, src, 0, r[0], r[1], r[2]);
           qk_red_addf64(&cx.gs64[(size_t)(comp * ST_PER_COMP + ST64_FQ) * cx.rep_pad], quantity);
           if (kind != QK_VECTOR_SINK && c->down >= 0) qk_vstock_add<LOG, SM>(cx, (uint32_t)c->down, r, src);
@@ -243,11 +247,11 @@ __device__ __forceinline__ void qk_update_vector(Ctx& cx, const DevComp* c, uint
     const bool tick = kind == QK_VECTOR_SOURCE ? (is_in_delay || is_in_process)
                                                : (!is_env_blocked && (is_in_delay || is_in_process));
     if (c->n_dm && tick) {
-      qk_tick_delays<LOG, SM>(cx, c, comp, &flags, dt, &src);
+      qk_tick_delays<LOG, SM>(cx, ha, hb, comp, &flags, dt, &src);
       if (cx.status) return;
     }
   }
-  if (c->env >= 0 || (flags & PF_ENV_STOPPED)) qk_refresh_env<LOG, SM>(cx, c, comp, &flags, &src);
+  if (c->env >= 0 || (flags & PF_ENV_STOPPED)) qk_refresh_env<LOG, SM>(cx, ha, c->env, comp, &flags, &src);
 
   const bool has_item = (flags & PF_HAS_ITEM) != 0;
   const uint32_t fixmask = (flags >> PF_FIX_SHIFT) & 0xFFu;
@@ -315,7 +319,7 @@ __device__ __forceinline__ void qk_update_vector(Ctx& cx, const DevComp* c, uint
         const double factor = __ddiv_rn(q, st);
         for (uint32_t k = 0; k < 3; ++k) got[0][k] = k < dim ? __dmul_rn(v->vinit[k], factor) : 0.0;
       } else {
-        src = qk_log<LOG, SM>(cx, c, comp, src, QK_LOG_WITHDRAW_REQUEST, 0, 0);
+        src = qk_log<LOG, SM>(cx, ha, comp, src, QK_LOG_WITHDRAW_REQUEST, 0, 0);
         if (kind == QK_VECTOR_COMBINER) {
           start_kind = QK_LOG_VPROC_COMBINE_START;
           ngot = v->n_ports;
@@ -346,12 +350,12 @@ __device__ __forceinline__ void qk_update_vector(Ctx& cx, const DevComp* c, uint
       } else {
         qk_vstore<SM>(cx, v->o64_res, dim, got[0]);
       }
-      const uint64_t id = qk_log<LOG, SM>(cx, c, comp, src, start_kind, 0, QK_D2U(q));
+      const uint64_t id = qk_log<LOG, SM>(cx, ha, comp, src, start_kind, 0, QK_D2U(q));
       for (uint32_t i = 0; i < ngot; ++i) qk_log_vec<LOG, SM>(cx, c, comp, id, i, got[i][0], got[i][1], got[i][2]);
       if (kind != QK_VECTOR_SINK) src = id; /* VectorSink drops the returned id (vector.rs:1747) */
       ttnpe = d;
     } else {
-      const uint64_t id = qk_log<LOG, SM>(cx, c, comp, src, QK_LOG_VPROC_FAILURE, fail, 0);
+      const uint64_t id = qk_log<LOG, SM>(cx, ha, comp, src, QK_LOG_VPROC_FAILURE, fail, 0);
       if (kind != QK_VECTOR_SINK) src = id;
     }
   } else if (has_item && !has_active_delay) {
@@ -374,7 +378,7 @@ __device__ __forceinline__ void qk_update_vector(Ctx& cx, const DevComp* c, uint
   }
   S32(c->o32 + P32_FLAGS) = flags;
   S64(c->o64 + P64_LEFT) = left;
-  qk_post<LOG, SM>(cx, c, next, src);
+  qk_post<LOG, SM>(cx, ha, next, src);
   S64(c->o64 + P64_PREV) = cx.now;
 }
 
