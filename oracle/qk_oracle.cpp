@@ -1189,6 +1189,18 @@ int orc_sim_comp_stats(orc_sim* s, uint32_t comp, orc_comp_stats* out) {
   if (comp >= s->c.size()) return -1;
   s->finalize_stats();
   *out = s->c[comp].st;
+  /* busy time is reported up to the CLOCK (not up to the component's last update_state): add the part of the
+   * countdown that has elapsed since previous_check_time but has not been applied yet */
+  const Comp& p = s->c[comp];
+  const uint32_t kind = s->m->comps[comp].kind;
+  if (is_process_like(kind) && !(s->dm_active(p) >= 0 || p.env_stopped)) {
+    const uint64_t dt = s->now - p.previous_check_time;
+    if (kind == ORC_DISCRETE_PARALLEL_PROCESS) {
+      for (size_t i = 0; i < p.in_progress.size(); ++i) out->t_a_ns += std::min(dt, p.in_progress[i].first);
+    } else if (p.has_item) {
+      out->t_a_ns += std::min(dt, p.left);
+    }
+  }
   return 0;
 }
 uint64_t orc_sim_stock_items(const orc_sim* s, uint32_t comp, uint32_t* buf, uint64_t cap) {

@@ -19,6 +19,7 @@ FLAGS = [
     "--fmad=false",  # fp64 parity: no contraction anywhere in the product
     "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off",
     "-Xptxas", "-v",
+    "--split-compile", "0",  # ptxas over the kernel instantiations in parallel (build time only)
     "-shared", "-cudart", "static",
 ]
 

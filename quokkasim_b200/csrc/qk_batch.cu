@@ -65,23 +65,27 @@ struct qk_batch {
 
 /* one instantiation per (logging, state placement, block size): the block size is a template constant so that
  * state-slot offsets become LDS/STS immediates */
-template <bool LOG>
-static StepKernel pick_kernel_log(bool hbm, uint32_t nt) {
-  if (hbm) return qk_step_kernel<LOG, 0>;
+template <bool LOG, int FT>
+static StepKernel pick_kernel_ft(uint32_t nt) {
   switch (nt) {
-    case 32: return qk_step_kernel<LOG, 32>;
-    case 64: return qk_step_kernel<LOG, 64>;
-    case 96: return qk_step_kernel<LOG, 96>;
-    case 128: return qk_step_kernel<LOG, 128>;
-    case 160: return qk_step_kernel<LOG, 160>;
-    case 192: return qk_step_kernel<LOG, 192>;
-    case 224: return qk_step_kernel<LOG, 224>;
-    case 256: return qk_step_kernel<LOG, 256>;
-    default: return qk_step_kernel<LOG, -1>;
+    case 32: return qk_step_kernel<LOG, 32, FT>;
+    case 64: return qk_step_kernel<LOG, 64, FT>;
+    case 96: return qk_step_kernel<LOG, 96, FT>;
+    case 128: return qk_step_kernel<LOG, 128, FT>;
+    case 160: return qk_step_kernel<LOG, 160, FT>;
+    case 192: return qk_step_kernel<LOG, 192, FT>;
+    case 224: return qk_step_kernel<LOG, 224, FT>;
+    case 256: return qk_step_kernel<LOG, 256, FT>;
+    default: return qk_step_kernel<LOG, -1, 1>;
   }
 }
-static StepKernel pick_kernel(bool log, bool hbm, uint32_t nt) {
-  return log ? pick_kernel_log<true>(hbm, nt) : pick_kernel_log<false>(hbm, nt);
+template <bool LOG>
+static StepKernel pick_kernel_log(bool hbm, uint32_t nt, uint32_t features) {
+  if (hbm) return qk_step_kernel<LOG, 0, 1>;
+  return features ? pick_kernel_ft<LOG, 1>(nt) : pick_kernel_ft<LOG, 0>(nt);
+}
+static StepKernel pick_kernel(bool log, bool hbm, uint32_t nt, uint32_t features) {
+  return log ? pick_kernel_log<true>(hbm, nt, features) : pick_kernel_log<false>(hbm, nt, features);
 }
 
 static uint32_t choose_nt(uint32_t per_rep_bytes, uint32_t table_bytes, uint32_t* threads_per_sm) {
@@ -89,7 +93,7 @@ static uint32_t choose_nt(uint32_t per_rep_bytes, uint32_t table_bytes, uint32_t
   for (uint32_t nt = 256; nt >= 32; nt -= 32) {
     const uint64_t bytes = (uint64_t)table_bytes + (uint64_t)per_rep_bytes * nt;
     if (bytes > 227u * 1024u) continue;
-    uint32_t bps = (uint32_t)((228u * 1024u) / (bytes + 1024u));
+    uint32_t bps = (uint32_t)((227u * 1024u) / (bytes + 1024u));
     if (bps > 32) bps = 32;
     uint32_t thr = bps * nt;
     if (thr > 2048) thr = 2048;
@@ -102,7 +106,7 @@ static uint32_t choose_nt(uint32_t per_rep_bytes, uint32_t table_bytes, uint32_t
    * until its slowest warp finishes, so small blocks recycle capacity sooner (measured: 64 beats 128..256) */
   for (uint32_t nt = 64; nt < best_nt; nt += 32) {
     const uint64_t bytes = (uint64_t)table_bytes + (uint64_t)per_rep_bytes * nt;
-    uint32_t bps = (uint32_t)((228u * 1024u) / (bytes + 1024u));
+    uint32_t bps = (uint32_t)((227u * 1024u) / (bytes + 1024u));
     if (bps > 32) bps = 32;
     uint32_t thr = bps * nt;
     if (thr > 2048) thr = 2048;
@@ -416,7 +420,7 @@ int qk_batch_create(const qk_model* m, const qk_batch_config* cfg, qk_batch** ou
   CUDA_TRY(cudaMalloc(&b->d_tape_len, sizeof(uint64_t) * (h.n_dist ? h.n_dist : 1)));
   CUDA_TRY(cudaMemset(b->d_tapes, 0, sizeof(double*) * (h.n_dist ? h.n_dist : 1)));
   CUDA_TRY(cudaMemset(b->d_tape_len, 0, sizeof(uint64_t) * (h.n_dist ? h.n_dist : 1)));
-  b->kernel = pick_kernel(b->log, b->hbm, b->nt);
+  b->kernel = pick_kernel(b->log, b->hbm, b->nt, h.features);
   CUDA_TRY(cudaFuncSetAttribute((const void*)b->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   b->red_blocks = 148 * 4;
   CUDA_TRY(cudaMalloc(&b->d_sums, sizeof(uint64_t) * 6 * h.n_comp));

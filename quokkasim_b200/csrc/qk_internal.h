@@ -66,6 +66,7 @@ enum { ST64_TIME = 0, ST64_DELAY = 1, ST64_FQ = 2, ST32_COUNT = 0, ST32_MAXOCC =
 enum { E32_STATE = 0, E32_COUNT = 1 };
 
 #define DC_LOGGED 1u
+#define DC_SIMPLE 2u /* single-server discrete component without delay modes or environment (quick path) */
 
 typedef struct {
   uint8_t kind;    /* qk_component_kind */
@@ -181,7 +182,8 @@ typedef struct {
   uint32_t total_bytes;
   uint32_t log_enabled;
   uint32_t off_hot; /* DevHot[n_comp], 16-byte aligned */
-  uint32_t pad[3];
+  uint32_t features; /* 0 = every process-like component is SIMPLE and nothing is scheduled externally ; 1 = general */
+  uint32_t pad[2];
 } DevHeader;
 
 #endif

@@ -51,7 +51,7 @@ struct Ctx {
   uint32_t stride;         /* on-chip: threads per block ; HBM: padded replication count */
   uint64_t* gs64;          /* statistics planes, offset to this replication; row stride = rep_pad */
   uint32_t* gs32;
-  uint64_t rep_pad;
+  uint32_t rep_pad; /* < 2^32 replications per batch */
   const DevHeader* hdr;
   const DevComp* comps;
   const DevDist* dists;
@@ -100,9 +100,10 @@ __device__ __forceinline__ auto qk_ix(uint32_t slot, uint32_t stride) {
 #define S64(slot) (qk_p64<SM>(cx)[qk_ix<SM>((uint32_t)(slot), cx.stride)])
 #define S32(slot) (qk_p32<SM>(cx)[qk_ix<SM>((uint32_t)(slot), cx.stride)])
 /* statistics accumulators: fire-and-forget RED atomics on the HBM planes (see qk_internal.h) */
-#define QK_ST64_ADD(comp, k, v) qk_red_add64(&cx.gs64[(size_t)((comp)*ST_PER_COMP + (k)) * cx.rep_pad], (v))
-#define QK_ST32_ADD(comp, k, v) qk_red_add32(&cx.gs32[(size_t)((comp)*ST_PER_COMP + (k)) * cx.rep_pad], (v))
-#define QK_ST32_MAX(comp, k, v) qk_red_max32(&cx.gs32[(size_t)((comp)*ST_PER_COMP + (k)) * cx.rep_pad], (v))
+#define QK_STROW(comp, k) ((uint64_t)(uint32_t)((comp)*ST_PER_COMP + (k)) * cx.rep_pad)
+#define QK_ST64_ADD(comp, k, v) qk_red_add64(&cx.gs64[QK_STROW(comp, k)], (v))
+#define QK_ST32_ADD(comp, k, v) qk_red_add32(&cx.gs32[QK_STROW(comp, k)], (v))
+#define QK_ST32_MAX(comp, k, v) qk_red_max32(&cx.gs32[QK_STROW(comp, k)], (v))
 #define SRC_INIT (((uint64_t)QK_SRC_INIT) << 32)
 #define SRC_SCH (((uint64_t)QK_SRC_SCH) << 32)
 
@@ -432,34 +433,37 @@ __device__ __forceinline__ void qk_pre(Ctx& cx, const DevHotA& c) {
 }
 
 /* ---- quick path ----------------------------------------------------------------------------------------------
- * Most update_state calls change nothing but the countdown: a stock's emit_change is broadcast to every connected
- * process, and a process that is busy (or idle and still blocked) only refreshes `previous_check_time`.  The event
- * loop handles those calls while it walks a call list, so that the UPDATE phase -- the long, divergent handler --
- * is only entered with calls that finish or start something.  Returns false (state untouched) when the call needs
- * the full handler; otherwise it has done exactly what qk_update_single would have done. */
-template <bool LOG, int SM>
+ * Most update_state calls change nothing: a stock's emit_change is broadcast to every connected process, and a
+ * process that is busy, or idle and still blocked, has nothing to do.  The event loop disposes of those calls while
+ * it walks a call list, so the UPDATE phase -- the long, divergent handler -- only sees calls that finish or start
+ * something.  Quick handling is limited to SIMPLE components (single-server, no delay modes, no environment), for
+ * which two invariants hold between calls:
+ *     busy  <=>  fire != NONE, and then fire == previous_check_time + left (the finish time);
+ *     idle   =>  the sink's persistent ttnpe is NONE.
+ * (left, previous_check_time) is only ever used as the pair "left at previous_check_time", so a busy no-op call may
+ * leave it untouched: the next real call subtracts the whole elapsed time at once (saturating subtraction composes),
+ * and statistics read-outs evaluate the countdown at the clock (qk_left_at_clock).  Hence a quick call of a busy
+ * component is one table quad + one state load, and it writes nothing.
+ * Returns false (state untouched) when the call needs the full handler. */
+template <bool LOG, int SM, int FT>
 __device__ __forceinline__ bool qk_try_quick(Ctx& cx, uint32_t comp, uint64_t src) {
   const DevHotA c = QK_HOT_A(comp);
-  const uint32_t kind = c.kind;
-  if (kind < QK_DISCRETE_PROCESS || kind > QK_DISCRETE_SINK || c.n_dm != 0) return false;
-  const DevHotB cb = QK_HOT_B(comp);
-  const uint32_t flags = S32(c.o32 + P32_FLAGS);
-  if (cb.env >= 0 || (flags & PF_ENV_STOPPED)) return false;
+  if (FT != 0 && !(c.flags & DC_SIMPLE)) return false;
   const uint64_t fire = S64(G64_FIRE0 + c.fire_idx);
-  if (fire <= cx.now) return false; /* pre_update_state would drop the handle (Q3) */
-  if (flags & PF_HAS_ITEM) {
-    const uint64_t left = S64(c.o64 + P64_LEFT);
-    const uint64_t dt = cx.now - S64(c.o64 + P64_PREV);
-    if (left <= dt) return false; /* finishes */
-    const uint64_t rest = left - dt;
-    /* ttnpe: Process (Some,false) / Source (Some,_) = what is left ; Sink keeps its previous value */
-    const uint64_t ttnpe = kind == QK_DISCRETE_SINK ? S64(QK_HOT_C(comp).o64_ttnpe) : rest;
-    if (ttnpe != QK_TIME_NONE && (ttnpe == 0 || cx.now + ttnpe < fire)) return false; /* fault / reschedule */
-    S64(c.o64 + P64_LEFT) = rest;
-    S64(c.o64 + P64_PREV) = cx.now;
-    return true;
+  if (fire != QK_TIME_NONE) {
+#ifdef QK_HOST_EMUL
+    if (fire > cx.now && (!(S32(c.o32 + P32_FLAGS) & PF_HAS_ITEM) ||
+                          S64(c.o64 + P64_PREV) + S64(c.o64 + P64_LEFT) != fire))
+      cx.status = 98; /* invariant check, CPU test build only */
+#endif
+    return fire > cx.now; /* busy and not due: nothing to do ; due (<= now): pre_update_state drops the handle (Q3) */
   }
+#ifdef QK_HOST_EMUL
+  if (S32(c.o32 + P32_FLAGS) & PF_HAS_ITEM) cx.status = 98;
+#endif
   /* idle: quick only if it stays idle */
+  const DevHotB cb = QK_HOT_B(comp);
+  const uint32_t kind = c.kind;
   const bool need_us = kind != QK_DISCRETE_SOURCE, need_ds = kind != QK_DISCRETE_SINK;
   const uint32_t us = need_us ? qk_stock_cat_of<SM>(cx, cb.up) : 1u;
   const uint32_t ds = need_ds ? qk_stock_cat_of<SM>(cx, cb.down) : 1u;
@@ -476,13 +480,11 @@ __device__ __forceinline__ bool qk_try_quick(Ctx& cx, uint32_t comp, uint64_t sr
       reason = QK_REASON_DOWNSTREAM_NOT_CONNECTED;
     qk_log<LOG, SM>(cx, c, comp, src, QK_LOG_PROCESS_NONSTART, reason, 0);
   }
-  if (kind == QK_DISCRETE_SINK) S64(QK_HOT_C(comp).o64_ttnpe) = QK_TIME_NONE;
-  S64(c.o64 + P64_PREV) = cx.now;
   return true;
 }
 
 /* ---- DiscreteProcess / DiscreteSource / DiscreteSink update_state, one code path ----------------------------- */
-template <bool LOG, int SM>
+template <bool LOG, int SM, int FT>
 __device__ __forceinline__ void qk_update_single(Ctx& cx, const DevHotA& c, uint32_t comp, uint64_t src) {
   const DevHotB cb = QK_HOT_B(comp);
   const uint32_t kind = c.kind;
@@ -508,16 +510,16 @@ __device__ __forceinline__ void qk_update_single(Ctx& cx, const DevHotA& c, uint
         }
       }
     }
-    if (c.n_dm && !is_env_blocked && (is_in_delay || is_in_process)) {
+    if (FT != 0 && c.n_dm && !is_env_blocked && (is_in_delay || is_in_process)) {
       qk_tick_delays<LOG, SM>(cx, c, cb, comp, &flags, dt, &src);
       if (cx.status) return;
     }
   }
-  if (cb.env >= 0 || (flags & PF_ENV_STOPPED)) qk_refresh_env<LOG, SM>(cx, c, cb.env, comp, &flags, &src);
+  if (FT != 0 && (cb.env >= 0 || (flags & PF_ENV_STOPPED))) qk_refresh_env<LOG, SM>(cx, c, cb.env, comp, &flags, &src);
 
   const bool has_item = (flags & PF_HAS_ITEM) != 0;
-  const uint32_t fixmask = (flags >> PF_FIX_SHIFT) & 0xFFu;
-  const bool has_active_delay = fixmask != 0 || (flags & PF_ENV_STOPPED) != 0;
+  const uint32_t fixmask = FT != 0 ? (flags >> PF_FIX_SHIFT) & 0xFFu : 0u;
+  const bool has_active_delay = FT != 0 && (fixmask != 0 || (flags & PF_ENV_STOPPED) != 0);
   if (!has_item && !has_active_delay) {
     /* match (&us_state, &ds_state) discrete.rs:480-516 / 854-872 / 1100-1125; 3 == not connected */
     const bool need_us = kind != QK_DISCRETE_SOURCE, need_ds = kind != QK_DISCRETE_SINK;
@@ -700,30 +702,32 @@ __device__ __forceinline__ void qk_update_parallel(Ctx& cx, const DevComp* c, ui
 #include "qk_vector.cuh"
 
 /* Process::update_state (core.rs:370-376) */
-template <bool LOG, int SM>
+template <bool LOG, int SM, int FT>
 __device__ __forceinline__ void qk_update_state(Ctx& cx, uint32_t comp, uint64_t src) {
   const DevHotA a = QK_HOT_A(comp);
-  if (a.kind >= QK_DISCRETE_PROCESS && a.kind <= QK_DISCRETE_SINK) {
+  if (FT == 0 || (a.kind >= QK_DISCRETE_PROCESS && a.kind <= QK_DISCRETE_SINK)) {
     qk_pre<LOG, SM>(cx, a);
-    qk_update_single<LOG, SM>(cx, a, comp, src);
+    qk_update_single<LOG, SM, FT>(cx, a, comp, src);
     return;
   }
-  const DevComp* c = &cx.comps[comp];
-  if (a.kind == QK_ENVIRONMENT) { /* only reached from the init list: BasicEnvironment::init logs its state */
-    qk_log<LOG, SM>(cx, a, comp, src, QK_LOG_ENV_STATE, S32(a.o32 + E32_STATE), 0);
-    return;
-  }
-  if (a.kind >= QK_VECTOR_PROCESS) {
-    /* Combiner / Splitter / VectorSource / VectorSink init with their own next id instead of INIT_000000
-     * (vector.rs:774,1111,1393,1619); SRC_INIT only ever arrives from the init list */
-    if (LOG && src == SRC_INIT && a.kind != QK_VECTOR_PROCESS)
-      src = ((uint64_t)comp << 32) | S32(a.olog32 + L32_SEQ);
+  if constexpr (FT != 0) {
+    const DevComp* c = &cx.comps[comp];
+    if (a.kind == QK_ENVIRONMENT) { /* only reached from the init list: BasicEnvironment::init logs its state */
+      qk_log<LOG, SM>(cx, a, comp, src, QK_LOG_ENV_STATE, S32(a.o32 + E32_STATE), 0);
+      return;
+    }
+    if (a.kind >= QK_VECTOR_PROCESS) {
+      /* Combiner / Splitter / VectorSource / VectorSink init with their own next id instead of INIT_000000
+       * (vector.rs:774,1111,1393,1619); SRC_INIT only ever arrives from the init list */
+      if (LOG && src == SRC_INIT && a.kind != QK_VECTOR_PROCESS)
+        src = ((uint64_t)comp << 32) | S32(a.olog32 + L32_SEQ);
+      qk_pre<LOG, SM>(cx, a);
+      qk_update_vector<LOG, SM>(cx, c, comp, src);
+      return;
+    }
     qk_pre<LOG, SM>(cx, a);
-    qk_update_vector<LOG, SM>(cx, c, comp, src);
-    return;
+    qk_update_parallel<LOG, SM>(cx, c, comp, src);
   }
-  qk_pre<LOG, SM>(cx, a);
-  qk_update_parallel<LOG, SM>(cx, c, comp, src);
 }
 
 /* ============================================ the kernel ============================================ */
@@ -737,7 +741,10 @@ constexpr int qk_lb_blocks(int sm) { return sm > 0 ? (512 / sm > 0 ? 512 / sm : 
 /* shared memory admits roughly 512 resident threads per SM for the models this path targets, so ask ptxas for that
  * occupancy explicitly (<= 128 registers); a bare __launch_bounds__(SM) made it cap some instantiations at 80
  * registers and spill */
-template <bool LOG, int SM>
+/* FT = feature set of the model: 0 = only SIMPLE single-server discrete components and stocks (no delay modes, no
+ * environment, no scheduled events, no parallel or vector components): the handlers for everything else are
+ * compiled out, which frees registers ; 1 = everything */
+template <bool LOG, int SM, int FT>
 __global__ void __launch_bounds__(qk_lb_threads(SM), qk_lb_blocks(SM)) qk_step_kernel(const __grid_constant__ KParams P) {
   uint8_t* const smem = qk_smem;
   const uint32_t tid = QK_TID, nt = SM > 0 ? (uint32_t)SM : QK_NT;
@@ -780,7 +787,7 @@ __global__ void __launch_bounds__(qk_lb_threads(SM), qk_lb_blocks(SM)) qk_step_k
   cx.rep_local = rep_local;
   cx.gs64 = P.gs64 + rep_local;
   cx.gs32 = P.gs32 + rep_local;
-  cx.rep_pad = P.rep_pad;
+  cx.rep_pad = (uint32_t)P.rep_pad;
   cx.key0 = (uint32_t)P.seed;
   cx.key1 = (uint32_t)(P.seed >> 32);
   cx.rep_lo = (uint32_t)rep_global;
@@ -866,12 +873,14 @@ __global__ void __launch_bounds__(qk_lb_threads(SM), qk_lb_blocks(SM)) qk_step_k
   uint64_t src = SRC_INIT;
   uint32_t ext_cursor = S32(G32_EXT_CURSOR);
   bool done = false;
+  bool keyed = false; /* the pending call is a component's own keyed event: its fire slot was just cleared, so the
+                         quick path's "fire == NONE means idle" does not apply -- always the full handler */
   for (;;) {
     QK_SYNCWARP();
 #pragma unroll 1
     for (int it = 0; it < QK_SCAN_ITERS; ++it) {
       /* dispose of the quick calls at the head of the list */
-      while (rem != 0 && qk_try_quick<LOG, SM>(cx, cx.subs[ptr], src)) {
+      while (rem != 0 && !keyed && qk_try_quick<LOG, SM, FT>(cx, cx.subs[ptr], src)) {
         ptr += 1;
         rem -= 1;
       }
@@ -879,7 +888,7 @@ __global__ void __launch_bounds__(qk_lb_threads(SM), qk_lb_blocks(SM)) qk_step_k
       if (!QK_ANY_SYNC(rem == 0 && !done)) break; /* every lane stands on a full call or has finished */
       if (rem == 0 && !done) {
         /* pop the scheduler queue: min over (time, rank); rank 0 = externally scheduled events */
-        uint64_t best = ext_cursor < n_ext ? cx.ext[ext_cursor].t : QK_TIME_NONE;
+        uint64_t best = (FT != 0 && ext_cursor < n_ext) ? cx.ext[ext_cursor].t : QK_TIME_NONE;
         int bi = -1;
         for (uint32_t i = 0; i < n_sched; ++i) {
           const uint64_t t = S64(G64_FIRE0 + i);
@@ -910,7 +919,7 @@ __global__ void __launch_bounds__(qk_lb_threads(SM), qk_lb_blocks(SM)) qk_step_k
           if (stale) S32(G32_STALE0 + stale_word) = stale_mask;
           cx.now = best;
           events_done += 1;
-          if (bi < 0) {
+          if (FT != 0 && bi < 0) {
             /* ScheduledEventConfig::SetEnvironmentState -> BasicEnvironment::set_state (core.rs:256-265, 1393-1396) */
             const DevExt* e = &cx.ext[ext_cursor];
             ext_cursor += 1;
@@ -944,7 +953,7 @@ __global__ void __launch_bounds__(qk_lb_threads(SM), qk_lb_blocks(SM)) qk_step_k
               }
               rem = a.n_subs;
               ptr = sb.subs_off;
-            } else if (a.kind == QK_VECTOR_STOCK) {
+            } else if (FT != 0 && a.kind == QK_VECTOR_STOCK) {
               /* VectorStock::emit_change (vector.rs:167-171) logs the state carried by the event */
               const DevHotSB sb = QK_HOT_SB(comp);
               const DevComp* c = &cx.comps[comp];
@@ -967,6 +976,7 @@ __global__ void __launch_bounds__(qk_lb_threads(SM), qk_lb_blocks(SM)) qk_step_k
               } else {
                 if (LOG) src = S64(a.olog64 + PL64_SCHED_SRC);
                 S64(G64_FIRE0 + bi) = QK_TIME_NONE;
+                keyed = true;
               }
               rem = 1;
               ptr = ident_off + comp;
@@ -994,7 +1004,8 @@ __global__ void __launch_bounds__(qk_lb_threads(SM), qk_lb_blocks(SM)) qk_step_k
       const uint32_t p = cx.subs[ptr];
       ptr += 1;
       rem -= 1;
-      qk_update_state<LOG, SM>(cx, p, src);
+      qk_update_state<LOG, SM, FT>(cx, p, src);
+      keyed = false;
       if (cx.status) rem = 0;
     }
   }
@@ -1010,6 +1021,14 @@ __global__ void __launch_bounds__(qk_lb_threads(SM), qk_lb_blocks(SM)) qk_step_k
     for (uint32_t s = 0; s < P.n64; ++s) P.g64[(size_t)s * P.rep_pad + rep_local] = S64(s);
     for (uint32_t s = 0; s < P.n32; ++s) P.g32[(size_t)s * P.rep_pad + rep_local] = S32(s);
   }
+}
+
+/* what is left of a countdown at the CLOCK: state keeps (left, previous_check_time) as of the component's last
+ * update_state; busy time is reported up to `now`, so the elapsed-but-unapplied part counts as consumed unless a
+ * delay or the environment has paused the countdown */
+__device__ __forceinline__ uint64_t qk_left_at_clock(uint32_t flags, uint64_t left, uint64_t dt) {
+  if (((flags >> PF_FIX_SHIFT) & 0xFFu) != 0 || (flags & PF_ENV_STOPPED)) return left;
+  return left - (dt < left ? dt : left);
 }
 
 /* per-replication (count, time_ns, aux, level) of component c, from the HBM state planes */
@@ -1047,7 +1066,7 @@ __device__ __forceinline__ void qk_comp_stats_dev(const DevComp* c, const DevVec
       r[2] = QK_U2D(G64(v->o64_res + 2));
     }
     o->count = GS32(ST32_COUNT);
-    o->time_ns = GS64(ST64_TIME) - (has ? G64(c->o64 + P64_LEFT) : 0);
+    o->time_ns = GS64(ST64_TIME) - (has ? qk_left_at_clock(flags, G64(c->o64 + P64_LEFT), now - G64(c->o64 + P64_PREV)) : 0);
     o->aux = GS64(ST64_DELAY);
     o->level = has ? 1 : 0;
     o->fvalue = QK_U2D(GS64(ST64_FQ));
@@ -1060,8 +1079,10 @@ __device__ __forceinline__ void qk_comp_stats_dev(const DevComp* c, const DevVec
     o->level = cnt;
   } else if (c->kind == QK_DISCRETE_PARALLEL_PROCESS) {
     const uint32_t nprog = G32(c->o32 + PP32_NPROG);
+    const uint32_t pflags = G32(c->o32 + PP32_FLAGS);
+    const uint64_t pdt = now - G64(c->o64 + PP64_PREV);
     uint64_t busy = GS64(ST64_TIME);
-    for (uint32_t i = 0; i < nprog; ++i) busy -= G64(c->o64_dm + c->n_dm + i);
+    for (uint32_t i = 0; i < nprog; ++i) busy -= qk_left_at_clock(pflags, G64(c->o64_dm + c->n_dm + i), pdt);
     o->count = GS32(ST32_COUNT);
     o->time_ns = busy;
     o->aux = GS64(ST64_DELAY);
@@ -1075,7 +1096,7 @@ __device__ __forceinline__ void qk_comp_stats_dev(const DevComp* c, const DevVec
     const uint32_t flags = G32(c->o32 + P32_FLAGS);
     const bool has = flags & PF_HAS_ITEM;
     o->count = GS32(ST32_COUNT);
-    o->time_ns = GS64(ST64_TIME) - (has ? G64(c->o64 + P64_LEFT) : 0);
+    o->time_ns = GS64(ST64_TIME) - (has ? qk_left_at_clock(flags, G64(c->o64 + P64_LEFT), now - G64(c->o64 + P64_PREV)) : 0);
     o->aux = GS64(ST64_DELAY);
     o->level = has ? 1 : 0;
   }

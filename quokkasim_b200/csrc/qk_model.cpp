@@ -670,6 +670,7 @@ int qk_lower(const qk_model* m, bool log, QkLowered* out) {
   off = align8(off + (uint32_t)(vecs.size() * sizeof(DevVec)));
   /* hot rows (see qk_internal.h) */
   std::vector<DevHot> hot(nc);
+  h.features = ext.empty() ? 0 : 1;
   for (size_t i = 0; i < nc; ++i) {
     const DevComp& d = dc[i];
     DevHot& q = hot[i];
@@ -682,6 +683,9 @@ int qk_lower(const qk_model* m, bool log, QkLowered* out) {
     q.a.o64 = d.o64;
     q.a.fire_idx = d.fire_idx;
     q.a.flags = d.flags;
+    const bool single = d.kind == QK_DISCRETE_PROCESS || d.kind == QK_DISCRETE_SOURCE || d.kind == QK_DISCRETE_SINK;
+    if (single && d.n_dm == 0 && d.env < 0) q.a.flags |= DC_SIMPLE;
+    if (!(d.kind == QK_DISCRETE_STOCK || (q.a.flags & DC_SIMPLE))) h.features = 1;
     q.a.olog32 = d.olog32;
     q.a.olog64 = d.olog64;
     if (qk_is_process_like(d.kind)) {

@@ -66,10 +66,15 @@ static int run(qk_batch* b, uint32_t do_init, uint64_t t0, uint64_t t_until, uin
   for (uint64_t r = 0; r < b->rep_pad; ++r) {
     qk_emul_bid = (uint32_t)r;
     const bool hbm = (b->cfg.flags & QK_BATCH_STATE_IN_HBM) != 0;
+    /* the product picks FT = 0 only for on-chip state; here both state placements run both feature sets so the
+     * CPU suite covers the lean kernel on every simple model */
+    const bool ft = b->low.hdr.features != 0;
     if (b->log) {
-      if (hbm) qk_step_kernel<true, 0>(P); else qk_step_kernel<true, -1>(P);
+      if (hbm) { if (ft) qk_step_kernel<true, 0, 1>(P); else qk_step_kernel<true, 0, 0>(P); }
+      else { if (ft) qk_step_kernel<true, -1, 1>(P); else qk_step_kernel<true, -1, 0>(P); }
     } else {
-      if (hbm) qk_step_kernel<false, 0>(P); else qk_step_kernel<false, -1>(P);
+      if (hbm) { if (ft) qk_step_kernel<false, 0, 1>(P); else qk_step_kernel<false, 0, 0>(P); }
+      else { if (ft) qk_step_kernel<false, -1, 1>(P); else qk_step_kernel<false, -1, 0>(P); }
     }
   }
   qk_emul_smem = nullptr;
