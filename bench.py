@@ -27,6 +27,7 @@ WORKLOADS = {
     "discrete_queue": ("discrete_queue", {}, 1048576, 10000),
     "serial_line": ("serial_line", {"n_proc": 32}, 100000, 100000),
     "haulage": ("haulage", {"n_src": 8, "per_queue": 8}, 262144, 10000),
+    "vector_flow": ("vector_flow", {"dim": 3}, 262144, 10000),
 }
 
 

@@ -81,7 +81,7 @@ static StepKernel pick_kernel_ft(uint32_t nt) {
 }
 template <bool LOG>
 static StepKernel pick_kernel_log(bool hbm, uint32_t nt, uint32_t features) {
-  if (hbm) return qk_step_kernel<LOG, 0, 1>;
+  if (hbm) return features ? qk_step_kernel<LOG, 0, 1> : qk_step_kernel<LOG, 0, 0>;
   return features ? pick_kernel_ft<LOG, 1>(nt) : pick_kernel_ft<LOG, 0>(nt);
 }
 static StepKernel pick_kernel(bool log, bool hbm, uint32_t nt, uint32_t features) {
@@ -102,15 +102,16 @@ static uint32_t choose_nt(uint32_t per_rep_bytes, uint32_t table_bytes, uint32_t
       best_nt = nt;
     }
   }
-  /* among block sizes within 6% of the best residency prefer the smallest (>= 64): a block holds its shared memory
-   * until its slowest warp finishes, so small blocks recycle capacity sooner (measured: 64 beats 128..256) */
+  /* among block sizes within 12% of the best residency prefer the smallest (>= 64): a block holds its shared memory
+   * until its slowest warp finishes, so small blocks recycle capacity sooner (measured on discrete_queue: 8 x 64
+   * threads per SM beats 3 x 192 although the latter holds two more warps) */
   for (uint32_t nt = 64; nt < best_nt; nt += 32) {
     const uint64_t bytes = (uint64_t)table_bytes + (uint64_t)per_rep_bytes * nt;
     uint32_t bps = (uint32_t)((227u * 1024u) / (bytes + 1024u));
     if (bps > 32) bps = 32;
     uint32_t thr = bps * nt;
     if (thr > 2048) thr = 2048;
-    if ((uint64_t)thr * 100 >= (uint64_t)best_thr * 94) {
+    if ((uint64_t)thr * 100 >= (uint64_t)best_thr * 88) {
       best_nt = nt;
       best_thr = thr;
       break;
@@ -314,6 +315,10 @@ extern "C" {
 int qk_batch_create(const qk_model* m, const qk_batch_config* cfg, qk_batch** out) {
   if (!m || !cfg || !out) {
     qk_set_error("qk_batch_create: NULL argument");
+    return QK_ERR_INVALID_ARG;
+  }
+  if (cfg->n_reps > 0xFFFF0000ull) {
+    qk_set_error("qk_batch_create: at most 2^32 - 65536 replications per batch (one GPU); shard across batches");
     return QK_ERR_INVALID_ARG;
   }
   if (cfg->n_reps == 0) {
