@@ -1,0 +1,140 @@
+//! `extern "C"` declarations for include/quokka_b200.h (ABI version 1).  Plain-old-data only.
+#![allow(non_camel_case_types, dead_code)]
+use core::ffi::{c_char, c_void};
+
+pub const QK_OK: i32 = 0;
+
+// qk_component_kind
+pub const QK_DISCRETE_STOCK: u32 = 1;
+pub const QK_DISCRETE_PROCESS: u32 = 2;
+pub const QK_DISCRETE_SOURCE: u32 = 3;
+pub const QK_DISCRETE_SINK: u32 = 4;
+pub const QK_DISCRETE_PARALLEL_PROCESS: u32 = 5;
+pub const QK_ENVIRONMENT: u32 = 6;
+pub const QK_VECTOR_STOCK: u32 = 16;
+pub const QK_VECTOR_PROCESS: u32 = 17;
+pub const QK_VECTOR_SOURCE: u32 = 18;
+pub const QK_VECTOR_SINK: u32 = 19;
+pub const QK_VECTOR_COMBINER: u32 = 20;
+pub const QK_VECTOR_SPLITTER: u32 = 21;
+
+// qk_dist_kind
+pub const QK_DIST_CONSTANT: u32 = 0;
+pub const QK_DIST_UNIFORM: u32 = 1;
+pub const QK_DIST_TRIANGULAR: u32 = 2;
+pub const QK_DIST_NORMAL: u32 = 3;
+pub const QK_DIST_TRUNCNORMAL: u32 = 4;
+pub const QK_DIST_EXPONENTIAL: u32 = 5;
+
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
+pub struct qk_dist_desc {
+    pub kind: u32,
+    pub stream: u32,
+    pub p: [f64; 4],
+}
+
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
+pub struct qk_component_desc {
+    pub kind: u32,
+    pub low_capacity: u32,
+    pub max_capacity: u32,
+    pub n_initial_items: u32,
+    pub capacity_hint: u32,
+    pub initial_env_state: u32,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy, Debug)]
+pub struct qk_batch_config {
+    pub n_reps: u64,
+    pub rep_offset: u64,
+    pub base_seed: u64,
+    pub device: i32,
+    pub log_capacity: u32,
+    pub threads_per_block: u32,
+    pub flags: u32,
+    pub stream: *mut c_void,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
+pub struct qk_log_record {
+    pub time_ns: u64,
+    pub comp: u16,
+    pub kind: u8,
+    pub reason: u8,
+    pub seq: u32,
+    pub src_comp: u16,
+    pub aux: u16,
+    pub src_seq: u32,
+    pub payload: u64,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
+pub struct qk_comp_stats {
+    pub count: u64,
+    pub time_ns: u64,
+    pub aux: u64,
+    pub level: u64,
+    pub fvalue: f64,
+    pub faux: f64,
+}
+
+pub enum qk_model {}
+pub enum qk_batch {}
+
+extern "C" {
+    pub fn qk_abi_version() -> i32;
+    pub fn qk_last_error() -> *const c_char;
+
+    pub fn qk_model_create(out: *mut *mut qk_model) -> i32;
+    pub fn qk_model_destroy(m: *mut qk_model);
+    pub fn qk_model_add_component(m: *mut qk_model, d: *const qk_component_desc, out_id: *mut u32) -> i32;
+    pub fn qk_model_set_dist(m: *mut qk_model, comp: u32, which: u32, d: *const qk_dist_desc, out_id: *mut u32) -> i32;
+    pub fn qk_model_add_delay_mode(
+        m: *mut qk_model,
+        comp: u32,
+        until_delay: *const qk_dist_desc,
+        until_fix: *const qk_dist_desc,
+        out_until_delay: *mut u32,
+        out_until_fix: *mut u32,
+    ) -> i32;
+    pub fn qk_model_set_vector(m: *mut qk_model, comp: u32, dim: u32, low: f64, max: f64, init3: *const f64) -> i32;
+    pub fn qk_model_set_ports(m: *mut qk_model, comp: u32, n_ports: u32, ratios5: *const f64) -> i32;
+    pub fn qk_model_connect(m: *mut qk_model, a: u32, b: u32, port_n: i32) -> i32;
+    pub fn qk_model_set_logged(m: *mut qk_model, comp: u32, enabled: i32) -> i32;
+    pub fn qk_model_schedule_env_state(m: *mut qk_model, t_ns: u64, env: u32, state: u32) -> i32;
+    pub fn qk_model_schedule_low_capacity(m: *mut qk_model, t_ns: u64, stock: u32, value: f64) -> i32;
+
+    pub fn qk_batch_create(m: *const qk_model, cfg: *const qk_batch_config, out: *mut *mut qk_batch) -> i32;
+    pub fn qk_batch_destroy(b: *mut qk_batch);
+    pub fn qk_batch_set_tape(b: *mut qk_batch, dist_id: u32, values: *const f64, per_rep_len: u64) -> i32;
+    pub fn qk_batch_init(b: *mut qk_batch, t0_ns: u64) -> i32;
+    pub fn qk_batch_step_until(b: *mut qk_batch, t_ns: u64) -> i32;
+    pub fn qk_batch_step_events(b: *mut qk_batch, n_events: u64) -> i32;
+    pub fn qk_batch_synchronize(b: *mut qk_batch) -> i32;
+    pub fn qk_batch_read_status(b: *mut qk_batch, rep0: u64, n: u64, status: *mut u32, now_ns: *mut u64, n_events: *mut u64) -> i32;
+    pub fn qk_batch_comp_stats(b: *mut qk_batch, rep0: u64, n: u64, comp: u32, out: *mut qk_comp_stats) -> i32;
+    pub fn qk_batch_read_log(b: *mut qk_batch, rep: u64, buf: *mut qk_log_record, cap: u64, n_out: *mut u64, n_total: *mut u64) -> i32;
+    pub fn qk_batch_read_stock(b: *mut qk_batch, rep: u64, comp: u32, items: *mut u32, cap: u64, n_out: *mut u64) -> i32;
+    pub fn qk_batch_read_vector(b: *mut qk_batch, rep: u64, comp: u32, out3: *mut f64) -> i32;
+}
+
+/// `Err(String)` carrying the library's thread-local message, like the reference's `Box<dyn Error>` strings.
+pub fn check(rc: i32) -> Result<(), Box<dyn std::error::Error>> {
+    if rc == QK_OK {
+        return Ok(());
+    }
+    let msg = unsafe {
+        let p = qk_last_error();
+        if p.is_null() {
+            format!("libquokka_b200: error {}", rc)
+        } else {
+            std::ffi::CStr::from_ptr(p).to_string_lossy().into_owned()
+        }
+    };
+    Err(msg.into())
+}
