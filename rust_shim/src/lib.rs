@@ -234,7 +234,14 @@ impl BatchedSimInit {
     pub fn init(self, t0: MonotonicTime, opt: BatchOptions) -> Result<BatchedSimulation, Box<dyn Error>> {
         let mut model: *mut ffi::qk_model = std::ptr::null_mut();
         ffi::check(unsafe { ffi::qk_model_create(&mut model) })?;
-        let mut sim = BatchedSimulation { model, batch: std::ptr::null_mut(), dist_ids: HashMap::new(), components: self.components.clone() };
+        let mut sim = BatchedSimulation {
+            model,
+            batch: std::ptr::null_mut(),
+            dist_ids: HashMap::new(),
+            components: self.components.clone(),
+            t0: 0,
+            initialised: false,
+        };
         for sh in &self.components {
             let c = sh.borrow();
             let d = ffi::qk_component_desc {
@@ -289,7 +296,7 @@ impl BatchedSimInit {
             stream: std::ptr::null_mut(),
         };
         ffi::check(unsafe { ffi::qk_batch_create(model, &cfg, &mut sim.batch) })?;
-        ffi::check(unsafe { ffi::qk_batch_init(sim.batch, t0.0) })?;
+        sim.t0 = t0.0; // Model::init runs with the first step, so that tapes set in between feed the init-time draws
         Ok(sim)
     }
 }
@@ -301,18 +308,28 @@ pub struct BatchedSimulation {
     batch: *mut ffi::qk_batch,
     dist_ids: HashMap<u64, Vec<u32>>,
     components: Vec<Shared>,
+    t0: u64,
+    initialised: bool,
 }
 
 impl BatchedSimulation {
+    fn ensure_init(&mut self) -> Result<(), Box<dyn Error>> {
+        if !self.initialised {
+            ffi::check(unsafe { ffi::qk_batch_init(self.batch, self.t0) })?;
+            self.initialised = true;
+        }
+        Ok(())
+    }
     pub fn step_until(&mut self, t: MonotonicTime) -> Result<(), Box<dyn Error>> {
+        self.ensure_init()?;
         ffi::check(unsafe { ffi::qk_batch_step_until(self.batch, t.0) })
     }
     pub fn step_events(&mut self, n: u64) -> Result<(), Box<dyn Error>> {
+        self.ensure_init()?;
         ffi::check(unsafe { ffi::qk_batch_step_events(self.batch, n) })
     }
     /// Pre-drawn variate tape: `values[rep * per_rep + i]` is what the i-th `.sample()` of `dist` returns in
-    /// replication `rep`.  Must be called before the first step.  (The library re-runs Model::init when a tape
-    /// arrives after qk_batch_init.)
+    /// replication `rep`.  Must be called before the first step (Model::init runs with the first step).
     pub fn set_tape(&mut self, dist: &Distribution, values: &[f64], per_rep: u64) -> Result<(), Box<dyn Error>> {
         for did in self.dist_ids.get(&dist.uid).cloned().unwrap_or_default() {
             ffi::check(unsafe { ffi::qk_batch_set_tape(self.batch, did, values.as_ptr(), per_rep) })?;
@@ -322,6 +339,7 @@ impl BatchedSimulation {
     /// (status, now_ns, n_events) of one replication; status != 0 is a per-replication fault such as the
     /// reference's panic "Time until next event is zero!" (discrete.rs:541).
     pub fn status(&mut self, rep: u64) -> Result<(u32, u64, u64), Box<dyn Error>> {
+        self.ensure_init()?;
         let (mut st, mut now, mut ev) = (0u32, 0u64, 0u64);
         ffi::check(unsafe { ffi::qk_batch_read_status(self.batch, rep, 1, &mut st, &mut now, &mut ev) })?;
         Ok((st, now, ev))
