@@ -195,7 +195,7 @@ def run_ours(args):
     torch.cuda.set_stream(stream)
 
     def new_sim(log_capacity):
-        return model.sim(None, reps_gpu, t0=0, base_seed=1234, rep_offset=rank * reps_gpu, log_capacity=log_capacity,
+        return model.sim(args.lib, reps_gpu, t0=0, base_seed=1234, rep_offset=rank * reps_gpu, log_capacity=log_capacity,
                          threads_per_block=args.threads_per_block, stream=stream.cuda_stream,
                          flags=1 if args.state == "hbm" else 0)
 
@@ -327,6 +327,7 @@ def main():
     ap.add_argument("--e2e-log-reps", type=int, default=256)
     ap.add_argument("--ref-step-seconds", type=float, default=6.0)
     ap.add_argument("--per-launch-timing", action="store_true")
+    ap.add_argument("--lib", default=None, help="path of an alternative build of libquokka_b200.so (A/B experiments)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

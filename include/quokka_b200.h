@@ -246,9 +246,9 @@ int qk_model_n_dists(const qk_model*, uint32_t* out);
 int qk_model_state_bytes(const qk_model*, int with_log, uint32_t* out_bytes);
 
 /* ---- batch of replications on one GPU -------------------------------------------------------- */
-/* State placement. Default: per-replication state is staged in shared memory for the whole launch; if the
- * model is too large for even one warp per block, the batch falls back to operating directly on the HBM
- * state planes (through L1/L2).  The two flags force one or the other. */
+/* State placement. Default: per-replication state is staged in shared memory for the whole launch when at
+ * least 12 warps of replications fit per SM that way; larger models operate directly on the HBM state planes
+ * (through L1/L2), where residency is limited by registers only.  The two flags force one or the other. */
 #define QK_BATCH_STATE_IN_HBM 1u
 #define QK_BATCH_STATE_ON_CHIP 2u
 typedef struct {
@@ -266,10 +266,10 @@ typedef struct {
 typedef struct {
   uint32_t threads_per_block, grid_blocks, shared_bytes_per_block, table_bytes;
   uint32_t slots64, slots32;         /* per-replication state: slots64 * 8 + slots32 * 4 bytes */
-  uint32_t state_bytes_per_rep;
+  uint32_t state_bytes_per_rep;      /* HOT state: loaded from / stored to HBM once per launch */
   uint32_t resident_blocks_per_sm;   /* occupancy of the step kernel as reported by the CUDA runtime */
   uint32_t state_in_hbm;             /* 1 if the batch operates on the HBM planes in place */
-  uint32_t reserved;
+  uint32_t cold_bytes_per_rep;       /* COLD state (item rings, source ids of pending events): global memory only */
   uint64_t replications_padded;
   uint64_t state_bytes_total, log_bytes_total;
 } qk_batch_info;

@@ -88,7 +88,7 @@ class BatchInfo(C.Structure):
         ("threads_per_block", C.c_uint32), ("grid_blocks", C.c_uint32), ("shared_bytes_per_block", C.c_uint32),
         ("table_bytes", C.c_uint32), ("slots64", C.c_uint32), ("slots32", C.c_uint32),
         ("state_bytes_per_rep", C.c_uint32), ("resident_blocks_per_sm", C.c_uint32),
-        ("state_in_hbm", C.c_uint32), ("reserved", C.c_uint32),
+        ("state_in_hbm", C.c_uint32), ("cold_bytes_per_rep", C.c_uint32),
         ("replications_padded", C.c_uint64), ("state_bytes_total", C.c_uint64), ("log_bytes_total", C.c_uint64),
     ]
 

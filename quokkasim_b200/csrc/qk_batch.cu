@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <vector>
 
 #include "qk_kernels.cuh"
@@ -40,6 +41,8 @@ struct qk_batch {
   uint32_t* g32;
   uint64_t* gs64; /* statistics planes */
   uint32_t* gs32;
+  uint64_t* gc64; /* cold state planes (item rings, source ids of pending events) */
+  uint32_t* gc32;
   uint8_t* d_tables;
   uint4* d_log;
   std::vector<double*> h_tapes; /* device pointers, host copy */
@@ -88,7 +91,8 @@ static StepKernel pick_kernel(bool log, bool hbm, uint32_t nt, uint32_t features
   return log ? pick_kernel_log<true>(hbm, nt, features) : pick_kernel_log<false>(hbm, nt, features);
 }
 
-static uint32_t choose_nt(uint32_t per_rep_bytes, uint32_t table_bytes, uint32_t* threads_per_sm) {
+/* max_thr: resident threads per SM the register allocation of the kernel variant allows (its launch bounds) */
+static uint32_t choose_nt(uint32_t per_rep_bytes, uint32_t table_bytes, uint32_t max_thr, uint32_t* threads_per_sm) {
   uint32_t best_nt = 0, best_thr = 0;
   for (uint32_t nt = 256; nt >= 32; nt -= 32) {
     const uint64_t bytes = (uint64_t)table_bytes + (uint64_t)per_rep_bytes * nt;
@@ -96,7 +100,7 @@ static uint32_t choose_nt(uint32_t per_rep_bytes, uint32_t table_bytes, uint32_t
     uint32_t bps = (uint32_t)((227u * 1024u) / (bytes + 1024u));
     if (bps > 32) bps = 32;
     uint32_t thr = bps * nt;
-    if (thr > 2048) thr = 2048;
+    if (thr > max_thr) thr = max_thr / nt * nt;
     if (thr > best_thr) {
       best_thr = thr;
       best_nt = nt;
@@ -110,7 +114,7 @@ static uint32_t choose_nt(uint32_t per_rep_bytes, uint32_t table_bytes, uint32_t
     uint32_t bps = (uint32_t)((227u * 1024u) / (bytes + 1024u));
     if (bps > 32) bps = 32;
     uint32_t thr = bps * nt;
-    if (thr > 2048) thr = 2048;
+    if (thr > max_thr) thr = max_thr / nt * nt;
     if ((uint64_t)thr * 100 >= (uint64_t)best_thr * 88) {
       best_nt = nt;
       best_thr = thr;
@@ -128,6 +132,10 @@ static int launch_step(qk_batch* b, uint32_t do_init, uint64_t t0, uint64_t t_un
   P.g32 = b->g32;
   P.gs64 = b->gs64;
   P.gs32 = b->gs32;
+  P.gc64 = b->gc64;
+  P.gc32 = b->gc32;
+  P.n64c = b->low.hdr.n64c;
+  P.n32c = b->low.hdr.n32c;
   P.tables = b->d_tables;
   P.table_bytes = b->table_bytes_padded;
   P.n64 = b->low.hdr.n64;
@@ -348,6 +356,8 @@ int qk_batch_create(const qk_model* m, const qk_batch_config* cfg, qk_batch** ou
   b->g32 = nullptr;
   b->gs64 = nullptr;
   b->gs32 = nullptr;
+  b->gc64 = nullptr;
+  b->gc32 = nullptr;
   b->d_tables = nullptr;
   b->d_log = nullptr;
   b->d_tapes = nullptr;
@@ -371,9 +381,18 @@ int qk_batch_create(const qk_model* m, const qk_batch_config* cfg, qk_batch** ou
   b->table_bytes_padded = (h.total_bytes + 15u) & ~15u;
   const uint32_t per_rep = h.n64 * 8 + h.n32 * 4;
   uint32_t nt = cfg->threads_per_block;
+  const uint32_t max_thr = h.features ? 512u : (uint32_t)QK_LEAN_THREADS; /* qk_lb_blocks: 128- / 80-register kernel variants */
   b->hbm = (cfg->flags & QK_BATCH_STATE_IN_HBM) != 0;
+  if (!b->hbm && nt == 0 && !(cfg->flags & QK_BATCH_STATE_ON_CHIP)) {
+    /* placement heuristic (measured, profiles/README.md): staging the state in shared memory wins while at least
+     * 12 warps fit per SM (discrete_queue: 8 x 64 threads); below that the L1/L2-cached HBM planes with
+     * register-limited residency are faster (vector_flow 1.3x, serial line / haulage 2x) */
+    uint32_t thr = 0;
+    choose_nt(per_rep, b->table_bytes_padded, max_thr, &thr);
+    if (thr < 384) b->hbm = true;
+  }
   if (!b->hbm) {
-    if (nt == 0) nt = choose_nt(per_rep, b->table_bytes_padded, nullptr);
+    if (nt == 0) nt = choose_nt(per_rep, b->table_bytes_padded, max_thr, nullptr);
     const bool fits = nt != 0 && nt <= QK_MAX_NT && !(nt & 31) &&
                       (uint64_t)b->table_bytes_padded + (uint64_t)per_rep * nt <= 227u * 1024u;
     if (!fits) {
@@ -398,6 +417,8 @@ int qk_batch_create(const qk_model* m, const qk_batch_config* cfg, qk_batch** ou
   }
   b->nt = nt;
   b->smem_bytes = b->table_bytes_padded + (b->hbm ? 0u : per_rep * nt);
+  if (const char* pad = getenv("QK_DEBUG_EXTRA_SMEM")) /* occupancy experiments only: lowers resident blocks per SM */
+    b->smem_bytes += (uint32_t)atoi(pad);
   b->grid = (uint32_t)((cfg->n_reps + nt - 1) / nt);
   b->rep_pad = (uint64_t)b->grid * nt;
   if (cfg->stream) {
@@ -412,6 +433,8 @@ int qk_batch_create(const qk_model* m, const qk_batch_config* cfg, qk_batch** ou
   CUDA_TRY(cudaMalloc(&b->g32, (size_t)h.n32 * b->rep_pad * 4));
   CUDA_TRY(cudaMalloc(&b->gs64, (size_t)h.n_comp * ST_PER_COMP * b->rep_pad * 8));
   CUDA_TRY(cudaMalloc(&b->gs32, (size_t)h.n_comp * ST_PER_COMP * b->rep_pad * 4));
+  CUDA_TRY(cudaMalloc(&b->gc64, (size_t)(h.n64c ? h.n64c : 1) * b->rep_pad * 8));
+  CUDA_TRY(cudaMalloc(&b->gc32, (size_t)(h.n32c ? h.n32c : 1) * b->rep_pad * 4));
   CUDA_TRY(cudaMalloc(&b->d_tables, b->table_bytes_padded));
   {
     std::vector<uint8_t> padded(b->table_bytes_padded, 0);
@@ -448,12 +471,13 @@ int qk_batch_info_get(qk_batch* b, qk_batch_info* out) {
   out->slots64 = b->low.hdr.n64;
   out->slots32 = b->low.hdr.n32;
   out->state_bytes_per_rep = b->low.hdr.n64 * 8 + b->low.hdr.n32 * 4;
+  out->cold_bytes_per_rep = b->low.hdr.n64c * 8 + b->low.hdr.n32c * 4;
   int nb = 0;
   CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)b->kernel, (int)b->nt, b->smem_bytes));
   out->state_in_hbm = b->hbm ? 1u : 0u;
   out->resident_blocks_per_sm = (uint32_t)nb;
   out->replications_padded = b->rep_pad;
-  out->state_bytes_total = (uint64_t)out->state_bytes_per_rep * b->rep_pad;
+  out->state_bytes_total = (uint64_t)(out->state_bytes_per_rep + out->cold_bytes_per_rep) * b->rep_pad;
   out->log_bytes_total = b->log ? (uint64_t)b->rep_pad * b->cfg.log_capacity * 32 : 0;
   return QK_OK;
 }
@@ -466,6 +490,8 @@ void qk_batch_destroy(qk_batch* b) {
   cudaFree(b->g32);
   cudaFree(b->gs64);
   cudaFree(b->gs32);
+  cudaFree(b->gc64);
+  cudaFree(b->gc32);
   cudaFree(b->d_tables);
   cudaFree(b->d_log);
   for (size_t i = 0; i < b->h_tapes.size(); ++i) cudaFree(b->h_tapes[i]);
@@ -749,7 +775,7 @@ int qk_batch_read_stock(qk_batch* b, uint64_t rep, uint32_t comp, uint32_t* item
   if (!items) return QK_OK;
   if (cap < cnt) return QK_ERR_BUFFER_TOO_SMALL;
   std::vector<uint32_t> ring(c.ring_cap);
-  CUDA_TRY(cudaMemcpy2D(ring.data(), 4, b->g32 + (size_t)(c.o32 + S32_RING) * b->rep_pad + rep, b->rep_pad * 4, 4,
+  CUDA_TRY(cudaMemcpy2D(ring.data(), 4, b->gc32 + (size_t)c.ocold32 * b->rep_pad + rep, b->rep_pad * 4, 4,
                         c.ring_cap, cudaMemcpyDeviceToHost));
   for (uint32_t i = 0; i < cnt; ++i) items[i] = ring[(head + i) % c.ring_cap];
   return QK_OK;

@@ -37,14 +37,24 @@ enum { P32_FLAGS = 0, P32_ITEM = 1, P32_BASE_COUNT = 2 }; /* optional: next item
 #define PF_HAS_ITEM 1u
 #define PF_ENV_STOPPED 2u
 #define PF_FIX_SHIFT 8 /* bits 8..15: delay mode k is in TimeUntilFix */
-/* LOG-only slots relative to olog64 / olog32 */
+/* LOG-only slots: the seq counter at hot slot olog32 ; the source ids of the pending / stale keyed event at COLD64
+ * slots olog64 + PL64_* */
 enum { PL64_SCHED_SRC = 0, PL64_STALE_SRC = 1, PL64_COUNT = 2 };
 enum { L32_SEQ = 0 };
 
+/* ---- cold planes ----------------------------------------------------------------------------------
+ * State that is touched once or twice per item and never decides control flow -- stock item rings, the source
+ * ids carried by pending events -- lives only in global memory ([slot][replication], like the hot planes in HBM)
+ * and is read and written in place through L1/L2.  Keeping it out of shared memory is what lets 22-24 warps of
+ * replications stay resident per SM instead of 12-16 (the step kernel's throughput is proportional to resident
+ * warps: profiles/README.md "occupancy experiment"). */
+
 /* ---- discrete stock slots ------------------------------------------------------------------------ */
 enum { S64_COUNT = 0 }; /* the fire slot holds emit_t0; nothing else is 64-bit */
-enum { S32_HC = 0, S32_EMIT = 1, S32_RING = 2 };
-/* S32_EMIT = n | split << 8 | head << 16 ; LOG: emit source seq ring at olog32 + 1 */
+enum { S32_HC = 0, S32_EMIT = 1, S32_COUNT = 2 };
+/* S32_EMIT = n | split << 8 | head << 16.
+ * COLD state (global memory only, never staged in shared memory -- see "cold planes" below): the item ring
+ * [ring_cap] at cold32 slot `ocold32`, followed (LOG) by the emit source-seq ring [emit_depth] */
 
 /* ---- parallel process slots ---------------------------------------------------------------------- */
 enum { PP64_PREV = 0, PP64_BASE_COUNT = 1 }; /* then dm durs, in-progress durations[cap] */
@@ -91,7 +101,8 @@ typedef struct {
   uint16_t o64_nextdur; /* absolute slot of the pre-drawn next process duration, 0xFFFF if none */
   uint16_t pf_idx;      /* bit index in the prefetch-pending mask */
   uint32_t const_dur_lo, const_dur_hi; /* process_time_distr is Constant: its duration in ns (or QK_DUR_FAULT code) */
-  uint32_t pad2;
+  uint16_t ocold32; /* cold32 slot: discrete stock item ring (+ emit source ring) ; vector stock emit source ring */
+  uint16_t pad2;
 } DevComp; /* 68 bytes = 17 words: an odd word stride keeps per-lane table reads of different components off the
               same shared-memory bank */
 
@@ -105,7 +116,8 @@ typedef struct {
   uint8_t kind, n_dm, n_subs, src_ord;
   uint16_t o32, o64;
   uint16_t fire_idx, flags; /* DC_LOGGED */
-  uint16_t olog32, olog64;
+  uint16_t olog32;
+  uint16_t olog64; /* process-like, vector stock: cold64 slot (LOG) ; discrete stock: cold32 slot of the item ring */
 } DevHotA; /* every kind */
 typedef struct {
   int16_t up, down;
@@ -171,7 +183,8 @@ typedef struct {
 /* header of the table blob (all offsets in bytes from the blob start, 8-byte aligned) */
 typedef struct {
   uint32_t n_comp, n_sched, n_dist, n_dm, n_subs, n_ext;
-  uint32_t n64, n32;         /* slots per replication (for the chosen LOG mode) */
+  uint32_t n64, n32;         /* hot slots per replication (for the chosen LOG mode) */
+  uint32_t n64c, n32c;       /* cold slots per replication */
   uint32_t n_stale_words;
   uint32_t ident_off;        /* index in subs[] of the identity list (subs[ident_off + c] == c) */
   uint32_t init_off, n_init; /* subs[init_off ..): components whose Model::init does something, registration order */
@@ -183,7 +196,6 @@ typedef struct {
   uint32_t log_enabled;
   uint32_t off_hot; /* DevHot[n_comp], 16-byte aligned */
   uint32_t features; /* 0 = every process-like component is SIMPLE and nothing is scheduled externally ; 1 = general */
-  uint32_t pad[2];
 } DevHeader;
 
 #endif

@@ -32,6 +32,9 @@ struct KParams {
   uint32_t* g32; /* [n32][rep_pad] */
   uint64_t* gs64; /* statistics planes [n_comp * 2][rep_pad], HBM only */
   uint32_t* gs32;
+  uint64_t* gc64; /* cold state planes [n64c][rep_pad] / [n32c][rep_pad], global memory only */
+  uint32_t* gc32;
+  uint32_t n64c, n32c;
   const uint8_t* tables;
   uint32_t table_bytes; /* multiple of 16 */
   uint32_t n64, n32;
@@ -51,6 +54,8 @@ struct Ctx {
   uint32_t stride;         /* on-chip: threads per block ; HBM: padded replication count */
   uint64_t* gs64;          /* statistics planes, offset to this replication; row stride = rep_pad */
   uint32_t* gs32;
+  uint64_t* gc64;          /* cold planes, offset to this replication */
+  uint32_t* gc32;
   uint32_t rep_pad; /* < 2^32 replications per batch */
   const DevHeader* hdr;
   const DevComp* comps;
@@ -99,11 +104,20 @@ __device__ __forceinline__ auto qk_ix(uint32_t slot, uint32_t stride) {
 }
 #define S64(slot) (qk_p64<SM>(cx)[qk_ix<SM>((uint32_t)(slot), cx.stride)])
 #define S32(slot) (qk_p32<SM>(cx)[qk_ix<SM>((uint32_t)(slot), cx.stride)])
+/* cold state: always global memory, whatever the placement of the hot planes */
+#define C64(slot) (cx.gc64[(uint64_t)(uint32_t)(slot) * cx.rep_pad])
+#define C32(slot) (cx.gc32[(uint64_t)(uint32_t)(slot) * cx.rep_pad])
 /* statistics accumulators: fire-and-forget RED atomics on the HBM planes (see qk_internal.h) */
+#ifdef QK_EXPERIMENT_NO_STATS /* perf experiment only: results are wrong */
+#define QK_ST64_ADD(comp, k, v) ((void)0)
+#define QK_ST32_ADD(comp, k, v) ((void)0)
+#define QK_ST32_MAX(comp, k, v) ((void)0)
+#else
 #define QK_STROW(comp, k) ((uint64_t)(uint32_t)((comp)*ST_PER_COMP + (k)) * cx.rep_pad)
 #define QK_ST64_ADD(comp, k, v) qk_red_add64(&cx.gs64[QK_STROW(comp, k)], (v))
 #define QK_ST32_ADD(comp, k, v) qk_red_add32(&cx.gs32[QK_STROW(comp, k)], (v))
 #define QK_ST32_MAX(comp, k, v) qk_red_max32(&cx.gs32[QK_STROW(comp, k)], (v))
+#endif
 #define SRC_INIT (((uint64_t)QK_SRC_INIT) << 32)
 #define SRC_SCH (((uint64_t)QK_SRC_SCH) << 32)
 
@@ -237,7 +251,8 @@ __device__ __forceinline__ uint32_t qk_stock_cat(uint32_t cnt, uint32_t low, uin
 
 /* cx.schedule_event(now + 1ns, Self::emit_change, ..) discrete.rs:193-194, 218-219 */
 template <bool LOG, int SM>
-__device__ __forceinline__ void qk_emit_push(Ctx& cx, const DevHotA& c, uint32_t emit_depth, uint32_t src_seq) {
+__device__ __forceinline__ void qk_emit_push(Ctx& cx, const DevHotA& c, uint32_t emit_depth, uint32_t oemit,
+                                             uint32_t src_seq) {
   const uint32_t fire = G64_FIRE0 + c.fire_idx;
   uint32_t e = S32(c.o32 + S32_EMIT);
   uint32_t n = e & 0xFFu, split = (e >> 8) & 0xFFu, head = (e >> 16) & 0xFFu;
@@ -257,18 +272,18 @@ __device__ __forceinline__ void qk_emit_push(Ctx& cx, const DevHotA& c, uint32_t
   if (LOG) {
     uint32_t pos = head + n - 1;
     if (pos >= emit_depth) pos -= emit_depth;
-    S32(c.olog32 + 1 + pos) = src_seq;
+    C32(oemit + pos) = src_seq;
   }
   S32(c.o32 + S32_EMIT) = n | (split << 8) | (head << 16);
 }
 
 template <bool LOG, int SM>
-__device__ __forceinline__ uint32_t qk_emit_pop(Ctx& cx, const DevHotA& c, uint32_t emit_depth) {
+__device__ __forceinline__ uint32_t qk_emit_pop(Ctx& cx, const DevHotA& c, uint32_t emit_depth, uint32_t oemit) {
   const uint32_t fire = G64_FIRE0 + c.fire_idx;
   uint32_t e = S32(c.o32 + S32_EMIT);
   uint32_t n = e & 0xFFu, split = (e >> 8) & 0xFFu, head = (e >> 16) & 0xFFu;
   uint32_t src_seq = 0;
-  if (LOG) src_seq = S32(c.olog32 + 1 + head);
+  if (LOG) src_seq = C32(oemit + head);
   head += 1;
   if (head >= emit_depth) head = 0;
   n -= 1;
@@ -297,14 +312,14 @@ __device__ __forceinline__ void qk_stock_add(Ctx& cx, uint32_t sidx, uint32_t it
   }
   uint32_t pos = head + cnt;
   if (pos >= sb.ring_cap) pos -= sb.ring_cap;
-  S32(c.o32 + S32_RING + pos) = item;
+  C32(c.olog64 + pos) = item; /* item ring: cold */
   cnt += 1;
   S32(c.o32 + S32_HC) = head | (cnt << 16);
   QK_ST64_ADD(sidx, ST64_TIME, 0ull - cx.now); /* occupancy integral = sum(t_remove) - sum(t_add) + cnt * T */
   QK_ST32_ADD(sidx, ST32_COUNT, 1u);
   QK_ST32_MAX(sidx, ST32_MAXOCC, cnt);
   const uint64_t id = qk_log<LOG, SM>(cx, c, sidx, src, QK_LOG_STOCK_ADD, 0, item);
-  if (prev != qk_stock_cat(cnt, sb.low, sb.max)) qk_emit_push<LOG, SM>(cx, c, sb.emit_depth, (uint32_t)id);
+  if (prev != qk_stock_cat(cnt, sb.low, sb.max)) qk_emit_push<LOG, SM>(cx, c, sb.emit_depth, c.olog64 + sb.ring_cap, (uint32_t)id);
 }
 
 /* Stock::remove (core.rs:197-204; discrete.rs:200-225); returns false for Remove(None) */
@@ -318,7 +333,7 @@ __device__ __forceinline__ bool qk_stock_remove(Ctx& cx, uint32_t sidx, uint64_t
   const bool some = cnt != 0;
   uint32_t item = 0;
   if (some) {
-    item = S32(c.o32 + S32_RING + head);
+    item = C32(c.olog64 + head);
     head += 1;
     if (head >= sb.ring_cap) head = 0;
     cnt -= 1;
@@ -326,7 +341,7 @@ __device__ __forceinline__ bool qk_stock_remove(Ctx& cx, uint32_t sidx, uint64_t
     QK_ST64_ADD(sidx, ST64_TIME, cx.now);
   }
   const uint64_t id = qk_log<LOG, SM>(cx, c, sidx, src, QK_LOG_STOCK_REMOVE, 0, some ? (uint64_t)item : QK_ITEM_NONE);
-  if (prev != qk_stock_cat(cnt, sb.low, sb.max)) qk_emit_push<LOG, SM>(cx, c, sb.emit_depth, (uint32_t)id);
+  if (prev != qk_stock_cat(cnt, sb.low, sb.max)) qk_emit_push<LOG, SM>(cx, c, sb.emit_depth, c.olog64 + sb.ring_cap, (uint32_t)id);
   *item_out = item;
   return some;
 }
@@ -415,7 +430,7 @@ __device__ __forceinline__ void qk_post(Ctx& cx, const DevHotA& c, uint64_t ttnp
     const uint32_t fire = G64_FIRE0 + c.fire_idx;
     if (next < S64(fire)) { /* NONE is the largest u64 */
       S64(fire) = next;
-      if (LOG) S64(c.olog64 + PL64_SCHED_SRC) = src;
+      if (LOG) C64(c.olog64 + PL64_SCHED_SRC) = src;
     }
   }
 }
@@ -428,7 +443,7 @@ __device__ __forceinline__ void qk_pre(Ctx& cx, const DevHotA& c) {
   if (S64(fire) <= cx.now) {
     S64(fire) = QK_TIME_NONE;
     S32(G32_STALE0 + (c.fire_idx >> 5)) |= 1u << (c.fire_idx & 31);
-    if (LOG) S64(c.olog64 + PL64_STALE_SRC) = S64(c.olog64 + PL64_SCHED_SRC);
+    if (LOG) C64(c.olog64 + PL64_STALE_SRC) = C64(c.olog64 + PL64_SCHED_SRC);
   }
 }
 
@@ -737,15 +752,20 @@ __device__ __forceinline__ void qk_update_state(Ctx& cx, uint32_t comp, uint64_t
 #endif
 
 constexpr int qk_lb_threads(int sm) { return sm > 0 ? sm : QK_MAX_NT; }
-constexpr int qk_lb_blocks(int sm) { return sm > 0 ? (512 / sm > 0 ? 512 / sm : 1) : 2; }
-/* shared memory admits roughly 512 resident threads per SM for the models this path targets, so ask ptxas for that
- * occupancy explicitly (<= 128 registers); a bare __launch_bounds__(SM) made it cap some instantiations at 80
- * registers and spill */
+/* resident threads per SM the register allocation must allow: the kernel is latency-bound and its throughput is
+ * proportional to resident warps (profiles/README.md), so the lean kernel (FT == 0: small models, ~250-280 B of hot
+ * state per replication) is held to 80 registers = 24 warps; the general kernel to 128 registers = 16 warps */
+#ifndef QK_LEAN_THREADS
+#define QK_LEAN_THREADS 640
+#endif
+constexpr int qk_lb_blocks(int sm, int ft) {
+  return sm > 0 ? ((ft == 0 ? QK_LEAN_THREADS : 512) / sm > 0 ? (ft == 0 ? QK_LEAN_THREADS : 512) / sm : 1) : (ft == 0 ? 3 : 2);
+}
 /* FT = feature set of the model: 0 = only SIMPLE single-server discrete components and stocks (no delay modes, no
  * environment, no scheduled events, no parallel or vector components): the handlers for everything else are
  * compiled out, which frees registers ; 1 = everything */
 template <bool LOG, int SM, int FT>
-__global__ void __launch_bounds__(qk_lb_threads(SM), qk_lb_blocks(SM)) qk_step_kernel(const __grid_constant__ KParams P) {
+__global__ void __launch_bounds__(qk_lb_threads(SM), qk_lb_blocks(SM, FT)) qk_step_kernel(const __grid_constant__ KParams P) {
   uint8_t* const smem = qk_smem;
   const uint32_t tid = QK_TID, nt = SM > 0 ? (uint32_t)SM : QK_NT;
 
@@ -787,6 +807,8 @@ __global__ void __launch_bounds__(qk_lb_threads(SM), qk_lb_blocks(SM)) qk_step_k
   cx.rep_local = rep_local;
   cx.gs64 = P.gs64 + rep_local;
   cx.gs32 = P.gs32 + rep_local;
+  cx.gc64 = P.gc64 + rep_local;
+  cx.gc32 = P.gc32 + rep_local;
   cx.rep_pad = (uint32_t)P.rep_pad;
   cx.key0 = (uint32_t)P.seed;
   cx.key1 = (uint32_t)(P.seed >> 32);
@@ -806,6 +828,8 @@ __global__ void __launch_bounds__(qk_lb_threads(SM), qk_lb_blocks(SM)) qk_step_k
     for (uint32_t s = 0; s < P.n64; ++s) S64(s) = 0;
     for (uint32_t s = 0; s < P.n32; ++s) S32(s) = 0;
     for (uint32_t i = 0; i < n_sched; ++i) S64(G64_FIRE0 + i) = QK_TIME_NONE;
+    for (uint32_t s = 0; s < P.n64c; ++s) C64(s) = 0;
+    for (uint32_t s = 0; s < P.n32c; ++s) C32(s) = 0;
     cx.now = P.t0;
     cx.log_cnt = 0;
     for (uint32_t s = 0; s < n_comp * ST_PER_COMP; ++s) {
@@ -827,7 +851,7 @@ __global__ void __launch_bounds__(qk_lb_threads(SM), qk_lb_blocks(SM)) qk_step_k
         if (c->kind == QK_DISCRETE_STOCK) {
           /* with_initial_resource: the count rides in DevComp.dist_time (unused for stocks) */
           const uint32_t n_init = c->dist_time;
-          for (uint32_t k = 0; k < n_init; ++k) S32(c->o32 + S32_RING + k) = (63u << 26) | (initial_base + k);
+          for (uint32_t k = 0; k < n_init; ++k) C32(c->ocold32 + k) = (63u << 26) | (initial_base + k);
           initial_base += n_init;
           S32(c->o32 + S32_HC) = n_init << 16;
           cx.gs32[(size_t)(i * ST_PER_COMP + ST32_MAXOCC) * P.rep_pad] = n_init;
@@ -944,7 +968,7 @@ __global__ void __launch_bounds__(qk_lb_threads(SM), qk_lb_blocks(SM)) qk_step_k
               /* emit_change (discrete.rs:227-233): log the state AT EMISSION TIME, then update_state on every
                * subscriber in connection order */
               const DevHotSB sb = QK_HOT_SB(comp);
-              const uint32_t src_seq = qk_emit_pop<LOG, SM>(cx, a, sb.emit_depth);
+              const uint32_t src_seq = qk_emit_pop<LOG, SM>(cx, a, sb.emit_depth, a.olog64 + sb.ring_cap);
               if (LOG) {
                 const uint32_t cnt = S32(a.o32 + S32_HC) >> 16;
                 const uint32_t empty = sb.max > cnt ? sb.max - cnt : 0;
@@ -961,9 +985,9 @@ __global__ void __launch_bounds__(qk_lb_threads(SM), qk_lb_blocks(SM)) qk_step_k
               uint64_t occ_bits = 0;
               if (LOG) {
                 const uint32_t head = (S32(a.o32 + S32_EMIT) >> 16) & 0xFFu;
-                occ_bits = S64(a.olog64 + head);
+                occ_bits = C64(a.olog64 + head);
               }
-              packed = qk_emit_pop<LOG, SM>(cx, a, sb.emit_depth);
+              packed = qk_emit_pop<LOG, SM>(cx, a, sb.emit_depth, c->ocold32);
               src = qk_log<LOG, SM>(cx, a, comp, ((uint64_t)comp << 32) | (packed & 0x3FFFFFFFu),
                                     QK_LOG_VSTOCK_STATE_CHANGE, packed >> 30, occ_bits);
               qk_log_vec<LOG, SM>(cx, c, comp, src, 0, __dsub_rn(cx.vecs[c->vec_idx].vmax, QK_U2D(occ_bits)), 0.0, 0.0);
@@ -972,9 +996,9 @@ __global__ void __launch_bounds__(qk_lb_threads(SM), qk_lb_blocks(SM)) qk_step_k
             } else {
               /* keyed update_state(source_event_id) (discrete.rs:549,556) */
               if (stale) {
-                if (LOG) src = S64(a.olog64 + PL64_STALE_SRC);
+                if (LOG) src = C64(a.olog64 + PL64_STALE_SRC);
               } else {
-                if (LOG) src = S64(a.olog64 + PL64_SCHED_SRC);
+                if (LOG) src = C64(a.olog64 + PL64_SCHED_SRC);
                 S64(G64_FIRE0 + bi) = QK_TIME_NONE;
                 keyed = true;
               }

@@ -423,6 +423,7 @@ int qk_lower(const qk_model* m, bool log, QkLowered* out) {
   }
   const uint32_t n_pf = (uint32_t)pf_comp.size();
   const uint32_t n_pf_words = (n_pf + 31) / 32;
+  uint32_t n64c = 0, n32c = 0; /* cold slots */
   uint32_t n64 = G64_FIRE0 + n_sched;
   const uint32_t pf32 = G32_STALE0 + n_stale_words;
   uint32_t n32 = pf32 + n_pf_words;
@@ -525,7 +526,9 @@ int qk_lower(const qk_model* m, bool log, QkLowered* out) {
       d.o64 = (uint16_t)n64;
       n64 += S64_COUNT;
       d.o32 = (uint16_t)n32;
-      n32 += S32_RING + d.ring_cap;
+      n32 += S32_COUNT;
+      d.ocold32 = (uint16_t)n32c;
+      n32c += d.ring_cap;
       uint32_t depth = 0;
       for (size_t j = 0; j < nc; ++j) {
         const QkHostComp& o = m->comps[j];
@@ -550,7 +553,7 @@ int qk_lower(const qk_model* m, bool log, QkLowered* out) {
       v.o64_low = (uint16_t)n64++;
       v.o64_last = (uint16_t)n64++;
       d.o32 = (uint16_t)n32;
-      n32 += S32_RING; /* S32_HC unused, S32_EMIT used */
+      n32 += S32_COUNT; /* S32_HC unused, S32_EMIT used */
       uint32_t depth = 0;
       for (size_t j = 0; j < nc; ++j) {
         const QkHostComp& o = m->comps[j];
@@ -602,17 +605,19 @@ int qk_lower(const qk_model* m, bool log, QkLowered* out) {
     if (log) {
       d.olog32 = (uint16_t)n32;
       n32 += 1; /* L32_SEQ */
-      if (kind == QK_DISCRETE_STOCK || kind == QK_VECTOR_STOCK) n32 += d.emit_depth;
+      if (kind == QK_DISCRETE_STOCK) n32c += d.emit_depth; /* emit source ring follows the item ring */
       if (kind == QK_VECTOR_STOCK) {
-        d.olog64 = (uint16_t)n64; /* occupied (f64) of each pending emit_change */
-        n64 += d.emit_depth;
+        d.ocold32 = (uint16_t)n32c;
+        n32c += d.emit_depth;
+        d.olog64 = (uint16_t)n64c; /* occupied (f64) of each pending emit_change */
+        n64c += d.emit_depth;
       }
       if (qk_is_process_like(kind)) {
-        d.olog64 = (uint16_t)n64;
-        n64 += PL64_COUNT;
+        d.olog64 = (uint16_t)n64c;
+        n64c += PL64_COUNT;
       }
     }
-    if (n64 > 0xFFF0 || n32 > 0xFFF0) {
+    if (n64 > 0xFFF0 || n32 > 0xFFF0 || n64c > 0xFFF0 || n32c > 0xFFF0) {
       qk_set_error("model state exceeds 65520 slots per replication");
       return QK_ERR_CAPACITY;
     }
@@ -642,6 +647,8 @@ int qk_lower(const qk_model* m, bool log, QkLowered* out) {
   h.n_ext = (uint32_t)ext.size();
   h.n64 = n64;
   h.n32 = n32;
+  h.n64c = n64c;
+  h.n32c = n32c;
   h.n_stale_words = n_stale_words;
   h.n_pf = n_pf;
   h.n_pf_words = n_pf_words;
@@ -687,7 +694,7 @@ int qk_lower(const qk_model* m, bool log, QkLowered* out) {
     if (single && d.n_dm == 0 && d.env < 0) q.a.flags |= DC_SIMPLE;
     if (!(d.kind == QK_DISCRETE_STOCK || (q.a.flags & DC_SIMPLE))) h.features = 1;
     q.a.olog32 = d.olog32;
-    q.a.olog64 = d.olog64;
+    q.a.olog64 = d.kind == QK_DISCRETE_STOCK ? d.ocold32 : d.olog64;
     if (qk_is_process_like(d.kind)) {
       q.b.up = d.up;
       q.b.down = d.down;

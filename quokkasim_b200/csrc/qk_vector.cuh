@@ -114,8 +114,8 @@ __device__ __forceinline__ void qk_vemit_push(Ctx& cx, const DevComp* c, uint32_
   if (LOG) {
     uint32_t pos = head + n - 1;
     if (pos >= c->emit_depth) pos -= c->emit_depth;
-    S32(c->olog32 + 1 + pos) = src_seq | (cat << 30);
-    S64(c->olog64 + pos) = QK_D2U(occ);
+    C32(c->ocold32 + pos) = src_seq | (cat << 30);
+    C64(c->olog64 + pos) = QK_D2U(occ);
   }
   S32(c->o32 + S32_EMIT) = n | (split << 8) | (head << 16);
 }

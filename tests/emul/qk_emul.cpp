@@ -28,6 +28,8 @@ struct qk_batch {
   std::vector<uint32_t> g32;
   std::vector<uint64_t> gs64;
   std::vector<uint32_t> gs32;
+  std::vector<uint64_t> gc64;
+  std::vector<uint32_t> gc32;
   std::vector<uint8_t> tables;
   std::vector<uint4> logbuf;
   std::vector<std::vector<double> > tapes;
@@ -44,6 +46,10 @@ static int run(qk_batch* b, uint32_t do_init, uint64_t t0, uint64_t t_until, uin
   P.g32 = b->g32.data();
   P.gs64 = b->gs64.data();
   P.gs32 = b->gs32.data();
+  P.gc64 = b->gc64.data();
+  P.gc32 = b->gc32.data();
+  P.n64c = b->low.hdr.n64c;
+  P.n32c = b->low.hdr.n32c;
   P.tables = b->tables.data();
   P.table_bytes = b->table_bytes_padded;
   P.n64 = b->low.hdr.n64;
@@ -101,6 +107,8 @@ int qk_batch_create(const qk_model* m, const qk_batch_config* cfg, qk_batch** ou
   b->g32.assign((size_t)h.n32 * b->rep_pad, 0);
   b->gs64.assign((size_t)h.n_comp * ST_PER_COMP * b->rep_pad, 0);
   b->gs32.assign((size_t)h.n_comp * ST_PER_COMP * b->rep_pad, 0);
+  b->gc64.assign((size_t)(h.n64c ? h.n64c : 1) * b->rep_pad, 0);
+  b->gc32.assign((size_t)(h.n32c ? h.n32c : 1) * b->rep_pad, 0);
   b->tables.assign(b->table_bytes_padded, 0);
   memcpy(b->tables.data(), b->low.blob.data(), b->low.blob.size());
   if (b->log) b->logbuf.assign((size_t)b->rep_pad * cfg->log_capacity * 2, uint4{0, 0, 0, 0});
@@ -123,9 +131,10 @@ int qk_batch_info_get(qk_batch* b, qk_batch_info* out) {
   out->slots64 = b->low.hdr.n64;
   out->slots32 = b->low.hdr.n32;
   out->state_bytes_per_rep = b->low.hdr.n64 * 8 + b->low.hdr.n32 * 4;
+  out->cold_bytes_per_rep = b->low.hdr.n64c * 8 + b->low.hdr.n32c * 4;
   out->shared_bytes_per_block = out->table_bytes + out->state_bytes_per_rep;
   out->replications_padded = b->rep_pad;
-  out->state_bytes_total = (uint64_t)out->state_bytes_per_rep * b->rep_pad;
+  out->state_bytes_total = (uint64_t)(out->state_bytes_per_rep + out->cold_bytes_per_rep) * b->rep_pad;
   out->log_bytes_total = b->log ? (uint64_t)b->rep_pad * b->cfg.log_capacity * 32 : 0;
   out->state_in_hbm = (b->cfg.flags & QK_BATCH_STATE_IN_HBM) ? 1u : 0u;
   return QK_OK;
@@ -271,7 +280,7 @@ int qk_batch_read_stock(qk_batch* b, uint64_t rep, uint32_t comp, uint32_t* item
   if (!items) return QK_OK;
   if (cap < cnt) return QK_ERR_BUFFER_TOO_SMALL;
   for (uint32_t i = 0; i < cnt; ++i)
-    items[i] = b->g32[(size_t)(c.o32 + S32_RING + (head + i) % c.ring_cap) * b->rep_pad + rep];
+    items[i] = b->gc32[(size_t)(c.ocold32 + (head + i) % c.ring_cap) * b->rep_pad + rep];
   return QK_OK;
 }
 

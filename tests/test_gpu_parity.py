@@ -263,3 +263,24 @@ def test_vector_mass_balance_at_scale(gpu_lib):
     assert rel.max() < 1e-9, rel.max()
     assert (stats["Source"]["count"] > 0).all()
     sim.close()
+
+
+def test_state_placement_does_not_change_results(gpu_lib):
+    """shared-memory staging (flag 2) and HBM-resident state (flag 1) are two placements of the same state"""
+    blobs = []
+    for flags in (1, 2):
+        m = H.haulage(n_src=3, per_queue=4)
+        sim = m.sim(gpu_lib, 96, base_seed=21, flags=flags, log_capacity=1024)
+        sim.step_events(5000)
+        assert sim.info()["state_in_hbm"] == (1 if flags == 1 else 0)
+        blob = b"".join(sim.comp_stats(ci).tobytes() for ci in range(len(m.components)))
+        blob += sim.read_log(95)[0].tobytes()
+        blobs.append(blob)
+        sim.close()
+    assert blobs[0] == blobs[1]
+    # the default picks by residency: the 7-component line is staged on chip, the 89-component network is not
+    a = H.discrete_queue().sim(gpu_lib, 64)
+    b = H.haulage(n_src=8, per_queue=8).sim(gpu_lib, 64)
+    assert a.info()["state_in_hbm"] == 0 and b.info()["state_in_hbm"] == 1
+    a.close()
+    b.close()
