@@ -12,14 +12,14 @@ CSRC = os.path.join(_HERE, "csrc")
 LIB = os.path.join(_HERE, "libquokka_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
-SOURCES = ["qk_model.cpp", "qk_batch.cu"]
+SOURCES = ["qk_model.cpp", "qk_batch.cu", "qk_step_l0f0.cu", "qk_step_l0f1.cu", "qk_step_l1f0.cu", "qk_step_l1f1.cu"]
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
     "--fmad=false",  # fp64 parity: no contraction anywhere in the product
     "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off",
     "-Xptxas", "-v",
-    "--split-compile", "0",  # ptxas over the kernel instantiations in parallel (build time only)
+    "--threads", "0",  # the translation units compile in parallel (reproducibly, unlike --split-compile)
     "-shared", "-cudart", "static",
 ]
 

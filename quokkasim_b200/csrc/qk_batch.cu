@@ -15,7 +15,7 @@
 #include <cstdlib>
 #include <vector>
 
-#include "qk_kernels.cuh"
+#include "qk_step_inst.cuh"
 #include "qk_model.h"
 
 #define CUDA_TRY(expr)                                                                    \
@@ -27,7 +27,6 @@
     }                                                                                     \
   } while (0)
 
-typedef void (*StepKernel)(const KParams);
 
 struct qk_batch {
   StepKernel kernel;
@@ -66,29 +65,15 @@ struct qk_batch {
   uint32_t red_blocks;
 };
 
-/* one instantiation per (logging, state placement, block size): the block size is a template constant so that
- * state-slot offsets become LDS/STS immediates */
-template <bool LOG, int FT>
-static StepKernel pick_kernel_ft(uint32_t nt) {
-  switch (nt) {
-    case 32: return qk_step_kernel<LOG, 32, FT>;
-    case 64: return qk_step_kernel<LOG, 64, FT>;
-    case 96: return qk_step_kernel<LOG, 96, FT>;
-    case 128: return qk_step_kernel<LOG, 128, FT>;
-    case 160: return qk_step_kernel<LOG, 160, FT>;
-    case 192: return qk_step_kernel<LOG, 192, FT>;
-    case 224: return qk_step_kernel<LOG, 224, FT>;
-    case 256: return qk_step_kernel<LOG, 256, FT>;
-    default: return qk_step_kernel<LOG, -1, 1>;
-  }
-}
-template <bool LOG>
-static StepKernel pick_kernel_log(bool hbm, uint32_t nt, uint32_t features) {
-  if (hbm) return features ? qk_step_kernel<LOG, 0, 1> : qk_step_kernel<LOG, 0, 0>;
-  return features ? pick_kernel_ft<LOG, 1>(nt) : pick_kernel_ft<LOG, 0>(nt);
-}
+/* the step kernel instantiations live in qk_step_l{0,1}f{0,1}.cu */
+StepKernel qk_pick_step_l0f0(uint32_t nt);
+StepKernel qk_pick_step_l0f1(uint32_t nt);
+StepKernel qk_pick_step_l1f0(uint32_t nt);
+StepKernel qk_pick_step_l1f1(uint32_t nt);
 static StepKernel pick_kernel(bool log, bool hbm, uint32_t nt, uint32_t features) {
-  return log ? pick_kernel_log<true>(hbm, nt, features) : pick_kernel_log<false>(hbm, nt, features);
+  const uint32_t key = hbm ? 0u : nt;
+  if (log) return features ? qk_pick_step_l1f1(key) : qk_pick_step_l1f0(key);
+  return features ? qk_pick_step_l0f1(key) : qk_pick_step_l0f0(key);
 }
 
 /* max_thr: resident threads per SM the register allocation of the kernel variant allows (its launch bounds) */

@@ -36,6 +36,16 @@ __device__ __forceinline__ void qk_red_max32(uint32_t* p, uint32_t v) { atomicMa
 __device__ __forceinline__ void qk_red_addf64(uint64_t* p, double v) { atomicAdd(reinterpret_cast<double*>(p), v); }
 #endif
 
+#ifndef QK_HOST_EMUL
+/* one 32-byte log record = ONE store: sm_100 has 256-bit global stores (STG.E.ENL2.256), which halves the L1 tag
+ * work of the scattered per-replication log writes compared with two STG.128 */
+__device__ __forceinline__ void qk_store_record(uint4* r, const uint4& a, const uint4& b) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(r), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w),
+               "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+               : "memory");
+}
+#endif
+
 #define QK_DEV __device__ __forceinline__
 #ifndef QK_REFILL_LANES
 #define QK_REFILL_LANES 20 /* run the REFILL phase when this many lanes of the warp wait for a variate */
@@ -161,7 +171,7 @@ struct QkVariate {
   double value;
   uint32_t draws;
 };
-__device__ __noinline__ QkVariate qk_sample_native(uint32_t kind, double p0, double p1, double p2, double p3,
+static __device__ __noinline__ QkVariate qk_sample_native(uint32_t kind, double p0, double p1, double p2, double p3,
                                                    uint32_t stream, uint32_t key0, uint32_t key1, uint32_t rep_lo,
                                                    uint32_t rep_hi, uint32_t draws) {
   const double p[4] = {p0, p1, p2, p3};

@@ -155,8 +155,7 @@ __device__ __forceinline__ uint64_t qk_log(Ctx& cx, const DevHotA& c, uint32_t c
     b.y = (uint32_t)src;
     b.z = (uint32_t)payload;
     b.w = (uint32_t)(payload >> 32);
-    r[0] = a;
-    r[1] = b;
+    qk_store_record(r, a, b);
     cx.log_cnt += 1;
   }
   return ((uint64_t)comp << 32) | seq;

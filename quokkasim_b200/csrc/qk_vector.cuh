@@ -35,8 +35,7 @@ __device__ __forceinline__ void qk_log_vec(Ctx& cx, const DevComp* c, uint32_t c
     b.y = (uint32_t)(b1 >> 32);
     b.z = (uint32_t)b2;
     b.w = (uint32_t)(b2 >> 32);
-    r[0] = a;
-    r[1] = b;
+    qk_store_record(r, a, b);
     cx.log_cnt += 1;
   }
 }

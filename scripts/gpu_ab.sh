@@ -1,7 +1,7 @@
 #!/bin/bash
-# A/B of two builds of the library at full size, same box, interleaved
+# A/B of builds of the library at full size, same box, interleaved.  LIBS="a.so b.so"
 for rep in 1 2; do
-for lib in quokkasim_b200/libqk_ab_old.so quokkasim_b200/libquokka_b200.so; do
+for lib in ${LIBS:-quokkasim_b200/libquokka_b200.so}; do
   for lg in off ring; do
     echo "== $lib log=$lg $(timeout 300 python bench.py --steps 3 --warmup 2 --no-cpu-baseline --e2e-steps 1 --log $lg --lib $lib 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.readline()); print('value %.4e kernel_ms %.2f' % (d['value'], d['roofline']['kernel_ms']))")"
   done

@@ -66,4 +66,9 @@ static inline double __ddiv_rn(double a, double b) { return a / b; }
 static inline double __dsqrt_rn(double a) { return std::sqrt(a); }
 static inline int __ffs(int v) { return __builtin_ffs(v); }
 
+
+static inline void qk_store_record(uint4* r, const uint4& a, const uint4& b) {
+  r[0] = a;
+  r[1] = b;
+}
 #endif
