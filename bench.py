@@ -22,6 +22,18 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# stdout carries exactly ONE line -- the JSON result.  Libraries print to file descriptor 1 behind Python's back (NCCL
+# writes "NCCL version ..." there), so keep a private duplicate of the original stdout for the result and point fd 1
+# at stderr for everybody else.
+_RESULT_FD = os.dup(1)
+os.dup2(2, 1)
+sys.stdout = sys.stderr
+
+
+def emit(obj):
+    os.write(_RESULT_FD, (json.dumps(obj) + "\n").encode())
+
+
 WORKLOADS = {
     # name: (builder kwargs, replications per GPU, events per replication)
     "discrete_queue": ("discrete_queue", {}, 1048576, 10000),
@@ -149,7 +161,7 @@ def run_reference(args):
     value = ev_sum / t_sum
     sample = ("each step = %d replications x %d events (bounded sample of the %d-replication workload), oracle port "
               "of the reference CPU path on %d host threads" % (reps, n_events, reps_gpu * args.gpus, threads))
-    print(json.dumps({
+    emit(({
         "impl": "reference", "metric": "simulated events/sec", "value": value, "unit": "events/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_sum / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
@@ -196,7 +208,7 @@ def run_ours(args):
 
     def new_sim(log_capacity):
         return model.sim(args.lib, reps_gpu, t0=0, base_seed=1234, rep_offset=rank * reps_gpu, log_capacity=log_capacity,
-                         threads_per_block=args.threads_per_block, stream=stream.cuda_stream,
+                         threads_per_block=args.threads_per_block, stream=stream.cuda_stream, device=local_rank,
                          flags=1 if args.state == "hbm" else 0)
 
     sim = new_sim(log_cap)
@@ -304,7 +316,7 @@ def run_ours(args):
         }
         if not args.no_cpu_baseline and world == 1:
             out["cpu_baseline"] = cpu_baseline(model, n_events, log_cap != 0)
-        print(json.dumps(out))
+        emit(out)
     if world > 1:
         dist.destroy_process_group()
 

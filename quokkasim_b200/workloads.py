@@ -19,11 +19,12 @@ class Model:
         self.by_name[cm.component.element_name] = cm
         return cm
 
-    def sim(self, lib, n_reps, t0=0, base_seed=0, rep_offset=0, log_capacity=0, threads_per_block=0, stream=None, flags=0):
+    def sim(self, lib, n_reps, t0=0, base_seed=0, rep_offset=0, log_capacity=0, threads_per_block=0, stream=None, flags=0,
+            device=0):
         si = qk.BatchedSimInit.new()
         for c in self.components:
             si = qk.register_component(si, c)
-        sim, sched = si.init(t0, n_replications=n_reps, base_seed=base_seed, rep_offset=rep_offset,
+        sim, sched = si.init(t0, n_replications=n_reps, base_seed=base_seed, device=device, rep_offset=rep_offset,
                              log_capacity=log_capacity, threads_per_block=threads_per_block, stream=stream,
                              lib=lib, flags=flags)
         for t, env, state in self.ext:
