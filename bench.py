@@ -178,6 +178,7 @@ def workload_config(args, reps_gpu, n_events):
             "replications_per_gpu": args.reps or reps_gpu, "events_per_replication": n_events,
             "logging": args.log, "log_ring_records": args.log_capacity if args.log != "off" else 0,
             "state": args.state, "threads_per_block": args.threads_per_block,
+            "events_per_launch": args.events_per_launch or n_events,
             "l2": "state planes (>= 0.5 GB) and log rings are larger than the 126 MB L2; no flush needed"}
 
 
@@ -216,9 +217,14 @@ def run_ours(args):
     L, b = sim.L, sim._batch
     state_bytes = sim.state_bytes()
 
+    K = args.events_per_launch or n_events
+
     def one_step():
         L.qk_batch_init(b, 0)
-        L.qk_batch_step_events(b, n_events)
+        if K >= n_events:
+            L.qk_batch_step_events(b, n_events)
+        else:
+            L.qk_batch_step_events_chunked(b, n_events, K)
 
     def barrier():
         if world > 1:
@@ -243,7 +249,9 @@ def run_ours(args):
     elapsed_ms = ev0.elapsed_time(ev1)
     clk = clocks.stop() if rank == 0 else None
     if not args.per_launch_timing:
-        kernel_ms.append(sim.last_step_ms()[0])  # the dominant kernel: last step launch, CUDA events on its stream
+        # the dominant kernel: the launches of the last step, CUDA events on their stream (average per launch)
+        ms_all, n_l = sim.last_step_ms()
+        kernel_ms.append(ms_all / max(1, n_l))
     summ = sim.summary()
     t = torch.tensor([elapsed_ms], dtype=torch.float64, device=device)
     ev_total = torch.tensor([summ["n_events"], summ["n_log_records"], summ["n_faulted"]], dtype=torch.int64,
@@ -293,10 +301,21 @@ def run_ours(args):
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
         # algorithmic bytes of one step launch on one GPU: B_alg = L + 2*S/K per event
         ev_gpu = events_per_step / world
-        log_bytes = 32.0 * records_per_step / world if log_cap else 0.0
-        alg_bytes = log_bytes + 2.0 * state_bytes * reps_gpu
+        launches_per_step = (n_events + K - 1) // K
+        log_bytes = 32.0 * records_per_step / world / launches_per_step if log_cap else 0.0
+        alg_bytes = log_bytes + 2.0 * state_bytes * reps_gpu  # per launch: state planes in and out + its log records
         k_ms = sorted(kernel_ms)[len(kernel_ms) // 2]
         achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+        # dram__bytes_read.sum + dram__bytes_write.sum of ONE step launch, from the committed ncu capture of this exact
+        # workload shape (profiles/r01_traffic.json); null for any other shape
+        traffic = None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+            rec = tr.get(args.workload, {}).get(args.log)
+            if rec and rec["replications"] == reps_gpu and rec["events"] == n_events:
+                traffic = rec["dram_bytes_per_launch"]
+        except Exception:
+            pass
         out = {
             "metric": "simulated events/sec", "value": value, "unit": "events/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
@@ -304,13 +323,14 @@ def run_ours(args):
             "config": workload_config(args, reps_gpu, n_events),
             "e2e": {"value": e2e_value, "unit": "events/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps},
-            "gpu_launches": 2 * args.steps,
+            "gpu_launches": (1 + launches_per_step) * args.steps,
             "clocks": clk,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "qk_step_kernel",
+                         "traffic": traffic, "peak_source": peak_src, "kernel": "qk_step_kernel",
                          "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg_bytes,
-                         "bytes_per_event": alg_bytes / ev_gpu, "state_bytes_per_replication": state_bytes,
-                         "events_per_residency_K": n_events},
+                         "bytes_per_event": alg_bytes * launches_per_step / ev_gpu,
+                         "state_bytes_per_replication": state_bytes, "events_per_residency_K": K,
+                         "launches_per_step": launches_per_step},
             "faulted_replications": int(ev_total[2].item()),
             "per_gpu_events_per_s": value / world,
         }
@@ -335,6 +355,9 @@ def main():
     ap.add_argument("--threads-per-block", type=int, default=0)
     ap.add_argument("--state", default="auto", choices=["auto", "hbm"],
                     help="auto: state staged in shared memory when it fits; hbm: operate on the HBM planes in place")
+    ap.add_argument("--events-per-launch", type=int, default=0,
+                    help="K: events advanced per state residency (default: all events of a step in one launch); small K "
+                         "makes the state round-trip HBM every K events -- the regime where the kernel is HBM-bound")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--e2e-log-reps", type=int, default=256)
     ap.add_argument("--ref-step-seconds", type=float, default=6.0)

@@ -283,6 +283,9 @@ int qk_batch_set_tape(qk_batch*, uint32_t dist_id, const double* values, uint64_
 int qk_batch_init(qk_batch*, uint64_t t0_ns);
 int qk_batch_step_until(qk_batch*, uint64_t t_ns);
 int qk_batch_step_events(qk_batch*, uint64_t n_events);
+/* same result as qk_batch_step_events, cut into launches of `chunk` events (state round-trips HBM between them);
+ * for measuring the kernel at a small number of events per state residency */
+int qk_batch_step_events_chunked(qk_batch*, uint64_t n_events, uint64_t chunk);
 int qk_batch_synchronize(qk_batch*);
 
 /* ---- results ------------------------------------------------------------------------------------ */

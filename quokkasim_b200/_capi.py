@@ -42,7 +42,7 @@ EXPORTED_SYMBOLS = [
     "qk_model_set_vector", "qk_model_set_ports", "qk_model_schedule_low_capacity", "qk_batch_read_vector",
     "qk_model_n_components", "qk_model_n_dists", "qk_model_state_bytes", "qk_batch_create", "qk_batch_destroy",
     "qk_batch_info_get",
-    "qk_batch_set_tape", "qk_batch_init", "qk_batch_step_until", "qk_batch_step_events", "qk_batch_synchronize",
+    "qk_batch_set_tape", "qk_batch_init", "qk_batch_step_until", "qk_batch_step_events", "qk_batch_step_events_chunked", "qk_batch_synchronize",
     "qk_batch_summary_get", "qk_batch_read_status", "qk_batch_comp_stats", "qk_batch_reduce_stats",
     "qk_batch_reduce_stats_device", "qk_batch_histograms_device", "qk_batch_read_log", "qk_batch_read_stock",
     "qk_batch_last_step_ms", "qk_last_error",
@@ -148,6 +148,7 @@ def load_library(path=None):
         "qk_batch_init": (C.c_int, [vp, u64]),
         "qk_batch_step_until": (C.c_int, [vp, u64]),
         "qk_batch_step_events": (C.c_int, [vp, u64]),
+        "qk_batch_step_events_chunked": (C.c_int, [vp, u64, u64]),
         "qk_batch_synchronize": (C.c_int, [vp]),
         "qk_batch_summary_get": (C.c_int, [vp, P(BatchSummary)]),
         "qk_batch_read_status": (C.c_int, [vp, u64, u64, vp, vp, vp]),

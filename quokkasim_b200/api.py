@@ -795,6 +795,11 @@ class BatchedSimulation:
         self._materialize()
         capi.check(self.L, self.L.qk_batch_step_events(self._batch, int(n_events)))
 
+    def step_events_chunked(self, n_events, chunk):
+        """step_events cut into launches of `chunk` events (state round-trips HBM between launches); same results."""
+        self._materialize()
+        capi.check(self.L, self.L.qk_batch_step_events_chunked(self._batch, int(n_events), int(chunk)))
+
     def synchronize(self):
         self._materialize()
         capi.check(self.L, self.L.qk_batch_synchronize(self._batch))

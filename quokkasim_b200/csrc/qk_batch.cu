@@ -110,7 +110,8 @@ static uint32_t choose_nt(uint32_t per_rep_bytes, uint32_t table_bytes, uint32_t
   return best_nt;
 }
 
-static int launch_step(qk_batch* b, uint32_t do_init, uint64_t t0, uint64_t t_until, uint64_t budget) {
+static int launch_step(qk_batch* b, uint32_t do_init, uint64_t t0, uint64_t t_until, uint64_t budget,
+                       bool record_begin = true, bool record_end = true) {
   KParams P;
   memset(&P, 0, sizeof(P));
   P.g64 = b->g64;
@@ -137,11 +138,14 @@ static int launch_step(qk_batch* b, uint32_t do_init, uint64_t t0, uint64_t t_un
   P.t_until = t_until;
   P.event_budget = budget;
   P.do_init = do_init;
-  CUDA_TRY(cudaEventRecord(b->ev0, b->stream));
+  if (record_begin) {
+    CUDA_TRY(cudaEventRecord(b->ev0, b->stream));
+    b->last_launches = 0;
+  }
   b->kernel<<<b->grid, b->nt, b->smem_bytes, b->stream>>>(P);
   CUDA_TRY(cudaGetLastError());
-  CUDA_TRY(cudaEventRecord(b->ev1, b->stream));
-  b->last_launches = 1;
+  if (record_end) CUDA_TRY(cudaEventRecord(b->ev1, b->stream));
+  b->last_launches += 1;
   b->total_launches += 1;
   return QK_OK;
 }
@@ -544,6 +548,29 @@ int qk_batch_step_events(qk_batch* b, uint64_t n_events) {
   }
   CUDA_TRY(cudaSetDevice(b->cfg.device));
   return launch_step(b, 0, 0, QK_TIME_NONE, n_events);
+}
+
+/* The same step cut into launches of `chunk` events each: every launch loads the hot state planes from HBM, advances
+ * each replication by at most `chunk` scheduler actions and stores the planes back (events advanced per state
+ * residency K = chunk; K = 1 is pure lockstep).  Results are identical to one launch (tests); this entry point exists
+ * to MEASURE the kernel where it is HBM-bound (bench.py --events-per-launch). */
+int qk_batch_step_events_chunked(qk_batch* b, uint64_t n_events, uint64_t chunk) {
+  if (!b || chunk == 0) return QK_ERR_INVALID_ARG;
+  if (!b->initialised) {
+    qk_set_error("qk_batch_step_events_chunked: call qk_batch_init first");
+    return QK_ERR_STATE;
+  }
+  CUDA_TRY(cudaSetDevice(b->cfg.device));
+  uint64_t left = n_events;
+  bool first = true;
+  while (left) {
+    const uint64_t k = left < chunk ? left : chunk;
+    left -= k;
+    const int rc = launch_step(b, 0, 0, QK_TIME_NONE, k, first, left == 0);
+    if (rc) return rc;
+    first = false;
+  }
+  return QK_OK;
 }
 
 int qk_batch_synchronize(qk_batch* b) {

@@ -37,12 +37,28 @@ __device__ __forceinline__ void qk_red_addf64(uint64_t* p, double v) { atomicAdd
 #endif
 
 #ifndef QK_HOST_EMUL
-/* one 32-byte log record = ONE store: sm_100 has 256-bit global stores (STG.E.ENL2.256), which halves the L1 tag
+/* one 32-byte log record = ONE streaming store (evict-first: log lines are never read back by the kernel and must not
+ * push the cold planes out of L2): sm_100 has 256-bit global stores (STG.E.EF.ENL2.256), which halves the L1 tag
  * work of the scattered per-replication log writes compared with two STG.128 */
 __device__ __forceinline__ void qk_store_record(uint4* r, const uint4& a, const uint4& b) {
-  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(r), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w),
+  asm volatile("st.global.cs.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(r), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w),
                "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
                : "memory");
+}
+#endif
+
+#ifndef QK_HOST_EMUL
+/* asynchronous global -> shared copies for staging the state planes (cp.async = LDGSTS) */
+__device__ __forceinline__ void qk_stage8(uint64_t* smem_dst, const uint64_t* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
+               : "memory");
+}
+__device__ __forceinline__ void qk_stage4(uint32_t* smem_dst, const uint32_t* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
+               : "memory");
+}
+__device__ __forceinline__ void qk_stage_wait() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
 #endif
 

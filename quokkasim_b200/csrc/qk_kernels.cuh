@@ -868,8 +868,13 @@ __global__ void __launch_bounds__(qk_lb_threads(SM), qk_lb_blocks(SM, FT)) qk_st
     S64(G64_NEVENTS) = 0;
   } else {
     if constexpr (SM != 0) {
-      for (uint32_t s = 0; s < P.n64; ++s) S64(s) = P.g64[(size_t)s * P.rep_pad + rep_local];
-      for (uint32_t s = 0; s < P.n32; ++s) S32(s) = P.g32[(size_t)s * P.rep_pad + rep_local];
+      /* stage this replication's hot planes: one asynchronous global->shared copy per slot (LDGSTS), all in flight at
+       * once and without a register round trip.  With few events per launch this load IS the kernel: issuing the
+       * slots as dependent LDG/STS pairs left it latency-bound at 44 % of the HBM roofline (profiles/README.md).
+       * Each thread reads back only what it copied itself, so waiting for its own group is enough. */
+      for (uint32_t s = 0; s < P.n64; ++s) qk_stage8(&S64(s), &P.g64[(size_t)s * P.rep_pad + rep_local]);
+      for (uint32_t s = 0; s < P.n32; ++s) qk_stage4(&S32(s), &P.g32[(size_t)s * P.rep_pad + rep_local]);
+      qk_stage_wait();
     }
     cx.now = S64(G64_NOW);
     cx.status = S32(G32_STATUS);
@@ -1041,7 +1046,9 @@ __global__ void __launch_bounds__(qk_lb_threads(SM), qk_lb_blocks(SM, FT)) qk_st
   S32(G32_EXT_CURSOR) = ext_cursor;
   S32(G32_LOGCNT) = cx.log_cnt;
   if constexpr (SM != 0) {
+#pragma unroll 4
     for (uint32_t s = 0; s < P.n64; ++s) P.g64[(size_t)s * P.rep_pad + rep_local] = S64(s);
+#pragma unroll 4
     for (uint32_t s = 0; s < P.n32; ++s) P.g32[(size_t)s * P.rep_pad + rep_local] = S32(s);
   }
 }

@@ -162,6 +162,16 @@ int qk_batch_step_events(qk_batch* b, uint64_t n) {
   if (!b || !b->initialised) return QK_ERR_STATE;
   return run(b, 0, 0, QK_TIME_NONE, n);
 }
+int qk_batch_step_events_chunked(qk_batch* b, uint64_t n, uint64_t chunk) {
+  if (!b || !b->initialised || chunk == 0) return QK_ERR_STATE;
+  while (n) {
+    const uint64_t k = n < chunk ? n : chunk;
+    n -= k;
+    const int rc = run(b, 0, 0, QK_TIME_NONE, k);
+    if (rc) return rc;
+  }
+  return QK_OK;
+}
 int qk_batch_synchronize(qk_batch*) { return QK_OK; }
 int qk_batch_last_step_ms(qk_batch*, float* ms, uint32_t* n) {
   if (ms) *ms = 0;

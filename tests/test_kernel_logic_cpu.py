@@ -209,3 +209,18 @@ def test_vector_flow_sink_delay_and_constant(emul_lib):
 def test_vector_hbm_resident_and_eager(emul_lib, emul_eager_lib):
     _check(emul_lib, H.vector_flow(3), 2, n_events=2000, log_capacity=32768, flags=1)
     _check(emul_eager_lib, H.vector_flow(3), 2, n_events=2000, log_capacity=32768)
+
+
+def test_chunked_stepping_equals_one_launch(emul_lib):
+    """qk_batch_step_events_chunked: K events per state residency, same trajectories (bench --events-per-launch)"""
+    m = H.discrete_queue()
+    a = m.sim(emul_lib, 3, base_seed=17, log_capacity=8192)
+    a.step_events(900)
+    for chunk in (1, 7, 900):
+        b = H.discrete_queue().sim(emul_lib, 3, base_seed=17, log_capacity=8192)
+        b.step_events_chunked(900, chunk)
+        for ci in range(len(m.components)):
+            assert a.comp_stats(ci).tobytes() == b.comp_stats(ci).tobytes()
+        assert a.read_log(2)[0].tobytes() == b.read_log(2)[0].tobytes()
+        b.close()
+    a.close()
