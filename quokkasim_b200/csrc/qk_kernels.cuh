@@ -821,12 +821,13 @@ __global__ void __launch_bounds__(qk_lb_threads(SM), qk_lb_blocks(SM, FT)) qk_st
   cx.npend = 0;
   const uint32_t n_comp = cx.hdr->n_comp, n_sched = cx.hdr->n_sched, n_ext = cx.hdr->n_ext;
   const uint32_t n_stale_words = cx.hdr->n_stale_words;
+  const uint32_t n_sched_pad = (n_sched + 3u) & ~3u;
 
   if (P.do_init) {
     /* fresh replication: zero state, no pending events, stocks hold their initial items */
     for (uint32_t s = 0; s < P.n64; ++s) S64(s) = 0;
     for (uint32_t s = 0; s < P.n32; ++s) S32(s) = 0;
-    for (uint32_t i = 0; i < n_sched; ++i) S64(G64_FIRE0 + i) = QK_TIME_NONE;
+    for (uint32_t i = 0; i < n_sched_pad; ++i) S64(G64_FIRE0 + i) = QK_TIME_NONE; /* incl. the padding slots */
     for (uint32_t s = 0; s < P.n64c; ++s) C64(s) = 0;
     for (uint32_t s = 0; s < P.n32c; ++s) C32(s) = 0;
     cx.now = P.t0;
@@ -918,11 +919,20 @@ __global__ void __launch_bounds__(qk_lb_threads(SM), qk_lb_blocks(SM, FT)) qk_st
         /* pop the scheduler queue: min over (time, rank); rank 0 = externally scheduled events */
         uint64_t best = (FT != 0 && ext_cursor < n_ext) ? cx.ext[ext_cursor].t : QK_TIME_NONE;
         int bi = -1;
-        for (uint32_t i = 0; i < n_sched; ++i) {
-          const uint64_t t = S64(G64_FIRE0 + i);
-          if (t < best) {
-            best = t;
-            bi = (int)i;
+        /* fire[] is padded with NONE to a multiple of four slots (lowering): groups of four independent loads and a
+         * two-level tournament instead of one long dependent chain of 64-bit compares.  Strict '<' everywhere keeps
+         * the LOWEST index among equal times, i.e. registration-rank order. */
+        for (uint32_t i = 0; i < n_sched_pad; i += 4) {
+          const uint64_t t0 = S64(G64_FIRE0 + i), t1 = S64(G64_FIRE0 + i + 1);
+          const uint64_t t2 = S64(G64_FIRE0 + i + 2), t3 = S64(G64_FIRE0 + i + 3);
+          const bool p01 = t1 < t0, p23 = t3 < t2;
+          const uint64_t a = p01 ? t1 : t0, b = p23 ? t3 : t2;
+          const uint32_t ai = p01 ? i + 1 : i, bj = p23 ? i + 3 : i + 2;
+          const bool pab = b < a;
+          const uint64_t m = pab ? b : a;
+          if (m < best) {
+            best = m;
+            bi = (int)(pab ? bj : ai);
           }
         }
         bool stale = false;

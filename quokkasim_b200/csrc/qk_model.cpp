@@ -424,7 +424,7 @@ int qk_lower(const qk_model* m, bool log, QkLowered* out) {
   const uint32_t n_pf = (uint32_t)pf_comp.size();
   const uint32_t n_pf_words = (n_pf + 31) / 32;
   uint32_t n64c = 0, n32c = 0; /* cold slots */
-  uint32_t n64 = G64_FIRE0 + n_sched;
+  uint32_t n64 = G64_FIRE0 + ((n_sched + 3u) & ~3u); /* fire[] padded to a multiple of four (scheduler scan) */
   const uint32_t pf32 = G32_STALE0 + n_stale_words;
   uint32_t n32 = pf32 + n_pf_words;
 

@@ -18,4 +18,6 @@ for lg in ring off; do
   C="python bench.py --steps 1 --warmup 0 --reps 131072 --events 1000 --no-cpu-baseline --e2e-steps 1 --log $lg"
   $C > $O/plain_small_$lg.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:qk_step_kernel -s 2 -c 1 -o $O/prof_small_$lg -f $C > $O/ncu_small_$lg.log 2>&1
 done
+# events per state residency K: where the kernel becomes HBM-bound (no profiler)
+bash scripts/gpu_lockstep.sh > $O/lockstep_sweep.txt 2>&1
 ls -la $O
