@@ -429,3 +429,112 @@ def vector_flow(dim=3, random=True, breakdowns=True, env_events=True, sink_delay
         m.reg(x)
     _log_all(m)
     return m
+
+
+def transport():
+    """quokkasim_examples/src/bin/transport.rs: Vector3 Stock -> Process (two delay modes, Uniform until-delay,
+    Constant until-fix) -> Stock; registration order stock_1, stock_2, process; seeds from DistributionFactory::new(1234)."""
+    m = Model()
+    c = qk.Distribution.Constant
+    df = qk.DistributionFactory.new(1234)
+    s1 = qk.ComponentModel.Vector3Stock(
+        qk.VectorStock.new().with_name("Stock 1").with_low_capacity(10.0).with_max_capacity(100.0)
+        .with_initial_resource(qk.Vector3([99.0, 0.0, 0.0])), qk.Mailbox.new())
+    d1 = df.create(qk.DistributionConfig.Uniform(5.0, 10.0))
+    d2 = df.create(qk.DistributionConfig.Uniform(40.0, 60.0))
+    m.random_dists += [d1, d2]
+    p = qk.ComponentModel.Vector3Process(
+        qk.VectorProcess.new().with_name("Process").with_process_quantity_distr(c(1.0)).with_process_time_distr(c(1.0))
+        .with_delay_mode(qk.DelayModeChange.Add(qk.DelayMode("ShortDelay", d1, c(1.0))))
+        .with_delay_mode(qk.DelayModeChange.Add(qk.DelayMode("LongDelay", d2, c(5.0)))), qk.Mailbox.new())
+    s2 = qk.ComponentModel.Vector3Stock(
+        qk.VectorStock.new().with_name("Stock 2").with_low_capacity(10.0).with_max_capacity(100.0)
+        .with_initial_resource(qk.Vector3([0.0, 0.0, 0.0])), qk.Mailbox.new())
+    qk.connect_components(s1, p)
+    qk.connect_components(p, s2)
+    for x in (s1, s2, p):
+        m.reg(x)
+    _log_all(m)
+    return m
+
+
+def delay_testing():
+    """quokkasim_examples/src/bin/delay_testing.rs: F64 Stock -> Process (DelayMode Constant 7 / 2) -> Stock, with a
+    BasicEnvironment stopped at 4 s and resumed at 24 s; horizon 40 s."""
+    m = Model()
+    c = qk.Distribution.Constant
+    s1 = qk.ComponentModel.F64Stock(
+        qk.VectorStock.new().with_name("Stock1").with_code("S1").with_initial_resource(100.0).with_low_capacity(10.0)
+        .with_max_capacity(1000.0), qk.Mailbox.new())
+    p = qk.ComponentModel.F64Process(
+        qk.VectorProcess.new().with_name("Process").with_code("P1").with_process_quantity_distr(c(10.0))
+        .with_process_time_distr(c(10.0))
+        .with_delay_mode(qk.DelayModeChange.Add(qk.DelayMode("ProcessDelay", c(7.0), c(2.0)))), qk.Mailbox.new())
+    s2 = qk.ComponentModel.F64Stock(
+        qk.VectorStock.new().with_name("Stock2").with_code("S2").with_low_capacity(10.0).with_max_capacity(1000.0),
+        qk.Mailbox.new())
+    env = qk.ComponentModel.BasicEnvironment(qk.BasicEnvironment.new().with_name("Environment").with_code("E1"),
+                                             qk.Mailbox.new())
+    qk.connect_components(s1, p)
+    qk.connect_components(p, s2, 0)  # the example passes Some(0); the arm ignores it (core.rs:578-583)
+    qk.connect_components(env, p)
+    for x in (s1, s2, p, env):
+        m.reg(x)
+    m.ext.append((qk.Duration.from_secs(4), env, qk.BasicEnvironmentState.Stopped))
+    m.ext.append((qk.Duration.from_secs(24), env, qk.BasicEnvironmentState.Normal))
+    _log_all(m)
+    return m
+
+
+def the_example():
+    """quokkasim_examples/src/bin/the_example.rs ("rocks"): two VectorSources into one stock, trucking process, a
+    Splitter2 with a breakdown mode, two sinks (one with Uniform time and TruncNormal quantity); t0 = 2025-06-22."""
+    m = Model()
+    c = qk.Distribution.Constant
+    df = qk.DistributionFactory.new(12345)
+    V = qk.Vector3
+
+    def cm(kind, comp):
+        return getattr(qk.ComponentModel, "Vector3" + kind)(comp, qk.Mailbox.new())
+
+    rs1 = cm("Source", qk.VectorSource.new().with_name("Rock Source 1").with_code("RS1").with_process_time_distr(c(600.0))
+             .with_process_quantity_distr(c(5000.0)).with_source_vector(V([300.0, 100.0, 0.0])))
+    rs2 = cm("Source", qk.VectorSource.new().with_name("Rock Source 2").with_code("RS2").with_process_time_distr(c(300.0))
+             .with_process_quantity_distr(c(2000.0)).with_source_vector(V([200.0, 200.0, 0.0])))
+    st1 = cm("Stock", qk.VectorStock.new().with_name("Rock Stock 1").with_code("RS1").with_low_capacity(100.0)
+             .with_max_capacity(2000.0).with_initial_resource(V([1600.0, 400.0, 0.0])))
+    trucking = cm("Process", qk.VectorProcess.new().with_name("Trucking").with_code("T1").with_process_time_distr(c(18.0))
+                  .with_process_quantity_distr(c(60.0)))
+    st2 = cm("Stock", qk.VectorStock.new().with_name("Rock Stock 2").with_code("RS2").with_low_capacity(100.0)
+             .with_max_capacity(2000.0).with_initial_resource(V([1600.0, 400.0, 0.0])))
+    ud = df.create(qk.DistributionConfig.Uniform(60.0, 180.0))
+    uf = df.create(qk.DistributionConfig.Uniform(10.0, 60.0))
+    conveyors = cm("Splitter2", qk.VectorSplitter.new().with_name("Conveyor").with_code("C1")
+                   .with_process_time_distr(c(18.0)).with_process_quantity_distr(c(60.0))
+                   .with_split_ratios([2.0 / 3.0, 1.0 / 3.0])
+                   .with_delay_mode(qk.DelayModeChange.Add(qk.DelayMode("Short Delay", ud, uf))))
+    pf1 = cm("Stock", qk.VectorStock.new().with_name("Process Feed 1").with_code("PF1").with_low_capacity(100.0)
+             .with_max_capacity(500.0))
+    p1 = cm("Sink", qk.VectorSink.new().with_name("Processing 1").with_code("P1").with_process_time_distr(c(18.0))
+            .with_process_quantity_distr(c(60.0)))
+    pf2 = cm("Stock", qk.VectorStock.new().with_name("Process Feed 2").with_code("PF2").with_low_capacity(100.0)
+             .with_max_capacity(500.0))
+    t2 = df.create(qk.DistributionConfig.Uniform(10.0, 26.0))
+    q2 = df.create(qk.DistributionConfig.TruncNormal(30.0, 10.0, min=1.0, max=None))
+    p2 = cm("Sink", qk.VectorSink.new().with_name("Processing 2").with_code("P2").with_process_time_distr(t2)
+            .with_process_quantity_distr(q2))
+    m.random_dists += [ud, uf, t2]  # q2 (TruncNormal) stays on its native stream in tape tests
+    qk.connect_components(rs1, st1)
+    qk.connect_components(rs2, st1)
+    qk.connect_components(st1, trucking)
+    qk.connect_components(trucking, st2)
+    qk.connect_components(st2, conveyors)
+    qk.connect_components(conveyors, pf1, 0)
+    qk.connect_components(conveyors, pf2, 1)
+    qk.connect_components(pf1, p1)
+    qk.connect_components(pf2, p2)
+    for x in (rs1, rs2, st1, trucking, st2, conveyors, pf1, p1, pf2, p2):
+        m.reg(x)
+    m.t0 = qk.MonotonicTime.try_from_date_time(2025, 6, 22, 0, 0, 0, 0)
+    _log_all(m)
+    return m

@@ -284,3 +284,11 @@ def test_state_placement_does_not_change_results(gpu_lib):
     assert a.info()["state_in_hbm"] == 0 and b.info()["state_in_hbm"] == 1
     a.close()
     b.close()
+
+
+def test_reference_vector_examples_transport_delay_testing_rocks(gpu_lib):
+    """transport.rs, delay_testing.rs, the_example.rs at their own horizons"""
+    _check(gpu_lib, H.transport(), 64, t_until=120 * S, sample=[0, 63], log_capacity=8192)
+    _check(gpu_lib, H.delay_testing(), 32, t_until=40 * S, sample=[0], log_capacity=1024)
+    m = H.the_example()
+    _check(gpu_lib, m, 64, t_until=m.t0 + 700 * S, t0=m.t0, sample=[0, 31, 63], log_capacity=8192)

@@ -224,3 +224,13 @@ def test_chunked_stepping_equals_one_launch(emul_lib):
         assert a.read_log(2)[0].tobytes() == b.read_log(2)[0].tobytes()
         b.close()
     a.close()
+
+
+def test_reference_vector_examples_transport_delay_testing_rocks(emul_lib):
+    """transport.rs (120 s), delay_testing.rs (40 s), the_example.rs (700 s from 2025-06-22): the remaining
+    reference examples that are built from the stock component set"""
+    _check(emul_lib, H.transport(), 3, t_until=120 * S, log_capacity=8192)
+    _check(emul_lib, H.transport(), 2, t_until=120 * S, tape_len=200, log_capacity=8192)
+    _check(emul_lib, H.delay_testing(), 1, t_until=40 * S, log_capacity=1024)
+    m = H.the_example()
+    _check(emul_lib, m, 3, t_until=m.t0 + 700 * S, t0=m.t0, log_capacity=8192)
