@@ -72,7 +72,18 @@ typedef enum {
   QK_VECTOR_SOURCE = 18,   /* VectorSource   vector.rs:1324-1358 */
   QK_VECTOR_SINK = 19,     /* VectorSink     vector.rs:1578-1612 */
   QK_VECTOR_COMBINER = 20, /* VectorCombiner vector.rs:726-765 */
-  QK_VECTOR_SPLITTER = 21  /* VectorSplitter vector.rs:1026-1065 */
+  QK_VECTOR_SPLITTER = 21, /* VectorSplitter vector.rs:1026-1065 */
+  /* container family (components/vector_container.rs; ComponentModel::Vector3Container*, core.rs:549-555): discrete
+   * items that carry an Option<Vector3> resource and a capacity.  Stock/Process/ParallelProcess/Source/Sink are the
+   * discrete components instantiated with Vector3Container; Load/Unload move resource between a Vector3Stock and the
+   * containers.  For Load/Unload `max_capacity` of the descriptor is max_process_count (default 1). */
+  QK_CONTAINER_STOCK = 32,            /* Vector3ContainerStock            core.rs:549 */
+  QK_CONTAINER_PROCESS = 33,          /* Vector3ContainerProcess          core.rs:550 */
+  QK_CONTAINER_SOURCE = 34,           /* Vector3ContainerSource           core.rs:552 */
+  QK_CONTAINER_SINK = 35,             /* Vector3ContainerSink             core.rs:553 */
+  QK_CONTAINER_PARALLEL_PROCESS = 36, /* Vector3ContainerParallelProcess  core.rs:551 */
+  QK_CONTAINER_LOAD_PROCESS = 37,     /* ContainerLoadingProcess          vector_container.rs:158-196 */
+  QK_CONTAINER_UNLOAD_PROCESS = 38    /* ContainerUnloadingProcess        vector_container.rs:445-483 */
 } qk_component_kind;
 
 /* DistributionConfig (common.rs:37-44) */
@@ -145,7 +156,10 @@ typedef enum {
   QK_REASON_AN_UPSTREAM_EMPTY = 9,        /* "At least one upstream is empty"   vector.rs:938 */
   QK_REASON_NO_UPSTREAMS = 10,            /* "No upstreams are connected"       vector.rs:942 */
   QK_REASON_A_DOWNSTREAM_FULL = 11,       /* "At least one downstream is full"  vector.rs:1231 */
-  QK_REASON_NO_DOWNSTREAMS = 12           /* "No downstreams are connected"     vector.rs:1235 */
+  QK_REASON_NO_DOWNSTREAMS = 12,          /* "No downstreams are connected"     vector.rs:1235 */
+  QK_REASON_NO_PROCESS_SLOTS = 13,        /* "No remaining process slots"          vector_container.rs:369,676 */
+  QK_REASON_DS_CONTAINERS_FULL = 14,      /* "Downstream container stock is full"  vector_container.rs:601 */
+  QK_REASON_DS_RESOURCE_FULL = 15         /* "Downstream resource stock is full"   vector_container.rs:605 */
 } qk_reason;
 
 #define QK_SRC_INIT 0xFFFFu /* source_event_id "INIT_000000" (common.rs:14) */
@@ -154,6 +168,10 @@ typedef enum {
 /* item handle = (source ordinal << 26) | index; ordinal 63 = initial stock contents */
 #define QK_ITEM_SOURCE(h) ((uint32_t)(h) >> 26)
 #define QK_ITEM_INDEX(h) ((uint32_t)(h)&0x3FFFFFFu)
+/* a container whose `resource` is None: the first double of its vector carries this (signalling-NaN) bit pattern.
+ * Records that serialise a container (ProcessStart / ProcessFinish / Add / Remove(Some)) of a container component are
+ * followed by ONE QK_LOG_VEC_DATA continuation record holding the container's resource. */
+#define QK_CONTAINER_NONE_BITS 0x7FF40000000000C0ull
 
 typedef struct {
   uint64_t time_ns;  /* absolute ns since MonotonicTime::EPOCH */
@@ -177,7 +195,8 @@ typedef enum {
   QK_REP_EMIT_OVERFLOW = 5,  /* too many pending emit_change events on one stock */
   QK_REP_PARALLEL_OVERFLOW = 6,
   QK_REP_ITEM_INDEX_OVERFLOW = 7,
-  QK_REP_SOURCE_VECTOR = 8 /* panic!("Source vector has total 0 or negative") vector.rs:1490 */
+  QK_REP_SOURCE_VECTOR = 8, /* panic!("Source vector has total 0 or negative") vector.rs:1490 */
+  QK_REP_NOT_CONNECTED = 9  /* `.next().unwrap()` on a port nobody connected (vector_container.rs:358) */
 } qk_rep_status;
 
 /* per-component, per-replication summary (exact integers) */
@@ -240,6 +259,15 @@ int qk_model_set_ports(qk_model*, uint32_t comp, uint32_t n_ports, const double*
 /* create_scheduled_event!(SetLowCapacity(v)) on an F64Stock (core.rs:1382-1386): setter + add(0.) at t */
 int qk_model_schedule_low_capacity(qk_model*, uint64_t t_ns, uint32_t stock, double value);
 int qk_model_schedule_env_state(qk_model*, uint64_t t_ns, uint32_t env, uint32_t state);
+/* Vector3ContainerFactory of a QK_CONTAINER_SOURCE (vector_container.rs:126-156): create_quantity_distr (NULL = None:
+ * containers are created empty), create_component_split[3], capacity.  *out_dist_id = the distribution instance
+ * (for tapes) or 0xFFFFFFFF */
+int qk_model_set_container_factory(qk_model*, uint32_t source, const qk_dist_desc* create_quantity, const double* split3,
+                                   double capacity, uint32_t* out_dist_id);
+/* with_initial_resource(ItemDeque<Vector3Container>) of a QK_CONTAINER_STOCK: n containers in FIFO order with
+ * resources[n][3] (ignored where has_resource[k] == 0), capacities[n].  Replaces n_initial_items of the descriptor. */
+int qk_model_set_initial_containers(qk_model*, uint32_t stock, uint32_t n, const double* resources,
+                                    const uint8_t* has_resource, const double* capacities);
 int qk_model_n_components(const qk_model*, uint32_t* out);
 int qk_model_n_dists(const qk_model*, uint32_t* out);
 /* bytes of on-chip state one replication needs (for capacity planning / roofline arithmetic) */
@@ -306,6 +334,11 @@ int qk_batch_read_log(qk_batch*, uint64_t rep, qk_log_record* buf, uint64_t cap,
 int qk_batch_read_vector(qk_batch*, uint64_t rep, uint32_t comp, double* out3);
 /* discrete stock contents in FIFO order */
 int qk_batch_read_stock(qk_batch*, uint64_t rep, uint32_t comp, uint32_t* items, uint64_t cap, uint64_t* n_out);
+/* containers held by a container stock (FIFO order) or by a container process-like component (in progress first, then
+ * completed-but-not-pushed): handles[cap], resources[cap][3] as raw fp64 bits (first word QK_CONTAINER_NONE_BITS for a
+ * container without resource) */
+int qk_batch_read_containers(qk_batch*, uint64_t rep, uint32_t comp, uint32_t* handles, uint64_t* resources,
+                             uint64_t cap, uint64_t* n_out);
 /* timing of the last step call measured with CUDA events on the batch's stream (ms) and kernels launched */
 int qk_batch_last_step_ms(qk_batch*, float* ms, uint32_t* n_launches);
 

@@ -13,11 +13,27 @@ def lower_to_oracle(model):
     comps = [c.component for c in model.components]
     index = {id(c): i for i, c in enumerate(comps)}
     for c in comps:
-        if c.KIND == O.DISCRETE_STOCK:
-            i = om.add_component(c.KIND, c.low_capacity, c.max_capacity, len(c.resource))
+        kind = getattr(c, "_container_kind", None) or c.KIND
+        if kind == O.DISCRETE_STOCK:
+            i = om.add_component(kind, c.low_capacity, c.max_capacity, len(c.resource))
+        elif kind == O.CONTAINER_STOCK:
+            i = om.add_component(kind, c.low_capacity, c.max_capacity, 0)
+            if len(c.resource):
+                om.set_initial_containers(
+                    i, [(it.resource.values if it.resource is not None else [0.0, 0.0, 0.0]) for it in c.resource],
+                    [it.resource is not None for it in c.resource], [it.capacity for it in c.resource])
+        elif hasattr(c, "max_process_count"):
+            i = om.add_component(kind, 0, c.max_process_count, 0)
         else:
-            i = om.add_component(c.KIND)
+            i = om.add_component(kind)
         assert i == index[id(c)]
+        if kind == O.CONTAINER_SOURCE:
+            f = c.item_factory
+            q = f.create_quantity_distr
+            did = om.set_container_factory(i, O.make_dist(q.kind, q.stream, q.params) if q is not None else None,
+                                           f.create_component_split, f.capacity)
+            if q is not None:
+                dist_ids.setdefault(id(q), []).append(did)
         if hasattr(c, "vector_rows"):
             dim, low, maxc, init = c.vector_rows()
             om.set_vector(i, dim, low, maxc, init)

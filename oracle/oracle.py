@@ -15,6 +15,9 @@ _LIB = None
 # numeric codes (restated from qk_oracle.h)
 DISCRETE_STOCK, DISCRETE_PROCESS, DISCRETE_SOURCE, DISCRETE_SINK, DISCRETE_PARALLEL_PROCESS, ENVIRONMENT = 1, 2, 3, 4, 5, 6
 VECTOR_STOCK, VECTOR_PROCESS, VECTOR_SOURCE, VECTOR_SINK, VECTOR_COMBINER, VECTOR_SPLITTER = 16, 17, 18, 19, 20, 21
+CONTAINER_STOCK, CONTAINER_PROCESS, CONTAINER_SOURCE, CONTAINER_SINK = 32, 33, 34, 35
+CONTAINER_PARALLEL_PROCESS, CONTAINER_LOAD_PROCESS, CONTAINER_UNLOAD_PROCESS = 36, 37, 38
+CONTAINER_NONE_BITS = 0x7FF40000000000C0
 DIST_CONSTANT, DIST_UNIFORM, DIST_TRIANGULAR, DIST_NORMAL, DIST_TRUNCNORMAL, DIST_EXPONENTIAL = 0, 1, 2, 3, 4, 5
 
 LOG_DTYPE = np.dtype(
@@ -92,6 +95,9 @@ def lib():
         "orc_sim_stock_items": (u64, [vp, u32, P(u32), u64]),
         "orc_sim_vector_resource": (C.c_int, [vp, u32, P(dbl)]),
         "orc_sim_draws": (u64, [vp, u32]),
+        "orc_model_set_container_factory": (C.c_int, [vp, u32, P(Dist), P(dbl), dbl, P(C.c_int)]),
+        "orc_model_set_initial_containers": (C.c_int, [vp, u32, u32, vp, vp, vp]),
+        "orc_sim_containers": (u64, [vp, u32, vp, vp, u64]),
         "orc_run_batch": (u64, [vp, u64, u64, u64, u64, u64, u64, C.c_int, C.c_int, vp, vp, vp, vp]),
         "orc_from_secs_f64": (C.c_int, [dbl, P(u64)]),
         "orc_philox4x32_10": (None, [P(u32), P(u32), P(u32)]),
@@ -166,6 +172,22 @@ class OracleModel:
         arr = (C.c_double * len(ratios))(*ratios)
         if self.L.orc_model_set_splits(self.h, comp, len(ratios), arr) != 0:
             raise RuntimeError("orc_model_set_splits failed")
+
+    def set_container_factory(self, source, create_quantity, split, capacity):
+        did = C.c_int(-1)
+        arr = (C.c_double * 3)(*[float(x) for x in split])
+        rc = self.L.orc_model_set_container_factory(self.h, source, C.byref(create_quantity) if create_quantity else None,
+                                                    arr, capacity, C.byref(did))
+        if rc != 0:
+            raise RuntimeError("orc_model_set_container_factory failed")
+        return did.value
+
+    def set_initial_containers(self, stock, resources, has, capacities):
+        r = np.ascontiguousarray(resources, dtype=np.float64).reshape(-1, 3)
+        h = np.ascontiguousarray(has, dtype=np.uint8)
+        c = np.ascontiguousarray(capacities, dtype=np.float64)
+        if self.L.orc_model_set_initial_containers(self.h, stock, len(h), r.ctypes.data, h.ctypes.data, c.ctypes.data) != 0:
+            raise RuntimeError("orc_model_set_initial_containers failed")
 
     def schedule_low_capacity(self, t_ns, stock, value):
         if self.L.orc_model_schedule_low_capacity(self.h, t_ns, stock, value) != 0:
@@ -242,6 +264,12 @@ class OracleSim:
         out = (C.c_double * 3)()
         self.L.orc_sim_vector_resource(self.h, comp, out)
         return list(out)
+
+    def containers(self, comp):
+        h = np.zeros(4096, dtype=np.uint32)
+        r = np.zeros((4096, 3), dtype=np.uint64)
+        n = self.L.orc_sim_containers(self.h, comp, h.ctypes.data, r.ctypes.data, 4096)
+        return h[:n], r[:n]
 
     def draws(self, dist_id):
         return self.L.orc_sim_draws(self.h, dist_id)

@@ -20,6 +20,7 @@
 #include <cmath>
 #include <cstring>
 #include <deque>
+#include <map>
 #include <queue>
 #include <thread>
 #include <vector>
@@ -265,9 +266,17 @@ struct CompDef {
   int ups[5], downs[5];
   uint32_t n_ports;
   double ratios[5];
+  /* container family (vector_container.rs): factory of a container source; initial contents of a container stock */
+  int dist_cqty; /* create_quantity_distr instance or -1 (None) */
+  double csplit[3], ccapacity;
+  std::vector<std::array<double, 3> > init_res;
+  std::vector<uint8_t> init_has;
+  std::vector<double> init_cap;
   CompDef()
       : kind(0), low(0), max(1), n_initial(0), initial_base(0), dist_time(-1), dist_qty(-1), upstream(-1),
-        downstream(-1), env(-1), source_ordinal(-1), dim(0), vlow(0), vmax(0), n_ports(0) {
+        downstream(-1), env(-1), source_ordinal(-1), dim(0), vlow(0), vmax(0), n_ports(0), dist_cqty(-1),
+        ccapacity(0) {
+    csplit[0] = csplit[1] = csplit[2] = 0;
     for (int i = 0; i < 5; ++i) {
       ups[i] = downs[i] = -1;
       ratios[i] = 0;
@@ -292,7 +301,13 @@ struct orc_model {
   std::vector<ExtEvent> ext;
   uint32_t n_sources;
   uint32_t n_initial_total;
-  orc_model() : n_sources(0), n_initial_total(0) {}
+  /* container capacities: immutable per container, so they are a function of the handle --
+   * by source ordinal (factory capacity) or by initial-item index */
+  double src_caps[64];
+  std::vector<double> init_caps;
+  orc_model() : n_sources(0), n_initial_total(0) {
+    for (int i = 0; i < 64; ++i) src_caps[i] = 0;
+  }
 };
 
 namespace {
@@ -300,7 +315,15 @@ namespace {
 inline bool is_process_like(uint32_t k) {
   return k == ORC_DISCRETE_PROCESS || k == ORC_DISCRETE_SOURCE || k == ORC_DISCRETE_SINK ||
          k == ORC_DISCRETE_PARALLEL_PROCESS || k == ORC_VECTOR_PROCESS || k == ORC_VECTOR_SOURCE ||
-         k == ORC_VECTOR_SINK || k == ORC_VECTOR_COMBINER || k == ORC_VECTOR_SPLITTER;
+         k == ORC_VECTOR_SINK || k == ORC_VECTOR_COMBINER || k == ORC_VECTOR_SPLITTER ||
+         (k >= ORC_CONTAINER_PROCESS && k <= ORC_CONTAINER_UNLOAD_PROCESS);
+}
+/* DiscreteStock<T> for T = String or Vector3Container (core.rs:541,549) */
+inline bool is_item_stock(uint32_t k) { return k == ORC_DISCRETE_STOCK || k == ORC_CONTAINER_STOCK; }
+inline bool is_container_kind(uint32_t k) { return k >= ORC_CONTAINER_STOCK && k <= ORC_CONTAINER_UNLOAD_PROCESS; }
+inline bool is_multi_server(uint32_t k) {
+  return k == ORC_DISCRETE_PARALLEL_PROCESS || k == ORC_CONTAINER_PARALLEL_PROCESS ||
+         k == ORC_CONTAINER_LOAD_PROCESS || k == ORC_CONTAINER_UNLOAD_PROCESS;
 }
 
 enum { CAT_EMPTY = 0, CAT_NORMAL = 1, CAT_FULL = 2, CAT_NONE = 3 };
@@ -395,6 +418,18 @@ struct orc_sim {
   int pay_cat_next = 0;
   double pay_occ_next = 0;
   std::vector<orc_log_record> logs;
+  /* container family: a container IS its handle; what it carries lives here (Vector3Container.resource) */
+  struct CPay {
+    bool has;
+    double v[3];
+  };
+  std::map<uint32_t, CPay> cpay;
+  double container_capacity(uint32_t h) const {
+    return (h >> 26) == 63u ? m->init_caps[h & 0x3FFFFFFu] : m->src_caps[h >> 26];
+  }
+  void impl_load(uint32_t, EvId*);   /* oracle/qk_oracle_container.inc */
+  void impl_unload(uint32_t, EvId*);
+  void create_container(const CompDef&, uint32_t);
 
   /* ---- sampling -------------------------------------------------------------------------- */
   double sample(int dist_id) {
@@ -430,6 +465,29 @@ struct orc_sim {
       r.src_seq = src.seq;
       r.payload = payload;
       logs.push_back(r);
+      /* records that serialise an item (discrete.rs:299-316, 612-631): a container's JSON carries its resource, so
+       * its vector follows as one continuation record (format: qk_oracle_vector.inc header) */
+      if (is_container_kind(m->comps[comp].kind) &&
+          (kind == ORC_LOG_PROCESS_START || kind == ORC_LOG_PROCESS_FINISH || kind == ORC_LOG_STOCK_ADD ||
+           (kind == ORC_LOG_STOCK_REMOVE && payload != ORC_ITEM_NONE))) {
+        const CPay& cp = cpay[(uint32_t)payload];
+        uint64_t w[3];
+        for (int k = 0; k < 3; ++k) std::memcpy(&w[k], &cp.v[k], 8);
+        if (!cp.has) {
+          w[0] = ORC_CONTAINER_NONE_BITS;
+          w[1] = w[2] = 0;
+        }
+        orc_log_record q;
+        std::memset(&q, 0, sizeof(q));
+        q.time_ns = w[0];
+        q.comp = (uint16_t)comp;
+        q.kind = ORC_LOG_VEC_DATA;
+        q.reason = 0;
+        q.seq = id.seq;
+        std::memcpy(&q.src_comp, &w[1], 8);
+        q.payload = w[2];
+        logs.push_back(q);
+      }
     }
     s.next_event_index += 1;
     return id;
@@ -603,17 +661,29 @@ struct orc_sim {
     /* pre_update_state (discrete.rs:404-412): forget (do NOT cancel) a handle whose time has come */
     if (p.sched_some && p.sched_time <= now) p.sched_some = false;
     switch (d.kind) {
+      /* Vector3ContainerProcess/Source/Sink/ParallelProcess ARE DiscreteProcess<.., Vector3Container> etc.
+       * (core.rs:550-553): same code, the item is a container */
       case ORC_DISCRETE_PROCESS:
+      case ORC_CONTAINER_PROCESS:
         impl_process(pidx, &src);
         break;
       case ORC_DISCRETE_SOURCE:
+      case ORC_CONTAINER_SOURCE:
         impl_source(pidx, &src);
         break;
       case ORC_DISCRETE_SINK:
+      case ORC_CONTAINER_SINK:
         impl_sink(pidx, &src);
         break;
       case ORC_DISCRETE_PARALLEL_PROCESS:
+      case ORC_CONTAINER_PARALLEL_PROCESS:
         impl_parallel(pidx, &src);
+        break;
+      case ORC_CONTAINER_LOAD_PROCESS:
+        impl_load(pidx, &src);
+        break;
+      case ORC_CONTAINER_UNLOAD_PROCESS:
+        impl_unload(pidx, &src);
         break;
       default:
         impl_vector(pidx, &src);
@@ -752,6 +822,7 @@ struct orc_sim {
           /* ItemFactory::create_item (discrete.rs:680-686): handle = (source ordinal, next_index) */
           uint32_t item = ((uint32_t)d.source_ordinal << 26) | (uint32_t)(p.next_item_index & 0x3FFFFFFu);
           p.next_item_index += 1;
+          if (d.kind == ORC_CONTAINER_SOURCE) create_container(d, item); /* Vector3ContainerFactory::create_item */
           p.left = dur_from(secs);
           p.item = item;
           p.has_item = true;
@@ -956,8 +1027,17 @@ struct orc_sim {
           c[i].vlow = d.vlow;
           c[i].area_last_t = t0;
         }
-        if (d.kind == ORC_DISCRETE_STOCK) {
-          for (uint32_t k = 0; k < d.n_initial; ++k) c[i].items.push_back((63u << 26) | (d.initial_base + k));
+        if (is_item_stock(d.kind)) {
+          for (uint32_t k = 0; k < d.n_initial; ++k) {
+            const uint32_t h = (63u << 26) | (d.initial_base + k);
+            c[i].items.push_back(h);
+            if (d.kind == ORC_CONTAINER_STOCK) {
+              CPay cp;
+              cp.has = d.init_has[k] != 0;
+              for (int j = 0; j < 3; ++j) cp.v[j] = cp.has ? d.init_res[k][(size_t)j] : 0.0;
+              cpay[h] = cp;
+            }
+          }
           c[i].area_last_t = t0;
           c[i].st.t_b_ns = d.n_initial;
         }
@@ -1000,7 +1080,7 @@ struct orc_sim {
             update_state(a.target, a.src);
             break;
           case ACT_EMIT:
-            if (m->comps[a.target].kind == ORC_DISCRETE_STOCK)
+            if (is_item_stock(m->comps[a.target].kind))
               stock_emit_change(a.target, a.src);
             else
               vstock_emit_change(a.target, a.src, a.pay_cat, a.pay_occ);
@@ -1029,13 +1109,13 @@ struct orc_sim {
 
   void finalize_stats() {
     for (size_t i = 0; i < c.size(); ++i)
-      if (m->comps[i].kind == ORC_DISCRETE_STOCK) stock_area((uint32_t)i);
+      if (is_item_stock(m->comps[i].kind)) stock_area((uint32_t)i);
       else if (m->comps[i].kind == ORC_VECTOR_STOCK) vstock_area((uint32_t)i);
   }
 };
 
-/* vector components are added in a later milestone; keep the link closed */
 #include "qk_oracle_vector.inc"
+#include "qk_oracle_container.inc"
 
 /* =========================================== C API ========================================== */
 extern "C" {
@@ -1051,7 +1131,8 @@ int orc_model_add_component(orc_model* m, uint32_t kind, uint32_t low, uint32_t 
   d.n_initial = n_initial;
   d.initial_base = m->n_initial_total;
   m->n_initial_total += n_initial;
-  if (kind == ORC_DISCRETE_SOURCE) d.source_ordinal = (int)m->n_sources++;
+  if (kind == ORC_DISCRETE_SOURCE || kind == ORC_CONTAINER_SOURCE) d.source_ordinal = (int)m->n_sources++;
+  if (is_container_kind(kind)) d.dim = 3;
   if (is_process_like(kind)) {
     /* Default::default() for Distribution is Constant(1.) (common.rs:181-185) */
     orc_dist one;
@@ -1110,7 +1191,8 @@ int orc_model_connect(orc_model* m, uint32_t a, uint32_t b, int32_t port_n) {
     A.downstream = (int)b;
     return 0;
   }
-  if (A.kind == ORC_ENVIRONMENT && is_process_like(B.kind)) { /* core.rs:1129-1148 */
+  /* core.rs:1129-1172; there is no (BasicEnvironment, Vector3ContainerParallelProcess) arm */
+  if (A.kind == ORC_ENVIRONMENT && is_process_like(B.kind) && B.kind != ORC_CONTAINER_PARALLEL_PROCESS) {
     if (B.env >= 0) return -2;
     A.subscribers.push_back((int)b);
     B.env = (int)a;
@@ -1118,6 +1200,8 @@ int orc_model_connect(orc_model* m, uint32_t a, uint32_t b, int32_t port_n) {
   }
   {
     int rc = orc_connect_vector(m, a, b, port_n);
+    if (rc != -3) return rc;
+    rc = orc_connect_container(m, a, b);
     if (rc != -3) return rc;
   }
   return -3; /* "No component connection defined from {} to {}" */
@@ -1195,7 +1279,7 @@ int orc_sim_comp_stats(orc_sim* s, uint32_t comp, orc_comp_stats* out) {
   const uint32_t kind = s->m->comps[comp].kind;
   if (is_process_like(kind) && !(s->dm_active(p) >= 0 || p.env_stopped)) {
     const uint64_t dt = s->now - p.previous_check_time;
-    if (kind == ORC_DISCRETE_PARALLEL_PROCESS) {
+    if (is_multi_server(kind)) {
       for (size_t i = 0; i < p.in_progress.size(); ++i) out->t_a_ns += std::min(dt, p.in_progress[i].first);
     } else if (p.has_item) {
       out->t_a_ns += std::min(dt, p.left);

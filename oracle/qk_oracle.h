@@ -42,7 +42,16 @@ enum {
   ORC_VECTOR_SOURCE = 18,
   ORC_VECTOR_SINK = 19,
   ORC_VECTOR_COMBINER = 20,
-  ORC_VECTOR_SPLITTER = 21
+  ORC_VECTOR_SPLITTER = 21,
+  /* container family (components/vector_container.rs; ComponentModel::Vector3Container*, core.rs:549-555):
+   * discrete items that carry an Option<Vector3> resource and a capacity */
+  ORC_CONTAINER_STOCK = 32,
+  ORC_CONTAINER_PROCESS = 33,
+  ORC_CONTAINER_SOURCE = 34,
+  ORC_CONTAINER_SINK = 35,
+  ORC_CONTAINER_PARALLEL_PROCESS = 36,
+  ORC_CONTAINER_LOAD_PROCESS = 37,
+  ORC_CONTAINER_UNLOAD_PROCESS = 38
 };
 
 /* distribution kinds (common.rs:37-44) */
@@ -97,7 +106,10 @@ enum {
   ORC_REASON_AN_UPSTREAM_EMPTY = 9,      /* "At least one upstream is empty" */
   ORC_REASON_NO_UPSTREAMS = 10,          /* "No upstreams are connected" */
   ORC_REASON_A_DOWNSTREAM_FULL = 11,     /* "At least one downstream is full" */
-  ORC_REASON_NO_DOWNSTREAMS = 12         /* "No downstreams are connected" */
+  ORC_REASON_NO_DOWNSTREAMS = 12,        /* "No downstreams are connected" */
+  ORC_REASON_NO_PROCESS_SLOTS = 13,      /* "No remaining process slots"          vector_container.rs:369,676 */
+  ORC_REASON_DS_CONTAINERS_FULL = 14,    /* "Downstream container stock is full"  vector_container.rs:601 */
+  ORC_REASON_DS_RESOURCE_FULL = 15       /* "Downstream resource stock is full"   vector_container.rs:605 */
 };
 
 /* per-replication status */
@@ -106,12 +118,15 @@ enum {
   ORC_FAULT_ZERO_DURATION = 1, /* panic!("Time until next event is zero!") discrete.rs:541 */
   ORC_FAULT_BAD_DURATION = 2,  /* Duration::from_secs_f64 panics: negative / NaN / overflow */
   ORC_FAULT_TAPE_EXHAUSTED = 3,
-  ORC_FAULT_SOURCE_VECTOR = 8 /* panic!("Source vector has total 0 or negative") vector.rs:1490 */
+  ORC_FAULT_SOURCE_VECTOR = 8, /* panic!("Source vector has total 0 or negative") vector.rs:1490 */
+  ORC_FAULT_NOT_CONNECTED = 9  /* `.next().unwrap()` on a Requestor nobody connected (vector_container.rs:358) */
 };
 
 #define ORC_SRC_INIT 0xFFFFu /* EventId::from_init()      common.rs:14 */
 #define ORC_SRC_SCH 0xFFFEu  /* EventId::from_scheduler() common.rs:18 */
 #define ORC_ITEM_NONE 0xFFFFFFFFFFFFFFFFull
+/* a container whose `resource` is None: first double of its vector carries this (signalling-NaN) bit pattern */
+#define ORC_CONTAINER_NONE_BITS 0x7FF40000000000C0ull
 
 typedef struct {
   uint64_t time_ns;
@@ -161,6 +176,14 @@ int orc_model_n_dists(const orc_model*);
 int orc_model_set_vector(orc_model*, uint32_t comp, uint32_t dim, double low, double max, const double* init);
 int orc_model_set_splits(orc_model*, uint32_t comp, uint32_t n, const double* ratios);
 int orc_model_schedule_low_capacity(orc_model*, uint64_t t_ns, uint32_t stock, double value);
+/* container family. Vector3ContainerFactory (vector_container.rs:126-156): create_quantity_distr (NULL = None),
+ * create_component_split, capacity; *dist_id_out = distribution instance id or -1 */
+int orc_model_set_container_factory(orc_model*, uint32_t source, const orc_dist* create_quantity, const double* split3,
+                                    double capacity, int* dist_id_out);
+/* with_initial_resource(ItemDeque<Vector3Container>) of a container stock: resources [n][3], has_resource [n],
+ * capacities [n] */
+int orc_model_set_initial_containers(orc_model*, uint32_t stock, uint32_t n, const double* resources,
+                                     const uint8_t* has_resource, const double* capacities);
 
 orc_sim* orc_sim_new(const orc_model*, uint64_t base_seed, uint64_t rep, uint64_t t0_ns, int log_enabled);
 void orc_sim_free(orc_sim*);
@@ -179,6 +202,9 @@ uint64_t orc_sim_stock_items(const orc_sim*, uint32_t comp, uint32_t* buf, uint6
 /* vector stock contents */
 int orc_sim_vector_resource(const orc_sim*, uint32_t comp, double* out3);
 uint64_t orc_sim_draws(const orc_sim*, uint32_t dist_id);
+/* containers held by a container stock (FIFO order) or a container process-like component (in progress, then
+ * complete): handles [cap], resources [cap][3] (first double = ORC_CONTAINER_NONE_BITS for None); returns count */
+uint64_t orc_sim_containers(const orc_sim*, uint32_t comp, uint32_t* handles, double* resources, uint64_t cap);
 
 /* batch runner (CPU baseline): runs reps [rep0, rep0+n) with native Philox streams on n_threads host threads.
  * stats_out: [n_reps][n_comp] orc_comp_stats or NULL; status_out: [n_reps] or NULL. returns total events executed. */

@@ -18,4 +18,9 @@ from .vector_api import (  # noqa: F401
     Vector3, VectorCombiner, VectorProcess, VectorSink, VectorSource, VectorSplitter, VectorStock,
 )
 
+from .api import ContainerProcessLogger, ContainerStockLogger  # noqa: F401
+from .container_api import (  # noqa: F401
+    ContainerLoadingProcess, ContainerUnloadingProcess, Vector3Container, Vector3ContainerFactory,
+)
+
 __version__ = "0.1.0"

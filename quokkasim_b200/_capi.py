@@ -14,6 +14,9 @@ DEFAULT_LIB = os.path.join(_HERE, "libquokka_b200.so")
 # qk_component_kind
 DISCRETE_STOCK, DISCRETE_PROCESS, DISCRETE_SOURCE, DISCRETE_SINK, DISCRETE_PARALLEL_PROCESS, ENVIRONMENT = 1, 2, 3, 4, 5, 6
 VECTOR_STOCK, VECTOR_PROCESS, VECTOR_SOURCE, VECTOR_SINK, VECTOR_COMBINER, VECTOR_SPLITTER = 16, 17, 18, 19, 20, 21
+CONTAINER_STOCK, CONTAINER_PROCESS, CONTAINER_SOURCE, CONTAINER_SINK = 32, 33, 34, 35
+CONTAINER_PARALLEL_PROCESS, CONTAINER_LOAD_PROCESS, CONTAINER_UNLOAD_PROCESS = 36, 37, 38
+CONTAINER_NONE_BITS = 0x7FF40000000000C0
 # qk_dist_kind
 DIST_CONSTANT, DIST_UNIFORM, DIST_TRIANGULAR, DIST_NORMAL, DIST_TRUNCNORMAL, DIST_EXPONENTIAL = 0, 1, 2, 3, 4, 5
 # qk_log_kind
@@ -46,6 +49,7 @@ EXPORTED_SYMBOLS = [
     "qk_batch_summary_get", "qk_batch_read_status", "qk_batch_comp_stats", "qk_batch_reduce_stats",
     "qk_batch_reduce_stats_device", "qk_batch_histograms_device", "qk_batch_read_log", "qk_batch_read_stock",
     "qk_batch_last_step_ms", "qk_last_error",
+    "qk_model_set_container_factory", "qk_model_set_initial_containers", "qk_batch_read_containers",
 ]
 
 
@@ -160,6 +164,9 @@ def load_library(path=None):
         "qk_batch_read_stock": (C.c_int, [vp, u64, u32, vp, u64, P(u64)]),
         "qk_batch_last_step_ms": (C.c_int, [vp, P(C.c_float), P(u32)]),
         "qk_last_error": (C.c_char_p, []),
+        "qk_model_set_container_factory": (C.c_int, [vp, u32, P(DistDesc), P(C.c_double), C.c_double, P(u32)]),
+        "qk_model_set_initial_containers": (C.c_int, [vp, u32, u32, vp, vp, vp]),
+        "qk_batch_read_containers": (C.c_int, [vp, u64, u32, vp, vp, u64, P(u64)]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)

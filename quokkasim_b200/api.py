@@ -349,13 +349,16 @@ class DiscreteSource(_ProcessLike):
     def __init__(self):
         super().__init__()
         self.item_factory = StringItemFactory()
+        self._factory_set = False  # F::default() until with_item_factory: the variant decides which F
 
     def with_item_factory(self, f):
         self.item_factory = f
+        self._factory_set = True
         return self
 
     def with_item_factory_inplace(self, f):
         self.item_factory = f
+        self._factory_set = True
 
 
 class DiscreteSink(_ProcessLike):
@@ -425,6 +428,8 @@ class ComponentModel:
         self.mailbox = mailbox
         if variant in _VECTOR_VARIANTS:
             _bind_vector_variant(variant, component)
+        if variant in _CONTAINER_VARIANTS:
+            _bind_container_variant(variant, component)
 
     def __str__(self):  # #[derive(Display)] prints the variant name
         return self.variant
@@ -467,8 +472,10 @@ def connect_components(a, b, n=None):
     ok = (
         (va == "StringStock" and vb in _STOCK_TO_PROC)
         or (vb == "StringStock" and va in _PROC_TO_STOCK)
-        or (va == "BasicEnvironment" and (vb in _ENV_TARGETS or (vb in _VECTOR_VARIANTS and not vb.endswith("Stock"))))
+        or (va == "BasicEnvironment" and (vb in _ENV_TARGETS or vb in _CONTAINER_ENV_TARGETS
+                                          or (vb in _VECTOR_VARIANTS and not vb.endswith("Stock"))))
         or _vector_connection_ok(va, vb, n)
+        or _container_connection_ok(va, vb, n)
     )
     if not ok:
         raise ComponentConnectionError(
@@ -501,6 +508,19 @@ class DiscreteProcessLogger(_Logger):
     ACCEPTS = ("StringProcess", "StringParallelProcess", "StringSource", "StringSink")
 
 
+class ContainerStockLogger(DiscreteStockLogger):
+    """DiscreteStockLogger<Vector3Container> (core.rs:1292, 1330)"""
+
+    ACCEPTS = ("Vector3ContainerStock",)
+
+
+class ContainerProcessLogger(DiscreteProcessLogger):
+    """DiscreteProcessLogger<Vector3Container> (core.rs:1293, 1331-1334): no Source / Sink arm"""
+
+    ACCEPTS = ("Vector3ContainerProcess", "Vector3ContainerParallelProcess", "Vector3ContainerLoadProcess",
+               "Vector3ContainerUnloadProcess")
+
+
 class BasicEnvironmentLogger(_Logger):
     ACCEPTS = ("BasicEnvironment",)
 
@@ -530,6 +550,8 @@ class ComponentLogger:
         "F64ProcessLogger": VectorProcessLogger,
         "Vector3StockLogger": VectorStockLogger,
         "Vector3ProcessLogger": VectorProcessLogger,
+        "Vector3ContainerStockLogger": ContainerStockLogger,
+        "Vector3ContainerProcessLogger": ContainerProcessLogger,
     }
 
     def __init__(self, variant, logger):
@@ -684,12 +706,15 @@ class BatchedSimulation:
         registered = set(id(c) for c in self.components)
         for c in self.components:
             d = capi.ComponentDesc()
-            d.kind = c.KIND
+            d.kind = getattr(c, "_container_kind", None) or c.KIND
+            is_container = d.kind >= capi.CONTAINER_STOCK
             if isinstance(c, DiscreteStock):
                 d.low_capacity = c.low_capacity
                 d.max_capacity = c.max_capacity
-                d.n_initial_items = len(c.resource)
+                d.n_initial_items = 0 if is_container else len(c.resource)
                 d.capacity_hint = c.capacity_hint
+            elif hasattr(c, "max_process_count"):
+                d.max_capacity = c.max_process_count
             elif isinstance(c, BasicEnvironment):
                 d.initial_env_state = c.state
             elif hasattr(c, "capacity_hint"):
@@ -697,6 +722,27 @@ class BatchedSimulation:
             out = C.c_uint32()
             capi.check(L, L.qk_model_add_component(self._model, C.byref(d), C.byref(out)))
             assert out.value == c._id
+            if is_container and isinstance(c, DiscreteStock) and len(c.resource):
+                n = len(c.resource)
+                res = np.zeros((n, 3), dtype=np.float64)
+                has = np.zeros(n, dtype=np.uint8)
+                caps = np.zeros(n, dtype=np.float64)
+                for k, it in enumerate(c.resource):
+                    caps[k] = it.capacity
+                    if it.resource is not None:
+                        has[k] = 1
+                        res[k] = it.resource.values
+                capi.check(L, L.qk_model_set_initial_containers(self._model, c._id, n, res.ctypes.data, has.ctypes.data,
+                                                                caps.ctypes.data))
+            if is_container and isinstance(c, DiscreteSource):
+                f = c.item_factory
+                split = (C.c_double * 3)(*f.create_component_split)
+                did = C.c_uint32()
+                desc = f.create_quantity_distr.desc() if f.create_quantity_distr is not None else None
+                capi.check(L, L.qk_model_set_container_factory(self._model, c._id, C.byref(desc) if desc else None, split,
+                                                               f.capacity, C.byref(did)))
+                if desc is not None:
+                    self._dist_ids.setdefault(id(f.create_quantity_distr), []).append(did.value)
             if hasattr(c, "vector_rows"):
                 if c.dim is None:
                     raise TypeError("vector component %r was never wrapped in a ComponentModel variant" % c.element_name)
@@ -885,6 +931,19 @@ class BatchedSimulation:
                                                       C.byref(n)))
         return buf[: n.value]
 
+    def read_containers(self, component, replication):
+        """Containers held by a container stock (FIFO order) or a container process-like component: (handles,
+        resources[n, 3]) with NaN rows for containers that carry nothing (resource None)."""
+        self._materialize()
+        n = C.c_uint64()
+        cid = self._cid(component)
+        capi.check(self.L, self.L.qk_batch_read_containers(self._batch, replication, cid, None, None, 0, C.byref(n)))
+        h = np.zeros(max(n.value, 1), dtype=np.uint32)
+        r = np.zeros((max(n.value, 1), 3), dtype=np.uint64)
+        capi.check(self.L, self.L.qk_batch_read_containers(self._batch, replication, cid, h.ctypes.data, r.ctypes.data,
+                                                           h.size, C.byref(n)))
+        return h[: n.value], r[: n.value]
+
     # device-resident reduction for the multi-GPU path (see parallel.py)
     def reduce_stats_device(self, d_sums_ptr, d_extrema_ptr):
         self._materialize()
@@ -907,5 +966,18 @@ for _v, (_cls, _dim, _ports) in _VECTOR_VARIANTS.items():
     setattr(ComponentModel, _v, _variant_ctor(_v))
 for _v in ("F64StockLogger", "F64ProcessLogger", "Vector3StockLogger", "Vector3ProcessLogger"):
     setattr(ComponentLogger, _v, staticmethod(lambda logger, _v=_v: ComponentLogger(_v, logger)))
+from . import container_api as _ca  # noqa: E402
+
+_CONTAINER_VARIANTS = _ca.CONTAINER_VARIANTS
+_bind_container_variant = _ca.bind_variant
+_container_connection_ok = _ca.connection_ok
+_CONTAINER_ENV_TARGETS = _ca.ENV_TARGETS
+for _v, (_cls, _kind) in _CONTAINER_VARIANTS.items():
+    ComponentModel._VARIANTS[_v] = _cls
+    setattr(ComponentModel, _v, _variant_ctor(_v))
+for _v in ("Vector3ContainerStockLogger", "Vector3ContainerProcessLogger"):
+    setattr(ComponentLogger, _v, staticmethod(lambda logger, _v=_v: ComponentLogger(_v, logger)))
+Vector3Container, Vector3ContainerFactory = _ca.Vector3Container, _ca.Vector3ContainerFactory
+ContainerLoadingProcess, ContainerUnloadingProcess = _ca.ContainerLoadingProcess, _ca.ContainerUnloadingProcess
 Vector3, VectorStock, VectorProcess, VectorSource = _va.Vector3, _va.VectorStock, _va.VectorProcess, _va.VectorSource
 VectorSink, VectorCombiner, VectorSplitter = _va.VectorSink, _va.VectorCombiner, _va.VectorSplitter

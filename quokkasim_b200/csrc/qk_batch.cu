@@ -70,8 +70,11 @@ StepKernel qk_pick_step_l0f0(uint32_t nt);
 StepKernel qk_pick_step_l0f1(uint32_t nt);
 StepKernel qk_pick_step_l1f0(uint32_t nt);
 StepKernel qk_pick_step_l1f1(uint32_t nt);
+StepKernel qk_pick_step_l0f2(uint32_t nt);
+StepKernel qk_pick_step_l1f2(uint32_t nt);
 static StepKernel pick_kernel(bool log, bool hbm, uint32_t nt, uint32_t features) {
   const uint32_t key = hbm ? 0u : nt;
+  if (features >= 2) return log ? qk_pick_step_l1f2(key) : qk_pick_step_l0f2(key);
   if (log) return features ? qk_pick_step_l1f1(key) : qk_pick_step_l1f0(key);
   return features ? qk_pick_step_l0f1(key) : qk_pick_step_l0f0(key);
 }
@@ -304,6 +307,14 @@ __global__ void qk_batch_summary_kernel(const uint64_t* g64, const uint32_t* g32
     atomicMin((unsigned long long*)&out[3], (unsigned long long)mn);
     atomicMin((unsigned long long*)&out[4], (unsigned long long)mx);
   }
+}
+
+/* one element of a [slot][replication] plane */
+static cudaError_t fetch(const uint32_t* plane, uint64_t rep_pad, uint32_t slot, uint64_t rep, uint32_t* out) {
+  return cudaMemcpy(out, plane + (size_t)slot * rep_pad + rep, 4, cudaMemcpyDeviceToHost);
+}
+static cudaError_t fetch(const uint64_t* plane, uint64_t rep_pad, uint32_t slot, uint64_t rep, uint64_t* out) {
+  return cudaMemcpy(out, plane + (size_t)slot * rep_pad + rep, 8, cudaMemcpyDeviceToHost);
 }
 
 /* ============================================ C ABI ============================================ */
@@ -757,7 +768,8 @@ int qk_batch_read_log(qk_batch* b, uint64_t rep, qk_log_record* buf, uint64_t ca
 int qk_batch_read_vector(qk_batch* b, uint64_t rep, uint32_t comp, double* out3) {
   int rc = check_range(b, rep, 1);
   if (rc) return rc;
-  if (comp >= b->low.hdr.n_comp || b->low.comps[comp].kind < QK_VECTOR_STOCK || !out3) {
+  if (comp >= b->low.hdr.n_comp || b->low.comps[comp].kind < QK_VECTOR_STOCK ||
+      b->low.comps[comp].kind > QK_VECTOR_SPLITTER || !out3) {
     qk_set_error("qk_batch_read_vector: component %u is not a vector component", comp);
     return QK_ERR_INVALID_ARG;
   }
@@ -790,6 +802,63 @@ int qk_batch_read_stock(qk_batch* b, uint64_t rep, uint32_t comp, uint32_t* item
   CUDA_TRY(cudaMemcpy2D(ring.data(), 4, b->gc32 + (size_t)c.ocold32 * b->rep_pad + rep, b->rep_pad * 4, 4,
                         c.ring_cap, cudaMemcpyDeviceToHost));
   for (uint32_t i = 0; i < cnt; ++i) items[i] = ring[(head + i) % c.ring_cap];
+  return QK_OK;
+}
+
+int qk_batch_read_containers(qk_batch* b, uint64_t rep, uint32_t comp, uint32_t* handles, uint64_t* resources,
+                             uint64_t cap, uint64_t* n_out) {
+  int rc = check_range(b, rep, 1);
+  if (rc) return rc;
+  if (comp >= b->low.hdr.n_comp || !(b->low.comps[comp].flags & DC_CONTAINER)) {
+    qk_set_error("qk_batch_read_containers: component %u does not hold containers", comp);
+    return QK_ERR_INVALID_ARG;
+  }
+  CUDA_TRY(cudaSetDevice(b->cfg.device));
+  CUDA_TRY(cudaStreamSynchronize(b->stream));
+  const DevComp& c = b->low.comps[comp];
+  /* (item slot in plane32 or cold32, payload slot in cold64) of every container held, in order */
+  std::vector<uint32_t> item_slot, pay_slot;
+  bool item_cold = false;
+  if (c.kind == QK_DISCRETE_STOCK) {
+    uint32_t hc = 0;
+    CUDA_TRY(fetch(b->g32, b->rep_pad, c.o32 + S32_HC, rep, &hc));
+    const uint32_t head = hc & 0xFFFFu, cnt = hc >> 16;
+    item_cold = true;
+    for (uint32_t i = 0; i < cnt; ++i) {
+      const uint32_t pos = (head + i) % c.ring_cap;
+      item_slot.push_back(c.ocold32 + pos);
+      pay_slot.push_back(c.ocold64 + 3u * pos);
+    }
+  } else if (c.kind == QK_DISCRETE_PARALLEL_PROCESS || c.kind == QK_CONTAINER_LOAD_PROCESS ||
+             c.kind == QK_CONTAINER_UNLOAD_PROCESS) {
+    uint32_t nprog = 0, cq = 0;
+    CUDA_TRY(fetch(b->g32, b->rep_pad, c.o32 + PP32_NPROG, rep, &nprog));
+    CUDA_TRY(fetch(b->g32, b->rep_pad, c.o32 + PP32_COMPLETE, rep, &cq));
+    const uint32_t ring = c.ring_cap, item0 = c.o32 + PP32_BASE_COUNT;
+    for (uint32_t i = 0; i < nprog; ++i) {
+      item_slot.push_back(item0 + i);
+      pay_slot.push_back(c.ocold64 + 3u * i);
+    }
+    for (uint32_t i = 0; i < (cq >> 16); ++i) {
+      const uint32_t pos = ((cq & 0xFFFFu) + i) % ring;
+      item_slot.push_back(item0 + ring + pos);
+      pay_slot.push_back(c.ocold64 + 3u * (ring + pos));
+    }
+  } else {
+    uint32_t flags = 0;
+    CUDA_TRY(fetch(b->g32, b->rep_pad, c.o32 + P32_FLAGS, rep, &flags));
+    if (flags & PF_HAS_ITEM) {
+      item_slot.push_back(c.o32 + P32_ITEM);
+      pay_slot.push_back(c.ocold64);
+    }
+  }
+  if (n_out) *n_out = item_slot.size();
+  if (!handles || !resources) return QK_OK;
+  if (cap < item_slot.size()) return QK_ERR_BUFFER_TOO_SMALL;
+  for (size_t i = 0; i < item_slot.size(); ++i) {
+    CUDA_TRY(fetch(item_cold ? b->gc32 : b->g32, b->rep_pad, item_slot[i], rep, &handles[i]));
+    for (uint32_t k = 0; k < 3; ++k) CUDA_TRY(fetch(b->gc64, b->rep_pad, pay_slot[i] + k, rep, &resources[i * 3 + k]));
+  }
   return QK_OK;
 }
 

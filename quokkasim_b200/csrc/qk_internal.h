@@ -77,6 +77,15 @@ enum { E32_STATE = 0, E32_COUNT = 1 };
 
 #define DC_LOGGED 1u
 #define DC_SIMPLE 2u /* single-server discrete component without delay modes or environment (quick path) */
+#define DC_CONTAINER 4u /* the items of this component are Vector3Containers: every slot that holds an item handle has
+                           three cold64 slots (from DevComp.ocold64) holding what the container carries */
+
+/* Container family (vector_container.rs).  Vector3ContainerStock / Process / Source / Sink / ParallelProcess are
+ * lowered to the DISCRETE kinds with DC_CONTAINER set (they are the discrete components instantiated with another item
+ * type, core.rs:549-553); ContainerLoadingProcess / ContainerUnloadingProcess keep their own kinds and share the
+ * multi-server layout of the parallel process (slots below), with max_process_count in DevComp.max / ring_cap.
+ * Payload layout at cold64 slot ocold64: stock -> [ring_cap][3]; single-server process-like -> [3];
+ * multi-server -> in-progress [ring_cap][3], then the complete ring [ring_cap][3]. */
 
 typedef struct {
   uint8_t kind;    /* qk_component_kind */
@@ -102,7 +111,7 @@ typedef struct {
   uint16_t pf_idx;      /* bit index in the prefetch-pending mask */
   uint32_t const_dur_lo, const_dur_hi; /* process_time_distr is Constant: its duration in ns (or QK_DUR_FAULT code) */
   uint16_t ocold32; /* cold32 slot: discrete stock item ring (+ emit source ring) ; vector stock emit source ring */
-  uint16_t pad2;
+  uint16_t ocold64; /* DC_CONTAINER: first cold64 payload slot */
 } DevComp; /* 68 bytes = 17 words: an odd word stride keeps per-lane table reads of different components off the
               same shared-memory bank */
 
@@ -195,7 +204,10 @@ typedef struct {
   uint32_t total_bytes;
   uint32_t log_enabled;
   uint32_t off_hot; /* DevHot[n_comp], 16-byte aligned */
-  uint32_t features; /* 0 = every process-like component is SIMPLE and nothing is scheduled externally ; 1 = general */
+  uint32_t off_ccap;  /* double ccap[64 + n_initial]: container capacity by source ordinal, then by initial-item index */
+  uint32_t off_cinit; /* uint64_t cinit[n_initial][3]: resource bits of the initial containers (NONE sentinel) */
+  uint32_t features; /* 0 = every process-like component is SIMPLE and nothing is scheduled externally ; 1 = general ;
+                        2 = general + container family (vector_container.rs) */
 } DevHeader;
 
 #endif

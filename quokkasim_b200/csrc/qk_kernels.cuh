@@ -27,6 +27,9 @@
 #define QK_KERNELS_CUH
 #include "qk_device.cuh"
 
+#define QK_D2U(d) ((uint64_t)__double_as_longlong(d))
+#define QK_U2D(u) (__longlong_as_double((long long)(u)))
+
 struct KParams {
   uint64_t* g64; /* [n64][rep_pad] */
   uint32_t* g32; /* [n32][rep_pad] */
@@ -66,6 +69,7 @@ struct Ctx {
   const DevExt* ext;
   const DevVec* vecs;
   const DevHot* hot;
+  const double* ccap;    /* container capacity by handle (DevHeader.off_ccap) */
   uint32_t pf32, n_pf_words; /* hoisted DevHeader fields (re-reading them after every state store is wasted LDS) */
   uint64_t now;
   uint32_t status;
@@ -159,6 +163,28 @@ __device__ __forceinline__ uint64_t qk_log(Ctx& cx, const DevHotA& c, uint32_t c
     cx.log_cnt += 1;
   }
   return ((uint64_t)comp << 32) | seq;
+}
+
+/* continuation record of a record that serialises a Vector3Container (ProcessStart / ProcessFinish / Add / Remove):
+ * the container's resource as three raw fp64 words (w[0] == QK_CONTAINER_NONE_BITS for None).  Same layout as the
+ * vector components' continuation records (quokka_b200.h, QK_LOG_VEC_DATA). */
+template <bool LOG, int SM>
+__device__ __forceinline__ void qk_log_pay(Ctx& cx, uint32_t flags, uint32_t comp, uint64_t id, const uint64_t* w) {
+  if (!LOG) return;
+  if (flags & DC_LOGGED) {
+    uint4* r = cx.log_base + 2 * (size_t)(cx.log_cnt & cx.log_mask);
+    uint4 a, b;
+    a.x = (uint32_t)w[0];
+    a.y = (uint32_t)(w[0] >> 32);
+    a.z = comp | ((uint32_t)QK_LOG_VEC_DATA << 16);
+    a.w = (uint32_t)id;
+    b.x = (uint32_t)w[1];
+    b.y = (uint32_t)(w[1] >> 32);
+    b.z = (uint32_t)w[2];
+    b.w = (uint32_t)(w[2] >> 32);
+    qk_store_record(r, a, b);
+    cx.log_cnt += 1;
+  }
 }
 
 /* ---- Distribution::sample (common.rs:152-178) + Duration::from_secs_f64 -------------------------------- */
@@ -298,8 +324,10 @@ __device__ __forceinline__ uint32_t qk_emit_pop(Ctx& cx, const DevHotA& c, uint3
 }
 
 /* Stock::add = pre_add, add_impl, post_add (core.rs:177-183; discrete.rs:181-198). No capacity check. */
+/* pay != nullptr: the item is a Vector3Container and pay[3] is what it carries (the stock is a container stock) */
 template <bool LOG, int SM>
-__device__ __forceinline__ void qk_stock_add(Ctx& cx, uint32_t sidx, uint32_t item, uint64_t src) {
+__device__ __forceinline__ void qk_stock_add(Ctx& cx, uint32_t sidx, uint32_t item, uint64_t src,
+                                             const uint64_t* pay = nullptr) {
   const DevHotA c = QK_HOT_A(sidx);
   const DevHotSB sb = QK_HOT_SB(sidx);
   const uint32_t hc = S32(c.o32 + S32_HC);
@@ -312,18 +340,26 @@ __device__ __forceinline__ void qk_stock_add(Ctx& cx, uint32_t sidx, uint32_t it
   uint32_t pos = head + cnt;
   if (pos >= sb.ring_cap) pos -= sb.ring_cap;
   C32(c.olog64 + pos) = item; /* item ring: cold */
+  if (pay) {
+    const uint32_t op = cx.comps[sidx].ocold64 + 3u * pos;
+    C64(op) = pay[0];
+    C64(op + 1) = pay[1];
+    C64(op + 2) = pay[2];
+  }
   cnt += 1;
   S32(c.o32 + S32_HC) = head | (cnt << 16);
   QK_ST64_ADD(sidx, ST64_TIME, 0ull - cx.now); /* occupancy integral = sum(t_remove) - sum(t_add) + cnt * T */
   QK_ST32_ADD(sidx, ST32_COUNT, 1u);
   QK_ST32_MAX(sidx, ST32_MAXOCC, cnt);
   const uint64_t id = qk_log<LOG, SM>(cx, c, sidx, src, QK_LOG_STOCK_ADD, 0, item);
+  if (pay) qk_log_pay<LOG, SM>(cx, c.flags, sidx, id, pay);
   if (prev != qk_stock_cat(cnt, sb.low, sb.max)) qk_emit_push<LOG, SM>(cx, c, sb.emit_depth, c.olog64 + sb.ring_cap, (uint32_t)id);
 }
 
 /* Stock::remove (core.rs:197-204; discrete.rs:200-225); returns false for Remove(None) */
 template <bool LOG, int SM>
-__device__ __forceinline__ bool qk_stock_remove(Ctx& cx, uint32_t sidx, uint64_t src, uint32_t* item_out) {
+__device__ __forceinline__ bool qk_stock_remove(Ctx& cx, uint32_t sidx, uint64_t src, uint32_t* item_out,
+                                                uint64_t* pay_out = nullptr) {
   const DevHotA c = QK_HOT_A(sidx);
   const DevHotSB sb = QK_HOT_SB(sidx);
   const uint32_t hc = S32(c.o32 + S32_HC);
@@ -333,6 +369,12 @@ __device__ __forceinline__ bool qk_stock_remove(Ctx& cx, uint32_t sidx, uint64_t
   uint32_t item = 0;
   if (some) {
     item = C32(c.olog64 + head);
+    if (pay_out) {
+      const uint32_t op = cx.comps[sidx].ocold64 + 3u * head;
+      pay_out[0] = C64(op);
+      pay_out[1] = C64(op + 1);
+      pay_out[2] = C64(op + 2);
+    }
     head += 1;
     if (head >= sb.ring_cap) head = 0;
     cnt -= 1;
@@ -340,6 +382,7 @@ __device__ __forceinline__ bool qk_stock_remove(Ctx& cx, uint32_t sidx, uint64_t
     QK_ST64_ADD(sidx, ST64_TIME, cx.now);
   }
   const uint64_t id = qk_log<LOG, SM>(cx, c, sidx, src, QK_LOG_STOCK_REMOVE, 0, some ? (uint64_t)item : QK_ITEM_NONE);
+  if (pay_out && some) qk_log_pay<LOG, SM>(cx, c.flags, sidx, id, pay_out);
   if (prev != qk_stock_cat(cnt, sb.low, sb.max)) qk_emit_push<LOG, SM>(cx, c, sb.emit_depth, c.olog64 + sb.ring_cap, (uint32_t)id);
   *item_out = item;
   return some;
@@ -506,6 +549,10 @@ __device__ __forceinline__ void qk_update_single(Ctx& cx, const DevHotA& c, uint
   uint64_t left = S64(c.o64 + P64_LEFT);
   const uint64_t dt = cx.now - S64(c.o64 + P64_PREV);
   uint64_t ttnpe = QK_TIME_NONE;
+  /* Vector3ContainerProcess / Source / Sink (core.rs:550-553): the item carries a resource, kept at cold64 `opay` */
+  const bool ctr = FT >= 2 && (c.flags & DC_CONTAINER) != 0;
+  const uint32_t opay = ctr ? cx.comps[comp].ocold64 : 0u;
+  uint64_t pay[3];
   {
     const bool is_in_delay = ((flags >> PF_FIX_SHIFT) & 0xFFu) != 0;
     const bool has_item0 = (flags & PF_HAS_ITEM) != 0;
@@ -517,9 +564,15 @@ __device__ __forceinline__ void qk_update_single(Ctx& cx, const DevHotA& c, uint
         flags &= ~PF_HAS_ITEM;
         const uint32_t item = S32(c.o32 + P32_ITEM);
         src = qk_log<LOG, SM>(cx, c, comp, src, QK_LOG_PROCESS_FINISH, 0, item);
+        if (ctr) {
+          pay[0] = C64(opay);
+          pay[1] = C64(opay + 1);
+          pay[2] = C64(opay + 2);
+          qk_log_pay<LOG, SM>(cx, c.flags, comp, src, pay);
+        }
         QK_ST32_ADD(comp, ST32_COUNT, 1u);
         if (kind != QK_DISCRETE_SINK && cb.down >= 0) { /* push_downstream: no downstream check at finish */
-          qk_stock_add<LOG, SM>(cx, (uint32_t)cb.down, item, src);
+          qk_stock_add<LOG, SM>(cx, (uint32_t)cb.down, item, src, ctr ? pay : nullptr);
           if (cx.status) return;
         }
       }
@@ -545,7 +598,7 @@ __device__ __forceinline__ void qk_update_single(Ctx& cx, const DevHotA& c, uint
       uint32_t item;
       if (need_us) {
         src = qk_log<LOG, SM>(cx, c, comp, src, QK_LOG_WITHDRAW_REQUEST, 0, 0);
-        got = qk_stock_remove<LOG, SM>(cx, (uint32_t)cb.up, src, &item);
+        got = qk_stock_remove<LOG, SM>(cx, (uint32_t)cb.up, src, &item, ctr ? pay : nullptr);
         if (cx.status) return;
       }
       if (got) {
@@ -569,6 +622,16 @@ __device__ __forceinline__ void qk_update_single(Ctx& cx, const DevHotA& c, uint
           }
           S32(cc.o32_next_item) = idx + 1;
           item = ((uint32_t)c.src_ord << 26) | idx;
+          if (ctr) { /* Vector3ContainerFactory::create_item (vector_container.rs:136-156) */
+            const DevVec* v = &cx.vecs[cc.vec_idx];
+            pay[0] = QK_CONTAINER_NONE_BITS;
+            pay[1] = pay[2] = 0;
+            if (v->dist_qty != 0xFFFF) {
+              const double q = qk_sample<SM>(cx, v->dist_qty);
+              if (cx.status) return;
+              for (int k = 0; k < 3; ++k) pay[k] = QK_D2U(__dmul_rn(q, v->vinit[k])); /* quantity * split[k] */
+            }
+          }
         }
         if (d >= QK_DUR_FAULT_BASE) { /* from_secs_f64 panicked / tape exhausted / (EMPTY: refill logic bug) */
           cx.status = d == QK_DUR_EMPTY ? 99u : (uint32_t)(d - QK_DUR_FAULT_BASE);
@@ -579,6 +642,12 @@ __device__ __forceinline__ void qk_update_single(Ctx& cx, const DevHotA& c, uint
         S32(c.o32 + P32_ITEM) = item;
         QK_ST64_ADD(comp, ST64_TIME, d);
         src = qk_log<LOG, SM>(cx, c, comp, src, QK_LOG_PROCESS_START, 0, item);
+        if (ctr) {
+          C64(opay) = pay[0];
+          C64(opay + 1) = pay[1];
+          C64(opay + 2) = pay[2];
+          qk_log_pay<LOG, SM>(cx, c.flags, comp, src, pay);
+        }
         ttnpe = d;
       } else {
         src = qk_log<LOG, SM>(cx, c, comp, src, QK_LOG_PROCESS_NONSTART, QK_REASON_UPSTREAM_NO_RESOURCE, 0);
@@ -610,27 +679,40 @@ __device__ __forceinline__ void qk_update_single(Ctx& cx, const DevHotA& c, uint
   S64(c.o64 + P64_PREV) = cx.now;
 }
 
-/* ---- DiscreteParallelProcess::update_state_impl (discrete.rs:1280-1417) ---------------------------------------- */
-template <bool LOG, int SM>
-__device__ __forceinline__ void qk_update_parallel(Ctx& cx, const DevComp* c, uint32_t comp, uint64_t src) {
+#include "qk_vector.cuh"
+
+/* ---- multi-server process-like components ------------------------------------------------------------------
+ * DiscreteParallelProcess::update_state_impl (discrete.rs:1280-1417), ContainerLoadingProcess (vector_container.rs:
+ * 263-393) and ContainerUnloadingProcess (vector_container.rs:550-707) share one skeleton: a Vec of (countdown, item)
+ * in progress, a deque of completed items drained while downstream accepts, a withdraw loop, ttnpe = min countdown.
+ * They differ in the drain condition, in what a finish/start moves, and in the withdraw test; `kind` selects. */
+template <bool LOG, int SM, int FT>
+__device__ __forceinline__ void qk_update_multi(Ctx& cx, const DevComp* c, uint32_t comp, uint64_t src) {
   const DevHotA ha = QK_HOT_A(comp);
   const DevHotB hb = QK_HOT_B(comp);
+  const uint32_t kind = c->kind;
+  /* the container family is compiled in only for models that have it (feature set 2) */
+  const bool ctr = FT >= 2 && (c->flags & DC_CONTAINER) != 0;
+  const bool is_load = FT >= 2 && kind == QK_CONTAINER_LOAD_PROCESS;
+  const bool is_unload = FT >= 2 && kind == QK_CONTAINER_UNLOAD_PROCESS;
   uint32_t flags = S32(c->o32 + PP32_FLAGS);
   const uint64_t dt = cx.now - S64(c->o64 + PP64_PREV);
   const uint32_t cap = c->ring_cap;
   const uint32_t dur0 = c->o64_dm + c->n_dm;
   const uint32_t item0 = c->o32 + PP32_BASE_COUNT;
   const uint32_t comp0 = item0 + cap;
+  const uint32_t pay0 = c->ocold64, cpay0 = c->ocold64 + 3u * cap; /* container payloads: in progress / complete ring */
   uint32_t nprog = S32(c->o32 + PP32_NPROG);
   uint32_t cq = S32(c->o32 + PP32_COMPLETE);
   uint32_t chead = cq & 0xFFFFu, ccnt = cq >> 16;
+  uint64_t pay[3];
   {
     const bool is_in_delay = ((flags >> PF_FIX_SHIFT) & 0xFFu) != 0;
     const bool is_in_process = nprog > 0 && !is_in_delay;
     const bool is_env_blocked = (flags & PF_ENV_STOPPED) != 0;
     if (!(is_in_delay || is_env_blocked)) {
       uint32_t w = 0;
-      for (uint32_t i = 0; i < nprog; ++i) { /* retain_mut :1298-1306 */
+      for (uint32_t i = 0; i < nprog; ++i) { /* retain_mut discrete.rs:1298-1306 */
         uint64_t d = S64(dur0 + i);
         const uint32_t it = S32(item0 + i);
         d -= (dt < d ? dt : d);
@@ -642,29 +724,70 @@ __device__ __forceinline__ void qk_update_parallel(Ctx& cx, const DevComp* c, ui
           uint32_t pos = chead + ccnt;
           if (pos >= cap) pos -= cap;
           S32(comp0 + pos) = it;
+          if (ctr)
+            for (uint32_t k = 0; k < 3; ++k) C64(cpay0 + 3u * pos + k) = C64(pay0 + 3u * i + k);
           ccnt += 1;
         } else {
           S64(dur0 + w) = d;
           S32(item0 + w) = it;
+          if (ctr && w != i)
+            for (uint32_t k = 0; k < 3; ++k) C64(pay0 + 3u * w + k) = C64(pay0 + 3u * i + k);
           w += 1;
         }
       }
       nprog = w;
-      while (ccnt) { /* :1311-1327 -- the popped item is lost when downstream is Full */
+      while (ccnt) { /* discrete.rs:1311-1327 -- the popped item is lost when downstream does not accept it */
         const uint32_t it = S32(comp0 + chead);
+        if (ctr)
+          for (uint32_t k = 0; k < 3; ++k) pay[k] = C64(cpay0 + 3u * chead + k);
         chead += 1;
         if (chead >= cap) chead = 0;
         ccnt -= 1;
         const uint32_t ds = c->down >= 0 ? qk_stock_cat_of<SM>(cx, c->down) : 3u;
-        if (ds == 0u || ds == 1u) {
-          src = qk_log<LOG, SM>(cx, ha, comp, src, QK_LOG_PROCESS_FINISH, 0, it);
-          QK_ST32_ADD(comp, ST32_COUNT, 1u);
-          qk_stock_add<LOG, SM>(cx, (uint32_t)c->down, it, src);
-          if (cx.status) return;
-        } else {
-          src = qk_log<LOG, SM>(cx, ha, comp, src, QK_LOG_PROCESS_NONSTART,
-                            ds == 2u ? QK_REASON_DOWNSTREAM_FULL : QK_REASON_DOWNSTREAM_NOT_CONNECTED, 0);
-          break;
+        if (!is_unload) {
+          if (ds == 0u || ds == 1u) {
+            src = qk_log<LOG, SM>(cx, ha, comp, src, QK_LOG_PROCESS_FINISH, 0, it);
+            if (ctr) qk_log_pay<LOG, SM>(cx, ha.flags, comp, src, pay);
+            QK_ST32_ADD(comp, ST32_COUNT, 1u);
+            qk_stock_add<LOG, SM>(cx, (uint32_t)c->down, it, src, ctr ? pay : nullptr);
+            if (cx.status) return;
+          } else {
+            src = qk_log<LOG, SM>(cx, ha, comp, src, QK_LOG_PROCESS_NONSTART,
+                                  ds == 2u ? QK_REASON_DOWNSTREAM_FULL : QK_REASON_DOWNSTREAM_NOT_CONNECTED, 0);
+            break;
+          }
+        } else { /* vector_container.rs:574-613 */
+          const DevVec* v = &cx.vecs[c->vec_idx];
+          const uint32_t dsr = qk_vstock_cat_of<SM>(cx, v->downs[0]);
+          if ((ds == 0u || ds == 1u) && (dsr == 0u || dsr == 1u)) {
+            src = qk_log<LOG, SM>(cx, ha, comp, src, QK_LOG_PROCESS_FINISH, 0, it); /* the container as it arrived */
+            qk_log_pay<LOG, SM>(cx, ha.flags, comp, src, pay);
+            QK_ST32_ADD(comp, ST32_COUNT, 1u);
+            const double proportion = qk_sample<SM>(cx, v->dist_qty); /* process_quantity_ratio_distr */
+            if (cx.status) return;
+            if (pay[0] != QK_CONTAINER_NONE_BITS) {
+              /* item.take_resource() (:582) leaves item.resource == None ... */
+              double taken[3] = {QK_U2D(pay[0]), QK_U2D(pay[1]), QK_U2D(pay[2])};
+              double moved[3] = {0.0, 0.0, 0.0};
+              pay[0] = QK_CONTAINER_NONE_BITS;
+              pay[1] = pay[2] = 0;
+              if (!(proportion >= 1.0)) {
+                qk_vremove(taken, __dmul_rn(qk_vtotal(taken, 3), proportion), 3, moved);
+                for (int k = 0; k < 3; ++k) pay[k] = QK_D2U(taken[k]); /* item.set_resource(Some(resource)) :590 */
+              }
+              /* ... so for proportion >= 1 item.remove_all() (:585) yields Vector3::default(): zeros reach the
+               * resource stock and what the container carried is dropped (reproduced on purpose) */
+              qk_vstock_add<LOG, SM>(cx, (uint32_t)v->downs[0], moved, src);
+              if (cx.status) return;
+            }
+            qk_stock_add<LOG, SM>(cx, (uint32_t)c->down, it, src, pay);
+            if (cx.status) return;
+          } else {
+            const uint32_t reason = ds == 2u ? QK_REASON_DS_CONTAINERS_FULL
+                                             : (dsr == 2u ? QK_REASON_DS_RESOURCE_FULL : QK_REASON_DOWNSTREAM_NOT_CONNECTED);
+            src = qk_log<LOG, SM>(cx, ha, comp, src, QK_LOG_PROCESS_NONSTART, reason, 0);
+            break;
+          }
         }
       }
     }
@@ -676,14 +799,35 @@ __device__ __forceinline__ void qk_update_parallel(Ctx& cx, const DevComp* c, ui
   if (c->env >= 0 || (flags & PF_ENV_STOPPED)) qk_refresh_env<LOG, SM>(cx, ha, c->env, comp, &flags, &src);
   uint64_t ttnpe = QK_TIME_NONE;
   if (!(flags & PF_ENV_STOPPED)) {
-    for (;;) { /* :1373-1398 */
+    for (;;) { /* discrete.rs:1373-1398 ; vector_container.rs:348-381, 659-688 */
       const uint32_t us = c->up >= 0 ? qk_stock_cat_of<SM>(cx, c->up) : 3u;
-      if (us == 0u || us == 1u) { /* Q4: withdraws while upstream is Empty|Normal */
+      /* Parallel and Load withdraw while upstream is Empty|Normal (Q4); Unload while it is Normal|Full */
+      const bool us_ok = is_unload ? (us == 1u || us == 2u) : (us == 0u || us == 1u);
+      const bool slots = !(is_load || is_unload) || nprog + ccnt < c->max; /* max_process_count - in progress - complete */
+      if (us_ok && slots) {
         src = qk_log<LOG, SM>(cx, ha, comp, src, QK_LOG_WITHDRAW_REQUEST, 0, 0);
         uint32_t it;
-        const bool got = qk_stock_remove<LOG, SM>(cx, (uint32_t)c->up, src, &it);
+        const bool got = qk_stock_remove<LOG, SM>(cx, (uint32_t)c->up, src, &it, ctr ? pay : nullptr);
         if (cx.status) return;
         if (!got) break;
+        if (is_load) { /* vector_container.rs:356-360 */
+          const DevVec* v = &cx.vecs[c->vec_idx];
+          const double proportion = qk_sample<SM>(cx, v->dist_qty); /* process_capacity_ratio_distr */
+          if (cx.status) return;
+          const bool has = pay[0] != QK_CONTAINER_NONE_BITS;
+          double held[3] = {has ? QK_U2D(pay[0]) : 0.0, has ? QK_U2D(pay[1]) : 0.0, has ? QK_U2D(pay[2]) : 0.0};
+          const uint32_t ord = it >> 26;
+          const double capacity = cx.ccap[ord == 63u ? 64u + (it & 0x3FFFFFFu) : ord];
+          const double quantity = __dmul_rn(__dsub_rn(capacity, has ? qk_vtotal(held, 3) : 0.0), proportion);
+          if (v->ups[0] < 0) {
+            cx.status = QK_REP_NOT_CONNECTED; /* withdraw_us_resource ... .next().unwrap() :358 */
+            return;
+          }
+          double got3[3];
+          qk_vstock_remove<LOG, SM>(cx, (uint32_t)v->ups[0], quantity, src, got3); /* no state check on that stock */
+          if (cx.status) return;
+          for (int k = 0; k < 3; ++k) pay[k] = QK_D2U(has ? __dadd_rn(held[k], got3[k]) : got3[k]); /* item.add :84-92 */
+        }
         const uint64_t d = qk_sample_duration<SM>(cx, c->dist_time);
         if (cx.status) return;
         if (nprog >= cap) {
@@ -692,16 +836,25 @@ __device__ __forceinline__ void qk_update_parallel(Ctx& cx, const DevComp* c, ui
         }
         S64(dur0 + nprog) = d;
         S32(item0 + nprog) = it;
+        if (ctr)
+          for (uint32_t k = 0; k < 3; ++k) C64(pay0 + 3u * nprog + k) = pay[k];
         nprog += 1;
         QK_ST64_ADD(comp, ST64_TIME, d);
         src = qk_log<LOG, SM>(cx, ha, comp, src, QK_LOG_PROCESS_START, 0, it);
+        if (ctr) qk_log_pay<LOG, SM>(cx, ha.flags, comp, src, pay);
       } else {
-        src = qk_log<LOG, SM>(cx, ha, comp, src, QK_LOG_PROCESS_NONSTART,
-                          us == 2u ? QK_REASON_UPSTREAM_FULL : QK_REASON_UPSTREAM_NOT_CONNECTED, 0);
+        uint32_t reason;
+        if (!slots)
+          reason = QK_REASON_NO_PROCESS_SLOTS; /* the (_, 0) arm precedes the state arms */
+        else if (us == 3u)
+          reason = QK_REASON_UPSTREAM_NOT_CONNECTED;
+        else
+          reason = is_unload ? QK_REASON_UPSTREAM_EMPTY : QK_REASON_UPSTREAM_FULL;
+        src = qk_log<LOG, SM>(cx, ha, comp, src, QK_LOG_PROCESS_NONSTART, reason, 0);
         break;
       }
     }
-    for (uint32_t i = 0; i < nprog; ++i) { /* :1400-1406 */
+    for (uint32_t i = 0; i < nprog; ++i) { /* discrete.rs:1400-1406 */
       const uint64_t d = S64(dur0 + i);
       if (d < ttnpe) ttnpe = d;
     }
@@ -713,7 +866,6 @@ __device__ __forceinline__ void qk_update_parallel(Ctx& cx, const DevComp* c, ui
   S64(c->o64 + PP64_PREV) = cx.now;
 }
 
-#include "qk_vector.cuh"
 
 /* Process::update_state (core.rs:370-376) */
 template <bool LOG, int SM, int FT>
@@ -730,7 +882,7 @@ __device__ __forceinline__ void qk_update_state(Ctx& cx, uint32_t comp, uint64_t
       qk_log<LOG, SM>(cx, a, comp, src, QK_LOG_ENV_STATE, S32(a.o32 + E32_STATE), 0);
       return;
     }
-    if (a.kind >= QK_VECTOR_PROCESS) {
+    if (a.kind >= QK_VECTOR_PROCESS && a.kind <= QK_VECTOR_SPLITTER) {
       /* Combiner / Splitter / VectorSource / VectorSink init with their own next id instead of INIT_000000
        * (vector.rs:774,1111,1393,1619); SRC_INIT only ever arrives from the init list */
       if (LOG && src == SRC_INIT && a.kind != QK_VECTOR_PROCESS)
@@ -740,7 +892,7 @@ __device__ __forceinline__ void qk_update_state(Ctx& cx, uint32_t comp, uint64_t
       return;
     }
     qk_pre<LOG, SM>(cx, a);
-    qk_update_parallel<LOG, SM>(cx, c, comp, src);
+    qk_update_multi<LOG, SM, FT>(cx, c, comp, src);
   }
 }
 
@@ -762,7 +914,7 @@ constexpr int qk_lb_blocks(int sm, int ft) {
 }
 /* FT = feature set of the model: 0 = only SIMPLE single-server discrete components and stocks (no delay modes, no
  * environment, no scheduled events, no parallel or vector components): the handlers for everything else are
- * compiled out, which frees registers ; 1 = everything */
+ * compiled out, which frees registers ; 1 = everything but the container family ; 2 = everything */
 template <bool LOG, int SM, int FT>
 __global__ void __launch_bounds__(qk_lb_threads(SM), qk_lb_blocks(SM, FT)) qk_step_kernel(const __grid_constant__ KParams P) {
   uint8_t* const smem = qk_smem;
@@ -786,6 +938,7 @@ __global__ void __launch_bounds__(qk_lb_threads(SM), qk_lb_blocks(SM, FT)) qk_st
   cx.ext = reinterpret_cast<const DevExt*>(smem + cx.hdr->off_ext);
   cx.vecs = reinterpret_cast<const DevVec*>(smem + cx.hdr->off_vecs);
   cx.hot = reinterpret_cast<const DevHot*>(smem + cx.hdr->off_hot);
+  cx.ccap = reinterpret_cast<const double*>(smem + cx.hdr->off_ccap);
   cx.pf32 = cx.hdr->pf32;
   cx.n_pf_words = cx.hdr->n_pf_words;
   const uint64_t rep_local = (uint64_t)QK_BID * nt + tid;
@@ -852,6 +1005,10 @@ __global__ void __launch_bounds__(qk_lb_threads(SM), qk_lb_blocks(SM, FT)) qk_st
           /* with_initial_resource: the count rides in DevComp.dist_time (unused for stocks) */
           const uint32_t n_init = c->dist_time;
           for (uint32_t k = 0; k < n_init; ++k) C32(c->ocold32 + k) = (63u << 26) | (initial_base + k);
+          if (FT >= 2 && (c->flags & DC_CONTAINER)) { /* with_initial_resource(ItemDeque<Vector3Container>) */
+            const uint64_t* cinit = reinterpret_cast<const uint64_t*>(smem + cx.hdr->off_cinit) + 3u * initial_base;
+            for (uint32_t k = 0; k < 3u * n_init; ++k) C64(c->ocold64 + k) = cinit[k];
+          }
           initial_base += n_init;
           S32(c->o32 + S32_HC) = n_init << 16;
           cx.gs32[(size_t)(i * ST_PER_COMP + ST32_MAXOCC) * P.rep_pad] = n_init;
@@ -1096,7 +1253,7 @@ __device__ __forceinline__ void qk_comp_stats_dev(const DevComp* c, const DevVec
     o->level = qk_vcat(total, QK_U2D(G64(v->o64_low)), v->vmax);
     o->fvalue = total;
     o->faux = __dadd_rn(QK_U2D(GS64(ST64_TIME)), __dmul_rn(total, __dmul_rn((double)(now - G64(v->o64_last)), 1e-9)));
-  } else if (c->kind >= QK_VECTOR_PROCESS) {
+  } else if (c->kind >= QK_VECTOR_PROCESS && c->kind <= QK_VECTOR_SPLITTER) {
     const DevVec* v = &vecs[c->vec_idx];
     const uint32_t flags = G32(c->o32 + P32_FLAGS);
     const bool has = flags & PF_HAS_ITEM;
@@ -1117,7 +1274,8 @@ __device__ __forceinline__ void qk_comp_stats_dev(const DevComp* c, const DevVec
     o->time_ns = GS64(ST64_TIME) + (uint64_t)cnt * now;
     o->aux = GS32(ST32_MAXOCC);
     o->level = cnt;
-  } else if (c->kind == QK_DISCRETE_PARALLEL_PROCESS) {
+  } else if (c->kind == QK_DISCRETE_PARALLEL_PROCESS || c->kind == QK_CONTAINER_LOAD_PROCESS ||
+             c->kind == QK_CONTAINER_UNLOAD_PROCESS) {
     const uint32_t nprog = G32(c->o32 + PP32_NPROG);
     const uint32_t pflags = G32(c->o32 + PP32_FLAGS);
     const uint64_t pdt = now - G64(c->o64 + PP64_PREV);

@@ -24,9 +24,27 @@ void qk_set_error(const char* fmt, ...) {
 
 int qk_is_process_like(uint32_t k) {
   return k == QK_DISCRETE_PROCESS || k == QK_DISCRETE_SOURCE || k == QK_DISCRETE_SINK ||
-         k == QK_DISCRETE_PARALLEL_PROCESS || (k >= QK_VECTOR_PROCESS && k <= QK_VECTOR_SPLITTER);
+         k == QK_DISCRETE_PARALLEL_PROCESS || (k >= QK_VECTOR_PROCESS && k <= QK_VECTOR_SPLITTER) ||
+         (k >= QK_CONTAINER_PROCESS && k <= QK_CONTAINER_UNLOAD_PROCESS);
 }
 static int is_vector_kind(uint32_t k) { return k >= QK_VECTOR_STOCK && k <= QK_VECTOR_SPLITTER; }
+static int is_container_kind(uint32_t k) { return k >= QK_CONTAINER_STOCK && k <= QK_CONTAINER_UNLOAD_PROCESS; }
+static int is_item_stock(uint32_t k) { return k == QK_DISCRETE_STOCK || k == QK_CONTAINER_STOCK; }
+static int is_multi_server(uint32_t k) {
+  return k == QK_DISCRETE_PARALLEL_PROCESS || k == QK_CONTAINER_PARALLEL_PROCESS || k == QK_CONTAINER_LOAD_PROCESS ||
+         k == QK_CONTAINER_UNLOAD_PROCESS;
+}
+/* the discrete kind a container component is an instantiation of (core.rs:549-553); Load / Unload have their own */
+static uint32_t device_kind(uint32_t k) {
+  switch (k) {
+    case QK_CONTAINER_STOCK: return QK_DISCRETE_STOCK;
+    case QK_CONTAINER_PROCESS: return QK_DISCRETE_PROCESS;
+    case QK_CONTAINER_SOURCE: return QK_DISCRETE_SOURCE;
+    case QK_CONTAINER_SINK: return QK_DISCRETE_SINK;
+    case QK_CONTAINER_PARALLEL_PROCESS: return QK_DISCRETE_PARALLEL_PROCESS;
+    default: return k;
+  }
+}
 
 static const char* kind_name(uint32_t k) {
   switch (k) {
@@ -42,6 +60,13 @@ static const char* kind_name(uint32_t k) {
     case QK_VECTOR_SINK: return "VectorSink";
     case QK_VECTOR_COMBINER: return "VectorCombiner";
     case QK_VECTOR_SPLITTER: return "VectorSplitter";
+    case QK_CONTAINER_STOCK: return "Vector3ContainerStock";
+    case QK_CONTAINER_PROCESS: return "Vector3ContainerProcess";
+    case QK_CONTAINER_SOURCE: return "Vector3ContainerSource";
+    case QK_CONTAINER_SINK: return "Vector3ContainerSink";
+    case QK_CONTAINER_PARALLEL_PROCESS: return "Vector3ContainerParallelProcess";
+    case QK_CONTAINER_LOAD_PROCESS: return "Vector3ContainerLoadProcess";
+    case QK_CONTAINER_UNLOAD_PROCESS: return "Vector3ContainerUnloadProcess";
     default: return "?";
   }
 }
@@ -70,7 +95,8 @@ int qk_model_add_component(qk_model* m, const qk_component_desc* d, uint32_t* ou
     qk_set_error("qk_model_add_component: NULL argument");
     return QK_ERR_INVALID_ARG;
   }
-  if (!((d->kind >= QK_DISCRETE_STOCK && d->kind <= QK_ENVIRONMENT) || is_vector_kind(d->kind))) {
+  if (!((d->kind >= QK_DISCRETE_STOCK && d->kind <= QK_ENVIRONMENT) || is_vector_kind(d->kind) ||
+        is_container_kind(d->kind))) {
     qk_set_error("qk_model_add_component: unknown component kind %u", d->kind);
     return QK_ERR_INVALID_ARG;
   }
@@ -84,7 +110,20 @@ int qk_model_add_component(qk_model* m, const qk_component_desc* d, uint32_t* ou
   c.dist_time = c.dist_qty = -1;
   c.logged = false;
   c.src_ord = -1;
-  c.dim = is_vector_kind(d->kind) ? 1 : 0;
+  c.dim = is_vector_kind(d->kind) ? 1 : (is_container_kind(d->kind) ? 3 : 0);
+  c.dist_cqty = -1;
+  c.csplit[0] = c.csplit[1] = c.csplit[2] = 0.0;
+  c.ccapacity = 0.0;
+  if (d->kind == QK_CONTAINER_STOCK && d->n_initial_items) {
+    qk_set_error("qk_model_add_component: a container stock takes its initial contents from "
+                 "qk_model_set_initial_containers (n_initial_items must be 0)");
+    return QK_ERR_INVALID_ARG;
+  }
+  if ((d->kind == QK_CONTAINER_LOAD_PROCESS || d->kind == QK_CONTAINER_UNLOAD_PROCESS) &&
+      (d->max_capacity == 0 || d->max_capacity > 4096)) {
+    qk_set_error("qk_model_add_component: max_process_count (max_capacity) of a load/unload process must be 1..4096");
+    return QK_ERR_INVALID_ARG;
+  }
   c.n_ports = (d->kind == QK_VECTOR_COMBINER || d->kind == QK_VECTOR_SPLITTER) ? 1 : 0;
   c.vlow = c.vmax = 0.0; /* VectorStock defaults (vector.rs:70-71) */
   for (int k = 0; k < 3; ++k) c.vinit[k] = 0.0;
@@ -92,9 +131,8 @@ int qk_model_add_component(qk_model* m, const qk_component_desc* d, uint32_t* ou
     c.ratios[k] = 0.0;
     c.ups[k] = c.downs[k] = -1;
   }
-  c.initial_base = m->n_initial_total;
-  if (d->kind == QK_DISCRETE_STOCK) m->n_initial_total += d->n_initial_items;
-  if (d->kind == QK_DISCRETE_SOURCE) {
+  c.initial_base = 0; /* assigned at lowering: initial items are numbered in registration order of their stocks */
+  if (d->kind == QK_DISCRETE_SOURCE || d->kind == QK_CONTAINER_SOURCE) {
     if (m->n_sources >= 63) {
       qk_set_error("qk_model_add_component: at most 63 DiscreteSource components (item handle ordinal)");
       return QK_ERR_CAPACITY;
@@ -208,8 +246,50 @@ int qk_model_connect(qk_model* m, uint32_t a, uint32_t b, int32_t port_n) {
     A.down = (int)b;
     return QK_OK;
   }
-  if (ka == QK_ENVIRONMENT && qk_is_process_like(kb)) {
-    /* core.rs:1129-1148: emit_change->update_state, req_environment */
+  /* container family (core.rs:923-995) */
+  if (ka == QK_CONTAINER_STOCK &&
+      (kb == QK_CONTAINER_PROCESS || kb == QK_CONTAINER_PARALLEL_PROCESS || kb == QK_CONTAINER_SINK ||
+       kb == QK_CONTAINER_LOAD_PROCESS || kb == QK_CONTAINER_UNLOAD_PROCESS)) {
+    if (B.up >= 0) {
+      qk_set_error("qk_model_connect: component %u already has an upstream container stock", b);
+      return QK_ERR_PORT_IN_USE;
+    }
+    A.subs.push_back((int)b);
+    B.up = (int)a;
+    return QK_OK;
+  }
+  if (kb == QK_CONTAINER_STOCK &&
+      (ka == QK_CONTAINER_PROCESS || ka == QK_CONTAINER_PARALLEL_PROCESS || ka == QK_CONTAINER_SOURCE ||
+       ka == QK_CONTAINER_LOAD_PROCESS || ka == QK_CONTAINER_UNLOAD_PROCESS)) {
+    if (A.down >= 0) {
+      qk_set_error("qk_model_connect: component %u already has a downstream container stock", a);
+      return QK_ERR_PORT_IN_USE;
+    }
+    B.subs.push_back((int)a);
+    A.down = (int)b;
+    return QK_OK;
+  }
+  if (ka == QK_VECTOR_STOCK && A.dim == 3 && kb == QK_CONTAINER_LOAD_PROCESS) { /* core.rs:960-965 */
+    if (B.ups[0] >= 0) {
+      qk_set_error("qk_model_connect: load process %u already has an upstream resource stock", b);
+      return QK_ERR_PORT_IN_USE;
+    }
+    A.subs.push_back((int)b);
+    B.ups[0] = (int)a;
+    return QK_OK;
+  }
+  if (kb == QK_VECTOR_STOCK && B.dim == 3 && ka == QK_CONTAINER_UNLOAD_PROCESS) { /* core.rs:990-995 */
+    if (A.downs[0] >= 0) {
+      qk_set_error("qk_model_connect: unload process %u already has a downstream resource stock", a);
+      return QK_ERR_PORT_IN_USE;
+    }
+    B.subs.push_back((int)a);
+    A.downs[0] = (int)b;
+    return QK_OK;
+  }
+  /* core.rs:1129-1172; there is no (BasicEnvironment, Vector3ContainerParallelProcess) arm */
+  if (ka == QK_ENVIRONMENT && qk_is_process_like(kb) && kb != QK_CONTAINER_PARALLEL_PROCESS) {
+    /* emit_change->update_state, req_environment */
     if (B.env >= 0) {
       qk_set_error("qk_model_connect: component %u already has an environment", b);
       return QK_ERR_PORT_IN_USE;
@@ -334,6 +414,53 @@ int qk_model_schedule_low_capacity(qk_model* m, uint64_t t_ns, uint32_t stock, d
   return QK_OK;
 }
 
+int qk_model_set_container_factory(qk_model* m, uint32_t source, const qk_dist_desc* create_quantity,
+                                   const double* split3, double capacity, uint32_t* out_dist_id) {
+  if (!m || source >= m->comps.size() || m->comps[source].d.kind != QK_CONTAINER_SOURCE) {
+    qk_set_error("qk_model_set_container_factory: component %u is not a container source", source);
+    return QK_ERR_INVALID_ARG;
+  }
+  if (create_quantity && !check_dist(create_quantity)) {
+    qk_set_error("qk_model_set_container_factory: invalid distribution parameters");
+    return QK_ERR_INVALID_ARG;
+  }
+  QkHostComp& c = m->comps[source];
+  if (create_quantity) {
+    if (c.dist_cqty < 0) {
+      c.dist_cqty = (int)m->dists.size();
+      m->dists.push_back(*create_quantity);
+    } else {
+      m->dists[(size_t)c.dist_cqty] = *create_quantity;
+    }
+  } else {
+    c.dist_cqty = -1;
+  }
+  for (int k = 0; k < 3; ++k) c.csplit[k] = split3 ? split3[k] : 0.0;
+  c.ccapacity = capacity;
+  if (out_dist_id) *out_dist_id = c.dist_cqty >= 0 ? (uint32_t)c.dist_cqty : 0xFFFFFFFFu;
+  return QK_OK;
+}
+
+int qk_model_set_initial_containers(qk_model* m, uint32_t stock, uint32_t n, const double* resources,
+                                    const uint8_t* has_resource, const double* capacities) {
+  if (!m || stock >= m->comps.size() || m->comps[stock].d.kind != QK_CONTAINER_STOCK || (n && !capacities)) {
+    qk_set_error("qk_model_set_initial_containers: component %u is not a container stock (or capacities is NULL)", stock);
+    return QK_ERR_INVALID_ARG;
+  }
+  QkHostComp& c = m->comps[stock];
+  c.d.n_initial_items = n;
+  c.init_res.assign((size_t)n * 3, 0.0);
+  c.init_has.assign(n, 0);
+  c.init_cap.assign(n, 0.0);
+  for (uint32_t k = 0; k < n; ++k) {
+    c.init_has[k] = (has_resource && resources) ? has_resource[k] : 0;
+    if (c.init_has[k])
+      for (int j = 0; j < 3; ++j) c.init_res[(size_t)k * 3 + j] = resources[(size_t)k * 3 + j];
+    c.init_cap[k] = capacities[k];
+  }
+  return QK_OK;
+}
+
 int qk_model_n_components(const qk_model* m, uint32_t* out) {
   if (!m || !out) return QK_ERR_INVALID_ARG;
   *out = (uint32_t)m->comps.size();
@@ -405,7 +532,7 @@ int qk_lower(const qk_model* m, bool log, QkLowered* out) {
     memset(&dc[i], 0, sizeof(DevComp));
     uint32_t k = m->comps[i].d.kind;
     dc[i].fire_idx = 0xFFFF;
-    if (k == QK_DISCRETE_STOCK || k == QK_VECTOR_STOCK || qk_is_process_like(k)) {
+    if (is_item_stock(k) || k == QK_VECTOR_STOCK || qk_is_process_like(k)) {
       dc[i].fire_idx = (uint16_t)sched.size();
       sched.push_back((uint16_t)i);
     }
@@ -416,7 +543,7 @@ int qk_lower(const qk_model* m, bool log, QkLowered* out) {
   /* prefetchable distributions: process_time_distr of single-server components when it is not Constant */
   std::vector<uint16_t> pf_comp;
   for (size_t i = 0; i < nc; ++i) {
-    uint32_t k = m->comps[i].d.kind;
+    uint32_t k = device_kind(m->comps[i].d.kind);
     if ((k == QK_DISCRETE_PROCESS || k == QK_DISCRETE_SOURCE || k == QK_DISCRETE_SINK) &&
         m->dists[(size_t)m->comps[i].dist_time].kind != QK_DIST_CONSTANT)
       pf_comp.push_back((uint16_t)i);
@@ -432,7 +559,7 @@ int qk_lower(const qk_model* m, bool log, QkLowered* out) {
   std::vector<uint32_t> cap(nc, 0);
   for (size_t i = 0; i < nc; ++i) { /* stock rings first */
     const QkHostComp& c = m->comps[i];
-    if (c.d.kind != QK_DISCRETE_STOCK) continue;
+    if (!is_item_stock(c.d.kind)) continue;
     uint32_t r;
     if (c.d.capacity_hint) {
       r = c.d.capacity_hint;
@@ -445,7 +572,7 @@ int qk_lower(const qk_model* m, bool log, QkLowered* out) {
       }
       uint32_t producers = 0;
       for (size_t j = 0; j < nc; ++j)
-        if (m->comps[j].down == (int)i && m->comps[j].d.kind != QK_DISCRETE_PARALLEL_PROCESS) producers++;
+        if (m->comps[j].down == (int)i && !is_multi_server(m->comps[j].d.kind)) producers++;
       /* capacity is advisory (discrete.rs:181-186 has no check): each single-server producer that saw
        * Empty/Normal when it started may still push when the stock is already at max */
       r = base + producers;
@@ -459,8 +586,10 @@ int qk_lower(const qk_model* m, bool log, QkLowered* out) {
   }
   for (size_t i = 0; i < nc; ++i) {
     const QkHostComp& c = m->comps[i];
-    if (c.d.kind != QK_DISCRETE_PARALLEL_PROCESS) continue;
+    if (!is_multi_server(c.d.kind)) continue;
     uint32_t r = c.d.capacity_hint ? c.d.capacity_hint : (c.up >= 0 ? 2 * cap[(size_t)c.up] + 8 : 8);
+    /* Load / Unload are bounded by max_process_count (vector_container.rs:350, 661) */
+    if (c.d.kind == QK_CONTAINER_LOAD_PROCESS || c.d.kind == QK_CONTAINER_UNLOAD_PROCESS) r = c.d.max_capacity;
     if (r > 0xFFFF) return QK_ERR_CAPACITY;
     cap[i] = r;
   }
@@ -468,7 +597,7 @@ int qk_lower(const qk_model* m, bool log, QkLowered* out) {
   for (size_t i = 0; i < nc; ++i) {
     const QkHostComp& c = m->comps[i];
     DevComp& d = dc[i];
-    d.kind = (uint8_t)c.d.kind;
+    d.kind = (uint8_t)device_kind(c.d.kind);
     d.n_dm = (uint8_t)c.dms.size();
     d.src_ord = (uint8_t)(c.src_ord >= 0 ? c.src_ord : 0);
     d.up = (int16_t)c.up;
@@ -479,6 +608,8 @@ int qk_lower(const qk_model* m, bool log, QkLowered* out) {
     d.ring_cap = (uint16_t)cap[i];
     d.dist_time = (uint16_t)(c.dist_time >= 0 ? c.dist_time : 0);
     d.flags = c.logged ? DC_LOGGED : 0;
+    const bool is_ctr = is_container_kind(c.d.kind) != 0;
+    if (is_ctr) d.flags |= DC_CONTAINER;
     d.o64_ttnpe = 0xFFFF;
     d.o32_next_item = 0xFFFF;
     d.o64_nextdur = 0xFFFF;
@@ -499,7 +630,7 @@ int qk_lower(const qk_model* m, bool log, QkLowered* out) {
     d.dm_off = (uint16_t)dms.size();
     for (size_t k = 0; k < c.dms.size(); ++k) dms.push_back(c.dms[k]);
 
-    uint32_t kind = c.d.kind;
+    uint32_t kind = device_kind(c.d.kind);
     if (kind == QK_DISCRETE_PROCESS || kind == QK_DISCRETE_SOURCE || kind == QK_DISCRETE_SINK) {
       d.o64 = (uint16_t)n64;
       n64 += P64_BASE_COUNT;
@@ -514,7 +645,24 @@ int qk_lower(const qk_model* m, bool log, QkLowered* out) {
           d.pf_idx = (uint16_t)k;
           d.o64_nextdur = (uint16_t)n64++;
         }
-    } else if (kind == QK_DISCRETE_PARALLEL_PROCESS) {
+      if (is_ctr) {
+        d.ocold64 = (uint16_t)n64c;
+        n64c += 3;
+        if (kind == QK_DISCRETE_SOURCE) { /* Vector3ContainerFactory (vector_container.rs:126-156) */
+          DevVec v;
+          memset(&v, 0, sizeof(v));
+          v.dim = 3;
+          for (int k = 0; k < 3; ++k) v.vinit[k] = c.csplit[k]; /* create_component_split */
+          v.vmax = c.ccapacity;
+          for (int k = 0; k < 5; ++k) v.ups[k] = v.downs[k] = -1;
+          v.dist_qty = (uint16_t)(c.dist_cqty >= 0 ? c.dist_cqty : 0xFFFF); /* create_quantity_distr or None */
+          if (c.dist_cqty >= 0 && m->dists[(size_t)c.dist_cqty].kind != QK_DIST_CONSTANT)
+            dd[(size_t)c.dist_cqty].draw_slot = n32++;
+          d.vec_idx = (uint16_t)vecs.size();
+          vecs.push_back(v);
+        }
+      }
+    } else if (is_multi_server(kind)) {
       d.o64 = (uint16_t)n64;
       n64 += PP64_BASE_COUNT;
       d.o64_dm = (uint16_t)n64;
@@ -522,6 +670,23 @@ int qk_lower(const qk_model* m, bool log, QkLowered* out) {
       n64 += d.ring_cap; /* in-progress durations */
       d.o32 = (uint16_t)n32;
       n32 += PP32_BASE_COUNT + 2u * d.ring_cap;
+      if (is_ctr) {
+        d.ocold64 = (uint16_t)n64c;
+        n64c += 6u * d.ring_cap; /* payload of the in-progress slots, then of the complete ring */
+      }
+      if (kind == QK_CONTAINER_LOAD_PROCESS || kind == QK_CONTAINER_UNLOAD_PROCESS) {
+        DevVec v;
+        memset(&v, 0, sizeof(v));
+        v.dim = 3;
+        for (int k = 0; k < 5; ++k) {
+          v.ups[k] = (int16_t)c.ups[k];     /* Load: ups[0] = the Vector3Stock it withdraws resource from */
+          v.downs[k] = (int16_t)c.downs[k]; /* Unload: downs[0] = the Vector3Stock it pushes resource to */
+        }
+        v.dist_qty = (uint16_t)c.dist_qty; /* process_capacity_ratio_distr / process_quantity_ratio_distr */
+        if (m->dists[(size_t)c.dist_qty].kind != QK_DIST_CONSTANT) dd[(size_t)c.dist_qty].draw_slot = n32++;
+        d.vec_idx = (uint16_t)vecs.size();
+        vecs.push_back(v);
+      }
     } else if (kind == QK_DISCRETE_STOCK) {
       d.o64 = (uint16_t)n64;
       n64 += S64_COUNT;
@@ -529,11 +694,14 @@ int qk_lower(const qk_model* m, bool log, QkLowered* out) {
       n32 += S32_COUNT;
       d.ocold32 = (uint16_t)n32c;
       n32c += d.ring_cap;
+      if (is_ctr) {
+        d.ocold64 = (uint16_t)n64c;
+        n64c += 3u * d.ring_cap;
+      }
       uint32_t depth = 0;
       for (size_t j = 0; j < nc; ++j) {
         const QkHostComp& o = m->comps[j];
-        if (o.up == (int)i || o.down == (int)i)
-          depth += 2u * (o.d.kind == QK_DISCRETE_PARALLEL_PROCESS ? cap[j] : 1u);
+        if (o.up == (int)i || o.down == (int)i) depth += 2u * (is_multi_server(o.d.kind) ? cap[j] : 1u);
       }
       if (depth < 2) depth = 2;
       if (depth > 250) depth = 250;
@@ -559,7 +727,7 @@ int qk_lower(const qk_model* m, bool log, QkLowered* out) {
         const QkHostComp& o = m->comps[j];
         if (o.up == (int)i || o.down == (int)i) depth += 2;
         for (int k = 0; k < 5; ++k)
-          if (o.ups[k] == (int)i || o.downs[k] == (int)i) depth += 2;
+          if (o.ups[k] == (int)i || o.downs[k] == (int)i) depth += 2u * (is_multi_server(o.d.kind) ? cap[j] : 1u);
       }
       depth += 2 * (uint32_t)m->ext.size(); /* SetLowCapacity's add(0.) can flip the state too */
       if (depth < 2) depth = 2;
@@ -628,7 +796,7 @@ int qk_lower(const qk_model* m, bool log, QkLowered* out) {
    * BasicEnvironment logs its state (core.rs:229-234); stocks use the default no-op init */
   uint32_t init_off = (uint32_t)subs.size(), n_init = 0;
   for (size_t i = 0; i < nc; ++i)
-    if (m->comps[i].d.kind != QK_DISCRETE_STOCK && m->comps[i].d.kind != QK_VECTOR_STOCK) {
+    if (!is_item_stock(m->comps[i].d.kind) && m->comps[i].d.kind != QK_VECTOR_STOCK) {
       subs.push_back((uint16_t)i);
       n_init++;
     }
@@ -691,8 +859,8 @@ int qk_lower(const qk_model* m, bool log, QkLowered* out) {
     q.a.fire_idx = d.fire_idx;
     q.a.flags = d.flags;
     const bool single = d.kind == QK_DISCRETE_PROCESS || d.kind == QK_DISCRETE_SOURCE || d.kind == QK_DISCRETE_SINK;
-    if (single && d.n_dm == 0 && d.env < 0) q.a.flags |= DC_SIMPLE;
-    if (!(d.kind == QK_DISCRETE_STOCK || (q.a.flags & DC_SIMPLE))) h.features = 1;
+    if (single && d.n_dm == 0 && d.env < 0 && !(d.flags & DC_CONTAINER)) q.a.flags |= DC_SIMPLE;
+    if (!(d.kind == QK_DISCRETE_STOCK || (q.a.flags & DC_SIMPLE)) || (d.flags & DC_CONTAINER)) h.features = 1;
     q.a.olog32 = d.olog32;
     q.a.olog64 = d.kind == QK_DISCRETE_STOCK ? d.ocold32 : d.olog64;
     if (qk_is_process_like(d.kind)) {
@@ -722,9 +890,48 @@ int qk_lower(const qk_model* m, bool log, QkLowered* out) {
   off = (off + 15u) & ~15u;
   h.off_hot = off;
   off = align8(off + (uint32_t)(nc * sizeof(DevHot)));
+  /* container tables: capacity by handle, resource of the initial containers (numbered in registration order of
+   * their stocks, like the handles the init kernel hands out) */
+  std::vector<double> ccap(64, 0.0);
+  std::vector<uint64_t> cinit;
+  {
+    uint32_t base = 0;
+    for (size_t i = 0; i < nc; ++i) {
+      const QkHostComp& c = m->comps[i];
+      if (c.d.kind == QK_CONTAINER_SOURCE) ccap[(size_t)c.src_ord] = c.ccapacity;
+      if (!is_item_stock(c.d.kind)) continue;
+      for (uint32_t k = 0; k < c.d.n_initial_items; ++k) {
+        const bool has = c.d.kind == QK_CONTAINER_STOCK && c.init_has[k];
+        ccap.push_back(c.d.kind == QK_CONTAINER_STOCK ? c.init_cap[k] : 0.0);
+        for (int j = 0; j < 3; ++j) {
+          uint64_t w = 0;
+          if (has) memcpy(&w, &c.init_res[(size_t)k * 3 + j], 8);
+          else if (j == 0) w = QK_CONTAINER_NONE_BITS;
+          cinit.push_back(w);
+        }
+      }
+      base += c.d.n_initial_items;
+    }
+    if (base > 0x3FFFFFFu) {
+      qk_set_error("more than 2^26 initial items");
+      return QK_ERR_CAPACITY;
+    }
+  }
+  const bool any_ctr = std::any_of(dc.begin(), dc.end(), [](const DevComp& d) { return (d.flags & DC_CONTAINER) != 0; });
+  if (any_ctr) {
+    h.features = 2;
+    h.off_ccap = off;
+    off = align8(off + (uint32_t)(ccap.size() * 8));
+    h.off_cinit = off;
+    off = align8(off + (uint32_t)(cinit.size() * 8));
+  }
   h.total_bytes = off;
 
   out->blob.assign(off, 0);
+  if (any_ctr) {
+    memcpy(out->blob.data() + h.off_ccap, ccap.data(), ccap.size() * 8);
+    if (!cinit.empty()) memcpy(out->blob.data() + h.off_cinit, cinit.data(), cinit.size() * 8);
+  }
   memcpy(out->blob.data() + h.off_hot, hot.data(), nc * sizeof(DevHot));
   memcpy(out->blob.data(), &h, sizeof(h));
   memcpy(out->blob.data() + h.off_comps, dc.data(), nc * sizeof(DevComp));

@@ -19,6 +19,12 @@ struct QkHostComp {
   uint32_t dim, n_ports;
   double vlow, vmax, vinit[3], ratios[5];
   int ups[5], downs[5];
+  /* container family: factory of a container source; initial contents of a container stock */
+  int dist_cqty; /* create_quantity_distr instance or -1 (None) */
+  double csplit[3], ccapacity;
+  std::vector<double> init_res; /* [n][3] */
+  std::vector<uint8_t> init_has;
+  std::vector<double> init_cap;
 };
 
 struct qk_model {

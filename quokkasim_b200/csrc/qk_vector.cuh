@@ -15,8 +15,7 @@
 #ifndef QK_VECTOR_CUH
 #define QK_VECTOR_CUH
 
-#define QK_D2U(d) ((uint64_t)__double_as_longlong(d))
-#define QK_U2D(u) (__longlong_as_double((long long)(u)))
+/* QK_D2U / QK_U2D: qk_kernels.cuh */
 
 /* continuation record carrying three doubles (see qk_log_record docs in quokka_b200.h) */
 template <bool LOG, int SM>

@@ -11,6 +11,10 @@
   VectorProcessLog     vector.rs:594-720    ...,event_type,total,inflows,outflows,reason
   BasicEnvironmentLog  core.rs:306-325      time,event_id,source_event_id,element_name,element_type,event
 
+The container family logs through DiscreteStockLog<Vector3Container> / DiscreteProcessLog<Vector3Container>: same
+columns, the `item` column is `serde_json::to_string` of the container (Serialize impl vector_container.rs:113-124):
+`{"id":"Truck_01","resource":{"x":1.0,"y":2.0,"z":3.0},"capacity":80.0}` with `"resource":null` for None.
+
 Formatting facts this relies on (third-party crates, not in /root/reference -- restated from their documented
 behaviour): the `csv` crate quotes a field only when it contains `,` `"` CR or LF and doubles embedded quotes,
 terminates records with LF, writes `None` as an empty field; `serde_json` and `csv` print f64 with `ryu`
@@ -34,6 +38,8 @@ _REASONS = {
     5: "Upstream did not provide resource", 6: "Stopped by environment", 7: "Resumed by environment",
     8: "Upstream is full", 9: "At least one upstream is empty", 10: "No upstreams are connected",
     11: "At least one downstream is full", 12: "No downstreams are connected",
+    13: "No remaining process slots", 14: "Downstream container stock is full",
+    15: "Downstream resource stock is full",
 }
 _STATE = ("Empty", "Normal", "Full")
 _EPOCH = datetime.datetime(1970, 1, 1)
@@ -133,6 +139,12 @@ def json_string(s):
     return "".join(out)
 
 
+def _json_f64(x):
+    """serde_json prints non-finite floats as null"""
+    x = float(x)
+    return ryu_f64(x) if x == x and x not in (float("inf"), float("-inf")) else "null"
+
+
 class LogDecoder:
     """Turns the records of one replication into reference-format rows, per logger."""
 
@@ -163,6 +175,32 @@ class LogDecoder:
         f = self.sources[ordn].item_factory
         return f.item_name(idx)
 
+    def is_container(self, comp):
+        return self.variants[comp].startswith("Vector3Container")
+
+    def is_vector(self, comp):
+        v = self.variants[comp]
+        return v.startswith(("F64", "Vector3")) and not v.startswith("Vector3Container")
+
+    def item_json(self, comp, handle, rec_vecs):
+        """serde_json::to_string(item): a String item, or a Vector3Container (vector_container.rs:113-124)"""
+        if not self.is_container(comp):
+            return json_string(self.item_name(handle))
+        handle = int(handle)
+        ordn, idx = (handle >> 26) & 63, handle & 0x3FFFFFF
+        if ordn == 63:
+            it = self.initial_items[idx]
+            name, capacity = it.id, it.capacity
+        else:
+            f = self.sources[ordn].item_factory
+            name, capacity = f.item_name(idx), f.capacity
+        raw = rec_vecs[0] if rec_vecs else None
+        if raw is None or raw[0] == capi.CONTAINER_NONE_BITS:
+            res = "null"
+        else:
+            res = '{"x":%s,"y":%s,"z":%s}' % tuple(_json_f64(self._f64(w)) for w in raw)
+        return '{"id":%s,"resource":%s,"capacity":%s}' % (json_string(name), res, _json_f64(capacity))
+
     def vector_json(self, comp, v3):
         if self.components[comp].dim == 1:
             return ryu_f64(v3[0])
@@ -191,14 +229,16 @@ class LogDecoder:
             kind = int(r["kind"])
             if kind == capi.LOG_VEC_DATA:
                 continue  # orphan (its main record fell out of the ring)
-            vecs = []
+            vecs, raws = [], []
             while i < n and int(records[i]["kind"]) == capi.LOG_VEC_DATA and int(records[i]["comp"]) == int(r["comp"]) \
                     and int(records[i]["seq"]) == int(r["seq"]):
                 vecs.append(self._vec_of(records[i]))
+                q = struct.unpack("<QQQQ", records[i].tobytes())
+                raws.append((q[0], q[2], q[3]))  # the three fp64 words as raw bits (container None sentinel)
                 i += 1
-            yield int(r["comp"]), self._row(r, kind, vecs)
+            yield int(r["comp"]), self._row(r, kind, vecs, raws)
 
-    def _row(self, r, kind, vecs):
+    def _row(self, r, kind, vecs, raws=()):
         comp = int(r["comp"])
         c = self.components[comp]
         variant = self.variants[comp]
@@ -213,27 +253,27 @@ class LogDecoder:
             return head + ["Stopped" if reason == 1 else "Normal"]
         head[0] = chrono_utc(t)
         if kind == capi.LOG_STOCK_ADD:
-            return head + ["Add", json_string(self.item_name(payload)), None]
+            return head + ["Add", self.item_json(comp, payload, raws), None]
         if kind == capi.LOG_STOCK_REMOVE:
-            item = "null" if payload == 0xFFFFFFFFFFFFFFFF else json_string(self.item_name(payload))
+            item = "null" if payload == 0xFFFFFFFFFFFFFFFF else self.item_json(comp, payload, raws)
             return head + ["Remove", item, None]
         if kind == capi.LOG_STOCK_STATE_CHANGE:
             st = '{"%s":{"occupied":%d,"empty":%d}}' % (_STATE[reason], payload >> 32, payload & 0xFFFFFFFF)
             return head + ["StateChange", st, None]
         if kind in (capi.LOG_PROCESS_START, capi.LOG_PROCESS_FINISH):
             name = "ProcessStart" if kind == capi.LOG_PROCESS_START else "ProcessFinish"
-            return head + [name, json_string(self.item_name(payload)), None]
+            return head + [name, self.item_json(comp, payload, raws), None]
         if kind in (capi.LOG_DELAY_START, capi.LOG_DELAY_END):
             name = "DelayStart" if kind == capi.LOG_DELAY_START else "DelayEnd"
             dm = c.delay_modes[payload].name
-            if variant.startswith(("F64", "Vector3")):  # vector.rs:693-706: the name travels in `reason`
+            if self.is_vector(comp):  # vector.rs:693-706: the name travels in `reason`
                 return head + [name, None, None, None, dm]
             return head + [name, dm, None]
         simple = {capi.LOG_PROCESS_CONTINUE: "ProcessContinue", capi.LOG_PROCESS_NONSTART: "ProcessNonStart",
                   capi.LOG_PROCESS_STOPPED: "ProcessStopped", capi.LOG_WITHDRAW_REQUEST: "WithdrawRequest"}
         if kind in simple:
             why = _REASONS.get(reason) if kind != capi.LOG_WITHDRAW_REQUEST else None
-            if variant.startswith(("F64", "Vector3")):
+            if self.is_vector(comp):
                 return head + [simple[kind], None, None, None, why]
             return head + [simple[kind], None, why]
         # ---- vector stock
@@ -265,6 +305,8 @@ HEADERS = {
                            "outflows,reason",
     "BasicEnvironmentLogger": "time,event_id,source_event_id,element_name,element_type,event",
 }
+HEADERS["ContainerStockLogger"] = HEADERS["DiscreteStockLogger"]
+HEADERS["ContainerProcessLogger"] = HEADERS["DiscreteProcessLogger"]
 
 
 def csv_text(component_logger, sim, replication=0):

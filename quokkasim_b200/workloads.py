@@ -42,9 +42,21 @@ def _log_all(m):
            for p in ("F64", "Vector3")}
     vpl = {p: qk.ComponentLogger(p + "ProcessLogger", qk.VectorProcessLogger.new(p + "ProcessLogger"))
            for p in ("F64", "Vector3")}
+    csl = qk.ComponentLogger.Vector3ContainerStockLogger(qk.ContainerStockLogger.new("ContainerStockLogger"))
+    cpl = qk.ComponentLogger.Vector3ContainerProcessLogger(qk.ContainerProcessLogger.new("ContainerProcessLogger"))
     for c in m.components:
         prefix = "F64" if c.variant.startswith("F64") else ("Vector3" if c.variant.startswith("Vector3") else None)
-        if prefix:
+        if c.variant.startswith("Vector3Container"):
+            if c.variant == "Vector3ContainerStock":
+                qk.connect_logger(csl, c)
+            elif c.variant in cpl.logger.ACCEPTS:
+                qk.connect_logger(cpl, c)
+            elif getattr(m, "log_unloggable", False):
+                # the reference has no logger arm for Vector3ContainerSource / Sink (core.rs:1331-1334); parity tests
+                # still want their records compared, so they switch logging on below the Python API
+                c.component._logged_by = cpl.logger
+                cpl.logger.components.append(c.component)
+        elif prefix:
             qk.connect_logger((vsl if c.variant.endswith("Stock") else vpl)[prefix], c)
         elif c.variant == "StringStock":
             qk.connect_logger(sl, c)
@@ -53,6 +65,7 @@ def _log_all(m):
         else:
             qk.connect_logger(pl, c)
     m.loggers = (sl, pl, el, vsl, vpl)
+    m.container_loggers = (csl, cpl)
 
 
 def discrete_queue(tri=(1.0, 10.0, 6.0), src_time=3.0, sink_time=1.0, cap=10):
@@ -536,5 +549,130 @@ def the_example():
     for x in (rs1, rs2, st1, trucking, st2, conveyors, pf1, p1, pf2, p2):
         m.reg(x)
     m.t0 = qk.MonotonicTime.try_from_date_time(2025, 6, 22, 0, 0, 0, 0)
+    _log_all(m)
+    return m
+
+
+# ---------------------------------------------------------------------------------------- container models
+def container_haulage(n_trucks=4, loaders=2, random=True, breakdowns=True, unload_ratio=(0.85, 0.98)):
+    """Payload-true truck cycle: a fixed fleet of Vector3Containers circulates
+    ReadyToLoad -> ContainerLoadingProcess (ore from a Vector3Stock) -> Loaded -> Vector3ContainerParallelProcess
+    (haul) -> AtDump -> ContainerUnloadingProcess (ore into a Vector3Stock) -> Emptied -> Vector3ContainerProcess
+    (return) -> ReadyToLoad.  With an unload ratio below 1 mass is conserved: ore + dumped + carried is constant."""
+    m = Model()
+    df = qk.DistributionFactory(base_seed=777, next_seed=0)
+
+    def dist(kind, *a):
+        if not random:
+            return qk.Distribution.Constant(sum(a[:2]) / 2.0)
+        d = df.create(getattr(qk.DistributionConfig, kind)(*a))
+        m.random_dists.append(d)
+        return d
+
+    ore = m.reg(qk.ComponentModel.Vector3Stock(
+        qk.VectorStock.new().with_name("Ore").with_code("ORE").with_low_capacity(0.0).with_max_capacity(1e9)
+        .with_initial_resource(qk.Vector3([60000.0, 30000.0, 10000.0])), qk.Mailbox.new()))
+    trucks = [qk.Vector3Container("Truck_%02d" % i, None if i % 3 else qk.Vector3([1.0, 0.5, 0.25]), 80.0 + 10.0 * (i % 4))
+              for i in range(n_trucks)]
+    ready = m.reg(qk.ComponentModel.Vector3ContainerStock(
+        qk.DiscreteStock.new().with_name("ReadyToLoad").with_code("RTL").with_low_capacity(0)
+        .with_max_capacity(n_trucks + 2).with_initial_resource(qk.ItemDeque(trucks)), qk.Mailbox.new()))
+    load_c = qk.ContainerLoadingProcess.new().with_name("Loader").with_code("LD").with_max_process_count(loaders) \
+        .with_process_time_distr(dist("Triangular", 20.0, 60.0, 30.0)) \
+        .with_process_capacity_ratio_distr(dist("Uniform", 0.8, 1.0))
+    if breakdowns:
+        load_c = load_c.with_delay_mode(qk.DelayModeChange.Add(
+            qk.DelayMode("Breakdown", dist("Uniform", 300.0, 600.0), dist("Uniform", 20.0, 60.0))))
+    load = m.reg(qk.ComponentModel.Vector3ContainerLoadProcess(load_c, qk.Mailbox.new()))
+    loaded = m.reg(qk.ComponentModel.Vector3ContainerStock(
+        qk.DiscreteStock.new().with_name("Loaded").with_code("LDD").with_max_capacity(n_trucks + 2), qk.Mailbox.new()))
+    haul = m.reg(qk.ComponentModel.Vector3ContainerParallelProcess(
+        qk.DiscreteParallelProcess.new().with_name("Haul").with_code("HL")
+        .with_process_time_distr(dist("Triangular", 100.0, 200.0, 140.0)), qk.Mailbox.new()))
+    at_dump = m.reg(qk.ComponentModel.Vector3ContainerStock(
+        qk.DiscreteStock.new().with_name("AtDump").with_code("ATD").with_max_capacity(n_trucks + 2), qk.Mailbox.new()))
+    unload_c = qk.ContainerUnloadingProcess.new().with_name("Dump").with_code("DMP").with_max_process_count(1) \
+        .with_process_time_distr(dist("Uniform", 15.0, 25.0))
+    if unload_ratio is not None:
+        unload_c = unload_c.with_process_quantity_ratio_distr(dist("Uniform", *unload_ratio))
+    unload = m.reg(qk.ComponentModel.Vector3ContainerUnloadProcess(unload_c, qk.Mailbox.new()))
+    dumped = m.reg(qk.ComponentModel.Vector3Stock(
+        qk.VectorStock.new().with_name("Dumped").with_code("DPD").with_low_capacity(0.0).with_max_capacity(1e9),
+        qk.Mailbox.new()))
+    emptied = m.reg(qk.ComponentModel.Vector3ContainerStock(
+        qk.DiscreteStock.new().with_name("Emptied").with_code("EMP").with_max_capacity(n_trucks + 2), qk.Mailbox.new()))
+    ret = m.reg(qk.ComponentModel.Vector3ContainerProcess(
+        qk.DiscreteProcess.new().with_name("Return").with_code("RET")
+        .with_process_time_distr(dist("Triangular", 30.0, 70.0, 45.0)), qk.Mailbox.new()))
+    env = m.reg(qk.ComponentModel.BasicEnvironment(qk.BasicEnvironment.new().with_name("Shift").with_code("ENV"),
+                                                   qk.Mailbox.new()))
+    qk.connect_components(ore, load)
+    qk.connect_components(ready, load)
+    qk.connect_components(load, loaded)
+    qk.connect_components(loaded, haul)
+    qk.connect_components(haul, at_dump)
+    qk.connect_components(at_dump, unload)
+    qk.connect_components(unload, emptied)
+    qk.connect_components(unload, dumped)
+    qk.connect_components(emptied, ret)
+    qk.connect_components(ret, ready)
+    for x in (load, unload, ret):
+        qk.connect_components(env, x)
+    m.ext.append((qk.Duration.from_secs(1500), env, qk.BasicEnvironmentState.Stopped))
+    m.ext.append((qk.Duration.from_secs(1700), env, qk.BasicEnvironmentState.Normal))
+    m.mass = dict(vector_stocks=[ore, dumped], container_holders=[ready, load, loaded, haul, at_dump, unload, emptied, ret])
+    _log_all(m)
+    return m
+
+
+def container_open(lossy_unload=True, log_unloggable=True):
+    """Open container line: Vector3ContainerSource (factory draws what each container arrives with) -> stock ->
+    ContainerLoadingProcess (tops it up) -> stock -> ContainerUnloadingProcess -> stock -> Vector3ContainerSink.
+    lossy_unload keeps the default process_quantity_ratio_distr Constant(1.): the reference then moves
+    Vector3::default() to the resource stock and drops what the container carried (vector_container.rs:582-586)."""
+    m = Model()
+    m.log_unloggable = log_unloggable
+    df = qk.DistributionFactory(base_seed=4242, next_seed=0)
+
+    def dist(kind, *a):
+        d = df.create(getattr(qk.DistributionConfig, kind)(*a))
+        m.random_dists.append(d)
+        return d
+
+    fac = qk.Vector3ContainerFactory("Bin", 1, 3, dist("Uniform", 2.0, 6.0), [0.5, 0.3, 0.2], 25.0)
+    src = m.reg(qk.ComponentModel.Vector3ContainerSource(
+        qk.DiscreteSource.new().with_name("Arrivals").with_code("ARR").with_item_factory(fac)
+        .with_process_time_distr(dist("Uniform", 4.0, 8.0)), qk.Mailbox.new()))
+    q0 = m.reg(qk.ComponentModel.Vector3ContainerStock(
+        qk.DiscreteStock.new().with_name("Q0").with_code("Q0").with_max_capacity(6), qk.Mailbox.new()))
+    bulk = m.reg(qk.ComponentModel.Vector3Stock(
+        qk.VectorStock.new().with_name("Bulk").with_code("BLK").with_low_capacity(10.0).with_max_capacity(5000.0)
+        .with_initial_resource(qk.Vector3([900.0, 500.0, 100.0])), qk.Mailbox.new()))
+    load = m.reg(qk.ComponentModel.Vector3ContainerLoadProcess(
+        qk.ContainerLoadingProcess.new().with_name("Fill").with_max_process_count(2)
+        .with_process_time_distr(dist("Triangular", 3.0, 9.0, 5.0)), qk.Mailbox.new()))
+    q1 = m.reg(qk.ComponentModel.Vector3ContainerStock(
+        qk.DiscreteStock.new().with_name("Q1").with_code("Q1").with_max_capacity(3), qk.Mailbox.new()))
+    un_c = qk.ContainerUnloadingProcess.new().with_name("Empty").with_code("UNL").with_max_process_count(2) \
+        .with_process_time_distr(dist("Uniform", 5.0, 12.0))
+    if not lossy_unload:
+        un_c = un_c.with_process_quantity_ratio_distr(dist("Uniform", 0.2, 0.9))
+    unl = m.reg(qk.ComponentModel.Vector3ContainerUnloadProcess(un_c, qk.Mailbox.new()))
+    out = m.reg(qk.ComponentModel.Vector3Stock(
+        qk.VectorStock.new().with_name("Out").with_code("OUT").with_low_capacity(0.0).with_max_capacity(400.0),
+        qk.Mailbox.new()))
+    q2 = m.reg(qk.ComponentModel.Vector3ContainerStock(
+        qk.DiscreteStock.new().with_name("Q2").with_code("Q2").with_max_capacity(2), qk.Mailbox.new()))
+    snk = m.reg(qk.ComponentModel.Vector3ContainerSink(
+        qk.DiscreteSink.new().with_name("Leave").with_code("LV")
+        .with_process_time_distr(dist("Uniform", 6.0, 10.0)), qk.Mailbox.new()))
+    qk.connect_components(src, q0)
+    qk.connect_components(q0, load)
+    qk.connect_components(bulk, load)
+    qk.connect_components(load, q1)
+    qk.connect_components(q1, unl)
+    qk.connect_components(unl, q2)
+    qk.connect_components(unl, out)
+    qk.connect_components(q2, snk)
     _log_all(m)
     return m

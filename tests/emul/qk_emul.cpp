@@ -74,13 +74,19 @@ static int run(qk_batch* b, uint32_t do_init, uint64_t t0, uint64_t t_until, uin
     const bool hbm = (b->cfg.flags & QK_BATCH_STATE_IN_HBM) != 0;
     /* the product picks FT = 0 only for on-chip state; here both state placements run both feature sets so the
      * CPU suite covers the lean kernel on every simple model */
-    const bool ft = b->low.hdr.features != 0;
+    const uint32_t ft = b->low.hdr.features;
+#define QK_EMUL_RUN(L, S)                         \
+  do {                                            \
+    if (ft >= 2) qk_step_kernel<L, S, 2>(P);      \
+    else if (ft == 1) qk_step_kernel<L, S, 1>(P); \
+    else qk_step_kernel<L, S, 0>(P);              \
+  } while (0)
     if (b->log) {
-      if (hbm) { if (ft) qk_step_kernel<true, 0, 1>(P); else qk_step_kernel<true, 0, 0>(P); }
-      else { if (ft) qk_step_kernel<true, -1, 1>(P); else qk_step_kernel<true, -1, 0>(P); }
+      if (hbm) QK_EMUL_RUN(true, 0);
+      else QK_EMUL_RUN(true, -1);
     } else {
-      if (hbm) { if (ft) qk_step_kernel<false, 0, 1>(P); else qk_step_kernel<false, 0, 0>(P); }
-      else { if (ft) qk_step_kernel<false, -1, 1>(P); else qk_step_kernel<false, -1, 0>(P); }
+      if (hbm) QK_EMUL_RUN(false, 0);
+      else QK_EMUL_RUN(false, -1);
     }
   }
   qk_emul_smem = nullptr;
@@ -272,7 +278,8 @@ int qk_batch_read_log(qk_batch* b, uint64_t rep, qk_log_record* buf, uint64_t ca
 }
 
 int qk_batch_read_vector(qk_batch* b, uint64_t rep, uint32_t comp, double* out3) {
-  if (!b || rep >= b->cfg.n_reps || comp >= b->low.hdr.n_comp || b->low.comps[comp].kind < QK_VECTOR_STOCK)
+  if (!b || rep >= b->cfg.n_reps || comp >= b->low.hdr.n_comp || b->low.comps[comp].kind < QK_VECTOR_STOCK ||
+      b->low.comps[comp].kind > QK_VECTOR_SPLITTER)
     return QK_ERR_INVALID_ARG;
   const DevVec& v = b->low.vecs[b->low.comps[comp].vec_idx];
   out3[0] = out3[1] = out3[2] = 0.0;
@@ -291,6 +298,49 @@ int qk_batch_read_stock(qk_batch* b, uint64_t rep, uint32_t comp, uint32_t* item
   if (cap < cnt) return QK_ERR_BUFFER_TOO_SMALL;
   for (uint32_t i = 0; i < cnt; ++i)
     items[i] = b->gc32[(size_t)(c.ocold32 + (head + i) % c.ring_cap) * b->rep_pad + rep];
+  return QK_OK;
+}
+
+int qk_batch_read_containers(qk_batch* b, uint64_t rep, uint32_t comp, uint32_t* handles, uint64_t* resources,
+                             uint64_t cap, uint64_t* n_out) {
+  if (!b || rep >= b->cfg.n_reps || comp >= b->low.hdr.n_comp || !(b->low.comps[comp].flags & DC_CONTAINER))
+    return QK_ERR_INVALID_ARG;
+  const DevComp& c = b->low.comps[comp];
+  auto h32 = [&](uint32_t slot) { return b->g32[(size_t)slot * b->rep_pad + rep]; };
+  auto c32 = [&](uint32_t slot) { return b->gc32[(size_t)slot * b->rep_pad + rep]; };
+  auto c64 = [&](uint32_t slot) { return b->gc64[(size_t)slot * b->rep_pad + rep]; };
+  std::vector<uint32_t> hs, ps;
+  if (c.kind == QK_DISCRETE_STOCK) {
+    const uint32_t hc = h32(c.o32 + S32_HC), head = hc & 0xFFFFu, cnt = hc >> 16;
+    for (uint32_t i = 0; i < cnt; ++i) {
+      const uint32_t pos = (head + i) % c.ring_cap;
+      hs.push_back(c32(c.ocold32 + pos));
+      ps.push_back(c.ocold64 + 3u * pos);
+    }
+  } else if (c.kind == QK_DISCRETE_PARALLEL_PROCESS || c.kind == QK_CONTAINER_LOAD_PROCESS ||
+             c.kind == QK_CONTAINER_UNLOAD_PROCESS) {
+    const uint32_t nprog = h32(c.o32 + PP32_NPROG), cq = h32(c.o32 + PP32_COMPLETE);
+    const uint32_t ring = c.ring_cap, item0 = c.o32 + PP32_BASE_COUNT;
+    for (uint32_t i = 0; i < nprog; ++i) {
+      hs.push_back(h32(item0 + i));
+      ps.push_back(c.ocold64 + 3u * i);
+    }
+    for (uint32_t i = 0; i < (cq >> 16); ++i) {
+      const uint32_t pos = ((cq & 0xFFFFu) + i) % ring;
+      hs.push_back(h32(item0 + ring + pos));
+      ps.push_back(c.ocold64 + 3u * (ring + pos));
+    }
+  } else if (h32(c.o32 + P32_FLAGS) & PF_HAS_ITEM) {
+    hs.push_back(h32(c.o32 + P32_ITEM));
+    ps.push_back(c.ocold64);
+  }
+  if (n_out) *n_out = hs.size();
+  if (!handles || !resources) return QK_OK;
+  if (cap < hs.size()) return QK_ERR_BUFFER_TOO_SMALL;
+  for (size_t i = 0; i < hs.size(); ++i) {
+    handles[i] = hs[i];
+    for (uint32_t k = 0; k < 3; ++k) resources[i * 3 + k] = c64(ps[i] + k);
+  }
   return QK_OK;
 }
 

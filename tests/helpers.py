@@ -11,7 +11,7 @@ from quokkasim_b200 import _capi as capi
 
 from quokkasim_b200.workloads import (Model, assembly_line, car_workshop, discrete_queue, haulage,  # noqa: F401
                                       material_blending, scheduled_event_f64, serial_line, source_sink, vector_flow,
-                                      transport, delay_testing, the_example)
+                                      transport, delay_testing, the_example, container_haulage, container_open)
 
 
 from oracle.lowering import lower_to_oracle  # noqa: F401,E402
@@ -71,7 +71,24 @@ def assert_rep_parity(sim, osim, model, rep_local_idx, check_log=True):
     for ci, cm in enumerate(model.components):
         gs = sim.comp_stats(ci, rep_local_idx, 1)[0]
         os_ = osim.comp_stats(ci)
-        if cm.variant.startswith(("F64", "Vector3")):
+        if cm.variant.startswith("Vector3Container"):
+            # container family: integer statistics as for the discrete components, and every container held (handle
+            # + the bits of what it carries) in order
+            gh, gr = sim.read_containers(ci, rep_local_idx)
+            oh, orr = osim.containers(ci)
+            assert list(gh) == list(oh), "comp %d containers %r vs %r" % (ci, list(gh), list(oh))
+            assert gr.tobytes() == orr.tobytes(), "comp %d container resources\n%r\nvs\n%r" % (ci, gr, orr)
+            if cm.variant.endswith("Stock"):
+                assert int(gs["count"]) == int(os_["n_a"]), "cstock %d n_add" % ci
+                assert int(gs["time_ns"]) == int(os_["t_a_ns"]), "cstock %d area" % ci
+                assert int(gs["aux"]) == int(os_["t_b_ns"]), "cstock %d max occupancy" % ci
+                assert int(gs["level"]) == len(oh)
+                assert list(sim.read_stock(ci, rep_local_idx)) == list(oh)
+            else:
+                assert int(gs["count"]) == int(os_["n_b"]), "cproc %d n_finish %d vs %d" % (ci, gs["count"], os_["n_b"])
+                assert int(gs["time_ns"]) == int(os_["t_a_ns"]), "cproc %d busy %d vs %d" % (ci, gs["time_ns"], os_["t_a_ns"])
+                assert int(gs["aux"]) == int(os_["t_b_ns"]), "cproc %d delay ns" % ci
+        elif cm.variant.startswith(("F64", "Vector3")):
             # continuous components: fp64 values are compared BIT-exactly (same operation order, no FMA); the
             # north_star tolerance would be 1e-9 relative
             assert float(gs["fvalue"]).hex() == float(os_["fvalue"]).hex(), "comp %d fvalue %r vs %r" % (

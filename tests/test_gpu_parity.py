@@ -292,3 +292,60 @@ def test_reference_vector_examples_transport_delay_testing_rocks(gpu_lib):
     _check(gpu_lib, H.delay_testing(), 32, t_until=40 * S, sample=[0], log_capacity=1024)
     m = H.the_example()
     _check(gpu_lib, m, 64, t_until=m.t0 + 700 * S, t0=m.t0, sample=[0, 31, 63], log_capacity=8192)
+
+
+# ------------------------------------------------------------------------------------- container family (row f3)
+def test_container_haulage_cycle(gpu_lib):
+    """payload-true truck cycle: ContainerLoadingProcess / Vector3ContainerParallelProcess / ContainerUnloadingProcess /
+    Vector3ContainerProcess over a fleet of initial Vector3Containers; bit-exact records, container payloads, stocks"""
+    _check(gpu_lib, H.container_haulage(), 256, n_events=6000, sample=[0, 1, 131, 255], log_capacity=65536)
+    _check(gpu_lib, H.container_haulage(n_trucks=7, loaders=3), 64, n_events=4000, tape_len=4000, sample=[0, 63],
+           log_capacity=65536)
+    _check(gpu_lib, H.container_haulage(random=False, breakdowns=False), 32, n_events=1500, sample=[0, 31],
+           log_capacity=32768)
+
+
+def test_container_open_line(gpu_lib):
+    """Vector3ContainerSource (factory quantity distribution) -> Load -> Unload -> Sink, incl. the lost-resource quirk"""
+    _check(gpu_lib, H.container_open(), 128, n_events=5000, sample=[0, 64, 127], log_capacity=65536)
+    _check(gpu_lib, H.container_open(lossy_unload=False), 128, n_events=5000, sample=[0, 127], log_capacity=65536)
+
+
+def test_container_state_in_shared_memory_and_in_hbm(gpu_lib):
+    """both state placements of the feature-set-2 kernel give the same trajectories"""
+    m = H.container_haulage()
+    a = m.sim(gpu_lib, 96, base_seed=9, log_capacity=32768, flags=1)  # QK_BATCH_STATE_IN_HBM
+    b = H.container_haulage().sim(gpu_lib, 96, base_seed=9, log_capacity=32768, flags=2)  # QK_BATCH_STATE_ON_CHIP
+    assert a.info()["state_in_hbm"] == 1 and b.info()["state_in_hbm"] == 0
+    a.step_events(3000)
+    b.step_events(3000)
+    for r in (0, 50, 95):
+        assert a.read_log(r)[0].tobytes() == b.read_log(r)[0].tobytes()
+    for ci in range(len(m.components)):
+        assert a.comp_stats(ci).tobytes() == b.comp_stats(ci).tobytes()
+    a.close()
+    b.close()
+
+
+def test_container_mass_balance_at_scale(gpu_lib):
+    """65,536 replications of the truck cycle: ore + dumped + carried by the fleet stays constant (1e-9 relative)"""
+    m = H.container_haulage()
+    n = 65536
+    sim = m.sim(gpu_lib, n, base_seed=77)
+    sim.step_events(3000)
+    st, _, ev = sim.status()
+    assert not st.any() and (ev == 3000).all()
+    from quokkasim_b200 import _capi as capi
+
+    for r in (0, 1, 4097, n - 1):
+        t = sum(sum(sim.read_vector(c.component._id, r)) for c in m.mass["vector_stocks"])
+        fleet = 0
+        for c in m.mass["container_holders"]:
+            h, res = sim.read_containers(c.component._id, r)
+            fleet += len(h)
+            for row in res:
+                if int(row[0]) != capi.CONTAINER_NONE_BITS:
+                    t += float(row.view(np.float64).sum())
+        assert fleet == 4
+        assert abs(t - (100000.0 + 1.75 * 2)) <= 1e-9 * t, t
+    sim.close()

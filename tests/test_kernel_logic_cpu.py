@@ -234,3 +234,151 @@ def test_reference_vector_examples_transport_delay_testing_rocks(emul_lib):
     _check(emul_lib, H.delay_testing(), 1, t_until=40 * S, log_capacity=1024)
     m = H.the_example()
     _check(emul_lib, m, 3, t_until=m.t0 + 700 * S, t0=m.t0, log_capacity=8192)
+
+
+# ------------------------------------------------------------------------------------- container family (row f3)
+def test_container_haulage_cycle(emul_lib):
+    """closed truck cycle: ContainerLoadingProcess / ParallelProcess / ContainerUnloadingProcess / Process on a fleet
+    of initial Vector3Containers, breakdowns on the loader, environment stop/resume"""
+    _check(emul_lib, H.container_haulage(), 3, n_events=3000, log_capacity=65536)
+    _check(emul_lib, H.container_haulage(n_trucks=7, loaders=3), 2, n_events=3000, tape_len=3000, log_capacity=65536)
+    _check(emul_lib, H.container_haulage(random=False, breakdowns=False), 1, n_events=1500, log_capacity=32768)
+
+
+def test_container_open_line(emul_lib, emul_eager_lib):
+    """Vector3ContainerSource with a factory quantity distribution -> Load -> Unload -> Sink; the default unload ratio
+    Constant(1.) reproduces the reference's lost-resource quirk (vector_container.rs:582-586)"""
+    _check(emul_lib, H.container_open(), 3, n_events=3000, log_capacity=65536)
+    _check(emul_lib, H.container_open(lossy_unload=False), 2, n_events=3000, log_capacity=65536)
+    _check(emul_eager_lib, H.container_open(lossy_unload=False), 2, n_events=2000, tape_len=2500, log_capacity=65536)
+    _check(emul_lib, H.container_open(), 2, n_events=2000, log_capacity=65536, flags=1)
+
+
+def test_container_mass_balance_and_lossy_quirk(emul_lib):
+    """with an unload ratio below 1 nothing is lost: ore + dumped + carried by the fleet is constant"""
+    import numpy as np
+
+    def total(sim, m, r):
+        t = sum(sum(sim.read_vector(c.component._id, r)) for c in m.mass["vector_stocks"])
+        for c in m.mass["container_holders"]:
+            _, res = sim.read_containers(c.component._id, r)
+            for row in res:
+                if int(row[0]) != capi.CONTAINER_NONE_BITS:
+                    t += float(row.view(np.float64).sum())
+        return t
+
+    m = H.container_haulage()
+    sim = m.sim(emul_lib, 2, base_seed=3)
+    t0 = [total(sim, m, r) for r in range(2)]
+    sim.step_events(4000)
+    for r in range(2):
+        assert abs(total(sim, m, r) - t0[r]) <= 1e-9 * t0[r]
+    dumped = m.by_name["Dumped"].component._id
+    assert sum(sim.read_vector(dumped, 0)) > 100.0
+    # default ratio Constant(1.): the resource stock receives zeros, the load vanishes
+    m2 = H.container_haulage(unload_ratio=None)
+    sim2 = m2.sim(emul_lib, 1, base_seed=3)
+    sim2.step_events(4000)
+    assert sum(sim2.read_vector(m2.by_name["Dumped"].component._id, 0)) == 0.0
+    assert total(sim2, m2, 0) < t0[0] - 100.0
+
+
+def test_container_connection_rules():
+    """connect_components / connect_logger arms of the container family (core.rs:923-995, 1149-1172, 1330-1334)"""
+    import pytest as _pt
+    import quokkasim_b200 as qk
+
+    cs = qk.ComponentModel.Vector3ContainerStock(qk.DiscreteStock.new(), qk.Mailbox.new())
+    ss = qk.ComponentModel.StringStock(qk.DiscreteStock.new(), qk.Mailbox.new())
+    vs = qk.ComponentModel.Vector3Stock(qk.VectorStock.new(), qk.Mailbox.new())
+    fs = qk.ComponentModel.F64Stock(qk.VectorStock.new(), qk.Mailbox.new())
+    ld = qk.ComponentModel.Vector3ContainerLoadProcess(qk.ContainerLoadingProcess.new(), qk.Mailbox.new())
+    un = qk.ComponentModel.Vector3ContainerUnloadProcess(qk.ContainerUnloadingProcess.new(), qk.Mailbox.new())
+    pp = qk.ComponentModel.Vector3ContainerParallelProcess(qk.DiscreteParallelProcess.new(), qk.Mailbox.new())
+    sp = qk.ComponentModel.StringProcess(qk.DiscreteProcess.new(), qk.Mailbox.new())
+    src = qk.ComponentModel.Vector3ContainerSource(qk.DiscreteSource.new(), qk.Mailbox.new())
+    env = qk.ComponentModel.BasicEnvironment(qk.BasicEnvironment.new(), qk.Mailbox.new())
+    assert isinstance(src.component.item_factory, qk.Vector3ContainerFactory)
+    for a, b in ((cs, ld), (vs, ld), (ld, cs), (cs, un), (un, cs), (un, vs), (cs, pp), (pp, cs), (src, cs), (env, ld),
+                 (env, un), (env, src)):
+        qk.connect_components(a, b)
+    for a, b in ((ss, ld), (cs, sp), (fs, ld), (un, fs), (ld, vs), (vs, un), (env, pp), (src, ss)):
+        with _pt.raises(qk.ComponentConnectionError, match="No component connection defined"):
+            qk.connect_components(a, b)
+    cpl = qk.ComponentLogger.Vector3ContainerProcessLogger(qk.ContainerProcessLogger.new("L"))
+    qk.connect_logger(cpl, ld)
+    qk.connect_logger(cpl, pp)
+    with _pt.raises(qk.ComponentConnectionError):
+        qk.connect_logger(cpl, src)  # no Source / Sink arm in the reference
+    assert ld.component.element_code == "CLP" and un.component.element_code == ""
+
+
+def _mini_container_model(kind):
+    import quokkasim_b200 as qk
+    from quokkasim_b200.workloads import Model, _log_all
+
+    m = Model()
+    C = qk.Distribution.Constant
+
+    def cstock(name, maxc, n_init=0, low=0):
+        items = [qk.Vector3Container("%s_%d" % (name, i), qk.Vector3([1.0 + i, 2.0, 0.5]) if i % 2 else None, 10.0 + i)
+                 for i in range(n_init)]
+        return m.reg(qk.ComponentModel.Vector3ContainerStock(
+            qk.DiscreteStock.new().with_name(name).with_code(name).with_low_capacity(low).with_max_capacity(maxc)
+            .with_initial_resource(qk.ItemDeque(items)), qk.Mailbox.new()))
+
+    def vstock(name, init, maxc=1000.0):
+        return m.reg(qk.ComponentModel.Vector3Stock(
+            qk.VectorStock.new().with_name(name).with_code(name).with_max_capacity(maxc)
+            .with_initial_resource(qk.Vector3(init)), qk.Mailbox.new()))
+
+    def load(name, n, t):
+        return m.reg(qk.ComponentModel.Vector3ContainerLoadProcess(
+            qk.ContainerLoadingProcess.new().with_name(name).with_max_process_count(n).with_process_time_distr(C(t)),
+            qk.Mailbox.new()))
+
+    def unload(name, n, t, ratio=0.5):
+        return m.reg(qk.ComponentModel.Vector3ContainerUnloadProcess(
+            qk.ContainerUnloadingProcess.new().with_name(name).with_code(name).with_max_process_count(n)
+            .with_process_time_distr(C(t)).with_process_quantity_ratio_distr(C(ratio)), qk.Mailbox.new()))
+
+    if kind == "upstream_full":  # 3 of max 3 -> Full -> "Upstream is full" (the Empty|Normal test, vector_container.rs:352)
+        a, b, l = cstock("A", 3, 3), vstock("B", [5.0, 5.0, 5.0]), load("L", 2, 4.0)
+        qk.connect_components(a, l)
+        qk.connect_components(b, l)
+    elif kind == "no_resource_stock":  # withdraw_us_resource...unwrap() on nothing -> fault
+        a, l, q = cstock("A", 5, 2), load("L", 2, 4.0), cstock("Q", 5)
+        qk.connect_components(a, l)
+        qk.connect_components(l, q)
+    elif kind == "downstream_full":  # drain loop loses containers when the downstream stock is Full
+        a, b, l, q = cstock("A", 6, 4), vstock("B", [50.0, 5.0, 5.0]), load("L", 3, 5.0), cstock("Q", 1)
+        snk = m.reg(qk.ComponentModel.Vector3ContainerSink(
+            qk.DiscreteSink.new().with_name("S").with_process_time_distr(C(100.0)), qk.Mailbox.new()))
+        for x, y in ((a, l), (b, l), (l, q), (q, snk)):
+            qk.connect_components(x, y)
+    elif kind == "lonely":
+        load("L", 1, 1.0)
+        unload("U", 1, 1.0)
+        m.reg(qk.ComponentModel.Vector3ContainerParallelProcess(qk.DiscreteParallelProcess.new().with_name("P"),
+                                                                qk.Mailbox.new()))
+        m.reg(qk.ComponentModel.Vector3ContainerProcess(qk.DiscreteProcess.new().with_name("X"), qk.Mailbox.new()))
+    elif kind == "unload_half_connected":  # "Downstream is not connected" / "Downstream resource stock is full"
+        a, u1, q = cstock("A", 8, 3, low=0), unload("U1", 2, 3.0), cstock("Q", 8)
+        qk.connect_components(a, u1)
+        qk.connect_components(u1, q)  # no resource stock: (_, _) arm
+        a2, u2, v = cstock("A2", 8, 3), unload("U2", 2, 3.0), vstock("V", [1.0, 1.0, 1.0], maxc=3.0)
+        qk.connect_components(a2, u2)
+        qk.connect_components(u2, v)  # no container stock; V is Full (3 of 3): (_, Some(Full)) arm
+    m.log_unloggable = True
+    _log_all(m)
+    return m
+
+
+@pytest.mark.parametrize("kind", ["upstream_full", "no_resource_stock", "downstream_full", "lonely",
+                                  "unload_half_connected"])
+def test_container_edge_arms(emul_lib, kind):
+    """the match arms the two example models do not reach (vector_container.rs:294-301, 358, 372-379, 600-611, 683-686)"""
+    m = _mini_container_model(kind)
+    s = _check(emul_lib, m, 1, t_until=400 * 10**9, log_capacity=4096)
+    if kind == "no_resource_stock":
+        assert s["n_faulted"] == 1
