@@ -40,6 +40,7 @@ WORKLOADS = {
     "serial_line": ("serial_line", {"n_proc": 32}, 100000, 100000),
     "haulage": ("haulage", {"n_src": 8, "per_queue": 8}, 262144, 10000),
     "vector_flow": ("vector_flow", {"dim": 3}, 262144, 10000),
+    "container_haulage": ("container_haulage", {"n_trucks": 8, "loaders": 2}, 262144, 10000),
 }
 
 

@@ -51,7 +51,7 @@ enum { L32_SEQ = 0 };
 
 /* ---- discrete stock slots ------------------------------------------------------------------------ */
 enum { S64_COUNT = 0 }; /* the fire slot holds emit_t0; nothing else is 64-bit */
-enum { S32_HC = 0, S32_EMIT = 1, S32_COUNT = 2 };
+enum { S32_HC = 0, S32_EMIT = 1, S32_COUNT = 2, S32_EMITSRC = 2 }; /* S32_EMITSRC: discrete stocks, LOG only */
 /* S32_EMIT = n | split << 8 | head << 16.
  * COLD state (global memory only, never staged in shared memory -- see "cold planes" below): the item ring
  * [ring_cap] at cold32 slot `ocold32`, followed (LOG) by the emit source-seq ring [emit_depth] */

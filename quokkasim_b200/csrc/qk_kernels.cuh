@@ -274,8 +274,11 @@ __device__ __forceinline__ uint32_t qk_stock_cat(uint32_t cnt, uint32_t low, uin
   return cnt <= low ? 0u : (cnt >= max ? 2u : 1u);
 }
 
-/* cx.schedule_event(now + 1ns, Self::emit_change, ..) discrete.rs:193-194, 218-219 */
-template <bool LOG, int SM>
+/* cx.schedule_event(now + 1ns, Self::emit_change, ..) discrete.rs:193-194, 218-219.
+ * HOT (discrete stocks): the source id of the OLDEST pending emit lives in the hot slot S32_EMITSRC, the cold ring only
+ * holds the ones queued behind it -- almost every emit_change is alone in its queue, so the pop (whose id goes
+ * straight into a log record) no longer waits for a global-memory load */
+template <bool LOG, int SM, bool HOT = false>
 __device__ __forceinline__ void qk_emit_push(Ctx& cx, const DevHotA& c, uint32_t emit_depth, uint32_t oemit,
                                              uint32_t src_seq) {
   const uint32_t fire = G64_FIRE0 + c.fire_idx;
@@ -295,24 +298,29 @@ __device__ __forceinline__ void qk_emit_push(Ctx& cx, const DevHotA& c, uint32_t
     return;
   }
   if (LOG) {
-    uint32_t pos = head + n - 1;
-    if (pos >= emit_depth) pos -= emit_depth;
-    C32(oemit + pos) = src_seq;
+    if (HOT && n == 1) {
+      S32(c.o32 + S32_EMITSRC) = src_seq;
+    } else {
+      uint32_t pos = head + n - 1;
+      if (pos >= emit_depth) pos -= emit_depth;
+      C32(oemit + pos) = src_seq;
+    }
   }
   S32(c.o32 + S32_EMIT) = n | (split << 8) | (head << 16);
 }
 
-template <bool LOG, int SM>
+template <bool LOG, int SM, bool HOT = false>
 __device__ __forceinline__ uint32_t qk_emit_pop(Ctx& cx, const DevHotA& c, uint32_t emit_depth, uint32_t oemit) {
   const uint32_t fire = G64_FIRE0 + c.fire_idx;
   uint32_t e = S32(c.o32 + S32_EMIT);
   uint32_t n = e & 0xFFu, split = (e >> 8) & 0xFFu, head = (e >> 16) & 0xFFu;
   uint32_t src_seq = 0;
-  if (LOG) src_seq = C32(oemit + head);
+  if (LOG) src_seq = HOT ? S32(c.o32 + S32_EMITSRC) : C32(oemit + head);
   head += 1;
   if (head >= emit_depth) head = 0;
   n -= 1;
   split -= 1;
+  if (LOG && HOT && n != 0) S32(c.o32 + S32_EMITSRC) = C32(oemit + head); /* the next one moves up (rare) */
   if (n == 0) {
     S64(fire) = QK_TIME_NONE;
   } else if (split == 0) {
@@ -353,13 +361,15 @@ __device__ __forceinline__ void qk_stock_add(Ctx& cx, uint32_t sidx, uint32_t it
   QK_ST32_MAX(sidx, ST32_MAXOCC, cnt);
   const uint64_t id = qk_log<LOG, SM>(cx, c, sidx, src, QK_LOG_STOCK_ADD, 0, item);
   if (pay) qk_log_pay<LOG, SM>(cx, c.flags, sidx, id, pay);
-  if (prev != qk_stock_cat(cnt, sb.low, sb.max)) qk_emit_push<LOG, SM>(cx, c, sb.emit_depth, c.olog64 + sb.ring_cap, (uint32_t)id);
+  if (prev != qk_stock_cat(cnt, sb.low, sb.max)) qk_emit_push<LOG, SM, true>(cx, c, sb.emit_depth, c.olog64 + sb.ring_cap, (uint32_t)id);
 }
 
 /* Stock::remove (core.rs:197-204; discrete.rs:200-225); returns false for Remove(None) */
+/* item_pre: the head item, already loaded by the caller (qk_update_single issues that global-memory load before it
+ * writes its WithdrawRequest record, so the latency is not on the path to the Remove record) */
 template <bool LOG, int SM>
 __device__ __forceinline__ bool qk_stock_remove(Ctx& cx, uint32_t sidx, uint64_t src, uint32_t* item_out,
-                                                uint64_t* pay_out = nullptr) {
+                                                uint64_t* pay_out = nullptr, const uint32_t* item_pre = nullptr) {
   const DevHotA c = QK_HOT_A(sidx);
   const DevHotSB sb = QK_HOT_SB(sidx);
   const uint32_t hc = S32(c.o32 + S32_HC);
@@ -368,7 +378,7 @@ __device__ __forceinline__ bool qk_stock_remove(Ctx& cx, uint32_t sidx, uint64_t
   const bool some = cnt != 0;
   uint32_t item = 0;
   if (some) {
-    item = C32(c.olog64 + head);
+    item = item_pre ? *item_pre : C32(c.olog64 + head);
     if (pay_out) {
       const uint32_t op = cx.comps[sidx].ocold64 + 3u * head;
       pay_out[0] = C64(op);
@@ -383,7 +393,7 @@ __device__ __forceinline__ bool qk_stock_remove(Ctx& cx, uint32_t sidx, uint64_t
   }
   const uint64_t id = qk_log<LOG, SM>(cx, c, sidx, src, QK_LOG_STOCK_REMOVE, 0, some ? (uint64_t)item : QK_ITEM_NONE);
   if (pay_out && some) qk_log_pay<LOG, SM>(cx, c.flags, sidx, id, pay_out);
-  if (prev != qk_stock_cat(cnt, sb.low, sb.max)) qk_emit_push<LOG, SM>(cx, c, sb.emit_depth, c.olog64 + sb.ring_cap, (uint32_t)id);
+  if (prev != qk_stock_cat(cnt, sb.low, sb.max)) qk_emit_push<LOG, SM, true>(cx, c, sb.emit_depth, c.olog64 + sb.ring_cap, (uint32_t)id);
   *item_out = item;
   return some;
 }
@@ -461,7 +471,10 @@ __device__ __forceinline__ void qk_refresh_env(Ctx& cx, const DevHotA& c, int en
 
 /* post_update_state (discrete.rs:535-564): keep the earlier of the pending keyed event and now+ttnpe.
  * Cancelling == overwriting the single fire slot. */
-template <bool LOG, int SM>
+/* LEAN (feature set 0, SIMPLE components only): a keyed event is only ever scheduled right after the component logged
+ * its ProcessStart, and a busy SIMPLE component logs nothing until that event fires (qk_try_quick), so the event's
+ * source id is always (component, seq counter - 1) and need not be stored */
+template <bool LOG, int SM, bool LEAN = false>
 __device__ __forceinline__ void qk_post(Ctx& cx, const DevHotA& c, uint64_t ttnpe, uint64_t src) {
   if (ttnpe != QK_TIME_NONE) {
     if (ttnpe == 0) {
@@ -472,20 +485,22 @@ __device__ __forceinline__ void qk_post(Ctx& cx, const DevHotA& c, uint64_t ttnp
     const uint32_t fire = G64_FIRE0 + c.fire_idx;
     if (next < S64(fire)) { /* NONE is the largest u64 */
       S64(fire) = next;
-      if (LOG) C64(c.olog64 + PL64_SCHED_SRC) = src;
+      if (LOG && !LEAN) C64(c.olog64 + PL64_SCHED_SRC) = src;
     }
   }
 }
 
 /* pre_update_state (discrete.rs:404-412): a handle whose time has come is forgotten, NOT cancelled; if its
  * event has not fired yet it stays queued (Q3) -> move it to the stale mask (it fires at `now`, in rank order) */
-template <bool LOG, int SM>
-__device__ __forceinline__ void qk_pre(Ctx& cx, const DevHotA& c) {
+template <bool LOG, int SM, bool LEAN = false>
+__device__ __forceinline__ void qk_pre(Ctx& cx, const DevHotA& c, uint32_t comp) {
   const uint32_t fire = G64_FIRE0 + c.fire_idx;
   if (S64(fire) <= cx.now) {
     S64(fire) = QK_TIME_NONE;
     S32(G32_STALE0 + (c.fire_idx >> 5)) |= 1u << (c.fire_idx & 31);
-    if (LOG) C64(c.olog64 + PL64_STALE_SRC) = C64(c.olog64 + PL64_SCHED_SRC);
+    if (LOG)
+      C64(c.olog64 + PL64_STALE_SRC) =
+          LEAN ? (((uint64_t)comp << 32) | (uint32_t)(S32(c.olog32 + L32_SEQ) - 1u)) : C64(c.olog64 + PL64_SCHED_SRC);
   }
 }
 
@@ -597,8 +612,13 @@ __device__ __forceinline__ void qk_update_single(Ctx& cx, const DevHotA& c, uint
       bool got = true;
       uint32_t item;
       if (need_us) {
+        uint32_t head_item = 0;
+        if (LOG) { /* us is Normal|Full, so the ring is not empty */
+          const DevHotA ua = QK_HOT_A(cb.up);
+          head_item = C32(ua.olog64 + (S32(ua.o32 + S32_HC) & 0xFFFFu));
+        }
         src = qk_log<LOG, SM>(cx, c, comp, src, QK_LOG_WITHDRAW_REQUEST, 0, 0);
-        got = qk_stock_remove<LOG, SM>(cx, (uint32_t)cb.up, src, &item, ctr ? pay : nullptr);
+        got = qk_stock_remove<LOG, SM>(cx, (uint32_t)cb.up, src, &item, ctr ? pay : nullptr, LOG ? &head_item : nullptr);
         if (cx.status) return;
       }
       if (got) {
@@ -675,7 +695,7 @@ __device__ __forceinline__ void qk_update_single(Ctx& cx, const DevHotA& c, uint
   if (kind == QK_DISCRETE_SINK) S64(QK_HOT_C(comp).o64_ttnpe) = ttnpe;
   S32(c.o32 + P32_FLAGS) = flags;
   S64(c.o64 + P64_LEFT) = left;
-  qk_post<LOG, SM>(cx, c, ttnpe, src);
+  qk_post<LOG, SM, FT == 0>(cx, c, ttnpe, src);
   S64(c.o64 + P64_PREV) = cx.now;
 }
 
@@ -872,7 +892,7 @@ template <bool LOG, int SM, int FT>
 __device__ __forceinline__ void qk_update_state(Ctx& cx, uint32_t comp, uint64_t src) {
   const DevHotA a = QK_HOT_A(comp);
   if (FT == 0 || (a.kind >= QK_DISCRETE_PROCESS && a.kind <= QK_DISCRETE_SINK)) {
-    qk_pre<LOG, SM>(cx, a);
+    qk_pre<LOG, SM, FT == 0>(cx, a, comp);
     qk_update_single<LOG, SM, FT>(cx, a, comp, src);
     return;
   }
@@ -887,11 +907,11 @@ __device__ __forceinline__ void qk_update_state(Ctx& cx, uint32_t comp, uint64_t
        * (vector.rs:774,1111,1393,1619); SRC_INIT only ever arrives from the init list */
       if (LOG && src == SRC_INIT && a.kind != QK_VECTOR_PROCESS)
         src = ((uint64_t)comp << 32) | S32(a.olog32 + L32_SEQ);
-      qk_pre<LOG, SM>(cx, a);
+      qk_pre<LOG, SM>(cx, a, comp);
       qk_update_vector<LOG, SM>(cx, c, comp, src);
       return;
     }
-    qk_pre<LOG, SM>(cx, a);
+    qk_pre<LOG, SM>(cx, a, comp);
     qk_update_multi<LOG, SM, FT>(cx, c, comp, src);
   }
 }
@@ -1139,7 +1159,7 @@ __global__ void __launch_bounds__(qk_lb_threads(SM), qk_lb_blocks(SM, FT)) qk_st
               /* emit_change (discrete.rs:227-233): log the state AT EMISSION TIME, then update_state on every
                * subscriber in connection order */
               const DevHotSB sb = QK_HOT_SB(comp);
-              const uint32_t src_seq = qk_emit_pop<LOG, SM>(cx, a, sb.emit_depth, a.olog64 + sb.ring_cap);
+              const uint32_t src_seq = qk_emit_pop<LOG, SM, true>(cx, a, sb.emit_depth, a.olog64 + sb.ring_cap);
               if (LOG) {
                 const uint32_t cnt = S32(a.o32 + S32_HC) >> 16;
                 const uint32_t empty = sb.max > cnt ? sb.max - cnt : 0;
@@ -1169,7 +1189,9 @@ __global__ void __launch_bounds__(qk_lb_threads(SM), qk_lb_blocks(SM, FT)) qk_st
               if (stale) {
                 if (LOG) src = C64(a.olog64 + PL64_STALE_SRC);
               } else {
-                if (LOG) src = C64(a.olog64 + PL64_SCHED_SRC);
+                if (LOG)
+                  src = FT == 0 ? (((uint64_t)comp << 32) | (uint32_t)(S32(a.olog32 + L32_SEQ) - 1u))
+                                : C64(a.olog64 + PL64_SCHED_SRC);
                 S64(G64_FIRE0 + bi) = QK_TIME_NONE;
                 keyed = true;
               }
