@@ -17,6 +17,16 @@ pub const QK_VECTOR_SOURCE: u32 = 18;
 pub const QK_VECTOR_SINK: u32 = 19;
 pub const QK_VECTOR_COMBINER: u32 = 20;
 pub const QK_VECTOR_SPLITTER: u32 = 21;
+// container family (components/vector_container.rs; ComponentModel::Vector3Container*, core.rs:549-555)
+pub const QK_CONTAINER_STOCK: u32 = 32;
+pub const QK_CONTAINER_PROCESS: u32 = 33;
+pub const QK_CONTAINER_SOURCE: u32 = 34;
+pub const QK_CONTAINER_SINK: u32 = 35;
+pub const QK_CONTAINER_PARALLEL_PROCESS: u32 = 36;
+pub const QK_CONTAINER_LOAD_PROCESS: u32 = 37; // max_capacity of the descriptor = max_process_count
+pub const QK_CONTAINER_UNLOAD_PROCESS: u32 = 38;
+/// first fp64 word of a container's resource when it is `None`
+pub const QK_CONTAINER_NONE_BITS: u64 = 0x7FF4_0000_0000_00C0;
 
 // qk_dist_kind
 pub const QK_DIST_CONSTANT: u32 = 0;
@@ -108,6 +118,24 @@ extern "C" {
     pub fn qk_model_set_logged(m: *mut qk_model, comp: u32, enabled: i32) -> i32;
     pub fn qk_model_schedule_env_state(m: *mut qk_model, t_ns: u64, env: u32, state: u32) -> i32;
     pub fn qk_model_schedule_low_capacity(m: *mut qk_model, t_ns: u64, stock: u32, value: f64) -> i32;
+    /// Vector3ContainerFactory (vector_container.rs:126-156); `create_quantity` null = None
+    pub fn qk_model_set_container_factory(
+        m: *mut qk_model,
+        source: u32,
+        create_quantity: *const qk_dist_desc,
+        split3: *const f64,
+        capacity: f64,
+        out_dist_id: *mut u32,
+    ) -> i32;
+    /// with_initial_resource(ItemDeque<Vector3Container>) of a container stock
+    pub fn qk_model_set_initial_containers(
+        m: *mut qk_model,
+        stock: u32,
+        n: u32,
+        resources: *const f64,
+        has_resource: *const u8,
+        capacities: *const f64,
+    ) -> i32;
 
     pub fn qk_batch_create(m: *const qk_model, cfg: *const qk_batch_config, out: *mut *mut qk_batch) -> i32;
     pub fn qk_batch_destroy(b: *mut qk_batch);
@@ -121,6 +149,15 @@ extern "C" {
     pub fn qk_batch_read_log(b: *mut qk_batch, rep: u64, buf: *mut qk_log_record, cap: u64, n_out: *mut u64, n_total: *mut u64) -> i32;
     pub fn qk_batch_read_stock(b: *mut qk_batch, rep: u64, comp: u32, items: *mut u32, cap: u64, n_out: *mut u64) -> i32;
     pub fn qk_batch_read_vector(b: *mut qk_batch, rep: u64, comp: u32, out3: *mut f64) -> i32;
+    pub fn qk_batch_read_containers(
+        b: *mut qk_batch,
+        rep: u64,
+        comp: u32,
+        handles: *mut u32,
+        resources: *mut u64,
+        cap: u64,
+        n_out: *mut u64,
+    ) -> i32;
 }
 
 /// `Err(String)` carrying the library's thread-local message, like the reference's `Box<dyn Error>` strings.
