@@ -382,3 +382,25 @@ def test_container_edge_arms(emul_lib, kind):
     s = _check(emul_lib, m, 1, t_until=400 * 10**9, log_capacity=4096)
     if kind == "no_resource_stock":
         assert s["n_faulted"] == 1
+
+
+def test_large_models_on_hbm_planes_with_ties(emul_lib):
+    """> 16 schedulable components on the HBM planes (the placement the product picks for them), including exact
+    same-timestamp ties between many components (constant tapes): the scheduler scan must keep registration order."""
+    import numpy as np
+
+    _check(emul_lib, H.haulage(n_src=3, per_queue=4), 2, n_events=6000, log_capacity=65536, flags=1)
+    _check(emul_lib, H.serial_line(n_proc=8), 2, n_events=8000, log_capacity=65536, flags=1)
+    _check(emul_lib, H.container_haulage(n_trucks=6), 2, n_events=3000, log_capacity=65536, flags=1)
+    # every process time identical -> many components fire at the same instant, in different groups
+    m = H.haulage(n_src=4, per_queue=5)
+    om, dist_ids = H.lower_to_oracle(m)
+    tapes = {id(d): (d, np.full((2, 3000), 2.0 if i % 2 else 4.0)) for i, d in enumerate(m.random_dists)}
+    sim = m.sim(emul_lib, 2, log_capacity=65536, flags=1)
+    for d, v in tapes.values():
+        sim.set_tape(d, v)
+    sim.step_events(5000)
+    assert sim.info()["state_in_hbm"] == 1
+    for r in range(2):
+        H.assert_rep_parity(sim, H.run_oracle(m, om, dist_ids, r, tapes=tapes, n_events=5000), m, r)
+    sim.close()
