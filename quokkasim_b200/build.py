@@ -37,7 +37,9 @@ def _stale():
 def build(force=False, verbose=False):
     if not force and not _stale():
         return LIB
-    cmd = [NVCC] + FLAGS + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    extra = os.environ.get("QK_EXTRA_NVCC_FLAGS", "").split()  # experiments: -DQK_..., with QK_LIB_OUT for the output
+    out = os.environ.get("QK_LIB_OUT", LIB)
+    cmd = [NVCC] + FLAGS + extra + ["-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     log = os.path.join(_HERE, "build.log")
     with open(log, "w") as f:

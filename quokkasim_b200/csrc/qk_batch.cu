@@ -381,7 +381,7 @@ int qk_batch_create(const qk_model* m, const qk_batch_config* cfg, qk_batch** ou
   b->table_bytes_padded = (h.total_bytes + 15u) & ~15u;
   const uint32_t per_rep = h.n64 * 8 + h.n32 * 4;
   uint32_t nt = cfg->threads_per_block;
-  const uint32_t max_thr = h.features ? 512u : (uint32_t)QK_LEAN_THREADS; /* qk_lb_blocks: 128- / 80-register kernel variants */
+  const uint32_t max_thr = (uint32_t)qk_lb_resident((int)h.features, b->log); /* the kernel variant's launch bounds */
   b->hbm = (cfg->flags & QK_BATCH_STATE_IN_HBM) != 0;
   if (!b->hbm && nt == 0 && !(cfg->flags & QK_BATCH_STATE_ON_CHIP)) {
     /* placement heuristic (measured, profiles/README.md): staging the state in shared memory wins while at least
@@ -558,7 +558,17 @@ int qk_batch_step_events(qk_batch* b, uint64_t n_events) {
     return QK_ERR_STATE;
   }
   CUDA_TRY(cudaSetDevice(b->cfg.device));
-  return launch_step(b, 0, 0, QK_TIME_NONE, n_events);
+  /* the kernel counts events in 32 bits: finite budgets go in launches of at most 2^32 - 2 events */
+  const uint64_t cap = 0xFFFFFFFEull;
+  bool first = true;
+  do {
+    const uint64_t k = n_events < cap ? n_events : cap;
+    n_events -= k;
+    const int rc = launch_step(b, 0, 0, QK_TIME_NONE, k, first, n_events == 0);
+    if (rc) return rc;
+    first = false;
+  } while (n_events);
+  return QK_OK;
 }
 
 /* The same step cut into launches of `chunk` events each: every launch loads the hot state planes from HBM, advances
@@ -566,7 +576,7 @@ int qk_batch_step_events(qk_batch* b, uint64_t n_events) {
  * residency K = chunk; K = 1 is pure lockstep).  Results are identical to one launch (tests); this entry point exists
  * to MEASURE the kernel where it is HBM-bound (bench.py --events-per-launch). */
 int qk_batch_step_events_chunked(qk_batch* b, uint64_t n_events, uint64_t chunk) {
-  if (!b || chunk == 0) return QK_ERR_INVALID_ARG;
+  if (!b || chunk == 0 || chunk > 0xFFFFFFFEull) return QK_ERR_INVALID_ARG;
   if (!b->initialised) {
     qk_set_error("qk_batch_step_events_chunked: call qk_batch_init first");
     return QK_ERR_STATE;

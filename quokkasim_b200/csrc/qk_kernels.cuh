@@ -278,8 +278,10 @@ __device__ __forceinline__ uint32_t qk_stock_cat(uint32_t cnt, uint32_t low, uin
  * HOT (discrete stocks): the source id of the OLDEST pending emit lives in the hot slot S32_EMITSRC, the cold ring only
  * holds the ones queued behind it -- almost every emit_change is alone in its queue, so the pop (whose id goes
  * straight into a log record) no longer waits for a global-memory load */
+/* Faults travel UP as return values (true = this replication has faulted, cx.status says why): the lean kernel keeps
+ * cx.status in local memory, and re-reading it after every call cost a local-memory round trip each time. */
 template <bool LOG, int SM, bool HOT = false>
-__device__ __forceinline__ void qk_emit_push(Ctx& cx, const DevHotA& c, uint32_t emit_depth, uint32_t oemit,
+__device__ __forceinline__ bool qk_emit_push(Ctx& cx, const DevHotA& c, uint32_t emit_depth, uint32_t oemit,
                                              uint32_t src_seq) {
   const uint32_t fire = G64_FIRE0 + c.fire_idx;
   uint32_t e = S32(c.o32 + S32_EMIT);
@@ -295,7 +297,7 @@ __device__ __forceinline__ void qk_emit_push(Ctx& cx, const DevHotA& c, uint32_t
   n += 1;
   if (n > emit_depth) {
     cx.status = QK_REP_EMIT_OVERFLOW;
-    return;
+    return true;
   }
   if (LOG) {
     if (HOT && n == 1) {
@@ -307,6 +309,7 @@ __device__ __forceinline__ void qk_emit_push(Ctx& cx, const DevHotA& c, uint32_t
     }
   }
   S32(c.o32 + S32_EMIT) = n | (split << 8) | (head << 16);
+  return false;
 }
 
 template <bool LOG, int SM, bool HOT = false>
@@ -334,7 +337,7 @@ __device__ __forceinline__ uint32_t qk_emit_pop(Ctx& cx, const DevHotA& c, uint3
 /* Stock::add = pre_add, add_impl, post_add (core.rs:177-183; discrete.rs:181-198). No capacity check. */
 /* pay != nullptr: the item is a Vector3Container and pay[3] is what it carries (the stock is a container stock) */
 template <bool LOG, int SM>
-__device__ __forceinline__ void qk_stock_add(Ctx& cx, uint32_t sidx, uint32_t item, uint64_t src,
+__device__ __forceinline__ bool qk_stock_add(Ctx& cx, uint32_t sidx, uint32_t item, uint64_t src,
                                              const uint64_t* pay = nullptr) {
   const DevHotA c = QK_HOT_A(sidx);
   const DevHotSB sb = QK_HOT_SB(sidx);
@@ -343,7 +346,7 @@ __device__ __forceinline__ void qk_stock_add(Ctx& cx, uint32_t sidx, uint32_t it
   const uint32_t prev = qk_stock_cat(cnt, sb.low, sb.max);
   if (cnt >= sb.ring_cap) {
     cx.status = QK_REP_STOCK_OVERFLOW;
-    return;
+    return true;
   }
   uint32_t pos = head + cnt;
   if (pos >= sb.ring_cap) pos -= sb.ring_cap;
@@ -361,15 +364,17 @@ __device__ __forceinline__ void qk_stock_add(Ctx& cx, uint32_t sidx, uint32_t it
   QK_ST32_MAX(sidx, ST32_MAXOCC, cnt);
   const uint64_t id = qk_log<LOG, SM>(cx, c, sidx, src, QK_LOG_STOCK_ADD, 0, item);
   if (pay) qk_log_pay<LOG, SM>(cx, c.flags, sidx, id, pay);
-  if (prev != qk_stock_cat(cnt, sb.low, sb.max)) qk_emit_push<LOG, SM, true>(cx, c, sb.emit_depth, c.olog64 + sb.ring_cap, (uint32_t)id);
+  if (prev != qk_stock_cat(cnt, sb.low, sb.max))
+    return qk_emit_push<LOG, SM, true>(cx, c, sb.emit_depth, c.olog64 + sb.ring_cap, (uint32_t)id);
+  return false;
 }
 
-/* Stock::remove (core.rs:197-204; discrete.rs:200-225); returns false for Remove(None) */
-/* item_pre: the head item, already loaded by the caller (qk_update_single issues that global-memory load before it
- * writes its WithdrawRequest record, so the latency is not on the path to the Remove record) */
+/* Stock::remove (core.rs:197-204; discrete.rs:200-225); returns QK_RM_GOT unless Remove(None), | QK_RM_FAULT */
+#define QK_RM_GOT 1u
+#define QK_RM_FAULT 2u
 template <bool LOG, int SM>
-__device__ __forceinline__ bool qk_stock_remove(Ctx& cx, uint32_t sidx, uint64_t src, uint32_t* item_out,
-                                                uint64_t* pay_out = nullptr, const uint32_t* item_pre = nullptr) {
+__device__ __forceinline__ uint32_t qk_stock_remove(Ctx& cx, uint32_t sidx, uint64_t src, uint32_t* item_out,
+                                                    uint64_t* pay_out = nullptr) {
   const DevHotA c = QK_HOT_A(sidx);
   const DevHotSB sb = QK_HOT_SB(sidx);
   const uint32_t hc = S32(c.o32 + S32_HC);
@@ -378,7 +383,7 @@ __device__ __forceinline__ bool qk_stock_remove(Ctx& cx, uint32_t sidx, uint64_t
   const bool some = cnt != 0;
   uint32_t item = 0;
   if (some) {
-    item = item_pre ? *item_pre : C32(c.olog64 + head);
+    item = C32(c.olog64 + head);
     if (pay_out) {
       const uint32_t op = cx.comps[sidx].ocold64 + 3u * head;
       pay_out[0] = C64(op);
@@ -393,9 +398,12 @@ __device__ __forceinline__ bool qk_stock_remove(Ctx& cx, uint32_t sidx, uint64_t
   }
   const uint64_t id = qk_log<LOG, SM>(cx, c, sidx, src, QK_LOG_STOCK_REMOVE, 0, some ? (uint64_t)item : QK_ITEM_NONE);
   if (pay_out && some) qk_log_pay<LOG, SM>(cx, c.flags, sidx, id, pay_out);
-  if (prev != qk_stock_cat(cnt, sb.low, sb.max)) qk_emit_push<LOG, SM, true>(cx, c, sb.emit_depth, c.olog64 + sb.ring_cap, (uint32_t)id);
   *item_out = item;
-  return some;
+  uint32_t rc = some ? QK_RM_GOT : 0u;
+  if (prev != qk_stock_cat(cnt, sb.low, sb.max) &&
+      qk_emit_push<LOG, SM, true>(cx, c, sb.emit_depth, c.olog64 + sb.ring_cap, (uint32_t)id))
+    rc |= QK_RM_FAULT;
+  return rc;
 }
 
 /* state category of stock `sidx` (3 = not connected): one table quad + one state word */
@@ -475,11 +483,11 @@ __device__ __forceinline__ void qk_refresh_env(Ctx& cx, const DevHotA& c, int en
  * its ProcessStart, and a busy SIMPLE component logs nothing until that event fires (qk_try_quick), so the event's
  * source id is always (component, seq counter - 1) and need not be stored */
 template <bool LOG, int SM, bool LEAN = false>
-__device__ __forceinline__ void qk_post(Ctx& cx, const DevHotA& c, uint64_t ttnpe, uint64_t src) {
+__device__ __forceinline__ bool qk_post(Ctx& cx, const DevHotA& c, uint64_t ttnpe, uint64_t src) {
   if (ttnpe != QK_TIME_NONE) {
     if (ttnpe == 0) {
       cx.status = QK_REP_ZERO_DURATION; /* panic!("Time until next event is zero!") */
-      return;
+      return true;
     }
     const uint64_t next = cx.now + ttnpe;
     const uint32_t fire = G64_FIRE0 + c.fire_idx;
@@ -488,6 +496,7 @@ __device__ __forceinline__ void qk_post(Ctx& cx, const DevHotA& c, uint64_t ttnp
       if (LOG && !LEAN) C64(c.olog64 + PL64_SCHED_SRC) = src;
     }
   }
+  return false;
 }
 
 /* pre_update_state (discrete.rs:404-412): a handle whose time has come is forgotten, NOT cancelled; if its
@@ -557,7 +566,7 @@ __device__ __forceinline__ bool qk_try_quick(Ctx& cx, uint32_t comp, uint64_t sr
 
 /* ---- DiscreteProcess / DiscreteSource / DiscreteSink update_state, one code path ----------------------------- */
 template <bool LOG, int SM, int FT>
-__device__ __forceinline__ void qk_update_single(Ctx& cx, const DevHotA& c, uint32_t comp, uint64_t src) {
+__device__ __forceinline__ bool qk_update_single(Ctx& cx, const DevHotA& c, uint32_t comp, uint64_t src) {
   const DevHotB cb = QK_HOT_B(comp);
   const uint32_t kind = c.kind;
   uint32_t flags = S32(c.o32 + P32_FLAGS);
@@ -568,6 +577,12 @@ __device__ __forceinline__ void qk_update_single(Ctx& cx, const DevHotA& c, uint
   const bool ctr = FT >= 2 && (c.flags & DC_CONTAINER) != 0;
   const uint32_t opay = ctr ? cx.comps[comp].ocold64 : 0u;
   uint64_t pay[3];
+  if (LOG && kind != QK_DISCRETE_SOURCE && cb.up >= 0) {
+    /* if this call starts a process, the head item of the upstream ring goes straight into a Remove record: start
+     * bringing it in now (no register is held: the lean kernel has none to spare, a held value was spilled) */
+    const DevHotA ua = QK_HOT_A(cb.up);
+    qk_prefetch(&C32(ua.olog64 + (S32(ua.o32 + S32_HC) & 0xFFFFu)));
+  }
   {
     const bool is_in_delay = ((flags >> PF_FIX_SHIFT) & 0xFFu) != 0;
     const bool has_item0 = (flags & PF_HAS_ITEM) != 0;
@@ -587,14 +602,13 @@ __device__ __forceinline__ void qk_update_single(Ctx& cx, const DevHotA& c, uint
         }
         QK_ST32_ADD(comp, ST32_COUNT, 1u);
         if (kind != QK_DISCRETE_SINK && cb.down >= 0) { /* push_downstream: no downstream check at finish */
-          qk_stock_add<LOG, SM>(cx, (uint32_t)cb.down, item, src, ctr ? pay : nullptr);
-          if (cx.status) return;
+          if (qk_stock_add<LOG, SM>(cx, (uint32_t)cb.down, item, src, ctr ? pay : nullptr)) return true;
         }
       }
     }
     if (FT != 0 && c.n_dm && !is_env_blocked && (is_in_delay || is_in_process)) {
       qk_tick_delays<LOG, SM>(cx, c, cb, comp, &flags, dt, &src);
-      if (cx.status) return;
+      if (cx.status) return true;
     }
   }
   if (FT != 0 && (cb.env >= 0 || (flags & PF_ENV_STOPPED))) qk_refresh_env<LOG, SM>(cx, c, cb.env, comp, &flags, &src);
@@ -612,14 +626,10 @@ __device__ __forceinline__ void qk_update_single(Ctx& cx, const DevHotA& c, uint
       bool got = true;
       uint32_t item;
       if (need_us) {
-        uint32_t head_item = 0;
-        if (LOG) { /* us is Normal|Full, so the ring is not empty */
-          const DevHotA ua = QK_HOT_A(cb.up);
-          head_item = C32(ua.olog64 + (S32(ua.o32 + S32_HC) & 0xFFFFu));
-        }
         src = qk_log<LOG, SM>(cx, c, comp, src, QK_LOG_WITHDRAW_REQUEST, 0, 0);
-        got = qk_stock_remove<LOG, SM>(cx, (uint32_t)cb.up, src, &item, ctr ? pay : nullptr, LOG ? &head_item : nullptr);
-        if (cx.status) return;
+        const uint32_t rc = qk_stock_remove<LOG, SM>(cx, (uint32_t)cb.up, src, &item, ctr ? pay : nullptr);
+        if (rc & QK_RM_FAULT) return true;
+        got = (rc & QK_RM_GOT) != 0;
       }
       if (got) {
         /* process_time_distr.sample() + Duration::from_secs_f64: Constant distributions were converted at
@@ -638,7 +648,7 @@ __device__ __forceinline__ void qk_update_single(Ctx& cx, const DevHotA& c, uint
           const uint32_t idx = S32(cc.o32_next_item);
           if (idx > 0x3FFFFFFu) {
             cx.status = QK_REP_ITEM_INDEX_OVERFLOW;
-            return;
+            return true;
           }
           S32(cc.o32_next_item) = idx + 1;
           item = ((uint32_t)c.src_ord << 26) | idx;
@@ -648,14 +658,14 @@ __device__ __forceinline__ void qk_update_single(Ctx& cx, const DevHotA& c, uint
             pay[1] = pay[2] = 0;
             if (v->dist_qty != 0xFFFF) {
               const double q = qk_sample<SM>(cx, v->dist_qty);
-              if (cx.status) return;
+              if (cx.status) return true;
               for (int k = 0; k < 3; ++k) pay[k] = QK_D2U(__dmul_rn(q, v->vinit[k])); /* quantity * split[k] */
             }
           }
         }
         if (d >= QK_DUR_FAULT_BASE) { /* from_secs_f64 panicked / tape exhausted / (EMPTY: refill logic bug) */
           cx.status = d == QK_DUR_EMPTY ? 99u : (uint32_t)(d - QK_DUR_FAULT_BASE);
-          return;
+          return true;
         }
         left = d;
         flags |= PF_HAS_ITEM;
@@ -695,8 +705,9 @@ __device__ __forceinline__ void qk_update_single(Ctx& cx, const DevHotA& c, uint
   if (kind == QK_DISCRETE_SINK) S64(QK_HOT_C(comp).o64_ttnpe) = ttnpe;
   S32(c.o32 + P32_FLAGS) = flags;
   S64(c.o64 + P64_LEFT) = left;
-  qk_post<LOG, SM, FT == 0>(cx, c, ttnpe, src);
+  const bool fault = qk_post<LOG, SM, FT == 0>(cx, c, ttnpe, src);
   S64(c.o64 + P64_PREV) = cx.now;
+  return fault;
 }
 
 #include "qk_vector.cuh"
@@ -827,9 +838,9 @@ __device__ __forceinline__ void qk_update_multi(Ctx& cx, const DevComp* c, uint3
       if (us_ok && slots) {
         src = qk_log<LOG, SM>(cx, ha, comp, src, QK_LOG_WITHDRAW_REQUEST, 0, 0);
         uint32_t it;
-        const bool got = qk_stock_remove<LOG, SM>(cx, (uint32_t)c->up, src, &it, ctr ? pay : nullptr);
-        if (cx.status) return;
-        if (!got) break;
+        const uint32_t rc = qk_stock_remove<LOG, SM>(cx, (uint32_t)c->up, src, &it, ctr ? pay : nullptr);
+        if (rc & QK_RM_FAULT) return;
+        if (!(rc & QK_RM_GOT)) break;
         if (is_load) { /* vector_container.rs:356-360 */
           const DevVec* v = &cx.vecs[c->vec_idx];
           const double proportion = qk_sample<SM>(cx, v->dist_qty); /* process_capacity_ratio_distr */
@@ -888,19 +899,19 @@ __device__ __forceinline__ void qk_update_multi(Ctx& cx, const DevComp* c, uint3
 
 
 /* Process::update_state (core.rs:370-376) */
+/* returns true when the replication has faulted (cx.status) */
 template <bool LOG, int SM, int FT>
-__device__ __forceinline__ void qk_update_state(Ctx& cx, uint32_t comp, uint64_t src) {
+__device__ __forceinline__ bool qk_update_state(Ctx& cx, uint32_t comp, uint64_t src) {
   const DevHotA a = QK_HOT_A(comp);
   if (FT == 0 || (a.kind >= QK_DISCRETE_PROCESS && a.kind <= QK_DISCRETE_SINK)) {
     qk_pre<LOG, SM, FT == 0>(cx, a, comp);
-    qk_update_single<LOG, SM, FT>(cx, a, comp, src);
-    return;
+    return qk_update_single<LOG, SM, FT>(cx, a, comp, src);
   }
   if constexpr (FT != 0) {
     const DevComp* c = &cx.comps[comp];
     if (a.kind == QK_ENVIRONMENT) { /* only reached from the init list: BasicEnvironment::init logs its state */
       qk_log<LOG, SM>(cx, a, comp, src, QK_LOG_ENV_STATE, S32(a.o32 + E32_STATE), 0);
-      return;
+      return cx.status != 0;
     }
     if (a.kind >= QK_VECTOR_PROCESS && a.kind <= QK_VECTOR_SPLITTER) {
       /* Combiner / Splitter / VectorSource / VectorSink init with their own next id instead of INIT_000000
@@ -909,11 +920,13 @@ __device__ __forceinline__ void qk_update_state(Ctx& cx, uint32_t comp, uint64_t
         src = ((uint64_t)comp << 32) | S32(a.olog32 + L32_SEQ);
       qk_pre<LOG, SM>(cx, a, comp);
       qk_update_vector<LOG, SM>(cx, c, comp, src);
-      return;
+      return cx.status != 0;
     }
     qk_pre<LOG, SM>(cx, a, comp);
     qk_update_multi<LOG, SM, FT>(cx, c, comp, src);
+    return cx.status != 0;
   }
+  return false;
 }
 
 /* ============================================ the kernel ============================================ */
@@ -929,14 +942,18 @@ constexpr int qk_lb_threads(int sm) { return sm > 0 ? sm : QK_MAX_NT; }
 #ifndef QK_LEAN_THREADS
 #define QK_LEAN_THREADS 640
 #endif
-constexpr int qk_lb_blocks(int sm, int ft) {
-  return sm > 0 ? ((ft == 0 ? QK_LEAN_THREADS : 512) / sm > 0 ? (ft == 0 ? QK_LEAN_THREADS : 512) / sm : 1) : (ft == 0 ? 3 : 2);
+#ifndef QK_LEAN_THREADS_LOG
+#define QK_LEAN_THREADS_LOG QK_LEAN_THREADS /* the lean kernel with logging compiled in */
+#endif
+constexpr int qk_lb_resident(int ft, bool log) { return ft == 0 ? (log ? QK_LEAN_THREADS_LOG : QK_LEAN_THREADS) : 512; }
+constexpr int qk_lb_blocks(int sm, int ft, bool log) {
+  return sm > 0 ? (qk_lb_resident(ft, log) / sm > 0 ? qk_lb_resident(ft, log) / sm : 1) : (ft == 0 ? 3 : 2);
 }
 /* FT = feature set of the model: 0 = only SIMPLE single-server discrete components and stocks (no delay modes, no
  * environment, no scheduled events, no parallel or vector components): the handlers for everything else are
  * compiled out, which frees registers ; 1 = everything but the container family ; 2 = everything */
 template <bool LOG, int SM, int FT>
-__global__ void __launch_bounds__(qk_lb_threads(SM), qk_lb_blocks(SM, FT)) qk_step_kernel(const __grid_constant__ KParams P) {
+__global__ void __launch_bounds__(qk_lb_threads(SM), qk_lb_blocks(SM, FT, LOG)) qk_step_kernel(const __grid_constant__ KParams P) {
   uint8_t* const smem = qk_smem;
   const uint32_t tid = QK_TID, nt = SM > 0 ? (uint32_t)SM : QK_NT;
 
@@ -1070,15 +1087,25 @@ __global__ void __launch_bounds__(qk_lb_threads(SM), qk_lb_blocks(SM, FT)) qk_st
    *           needs the full handler (at most QK_SCAN_ITERS pops per trip, so no lane holds the warp for long);
    *   REFILL  deferred variate prefetch (see below);
    *   UPDATE  one full update_state per lane that has one. */
+  /* events left in this launch, as a 32-bit count-down (registers are what limits residency): the host cuts finite
+   * budgets into launches of at most 2^32 - 2 events; ~0 means no limit, and then the counter is re-armed when it
+   * runs out (4.29e9 events of one replication in one launch) */
+  /* (which counter is cheaper is a matter of register allocation, measured per kernel family on the box: the logging
+   * kernels gain 1.5 % from the 32-bit count-down, the statistics-only kernels lose 2 % with it) */
+  constexpr bool EV32 = LOG;
   uint64_t events_done = 0;
   const uint64_t budget = live ? P.event_budget : 0;
+  const bool unlimited = P.event_budget == ~0ull;
+  const uint32_t ev_initial = live ? (unlimited ? 0xFFFFFFFFu : (uint32_t)P.event_budget) : 0u;
+  uint32_t ev_left = ev_initial;
   const uint64_t t_until = P.t_until;
   /* Model::init of every component in registration order is the first call list of the loop */
   uint32_t rem = (P.do_init && live) ? cx.hdr->n_init : 0, ptr = cx.hdr->init_off;
   const uint32_t ident_off = cx.hdr->ident_off;
   uint64_t src = SRC_INIT;
-  uint32_t ext_cursor = S32(G32_EXT_CURSOR);
-  bool done = false;
+  uint32_t ext_cursor = FT != 0 ? S32(G32_EXT_CURSOR) : 0u; /* the lean kernel has no external events */
+  bool done = cx.status != 0; /* a faulted replication stays frozen; later faults arrive as return values */
+  if (done) rem = 0;
   bool keyed = false; /* the pending call is a component's own keyed event: its fire slot was just cleared, so the
                          quick path's "fire == NONE means idle" does not apply -- always the full handler */
   for (;;) {
@@ -1090,7 +1117,17 @@ __global__ void __launch_bounds__(qk_lb_threads(SM), qk_lb_blocks(SM, FT)) qk_st
         ptr += 1;
         rem -= 1;
       }
-      if (rem == 0 && !done) done = cx.status != 0 || events_done >= budget;
+      if (rem == 0 && !done) {
+        if constexpr (EV32) {
+          if (ev_left == 0 && unlimited && live) { /* re-arm (see above) */
+            S64(G64_NEVENTS) += 0xFFFFFFFFull;
+            ev_left = 0xFFFFFFFFu;
+          }
+          done = ev_left == 0;
+        } else {
+          done = events_done >= budget;
+        }
+      }
       if (!QK_ANY_SYNC(rem == 0 && !done)) break; /* every lane stands on a full call or has finished */
       if (rem == 0 && !done) {
         /* pop the scheduler queue: min over (time, rank); rank 0 = externally scheduled events */
@@ -1133,7 +1170,7 @@ __global__ void __launch_bounds__(qk_lb_threads(SM), qk_lb_blocks(SM, FT)) qk_st
         } else {
           if (stale) S32(G32_STALE0 + stale_word) = stale_mask;
           cx.now = best;
-          events_done += 1;
+          if constexpr (EV32) ev_left -= 1; else events_done += 1;
           if (FT != 0 && bi < 0) {
             /* ScheduledEventConfig::SetEnvironmentState -> BasicEnvironment::set_state (core.rs:256-265, 1393-1396) */
             const DevExt* e = &cx.ext[ext_cursor];
@@ -1145,6 +1182,7 @@ __global__ void __launch_bounds__(qk_lb_threads(SM), qk_lb_blocks(SM, FT)) qk_st
               S64(cx.vecs[cx.comps[target].vec_idx].o64_low) = QK_D2U(e->value);
               const double zero[3] = {0.0, 0.0, 0.0};
               qk_vstock_add<LOG, SM>(cx, target, zero, SRC_SCH);
+              if (cx.status) done = true;
             } else if (S32(a.o32 + E32_STATE) != e->state) {
               const uint32_t st = e->state;
               S32(a.o32 + E32_STATE) = st;
@@ -1221,18 +1259,21 @@ __global__ void __launch_bounds__(qk_lb_threads(SM), qk_lb_blocks(SM, FT)) qk_st
       const uint32_t p = cx.subs[ptr];
       ptr += 1;
       rem -= 1;
-      qk_update_state<LOG, SM, FT>(cx, p, src);
+      const bool fault = qk_update_state<LOG, SM, FT>(cx, p, src);
       keyed = false;
-      if (cx.status) rem = 0;
+      if (fault) {
+        rem = 0;
+        done = true;
+      }
     }
   }
   /* step_until(t) leaves the clock at t */
   if (!cx.status && live && P.t_until != QK_TIME_NONE && P.t_until > cx.now) cx.now = P.t_until;
 
   S64(G64_NOW) = cx.now;
-  S64(G64_NEVENTS) += events_done;
+  S64(G64_NEVENTS) += EV32 ? (uint64_t)(ev_initial - ev_left) : events_done;
   S32(G32_STATUS) = cx.status;
-  S32(G32_EXT_CURSOR) = ext_cursor;
+  if (FT != 0) S32(G32_EXT_CURSOR) = ext_cursor;
   S32(G32_LOGCNT) = cx.log_cnt;
   if constexpr (SM != 0) {
 #pragma unroll 4

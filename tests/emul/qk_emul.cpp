@@ -166,7 +166,13 @@ int qk_batch_step_until(qk_batch* b, uint64_t t_ns) {
 }
 int qk_batch_step_events(qk_batch* b, uint64_t n) {
   if (!b || !b->initialised) return QK_ERR_STATE;
-  return run(b, 0, 0, QK_TIME_NONE, n);
+  do { /* 32-bit event counter in the kernel: finite budgets go in launches of at most 2^32 - 2 events */
+    const uint64_t k = n < 0xFFFFFFFEull ? n : 0xFFFFFFFEull;
+    n -= k;
+    const int rc = run(b, 0, 0, QK_TIME_NONE, k);
+    if (rc) return rc;
+  } while (n);
+  return QK_OK;
 }
 int qk_batch_step_events_chunked(qk_batch* b, uint64_t n, uint64_t chunk) {
   if (!b || !b->initialised || chunk == 0) return QK_ERR_STATE;
