@@ -65,6 +65,8 @@ __device__ __forceinline__ void qk_stage4(uint32_t* smem_dst, const uint32_t* gs
 __device__ __forceinline__ void qk_stage_wait() {
   asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
+/* every asynchronous copy this thread has issued has landed */
+__device__ __forceinline__ void qk_async_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 #endif
 
 #define QK_DEV __device__ __forceinline__

@@ -51,7 +51,9 @@ enum { L32_SEQ = 0 };
 
 /* ---- discrete stock slots ------------------------------------------------------------------------ */
 enum { S64_COUNT = 0 }; /* the fire slot holds emit_t0; nothing else is 64-bit */
-enum { S32_HC = 0, S32_EMIT = 1, S32_COUNT = 2, S32_EMITSRC = 2 }; /* S32_EMITSRC: discrete stocks, LOG only */
+enum { S32_HC = 0, S32_EMIT = 1, S32_COUNT = 2, S32_EMITSRC = 2, S32_HEADITEM = 3 };
+/* LOG only, discrete stocks: S32_EMITSRC = source id of the oldest pending emit_change ; S32_HEADITEM = copy of the
+ * ring's head item (on-chip kernels; refilled by an asynchronous global->shared copy, see qk_stock_remove) */
 /* S32_EMIT = n | split << 8 | head << 16.
  * COLD state (global memory only, never staged in shared memory -- see "cold planes" below): the item ring
  * [ring_cap] at cold32 slot `ocold32`, followed (LOG) by the emit source-seq ring [emit_depth] */

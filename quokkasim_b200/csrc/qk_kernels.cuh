@@ -351,6 +351,7 @@ __device__ __forceinline__ bool qk_stock_add(Ctx& cx, uint32_t sidx, uint32_t it
   uint32_t pos = head + cnt;
   if (pos >= sb.ring_cap) pos -= sb.ring_cap;
   C32(c.olog64 + pos) = item; /* item ring: cold */
+  if (LOG && SM != 0 && cnt == 0) S32(c.o32 + S32_HEADITEM) = item; /* the ring was empty: this is its head */
   if (pay) {
     const uint32_t op = cx.comps[sidx].ocold64 + 3u * pos;
     C64(op) = pay[0];
@@ -383,7 +384,16 @@ __device__ __forceinline__ uint32_t qk_stock_remove(Ctx& cx, uint32_t sidx, uint
   const bool some = cnt != 0;
   uint32_t item = 0;
   if (some) {
-    item = C32(c.olog64 + head);
+    /* With logging the head item goes straight into the Remove record, so a global-memory load here is a stall of
+     * a few hundred cycles in every start.  On-chip kernels therefore keep a copy of the HEAD item in a hot slot:
+     * reading it is a shared-memory load, and the copy of the NEXT head is fetched by an asynchronous
+     * global->shared copy (LDGSTS) that nobody waits for until this stock's next remove. */
+    if (LOG && SM != 0) {
+      qk_async_wait();
+      item = S32(c.o32 + S32_HEADITEM);
+    } else {
+      item = C32(c.olog64 + head);
+    }
     if (pay_out) {
       const uint32_t op = cx.comps[sidx].ocold64 + 3u * head;
       pay_out[0] = C64(op);
@@ -394,6 +404,7 @@ __device__ __forceinline__ uint32_t qk_stock_remove(Ctx& cx, uint32_t sidx, uint
     if (head >= sb.ring_cap) head = 0;
     cnt -= 1;
     S32(c.o32 + S32_HC) = head | (cnt << 16);
+    if (LOG && SM != 0 && cnt != 0) qk_stage4(&S32(c.o32 + S32_HEADITEM), &C32(c.olog64 + head));
     QK_ST64_ADD(sidx, ST64_TIME, cx.now);
   }
   const uint64_t id = qk_log<LOG, SM>(cx, c, sidx, src, QK_LOG_STOCK_REMOVE, 0, some ? (uint64_t)item : QK_ITEM_NONE);
@@ -577,12 +588,6 @@ __device__ __forceinline__ bool qk_update_single(Ctx& cx, const DevHotA& c, uint
   const bool ctr = FT >= 2 && (c.flags & DC_CONTAINER) != 0;
   const uint32_t opay = ctr ? cx.comps[comp].ocold64 : 0u;
   uint64_t pay[3];
-  if (LOG && kind != QK_DISCRETE_SOURCE && cb.up >= 0) {
-    /* if this call starts a process, the head item of the upstream ring goes straight into a Remove record: start
-     * bringing it in now (no register is held: the lean kernel has none to spare, a held value was spilled) */
-    const DevHotA ua = QK_HOT_A(cb.up);
-    qk_prefetch(&C32(ua.olog64 + (S32(ua.o32 + S32_HC) & 0xFFFFu)));
-  }
   {
     const bool is_in_delay = ((flags >> PF_FIX_SHIFT) & 0xFFu) != 0;
     const bool has_item0 = (flags & PF_HAS_ITEM) != 0;
@@ -1048,6 +1053,7 @@ __global__ void __launch_bounds__(qk_lb_threads(SM), qk_lb_blocks(SM, FT, LOG)) 
           }
           initial_base += n_init;
           S32(c->o32 + S32_HC) = n_init << 16;
+          if (LOG && n_init) S32(c->o32 + S32_HEADITEM) = (63u << 26) | (initial_base - n_init);
           cx.gs32[(size_t)(i * ST_PER_COMP + ST32_MAXOCC) * P.rep_pad] = n_init;
           cx.gs64[(size_t)(i * ST_PER_COMP + ST64_TIME) * P.rep_pad] = 0ull - (uint64_t)n_init * P.t0;
         } else if (c->kind == QK_ENVIRONMENT) {
@@ -1270,6 +1276,7 @@ __global__ void __launch_bounds__(qk_lb_threads(SM), qk_lb_blocks(SM, FT, LOG)) 
   /* step_until(t) leaves the clock at t */
   if (!cx.status && live && P.t_until != QK_TIME_NONE && P.t_until > cx.now) cx.now = P.t_until;
 
+  if constexpr (LOG && SM != 0) qk_async_wait(); /* head-item copies still in flight land before the write-back */
   S64(G64_NOW) = cx.now;
   S64(G64_NEVENTS) += EV32 ? (uint64_t)(ev_initial - ev_left) : events_done;
   S32(G32_STATUS) = cx.status;

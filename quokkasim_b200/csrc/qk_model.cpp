@@ -692,7 +692,7 @@ int qk_lower(const qk_model* m, bool log, QkLowered* out) {
       n64 += S64_COUNT;
       d.o32 = (uint16_t)n32;
       n32 += S32_COUNT;
-      if (log) n32 += 1; /* S32_EMITSRC: source id of the oldest pending emit_change */
+      if (log) n32 += 2; /* S32_EMITSRC, S32_HEADITEM */
       d.ocold32 = (uint16_t)n32c;
       n32c += d.ring_cap;
       if (is_ctr) {
