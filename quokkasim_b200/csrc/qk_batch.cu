@@ -804,7 +804,7 @@ int qk_batch_read_stock(qk_batch* b, uint64_t rep, uint32_t comp, uint32_t* item
   const DevComp& c = b->low.comps[comp];
   uint32_t hc = 0;
   CUDA_TRY(cudaMemcpy(&hc, b->g32 + (size_t)(c.o32 + S32_HC) * b->rep_pad + rep, 4, cudaMemcpyDeviceToHost));
-  const uint32_t head = hc & 0xFFFFu, cnt = hc >> 16;
+  const uint32_t head = QK_HC_HEAD(hc), cnt = QK_HC_CNT(hc);
   if (n_out) *n_out = cnt;
   if (!items) return QK_OK;
   if (cap < cnt) return QK_ERR_BUFFER_TOO_SMALL;
@@ -832,7 +832,7 @@ int qk_batch_read_containers(qk_batch* b, uint64_t rep, uint32_t comp, uint32_t*
   if (c.kind == QK_DISCRETE_STOCK) {
     uint32_t hc = 0;
     CUDA_TRY(fetch(b->g32, b->rep_pad, c.o32 + S32_HC, rep, &hc));
-    const uint32_t head = hc & 0xFFFFu, cnt = hc >> 16;
+    const uint32_t head = QK_HC_HEAD(hc), cnt = QK_HC_CNT(hc);
     item_cold = true;
     for (uint32_t i = 0; i < cnt; ++i) {
       const uint32_t pos = (head + i) % c.ring_cap;

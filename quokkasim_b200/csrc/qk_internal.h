@@ -52,6 +52,15 @@ enum { L32_SEQ = 0 };
 /* ---- discrete stock slots ------------------------------------------------------------------------ */
 enum { S64_COUNT = 0 }; /* the fire slot holds emit_t0; nothing else is 64-bit */
 enum { S32_HC = 0, S32_EMIT = 1, S32_COUNT = 2, S32_EMITSRC = 2, S32_HEADITEM = 3 };
+/* S32_HC = ring head (15 bits) | item count (15 bits) | state category (2 bits: 0 Empty, 1 Normal, 2 Full).  The
+ * category is a function of the count (get_state, discrete.rs:161-171) and is cached in the word so that the many
+ * "what state is my neighbour in" questions of the event loop are ONE state load -- DevHotB.up_hc / down_hc name this
+ * word directly -- instead of a table quad, a state load and two compares. */
+#define QK_HC_HEAD(hc) ((hc)&0x7FFFu)
+#define QK_HC_CNT(hc) (((hc) >> 15) & 0x7FFFu)
+#define QK_HC_CAT(hc) ((hc) >> 30)
+#define QK_HC_PACK(head, cnt, cat) ((head) | ((cnt) << 15) | ((cat) << 30))
+#define QK_HC_NONE 0xFFFFu /* up_hc / down_hc of a port nobody connected */
 /* LOG only, discrete stocks: S32_EMITSRC = source id of the oldest pending emit_change ; S32_HEADITEM = copy of the
  * ring's head item (on-chip kernels; refilled by an asynchronous global->shared copy, see qk_stock_remove) */
 /* S32_EMIT = n | split << 8 | head << 16.
@@ -131,7 +140,8 @@ typedef struct {
   uint16_t olog64; /* process-like, vector stock: cold64 slot (LOG) ; discrete stock: cold32 slot of the item ring */
 } DevHotA; /* every kind */
 typedef struct {
-  int16_t up, down;
+  uint16_t up_hc, down_hc; /* single-server discrete components: plane32 slot of the S32_HC word of the upstream /
+                              downstream stock (QK_HC_NONE if not connected); the stock ids are in DevComp.up / down */
   int16_t env;
   uint16_t dist_time;
   uint16_t o64_dm, dm_off;

@@ -342,8 +342,8 @@ __device__ __forceinline__ bool qk_stock_add(Ctx& cx, uint32_t sidx, uint32_t it
   const DevHotA c = QK_HOT_A(sidx);
   const DevHotSB sb = QK_HOT_SB(sidx);
   const uint32_t hc = S32(c.o32 + S32_HC);
-  uint32_t head = hc & 0xFFFFu, cnt = hc >> 16;
-  const uint32_t prev = qk_stock_cat(cnt, sb.low, sb.max);
+  uint32_t head = QK_HC_HEAD(hc), cnt = QK_HC_CNT(hc);
+  const uint32_t prev = QK_HC_CAT(hc);
   if (cnt >= sb.ring_cap) {
     cx.status = QK_REP_STOCK_OVERFLOW;
     return true;
@@ -359,13 +359,14 @@ __device__ __forceinline__ bool qk_stock_add(Ctx& cx, uint32_t sidx, uint32_t it
     C64(op + 2) = pay[2];
   }
   cnt += 1;
-  S32(c.o32 + S32_HC) = head | (cnt << 16);
+  const uint32_t cur = qk_stock_cat(cnt, sb.low, sb.max);
+  S32(c.o32 + S32_HC) = QK_HC_PACK(head, cnt, cur);
   QK_ST64_ADD(sidx, ST64_TIME, 0ull - cx.now); /* occupancy integral = sum(t_remove) - sum(t_add) + cnt * T */
   QK_ST32_ADD(sidx, ST32_COUNT, 1u);
   QK_ST32_MAX(sidx, ST32_MAXOCC, cnt);
   const uint64_t id = qk_log<LOG, SM>(cx, c, sidx, src, QK_LOG_STOCK_ADD, 0, item);
   if (pay) qk_log_pay<LOG, SM>(cx, c.flags, sidx, id, pay);
-  if (prev != qk_stock_cat(cnt, sb.low, sb.max))
+  if (prev != cur)
     return qk_emit_push<LOG, SM, true>(cx, c, sb.emit_depth, c.olog64 + sb.ring_cap, (uint32_t)id);
   return false;
 }
@@ -379,8 +380,9 @@ __device__ __forceinline__ uint32_t qk_stock_remove(Ctx& cx, uint32_t sidx, uint
   const DevHotA c = QK_HOT_A(sidx);
   const DevHotSB sb = QK_HOT_SB(sidx);
   const uint32_t hc = S32(c.o32 + S32_HC);
-  uint32_t head = hc & 0xFFFFu, cnt = hc >> 16;
-  const uint32_t prev = qk_stock_cat(cnt, sb.low, sb.max);
+  uint32_t head = QK_HC_HEAD(hc), cnt = QK_HC_CNT(hc);
+  const uint32_t prev = QK_HC_CAT(hc);
+  uint32_t cur = prev;
   const bool some = cnt != 0;
   uint32_t item = 0;
   if (some) {
@@ -403,7 +405,8 @@ __device__ __forceinline__ uint32_t qk_stock_remove(Ctx& cx, uint32_t sidx, uint
     head += 1;
     if (head >= sb.ring_cap) head = 0;
     cnt -= 1;
-    S32(c.o32 + S32_HC) = head | (cnt << 16);
+    cur = qk_stock_cat(cnt, sb.low, sb.max);
+    S32(c.o32 + S32_HC) = QK_HC_PACK(head, cnt, cur);
     if (LOG && SM != 0 && cnt != 0) qk_stage4(&S32(c.o32 + S32_HEADITEM), &C32(c.olog64 + head));
     QK_ST64_ADD(sidx, ST64_TIME, cx.now);
   }
@@ -411,10 +414,16 @@ __device__ __forceinline__ uint32_t qk_stock_remove(Ctx& cx, uint32_t sidx, uint
   if (pay_out && some) qk_log_pay<LOG, SM>(cx, c.flags, sidx, id, pay_out);
   *item_out = item;
   uint32_t rc = some ? QK_RM_GOT : 0u;
-  if (prev != qk_stock_cat(cnt, sb.low, sb.max) &&
+  if (prev != cur &&
       qk_emit_push<LOG, SM, true>(cx, c, sb.emit_depth, c.olog64 + sb.ring_cap, (uint32_t)id))
     rc |= QK_RM_FAULT;
   return rc;
+}
+
+/* state category through DevHotB.up_hc / down_hc (3 = not connected): one state word, no table access */
+template <int SM>
+__device__ __forceinline__ uint32_t qk_cat_at(Ctx& cx, uint32_t hc_slot) {
+  return hc_slot == QK_HC_NONE ? 3u : QK_HC_CAT(S32(hc_slot));
 }
 
 /* state category of stock `sidx` (3 = not connected): one table quad + one state word */
@@ -422,7 +431,7 @@ template <int SM>
 __device__ __forceinline__ uint32_t qk_stock_cat_of(Ctx& cx, int sidx) {
   if (sidx < 0) return 3u;
   const DevHotSB sb = QK_HOT_SB(sidx);
-  return qk_stock_cat(S32(sb.o32 + S32_HC) >> 16, sb.low, sb.max);
+  return QK_HC_CAT(S32(sb.o32 + S32_HC));
 }
 
 /* ---- DelayModes::update_state (delays.rs:86-142) + DelayEnd/DelayStart logs (discrete.rs:441-451) ------- */
@@ -557,8 +566,8 @@ __device__ __forceinline__ bool qk_try_quick(Ctx& cx, uint32_t comp, uint64_t sr
   const DevHotB cb = QK_HOT_B(comp);
   const uint32_t kind = c.kind;
   const bool need_us = kind != QK_DISCRETE_SOURCE, need_ds = kind != QK_DISCRETE_SINK;
-  const uint32_t us = need_us ? qk_stock_cat_of<SM>(cx, cb.up) : 1u;
-  const uint32_t ds = need_ds ? qk_stock_cat_of<SM>(cx, cb.down) : 1u;
+  const uint32_t us = need_us ? qk_cat_at<SM>(cx, cb.up_hc) : 1u;
+  const uint32_t ds = need_ds ? qk_cat_at<SM>(cx, cb.down_hc) : 1u;
   if ((us == 1u || us == 2u) && (ds == 0u || ds == 1u)) return false; /* starts */
   if (LOG) {
     uint32_t reason;
@@ -606,8 +615,8 @@ __device__ __forceinline__ bool qk_update_single(Ctx& cx, const DevHotA& c, uint
           qk_log_pay<LOG, SM>(cx, c.flags, comp, src, pay);
         }
         QK_ST32_ADD(comp, ST32_COUNT, 1u);
-        if (kind != QK_DISCRETE_SINK && cb.down >= 0) { /* push_downstream: no downstream check at finish */
-          if (qk_stock_add<LOG, SM>(cx, (uint32_t)cb.down, item, src, ctr ? pay : nullptr)) return true;
+        if (kind != QK_DISCRETE_SINK && cb.down_hc != QK_HC_NONE) { /* push_downstream: no downstream check at finish */
+          if (qk_stock_add<LOG, SM>(cx, (uint32_t)cx.comps[comp].down, item, src, ctr ? pay : nullptr)) return true;
         }
       }
     }
@@ -624,15 +633,15 @@ __device__ __forceinline__ bool qk_update_single(Ctx& cx, const DevHotA& c, uint
   if (!has_item && !has_active_delay) {
     /* match (&us_state, &ds_state) discrete.rs:480-516 / 854-872 / 1100-1125; 3 == not connected */
     const bool need_us = kind != QK_DISCRETE_SOURCE, need_ds = kind != QK_DISCRETE_SINK;
-    const uint32_t us = need_us ? qk_stock_cat_of<SM>(cx, cb.up) : 1u;
-    const uint32_t ds = need_ds ? qk_stock_cat_of<SM>(cx, cb.down) : 1u;
+    const uint32_t us = need_us ? qk_cat_at<SM>(cx, cb.up_hc) : 1u;
+    const uint32_t ds = need_ds ? qk_cat_at<SM>(cx, cb.down_hc) : 1u;
     const bool ok = (us == 1u || us == 2u) && (ds == 0u || ds == 1u);
     if (ok) {
       bool got = true;
       uint32_t item;
       if (need_us) {
         src = qk_log<LOG, SM>(cx, c, comp, src, QK_LOG_WITHDRAW_REQUEST, 0, 0);
-        const uint32_t rc = qk_stock_remove<LOG, SM>(cx, (uint32_t)cb.up, src, &item, ctr ? pay : nullptr);
+        const uint32_t rc = qk_stock_remove<LOG, SM>(cx, (uint32_t)cx.comps[comp].up, src, &item, ctr ? pay : nullptr);
         if (rc & QK_RM_FAULT) return true;
         got = (rc & QK_RM_GOT) != 0;
       }
@@ -1052,7 +1061,7 @@ __global__ void __launch_bounds__(qk_lb_threads(SM), qk_lb_blocks(SM, FT, LOG)) 
             for (uint32_t k = 0; k < 3u * n_init; ++k) C64(c->ocold64 + k) = cinit[k];
           }
           initial_base += n_init;
-          S32(c->o32 + S32_HC) = n_init << 16;
+          S32(c->o32 + S32_HC) = QK_HC_PACK(0u, n_init, qk_stock_cat(n_init, c->low, c->max));
           if (LOG && n_init) S32(c->o32 + S32_HEADITEM) = (63u << 26) | (initial_base - n_init);
           cx.gs32[(size_t)(i * ST_PER_COMP + ST32_MAXOCC) * P.rep_pad] = n_init;
           cx.gs64[(size_t)(i * ST_PER_COMP + ST64_TIME) * P.rep_pad] = 0ull - (uint64_t)n_init * P.t0;
@@ -1205,7 +1214,7 @@ __global__ void __launch_bounds__(qk_lb_threads(SM), qk_lb_blocks(SM, FT, LOG)) 
               const DevHotSB sb = QK_HOT_SB(comp);
               const uint32_t src_seq = qk_emit_pop<LOG, SM, true>(cx, a, sb.emit_depth, a.olog64 + sb.ring_cap);
               if (LOG) {
-                const uint32_t cnt = S32(a.o32 + S32_HC) >> 16;
+                const uint32_t cnt = QK_HC_CNT(S32(a.o32 + S32_HC));
                 const uint32_t empty = sb.max > cnt ? sb.max - cnt : 0;
                 src = qk_log<LOG, SM>(cx, a, comp, ((uint64_t)comp << 32) | src_seq, QK_LOG_STOCK_STATE_CHANGE,
                                       qk_stock_cat(cnt, sb.low, sb.max), ((uint64_t)cnt << 32) | empty);
@@ -1339,7 +1348,7 @@ __device__ __forceinline__ void qk_comp_stats_dev(const DevComp* c, const DevVec
     o->fvalue = QK_U2D(GS64(ST64_FQ));
     o->faux = !has ? 0.0 : (c->kind == QK_VECTOR_COMBINER ? QK_U2D(G64(v->o64_res + v->dim)) : qk_vtotal(r, v->dim));
   } else if (c->kind == QK_DISCRETE_STOCK) {
-    const uint32_t cnt = G32(c->o32 + S32_HC) >> 16;
+    const uint32_t cnt = QK_HC_CNT(G32(c->o32 + S32_HC));
     o->count = GS32(ST32_COUNT);
     o->time_ns = GS64(ST64_TIME) + (uint64_t)cnt * now;
     o->aux = GS32(ST32_MAXOCC);

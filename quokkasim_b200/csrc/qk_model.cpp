@@ -578,7 +578,7 @@ int qk_lower(const qk_model* m, bool log, QkLowered* out) {
       r = base + producers;
       if (r == 0) r = 1;
     }
-    if (r < c.d.n_initial_items || r > 0xFFFF) {
+    if (r < c.d.n_initial_items || r > 0x7FFF) { /* head and count are 15-bit fields of S32_HC */
       qk_set_error("component %zu: item ring of %u slots is out of range", i, r);
       return QK_ERR_CAPACITY;
     }
@@ -865,8 +865,8 @@ int qk_lower(const qk_model* m, bool log, QkLowered* out) {
     q.a.olog32 = d.olog32;
     q.a.olog64 = d.kind == QK_DISCRETE_STOCK ? d.ocold32 : d.olog64;
     if (qk_is_process_like(d.kind)) {
-      q.b.up = d.up;
-      q.b.down = d.down;
+      q.b.up_hc = d.up >= 0 ? (uint16_t)(dc[(size_t)d.up].o32 + S32_HC) : (uint16_t)QK_HC_NONE;
+      q.b.down_hc = d.down >= 0 ? (uint16_t)(dc[(size_t)d.down].o32 + S32_HC) : (uint16_t)QK_HC_NONE;
       q.b.env = d.env;
       q.b.dist_time = d.dist_time;
       q.b.o64_dm = d.o64_dm;

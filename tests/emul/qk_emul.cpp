@@ -298,7 +298,7 @@ int qk_batch_read_stock(qk_batch* b, uint64_t rep, uint32_t comp, uint32_t* item
     return QK_ERR_INVALID_ARG;
   const DevComp& c = b->low.comps[comp];
   const uint32_t hc = b->g32[(size_t)(c.o32 + S32_HC) * b->rep_pad + rep];
-  const uint32_t head = hc & 0xFFFFu, cnt = hc >> 16;
+  const uint32_t head = QK_HC_HEAD(hc), cnt = QK_HC_CNT(hc);
   if (n_out) *n_out = cnt;
   if (!items) return QK_OK;
   if (cap < cnt) return QK_ERR_BUFFER_TOO_SMALL;
@@ -317,7 +317,7 @@ int qk_batch_read_containers(qk_batch* b, uint64_t rep, uint32_t comp, uint32_t*
   auto c64 = [&](uint32_t slot) { return b->gc64[(size_t)slot * b->rep_pad + rep]; };
   std::vector<uint32_t> hs, ps;
   if (c.kind == QK_DISCRETE_STOCK) {
-    const uint32_t hc = h32(c.o32 + S32_HC), head = hc & 0xFFFFu, cnt = hc >> 16;
+    const uint32_t hc = h32(c.o32 + S32_HC), head = QK_HC_HEAD(hc), cnt = QK_HC_CNT(hc);
     for (uint32_t i = 0; i < cnt; ++i) {
       const uint32_t pos = (head + i) % c.ring_cap;
       hs.push_back(c32(c.ocold32 + pos));
