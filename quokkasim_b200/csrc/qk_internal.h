@@ -166,6 +166,20 @@ typedef struct {
   DevHotC c;
 } DevHot; /* 48 bytes */
 
+/* One per entry of subs[] (same index): what the quick path of the event loop needs to know about the callee, in one
+ * 8-byte load -- where its fire slot is and which state words tell whether it could start -- instead of walking
+ * subs[] -> hot row A -> fire slot -> hot row B -> neighbour words one dependent shared-memory access after the other. */
+typedef struct {
+  uint16_t fire_slot;        /* absolute plane64 slot of the callee's fire time */
+  uint16_t up_hc, down_hc;   /* plane32 slots of the S32_HC words of its upstream / downstream stock (0 if forced) */
+  uint16_t flags;            /* SQ_* */
+} DevSubQ;
+#define SQ_QUICK 1u      /* the callee is a SIMPLE component: the quick path applies */
+#define SQ_US_FORCED 2u  /* upstream category is the constant in bits 4-5 (1: a source needs none ; 3: not connected) */
+#define SQ_DS_FORCED 4u  /* downstream category is the constant in bits 6-7 */
+#define SQ_US_SHIFT 4
+#define SQ_DS_SHIFT 6
+
 typedef struct {
   uint32_t kind, stream;
   double p[4];
@@ -216,6 +230,7 @@ typedef struct {
   uint32_t total_bytes;
   uint32_t log_enabled;
   uint32_t off_hot; /* DevHot[n_comp], 16-byte aligned */
+  uint32_t off_subq;  /* DevSubQ[n_subs], 8-byte aligned */
   uint32_t off_ccap;  /* double ccap[64 + n_initial]: container capacity by source ordinal, then by initial-item index */
   uint32_t off_cinit; /* uint64_t cinit[n_initial][3]: resource bits of the initial containers (NONE sentinel) */
   uint32_t features; /* 0 = every process-like component is SIMPLE and nothing is scheduled externally ; 1 = general ;

@@ -69,6 +69,7 @@ struct Ctx {
   const DevExt* ext;
   const DevVec* vecs;
   const DevHot* hot;
+  const DevSubQ* subq;   /* quick-path descriptor of every subs[] entry */
   const double* ccap;    /* container capacity by handle (DevHeader.off_ccap) */
   uint32_t pf32, n_pf_words; /* hoisted DevHeader fields (re-reading them after every state store is wasted LDS) */
   uint64_t now;
@@ -547,12 +548,27 @@ __device__ __forceinline__ void qk_pre(Ctx& cx, const DevHotA& c, uint32_t comp)
  * component is one table quad + one state load, and it writes nothing.
  * Returns false (state untouched) when the call needs the full handler. */
 template <bool LOG, int SM, int FT>
-__device__ __forceinline__ bool qk_try_quick(Ctx& cx, uint32_t comp, uint64_t src) {
-  const DevHotA c = QK_HOT_A(comp);
-  if (FT != 0 && !(c.flags & DC_SIMPLE)) return false;
-  const uint64_t fire = S64(G64_FIRE0 + c.fire_idx);
+__device__ __forceinline__ bool qk_try_quick(Ctx& cx, uint32_t ptr, uint64_t src) {
+  union {
+    uint2 v;
+    DevSubQ q;
+  } u;
+  u.v = *reinterpret_cast<const uint2*>(&cx.subq[ptr]); /* one LDS.64 */
+  const DevSubQ q = u.q;
+  if (FT != 0 && !(q.flags & SQ_QUICK)) return false;
+  /* the three state words are independent loads: one shared-memory latency, not three.  (On the HBM planes the
+   * neighbour words are only fetched when the callee turns out to be idle: there a load is a memory transaction; the
+   * logging kernels do the same because they have no registers to hold the two words: measured.) */
+  constexpr bool EAGER = SM != 0 && !LOG;
+  const uint64_t fire = S64(q.fire_slot);
+  uint32_t uw = 0, dw = 0;
+  if constexpr (EAGER) {
+    uw = S32(q.up_hc);
+    dw = S32(q.down_hc);
+  }
   if (fire != QK_TIME_NONE) {
 #ifdef QK_HOST_EMUL
+    const DevHotA c = QK_HOT_A(cx.subs[ptr]);
     if (fire > cx.now && (!(S32(c.o32 + P32_FLAGS) & PF_HAS_ITEM) ||
                           S64(c.o64 + P64_PREV) + S64(c.o64 + P64_LEFT) != fire))
       cx.status = 98; /* invariant check, CPU test build only */
@@ -560,26 +576,24 @@ __device__ __forceinline__ bool qk_try_quick(Ctx& cx, uint32_t comp, uint64_t sr
     return fire > cx.now; /* busy and not due: nothing to do ; due (<= now): pre_update_state drops the handle (Q3) */
   }
 #ifdef QK_HOST_EMUL
-  if (S32(c.o32 + P32_FLAGS) & PF_HAS_ITEM) cx.status = 98;
+  if (S32(QK_HOT_A(cx.subs[ptr]).o32 + P32_FLAGS) & PF_HAS_ITEM) cx.status = 98;
 #endif
   /* idle: quick only if it stays idle */
-  const DevHotB cb = QK_HOT_B(comp);
-  const uint32_t kind = c.kind;
-  const bool need_us = kind != QK_DISCRETE_SOURCE, need_ds = kind != QK_DISCRETE_SINK;
-  const uint32_t us = need_us ? qk_cat_at<SM>(cx, cb.up_hc) : 1u;
-  const uint32_t ds = need_ds ? qk_cat_at<SM>(cx, cb.down_hc) : 1u;
+  if constexpr (!EAGER) {
+    uw = S32(q.up_hc);
+    dw = S32(q.down_hc);
+  }
+  const uint32_t us = (q.flags & SQ_US_FORCED) ? (q.flags >> SQ_US_SHIFT) & 3u : QK_HC_CAT(uw);
+  const uint32_t ds = (q.flags & SQ_DS_FORCED) ? (q.flags >> SQ_DS_SHIFT) & 3u : QK_HC_CAT(dw);
   if ((us == 1u || us == 2u) && (ds == 0u || ds == 1u)) return false; /* starts */
   if (LOG) {
-    uint32_t reason;
-    if (need_us && us == 0u)
-      reason = QK_REASON_UPSTREAM_EMPTY;
-    else if (need_us && us == 3u)
-      reason = QK_REASON_UPSTREAM_NOT_CONNECTED;
-    else if (ds == 2u)
-      reason = QK_REASON_DOWNSTREAM_FULL;
-    else
-      reason = QK_REASON_DOWNSTREAM_NOT_CONNECTED;
-    qk_log<LOG, SM>(cx, c, comp, src, QK_LOG_PROCESS_NONSTART, reason, 0);
+    /* a source's forced upstream category is 1, so the first two tests can only fire for components that need one */
+    const uint32_t reason = us == 0u   ? QK_REASON_UPSTREAM_EMPTY
+                            : us == 3u ? QK_REASON_UPSTREAM_NOT_CONNECTED
+                            : ds == 2u ? QK_REASON_DOWNSTREAM_FULL
+                                       : QK_REASON_DOWNSTREAM_NOT_CONNECTED;
+    const uint32_t comp = cx.subs[ptr];
+    qk_log<LOG, SM>(cx, QK_HOT_A(comp), comp, src, QK_LOG_PROCESS_NONSTART, reason, 0);
   }
   return true;
 }
@@ -989,6 +1003,7 @@ __global__ void __launch_bounds__(qk_lb_threads(SM), qk_lb_blocks(SM, FT, LOG)) 
   cx.ext = reinterpret_cast<const DevExt*>(smem + cx.hdr->off_ext);
   cx.vecs = reinterpret_cast<const DevVec*>(smem + cx.hdr->off_vecs);
   cx.hot = reinterpret_cast<const DevHot*>(smem + cx.hdr->off_hot);
+  cx.subq = reinterpret_cast<const DevSubQ*>(smem + cx.hdr->off_subq);
   cx.ccap = reinterpret_cast<const double*>(smem + cx.hdr->off_ccap);
   cx.pf32 = cx.hdr->pf32;
   cx.n_pf_words = cx.hdr->n_pf_words;
@@ -1128,7 +1143,7 @@ __global__ void __launch_bounds__(qk_lb_threads(SM), qk_lb_blocks(SM, FT, LOG)) 
 #pragma unroll 1
     for (int it = 0; it < QK_SCAN_ITERS; ++it) {
       /* dispose of the quick calls at the head of the list */
-      while (rem != 0 && !keyed && qk_try_quick<LOG, SM, FT>(cx, cx.subs[ptr], src)) {
+      while (rem != 0 && !keyed && qk_try_quick<LOG, SM, FT>(cx, ptr, src)) {
         ptr += 1;
         rem -= 1;
       }

@@ -891,6 +891,25 @@ int qk_lower(const qk_model* m, bool log, QkLowered* out) {
   off = (off + 15u) & ~15u;
   h.off_hot = off;
   off = align8(off + (uint32_t)(nc * sizeof(DevHot)));
+  /* quick-path descriptors, one per subs[] entry */
+  std::vector<DevSubQ> subq(subs.size());
+  for (size_t i = 0; i < subs.size(); ++i) {
+    const DevComp& d = dc[subs[i]];
+    const DevHot& q = hot[subs[i]];
+    DevSubQ& s = subq[i];
+    memset(&s, 0, sizeof(s));
+    if (!(q.a.flags & DC_SIMPLE)) continue; /* flags == 0: always the full handler */
+    s.flags = SQ_QUICK;
+    s.fire_slot = (uint16_t)(G64_FIRE0 + d.fire_idx);
+    if (d.kind == QK_DISCRETE_SOURCE) s.flags |= SQ_US_FORCED | (1u << SQ_US_SHIFT);
+    else if (d.up < 0) s.flags |= SQ_US_FORCED | (3u << SQ_US_SHIFT);
+    else s.up_hc = q.b.up_hc;
+    if (d.kind == QK_DISCRETE_SINK) s.flags |= SQ_DS_FORCED | (1u << SQ_DS_SHIFT);
+    else if (d.down < 0) s.flags |= SQ_DS_FORCED | (3u << SQ_DS_SHIFT);
+    else s.down_hc = q.b.down_hc;
+  }
+  h.off_subq = off;
+  off = align8(off + (uint32_t)(subq.size() * sizeof(DevSubQ)));
   /* container tables: capacity by handle, resource of the initial containers (numbered in registration order of
    * their stocks, like the handles the init kernel hands out) */
   std::vector<double> ccap(64, 0.0);
@@ -934,6 +953,7 @@ int qk_lower(const qk_model* m, bool log, QkLowered* out) {
     if (!cinit.empty()) memcpy(out->blob.data() + h.off_cinit, cinit.data(), cinit.size() * 8);
   }
   memcpy(out->blob.data() + h.off_hot, hot.data(), nc * sizeof(DevHot));
+  memcpy(out->blob.data() + h.off_subq, subq.data(), subq.size() * sizeof(DevSubQ));
   memcpy(out->blob.data(), &h, sizeof(h));
   memcpy(out->blob.data() + h.off_comps, dc.data(), nc * sizeof(DevComp));
   if (!dd.empty()) memcpy(out->blob.data() + h.off_dists, dd.data(), dd.size() * sizeof(DevDist));

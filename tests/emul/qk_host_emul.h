@@ -22,6 +22,9 @@
 struct uint4 {
   uint32_t x, y, z, w;
 };
+struct uint2 {
+  uint32_t x, y;
+};
 
 extern thread_local uint8_t* qk_emul_smem;
 extern thread_local uint32_t qk_emul_bid;

@@ -349,3 +349,37 @@ def test_container_mass_balance_at_scale(gpu_lib):
         assert fleet == 4
         assert abs(t - (100000.0 + 1.75 * 2)) <= 1e-9 * t, t
     sim.close()
+
+
+def test_c2_full_size_invariants_and_sampled_oracle_parity(gpu_lib):
+    """BASELINE config C2 at its full size -- 1,048,576 replications x 10,000 events, Philox seeds, the bench's own
+    shape (newest 64 records kept per replication): conservation and bound invariants on EVERY replication, and
+    bit-exact agreement with the CPU oracle (status, clock, statistics, stock contents, the retained log records) on a
+    sample of replications spread over the batch."""
+    m = H.discrete_queue()
+    n, n_events, seed = 1048576, 10000, 1234
+    sim = m.sim(gpu_lib, n, base_seed=seed, log_capacity=64)
+    sim.step_events(n_events)
+    st, now, ev = sim.status()
+    assert (st == 0).all() and (ev == n_events).all()
+    src, q1, p1, q2, p2, q3, snk = [sim.comp_stats(ci) for ci in range(len(m.components))]
+    in_system = q1["level"] + p1["level"] + q2["level"] + p2["level"] + q3["level"] + snk["level"] + src["level"]
+    assert (src["count"] + src["level"] == in_system + snk["count"]).all()
+    assert (q1["count"] - (p1["count"] + p1["level"]) == q1["level"]).all()
+    assert (q2["count"] - (p2["count"] + p2["level"]) == q2["level"]).all()
+    assert (q3["count"] - (snk["count"] + snk["level"]) == q3["level"]).all()
+    for q in (q1, q2, q3):
+        assert (q["aux"] <= 10).all() and (q["time_ns"] <= 10 * now).all()
+    for p in (src, p1, p2, snk):
+        assert (p["time_ns"] <= now).all()
+    summ = sim.summary()
+    assert summ["n_events"] == n * n_events and summ["n_faulted"] == 0
+    om, dist_ids = H.lower_to_oracle(m)
+    for r in (0, 1, 63, 64, 4099, 524288, n - 2, n - 1):
+        osim = H.run_oracle(m, om, dist_ids, r, base_seed=seed, n_events=n_events)
+        H.assert_rep_parity(sim, osim, m, r, check_log=False)
+        glog, total = sim.read_log(r)
+        olog = osim.log()
+        assert total == len(olog) and len(glog) == 64
+        assert glog.tobytes() == olog[-64:].tobytes()
+    sim.close()
