@@ -211,13 +211,14 @@ static __device__ __noinline__ QkVariate qk_sample_native(uint32_t kind, double 
       const double diff_mode_min = __dsub_rn(mode, mn);
       const double range = __dsub_rn(mx, mn);
       const double f_range = __dmul_rn(u, range);
-      if (f_range < diff_mode_min) {
-        return QkVariate{__dadd_rn(mn, __dsqrt_rn(__dmul_rn(f_range, diff_mode_min))), draws};
-      } else {
-        const double a = __dsub_rn(range, f_range);
-        const double b = __dsub_rn(mx, mode);
-        return QkVariate{__dsub_rn(mx, __dsqrt_rn(__dmul_rn(a, b))), draws};
-      }
+      /* both arms of rand_distr's Triangular::sample, selected per lane: ONE square root for the whole warp instead
+       * of two half-empty passes through the fp64 sqrt sequence (same operations on the selected arm, same bits) */
+      const bool lo = f_range < diff_mode_min;
+      const double a = __dsub_rn(range, f_range);
+      const double b = __dsub_rn(mx, mode);
+      const double arg = lo ? __dmul_rn(f_range, diff_mode_min) : __dmul_rn(a, b);
+      const double r = __dsqrt_rn(arg);
+      return QkVariate{lo ? __dadd_rn(mn, r) : __dsub_rn(mx, r), draws};
     } else if (kind == QK_DIST_EXPONENTIAL) {
       const double om = __dsub_rn(1.0, u);
       const double l = qk_det_ln(om);
