@@ -48,11 +48,6 @@ __device__ __forceinline__ void qk_store_record(uint4* r, const uint4& a, const 
 #endif
 
 #ifndef QK_HOST_EMUL
-/* start bringing a global-memory line into L1 without tying up a register */
-__device__ __forceinline__ void qk_prefetch(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
-#endif
-
-#ifndef QK_HOST_EMUL
 /* asynchronous global -> shared copies for staging the state planes (cp.async = LDGSTS) */
 __device__ __forceinline__ void qk_stage8(uint64_t* smem_dst, const uint64_t* gsrc) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)

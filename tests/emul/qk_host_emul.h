@@ -73,7 +73,6 @@ static inline int __ffs(int v) { return __builtin_ffs(v); }
 static inline void qk_stage8(uint64_t* dst, const uint64_t* src) { *dst = *src; }
 static inline void qk_stage4(uint32_t* dst, const uint32_t* src) { *dst = *src; }
 static inline void qk_stage_wait() {}
-static inline void qk_prefetch(const void*) {}
 static inline void qk_async_wait() {}
 static inline void qk_store_record(uint4* r, const uint4& a, const uint4& b) {
   r[0] = a;
