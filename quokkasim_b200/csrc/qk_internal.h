@@ -45,7 +45,7 @@ enum { L32_SEQ = 0 };
 /* ---- cold planes ----------------------------------------------------------------------------------
  * State that is touched once or twice per item and never decides control flow -- stock item rings, the source
  * ids carried by pending events -- lives only in global memory ([slot][replication], like the hot planes in HBM)
- * and is read and written in place through L1/L2.  Keeping it out of shared memory is what lets 22-24 warps of
+ * and is read and written in place through L1/L2.  Keeping it out of shared memory is what lets 20 warps of
  * replications stay resident per SM instead of 12-16 (the step kernel's throughput is proportional to resident
  * warps: profiles/README.md "occupancy experiment"). */
 

@@ -966,7 +966,8 @@ __device__ __forceinline__ bool qk_update_state(Ctx& cx, uint32_t comp, uint64_t
 constexpr int qk_lb_threads(int sm) { return sm > 0 ? sm : QK_MAX_NT; }
 /* resident threads per SM the register allocation must allow: the kernel is latency-bound and its throughput is
  * proportional to resident warps (profiles/README.md), so the lean kernel (FT == 0: small models, ~250-280 B of hot
- * state per replication) is held to 80 registers = 24 warps; the general kernel to 128 registers = 16 warps */
+ * state per replication) is held to 96 registers = 20 warps (10 blocks of 64); the general kernels to 128
+ * registers = 16 warps */
 #ifndef QK_LEAN_THREADS
 #define QK_LEAN_THREADS 640
 #endif
