@@ -158,3 +158,106 @@ def test_random_models_are_mostly_comparable(emul_lib):
 @pytest.mark.parametrize("seed", range(100, 112))
 def test_random_models_match_the_oracle_on_gpu(gpu_lib, seed):
     assert _run(gpu_lib, seed, 96) >= 0
+
+
+# ------------------------------------------------------------------------------------------ continuous family
+def random_vector_model(seed):
+    """A random chain of the continuous components: Source -> stocks -> Process / Combiner2 / Splitter2 -> Sink, f64 or
+    Vector3, random capacities around the flow so that Full / Empty flips happen, breakdown modes, environment."""
+    rng = random.Random(10_000 + seed)
+    m = Model()
+    df = qk.DistributionFactory(base_seed=77 + seed, next_seed=0)
+    dim = rng.choice([1, 3])
+    P = "Vector3" if dim == 3 else "F64"
+    V = (lambda v: qk.Vector3(v)) if dim == 3 else (lambda v: float(sum(v)))
+
+    def dist(a):
+        k = rng.choice(["const", "uniform", "uniform", "tri"])
+        if k == "const":
+            return qk.Distribution.Constant(a)
+        if k == "uniform":
+            d = df.create(qk.DistributionConfig.Uniform(0.5 * a, 1.5 * a))
+        else:
+            d = df.create(qk.DistributionConfig.Triangular(0.5 * a, 2.0 * a, a))
+        m.random_dists.append(d)
+        return d
+
+    def cm(kind, comp):
+        return m.reg(getattr(qk.ComponentModel, P + kind)(comp, qk.Mailbox.new()))
+
+    def stock(name):
+        init = [rng.uniform(0, 4), rng.uniform(0, 4), rng.uniform(0, 4)]
+        return cm("Stock", qk.VectorStock.new().with_name(name).with_code(name)
+                  .with_low_capacity(rng.choice([0.0, 1.0, 3.0])).with_max_capacity(rng.choice([8.0, 15.0, 40.0]))
+                  .with_initial_resource(V(init)))
+
+    def proc(c):
+        c = c.with_process_quantity_distr(dist(rng.choice([0.5, 1.0, 2.0]))).with_process_time_distr(dist(rng.choice([1.0, 2.0])))
+        if rng.random() < 0.35:
+            c = c.with_delay_mode(qk.DelayModeChange.Add(qk.DelayMode("Brk", dist(15.0), dist(3.0))))
+        return c
+
+    src = cm("Source", proc(qk.VectorSource.new().with_name("Src").with_code("SRC").with_source_vector(V([1.0, 2.0, 3.0]))))
+    s = stock("S0")
+    qk.connect_components(src, s)
+    actors = [src]
+    for i in range(rng.randint(1, 3)):
+        kind = rng.choice(["Process", "Combiner2", "Splitter2"])
+        nxt = stock("S%d" % (i + 1))
+        if kind == "Process":
+            p = cm("Process", proc(qk.VectorProcess.new().with_name("P%d" % i).with_code("P%d" % i)))
+            qk.connect_components(s, p)
+            qk.connect_components(p, nxt)
+        elif kind == "Combiner2":
+            side = stock("X%d" % i)
+            p = cm("Combiner2", proc(qk.VectorCombiner.new().with_name("C%d" % i).with_code("C%d" % i)))
+            qk.connect_components(s, p, 0)
+            qk.connect_components(side, p, 1)
+            qk.connect_components(p, nxt)
+        else:
+            side = stock("Y%d" % i)
+            r = rng.choice([0.3, 0.5])
+            p = cm("Splitter2", proc(qk.VectorSplitter.new().with_name("L%d" % i).with_code("L%d" % i)
+                                      .with_split_ratios([r, 1.0 - r])))
+            qk.connect_components(s, p)
+            qk.connect_components(p, nxt, 0)
+            qk.connect_components(p, side, 1)
+        actors.append(p)
+        s = nxt
+    snk = cm("Sink", proc(qk.VectorSink.new().with_name("Snk").with_code("SNK")))
+    qk.connect_components(s, snk)
+    actors.append(snk)
+    if rng.random() < 0.5:
+        env = m.reg(qk.ComponentModel.BasicEnvironment(qk.BasicEnvironment.new().with_name("Env").with_code("ENV"),
+                                                       qk.Mailbox.new()))
+        for a in actors:
+            if rng.random() < 0.7:
+                qk.connect_components(env, a)
+        m.ext.append((qk.Duration.from_secs(rng.randint(5, 30)), env, qk.BasicEnvironmentState.Stopped))
+        m.ext.append((qk.Duration.from_secs(rng.randint(31, 60)), env, qk.BasicEnvironmentState.Normal))
+    _log_all(m)
+    return m
+
+
+def _run_vector(lib, seed, n_reps, flags=0):
+    m = random_vector_model(seed)
+    om, dist_ids = H.lower_to_oracle(m)
+    sim = m.sim(lib, n_reps, base_seed=seed, log_capacity=32768, flags=flags)
+    sim.step_until(90 * 10**9)
+    st, _, _ = sim.status()
+    for r in range(n_reps):
+        if int(st[r]) in CAPACITY_FAULTS:
+            continue
+        H.assert_rep_parity(sim, H.run_oracle(m, om, dist_ids, r, base_seed=seed, t_until=90 * 10**9), m, r)
+    sim.close()
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_vector_models_match_the_oracle(emul_lib, seed):
+    _run_vector(emul_lib, seed, 2, flags=seed % 2)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(200, 208))
+def test_random_vector_models_match_the_oracle_on_gpu(gpu_lib, seed):
+    _run_vector(gpu_lib, seed, 64)
