@@ -9,7 +9,10 @@ replication of the batch (1.05e10 events per GPU).
   python bench.py --impl reference [--gpus N ...]            # CPU arm: the oracle port of the reference engine on
                                                              # all host cores, bounded sample of the same workload
 
-Prints ONE JSON line on rank 0.  See DESIGN.md "Measurement" for what every key means.
+Prints ONE JSON line on rank 0.  See DESIGN.md "Measurement" for what every key means.  `roofline` describes the step
+launch of the bench itself (K = 10,000 events per state residency: the state planes cross HBM once per launch, so the
+algorithmic bytes are the log records); `roofline.lockstep_K1` is a short probe of the SAME kernel at one event per
+launch, where the state planes cross HBM for every event (profiles/README.md section 2 has the whole K sweep).
 """
 import argparse
 import json
@@ -265,6 +268,19 @@ def run_ours(args):
     records_per_step = int(ev_total[1].item())
     value = events_per_step * args.steps / (elapsed_ms * 1e-3)
 
+    # ---- the same kernel where it IS an HBM kernel: one event per state residency (K = 1, pure lockstep).  Every launch
+    # stages the hot planes from HBM and stores them back; short probe on the resident batch, CUDA events on its stream.
+    lockstep = None
+    if K >= n_events and not args.no_lockstep_probe:
+        L.qk_batch_init(b, 0)
+        L.qk_batch_step_events_chunked(b, 64, 1)
+        s0 = sim.summary()
+        L.qk_batch_step_events_chunked(b, 256, 1)
+        ms_k1, nl_k1 = sim.last_step_ms()
+        s1 = sim.summary()
+        recs_k1 = (s1["n_log_records"] - s0["n_log_records"]) / max(1, nl_k1)
+        lockstep = (ms_k1 / max(1, nl_k1), recs_k1, (s1["n_events"] - s0["n_events"]) / (ms_k1 * 1e-3))
+
     # ---- end to end through the public API with host buffers: build tables on the host, create the batch (H2D),
     # init + step, reduce the summary statistics (NCCL when N>1), read them and a log sample back (D2H)
     sim.close()
@@ -338,6 +354,15 @@ def run_ours(args):
             "faulted_replications": int(ev_total[2].item()),
             "per_gpu_events_per_s": value / world,
         }
+        if lockstep is not None:
+            ms1, recs1, evps1 = lockstep
+            alg1 = 2.0 * state_bytes * reps_gpu + (32.0 * recs1 if log_cap else 0.0)
+            out["roofline"]["lockstep_K1"] = {
+                "events_per_residency_K": 1, "kernel_ms": ms1, "algorithmic_bytes_per_launch": alg1,
+                "achieved": alg1 / (ms1 * 1e-3) / 1e9, "frac": alg1 / (ms1 * 1e-3) / 1e9 / peak,
+                "events_per_s_this_gpu": evps1,
+                "note": "same kernel, 256 launches of one event each on the resident batch: the operating point where "
+                        "the state planes cross HBM for every event (the bench itself runs K = events per step)"}
         if not args.no_cpu_baseline and world == 1:
             out["cpu_baseline"] = cpu_baseline(model, n_events, log_cap != 0)
         emit(out)
@@ -368,6 +393,7 @@ def main():
     ap.add_argument("--per-launch-timing", action="store_true")
     ap.add_argument("--lib", default=None, help="path of an alternative build of libquokka_b200.so (A/B experiments)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-lockstep-probe", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         sys.stderr.write("bench.py: note: the timing rules ask for >= 3 warm-up steps\n")
