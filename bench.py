@@ -287,6 +287,16 @@ def run_ours(args):
     del sim
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
     h2d = d2h = 0
+    # untimed warm-up of the end-to-end path on a small batch: the first call of the reduction loads torch / NCCL kernels
+    # (0.1 s once per process), which is not part of a step
+    w = model.sim(args.lib, 4096, t0=0, base_seed=1, rep_offset=rank * 4096, log_capacity=log_cap,
+                  stream=stream.cuda_stream, device=local_rank, flags=1 if args.state == "hbm" else 0)
+    w.step_events(16)
+    parallel.allreduce_summary(w, device)
+    w.summary()
+    if log_cap:
+        w.read_log(0)
+    w.close()
     done_sims = []
     barrier()
     t0 = time.perf_counter()
