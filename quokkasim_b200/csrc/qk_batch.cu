@@ -320,6 +320,19 @@ static cudaError_t fetch(const uint64_t* plane, uint64_t rep_pad, uint32_t slot,
 /* ============================================ C ABI ============================================ */
 extern "C" {
 
+/* inside qk_batch_create, once `b` exists: a failed CUDA call (typically cudaMalloc on a batch that does not fit the
+ * GPU) releases what was allocated so far */
+#define CREATE_TRY(expr)                                                                         \
+  do {                                                                                           \
+    cudaError_t _e = (expr);                                                                     \
+    if (_e != cudaSuccess) {                                                                     \
+      qk_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      cudaGetLastError();                                                                        \
+      qk_batch_destroy(b);                                                                       \
+      return QK_ERR_CUDA;                                                                        \
+    }                                                                                            \
+  } while (0)
+
 int qk_batch_create(const qk_model* m, const qk_batch_config* cfg, qk_batch** out) {
   if (!m || !cfg || !out) {
     qk_set_error("qk_batch_create: NULL argument");
@@ -424,38 +437,38 @@ int qk_batch_create(const qk_model* m, const qk_batch_config* cfg, qk_batch** ou
   if (cfg->stream) {
     b->stream = (cudaStream_t)cfg->stream;
   } else {
-    CUDA_TRY(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+    CREATE_TRY(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
     b->own_stream = true;
   }
-  CUDA_TRY(cudaEventCreate(&b->ev0));
-  CUDA_TRY(cudaEventCreate(&b->ev1));
-  CUDA_TRY(cudaMalloc(&b->g64, (size_t)h.n64 * b->rep_pad * 8));
-  CUDA_TRY(cudaMalloc(&b->g32, (size_t)h.n32 * b->rep_pad * 4));
-  CUDA_TRY(cudaMalloc(&b->gs64, (size_t)h.n_comp * ST_PER_COMP * b->rep_pad * 8));
-  CUDA_TRY(cudaMalloc(&b->gs32, (size_t)h.n_comp * ST_PER_COMP * b->rep_pad * 4));
-  CUDA_TRY(cudaMalloc(&b->gc64, (size_t)(h.n64c ? h.n64c : 1) * b->rep_pad * 8));
-  CUDA_TRY(cudaMalloc(&b->gc32, (size_t)(h.n32c ? h.n32c : 1) * b->rep_pad * 4));
-  CUDA_TRY(cudaMalloc(&b->d_tables, b->table_bytes_padded));
+  CREATE_TRY(cudaEventCreate(&b->ev0));
+  CREATE_TRY(cudaEventCreate(&b->ev1));
+  CREATE_TRY(cudaMalloc(&b->g64, (size_t)h.n64 * b->rep_pad * 8));
+  CREATE_TRY(cudaMalloc(&b->g32, (size_t)h.n32 * b->rep_pad * 4));
+  CREATE_TRY(cudaMalloc(&b->gs64, (size_t)h.n_comp * ST_PER_COMP * b->rep_pad * 8));
+  CREATE_TRY(cudaMalloc(&b->gs32, (size_t)h.n_comp * ST_PER_COMP * b->rep_pad * 4));
+  CREATE_TRY(cudaMalloc(&b->gc64, (size_t)(h.n64c ? h.n64c : 1) * b->rep_pad * 8));
+  CREATE_TRY(cudaMalloc(&b->gc32, (size_t)(h.n32c ? h.n32c : 1) * b->rep_pad * 4));
+  CREATE_TRY(cudaMalloc(&b->d_tables, b->table_bytes_padded));
   {
     std::vector<uint8_t> padded(b->table_bytes_padded, 0);
     memcpy(padded.data(), b->low.blob.data(), b->low.blob.size());
-    CUDA_TRY(cudaMemcpy(b->d_tables, padded.data(), padded.size(), cudaMemcpyHostToDevice));
+    CREATE_TRY(cudaMemcpy(b->d_tables, padded.data(), padded.size(), cudaMemcpyHostToDevice));
   }
-  if (b->log) CUDA_TRY(cudaMalloc(&b->d_log, (size_t)b->rep_pad * cfg->log_capacity * 32));
+  if (b->log) CREATE_TRY(cudaMalloc(&b->d_log, (size_t)b->rep_pad * cfg->log_capacity * 32));
   b->h_tapes.assign(h.n_dist, nullptr);
   b->h_tape_len.assign(h.n_dist, 0);
-  CUDA_TRY(cudaMalloc(&b->d_tapes, sizeof(double*) * (h.n_dist ? h.n_dist : 1)));
-  CUDA_TRY(cudaMalloc(&b->d_tape_len, sizeof(uint64_t) * (h.n_dist ? h.n_dist : 1)));
-  CUDA_TRY(cudaMemset(b->d_tapes, 0, sizeof(double*) * (h.n_dist ? h.n_dist : 1)));
-  CUDA_TRY(cudaMemset(b->d_tape_len, 0, sizeof(uint64_t) * (h.n_dist ? h.n_dist : 1)));
+  CREATE_TRY(cudaMalloc(&b->d_tapes, sizeof(double*) * (h.n_dist ? h.n_dist : 1)));
+  CREATE_TRY(cudaMalloc(&b->d_tape_len, sizeof(uint64_t) * (h.n_dist ? h.n_dist : 1)));
+  CREATE_TRY(cudaMemset(b->d_tapes, 0, sizeof(double*) * (h.n_dist ? h.n_dist : 1)));
+  CREATE_TRY(cudaMemset(b->d_tape_len, 0, sizeof(uint64_t) * (h.n_dist ? h.n_dist : 1)));
   b->kernel = pick_kernel(b->log, b->hbm, b->nt, h.features);
-  CUDA_TRY(cudaFuncSetAttribute((const void*)b->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  CREATE_TRY(cudaFuncSetAttribute((const void*)b->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   b->red_blocks = 148 * 4;
-  CUDA_TRY(cudaMalloc(&b->d_sums, sizeof(uint64_t) * 6 * h.n_comp));
-  CUDA_TRY(cudaMalloc(&b->d_ext, sizeof(uint64_t) * 4 * h.n_comp));
-  CUDA_TRY(cudaMalloc(&b->d_hist, sizeof(uint64_t) * 2 * QK_HIST_BINS * h.n_comp));
-  CUDA_TRY(cudaMalloc(&b->d_sq_partial, sizeof(double) * 2 * b->red_blocks * h.n_comp));
-  CUDA_TRY(cudaMalloc(&b->d_sq, sizeof(double) * 2 * h.n_comp));
+  CREATE_TRY(cudaMalloc(&b->d_sums, sizeof(uint64_t) * 6 * h.n_comp));
+  CREATE_TRY(cudaMalloc(&b->d_ext, sizeof(uint64_t) * 4 * h.n_comp));
+  CREATE_TRY(cudaMalloc(&b->d_hist, sizeof(uint64_t) * 2 * QK_HIST_BINS * h.n_comp));
+  CREATE_TRY(cudaMalloc(&b->d_sq_partial, sizeof(double) * 2 * b->red_blocks * h.n_comp));
+  CREATE_TRY(cudaMalloc(&b->d_sq, sizeof(double) * 2 * h.n_comp));
   *out = b;
   return QK_OK;
 }

@@ -383,3 +383,22 @@ def test_c2_full_size_invariants_and_sampled_oracle_parity(gpu_lib):
         assert total == len(olog) and len(glog) == 64
         assert glog.tobytes() == olog[-64:].tobytes()
     sim.close()
+
+
+def test_batch_that_does_not_fit_fails_cleanly(gpu_lib):
+    """a batch larger than the GPU's memory: qk_batch_create reports the CUDA error, releases what it had allocated,
+    and the device is as usable as before"""
+    from quokkasim_b200 import _capi as capi
+
+    m = H.discrete_queue()
+    huge = m.sim(gpu_lib, 1 << 31, base_seed=1, log_capacity=64)  # ~ 1 TB of state + 4 TB of log rings
+    with pytest.raises(capi.QkError) as e:
+        huge.step_events(1)
+    assert e.value.status == -5 and "cudaMalloc" in e.value.detail
+    for _ in range(3):  # repeated failures do not eat memory either
+        with pytest.raises(capi.QkError):
+            H.discrete_queue().sim(gpu_lib, 1 << 31, log_capacity=64).step_events(1)
+    ok = H.discrete_queue().sim(gpu_lib, 1 << 20, base_seed=1, log_capacity=64)
+    ok.step_events(100)
+    assert ok.summary()["n_events"] == 100 << 20
+    ok.close()
