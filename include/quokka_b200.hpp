@@ -1,0 +1,623 @@
+/*
+ * quokka_b200.hpp -- C++ host side above the C ABI (include/quokka_b200.h): the model-builder surface of
+ * jajetloh/quokkasim v0.2.2 for the DISCRETE family and BasicEnvironment, restated as plain descriptions that are
+ * lowered to C-ABI rows.  Header only, C++17, no dependencies beyond the C header.
+ *
+ * The reference is Rust; there is no Rust toolchain in the build image, so this is the compiled-language host mirror
+ * of its operator interface (same names, argument meaning and error behaviour), next to the Python mirror
+ * (quokkasim_b200/api.py, which also covers the continuous and container families) and the source-only Rust shim.
+ *
+ *   reference (paths relative to /root/reference/quokkasim/src)                   here (namespace quokka)
+ *   ------------------------------------------------------------------------     -------------------------------------
+ *   DistributionConfig / DistributionFactory::create      common.rs:37-148       DistributionConfig / DistributionFactory
+ *   #[derive(WithMethods)] builders  quokkasim_derive_macros/src/lib.rs:22-94    .with_name() .with_code() ... (by value)
+ *   DiscreteStock / Process / Source / Sink / ParallelProcess  components/discrete.rs   DiscreteStock::new_() ...
+ *   ComponentModel::StringStock(c, Mailbox::new()) ...    core.rs:505-557        ComponentModel::StringStock(c, Mailbox::new_())
+ *   connect_components!(&mut a, &mut b)                   core.rs:565-1178       connect_components(a, b)  (throws the Err text)
+ *   connect_logger!(&mut logger, &mut c)                  core.rs:1303-1338      connect_logger(logger, c)
+ *   register_component!(sim_init, c)                      core.rs:1424-1428      sim_init = register_component(sim_init, c)
+ *   create_scheduled_event!(.., SetEnvironmentState, ..)  core.rs:1377-1401      create_scheduled_event(sim, t, cfg, addr)
+ *   sim_init.init(t0) / simu.step_until(t)                discrete_queue.rs:109-111   BatchedSimInit::init / step_until
+ *   logger.write_csv(dir)                                 core.rs:388-401        logger.write_csv(dir, sim, replication)
+ *
+ * All simulation work happens in libquokka_b200.so on the GPU; nothing here can advance a replication.
+ */
+#ifndef QUOKKA_B200_HPP
+#define QUOKKA_B200_HPP
+
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <ctime>
+#include <fstream>
+#include <memory>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "quokka_b200.h"
+
+namespace quokka {
+
+/* ---- errors: the reference's `Box<dyn Error>` strings ---------------------------------------------------------- */
+struct Error : std::runtime_error {
+  int status;
+  Error(const std::string& msg, int st) : std::runtime_error(msg), status(st) {}
+};
+inline void check(int rc) {
+  if (rc != QK_OK) throw Error(qk_last_error(), rc);
+}
+
+/* ---- time ------------------------------------------------------------------------------------------------------- */
+struct Duration {
+  static uint64_t from_secs(uint64_t s) { return s * 1000000000ull; }
+  static uint64_t from_millis(uint64_t ms) { return ms * 1000000ull; }
+  static uint64_t from_nanos(uint64_t ns) { return ns; }
+};
+struct MonotonicTime {
+  static constexpr uint64_t EPOCH = 0; /* absolute ns since the TAI epoch */
+};
+
+/* ---- distributions (common.rs:25-148) --------------------------------------------------------------------------- */
+struct Distribution {
+  qk_dist_desc desc;
+  std::shared_ptr<int> identity; /* components that share one Distribution value share its variate tape */
+  static Distribution Constant(double v) {
+    Distribution d;
+    std::memset(&d.desc, 0, sizeof(d.desc));
+    d.desc.kind = QK_DIST_CONSTANT;
+    d.desc.p[0] = v;
+    d.identity = std::make_shared<int>(0);
+    return d;
+  }
+  static Distribution default_() { return Constant(1.0); } /* common.rs:181-185 */
+};
+
+struct DistributionConfig {
+  uint32_t kind;
+  double p[4];
+  static DistributionConfig make(uint32_t k, double a = 0, double b = 0, double c = 0, double d = 0) {
+    DistributionConfig x;
+    x.kind = k;
+    x.p[0] = a, x.p[1] = b, x.p[2] = c, x.p[3] = d;
+    return x;
+  }
+  static DistributionConfig Uniform(double min, double max) { return make(QK_DIST_UNIFORM, min, max); }
+  static DistributionConfig Triangular(double min, double max, double mode) { return make(QK_DIST_TRIANGULAR, min, max, mode); }
+  static DistributionConfig Constant(double v) { return make(QK_DIST_CONSTANT, v); }
+  static DistributionConfig Normal(double mean, double std) { return make(QK_DIST_NORMAL, mean, std); }
+  static DistributionConfig Exponential(double mean) { return make(QK_DIST_EXPONENTIAL, mean); }
+};
+
+/* Seeds increment per created distribution, EXCEPT that the Normal / TruncNormal / Exponential arms of the reference
+ * return early and skip the increment (common.rs:98,121,134 vs :145): reproduced, the stream id decides which
+ * instances share a variate sequence. */
+struct DistributionFactory {
+  uint64_t base_seed, next_seed;
+  explicit DistributionFactory(uint64_t seed) : base_seed(seed), next_seed(seed) {}
+  Distribution create(const DistributionConfig& c) {
+    if (c.kind == QK_DIST_CONSTANT) {
+      next_seed += 1;
+      return Distribution::Constant(c.p[0]);
+    }
+    if (c.kind == QK_DIST_TRIANGULAR && (!(c.p[1] >= c.p[2] && c.p[2] >= c.p[0]) || !(c.p[1] > c.p[0])))
+      throw Error("invalid Triangular parameters", QK_ERR_INVALID_ARG);
+    if (c.kind == QK_DIST_EXPONENTIAL && !(c.p[0] > 0)) throw Error("invalid Exponential parameters", QK_ERR_INVALID_ARG);
+    Distribution d;
+    std::memset(&d.desc, 0, sizeof(d.desc));
+    d.desc.kind = c.kind;
+    d.desc.stream = (uint32_t)next_seed;
+    for (int i = 0; i < 4; ++i) d.desc.p[i] = c.p[i];
+    d.identity = std::make_shared<int>(0);
+    if (c.kind == QK_DIST_UNIFORM || c.kind == QK_DIST_TRIANGULAR) next_seed += 1;
+    return d;
+  }
+};
+
+struct DelayMode {
+  std::string name;
+  Distribution until_delay_distr, until_fix_distr;
+};
+
+/* discrete.rs:664-686: items are "{prefix}_{index:0>num_digits}" */
+struct StringItemFactory {
+  std::string prefix = "Item";
+  uint64_t next_index = 0;
+  size_t num_digits = 4;
+  std::string item_name(uint64_t index) const {
+    std::string n = std::to_string(next_index + index);
+    if (n.size() < num_digits) n = std::string(num_digits - n.size(), '0') + n;
+    return prefix + "_" + n;
+  }
+};
+
+enum class BasicEnvironmentState { Normal = 0, Stopped = 1 };
+
+/* ---- components: every component is one row -------------------------------------------------------------------- */
+struct ComponentData {
+  uint32_t kind = 0;
+  std::string element_name, element_code, element_type;
+  uint32_t low_capacity = 0, max_capacity = 1; /* discrete.rs:70-71 */
+  std::vector<std::string> resource;            /* ItemDeque<String> */
+  Distribution process_time_distr = Distribution::default_();
+  std::vector<DelayMode> delay_modes;
+  StringItemFactory item_factory;
+  BasicEnvironmentState state = BasicEnvironmentState::Normal;
+  int id = -1;
+  bool logged = false;
+};
+
+class Component {
+ public:
+  std::shared_ptr<ComponentData> d;
+  Component(uint32_t kind, const char* type_name) : d(std::make_shared<ComponentData>()) {
+    d->kind = kind;
+    d->element_name = type_name;
+    d->element_type = type_name;
+  }
+  Component with_name(const std::string& v) { d->element_name = v; return *this; }
+  Component with_code(const std::string& v) { d->element_code = v; return *this; }
+  Component with_type(const std::string& v) { d->element_type = v; return *this; }
+  Component with_low_capacity(uint32_t v) { d->low_capacity = v; return *this; }
+  Component with_max_capacity(uint32_t v) { d->max_capacity = v; return *this; }
+  Component with_initial_resource(std::vector<std::string> items) { d->resource = std::move(items); return *this; }
+  Component with_process_time_distr(const Distribution& x) { d->process_time_distr = x; return *this; }
+  Component with_item_factory(const StringItemFactory& f) { d->item_factory = f; return *this; }
+  Component with_state(BasicEnvironmentState s) { d->state = s; return *this; }
+  /* DelayModes::modify(Add) (delays.rs:157-164): an existing name keeps its position */
+  Component with_delay_mode(const DelayMode& m) {
+    for (auto& x : d->delay_modes)
+      if (x.name == m.name) {
+        x = m;
+        return *this;
+      }
+    d->delay_modes.push_back(m);
+    return *this;
+  }
+};
+
+#define QUOKKA_COMPONENT_TYPE(Name, Kind) \
+  struct Name {                           \
+    static Component new_() { return Component(Kind, #Name); } \
+  };
+QUOKKA_COMPONENT_TYPE(DiscreteStock, QK_DISCRETE_STOCK)
+QUOKKA_COMPONENT_TYPE(DiscreteProcess, QK_DISCRETE_PROCESS)
+QUOKKA_COMPONENT_TYPE(DiscreteSource, QK_DISCRETE_SOURCE)
+QUOKKA_COMPONENT_TYPE(DiscreteSink, QK_DISCRETE_SINK)
+QUOKKA_COMPONENT_TYPE(DiscreteParallelProcess, QK_DISCRETE_PARALLEL_PROCESS)
+#undef QUOKKA_COMPONENT_TYPE
+struct BasicEnvironment {
+  static Component new_() {
+    Component c(QK_ENVIRONMENT, "BasicEnvironment");
+    c.d->element_name.clear();
+    return c;
+  }
+};
+
+/* kept so that `ComponentModel::StringStock(component, Mailbox::new_())` reads like the reference; inert */
+struct Mailbox {
+  static Mailbox new_() { return Mailbox(); }
+};
+
+struct Connection {
+  std::shared_ptr<ComponentData> a, b;
+  int n;
+  uint64_t stamp;
+};
+inline uint64_t& connection_stamp() {
+  static uint64_t s = 0;
+  return s;
+}
+
+/* the generated enum of core.rs:504-562 (discrete family + BasicEnvironment) */
+class ComponentModel {
+ public:
+  std::string variant;
+  Component component;
+  std::shared_ptr<std::vector<Connection>> conns = std::make_shared<std::vector<Connection>>();
+  ComponentModel(std::string v, Component c) : variant(std::move(v)), component(std::move(c)) {}
+#define QUOKKA_VARIANT(Name, Kind)                                                          \
+  static ComponentModel Name(Component c, Mailbox) {                                         \
+    if (c.d->kind != Kind) throw Error("ComponentModel::" #Name " expects another component type", QK_ERR_INVALID_ARG); \
+    return ComponentModel(#Name, std::move(c));                                              \
+  }
+  QUOKKA_VARIANT(StringStock, QK_DISCRETE_STOCK)
+  QUOKKA_VARIANT(StringProcess, QK_DISCRETE_PROCESS)
+  QUOKKA_VARIANT(StringParallelProcess, QK_DISCRETE_PARALLEL_PROCESS)
+  QUOKKA_VARIANT(StringSource, QK_DISCRETE_SOURCE)
+  QUOKKA_VARIANT(StringSink, QK_DISCRETE_SINK)
+  QUOKKA_VARIANT(BasicEnvironment, QK_ENVIRONMENT)
+#undef QUOKKA_VARIANT
+};
+
+/* connect_components!(&mut a, &mut b[, n]) (core.rs:565-1178; discrete arms :886-921, environment arms :1129-1148):
+ * an undefined pair is the reference's Err("No component connection defined from {} to {} (n={:?})") */
+inline void connect_components(ComponentModel& a, ComponentModel& b, int n = -1) {
+  const std::string &va = a.variant, &vb = b.variant;
+  auto in = [](const std::string& v, std::initializer_list<const char*> l) {
+    for (auto x : l)
+      if (v == x) return true;
+    return false;
+  };
+  const bool ok = (va == "StringStock" && in(vb, {"StringProcess", "StringParallelProcess", "StringSink"})) ||
+                  (vb == "StringStock" && in(va, {"StringProcess", "StringParallelProcess", "StringSource"})) ||
+                  (va == "BasicEnvironment" && in(vb, {"StringProcess", "StringParallelProcess", "StringSource", "StringSink"}));
+  if (!ok)
+    throw Error("No component connection defined from " + va + " to " + vb + " (n=" +
+                    (n < 0 ? std::string("None") : "Some(" + std::to_string(n) + ")") + ")",
+                QK_ERR_UNSUPPORTED_CONNECTION);
+  a.conns->push_back(Connection{a.component.d, b.component.d, n, connection_stamp()++});
+}
+
+/* ---- loggers (core.rs:1216-1365) --------------------------------------------------------------------------------- */
+class BatchedSimulation;
+class ComponentLogger {
+ public:
+  std::string variant, name;
+  std::vector<std::shared_ptr<ComponentData>> components;
+  ComponentLogger(std::string v, std::string n) : variant(std::move(v)), name(std::move(n)) {}
+  static ComponentLogger StringStockLogger(const std::string& name) { return ComponentLogger("StringStockLogger", name); }
+  static ComponentLogger StringProcessLogger(const std::string& name) { return ComponentLogger("StringProcessLogger", name); }
+  static ComponentLogger BasicEnvironmentLogger(const std::string& name) { return ComponentLogger("BasicEnvironmentLogger", name); }
+  /* the CSV text Logger::write_csv (core.rs:388-401) produces for one replication */
+  std::string csv_text(BatchedSimulation& sim, uint64_t replication = 0) const;
+  std::string write_csv(const std::string& dir, BatchedSimulation& sim, uint64_t replication = 0) const {
+    const std::string path = dir + "/" + name + ".csv";
+    std::ofstream f(path, std::ios::binary);
+    f << csv_text(sim, replication);
+    return path;
+  }
+};
+
+inline void connect_logger(ComponentLogger& logger, ComponentModel& c) {
+  const std::string& v = c.variant;
+  const bool ok = (logger.variant == "StringStockLogger" && v == "StringStock") ||
+                  (logger.variant == "StringProcessLogger" &&
+                   (v == "StringProcess" || v == "StringParallelProcess" || v == "StringSource" || v == "StringSink")) ||
+                  (logger.variant == "BasicEnvironmentLogger" && v == "BasicEnvironment");
+  if (!ok)
+    throw Error("No logger connection defined from " + logger.variant + " to " + v + " (n=None)",
+                QK_ERR_UNSUPPORTED_CONNECTION);
+  logger.components.push_back(c.component.d);
+  c.component.d->logged = true;
+}
+
+/* ---- scheduled events (core.rs:1367-1401) ------------------------------------------------------------------------ */
+struct ScheduledEventConfig {
+  std::string kind;
+  int value;
+  static ScheduledEventConfig SetEnvironmentState(BasicEnvironmentState s) { return ScheduledEventConfig{"SetEnvironmentState", (int)s}; }
+};
+
+/* ---- SimInit / Simulation ----------------------------------------------------------------------------------------- */
+struct BatchOptions {
+  uint64_t n_replications = 1, base_seed = 0, rep_offset = 0;
+  int device = 0;
+  uint32_t log_capacity = 0, threads_per_block = 0, flags = 0;
+};
+
+class BatchedSimulation {
+ public:
+  std::vector<ComponentModel> components;
+  uint64_t t0;
+  BatchOptions opt;
+
+  BatchedSimulation(std::vector<ComponentModel> comps, uint64_t t0_ns, const BatchOptions& o)
+      : components(std::move(comps)), t0(t0_ns), opt(o) {
+    for (size_t i = 0; i < components.size(); ++i) {
+      auto& d = *components[i].component.d;
+      if (d.id >= 0 && d.id != (int)i) throw Error("component " + d.element_name + " registered twice", QK_ERR_INVALID_ARG);
+      d.id = (int)i;
+    }
+  }
+  BatchedSimulation(const BatchedSimulation&) = delete;
+  BatchedSimulation& operator=(const BatchedSimulation&) = delete;
+  BatchedSimulation(BatchedSimulation&& o) noexcept
+      : components(std::move(o.components)), t0(o.t0), opt(o.opt), model_(o.model_), batch_(o.batch_), ext_(std::move(o.ext_)),
+        tapes_(std::move(o.tapes_)), dist_ids_(std::move(o.dist_ids_)) {
+    o.model_ = nullptr;
+    o.batch_ = nullptr;
+  }
+  ~BatchedSimulation() {
+    if (batch_) qk_batch_destroy(batch_);
+    if (model_) qk_model_destroy(model_);
+  }
+
+  /* create_scheduled_event!(&mut sched, &time, &cfg, &addr, &mut df): only before the first step */
+  void schedule_env_state(uint64_t t_ns, const ComponentModel& env, BasicEnvironmentState s) {
+    if (batch_) throw Error("scheduled events must be created before the first step of a BatchedSimulation", QK_ERR_STATE);
+    if (env.variant != "BasicEnvironment")
+      throw Error("schedule_event not implemented for types (SetEnvironmentState, " + env.variant + ")", QK_ERR_INVALID_ARG);
+    ext_.push_back({t_ns, env.component.d, (uint32_t)s});
+  }
+  /* pre-drawn variate tape of one Distribution instance: values[replication * len + i] (parity mode) */
+  void set_tape(const Distribution& dist, const std::vector<double>& values, uint64_t per_rep_len) {
+    if (batch_) throw Error("set_tape must be called before the first step", QK_ERR_STATE);
+    if (values.size() != per_rep_len * opt.n_replications) throw Error("tape must hold n_replications * len values", QK_ERR_INVALID_ARG);
+    tapes_.push_back({dist.identity.get(), values, per_rep_len});
+  }
+  void step_until(uint64_t t_ns) {
+    materialize();
+    check(qk_batch_step_until(batch_, t_ns));
+  }
+  void step_events(uint64_t n) {
+    materialize();
+    check(qk_batch_step_events(batch_, n));
+  }
+  qk_batch_summary summary() {
+    materialize();
+    qk_batch_summary s;
+    check(qk_batch_summary_get(batch_, &s));
+    return s;
+  }
+  std::vector<qk_comp_stats> comp_stats(const ComponentModel& c, uint64_t rep0, uint64_t n) {
+    materialize();
+    std::vector<qk_comp_stats> out(n);
+    check(qk_batch_comp_stats(batch_, rep0, n, (uint32_t)c.component.d->id, out.data()));
+    return out;
+  }
+  /* records of one replication, oldest first; *total = records ever written */
+  std::vector<qk_log_record> read_log(uint64_t rep, uint64_t* total = nullptr) {
+    materialize();
+    uint64_t n = 0, tot = 0;
+    check(qk_batch_read_log(batch_, rep, nullptr, 0, &n, &tot));
+    const uint64_t kept = tot < opt.log_capacity ? tot : opt.log_capacity;
+    std::vector<qk_log_record> buf(kept);
+    if (kept) check(qk_batch_read_log(batch_, rep, buf.data(), kept, &n, &tot));
+    if (total) *total = tot;
+    return buf;
+  }
+  qk_batch* handle() {
+    materialize();
+    return batch_;
+  }
+
+ private:
+  struct Ext {
+    uint64_t t;
+    std::shared_ptr<ComponentData> env;
+    uint32_t state;
+  };
+  struct Tape {
+    const int* identity;
+    std::vector<double> values;
+    uint64_t len;
+  };
+  qk_model* model_ = nullptr;
+  qk_batch* batch_ = nullptr;
+  std::vector<Ext> ext_;
+  std::vector<Tape> tapes_;
+  std::vector<std::pair<const int*, uint32_t>> dist_ids_;
+
+  /* component objects -> C-ABI rows; the batch is created lazily so that scheduled events created after init()
+   * (assembly_line.rs:240-246) still land in the model tables */
+  void materialize() {
+    if (batch_) return;
+    check(qk_model_create(&model_));
+    for (auto& cm : components) {
+      auto& c = *cm.component.d;
+      qk_component_desc d;
+      std::memset(&d, 0, sizeof(d));
+      d.kind = c.kind;
+      d.low_capacity = c.low_capacity;
+      d.max_capacity = c.max_capacity;
+      d.n_initial_items = c.kind == QK_DISCRETE_STOCK ? (uint32_t)c.resource.size() : 0;
+      d.initial_env_state = (uint32_t)c.state;
+      uint32_t id = 0;
+      check(qk_model_add_component(model_, &d, &id));
+      if (c.kind >= QK_DISCRETE_PROCESS && c.kind <= QK_DISCRETE_PARALLEL_PROCESS) {
+        uint32_t did = 0;
+        check(qk_model_set_dist(model_, id, 0, &c.process_time_distr.desc, &did));
+        dist_ids_.push_back({c.process_time_distr.identity.get(), did});
+        for (auto& m : c.delay_modes) {
+          uint32_t a = 0, b = 0;
+          check(qk_model_add_delay_mode(model_, id, &m.until_delay_distr.desc, &m.until_fix_distr.desc, &a, &b));
+          dist_ids_.push_back({m.until_delay_distr.identity.get(), a});
+          dist_ids_.push_back({m.until_fix_distr.identity.get(), b});
+        }
+      }
+      if (c.logged) check(qk_model_set_logged(model_, id, 1));
+    }
+    /* connections in the order connect_components! was called: subscriber order is broadcast order */
+    std::vector<Connection> all;
+    for (auto& cm : components) all.insert(all.end(), cm.conns->begin(), cm.conns->end());
+    for (size_t i = 1; i < all.size(); ++i)
+      for (size_t j = i; j > 0 && all[j].stamp < all[j - 1].stamp; --j) std::swap(all[j], all[j - 1]);
+    for (auto& k : all) {
+      if (k.a->id < 0 || k.b->id < 0) throw Error("connect_components involves a component that was never registered", QK_ERR_INVALID_ARG);
+      check(qk_model_connect(model_, (uint32_t)k.a->id, (uint32_t)k.b->id, k.n));
+    }
+    for (auto& e : ext_) check(qk_model_schedule_env_state(model_, e.t, (uint32_t)e.env->id, e.state));
+    qk_batch_config cfg;
+    std::memset(&cfg, 0, sizeof(cfg));
+    cfg.n_reps = opt.n_replications;
+    cfg.rep_offset = opt.rep_offset;
+    cfg.base_seed = opt.base_seed;
+    cfg.device = opt.device;
+    cfg.log_capacity = opt.log_capacity;
+    cfg.threads_per_block = opt.threads_per_block;
+    cfg.flags = opt.flags;
+    check(qk_batch_create(model_, &cfg, &batch_));
+    for (auto& t : tapes_)
+      for (auto& di : dist_ids_)
+        if (di.first == t.identity) check(qk_batch_set_tape(batch_, di.second, t.values.data(), t.len));
+    check(qk_batch_init(batch_, t0));
+  }
+};
+
+/* stands where nexosim::SimInit stands in the examples */
+class BatchedSimInit {
+ public:
+  std::vector<ComponentModel> components;
+  static BatchedSimInit new_() { return BatchedSimInit(); }
+  /* returns the simulation, like SimInit::init returns (Simulation, Scheduler) */
+  BatchedSimulation init(uint64_t t0_ns, const BatchOptions& opt = BatchOptions()) { return BatchedSimulation(components, t0_ns, opt); }
+};
+/* register_component!(sim_init, c): registration order = component id = scheduler origin rank - 1 */
+inline BatchedSimInit register_component(BatchedSimInit s, const ComponentModel& c) {
+  s.components.push_back(c);
+  return s;
+}
+inline void create_scheduled_event(BatchedSimulation& sim, uint64_t t_ns, const ScheduledEventConfig& cfg, const ComponentModel& addr) {
+  if (cfg.kind != "SetEnvironmentState")
+    throw Error("schedule_event not implemented for types (" + cfg.kind + ", " + addr.variant + ")", QK_ERR_INVALID_ARG);
+  sim.schedule_env_state(t_ns, addr, (BasicEnvironmentState)cfg.value);
+}
+
+/* ---- CSV (discrete.rs:295-318, 608-633; core.rs:306-325) ---------------------------------------------------------- */
+namespace detail {
+inline std::string two(int v) {
+  char b[8];
+  std::snprintf(b, sizeof(b), "%02d", v);
+  return b;
+}
+inline std::string date_time(uint64_t t_ns, uint32_t* nanos) {
+  const uint64_t secs = t_ns / 1000000000ull;
+  *nanos = (uint32_t)(t_ns % 1000000000ull);
+  /* civil-from-days (proleptic Gregorian), days since 1970-01-01 */
+  int64_t z = (int64_t)(secs / 86400) + 719468;
+  const int64_t era = z / 146097;
+  const unsigned doe = (unsigned)(z - era * 146097);
+  const unsigned yoe = (doe - doe / 1460 + doe / 36524 - doe / 146096) / 365;
+  int64_t y = (int64_t)yoe + era * 400;
+  const unsigned doy = doe - (365 * yoe + yoe / 4 - yoe / 100);
+  const unsigned mp = (5 * doy + 2) / 153;
+  const unsigned d = doy - (153 * mp + 2) / 5 + 1;
+  const unsigned m = mp < 10 ? mp + 3 : mp - 9;
+  if (m <= 2) y += 1;
+  const unsigned sod = (unsigned)(secs % 86400);
+  char b[64];
+  std::snprintf(b, sizeof(b), "%04lld-%02u-%02u %02u:%02u:%02u", (long long)y, m, d, sod / 3600, (sod / 60) % 60, sod % 60);
+  return b;
+}
+/* MonotonicTime::to_chrono_date_time(0).unwrap().to_string(): "%Y-%m-%d %H:%M:%S%.f UTC" with 0/3/6/9 digits */
+inline std::string chrono_utc(uint64_t t_ns) {
+  uint32_t nanos;
+  std::string s = date_time(t_ns, &nanos);
+  char b[16];
+  if (nanos) {
+    if (nanos % 1000000 == 0) std::snprintf(b, sizeof(b), ".%03u", nanos / 1000000);
+    else if (nanos % 1000 == 0) std::snprintf(b, sizeof(b), ".%06u", nanos / 1000);
+    else std::snprintf(b, sizeof(b), ".%09u", nanos);
+    s += b;
+  }
+  return s + " UTC";
+}
+/* tai-time's own Display (core.rs:277) */
+inline std::string tai_display(uint64_t t_ns) {
+  uint32_t nanos;
+  std::string s = date_time(t_ns, &nanos);
+  if (nanos) {
+    char b[16];
+    std::snprintf(b, sizeof(b), ".%09u", nanos);
+    s += b;
+  }
+  return s;
+}
+inline std::string csv_field(const std::string& s) {
+  if (s.find_first_of(",\"\r\n") == std::string::npos) return s;
+  std::string o = "\"";
+  for (char ch : s) {
+    if (ch == '"') o += '"';
+    o += ch;
+  }
+  return o + "\"";
+}
+inline std::string json_string(const std::string& s) {
+  std::string o = "\"";
+  for (char ch : s) {
+    if (ch == '"') o += "\\\"";
+    else if (ch == '\\') o += "\\\\";
+    else if (ch == '\n') o += "\\n";
+    else if (ch == '\r') o += "\\r";
+    else if (ch == '\t') o += "\\t";
+    else o += ch;
+  }
+  return o + "\"";
+}
+inline const char* reason_text(uint32_t r) {
+  static const char* T[] = {"", "Upstream is empty", "Upstream is not connected", "Downstream is full", "Downstream is not connected",
+                            "Upstream did not provide resource", "Stopped by environment", "Resumed by environment", "Upstream is full"};
+  return r < sizeof(T) / sizeof(T[0]) ? T[r] : "";
+}
+}  // namespace detail
+
+inline std::string ComponentLogger::csv_text(BatchedSimulation& sim, uint64_t replication) const {
+  uint64_t total = 0;
+  const std::vector<qk_log_record> recs = sim.read_log(replication, &total);
+  if (total > recs.size()) throw Error("log ring kept fewer records than were written: raise log_capacity for CSV export", QK_ERR_BUFFER_TOO_SMALL);
+  std::vector<std::shared_ptr<ComponentData>> by_id;
+  std::vector<const ComponentData*> sources;
+  std::vector<std::string> initial_items;
+  for (auto& cm : sim.components) {
+    by_id.push_back(cm.component.d);
+    if (cm.component.d->kind == QK_DISCRETE_SOURCE) sources.push_back(cm.component.d.get());
+    if (cm.component.d->kind == QK_DISCRETE_STOCK)
+      initial_items.insert(initial_items.end(), cm.component.d->resource.begin(), cm.component.d->resource.end());
+  }
+  auto event_id = [&](uint32_t comp, uint32_t seq) -> std::string {
+    if (comp == QK_SRC_INIT) return "INIT_000000";
+    if (comp == QK_SRC_SCH) return "SCH_000000";
+    char b[16];
+    std::snprintf(b, sizeof(b), "_%06u", seq);
+    return by_id[comp]->element_code + b;
+  };
+  auto item_name = [&](uint64_t h) -> std::string {
+    const uint32_t ord = QK_ITEM_SOURCE(h), idx = QK_ITEM_INDEX(h);
+    return ord == 63 ? initial_items[idx] : sources[ord]->item_factory.item_name(idx);
+  };
+  auto member = [&](uint32_t comp) {
+    for (auto& c : components)
+      if (c.get() == by_id[comp].get()) return true;
+    return false;
+  };
+  std::ostringstream out;
+  bool any = false;
+  const bool env_logger = variant == "BasicEnvironmentLogger";
+  for (const qk_log_record& r : recs) {
+    if (r.kind == QK_LOG_VEC_DATA || !member(r.comp)) continue;
+    const ComponentData& c = *by_id[r.comp];
+    if (!any) {
+      any = true; /* csv::Writer writes the header with the first record: an empty log is an empty file */
+      if (env_logger) out << "time,event_id,source_event_id,element_name,element_type,event\n";
+      else if (variant == "StringStockLogger") out << "time,event_id,source_event_id,element_name,element_type,log_type,item,reason\n";
+      else out << "time,event_id,source_event_id,element_name,element_type,event_type,item,reason\n";
+    }
+    std::string type, item, reason;
+    switch (r.kind) {
+      case QK_LOG_ENV_STATE:
+        out << detail::tai_display(r.time_ns) << ',' << event_id(r.comp, r.seq) << ',' << event_id(r.src_comp, r.src_seq) << ','
+            << detail::csv_field(c.element_name) << ",BasicEnvironment," << (r.reason == 1 ? "Stopped" : "Normal") << '\n';
+        continue;
+      case QK_LOG_STOCK_ADD: type = "Add", item = detail::json_string(item_name(r.payload)); break;
+      case QK_LOG_STOCK_REMOVE:
+        type = "Remove", item = r.payload == QK_ITEM_NONE ? "null" : detail::json_string(item_name(r.payload));
+        break;
+      case QK_LOG_STOCK_STATE_CHANGE: {
+        static const char* S[] = {"Empty", "Normal", "Full"};
+        type = "StateChange";
+        item = std::string("{\"") + S[r.reason] + "\":{\"occupied\":" + std::to_string(r.payload >> 32) +
+               ",\"empty\":" + std::to_string(r.payload & 0xFFFFFFFFull) + "}}";
+        break;
+      }
+      case QK_LOG_PROCESS_START: type = "ProcessStart", item = detail::json_string(item_name(r.payload)); break;
+      case QK_LOG_PROCESS_FINISH: type = "ProcessFinish", item = detail::json_string(item_name(r.payload)); break;
+      case QK_LOG_DELAY_START: type = "DelayStart", item = c.delay_modes[r.payload].name; break;
+      case QK_LOG_DELAY_END: type = "DelayEnd", item = c.delay_modes[r.payload].name; break;
+      case QK_LOG_PROCESS_CONTINUE: type = "ProcessContinue", reason = detail::reason_text(r.reason); break;
+      case QK_LOG_PROCESS_NONSTART: type = "ProcessNonStart", reason = detail::reason_text(r.reason); break;
+      case QK_LOG_PROCESS_STOPPED: type = "ProcessStopped", reason = detail::reason_text(r.reason); break;
+      case QK_LOG_WITHDRAW_REQUEST: type = "WithdrawRequest"; break;
+      default: continue;
+    }
+    out << detail::chrono_utc(r.time_ns) << ',' << event_id(r.comp, r.seq) << ',' << event_id(r.src_comp, r.src_seq) << ','
+        << detail::csv_field(c.element_name) << ',' << detail::csv_field(c.element_type) << ',' << type << ','
+        << detail::csv_field(item) << ',' << detail::csv_field(reason) << '\n';
+  }
+  return out.str();
+}
+
+}  // namespace quokka
+#endif /* QUOKKA_B200_HPP */
