@@ -150,3 +150,36 @@ def test_delay_mode_builder_follows_indexmap_semantics():
     assert [m.name for m in p.delay_modes] == ["B"]
     p.with_delay_mode(qk.DelayModeChange.RemoveAll())
     assert p.delay_modes == []
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """include/quokka_b200.h is a C header (extern "C", plain pointers and sizes): a strict C99 translation unit
+    compiles against it, links the product library and drives the model half of the ABI (no GPU needed)."""
+    import os
+    import subprocess
+
+    from quokkasim_b200 import _capi
+
+    src = tmp_path / "abi.c"
+    src.write_text(r'''
+#include "quokka_b200.h"
+#include <stdio.h>
+int main(void) {
+  qk_model* m = 0;
+  qk_component_desc d = {QK_DISCRETE_STOCK, 0, 3, 0, 0, 0};
+  unsigned id = 99;
+  if (qk_model_create(&m)) return 1;
+  if (qk_model_add_component(m, &d, &id)) return 2;
+  if (qk_model_connect(m, 0, 0, -1) != QK_ERR_UNSUPPORTED_CONNECTION) return 3;
+  printf("%d %u %s\n", qk_abi_version(), id, qk_last_error());
+  qk_model_destroy(m);
+  return 0;
+}
+''')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir, libname = os.path.dirname(_capi.DEFAULT_LIB), os.path.basename(_capi.DEFAULT_LIB)
+    exe = str(tmp_path / "abi")
+    subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I" + os.path.join(root, "include"),
+                           str(src), "-o", exe, "-L" + libdir, "-l:" + libname, "-Wl,-rpath," + libdir])
+    out = subprocess.check_output([exe], text=True)
+    assert out.strip() == "1 0 No component connection defined from StringStock to StringStock (n=None)"
