@@ -1,17 +1,21 @@
 /*
  * quokka_b200.hpp -- C++ host side above the C ABI (include/quokka_b200.h): the model-builder surface of
- * jajetloh/quokkasim v0.2.2 for the DISCRETE family and BasicEnvironment, restated as plain descriptions that are
- * lowered to C-ABI rows.  Header only, C++17, no dependencies beyond the C header.
+ * jajetloh/quokkasim v0.2.2 -- the discrete family, the continuous (vector) family, the container family and
+ * BasicEnvironment -- restated as plain descriptions that are lowered to C-ABI rows.  Header only, C++17, no
+ * dependencies beyond the C header.  (CSV export covers the discrete loggers; the Python mirror has all of them.)
  *
  * The reference is Rust; there is no Rust toolchain in the build image, so this is the compiled-language host mirror
  * of its operator interface (same names, argument meaning and error behaviour), next to the Python mirror
- * (quokkasim_b200/api.py, which also covers the continuous and container families) and the source-only Rust shim.
+ * (quokkasim_b200/api.py) and the source-only Rust shim.
  *
  *   reference (paths relative to /root/reference/quokkasim/src)                   here (namespace quokka)
  *   ------------------------------------------------------------------------     -------------------------------------
  *   DistributionConfig / DistributionFactory::create      common.rs:37-148       DistributionConfig / DistributionFactory
  *   #[derive(WithMethods)] builders  quokkasim_derive_macros/src/lib.rs:22-94    .with_name() .with_code() ... (by value)
  *   DiscreteStock / Process / Source / Sink / ParallelProcess  components/discrete.rs   DiscreteStock::new_() ...
+ *   VectorStock / Process / Source / Sink / Combiner / Splitter  components/vector.rs   VectorStock::new_() ...
+ *   Vector3Container, Vector3ContainerFactory, ContainerLoadingProcess,
+ *   ContainerUnloadingProcess                      components/vector_container.rs     same names
  *   ComponentModel::StringStock(c, Mailbox::new()) ...    core.rs:505-557        ComponentModel::StringStock(c, Mailbox::new_())
  *   connect_components!(&mut a, &mut b)                   core.rs:565-1178       connect_components(a, b)  (throws the Err text)
  *   connect_logger!(&mut logger, &mut c)                  core.rs:1303-1338      connect_logger(logger, c)
@@ -135,6 +139,23 @@ struct StringItemFactory {
 
 enum class BasicEnvironmentState { Normal = 0, Stopped = 1 };
 
+/* core.rs:47-128 */
+struct Vector3 {
+  double values[3];
+  Vector3(double x = 0, double y = 0, double z = 0) : values{x, y, z} {}
+  double total() const { return (values[0] + values[1]) + values[2]; }
+};
+/* vector_container.rs:71-76 */
+struct Vector3Container {
+  std::string id;
+  bool has_resource = false;
+  Vector3 resource;
+  double capacity = 0;
+  Vector3Container() {}
+  Vector3Container(std::string i, double cap) : id(std::move(i)), capacity(cap) {}
+  Vector3Container(std::string i, const Vector3& r, double cap) : id(std::move(i)), has_resource(true), resource(r), capacity(cap) {}
+};
+
 /* ---- components: every component is one row -------------------------------------------------------------------- */
 struct ComponentData {
   uint32_t kind = 0;
@@ -147,6 +168,34 @@ struct ComponentData {
   BasicEnvironmentState state = BasicEnvironmentState::Normal;
   int id = -1;
   bool logged = false;
+  /* continuous family (vector.rs): resource type decided by the ComponentModel variant (dim 1 = f64, 3 = Vector3) */
+  uint32_t dim = 0, n_ports = 0;
+  double vlow = 0, vmax = 0;        /* VectorStock capacities (vector.rs:70-71) */
+  bool vinit_set = false;
+  Vector3 vinit;                    /* VectorStock initial resource / VectorSource source_vector */
+  std::vector<double> split_ratios; /* VectorSplitter (default 1/N each), VectorCombiner (unused by the reference) */
+  Distribution process_quantity_distr = Distribution::default_(); /* also the load / unload ratio distribution */
+  /* container family (vector_container.rs) */
+  std::vector<Vector3Container> containers; /* ItemDeque<Vector3Container> of a container stock */
+  bool cfactory_set = false, cfactory_has_quantity = false;
+  Distribution cfactory_quantity = Distribution::default_();
+  double cfactory_split[3] = {0, 0, 0}, cfactory_capacity = 0;
+  std::string cfactory_prefix;
+  uint64_t cfactory_next_index = 0;
+  size_t cfactory_num_digits = 0;
+  uint32_t max_process_count = 1;
+  uint32_t container_kind = 0; /* QK_CONTAINER_* once wrapped in a Vector3Container* variant */
+};
+
+/* vector_container.rs:126-156 */
+struct Vector3ContainerFactory {
+  std::string prefix;
+  uint64_t next_index = 0;
+  size_t num_digits = 0;
+  bool has_quantity = false;
+  Distribution create_quantity_distr = Distribution::default_();
+  double create_component_split[3] = {0, 0, 0};
+  double capacity = 0;
 };
 
 class Component {
@@ -166,6 +215,31 @@ class Component {
   Component with_process_time_distr(const Distribution& x) { d->process_time_distr = x; return *this; }
   Component with_item_factory(const StringItemFactory& f) { d->item_factory = f; return *this; }
   Component with_state(BasicEnvironmentState s) { d->state = s; return *this; }
+  /* continuous family */
+  Component with_low_capacity_f(double v) { d->vlow = v; return *this; }
+  Component with_max_capacity_f(double v) { d->vmax = v; return *this; }
+  Component with_initial_resource(const Vector3& v) { d->vinit = v; d->vinit_set = true; return *this; }
+  Component with_initial_resource(double v) { d->vinit = Vector3(v, 0, 0); d->vinit_set = true; return *this; }
+  Component with_source_vector(const Vector3& v) { d->vinit = v; d->vinit_set = true; return *this; }
+  Component with_source_vector(double v) { d->vinit = Vector3(v, 0, 0); d->vinit_set = true; return *this; }
+  Component with_process_quantity_distr(const Distribution& x) { d->process_quantity_distr = x; return *this; }
+  Component with_split_ratios(std::vector<double> r) { d->split_ratios = std::move(r); return *this; }
+  /* container family */
+  Component with_initial_resource(std::vector<Vector3Container> items) { d->containers = std::move(items); return *this; }
+  Component with_item_factory(const Vector3ContainerFactory& f) {
+    d->cfactory_set = true;
+    d->cfactory_has_quantity = f.has_quantity;
+    d->cfactory_quantity = f.create_quantity_distr;
+    for (int k = 0; k < 3; ++k) d->cfactory_split[k] = f.create_component_split[k];
+    d->cfactory_capacity = f.capacity;
+    d->cfactory_prefix = f.prefix;
+    d->cfactory_next_index = f.next_index;
+    d->cfactory_num_digits = f.num_digits;
+    return *this;
+  }
+  Component with_max_process_count(uint32_t n) { d->max_process_count = n; return *this; }
+  Component with_process_capacity_ratio_distr(const Distribution& x) { d->process_quantity_distr = x; return *this; }
+  Component with_process_quantity_ratio_distr(const Distribution& x) { d->process_quantity_distr = x; return *this; }
   /* DelayModes::modify(Add) (delays.rs:157-164): an existing name keeps its position */
   Component with_delay_mode(const DelayMode& m) {
     for (auto& x : d->delay_modes)
@@ -187,7 +261,21 @@ QUOKKA_COMPONENT_TYPE(DiscreteProcess, QK_DISCRETE_PROCESS)
 QUOKKA_COMPONENT_TYPE(DiscreteSource, QK_DISCRETE_SOURCE)
 QUOKKA_COMPONENT_TYPE(DiscreteSink, QK_DISCRETE_SINK)
 QUOKKA_COMPONENT_TYPE(DiscreteParallelProcess, QK_DISCRETE_PARALLEL_PROCESS)
+QUOKKA_COMPONENT_TYPE(VectorStock, QK_VECTOR_STOCK)
+QUOKKA_COMPONENT_TYPE(VectorProcess, QK_VECTOR_PROCESS)
+QUOKKA_COMPONENT_TYPE(VectorSource, QK_VECTOR_SOURCE)
+QUOKKA_COMPONENT_TYPE(VectorSink, QK_VECTOR_SINK)
+QUOKKA_COMPONENT_TYPE(VectorCombiner, QK_VECTOR_COMBINER)
+QUOKKA_COMPONENT_TYPE(VectorSplitter, QK_VECTOR_SPLITTER)
+QUOKKA_COMPONENT_TYPE(ContainerUnloadingProcess, QK_CONTAINER_UNLOAD_PROCESS)
 #undef QUOKKA_COMPONENT_TYPE
+struct ContainerLoadingProcess {
+  static Component new_() {
+    Component c(QK_CONTAINER_LOAD_PROCESS, "ContainerLoadingProcess");
+    c.d->element_code = "CLP"; /* vector_container.rs:205 */
+    return c;
+  }
+};
 struct BasicEnvironment {
   static Component new_() {
     Component c(QK_ENVIRONMENT, "BasicEnvironment");
@@ -230,6 +318,51 @@ class ComponentModel {
   QUOKKA_VARIANT(StringSink, QK_DISCRETE_SINK)
   QUOKKA_VARIANT(BasicEnvironment, QK_ENVIRONMENT)
 #undef QUOKKA_VARIANT
+  /* continuous family (core.rs:505-533): the variant fixes the resource type and, for combiners / splitters, M / N */
+#define QUOKKA_VVARIANT(Name, Kind, Dim, Ports)                                                          \
+  static ComponentModel Name(Component c, Mailbox) {                                                     \
+    if (c.d->kind != Kind) throw Error("ComponentModel::" #Name " expects another component type", QK_ERR_INVALID_ARG); \
+    c.d->dim = Dim;                                                                                      \
+    c.d->n_ports = Ports;                                                                                \
+    if (Ports && c.d->split_ratios.empty()) c.d->split_ratios.assign(Ports, 1.0 / (Ports ? Ports : 1)); \
+    if (Ports && c.d->split_ratios.size() != Ports) throw Error(#Name " needs one split ratio per port", QK_ERR_INVALID_ARG); \
+    return ComponentModel(#Name, std::move(c));                                                          \
+  }
+#define QUOKKA_VFAMILY(P, Dim)                                   \
+  QUOKKA_VVARIANT(P##Stock, QK_VECTOR_STOCK, Dim, 0)             \
+  QUOKKA_VVARIANT(P##Process, QK_VECTOR_PROCESS, Dim, 0)         \
+  QUOKKA_VVARIANT(P##Source, QK_VECTOR_SOURCE, Dim, 0)           \
+  QUOKKA_VVARIANT(P##Sink, QK_VECTOR_SINK, Dim, 0)               \
+  QUOKKA_VVARIANT(P##Combiner1, QK_VECTOR_COMBINER, Dim, 1)      \
+  QUOKKA_VVARIANT(P##Combiner2, QK_VECTOR_COMBINER, Dim, 2)      \
+  QUOKKA_VVARIANT(P##Combiner3, QK_VECTOR_COMBINER, Dim, 3)      \
+  QUOKKA_VVARIANT(P##Combiner4, QK_VECTOR_COMBINER, Dim, 4)      \
+  QUOKKA_VVARIANT(P##Combiner5, QK_VECTOR_COMBINER, Dim, 5)      \
+  QUOKKA_VVARIANT(P##Splitter1, QK_VECTOR_SPLITTER, Dim, 1)      \
+  QUOKKA_VVARIANT(P##Splitter2, QK_VECTOR_SPLITTER, Dim, 2)      \
+  QUOKKA_VVARIANT(P##Splitter3, QK_VECTOR_SPLITTER, Dim, 3)      \
+  QUOKKA_VVARIANT(P##Splitter4, QK_VECTOR_SPLITTER, Dim, 4)      \
+  QUOKKA_VVARIANT(P##Splitter5, QK_VECTOR_SPLITTER, Dim, 5)
+  QUOKKA_VFAMILY(F64, 1)
+  QUOKKA_VFAMILY(Vector3, 3)
+#undef QUOKKA_VFAMILY
+#undef QUOKKA_VVARIANT
+  /* container family (core.rs:549-555): the discrete component classes instantiated with Vector3Container */
+#define QUOKKA_CVARIANT(Name, BaseKind, CKind)                                                           \
+  static ComponentModel Name(Component c, Mailbox) {                                                     \
+    if (c.d->kind != BaseKind) throw Error("ComponentModel::" #Name " expects another component type", QK_ERR_INVALID_ARG); \
+    c.d->container_kind = CKind;                                                                         \
+    c.d->dim = 3;                                                                                        \
+    return ComponentModel(#Name, std::move(c));                                                          \
+  }
+  QUOKKA_CVARIANT(Vector3ContainerStock, QK_DISCRETE_STOCK, QK_CONTAINER_STOCK)
+  QUOKKA_CVARIANT(Vector3ContainerProcess, QK_DISCRETE_PROCESS, QK_CONTAINER_PROCESS)
+  QUOKKA_CVARIANT(Vector3ContainerParallelProcess, QK_DISCRETE_PARALLEL_PROCESS, QK_CONTAINER_PARALLEL_PROCESS)
+  QUOKKA_CVARIANT(Vector3ContainerSource, QK_DISCRETE_SOURCE, QK_CONTAINER_SOURCE)
+  QUOKKA_CVARIANT(Vector3ContainerSink, QK_DISCRETE_SINK, QK_CONTAINER_SINK)
+  QUOKKA_CVARIANT(Vector3ContainerLoadProcess, QK_CONTAINER_LOAD_PROCESS, QK_CONTAINER_LOAD_PROCESS)
+  QUOKKA_CVARIANT(Vector3ContainerUnloadProcess, QK_CONTAINER_UNLOAD_PROCESS, QK_CONTAINER_UNLOAD_PROCESS)
+#undef QUOKKA_CVARIANT
 };
 
 /* connect_components!(&mut a, &mut b[, n]) (core.rs:565-1178; discrete arms :886-921, environment arms :1129-1148):
@@ -241,9 +374,36 @@ inline void connect_components(ComponentModel& a, ComponentModel& b, int n = -1)
       if (v == x) return true;
     return false;
   };
-  const bool ok = (va == "StringStock" && in(vb, {"StringProcess", "StringParallelProcess", "StringSink"})) ||
-                  (vb == "StringStock" && in(va, {"StringProcess", "StringParallelProcess", "StringSource"})) ||
-                  (va == "BasicEnvironment" && in(vb, {"StringProcess", "StringParallelProcess", "StringSource", "StringSink"}));
+  bool ok = (va == "StringStock" && in(vb, {"StringProcess", "StringParallelProcess", "StringSink"})) ||
+            (vb == "StringStock" && in(va, {"StringProcess", "StringParallelProcess", "StringSource"})) ||
+            (va == "BasicEnvironment" && in(vb, {"StringProcess", "StringParallelProcess", "StringSource", "StringSink"}));
+  /* continuous arms (core.rs:572-883): same resource type on both sides; Stock -> CombinerM and SplitterN -> Stock
+   * take Some(n) */
+  for (const char* P : {"F64", "Vector3"}) {
+    const std::string p(P);
+    if (va.compare(0, p.size(), p) != 0 || vb.compare(0, p.size(), p) != 0) continue;
+    if (va.compare(0, 16, "Vector3Container") == 0 || vb.compare(0, 16, "Vector3Container") == 0) continue;
+    const std::string x = va.substr(p.size()), y = vb.substr(p.size());
+    const bool xc = x.compare(0, 8, "Combiner") == 0, xs = x.compare(0, 8, "Splitter") == 0;
+    const bool yc = y.compare(0, 8, "Combiner") == 0, ys = y.compare(0, 8, "Splitter") == 0;
+    if (x == "Stock" && (y == "Process" || y == "Sink" || ys)) ok = true;
+    if (x == "Stock" && yc) ok = n >= 0 && n < y.back() - '0';
+    if (y == "Stock" && (x == "Process" || x == "Source" || xc)) ok = true;
+    if (y == "Stock" && xs) ok = n >= 0 && n < x.back() - '0';
+  }
+  if (va == "BasicEnvironment" && (vb.compare(0, 3, "F64") == 0 || vb.compare(0, 7, "Vector3") == 0) &&
+      vb.compare(0, 16, "Vector3Container") != 0 && vb.find("Stock") == std::string::npos)
+    ok = true;
+  /* container arms (core.rs:923-995) and their environment arms (core.rs:1149-1172: no ParallelProcess arm) */
+  const char* CS = "Vector3ContainerStock";
+  if (va == CS && in(vb, {"Vector3ContainerProcess", "Vector3ContainerParallelProcess", "Vector3ContainerSink",
+                          "Vector3ContainerLoadProcess", "Vector3ContainerUnloadProcess"})) ok = true;
+  if (vb == CS && in(va, {"Vector3ContainerProcess", "Vector3ContainerParallelProcess", "Vector3ContainerSource",
+                          "Vector3ContainerLoadProcess", "Vector3ContainerUnloadProcess"})) ok = true;
+  if (va == "Vector3Stock" && vb == "Vector3ContainerLoadProcess") ok = true;
+  if (va == "Vector3ContainerUnloadProcess" && vb == "Vector3Stock") ok = true;
+  if (va == "BasicEnvironment" && in(vb, {"Vector3ContainerProcess", "Vector3ContainerSource", "Vector3ContainerSink",
+                                          "Vector3ContainerLoadProcess", "Vector3ContainerUnloadProcess"})) ok = true;
   if (!ok)
     throw Error("No component connection defined from " + va + " to " + vb + " (n=" +
                     (n < 0 ? std::string("None") : "Some(" + std::to_string(n) + ")") + ")",
@@ -261,6 +421,13 @@ class ComponentLogger {
   static ComponentLogger StringStockLogger(const std::string& name) { return ComponentLogger("StringStockLogger", name); }
   static ComponentLogger StringProcessLogger(const std::string& name) { return ComponentLogger("StringProcessLogger", name); }
   static ComponentLogger BasicEnvironmentLogger(const std::string& name) { return ComponentLogger("BasicEnvironmentLogger", name); }
+  /* records of these are read with BatchedSimulation::read_log; their CSV layouts live in the Python mirror (csvlog.py) */
+  static ComponentLogger F64StockLogger(const std::string& name) { return ComponentLogger("F64StockLogger", name); }
+  static ComponentLogger F64ProcessLogger(const std::string& name) { return ComponentLogger("F64ProcessLogger", name); }
+  static ComponentLogger Vector3StockLogger(const std::string& name) { return ComponentLogger("Vector3StockLogger", name); }
+  static ComponentLogger Vector3ProcessLogger(const std::string& name) { return ComponentLogger("Vector3ProcessLogger", name); }
+  static ComponentLogger Vector3ContainerStockLogger(const std::string& name) { return ComponentLogger("Vector3ContainerStockLogger", name); }
+  static ComponentLogger Vector3ContainerProcessLogger(const std::string& name) { return ComponentLogger("Vector3ContainerProcessLogger", name); }
   /* the CSV text Logger::write_csv (core.rs:388-401) produces for one replication */
   std::string csv_text(BatchedSimulation& sim, uint64_t replication = 0) const;
   std::string write_csv(const std::string& dir, BatchedSimulation& sim, uint64_t replication = 0) const {
@@ -273,10 +440,21 @@ class ComponentLogger {
 
 inline void connect_logger(ComponentLogger& logger, ComponentModel& c) {
   const std::string& v = c.variant;
-  const bool ok = (logger.variant == "StringStockLogger" && v == "StringStock") ||
-                  (logger.variant == "StringProcessLogger" &&
-                   (v == "StringProcess" || v == "StringParallelProcess" || v == "StringSource" || v == "StringSink")) ||
-                  (logger.variant == "BasicEnvironmentLogger" && v == "BasicEnvironment");
+  bool ok = (logger.variant == "StringStockLogger" && v == "StringStock") ||
+            (logger.variant == "StringProcessLogger" &&
+             (v == "StringProcess" || v == "StringParallelProcess" || v == "StringSource" || v == "StringSink")) ||
+            (logger.variant == "BasicEnvironmentLogger" && v == "BasicEnvironment");
+  for (const char* P : {"F64", "Vector3"}) { /* core.rs:1311-1322 */
+    const std::string p(P);
+    if (v.compare(0, p.size(), p) != 0 || v.compare(0, 16, "Vector3Container") == 0) continue;
+    if (logger.variant == p + "StockLogger" && v == p + "Stock") ok = true;
+    if (logger.variant == p + "ProcessLogger" && v != p + "Stock") ok = true;
+  }
+  if (logger.variant == "Vector3ContainerStockLogger" && v == "Vector3ContainerStock") ok = true;
+  if (logger.variant == "Vector3ContainerProcessLogger" && /* core.rs:1331-1334: no Source / Sink arm */
+      (v == "Vector3ContainerProcess" || v == "Vector3ContainerParallelProcess" || v == "Vector3ContainerLoadProcess" ||
+       v == "Vector3ContainerUnloadProcess"))
+    ok = true;
   if (!ok)
     throw Error("No logger connection defined from " + logger.variant + " to " + v + " (n=None)",
                 QK_ERR_UNSUPPORTED_CONNECTION);
@@ -369,6 +547,32 @@ class BatchedSimulation {
     if (total) *total = tot;
     return buf;
   }
+  /* resource of a vector stock / in-flight vector of a vector process-like component */
+  Vector3 read_vector(const ComponentModel& c, uint64_t rep) {
+    materialize();
+    Vector3 v;
+    check(qk_batch_read_vector(batch_, rep, (uint32_t)c.component.d->id, v.values));
+    return v;
+  }
+  /* containers held by a container stock (FIFO order) or a container process-like component: (handle, resource) pairs;
+   * has_resource == false for a container that carries nothing.  id / capacity are not device state: the id is the
+   * item name of the handle, the capacity is the factory's or the initial item's. */
+  std::vector<std::pair<uint32_t, Vector3Container>> read_containers(const ComponentModel& c, uint64_t rep) {
+    materialize();
+    uint64_t n = 0;
+    check(qk_batch_read_containers(batch_, rep, (uint32_t)c.component.d->id, nullptr, nullptr, 0, &n));
+    std::vector<uint32_t> h(n ? n : 1);
+    std::vector<uint64_t> r(3 * (n ? n : 1));
+    check(qk_batch_read_containers(batch_, rep, (uint32_t)c.component.d->id, h.data(), r.data(), h.size(), &n));
+    std::vector<std::pair<uint32_t, Vector3Container>> out;
+    for (uint64_t i = 0; i < n; ++i) {
+      Vector3Container k;
+      k.has_resource = r[3 * i] != QK_CONTAINER_NONE_BITS;
+      if (k.has_resource) std::memcpy(k.resource.values, &r[3 * i], 24);
+      out.push_back({h[i], k});
+    }
+    return out;
+  }
   qk_batch* handle() {
     materialize();
     return batch_;
@@ -400,15 +604,42 @@ class BatchedSimulation {
       auto& c = *cm.component.d;
       qk_component_desc d;
       std::memset(&d, 0, sizeof(d));
-      d.kind = c.kind;
+      d.kind = c.container_kind ? c.container_kind : c.kind;
       d.low_capacity = c.low_capacity;
       d.max_capacity = c.max_capacity;
-      d.n_initial_items = c.kind == QK_DISCRETE_STOCK ? (uint32_t)c.resource.size() : 0;
+      d.n_initial_items = (c.kind == QK_DISCRETE_STOCK && !c.container_kind) ? (uint32_t)c.resource.size() : 0;
       d.initial_env_state = (uint32_t)c.state;
+      if (c.kind == QK_CONTAINER_LOAD_PROCESS || c.kind == QK_CONTAINER_UNLOAD_PROCESS) d.max_capacity = c.max_process_count;
       uint32_t id = 0;
       check(qk_model_add_component(model_, &d, &id));
-      if (c.kind >= QK_DISCRETE_PROCESS && c.kind <= QK_DISCRETE_PARALLEL_PROCESS) {
+      if (c.kind >= QK_VECTOR_STOCK && c.kind <= QK_VECTOR_SPLITTER) {
+        if (!c.dim) throw Error("vector component " + c.element_name + " was never wrapped in a ComponentModel variant", QK_ERR_INVALID_ARG);
+        check(qk_model_set_vector(model_, id, c.dim, c.vlow, c.vmax, c.vinit.values));
+        if (c.n_ports) check(qk_model_set_ports(model_, id, c.n_ports, c.split_ratios.data()));
+      }
+      if (c.container_kind == QK_CONTAINER_STOCK && !c.containers.empty()) {
+        std::vector<double> res, caps;
+        std::vector<uint8_t> has;
+        for (auto& k : c.containers) {
+          for (int j = 0; j < 3; ++j) res.push_back(k.resource.values[j]);
+          has.push_back(k.has_resource ? 1 : 0);
+          caps.push_back(k.capacity);
+        }
+        check(qk_model_set_initial_containers(model_, id, (uint32_t)has.size(), res.data(), has.data(), caps.data()));
+      }
+      if (c.container_kind == QK_CONTAINER_SOURCE) {
         uint32_t did = 0;
+        check(qk_model_set_container_factory(model_, id, c.cfactory_has_quantity ? &c.cfactory_quantity.desc : nullptr,
+                                             c.cfactory_split, c.cfactory_capacity, &did));
+        if (c.cfactory_has_quantity) dist_ids_.push_back({c.cfactory_quantity.identity.get(), did});
+      }
+      const bool process_like = (c.kind >= QK_DISCRETE_PROCESS && c.kind <= QK_DISCRETE_PARALLEL_PROCESS) ||
+                                (c.kind >= QK_VECTOR_PROCESS && c.kind <= QK_VECTOR_SPLITTER) ||
+                                c.kind == QK_CONTAINER_LOAD_PROCESS || c.kind == QK_CONTAINER_UNLOAD_PROCESS;
+      if (process_like) {
+        uint32_t did = 0;
+        check(qk_model_set_dist(model_, id, 1, &c.process_quantity_distr.desc, &did));
+        dist_ids_.push_back({c.process_quantity_distr.identity.get(), did});
         check(qk_model_set_dist(model_, id, 0, &c.process_time_distr.desc, &did));
         dist_ids_.push_back({c.process_time_distr.identity.get(), did});
         for (auto& m : c.delay_modes) {

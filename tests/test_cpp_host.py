@@ -13,10 +13,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
-def _build(tmp_path, libdir, libname):
-    exe = str(tmp_path / "discrete_queue")
+def _build(tmp_path, libdir, libname, example="discrete_queue"):
+    exe = str(tmp_path / example)
     subprocess.check_call(["g++", "-std=c++17", "-Wall", "-Wextra", "-Werror", "-I" + os.path.join(ROOT, "include"),
-                           os.path.join(ROOT, "examples", "discrete_queue.cpp"), "-o", exe, "-L" + libdir,
+                           os.path.join(ROOT, "examples", example + ".cpp"), "-o", exe, "-L" + libdir,
                            "-l:" + libname, "-Wl,-rpath," + libdir])
     return exe
 
@@ -53,3 +53,29 @@ def test_cpp_example_on_gpu(gpu_lib, tmp_path):
     sim.close()
     out = subprocess.check_output([exe, "--replications", "2", "--out", str(tmp_path), "--kat0"], text=True)
     assert open(tmp_path / "QueueLogger.csv").read() == open(os.path.join(GOLDEN, "kat0_StockLogger.csv")).read()
+
+
+def _check_container_example(lib, tmp_path, n_reps):
+    """examples/container_haulage.cpp (continuous + container families through the C++ mirror) against the Python host:
+    same clock, same dumped tonnage to the last bit, fleet and mass conserved"""
+    exe = _build(tmp_path, os.path.dirname(lib), os.path.basename(lib), "container_haulage")
+    out = subprocess.check_output([exe, "--replications", str(n_reps), "--events", "3000"], text=True)
+    m = H.container_haulage()
+    sim = m.sim(lib, n_reps, base_seed=42)
+    sim.step_events(3000)
+    s = sim.summary()
+    assert "faulted 0" in out and _events(out) == s["n_events"]
+    assert int(re.search(r"clock_ns (\d+)", out).group(1)) == s["max_now_ns"]
+    dumped = sum(sim.read_vector(m.by_name["Dumped"].component._id, n_reps - 1))
+    assert float(re.search(r"dumped (\S+)", out).group(1)) == dumped
+    assert "fleet 4" in out
+    sim.close()
+
+
+def test_cpp_container_example_matches_python_host(emul_lib, tmp_path):
+    _check_container_example(emul_lib, tmp_path, 3)
+
+
+@pytest.mark.gpu
+def test_cpp_container_example_on_gpu(gpu_lib, tmp_path):
+    _check_container_example(gpu_lib, tmp_path, 4096)
