@@ -188,44 +188,74 @@ __device__ __forceinline__ void qk_log_pay(Ctx& cx, uint32_t flags, uint32_t com
   }
 }
 
-/* ---- Distribution::sample (common.rs:152-178) + Duration::from_secs_f64 -------------------------------- */
+/* ---- Distribution::sample (common.rs:152-178) + Duration::from_secs_f64 --------------------------------
+ * ONE out-of-line copy of "next variate of this instance (tape or Philox), optionally converted to a Duration": it is
+ * needed at some fifteen places of the general kernels, and inlined there it was a fifth of their code (the general
+ * kernels are 140-240 KB of SASS against a 32 KB L1.5 instruction cache, and the container model spent 61 % of its stall
+ * samples waiting for instructions).  Everything travels by value, so no caller state is forced into memory. */
+struct QkDrawn {
+  double value;
+  uint64_t ns;
+  uint32_t draws, fault;
+};
+static __device__ __noinline__ QkDrawn qk_draw(uint32_t kind, double p0, double p1, double p2, double p3, uint32_t stream,
+                                               uint32_t key0, uint32_t key1, uint32_t rep_lo, uint32_t rep_hi,
+                                               uint32_t draws, const double* tape, uint64_t tape_len, uint64_t rep_local,
+                                               uint32_t want_duration) {
+  QkDrawn r;
+  r.ns = 0;
+  r.fault = 0;
+  if (kind == QK_DIST_CONSTANT) { /* a tape on a Constant is never consulted (common.rs:155) */
+    r.value = p0;
+    r.draws = draws;
+  } else if (tape) {
+    if (draws >= tape_len) {
+      r.value = 1.0;
+      r.draws = draws;
+      r.fault = QK_REP_TAPE_EXHAUSTED;
+      return r;
+    }
+    r.value = tape[rep_local * tape_len + draws];
+    r.draws = draws + 1;
+  } else {
+    const QkVariate v = qk_sample_native(kind, p0, p1, p2, p3, stream, key0, key1, rep_lo, rep_hi, draws);
+    r.value = v.value;
+    r.draws = v.draws;
+  }
+  if (want_duration) r.fault = qk_from_secs_f64(r.value, &r.ns);
+  return r;
+}
+
+template <int SM>
+__device__ __forceinline__ QkDrawn qk_draw_for(Ctx& cx, uint32_t dist_id, uint32_t want_duration) {
+  const DevDist* d = &cx.dists[dist_id];
+  const bool constant = d->kind == QK_DIST_CONSTANT; /* has no draw counter */
+  const double* tape = cx.tapes ? cx.tapes[dist_id] : nullptr;
+  const QkDrawn r = qk_draw(d->kind, d->p[0], d->p[1], d->p[2], d->p[3], d->stream, cx.key0, cx.key1, cx.rep_lo, cx.rep_hi,
+                            constant ? 0u : S32(d->draw_slot), tape, tape ? cx.tape_len[dist_id] : 0ull, cx.rep_local,
+                            want_duration);
+  if (!constant) S32(d->draw_slot) = r.draws;
+  return r;
+}
+
 template <int SM>
 __device__ __forceinline__ double qk_sample(Ctx& cx, uint32_t dist_id) {
   const DevDist* d = &cx.dists[dist_id];
   if (d->kind == QK_DIST_CONSTANT) return d->p[0];
-  uint32_t draws = S32(d->draw_slot);
-  double v;
-  const double* tape = cx.tapes ? cx.tapes[dist_id] : nullptr;
-  if (tape) {
-    const uint64_t len = cx.tape_len[dist_id];
-    if (draws >= len) {
-      cx.status = QK_REP_TAPE_EXHAUSTED;
-      return 1.0;
-    }
-    v = tape[cx.rep_local * len + draws];
-    draws += 1;
-  } else {
-    const QkVariate r = qk_sample_native(d->kind, d->p[0], d->p[1], d->p[2], d->p[3], d->stream, cx.key0, cx.key1,
-                                         cx.rep_lo, cx.rep_hi, draws);
-    v = r.value;
-    draws = r.draws;
-  }
-  S32(d->draw_slot) = draws;
-  return v;
+  const QkDrawn r = qk_draw_for<SM>(cx, dist_id, 0u);
+  if (r.fault) cx.status = r.fault;
+  return r.value;
 }
 
 /* sample + convert; on a fault sets cx.status and returns 1 (callers abandon the handler) */
 template <int SM>
 __device__ __forceinline__ uint64_t qk_sample_duration(Ctx& cx, uint32_t dist_id) {
-  const double secs = qk_sample<SM>(cx, dist_id);
-  if (cx.status) return 1;
-  uint64_t ns;
-  const uint32_t f = qk_from_secs_f64(secs, &ns);
-  if (f) {
-    cx.status = f;
+  const QkDrawn r = qk_draw_for<SM>(cx, dist_id, 1u);
+  if (r.fault) {
+    cx.status = r.fault;
     return 1;
   }
-  return ns;
+  return r.ns;
 }
 
 /* sample + convert for the prefetch slots: never raises, faults are encoded and raised when the value is consumed */

@@ -59,6 +59,23 @@ __device__ __forceinline__ void qk_vstore(Ctx& cx, uint32_t slot, uint32_t dim, 
 }
 
 /* ResourceRemove: f64 `*self -= q; q` (core.rs:13-18); Vector3 proportional (core.rs:73-94) */
+struct QkRemoved {
+  double self[3], out[3];
+};
+/* one out-of-line copy (fp64 division and six multiplications; by value, see qk_draw) */
+static __device__ __noinline__ QkRemoved qk_vremove3(double s0, double s1, double s2, double q) {
+  QkRemoved r;
+  const double total = __dadd_rn(__dadd_rn(s0, s1), s2);
+  const double ps = __ddiv_rn(q, total);
+  const double pr = __dsub_rn(1.0, ps);
+  r.out[0] = __dmul_rn(s0, ps);
+  r.out[1] = __dmul_rn(s1, ps);
+  r.out[2] = __dmul_rn(s2, ps);
+  r.self[0] = __dmul_rn(s0, pr);
+  r.self[1] = __dmul_rn(s1, pr);
+  r.self[2] = __dmul_rn(s2, pr);
+  return r;
+}
 __device__ __forceinline__ void qk_vremove(double* self, double q, uint32_t dim, double* out) {
   if (dim == 1) {
     self[0] = __dsub_rn(self[0], q);
@@ -66,12 +83,11 @@ __device__ __forceinline__ void qk_vremove(double* self, double q, uint32_t dim,
     out[1] = out[2] = 0.0;
     return;
   }
-  const double ps = __ddiv_rn(q, qk_vtotal(self, dim));
-  const double pr = __dsub_rn(1.0, ps);
+  const QkRemoved r = qk_vremove3(self[0], self[1], self[2], q);
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
-    out[k] = __dmul_rn(self[k], ps);
-    self[k] = __dmul_rn(self[k], pr);
+    out[k] = r.out[k];
+    self[k] = r.self[k];
   }
 }
 
