@@ -442,19 +442,30 @@ int qk_batch_create(const qk_model* m, const qk_batch_config* cfg, qk_batch** ou
   }
   CREATE_TRY(cudaEventCreate(&b->ev0));
   CREATE_TRY(cudaEventCreate(&b->ev1));
-  CREATE_TRY(cudaMalloc(&b->g64, (size_t)h.n64 * b->rep_pad * 8));
-  CREATE_TRY(cudaMalloc(&b->g32, (size_t)h.n32 * b->rep_pad * 4));
-  CREATE_TRY(cudaMalloc(&b->gs64, (size_t)h.n_comp * ST_PER_COMP * b->rep_pad * 8));
-  CREATE_TRY(cudaMalloc(&b->gs32, (size_t)h.n_comp * ST_PER_COMP * b->rep_pad * 4));
-  CREATE_TRY(cudaMalloc(&b->gc64, (size_t)(h.n64c ? h.n64c : 1) * b->rep_pad * 8));
-  CREATE_TRY(cudaMalloc(&b->gc32, (size_t)(h.n32c ? h.n32c : 1) * b->rep_pad * 4));
+  /* The planes and the log rings (gigabytes) come from the device's stream-ordered memory pool, which keeps what a
+   * destroyed batch hands back: cudaMalloc / cudaFree of such buffers cost tens to hundreds of milliseconds each
+   * (page mapping, device-wide synchronisation), which is what a user who builds one batch after another would wait
+   * for -- and what made the end-to-end leg of the bench noisy. */
+  {
+    cudaMemPool_t pool;
+    CREATE_TRY(cudaDeviceGetDefaultMemPool(&pool, cfg->device));
+    uint64_t keep = ~0ull;
+    CREATE_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+  }
+  CREATE_TRY(cudaMallocAsync(&b->g64, (size_t)h.n64 * b->rep_pad * 8, b->stream));
+  CREATE_TRY(cudaMallocAsync(&b->g32, (size_t)h.n32 * b->rep_pad * 4, b->stream));
+  CREATE_TRY(cudaMallocAsync(&b->gs64, (size_t)h.n_comp * ST_PER_COMP * b->rep_pad * 8, b->stream));
+  CREATE_TRY(cudaMallocAsync(&b->gs32, (size_t)h.n_comp * ST_PER_COMP * b->rep_pad * 4, b->stream));
+  CREATE_TRY(cudaMallocAsync(&b->gc64, (size_t)(h.n64c ? h.n64c : 1) * b->rep_pad * 8, b->stream));
+  CREATE_TRY(cudaMallocAsync(&b->gc32, (size_t)(h.n32c ? h.n32c : 1) * b->rep_pad * 4, b->stream));
+  if (b->log) CREATE_TRY(cudaMallocAsync(&b->d_log, (size_t)b->rep_pad * cfg->log_capacity * 32, b->stream));
+  CREATE_TRY(cudaStreamSynchronize(b->stream)); /* allocation failures of the pool surface here at the latest */
   CREATE_TRY(cudaMalloc(&b->d_tables, b->table_bytes_padded));
   {
     std::vector<uint8_t> padded(b->table_bytes_padded, 0);
     memcpy(padded.data(), b->low.blob.data(), b->low.blob.size());
     CREATE_TRY(cudaMemcpy(b->d_tables, padded.data(), padded.size(), cudaMemcpyHostToDevice));
   }
-  if (b->log) CREATE_TRY(cudaMalloc(&b->d_log, (size_t)b->rep_pad * cfg->log_capacity * 32));
   b->h_tapes.assign(h.n_dist, nullptr);
   b->h_tape_len.assign(h.n_dist, 0);
   CREATE_TRY(cudaMalloc(&b->d_tapes, sizeof(double*) * (h.n_dist ? h.n_dist : 1)));
@@ -499,14 +510,13 @@ void qk_batch_destroy(qk_batch* b) {
   if (!b) return;
   cudaSetDevice(b->cfg.device);
   if (b->stream) cudaStreamSynchronize(b->stream);
-  cudaFree(b->g64);
-  cudaFree(b->g32);
-  cudaFree(b->gs64);
-  cudaFree(b->gs32);
-  cudaFree(b->gc64);
-  cudaFree(b->gc32);
+  if (b->stream) { /* back to the pool, in stream order */
+    void* pooled[] = {b->g64, b->g32, b->gs64, b->gs32, b->gc64, b->gc32, b->d_log};
+    for (void* p : pooled)
+      if (p) cudaFreeAsync(p, b->stream);
+    cudaStreamSynchronize(b->stream);
+  }
   cudaFree(b->d_tables);
-  cudaFree(b->d_log);
   for (size_t i = 0; i < b->h_tapes.size(); ++i) cudaFree(b->h_tapes[i]);
   cudaFree(b->d_tapes);
   cudaFree(b->d_tape_len);
