@@ -13,8 +13,12 @@
  * cannot be run here.  The only value-pinning tests the reference holds for this path
  * are the two DelayModes unit tests (quokkasim/src/delays.rs:182-242); the oracle is
  * checked against both (tests/test_oracle_kat.py).  Everything else is pinned by the
- * hand-derived KAT-0 trace, Rust std's documented
+ * hand-derived KAT-0 trace and, for the container family, the hand-derived KAT-1 trace
+ * (tests/test_csv_export.py, tests/golden/kat1_*.csv), Rust std's documented
  * Duration::try_from_secs_f64 examples, and the Random123 Philox4x32-10 known answers.
+ * The continuous (vector.rs) and container (vector_container.rs) restatements have no reference test or golden
+ * file to pin them: "parity unpinned" against the real engine, anchored on the reference's call sites and checked by
+ * conservation laws.
  * Scheduler tie-break order is "parity unpinned" against the real engine
  * (the reference itself leaves same-timestamp cross-model order unspecified).
  *

