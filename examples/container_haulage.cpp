@@ -8,7 +8,7 @@
  *
  *   g++ -std=c++17 -Iinclude examples/container_haulage.cpp -o container_haulage \
  *       -Lquokkasim_b200 -l:libquokka_b200.so -Wl,-rpath,$PWD/quokkasim_b200
- *   ./container_haulage [--replications N] [--events E]
+ *   ./container_haulage [--replications N] [--events E] [--out DIR]     (--out: CSV files of the last replication)
  */
 #include <cstdlib>
 #include <iomanip>
@@ -20,10 +20,12 @@ using namespace quokka;
 
 int main(int argc, char** argv) {
   uint64_t n_replications = 256, n_events = 3000;
+  std::string out_dir;
   for (int i = 1; i < argc; ++i) {
     const std::string a = argv[i];
     if (a == "--replications" && i + 1 < argc) n_replications = std::strtoull(argv[++i], nullptr, 10);
     else if (a == "--events" && i + 1 < argc) n_events = std::strtoull(argv[++i], nullptr, 10);
+    else if (a == "--out" && i + 1 < argc) out_dir = argv[++i];
   }
   try {
     const int n_trucks = 4;
@@ -91,12 +93,19 @@ int main(int argc, char** argv) {
     } catch (const Error&) {
     }
 
+    /* DiscreteStockLogger<Vector3Container> / DiscreteProcessLogger<Vector3Container> (core.rs:1292-1293, 1330-1334) */
+    auto stock_logger = ComponentLogger::Vector3ContainerStockLogger("ContainerStockLogger");
+    auto process_logger = ComponentLogger::Vector3ContainerProcessLogger("ContainerProcessLogger");
+    for (auto* c : {&ready, &loaded, &at_dump, &emptied}) connect_logger(stock_logger, *c);
+    for (auto* c : {&load, &haul, &unload, &ret}) connect_logger(process_logger, *c);
+
     auto sim_builder = BatchedSimInit::new_();
     for (auto* c : {&ore, &ready, &load, &loaded, &haul, &at_dump, &unload, &dumped, &emptied, &ret, &env})
       sim_builder = register_component(sim_builder, *c);
     BatchOptions opt;
     opt.n_replications = n_replications;
     opt.base_seed = 42;
+    opt.log_capacity = out_dir.empty() ? 0 : 65536;
     auto simu = sim_builder.init(MonotonicTime::EPOCH, opt);
     create_scheduled_event(simu, Duration::from_secs(1500), ScheduledEventConfig::SetEnvironmentState(BasicEnvironmentState::Stopped), env);
     create_scheduled_event(simu, Duration::from_secs(1700), ScheduledEventConfig::SetEnvironmentState(BasicEnvironmentState::Normal), env);
@@ -116,6 +125,10 @@ int main(int argc, char** argv) {
       }
     std::cout << std::setprecision(17) << "fleet " << fleet << " dumped " << simu.read_vector(dumped, r).total() << " total " << total
               << "\n";
+    if (!out_dir.empty()) {
+      std::cout << stock_logger.write_csv(out_dir, simu, r) << "\n";
+      std::cout << process_logger.write_csv(out_dir, simu, r) << "\n";
+    }
     return (s.n_faulted == 0 && fleet == (size_t)n_trucks && std::abs(total - 100003.5) < 1e-4) ? 0 : 4;
   } catch (const Error& e) {
     std::cerr << "error (" << e.status << "): " << e.what() << "\n";

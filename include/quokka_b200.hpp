@@ -2,7 +2,8 @@
  * quokka_b200.hpp -- C++ host side above the C ABI (include/quokka_b200.h): the model-builder surface of
  * jajetloh/quokkasim v0.2.2 -- the discrete family, the continuous (vector) family, the container family and
  * BasicEnvironment -- restated as plain descriptions that are lowered to C-ABI rows.  Header only, C++17, no
- * dependencies beyond the C header.  (CSV export covers the discrete loggers; the Python mirror has all of them.)
+ * dependencies beyond the C header.  (CSV export covers the discrete and container loggers; the continuous ones are
+ * in the Python mirror.)
  *
  * The reference is Rust; there is no Rust toolchain in the build image, so this is the compiled-language host mirror
  * of its operator interface (same names, argument meaning and error behaviour), next to the Python mirror
@@ -29,6 +30,8 @@
 #ifndef QUOKKA_B200_HPP
 #define QUOKKA_B200_HPP
 
+#include <charconv>
+#include <cmath>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -770,8 +773,33 @@ inline std::string json_string(const std::string& s) {
 }
 inline const char* reason_text(uint32_t r) {
   static const char* T[] = {"", "Upstream is empty", "Upstream is not connected", "Downstream is full", "Downstream is not connected",
-                            "Upstream did not provide resource", "Stopped by environment", "Resumed by environment", "Upstream is full"};
+                            "Upstream did not provide resource", "Stopped by environment", "Resumed by environment", "Upstream is full",
+                            "At least one upstream is empty", "No upstreams are connected", "At least one downstream is full",
+                            "No downstreams are connected", "No remaining process slots", "Downstream container stock is full",
+                            "Downstream resource stock is full"};
   return r < sizeof(T) / sizeof(T[0]) ? T[r] : "";
+}
+/* f64 -> text the way serde_json / ryu print it: shortest round-trip digits, "1.0" not "1", exponent form outside
+ * [1e-5, 1e16); non-finite values are JSON null */
+inline std::string json_f64(double x) {
+  if (!std::isfinite(x)) return "null";
+  if (x == 0.0) return std::signbit(x) ? "-0.0" : "0.0";
+  char buf[64];
+  const auto res = std::to_chars(buf, buf + sizeof(buf), std::fabs(x), std::chars_format::scientific);
+  std::string sci(buf, res.ptr); /* d[.ddd]e[+-]XX, shortest digits */
+  const size_t e = sci.find('e');
+  std::string digits;
+  for (size_t i = 0; i < e; ++i)
+    if (sci[i] != '.') digits += sci[i];
+  while (digits.size() > 1 && digits.back() == '0') digits.pop_back();
+  const int kk = std::atoi(sci.c_str() + e + 1) + 1; /* value = 0.d1d2... * 10^kk */
+  const int n = (int)digits.size();
+  std::string out = x < 0 ? "-" : "";
+  if (0 < kk && kk <= 16 && n <= kk) out += digits + std::string((size_t)(kk - n), '0') + ".0";
+  else if (0 < kk && kk <= 16) out += digits.substr(0, (size_t)kk) + "." + digits.substr((size_t)kk);
+  else if (-5 < kk && kk <= 0) out += "0." + std::string((size_t)(-kk), '0') + digits;
+  else out += (n == 1 ? digits : digits.substr(0, 1) + "." + digits.substr(1)) + "e" + std::to_string(kk - 1);
+  return out;
 }
 }  // namespace detail
 
@@ -781,12 +809,22 @@ inline std::string ComponentLogger::csv_text(BatchedSimulation& sim, uint64_t re
   if (total > recs.size()) throw Error("log ring kept fewer records than were written: raise log_capacity for CSV export", QK_ERR_BUFFER_TOO_SMALL);
   std::vector<std::shared_ptr<ComponentData>> by_id;
   std::vector<const ComponentData*> sources;
-  std::vector<std::string> initial_items;
+  std::vector<std::string> initial_items; /* initial stock contents, numbered in registration order of their stocks */
+  std::vector<double> initial_caps;
   for (auto& cm : sim.components) {
+    const ComponentData& d = *cm.component.d;
     by_id.push_back(cm.component.d);
-    if (cm.component.d->kind == QK_DISCRETE_SOURCE) sources.push_back(cm.component.d.get());
-    if (cm.component.d->kind == QK_DISCRETE_STOCK)
-      initial_items.insert(initial_items.end(), cm.component.d->resource.begin(), cm.component.d->resource.end());
+    if (d.kind == QK_DISCRETE_SOURCE) sources.push_back(&d);
+    if (d.kind == QK_DISCRETE_STOCK && d.container_kind)
+      for (auto& k : d.containers) {
+        initial_items.push_back(k.id);
+        initial_caps.push_back(k.capacity);
+      }
+    else if (d.kind == QK_DISCRETE_STOCK)
+      for (auto& k : d.resource) {
+        initial_items.push_back(k);
+        initial_caps.push_back(0.0);
+      }
   }
   auto event_id = [&](uint32_t comp, uint32_t seq) -> std::string {
     if (comp == QK_SRC_INIT) return "INIT_000000";
@@ -797,7 +835,29 @@ inline std::string ComponentLogger::csv_text(BatchedSimulation& sim, uint64_t re
   };
   auto item_name = [&](uint64_t h) -> std::string {
     const uint32_t ord = QK_ITEM_SOURCE(h), idx = QK_ITEM_INDEX(h);
-    return ord == 63 ? initial_items[idx] : sources[ord]->item_factory.item_name(idx);
+    if (ord == 63) return initial_items[idx];
+    const ComponentData& f = *sources[ord];
+    if (!f.container_kind) return f.item_factory.item_name(idx);
+    std::string n = std::to_string(f.cfactory_next_index + idx); /* "{prefix}{index:0width$}" vector_container.rs:138 */
+    if (n.size() < f.cfactory_num_digits) n = std::string(f.cfactory_num_digits - n.size(), '0') + n;
+    return f.cfactory_prefix + n;
+  };
+  /* serde_json::to_string(item): a String, or a Vector3Container (Serialize impl vector_container.rs:113-124) whose
+   * resource arrived in the continuation record `cont` that follows the main record */
+  auto item_json = [&](const qk_log_record& r, const qk_log_record* cont) -> std::string {
+    if (!by_id[r.comp]->container_kind) return detail::json_string(item_name(r.payload));
+    const uint32_t ord = QK_ITEM_SOURCE(r.payload), idx = QK_ITEM_INDEX(r.payload);
+    const double cap = ord == 63 ? initial_caps[idx] : sources[ord]->cfactory_capacity;
+    std::string res = "null";
+    if (cont && cont->time_ns != QK_CONTAINER_NONE_BITS) {
+      double v[3];
+      std::memcpy(&v[0], &cont->time_ns, 8);
+      std::memcpy(&v[1], &cont->src_comp, 8); /* src_comp | aux | src_seq overlay the second double */
+      std::memcpy(&v[2], &cont->payload, 8);
+      res = "{\"x\":" + detail::json_f64(v[0]) + ",\"y\":" + detail::json_f64(v[1]) + ",\"z\":" + detail::json_f64(v[2]) + "}";
+    }
+    return "{\"id\":" + detail::json_string(item_name(r.payload)) + ",\"resource\":" + res + ",\"capacity\":" +
+           detail::json_f64(cap) + "}";
   };
   auto member = [&](uint32_t comp) {
     for (auto& c : components)
@@ -807,13 +867,19 @@ inline std::string ComponentLogger::csv_text(BatchedSimulation& sim, uint64_t re
   std::ostringstream out;
   bool any = false;
   const bool env_logger = variant == "BasicEnvironmentLogger";
-  for (const qk_log_record& r : recs) {
+  if (variant.compare(0, 3, "F64") == 0 || (variant.compare(0, 7, "Vector3") == 0 && variant.compare(0, 16, "Vector3Container") != 0))
+    throw Error("CSV export of the continuous loggers is in the Python mirror (quokkasim_b200/csvlog.py)", QK_ERR_INVALID_ARG);
+  for (size_t ri = 0; ri < recs.size(); ++ri) {
+    const qk_log_record& r = recs[ri];
     if (r.kind == QK_LOG_VEC_DATA || !member(r.comp)) continue;
+    const qk_log_record* cont = (ri + 1 < recs.size() && recs[ri + 1].kind == QK_LOG_VEC_DATA && recs[ri + 1].comp == r.comp &&
+                                 recs[ri + 1].seq == r.seq) ? &recs[ri + 1] : nullptr;
     const ComponentData& c = *by_id[r.comp];
     if (!any) {
       any = true; /* csv::Writer writes the header with the first record: an empty log is an empty file */
       if (env_logger) out << "time,event_id,source_event_id,element_name,element_type,event\n";
-      else if (variant == "StringStockLogger") out << "time,event_id,source_event_id,element_name,element_type,log_type,item,reason\n";
+      else if (variant == "StringStockLogger" || variant == "Vector3ContainerStockLogger")
+        out << "time,event_id,source_event_id,element_name,element_type,log_type,item,reason\n";
       else out << "time,event_id,source_event_id,element_name,element_type,event_type,item,reason\n";
     }
     std::string type, item, reason;
@@ -822,9 +888,9 @@ inline std::string ComponentLogger::csv_text(BatchedSimulation& sim, uint64_t re
         out << detail::tai_display(r.time_ns) << ',' << event_id(r.comp, r.seq) << ',' << event_id(r.src_comp, r.src_seq) << ','
             << detail::csv_field(c.element_name) << ",BasicEnvironment," << (r.reason == 1 ? "Stopped" : "Normal") << '\n';
         continue;
-      case QK_LOG_STOCK_ADD: type = "Add", item = detail::json_string(item_name(r.payload)); break;
+      case QK_LOG_STOCK_ADD: type = "Add", item = item_json(r, cont); break;
       case QK_LOG_STOCK_REMOVE:
-        type = "Remove", item = r.payload == QK_ITEM_NONE ? "null" : detail::json_string(item_name(r.payload));
+        type = "Remove", item = r.payload == QK_ITEM_NONE ? "null" : item_json(r, cont);
         break;
       case QK_LOG_STOCK_STATE_CHANGE: {
         static const char* S[] = {"Empty", "Normal", "Full"};
@@ -833,8 +899,8 @@ inline std::string ComponentLogger::csv_text(BatchedSimulation& sim, uint64_t re
                ",\"empty\":" + std::to_string(r.payload & 0xFFFFFFFFull) + "}}";
         break;
       }
-      case QK_LOG_PROCESS_START: type = "ProcessStart", item = detail::json_string(item_name(r.payload)); break;
-      case QK_LOG_PROCESS_FINISH: type = "ProcessFinish", item = detail::json_string(item_name(r.payload)); break;
+      case QK_LOG_PROCESS_START: type = "ProcessStart", item = item_json(r, cont); break;
+      case QK_LOG_PROCESS_FINISH: type = "ProcessFinish", item = item_json(r, cont); break;
       case QK_LOG_DELAY_START: type = "DelayStart", item = c.delay_modes[r.payload].name; break;
       case QK_LOG_DELAY_END: type = "DelayEnd", item = c.delay_modes[r.payload].name; break;
       case QK_LOG_PROCESS_CONTINUE: type = "ProcessContinue", reason = detail::reason_text(r.reason); break;

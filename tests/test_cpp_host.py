@@ -70,6 +70,19 @@ def _check_container_example(lib, tmp_path, n_reps):
     assert float(re.search(r"dumped (\S+)", out).group(1)) == dumped
     assert "fleet 4" in out
     sim.close()
+    # CSV export of the container loggers: the C++ writer and the Python writer (which is pinned by the hand-derived
+    # KAT-1 golden files) agree byte for byte on a few thousand records full of fp64 values
+    from quokkasim_b200 import csvlog
+
+    n_small = 2
+    subprocess.check_output([exe, "--replications", str(n_small), "--events", "2500", "--out", str(tmp_path)], text=True)
+    m = H.container_haulage()
+    sim = m.sim(lib, n_small, base_seed=42, log_capacity=65536)
+    sim.step_events(2500)
+    csl, cpl = m.container_loggers
+    assert open(tmp_path / "ContainerStockLogger.csv").read() == csvlog.csv_text(csl, sim, n_small - 1)
+    assert open(tmp_path / "ContainerProcessLogger.csv").read() == csvlog.csv_text(cpl, sim, n_small - 1)
+    sim.close()
 
 
 def test_cpp_container_example_matches_python_host(emul_lib, tmp_path):
