@@ -1,9 +1,11 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the B200 batched-replication executor.
 
-Metric (BASELINE.json): simulated events/sec (whole box) of the discrete_queue model, 1,048,576 replications x
-10,000 events per GPU, Philox seeds.  One "step" = Model::init + 10,000 executed scheduler actions of every
-replication of the batch (1.05e10 events per GPU).
+Metric (BASELINE.json): simulated events/sec (whole box, 1M replications) of the discrete_queue model: 1,048,576
+replications x 10,000 events, Philox seeds, split evenly over the N GPUs ("scaling": "strong"; --scaling weak keeps the
+replications PER GPU fixed instead).  One "step" = Model::init + 10,000 executed scheduler actions of every
+replication (1.05e10 events over the whole box).  --workload selects the other BASELINE configs (C3 vector_flow,
+C4 serial_line, C5 haulage) at their stated sizes.
 
   python bench.py [--gpus N --steps K --warmup W]            # our arm (N>1: launched by torchrun, one rank per GPU)
   python bench.py --impl reference [--gpus N ...]            # CPU arm: the oracle port of the reference engine on
@@ -38,12 +40,12 @@ def emit(obj):
 
 
 WORKLOADS = {
-    # name: (builder kwargs, replications per GPU, events per replication)
-    "discrete_queue": ("discrete_queue", {}, 1048576, 10000),
-    "serial_line": ("serial_line", {"n_proc": 32}, 100000, 100000),
-    "haulage": ("haulage", {"n_src": 8, "per_queue": 8}, 262144, 10000),
-    "vector_flow": ("vector_flow", {"dim": 3}, 262144, 10000),
-    "container_haulage": ("container_haulage", {"n_trucks": 8, "loaders": 2}, 262144, 10000),
+    # name: (builder, kwargs, replications (whole job), events per replication) -- BASELINE.json configs / SURVEY 8d
+    "discrete_queue": ("discrete_queue", {}, 1048576, 10000),                      # C2
+    "vector_flow": ("vector_flow", {"dim": 3}, 262144, 10000),                     # C3
+    "serial_line": ("serial_line", {"n_proc": 32}, 100000, 1000000),               # C4
+    "haulage": ("haulage", {"n_src": 8, "per_queue": 8}, 262144, 10000),           # C5 (one point of the sweep)
+    "container_haulage": ("container_haulage", {"n_trucks": 8, "loaders": 2}, 262144, 10000),  # row f3
 }
 
 
@@ -164,22 +166,28 @@ def run_reference(args):
         ev_sum += total
     value = ev_sum / t_sum
     sample = ("each step = %d replications x %d events (bounded sample of the %d-replication workload), oracle port "
-              "of the reference CPU path on %d host threads" % (reps, n_events, reps_gpu * args.gpus, threads))
+              "of the reference CPU path on %d host threads" % (reps, n_events, args.reps or reps_gpu, threads))
+    cfg = workload_config(args, args.reps or reps_gpu, n_events, 1)
+    # same workload definition as our arm; what the reference arm actually runs per step is stated next to it
+    cfg["reference_sample"] = ("each step of the reference arm = %d replications x %d events: a bounded sample of the "
+                               "workload's %d replications" % (reps, n_events, args.reps or reps_gpu))
+    cfg["reference_sample_replications_per_step"] = reps
     emit(({
         "impl": "reference", "metric": "simulated events/sec", "value": value, "unit": "events/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_sum / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": workload_config(args, reps_gpu, n_events),
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": cfg,
         "cpu_baseline": {"value": value, "unit": "events/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
 
 
-def workload_config(args, reps_gpu, n_events):
-    return {"workload": "%s batched: %d replications per GPU x %d events, Philox4x32-10 seeds"
-                        % (args.workload, args.reps or reps_gpu, n_events),
-            "replications_per_gpu": args.reps or reps_gpu, "events_per_replication": n_events,
+def workload_config(args, reps_total, n_events, world):
+    return {"workload": "%s batched: %d replications x %d events over %d GPU(s), Philox4x32-10 seeds"
+                        % (args.workload, reps_total, n_events, world),
+            "replications_total": reps_total, "replications_per_gpu": reps_total // world,
+            "events_per_replication": n_events,
             "logging": args.log, "log_ring_records": args.log_capacity if args.log != "off" else 0,
             "state": args.state, "threads_per_block": args.threads_per_block,
             "events_per_launch": args.events_per_launch or n_events,
@@ -187,6 +195,23 @@ def workload_config(args, reps_gpu, n_events):
 
 
 # ----------------------------------------------------------------------------------------------- GPU arm
+def lib_sha256(path=None):
+    import hashlib
+
+    from quokkasim_b200 import _capi
+
+    h = hashlib.sha256()
+    with open(path or _capi.DEFAULT_LIB, "rb") as f:
+        for blk in iter(lambda: f.read(1 << 20), b""):
+            h.update(blk)
+    return h.hexdigest()
+
+
+def median(xs):
+    xs = sorted(xs)
+    return xs[len(xs) // 2] if len(xs) % 2 else 0.5 * (xs[len(xs) // 2 - 1] + xs[len(xs) // 2])
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -202,24 +227,32 @@ def run_ours(args):
     device = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
-    _, _, reps_gpu, n_events = WORKLOADS[args.workload]
-    reps_gpu = args.reps or reps_gpu
+    _, _, reps_job, n_events = WORKLOADS[args.workload]
+    reps_job = args.reps or reps_job
+    if args.scaling == "weak":
+        reps_total = reps_job * world  # fixed work per GPU
+    else:
+        reps_total = reps_job          # BASELINE: the whole box shares the job's replications
+    rep_lo, rep_hi = parallel.shard_range(reps_total, rank, world)
+    reps_gpu = rep_hi - rep_lo
     n_events = args.events or n_events
     log_cap = args.log_capacity if args.log != "off" else 0
     model = build_model(args.workload)
     # a real (non-NULL) stream: the library launches on it, torch events and NCCL order against it
     stream = torch.cuda.Stream(device)
     torch.cuda.set_stream(stream)
+    flags = {"auto": 0, "hbm": 1, "chip": 2, "group": 4}[args.state]
 
-    def new_sim(log_capacity):
-        return model.sim(args.lib, reps_gpu, t0=0, base_seed=1234, rep_offset=rank * reps_gpu, log_capacity=log_capacity,
+    def new_sim(log_capacity, n=reps_gpu, off=rep_lo, seed=1234):
+        return model.sim(args.lib, n, t0=0, base_seed=seed, rep_offset=off, log_capacity=log_capacity,
                          threads_per_block=args.threads_per_block, stream=stream.cuda_stream, device=local_rank,
-                         flags=1 if args.state == "hbm" else 0)
+                         flags=flags)
 
     sim = new_sim(log_cap)
     sim._materialize()  # device state allocated; inputs (model tables, seeds) resident before the timed region
     L, b = sim.L, sim._batch
-    state_bytes = sim.state_bytes()
+    info = sim.info()
+    state_bytes = info["state_bytes_per_rep"]
 
     K = args.events_per_launch or n_events
 
@@ -242,21 +275,21 @@ def run_ours(args):
     if rank == 0:
         clocks.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kernel_ms = []
+    kernel_ms, launches = [], []
     ev0.record(stream)
     for _ in range(args.steps):
         one_step()
-        if args.per_launch_timing:
-            kernel_ms.append(sim.last_step_ms()[0])
+        # (reading the library's own CUDA events of the step just issued waits for that step: the next step's launch
+        # is issued a few microseconds late, once per step of >= tens of milliseconds)
+        ms_all, n_l = sim.last_step_ms()
+        kernel_ms.append(ms_all / max(1, n_l))
+        launches.append(n_l)
     ev1.record(stream)
     barrier()
     elapsed_ms = ev0.elapsed_time(ev1)
     clk = clocks.stop() if rank == 0 else None
-    if not args.per_launch_timing:
-        # the dominant kernel: the launches of the last step, CUDA events on their stream (average per launch)
-        ms_all, n_l = sim.last_step_ms()
-        kernel_ms.append(ms_all / max(1, n_l))
     summ = sim.summary()
+    step_chunks = sim.info()["last_step_chunks"]  # > 1 when the library cut the step into wave-sized launches
     t = torch.tensor([elapsed_ms], dtype=torch.float64, device=device)
     ev_total = torch.tensor([summ["n_events"], summ["n_log_records"], summ["n_faulted"]], dtype=torch.int64,
                             device=device)
@@ -281,45 +314,57 @@ def run_ours(args):
         recs_k1 = (s1["n_log_records"] - s0["n_log_records"]) / max(1, nl_k1)
         lockstep = (ms_k1 / max(1, nl_k1), recs_k1, (s1["n_events"] - s0["n_events"]) / (ms_k1 * 1e-3))
 
-    # ---- end to end through the public API with host buffers: build tables on the host, create the batch (H2D),
-    # init + step, reduce the summary statistics (NCCL when N>1), read them and a log sample back (D2H)
+    # ---- end to end through the public API with host buffers, every step: build the model tables on the host, create
+    # the batch (H2D), init + step, reduce the summary statistics over the replications (and over the GPUs: one
+    # all-gather + one all-reduce over NCCL), read them and a sample of the logs back (D2H).  Timed per step with the
+    # host clock around a barrier + device synchronisation; the reported value uses the MEDIAN step (max over ranks).
     sim.close()
     del sim
-    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    e2e_steps = max(1, args.e2e_steps)
     h2d = d2h = 0
     # untimed warm-up of the end-to-end path on a small batch: the first call of the reduction loads torch / NCCL kernels
     # (0.1 s once per process), which is not part of a step
-    w = model.sim(args.lib, 4096, t0=0, base_seed=1, rep_offset=rank * 4096, log_capacity=log_cap,
-                  stream=stream.cuda_stream, device=local_rank, flags=1 if args.state == "hbm" else 0)
+    w = new_sim(log_cap, n=4096, off=rank * 4096, seed=1)
     w.step_events(16)
     parallel.allreduce_summary(w, device)
     w.summary()
     if log_cap:
-        w.read_log(0)
+        w.read_logs(0, min(4096, args.e2e_log_reps))
     w.close()
     done_sims = []
-    barrier()
-    t0 = time.perf_counter()
+    step_s, phases = [], {"create": [], "init_step": [], "reduce": [], "d2h_logs": []}
     for _ in range(e2e_steps):
+        barrier()
+        t0 = time.perf_counter()
         s2 = new_sim(log_cap)
+        s2._materialize()  # lowering + allocation + H2D of the tables + the init launch (asynchronous)
+        t1 = time.perf_counter()
         s2.step_events(n_events)
+        s2.synchronize()
+        t2 = time.perf_counter()
         comp, n_ev, n_fault = parallel.allreduce_summary(s2, device)
-        sm2 = s2.summary()
-        d2h = s2.n_comp * (6 + 2 + 2 + 64) * 8 + 48
+        d2h = s2.n_comp * (20 + 64) * 8
+        t3 = time.perf_counter()
         if log_cap:
-            for r in range(0, min(reps_gpu, args.e2e_log_reps)):
-                recs, _ = s2.read_log(r)
-                d2h += recs.nbytes + 4
+            k = min(reps_gpu, args.e2e_log_reps)
+            logs, totals = s2.read_logs(0, k)
+            d2h += k * (log_cap * 32 + 12)
+        torch.cuda.synchronize(device)
+        t4 = time.perf_counter()
         h2d = s2.info()["table_bytes"] + 64  # model tables + batch config: the path's only host inputs
         done_sims.append(s2)
+        step_s.append(t4 - t0)
+        for kname, dt in (("create", t1 - t0), ("init_step", t2 - t1), ("reduce", t3 - t2), ("d2h_logs", t4 - t3)):
+            phases[kname].append(dt)
     barrier()
-    e2e_s = time.perf_counter() - t0
     for s2 in done_sims:  # cudaFree of multi-GB buffers is not part of the path (and sporadically takes 0.3 s)
         s2.close()
-    e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device=device)
+    e2e_t = torch.tensor(step_s, dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-    e2e_value = events_per_step * e2e_steps / float(e2e_t.item())
+    e2e_list = [float(x) for x in e2e_t.tolist()]
+    e2e_med = median(e2e_list)
+    e2e_value = events_per_step / e2e_med
 
     if rank == 0:
         peaks = {}
@@ -329,40 +374,56 @@ def run_ours(args):
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
-        # algorithmic bytes of one step launch on one GPU: B_alg = L + 2*S/K per event
+        # algorithmic bytes of one step on one GPU: B_alg = L + 2*S/K per event; the launches of a step
+        # (one, or the wave-sliced / K-chunked sequence) each move the state planes of the replications they advance
         ev_gpu = events_per_step / world
-        launches_per_step = (n_events + K - 1) // K
-        log_bytes = 32.0 * records_per_step / world / launches_per_step if log_cap else 0.0
-        alg_bytes = log_bytes + 2.0 * state_bytes * reps_gpu  # per launch: state planes in and out + its log records
-        k_ms = sorted(kernel_ms)[len(kernel_ms) // 2]
-        achieved = alg_bytes / (k_ms * 1e-3) / 1e9
-        # dram__bytes_read.sum + dram__bytes_write.sum of ONE step launch, from the committed ncu capture of this exact
-        # workload shape (profiles/r01_traffic.json); null for any other shape
+        launches_per_step = int(median(launches))
+        residencies = (n_events + K - 1) // K if K < n_events else max(1, step_chunks)
+        log_bytes = 32.0 * records_per_step / world if log_cap else 0.0
+        alg_bytes_step = log_bytes + 2.0 * state_bytes * reps_gpu * residencies
+        k_ms = median(kernel_ms)
+        step_kernel_ms = k_ms * launches_per_step
+        achieved = alg_bytes_step / (step_kernel_ms * 1e-3) / 1e9
+        # dram__bytes_read.sum + dram__bytes_write.sum of ONE step, from the committed ncu capture of this exact
+        # workload shape AND this exact build (sha256 of libquokka_b200.so); null otherwise
         traffic = None
         try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
             rec = tr.get(args.workload, {}).get(args.log)
-            if rec and rec["replications"] == reps_gpu and rec["events"] == n_events:
-                traffic = rec["dram_bytes_per_launch"]
+            if (rec and rec["replications"] == reps_gpu and rec["events"] == n_events
+                    and rec.get("lib_sha256") == lib_sha256(args.lib)):
+                traffic = rec["dram_bytes_per_step"]
         except Exception:
             pass
         out = {
             "metric": "simulated events/sec", "value": value, "unit": "events/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": workload_config(args, reps_gpu, n_events),
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "u64",
+            "data": "synthetic",
+            "config": workload_config(args, reps_total, n_events, world),
             "e2e": {"value": e2e_value, "unit": "events/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps},
+                    "steps": e2e_steps, "step_s": e2e_list, "median_step_s": e2e_med,
+                    "spread": (max(e2e_list) - min(e2e_list)) / e2e_med,
+                    "phases_s_median_rank0": {k: median(v) for k, v in phases.items()},
+                    "log_sample_replications": min(reps_gpu, args.e2e_log_reps) if log_cap else 0},
             "gpu_launches": (1 + launches_per_step) * args.steps,
             "clocks": clk,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel": "qk_step_kernel",
-                         "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg_bytes,
-                         "bytes_per_event": alg_bytes * launches_per_step / ev_gpu,
-                         "state_bytes_per_replication": state_bytes, "events_per_residency_K": K,
-                         "launches_per_step": launches_per_step},
+                         "traffic": traffic, "peak_source": peak_src, "kernel": "qk_group_kernel" if info["lanes_per_replication"] > 1 else "qk_step_kernel",
+                         "kernel_ms": k_ms, "step_kernel_ms": step_kernel_ms,
+                         "algorithmic_bytes_per_launch": alg_bytes_step / launches_per_step,
+                         "algorithmic_bytes_per_step": alg_bytes_step,
+                         "bytes_per_event": alg_bytes_step / ev_gpu,
+                         "state_bytes_per_replication": state_bytes, "events_per_residency_K": n_events // residencies,
+                         "launches_per_step": launches_per_step, "lib_sha256": lib_sha256(args.lib)},
             "faulted_replications": int(ev_total[2].item()),
             "per_gpu_events_per_s": value / world,
+            "placement": {"state": "hbm" if info["state_in_hbm"] else (
+                              "lane-group" if info["lanes_per_replication"] > 1 else "shared-memory"),
+                          "lanes_per_replication": info["lanes_per_replication"],
+                          "threads_per_block": info["threads_per_block"], "grid_blocks": info["grid_blocks"],
+                          "resident_blocks_per_sm": info["resident_blocks_per_sm"],
+                          "wave_blocks": info["wave_blocks"], "step_chunks": step_chunks},
         }
         if lockstep is not None:
             ms1, recs1, evps1 = lockstep
@@ -392,15 +453,18 @@ def main():
     ap.add_argument("--log", default="ring", choices=["ring", "off"])
     ap.add_argument("--log-capacity", type=int, default=64)
     ap.add_argument("--threads-per-block", type=int, default=0)
-    ap.add_argument("--state", default="auto", choices=["auto", "hbm"],
-                    help="auto: state staged in shared memory when it fits; hbm: operate on the HBM planes in place")
+    ap.add_argument("--state", default="auto", choices=["auto", "hbm", "chip", "group"],
+                    help="auto: the library chooses; hbm: operate on the HBM planes in place; chip: one thread per "
+                         "replication, state staged in shared memory; group: a lane group per replication, state in "
+                         "shared memory (large models)")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="strong (BASELINE): the job's replications are split over the GPUs; weak: that many PER GPU")
     ap.add_argument("--events-per-launch", type=int, default=0,
                     help="K: events advanced per state residency (default: all events of a step in one launch); small K "
                          "makes the state round-trip HBM every K events -- the regime where the kernel is HBM-bound")
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--e2e-log-reps", type=int, default=256)
     ap.add_argument("--ref-step-seconds", type=float, default=6.0)
-    ap.add_argument("--per-launch-timing", action="store_true")
     ap.add_argument("--lib", default=None, help="path of an alternative build of libquokka_b200.so (A/B experiments)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-lockstep-probe", action="store_true")

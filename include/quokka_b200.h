@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define QK_ABI_VERSION 1
+#define QK_ABI_VERSION 2
 
 typedef enum {
   QK_OK = 0,
@@ -219,12 +219,32 @@ typedef struct {
   uint64_t sum_level;
   uint64_t min_count, max_count;
   uint64_t min_time, max_time;
-  double sumsq_time; /* sum over replications of (time_ns * 1e-9)^2, fixed reduction order */
+  double sumsq_time; /* sum over replications of (time_ns * 1e-9)^2: the exact integer below, rounded once */
   double sumsq_count;
   uint64_t hist_time[QK_HIST_BINS]; /* replications binned on time_ns over [hist_lo_time, hist_hi_time] */
   uint64_t hist_count[QK_HIST_BINS];
   uint64_t hist_lo_time, hist_hi_time, hist_lo_count, hist_hi_count;
+  /* exact second moments (ABI 2): independent of how the replications are spread over blocks or GPUs */
+  uint64_t sumsq_time_ns2[3];              /* sum of time_ns^2 as a 192-bit integer, least significant limb first */
+  uint64_t sumsq_count_lo, sumsq_count_hi; /* sum of count^2, 128-bit */
+  uint64_t sumsq_level;                    /* sum of level^2 (stock occupancy now / items in progress now) */
 } qk_comp_summary;
+
+/* Packed partial sums of one component over the replications of one batch: QK_PARTIAL_WORDS u64 words.  This is what
+ * crosses GPUs -- ONE all-gather of [n_comp][QK_PARTIAL_WORDS] per rank, then qk_batch_combine_partials_device -- and
+ * every word is an exact integer: the four extrema words combine with unsigned MIN (maxima are stored complemented),
+ * all others with a wrapping SUM.  Sums that can exceed 64 bits travel as the sums of their low and high 32-bit halves:
+ * time_ns = a * 2^32 + b gives sum(time_ns) = TIME_HI * 2^32 + TIME_LO and sum(time_ns^2) = AA * 2^64 + 2 * AB * 2^32 +
+ * BB with AA = AA_HI * 2^32 + AA_LO the sum of a^2 (AB, BB, CC = sum of count^2 alike). */
+#define QK_PARTIAL_WORDS 20
+enum {
+  QP_COUNT = 0, QP_TIME_LO = 1, QP_TIME_HI = 2, QP_LEVEL = 3,
+  QP_NEVENTS = 4, QP_NFAULTED = 5, /* whole batch, stored with component 0 only */
+  QP_MIN_COUNT = 6, QP_MIN_TIME = 7, QP_NMAX_COUNT = 8, QP_NMAX_TIME = 9, /* ~max so that MIN serves both */
+  QP_AA_LO = 10, QP_AA_HI = 11, QP_AB_LO = 12, QP_AB_HI = 13, QP_BB_LO = 14, QP_BB_HI = 15,
+  QP_CC_LO = 16, QP_CC_HI = 17, QP_LEVEL_SQ = 18,
+  QP_NREPS = 19 /* replications reduced, stored with component 0 only */
+};
 
 typedef struct {
   uint64_t n_reps;
@@ -300,6 +320,11 @@ typedef struct {
   uint32_t cold_bytes_per_rep;       /* COLD state (item rings, source ids of pending events): global memory only */
   uint64_t replications_padded;
   uint64_t state_bytes_total, log_bytes_total;
+  /* ABI 2 */
+  uint32_t lanes_per_replication; /* 1: one thread per replication ; 4/8/16: a lane group per replication */
+  uint32_t wave_blocks;           /* blocks of the step kernel resident on the whole GPU at once */
+  uint32_t last_step_chunks;      /* state residencies of the last step call: 1, or the chunks of a wave-sliced step */
+  uint32_t reserved;
 } qk_batch_info;
 
 int qk_batch_create(const qk_model*, const qk_batch_config*, qk_batch** out);
@@ -314,6 +339,10 @@ int qk_batch_step_events(qk_batch*, uint64_t n_events);
 /* same result as qk_batch_step_events, cut into launches of `chunk` events (state round-trips HBM between them);
  * for measuring the kernel at a small number of events per state residency */
 int qk_batch_step_events_chunked(qk_batch*, uint64_t n_events, uint64_t chunk);
+/* same result again, as the wave-sliced schedule qk_batch_step_events chooses by itself when a launch would end in a
+ * mostly empty last wave: the step is cut into n_chunks chunks of events and the (block, chunk) work items are issued
+ * as launches of exactly one GPU-filling wave each (n_chunks = 0: let the library decide) */
+int qk_batch_step_events_sliced(qk_batch*, uint64_t n_events, uint32_t n_chunks);
 int qk_batch_synchronize(qk_batch*);
 
 /* ---- results ------------------------------------------------------------------------------------ */
@@ -321,15 +350,23 @@ int qk_batch_summary_get(qk_batch*, qk_batch_summary* out);
 int qk_batch_read_status(qk_batch*, uint64_t rep0, uint64_t n, uint32_t* status, uint64_t* now_ns, uint64_t* n_events);
 int qk_batch_comp_stats(qk_batch*, uint64_t rep0, uint64_t n, uint32_t comp, qk_comp_stats* out);
 int qk_batch_reduce_stats(qk_batch*, qk_comp_summary* out, uint32_t n_comp);
-/* device-resident variant for multi-GPU: fills caller-provided DEVICE arrays so that the caller can
- * all-reduce them (NCCL) without a host round trip. sums: [n_comp][6] u64 (count, time_lo, time_hi, level,
- * n_events(comp 0 only), n_faulted(comp 0 only)); extrema: [n_comp][4] u64 (min_count, min_time, then
- * ~max_count, ~max_time so that one MIN all-reduce serves both). */
-int qk_batch_reduce_stats_device(qk_batch*, uint64_t* d_sums, uint64_t* d_extrema, uint32_t n_comp);
-/* histograms over caller-supplied global ranges (after the extrema all-reduce): d_hist [n_comp][2][QK_HIST_BINS] */
-int qk_batch_histograms_device(qk_batch*, const uint64_t* d_extrema, uint64_t* d_hist, uint32_t n_comp);
+/* the packed partials of this batch on the host: partials[n_comp][QK_PARTIAL_WORDS] */
+int qk_batch_reduce_partials(qk_batch*, uint64_t* partials, uint32_t n_comp);
+/* device-resident variants for multi-GPU callers that own the collective (quokkasim_b200/parallel.py; qk_multi_* below
+ * does the same inside the library): fill a caller-provided DEVICE array with this batch's packed partials, enqueued on
+ * the batch's stream ... */
+int qk_batch_reduce_partials_device(qk_batch*, uint64_t* d_partials, uint32_t n_comp);
+/* ... combine n_parts such arrays laid end to end (the result of an all-gather) into d_out (may alias none of them) */
+int qk_batch_combine_partials_device(qk_batch*, const uint64_t* d_parts, uint32_t n_parts, uint64_t* d_out,
+                                     uint32_t n_comp);
+/* ... and bin this batch's replications over the GLOBAL ranges found in the combined partials:
+ * d_hist [n_comp][2][QK_HIST_BINS] (time_ns, count); the histograms of the ranks then add */
+int qk_batch_histograms_device(qk_batch*, const uint64_t* d_partials, uint64_t* d_hist, uint32_t n_comp);
 /* records of one replication, oldest first (at most log_capacity newest); *n_total = records ever written */
 int qk_batch_read_log(qk_batch*, uint64_t rep, qk_log_record* buf, uint64_t cap, uint64_t* n_out, uint64_t* n_total);
+/* the same for replications [rep0, rep0 + n) with ONE gather kernel and one copy: buf[n][log_capacity] (the first
+ * kept[i] records of row i are valid, oldest first), kept[n], total[n] */
+int qk_batch_read_logs(qk_batch*, uint64_t rep0, uint64_t n, qk_log_record* buf, uint32_t* kept, uint64_t* total);
 /* resource of a vector stock / in-flight vector of a vector process-like component (3 doubles) */
 int qk_batch_read_vector(qk_batch*, uint64_t rep, uint32_t comp, double* out3);
 /* discrete stock contents in FIFO order */

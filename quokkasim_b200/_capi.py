@@ -45,9 +45,11 @@ EXPORTED_SYMBOLS = [
     "qk_model_set_vector", "qk_model_set_ports", "qk_model_schedule_low_capacity", "qk_batch_read_vector",
     "qk_model_n_components", "qk_model_n_dists", "qk_model_state_bytes", "qk_batch_create", "qk_batch_destroy",
     "qk_batch_info_get",
-    "qk_batch_set_tape", "qk_batch_init", "qk_batch_step_until", "qk_batch_step_events", "qk_batch_step_events_chunked", "qk_batch_synchronize",
+    "qk_batch_set_tape", "qk_batch_init", "qk_batch_step_until", "qk_batch_step_events", "qk_batch_step_events_chunked", "qk_batch_step_events_sliced",
+    "qk_batch_synchronize",
     "qk_batch_summary_get", "qk_batch_read_status", "qk_batch_comp_stats", "qk_batch_reduce_stats",
-    "qk_batch_reduce_stats_device", "qk_batch_histograms_device", "qk_batch_read_log", "qk_batch_read_stock",
+    "qk_batch_reduce_partials", "qk_batch_reduce_partials_device", "qk_batch_combine_partials_device",
+    "qk_batch_histograms_device", "qk_batch_read_log", "qk_batch_read_logs", "qk_batch_read_stock",
     "qk_batch_last_step_ms", "qk_last_error",
     "qk_model_set_container_factory", "qk_model_set_initial_containers", "qk_batch_read_containers",
 ]
@@ -94,6 +96,8 @@ class BatchInfo(C.Structure):
         ("state_bytes_per_rep", C.c_uint32), ("resident_blocks_per_sm", C.c_uint32),
         ("state_in_hbm", C.c_uint32), ("cold_bytes_per_rep", C.c_uint32),
         ("replications_padded", C.c_uint64), ("state_bytes_total", C.c_uint64), ("log_bytes_total", C.c_uint64),
+        ("lanes_per_replication", C.c_uint32), ("wave_blocks", C.c_uint32), ("last_step_chunks", C.c_uint32),
+        ("reserved", C.c_uint32),
     ]
 
 
@@ -108,8 +112,14 @@ COMP_SUMMARY_DTYPE = np.dtype(
      ("min_count", "<u8"), ("max_count", "<u8"), ("min_time", "<u8"), ("max_time", "<u8"),
      ("sumsq_time", "<f8"), ("sumsq_count", "<f8"), ("hist_time", "<u8", (HIST_BINS,)),
      ("hist_count", "<u8", (HIST_BINS,)), ("hist_lo_time", "<u8"), ("hist_hi_time", "<u8"),
-     ("hist_lo_count", "<u8"), ("hist_hi_count", "<u8")]
+     ("hist_lo_count", "<u8"), ("hist_hi_count", "<u8"), ("sumsq_time_ns2", "<u8", (3,)),
+     ("sumsq_count_lo", "<u8"), ("sumsq_count_hi", "<u8"), ("sumsq_level", "<u8")]
 )
+# packed partials (quokka_b200.h QK_PARTIAL_WORDS / QP_*)
+PARTIAL_WORDS = 20
+(QP_COUNT, QP_TIME_LO, QP_TIME_HI, QP_LEVEL, QP_NEVENTS, QP_NFAULTED, QP_MIN_COUNT, QP_MIN_TIME, QP_NMAX_COUNT,
+ QP_NMAX_TIME, QP_AA_LO, QP_AA_HI, QP_AB_LO, QP_AB_HI, QP_BB_LO, QP_BB_HI, QP_CC_LO, QP_CC_HI, QP_LEVEL_SQ,
+ QP_NREPS) = range(20)
 assert LOG_DTYPE.itemsize == 32 and COMP_STATS_DTYPE.itemsize == 48
 
 _LIBS = {}
@@ -153,13 +163,17 @@ def load_library(path=None):
         "qk_batch_step_until": (C.c_int, [vp, u64]),
         "qk_batch_step_events": (C.c_int, [vp, u64]),
         "qk_batch_step_events_chunked": (C.c_int, [vp, u64, u64]),
+        "qk_batch_step_events_sliced": (C.c_int, [vp, u64, u32]),
         "qk_batch_synchronize": (C.c_int, [vp]),
         "qk_batch_summary_get": (C.c_int, [vp, P(BatchSummary)]),
         "qk_batch_read_status": (C.c_int, [vp, u64, u64, vp, vp, vp]),
         "qk_batch_comp_stats": (C.c_int, [vp, u64, u64, u32, vp]),
         "qk_batch_reduce_stats": (C.c_int, [vp, vp, u32]),
-        "qk_batch_reduce_stats_device": (C.c_int, [vp, vp, vp, u32]),
+        "qk_batch_reduce_partials": (C.c_int, [vp, vp, u32]),
+        "qk_batch_reduce_partials_device": (C.c_int, [vp, vp, u32]),
+        "qk_batch_combine_partials_device": (C.c_int, [vp, vp, u32, vp, u32]),
         "qk_batch_histograms_device": (C.c_int, [vp, vp, vp, u32]),
+        "qk_batch_read_logs": (C.c_int, [vp, u64, u64, vp, vp, vp]),
         "qk_batch_read_log": (C.c_int, [vp, u64, vp, u64, P(u64), P(u64)]),
         "qk_batch_read_stock": (C.c_int, [vp, u64, u32, vp, u64, P(u64)]),
         "qk_batch_last_step_ms": (C.c_int, [vp, P(C.c_float), P(u32)]),

@@ -846,6 +846,11 @@ class BatchedSimulation:
         self._materialize()
         capi.check(self.L, self.L.qk_batch_step_events_chunked(self._batch, int(n_events), int(chunk)))
 
+    def step_events_sliced(self, n_events, n_chunks):
+        """step_events as wave-sized launches over (block, chunk) work items; same results."""
+        self._materialize()
+        capi.check(self.L, self.L.qk_batch_step_events_sliced(self._batch, int(n_events), int(n_chunks)))
+
     def synchronize(self):
         self._materialize()
         capi.check(self.L, self.L.qk_batch_synchronize(self._batch))
@@ -944,14 +949,37 @@ class BatchedSimulation:
                                                            h.size, C.byref(n)))
         return h[: n.value], r[: n.value]
 
-    # device-resident reduction for the multi-GPU path (see parallel.py)
-    def reduce_stats_device(self, d_sums_ptr, d_extrema_ptr):
+    def read_logs(self, rep0, n):
+        """Retained records of replications [rep0, rep0 + n): ONE gather kernel and one device-to-host copy.
+        Returns (list of record arrays, oldest first; array of records ever written)."""
         self._materialize()
-        capi.check(self.L, self.L.qk_batch_reduce_stats_device(self._batch, d_sums_ptr, d_extrema_ptr, self.n_comp))
+        buf = np.zeros((n, max(self.log_capacity, 1)), dtype=capi.LOG_DTYPE)
+        kept = np.zeros(n, dtype=np.uint32)
+        total = np.zeros(n, dtype=np.uint64)
+        capi.check(self.L, self.L.qk_batch_read_logs(self._batch, rep0, n, buf.ctypes.data, kept.ctypes.data,
+                                                     total.ctypes.data))
+        return [buf[i, : kept[i]] for i in range(n)], total
 
-    def histograms_device(self, d_extrema_ptr, d_hist_ptr):
+    def reduce_partials(self):
+        """Packed partial sums of this batch, (n_comp, PARTIAL_WORDS) uint64 (quokka_b200.h QP_*)."""
         self._materialize()
-        capi.check(self.L, self.L.qk_batch_histograms_device(self._batch, d_extrema_ptr, d_hist_ptr, self.n_comp))
+        out = np.zeros((self.n_comp, capi.PARTIAL_WORDS), dtype=np.uint64)
+        capi.check(self.L, self.L.qk_batch_reduce_partials(self._batch, out.ctypes.data, self.n_comp))
+        return out
+
+    # device-resident reduction for the multi-GPU path (see parallel.py)
+    def reduce_partials_device(self, d_partials_ptr):
+        self._materialize()
+        capi.check(self.L, self.L.qk_batch_reduce_partials_device(self._batch, d_partials_ptr, self.n_comp))
+
+    def combine_partials_device(self, d_parts_ptr, n_parts, d_out_ptr):
+        self._materialize()
+        capi.check(self.L, self.L.qk_batch_combine_partials_device(self._batch, d_parts_ptr, n_parts, d_out_ptr,
+                                                                   self.n_comp))
+
+    def histograms_device(self, d_partials_ptr, d_hist_ptr):
+        self._materialize()
+        capi.check(self.L, self.L.qk_batch_histograms_device(self._batch, d_partials_ptr, d_hist_ptr, self.n_comp))
 
 
 # --------------------------------------------------------------------------------------- vector family

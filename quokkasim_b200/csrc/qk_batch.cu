@@ -57,12 +57,18 @@ struct qk_batch {
   uint32_t last_launches;
   uint64_t total_launches;
   /* reduction scratch */
-  uint64_t* d_sums;
-  uint64_t* d_ext;
+  uint64_t* d_part; /* packed partials [n_comp][QK_PARTIAL_WORDS] */
   uint64_t* d_hist;
-  double* d_sq_partial;
-  double* d_sq;
   uint32_t red_blocks;
+  /* small persistent buffers for the result calls (no cudaMalloc / cudaFree -- a device-wide synchronisation each --
+   * on the read-back path) */
+  uint8_t* d_scratch;
+  size_t scratch_bytes;
+  uint8_t* h_pinned;
+  size_t pinned_bytes;
+  uint32_t lanes;       /* lanes per replication: 1, or the group width of the lane-group kernel */
+  uint32_t last_chunks; /* state residencies of the last step call */
+  uint32_t n_sm, wave_blocks; /* SMs of the device ; blocks of the step kernel resident on the whole GPU at once */
 };
 
 /* the step kernel instantiations live in qk_step_l{0,1}f{0,1}.cu */
@@ -113,8 +119,13 @@ static uint32_t choose_nt(uint32_t per_rep_bytes, uint32_t table_bytes, uint32_t
   return best_nt;
 }
 
+struct QkSlice {
+  uint32_t item0, n_items; /* n_items == 0: a plain launch over every tile */
+  uint64_t chunk_events, total_events;
+};
+
 static int launch_step(qk_batch* b, uint32_t do_init, uint64_t t0, uint64_t t_until, uint64_t budget,
-                       bool record_begin = true, bool record_end = true) {
+                       bool record_begin = true, bool record_end = true, const QkSlice* slice = nullptr) {
   KParams P;
   memset(&P, 0, sizeof(P));
   P.g64 = b->g64;
@@ -141,11 +152,19 @@ static int launch_step(qk_batch* b, uint32_t do_init, uint64_t t0, uint64_t t_un
   P.t_until = t_until;
   P.event_budget = budget;
   P.do_init = do_init;
+  uint32_t grid = b->grid;
+  if (slice && slice->n_items) {
+    P.item0 = slice->item0;
+    P.n_tiles = b->grid;
+    P.chunk_events = slice->chunk_events;
+    P.sliced_total = slice->total_events;
+    grid = slice->n_items;
+  }
   if (record_begin) {
     CUDA_TRY(cudaEventRecord(b->ev0, b->stream));
     b->last_launches = 0;
   }
-  b->kernel<<<b->grid, b->nt, b->smem_bytes, b->stream>>>(P);
+  b->kernel<<<grid, b->nt, b->smem_bytes, b->stream>>>(P);
   CUDA_TRY(cudaGetLastError());
   if (record_end) CUDA_TRY(cudaEventRecord(b->ev1, b->stream));
   b->last_launches += 1;
@@ -180,87 +199,97 @@ __device__ __forceinline__ double warp_sum_f64(double v) {
   return v;
 }
 
-/* grid = (red_blocks, n_comp).  sums[c] = {count, time_lo32 sum, time_hi32 sum, level, n_events, n_faulted};
- * ext[c] = {min_count, min_time, ~max_count, ~max_time}; sq_partial[c][block] = {sum t^2, sum count^2} */
+/* grid = (red_blocks, n_comp): the packed partials of one component (quokka_b200.h, QK_PARTIAL_WORDS / QP_*) over the
+ * replications of this batch.  Everything is an exact integer -- second moments too: time_ns = a * 2^32 + b, so
+ * time_ns^2 = a^2 * 2^64 + 2ab * 2^32 + b^2, and each of a^2, ab, b^2 (< 2^64) is summed as its low and high 32-bit
+ * halves -- so the result does not depend on how the replications are partitioned over blocks or GPUs. */
 __global__ void __launch_bounds__(256) qk_reduce_kernel(const uint8_t* tables, const uint64_t* g64,
                                                         const uint32_t* g32, const uint64_t* gs64,
                                                         const uint32_t* gs32, uint64_t rep_pad, uint64_t n_reps,
-                                                        uint64_t* sums, uint64_t* ext, double* sq_partial) {
+                                                        uint64_t* part) {
   const DevHeader* h = reinterpret_cast<const DevHeader*>(tables);
   const uint32_t comp = blockIdx.y;
   const DevComp* c = reinterpret_cast<const DevComp*>(tables + h->off_comps) + comp;
-  uint64_t a[6] = {0, 0, 0, 0, 0, 0};
-  uint64_t mn[4] = {~0ull, ~0ull, ~0ull, ~0ull};
-  double sq[2] = {0.0, 0.0};
+  uint64_t a[QK_PARTIAL_WORDS];
+  for (int k = 0; k < QK_PARTIAL_WORDS; ++k) a[k] = (k >= QP_MIN_COUNT && k <= QP_NMAX_TIME) ? ~0ull : 0ull;
   for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_reps; r += (uint64_t)gridDim.x * blockDim.x) {
     qk_comp_stats s;
     qk_comp_stats_dev(c, reinterpret_cast<const DevVec*>(tables + h->off_vecs), comp, g64, g32, gs64, gs32, rep_pad, r, &s);
-    a[0] += s.count;
-    a[1] += s.time_ns & 0xFFFFFFFFull;
-    a[2] += s.time_ns >> 32;
-    a[3] += s.level;
+    const uint64_t lo = s.time_ns & 0xFFFFFFFFull, hi = s.time_ns >> 32;
+    a[QP_COUNT] += s.count;
+    a[QP_TIME_LO] += lo;
+    a[QP_TIME_HI] += hi;
+    a[QP_LEVEL] += s.level;
     if (comp == 0) {
-      a[4] += g64[(size_t)G64_NEVENTS * rep_pad + r];
-      a[5] += g32[(size_t)G32_STATUS * rep_pad + r] ? 1 : 0;
+      a[QP_NEVENTS] += g64[(size_t)G64_NEVENTS * rep_pad + r];
+      a[QP_NFAULTED] += g32[(size_t)G32_STATUS * rep_pad + r] ? 1 : 0;
+      a[QP_NREPS] += 1;
     }
-    mn[0] = s.count < mn[0] ? s.count : mn[0];
-    mn[1] = s.time_ns < mn[1] ? s.time_ns : mn[1];
-    mn[2] = ~s.count < mn[2] ? ~s.count : mn[2];
-    mn[3] = ~s.time_ns < mn[3] ? ~s.time_ns : mn[3];
-    const double ts = (double)s.time_ns * 1e-9;
-    sq[0] += ts * ts;
-    sq[1] += (double)s.count * (double)s.count;
+    a[QP_MIN_COUNT] = s.count < a[QP_MIN_COUNT] ? s.count : a[QP_MIN_COUNT];
+    a[QP_MIN_TIME] = s.time_ns < a[QP_MIN_TIME] ? s.time_ns : a[QP_MIN_TIME];
+    a[QP_NMAX_COUNT] = ~s.count < a[QP_NMAX_COUNT] ? ~s.count : a[QP_NMAX_COUNT];
+    a[QP_NMAX_TIME] = ~s.time_ns < a[QP_NMAX_TIME] ? ~s.time_ns : a[QP_NMAX_TIME];
+    const uint64_t aa = hi * hi, ab = hi * lo, bb = lo * lo;
+    a[QP_AA_LO] += aa & 0xFFFFFFFFull;
+    a[QP_AA_HI] += aa >> 32;
+    a[QP_AB_LO] += ab & 0xFFFFFFFFull;
+    a[QP_AB_HI] += ab >> 32;
+    a[QP_BB_LO] += bb & 0xFFFFFFFFull;
+    a[QP_BB_HI] += bb >> 32;
+    const uint64_t cn = s.count & 0xFFFFFFFFull; /* counts are 32-bit accumulators (ST32_COUNT) */
+    const uint64_t cc = cn * cn;
+    a[QP_CC_LO] += cc & 0xFFFFFFFFull;
+    a[QP_CC_HI] += cc >> 32;
+    a[QP_LEVEL_SQ] += s.level * s.level;
   }
-  __shared__ uint64_t sh_a[8][6];
-  __shared__ uint64_t sh_m[8][4];
-  __shared__ double sh_q[8][2];
+  __shared__ uint64_t sh[8][QK_PARTIAL_WORDS];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  for (int k = 0; k < 6; ++k) {
-    const uint64_t v = warp_sum_u64(a[k]);
-    if (lane == 0) sh_a[wid][k] = v;
-  }
-  for (int k = 0; k < 4; ++k) {
-    const uint64_t v = warp_min_u64(mn[k]);
-    if (lane == 0) sh_m[wid][k] = v;
-  }
-  for (int k = 0; k < 2; ++k) {
-    const double v = warp_sum_f64(sq[k]);
-    if (lane == 0) sh_q[wid][k] = v;
+  for (int k = 0; k < QK_PARTIAL_WORDS; ++k) {
+    const bool is_min = k >= QP_MIN_COUNT && k <= QP_NMAX_TIME;
+    const uint64_t v = is_min ? warp_min_u64(a[k]) : warp_sum_u64(a[k]);
+    if (lane == 0) sh[wid][k] = v;
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    const int nw = blockDim.x >> 5;
-    for (int k = 0; k < 6; ++k) {
-      uint64_t v = 0;
-      for (int w = 0; w < nw; ++w) v += sh_a[w][k];
-      atomicAdd((unsigned long long*)&sums[comp * 6 + k], (unsigned long long)v);
-    }
-    for (int k = 0; k < 4; ++k) {
-      uint64_t v = ~0ull;
-      for (int w = 0; w < nw; ++w) v = sh_m[w][k] < v ? sh_m[w][k] : v;
-      atomicMin((unsigned long long*)&ext[comp * 4 + k], (unsigned long long)v);
-    }
-    for (int k = 0; k < 2; ++k) {
-      double v = 0;
-      for (int w = 0; w < nw; ++w) v += sh_q[w][k];
-      sq_partial[((size_t)comp * gridDim.x + blockIdx.x) * 2 + k] = v;
-    }
+  if (threadIdx.x < QK_PARTIAL_WORDS) {
+    const int k = threadIdx.x, nw = blockDim.x >> 5;
+    const bool is_min = k >= QP_MIN_COUNT && k <= QP_NMAX_TIME;
+    uint64_t v = is_min ? ~0ull : 0ull;
+    for (int w = 0; w < nw; ++w) v = is_min ? (sh[w][k] < v ? sh[w][k] : v) : v + sh[w][k];
+    unsigned long long* dst = (unsigned long long*)&part[(size_t)comp * QK_PARTIAL_WORDS + k];
+    if (is_min)
+      atomicMin(dst, (unsigned long long)v);
+    else if (v)
+      atomicAdd(dst, (unsigned long long)v);
   }
 }
 
-/* fixed-order final sum of the per-block partials: deterministic fp64 result */
-__global__ void qk_reduce_sq_kernel(const double* sq_partial, uint32_t n_blocks, double* sq) {
-  const uint32_t comp = blockIdx.x;
-  if (threadIdx.x < 2) {
-    double v = 0;
-    for (uint32_t b = 0; b < n_blocks; ++b) v += sq_partial[((size_t)comp * n_blocks + b) * 2 + threadIdx.x];
-    sq[comp * 2 + threadIdx.x] = v;
+/* the neutral element of the combination: 0 for the sums, ~0 for the four extrema words */
+__global__ void qk_partials_clear_kernel(uint64_t* part, uint32_t n_words) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_words) {
+    const uint32_t k = i % QK_PARTIAL_WORDS;
+    part[i] = (k >= QP_MIN_COUNT && k <= QP_NMAX_TIME) ? ~0ull : 0ull;
   }
 }
 
-/* hist[c][0][bin] over time_ns, hist[c][1][bin] over count; ranges from ext (min, ~max) */
+/* out = combination of n_parts packed partial arrays laid end to end (what an all-gather over the GPUs delivers):
+ * unsigned min on the extrema words, wrapping sum on everything else */
+__global__ void qk_partials_combine_kernel(const uint64_t* parts, uint32_t n_parts, uint32_t n_words, uint64_t* out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_words) return;
+  const uint32_t k = i % QK_PARTIAL_WORDS;
+  const bool is_min = k >= QP_MIN_COUNT && k <= QP_NMAX_TIME;
+  uint64_t v = is_min ? ~0ull : 0ull;
+  for (uint32_t p = 0; p < n_parts; ++p) {
+    const uint64_t w = parts[(size_t)p * n_words + i];
+    v = is_min ? (w < v ? w : v) : v + w;
+  }
+  out[i] = v;
+}
+
+/* hist[c][0][bin] over time_ns, hist[c][1][bin] over count; ranges from the extrema words of (combined) partials */
 __global__ void __launch_bounds__(256) qk_hist_kernel(const uint8_t* tables, const uint64_t* g64, const uint32_t* g32,
-                                                      const uint64_t* gs64, const uint32_t* gs32, uint64_t rep_pad, uint64_t n_reps, const uint64_t* ext,
+                                                      const uint64_t* gs64, const uint32_t* gs32, uint64_t rep_pad, uint64_t n_reps, const uint64_t* part,
                                                       uint64_t* hist) {
   const DevHeader* h = reinterpret_cast<const DevHeader*>(tables);
   const uint32_t comp = blockIdx.y;
@@ -268,8 +297,9 @@ __global__ void __launch_bounds__(256) qk_hist_kernel(const uint8_t* tables, con
   __shared__ unsigned long long sh[2][QK_HIST_BINS];
   if (threadIdx.x < 2 * QK_HIST_BINS) sh[threadIdx.x / QK_HIST_BINS][threadIdx.x % QK_HIST_BINS] = 0;
   __syncthreads();
-  const uint64_t lo_c = ext[comp * 4 + 0], lo_t = ext[comp * 4 + 1];
-  const uint64_t hi_c = ~ext[comp * 4 + 2], hi_t = ~ext[comp * 4 + 3];
+  const uint64_t* ext = part + (size_t)comp * QK_PARTIAL_WORDS;
+  const uint64_t lo_c = ext[QP_MIN_COUNT], lo_t = ext[QP_MIN_TIME];
+  const uint64_t hi_c = ~ext[QP_NMAX_COUNT], hi_t = ~ext[QP_NMAX_TIME];
   const uint64_t w_c = (hi_c - lo_c) / QK_HIST_BINS + 1, w_t = (hi_t - lo_t) / QK_HIST_BINS + 1;
   for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_reps; r += (uint64_t)gridDim.x * blockDim.x) {
     qk_comp_stats s;
@@ -281,6 +311,29 @@ __global__ void __launch_bounds__(256) qk_hist_kernel(const uint8_t* tables, con
   if (threadIdx.x < 2 * QK_HIST_BINS) {
     const unsigned long long v = sh[threadIdx.x / QK_HIST_BINS][threadIdx.x % QK_HIST_BINS];
     if (v) atomicAdd((unsigned long long*)&hist[(size_t)comp * 2 * QK_HIST_BINS + threadIdx.x], v);
+  }
+}
+
+/* the retained records of replications [rep0, rep0 + n) in canonical order (oldest first), one block per replication:
+ * out[(r - rep0) * log_cap + i], kept[r - rep0] = records retained, total[r - rep0] = records ever written */
+__global__ void qk_gather_logs_kernel(const uint4* log, const uint32_t* g32, uint64_t rep_pad, uint64_t rep0,
+                                      uint32_t log_cap, uint4* out, uint32_t* kept_out, uint64_t* total_out) {
+  const uint64_t r = rep0 + blockIdx.x;
+  const uint32_t cnt = g32[(size_t)G32_LOGCNT * rep_pad + r];
+  const uint32_t kept = cnt < log_cap ? cnt : log_cap;
+  const uint32_t first = cnt - kept;
+  const uint4* ring = log + 2 * (size_t)r * log_cap;
+  uint4* dst = out + 2 * (size_t)blockIdx.x * log_cap;
+  for (uint32_t i = threadIdx.x; i < kept; i += blockDim.x) {
+    const uint32_t pos = (first + i) & (log_cap - 1);
+    uint4 a = ring[2 * pos], b = ring[2 * pos + 1];
+    if (((a.z >> 16) & 0xFFu) != QK_LOG_VEC_DATA) b.x &= 0xFFFFu; /* aux: device-internal, cleared on read */
+    dst[2 * i] = a;
+    dst[2 * i + 1] = b;
+  }
+  if (threadIdx.x == 0) {
+    kept_out[blockIdx.x] = kept;
+    total_out[blockIdx.x] = cnt;
   }
 }
 
@@ -383,8 +436,14 @@ int qk_batch_create(const qk_model* m, const qk_batch_config* cfg, qk_batch** ou
   b->last_ms = 0;
   b->last_launches = 0;
   b->total_launches = 0;
-  b->d_sums = b->d_ext = b->d_hist = nullptr;
-  b->d_sq_partial = b->d_sq = nullptr;
+  b->d_part = b->d_hist = nullptr;
+  b->d_scratch = nullptr;
+  b->h_pinned = nullptr;
+  b->scratch_bytes = b->pinned_bytes = 0;
+  b->n_sm = 148;
+  b->wave_blocks = 0;
+  b->lanes = 1;
+  b->last_chunks = 1;
   int rc = qk_lower(m, b->log, &b->low);
   if (rc) {
     delete b;
@@ -474,12 +533,20 @@ int qk_batch_create(const qk_model* m, const qk_batch_config* cfg, qk_batch** ou
   CREATE_TRY(cudaMemset(b->d_tape_len, 0, sizeof(uint64_t) * (h.n_dist ? h.n_dist : 1)));
   b->kernel = pick_kernel(b->log, b->hbm, b->nt, h.features);
   CREATE_TRY(cudaFuncSetAttribute((const void*)b->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  b->red_blocks = 148 * 4;
-  CREATE_TRY(cudaMalloc(&b->d_sums, sizeof(uint64_t) * 6 * h.n_comp));
-  CREATE_TRY(cudaMalloc(&b->d_ext, sizeof(uint64_t) * 4 * h.n_comp));
+  {
+    int sms = 0, nb = 0;
+    CREATE_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device));
+    CREATE_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)b->kernel, (int)b->nt, b->smem_bytes));
+    b->n_sm = (uint32_t)sms;
+    b->wave_blocks = (uint32_t)(sms * nb);
+  }
+  b->red_blocks = b->n_sm * 4;
+  CREATE_TRY(cudaMalloc(&b->d_part, sizeof(uint64_t) * QK_PARTIAL_WORDS * h.n_comp));
   CREATE_TRY(cudaMalloc(&b->d_hist, sizeof(uint64_t) * 2 * QK_HIST_BINS * h.n_comp));
-  CREATE_TRY(cudaMalloc(&b->d_sq_partial, sizeof(double) * 2 * b->red_blocks * h.n_comp));
-  CREATE_TRY(cudaMalloc(&b->d_sq, sizeof(double) * 2 * h.n_comp));
+  b->scratch_bytes = std::max<size_t>(1u << 20, (size_t)h.n_comp * (QK_PARTIAL_WORDS + 2 * QK_HIST_BINS) * 8);
+  CREATE_TRY(cudaMalloc(&b->d_scratch, b->scratch_bytes));
+  b->pinned_bytes = b->scratch_bytes;
+  CREATE_TRY(cudaHostAlloc(&b->h_pinned, b->pinned_bytes, cudaHostAllocDefault));
   *out = b;
   return QK_OK;
 }
@@ -503,6 +570,9 @@ int qk_batch_info_get(qk_batch* b, qk_batch_info* out) {
   out->replications_padded = b->rep_pad;
   out->state_bytes_total = (uint64_t)(out->state_bytes_per_rep + out->cold_bytes_per_rep) * b->rep_pad;
   out->log_bytes_total = b->log ? (uint64_t)b->rep_pad * b->cfg.log_capacity * 32 : 0;
+  out->lanes_per_replication = b->lanes;
+  out->wave_blocks = b->wave_blocks;
+  out->last_step_chunks = b->last_chunks;
   return QK_OK;
 }
 
@@ -520,11 +590,10 @@ void qk_batch_destroy(qk_batch* b) {
   for (size_t i = 0; i < b->h_tapes.size(); ++i) cudaFree(b->h_tapes[i]);
   cudaFree(b->d_tapes);
   cudaFree(b->d_tape_len);
-  cudaFree(b->d_sums);
-  cudaFree(b->d_ext);
+  cudaFree(b->d_part);
   cudaFree(b->d_hist);
-  cudaFree(b->d_sq_partial);
-  cudaFree(b->d_sq);
+  cudaFree(b->d_scratch);
+  if (b->h_pinned) cudaFreeHost(b->h_pinned);
   if (b->ev0) cudaEventDestroy(b->ev0);
   if (b->ev1) cudaEventDestroy(b->ev1);
   if (b->own_stream) cudaStreamDestroy(b->stream);
@@ -537,6 +606,7 @@ int qk_batch_set_tape(qk_batch* b, uint32_t dist_id, const double* values, uint6
     return QK_ERR_INVALID_ARG;
   }
   CUDA_TRY(cudaSetDevice(b->cfg.device));
+  CUDA_TRY(cudaStreamSynchronize(b->stream)); /* launches in flight read the tape table this call rewrites */
   if (b->h_tapes[dist_id]) {
     CUDA_TRY(cudaFree(b->h_tapes[dist_id]));
     b->h_tapes[dist_id] = nullptr;
@@ -574,6 +644,56 @@ int qk_batch_step_until(qk_batch* b, uint64_t t_ns) {
   return launch_step(b, 0, 0, t_ns, ~0ull);
 }
 
+/* Wave-sliced stepping.  A launch of `grid` blocks runs in ceil(grid / wave_blocks) waves, and the last, partial wave
+ * runs on a mostly idle GPU at the pace of a full one: 2048 blocks over 1480 resident ones (1M replications of
+ * discrete_queue split over 8 GPUs) take two wave times for 1.38 waves of work.  Replications are independent and a
+ * step of n events can be cut anywhere (qk_batch_step_events_chunked), so the step is cut into `c` chunks of events and
+ * the grid x c work items (chunk-major) are issued as launches of exactly one wave each: every wave but the last is
+ * full, and stream order guarantees that a tile's chunk k has finished before its chunk k + 1 starts.  c is chosen so
+ * that the last wave is nearly full too.  Costs one state round trip through HBM per chunk (2 * S bytes per
+ * replication per >= 250 events) and the drain at the end of every wave. */
+static bool plan_slices(const qk_batch* b, uint64_t n_events, uint32_t* n_chunks) {
+  static const char* env = getenv("QK_SLICE"); /* "0": never ; "1": whenever more than one wave ; default: when it pays */
+  if (env && env[0] == '0') return false;
+  const uint64_t W = b->wave_blocks, T = b->grid;
+  if (W == 0 || T <= W || n_events < 1000 || n_events > 0xFFFFFFFEull) return false;
+  const double waves = (double)T / (double)W;
+  const double plain_eff = waves / (double)((T + W - 1) / W);
+  if (!(env && env[0] == '1') && plain_eff > 0.93) return false;
+  double best_eff = 0;
+  uint32_t best_c = 0;
+  for (uint32_t c = 2; c <= 40 && n_events / c >= 250; ++c) {
+    const uint64_t items = T * c;
+    if (items > 0xFFFFFFFFull - W) break;
+    const double eff = (double)items / (double)(((items + W - 1) / W) * W);
+    if (eff > best_eff + 0.005) { /* prefer fewer chunks unless more buys at least half a percent */
+      best_eff = eff;
+      best_c = c;
+    }
+  }
+  if (best_c == 0 || best_eff <= plain_eff + 0.02) return false;
+  *n_chunks = best_c;
+  return true;
+}
+
+static int step_sliced(qk_batch* b, uint64_t n_events, uint32_t n_chunks) {
+  QkSlice sl;
+  sl.chunk_events = (n_events + n_chunks - 1) / n_chunks;
+  sl.total_events = n_events;
+  const uint64_t c = (n_events + sl.chunk_events - 1) / sl.chunk_events;
+  const uint64_t items = (uint64_t)b->grid * c;
+  b->last_chunks = (uint32_t)c;
+  bool first = true;
+  for (uint64_t i0 = 0; i0 < items; i0 += b->wave_blocks) {
+    sl.item0 = (uint32_t)i0;
+    sl.n_items = (uint32_t)std::min<uint64_t>(b->wave_blocks, items - i0);
+    const int rc = launch_step(b, 0, 0, QK_TIME_NONE, 0, first, i0 + b->wave_blocks >= items, &sl);
+    if (rc) return rc;
+    first = false;
+  }
+  return QK_OK;
+}
+
 int qk_batch_step_events(qk_batch* b, uint64_t n_events) {
   if (!b) return QK_ERR_INVALID_ARG;
   if (!b->initialised) {
@@ -581,6 +701,9 @@ int qk_batch_step_events(qk_batch* b, uint64_t n_events) {
     return QK_ERR_STATE;
   }
   CUDA_TRY(cudaSetDevice(b->cfg.device));
+  uint32_t n_chunks = 0;
+  if (plan_slices(b, n_events, &n_chunks)) return step_sliced(b, n_events, n_chunks);
+  b->last_chunks = 1;
   /* the kernel counts events in 32 bits: finite budgets go in launches of at most 2^32 - 2 events */
   const uint64_t cap = 0xFFFFFFFEull;
   bool first = true;
@@ -592,6 +715,27 @@ int qk_batch_step_events(qk_batch* b, uint64_t n_events) {
     first = false;
   } while (n_events);
   return QK_OK;
+}
+
+/* the wave-sliced schedule with an explicit number of chunks (tests, measurements); n_chunks == 0: as step_events */
+int qk_batch_step_events_sliced(qk_batch* b, uint64_t n_events, uint32_t n_chunks) {
+  if (!b) return QK_ERR_INVALID_ARG;
+  if (n_chunks == 0) return qk_batch_step_events(b, n_events);
+  if (!b->initialised) {
+    qk_set_error("qk_batch_step_events_sliced: call qk_batch_init first");
+    return QK_ERR_STATE;
+  }
+  if (n_events == 0 || n_events > 0xFFFFFFFEull || n_chunks > n_events || b->wave_blocks == 0 ||
+      (uint64_t)b->grid * n_chunks > 0xFFFFFFFFull - b->wave_blocks) {
+    qk_set_error("qk_batch_step_events_sliced: invalid argument");
+    return QK_ERR_INVALID_ARG;
+  }
+  CUDA_TRY(cudaSetDevice(b->cfg.device));
+  if (b->grid <= b->wave_blocks) { /* one (partial) wave holds every tile: chunks are simply launches */
+    b->last_chunks = n_chunks;
+    return qk_batch_step_events_chunked(b, n_events, (n_events + n_chunks - 1) / n_chunks);
+  }
+  return step_sliced(b, n_events, n_chunks);
 }
 
 /* The same step cut into launches of `chunk` events each: every launch loads the hot state planes from HBM, advances
@@ -638,15 +782,15 @@ int qk_batch_last_step_ms(qk_batch* b, float* ms, uint32_t* n_launches) {
 int qk_batch_summary_get(qk_batch* b, qk_batch_summary* out) {
   if (!b || !out) return QK_ERR_INVALID_ARG;
   CUDA_TRY(cudaSetDevice(b->cfg.device));
-  uint64_t h[5] = {0, 0, 0, ~0ull, ~0ull};
-  uint64_t* d = nullptr;
-  CUDA_TRY(cudaMalloc(&d, sizeof(h)));
-  CUDA_TRY(cudaMemcpyAsync(d, h, sizeof(h), cudaMemcpyHostToDevice, b->stream));
-  qk_batch_summary_kernel<<<148, 256, 0, b->stream>>>(b->g64, b->g32, b->rep_pad, b->cfg.n_reps, d);
+  uint64_t* h = reinterpret_cast<uint64_t*>(b->h_pinned);
+  uint64_t* d = reinterpret_cast<uint64_t*>(b->d_scratch);
+  h[0] = h[1] = h[2] = 0;
+  h[3] = h[4] = ~0ull;
+  CUDA_TRY(cudaMemcpyAsync(d, h, 5 * sizeof(uint64_t), cudaMemcpyHostToDevice, b->stream));
+  qk_batch_summary_kernel<<<b->n_sm, 256, 0, b->stream>>>(b->g64, b->g32, b->rep_pad, b->cfg.n_reps, d);
   CUDA_TRY(cudaGetLastError());
-  CUDA_TRY(cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, b->stream));
+  CUDA_TRY(cudaMemcpyAsync(h, d, 5 * sizeof(uint64_t), cudaMemcpyDeviceToHost, b->stream));
   CUDA_TRY(cudaStreamSynchronize(b->stream));
-  cudaFree(d);
   out->n_reps = b->cfg.n_reps;
   out->n_events = h[0];
   out->n_faulted = h[1];
@@ -685,83 +829,177 @@ int qk_batch_comp_stats(qk_batch* b, uint64_t rep0, uint64_t n, uint32_t comp, q
   if (comp >= b->low.hdr.n_comp || !out) return QK_ERR_INVALID_ARG;
   if (n == 0) return QK_OK;
   CUDA_TRY(cudaSetDevice(b->cfg.device));
-  qk_comp_stats* d = nullptr;
-  CUDA_TRY(cudaMalloc(&d, n * sizeof(qk_comp_stats)));
-  qk_comp_stats_kernel<<<(unsigned)((n + 255) / 256), 256, 0, b->stream>>>(b->d_tables, b->g64, b->g32, b->gs64, b->gs32, b->rep_pad,
-                                                                            rep0, n, comp, d);
-  CUDA_TRY(cudaGetLastError());
-  CUDA_TRY(cudaMemcpyAsync(out, d, n * sizeof(qk_comp_stats), cudaMemcpyDeviceToHost, b->stream));
-  CUDA_TRY(cudaStreamSynchronize(b->stream));
-  cudaFree(d);
+  qk_comp_stats* d = reinterpret_cast<qk_comp_stats*>(b->d_scratch);
+  const uint64_t piece = b->scratch_bytes / sizeof(qk_comp_stats);
+  for (uint64_t done = 0; done < n; done += piece) {
+    const uint64_t k = std::min<uint64_t>(piece, n - done);
+    qk_comp_stats_kernel<<<(unsigned)((k + 255) / 256), 256, 0, b->stream>>>(b->d_tables, b->g64, b->g32, b->gs64, b->gs32,
+                                                                              b->rep_pad, rep0 + done, k, comp, d);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(out + done, d, k * sizeof(qk_comp_stats), cudaMemcpyDeviceToHost, b->stream));
+    CUDA_TRY(cudaStreamSynchronize(b->stream));
+  }
   return QK_OK;
 }
 
-int qk_batch_reduce_stats_device(qk_batch* b, uint64_t* d_sums, uint64_t* d_extrema, uint32_t n_comp) {
-  if (!b || !d_sums || !d_extrema || n_comp != b->low.hdr.n_comp) {
-    qk_set_error("qk_batch_reduce_stats_device: invalid argument (n_comp must equal the model's)");
+int qk_batch_reduce_partials_device(qk_batch* b, uint64_t* d_partials, uint32_t n_comp) {
+  if (!b || !d_partials || n_comp != b->low.hdr.n_comp) {
+    qk_set_error("qk_batch_reduce_partials_device: invalid argument (n_comp must equal the model's)");
     return QK_ERR_INVALID_ARG;
   }
   CUDA_TRY(cudaSetDevice(b->cfg.device));
-  CUDA_TRY(cudaMemsetAsync(d_sums, 0, sizeof(uint64_t) * 6 * n_comp, b->stream));
-  CUDA_TRY(cudaMemsetAsync(d_extrema, 0xFF, sizeof(uint64_t) * 4 * n_comp, b->stream));
-  dim3 grid(b->red_blocks, n_comp);
-  qk_reduce_kernel<<<grid, 256, 0, b->stream>>>(b->d_tables, b->g64, b->g32, b->gs64, b->gs32, b->rep_pad, b->cfg.n_reps, d_sums,
-                                                d_extrema, b->d_sq_partial);
+  const uint32_t n_words = n_comp * QK_PARTIAL_WORDS;
+  qk_partials_clear_kernel<<<(n_words + 255) / 256, 256, 0, b->stream>>>(d_partials, n_words);
   CUDA_TRY(cudaGetLastError());
-  qk_reduce_sq_kernel<<<n_comp, 32, 0, b->stream>>>(b->d_sq_partial, b->red_blocks, b->d_sq);
+  dim3 grid(b->red_blocks, n_comp);
+  qk_reduce_kernel<<<grid, 256, 0, b->stream>>>(b->d_tables, b->g64, b->g32, b->gs64, b->gs32, b->rep_pad, b->cfg.n_reps,
+                                                d_partials);
   CUDA_TRY(cudaGetLastError());
   return QK_OK;
 }
 
-int qk_batch_histograms_device(qk_batch* b, const uint64_t* d_extrema, uint64_t* d_hist, uint32_t n_comp) {
-  if (!b || !d_extrema || !d_hist || n_comp != b->low.hdr.n_comp) return QK_ERR_INVALID_ARG;
+int qk_batch_combine_partials_device(qk_batch* b, const uint64_t* d_parts, uint32_t n_parts, uint64_t* d_out,
+                                     uint32_t n_comp) {
+  if (!b || !d_parts || !d_out || !n_parts || n_comp != b->low.hdr.n_comp) {
+    qk_set_error("qk_batch_combine_partials_device: invalid argument");
+    return QK_ERR_INVALID_ARG;
+  }
+  CUDA_TRY(cudaSetDevice(b->cfg.device));
+  const uint32_t n_words = n_comp * QK_PARTIAL_WORDS;
+  qk_partials_combine_kernel<<<(n_words + 255) / 256, 256, 0, b->stream>>>(d_parts, n_parts, n_words, d_out);
+  CUDA_TRY(cudaGetLastError());
+  return QK_OK;
+}
+
+int qk_batch_histograms_device(qk_batch* b, const uint64_t* d_partials, uint64_t* d_hist, uint32_t n_comp) {
+  if (!b || !d_partials || !d_hist || n_comp != b->low.hdr.n_comp) return QK_ERR_INVALID_ARG;
   CUDA_TRY(cudaSetDevice(b->cfg.device));
   CUDA_TRY(cudaMemsetAsync(d_hist, 0, sizeof(uint64_t) * 2 * QK_HIST_BINS * n_comp, b->stream));
   dim3 grid(b->red_blocks, n_comp);
-  qk_hist_kernel<<<grid, 256, 0, b->stream>>>(b->d_tables, b->g64, b->g32, b->gs64, b->gs32, b->rep_pad, b->cfg.n_reps, d_extrema,
-                                              d_hist);
+  qk_hist_kernel<<<grid, 256, 0, b->stream>>>(b->d_tables, b->g64, b->g32, b->gs64, b->gs32, b->rep_pad, b->cfg.n_reps,
+                                              d_partials, d_hist);
   CUDA_TRY(cudaGetLastError());
+  return QK_OK;
+}
+
+} /* extern "C" */
+
+/* exact sum of squares from its six half-sums: S = AA * 2^64 + 2 * AB * 2^32 + BB as 32-bit digits with carries */
+static void qk_sumsq_limbs(const uint64_t* w, uint64_t limbs[3]) {
+  unsigned __int128 d[7] = {0, 0, 0, 0, 0, 0, 0};
+  d[0] += w[QP_BB_LO];
+  d[1] += w[QP_BB_HI];
+  d[1] += (unsigned __int128)w[QP_AB_LO] * 2;
+  d[2] += (unsigned __int128)w[QP_AB_HI] * 2;
+  d[2] += w[QP_AA_LO];
+  d[3] += w[QP_AA_HI];
+  for (int k = 0; k < 6; ++k) {
+    d[k + 1] += d[k] >> 32;
+    d[k] &= 0xFFFFFFFFull;
+  }
+  for (int k = 0; k < 3; ++k) limbs[k] = (uint64_t)d[2 * k] | ((uint64_t)d[2 * k + 1] << 32);
+}
+
+void qk_fill_comp_summary(const uint64_t* w, const uint64_t* hist, qk_comp_summary* out) {
+  qk_comp_summary& o = *out;
+  memset(&o, 0, sizeof(o));
+  o.sum_count = w[QP_COUNT];
+  const uint64_t lo = w[QP_TIME_LO], hi = w[QP_TIME_HI];
+  /* the kernel sums the low and high 32-bit halves separately; recombine into a 128-bit total */
+  const uint64_t low64 = (hi << 32) + lo;
+  o.sum_time_lo = low64;
+  o.sum_time_hi = (hi >> 32) + (low64 < lo ? 1 : 0);
+  o.sum_level = w[QP_LEVEL];
+  o.min_count = w[QP_MIN_COUNT];
+  o.min_time = w[QP_MIN_TIME];
+  o.max_count = ~w[QP_NMAX_COUNT];
+  o.max_time = ~w[QP_NMAX_TIME];
+  qk_sumsq_limbs(w, o.sumsq_time_ns2);
+  const unsigned __int128 cc = ((unsigned __int128)w[QP_CC_HI] << 32) + w[QP_CC_LO];
+  o.sumsq_count_lo = (uint64_t)cc;
+  o.sumsq_count_hi = (uint64_t)(cc >> 64);
+  o.sumsq_level = w[QP_LEVEL_SQ];
+  o.sumsq_time = ((long double)o.sumsq_time_ns2[2] * 18446744073709551616.0L * 18446744073709551616.0L +
+                  (long double)o.sumsq_time_ns2[1] * 18446744073709551616.0L + (long double)o.sumsq_time_ns2[0]) *
+                 1e-18L;
+  o.sumsq_count = (double)((long double)o.sumsq_count_hi * 18446744073709551616.0L + (long double)o.sumsq_count_lo);
+  if (hist) {
+    for (int k = 0; k < QK_HIST_BINS; ++k) {
+      o.hist_time[k] = hist[k];
+      o.hist_count[k] = hist[QK_HIST_BINS + k];
+    }
+  }
+  o.hist_lo_time = o.min_time;
+  o.hist_hi_time = o.max_time;
+  o.hist_lo_count = o.min_count;
+  o.hist_hi_count = o.max_count;
+}
+
+extern "C" {
+
+int qk_batch_reduce_partials(qk_batch* b, uint64_t* partials, uint32_t n_comp) {
+  if (!b || !partials || n_comp != b->low.hdr.n_comp) return QK_ERR_INVALID_ARG;
+  int rc = qk_batch_reduce_partials_device(b, b->d_part, n_comp);
+  if (rc) return rc;
+  CUDA_TRY(cudaMemcpyAsync(b->h_pinned, b->d_part, sizeof(uint64_t) * QK_PARTIAL_WORDS * n_comp, cudaMemcpyDeviceToHost,
+                           b->stream));
+  CUDA_TRY(cudaStreamSynchronize(b->stream));
+  memcpy(partials, b->h_pinned, sizeof(uint64_t) * QK_PARTIAL_WORDS * n_comp);
   return QK_OK;
 }
 
 int qk_batch_reduce_stats(qk_batch* b, qk_comp_summary* out, uint32_t n_comp) {
   if (!b || !out || n_comp != b->low.hdr.n_comp) return QK_ERR_INVALID_ARG;
-  int rc = qk_batch_reduce_stats_device(b, b->d_sums, b->d_ext, n_comp);
+  int rc = qk_batch_reduce_partials_device(b, b->d_part, n_comp);
   if (rc) return rc;
-  rc = qk_batch_histograms_device(b, b->d_ext, b->d_hist, n_comp);
+  rc = qk_batch_histograms_device(b, b->d_part, b->d_hist, n_comp);
   if (rc) return rc;
-  std::vector<uint64_t> sums(6 * n_comp), ext(4 * n_comp), hist(2 * QK_HIST_BINS * n_comp);
-  std::vector<double> sq(2 * n_comp);
-  CUDA_TRY(cudaMemcpyAsync(sums.data(), b->d_sums, sums.size() * 8, cudaMemcpyDeviceToHost, b->stream));
-  CUDA_TRY(cudaMemcpyAsync(ext.data(), b->d_ext, ext.size() * 8, cudaMemcpyDeviceToHost, b->stream));
-  CUDA_TRY(cudaMemcpyAsync(hist.data(), b->d_hist, hist.size() * 8, cudaMemcpyDeviceToHost, b->stream));
-  CUDA_TRY(cudaMemcpyAsync(sq.data(), b->d_sq, sq.size() * 8, cudaMemcpyDeviceToHost, b->stream));
+  uint64_t* hp = reinterpret_cast<uint64_t*>(b->h_pinned);
+  const size_t n_part = (size_t)QK_PARTIAL_WORDS * n_comp, n_hist = (size_t)2 * QK_HIST_BINS * n_comp;
+  CUDA_TRY(cudaMemcpyAsync(hp, b->d_part, n_part * 8, cudaMemcpyDeviceToHost, b->stream));
+  CUDA_TRY(cudaMemcpyAsync(hp + n_part, b->d_hist, n_hist * 8, cudaMemcpyDeviceToHost, b->stream));
   CUDA_TRY(cudaStreamSynchronize(b->stream));
-  for (uint32_t c = 0; c < n_comp; ++c) {
-    qk_comp_summary& o = out[c];
-    memset(&o, 0, sizeof(o));
-    o.sum_count = sums[c * 6 + 0];
-    const uint64_t lo = sums[c * 6 + 1], hi = sums[c * 6 + 2];
-    /* the kernel sums the low and high 32-bit halves separately; recombine into a 128-bit total */
-    const uint64_t low64 = (hi << 32) + lo;
-    o.sum_time_lo = low64;
-    o.sum_time_hi = (hi >> 32) + (low64 < lo ? 1 : 0);
-    o.sum_level = sums[c * 6 + 3];
-    o.min_count = ext[c * 4 + 0];
-    o.min_time = ext[c * 4 + 1];
-    o.max_count = ~ext[c * 4 + 2];
-    o.max_time = ~ext[c * 4 + 3];
-    o.sumsq_time = sq[c * 2 + 0];
-    o.sumsq_count = sq[c * 2 + 1];
-    for (int k = 0; k < QK_HIST_BINS; ++k) {
-      o.hist_time[k] = hist[(size_t)c * 2 * QK_HIST_BINS + k];
-      o.hist_count[k] = hist[(size_t)c * 2 * QK_HIST_BINS + QK_HIST_BINS + k];
-    }
-    o.hist_lo_time = o.min_time;
-    o.hist_hi_time = o.max_time;
-    o.hist_lo_count = o.min_count;
-    o.hist_hi_count = o.max_count;
+  for (uint32_t c = 0; c < n_comp; ++c)
+    qk_fill_comp_summary(hp + (size_t)c * QK_PARTIAL_WORDS, hp + n_part + (size_t)c * 2 * QK_HIST_BINS, &out[c]);
+  return QK_OK;
+}
+
+int qk_batch_read_logs(qk_batch* b, uint64_t rep0, uint64_t n, qk_log_record* buf, uint32_t* kept, uint64_t* total) {
+  int rc = check_range(b, rep0, n);
+  if (rc) return rc;
+  if (!b->log) {
+    qk_set_error("qk_batch_read_logs: batch was created with log_capacity 0");
+    return QK_ERR_STATE;
   }
+  if (!buf || !kept || !total) return QK_ERR_INVALID_ARG;
+  if (n == 0) return QK_OK;
+  CUDA_TRY(cudaSetDevice(b->cfg.device));
+  const uint32_t lc = b->cfg.log_capacity;
+  const size_t per_rep = (size_t)lc * 32 + 16; /* records + (kept, total) */
+  uint64_t piece = b->scratch_bytes / per_rep;
+  uint8_t* d = b->d_scratch;
+  bool pooled = false;
+  if (piece < n && piece < 4096) { /* large requests: one temporary from the stream-ordered pool instead of many pieces */
+    piece = std::min<uint64_t>(n, (256u << 20) / per_rep);
+    if (piece == 0) piece = 1;
+    CUDA_TRY(cudaMallocAsync(&d, piece * per_rep, b->stream));
+    pooled = true;
+  }
+  for (uint64_t done = 0; done < n; done += piece) {
+    const uint64_t k = std::min<uint64_t>(piece, n - done);
+    uint4* d_rec = reinterpret_cast<uint4*>(d);
+    uint64_t* d_total = reinterpret_cast<uint64_t*>(d + k * (size_t)lc * 32);
+    uint32_t* d_kept = reinterpret_cast<uint32_t*>(d_total + k);
+    qk_gather_logs_kernel<<<(unsigned)k, 64, 0, b->stream>>>(b->d_log, b->g32, b->rep_pad, rep0 + done, lc, d_rec, d_kept,
+                                                             d_total);
+    CUDA_TRY(cudaGetLastError());
+    /* one gather kernel and one copy per array instead of a round trip per replication */
+    CUDA_TRY(cudaMemcpyAsync(buf + done * lc, d_rec, k * (size_t)lc * 32, cudaMemcpyDeviceToHost, b->stream));
+    CUDA_TRY(cudaMemcpyAsync(total + done, d_total, k * 8, cudaMemcpyDeviceToHost, b->stream));
+    CUDA_TRY(cudaMemcpyAsync(kept + done, d_kept, k * 4, cudaMemcpyDeviceToHost, b->stream));
+    CUDA_TRY(cudaStreamSynchronize(b->stream));
+  }
+  if (pooled) CUDA_TRY(cudaFreeAsync(d, b->stream));
   return QK_OK;
 }
 

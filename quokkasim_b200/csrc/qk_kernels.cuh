@@ -48,7 +48,34 @@ struct KParams {
   const uint64_t* tape_len;   /* [n_dist] per-replication length */
   uint64_t t0, t_until, event_budget;
   uint32_t do_init;
+  /* wave-sliced stepping (qk_batch.cu, step_sliced): when n_tiles != 0 the blocks of this launch are the work items
+   * [item0, item0 + gridDim.x) of the chunk-major sequence item -> (chunk = item / n_tiles, tile = item % n_tiles);
+   * a tile is one block's worth of replications, a chunk is chunk_events scheduler actions (the last one shorter:
+   * sliced_total events in all).  Launches follow each other on one stream, so chunk c of a tile has finished
+   * before chunk c + 1 starts. */
+  uint32_t item0, n_tiles;
+  uint64_t chunk_events, sliced_total;
 };
+
+/* which replications this block owns and how many events it may advance them by */
+struct QkWork {
+  uint32_t tile;
+  uint64_t budget;
+};
+__device__ __forceinline__ QkWork qk_work_item(const KParams& P) {
+  QkWork w;
+  w.tile = QK_BID;
+  w.budget = P.event_budget;
+  if (P.n_tiles) {
+    const uint32_t item = P.item0 + QK_BID;
+    const uint32_t chunk = item / P.n_tiles;
+    w.tile = item - chunk * P.n_tiles;
+    const uint64_t before = (uint64_t)chunk * P.chunk_events;
+    const uint64_t left = P.sliced_total - before;
+    w.budget = left < P.chunk_events ? left : P.chunk_events;
+  }
+  return w;
+}
 
 struct Ctx {
   uint32_t base64, base32; /* on-chip: element offsets of this lane's slot 0 inside qk_smem */
@@ -1038,7 +1065,8 @@ __global__ void __launch_bounds__(qk_lb_threads(SM), qk_lb_blocks(SM, FT, LOG)) 
   cx.ccap = reinterpret_cast<const double*>(smem + cx.hdr->off_ccap);
   cx.pf32 = cx.hdr->pf32;
   cx.n_pf_words = cx.hdr->n_pf_words;
-  const uint64_t rep_local = (uint64_t)QK_BID * nt + tid;
+  const QkWork work = qk_work_item(P);
+  const uint64_t rep_local = (uint64_t)work.tile * nt + tid;
   if constexpr (SM == 0) {
     cx.g64 = P.g64 + rep_local;
     cx.g32 = P.g32 + rep_local;
@@ -1155,9 +1183,9 @@ __global__ void __launch_bounds__(qk_lb_threads(SM), qk_lb_blocks(SM, FT, LOG)) 
    * kernels gain 1.5 % from the 32-bit count-down, the statistics-only kernels lose 2 % with it) */
   constexpr bool EV32 = LOG;
   uint64_t events_done = 0;
-  const uint64_t budget = live ? P.event_budget : 0;
-  const bool unlimited = P.event_budget == ~0ull;
-  const uint32_t ev_initial = live ? (unlimited ? 0xFFFFFFFFu : (uint32_t)P.event_budget) : 0u;
+  const uint64_t budget = live ? work.budget : 0;
+  const bool unlimited = work.budget == ~0ull;
+  const uint32_t ev_initial = live ? (unlimited ? 0xFFFFFFFFu : (uint32_t)work.budget) : 0u;
   uint32_t ev_left = ev_initial;
   const uint64_t t_until = P.t_until;
   /* Model::init of every component in registration order is the first call list of the loop */

@@ -37,9 +37,10 @@ struct qk_batch {
   std::vector<uint64_t> tape_len;
   bool any_tape;
   bool initialised;
+  uint64_t slice_chunk = 0, slice_total = 0;
 };
 
-static int run(qk_batch* b, uint32_t do_init, uint64_t t0, uint64_t t_until, uint64_t budget) {
+static int run(qk_batch* b, uint32_t do_init, uint64_t t0, uint64_t t_until, uint64_t budget, uint32_t n_items = 0) {
   KParams P;
   memset(&P, 0, sizeof(P));
   P.g64 = b->g64.data();
@@ -66,10 +67,16 @@ static int run(qk_batch* b, uint32_t do_init, uint64_t t0, uint64_t t_until, uin
   P.t_until = t_until;
   P.event_budget = budget;
   P.do_init = do_init;
+  if (n_items) {
+    P.item0 = 0;
+    P.n_tiles = (uint32_t)b->rep_pad;
+    P.chunk_events = b->slice_chunk;
+    P.sliced_total = b->slice_total;
+  }
   const size_t smem_bytes = b->table_bytes_padded + (size_t)P.n64 * 8 + (size_t)P.n32 * 4;
   std::vector<uint64_t> smem((smem_bytes + 7) / 8 + 2);
   qk_emul_smem = reinterpret_cast<uint8_t*>(smem.data());
-  for (uint64_t r = 0; r < b->rep_pad; ++r) {
+  for (uint64_t r = 0; r < (n_items ? n_items : b->rep_pad); ++r) {
     qk_emul_bid = (uint32_t)r;
     const bool hbm = (b->cfg.flags & QK_BATCH_STATE_IN_HBM) != 0;
     /* the product picks FT = 0 only for on-chip state; here both state placements run both feature sets so the
@@ -143,6 +150,8 @@ int qk_batch_info_get(qk_batch* b, qk_batch_info* out) {
   out->state_bytes_total = (uint64_t)(out->state_bytes_per_rep + out->cold_bytes_per_rep) * b->rep_pad;
   out->log_bytes_total = b->log ? (uint64_t)b->rep_pad * b->cfg.log_capacity * 32 : 0;
   out->state_in_hbm = (b->cfg.flags & QK_BATCH_STATE_IN_HBM) ? 1u : 0u;
+  out->lanes_per_replication = 1;
+  out->last_step_chunks = 1;
   return QK_OK;
 }
 
@@ -183,6 +192,18 @@ int qk_batch_step_events_chunked(qk_batch* b, uint64_t n, uint64_t chunk) {
     if (rc) return rc;
   }
   return QK_OK;
+}
+int qk_batch_step_events_sliced(qk_batch* b, uint64_t n, uint32_t n_chunks) {
+  /* the emulator runs one replication per block, so a "wave" here is a run of consecutive work items: the same
+   * chunk-major item -> (chunk, tile) mapping and per-chunk budgets as the product's step_sliced */
+  if (!b || !b->initialised) return QK_ERR_STATE;
+  if (n_chunks == 0) return qk_batch_step_events(b, n);
+  b->slice_chunk = (n + n_chunks - 1) / n_chunks;
+  b->slice_total = n;
+  const uint64_t c = (n + b->slice_chunk - 1) / b->slice_chunk;
+  const int rc = run(b, 0, 0, QK_TIME_NONE, 0, (uint32_t)(b->rep_pad * c));
+  b->slice_chunk = 0;
+  return rc;
 }
 int qk_batch_synchronize(qk_batch*) { return QK_OK; }
 int qk_batch_last_step_ms(qk_batch*, float* ms, uint32_t* n) {
@@ -226,13 +247,53 @@ int qk_batch_comp_stats(qk_batch* b, uint64_t rep0, uint64_t n, uint32_t comp, q
   return QK_OK;
 }
 
+/* the packed partials (quokka_b200.h QP_*) stated the slow, obvious way: the CPU suite uses them to check the host
+ * logic that combines the ranks (gloo) and qk_fill_comp_summary's 192-bit arithmetic */
+int qk_batch_reduce_partials(qk_batch* b, uint64_t* part, uint32_t n_comp) {
+  if (!b || !part || n_comp != b->low.hdr.n_comp) return QK_ERR_INVALID_ARG;
+  for (uint32_t c = 0; c < n_comp; ++c) {
+    uint64_t* w = part + (size_t)c * QK_PARTIAL_WORDS;
+    for (int k = 0; k < QK_PARTIAL_WORDS; ++k) w[k] = (k >= QP_MIN_COUNT && k <= QP_NMAX_TIME) ? ~0ull : 0ull;
+    std::vector<qk_comp_stats> st(b->cfg.n_reps);
+    qk_batch_comp_stats(b, 0, b->cfg.n_reps, c, st.data());
+    for (uint64_t r = 0; r < b->cfg.n_reps; ++r) {
+      const uint64_t t = st[r].time_ns, lo = t & 0xFFFFFFFFull, hi = t >> 32, cn = st[r].count & 0xFFFFFFFFull;
+      w[QP_COUNT] += st[r].count;
+      w[QP_TIME_LO] += lo;
+      w[QP_TIME_HI] += hi;
+      w[QP_LEVEL] += st[r].level;
+      w[QP_MIN_COUNT] = std::min(w[QP_MIN_COUNT], st[r].count);
+      w[QP_MIN_TIME] = std::min(w[QP_MIN_TIME], t);
+      w[QP_NMAX_COUNT] = std::min(w[QP_NMAX_COUNT], ~st[r].count);
+      w[QP_NMAX_TIME] = std::min(w[QP_NMAX_TIME], ~t);
+      w[QP_AA_LO] += (hi * hi) & 0xFFFFFFFFull;
+      w[QP_AA_HI] += (hi * hi) >> 32;
+      w[QP_AB_LO] += (hi * lo) & 0xFFFFFFFFull;
+      w[QP_AB_HI] += (hi * lo) >> 32;
+      w[QP_BB_LO] += (lo * lo) & 0xFFFFFFFFull;
+      w[QP_BB_HI] += (lo * lo) >> 32;
+      w[QP_CC_LO] += (cn * cn) & 0xFFFFFFFFull;
+      w[QP_CC_HI] += (cn * cn) >> 32;
+      w[QP_LEVEL_SQ] += st[r].level * st[r].level;
+      if (c == 0) {
+        w[QP_NEVENTS] += b->g64[(size_t)G64_NEVENTS * b->rep_pad + r];
+        w[QP_NFAULTED] += b->g32[(size_t)G32_STATUS * b->rep_pad + r] ? 1 : 0;
+        w[QP_NREPS] += 1;
+      }
+    }
+  }
+  return QK_OK;
+}
+
 int qk_batch_reduce_stats(qk_batch* b, qk_comp_summary* out, uint32_t n_comp) {
   if (!b || !out || n_comp != b->low.hdr.n_comp) return QK_ERR_INVALID_ARG;
   for (uint32_t c = 0; c < n_comp; ++c) {
     qk_comp_summary& o = out[c];
     memset(&o, 0, sizeof(o));
     o.min_count = o.min_time = ~0ull;
-    unsigned __int128 tsum = 0;
+    unsigned __int128 tsum = 0, csq = 0;
+    /* sum of time_ns^2 in 32-bit digits (independent of the product's half-sum scheme) */
+    unsigned __int128 dig[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     std::vector<qk_comp_stats> st(b->cfg.n_reps);
     qk_batch_comp_stats(b, 0, b->cfg.n_reps, c, st.data());
     for (uint64_t r = 0; r < b->cfg.n_reps; ++r) {
@@ -243,10 +304,22 @@ int qk_batch_reduce_stats(qk_batch* b, qk_comp_summary* out, uint32_t n_comp) {
       o.max_count = std::max(o.max_count, st[r].count);
       o.min_time = std::min(o.min_time, st[r].time_ns);
       o.max_time = std::max(o.max_time, st[r].time_ns);
-      const double ts = (double)st[r].time_ns * 1e-9;
-      o.sumsq_time += ts * ts;
-      o.sumsq_count += (double)st[r].count * (double)st[r].count;
+      const unsigned __int128 sq = (unsigned __int128)st[r].time_ns * st[r].time_ns;
+      for (int k = 0; k < 4; ++k) dig[k] += (uint64_t)(sq >> (32 * k)) & 0xFFFFFFFFull;
+      csq += (unsigned __int128)st[r].count * st[r].count;
+      o.sumsq_level += st[r].level * st[r].level;
     }
+    for (int k = 0; k < 7; ++k) {
+      dig[k + 1] += dig[k] >> 32;
+      dig[k] &= 0xFFFFFFFFull;
+    }
+    for (int k = 0; k < 3; ++k) o.sumsq_time_ns2[k] = (uint64_t)dig[2 * k] | ((uint64_t)dig[2 * k + 1] << 32);
+    o.sumsq_count_lo = (uint64_t)csq;
+    o.sumsq_count_hi = (uint64_t)(csq >> 64);
+    o.sumsq_time = ((long double)o.sumsq_time_ns2[2] * 18446744073709551616.0L * 18446744073709551616.0L +
+                    (long double)o.sumsq_time_ns2[1] * 18446744073709551616.0L + (long double)o.sumsq_time_ns2[0]) *
+                   1e-18L;
+    o.sumsq_count = (double)((long double)o.sumsq_count_hi * 18446744073709551616.0L + (long double)o.sumsq_count_lo);
     o.sum_time_lo = (uint64_t)tsum;
     o.sum_time_hi = (uint64_t)(tsum >> 64);
     o.hist_lo_time = o.min_time;
@@ -261,7 +334,8 @@ int qk_batch_reduce_stats(qk_batch* b, qk_comp_summary* out, uint32_t n_comp) {
   }
   return QK_OK;
 }
-int qk_batch_reduce_stats_device(qk_batch*, uint64_t*, uint64_t*, uint32_t) { return QK_ERR_NO_DEVICE; }
+int qk_batch_reduce_partials_device(qk_batch*, uint64_t*, uint32_t) { return QK_ERR_NO_DEVICE; }
+int qk_batch_combine_partials_device(qk_batch*, const uint64_t*, uint32_t, uint64_t*, uint32_t) { return QK_ERR_NO_DEVICE; }
 int qk_batch_histograms_device(qk_batch*, const uint64_t*, uint64_t*, uint32_t) { return QK_ERR_NO_DEVICE; }
 
 int qk_batch_read_log(qk_batch* b, uint64_t rep, qk_log_record* buf, uint64_t cap, uint64_t* n_out,
@@ -279,6 +353,18 @@ int qk_batch_read_log(qk_batch* b, uint64_t rep, qk_log_record* buf, uint64_t ca
   for (uint64_t i = 0; i < kept; ++i) {
     buf[i] = ring[(first + i) & (lc - 1)];
     if (buf[i].kind != QK_LOG_VEC_DATA) buf[i].aux = 0; /* continuation records carry fp64 bits there */
+  }
+  return QK_OK;
+}
+
+int qk_batch_read_logs(qk_batch* b, uint64_t rep0, uint64_t n, qk_log_record* buf, uint32_t* kept, uint64_t* total) {
+  if (!b || rep0 + n > b->cfg.n_reps || !b->log || !buf || !kept || !total) return QK_ERR_INVALID_ARG;
+  for (uint64_t i = 0; i < n; ++i) {
+    uint64_t k = 0, t = 0;
+    const int rc = qk_batch_read_log(b, rep0 + i, buf + i * b->cfg.log_capacity, b->cfg.log_capacity, &k, &t);
+    if (rc) return rc;
+    kept[i] = (uint32_t)k;
+    total[i] = t;
   }
   return QK_OK;
 }

@@ -22,7 +22,7 @@ def test_library_exports_every_symbol_in_the_header():
     for sym in sorted(declared):
         assert hasattr(L, sym), "libquokka_b200.so does not export %s" % sym
     assert declared == set(capi.EXPORTED_SYMBOLS), declared ^ set(capi.EXPORTED_SYMBOLS)
-    assert L.qk_abi_version() == 1
+    assert L.qk_abi_version() == 2
 
 
 def test_library_contains_sm_100a_code_only():
@@ -182,7 +182,7 @@ int main(void) {
     subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I" + os.path.join(root, "include"),
                            str(src), "-o", exe, "-L" + libdir, "-l:" + libname, "-Wl,-rpath," + libdir])
     out = subprocess.check_output([exe], text=True)
-    assert out.strip() == "1 0 No component connection defined from StringStock to StringStock (n=None)"
+    assert out.strip() == "2 0 No component connection defined from StringStock to StringStock (n=None)"
 
 
 def test_container_abi_argument_checks():

@@ -404,3 +404,29 @@ def test_large_models_on_hbm_planes_with_ties(emul_lib):
     for r in range(2):
         H.assert_rep_parity(sim, H.run_oracle(m, om, dist_ids, r, tapes=tapes, n_events=5000), m, r)
     sim.close()
+
+
+def test_wave_sliced_stepping_equals_one_step(emul_lib):
+    """the (block, chunk) work-item schedule of qk_batch_step_events_sliced: same trajectories as one launch, for
+    chunk counts that do and do not divide the event budget"""
+    for chunks in (1, 3, 7, 16):
+        m = H.discrete_queue()
+        a = m.sim(emul_lib, 5, base_seed=11, log_capacity=8192)
+        a.step_events(1000)
+        b = H.discrete_queue().sim(emul_lib, 5, base_seed=11, log_capacity=8192)
+        b.step_events_sliced(1000, chunks)
+        assert (b.status()[2] == 1000).all()
+        for r in range(5):
+            assert a.read_log(r)[0].tobytes() == b.read_log(r)[0].tobytes()
+        for ci in range(len(m.components)):
+            assert a.comp_stats(ci).tobytes() == b.comp_stats(ci).tobytes()
+
+
+def test_read_logs_equals_read_log(emul_lib):
+    m = H.discrete_queue()
+    s = m.sim(emul_lib, 6, base_seed=3, log_capacity=64)
+    s.step_events(300)
+    logs, totals = s.read_logs(1, 4)
+    for i in range(4):
+        one, tot = s.read_log(1 + i)
+        assert tot == totals[i] and logs[i].tobytes() == one.tobytes()

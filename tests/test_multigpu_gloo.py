@@ -18,22 +18,34 @@ N_TOTAL, N_EVENTS, SEED = 24, 800, 321
 
 
 def _partials(sim, n_comp):
-    """what qk_reduce_kernel writes: sums[c] = {count, time_lo32, time_hi32, level, n_events, n_faulted}"""
-    sums = np.zeros((n_comp, 6), dtype=np.uint64)
-    mins = np.zeros((n_comp, 2), dtype=np.uint64)
-    maxs = np.zeros((n_comp, 2), dtype=np.uint64)
+    """what qk_reduce_kernel writes (quokka_b200.h QP_*), formed in numpy from the per-replication statistics --
+    independently of the library's own qk_batch_reduce_partials, which must agree with it"""
+    from quokkasim_b200 import _capi as capi
+
+    w = np.zeros((n_comp, capi.PARTIAL_WORDS), dtype=np.uint64)
     st, _, ev = sim.status()
+    m32 = np.uint64(0xFFFFFFFF)
+    s32 = np.uint64(32)
     for c in range(n_comp):
         s = sim.comp_stats(c)
-        sums[c, 0] = s["count"].sum()
-        sums[c, 1] = (s["time_ns"] & np.uint64(0xFFFFFFFF)).sum()
-        sums[c, 2] = (s["time_ns"] >> np.uint64(32)).sum()
-        sums[c, 3] = s["level"].sum()
-        mins[c] = (s["count"].min(), s["time_ns"].min())
-        maxs[c] = (s["count"].max(), s["time_ns"].max())
-    sums[0, 4] = ev.sum()
-    sums[0, 5] = (st != 0).sum()
-    return sums, mins, maxs
+        t, cnt, lvl = s["time_ns"], s["count"], s["level"]
+        lo, hi = t & m32, t >> s32
+        w[c, capi.QP_COUNT] = cnt.sum()
+        w[c, capi.QP_TIME_LO] = lo.sum()
+        w[c, capi.QP_TIME_HI] = hi.sum()
+        w[c, capi.QP_LEVEL] = lvl.sum()
+        w[c, capi.QP_MIN_COUNT], w[c, capi.QP_MIN_TIME] = cnt.min(), t.min()
+        w[c, capi.QP_NMAX_COUNT], w[c, capi.QP_NMAX_TIME] = ~cnt.max(), ~t.max()
+        for k, v in ((capi.QP_AA_LO, hi * hi), (capi.QP_AB_LO, hi * lo), (capi.QP_BB_LO, lo * lo),
+                     (capi.QP_CC_LO, cnt * cnt)):
+            w[c, k] = (v & m32).sum()
+            w[c, k + 1] = (v >> s32).sum()
+        w[c, capi.QP_LEVEL_SQ] = (lvl * lvl).sum()
+    w[0, capi.QP_NEVENTS] = ev.sum()
+    w[0, capi.QP_NFAULTED] = (st != 0).sum()
+    w[0, capi.QP_NREPS] = len(st)
+    assert sim.reduce_partials().tobytes() == w.tobytes()
+    return w
 
 
 def _worker(rank, world, port, emul_lib, out):
@@ -42,6 +54,7 @@ def _worker(rank, world, port, emul_lib, out):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
+    from quokkasim_b200 import _capi as capi
     from quokkasim_b200 import parallel, workloads
 
     lo, hi = parallel.shard_range(N_TOTAL, rank, world)
@@ -49,17 +62,27 @@ def _worker(rank, world, port, emul_lib, out):
     sim = m.sim(emul_lib, hi - lo, base_seed=SEED, rep_offset=lo)
     sim.step_events(N_EVENTS)
     n_comp = len(m.components)
-    sums, mins, maxs = _partials(sim, n_comp)
-    t_sums = torch.from_numpy(sums.view(np.int64).copy())
-    t_mins = torch.from_numpy(mins.view(np.int64).copy())
-    t_maxs = torch.from_numpy(maxs.view(np.int64).copy())
-    dist.all_reduce(t_sums, op=dist.ReduceOp.SUM)
-    dist.all_reduce(t_mins, op=dist.ReduceOp.MIN)
-    dist.all_reduce(t_maxs, op=dist.ReduceOp.MAX)
-    comp, n_ev, n_fault = parallel.summarize(t_sums.numpy().view(np.uint64), t_mins.numpy().view(np.uint64),
-                                             t_maxs.numpy().view(np.uint64), None, n_comp)
+    mine = torch.from_numpy(_partials(sim, n_comp).view(np.int64).reshape(-1).copy())
+    # the one exchange of the multi-GPU path: all-gather of the packed partials, combined locally
+    gathered = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(gathered, mine)
+    combined = parallel.combine_partials([g.numpy().view(np.uint64).reshape(n_comp, capi.PARTIAL_WORDS)
+                                          for g in gathered])
+    # histograms over the GLOBAL ranges, then a sum all-reduce
+    hist = np.zeros((n_comp, 2, capi.HIST_BINS), dtype=np.int64)
+    for c in range(n_comp):
+        s = sim.comp_stats(c)
+        for k, (key, lo_w, hi_w) in enumerate((("time_ns", capi.QP_MIN_TIME, capi.QP_NMAX_TIME),
+                                               ("count", capi.QP_MIN_COUNT, capi.QP_NMAX_COUNT))):
+            lo_v, hi_v = int(combined[c, lo_w]), int(combined[c, hi_w]) ^ ((1 << 64) - 1)
+            width = (hi_v - lo_v) // capi.HIST_BINS + 1
+            for v in s[key]:
+                hist[c, k, (int(v) - lo_v) // width] += 1
+    t_hist = torch.from_numpy(hist)
+    dist.all_reduce(t_hist, op=dist.ReduceOp.SUM)
+    comp, n_ev, n_fault, n_reps = parallel.summarize(combined, t_hist.numpy().view(np.uint64), n_comp)
     if rank == 0:
-        torch.save({"comp": comp, "n_ev": n_ev, "n_fault": n_fault}, out)
+        torch.save({"comp": comp, "n_ev": n_ev, "n_fault": n_fault, "n_reps": n_reps}, out)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -80,22 +103,41 @@ def test_two_rank_reduction_equals_single_batch(emul_lib, tmp_path):
     mp.spawn(_worker, args=(2, port, emul_lib, out), nprocs=2, join=True)
     got = torch.load(out, weights_only=False)
     sys.path.insert(0, ROOT)
+    from quokkasim_b200 import _capi as capi
     from quokkasim_b200 import parallel, workloads
 
     m = workloads.discrete_queue()
+    n_comp = len(m.components)
     sim = m.sim(emul_lib, N_TOTAL, base_seed=SEED)
     sim.step_events(N_EVENTS)
-    sums, mins, maxs = _partials(sim, len(m.components))
-    want, n_ev, n_fault = parallel.summarize(sums, mins, maxs, None, len(m.components))
-    assert got["n_ev"] == n_ev == N_TOTAL * N_EVENTS and got["n_fault"] == n_fault == 0
-    assert got["comp"] == want
-    # and the host-side statement of the collective agrees with gloo
-    lo0, hi0 = parallel.shard_range(N_TOTAL, 0, 2)
+    # the single-batch answer, from the library's own summary (exact integers: moments and histograms included)
+    red = sim.reduce_stats()
+    assert got["n_ev"] == N_TOTAL * N_EVENTS and got["n_fault"] == 0 and got["n_reps"] == N_TOTAL
+    for c in range(n_comp):
+        g, r = got["comp"][c], red[c]
+        assert g["sum_count"] == int(r["sum_count"]) and g["sum_level"] == int(r["sum_level"])
+        assert g["sum_time_ns"] == (int(r["sum_time_hi"]) << 64) + int(r["sum_time_lo"])
+        assert (g["min_count"], g["max_count"]) == (int(r["min_count"]), int(r["max_count"]))
+        assert (g["min_time_ns"], g["max_time_ns"]) == (int(r["min_time"]), int(r["max_time"]))
+        assert g["sumsq_time_ns"] == sum(int(r["sumsq_time_ns2"][k]) << (64 * k) for k in range(3))
+        assert g["sumsq_count"] == (int(r["sumsq_count_hi"]) << 64) + int(r["sumsq_count_lo"])
+        assert g["sumsq_level"] == int(r["sumsq_level"])
+        assert g["hist_time"] == r["hist_time"].tolist() and g["hist_count"] == r["hist_count"].tolist()
+        # and against the per-replication values themselves
+        s = sim.comp_stats(c)
+        assert g["sumsq_time_ns"] == sum(int(t) ** 2 for t in s["time_ns"])
+        assert g["sumsq_count"] == sum(int(t) ** 2 for t in s["count"])
+        mom = parallel.moments(g, N_TOTAL)
+        ts = s["time_ns"].astype(np.float64)
+        assert abs(mom["time_ns"][0] - ts.mean()) <= 1e-9 * max(1.0, ts.mean())
+        assert abs(mom["time_ns"][1] - ts.var()) <= 1e-6 * max(1.0, ts.var())
+    # the host-side statement of the combine agrees with what the ranks exchanged
     parts = []
-    for lo, hi in ((lo0, hi0), parallel.shard_range(N_TOTAL, 1, 2)):
+    for r in range(2):
+        lo, hi = parallel.shard_range(N_TOTAL, r, 2)
         s = workloads.discrete_queue().sim(emul_lib, hi - lo, base_seed=SEED, rep_offset=lo)
         s.step_events(N_EVENTS)
-        parts.append(_partials(s, len(m.components)))
-    c_sums, c_mins, c_maxs = parallel.combine_partials([p[0] for p in parts], [p[1] for p in parts],
-                                                       [p[2] for p in parts])
-    assert parallel.summarize(c_sums, c_mins, c_maxs, None, len(m.components))[0] == want
+        parts.append(_partials(s, n_comp))
+    whole = _partials(sim, n_comp)
+    assert parallel.combine_partials(parts).tobytes() == whole.tobytes()
+    assert parallel.summarize(whole, None, n_comp)[0][3]["sum_count"] == got["comp"][3]["sum_count"]
