@@ -331,7 +331,6 @@ def run_ours(args):
     if log_cap:
         w.read_logs(0, min(4096, args.e2e_log_reps))
     w.close()
-    done_sims = []
     step_s, phases = [], {"create": [], "init_step": [], "reduce": [], "d2h_logs": []}
     for _ in range(e2e_steps):
         barrier()
@@ -352,13 +351,14 @@ def run_ours(args):
         torch.cuda.synchronize(device)
         t4 = time.perf_counter()
         h2d = s2.info()["table_bytes"] + 64  # model tables + batch config: the path's only host inputs
-        done_sims.append(s2)
         step_s.append(t4 - t0)
         for kname, dt in (("create", t1 - t0), ("init_step", t2 - t1), ("reduce", t3 - t2), ("d2h_logs", t4 - t3)):
             phases[kname].append(dt)
-    barrier()
-    for s2 in done_sims:  # cudaFree of multi-GB buffers is not part of the path (and sporadically takes 0.3 s)
+        # releasing the batch is outside the timed region: its planes and log rings go back to the device's
+        # stream-ordered pool, which is what the next step's batch is carved from (a batch that had to get its
+        # gigabytes from the driver instead paid 0.1-0.8 s in `create`: the 1.26 spread of the first r02 run)
         s2.close()
+    barrier()
     e2e_t = torch.tensor(step_s, dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)

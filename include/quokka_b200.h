@@ -323,7 +323,7 @@ typedef struct {
   /* ABI 2 */
   uint32_t lanes_per_replication; /* 1: one thread per replication ; 4/8/16: a lane group per replication */
   uint32_t wave_blocks;           /* blocks of the step kernel resident on the whole GPU at once */
-  uint32_t last_step_chunks;      /* state residencies of the last step call: 1, or the chunks of a wave-sliced step */
+  uint32_t last_step_chunks;      /* state residencies of the last step call: 1, or the chunks of a sliced step */
   uint32_t reserved;
 } qk_batch_info;
 
@@ -339,9 +339,10 @@ int qk_batch_step_events(qk_batch*, uint64_t n_events);
 /* same result as qk_batch_step_events, cut into launches of `chunk` events (state round-trips HBM between them);
  * for measuring the kernel at a small number of events per state residency */
 int qk_batch_step_events_chunked(qk_batch*, uint64_t n_events, uint64_t chunk);
-/* same result again, as the wave-sliced schedule qk_batch_step_events chooses by itself when a launch would end in a
- * mostly empty last wave: the step is cut into n_chunks chunks of events and the (block, chunk) work items are issued
- * as launches of exactly one GPU-filling wave each (n_chunks = 0: let the library decide) */
+/* same result again, as the sliced schedule qk_batch_step_events chooses by itself when a launch would end in a
+ * mostly empty last wave: the step is cut into n_chunks chunks of events and the blocks of replications into
+ * parts, each part advanced chunk by chunk on its own stream so that the launches overlap and the GPU stays full
+ * (n_chunks = 0: let the library decide) */
 int qk_batch_step_events_sliced(qk_batch*, uint64_t n_events, uint32_t n_chunks);
 int qk_batch_synchronize(qk_batch*);
 

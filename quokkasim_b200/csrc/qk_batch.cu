@@ -28,6 +28,8 @@
   } while (0)
 
 
+#define QK_SLICE_PARTS 8
+
 struct qk_batch {
   StepKernel kernel;
   qk_batch_config cfg;
@@ -66,6 +68,11 @@ struct qk_batch {
   size_t scratch_bytes;
   uint8_t* h_pinned;
   size_t pinned_bytes;
+  uint32_t grp_reps, grp_stride64, grp_stride32, grp_bar_off; /* lane-group kernel geometry (qk_group.cuh) */
+  /* sliced stepping: the tiles are split into QK_SLICE_PARTS parts, each advanced chunk by chunk on its own stream */
+  cudaStream_t side[QK_SLICE_PARTS - 1];
+  cudaEvent_t ev_fork, ev_join[QK_SLICE_PARTS - 1];
+  bool have_side;
   uint32_t lanes;       /* lanes per replication: 1, or the group width of the lane-group kernel */
   uint32_t last_chunks; /* state residencies of the last step call */
   uint32_t n_sm, wave_blocks; /* SMs of the device ; blocks of the step kernel resident on the whole GPU at once */
@@ -120,8 +127,8 @@ static uint32_t choose_nt(uint32_t per_rep_bytes, uint32_t table_bytes, uint32_t
 }
 
 struct QkSlice {
-  uint32_t item0, n_items; /* n_items == 0: a plain launch over every tile */
-  uint64_t chunk_events, total_events;
+  uint32_t tile0, n_tiles; /* n_tiles == 0: every tile of the batch */
+  cudaStream_t stream;
 };
 
 static int launch_step(qk_batch* b, uint32_t do_init, uint64_t t0, uint64_t t_until, uint64_t budget,
@@ -153,18 +160,21 @@ static int launch_step(qk_batch* b, uint32_t do_init, uint64_t t0, uint64_t t_un
   P.event_budget = budget;
   P.do_init = do_init;
   uint32_t grid = b->grid;
-  if (slice && slice->n_items) {
-    P.item0 = slice->item0;
-    P.n_tiles = b->grid;
-    P.chunk_events = slice->chunk_events;
-    P.sliced_total = slice->total_events;
-    grid = slice->n_items;
+  P.grp_reps = b->grp_reps;
+  P.grp_stride64 = b->grp_stride64;
+  P.grp_stride32 = b->grp_stride32;
+  P.grp_bar_off = b->grp_bar_off;
+  cudaStream_t stream = b->stream;
+  if (slice && slice->n_tiles) {
+    P.tile0 = slice->tile0;
+    grid = slice->n_tiles;
+    stream = slice->stream;
   }
   if (record_begin) {
     CUDA_TRY(cudaEventRecord(b->ev0, b->stream));
     b->last_launches = 0;
   }
-  b->kernel<<<grid, b->nt, b->smem_bytes, b->stream>>>(P);
+  b->kernel<<<grid, b->nt, b->smem_bytes, stream>>>(P);
   CUDA_TRY(cudaGetLastError());
   if (record_end) CUDA_TRY(cudaEventRecord(b->ev1, b->stream));
   b->last_launches += 1;
@@ -444,6 +454,8 @@ int qk_batch_create(const qk_model* m, const qk_batch_config* cfg, qk_batch** ou
   b->wave_blocks = 0;
   b->lanes = 1;
   b->last_chunks = 1;
+  b->grp_reps = b->grp_stride64 = b->grp_stride32 = b->grp_bar_off = 0;
+  b->have_side = false;
   int rc = qk_lower(m, b->log, &b->low);
   if (rc) {
     delete b;
@@ -590,6 +602,13 @@ void qk_batch_destroy(qk_batch* b) {
   for (size_t i = 0; i < b->h_tapes.size(); ++i) cudaFree(b->h_tapes[i]);
   cudaFree(b->d_tapes);
   cudaFree(b->d_tape_len);
+  if (b->have_side) {
+    for (int i = 0; i < QK_SLICE_PARTS - 1; ++i) {
+      cudaStreamDestroy(b->side[i]);
+      cudaEventDestroy(b->ev_join[i]);
+    }
+    cudaEventDestroy(b->ev_fork);
+  }
   cudaFree(b->d_part);
   cudaFree(b->d_hist);
   cudaFree(b->d_scratch);
@@ -644,53 +663,64 @@ int qk_batch_step_until(qk_batch* b, uint64_t t_ns) {
   return launch_step(b, 0, 0, t_ns, ~0ull);
 }
 
-/* Wave-sliced stepping.  A launch of `grid` blocks runs in ceil(grid / wave_blocks) waves, and the last, partial wave
- * runs on a mostly idle GPU at the pace of a full one: 2048 blocks over 1480 resident ones (1M replications of
+/* Sliced stepping.  A launch of `grid` blocks runs in ceil(grid / wave_blocks) waves, and the last, partial wave runs
+ * on a mostly idle GPU at the pace of a full one: 2048 blocks over 1480 resident ones (1M replications of
  * discrete_queue split over 8 GPUs) take two wave times for 1.38 waves of work.  Replications are independent and a
  * step of n events can be cut anywhere (qk_batch_step_events_chunked), so the step is cut into `c` chunks of events and
- * the grid x c work items (chunk-major) are issued as launches of exactly one wave each: every wave but the last is
- * full, and stream order guarantees that a tile's chunk k has finished before its chunk k + 1 starts.  c is chosen so
- * that the last wave is nearly full too.  Costs one state round trip through HBM per chunk (2 * S bytes per
- * replication per >= 250 events) and the drain at the end of every wave. */
+ * the tiles into QK_SLICE_PARTS parts; each part is advanced chunk by chunk by launches on its OWN stream.  Launches of
+ * different parts overlap -- when one part's launch drains, blocks of the others fill the SMs -- while stream order
+ * keeps a part's chunk k + 1 behind its chunk k.  The GPU stays full until the last chunk of the last parts: a tail of
+ * about 1 / (waves * c) of the step instead of the last wave's.  Costs one state round trip through HBM per chunk
+ * (2 * S bytes per replication per >= 200 events) and c * QK_SLICE_PARTS launches. */
 static bool plan_slices(const qk_batch* b, uint64_t n_events, uint32_t* n_chunks) {
   static const char* env = getenv("QK_SLICE"); /* "0": never ; "1": whenever more than one wave ; default: when it pays */
   if (env && env[0] == '0') return false;
   const uint64_t W = b->wave_blocks, T = b->grid;
-  if (W == 0 || T <= W || n_events < 1000 || n_events > 0xFFFFFFFEull) return false;
+  if (W == 0 || T <= W || T < 4 * QK_SLICE_PARTS || n_events < 400 || n_events > 0xFFFFFFFEull) return false;
   const double waves = (double)T / (double)W;
   const double plain_eff = waves / (double)((T + W - 1) / W);
-  if (!(env && env[0] == '1') && plain_eff > 0.93) return false;
-  double best_eff = 0;
-  uint32_t best_c = 0;
-  for (uint32_t c = 2; c <= 40 && n_events / c >= 250; ++c) {
-    const uint64_t items = T * c;
-    if (items > 0xFFFFFFFFull - W) break;
-    const double eff = (double)items / (double)(((items + W - 1) / W) * W);
-    if (eff > best_eff + 0.005) { /* prefer fewer chunks unless more buys at least half a percent */
-      best_eff = eff;
-      best_c = c;
-    }
-  }
-  if (best_c == 0 || best_eff <= plain_eff + 0.02) return false;
-  *n_chunks = best_c;
+  if (!(env && env[0] == '1') && plain_eff > 0.97) return false;
+  /* the tail is about one chunk of one wave: 1 / (waves * c) of the step; aim at 2 % */
+  uint64_t c = (uint64_t)(1.0 / (0.02 * waves)) + 1;
+  if (c < 2) c = 2;
+  if (c > 32) c = 32;
+  while (c > 2 && n_events / c < 200) --c;
+  *n_chunks = (uint32_t)c;
   return true;
 }
 
 static int step_sliced(qk_batch* b, uint64_t n_events, uint32_t n_chunks) {
-  QkSlice sl;
-  sl.chunk_events = (n_events + n_chunks - 1) / n_chunks;
-  sl.total_events = n_events;
-  const uint64_t c = (n_events + sl.chunk_events - 1) / sl.chunk_events;
-  const uint64_t items = (uint64_t)b->grid * c;
-  b->last_chunks = (uint32_t)c;
-  bool first = true;
-  for (uint64_t i0 = 0; i0 < items; i0 += b->wave_blocks) {
-    sl.item0 = (uint32_t)i0;
-    sl.n_items = (uint32_t)std::min<uint64_t>(b->wave_blocks, items - i0);
-    const int rc = launch_step(b, 0, 0, QK_TIME_NONE, 0, first, i0 + b->wave_blocks >= items, &sl);
-    if (rc) return rc;
-    first = false;
+  if (!b->have_side) {
+    CUDA_TRY(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming));
+    for (int i = 0; i < QK_SLICE_PARTS - 1; ++i) {
+      CUDA_TRY(cudaStreamCreateWithFlags(&b->side[i], cudaStreamNonBlocking));
+      CUDA_TRY(cudaEventCreateWithFlags(&b->ev_join[i], cudaEventDisableTiming));
+    }
+    b->have_side = true;
   }
+  const uint64_t chunk = (n_events + n_chunks - 1) / n_chunks;
+  const uint32_t parts = b->grid >= QK_SLICE_PARTS ? QK_SLICE_PARTS : 1;
+  b->last_chunks = (uint32_t)((n_events + chunk - 1) / chunk);
+  CUDA_TRY(cudaEventRecord(b->ev0, b->stream));
+  b->last_launches = 0;
+  CUDA_TRY(cudaEventRecord(b->ev_fork, b->stream));
+  for (uint32_t p = 1; p < parts; ++p) CUDA_TRY(cudaStreamWaitEvent(b->side[p - 1], b->ev_fork, 0));
+  for (uint64_t done = 0; done < n_events; done += chunk) {
+    const uint64_t k = std::min<uint64_t>(chunk, n_events - done);
+    for (uint32_t p = 0; p < parts; ++p) {
+      QkSlice sl;
+      sl.tile0 = (uint32_t)((uint64_t)b->grid * p / parts);
+      sl.n_tiles = (uint32_t)((uint64_t)b->grid * (p + 1) / parts) - sl.tile0;
+      sl.stream = p == 0 ? b->stream : b->side[p - 1];
+      const int rc = launch_step(b, 0, 0, QK_TIME_NONE, k, false, false, &sl);
+      if (rc) return rc;
+    }
+  }
+  for (uint32_t p = 1; p < parts; ++p) {
+    CUDA_TRY(cudaEventRecord(b->ev_join[p - 1], b->side[p - 1]));
+    CUDA_TRY(cudaStreamWaitEvent(b->stream, b->ev_join[p - 1], 0));
+  }
+  CUDA_TRY(cudaEventRecord(b->ev1, b->stream));
   return QK_OK;
 }
 
@@ -717,7 +747,7 @@ int qk_batch_step_events(qk_batch* b, uint64_t n_events) {
   return QK_OK;
 }
 
-/* the wave-sliced schedule with an explicit number of chunks (tests, measurements); n_chunks == 0: as step_events */
+/* the sliced schedule with an explicit number of chunks (tests, measurements); n_chunks == 0: as step_events */
 int qk_batch_step_events_sliced(qk_batch* b, uint64_t n_events, uint32_t n_chunks) {
   if (!b) return QK_ERR_INVALID_ARG;
   if (n_chunks == 0) return qk_batch_step_events(b, n_events);
@@ -725,16 +755,11 @@ int qk_batch_step_events_sliced(qk_batch* b, uint64_t n_events, uint32_t n_chunk
     qk_set_error("qk_batch_step_events_sliced: call qk_batch_init first");
     return QK_ERR_STATE;
   }
-  if (n_events == 0 || n_events > 0xFFFFFFFEull || n_chunks > n_events || b->wave_blocks == 0 ||
-      (uint64_t)b->grid * n_chunks > 0xFFFFFFFFull - b->wave_blocks) {
+  if (n_events == 0 || n_events > 0xFFFFFFFEull || n_chunks > n_events) {
     qk_set_error("qk_batch_step_events_sliced: invalid argument");
     return QK_ERR_INVALID_ARG;
   }
   CUDA_TRY(cudaSetDevice(b->cfg.device));
-  if (b->grid <= b->wave_blocks) { /* one (partial) wave holds every tile: chunks are simply launches */
-    b->last_chunks = n_chunks;
-    return qk_batch_step_events_chunked(b, n_events, (n_events + n_chunks - 1) / n_chunks);
-  }
   return step_sliced(b, n_events, n_chunks);
 }
 

@@ -48,40 +48,20 @@ struct KParams {
   const uint64_t* tape_len;   /* [n_dist] per-replication length */
   uint64_t t0, t_until, event_budget;
   uint32_t do_init;
-  /* wave-sliced stepping (qk_batch.cu, step_sliced): when n_tiles != 0 the blocks of this launch are the work items
-   * [item0, item0 + gridDim.x) of the chunk-major sequence item -> (chunk = item / n_tiles, tile = item % n_tiles);
-   * a tile is one block's worth of replications, a chunk is chunk_events scheduler actions (the last one shorter:
-   * sliced_total events in all).  Launches follow each other on one stream, so chunk c of a tile has finished
-   * before chunk c + 1 starts. */
-  uint32_t item0, n_tiles;
-  uint64_t chunk_events, sliced_total;
+  /* sliced stepping (qk_batch.cu, step_sliced): a launch may cover only the tiles [tile0, tile0 + gridDim.x) of the
+   * batch (a tile = one block's worth of replications) */
+  uint32_t tile0;
+  /* lane-group kernel (qk_group.cuh): replications per block, row strides of the shared-memory state (elements),
+   * byte offset of the mbarrier */
+  uint32_t grp_reps, grp_stride64, grp_stride32, grp_bar_off;
 };
-
-/* which replications this block owns and how many events it may advance them by */
-struct QkWork {
-  uint32_t tile;
-  uint64_t budget;
-};
-__device__ __forceinline__ QkWork qk_work_item(const KParams& P) {
-  QkWork w;
-  w.tile = QK_BID;
-  w.budget = P.event_budget;
-  if (P.n_tiles) {
-    const uint32_t item = P.item0 + QK_BID;
-    const uint32_t chunk = item / P.n_tiles;
-    w.tile = item - chunk * P.n_tiles;
-    const uint64_t before = (uint64_t)chunk * P.chunk_events;
-    const uint64_t left = P.sliced_total - before;
-    w.budget = left < P.chunk_events ? left : P.chunk_events;
-  }
-  return w;
-}
 
 struct Ctx {
   uint32_t base64, base32; /* on-chip: element offsets of this lane's slot 0 inside qk_smem */
   uint64_t* g64;           /* HBM-resident state: plane pointers offset to this replication */
   uint32_t* g32;
   uint32_t stride;         /* on-chip: threads per block ; HBM: padded replication count */
+  uint32_t stride32;       /* run-time-stride on-chip mode only (SM < 0): row stride of the 32-bit slots */
   uint64_t* gs64;          /* statistics planes, offset to this replication; row stride = rep_pad */
   uint32_t* gs32;
   uint64_t* gc64;          /* cold planes, offset to this replication */
@@ -135,7 +115,7 @@ __device__ __forceinline__ auto qk_ix(uint32_t slot, uint32_t stride) {
     return slot * stride;
 }
 #define S64(slot) (qk_p64<SM>(cx)[qk_ix<SM>((uint32_t)(slot), cx.stride)])
-#define S32(slot) (qk_p32<SM>(cx)[qk_ix<SM>((uint32_t)(slot), cx.stride)])
+#define S32(slot) (qk_p32<SM>(cx)[qk_ix<SM>((uint32_t)(slot), SM < 0 ? cx.stride32 : cx.stride)])
 /* cold state: always global memory, whatever the placement of the hot planes */
 #define C64(slot) (cx.gc64[(uint64_t)(uint32_t)(slot) * cx.rep_pad])
 #define C32(slot) (cx.gc32[(uint64_t)(uint32_t)(slot) * cx.rep_pad])
@@ -1065,17 +1045,18 @@ __global__ void __launch_bounds__(qk_lb_threads(SM), qk_lb_blocks(SM, FT, LOG)) 
   cx.ccap = reinterpret_cast<const double*>(smem + cx.hdr->off_ccap);
   cx.pf32 = cx.hdr->pf32;
   cx.n_pf_words = cx.hdr->n_pf_words;
-  const QkWork work = qk_work_item(P);
-  const uint64_t rep_local = (uint64_t)work.tile * nt + tid;
+  const uint64_t rep_local = (uint64_t)(P.tile0 + QK_BID) * nt + tid;
   if constexpr (SM == 0) {
     cx.g64 = P.g64 + rep_local;
     cx.g32 = P.g32 + rep_local;
     cx.stride = (uint32_t)P.rep_pad;
+    cx.stride32 = cx.stride;
     cx.base64 = cx.base32 = 0;
   } else {
     cx.g64 = nullptr;
     cx.g32 = nullptr;
     cx.stride = nt;
+    cx.stride32 = nt;
     cx.base64 = P.table_bytes / 8 + tid;
     cx.base32 = (P.table_bytes + P.n64 * nt * 8) / 4 + tid;
   }
@@ -1183,9 +1164,9 @@ __global__ void __launch_bounds__(qk_lb_threads(SM), qk_lb_blocks(SM, FT, LOG)) 
    * kernels gain 1.5 % from the 32-bit count-down, the statistics-only kernels lose 2 % with it) */
   constexpr bool EV32 = LOG;
   uint64_t events_done = 0;
-  const uint64_t budget = live ? work.budget : 0;
-  const bool unlimited = work.budget == ~0ull;
-  const uint32_t ev_initial = live ? (unlimited ? 0xFFFFFFFFu : (uint32_t)work.budget) : 0u;
+  const uint64_t budget = live ? P.event_budget : 0;
+  const bool unlimited = P.event_budget == ~0ull;
+  const uint32_t ev_initial = live ? (unlimited ? 0xFFFFFFFFu : (uint32_t)P.event_budget) : 0u;
   uint32_t ev_left = ev_initial;
   const uint64_t t_until = P.t_until;
   /* Model::init of every component in registration order is the first call list of the loop */

@@ -9,12 +9,17 @@
  */
 #define QK_HOST_EMUL 1
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <vector>
 
 #include "qk_kernels.cuh"
 #include "qk_model.h"
 
+void qk_emul_fail(const char* what) {
+  fprintf(stderr, "qk_emul: %s\n", what);
+  abort();
+}
 thread_local uint8_t* qk_emul_smem = nullptr;
 thread_local uint32_t qk_emul_bid = 0;
 
@@ -37,10 +42,10 @@ struct qk_batch {
   std::vector<uint64_t> tape_len;
   bool any_tape;
   bool initialised;
-  uint64_t slice_chunk = 0, slice_total = 0;
 };
 
-static int run(qk_batch* b, uint32_t do_init, uint64_t t0, uint64_t t_until, uint64_t budget, uint32_t n_items = 0) {
+static int run(qk_batch* b, uint32_t do_init, uint64_t t0, uint64_t t_until, uint64_t budget, uint32_t tile0 = 0,
+               uint32_t n_tiles = 0) {
   KParams P;
   memset(&P, 0, sizeof(P));
   P.g64 = b->g64.data();
@@ -67,16 +72,11 @@ static int run(qk_batch* b, uint32_t do_init, uint64_t t0, uint64_t t_until, uin
   P.t_until = t_until;
   P.event_budget = budget;
   P.do_init = do_init;
-  if (n_items) {
-    P.item0 = 0;
-    P.n_tiles = (uint32_t)b->rep_pad;
-    P.chunk_events = b->slice_chunk;
-    P.sliced_total = b->slice_total;
-  }
+  P.tile0 = tile0;
   const size_t smem_bytes = b->table_bytes_padded + (size_t)P.n64 * 8 + (size_t)P.n32 * 4;
   std::vector<uint64_t> smem((smem_bytes + 7) / 8 + 2);
   qk_emul_smem = reinterpret_cast<uint8_t*>(smem.data());
-  for (uint64_t r = 0; r < (n_items ? n_items : b->rep_pad); ++r) {
+  for (uint64_t r = 0; r < (n_tiles ? n_tiles : b->rep_pad); ++r) {
     qk_emul_bid = (uint32_t)r;
     const bool hbm = (b->cfg.flags & QK_BATCH_STATE_IN_HBM) != 0;
     /* the product picks FT = 0 only for on-chip state; here both state placements run both feature sets so the
@@ -194,16 +194,18 @@ int qk_batch_step_events_chunked(qk_batch* b, uint64_t n, uint64_t chunk) {
   return QK_OK;
 }
 int qk_batch_step_events_sliced(qk_batch* b, uint64_t n, uint32_t n_chunks) {
-  /* the emulator runs one replication per block, so a "wave" here is a run of consecutive work items: the same
-   * chunk-major item -> (chunk, tile) mapping and per-chunk budgets as the product's step_sliced */
+  /* the product's step_sliced: tiles in parts, each part chunk by chunk (here: one after the other, tile0 offsets) */
   if (!b || !b->initialised) return QK_ERR_STATE;
   if (n_chunks == 0) return qk_batch_step_events(b, n);
-  b->slice_chunk = (n + n_chunks - 1) / n_chunks;
-  b->slice_total = n;
-  const uint64_t c = (n + b->slice_chunk - 1) / b->slice_chunk;
-  const int rc = run(b, 0, 0, QK_TIME_NONE, 0, (uint32_t)(b->rep_pad * c));
-  b->slice_chunk = 0;
-  return rc;
+  const uint64_t chunk = (n + n_chunks - 1) / n_chunks;
+  const uint32_t parts = b->rep_pad >= 3 ? 3 : 1;
+  for (uint64_t done = 0; done < n; done += chunk)
+    for (uint32_t p = 0; p < parts; ++p) {
+      const uint32_t t0 = (uint32_t)(b->rep_pad * p / parts), t1 = (uint32_t)(b->rep_pad * (p + 1) / parts);
+      const int rc = run(b, 0, 0, QK_TIME_NONE, std::min<uint64_t>(chunk, n - done), t0, t1 - t0);
+      if (rc) return rc;
+    }
+  return QK_OK;
 }
 int qk_batch_synchronize(qk_batch*) { return QK_OK; }
 int qk_batch_last_step_ms(qk_batch*, float* ms, uint32_t* n) {

@@ -46,7 +46,6 @@ static inline void qk_red_addf64(uint64_t* p, double v) {
   std::memcpy(p, &d, 8);
 }
 static inline void __syncthreads() {}
-
 static inline uint64_t __umul64hi(uint64_t a, uint64_t b) {
   return (uint64_t)(((unsigned __int128)a * b) >> 64);
 }
