@@ -294,11 +294,15 @@ int qk_model_n_dists(const qk_model*, uint32_t* out);
 int qk_model_state_bytes(const qk_model*, int with_log, uint32_t* out_bytes);
 
 /* ---- batch of replications on one GPU -------------------------------------------------------- */
-/* State placement. Default: per-replication state is staged in shared memory for the whole launch when at
- * least 12 warps of replications fit per SM that way; larger models operate directly on the HBM state planes
- * (through L1/L2), where residency is limited by registers only.  The two flags force one or the other. */
+/* State placement. Default: per-replication state is staged in shared memory for the whole launch, one thread per
+ * replication, when at least 12 warps of replications fit per SM that way; larger models get a lane group per
+ * replication (state still in shared memory), and models too large even for that operate directly on the HBM state
+ * planes (through L1/L2).  The flags force one placement. */
 #define QK_BATCH_STATE_IN_HBM 1u
 #define QK_BATCH_STATE_ON_CHIP 2u
+/* large models: a group of `lanes_per_replication` lanes (4, 8 or 16; 0 = choose) owns one replication, whose state
+ * stays in shared memory: the scheduler pop and the emit_change broadcast are done by the group's lanes side by side */
+#define QK_BATCH_STATE_LANE_GROUP 4u
 typedef struct {
   uint64_t n_reps;
   uint64_t rep_offset;   /* global index of this batch's first replication (Philox counter words 0,1) */
@@ -308,6 +312,8 @@ typedef struct {
   uint32_t threads_per_block; /* 0 = choose */
   uint32_t flags;        /* QK_BATCH_* bits */
   void* stream;          /* cudaStream_t to launch on, NULL = the library creates its own */
+  uint32_t lanes_per_replication; /* ABI 2: with QK_BATCH_STATE_LANE_GROUP: 4, 8 or 16 ; 0 = choose */
+  uint32_t reserved;
 } qk_batch_config;
 
 /* launch geometry and memory footprint chosen for a batch (for roofline arithmetic and capacity planning) */

@@ -79,6 +79,7 @@ class BatchConfig(C.Structure):
     _fields_ = [
         ("n_reps", C.c_uint64), ("rep_offset", C.c_uint64), ("base_seed", C.c_uint64), ("device", C.c_int32),
         ("log_capacity", C.c_uint32), ("threads_per_block", C.c_uint32), ("flags", C.c_uint32), ("stream", C.c_void_p),
+        ("lanes_per_replication", C.c_uint32), ("reserved", C.c_uint32),
     ]
 
 

@@ -810,7 +810,8 @@ class BatchedSimulation:
         cfg.device = self.device
         cfg.log_capacity = self.log_capacity
         cfg.threads_per_block = self.threads_per_block
-        cfg.flags = self.flags
+        cfg.flags = self.flags & 0xFF
+        cfg.lanes_per_replication = (self.flags >> 8) & 0xFF  # Python-level convention: flags = placement | lanes << 8
         cfg.stream = self.stream
         capi.check(L, L.qk_batch_create(self._model, C.byref(cfg), C.byref(self._batch)))
         for dist, v in self._tapes:

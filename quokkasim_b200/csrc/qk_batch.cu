@@ -85,6 +85,19 @@ StepKernel qk_pick_step_l1f0(uint32_t nt);
 StepKernel qk_pick_step_l1f1(uint32_t nt);
 StepKernel qk_pick_step_l0f2(uint32_t nt);
 StepKernel qk_pick_step_l1f2(uint32_t nt);
+/* ... the lane-group kernels in qk_group_l{0,1}f{0,1,2}.cu */
+StepKernel qk_pick_group_l0f0(uint32_t g);
+StepKernel qk_pick_group_l0f1(uint32_t g);
+StepKernel qk_pick_group_l0f2(uint32_t g);
+StepKernel qk_pick_group_l1f0(uint32_t g);
+StepKernel qk_pick_group_l1f1(uint32_t g);
+StepKernel qk_pick_group_l1f2(uint32_t g);
+static StepKernel pick_group_kernel(bool log, uint32_t g, uint32_t features) {
+  if (features >= 2) return log ? qk_pick_group_l1f2(g) : qk_pick_group_l0f2(g);
+  if (log) return features ? qk_pick_group_l1f1(g) : qk_pick_group_l1f0(g);
+  return features ? qk_pick_group_l0f1(g) : qk_pick_group_l0f0(g);
+}
+static uint32_t group_max_threads(uint32_t g) { return g <= 4 ? 256u : (g == 8 ? 512u : 768u); } /* qk_group_max_threads */
 static StepKernel pick_kernel(bool log, bool hbm, uint32_t nt, uint32_t features) {
   const uint32_t key = hbm ? 0u : nt;
   if (features >= 2) return log ? qk_pick_step_l1f2(key) : qk_pick_step_l0f2(key);
@@ -467,15 +480,51 @@ int qk_batch_create(const qk_model* m, const qk_batch_config* cfg, qk_batch** ou
   uint32_t nt = cfg->threads_per_block;
   const uint32_t max_thr = (uint32_t)qk_lb_resident((int)h.features, b->log); /* the kernel variant's launch bounds */
   b->hbm = (cfg->flags & QK_BATCH_STATE_IN_HBM) != 0;
-  if (!b->hbm && nt == 0 && !(cfg->flags & QK_BATCH_STATE_ON_CHIP)) {
-    /* placement heuristic (measured, profiles/README.md): staging the state in shared memory wins while at least
-     * 12 warps fit per SM (discrete_queue: 8 x 64 threads); below that the L1/L2-cached HBM planes with
-     * register-limited residency are faster (vector_flow 1.3x, serial line / haulage 2x) */
+  bool group = (cfg->flags & QK_BATCH_STATE_LANE_GROUP) != 0;
+  uint32_t G = cfg->lanes_per_replication;
+  if (const char* e = getenv("QK_GROUP_LANES")) /* experiments: overrides the group width wherever groups are used */
+    if (atoi(e) > 0) G = (uint32_t)atoi(e);
+  if (!b->hbm && !group && nt == 0 && !(cfg->flags & QK_BATCH_STATE_ON_CHIP)) {
+    /* placement heuristic (measured, profiles/README.md): one thread per replication with the state staged in shared
+     * memory wins while at least 12 warps fit per SM (discrete_queue: 8 x 64 threads); below that a lane group per
+     * replication keeps the state on chip with fewer replications and more warps */
     uint32_t thr = 0;
     choose_nt(per_rep, b->table_bytes_padded, max_thr, &thr);
-    if (thr < 384) b->hbm = true;
+    if (thr < 384) {
+      const char* e = getenv("QK_AUTO_PLACEMENT"); /* "hbm": the round-1 choice for large models */
+      if (e && e[0] == 'h') b->hbm = true; else group = true;
+    }
   }
-  if (!b->hbm) {
+  if (group) {
+    if (G == 0) G = 8;
+    QkGroupGeom geo;
+    const bool ok = (G == 4 || G == 8 || G == 16) &&
+                    qk_group_geometry(G, 32u, h.n64, h.n32, b->table_bytes_padded, group_max_threads(G), 227u * 1024u, 1024u, 4u,
+                                      &geo) != 0 &&
+                    geo.reps >= 8;
+    if (!ok) {
+      if (cfg->flags & QK_BATCH_STATE_LANE_GROUP) {
+        qk_set_error("qk_batch_create: no lane-group geometry for %u lanes per replication (%u B of state per "
+                     "replication, %u B of tables)", G, per_rep, b->table_bytes_padded);
+        delete b;
+        return QK_ERR_CAPACITY;
+      }
+      group = false;
+      b->hbm = true; /* too large even for a lane group per replication */
+    } else {
+      /* prefer the largest block that still leaves the SM full: several small blocks recycle capacity sooner, but
+       * every block carries its own copy of the tables */
+      b->lanes = G;
+      b->grp_reps = geo.reps;
+      b->grp_stride64 = geo.stride64;
+      b->grp_stride32 = geo.stride32;
+      b->grp_bar_off = geo.bar_off;
+      nt = geo.threads;
+    }
+  }
+  if (group) {
+    /* geometry chosen above */
+  } else if (!b->hbm) {
     if (nt == 0) nt = choose_nt(per_rep, b->table_bytes_padded, max_thr, nullptr);
     const bool fits = nt != 0 && nt <= QK_MAX_NT && !(nt & 31) &&
                       (uint64_t)b->table_bytes_padded + (uint64_t)per_rep * nt <= 227u * 1024u;
@@ -500,11 +549,12 @@ int qk_batch_create(const qk_model* m, const qk_batch_config* cfg, qk_batch** ou
     }
   }
   b->nt = nt;
-  b->smem_bytes = b->table_bytes_padded + (b->hbm ? 0u : per_rep * nt);
+  const uint32_t reps_per_block = group ? b->grp_reps : nt;
+  b->smem_bytes = group ? b->grp_bar_off + 16u : b->table_bytes_padded + (b->hbm ? 0u : per_rep * nt);
   if (const char* pad = getenv("QK_DEBUG_EXTRA_SMEM")) /* occupancy experiments only: lowers resident blocks per SM */
     b->smem_bytes += (uint32_t)atoi(pad);
-  b->grid = (uint32_t)((cfg->n_reps + nt - 1) / nt);
-  b->rep_pad = (uint64_t)b->grid * nt;
+  b->grid = (uint32_t)((cfg->n_reps + reps_per_block - 1) / reps_per_block);
+  b->rep_pad = (uint64_t)b->grid * reps_per_block;
   if (cfg->stream) {
     b->stream = (cudaStream_t)cfg->stream;
   } else {
@@ -543,7 +593,7 @@ int qk_batch_create(const qk_model* m, const qk_batch_config* cfg, qk_batch** ou
   CREATE_TRY(cudaMalloc(&b->d_tape_len, sizeof(uint64_t) * (h.n_dist ? h.n_dist : 1)));
   CREATE_TRY(cudaMemset(b->d_tapes, 0, sizeof(double*) * (h.n_dist ? h.n_dist : 1)));
   CREATE_TRY(cudaMemset(b->d_tape_len, 0, sizeof(uint64_t) * (h.n_dist ? h.n_dist : 1)));
-  b->kernel = pick_kernel(b->log, b->hbm, b->nt, h.features);
+  b->kernel = group ? pick_group_kernel(b->log, b->lanes, h.features) : pick_kernel(b->log, b->hbm, b->nt, h.features);
   CREATE_TRY(cudaFuncSetAttribute((const void*)b->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   {
     int sms = 0, nb = 0;

@@ -113,7 +113,6 @@ constexpr int qk_group_max_threads(int g) { return g <= 4 ? 256 : (g == 8 ? 512 
 template <bool LOG, int G, int FT>
 __global__ void __launch_bounds__(qk_group_max_threads(G), 1) qk_group_kernel(const __grid_constant__ KParams P) {
   constexpr int SM = QK_SMG;
-  constexpr uint32_t GPW = QK_WARP / G; /* groups per warp */
   static_assert(G == 2 || G == 4 || G == 8 || G == 16 || G == 32, "group width");
   uint8_t* const smem = qk_smem;
   const uint32_t tid = QK_TID, nt = QK_NT;
@@ -124,7 +123,6 @@ __global__ void __launch_bounds__(qk_group_max_threads(G), 1) qk_group_kernel(co
   const bool leader = j == 0;
   const uint32_t gshift = lead; /* this group's bits inside a warp ballot */
   const uint32_t gmask = G == 32 ? 0xFFFFFFFFu : ((1u << G) - 1u);
-  (void)GPW;
 
   const uint64_t rep0 = (uint64_t)(P.tile0 + QK_BID) * R; /* first replication of this block */
 
@@ -133,6 +131,7 @@ __global__ void __launch_bounds__(qk_group_max_threads(G), 1) qk_group_kernel(co
   uint64_t* const s64 = reinterpret_cast<uint64_t*>(smem + P.table_bytes);
   uint32_t* const s32 = reinterpret_cast<uint32_t*>(smem + P.table_bytes + (size_t)P.n64 * P.grp_stride64 * 8);
   uint64_t* const bar = reinterpret_cast<uint64_t*>(smem + P.grp_bar_off);
+  (void)bar;
 #ifndef QK_HOST_EMUL
   if (!P.do_init) {
     if (tid == 0) {
@@ -287,70 +286,14 @@ __global__ void __launch_bounds__(qk_group_max_threads(G), 1) qk_group_kernel(co
   uint32_t ext_cursor = (FT != 0 && leader) ? S32(G32_EXT_CURSOR) : 0u;
   bool done = !leader || cx.status != 0;
   if (done) rem = 0;
-  bool keyed = false;
+  /* stand: the call at the head of the group's list is known to need the full handler (a component's own keyed event,
+   * whose fire slot was just cleared so that "fire == NONE means idle" does not hold; or a call qk_quick_eval sent on) */
+  bool stand = false;
   const uint16_t* pf_comp = reinterpret_cast<const uint16_t*>(reinterpret_cast<const uint8_t*>(cx.hdr) + cx.hdr->off_pf);
   for (;;) {
     QK_SYNCWARP();
 #pragma unroll 1
     for (int it = 0; it < QK_SCAN_ITERS; ++it) {
-      /* -- QUICK: the calls at the head of the group's list, G at a time, one lane each */
-      for (;;) {
-        const uint32_t g_rem = QK_SHFL32(keyed ? 0u : rem, lead);
-        if (!QK_ANY_SYNC(g_rem != 0)) break;
-        const uint32_t g_ptr = QK_SHFL32(ptr, lead);
-        const uint64_t g_now = qk_shfl64(cx.now, lead);
-        const uint32_t n_here = g_rem < (uint32_t)G ? g_rem : (uint32_t)G;
-        uint32_t code = 1u;
-        if (j < n_here) code = qk_quick_eval<LOG, SM, FT>(cx, g_ptr + j, g_now);
-        const uint32_t full = (QK_BALLOT(code == 0u) >> gshift) & gmask;
-        const uint32_t n_take = full ? (uint32_t)__ffs((int)full) - 1u : n_here; /* calls disposed of right here */
-        if (LOG) {
-          /* their ProcessNonStart records, in list order: lane j's is record number (popcount of the logging lanes
-           * below it) after the replication's current count */
-          const uint64_t g_src = qk_shfl64(src, lead);
-          const uint32_t g_cnt = QK_SHFL32(cx.log_cnt, lead);
-          bool writes = false;
-          uint32_t comp = 0, seq = 0;
-          if (j < n_take && code >= 0x100u) {
-            comp = cx.subs[g_ptr + j];
-            const DevHotA a = QK_HOT_A(comp);
-            seq = S32(a.olog32 + L32_SEQ);
-            S32(a.olog32 + L32_SEQ) = seq + 1;
-            writes = (a.flags & DC_LOGGED) != 0;
-          }
-          const uint32_t wmask = (QK_BALLOT(writes) >> gshift) & gmask;
-          if (writes) {
-            const uint32_t pos = g_cnt + (uint32_t)QK_POPC(wmask & ((1u << j) - 1u));
-            uint4* r = cx.log_base + 2 * (size_t)(pos & cx.log_mask);
-            uint4 a, b;
-            a.x = (uint32_t)g_now;
-            a.y = (uint32_t)(g_now >> 32);
-            a.z = comp | ((uint32_t)QK_LOG_PROCESS_NONSTART << 16) | ((code & 0xFFu) << 24);
-            a.w = seq;
-            b.x = (uint32_t)(g_src >> 32) & 0xFFFFu;
-            b.y = (uint32_t)g_src;
-            b.z = 0;
-            b.w = 0;
-            qk_store_record(r, a, b);
-          }
-          if (leader) cx.log_cnt += (uint32_t)QK_POPC(wmask);
-        }
-        if (leader && !keyed) {
-          ptr += n_take;
-          rem -= n_take;
-        }
-        QK_SYNCWARP();
-        /* a group goes round again only if its whole chunk was quick and calls are left */
-        const bool again = leader && !keyed && rem != 0 && n_take == (uint32_t)G && !full;
-        if (!QK_ANY_SYNC(again)) break;
-        if (!again) keyed = keyed || false;
-        /* groups that stand on a full call must not be re-evaluated: mask them by pretending the list is keyed for the
-         * rest of this inner loop */
-        if (leader && !again && rem != 0) keyed = keyed || true, src = src; /* see `stand` below */
-      }
-      /* (`keyed` doubles as "stands on a call that needs the full handler"; UPDATE clears it) */
-      if (leader && rem != 0) keyed = true;
-
       /* -- POP: groups whose list is empty take the next action from their scheduler queue */
       if (leader && rem == 0 && !done) {
         if constexpr (EV32) {
@@ -364,7 +307,9 @@ __global__ void __launch_bounds__(qk_group_max_threads(G), 1) qk_group_kernel(co
         }
       }
       const bool want = QK_SHFL32((leader && rem == 0 && !done) ? 1u : 0u, lead) != 0;
-      if (!QK_ANY_SYNC(want)) break; /* every group stands on a full call or has finished */
+      const bool any_want = QK_ANY_SYNC(want);
+      if (!any_want && !QK_ANY_SYNC(leader && rem != 0 && !stand)) break; /* every group stands on a full call or has finished */
+      if (any_want) {
       uint64_t best = QK_TIME_NONE;
       uint32_t bidx = 0xFFFFFFFFu;
       if (want) {
@@ -476,7 +421,7 @@ __global__ void __launch_bounds__(qk_group_max_threads(G), 1) qk_group_kernel(co
                   src = FT == 0 ? (((uint64_t)comp << 32) | (uint32_t)(S32(a.olog32 + L32_SEQ) - 1u))
                                 : C64(a.olog64 + PL64_SCHED_SRC);
                 S64(G64_FIRE0 + bi) = QK_TIME_NONE;
-                keyed = true;
+                stand = true;
               }
               rem = 1;
               ptr = ident_off + comp;
@@ -485,6 +430,57 @@ __global__ void __launch_bounds__(qk_group_max_threads(G), 1) qk_group_kernel(co
         } /* an action was popped */
       }
       QK_SYNCWARP();
+      } /* any_want */
+
+      /* -- QUICK: the calls at the head of each group's list, G at a time, one lane each */
+      for (;;) {
+        const uint32_t g_rem = QK_SHFL32((leader && !stand) ? rem : 0u, lead);
+        if (!QK_ANY_SYNC(g_rem != 0)) break;
+        const uint32_t g_ptr = QK_SHFL32(ptr, lead);
+        const uint64_t g_now = qk_shfl64(cx.now, lead);
+        const uint32_t n_here = g_rem < (uint32_t)G ? g_rem : (uint32_t)G;
+        uint32_t code = 1u;
+        if (j < n_here) code = qk_quick_eval<LOG, SM, FT>(cx, g_ptr + j, g_now);
+        const uint32_t full = (QK_BALLOT(code == 0u) >> gshift) & gmask;
+        const uint32_t n_take = full ? (uint32_t)__ffs((int)full) - 1u : n_here; /* calls disposed of right here */
+        if (LOG) {
+          /* their ProcessNonStart records, in list order: lane j's is record number (popcount of the writing lanes
+           * below it) after the replication's current count */
+          const uint64_t g_src = qk_shfl64(src, lead);
+          const uint32_t g_cnt = QK_SHFL32(cx.log_cnt, lead);
+          bool writes = false;
+          uint32_t comp = 0, seq = 0;
+          if (j < n_take && code >= 0x100u) {
+            comp = cx.subs[g_ptr + j];
+            const DevHotA a = QK_HOT_A(comp);
+            seq = S32(a.olog32 + L32_SEQ);
+            S32(a.olog32 + L32_SEQ) = seq + 1;
+            writes = (a.flags & DC_LOGGED) != 0;
+          }
+          const uint32_t wmask = (QK_BALLOT(writes) >> gshift) & gmask;
+          if (writes) {
+            const uint32_t pos = g_cnt + (uint32_t)QK_POPC(wmask & ((1u << j) - 1u));
+            uint4* r = cx.log_base + 2 * (size_t)(pos & cx.log_mask);
+            uint4 a, b;
+            a.x = (uint32_t)g_now;
+            a.y = (uint32_t)(g_now >> 32);
+            a.z = comp | ((uint32_t)QK_LOG_PROCESS_NONSTART << 16) | ((code & 0xFFu) << 24);
+            a.w = seq;
+            b.x = (uint32_t)(g_src >> 32) & 0xFFFFu;
+            b.y = (uint32_t)g_src;
+            b.z = 0;
+            b.w = 0;
+            qk_store_record(r, a, b);
+          }
+          if (leader) cx.log_cnt += (uint32_t)QK_POPC(wmask);
+        }
+        if (leader && g_rem != 0) {
+          ptr += n_take;
+          rem -= n_take;
+          if (full) stand = true; /* the head of the list is now a call for the full handler */
+        }
+        QK_SYNCWARP();
+      }
     }
     QK_SYNCWARP();
     if (!QK_ANY_SYNC(!done || rem != 0)) break; /* uniform exit: every group of the warp has finished */
@@ -528,7 +524,7 @@ __global__ void __launch_bounds__(qk_group_max_threads(G), 1) qk_group_kernel(co
         done = true;
       }
     }
-    keyed = false;
+    stand = false;
   }
   /* step_until(t) leaves the clock at t */
   if (leader) {

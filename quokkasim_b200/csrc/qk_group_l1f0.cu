@@ -1,0 +1,4 @@
+/* lane-group kernel instantiations: logging on, feature set 0 (see qk_group_inst.cuh) */
+#include "qk_group_inst.cuh"
+
+StepKernel qk_pick_group_l1f0(uint32_t g) { return qk_pick_group<true, 0>(g); }

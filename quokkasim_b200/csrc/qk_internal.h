@@ -179,6 +179,9 @@ typedef struct {
 #define SQ_DS_FORCED 4u  /* downstream category is the constant in bits 6-7 */
 #define SQ_US_SHIFT 4
 #define SQ_DS_SHIFT 6
+#define SQ_DUP 256u      /* the callee appears more than once in this call list (a process whose upstream and downstream
+                            are the same stock): the lane-group kernel, which lets the lanes of a group write the
+                            ProcessNonStart records of a list side by side, takes such entries one at a time */
 
 typedef struct {
   uint32_t kind, stream;
@@ -236,5 +239,37 @@ typedef struct {
   uint32_t features; /* 0 = every process-like component is SIMPLE and nothing is scheduled externally ; 1 = general ;
                         2 = general + container family (vector_container.rs) */
 } DevHeader;
+
+/* ---- lane-group kernel geometry (qk_group.cuh): R replications per block, G lanes each ----------------------------
+ * Shared memory holds the block's state slot-major: 64-bit rows of stride64 elements, then 32-bit rows of stride32.
+ * Rows are moved by bulk asynchronous copies, so R * 4 bytes must be a multiple of 16 and the row starts 16-byte aligned
+ * (R a multiple of 4; stride64 even; stride32 a multiple of 4).  Bank spread: the G lanes of a group read G consecutive
+ * slots of ONE replication, i.e. addresses one row stride apart -- stride64 = 2 (mod 4) puts 8 consecutive 64-bit
+ * rows on 8 different bank pairs, stride32 = 4 (mod 8) 8 consecutive 32-bit rows on 8 different banks. */
+typedef struct {
+  uint32_t reps, stride64, stride32, bar_off, smem_bytes, threads;
+} QkGroupGeom;
+static inline int qk_group_geometry(uint32_t G, uint32_t warp, uint32_t n64, uint32_t n32, uint32_t table_bytes,
+                                    uint32_t max_threads, uint32_t max_smem, uint32_t reps_cap, uint32_t rep_multiple,
+                                    QkGroupGeom* out) {
+  uint32_t unit = G >= warp ? 1u : warp / G; /* whole warps */
+  if (unit < rep_multiple) unit = rep_multiple;
+  int found = 0;
+  for (uint32_t R = unit; R * G <= max_threads && R <= reps_cap; R += unit) {
+    uint32_t s64 = R, s32 = R;
+    while ((s64 & 3u) != 2u) ++s64;
+    while ((s32 & 7u) != 4u) ++s32;
+    const uint32_t bar = (table_bytes + n64 * s64 * 8u + n32 * s32 * 4u + 7u) & ~7u;
+    if (bar + 16u > max_smem) break;
+    found = 1;
+    out->reps = R;
+    out->stride64 = s64;
+    out->stride32 = s32;
+    out->bar_off = bar;
+    out->smem_bytes = bar + 16u;
+    out->threads = R * G;
+  }
+  return found;
+}
 
 #endif

@@ -908,6 +908,12 @@ int qk_lower(const qk_model* m, bool log, QkLowered* out) {
     else if (d.down < 0) s.flags |= SQ_DS_FORCED | (3u << SQ_DS_SHIFT);
     else s.down_hc = q.b.down_hc;
   }
+  for (size_t i = 0; i < nc; ++i) { /* SQ_DUP: duplicates within one subscriber list */
+    const DevComp& d = dc[i];
+    for (uint32_t a = 0; a < d.n_subs; ++a)
+      for (uint32_t b2 = 0; b2 < d.n_subs; ++b2)
+        if (a != b2 && subs[d.subs_off + a] == subs[d.subs_off + b2]) subq[d.subs_off + a].flags |= SQ_DUP;
+  }
   h.off_subq = off;
   off = align8(off + (uint32_t)(subq.size() * sizeof(DevSubQ)));
   /* container tables: capacity by handle, resource of the initial containers (numbered in registration order of

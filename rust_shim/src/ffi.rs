@@ -66,6 +66,8 @@ pub struct qk_batch_config {
     pub threads_per_block: u32,
     pub flags: u32,
     pub stream: *mut c_void,
+    pub lanes_per_replication: u32, // ABI 2: with QK_BATCH_STATE_LANE_GROUP (4): 4, 8 or 16; 0 = choose
+    pub reserved: u32,
 }
 
 #[repr(C)]

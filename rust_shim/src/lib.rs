@@ -294,6 +294,8 @@ impl BatchedSimInit {
             threads_per_block: 0,
             flags: 0,
             stream: std::ptr::null_mut(),
+            lanes_per_replication: 0,
+            reserved: 0,
         };
         ffi::check(unsafe { ffi::qk_batch_create(model, &cfg, &mut sim.batch) })?;
         sim.t0 = t0.0; // Model::init runs with the first step, so that tapes set in between feed the init-time draws

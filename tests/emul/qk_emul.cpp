@@ -13,7 +13,9 @@
 #include <cstdlib>
 #include <vector>
 
-#include "qk_kernels.cuh"
+#include <thread>
+
+#include "qk_group.cuh"
 #include "qk_model.h"
 
 void qk_emul_fail(const char* what) {
@@ -22,6 +24,8 @@ void qk_emul_fail(const char* what) {
 }
 thread_local uint8_t* qk_emul_smem = nullptr;
 thread_local uint32_t qk_emul_bid = 0;
+thread_local QkEmulTeam* qk_emul_team = nullptr;
+thread_local uint32_t qk_emul_tid = 0, qk_emul_nt = 1;
 
 struct qk_batch {
   qk_batch_config cfg;
@@ -42,7 +46,53 @@ struct qk_batch {
   std::vector<uint64_t> tape_len;
   bool any_tape;
   bool initialised;
+  uint32_t lanes; /* 0: one "thread" per replication ; else the lane-group kernel with this group width */
+  QkGroupGeom geo;
 };
+
+/* the lane-group kernel: one block = geo.reps replications x `lanes` lanes = one team of host threads */
+template <bool L, int G>
+static void group_block(const KParams& P, uint32_t ft) {
+  if (ft >= 2) qk_group_kernel<L, G, 2>(P);
+  else if (ft == 1) qk_group_kernel<L, G, 1>(P);
+  else qk_group_kernel<L, G, 0>(P);
+}
+static int run_group(qk_batch* b, KParams& P, uint32_t tile0, uint32_t n_tiles) {
+  P.grp_reps = b->geo.reps;
+  P.grp_stride64 = b->geo.stride64;
+  P.grp_stride32 = b->geo.stride32;
+  P.grp_bar_off = b->geo.bar_off;
+  const uint32_t nt = b->geo.threads, ft = b->low.hdr.features, G = b->lanes;
+  const uint32_t blocks = n_tiles ? n_tiles : (uint32_t)(b->rep_pad / b->geo.reps);
+  std::vector<uint64_t> smem(b->geo.smem_bytes / 8 + 2);
+  for (uint32_t blk = 0; blk < blocks; ++blk) {
+    QkEmulTeam team;
+    team.n = nt;
+    team.count.store(0);
+    team.gen.store(0);
+    std::vector<std::thread> th;
+    for (uint32_t t = 0; t < nt; ++t)
+      th.emplace_back([&, t]() {
+        qk_emul_smem = reinterpret_cast<uint8_t*>(smem.data());
+        qk_emul_bid = blk;
+        qk_emul_tid = t;
+        qk_emul_nt = nt;
+        qk_emul_team = &team;
+        if (b->log) {
+          if (G == 2) group_block<true, 2>(P, ft);
+          else if (G == 4) group_block<true, 4>(P, ft);
+          else group_block<true, 8>(P, ft);
+        } else {
+          if (G == 2) group_block<false, 2>(P, ft);
+          else if (G == 4) group_block<false, 4>(P, ft);
+          else group_block<false, 8>(P, ft);
+        }
+      });
+    for (auto& x : th) x.join();
+  }
+  (void)tile0;
+  return QK_OK;
+}
 
 static int run(qk_batch* b, uint32_t do_init, uint64_t t0, uint64_t t_until, uint64_t budget, uint32_t tile0 = 0,
                uint32_t n_tiles = 0) {
@@ -73,6 +123,7 @@ static int run(qk_batch* b, uint32_t do_init, uint64_t t0, uint64_t t_until, uin
   P.event_budget = budget;
   P.do_init = do_init;
   P.tile0 = tile0;
+  if (b->lanes) return run_group(b, P, tile0, n_tiles);
   const size_t smem_bytes = b->table_bytes_padded + (size_t)P.n64 * 8 + (size_t)P.n32 * 4;
   std::vector<uint64_t> smem((smem_bytes + 7) / 8 + 2);
   qk_emul_smem = reinterpret_cast<uint8_t*>(smem.data());
@@ -116,6 +167,21 @@ int qk_batch_create(const qk_model* m, const qk_batch_config* cfg, qk_batch** ou
   const DevHeader& h = b->low.hdr;
   b->table_bytes_padded = (h.total_bytes + 15u) & ~15u;
   b->rep_pad = cfg->n_reps;
+  b->lanes = 0;
+  if (cfg->flags & QK_BATCH_STATE_LANE_GROUP) {
+    b->lanes = cfg->lanes_per_replication ? cfg->lanes_per_replication : 4;
+    if (b->lanes != 2 && b->lanes != 4 && b->lanes != 8) {
+      delete b;
+      return QK_ERR_INVALID_ARG;
+    }
+    /* small blocks: `threads_per_block` (if given) = replications per block here; the whole block is one warp */
+    const uint32_t cap = cfg->threads_per_block ? cfg->threads_per_block : 2;
+    if (!qk_group_geometry(b->lanes, b->lanes, h.n64, h.n32, b->table_bytes_padded, 32u, 1u << 30, cap, 1u, &b->geo)) {
+      delete b;
+      return QK_ERR_CAPACITY;
+    }
+    b->rep_pad = (cfg->n_reps + b->geo.reps - 1) / b->geo.reps * b->geo.reps;
+  }
   b->g64.assign((size_t)h.n64 * b->rep_pad, 0);
   b->g32.assign((size_t)h.n32 * b->rep_pad, 0);
   b->gs64.assign((size_t)h.n_comp * ST_PER_COMP * b->rep_pad, 0);
@@ -150,7 +216,12 @@ int qk_batch_info_get(qk_batch* b, qk_batch_info* out) {
   out->state_bytes_total = (uint64_t)(out->state_bytes_per_rep + out->cold_bytes_per_rep) * b->rep_pad;
   out->log_bytes_total = b->log ? (uint64_t)b->rep_pad * b->cfg.log_capacity * 32 : 0;
   out->state_in_hbm = (b->cfg.flags & QK_BATCH_STATE_IN_HBM) ? 1u : 0u;
-  out->lanes_per_replication = 1;
+  out->lanes_per_replication = b->lanes ? b->lanes : 1;
+  if (b->lanes) {
+    out->threads_per_block = b->geo.threads;
+    out->grid_blocks = (uint32_t)(b->rep_pad / b->geo.reps);
+    out->shared_bytes_per_block = b->geo.smem_bytes;
+  }
   out->last_step_chunks = 1;
   return QK_OK;
 }
@@ -198,10 +269,11 @@ int qk_batch_step_events_sliced(qk_batch* b, uint64_t n, uint32_t n_chunks) {
   if (!b || !b->initialised) return QK_ERR_STATE;
   if (n_chunks == 0) return qk_batch_step_events(b, n);
   const uint64_t chunk = (n + n_chunks - 1) / n_chunks;
-  const uint32_t parts = b->rep_pad >= 3 ? 3 : 1;
+  const uint64_t tiles = b->lanes ? b->rep_pad / b->geo.reps : b->rep_pad;
+  const uint32_t parts = tiles >= 3 ? 3 : 1;
   for (uint64_t done = 0; done < n; done += chunk)
     for (uint32_t p = 0; p < parts; ++p) {
-      const uint32_t t0 = (uint32_t)(b->rep_pad * p / parts), t1 = (uint32_t)(b->rep_pad * (p + 1) / parts);
+      const uint32_t t0 = (uint32_t)(tiles * p / parts), t1 = (uint32_t)(tiles * (p + 1) / parts);
       const int rc = run(b, 0, 0, QK_TIME_NONE, std::min<uint64_t>(chunk, n - done), t0, t1 - t0);
       if (rc) return rc;
     }

@@ -149,6 +149,12 @@ def test_random_models_match_the_oracle(emul_lib, seed):
     _run(emul_lib, seed, 2, flags=seed % 2)  # both state placements
 
 
+@pytest.mark.parametrize("seed", range(300, 324))
+def test_random_models_match_the_oracle_lane_groups(emul_lib, seed):
+    """the lane-group kernel (qk_group.cuh), 2 / 4 / 8 lanes per replication"""
+    _run(emul_lib, seed, 2, flags=4 | ((2, 4, 8)[seed % 3] << 8))
+
+
 def test_random_models_are_mostly_comparable(emul_lib):
     """the generator must not hide behind capacity faults"""
     assert sum(_run(emul_lib, s, 1) for s in range(40, 60)) >= 17
@@ -255,6 +261,19 @@ def _run_vector(lib, seed, n_reps, flags=0):
 @pytest.mark.parametrize("seed", range(24))
 def test_random_vector_models_match_the_oracle(emul_lib, seed):
     _run_vector(emul_lib, seed, 2, flags=seed % 2)
+
+
+@pytest.mark.parametrize("seed", range(400, 408))
+def test_random_vector_models_match_the_oracle_lane_groups(emul_lib, seed):
+    _run_vector(emul_lib, seed, 2, flags=4 | ((2, 4, 8)[seed % 3] << 8))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(500, 512))
+def test_random_models_match_the_oracle_lane_groups_on_gpu(gpu_lib, seed):
+    _run(gpu_lib, seed, 48, flags=4 | ((4, 8, 16)[seed % 3] << 8))
+    if seed < 504:
+        _run_vector(gpu_lib, seed, 48, flags=4 | ((4, 8, 16)[seed % 3] << 8))
 
 
 @pytest.mark.gpu

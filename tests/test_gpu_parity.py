@@ -12,11 +12,11 @@ pytestmark = pytest.mark.gpu
 
 
 def _check(lib, model, n_reps, n_events=None, t_until=None, tape_len=None, t0=0, seed=42, sample=None,
-           log_capacity=65536, rep_offset=0, threads_per_block=0):
+           log_capacity=65536, rep_offset=0, threads_per_block=0, flags=0):
     om, dist_ids = H.lower_to_oracle(model)
     tapes = H.make_tapes(model, n_reps, tape_len, seed=3) if tape_len else None
     sim = model.sim(lib, n_reps, t0=t0, base_seed=seed, log_capacity=log_capacity, rep_offset=rep_offset,
-                    threads_per_block=threads_per_block)
+                    threads_per_block=threads_per_block, flags=flags)
     if tapes:
         for d, v in tapes.values():
             sim.set_tape(d, v)
@@ -278,12 +278,70 @@ def test_state_placement_does_not_change_results(gpu_lib):
         blobs.append(blob)
         sim.close()
     assert blobs[0] == blobs[1]
-    # the default picks by residency: the 7-component line is staged on chip, the 89-component network is not
+    # the default picks by residency: the 7-component line is staged on chip one thread per replication, the
+    # 96-component network gets a lane group per replication (state still on chip)
     a = H.discrete_queue().sim(gpu_lib, 64)
     b = H.haulage(n_src=8, per_queue=8).sim(gpu_lib, 64)
-    assert a.info()["state_in_hbm"] == 0 and b.info()["state_in_hbm"] == 1
+    ia, ib = a.info(), b.info()
+    assert ia["state_in_hbm"] == 0 and ia["lanes_per_replication"] == 1
+    assert ib["state_in_hbm"] == 0 and ib["lanes_per_replication"] == 8
     a.close()
     b.close()
+
+
+# ------------------------------------------------------------------------------------- lane-group kernel (qk_group.cuh)
+def _gflags(lanes):
+    return 4 | (lanes << 8)  # QK_BATCH_STATE_LANE_GROUP | lanes_per_replication << 8 (api.py convention)
+
+
+@pytest.mark.parametrize("lanes", [4, 8, 16])
+def test_group_kernel_matches_the_oracle(gpu_lib, lanes):
+    """a lane group per replication: records, statistics, stocks bit-exact against the oracle; replication counts that
+    do not fill the last block"""
+    f = _gflags(lanes)
+    _check(gpu_lib, H.haulage(n_src=8, per_queue=8), 101, n_events=20000, sample=[0, 50, 100], log_capacity=131072, flags=f)
+    _check(gpu_lib, H.serial_line(n_proc=32), 70, n_events=30000, sample=[0, 69], log_capacity=131072, flags=f)
+    _check(gpu_lib, H.discrete_queue(), 300, n_events=3000, tape_len=1200, sample=[0, 1, 150, 299], log_capacity=16384,
+           flags=f)
+    m = H.car_workshop()
+    _check(gpu_lib, m, 33, t_until=m.t0 + 9 * 3600 * 10**9, t0=m.t0, sample=[0, 32], log_capacity=4096, flags=f)
+
+
+def test_group_kernel_general_components(gpu_lib):
+    f = _gflags(8)
+    m = H.assembly_line()
+    _check(gpu_lib, m, 64, t_until=m.t0 + 3 * 24 * 3600 * 10**9, t0=m.t0, sample=[0, 63], log_capacity=16384, flags=f)
+    _check(gpu_lib, H.vector_flow(3), 200, n_events=6000, sample=[0, 99, 199], log_capacity=65536, flags=f)
+    _check(gpu_lib, H.container_haulage(), 128, n_events=6000, sample=[0, 127], log_capacity=65536, flags=f)
+
+
+def test_group_kernel_state_round_trip_and_placements_agree(gpu_lib):
+    """the bulk-copy staging (one cp.async.bulk per slot row in, one out): a step cut into launches, and sliced into
+    parts on side streams, equals one launch; and equals the thread-per-replication placements"""
+    blobs = []
+    for flags, how in ((_gflags(8), "one"), (_gflags(8), "pieces"), (_gflags(4), "sliced"), (_gflags(16), "chunked"),
+                       (1, "one"), (2, "one")):
+        m = H.haulage(n_src=3, per_queue=4)
+        sim = m.sim(gpu_lib, 1000, base_seed=21, flags=flags, log_capacity=256)
+        if how == "one":
+            sim.step_events(6000)
+        elif how == "pieces":
+            sim.step_events(1)
+            sim.step_events(2999)
+            sim.step_events(3000)
+        elif how == "sliced":
+            sim.step_events_sliced(6000, 5)
+        else:
+            sim.step_events_chunked(6000, 700)
+        blob = b"".join(sim.comp_stats(ci).tobytes() for ci in range(len(m.components)))
+        logs, totals = sim.read_logs(0, 1000)
+        blob += b"".join(x.tobytes() for x in logs) + totals.tobytes()
+        for ci, c in enumerate(m.components):
+            if c.variant == "StringStock":
+                blob += sim.read_stock(ci, 999).tobytes()
+        blobs.append(blob)
+        sim.close()
+    assert all(b == blobs[0] for b in blobs[1:])
 
 
 def test_reference_vector_examples_transport_delay_testing_rocks(gpu_lib):
