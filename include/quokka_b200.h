@@ -386,6 +386,39 @@ int qk_batch_read_containers(qk_batch*, uint64_t rep, uint32_t comp, uint32_t* h
 /* timing of the last step call measured with CUDA events on the batch's stream (ms) and kernels launched */
 int qk_batch_last_step_ms(qk_batch*, float* ms, uint32_t* n_launches);
 
+/* ---- one job on several GPUs of one box (`devices, n_dev`, statistics "after internal NCCL reduce") ----------
+ * The replications [0, n_reps) of the job are sharded over the devices by contiguous range (device d of D owns
+ * [n_reps*d/D, n_reps*(d+1)/D), = its Philox counter range); each shard is a qk_batch on its own stream, driven from
+ * the calling thread (every step call only enqueues).  Replaces running one `Simulation` per replication
+ * (quokkasim_examples/src/bin/discrete_queue.rs:109-111) on a box with several GPUs; there is no data-path collective.
+ * qk_multi_stats is the one exchange: packed partials -> ncclAllGather -> combine -> global-range histograms ->
+ * ncclAllReduce(sum); it returns the same qk_comp_summary a single batch holding all the replications would.
+ * NCCL (libnccl.so.2) is loaded at run time, and only when a job has more than one device. */
+typedef struct qk_multi qk_multi;
+typedef struct {
+  uint64_t n_reps;        /* replications of the whole job */
+  uint64_t rep_offset;    /* global index of the job's first replication */
+  uint64_t base_seed;
+  const int32_t* devices; /* CUDA ordinals, n_devices of them; NULL / 0 = every visible device */
+  uint32_t n_devices;
+  uint32_t log_capacity, threads_per_block, flags, lanes_per_replication; /* as qk_batch_config, for every shard */
+} qk_multi_config;
+int qk_multi_create(const qk_model*, const qk_multi_config*, qk_multi** out);
+void qk_multi_destroy(qk_multi*);
+int qk_multi_n_shards(qk_multi*, uint32_t* n);
+/* shard i: its batch (for the per-replication read-back calls qk_batch_read_*), first replication, count, device */
+int qk_multi_shard(qk_multi*, uint32_t i, qk_batch** batch, uint64_t* rep0, uint64_t* n_reps, int32_t* device);
+/* values[rep * per_rep_len + i] for the replications of the whole job */
+int qk_multi_set_tape(qk_multi*, uint32_t dist_id, const double* values, uint64_t per_rep_len);
+int qk_multi_init(qk_multi*, uint64_t t0_ns);
+int qk_multi_step_until(qk_multi*, uint64_t t_ns);
+int qk_multi_step_events(qk_multi*, uint64_t n_events);
+int qk_multi_synchronize(qk_multi*);
+/* device-timed duration of the last step call: the maximum over the GPUs */
+int qk_multi_last_step_ms(qk_multi*, float* ms_max);
+/* globally reduced summary: out[n_comp]; *total (optional) = whole-job counts and clock range */
+int qk_multi_stats(qk_multi*, qk_comp_summary* out, uint32_t n_comp, qk_batch_summary* total);
+
 const char* qk_last_error(void);
 
 #ifdef __cplusplus

@@ -476,7 +476,12 @@ struct ScheduledEventConfig {
 struct BatchOptions {
   uint64_t n_replications = 1, base_seed = 0, rep_offset = 0;
   int device = 0;
-  uint32_t log_capacity = 0, threads_per_block = 0, flags = 0;
+  uint32_t log_capacity = 0, threads_per_block = 0, flags = 0, lanes_per_replication = 0;
+  /* more than one GPU: the replications are sharded over `devices` (or over every visible device) by the library's
+   * qk_multi_* plane, and stats() returns the globally reduced summary (NCCL inside the library) */
+  std::vector<int32_t> devices;
+  bool all_devices = false;
+  bool multi() const { return all_devices || devices.size() > 1; }
 };
 
 class BatchedSimulation {
@@ -497,11 +502,13 @@ class BatchedSimulation {
   BatchedSimulation& operator=(const BatchedSimulation&) = delete;
   BatchedSimulation(BatchedSimulation&& o) noexcept
       : components(std::move(o.components)), t0(o.t0), opt(o.opt), model_(o.model_), batch_(o.batch_), ext_(std::move(o.ext_)),
-        tapes_(std::move(o.tapes_)), dist_ids_(std::move(o.dist_ids_)) {
+        tapes_(std::move(o.tapes_)), dist_ids_(std::move(o.dist_ids_)), multi_(o.multi_) {
     o.model_ = nullptr;
     o.batch_ = nullptr;
+    o.multi_ = nullptr;
   }
   ~BatchedSimulation() {
+    if (multi_) qk_multi_destroy(multi_);
     if (batch_) qk_batch_destroy(batch_);
     if (model_) qk_model_destroy(model_);
   }
@@ -521,16 +528,47 @@ class BatchedSimulation {
   }
   void step_until(uint64_t t_ns) {
     materialize();
-    check(qk_batch_step_until(batch_, t_ns));
+    check(multi_ ? qk_multi_step_until(multi_, t_ns) : qk_batch_step_until(batch_, t_ns));
   }
   void step_events(uint64_t n) {
     materialize();
-    check(qk_batch_step_events(batch_, n));
+    check(multi_ ? qk_multi_step_events(multi_, n) : qk_batch_step_events(batch_, n));
+  }
+  /* per-component summaries over ALL replications (on several GPUs: reduced inside the library with NCCL) and the
+   * whole-job totals */
+  std::vector<qk_comp_summary> stats(qk_batch_summary* total = nullptr) {
+    materialize();
+    std::vector<qk_comp_summary> out(components.size());
+    if (multi_) {
+      check(qk_multi_stats(multi_, out.data(), (uint32_t)out.size(), total));
+    } else {
+      check(qk_batch_reduce_stats(batch_, out.data(), (uint32_t)out.size()));
+      if (total) check(qk_batch_summary_get(batch_, total));
+    }
+    return out;
+  }
+  /* device-timed duration of the last step call (maximum over the GPUs) */
+  float last_step_ms() {
+    materialize();
+    float ms = 0;
+    check(multi_ ? qk_multi_last_step_ms(multi_, &ms) : qk_batch_last_step_ms(batch_, &ms, nullptr));
+    return ms;
+  }
+  uint32_t n_shards() {
+    materialize();
+    uint32_t n = 1;
+    if (multi_) check(qk_multi_n_shards(multi_, &n));
+    return n;
   }
   qk_batch_summary summary() {
     materialize();
     qk_batch_summary s;
-    check(qk_batch_summary_get(batch_, &s));
+    if (multi_) {
+      std::vector<qk_comp_summary> tmp(components.size());
+      check(qk_multi_stats(multi_, tmp.data(), (uint32_t)tmp.size(), &s));
+    } else {
+      check(qk_batch_summary_get(batch_, &s));
+    }
     return s;
   }
   std::vector<qk_comp_stats> comp_stats(const ComponentModel& c, uint64_t rep0, uint64_t n) {
@@ -593,7 +631,8 @@ class BatchedSimulation {
     uint64_t len;
   };
   qk_model* model_ = nullptr;
-  qk_batch* batch_ = nullptr;
+  qk_batch* batch_ = nullptr; /* one GPU: the batch ; several GPUs: shard 0 (per-replication reads address shard 0) */
+  qk_multi* multi_ = nullptr;
   std::vector<Ext> ext_;
   std::vector<Tape> tapes_;
   std::vector<std::pair<const int*, uint32_t>> dist_ids_;
@@ -601,7 +640,7 @@ class BatchedSimulation {
   /* component objects -> C-ABI rows; the batch is created lazily so that scheduled events created after init()
    * (assembly_line.rs:240-246) still land in the model tables */
   void materialize() {
-    if (batch_) return;
+    if (batch_ || multi_) return;
     check(qk_model_create(&model_));
     for (auto& cm : components) {
       auto& c = *cm.component.d;
@@ -664,8 +703,28 @@ class BatchedSimulation {
       check(qk_model_connect(model_, (uint32_t)k.a->id, (uint32_t)k.b->id, k.n));
     }
     for (auto& e : ext_) check(qk_model_schedule_env_state(model_, e.t, (uint32_t)e.env->id, e.state));
+    if (opt.multi()) {
+      qk_multi_config mc;
+      std::memset(&mc, 0, sizeof(mc));
+      mc.n_reps = opt.n_replications;
+      mc.rep_offset = opt.rep_offset;
+      mc.base_seed = opt.base_seed;
+      mc.devices = opt.all_devices ? nullptr : opt.devices.data();
+      mc.n_devices = opt.all_devices ? 0u : (uint32_t)opt.devices.size();
+      mc.log_capacity = opt.log_capacity;
+      mc.threads_per_block = opt.threads_per_block;
+      mc.flags = opt.flags;
+      mc.lanes_per_replication = opt.lanes_per_replication;
+      check(qk_multi_create(model_, &mc, &multi_));
+      for (auto& t : tapes_)
+        for (auto& di : dist_ids_)
+          if (di.first == t.identity) check(qk_multi_set_tape(multi_, di.second, t.values.data(), t.len));
+      check(qk_multi_init(multi_, t0));
+      return;
+    }
     qk_batch_config cfg;
     std::memset(&cfg, 0, sizeof(cfg));
+    cfg.lanes_per_replication = opt.lanes_per_replication;
     cfg.n_reps = opt.n_replications;
     cfg.rep_offset = opt.rep_offset;
     cfg.base_seed = opt.base_seed;

@@ -52,6 +52,8 @@ EXPORTED_SYMBOLS = [
     "qk_batch_histograms_device", "qk_batch_read_log", "qk_batch_read_logs", "qk_batch_read_stock",
     "qk_batch_last_step_ms", "qk_last_error",
     "qk_model_set_container_factory", "qk_model_set_initial_containers", "qk_batch_read_containers",
+    "qk_multi_create", "qk_multi_destroy", "qk_multi_n_shards", "qk_multi_shard", "qk_multi_set_tape", "qk_multi_init",
+    "qk_multi_step_until", "qk_multi_step_events", "qk_multi_synchronize", "qk_multi_last_step_ms", "qk_multi_stats",
 ]
 
 
@@ -80,6 +82,14 @@ class BatchConfig(C.Structure):
         ("n_reps", C.c_uint64), ("rep_offset", C.c_uint64), ("base_seed", C.c_uint64), ("device", C.c_int32),
         ("log_capacity", C.c_uint32), ("threads_per_block", C.c_uint32), ("flags", C.c_uint32), ("stream", C.c_void_p),
         ("lanes_per_replication", C.c_uint32), ("reserved", C.c_uint32),
+    ]
+
+
+class MultiConfig(C.Structure):
+    _fields_ = [
+        ("n_reps", C.c_uint64), ("rep_offset", C.c_uint64), ("base_seed", C.c_uint64), ("devices", C.POINTER(C.c_int32)),
+        ("n_devices", C.c_uint32), ("log_capacity", C.c_uint32), ("threads_per_block", C.c_uint32), ("flags", C.c_uint32),
+        ("lanes_per_replication", C.c_uint32),
     ]
 
 
@@ -182,6 +192,17 @@ def load_library(path=None):
         "qk_model_set_container_factory": (C.c_int, [vp, u32, P(DistDesc), P(C.c_double), C.c_double, P(u32)]),
         "qk_model_set_initial_containers": (C.c_int, [vp, u32, u32, vp, vp, vp]),
         "qk_batch_read_containers": (C.c_int, [vp, u64, u32, vp, vp, u64, P(u64)]),
+        "qk_multi_create": (C.c_int, [vp, P(MultiConfig), P(vp)]),
+        "qk_multi_destroy": (None, [vp]),
+        "qk_multi_n_shards": (C.c_int, [vp, P(u32)]),
+        "qk_multi_shard": (C.c_int, [vp, u32, P(vp), P(u64), P(u64), P(i32)]),
+        "qk_multi_set_tape": (C.c_int, [vp, u32, vp, u64]),
+        "qk_multi_init": (C.c_int, [vp, u64]),
+        "qk_multi_step_until": (C.c_int, [vp, u64]),
+        "qk_multi_step_events": (C.c_int, [vp, u64]),
+        "qk_multi_synchronize": (C.c_int, [vp]),
+        "qk_multi_last_step_ms": (C.c_int, [vp, P(C.c_float)]),
+        "qk_multi_stats": (C.c_int, [vp, vp, u32, P(BatchSummary)]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)

@@ -821,7 +821,8 @@ class BatchedSimulation:
 
     def close(self):
         if self._batch:
-            self.L.qk_batch_destroy(self._batch)
+            if getattr(self, "_owns", True):  # a shard view of a MultiGpuSimulation does not own its batch
+                self.L.qk_batch_destroy(self._batch)
             self._batch = C.c_void_p()
         if self._model:
             self.L.qk_model_destroy(self._model)

@@ -12,7 +12,7 @@ CSRC = os.path.join(_HERE, "csrc")
 LIB = os.path.join(_HERE, "libquokka_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
-SOURCES = ["qk_model.cpp", "qk_batch.cu", "qk_step_l0f0.cu", "qk_step_l0f1.cu", "qk_step_l1f0.cu", "qk_step_l1f1.cu",
+SOURCES = ["qk_model.cpp", "qk_batch.cu", "qk_multi.cu", "qk_step_l0f0.cu", "qk_step_l0f1.cu", "qk_step_l1f0.cu", "qk_step_l1f1.cu",
            "qk_step_l0f2.cu", "qk_step_l1f2.cu", "qk_group_l0f0.cu", "qk_group_l0f1.cu", "qk_group_l0f2.cu",
            "qk_group_l1f0.cu", "qk_group_l1f1.cu", "qk_group_l1f2.cu"]
 FLAGS = [
@@ -23,6 +23,8 @@ FLAGS = [
     "-Xptxas", "-v",
     "--threads", "0",  # the translation units compile in parallel (reproducibly, unlike --split-compile)
     "-shared", "-cudart", "static",
+    "-I/usr/include",  # nccl.h (types only: libnccl.so.2 is loaded at run time by qk_multi_create)
+    "-ldl",
 ]
 
 

@@ -31,6 +31,7 @@
 #define QK_LANE (threadIdx.x & 31u)
 #define QK_SHFL32(v, src) __shfl_sync(0xFFFFFFFFu, (v), (int)(src))
 #define QK_SHFL_XOR32(v, m) __shfl_xor_sync(0xFFFFFFFFu, (v), (int)(m))
+#define QK_REDUCE_MIN32(mask, v) __reduce_min_sync((mask), (v)) /* REDUX over the lanes of `mask` (the caller's group) */
 #define QK_SYNCBLOCK() __syncthreads()
 
 /* ---- bulk asynchronous copies (TMA engine, 1-D): one instruction moves a whole slot row ------------------------- */
@@ -80,19 +81,25 @@ __device__ __forceinline__ uint64_t qk_shfl_xor64(uint64_t v, uint32_t m) {
 }
 
 /* What would update_state(subs[ptr]) do right now?  The side-effect-free half of qk_try_quick:
- *   0              it finishes or starts something (or is not a SIMPLE component): the full handler
+ *   0              it finishes or starts something (or has no quick path): the full handler
  *   1              busy and not due: nothing
+ *   2              a busy component with delay modes: its countdowns lose *dt (qk_dm_apply)
  *   0x100 | reason idle and it stays blocked: only its ProcessNonStart record */
 template <bool LOG, int SM, int FT>
-__device__ __forceinline__ uint32_t qk_quick_eval(Ctx& cx, uint32_t ptr, uint64_t now) {
+__device__ __forceinline__ uint32_t qk_quick_eval(Ctx& cx, uint32_t ptr, uint64_t now, uint64_t* dt) {
   union {
     uint2 v;
     DevSubQ q;
   } u;
   u.v = *reinterpret_cast<const uint2*>(&cx.subq[ptr]);
   const DevSubQ q = u.q;
-  if (!(q.flags & SQ_QUICK)) return 0u;
   if (LOG && (q.flags & SQ_DUP)) return 0u; /* the component is in this list twice: its records must be written in turn */
+  if (FT != 0 && (q.flags & SQ_DM)) {
+    uint32_t reason = 0;
+    const uint32_t code = qk_dm_quick<SM>(cx, q, cx.subs[ptr], now, &reason, dt);
+    return code == 1u ? (0x100u | reason) : code;
+  }
+  if (!(q.flags & SQ_QUICK)) return 0u;
   const uint64_t fire = S64(q.fire_slot);
   if (fire != QK_TIME_NONE) return fire > now ? 1u : 0u;
   const uint32_t us = (q.flags & SQ_US_FORCED) ? (q.flags >> SQ_US_SHIFT) & 3u : QK_HC_CAT(S32(q.up_hc));
@@ -314,6 +321,7 @@ __global__ void __launch_bounds__(qk_group_max_threads(G), 1) qk_group_kernel(co
       uint32_t bidx = 0xFFFFFFFFu;
       if (want) {
         /* lane j owns fire slots j, j + G, ...: independent loads, ascending, strict '<' keeps the lowest index */
+#pragma unroll 4
         for (uint32_t i = j; i < n_sched; i += G) {
           const uint64_t t = S64(G64_FIRE0 + i);
           if (t < best) {
@@ -322,14 +330,16 @@ __global__ void __launch_bounds__(qk_group_max_threads(G), 1) qk_group_kernel(co
           }
         }
       }
-#pragma unroll
-      for (uint32_t m = G / 2; m > 0; m >>= 1) { /* min over (time, registration rank) */
-        const uint64_t ot = qk_shfl_xor64(best, m);
-        const uint32_t oi = QK_SHFL_XOR32(bidx, m);
-        if (ot < best || (ot == best && oi < bidx)) {
-          best = ot;
-          bidx = oi;
-        }
+      {
+        /* min over (time, registration rank) of the group's lanes: three warp reductions (REDUX) on the 32-bit halves
+         * and the index, each over this group's lanes only -- the groups of a warp reduce side by side */
+        const uint32_t wm = gmask << gshift;
+        const uint32_t hi = (uint32_t)(best >> 32), lo = (uint32_t)best;
+        const uint32_t mhi = QK_REDUCE_MIN32(wm, hi);
+        const uint32_t mlo = QK_REDUCE_MIN32(wm, hi == mhi ? lo : 0xFFFFFFFFu);
+        const uint32_t mid = QK_REDUCE_MIN32(wm, (hi == mhi && lo == mlo) ? bidx : 0xFFFFFFFFu);
+        best = ((uint64_t)mhi << 32) | mlo;
+        bidx = mid;
       }
       if (leader && rem == 0 && !done) {
         int bi = best == QK_TIME_NONE ? -1 : (int)bidx;
@@ -440,9 +450,14 @@ __global__ void __launch_bounds__(qk_group_max_threads(G), 1) qk_group_kernel(co
         const uint64_t g_now = qk_shfl64(cx.now, lead);
         const uint32_t n_here = g_rem < (uint32_t)G ? g_rem : (uint32_t)G;
         uint32_t code = 1u;
-        if (j < n_here) code = qk_quick_eval<LOG, SM, FT>(cx, g_ptr + j, g_now);
+        uint64_t tick_dt = 0;
+        if (j < n_here) code = qk_quick_eval<LOG, SM, FT>(cx, g_ptr + j, g_now, &tick_dt);
         const uint32_t full = (QK_BALLOT(code == 0u) >> gshift) & gmask;
         const uint32_t n_take = full ? (uint32_t)__ffs((int)full) - 1u : n_here; /* calls disposed of right here */
+        if (FT != 0 && code == 2u && j < n_take) qk_dm_apply<SM>(cx, cx.subs[g_ptr + j], g_now, tick_dt);
+#ifdef QK_HOST_EMUL
+        if (FT != 0 && code >= 0x100u && j < n_take && (cx.subq[g_ptr + j].flags & SQ_DM)) qk_emul_count(1);
+#endif
         if (LOG) {
           /* their ProcessNonStart records, in list order: lane j's is record number (popcount of the writing lanes
            * below it) after the replication's current count */
@@ -485,11 +500,12 @@ __global__ void __launch_bounds__(qk_group_max_threads(G), 1) qk_group_kernel(co
     QK_SYNCWARP();
     if (!QK_ANY_SYNC(!done || rem != 0)) break; /* uniform exit: every group of the warp has finished */
 
-    /* -- REFILL (deferred variate prefetch): when a group's next call may start a process whose pre-drawn duration is
-     * missing, or half the group's lanes would have one to draw, the pending slots are re-drawn -- one per lane */
+    /* -- REFILL (variate prefetch): the durations consumed by the starts of the previous trip are re-drawn before the
+     * next handler runs -- one pending slot per lane, the groups of the warp side by side (a process that finishes and
+     * restarts in one call needs its slot full again by then, so waiting for several to accumulate does not pay here:
+     * measured, 1.2 lanes per sampler instruction with a threshold of G / 2) */
     {
-      const bool must = leader && rem != 0 && cx.npend != 0 && qk_needs_refill_now<SM>(cx, cx.subs[ptr]);
-      const bool go = QK_SHFL32((must || (leader && cx.npend >= (uint32_t)(G >= 4 ? G / 2 : 1))) ? 1u : 0u, lead) != 0;
+      const bool go = QK_SHFL32((leader && cx.npend != 0) ? 1u : 0u, lead) != 0;
       if (QK_ANY_SYNC(go)) {
         if (go) {
           uint32_t k = 0;

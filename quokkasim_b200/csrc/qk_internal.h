@@ -179,6 +179,10 @@ typedef struct {
 #define SQ_DS_FORCED 4u  /* downstream category is the constant in bits 6-7 */
 #define SQ_US_SHIFT 4
 #define SQ_DS_SHIFT 6
+#define SQ_DM 512u       /* the callee is a single-server discrete component WITH delay modes (no environment, no
+                            container items): not SIMPLE, but two of its calls still change nothing that needs the full
+                            handler -- idle and still blocked (as for SIMPLE components), and busy with neither the
+                            process countdown nor any until-delay countdown running out (qk_dm_quick) */
 #define SQ_DUP 256u      /* the callee appears more than once in this call list (a process whose upstream and downstream
                             are the same stock): the lane-group kernel, which lets the lanes of a group write the
                             ProcessNonStart records of a list side by side, takes such entries one at a time */

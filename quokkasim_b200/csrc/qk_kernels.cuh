@@ -584,6 +584,59 @@ __device__ __forceinline__ void qk_pre(Ctx& cx, const DevHotA& c, uint32_t comp)
  * and statistics read-outs evaluate the countdown at the clock (qk_left_at_clock).  Hence a quick call of a busy
  * component is one table quad + one state load, and it writes nothing.
  * Returns false (state untouched) when the call needs the full handler. */
+/* Quick handling of a single-server discrete component WITH delay modes (SQ_DM; no environment).  Its update_state
+ * (discrete.rs:404-564) changes nothing but countdowns in two frequent cases:
+ *   idle   -- no item, no mode in TimeUntilFix, no pending keyed event: the delay modes do not tick (discrete.rs:436,
+ *             `is_in_delay || is_in_process`), so the call is the start test alone; if the component stays blocked it
+ *             logs ProcessNonStart and nothing else (previous_check_time is not read again before the next start, which
+ *             rewrites it);
+ *   busy   -- an item in process, no mode in TimeUntilFix, the pending keyed event neither due nor later than the finish
+ *             time, and dt shorter than every until-delay countdown: the process countdown and the until-delay countdowns
+ *             lose dt, previous_check_time = now, no record, and post_update_state keeps the pending event
+ *             (now + left is not earlier than it).  Not for sinks, whose ttnpe is not recomputed while busy
+ *             (discrete.rs:1127-1129).
+ * Returns 0 = needs the full handler, 1 = idle and blocked (reason in *reason), 2 = busy: *dt_out to be applied with
+ * qk_dm_apply.  Reads only. */
+template <int SM>
+__device__ __forceinline__ uint32_t qk_dm_quick(Ctx& cx, const DevSubQ& q, uint32_t comp, uint64_t now, uint32_t* reason,
+                                                uint64_t* dt_out) {
+  const DevHotA a = QK_HOT_A(comp);
+  const uint32_t flags = S32(a.o32 + P32_FLAGS);
+  const uint64_t fire = S64(q.fire_slot);
+  if (flags & ~PF_HAS_ITEM) return 0u; /* a mode in TimeUntilFix (or environment-stopped) */
+  if (!(flags & PF_HAS_ITEM)) {
+    if (fire != QK_TIME_NONE) return 0u;
+    const uint32_t us = (q.flags & SQ_US_FORCED) ? (q.flags >> SQ_US_SHIFT) & 3u : QK_HC_CAT(S32(q.up_hc));
+    const uint32_t ds = (q.flags & SQ_DS_FORCED) ? (q.flags >> SQ_DS_SHIFT) & 3u : QK_HC_CAT(S32(q.down_hc));
+    if ((us == 1u || us == 2u) && (ds == 0u || ds == 1u)) return 0u; /* starts */
+    *reason = us == 0u   ? QK_REASON_UPSTREAM_EMPTY
+              : us == 3u ? QK_REASON_UPSTREAM_NOT_CONNECTED
+              : ds == 2u ? QK_REASON_DOWNSTREAM_FULL
+                         : QK_REASON_DOWNSTREAM_NOT_CONNECTED;
+    return 1u;
+  }
+  if (a.kind == QK_DISCRETE_SINK || fire == QK_TIME_NONE || fire <= now) return 0u;
+  const uint64_t prev = S64(a.o64 + P64_PREV), left = S64(a.o64 + P64_LEFT);
+  if (prev + left < fire) return 0u; /* post_update_state would move the keyed event */
+  const uint64_t dt = now - prev;
+  const DevHotB b = QK_HOT_B(comp);
+  for (uint32_t k = 0; k < a.n_dm; ++k)
+    if (S64(b.o64_dm + k) <= dt) return 0u; /* a breakdown starts in this call */
+  *dt_out = dt;
+  return 2u;
+}
+template <int SM>
+__device__ __forceinline__ void qk_dm_apply(Ctx& cx, uint32_t comp, uint64_t now, uint64_t dt) {
+  const DevHotA a = QK_HOT_A(comp);
+  const DevHotB b = QK_HOT_B(comp);
+  for (uint32_t k = 0; k < a.n_dm; ++k) S64(b.o64_dm + k) -= dt;
+  S64(a.o64 + P64_LEFT) -= dt;
+  S64(a.o64 + P64_PREV) = now;
+#ifdef QK_HOST_EMUL
+  qk_emul_count(0); /* the CPU suite checks that its delay-mode models actually take this path */
+#endif
+}
+
 template <bool LOG, int SM, int FT>
 __device__ __forceinline__ bool qk_try_quick(Ctx& cx, uint32_t ptr, uint64_t src) {
   union {
@@ -592,7 +645,22 @@ __device__ __forceinline__ bool qk_try_quick(Ctx& cx, uint32_t ptr, uint64_t src
   } u;
   u.v = *reinterpret_cast<const uint2*>(&cx.subq[ptr]); /* one LDS.64 */
   const DevSubQ q = u.q;
-  if (FT != 0 && !(q.flags & SQ_QUICK)) return false;
+  if (FT != 0 && !(q.flags & SQ_QUICK)) {
+    if (!(q.flags & SQ_DM)) return false;
+    const uint32_t comp = cx.subs[ptr];
+    uint32_t reason = 0;
+    uint64_t dt = 0;
+    const uint32_t code = qk_dm_quick<SM>(cx, q, comp, cx.now, &reason, &dt);
+    if (code == 0u) return false;
+    if (code == 2u)
+      qk_dm_apply<SM>(cx, comp, cx.now, dt);
+    else if (LOG)
+      qk_log<LOG, SM>(cx, QK_HOT_A(comp), comp, src, QK_LOG_PROCESS_NONSTART, reason, 0);
+#ifdef QK_HOST_EMUL
+    if (code == 1u) qk_emul_count(1);
+#endif
+    return true;
+  }
   /* the three state words are independent loads: one shared-memory latency, not three.  (On the HBM planes the
    * neighbour words are only fetched when the callee turns out to be idle: there a load is a memory transaction; the
    * logging kernels do the same because they have no registers to hold the two words: measured.) */

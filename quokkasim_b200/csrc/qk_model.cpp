@@ -898,8 +898,10 @@ int qk_lower(const qk_model* m, bool log, QkLowered* out) {
     const DevHot& q = hot[subs[i]];
     DevSubQ& s = subq[i];
     memset(&s, 0, sizeof(s));
-    if (!(q.a.flags & DC_SIMPLE)) continue; /* flags == 0: always the full handler */
-    s.flags = SQ_QUICK;
+    const bool single_k = d.kind == QK_DISCRETE_PROCESS || d.kind == QK_DISCRETE_SOURCE || d.kind == QK_DISCRETE_SINK;
+    const bool dm_quick = single_k && d.n_dm > 0 && d.env < 0 && !(d.flags & DC_CONTAINER);
+    if (!(q.a.flags & DC_SIMPLE) && !dm_quick) continue; /* flags == 0: always the full handler */
+    s.flags = dm_quick ? SQ_DM : SQ_QUICK;
     s.fire_slot = (uint16_t)(G64_FIRE0 + d.fire_idx);
     if (d.kind == QK_DISCRETE_SOURCE) s.flags |= SQ_US_FORCED | (1u << SQ_US_SHIFT);
     else if (d.up < 0) s.flags |= SQ_US_FORCED | (3u << SQ_US_SHIFT);

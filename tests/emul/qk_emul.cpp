@@ -22,6 +22,8 @@ void qk_emul_fail(const char* what) {
   fprintf(stderr, "qk_emul: %s\n", what);
   abort();
 }
+std::atomic<uint64_t> qk_emul_counters[4];
+extern "C" uint64_t qk_emul_counter(int k) { return qk_emul_counters[k].load(); }
 thread_local uint8_t* qk_emul_smem = nullptr;
 thread_local uint32_t qk_emul_bid = 0;
 thread_local QkEmulTeam* qk_emul_team = nullptr;
@@ -509,5 +511,18 @@ int qk_batch_read_containers(qk_batch* b, uint64_t rep, uint32_t comp, uint32_t*
   }
   return QK_OK;
 }
+
+/* the multi-GPU plane needs GPUs */
+int qk_multi_create(const qk_model*, const qk_multi_config*, qk_multi**) { return QK_ERR_NO_DEVICE; }
+void qk_multi_destroy(qk_multi*) {}
+int qk_multi_n_shards(qk_multi*, uint32_t*) { return QK_ERR_NO_DEVICE; }
+int qk_multi_shard(qk_multi*, uint32_t, qk_batch**, uint64_t*, uint64_t*, int32_t*) { return QK_ERR_NO_DEVICE; }
+int qk_multi_set_tape(qk_multi*, uint32_t, const double*, uint64_t) { return QK_ERR_NO_DEVICE; }
+int qk_multi_init(qk_multi*, uint64_t) { return QK_ERR_NO_DEVICE; }
+int qk_multi_step_until(qk_multi*, uint64_t) { return QK_ERR_NO_DEVICE; }
+int qk_multi_step_events(qk_multi*, uint64_t) { return QK_ERR_NO_DEVICE; }
+int qk_multi_synchronize(qk_multi*) { return QK_ERR_NO_DEVICE; }
+int qk_multi_last_step_ms(qk_multi*, float*) { return QK_ERR_NO_DEVICE; }
+int qk_multi_stats(qk_multi*, qk_comp_summary*, uint32_t, qk_batch_summary*) { return QK_ERR_NO_DEVICE; }
 
 } /* extern "C" */

@@ -75,6 +75,8 @@ static inline uint32_t qk_emul_ballot(bool p) {
   qk_emul_barrier();
   return m;
 }
+extern std::atomic<uint64_t> qk_emul_counters[4];
+static inline void qk_emul_count(int k) { qk_emul_counters[k].fetch_add(1, std::memory_order_relaxed); }
 #define qk_smem qk_emul_smem
 #define QK_TID qk_emul_tid
 #define QK_NT qk_emul_nt
@@ -86,6 +88,18 @@ static inline uint32_t qk_emul_ballot(bool p) {
 #define QK_BALLOT(p) qk_emul_ballot(p)
 #define QK_SHFL32(v, src) ((uint32_t)qk_emul_shfl((uint64_t)(v), (uint32_t)(src)))
 #define QK_SHFL_XOR32(v, m) ((uint32_t)qk_emul_shfl((uint64_t)(v), qk_emul_tid ^ (uint32_t)(m)))
+static inline uint32_t qk_emul_reduce_min(uint32_t mask, uint32_t v) {
+  QkEmulTeam* t = qk_emul_team;
+  if (!t) return v;
+  t->slot[qk_emul_tid] = v;
+  qk_emul_barrier();
+  uint32_t m = 0xFFFFFFFFu;
+  for (uint32_t i = 0; i < t->n; ++i)
+    if ((mask >> i) & 1u) m = (uint32_t)t->slot[i] < m ? (uint32_t)t->slot[i] : m;
+  qk_emul_barrier();
+  return m;
+}
+#define QK_REDUCE_MIN32(mask, v) qk_emul_reduce_min((mask), (v))
 #define QK_POPC(x) __builtin_popcount(x)
 static inline void qk_red_add64(uint64_t* p, uint64_t v) { *p += v; }
 static inline void qk_red_add32(uint32_t* p, uint32_t v) { *p += v; }

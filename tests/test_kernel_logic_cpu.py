@@ -492,3 +492,17 @@ def test_group_kernel_faults(emul_lib):
     sim.step_events(600)
     st, _, _ = sim.status()
     assert list(st) == [0, 1, 2, 0]
+
+
+def test_delay_mode_quick_paths_are_taken(emul_lib):
+    """the quick handling of components WITH delay modes (qk_dm_quick: busy tick, idle and blocked) is exercised by the
+    serial line, in both kernels, and agrees with the oracle"""
+    import ctypes
+
+    L = ctypes.CDLL(emul_lib)
+    L.qk_emul_counter.restype = ctypes.c_uint64
+    for flags in (0, 1, _gflags(4)):
+        before = (L.qk_emul_counter(0), L.qk_emul_counter(1))
+        _check(emul_lib, H.serial_line(n_proc=6), 2, n_events=6000, log_capacity=65536, flags=flags)
+        assert L.qk_emul_counter(0) - before[0] > 500, "busy-tick quick path never taken"
+        assert L.qk_emul_counter(1) - before[1] > 20, "idle-and-blocked quick path never taken"
