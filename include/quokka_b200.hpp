@@ -501,8 +501,8 @@ class BatchedSimulation {
   BatchedSimulation(const BatchedSimulation&) = delete;
   BatchedSimulation& operator=(const BatchedSimulation&) = delete;
   BatchedSimulation(BatchedSimulation&& o) noexcept
-      : components(std::move(o.components)), t0(o.t0), opt(o.opt), model_(o.model_), batch_(o.batch_), ext_(std::move(o.ext_)),
-        tapes_(std::move(o.tapes_)), dist_ids_(std::move(o.dist_ids_)), multi_(o.multi_) {
+      : components(std::move(o.components)), t0(o.t0), opt(o.opt), model_(o.model_), batch_(o.batch_), multi_(o.multi_),
+        ext_(std::move(o.ext_)), tapes_(std::move(o.tapes_)), dist_ids_(std::move(o.dist_ids_)) {
     o.model_ = nullptr;
     o.batch_ = nullptr;
     o.multi_ = nullptr;
