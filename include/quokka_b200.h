@@ -17,6 +17,8 @@
  *   qk_model_set_logged                        <- connect_logger!(&mut logger,&mut c)   core.rs:1303-1338
  *   qk_model_schedule_env_state                <- create_scheduled_event!(SetEnvironmentState)
  *                                                                                      core.rs:1393-1396
+ *   qk_model_schedule_low_capacity             <- create_scheduled_event!(SetLowCapacity)  core.rs:1382-1386
+ *   qk_model_schedule_process_quantity         <- create_scheduled_event!(SetProcessQuantity) core.rs:1387-1391
  *   qk_batch_create + qk_batch_init            <- SimInit::init(t0) (one Simulation per replication)
  *                                                 quokkasim_examples/src/bin/discrete_queue.rs:109
  *   qk_batch_step_until / qk_batch_step_events <- Simulation::step_until / step   discrete_queue.rs:111
@@ -279,6 +281,11 @@ int qk_model_set_ports(qk_model*, uint32_t comp, uint32_t n_ports, const double*
 /* create_scheduled_event!(SetLowCapacity(v)) on an F64Stock (core.rs:1382-1386): setter + add(0.) at t */
 int qk_model_schedule_low_capacity(qk_model*, uint64_t t_ns, uint32_t stock, double value);
 int qk_model_schedule_env_state(qk_model*, uint64_t t_ns, uint32_t env, uint32_t state);
+/* create_scheduled_event!(SetProcessQuantity(cfg)) on an F64Process (core.rs:1387-1391): `dist` is the instance
+ * DistributionFactory::create made when the event was scheduled (its seed in `stream`); at t it replaces
+ * process_quantity_distr and the process gets update_state(SCH_000000).  *out_dist_id identifies it for tapes. */
+int qk_model_schedule_process_quantity(qk_model*, uint64_t t_ns, uint32_t process, const qk_dist_desc* dist,
+                                       uint32_t* out_dist_id);
 /* Vector3ContainerFactory of a QK_CONTAINER_SOURCE (vector_container.rs:126-156): create_quantity_distr (NULL = None:
  * containers are created empty), create_component_split[3], capacity.  *out_dist_id = the distribution instance
  * (for tapes) or 0xFFFFFFFF */

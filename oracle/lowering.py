@@ -56,4 +56,7 @@ def lower_to_oracle(model):
         om.schedule_env(t, index[id(env.component)], state)
     for t, stock, value in getattr(model, "ext_low", []):
         om.schedule_low_capacity(t, index[id(stock.component)], value)
+    for t, proc, d in getattr(model, "ext_qty", []):
+        did = om.schedule_process_quantity(t, index[id(proc.component)], O.make_dist(d.kind, d.stream, d.params))
+        dist_ids.setdefault(id(d), []).append(did)
     return om, dist_ids

@@ -80,6 +80,7 @@ def lib():
         "orc_model_set_vector": (C.c_int, [vp, u32, u32, dbl, dbl, P(dbl)]),
         "orc_model_set_splits": (C.c_int, [vp, u32, u32, P(dbl)]),
         "orc_model_schedule_low_capacity": (C.c_int, [vp, u64, u32, dbl]),
+        "orc_model_schedule_process_quantity": (C.c_int, [vp, u64, u32, vp]),
         "orc_sim_new": (vp, [vp, u64, u64, u64, C.c_int]),
         "orc_sim_free": (None, [vp]),
         "orc_sim_set_tape": (C.c_int, [vp, u32, P(dbl), u64]),
@@ -192,6 +193,12 @@ class OracleModel:
     def schedule_low_capacity(self, t_ns, stock, value):
         if self.L.orc_model_schedule_low_capacity(self.h, t_ns, stock, value) != 0:
             raise RuntimeError("orc_model_schedule_low_capacity failed")
+
+    def schedule_process_quantity(self, t_ns, process, dist):
+        did = self.L.orc_model_schedule_process_quantity(self.h, t_ns, process, C.byref(dist))
+        if did < 0:
+            raise RuntimeError("orc_model_schedule_process_quantity failed")
+        return did
 
     def run_batch(self, base_seed, rep0, n_reps, t0_ns=0, n_events=0, t_until_ns=0, log=False, threads=1,
                   want_stats=True):

@@ -287,7 +287,8 @@ struct CompDef {
 
 struct ExtEvent {
   uint64_t t;
-  uint32_t type; /* 0 = SetEnvironmentState, 1 = SetLowCapacity(F64Stock) */
+  uint32_t type; /* 0 = SetEnvironmentState, 1 = SetLowCapacity(F64Stock), 2 = SetProcessQuantity(F64Process): `state` =
+                    the distribution instance df.create made at schedule time (core.rs:1388) */
   uint32_t target;
   uint32_t state;
   double value;
@@ -364,6 +365,7 @@ struct Comp {
   double vres[3];
   std::vector<std::array<double, 3> > parts;
   double vlow; /* low_capacity is mutable at run time (SetLowCapacity, core.rs:1382-1386) */
+  int qty_dist; /* process_quantity_distr is too (SetProcessQuantity, core.rs:1387-1391): -1 = the model's */
   bool ttnde_some;
   uint64_t ttnde;
   /* stats */
@@ -372,7 +374,7 @@ struct Comp {
   Comp()
       : has_item(false), left(0), item(0), env_stopped(false), ttnpe_some(false), ttnpe(0), sched_some(false),
         sched_time(0), sched_key(0), next_event_index(0), previous_check_time(0), next_item_index(0), env_state(0),
-        vlow(0), ttnde_some(false), ttnde(0), area_last_t(0) {
+        vlow(0), qty_dist(-1), ttnde_some(false), ttnde(0), area_last_t(0) {
     std::memset(&st, 0, sizeof(st));
     vres[0] = vres[1] = vres[2] = 0;
   }
@@ -1098,10 +1100,16 @@ struct orc_sim {
   }
   void ext_fire(const Action& a) {
     const ExtEvent& e = m->ext[a.ext_index];
-    if (e.type == 0)
+    if (e.type == 0) {
       env_set_state(e.target, e.state, a.src);
-    else
+    } else if (e.type == 1) {
       ext_set_low_capacity(e);
+    } else {
+      /* with_process_quantity_distr_inplace(distr_instance), then update_state(SCH_000000): two scheduler actions of
+       * origin 0 at the same time, nothing can come between them (core.rs:1389-1390) */
+      c[e.target].qty_dist = (int)e.state;
+      update_state(e.target, a.src);
+    }
   }
   void vstock_emit_change(uint32_t, EvId, int, double);
   void ext_set_low_capacity(const ExtEvent&);

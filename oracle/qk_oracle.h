@@ -180,6 +180,7 @@ int orc_model_n_dists(const orc_model*);
 int orc_model_set_vector(orc_model*, uint32_t comp, uint32_t dim, double low, double max, const double* init);
 int orc_model_set_splits(orc_model*, uint32_t comp, uint32_t n, const double* ratios);
 int orc_model_schedule_low_capacity(orc_model*, uint64_t t_ns, uint32_t stock, double value);
+int orc_model_schedule_process_quantity(orc_model*, uint64_t t_ns, uint32_t process, const orc_dist* d);
 /* container family. Vector3ContainerFactory (vector_container.rs:126-156): create_quantity_distr (NULL = None),
  * create_component_split, capacity; *dist_id_out = distribution instance id or -1 */
 int orc_model_set_container_factory(orc_model*, uint32_t source, const orc_dist* create_quantity, const double* split3,

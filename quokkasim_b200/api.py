@@ -632,6 +632,16 @@ def create_scheduled_event(scheduler, time, event_config, component_addr, df=Non
     if event_config.kind == "SetLowCapacity" and component_addr.variant == "F64Stock":  # core.rs:1382-1386
         scheduler._sim._schedule_low(int(time), component_addr.component, float(event_config.value))
         return
+    if event_config.kind == "SetProcessQuantity" and component_addr.variant == "F64Process":  # core.rs:1387-1391
+        # `df.create(distr.clone())?` runs NOW, at schedule time: the factory hands out its next seed (and skips the
+        # increment for Normal / TruncNormal / Exponential); the instance replaces
+        # process_quantity_distr at `time`, followed by update_state(SCH_000000)
+        if df is None:
+            raise TypeError("create_scheduled_event(SetProcessQuantity) needs the DistributionFactory (`&mut df`)")
+        cfg = event_config.value
+        dist = cfg if isinstance(cfg, Distribution) else df.create(cfg)
+        scheduler._sim._schedule_qty(int(time), component_addr.component, dist)
+        return dist
     raise NotImplementedError(
         "schedule_event not implemented for types (%s, %s)" % (event_config, component_addr.variant)
     )
@@ -775,6 +785,11 @@ class BatchedSimulation:
         for kind, t, comp, value in self._ext:
             if kind == "env":
                 capi.check(L, L.qk_model_schedule_env_state(self._model, t, comp._id, value))
+            elif kind == "qty":
+                did = C.c_uint32()
+                desc = value.desc()
+                capi.check(L, L.qk_model_schedule_process_quantity(self._model, t, comp._id, C.byref(desc), C.byref(did)))
+                self._dist_ids.setdefault(id(value), []).append(did.value)
             else:
                 capi.check(L, L.qk_model_schedule_low_capacity(self._model, t, comp._id, value))
 
@@ -782,6 +797,11 @@ class BatchedSimulation:
         if self._batch:
             raise RuntimeError("scheduled events must be created before the first step of a BatchedSimulation")
         self._ext.append(("env", t_ns, env, state))
+
+    def _schedule_qty(self, t_ns, process, dist):
+        if self._batch:
+            raise RuntimeError("scheduled events must be created before the first step of a BatchedSimulation")
+        self._ext.append(("qty", t_ns, process, dist))
 
     def _schedule_low(self, t_ns, stock, value):
         if self._batch:

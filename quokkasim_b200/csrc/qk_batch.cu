@@ -491,8 +491,13 @@ int qk_batch_create(const qk_model* m, const qk_batch_config* cfg, qk_batch** ou
     uint32_t thr = 0;
     choose_nt(per_rep, b->table_bytes_padded, max_thr, &thr);
     if (thr < 384) {
-      const char* e = getenv("QK_AUTO_PLACEMENT"); /* "hbm": the round-1 choice for large models */
-      if (e && e[0] == 'h') b->hbm = true; else group = true;
+      /* ... when the scheduler queue is long enough for the cooperative pop to matter (measured: the 96- and
+       * 67-component networks gain 10-45 %, the 10- and 13-component vector / container models lose a factor of two
+       * against operating on the L1/L2-cached HBM planes, profiles/README.md) */
+      const char* e = getenv("QK_AUTO_PLACEMENT"); /* "hbm" / "group": force the choice for models of this class */
+      if (e && e[0] == 'h') b->hbm = true;
+      else if ((e && e[0] == 'g') || h.n_sched >= 32) group = true;
+      else b->hbm = true;
     }
   }
   if (group) {

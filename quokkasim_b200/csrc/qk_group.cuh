@@ -112,6 +112,13 @@ __device__ __forceinline__ uint32_t qk_quick_eval(Ctx& cx, uint32_t ptr, uint64_
   return 0x100u | reason;
 }
 
+#ifndef QK_GROUP_REDUX
+#define QK_GROUP_REDUX 1
+#endif
+#ifndef QK_GROUP_REFILL_EAGER
+#define QK_GROUP_REFILL_EAGER 0
+#endif
+
 /* GROUP-mode state accessors are the run-time-stride ones of qk_kernels.cuh (SM < 0): slot * row stride + replication */
 #define QK_SMG (-1)
 
@@ -264,6 +271,8 @@ __global__ void __launch_bounds__(qk_group_max_threads(G), 1) qk_group_kernel(co
             qk_vstore<SM>(cx, v->o64_res, v->dim, v->vinit);
             S64(v->o64_low) = QK_D2U(v->vlow);
             S64(v->o64_last) = P.t0;
+          } else if (FT != 0 && c->kind == QK_VECTOR_PROCESS && cx.vecs[c->vec_idx].o32_qty != 0xFFFF) {
+            S32(cx.vecs[c->vec_idx].o32_qty) = cx.vecs[c->vec_idx].dist_qty;
           }
         }
       }
@@ -330,6 +339,7 @@ __global__ void __launch_bounds__(qk_group_max_threads(G), 1) qk_group_kernel(co
           }
         }
       }
+#if QK_GROUP_REDUX
       {
         /* min over (time, registration rank) of the group's lanes: three warp reductions (REDUX) on the 32-bit halves
          * and the index, each over this group's lanes only -- the groups of a warp reduce side by side */
@@ -341,6 +351,17 @@ __global__ void __launch_bounds__(qk_group_max_threads(G), 1) qk_group_kernel(co
         best = ((uint64_t)mhi << 32) | mlo;
         bidx = mid;
       }
+#else
+#pragma unroll
+      for (uint32_t m = G / 2; m > 0; m >>= 1) { /* min over (time, registration rank): xor butterfly inside the group */
+        const uint64_t ot = qk_shfl_xor64(best, m);
+        const uint32_t oi = QK_SHFL_XOR32(bidx, m);
+        if (ot < best || (ot == best && oi < bidx)) {
+          best = ot;
+          bidx = oi;
+        }
+      }
+#endif
       if (leader && rem == 0 && !done) {
         int bi = best == QK_TIME_NONE ? -1 : (int)bidx;
         if (FT != 0 && ext_cursor < n_ext) { /* rank 0 = externally scheduled events: they win ties */
@@ -383,6 +404,13 @@ __global__ void __launch_bounds__(qk_group_max_threads(G), 1) qk_group_kernel(co
               const double zero[3] = {0.0, 0.0, 0.0};
               qk_vstock_add<LOG, SM>(cx, target, zero, SRC_SCH);
               if (cx.status) done = true;
+            } else if (e->type == 2) {
+              /* SetProcessQuantity on an F64Process: with_process_quantity_distr_inplace(instance), then
+               * update_state(SCH_000000) (core.rs:1389-1390) */
+              S32(cx.vecs[cx.comps[target].vec_idx].o32_qty) = e->state;
+              src = SRC_SCH;
+              rem = 1;
+              ptr = ident_off + target;
             } else if (S32(a.o32 + E32_STATE) != e->state) {
               const uint32_t st = e->state;
               S32(a.o32 + E32_STATE) = st;
@@ -500,12 +528,19 @@ __global__ void __launch_bounds__(qk_group_max_threads(G), 1) qk_group_kernel(co
     QK_SYNCWARP();
     if (!QK_ANY_SYNC(!done || rem != 0)) break; /* uniform exit: every group of the warp has finished */
 
-    /* -- REFILL (variate prefetch): the durations consumed by the starts of the previous trip are re-drawn before the
-     * next handler runs -- one pending slot per lane, the groups of the warp side by side (a process that finishes and
-     * restarts in one call needs its slot full again by then, so waiting for several to accumulate does not pay here:
-     * measured, 1.2 lanes per sampler instruction with a threshold of G / 2) */
+    /* -- REFILL (deferred variate prefetch): starts consume a pre-drawn duration.  When some group's next call may start
+     * a process whose slot is still empty (a process that finishes and restarts in one call is the usual case), EVERY
+     * group of the warp re-draws all its pending slots, one per lane: the sampler -- Philox, inverse CDF, from_secs_f64,
+     * ~150 instructions -- then runs once for several lanes instead of once per lane.  (Measured alternatives: re-draw
+     * every trip = more sampler passes, 1.52e9 -> 1.37e9 events/s on the haulage network; per-group threshold of G / 2
+     * pending = 1.2 lanes per sampler instruction.) */
     {
+#if QK_GROUP_REFILL_EAGER
       const bool go = QK_SHFL32((leader && cx.npend != 0) ? 1u : 0u, lead) != 0;
+#else
+      const bool must = leader && rem != 0 && cx.npend != 0 && qk_needs_refill_now<SM>(cx, cx.subs[ptr]);
+      const bool go = QK_ANY_SYNC(must) && QK_SHFL32((leader && cx.npend != 0) ? 1u : 0u, lead) != 0;
+#endif
       if (QK_ANY_SYNC(go)) {
         if (go) {
           uint32_t k = 0;

@@ -200,7 +200,8 @@ typedef struct {
 
 typedef struct {
   uint64_t t;
-  uint32_t type; /* 0 SetEnvironmentState, 1 SetLowCapacity (F64Stock) */
+  uint32_t type; /* 0 SetEnvironmentState, 1 SetLowCapacity (F64Stock), 2 SetProcessQuantity (F64Process): `state` = the
+                    distribution instance created at schedule time */
   uint32_t target;
   uint32_t state;
   uint32_t pad;
@@ -220,7 +221,10 @@ typedef struct {
   uint16_t o64_low;  /* stock: run-time low_capacity (f64 bits) */
   uint16_t o64_last; /* stock: time of the last level change (for the integral) */
   double vlow;       /* VectorStock.low_capacity at t0 */
-} DevVec; /* 112 bytes */
+  uint16_t o32_qty;  /* F64Process that a SetProcessQuantity event targets: plane32 slot holding the distribution instance
+                        process_quantity_distr currently is (0xFFFF: it never changes, dist_qty) */
+  uint16_t pad[3];
+} DevVec; /* 120 bytes */
 
 /* header of the table blob (all offsets in bytes from the blob start, 8-byte aligned) */
 typedef struct {

@@ -1195,6 +1195,8 @@ __global__ void __launch_bounds__(qk_lb_threads(SM), qk_lb_blocks(SM, FT, LOG)) 
           qk_vstore<SM>(cx, v->o64_res, v->dim, v->vinit);
           S64(v->o64_low) = QK_D2U(v->vlow);
           S64(v->o64_last) = P.t0;
+        } else if (FT != 0 && c->kind == QK_VECTOR_PROCESS && cx.vecs[c->vec_idx].o32_qty != 0xFFFF) {
+          S32(cx.vecs[c->vec_idx].o32_qty) = cx.vecs[c->vec_idx].dist_qty;
         }
       }
     }
@@ -1321,6 +1323,13 @@ __global__ void __launch_bounds__(qk_lb_threads(SM), qk_lb_blocks(SM, FT, LOG)) 
               const double zero[3] = {0.0, 0.0, 0.0};
               qk_vstock_add<LOG, SM>(cx, target, zero, SRC_SCH);
               if (cx.status) done = true;
+            } else if (e->type == 2) {
+              /* SetProcessQuantity on an F64Process: with_process_quantity_distr_inplace(instance), then
+               * update_state(SCH_000000) (core.rs:1389-1390) */
+              S32(cx.vecs[cx.comps[target].vec_idx].o32_qty) = e->state;
+              src = SRC_SCH;
+              rem = 1;
+              ptr = ident_off + target;
             } else if (S32(a.o32 + E32_STATE) != e->state) {
               const uint32_t st = e->state;
               S32(a.o32 + E32_STATE) = st;

@@ -414,6 +414,32 @@ int qk_model_schedule_low_capacity(qk_model* m, uint64_t t_ns, uint32_t stock, d
   return QK_OK;
 }
 
+/* create_scheduled_event!(SetProcessQuantity(cfg)) on an F64Process (core.rs:1387-1391): df.create(cfg) happens at
+ * schedule time (the caller passes the resulting instance), with_process_quantity_distr_inplace + update_state at t */
+int qk_model_schedule_process_quantity(qk_model* m, uint64_t t_ns, uint32_t process, const qk_dist_desc* dist,
+                                       uint32_t* out_dist_id) {
+  if (!m || process >= m->comps.size() || m->comps[process].d.kind != QK_VECTOR_PROCESS || m->comps[process].dim != 1) {
+    /* core.rs:1397-1399: only (SetProcessQuantity, F64Process) has an arm */
+    qk_set_error("schedule_event not implemented for types (SetProcessQuantity, %s)",
+                 (m && process < m->comps.size()) ? kind_name(m->comps[process].d.kind) : "?");
+    return QK_ERR_INVALID_ARG;
+  }
+  if (!dist || !check_dist(dist)) {
+    qk_set_error("qk_model_schedule_process_quantity: invalid distribution parameters");
+    return QK_ERR_INVALID_ARG;
+  }
+  DevExt e;
+  memset(&e, 0, sizeof(e));
+  e.t = t_ns;
+  e.type = 2;
+  e.target = process;
+  e.state = (uint32_t)m->dists.size();
+  m->dists.push_back(*dist);
+  m->ext.push_back(e);
+  if (out_dist_id) *out_dist_id = e.state;
+  return QK_OK;
+}
+
 int qk_model_set_container_factory(qk_model* m, uint32_t source, const qk_dist_desc* create_quantity,
                                    const double* split3, double capacity, uint32_t* out_dist_id) {
   if (!m || source >= m->comps.size() || m->comps[source].d.kind != QK_CONTAINER_SOURCE) {
@@ -748,6 +774,7 @@ int qk_lower(const qk_model* m, bool log, QkLowered* out) {
         v.downs[k] = (int16_t)c.downs[k];
       }
       v.dist_qty = (uint16_t)c.dist_qty;
+      v.o32_qty = 0xFFFF;
       d.o64 = (uint16_t)n64;
       n64 += P64_BASE_COUNT;
       d.o64_dm = (uint16_t)n64;
@@ -757,6 +784,12 @@ int qk_lower(const qk_model* m, bool log, QkLowered* out) {
       d.o32 = (uint16_t)n32;
       n32 += P32_BASE_COUNT;
       if (m->dists[(size_t)c.dist_qty].kind != QK_DIST_CONSTANT) dd[(size_t)c.dist_qty].draw_slot = n32++;
+      for (size_t k = 0; k < m->ext.size(); ++k) /* SetProcessQuantity events: the instance they bring, and where the
+                                                    component keeps which instance is current */
+        if (m->ext[k].type == 2 && m->ext[k].target == i) {
+          if (v.o32_qty == 0xFFFF) v.o32_qty = (uint16_t)n32++;
+          if (m->dists[m->ext[k].state].kind != QK_DIST_CONSTANT) dd[m->ext[k].state].draw_slot = n32++;
+        }
       d.vec_idx = (uint16_t)vecs.size();
       vecs.push_back(v);
     } else { /* environment */

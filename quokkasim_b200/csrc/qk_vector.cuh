@@ -320,7 +320,8 @@ __device__ __forceinline__ void qk_update_vector(Ctx& cx, const DevComp* c, uint
       else fail = QK_REASON_UPSTREAM_EMPTY;
     }
     if (ok) {
-      const double q = qk_sample<SM>(cx, v->dist_qty);
+      /* process_quantity_distr: the model's, or the instance the latest SetProcessQuantity event brought (core.rs:1387-1391) */
+      const double q = qk_sample<SM>(cx, v->o32_qty != 0xFFFF ? S32(v->o32_qty) : (uint32_t)v->dist_qty);
       if (cx.status) return;
       double got[5][3];
       uint32_t ngot = 1, start_kind = QK_LOG_VPROC_START;

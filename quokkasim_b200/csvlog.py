@@ -286,7 +286,9 @@ class LogDecoder:
         # ---- vector process-like
         family = "Combine" if "Combiner" in variant else ("Split" if "Splitter" in variant else "Process")
         if kind == capi.LOG_VPROC_FAILURE:
-            return head + [family + "Failure", None, None, None, _REASONS.get(reason)]
+            # combiners and splitters log VectorProcessLogType::ProcessFailure too (vector.rs:937-949, 1235-1247), which
+            # serialises as "ProcessFailure" (vector.rs:621-622): only Start / Success carry the Combine / Split prefix
+            return head + ["ProcessFailure", None, None, None, _REASONS.get(reason)]
         q = ryu_f64(self._f64(payload))
         js = "[" + ",".join(self.vector_json(comp, v) for v in vecs) + "]"
         if kind in (capi.LOG_VPROC_START, capi.LOG_VPROC_COMBINE_START, capi.LOG_VPROC_SPLIT_START):

@@ -11,6 +11,7 @@ class Model:
         self.components = []
         self.ext = []  # (t_ns, env ComponentModel, state)
         self.ext_low = []  # (t_ns, F64Stock ComponentModel, new low_capacity)
+        self.ext_qty = []  # (t_ns, F64Process ComponentModel, Distribution instance made by df.create at schedule time)
         self.random_dists = []  # Distribution objects that need tapes in tape mode
         self.by_name = {}
 
@@ -31,6 +32,9 @@ class Model:
             qk.create_scheduled_event(sched, t, qk.ScheduledEventConfig.SetEnvironmentState(state), env.get_address())
         for t, stock, value in self.ext_low:
             qk.create_scheduled_event(sched, t, qk.ScheduledEventConfig.SetLowCapacity(value), stock.get_address())
+        for t, proc, dist in self.ext_qty:
+            qk.create_scheduled_event(sched, t, qk.ScheduledEventConfig.SetProcessQuantity(dist), proc.get_address(),
+                                      qk.DistributionFactory(base_seed=0, next_seed=0))
         return sim
 
 
@@ -369,6 +373,50 @@ def scheduled_event_f64():
     for x in (s1, p, s2):
         m.reg(x)
     m.ext_low.append((qk.Duration.from_secs(60), s1, 10.0))
+    _log_all(m)
+    return m
+
+
+def scheduled_process_quantity(random=True):
+    """create_scheduled_event!(SetProcessQuantity(..)) on an F64Process (core.rs:1387-1391): F64 Source -> Stock ->
+    Process -> Stock -> Sink; the process moves U(0.5, 1.5) per cycle until 20 s, Tri(2, 4, 3) from then on, and a
+    Constant(0.25) from 45 s.  The instances come from the factory at schedule time (seeds 2 and 3 after the model's
+    own two)."""
+    m = Model()
+    df = qk.DistributionFactory(base_seed=31, next_seed=0)
+    c = qk.Distribution.Constant
+
+    def dist(cfg, const):
+        if not random:
+            return c(const)
+        d = df.create(cfg)
+        m.random_dists.append(d)
+        return d
+
+    src = qk.ComponentModel.F64Source(
+        qk.VectorSource.new().with_name("Source").with_code("SRC").with_source_vector(1.0)
+        .with_process_quantity_distr(c(2.0)).with_process_time_distr(c(1.0)), qk.Mailbox.new())
+    s1 = qk.ComponentModel.F64Stock(
+        qk.VectorStock.new().with_name("S1").with_code("S1").with_low_capacity(1.0).with_max_capacity(200.0)
+        .with_initial_resource(20.0), qk.Mailbox.new())
+    p = qk.ComponentModel.F64Process(
+        qk.VectorProcess.new().with_name("Process").with_code("P")
+        .with_process_quantity_distr(dist(qk.DistributionConfig.Uniform(0.5, 1.5), 1.0))
+        .with_process_time_distr(dist(qk.DistributionConfig.Uniform(0.5, 1.5), 1.0)), qk.Mailbox.new())
+    s2 = qk.ComponentModel.F64Stock(
+        qk.VectorStock.new().with_name("S2").with_code("S2").with_low_capacity(1.0).with_max_capacity(500.0)
+        .with_initial_resource(0.0), qk.Mailbox.new())
+    snk = qk.ComponentModel.F64Sink(
+        qk.VectorSink.new().with_name("Sink").with_code("SNK").with_process_quantity_distr(c(1.0))
+        .with_process_time_distr(c(2.0)), qk.Mailbox.new())
+    qk.connect_components(src, s1)
+    qk.connect_components(s1, p)
+    qk.connect_components(p, s2)
+    qk.connect_components(s2, snk)
+    for x in (src, s1, p, s2, snk):
+        m.reg(x)
+    m.ext_qty.append((qk.Duration.from_secs(20), p, dist(qk.DistributionConfig.Triangular(min=2.0, max=4.0, mode=3.0), 3.0)))
+    m.ext_qty.append((qk.Duration.from_secs(45), p, c(0.25)))
     _log_all(m)
     return m
 

@@ -10,7 +10,8 @@ from quokkasim_b200 import _capi as capi
 
 
 from quokkasim_b200.workloads import (Model, assembly_line, car_workshop, discrete_queue, haulage,  # noqa: F401
-                                      material_blending, scheduled_event_f64, serial_line, source_sink, vector_flow,
+                                      material_blending, scheduled_event_f64, scheduled_process_quantity,
+                                      serial_line, source_sink, vector_flow,
                                       transport, delay_testing, the_example, container_haulage, container_open)
 
 

@@ -164,3 +164,45 @@ def test_kat1_container_csv_matches_hand_derived_trace(emul_lib):
 @pytest.mark.gpu
 def test_kat1_container_csv_on_gpu(gpu_lib):
     _check_kat1(gpu_lib)
+
+
+def test_combiner_and_splitter_failures_are_process_failure_rows(emul_lib):
+    """vector.rs:937-949, 1235-1247: a combiner / splitter that cannot start logs VectorProcessLogType::ProcessFailure,
+    which serialises as event_type "ProcessFailure" (vector.rs:621-622) -- only Start and Success carry the Combine /
+    Split prefix.  Hand-derived model: the combiner's second upstream is below its low capacity (state Empty) at init,
+    the splitter's upstream (what the combiner feeds) is Empty too."""
+    import quokkasim_b200 as qk
+    from quokkasim_b200.workloads import Model, _log_all
+
+    m = Model()
+    c = qk.Distribution.Constant
+
+    def pile(name, low, maxc, init):
+        return m.reg(qk.ComponentModel.F64Stock(
+            qk.VectorStock.new().with_name(name).with_code(name).with_low_capacity(low).with_max_capacity(maxc)
+            .with_initial_resource(init), qk.Mailbox.new()))
+
+    a, b, mid, o1, o2 = pile("A", 1.0, 100.0, 50.0), pile("B", 1.0, 100.0, 0.0), pile("M", 1.0, 100.0, 0.0), \
+        pile("O1", 0.0, 100.0, 0.0), pile("O2", 0.0, 100.0, 0.0)
+    cmb = m.reg(qk.ComponentModel.F64Combiner2(
+        qk.VectorCombiner.new().with_name("Combiner").with_code("CMB").with_process_quantity_distr(c(5.0))
+        .with_process_time_distr(c(3.0)), qk.Mailbox.new()))
+    spl = m.reg(qk.ComponentModel.F64Splitter2(
+        qk.VectorSplitter.new().with_name("Splitter").with_code("SPL").with_split_ratios([0.5, 0.5])
+        .with_process_quantity_distr(c(5.0)).with_process_time_distr(c(3.0)), qk.Mailbox.new()))
+    qk.connect_components(a, cmb, 0)
+    qk.connect_components(b, cmb, 1)
+    qk.connect_components(cmb, mid)
+    qk.connect_components(mid, spl)
+    qk.connect_components(spl, o1, 0)
+    qk.connect_components(spl, o2, 1)
+    _log_all(m)
+    sim = m.sim(emul_lib, 1, log_capacity=256)
+    sim.step_until(10 * 10**9)
+    rows = csvlog.csv_text(m.loggers[4]["F64"], sim).splitlines()
+    assert "Failure" in "\n".join(rows) and "CombineFailure" not in "\n".join(rows) and "SplitFailure" not in "\n".join(rows)
+    # Combiner / Splitter init carry their own next id as source (vector.rs:774, 1111)
+    assert rows[1] == ("1970-01-01 00:00:00 UTC,CMB_000000,CMB_000000,Combiner,VectorCombiner,ProcessFailure,,,,"
+                       "At least one upstream is empty")
+    assert rows[2] == "1970-01-01 00:00:00 UTC,SPL_000000,SPL_000000,Splitter,VectorSplitter,ProcessFailure,,,,Upstream is empty"
+    sim.close()

@@ -460,3 +460,17 @@ def test_batch_that_does_not_fit_fails_cleanly(gpu_lib):
     ok.step_events(100)
     assert ok.summary()["n_events"] == 100 << 20
     ok.close()
+
+
+def test_scheduled_process_quantity_on_gpu(gpu_lib):
+    """create_scheduled_event!(SetProcessQuantity) on an F64Process (core.rs:1387-1391), every placement"""
+    for flags in (0, 1, 2, _gflags(8)):
+        _check(gpu_lib, H.scheduled_process_quantity(), 64, t_until=70 * 10**9, sample=[0, 63], log_capacity=8192,
+               flags=flags)
+
+
+def test_delay_mode_quick_path_at_scale(gpu_lib):
+    """the quick handling of busy / idle components with delay modes: a longer serial line run, thread-per-replication
+    (HBM planes) and lane groups, against the oracle"""
+    for flags in (1, _gflags(8)):
+        _check(gpu_lib, H.serial_line(n_proc=12), 200, n_events=60000, sample=[0, 199], log_capacity=262144, flags=flags)

@@ -2,6 +2,7 @@
 test-only shim in tests/emul, driven through the same C ABI and Python wrapper as the GPU library, compared bit
 for bit with the oracle.  This keeps the CPU suite meaningful between GPU sessions; the parity tests proper are
 tests/test_gpu_parity.py (-m gpu), which run the CUDA build of the same source."""
+import numpy as np
 import pytest
 
 import helpers as H
@@ -506,3 +507,51 @@ def test_delay_mode_quick_paths_are_taken(emul_lib):
         _check(emul_lib, H.serial_line(n_proc=6), 2, n_events=6000, log_capacity=65536, flags=flags)
         assert L.qk_emul_counter(0) - before[0] > 500, "busy-tick quick path never taken"
         assert L.qk_emul_counter(1) - before[1] > 20, "idle-and-blocked quick path never taken"
+
+
+def test_scheduled_process_quantity(emul_lib):
+    """create_scheduled_event!(SetProcessQuantity) on an F64Process (core.rs:1387-1391): the instance made at schedule
+    time replaces process_quantity_distr at t and the process gets update_state(SCH_000000) -- both kernels, native and
+    tape, against the oracle; and by hand on the all-Constant variant"""
+    for flags in (0, 1, _gflags(4)):
+        _check(emul_lib, H.scheduled_process_quantity(), 3, t_until=70 * 10**9, log_capacity=8192, flags=flags)
+    _check(emul_lib, H.scheduled_process_quantity(), 2, t_until=70 * 10**9, tape_len=200, log_capacity=8192)
+    # Constant variant: 1.0 per 1 s cycle until 20 s (the cycle started at 19 s still moves 1.0), 3.0 per cycle from the
+    # cycle that starts at 20 s, 0.25 from the one that starts at 45 s
+    m = H.scheduled_process_quantity(random=False)
+    sim = m.sim(emul_lib, 1, log_capacity=8192)
+    sim.step_until(70 * 10**9)
+    log, _ = sim.read_log(0)
+    from quokkasim_b200 import _capi as capi
+
+    pid = m.by_name["Process"].component._id
+    starts = [(int(r["time_ns"]) // 10**9, float(np.array([r["payload"]], dtype=np.uint64).view(np.float64)[0]))
+              for r in log if r["comp"] == pid and r["kind"] == capi.LOG_VPROC_START]
+    assert [q for t, q in starts if t < 20] == [1.0] * 20
+    assert all(q == 3.0 for t, q in starts if 20 <= t < 45) and all(q == 0.25 for t, q in starts if t >= 45)
+    assert {q for _, q in starts} == {1.0, 3.0, 0.25}
+    # the scheduled update_state arrives with source SCH_000000 at exactly 20 s and 45 s
+    sch = [int(r["time_ns"]) for r in log if r["comp"] == pid and r["src_comp"] == capi.SRC_SCH]
+    assert sorted(set(sch)) == [20 * 10**9, 45 * 10**9]
+
+
+def test_scheduled_event_arms_the_reference_does_not_have():
+    """core.rs:1397-1399: every other (event, component) pair is the reference's Err string"""
+    import quokkasim_b200 as qk
+
+    m = H.scheduled_process_quantity()
+    si = qk.BatchedSimInit.new()
+    for c in m.components:
+        si = qk.register_component(si, c)
+    _, sched = si.init(0)
+    df = qk.DistributionFactory(base_seed=0, next_seed=0)
+    cfg = qk.DistributionConfig.Uniform(1.0, 2.0)
+    for ev, target in ((qk.ScheduledEventConfig.SetProcessQuantity(cfg), m.by_name["Source"]),
+                       (qk.ScheduledEventConfig.SetProcessTime(cfg), m.by_name["Process"]),
+                       (qk.ScheduledEventConfig.SetMaxCapacity(5.0), m.by_name["S1"])):
+        with pytest.raises(NotImplementedError, match="schedule_event not implemented for types"):
+            qk.create_scheduled_event(sched, 10**9, ev, target.get_address(), df)
+    # the factory is consulted at schedule time: two events in a row get consecutive seeds
+    a = qk.create_scheduled_event(sched, 10**9, qk.ScheduledEventConfig.SetProcessQuantity(cfg), m.by_name["Process"].get_address(), df)
+    b = qk.create_scheduled_event(sched, 2 * 10**9, qk.ScheduledEventConfig.SetProcessQuantity(cfg), m.by_name["Process"].get_address(), df)
+    assert (a.stream, b.stream) == (0, 1)
