@@ -34,41 +34,6 @@
 #define QK_REDUCE_MIN32(mask, v) __reduce_min_sync((mask), (v)) /* REDUX over the lanes of `mask` (the caller's group) */
 #define QK_SYNCBLOCK() __syncthreads()
 
-/* ---- bulk asynchronous copies (TMA engine, 1-D): one instruction moves a whole slot row ------------------------- */
-__device__ __forceinline__ void qk_mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count)
-               : "memory");
-}
-__device__ __forceinline__ void qk_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)),
-               "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void qk_mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tQK_WAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra QK_DONE_%=;\n\t"
-      "bra QK_WAIT_%=;\n\tQK_DONE_%=:\n\t}" ::"r"((uint32_t)__cvta_generic_to_shared(bar)),
-      "r"(parity)
-      : "memory");
-}
-/* global -> shared, `bytes` a multiple of 16, both addresses 16-byte aligned; completes on the mbarrier */
-__device__ __forceinline__ void qk_bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   (uint32_t)__cvta_generic_to_shared(smem_dst)),
-               "l"(gsrc), "r"(bytes), "r"((uint32_t)__cvta_generic_to_shared(bar))
-               : "memory");
-}
-/* shared -> global */
-__device__ __forceinline__ void qk_bulk_store(void* gdst, const void* smem_src, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
-               "r"((uint32_t)__cvta_generic_to_shared(smem_src)), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void qk_bulk_store_wait() {
-  asm volatile("cp.async.bulk.commit_group;\n\tcp.async.bulk.wait_group 0;" ::: "memory");
-}
-/* writes made through the generic proxy (ordinary STS) become visible to the asynchronous proxy (bulk stores) */
-__device__ __forceinline__ void qk_fence_async_proxy() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 #endif
 
 __device__ __forceinline__ uint64_t qk_shfl64(uint64_t v, uint32_t src) {

@@ -1203,13 +1203,38 @@ __global__ void __launch_bounds__(qk_lb_threads(SM), qk_lb_blocks(SM, FT, LOG)) 
     S64(G64_NEVENTS) = 0;
   } else {
     if constexpr (SM != 0) {
-      /* stage this replication's hot planes: one asynchronous global->shared copy per slot (LDGSTS), all in flight at
-       * once and without a register round trip.  With few events per launch this load IS the kernel: issuing the
-       * slots as dependent LDG/STS pairs left it latency-bound at 44 % of the HBM roofline (profiles/README.md).
-       * Each thread reads back only what it copied itself, so waiting for its own group is enough. */
+      /* stage the block's hot planes.  Slot row s of the block -- nt consecutive replications -- is contiguous both in
+       * the HBM plane ([slot][replication]) and in shared memory (slot * nt + tid), so ONE bulk asynchronous copy per row
+       * (cp.async.bulk: the TMA engine moves 256-512 bytes per instruction, no register round trip) brings it in, all
+       * rows in flight at once, completing on an mbarrier.  With few events per launch this load IS the kernel: as
+       * dependent LDG/STS pairs it ran at 44 % of the HBM roofline, as one 4/8-byte cp.async (LDGSTS) per thread and slot
+       * at 50-55 % (profiles/README.md). */
+#ifndef QK_HOST_EMUL
+      __shared__ __align__(8) uint64_t stage_bar;
+      const uint64_t block_rep0 = (uint64_t)(P.tile0 + QK_BID) * nt;
+      if (tid == 0) {
+        qk_mbar_init(&stage_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      }
+      __syncthreads();
+      if (tid == 0) qk_mbar_expect_tx(&stage_bar, (P.n64 * 8u + P.n32 * 4u) * nt);
+      {
+        uint64_t* const row64 = reinterpret_cast<uint64_t*>(qk_smem) + P.table_bytes / 8;
+        uint32_t* const row32 = reinterpret_cast<uint32_t*>(qk_smem) + (P.table_bytes + P.n64 * nt * 8) / 4;
+        for (uint32_t s = tid; s < P.n64 + P.n32; s += nt) {
+          if (s < P.n64)
+            qk_bulk_load(row64 + (size_t)s * nt, P.g64 + (size_t)s * P.rep_pad + block_rep0, nt * 8u, &stage_bar);
+          else
+            qk_bulk_load(row32 + (size_t)(s - P.n64) * nt, P.g32 + (size_t)(s - P.n64) * P.rep_pad + block_rep0, nt * 4u,
+                         &stage_bar);
+        }
+      }
+      qk_mbar_wait(&stage_bar, 0);
+#else
       for (uint32_t s = 0; s < P.n64; ++s) qk_stage8(&S64(s), &P.g64[(size_t)s * P.rep_pad + rep_local]);
       for (uint32_t s = 0; s < P.n32; ++s) qk_stage4(&S32(s), &P.g32[(size_t)s * P.rep_pad + rep_local]);
       qk_stage_wait();
+#endif
     }
     cx.now = S64(G64_NOW);
     cx.status = S32(G32_STATUS);
@@ -1424,10 +1449,30 @@ __global__ void __launch_bounds__(qk_lb_threads(SM), qk_lb_blocks(SM, FT, LOG)) 
   if (FT != 0) S32(G32_EXT_CURSOR) = ext_cursor;
   S32(G32_LOGCNT) = cx.log_cnt;
   if constexpr (SM != 0) {
+#ifndef QK_HOST_EMUL
+    /* write-back: one bulk asynchronous store per slot row (shared -> global) */
+    qk_fence_async_proxy();
+    __syncthreads();
+    {
+      const uint64_t block_rep0 = (uint64_t)(P.tile0 + QK_BID) * nt;
+      uint64_t* const row64 = reinterpret_cast<uint64_t*>(qk_smem) + P.table_bytes / 8;
+      uint32_t* const row32 = reinterpret_cast<uint32_t*>(qk_smem) + (P.table_bytes + P.n64 * nt * 8) / 4;
+      bool stored = false;
+      for (uint32_t s = tid; s < P.n64 + P.n32; s += nt) {
+        if (s < P.n64)
+          qk_bulk_store(P.g64 + (size_t)s * P.rep_pad + block_rep0, row64 + (size_t)s * nt, nt * 8u);
+        else
+          qk_bulk_store(P.g32 + (size_t)(s - P.n64) * P.rep_pad + block_rep0, row32 + (size_t)(s - P.n64) * nt, nt * 4u);
+        stored = true;
+      }
+      if (stored) qk_bulk_store_wait();
+    }
+#else
 #pragma unroll 4
     for (uint32_t s = 0; s < P.n64; ++s) P.g64[(size_t)s * P.rep_pad + rep_local] = S64(s);
 #pragma unroll 4
     for (uint32_t s = 0; s < P.n32; ++s) P.g32[(size_t)s * P.rep_pad + rep_local] = S32(s);
+#endif
   }
 }
 

@@ -24,6 +24,20 @@ for wl in haulage serial_line; do
     done
   done
 done
+# thread-per-replication kernel: slot rows staged by bulk asynchronous copies (this tree) against the per-thread LDGSTS
+# staging of the commit before (build/ab/lib_notma.so): full-size C2 line, with the K = 1 lockstep probe
+for lib in default build/ab/lib_notma.so; do
+  for lg in ring off; do
+    tag=$(basename $lib .so)
+    L=""; [ $lib != default ] && L="--lib $lib"
+    timeout 600 python bench.py --no-cpu-baseline --log $lg $L > $O/tma_c2_${tag}_$lg.json 2> $O/tma_c2_${tag}_$lg.err
+    show $O/tma_c2_${tag}_$lg.json
+    python -c "
+import json,sys
+d=json.loads(open('$O/tma_c2_${tag}_$lg.json').readline()); k=d['roofline']['lockstep_K1']
+print('   lockstep K=1: %.4f ms  achieved %.0f GB/s  frac %.3f  events/s %.3e' % (k['kernel_ms'], k['achieved'], k['frac'], k['events_per_s_this_gpu']))"
+  done
+done
 # BASELINE sizes, default placement, statistics only and with the 64-record log ring
 for wl in vector_flow haulage; do
   for lg in off ring; do
