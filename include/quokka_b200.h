@@ -261,6 +261,8 @@ typedef struct qk_batch qk_batch;
 
 /* ---- model description (host only) ---------------------------------------------------------- */
 int qk_abi_version(void);
+/* identifies the sources and compiler flags this library was built from (quokkasim_b200/build.py: source_id) */
+const char* qk_build_id(void);
 int qk_model_create(qk_model** out);
 void qk_model_destroy(qk_model*);
 /* registration order = component id = scheduler origin rank - 1 */
@@ -310,6 +312,9 @@ int qk_model_state_bytes(const qk_model*, int with_log, uint32_t* out_bytes);
 /* large models: a group of `lanes_per_replication` lanes (4, 8 or 16; 0 = choose) owns one replication, whose state
  * stays in shared memory: the scheduler pop and the emit_change broadcast are done by the group's lanes side by side */
 #define QK_BATCH_STATE_LANE_GROUP 4u
+/* with QK_BATCH_STATE_LANE_GROUP: the phased variant -- the lane groups do the scheduler pop and the subscriber broadcast,
+ * then one thread per replication runs the full handlers of the whole block side by side (qk_group.cuh) */
+#define QK_BATCH_GROUP_PHASED 8u
 typedef struct {
   uint64_t n_reps;
   uint64_t rep_offset;   /* global index of this batch's first replication (Philox counter words 0,1) */

@@ -40,7 +40,7 @@ STATUS_NAMES = {
 
 # every symbol include/quokka_b200.h declares (tests check the library exports all of them)
 EXPORTED_SYMBOLS = [
-    "qk_abi_version", "qk_model_create", "qk_model_destroy", "qk_model_add_component", "qk_model_set_dist",
+    "qk_abi_version", "qk_build_id", "qk_model_create", "qk_model_destroy", "qk_model_add_component", "qk_model_set_dist",
     "qk_model_add_delay_mode", "qk_model_connect", "qk_model_set_logged", "qk_model_schedule_env_state",
     "qk_model_set_vector", "qk_model_set_ports", "qk_model_schedule_low_capacity", "qk_model_schedule_process_quantity", "qk_batch_read_vector",
     "qk_model_n_components", "qk_model_n_dists", "qk_model_state_bytes", "qk_batch_create", "qk_batch_destroy",
@@ -151,6 +151,7 @@ def load_library(path=None):
     P = C.POINTER
     sig = {
         "qk_abi_version": (C.c_int, []),
+        "qk_build_id": (C.c_char_p, []),
         "qk_model_create": (C.c_int, [P(vp)]),
         "qk_model_destroy": (None, [vp]),
         "qk_model_add_component": (C.c_int, [vp, P(ComponentDesc), P(u32)]),

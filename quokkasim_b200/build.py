@@ -28,21 +28,55 @@ FLAGS = [
 ]
 
 
-def _stale():
-    if not os.path.exists(LIB):
-        return True
-    t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
-    deps.append(os.path.join(_HERE, "..", "include", "quokka_b200.h"))
-    return any(os.path.getmtime(d) > t for d in deps)
+_MARKER = b"QKBUILDID:"
+
+
+def source_id(extra=()):
+    """What the library is built FROM: sha256 over every file of csrc/ and the public header (names and contents, in
+    sorted order) and over the compiler flags.  The same string is compiled into the library (qk_build_id())."""
+    import hashlib
+
+    h = hashlib.sha256()
+    files = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if not f.startswith("."))
+    files.append(os.path.join(_HERE, "..", "include", "quokka_b200.h"))
+    for f in files:
+        h.update(os.path.basename(f).encode() + b"\0")
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+        h.update(b"\0")
+    h.update(" ".join(FLAGS + list(extra) + SOURCES).encode())
+    return h.hexdigest()[:24]
+
+
+def built_id(path=None):
+    """The source id compiled into an existing library, read from the file (no dlopen), or None."""
+    path = path or LIB
+    try:
+        with open(path, "rb") as fh:
+            blob = fh.read()
+    except OSError:
+        return None
+    k = blob.find(_MARKER)
+    if k < 0:
+        return None
+    end = blob.find(b"\0", k)
+    return blob[k + len(_MARKER):end].decode("ascii", "replace")
+
+
+def _stale(extra=()):
+    """Rebuild when the library is missing or was built from other sources / flags than the tree holds now -- decided by
+    content, not by file times (a library shipped with a snapshot is newer than every source file, whatever it was
+    built from)."""
+    return built_id() != source_id(extra)
 
 
 def build(force=False, verbose=False):
-    if not force and not _stale():
-        return LIB
     extra = os.environ.get("QK_EXTRA_NVCC_FLAGS", "").split()  # experiments: -DQK_..., with QK_LIB_OUT for the output
     out = os.environ.get("QK_LIB_OUT", LIB)
-    cmd = [NVCC] + FLAGS + extra + ["-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
+    if not force and out == LIB and not _stale(extra):
+        return LIB
+    cmd = [NVCC] + FLAGS + extra + ['-DQK_BUILD_ID="%s"' % source_id(extra), "-o", out] + \
+        [os.path.join(CSRC, s) for s in SOURCES]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     log = os.path.join(_HERE, "build.log")
     with open(log, "w") as f:

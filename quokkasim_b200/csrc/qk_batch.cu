@@ -68,7 +68,8 @@ struct qk_batch {
   size_t scratch_bytes;
   uint8_t* h_pinned;
   size_t pinned_bytes;
-  uint32_t grp_reps, grp_stride64, grp_stride32, grp_bar_off; /* lane-group kernel geometry (qk_group.cuh) */
+  uint32_t grp_reps, grp_stride64, grp_stride32, grp_bar_off, grp_x64; /* lane-group kernel geometry (qk_group.cuh) */
+  bool phased;
   /* sliced stepping: the tiles are split into QK_SLICE_PARTS parts, each advanced chunk by chunk on its own stream */
   cudaStream_t side[QK_SLICE_PARTS - 1];
   cudaEvent_t ev_fork, ev_join[QK_SLICE_PARTS - 1];
@@ -92,6 +93,17 @@ StepKernel qk_pick_group_l0f2(uint32_t g);
 StepKernel qk_pick_group_l1f0(uint32_t g);
 StepKernel qk_pick_group_l1f1(uint32_t g);
 StepKernel qk_pick_group_l1f2(uint32_t g);
+StepKernel qk_pick_phased_l0f0(uint32_t g);
+StepKernel qk_pick_phased_l0f1(uint32_t g);
+StepKernel qk_pick_phased_l0f2(uint32_t g);
+StepKernel qk_pick_phased_l1f0(uint32_t g);
+StepKernel qk_pick_phased_l1f1(uint32_t g);
+StepKernel qk_pick_phased_l1f2(uint32_t g);
+static StepKernel pick_phased_kernel(bool log, uint32_t g, uint32_t features) {
+  if (features >= 2) return log ? qk_pick_phased_l1f2(g) : qk_pick_phased_l0f2(g);
+  if (log) return features ? qk_pick_phased_l1f1(g) : qk_pick_phased_l1f0(g);
+  return features ? qk_pick_phased_l0f1(g) : qk_pick_phased_l0f0(g);
+}
 static StepKernel pick_group_kernel(bool log, uint32_t g, uint32_t features) {
   if (features >= 2) return log ? qk_pick_group_l1f2(g) : qk_pick_group_l0f2(g);
   if (log) return features ? qk_pick_group_l1f1(g) : qk_pick_group_l1f0(g);
@@ -110,7 +122,7 @@ static uint32_t choose_nt(uint32_t per_rep_bytes, uint32_t table_bytes, uint32_t
   uint32_t best_nt = 0, best_thr = 0;
   for (uint32_t nt = 256; nt >= 32; nt -= 32) {
     const uint64_t bytes = (uint64_t)table_bytes + (uint64_t)per_rep_bytes * nt;
-    if (bytes > 227u * 1024u) continue;
+    if (bytes > 227u * 1024u - 64u) continue; /* 64 B: the kernels' static shared memory (an mbarrier) */
     uint32_t bps = (uint32_t)((227u * 1024u) / (bytes + 1024u));
     if (bps > 32) bps = 32;
     uint32_t thr = bps * nt;
@@ -177,6 +189,7 @@ static int launch_step(qk_batch* b, uint32_t do_init, uint64_t t0, uint64_t t_un
   P.grp_stride64 = b->grp_stride64;
   P.grp_stride32 = b->grp_stride32;
   P.grp_bar_off = b->grp_bar_off;
+  P.grp_x64 = b->grp_x64;
   cudaStream_t stream = b->stream;
   if (slice && slice->n_tiles) {
     P.tile0 = slice->tile0;
@@ -467,7 +480,8 @@ int qk_batch_create(const qk_model* m, const qk_batch_config* cfg, qk_batch** ou
   b->wave_blocks = 0;
   b->lanes = 1;
   b->last_chunks = 1;
-  b->grp_reps = b->grp_stride64 = b->grp_stride32 = b->grp_bar_off = 0;
+  b->grp_reps = b->grp_stride64 = b->grp_stride32 = b->grp_bar_off = b->grp_x64 = 0;
+  b->phased = false;
   b->have_side = false;
   int rc = qk_lower(m, b->log, &b->low);
   if (rc) {
@@ -500,12 +514,21 @@ int qk_batch_create(const qk_model* m, const qk_batch_config* cfg, qk_batch** ou
       else b->hbm = true;
     }
   }
+  bool phased = group && (cfg->flags & QK_BATCH_GROUP_PHASED) != 0;
+  if (const char* e = getenv("QK_GROUP_PHASED")) /* experiments: "1" / "0" overrides the variant wherever groups are used */
+    phased = group && e[0] == '1';
+  uint32_t phased_blocks = 2; /* blocks per SM the phased geometry aims at: they overlap each other's phases */
+  if (const char* e = getenv("QK_PHASED_BLOCKS"))
+    if (atoi(e) >= 1 && atoi(e) <= 8) phased_blocks = (uint32_t)atoi(e);
   if (group) {
     if (G == 0) G = 8;
     QkGroupGeom geo;
+    /* per-block budget: the SM's 228 KB over the blocks, less the 1 KB the system reserves per block and the static part */
+    const uint32_t budget = phased ? (228u * 1024u) / phased_blocks - 1024u - 64u : 227u * 1024u - 64u;
     const bool ok = (G == 4 || G == 8 || G == 16) &&
-                    qk_group_geometry(G, 32u, h.n64, h.n32, b->table_bytes_padded, group_max_threads(G), 227u * 1024u, 1024u, 4u,
-                                      &geo) != 0 &&
+                    qk_group_geometry(G, 32u, h.n64, h.n32, phased ? 2u : 0u, phased ? 6u : 0u, b->table_bytes_padded,
+                                      group_max_threads(G), budget < 227u * 1024u - 64u ? budget : 227u * 1024u - 64u,
+                                      1024u, 4u, &geo) != 0 &&
                     geo.reps >= 8;
     if (!ok) {
       if (cfg->flags & QK_BATCH_STATE_LANE_GROUP) {
@@ -524,6 +547,8 @@ int qk_batch_create(const qk_model* m, const qk_batch_config* cfg, qk_batch** ou
       b->grp_stride64 = geo.stride64;
       b->grp_stride32 = geo.stride32;
       b->grp_bar_off = geo.bar_off;
+      b->grp_x64 = phased ? 2u : 0u;
+      b->phased = phased;
       nt = geo.threads;
     }
   }
@@ -532,7 +557,7 @@ int qk_batch_create(const qk_model* m, const qk_batch_config* cfg, qk_batch** ou
   } else if (!b->hbm) {
     if (nt == 0) nt = choose_nt(per_rep, b->table_bytes_padded, max_thr, nullptr);
     const bool fits = nt != 0 && nt <= QK_MAX_NT && !(nt & 31) &&
-                      (uint64_t)b->table_bytes_padded + (uint64_t)per_rep * nt <= 227u * 1024u;
+                      (uint64_t)b->table_bytes_padded + (uint64_t)per_rep * nt <= 227u * 1024u - 64u;
     if (!fits) {
       if (cfg->flags & QK_BATCH_STATE_ON_CHIP) {
         qk_set_error("qk_batch_create: model needs %u B of on-chip state per replication (+%u B tables); "
@@ -598,8 +623,21 @@ int qk_batch_create(const qk_model* m, const qk_batch_config* cfg, qk_batch** ou
   CREATE_TRY(cudaMalloc(&b->d_tape_len, sizeof(uint64_t) * (h.n_dist ? h.n_dist : 1)));
   CREATE_TRY(cudaMemset(b->d_tapes, 0, sizeof(double*) * (h.n_dist ? h.n_dist : 1)));
   CREATE_TRY(cudaMemset(b->d_tape_len, 0, sizeof(uint64_t) * (h.n_dist ? h.n_dist : 1)));
-  b->kernel = group ? pick_group_kernel(b->log, b->lanes, h.features) : pick_kernel(b->log, b->hbm, b->nt, h.features);
-  CREATE_TRY(cudaFuncSetAttribute((const void*)b->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  b->kernel = group ? (b->phased ? pick_phased_kernel(b->log, b->lanes, h.features) : pick_group_kernel(b->log, b->lanes, h.features))
+                    : pick_kernel(b->log, b->hbm, b->nt, h.features);
+  {
+    /* the opt-in limit covers static + dynamic shared memory: the kernels keep an mbarrier (and little else) in static */
+    cudaFuncAttributes fa;
+    CREATE_TRY(cudaFuncGetAttributes(&fa, (const void*)b->kernel));
+    CREATE_TRY(cudaFuncSetAttribute((const void*)b->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    227 * 1024 - (int)fa.sharedSizeBytes));
+    if (b->smem_bytes + fa.sharedSizeBytes > 227u * 1024u) {
+      qk_set_error("qk_batch_create: %u B of dynamic + %zu B of static shared memory exceed the 227 KB of an SM",
+                   b->smem_bytes, fa.sharedSizeBytes);
+      qk_batch_destroy(b);
+      return QK_ERR_CAPACITY;
+    }
+  }
   {
     int sms = 0, nb = 0;
     CREATE_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device));

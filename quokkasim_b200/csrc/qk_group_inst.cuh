@@ -17,4 +17,13 @@ static StepKernel qk_pick_group(uint32_t g) {
     default: return nullptr;
   }
 }
+template <bool LOG, int FT>
+static StepKernel qk_pick_phased(uint32_t g) {
+  switch (g) {
+    case 4: return qk_phased_kernel<LOG, 4, FT>;
+    case 8: return qk_phased_kernel<LOG, 8, FT>;
+    case 16: return qk_phased_kernel<LOG, 16, FT>;
+    default: return nullptr;
+  }
+}
 #endif

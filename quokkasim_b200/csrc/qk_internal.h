@@ -257,9 +257,10 @@ typedef struct {
 typedef struct {
   uint32_t reps, stride64, stride32, bar_off, smem_bytes, threads;
 } QkGroupGeom;
-static inline int qk_group_geometry(uint32_t G, uint32_t warp, uint32_t n64, uint32_t n32, uint32_t table_bytes,
-                                    uint32_t max_threads, uint32_t max_smem, uint32_t reps_cap, uint32_t rep_multiple,
-                                    QkGroupGeom* out) {
+/* x64 / x32: extra rows after the state rows (the phased kernel keeps each replication's loop state there) */
+static inline int qk_group_geometry(uint32_t G, uint32_t warp, uint32_t n64, uint32_t n32, uint32_t x64, uint32_t x32,
+                                    uint32_t table_bytes, uint32_t max_threads, uint32_t max_smem, uint32_t reps_cap,
+                                    uint32_t rep_multiple, QkGroupGeom* out) {
   uint32_t unit = G >= warp ? 1u : warp / G; /* whole warps */
   if (unit < rep_multiple) unit = rep_multiple;
   int found = 0;
@@ -267,7 +268,7 @@ static inline int qk_group_geometry(uint32_t G, uint32_t warp, uint32_t n64, uin
     uint32_t s64 = R, s32 = R;
     while ((s64 & 3u) != 2u) ++s64;
     while ((s32 & 7u) != 4u) ++s32;
-    const uint32_t bar = (table_bytes + n64 * s64 * 8u + n32 * s32 * 4u + 7u) & ~7u;
+    const uint32_t bar = (table_bytes + (n64 + x64) * s64 * 8u + (n32 + x32) * s32 * 4u + 7u) & ~7u;
     if (bar + 16u > max_smem) break;
     found = 1;
     out->reps = R;

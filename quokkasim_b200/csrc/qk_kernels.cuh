@@ -54,6 +54,7 @@ struct KParams {
   /* lane-group kernel (qk_group.cuh): replications per block, row strides of the shared-memory state (elements),
    * byte offset of the mbarrier */
   uint32_t grp_reps, grp_stride64, grp_stride32, grp_bar_off;
+  uint32_t grp_x64; /* extra 64-bit rows after the state rows (the phased kernel's loop state); the 32-bit rows follow */
 };
 
 struct Ctx {

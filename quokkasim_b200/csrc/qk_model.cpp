@@ -76,6 +76,14 @@ extern "C" {
 const char* qk_last_error(void) { return g_err; }
 int qk_abi_version(void) { return QK_ABI_VERSION; }
 
+/* what this library was built from: quokkasim_b200/build.py hashes csrc/, the public header and the compiler flags and
+ * passes the result in; build.py finds the marker in the file to decide whether the library in the tree is current */
+#ifndef QK_BUILD_ID
+#define QK_BUILD_ID "unknown"
+#endif
+static const char qk_build_marker[] = "QKBUILDID:" QK_BUILD_ID;
+const char* qk_build_id(void) { return qk_build_marker + 10; }
+
 int qk_model_create(qk_model** out) {
   if (!out) {
     qk_set_error("qk_model_create: out is NULL");
@@ -616,7 +624,10 @@ int qk_lower(const qk_model* m, bool log, QkLowered* out) {
     uint32_t r = c.d.capacity_hint ? c.d.capacity_hint : (c.up >= 0 ? 2 * cap[(size_t)c.up] + 8 : 8);
     /* Load / Unload are bounded by max_process_count (vector_container.rs:350, 661) */
     if (c.d.kind == QK_CONTAINER_LOAD_PROCESS || c.d.kind == QK_CONTAINER_UNLOAD_PROCESS) r = c.d.max_capacity;
-    if (r > 0xFFFF) return QK_ERR_CAPACITY;
+    if (r > 0xFFFF) {
+      qk_set_error("component %zu: more than 65535 in-flight slots (capacity_hint / max_process_count %u)", i, r);
+      return QK_ERR_CAPACITY;
+    }
     cap[i] = r;
   }
 

@@ -49,12 +49,19 @@ struct qk_batch {
   bool any_tape;
   bool initialised;
   uint32_t lanes; /* 0: one "thread" per replication ; else the lane-group kernel with this group width */
+  bool phased;    /* ... its phased variant */
   QkGroupGeom geo;
 };
 
 /* the lane-group kernel: one block = geo.reps replications x `lanes` lanes = one team of host threads */
 template <bool L, int G>
-static void group_block(const KParams& P, uint32_t ft) {
+static void group_block(const KParams& P, uint32_t ft, bool phased) {
+  if (phased) {
+    if (ft >= 2) qk_phased_kernel<L, G, 2>(P);
+    else if (ft == 1) qk_phased_kernel<L, G, 1>(P);
+    else qk_phased_kernel<L, G, 0>(P);
+    return;
+  }
   if (ft >= 2) qk_group_kernel<L, G, 2>(P);
   else if (ft == 1) qk_group_kernel<L, G, 1>(P);
   else qk_group_kernel<L, G, 0>(P);
@@ -64,6 +71,8 @@ static int run_group(qk_batch* b, KParams& P, uint32_t tile0, uint32_t n_tiles) 
   P.grp_stride64 = b->geo.stride64;
   P.grp_stride32 = b->geo.stride32;
   P.grp_bar_off = b->geo.bar_off;
+  P.grp_x64 = b->phased ? 2u : 0u;
+  const bool phased = b->phased;
   const uint32_t nt = b->geo.threads, ft = b->low.hdr.features, G = b->lanes;
   const uint32_t blocks = n_tiles ? n_tiles : (uint32_t)(b->rep_pad / b->geo.reps);
   std::vector<uint64_t> smem(b->geo.smem_bytes / 8 + 2);
@@ -81,13 +90,13 @@ static int run_group(qk_batch* b, KParams& P, uint32_t tile0, uint32_t n_tiles) 
         qk_emul_nt = nt;
         qk_emul_team = &team;
         if (b->log) {
-          if (G == 2) group_block<true, 2>(P, ft);
-          else if (G == 4) group_block<true, 4>(P, ft);
-          else group_block<true, 8>(P, ft);
+          if (G == 2) group_block<true, 2>(P, ft, phased);
+          else if (G == 4) group_block<true, 4>(P, ft, phased);
+          else group_block<true, 8>(P, ft, phased);
         } else {
-          if (G == 2) group_block<false, 2>(P, ft);
-          else if (G == 4) group_block<false, 4>(P, ft);
-          else group_block<false, 8>(P, ft);
+          if (G == 2) group_block<false, 2>(P, ft, phased);
+          else if (G == 4) group_block<false, 4>(P, ft, phased);
+          else group_block<false, 8>(P, ft, phased);
         }
       });
     for (auto& x : th) x.join();
@@ -170,6 +179,7 @@ int qk_batch_create(const qk_model* m, const qk_batch_config* cfg, qk_batch** ou
   b->table_bytes_padded = (h.total_bytes + 15u) & ~15u;
   b->rep_pad = cfg->n_reps;
   b->lanes = 0;
+  b->phased = (cfg->flags & QK_BATCH_STATE_LANE_GROUP) && (cfg->flags & QK_BATCH_GROUP_PHASED);
   if (cfg->flags & QK_BATCH_STATE_LANE_GROUP) {
     b->lanes = cfg->lanes_per_replication ? cfg->lanes_per_replication : 4;
     if (b->lanes != 2 && b->lanes != 4 && b->lanes != 8) {
@@ -178,7 +188,8 @@ int qk_batch_create(const qk_model* m, const qk_batch_config* cfg, qk_batch** ou
     }
     /* small blocks: `threads_per_block` (if given) = replications per block here; the whole block is one warp */
     const uint32_t cap = cfg->threads_per_block ? cfg->threads_per_block : 2;
-    if (!qk_group_geometry(b->lanes, b->lanes, h.n64, h.n32, b->table_bytes_padded, 32u, 1u << 30, cap, 1u, &b->geo)) {
+    if (!qk_group_geometry(b->lanes, b->lanes, h.n64, h.n32, b->phased ? 2u : 0u, b->phased ? 6u : 0u, b->table_bytes_padded,
+                           32u, 1u << 30, cap, 1u, &b->geo)) {
       delete b;
       return QK_ERR_CAPACITY;
     }

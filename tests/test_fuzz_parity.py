@@ -155,6 +155,14 @@ def test_random_models_match_the_oracle_lane_groups(emul_lib, seed):
     _run(emul_lib, seed, 2, flags=4 | ((2, 4, 8)[seed % 3] << 8))
 
 
+@pytest.mark.parametrize("seed", range(600, 624))
+def test_random_models_match_the_oracle_phased(emul_lib, seed):
+    """the phased lane-group kernel (pop + quick by lane groups, handlers one thread per replication)"""
+    _run(emul_lib, seed, 3, flags=4 | 8 | ((2, 4, 8)[seed % 3] << 8))
+    if seed < 608:
+        _run_vector(emul_lib, seed, 2, flags=4 | 8 | ((2, 4, 8)[seed % 3] << 8))
+
+
 def test_random_models_are_mostly_comparable(emul_lib):
     """the generator must not hide behind capacity faults"""
     assert sum(_run(emul_lib, s, 1) for s in range(40, 60)) >= 17

@@ -290,8 +290,9 @@ def test_state_placement_does_not_change_results(gpu_lib):
 
 
 # ------------------------------------------------------------------------------------- lane-group kernel (qk_group.cuh)
-def _gflags(lanes):
-    return 4 | (lanes << 8)  # QK_BATCH_STATE_LANE_GROUP | lanes_per_replication << 8 (api.py convention)
+def _gflags(lanes, phased=False):
+    # QK_BATCH_STATE_LANE_GROUP [| QK_BATCH_GROUP_PHASED] | lanes_per_replication << 8 (api.py convention)
+    return 4 | (8 if phased else 0) | (lanes << 8)
 
 
 @pytest.mark.parametrize("lanes", [4, 8, 16])
@@ -474,3 +475,39 @@ def test_delay_mode_quick_path_at_scale(gpu_lib):
     (HBM planes) and lane groups, against the oracle"""
     for flags in (1, _gflags(8)):
         _check(gpu_lib, H.serial_line(n_proc=12), 200, n_events=60000, sample=[0, 199], log_capacity=262144, flags=flags)
+
+
+@pytest.mark.parametrize("lanes", [4, 8, 16])
+def test_phased_kernel_matches_the_oracle(gpu_lib, lanes):
+    """the phased variant: pop + quick by lane groups, the handlers of a whole block side by side in one or two warps"""
+    f = _gflags(lanes, True)
+    _check(gpu_lib, H.haulage(n_src=8, per_queue=8), 101, n_events=20000, sample=[0, 50, 100], log_capacity=131072, flags=f)
+    _check(gpu_lib, H.serial_line(n_proc=32), 70, n_events=30000, sample=[0, 69], log_capacity=131072, flags=f)
+    _check(gpu_lib, H.discrete_queue(), 300, n_events=3000, tape_len=1200, sample=[0, 1, 150, 299], log_capacity=16384,
+           flags=f)
+    m = H.assembly_line()
+    _check(gpu_lib, m, 64, t_until=m.t0 + 3 * 24 * 3600 * 10**9, t0=m.t0, sample=[0, 63], log_capacity=16384, flags=f)
+    _check(gpu_lib, H.vector_flow(3), 200, n_events=6000, sample=[0, 99, 199], log_capacity=65536, flags=f)
+    _check(gpu_lib, H.container_haulage(), 128, n_events=6000, sample=[0, 127], log_capacity=65536, flags=f)
+
+
+def test_phased_kernel_round_trips_and_agrees_with_the_other_placements(gpu_lib):
+    blobs = []
+    for flags, how in ((_gflags(8, True), "one"), (_gflags(8, True), "pieces"), (_gflags(4, True), "sliced"),
+                       (_gflags(8), "one"), (1, "one")):
+        m = H.haulage(n_src=3, per_queue=4)
+        sim = m.sim(gpu_lib, 1000, base_seed=21, flags=flags, log_capacity=256)
+        if how == "one":
+            sim.step_events(6000)
+        elif how == "pieces":
+            sim.step_events(1)
+            sim.step_events(2999)
+            sim.step_events(3000)
+        else:
+            sim.step_events_sliced(6000, 5)
+        blob = b"".join(sim.comp_stats(ci).tobytes() for ci in range(len(m.components)))
+        logs, totals = sim.read_logs(0, 1000)
+        blob += b"".join(x.tobytes() for x in logs) + totals.tobytes()
+        blobs.append(blob)
+        sim.close()
+    assert all(b == blobs[0] for b in blobs[1:])

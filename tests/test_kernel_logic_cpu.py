@@ -436,8 +436,8 @@ def test_read_logs_equals_read_log(emul_lib):
 # ---------------------------------------------------------------------------------------------- lane-group kernel
 # qk_group.cuh under the host shim: every lane is a host thread, the block's only warp is the team, shuffles / ballots
 # go through an exchange array between barriers.  flags = QK_BATCH_STATE_LANE_GROUP | lanes << 8.
-def _gflags(lanes):
-    return 4 | (lanes << 8)
+def _gflags(lanes, phased=False):
+    return 4 | (8 if phased else 0) | (lanes << 8)
 
 
 @pytest.mark.parametrize("lanes", [2, 4, 8])
@@ -555,3 +555,50 @@ def test_scheduled_event_arms_the_reference_does_not_have():
     a = qk.create_scheduled_event(sched, 10**9, qk.ScheduledEventConfig.SetProcessQuantity(cfg), m.by_name["Process"].get_address(), df)
     b = qk.create_scheduled_event(sched, 2 * 10**9, qk.ScheduledEventConfig.SetProcessQuantity(cfg), m.by_name["Process"].get_address(), df)
     assert (a.stream, b.stream) == (0, 1)
+
+
+# the PHASED variant of the lane-group kernel: pop + quick by lane groups, then one thread per replication runs the
+# handlers of the whole block (here: blocks of 2-3 replications, a team of lanes x replications host threads)
+@pytest.mark.parametrize("lanes", [2, 4, 8])
+def test_phased_kernel_discrete_queue(emul_lib, lanes):
+    s = _check(emul_lib, H.discrete_queue(), 5, n_events=1200, log_capacity=8192, flags=_gflags(lanes, True))
+    assert s["n_events"] == 6000
+    _check(emul_lib, H.discrete_queue(), 3, t_until=150 * 10**9, tape_len=200, log_capacity=2048, flags=_gflags(lanes, True))
+
+
+def test_phased_kernel_models(emul_lib):
+    f = _gflags(4, True)
+    m = H.car_workshop()
+    _check(emul_lib, m, 3, t_until=m.t0 + 9 * 3600 * 10**9, t0=m.t0, log_capacity=2048, flags=f)
+    _check(emul_lib, H.haulage(), 3, n_events=5000, tape_len=3000, log_capacity=16384, flags=f)
+    _check(emul_lib, H.haulage(n_src=3, per_queue=4), 2, n_events=8000, log_capacity=65536, flags=_gflags(8, True))
+    _check(emul_lib, H.serial_line(), 3, n_events=6000, tape_len=3000, log_capacity=32768, flags=f)
+    _check(emul_lib, H.serial_line(), 2, n_events=9000, log_capacity=65536, flags=_gflags(2, True))
+    m = H.assembly_line()
+    _check(emul_lib, m, 2, t_until=m.t0 + 24 * 3600 * 10**9, t0=m.t0, log_capacity=16384, flags=f)
+    _check(emul_lib, H.vector_flow(3), 2, n_events=2500, log_capacity=32768, flags=f)
+    _check(emul_lib, H.container_haulage(), 2, n_events=1500, log_capacity=32768, flags=f)
+    _check(emul_lib, H.scheduled_process_quantity(), 3, t_until=70 * 10**9, log_capacity=8192, flags=f)
+
+
+def test_phased_kernel_statistics_only_split_steps_and_faults(emul_lib):
+    m = H.haulage()
+    a = m.sim(emul_lib, 5, base_seed=5, log_capacity=0, flags=_gflags(4, True), threads_per_block=3)
+    a.step_events(700)
+    a.step_events(1)
+    a.step_events_sliced(1299, 4)
+    b = H.haulage().sim(emul_lib, 5, base_seed=5, log_capacity=16384)
+    b.step_events(2000)
+    for ci in range(len(m.components)):
+        assert a.comp_stats(ci).tobytes() == b.comp_stats(ci).tobytes()
+    assert a.status()[1].tobytes() == b.status()[1].tobytes()
+    m = H.discrete_queue()
+    tapes = H.make_tapes(m, 4, 300, seed=9)
+    _, v0 = list(tapes.values())[0]
+    v0[1, 3] = 0.0
+    v0[2, 2] = -1.0
+    sim = m.sim(emul_lib, 4, log_capacity=4096, flags=_gflags(4, True))
+    for d, v in tapes.values():
+        sim.set_tape(d, v)
+    sim.step_events(600)
+    assert list(sim.status()[0]) == [0, 1, 2, 0]
