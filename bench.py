@@ -241,7 +241,7 @@ def run_ours(args):
     # a real (non-NULL) stream: the library launches on it, torch events and NCCL order against it
     stream = torch.cuda.Stream(device)
     torch.cuda.set_stream(stream)
-    flags = {"auto": 0, "hbm": 1, "chip": 2, "group": 4, "phased": 12}[args.state]
+    flags = {"auto": 0, "hbm": 1, "chip": 2, "group": 4, "phased": 12, "split": 16}[args.state]
 
     def new_sim(log_capacity, n=reps_gpu, off=rep_lo, seed=1234):
         return model.sim(args.lib, n, t0=0, base_seed=seed, rep_offset=off, log_capacity=log_capacity,
@@ -419,7 +419,8 @@ def run_ours(args):
             "faulted_replications": int(ev_total[2].item()),
             "per_gpu_events_per_s": value / world,
             "placement": {"state": "hbm" if info["state_in_hbm"] else (
-                              "lane-group" if info["lanes_per_replication"] > 1 else "shared-memory"),
+                              "lane-group" if info["lanes_per_replication"] > 1 else (
+                                  "split" if info.get("state_split") else "shared-memory")),
                           "lanes_per_replication": info["lanes_per_replication"],
                           "threads_per_block": info["threads_per_block"], "grid_blocks": info["grid_blocks"],
                           "resident_blocks_per_sm": info["resident_blocks_per_sm"],
@@ -453,7 +454,7 @@ def main():
     ap.add_argument("--log", default="ring", choices=["ring", "off"])
     ap.add_argument("--log-capacity", type=int, default=64)
     ap.add_argument("--threads-per-block", type=int, default=0)
-    ap.add_argument("--state", default="auto", choices=["auto", "hbm", "chip", "group", "phased"],
+    ap.add_argument("--state", default="auto", choices=["auto", "hbm", "chip", "group", "phased", "split"],
                     help="auto: the library chooses; hbm: operate on the HBM planes in place; chip: one thread per "
                          "replication, state staged in shared memory; group: a lane group per replication, state in "
                          "shared memory (large models)")

@@ -315,6 +315,11 @@ int qk_model_state_bytes(const qk_model*, int with_log, uint32_t* out_bytes);
 /* with QK_BATCH_STATE_LANE_GROUP: the phased variant -- the lane groups do the scheduler pop and the subscriber broadcast,
  * then one thread per replication runs the full handlers of the whole block side by side (qk_group.cuh) */
 #define QK_BATCH_GROUP_PHASED 8u
+/* large models, one thread per replication: only the scheduler queue (the fire slots), the stocks' state words and the
+ * event-id counters are staged in shared memory; the component records (countdowns, flags, items in process, pre-drawn
+ * durations, draw counters, resources) stay in global memory and are read and written in place, through L2, by the
+ * handlers alone -- the scheduler pop and the emit_change broadcast never leave the chip */
+#define QK_BATCH_STATE_SPLIT 16u
 typedef struct {
   uint64_t n_reps;
   uint64_t rep_offset;   /* global index of this batch's first replication (Philox counter words 0,1) */
@@ -342,7 +347,7 @@ typedef struct {
   uint32_t lanes_per_replication; /* 1: one thread per replication ; 4/8/16: a lane group per replication */
   uint32_t wave_blocks;           /* blocks of the step kernel resident on the whole GPU at once */
   uint32_t last_step_chunks;      /* state residencies of the last step call: 1, or the chunks of a sliced step */
-  uint32_t reserved;
+  uint32_t state_split;           /* 1: QK_BATCH_STATE_SPLIT placement (state_bytes_per_rep = the staged part) */
 } qk_batch_info;
 
 int qk_batch_create(const qk_model*, const qk_batch_config*, qk_batch** out);

@@ -108,7 +108,7 @@ class BatchInfo(C.Structure):
         ("state_in_hbm", C.c_uint32), ("cold_bytes_per_rep", C.c_uint32),
         ("replications_padded", C.c_uint64), ("state_bytes_total", C.c_uint64), ("log_bytes_total", C.c_uint64),
         ("lanes_per_replication", C.c_uint32), ("wave_blocks", C.c_uint32), ("last_step_chunks", C.c_uint32),
-        ("reserved", C.c_uint32),
+        ("state_split", C.c_uint32),
     ]
 
 

@@ -70,6 +70,7 @@ struct qk_batch {
   size_t pinned_bytes;
   uint32_t grp_reps, grp_stride64, grp_stride32, grp_bar_off, grp_x64; /* lane-group kernel geometry (qk_group.cuh) */
   bool phased;
+  bool split; /* QK_BATCH_STATE_SPLIT: component records live in the cold planes (DevHeader.split) */
   /* sliced stepping: the tiles are split into QK_SLICE_PARTS parts, each advanced chunk by chunk on its own stream */
   cudaStream_t side[QK_SLICE_PARTS - 1];
   cudaEvent_t ev_fork, ev_join[QK_SLICE_PARTS - 1];
@@ -78,6 +79,10 @@ struct qk_batch {
   uint32_t last_chunks; /* state residencies of the last step call */
   uint32_t n_sm, wave_blocks; /* SMs of the device ; blocks of the step kernel resident on the whole GPU at once */
 };
+
+/* the planes the component records live in: the hot planes, or (split placement) the cold ones */
+static inline uint64_t* warm64(const qk_batch* b) { return b->split ? b->gc64 : b->g64; }
+static inline uint32_t* warm32(const qk_batch* b) { return b->split ? b->gc32 : b->g32; }
 
 /* the step kernel instantiations live in qk_step_l{0,1}f{0,1}.cu */
 StepKernel qk_pick_step_l0f0(uint32_t nt);
@@ -110,8 +115,8 @@ static StepKernel pick_group_kernel(bool log, uint32_t g, uint32_t features) {
   return features ? qk_pick_group_l0f1(g) : qk_pick_group_l0f0(g);
 }
 static uint32_t group_max_threads(uint32_t g) { return g <= 4 ? 256u : (g == 8 ? 512u : 768u); } /* qk_group_max_threads */
-static StepKernel pick_kernel(bool log, bool hbm, uint32_t nt, uint32_t features) {
-  const uint32_t key = hbm ? 0u : nt;
+static StepKernel pick_kernel(bool log, bool hbm, uint32_t nt, uint32_t features, bool split = false) {
+  const uint32_t key = split ? 0xFFFFFFFEu : (hbm ? 0u : nt);
   if (features >= 2) return log ? qk_pick_step_l1f2(key) : qk_pick_step_l0f2(key);
   if (log) return features ? qk_pick_step_l1f1(key) : qk_pick_step_l1f0(key);
   return features ? qk_pick_step_l0f1(key) : qk_pick_step_l0f0(key);
@@ -211,12 +216,12 @@ static int launch_step(qk_batch* b, uint32_t do_init, uint64_t t0, uint64_t t_un
 /* ================================= per-GPU summary reduction ================================= */
 
 __global__ void qk_comp_stats_kernel(const uint8_t* tables, const uint64_t* g64, const uint32_t* g32,
-                                     const uint64_t* gs64, const uint32_t* gs32, uint64_t rep_pad, uint64_t rep0, uint64_t n, uint32_t comp, qk_comp_stats* out) {
+                                     const uint64_t* w64, const uint32_t* w32, const uint64_t* gs64, const uint32_t* gs32, uint64_t rep_pad, uint64_t rep0, uint64_t n, uint32_t comp, qk_comp_stats* out) {
   const DevHeader* h = reinterpret_cast<const DevHeader*>(tables);
   const DevComp* c = reinterpret_cast<const DevComp*>(tables + h->off_comps) + comp;
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const DevVec* vecs = reinterpret_cast<const DevVec*>(tables + h->off_vecs);
-  if (i < n) qk_comp_stats_dev(c, vecs, comp, g64, g32, gs64, gs32, rep_pad, rep0 + i, &out[i]);
+  if (i < n) qk_comp_stats_dev(c, vecs, comp, g64, g32, w64, w32, gs64, gs32, rep_pad, rep0 + i, &out[i]);
 }
 
 __device__ __forceinline__ uint64_t warp_sum_u64(uint64_t v) {
@@ -240,7 +245,8 @@ __device__ __forceinline__ double warp_sum_f64(double v) {
  * time_ns^2 = a^2 * 2^64 + 2ab * 2^32 + b^2, and each of a^2, ab, b^2 (< 2^64) is summed as its low and high 32-bit
  * halves -- so the result does not depend on how the replications are partitioned over blocks or GPUs. */
 __global__ void __launch_bounds__(256) qk_reduce_kernel(const uint8_t* tables, const uint64_t* g64,
-                                                        const uint32_t* g32, const uint64_t* gs64,
+                                                        const uint32_t* g32, const uint64_t* w64, const uint32_t* w32,
+                                                        const uint64_t* gs64,
                                                         const uint32_t* gs32, uint64_t rep_pad, uint64_t n_reps,
                                                         uint64_t* part) {
   const DevHeader* h = reinterpret_cast<const DevHeader*>(tables);
@@ -250,7 +256,7 @@ __global__ void __launch_bounds__(256) qk_reduce_kernel(const uint8_t* tables, c
   for (int k = 0; k < QK_PARTIAL_WORDS; ++k) a[k] = (k >= QP_MIN_COUNT && k <= QP_NMAX_TIME) ? ~0ull : 0ull;
   for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_reps; r += (uint64_t)gridDim.x * blockDim.x) {
     qk_comp_stats s;
-    qk_comp_stats_dev(c, reinterpret_cast<const DevVec*>(tables + h->off_vecs), comp, g64, g32, gs64, gs32, rep_pad, r, &s);
+    qk_comp_stats_dev(c, reinterpret_cast<const DevVec*>(tables + h->off_vecs), comp, g64, g32, w64, w32, gs64, gs32, rep_pad, r, &s);
     const uint64_t lo = s.time_ns & 0xFFFFFFFFull, hi = s.time_ns >> 32;
     a[QP_COUNT] += s.count;
     a[QP_TIME_LO] += lo;
@@ -325,7 +331,7 @@ __global__ void qk_partials_combine_kernel(const uint64_t* parts, uint32_t n_par
 
 /* hist[c][0][bin] over time_ns, hist[c][1][bin] over count; ranges from the extrema words of (combined) partials */
 __global__ void __launch_bounds__(256) qk_hist_kernel(const uint8_t* tables, const uint64_t* g64, const uint32_t* g32,
-                                                      const uint64_t* gs64, const uint32_t* gs32, uint64_t rep_pad, uint64_t n_reps, const uint64_t* part,
+                                                      const uint64_t* w64, const uint32_t* w32, const uint64_t* gs64, const uint32_t* gs32, uint64_t rep_pad, uint64_t n_reps, const uint64_t* part,
                                                       uint64_t* hist) {
   const DevHeader* h = reinterpret_cast<const DevHeader*>(tables);
   const uint32_t comp = blockIdx.y;
@@ -339,7 +345,7 @@ __global__ void __launch_bounds__(256) qk_hist_kernel(const uint8_t* tables, con
   const uint64_t w_c = (hi_c - lo_c) / QK_HIST_BINS + 1, w_t = (hi_t - lo_t) / QK_HIST_BINS + 1;
   for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_reps; r += (uint64_t)gridDim.x * blockDim.x) {
     qk_comp_stats s;
-    qk_comp_stats_dev(c, reinterpret_cast<const DevVec*>(tables + h->off_vecs), comp, g64, g32, gs64, gs32, rep_pad, r, &s);
+    qk_comp_stats_dev(c, reinterpret_cast<const DevVec*>(tables + h->off_vecs), comp, g64, g32, w64, w32, gs64, gs32, rep_pad, r, &s);
     if (s.time_ns >= lo_t && s.time_ns <= hi_t) atomicAdd(&sh[0][(s.time_ns - lo_t) / w_t], 1ull);
     if (s.count >= lo_c && s.count <= hi_c) atomicAdd(&sh[1][(s.count - lo_c) / w_c], 1ull);
   }
@@ -482,23 +488,30 @@ int qk_batch_create(const qk_model* m, const qk_batch_config* cfg, qk_batch** ou
   b->last_chunks = 1;
   b->grp_reps = b->grp_stride64 = b->grp_stride32 = b->grp_bar_off = b->grp_x64 = 0;
   b->phased = false;
+  b->split = false;
   b->have_side = false;
-  int rc = qk_lower(m, b->log, &b->low);
+  int rc = qk_lower(m, b->log, false, &b->low);
   if (rc) {
     delete b;
     return rc;
   }
-  const DevHeader& h = b->low.hdr;
+  const DevHeader& h = b->low.hdr; /* (a reference: a second lowering below is seen through it) */
   b->table_bytes_padded = (h.total_bytes + 15u) & ~15u;
-  const uint32_t per_rep = h.n64 * 8 + h.n32 * 4;
+  uint32_t per_rep = h.n64 * 8 + h.n32 * 4;
   uint32_t nt = cfg->threads_per_block;
   const uint32_t max_thr = (uint32_t)qk_lb_resident((int)h.features, b->log); /* the kernel variant's launch bounds */
   b->hbm = (cfg->flags & QK_BATCH_STATE_IN_HBM) != 0;
   bool group = (cfg->flags & QK_BATCH_STATE_LANE_GROUP) != 0;
+  bool split = (cfg->flags & QK_BATCH_STATE_SPLIT) != 0;
+  if (split && (b->hbm || group || (cfg->flags & QK_BATCH_STATE_ON_CHIP))) {
+    qk_set_error("qk_batch_create: QK_BATCH_STATE_SPLIT excludes the other placement flags");
+    delete b;
+    return QK_ERR_INVALID_ARG;
+  }
   uint32_t G = cfg->lanes_per_replication;
   if (const char* e = getenv("QK_GROUP_LANES")) /* experiments: overrides the group width wherever groups are used */
     if (atoi(e) > 0) G = (uint32_t)atoi(e);
-  if (!b->hbm && !group && nt == 0 && !(cfg->flags & QK_BATCH_STATE_ON_CHIP)) {
+  if (!b->hbm && !group && !split && nt == 0 && !(cfg->flags & QK_BATCH_STATE_ON_CHIP)) {
     /* placement heuristic (measured, profiles/README.md): one thread per replication with the state staged in shared
      * memory wins while at least 12 warps fit per SM (discrete_queue: 8 x 64 threads); below that a lane group per
      * replication keeps the state on chip with fewer replications and more warps */
@@ -510,9 +523,21 @@ int qk_batch_create(const qk_model* m, const qk_batch_config* cfg, qk_batch** ou
        * against operating on the L1/L2-cached HBM planes, profiles/README.md) */
       const char* e = getenv("QK_AUTO_PLACEMENT"); /* "hbm" / "group": force the choice for models of this class */
       if (e && e[0] == 'h') b->hbm = true;
+      else if (e && e[0] == 's') split = true;
       else if ((e && e[0] == 'g') || h.n_sched >= 32) group = true;
       else b->hbm = true;
     }
+  }
+  if (split) {
+    /* lower again with the component records in the cold planes; what is staged is the scheduler queue and the stocks */
+    rc = qk_lower(m, b->log, true, &b->low);
+    if (rc) {
+      delete b;
+      return rc;
+    }
+    b->split = true;
+    b->table_bytes_padded = (h.total_bytes + 15u) & ~15u;
+    per_rep = h.n64 * 8 + h.n32 * 4;
   }
   bool phased = group && (cfg->flags & QK_BATCH_GROUP_PHASED) != 0;
   if (const char* e = getenv("QK_GROUP_PHASED")) /* experiments: "1" / "0" overrides the variant wherever groups are used */
@@ -555,11 +580,11 @@ int qk_batch_create(const qk_model* m, const qk_batch_config* cfg, qk_batch** ou
   if (group) {
     /* geometry chosen above */
   } else if (!b->hbm) {
-    if (nt == 0) nt = choose_nt(per_rep, b->table_bytes_padded, max_thr, nullptr);
+    if (nt == 0) nt = choose_nt(per_rep, b->table_bytes_padded, split ? 256u : max_thr, nullptr);
     const bool fits = nt != 0 && nt <= QK_MAX_NT && !(nt & 31) &&
                       (uint64_t)b->table_bytes_padded + (uint64_t)per_rep * nt <= 227u * 1024u - 64u;
     if (!fits) {
-      if (cfg->flags & QK_BATCH_STATE_ON_CHIP) {
+      if ((cfg->flags & QK_BATCH_STATE_ON_CHIP) || split) {
         qk_set_error("qk_batch_create: model needs %u B of on-chip state per replication (+%u B tables); "
                      "no block size fits the 227 KB of shared memory", per_rep, b->table_bytes_padded);
         delete b;
@@ -624,7 +649,7 @@ int qk_batch_create(const qk_model* m, const qk_batch_config* cfg, qk_batch** ou
   CREATE_TRY(cudaMemset(b->d_tapes, 0, sizeof(double*) * (h.n_dist ? h.n_dist : 1)));
   CREATE_TRY(cudaMemset(b->d_tape_len, 0, sizeof(uint64_t) * (h.n_dist ? h.n_dist : 1)));
   b->kernel = group ? (b->phased ? pick_phased_kernel(b->log, b->lanes, h.features) : pick_group_kernel(b->log, b->lanes, h.features))
-                    : pick_kernel(b->log, b->hbm, b->nt, h.features);
+                    : pick_kernel(b->log, b->hbm, b->nt, h.features, b->split);
   {
     /* the opt-in limit covers static + dynamic shared memory: the kernels keep an mbarrier (and little else) in static */
     cudaFuncAttributes fa;
@@ -671,6 +696,7 @@ int qk_batch_info_get(qk_batch* b, qk_batch_info* out) {
   int nb = 0;
   CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)b->kernel, (int)b->nt, b->smem_bytes));
   out->state_in_hbm = b->hbm ? 1u : 0u;
+  out->state_split = b->split ? 1u : 0u;
   out->resident_blocks_per_sm = (uint32_t)nb;
   out->replications_padded = b->rep_pad;
   out->state_bytes_total = (uint64_t)(out->state_bytes_per_rep + out->cold_bytes_per_rep) * b->rep_pad;
@@ -951,7 +977,7 @@ int qk_batch_comp_stats(qk_batch* b, uint64_t rep0, uint64_t n, uint32_t comp, q
   const uint64_t piece = b->scratch_bytes / sizeof(qk_comp_stats);
   for (uint64_t done = 0; done < n; done += piece) {
     const uint64_t k = std::min<uint64_t>(piece, n - done);
-    qk_comp_stats_kernel<<<(unsigned)((k + 255) / 256), 256, 0, b->stream>>>(b->d_tables, b->g64, b->g32, b->gs64, b->gs32,
+    qk_comp_stats_kernel<<<(unsigned)((k + 255) / 256), 256, 0, b->stream>>>(b->d_tables, b->g64, b->g32, warm64(b), warm32(b), b->gs64, b->gs32,
                                                                               b->rep_pad, rep0 + done, k, comp, d);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(out + done, d, k * sizeof(qk_comp_stats), cudaMemcpyDeviceToHost, b->stream));
@@ -970,7 +996,7 @@ int qk_batch_reduce_partials_device(qk_batch* b, uint64_t* d_partials, uint32_t 
   qk_partials_clear_kernel<<<(n_words + 255) / 256, 256, 0, b->stream>>>(d_partials, n_words);
   CUDA_TRY(cudaGetLastError());
   dim3 grid(b->red_blocks, n_comp);
-  qk_reduce_kernel<<<grid, 256, 0, b->stream>>>(b->d_tables, b->g64, b->g32, b->gs64, b->gs32, b->rep_pad, b->cfg.n_reps,
+  qk_reduce_kernel<<<grid, 256, 0, b->stream>>>(b->d_tables, b->g64, b->g32, warm64(b), warm32(b), b->gs64, b->gs32, b->rep_pad, b->cfg.n_reps,
                                                 d_partials);
   CUDA_TRY(cudaGetLastError());
   return QK_OK;
@@ -994,7 +1020,7 @@ int qk_batch_histograms_device(qk_batch* b, const uint64_t* d_partials, uint64_t
   CUDA_TRY(cudaSetDevice(b->cfg.device));
   CUDA_TRY(cudaMemsetAsync(d_hist, 0, sizeof(uint64_t) * 2 * QK_HIST_BINS * n_comp, b->stream));
   dim3 grid(b->red_blocks, n_comp);
-  qk_hist_kernel<<<grid, 256, 0, b->stream>>>(b->d_tables, b->g64, b->g32, b->gs64, b->gs32, b->rep_pad, b->cfg.n_reps,
+  qk_hist_kernel<<<grid, 256, 0, b->stream>>>(b->d_tables, b->g64, b->g32, warm64(b), warm32(b), b->gs64, b->gs32, b->rep_pad, b->cfg.n_reps,
                                               d_partials, d_hist);
   CUDA_TRY(cudaGetLastError());
   return QK_OK;
@@ -1167,7 +1193,7 @@ int qk_batch_read_vector(qk_batch* b, uint64_t rep, uint32_t comp, double* out3)
   const DevVec& v = b->low.vecs[b->low.comps[comp].vec_idx];
   out3[0] = out3[1] = out3[2] = 0.0;
   for (uint32_t k = 0; k < v.dim; ++k)
-    CUDA_TRY(cudaMemcpy(&out3[k], b->g64 + (size_t)(v.o64_res + k) * b->rep_pad + rep, 8, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(&out3[k], warm64(b) + (size_t)(v.o64_res + k) * b->rep_pad + rep, 8, cudaMemcpyDeviceToHost));
   return QK_OK;
 }
 
@@ -1221,8 +1247,8 @@ int qk_batch_read_containers(qk_batch* b, uint64_t rep, uint32_t comp, uint32_t*
   } else if (c.kind == QK_DISCRETE_PARALLEL_PROCESS || c.kind == QK_CONTAINER_LOAD_PROCESS ||
              c.kind == QK_CONTAINER_UNLOAD_PROCESS) {
     uint32_t nprog = 0, cq = 0;
-    CUDA_TRY(fetch(b->g32, b->rep_pad, c.o32 + PP32_NPROG, rep, &nprog));
-    CUDA_TRY(fetch(b->g32, b->rep_pad, c.o32 + PP32_COMPLETE, rep, &cq));
+    CUDA_TRY(fetch(warm32(b), b->rep_pad, c.o32 + PP32_NPROG, rep, &nprog));
+    CUDA_TRY(fetch(warm32(b), b->rep_pad, c.o32 + PP32_COMPLETE, rep, &cq));
     const uint32_t ring = c.ring_cap, item0 = c.o32 + PP32_BASE_COUNT;
     for (uint32_t i = 0; i < nprog; ++i) {
       item_slot.push_back(item0 + i);
@@ -1235,7 +1261,7 @@ int qk_batch_read_containers(qk_batch* b, uint64_t rep, uint32_t comp, uint32_t*
     }
   } else {
     uint32_t flags = 0;
-    CUDA_TRY(fetch(b->g32, b->rep_pad, c.o32 + P32_FLAGS, rep, &flags));
+    CUDA_TRY(fetch(warm32(b), b->rep_pad, c.o32 + P32_FLAGS, rep, &flags));
     if (flags & PF_HAS_ITEM) {
       item_slot.push_back(c.o32 + P32_ITEM);
       pay_slot.push_back(c.ocold64);
@@ -1245,7 +1271,7 @@ int qk_batch_read_containers(qk_batch* b, uint64_t rep, uint32_t comp, uint32_t*
   if (!handles || !resources) return QK_OK;
   if (cap < item_slot.size()) return QK_ERR_BUFFER_TOO_SMALL;
   for (size_t i = 0; i < item_slot.size(); ++i) {
-    CUDA_TRY(fetch(item_cold ? b->gc32 : b->g32, b->rep_pad, item_slot[i], rep, &handles[i]));
+    CUDA_TRY(fetch(item_cold ? b->gc32 : warm32(b), b->rep_pad, item_slot[i], rep, &handles[i]));
     for (uint32_t k = 0; k < 3; ++k) CUDA_TRY(fetch(b->gc64, b->rep_pad, pay_slot[i] + k, rep, &resources[i * 3 + k]));
   }
   return QK_OK;

@@ -198,20 +198,20 @@ __device__ __forceinline__ void qk_scan_phase(Ctx& cx, uint32_t& rem, uint32_t& 
           const uint32_t target = e->target;
           const DevHotA a = QK_HOT_A(target);
           if (e->type == 1) {
-            S64(cx.vecs[cx.comps[target].vec_idx].o64_low) = QK_D2U(e->value);
+            W64(cx.vecs[cx.comps[target].vec_idx].o64_low) = QK_D2U(e->value);
             const double zero[3] = {0.0, 0.0, 0.0};
             qk_vstock_add<LOG, SM>(cx, target, zero, SRC_SCH);
             if (cx.status) done = true;
           } else if (e->type == 2) {
             /* SetProcessQuantity on an F64Process: with_process_quantity_distr_inplace(instance), then
              * update_state(SCH_000000) (core.rs:1389-1390) */
-            S32(cx.vecs[cx.comps[target].vec_idx].o32_qty) = e->state;
+            W32(cx.vecs[cx.comps[target].vec_idx].o32_qty) = e->state;
             src = SRC_SCH;
             rem = 1;
             ptr = ident_off + target;
-          } else if (S32(a.o32 + E32_STATE) != e->state) {
+          } else if (W32(a.o32 + E32_STATE) != e->state) {
             const uint32_t st = e->state;
-            S32(a.o32 + E32_STATE) = st;
+            W32(a.o32 + E32_STATE) = st;
             src = qk_log<LOG, SM>(cx, a, target, SRC_SCH, QK_LOG_ENV_STATE, st, 0);
             rem = a.n_subs;
             ptr = QK_HOT_SB(target).subs_off;
@@ -447,14 +447,14 @@ __global__ void __launch_bounds__(qk_group_max_threads(G), 1) qk_group_kernel(co
         uint32_t initial_base = 0;
         for (uint32_t i = 0; i < n_comp; ++i) {
           const DevComp* c = &cx.comps[i];
-          if (c->o64_ttnpe != 0xFFFF) S64(c->o64_ttnpe) = QK_TIME_NONE;
+          if (c->o64_ttnpe != 0xFFFF) W64(c->o64_ttnpe) = QK_TIME_NONE;
           if (c->o64_nextdur != 0xFFFF) {
-            S64(c->o64_nextdur) = QK_DUR_EMPTY;
+            W64(c->o64_nextdur) = QK_DUR_EMPTY;
             S32(cx.pf32 + (c->pf_idx >> 5)) |= 1u << (c->pf_idx & 31);
           }
           /* DelayModes::modify(Add) samples until_delay when the mode is added (delays.rs:159-164) */
           for (int k = 0; k < c->n_dm && !cx.status; ++k)
-            S64(c->o64_dm + k) = qk_sample_duration<SM>(cx, cx.dms[c->dm_off + k].until_delay);
+            W64(c->o64_dm + k) = qk_sample_duration<SM>(cx, cx.dms[c->dm_off + k].until_delay);
           if (c->kind == QK_DISCRETE_STOCK) {
             const uint32_t n_init = c->dist_time; /* with_initial_resource: the count rides in DevComp.dist_time */
             for (uint32_t k = 0; k < n_init; ++k) C32(c->ocold32 + k) = (63u << 26) | (initial_base + k);
@@ -468,14 +468,14 @@ __global__ void __launch_bounds__(qk_group_max_threads(G), 1) qk_group_kernel(co
             cx.gs32[(size_t)(i * ST_PER_COMP + ST32_MAXOCC) * P.rep_pad] = n_init;
             cx.gs64[(size_t)(i * ST_PER_COMP + ST64_TIME) * P.rep_pad] = 0ull - (uint64_t)n_init * P.t0;
           } else if (c->kind == QK_ENVIRONMENT) {
-            S32(c->o32 + E32_STATE) = c->low; /* initial state rides in `low` */
+            W32(c->o32 + E32_STATE) = c->low; /* initial state rides in `low` */
           } else if (c->kind == QK_VECTOR_STOCK) {
             const DevVec* v = &cx.vecs[c->vec_idx];
             qk_vstore<SM>(cx, v->o64_res, v->dim, v->vinit);
-            S64(v->o64_low) = QK_D2U(v->vlow);
-            S64(v->o64_last) = P.t0;
+            W64(v->o64_low) = QK_D2U(v->vlow);
+            W64(v->o64_last) = P.t0;
           } else if (FT != 0 && c->kind == QK_VECTOR_PROCESS && cx.vecs[c->vec_idx].o32_qty != 0xFFFF) {
-            S32(cx.vecs[c->vec_idx].o32_qty) = cx.vecs[c->vec_idx].dist_qty;
+            W32(cx.vecs[c->vec_idx].o32_qty) = cx.vecs[c->vec_idx].dist_qty;
           }
         }
       }
@@ -539,7 +539,7 @@ __global__ void __launch_bounds__(qk_group_max_threads(G), 1) qk_group_kernel(co
               m &= m - 1;
               if ((k++ % G) == j) {
                 const DevHotB b = QK_HOT_B(pf_comp[w * 32 + i]);
-                S64(b.o64_nextdur) = qk_sample_duration_code<SM>(cx, b.dist_time);
+                W64(b.o64_nextdur) = qk_sample_duration_code<SM>(cx, b.dist_time);
               }
             }
           }
@@ -755,14 +755,14 @@ __global__ void __launch_bounds__(qk_group_max_threads(G), 1) qk_phased_kernel(c
         uint32_t initial_base = 0;
         for (uint32_t i = 0; i < n_comp; ++i) {
           const DevComp* c = &cx.comps[i];
-          if (c->o64_ttnpe != 0xFFFF) S64(c->o64_ttnpe) = QK_TIME_NONE;
+          if (c->o64_ttnpe != 0xFFFF) W64(c->o64_ttnpe) = QK_TIME_NONE;
           if (c->o64_nextdur != 0xFFFF) {
-            S64(c->o64_nextdur) = QK_DUR_EMPTY;
+            W64(c->o64_nextdur) = QK_DUR_EMPTY;
             S32(cx.pf32 + (c->pf_idx >> 5)) |= 1u << (c->pf_idx & 31);
           }
           /* DelayModes::modify(Add) samples until_delay when the mode is added (delays.rs:159-164) */
           for (int k = 0; k < c->n_dm && !cx.status; ++k)
-            S64(c->o64_dm + k) = qk_sample_duration<SM>(cx, cx.dms[c->dm_off + k].until_delay);
+            W64(c->o64_dm + k) = qk_sample_duration<SM>(cx, cx.dms[c->dm_off + k].until_delay);
           if (c->kind == QK_DISCRETE_STOCK) {
             const uint32_t n_init = c->dist_time; /* with_initial_resource: the count rides in DevComp.dist_time */
             for (uint32_t k = 0; k < n_init; ++k) C32(c->ocold32 + k) = (63u << 26) | (initial_base + k);
@@ -776,14 +776,14 @@ __global__ void __launch_bounds__(qk_group_max_threads(G), 1) qk_phased_kernel(c
             cx.gs32[(size_t)(i * ST_PER_COMP + ST32_MAXOCC) * P.rep_pad] = n_init;
             cx.gs64[(size_t)(i * ST_PER_COMP + ST64_TIME) * P.rep_pad] = 0ull - (uint64_t)n_init * P.t0;
           } else if (c->kind == QK_ENVIRONMENT) {
-            S32(c->o32 + E32_STATE) = c->low; /* initial state rides in `low` */
+            W32(c->o32 + E32_STATE) = c->low; /* initial state rides in `low` */
           } else if (c->kind == QK_VECTOR_STOCK) {
             const DevVec* v = &cx.vecs[c->vec_idx];
             qk_vstore<SM>(cx, v->o64_res, v->dim, v->vinit);
-            S64(v->o64_low) = QK_D2U(v->vlow);
-            S64(v->o64_last) = P.t0;
+            W64(v->o64_low) = QK_D2U(v->vlow);
+            W64(v->o64_last) = P.t0;
           } else if (FT != 0 && c->kind == QK_VECTOR_PROCESS && cx.vecs[c->vec_idx].o32_qty != 0xFFFF) {
-            S32(cx.vecs[c->vec_idx].o32_qty) = cx.vecs[c->vec_idx].dist_qty;
+            W32(cx.vecs[c->vec_idx].o32_qty) = cx.vecs[c->vec_idx].dist_qty;
           }
         }
         rem = cx.hdr->n_init;

@@ -117,6 +117,22 @@ __device__ __forceinline__ auto qk_ix(uint32_t slot, uint32_t stride) {
 }
 #define S64(slot) (qk_p64<SM>(cx)[qk_ix<SM>((uint32_t)(slot), cx.stride)])
 #define S32(slot) (qk_p32<SM>(cx)[qk_ix<SM>((uint32_t)(slot), SM < 0 ? cx.stride32 : cx.stride)])
+/* component records ("warm" state: countdowns, flags, items, pre-drawn durations, draw counters, resources): hot-plane
+ * slots, except under the SPLIT placement (SM == QK_SM_SPLIT, DevHeader.split), where the lowering allocated them in the
+ * cold planes so that only the scheduler queue and the stocks' state words occupy shared memory */
+#define QK_SM_SPLIT (-2)
+template <int SM>
+__device__ __forceinline__ uint64_t& qk_w64(const Ctx& cx, uint32_t slot) {
+  if constexpr (SM == QK_SM_SPLIT) return cx.gc64[(uint64_t)slot * cx.rep_pad];
+  else return qk_p64<SM>(cx)[qk_ix<SM>(slot, cx.stride)];
+}
+template <int SM>
+__device__ __forceinline__ uint32_t& qk_w32(const Ctx& cx, uint32_t slot) {
+  if constexpr (SM == QK_SM_SPLIT) return cx.gc32[(uint64_t)slot * cx.rep_pad];
+  else return qk_p32<SM>(cx)[qk_ix<SM>(slot, SM < 0 ? cx.stride32 : cx.stride)];
+}
+#define W64(slot) (qk_w64<SM>(cx, (uint32_t)(slot)))
+#define W32(slot) (qk_w32<SM>(cx, (uint32_t)(slot)))
 /* cold state: always global memory, whatever the placement of the hot planes */
 #define C64(slot) (cx.gc64[(uint64_t)(uint32_t)(slot) * cx.rep_pad])
 #define C32(slot) (cx.gc32[(uint64_t)(uint32_t)(slot) * cx.rep_pad])
@@ -240,9 +256,9 @@ __device__ __forceinline__ QkDrawn qk_draw_for(Ctx& cx, uint32_t dist_id, uint32
   const bool constant = d->kind == QK_DIST_CONSTANT; /* has no draw counter */
   const double* tape = cx.tapes ? cx.tapes[dist_id] : nullptr;
   const QkDrawn r = qk_draw(d->kind, d->p[0], d->p[1], d->p[2], d->p[3], d->stream, cx.key0, cx.key1, cx.rep_lo, cx.rep_hi,
-                            constant ? 0u : S32(d->draw_slot), tape, tape ? cx.tape_len[dist_id] : 0ull, cx.rep_local,
+                            constant ? 0u : W32(d->draw_slot), tape, tape ? cx.tape_len[dist_id] : 0ull, cx.rep_local,
                             want_duration);
-  if (!constant) S32(d->draw_slot) = r.draws;
+  if (!constant) W32(d->draw_slot) = r.draws;
   return r;
 }
 
@@ -282,11 +298,17 @@ template <int SM>
 __device__ __forceinline__ bool qk_needs_refill_now(Ctx& cx, uint32_t comp) {
   const DevHotB b = QK_HOT_B(comp); /* stocks never appear in a call list */
   if (b.o64_nextdur == 0xFFFF) return false;
-  if (S64(b.o64_nextdur) != QK_DUR_EMPTY) return false;
+  if constexpr (SM == QK_SM_SPLIT) {
+    /* the component record is in global memory: ask the pending mask (a hot word) instead -- its bit is set exactly while
+     * the slot holds QK_DUR_EMPTY -- and do not look at the countdown at all.  Refilling a little early only changes WHEN
+     * a variate is drawn, never which one (every distribution instance has its own counter / tape position) */
+    return ((S32(cx.pf32 + (b.pf_idx >> 5)) >> (b.pf_idx & 31)) & 1u) != 0;
+  }
+  if (W64(b.o64_nextdur) != QK_DUR_EMPTY) return false;
   const DevHotA a = QK_HOT_A(comp);
-  const uint32_t flags = S32(a.o32 + P32_FLAGS);
+  const uint32_t flags = W32(a.o32 + P32_FLAGS);
   if (!(flags & PF_HAS_ITEM)) return true;
-  return S64(a.o64 + P64_LEFT) <= cx.now - S64(a.o64 + P64_PREV); /* finishes in this call, may restart */
+  return W64(a.o64 + P64_LEFT) <= cx.now - W64(a.o64 + P64_PREV); /* finishes in this call, may restart */
 }
 
 /* REFILL: every lane with consumed slots draws their next durations (Distribution::sample, common.rs:152-178) */
@@ -301,7 +323,7 @@ __device__ __forceinline__ void qk_refill(Ctx& cx) {
       const uint32_t i = (uint32_t)__ffs((int)m) - 1;
       m &= m - 1;
       const DevHotB b = QK_HOT_B(pf_comp[w * 32 + i]);
-      S64(b.o64_nextdur) = qk_sample_duration_code<SM>(cx, b.dist_time);
+      W64(b.o64_nextdur) = qk_sample_duration_code<SM>(cx, b.dist_time);
     }
   }
   cx.npend = 0;
@@ -482,7 +504,7 @@ __device__ __forceinline__ void qk_tick_delays(Ctx& cx, const DevHotA& c, const 
   int from = -1, to = -1;
   if (mask) {
     const int a = __ffs((int)mask) - 1; /* active_delay: first mode in TimeUntilFix, insertion order */
-    uint64_t dur = S64(cb.o64_dm + a);
+    uint64_t dur = W64(cb.o64_dm + a);
     const uint64_t applied = dt < dur ? dt : dur;
     QK_ST64_ADD(comp, ST64_DELAY, applied);
     dur -= applied;
@@ -491,22 +513,22 @@ __device__ __forceinline__ void qk_tick_delays(Ctx& cx, const DevHotA& c, const 
       if (cx.status) return;
       mask &= ~(1u << a);
     }
-    S64(cb.o64_dm + a) = dur;
+    W64(cb.o64_dm + a) = dur;
     from = a;
   } else {
     for (int k = 0; k < c.n_dm; ++k) {
-      const uint64_t dur = S64(cb.o64_dm + k);
-      S64(cb.o64_dm + k) = dur - (dt < dur ? dt : dur);
+      const uint64_t dur = W64(cb.o64_dm + k);
+      W64(cb.o64_dm + k) = dur - (dt < dur ? dt : dur);
     }
   }
   if (mask) {
     to = __ffs((int)mask) - 1;
   } else {
     for (int k = 0; k < c.n_dm; ++k) {
-      if (S64(cb.o64_dm + k) == 0) {
+      if (W64(cb.o64_dm + k) == 0) {
         const uint64_t dur = qk_sample_duration<SM>(cx, cx.dms[cb.dm_off + k].until_fix);
         if (cx.status) return;
-        S64(cb.o64_dm + k) = dur;
+        W64(cb.o64_dm + k) = dur;
         mask |= 1u << k;
         to = k;
         break;
@@ -525,7 +547,7 @@ __device__ __forceinline__ void qk_tick_delays(Ctx& cx, const DevHotA& c, const 
 template <bool LOG, int SM>
 __device__ __forceinline__ void qk_refresh_env(Ctx& cx, const DevHotA& c, int env, uint32_t comp, uint32_t* flags,
                                                uint64_t* src) {
-  const bool new_stopped = env >= 0 ? (S32(QK_HOT_SB(env).o32 + E32_STATE) == 1u) : false;
+  const bool new_stopped = env >= 0 ? (W32(QK_HOT_SB(env).o32 + E32_STATE) == 1u) : false;
   const bool old_stopped = (*flags & PF_ENV_STOPPED) != 0;
   if (!old_stopped && new_stopped) {
     *src = qk_log<LOG, SM>(cx, c, comp, *src, QK_LOG_PROCESS_STOPPED, QK_REASON_STOPPED_BY_ENV, 0);
@@ -602,7 +624,7 @@ template <int SM>
 __device__ __forceinline__ uint32_t qk_dm_quick(Ctx& cx, const DevSubQ& q, uint32_t comp, uint64_t now, uint32_t* reason,
                                                 uint64_t* dt_out) {
   const DevHotA a = QK_HOT_A(comp);
-  const uint32_t flags = S32(a.o32 + P32_FLAGS);
+  const uint32_t flags = W32(a.o32 + P32_FLAGS);
   const uint64_t fire = S64(q.fire_slot);
   if (flags & ~PF_HAS_ITEM) return 0u; /* a mode in TimeUntilFix (or environment-stopped) */
   if (!(flags & PF_HAS_ITEM)) {
@@ -617,12 +639,12 @@ __device__ __forceinline__ uint32_t qk_dm_quick(Ctx& cx, const DevSubQ& q, uint3
     return 1u;
   }
   if (a.kind == QK_DISCRETE_SINK || fire == QK_TIME_NONE || fire <= now) return 0u;
-  const uint64_t prev = S64(a.o64 + P64_PREV), left = S64(a.o64 + P64_LEFT);
+  const uint64_t prev = W64(a.o64 + P64_PREV), left = W64(a.o64 + P64_LEFT);
   if (prev + left < fire) return 0u; /* post_update_state would move the keyed event */
   const uint64_t dt = now - prev;
   const DevHotB b = QK_HOT_B(comp);
   for (uint32_t k = 0; k < a.n_dm; ++k)
-    if (S64(b.o64_dm + k) <= dt) return 0u; /* a breakdown starts in this call */
+    if (W64(b.o64_dm + k) <= dt) return 0u; /* a breakdown starts in this call */
   *dt_out = dt;
   return 2u;
 }
@@ -630,9 +652,9 @@ template <int SM>
 __device__ __forceinline__ void qk_dm_apply(Ctx& cx, uint32_t comp, uint64_t now, uint64_t dt) {
   const DevHotA a = QK_HOT_A(comp);
   const DevHotB b = QK_HOT_B(comp);
-  for (uint32_t k = 0; k < a.n_dm; ++k) S64(b.o64_dm + k) -= dt;
-  S64(a.o64 + P64_LEFT) -= dt;
-  S64(a.o64 + P64_PREV) = now;
+  for (uint32_t k = 0; k < a.n_dm; ++k) W64(b.o64_dm + k) -= dt;
+  W64(a.o64 + P64_LEFT) -= dt;
+  W64(a.o64 + P64_PREV) = now;
 #ifdef QK_HOST_EMUL
   qk_emul_count(0); /* the CPU suite checks that its delay-mode models actually take this path */
 #endif
@@ -675,14 +697,14 @@ __device__ __forceinline__ bool qk_try_quick(Ctx& cx, uint32_t ptr, uint64_t src
   if (fire != QK_TIME_NONE) {
 #ifdef QK_HOST_EMUL
     const DevHotA c = QK_HOT_A(cx.subs[ptr]);
-    if (fire > cx.now && (!(S32(c.o32 + P32_FLAGS) & PF_HAS_ITEM) ||
-                          S64(c.o64 + P64_PREV) + S64(c.o64 + P64_LEFT) != fire))
+    if (fire > cx.now && (!(W32(c.o32 + P32_FLAGS) & PF_HAS_ITEM) ||
+                          W64(c.o64 + P64_PREV) + W64(c.o64 + P64_LEFT) != fire))
       cx.status = 98; /* invariant check, CPU test build only */
 #endif
     return fire > cx.now; /* busy and not due: nothing to do ; due (<= now): pre_update_state drops the handle (Q3) */
   }
 #ifdef QK_HOST_EMUL
-  if (S32(QK_HOT_A(cx.subs[ptr]).o32 + P32_FLAGS) & PF_HAS_ITEM) cx.status = 98;
+  if (W32(QK_HOT_A(cx.subs[ptr]).o32 + P32_FLAGS) & PF_HAS_ITEM) cx.status = 98;
 #endif
   /* idle: quick only if it stays idle */
   if constexpr (!EAGER) {
@@ -709,9 +731,9 @@ template <bool LOG, int SM, int FT>
 __device__ __forceinline__ bool qk_update_single(Ctx& cx, const DevHotA& c, uint32_t comp, uint64_t src) {
   const DevHotB cb = QK_HOT_B(comp);
   const uint32_t kind = c.kind;
-  uint32_t flags = S32(c.o32 + P32_FLAGS);
-  uint64_t left = S64(c.o64 + P64_LEFT);
-  const uint64_t dt = cx.now - S64(c.o64 + P64_PREV);
+  uint32_t flags = W32(c.o32 + P32_FLAGS);
+  uint64_t left = W64(c.o64 + P64_LEFT);
+  const uint64_t dt = cx.now - W64(c.o64 + P64_PREV);
   uint64_t ttnpe = QK_TIME_NONE;
   /* Vector3ContainerProcess / Source / Sink (core.rs:550-553): the item carries a resource, kept at cold64 `opay` */
   const bool ctr = FT >= 2 && (c.flags & DC_CONTAINER) != 0;
@@ -726,7 +748,7 @@ __device__ __forceinline__ bool qk_update_single(Ctx& cx, const DevHotA& c, uint
       left -= (dt < left ? dt : left); /* saturating_sub */
       if (left == 0) {
         flags &= ~PF_HAS_ITEM;
-        const uint32_t item = S32(c.o32 + P32_ITEM);
+        const uint32_t item = W32(c.o32 + P32_ITEM);
         src = qk_log<LOG, SM>(cx, c, comp, src, QK_LOG_PROCESS_FINISH, 0, item);
         if (ctr) {
           pay[0] = C64(opay);
@@ -771,20 +793,20 @@ __device__ __forceinline__ bool qk_update_single(Ctx& cx, const DevHotA& c, uint
         const DevHotC cc = QK_HOT_C(comp);
         uint64_t d;
         if (cb.o64_nextdur != 0xFFFF) {
-          d = S64(cb.o64_nextdur);
-          S64(cb.o64_nextdur) = QK_DUR_EMPTY;
+          d = W64(cb.o64_nextdur);
+          W64(cb.o64_nextdur) = QK_DUR_EMPTY;
           S32(cx.pf32 + (cb.pf_idx >> 5)) |= 1u << (cb.pf_idx & 31);
           cx.npend += 1;
         } else {
           d = ((uint64_t)cc.const_dur_hi << 32) | cc.const_dur_lo;
         }
         if (!need_us) { /* ItemFactory::create_item discrete.rs:680-686 */
-          const uint32_t idx = S32(cc.o32_next_item);
+          const uint32_t idx = W32(cc.o32_next_item);
           if (idx > 0x3FFFFFFu) {
             cx.status = QK_REP_ITEM_INDEX_OVERFLOW;
             return true;
           }
-          S32(cc.o32_next_item) = idx + 1;
+          W32(cc.o32_next_item) = idx + 1;
           item = ((uint32_t)c.src_ord << 26) | idx;
           if (ctr) { /* Vector3ContainerFactory::create_item (vector_container.rs:136-156) */
             const DevVec* v = &cx.vecs[cc.vec_idx];
@@ -803,7 +825,7 @@ __device__ __forceinline__ bool qk_update_single(Ctx& cx, const DevHotA& c, uint
         }
         left = d;
         flags |= PF_HAS_ITEM;
-        S32(c.o32 + P32_ITEM) = item;
+        W32(c.o32 + P32_ITEM) = item;
         QK_ST64_ADD(comp, ST64_TIME, d);
         src = qk_log<LOG, SM>(cx, c, comp, src, QK_LOG_PROCESS_START, 0, item);
         if (ctr) {
@@ -830,17 +852,17 @@ __device__ __forceinline__ bool qk_update_single(Ctx& cx, const DevHotA& c, uint
     }
   } else if (kind == QK_DISCRETE_SINK) {
     /* (Some, _) leaves ttnpe untouched (discrete.rs:1127-1129); (_, true) clears it (Q2, :1130-1132) */
-    ttnpe = has_item ? S64(QK_HOT_C(comp).o64_ttnpe) : QK_TIME_NONE;
+    ttnpe = has_item ? W64(QK_HOT_C(comp).o64_ttnpe) : QK_TIME_NONE;
   } else if (has_item && (!has_active_delay || kind == QK_DISCRETE_SOURCE)) {
     ttnpe = left; /* Process (Some,false) :518-520 ; Source (Some,_) :874-876 */
   } else {
-    ttnpe = fixmask ? S64(cb.o64_dm + (__ffs((int)fixmask) - 1)) : QK_TIME_NONE; /* (_, true) :521-523 */
+    ttnpe = fixmask ? W64(cb.o64_dm + (__ffs((int)fixmask) - 1)) : QK_TIME_NONE; /* (_, true) :521-523 */
   }
-  if (kind == QK_DISCRETE_SINK) S64(QK_HOT_C(comp).o64_ttnpe) = ttnpe;
-  S32(c.o32 + P32_FLAGS) = flags;
-  S64(c.o64 + P64_LEFT) = left;
+  if (kind == QK_DISCRETE_SINK) W64(QK_HOT_C(comp).o64_ttnpe) = ttnpe;
+  W32(c.o32 + P32_FLAGS) = flags;
+  W64(c.o64 + P64_LEFT) = left;
   const bool fault = qk_post<LOG, SM, FT == 0>(cx, c, ttnpe, src);
-  S64(c.o64 + P64_PREV) = cx.now;
+  W64(c.o64 + P64_PREV) = cx.now;
   return fault;
 }
 
@@ -860,15 +882,15 @@ __device__ __forceinline__ void qk_update_multi(Ctx& cx, const DevComp* c, uint3
   const bool ctr = FT >= 2 && (c->flags & DC_CONTAINER) != 0;
   const bool is_load = FT >= 2 && kind == QK_CONTAINER_LOAD_PROCESS;
   const bool is_unload = FT >= 2 && kind == QK_CONTAINER_UNLOAD_PROCESS;
-  uint32_t flags = S32(c->o32 + PP32_FLAGS);
-  const uint64_t dt = cx.now - S64(c->o64 + PP64_PREV);
+  uint32_t flags = W32(c->o32 + PP32_FLAGS);
+  const uint64_t dt = cx.now - W64(c->o64 + PP64_PREV);
   const uint32_t cap = c->ring_cap;
   const uint32_t dur0 = c->o64_dm + c->n_dm;
   const uint32_t item0 = c->o32 + PP32_BASE_COUNT;
   const uint32_t comp0 = item0 + cap;
   const uint32_t pay0 = c->ocold64, cpay0 = c->ocold64 + 3u * cap; /* container payloads: in progress / complete ring */
-  uint32_t nprog = S32(c->o32 + PP32_NPROG);
-  uint32_t cq = S32(c->o32 + PP32_COMPLETE);
+  uint32_t nprog = W32(c->o32 + PP32_NPROG);
+  uint32_t cq = W32(c->o32 + PP32_COMPLETE);
   uint32_t chead = cq & 0xFFFFu, ccnt = cq >> 16;
   uint64_t pay[3];
   {
@@ -878,8 +900,8 @@ __device__ __forceinline__ void qk_update_multi(Ctx& cx, const DevComp* c, uint3
     if (!(is_in_delay || is_env_blocked)) {
       uint32_t w = 0;
       for (uint32_t i = 0; i < nprog; ++i) { /* retain_mut discrete.rs:1298-1306 */
-        uint64_t d = S64(dur0 + i);
-        const uint32_t it = S32(item0 + i);
+        uint64_t d = W64(dur0 + i);
+        const uint32_t it = W32(item0 + i);
         d -= (dt < d ? dt : d);
         if (d == 0) {
           if (ccnt >= cap) {
@@ -888,13 +910,13 @@ __device__ __forceinline__ void qk_update_multi(Ctx& cx, const DevComp* c, uint3
           }
           uint32_t pos = chead + ccnt;
           if (pos >= cap) pos -= cap;
-          S32(comp0 + pos) = it;
+          W32(comp0 + pos) = it;
           if (ctr)
             for (uint32_t k = 0; k < 3; ++k) C64(cpay0 + 3u * pos + k) = C64(pay0 + 3u * i + k);
           ccnt += 1;
         } else {
-          S64(dur0 + w) = d;
-          S32(item0 + w) = it;
+          W64(dur0 + w) = d;
+          W32(item0 + w) = it;
           if (ctr && w != i)
             for (uint32_t k = 0; k < 3; ++k) C64(pay0 + 3u * w + k) = C64(pay0 + 3u * i + k);
           w += 1;
@@ -902,7 +924,7 @@ __device__ __forceinline__ void qk_update_multi(Ctx& cx, const DevComp* c, uint3
       }
       nprog = w;
       while (ccnt) { /* discrete.rs:1311-1327 -- the popped item is lost when downstream does not accept it */
-        const uint32_t it = S32(comp0 + chead);
+        const uint32_t it = W32(comp0 + chead);
         if (ctr)
           for (uint32_t k = 0; k < 3; ++k) pay[k] = C64(cpay0 + 3u * chead + k);
         chead += 1;
@@ -999,8 +1021,8 @@ __device__ __forceinline__ void qk_update_multi(Ctx& cx, const DevComp* c, uint3
           cx.status = QK_REP_PARALLEL_OVERFLOW;
           return;
         }
-        S64(dur0 + nprog) = d;
-        S32(item0 + nprog) = it;
+        W64(dur0 + nprog) = d;
+        W32(item0 + nprog) = it;
         if (ctr)
           for (uint32_t k = 0; k < 3; ++k) C64(pay0 + 3u * nprog + k) = pay[k];
         nprog += 1;
@@ -1020,15 +1042,15 @@ __device__ __forceinline__ void qk_update_multi(Ctx& cx, const DevComp* c, uint3
       }
     }
     for (uint32_t i = 0; i < nprog; ++i) { /* discrete.rs:1400-1406 */
-      const uint64_t d = S64(dur0 + i);
+      const uint64_t d = W64(dur0 + i);
       if (d < ttnpe) ttnpe = d;
     }
   }
-  S32(c->o32 + PP32_FLAGS) = flags;
-  S32(c->o32 + PP32_NPROG) = nprog;
-  S32(c->o32 + PP32_COMPLETE) = chead | (ccnt << 16);
+  W32(c->o32 + PP32_FLAGS) = flags;
+  W32(c->o32 + PP32_NPROG) = nprog;
+  W32(c->o32 + PP32_COMPLETE) = chead | (ccnt << 16);
   qk_post<LOG, SM>(cx, ha, ttnpe, src);
-  S64(c->o64 + PP64_PREV) = cx.now;
+  W64(c->o64 + PP64_PREV) = cx.now;
 }
 
 
@@ -1044,7 +1066,7 @@ __device__ __forceinline__ bool qk_update_state(Ctx& cx, uint32_t comp, uint64_t
   if constexpr (FT != 0) {
     const DevComp* c = &cx.comps[comp];
     if (a.kind == QK_ENVIRONMENT) { /* only reached from the init list: BasicEnvironment::init logs its state */
-      qk_log<LOG, SM>(cx, a, comp, src, QK_LOG_ENV_STATE, S32(a.o32 + E32_STATE), 0);
+      qk_log<LOG, SM>(cx, a, comp, src, QK_LOG_ENV_STATE, W32(a.o32 + E32_STATE), 0);
       return cx.status != 0;
     }
     if (a.kind >= QK_VECTOR_PROCESS && a.kind <= QK_VECTOR_SPLITTER) {
@@ -1082,7 +1104,8 @@ constexpr int qk_lb_threads(int sm) { return sm > 0 ? sm : QK_MAX_NT; }
 #endif
 constexpr int qk_lb_resident(int ft, bool log) { return ft == 0 ? (log ? QK_LEAN_THREADS_LOG : QK_LEAN_THREADS) : 512; }
 constexpr int qk_lb_blocks(int sm, int ft, bool log) {
-  return sm > 0 ? (qk_lb_resident(ft, log) / sm > 0 ? qk_lb_resident(ft, log) / sm : 1) : (ft == 0 ? 3 : 2);
+  /* split placement: shared memory holds at most ~240 replications per SM, so registers are not what limits residency */
+  return sm == QK_SM_SPLIT ? 1 : sm > 0 ? (qk_lb_resident(ft, log) / sm > 0 ? qk_lb_resident(ft, log) / sm : 1) : (ft == 0 ? 3 : 2);
 }
 /* FT = feature set of the model: 0 = only SIMPLE single-server discrete components and stocks (no delay modes, no
  * environment, no scheduled events, no parallel or vector components): the handlers for everything else are
@@ -1168,14 +1191,14 @@ __global__ void __launch_bounds__(qk_lb_threads(SM), qk_lb_blocks(SM, FT, LOG)) 
       uint32_t initial_base = 0;
       for (uint32_t i = 0; i < n_comp; ++i) {
         const DevComp* c = &cx.comps[i];
-        if (c->o64_ttnpe != 0xFFFF) S64(c->o64_ttnpe) = QK_TIME_NONE;
+        if (c->o64_ttnpe != 0xFFFF) W64(c->o64_ttnpe) = QK_TIME_NONE;
         if (c->o64_nextdur != 0xFFFF) {
-          S64(c->o64_nextdur) = QK_DUR_EMPTY;
+          W64(c->o64_nextdur) = QK_DUR_EMPTY;
           S32(cx.pf32 + (c->pf_idx >> 5)) |= 1u << (c->pf_idx & 31);
         }
         /* DelayModes::modify(Add) samples until_delay when the mode is added (delays.rs:159-164) */
         for (int k = 0; k < c->n_dm && !cx.status; ++k)
-          S64(c->o64_dm + k) = qk_sample_duration<SM>(cx, cx.dms[c->dm_off + k].until_delay);
+          W64(c->o64_dm + k) = qk_sample_duration<SM>(cx, cx.dms[c->dm_off + k].until_delay);
         if (c->kind == QK_DISCRETE_STOCK) {
           /* with_initial_resource: the count rides in DevComp.dist_time (unused for stocks) */
           const uint32_t n_init = c->dist_time;
@@ -1190,14 +1213,14 @@ __global__ void __launch_bounds__(qk_lb_threads(SM), qk_lb_blocks(SM, FT, LOG)) 
           cx.gs32[(size_t)(i * ST_PER_COMP + ST32_MAXOCC) * P.rep_pad] = n_init;
           cx.gs64[(size_t)(i * ST_PER_COMP + ST64_TIME) * P.rep_pad] = 0ull - (uint64_t)n_init * P.t0;
         } else if (c->kind == QK_ENVIRONMENT) {
-          S32(c->o32 + E32_STATE) = c->low; /* initial state rides in `low` */
+          W32(c->o32 + E32_STATE) = c->low; /* initial state rides in `low` */
         } else if (c->kind == QK_VECTOR_STOCK) {
           const DevVec* v = &cx.vecs[c->vec_idx];
           qk_vstore<SM>(cx, v->o64_res, v->dim, v->vinit);
-          S64(v->o64_low) = QK_D2U(v->vlow);
-          S64(v->o64_last) = P.t0;
+          W64(v->o64_low) = QK_D2U(v->vlow);
+          W64(v->o64_last) = P.t0;
         } else if (FT != 0 && c->kind == QK_VECTOR_PROCESS && cx.vecs[c->vec_idx].o32_qty != 0xFFFF) {
-          S32(cx.vecs[c->vec_idx].o32_qty) = cx.vecs[c->vec_idx].dist_qty;
+          W32(cx.vecs[c->vec_idx].o32_qty) = cx.vecs[c->vec_idx].dist_qty;
         }
       }
     }
@@ -1345,20 +1368,20 @@ __global__ void __launch_bounds__(qk_lb_threads(SM), qk_lb_blocks(SM, FT, LOG)) 
             const DevHotA a = QK_HOT_A(target);
             if (e->type == 1) {
               /* SetLowCapacity on an F64Stock: with_low_capacity_inplace, then add((0., SCH_000000)) (core.rs:1382-1386) */
-              S64(cx.vecs[cx.comps[target].vec_idx].o64_low) = QK_D2U(e->value);
+              W64(cx.vecs[cx.comps[target].vec_idx].o64_low) = QK_D2U(e->value);
               const double zero[3] = {0.0, 0.0, 0.0};
               qk_vstock_add<LOG, SM>(cx, target, zero, SRC_SCH);
               if (cx.status) done = true;
             } else if (e->type == 2) {
               /* SetProcessQuantity on an F64Process: with_process_quantity_distr_inplace(instance), then
                * update_state(SCH_000000) (core.rs:1389-1390) */
-              S32(cx.vecs[cx.comps[target].vec_idx].o32_qty) = e->state;
+              W32(cx.vecs[cx.comps[target].vec_idx].o32_qty) = e->state;
               src = SRC_SCH;
               rem = 1;
               ptr = ident_off + target;
-            } else if (S32(a.o32 + E32_STATE) != e->state) {
+            } else if (W32(a.o32 + E32_STATE) != e->state) {
               const uint32_t st = e->state;
-              S32(a.o32 + E32_STATE) = st;
+              W32(a.o32 + E32_STATE) = st;
               src = qk_log<LOG, SM>(cx, a, target, SRC_SCH, QK_LOG_ENV_STATE, st, 0);
               rem = a.n_subs;
               ptr = QK_HOT_SB(target).subs_off;
@@ -1485,12 +1508,16 @@ __device__ __forceinline__ uint64_t qk_left_at_clock(uint32_t flags, uint64_t le
   return left - (dt < left ? dt : left);
 }
 
-/* per-replication (count, time_ns, aux, level) of component c, from the HBM state planes */
+/* per-replication (count, time_ns, aux, level) of component c, from the HBM state planes; w64 / w32 = the planes the
+ * component records live in (the hot planes, or the cold ones under the split placement: DevHeader.split) */
 __device__ __forceinline__ void qk_comp_stats_dev(const DevComp* c, const DevVec* vecs, uint32_t comp, const uint64_t* g64,
-                                                  const uint32_t* g32, const uint64_t* gs64, const uint32_t* gs32,
+                                                  const uint32_t* g32, const uint64_t* w64, const uint32_t* w32,
+                                                  const uint64_t* gs64, const uint32_t* gs32,
                                                   uint64_t rep_pad, uint64_t rep, qk_comp_stats* o) {
 #define G64(slot) g64[(size_t)(slot)*rep_pad + rep]
 #define G32(slot) g32[(size_t)(slot)*rep_pad + rep]
+#define WG64(slot) w64[(size_t)(slot)*rep_pad + rep]
+#define WG32(slot) w32[(size_t)(slot)*rep_pad + rep]
 #define GS64(k) gs64[(size_t)(comp * ST_PER_COMP + (k)) * rep_pad + rep]
 #define GS32(k) gs32[(size_t)(comp * ST_PER_COMP + (k)) * rep_pad + rep]
   const uint64_t now = G64(G64_NOW);
@@ -1498,33 +1525,33 @@ __device__ __forceinline__ void qk_comp_stats_dev(const DevComp* c, const DevVec
   o->faux = 0.0;
   if (c->kind == QK_VECTOR_STOCK) {
     const DevVec* v = &vecs[c->vec_idx];
-    double r[3] = {QK_U2D(G64(v->o64_res)), 0.0, 0.0};
+    double r[3] = {QK_U2D(WG64(v->o64_res)), 0.0, 0.0};
     if (v->dim == 3) {
-      r[1] = QK_U2D(G64(v->o64_res + 1));
-      r[2] = QK_U2D(G64(v->o64_res + 2));
+      r[1] = QK_U2D(WG64(v->o64_res + 1));
+      r[2] = QK_U2D(WG64(v->o64_res + 2));
     }
     const double total = qk_vtotal(r, v->dim);
     o->count = GS32(ST32_COUNT);
     o->time_ns = 0;
     o->aux = 0;
-    o->level = qk_vcat(total, QK_U2D(G64(v->o64_low)), v->vmax);
+    o->level = qk_vcat(total, QK_U2D(WG64(v->o64_low)), v->vmax);
     o->fvalue = total;
-    o->faux = __dadd_rn(QK_U2D(GS64(ST64_TIME)), __dmul_rn(total, __dmul_rn((double)(now - G64(v->o64_last)), 1e-9)));
+    o->faux = __dadd_rn(QK_U2D(GS64(ST64_TIME)), __dmul_rn(total, __dmul_rn((double)(now - WG64(v->o64_last)), 1e-9)));
   } else if (c->kind >= QK_VECTOR_PROCESS && c->kind <= QK_VECTOR_SPLITTER) {
     const DevVec* v = &vecs[c->vec_idx];
-    const uint32_t flags = G32(c->o32 + P32_FLAGS);
+    const uint32_t flags = WG32(c->o32 + P32_FLAGS);
     const bool has = flags & PF_HAS_ITEM;
-    double r[3] = {QK_U2D(G64(v->o64_res)), 0.0, 0.0};
+    double r[3] = {QK_U2D(WG64(v->o64_res)), 0.0, 0.0};
     if (v->dim == 3) {
-      r[1] = QK_U2D(G64(v->o64_res + 1));
-      r[2] = QK_U2D(G64(v->o64_res + 2));
+      r[1] = QK_U2D(WG64(v->o64_res + 1));
+      r[2] = QK_U2D(WG64(v->o64_res + 2));
     }
     o->count = GS32(ST32_COUNT);
-    o->time_ns = GS64(ST64_TIME) - (has ? qk_left_at_clock(flags, G64(c->o64 + P64_LEFT), now - G64(c->o64 + P64_PREV)) : 0);
+    o->time_ns = GS64(ST64_TIME) - (has ? qk_left_at_clock(flags, WG64(c->o64 + P64_LEFT), now - WG64(c->o64 + P64_PREV)) : 0);
     o->aux = GS64(ST64_DELAY);
     o->level = has ? 1 : 0;
     o->fvalue = QK_U2D(GS64(ST64_FQ));
-    o->faux = !has ? 0.0 : (c->kind == QK_VECTOR_COMBINER ? QK_U2D(G64(v->o64_res + v->dim)) : qk_vtotal(r, v->dim));
+    o->faux = !has ? 0.0 : (c->kind == QK_VECTOR_COMBINER ? QK_U2D(WG64(v->o64_res + v->dim)) : qk_vtotal(r, v->dim));
   } else if (c->kind == QK_DISCRETE_STOCK) {
     const uint32_t cnt = QK_HC_CNT(G32(c->o32 + S32_HC));
     o->count = GS32(ST32_COUNT);
@@ -1533,11 +1560,11 @@ __device__ __forceinline__ void qk_comp_stats_dev(const DevComp* c, const DevVec
     o->level = cnt;
   } else if (c->kind == QK_DISCRETE_PARALLEL_PROCESS || c->kind == QK_CONTAINER_LOAD_PROCESS ||
              c->kind == QK_CONTAINER_UNLOAD_PROCESS) {
-    const uint32_t nprog = G32(c->o32 + PP32_NPROG);
-    const uint32_t pflags = G32(c->o32 + PP32_FLAGS);
-    const uint64_t pdt = now - G64(c->o64 + PP64_PREV);
+    const uint32_t nprog = WG32(c->o32 + PP32_NPROG);
+    const uint32_t pflags = WG32(c->o32 + PP32_FLAGS);
+    const uint64_t pdt = now - WG64(c->o64 + PP64_PREV);
     uint64_t busy = GS64(ST64_TIME);
-    for (uint32_t i = 0; i < nprog; ++i) busy -= qk_left_at_clock(pflags, G64(c->o64_dm + c->n_dm + i), pdt);
+    for (uint32_t i = 0; i < nprog; ++i) busy -= qk_left_at_clock(pflags, WG64(c->o64_dm + c->n_dm + i), pdt);
     o->count = GS32(ST32_COUNT);
     o->time_ns = busy;
     o->aux = GS64(ST64_DELAY);
@@ -1546,15 +1573,17 @@ __device__ __forceinline__ void qk_comp_stats_dev(const DevComp* c, const DevVec
     o->count = 0;
     o->time_ns = 0;
     o->aux = 0;
-    o->level = G32(c->o32 + E32_STATE);
+    o->level = WG32(c->o32 + E32_STATE);
   } else {
-    const uint32_t flags = G32(c->o32 + P32_FLAGS);
+    const uint32_t flags = WG32(c->o32 + P32_FLAGS);
     const bool has = flags & PF_HAS_ITEM;
     o->count = GS32(ST32_COUNT);
-    o->time_ns = GS64(ST64_TIME) - (has ? qk_left_at_clock(flags, G64(c->o64 + P64_LEFT), now - G64(c->o64 + P64_PREV)) : 0);
+    o->time_ns = GS64(ST64_TIME) - (has ? qk_left_at_clock(flags, WG64(c->o64 + P64_LEFT), now - WG64(c->o64 + P64_PREV)) : 0);
     o->aux = GS64(ST64_DELAY);
     o->level = has ? 1 : 0;
   }
+#undef WG64
+#undef WG32
 #undef G64
 #undef G32
 #undef GS64

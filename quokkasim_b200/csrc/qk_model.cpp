@@ -508,7 +508,7 @@ int qk_model_n_dists(const qk_model* m, uint32_t* out) {
 int qk_model_state_bytes(const qk_model* m, int with_log, uint32_t* out) {
   if (!m || !out) return QK_ERR_INVALID_ARG;
   QkLowered l;
-  int rc = qk_lower(m, with_log != 0, &l);
+  int rc = qk_lower(m, with_log != 0, false, &l);
   if (rc) return rc;
   *out = l.hdr.n64 * 8 + l.hdr.n32 * 4;
   return QK_OK;
@@ -540,7 +540,7 @@ static uint64_t host_duration_code(double secs) {
   return (uint64_t)q;
 }
 
-int qk_lower(const qk_model* m, bool log, QkLowered* out) {
+int qk_lower(const qk_model* m, bool log, bool split, QkLowered* out) {
   const size_t nc = m->comps.size();
   if (nc == 0) {
     qk_set_error("qk_lower: model has no components");
@@ -588,6 +588,12 @@ int qk_lower(const qk_model* m, bool log, QkLowered* out) {
   uint32_t n64 = G64_FIRE0 + ((n_sched + 3u) & ~3u); /* fire[] padded to a multiple of four (scheduler scan) */
   const uint32_t pf32 = G32_STALE0 + n_stale_words;
   uint32_t n32 = pf32 + n_pf_words;
+  /* split placement (qk_batch_create, QK_BATCH_STATE_SPLIT): only what the scheduler pop and the quick path read stays in
+   * the hot planes -- the fire slots, the stocks' head|count and pending-emit words, the seq counters -- and every
+   * component record (countdowns, flags, items, pre-drawn durations, draw counters, resources) is allocated in the
+   * cold planes, i.e. lives in global memory only */
+  uint32_t& w64 = split ? n64c : n64;
+  uint32_t& w32 = split ? n32c : n32;
 
   /* capacities that depend on neighbours */
   std::vector<uint32_t> cap(nc, 0);
@@ -669,18 +675,18 @@ int qk_lower(const qk_model* m, bool log, QkLowered* out) {
 
     uint32_t kind = device_kind(c.d.kind);
     if (kind == QK_DISCRETE_PROCESS || kind == QK_DISCRETE_SOURCE || kind == QK_DISCRETE_SINK) {
-      d.o64 = (uint16_t)n64;
-      n64 += P64_BASE_COUNT;
-      if (kind == QK_DISCRETE_SINK) d.o64_ttnpe = (uint16_t)n64++;
-      d.o64_dm = (uint16_t)n64;
-      n64 += d.n_dm;
-      d.o32 = (uint16_t)n32;
-      n32 += P32_BASE_COUNT;
-      if (kind == QK_DISCRETE_SOURCE) d.o32_next_item = (uint16_t)n32++;
+      d.o64 = (uint16_t)w64;
+      w64 += P64_BASE_COUNT;
+      if (kind == QK_DISCRETE_SINK) d.o64_ttnpe = (uint16_t)w64++;
+      d.o64_dm = (uint16_t)w64;
+      w64 += d.n_dm;
+      d.o32 = (uint16_t)w32;
+      w32 += P32_BASE_COUNT;
+      if (kind == QK_DISCRETE_SOURCE) d.o32_next_item = (uint16_t)w32++;
       for (uint32_t k = 0; k < n_pf; ++k)
         if (pf_comp[k] == i) {
           d.pf_idx = (uint16_t)k;
-          d.o64_nextdur = (uint16_t)n64++;
+          d.o64_nextdur = (uint16_t)w64++;
         }
       if (is_ctr) {
         d.ocold64 = (uint16_t)n64c;
@@ -694,19 +700,19 @@ int qk_lower(const qk_model* m, bool log, QkLowered* out) {
           for (int k = 0; k < 5; ++k) v.ups[k] = v.downs[k] = -1;
           v.dist_qty = (uint16_t)(c.dist_cqty >= 0 ? c.dist_cqty : 0xFFFF); /* create_quantity_distr or None */
           if (c.dist_cqty >= 0 && m->dists[(size_t)c.dist_cqty].kind != QK_DIST_CONSTANT)
-            dd[(size_t)c.dist_cqty].draw_slot = n32++;
+            dd[(size_t)c.dist_cqty].draw_slot = w32++;
           d.vec_idx = (uint16_t)vecs.size();
           vecs.push_back(v);
         }
       }
     } else if (is_multi_server(kind)) {
-      d.o64 = (uint16_t)n64;
-      n64 += PP64_BASE_COUNT;
-      d.o64_dm = (uint16_t)n64;
-      n64 += d.n_dm;
-      n64 += d.ring_cap; /* in-progress durations */
-      d.o32 = (uint16_t)n32;
-      n32 += PP32_BASE_COUNT + 2u * d.ring_cap;
+      d.o64 = (uint16_t)w64;
+      w64 += PP64_BASE_COUNT;
+      d.o64_dm = (uint16_t)w64;
+      w64 += d.n_dm;
+      w64 += d.ring_cap; /* in-progress durations */
+      d.o32 = (uint16_t)w32;
+      w32 += PP32_BASE_COUNT + 2u * d.ring_cap;
       if (is_ctr) {
         d.ocold64 = (uint16_t)n64c;
         n64c += 6u * d.ring_cap; /* payload of the in-progress slots, then of the complete ring */
@@ -720,7 +726,7 @@ int qk_lower(const qk_model* m, bool log, QkLowered* out) {
           v.downs[k] = (int16_t)c.downs[k]; /* Unload: downs[0] = the Vector3Stock it pushes resource to */
         }
         v.dist_qty = (uint16_t)c.dist_qty; /* process_capacity_ratio_distr / process_quantity_ratio_distr */
-        if (m->dists[(size_t)c.dist_qty].kind != QK_DIST_CONSTANT) dd[(size_t)c.dist_qty].draw_slot = n32++;
+        if (m->dists[(size_t)c.dist_qty].kind != QK_DIST_CONSTANT) dd[(size_t)c.dist_qty].draw_slot = w32++;
         d.vec_idx = (uint16_t)vecs.size();
         vecs.push_back(v);
       }
@@ -753,11 +759,11 @@ int qk_lower(const qk_model* m, bool log, QkLowered* out) {
       v.vlow = c.vlow;
       for (int k = 0; k < 3; ++k) v.vinit[k] = c.vinit[k];
       for (int k = 0; k < 5; ++k) v.ups[k] = v.downs[k] = -1;
-      d.o64 = (uint16_t)n64;
-      v.o64_res = (uint16_t)n64;
-      n64 += c.dim;
-      v.o64_low = (uint16_t)n64++;
-      v.o64_last = (uint16_t)n64++;
+      d.o64 = (uint16_t)w64;
+      v.o64_res = (uint16_t)w64;
+      w64 += c.dim;
+      v.o64_low = (uint16_t)w64++;
+      v.o64_last = (uint16_t)w64++;
       d.o32 = (uint16_t)n32;
       n32 += S32_COUNT; /* S32_HC unused, S32_EMIT used */
       uint32_t depth = 0;
@@ -786,33 +792,33 @@ int qk_lower(const qk_model* m, bool log, QkLowered* out) {
       }
       v.dist_qty = (uint16_t)c.dist_qty;
       v.o32_qty = 0xFFFF;
-      d.o64 = (uint16_t)n64;
-      n64 += P64_BASE_COUNT;
-      d.o64_dm = (uint16_t)n64;
-      n64 += d.n_dm;
-      v.o64_res = (uint16_t)n64;
-      n64 += c.dim + (kind == QK_VECTOR_COMBINER ? 1u : 0u);
-      d.o32 = (uint16_t)n32;
-      n32 += P32_BASE_COUNT;
-      if (m->dists[(size_t)c.dist_qty].kind != QK_DIST_CONSTANT) dd[(size_t)c.dist_qty].draw_slot = n32++;
+      d.o64 = (uint16_t)w64;
+      w64 += P64_BASE_COUNT;
+      d.o64_dm = (uint16_t)w64;
+      w64 += d.n_dm;
+      v.o64_res = (uint16_t)w64;
+      w64 += c.dim + (kind == QK_VECTOR_COMBINER ? 1u : 0u);
+      d.o32 = (uint16_t)w32;
+      w32 += P32_BASE_COUNT;
+      if (m->dists[(size_t)c.dist_qty].kind != QK_DIST_CONSTANT) dd[(size_t)c.dist_qty].draw_slot = w32++;
       for (size_t k = 0; k < m->ext.size(); ++k) /* SetProcessQuantity events: the instance they bring, and where the
                                                     component keeps which instance is current */
         if (m->ext[k].type == 2 && m->ext[k].target == i) {
-          if (v.o32_qty == 0xFFFF) v.o32_qty = (uint16_t)n32++;
-          if (m->dists[m->ext[k].state].kind != QK_DIST_CONSTANT) dd[m->ext[k].state].draw_slot = n32++;
+          if (v.o32_qty == 0xFFFF) v.o32_qty = (uint16_t)w32++;
+          if (m->dists[m->ext[k].state].kind != QK_DIST_CONSTANT) dd[m->ext[k].state].draw_slot = w32++;
         }
       d.vec_idx = (uint16_t)vecs.size();
       vecs.push_back(v);
     } else { /* environment */
-      d.o32 = (uint16_t)n32;
-      n32 += E32_COUNT;
+      d.o32 = (uint16_t)w32;
+      w32 += E32_COUNT;
       d.low = c.d.initial_env_state ? 1u : 0u; /* table field reuse: initial BasicEnvironmentState */
     }
     if (qk_is_process_like(kind)) {
-      if (m->dists[(size_t)c.dist_time].kind != QK_DIST_CONSTANT) dd[(size_t)c.dist_time].draw_slot = n32++;
+      if (m->dists[(size_t)c.dist_time].kind != QK_DIST_CONSTANT) dd[(size_t)c.dist_time].draw_slot = w32++;
       for (size_t k = 0; k < c.dms.size(); ++k) {
-        if (m->dists[c.dms[k].until_delay].kind != QK_DIST_CONSTANT) dd[c.dms[k].until_delay].draw_slot = n32++;
-        if (m->dists[c.dms[k].until_fix].kind != QK_DIST_CONSTANT) dd[c.dms[k].until_fix].draw_slot = n32++;
+        if (m->dists[c.dms[k].until_delay].kind != QK_DIST_CONSTANT) dd[c.dms[k].until_delay].draw_slot = w32++;
+        if (m->dists[c.dms[k].until_fix].kind != QK_DIST_CONSTANT) dd[c.dms[k].until_fix].draw_slot = w32++;
       }
     }
     if (log) {
@@ -870,6 +876,7 @@ int qk_lower(const qk_model* m, bool log, QkLowered* out) {
   h.init_off = init_off;
   h.n_init = n_init;
   h.log_enabled = log ? 1 : 0;
+  h.split = split ? 1 : 0;
   uint32_t off = align8((uint32_t)sizeof(DevHeader));
   h.off_comps = off;
   off = align8(off + (uint32_t)(nc * sizeof(DevComp)));

@@ -45,7 +45,8 @@ struct QkLowered {
 
 void qk_set_error(const char* fmt, ...);
 int qk_is_process_like(uint32_t kind);
-/* lowers the model for the given logging mode; returns QK_OK or an error */
-int qk_lower(const qk_model* m, bool log, QkLowered* out);
+/* lowers the model for the given logging mode and state placement (split: component records in the cold planes, see
+ * qk_lower); returns QK_OK or an error */
+int qk_lower(const qk_model* m, bool log, bool split, QkLowered* out);
 
 #endif

@@ -23,6 +23,7 @@ static StepKernel qk_pick_step(uint32_t nt) {
     case 192: return qk_step_kernel<LOG, 192, FT>;
     case 224: return qk_step_kernel<LOG, 224, FT>;
     case 256: return qk_step_kernel<LOG, 256, FT>;
+    case 0xFFFFFFFEu: return qk_step_kernel<LOG, QK_SM_SPLIT, FT>; /* split placement, run-time block size */
     default: return qk_step_kernel<LOG, -1, FT>;
   }
 }

@@ -45,16 +45,16 @@ __device__ __forceinline__ double qk_vtotal(const double* v, uint32_t dim) {
 
 template <int SM>
 __device__ __forceinline__ void qk_vload(Ctx& cx, uint32_t slot, uint32_t dim, double* v) {
-  v[0] = QK_U2D(S64(slot));
-  v[1] = dim == 3 ? QK_U2D(S64(slot + 1)) : 0.0;
-  v[2] = dim == 3 ? QK_U2D(S64(slot + 2)) : 0.0;
+  v[0] = QK_U2D(W64(slot));
+  v[1] = dim == 3 ? QK_U2D(W64(slot + 1)) : 0.0;
+  v[2] = dim == 3 ? QK_U2D(W64(slot + 2)) : 0.0;
 }
 template <int SM>
 __device__ __forceinline__ void qk_vstore(Ctx& cx, uint32_t slot, uint32_t dim, const double* v) {
-  S64(slot) = QK_D2U(v[0]);
+  W64(slot) = QK_D2U(v[0]);
   if (dim == 3) {
-    S64(slot + 1) = QK_D2U(v[1]);
-    S64(slot + 2) = QK_D2U(v[2]);
+    W64(slot + 1) = QK_D2U(v[1]);
+    W64(slot + 2) = QK_D2U(v[2]);
   }
 }
 
@@ -103,7 +103,7 @@ __device__ __forceinline__ uint32_t qk_vstock_cat_of(Ctx& cx, int sidx) {
   const DevVec* v = &cx.vecs[c->vec_idx];
   double r[3];
   qk_vload<SM>(cx, v->o64_res, v->dim, r);
-  return qk_vcat(qk_vtotal(r, v->dim), QK_U2D(S64(v->o64_low)), v->vmax);
+  return qk_vcat(qk_vtotal(r, v->dim), QK_U2D(W64(v->o64_low)), v->vmax);
 }
 
 /* cx.schedule_event(now + 1ns, emit_change, (state, id)) -- the emit carries the state computed NOW */
@@ -136,10 +136,10 @@ __device__ __forceinline__ void qk_vemit_push(Ctx& cx, const DevComp* c, uint32_
 
 template <int SM>
 __device__ __forceinline__ void qk_vstock_area(Ctx& cx, uint32_t sidx, const DevVec* v, double total) {
-  const uint64_t last = S64(v->o64_last);
+  const uint64_t last = W64(v->o64_last);
   const double dt = __dmul_rn((double)(cx.now - last), 1e-9);
   qk_red_addf64(&cx.gs64[(size_t)(sidx * ST_PER_COMP + ST64_TIME) * cx.rep_pad], __dmul_rn(total, dt));
-  S64(v->o64_last) = cx.now;
+  W64(v->o64_last) = cx.now;
 }
 
 /* Stock::add (core.rs:177-183; vector.rs:110-135) */
@@ -151,7 +151,7 @@ __device__ __forceinline__ void qk_vstock_add(Ctx& cx, uint32_t sidx, const doub
   const uint32_t dim = v->dim;
   double r[3];
   qk_vload<SM>(cx, v->o64_res, dim, r);
-  const double low = QK_U2D(S64(v->o64_low));
+  const double low = QK_U2D(W64(v->o64_low));
   const double before = qk_vtotal(r, dim);
   const uint32_t prev = qk_vcat(before, low, v->vmax);
   qk_vstock_area<SM>(cx, sidx, v, before);
@@ -174,7 +174,7 @@ __device__ __forceinline__ void qk_vstock_remove(Ctx& cx, uint32_t sidx, double 
   const uint32_t dim = v->dim;
   double r[3];
   qk_vload<SM>(cx, v->o64_res, dim, r);
-  const double low = QK_U2D(S64(v->o64_low));
+  const double low = QK_U2D(W64(v->o64_low));
   const double before = qk_vtotal(r, dim);
   const uint32_t prev = qk_vcat(before, low, v->vmax);
   qk_vstock_area<SM>(cx, sidx, v, before);
@@ -190,10 +190,10 @@ __device__ __forceinline__ void qk_vstock_remove(Ctx& cx, uint32_t sidx, double 
 /* DelayModes::get_next_event (delays.rs:144-155): active fix, else the smallest time-until-delay */
 template <int SM>
 __device__ __forceinline__ uint64_t qk_dm_next_event(Ctx& cx, const DevComp* c, uint32_t fixmask) {
-  if (fixmask) return S64(c->o64_dm + (__ffs((int)fixmask) - 1));
+  if (fixmask) return W64(c->o64_dm + (__ffs((int)fixmask) - 1));
   uint64_t best = QK_TIME_NONE;
   for (int k = 0; k < c->n_dm; ++k) {
-    const uint64_t d = S64(c->o64_dm + k);
+    const uint64_t d = W64(c->o64_dm + k);
     if (d < best) best = d;
   }
   return best;
@@ -206,9 +206,9 @@ __device__ __forceinline__ void qk_update_vector(Ctx& cx, const DevComp* c, uint
   const DevHotB hb = QK_HOT_B(comp);
   const DevVec* v = &cx.vecs[c->vec_idx];
   const uint32_t kind = c->kind, dim = v->dim;
-  uint32_t flags = S32(c->o32 + P32_FLAGS);
-  uint64_t left = S64(c->o64 + P64_LEFT);
-  const uint64_t dt = cx.now - S64(c->o64 + P64_PREV);
+  uint32_t flags = W32(c->o32 + P32_FLAGS);
+  uint64_t left = W64(c->o64 + P64_LEFT);
+  const uint64_t dt = cx.now - W64(c->o64 + P64_PREV);
   uint64_t ttnpe = QK_TIME_NONE;
   {
     const bool is_in_delay = ((flags >> PF_FIX_SHIFT) & 0xFFu) != 0;
@@ -224,7 +224,7 @@ __device__ __forceinline__ void qk_update_vector(Ctx& cx, const DevComp* c, uint
         QK_ST32_ADD(comp, ST32_COUNT, 1u);
         if (kind == QK_VECTOR_COMBINER) {
           /* the running total and quantity were accumulated at CombineStart in the reference's order */
-          const double quantity = QK_U2D(S64(v->o64_res + dim));
+          const double quantity = QK_U2D(W64(v->o64_res + dim));
           src = qk_log<LOG, SM>(cx, ha, comp, src, QK_LOG_VPROC_COMBINE_SUCCESS, 0, QK_D2U(quantity));
           qk_log_vec<LOG, SM>(cx, c, comp, src, 0, r[0], r[1], r[2]);
           qk_red_addf64(&cx.gs64[(size_t)(comp * ST_PER_COMP + ST64_FQ) * cx.rep_pad], quantity);
@@ -254,7 +254,7 @@ __device__ __forceinline__ void qk_update_vector(Ctx& cx, const DevComp* c, uint
         if (cx.status) return;
         const double zero[3] = {0.0, 0.0, 0.0};
         qk_vstore<SM>(cx, v->o64_res, dim, zero);
-        if (kind == QK_VECTOR_COMBINER) S64(v->o64_res + dim) = 0;
+        if (kind == QK_VECTOR_COMBINER) W64(v->o64_res + dim) = 0;
       }
     }
     /* VectorSource ticks its delay modes even while the environment has stopped it (vector.rs:1444) */
@@ -321,7 +321,7 @@ __device__ __forceinline__ void qk_update_vector(Ctx& cx, const DevComp* c, uint
     }
     if (ok) {
       /* process_quantity_distr: the model's, or the instance the latest SetProcessQuantity event brought (core.rs:1387-1391) */
-      const double q = qk_sample<SM>(cx, v->o32_qty != 0xFFFF ? S32(v->o32_qty) : (uint32_t)v->dist_qty);
+      const double q = qk_sample<SM>(cx, v->o32_qty != 0xFFFF ? W32(v->o32_qty) : (uint32_t)v->dist_qty);
       if (cx.status) return;
       double got[5][3];
       uint32_t ngot = 1, start_kind = QK_LOG_VPROC_START;
@@ -361,7 +361,7 @@ __device__ __forceinline__ void qk_update_vector(Ctx& cx, const DevComp* c, uint
           qsum = __dadd_rn(qsum, qk_vtotal(got[i], dim));
         }
         qk_vstore<SM>(cx, v->o64_res, dim, total);
-        S64(v->o64_res + dim) = QK_D2U(qsum);
+        W64(v->o64_res + dim) = QK_D2U(qsum);
       } else {
         qk_vstore<SM>(cx, v->o64_res, dim, got[0]);
       }
@@ -376,7 +376,7 @@ __device__ __forceinline__ void qk_update_vector(Ctx& cx, const DevComp* c, uint
   } else if (has_item && !has_active_delay) {
     ttnpe = left;
   } else if (kind != QK_VECTOR_SINK) {
-    ttnpe = fixmask ? S64(c->o64_dm + (__ffs((int)fixmask) - 1)) : QK_TIME_NONE;
+    ttnpe = fixmask ? W64(c->o64_dm + (__ffs((int)fixmask) - 1)) : QK_TIME_NONE;
   }
   /* flags may have gained PF_HAS_ITEM above */
   const bool has_item2 = (flags & PF_HAS_ITEM) != 0;
@@ -391,10 +391,10 @@ __device__ __forceinline__ void qk_update_vector(Ctx& cx, const DevComp* c, uint
   } else {
     next = ttnpe < ttnde ? ttnpe : ttnde; /* min of those that exist (vector.rs:495) */
   }
-  S32(c->o32 + P32_FLAGS) = flags;
-  S64(c->o64 + P64_LEFT) = left;
+  W32(c->o32 + P32_FLAGS) = flags;
+  W64(c->o64 + P64_LEFT) = left;
   qk_post<LOG, SM>(cx, ha, next, src);
-  S64(c->o64 + P64_PREV) = cx.now;
+  W64(c->o64 + P64_PREV) = cx.now;
 }
 
 #endif

@@ -141,6 +141,7 @@ static int run(qk_batch* b, uint32_t do_init, uint64_t t0, uint64_t t_until, uin
   for (uint64_t r = 0; r < (n_tiles ? n_tiles : b->rep_pad); ++r) {
     qk_emul_bid = (uint32_t)r;
     const bool hbm = (b->cfg.flags & QK_BATCH_STATE_IN_HBM) != 0;
+    const bool split = (b->cfg.flags & QK_BATCH_STATE_SPLIT) != 0;
     /* the product picks FT = 0 only for on-chip state; here both state placements run both feature sets so the
      * CPU suite covers the lean kernel on every simple model */
     const uint32_t ft = b->low.hdr.features;
@@ -152,9 +153,11 @@ static int run(qk_batch* b, uint32_t do_init, uint64_t t0, uint64_t t_until, uin
   } while (0)
     if (b->log) {
       if (hbm) QK_EMUL_RUN(true, 0);
+      else if (split) QK_EMUL_RUN(true, QK_SM_SPLIT);
       else QK_EMUL_RUN(true, -1);
     } else {
       if (hbm) QK_EMUL_RUN(false, 0);
+      else if (split) QK_EMUL_RUN(false, QK_SM_SPLIT);
       else QK_EMUL_RUN(false, -1);
     }
   }
@@ -170,7 +173,7 @@ int qk_batch_create(const qk_model* m, const qk_batch_config* cfg, qk_batch** ou
   qk_batch* b = new qk_batch();
   b->cfg = *cfg;
   b->log = cfg->log_capacity != 0;
-  int rc = qk_lower(m, b->log, &b->low);
+  int rc = qk_lower(m, b->log, (cfg->flags & QK_BATCH_STATE_SPLIT) != 0, &b->low);
   if (rc) {
     delete b;
     return rc;
@@ -229,6 +232,7 @@ int qk_batch_info_get(qk_batch* b, qk_batch_info* out) {
   out->state_bytes_total = (uint64_t)(out->state_bytes_per_rep + out->cold_bytes_per_rep) * b->rep_pad;
   out->log_bytes_total = b->log ? (uint64_t)b->rep_pad * b->cfg.log_capacity * 32 : 0;
   out->state_in_hbm = (b->cfg.flags & QK_BATCH_STATE_IN_HBM) ? 1u : 0u;
+  out->state_split = (b->cfg.flags & QK_BATCH_STATE_SPLIT) ? 1u : 0u;
   out->lanes_per_replication = b->lanes ? b->lanes : 1;
   if (b->lanes) {
     out->threads_per_block = b->geo.threads;
@@ -329,8 +333,9 @@ int qk_batch_read_status(qk_batch* b, uint64_t rep0, uint64_t n, uint32_t* statu
 int qk_batch_comp_stats(qk_batch* b, uint64_t rep0, uint64_t n, uint32_t comp, qk_comp_stats* out) {
   if (!b || rep0 + n > b->cfg.n_reps || comp >= b->low.hdr.n_comp) return QK_ERR_INVALID_ARG;
   for (uint64_t i = 0; i < n; ++i)
-    qk_comp_stats_dev(&b->low.comps[comp], b->low.vecs.data(), comp, b->g64.data(), b->g32.data(), b->gs64.data(), b->gs32.data(),
-                      b->rep_pad, rep0 + i, &out[i]);
+    qk_comp_stats_dev(&b->low.comps[comp], b->low.vecs.data(), comp, b->g64.data(), b->g32.data(),
+                      b->low.hdr.split ? b->gc64.data() : b->g64.data(), b->low.hdr.split ? b->gc32.data() : b->g32.data(),
+                      b->gs64.data(), b->gs32.data(), b->rep_pad, rep0 + i, &out[i]);
   return QK_OK;
 }
 
@@ -462,7 +467,7 @@ int qk_batch_read_vector(qk_batch* b, uint64_t rep, uint32_t comp, double* out3)
     return QK_ERR_INVALID_ARG;
   const DevVec& v = b->low.vecs[b->low.comps[comp].vec_idx];
   out3[0] = out3[1] = out3[2] = 0.0;
-  for (uint32_t k = 0; k < v.dim; ++k) memcpy(&out3[k], &b->g64[(size_t)(v.o64_res + k) * b->rep_pad + rep], 8);
+  for (uint32_t k = 0; k < v.dim; ++k) memcpy(&out3[k], &(b->low.hdr.split ? b->gc64 : b->g64)[(size_t)(v.o64_res + k) * b->rep_pad + rep], 8);
   return QK_OK;
 }
 
@@ -486,6 +491,7 @@ int qk_batch_read_containers(qk_batch* b, uint64_t rep, uint32_t comp, uint32_t*
     return QK_ERR_INVALID_ARG;
   const DevComp& c = b->low.comps[comp];
   auto h32 = [&](uint32_t slot) { return b->g32[(size_t)slot * b->rep_pad + rep]; };
+  auto w32 = [&](uint32_t slot) { return (b->low.hdr.split ? b->gc32 : b->g32)[(size_t)slot * b->rep_pad + rep]; };
   auto c32 = [&](uint32_t slot) { return b->gc32[(size_t)slot * b->rep_pad + rep]; };
   auto c64 = [&](uint32_t slot) { return b->gc64[(size_t)slot * b->rep_pad + rep]; };
   std::vector<uint32_t> hs, ps;
@@ -498,19 +504,19 @@ int qk_batch_read_containers(qk_batch* b, uint64_t rep, uint32_t comp, uint32_t*
     }
   } else if (c.kind == QK_DISCRETE_PARALLEL_PROCESS || c.kind == QK_CONTAINER_LOAD_PROCESS ||
              c.kind == QK_CONTAINER_UNLOAD_PROCESS) {
-    const uint32_t nprog = h32(c.o32 + PP32_NPROG), cq = h32(c.o32 + PP32_COMPLETE);
+    const uint32_t nprog = w32(c.o32 + PP32_NPROG), cq = w32(c.o32 + PP32_COMPLETE);
     const uint32_t ring = c.ring_cap, item0 = c.o32 + PP32_BASE_COUNT;
     for (uint32_t i = 0; i < nprog; ++i) {
-      hs.push_back(h32(item0 + i));
+      hs.push_back(w32(item0 + i));
       ps.push_back(c.ocold64 + 3u * i);
     }
     for (uint32_t i = 0; i < (cq >> 16); ++i) {
       const uint32_t pos = ((cq & 0xFFFFu) + i) % ring;
-      hs.push_back(h32(item0 + ring + pos));
+      hs.push_back(w32(item0 + ring + pos));
       ps.push_back(c.ocold64 + 3u * (ring + pos));
     }
-  } else if (h32(c.o32 + P32_FLAGS) & PF_HAS_ITEM) {
-    hs.push_back(h32(c.o32 + P32_ITEM));
+  } else if (w32(c.o32 + P32_FLAGS) & PF_HAS_ITEM) {
+    hs.push_back(w32(c.o32 + P32_ITEM));
     ps.push_back(c.ocold64);
   }
   if (n_out) *n_out = hs.size();

@@ -163,6 +163,14 @@ def test_random_models_match_the_oracle_phased(emul_lib, seed):
         _run_vector(emul_lib, seed, 2, flags=4 | 8 | ((2, 4, 8)[seed % 3] << 8))
 
 
+@pytest.mark.parametrize("seed", range(700, 732))
+def test_random_models_match_the_oracle_split_placement(emul_lib, seed):
+    """QK_BATCH_STATE_SPLIT: scheduler queue + stock words in the hot planes, component records in the cold planes"""
+    _run(emul_lib, seed, 2, flags=16)
+    if seed < 712:
+        _run_vector(emul_lib, seed, 2, flags=16)
+
+
 def test_random_models_are_mostly_comparable(emul_lib):
     """the generator must not hide behind capacity faults"""
     assert sum(_run(emul_lib, s, 1) for s in range(40, 60)) >= 17
@@ -282,6 +290,14 @@ def test_random_models_match_the_oracle_lane_groups_on_gpu(gpu_lib, seed):
     _run(gpu_lib, seed, 48, flags=4 | ((4, 8, 16)[seed % 3] << 8))
     if seed < 504:
         _run_vector(gpu_lib, seed, 48, flags=4 | ((4, 8, 16)[seed % 3] << 8))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(800, 812))
+def test_random_models_match_the_oracle_split_placement_on_gpu(gpu_lib, seed):
+    _run(gpu_lib, seed, 96, flags=16)
+    if seed < 804:
+        _run_vector(gpu_lib, seed, 96, flags=16)
 
 
 @pytest.mark.gpu

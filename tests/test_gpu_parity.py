@@ -491,6 +491,42 @@ def test_phased_kernel_matches_the_oracle(gpu_lib, lanes):
     _check(gpu_lib, H.container_haulage(), 128, n_events=6000, sample=[0, 127], log_capacity=65536, flags=f)
 
 
+@pytest.mark.parametrize("tpb", [0, 64, 128])
+def test_split_placement_matches_the_oracle(gpu_lib, tpb):
+    """QK_BATCH_STATE_SPLIT: the scheduler queue and the stocks' state words staged in shared memory, the component
+    records in global memory -- every model family, in one launch and across launches (state round trips)"""
+    f = 16
+    kw = dict(flags=f, threads_per_block=tpb)
+    _check(gpu_lib, H.haulage(n_src=8, per_queue=8), 301, n_events=20000, sample=[0, 150, 300], log_capacity=131072, **kw)
+    _check(gpu_lib, H.serial_line(n_proc=32), 170, n_events=30000, sample=[0, 169], log_capacity=131072, **kw)
+    _check(gpu_lib, H.discrete_queue(), 300, n_events=3000, tape_len=1200, sample=[0, 1, 150, 299], log_capacity=16384, **kw)
+    m = H.assembly_line()
+    _check(gpu_lib, m, 64, t_until=m.t0 + 3 * 24 * 3600 * 10**9, t0=m.t0, sample=[0, 63], log_capacity=16384, **kw)
+    _check(gpu_lib, H.vector_flow(3), 200, n_events=6000, sample=[0, 99, 199], log_capacity=65536, **kw)
+    _check(gpu_lib, H.container_haulage(), 128, n_events=6000, sample=[0, 127], log_capacity=65536, **kw)
+
+
+def test_split_placement_round_trips_and_agrees_with_the_other_placements(gpu_lib):
+    blobs = []
+    for flags, how in ((16, "one"), (16, "pieces"), (16, "sliced"), (_gflags(8), "one"), (1, "one")):
+        m = H.haulage(n_src=3, per_queue=4)
+        sim = m.sim(gpu_lib, 1000, base_seed=21, flags=flags, log_capacity=256)
+        if how == "one":
+            sim.step_events(6000)
+        elif how == "pieces":
+            sim.step_events(1)
+            sim.step_events(2999)
+            sim.step_events(3000)
+        else:
+            sim.step_events_sliced(6000, 5)
+        blob = b"".join(sim.comp_stats(ci).tobytes() for ci in range(len(m.components)))
+        logs, totals = sim.read_logs(0, 1000)
+        blob += b"".join(x.tobytes() for x in logs) + totals.tobytes()
+        blobs.append(blob)
+        sim.close()
+    assert all(b == blobs[0] for b in blobs[1:])
+
+
 def test_phased_kernel_round_trips_and_agrees_with_the_other_placements(gpu_lib):
     blobs = []
     for flags, how in ((_gflags(8, True), "one"), (_gflags(8, True), "pieces"), (_gflags(4, True), "sliced"),
