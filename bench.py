@@ -241,7 +241,7 @@ def run_ours(args):
     # a real (non-NULL) stream: the library launches on it, torch events and NCCL order against it
     stream = torch.cuda.Stream(device)
     torch.cuda.set_stream(stream)
-    flags = {"auto": 0, "hbm": 1, "chip": 2, "group": 4, "phased": 12, "split": 16}[args.state]
+    flags = {"auto": 0, "hbm": 1, "chip": 2, "group": 4, "phased": 12, "split": 16, "qsplit": 48}[args.state]
 
     def new_sim(log_capacity, n=reps_gpu, off=rep_lo, seed=1234):
         return model.sim(args.lib, n, t0=0, base_seed=seed, rep_offset=off, log_capacity=log_capacity,
@@ -454,7 +454,7 @@ def main():
     ap.add_argument("--log", default="ring", choices=["ring", "off"])
     ap.add_argument("--log-capacity", type=int, default=64)
     ap.add_argument("--threads-per-block", type=int, default=0)
-    ap.add_argument("--state", default="auto", choices=["auto", "hbm", "chip", "group", "phased", "split"],
+    ap.add_argument("--state", default="auto", choices=["auto", "hbm", "chip", "group", "phased", "split", "qsplit"],
                     help="auto: the library chooses; hbm: operate on the HBM planes in place; chip: one thread per "
                          "replication, state staged in shared memory; group: a lane group per replication, state in "
                          "shared memory (large models)")

@@ -320,6 +320,11 @@ int qk_model_state_bytes(const qk_model*, int with_log, uint32_t* out_bytes);
  * durations, draw counters, resources) stay in global memory and are read and written in place, through L2, by the
  * handlers alone -- the scheduler pop and the emit_change broadcast never leave the chip */
 #define QK_BATCH_STATE_SPLIT 16u
+/* with QK_BATCH_STATE_SPLIT: a two-tier scheduler queue.  Only the stocks' pending emit_change events (due one nanosecond
+ * after they are scheduled) are kept in shared memory; the keyed events of the process-like components live in a global
+ * array by rank, summarised on chip by a busy mask and a cached minimum that is re-established by a scan of that array
+ * only after the minimum itself has fired.  A third of the shared memory per replication: three times the warps. */
+#define QK_BATCH_QUEUE_TWO_TIER 32u
 typedef struct {
   uint64_t n_reps;
   uint64_t rep_offset;   /* global index of this batch's first replication (Philox counter words 0,1) */

@@ -83,6 +83,21 @@ struct qk_batch {
 /* the planes the component records live in: the hot planes, or (split placement) the cold ones */
 static inline uint64_t* warm64(const qk_batch* b) { return b->split ? b->gc64 : b->g64; }
 static inline uint32_t* warm32(const qk_batch* b) { return b->split ? b->gc32 : b->g32; }
+/* the cold planes are [slot][replication], except under the split placements: [replication][slot] (qk_kernels.cuh) */
+static inline const uint64_t* cold64_at(const qk_batch* b, uint32_t slot, uint64_t rep) {
+  return b->split ? b->gc64 + (size_t)rep * b->low.hdr.n64c + slot : b->gc64 + (size_t)slot * b->rep_pad + rep;
+}
+static inline const uint32_t* cold32_at(const qk_batch* b, uint32_t slot, uint64_t rep) {
+  return b->split ? b->gc32 + (size_t)rep * b->low.hdr.n32c + slot : b->gc32 + (size_t)slot * b->rep_pad + rep;
+}
+static inline const uint64_t* warm64_at(const qk_batch* b, uint32_t slot, uint64_t rep) {
+  return b->split ? cold64_at(b, slot, rep) : b->g64 + (size_t)slot * b->rep_pad + rep;
+}
+static inline const uint32_t* warm32_at(const qk_batch* b, uint32_t slot, uint64_t rep) {
+  return b->split ? cold32_at(b, slot, rep) : b->g32 + (size_t)slot * b->rep_pad + rep;
+}
+static inline uint32_t aos64(const qk_batch* b) { return b->split ? b->low.hdr.n64c : 0u; }
+static inline uint32_t aos32(const qk_batch* b) { return b->split ? b->low.hdr.n32c : 0u; }
 
 /* the step kernel instantiations live in qk_step_l{0,1}f{0,1}.cu */
 StepKernel qk_pick_step_l0f0(uint32_t nt);
@@ -115,8 +130,8 @@ static StepKernel pick_group_kernel(bool log, uint32_t g, uint32_t features) {
   return features ? qk_pick_group_l0f1(g) : qk_pick_group_l0f0(g);
 }
 static uint32_t group_max_threads(uint32_t g) { return g <= 4 ? 256u : (g == 8 ? 512u : 768u); } /* qk_group_max_threads */
-static StepKernel pick_kernel(bool log, bool hbm, uint32_t nt, uint32_t features, bool split = false) {
-  const uint32_t key = split ? 0xFFFFFFFEu : (hbm ? 0u : nt);
+static StepKernel pick_kernel(bool log, bool hbm, uint32_t nt, uint32_t features, uint32_t split = 0) {
+  const uint32_t key = split == 2 ? 0xFFFFFFFDu : (split ? 0xFFFFFFFEu : (hbm ? 0u : nt));
   if (features >= 2) return log ? qk_pick_step_l1f2(key) : qk_pick_step_l0f2(key);
   if (log) return features ? qk_pick_step_l1f1(key) : qk_pick_step_l1f0(key);
   return features ? qk_pick_step_l0f1(key) : qk_pick_step_l0f0(key);
@@ -216,12 +231,12 @@ static int launch_step(qk_batch* b, uint32_t do_init, uint64_t t0, uint64_t t_un
 /* ================================= per-GPU summary reduction ================================= */
 
 __global__ void qk_comp_stats_kernel(const uint8_t* tables, const uint64_t* g64, const uint32_t* g32,
-                                     const uint64_t* w64, const uint32_t* w32, const uint64_t* gs64, const uint32_t* gs32, uint64_t rep_pad, uint64_t rep0, uint64_t n, uint32_t comp, qk_comp_stats* out) {
+                                     const uint64_t* w64, const uint32_t* w32, uint32_t wa64, uint32_t wa32, const uint64_t* gs64, const uint32_t* gs32, uint64_t rep_pad, uint64_t rep0, uint64_t n, uint32_t comp, qk_comp_stats* out) {
   const DevHeader* h = reinterpret_cast<const DevHeader*>(tables);
   const DevComp* c = reinterpret_cast<const DevComp*>(tables + h->off_comps) + comp;
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const DevVec* vecs = reinterpret_cast<const DevVec*>(tables + h->off_vecs);
-  if (i < n) qk_comp_stats_dev(c, vecs, comp, g64, g32, w64, w32, gs64, gs32, rep_pad, rep0 + i, &out[i]);
+  if (i < n) qk_comp_stats_dev(c, vecs, comp, g64, g32, w64, w32, wa64, wa32, gs64, gs32, rep_pad, rep0 + i, &out[i]);
 }
 
 __device__ __forceinline__ uint64_t warp_sum_u64(uint64_t v) {
@@ -246,7 +261,7 @@ __device__ __forceinline__ double warp_sum_f64(double v) {
  * halves -- so the result does not depend on how the replications are partitioned over blocks or GPUs. */
 __global__ void __launch_bounds__(256) qk_reduce_kernel(const uint8_t* tables, const uint64_t* g64,
                                                         const uint32_t* g32, const uint64_t* w64, const uint32_t* w32,
-                                                        const uint64_t* gs64,
+                                                        uint32_t wa64, uint32_t wa32, const uint64_t* gs64,
                                                         const uint32_t* gs32, uint64_t rep_pad, uint64_t n_reps,
                                                         uint64_t* part) {
   const DevHeader* h = reinterpret_cast<const DevHeader*>(tables);
@@ -256,7 +271,7 @@ __global__ void __launch_bounds__(256) qk_reduce_kernel(const uint8_t* tables, c
   for (int k = 0; k < QK_PARTIAL_WORDS; ++k) a[k] = (k >= QP_MIN_COUNT && k <= QP_NMAX_TIME) ? ~0ull : 0ull;
   for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_reps; r += (uint64_t)gridDim.x * blockDim.x) {
     qk_comp_stats s;
-    qk_comp_stats_dev(c, reinterpret_cast<const DevVec*>(tables + h->off_vecs), comp, g64, g32, w64, w32, gs64, gs32, rep_pad, r, &s);
+    qk_comp_stats_dev(c, reinterpret_cast<const DevVec*>(tables + h->off_vecs), comp, g64, g32, w64, w32, wa64, wa32, gs64, gs32, rep_pad, r, &s);
     const uint64_t lo = s.time_ns & 0xFFFFFFFFull, hi = s.time_ns >> 32;
     a[QP_COUNT] += s.count;
     a[QP_TIME_LO] += lo;
@@ -331,7 +346,7 @@ __global__ void qk_partials_combine_kernel(const uint64_t* parts, uint32_t n_par
 
 /* hist[c][0][bin] over time_ns, hist[c][1][bin] over count; ranges from the extrema words of (combined) partials */
 __global__ void __launch_bounds__(256) qk_hist_kernel(const uint8_t* tables, const uint64_t* g64, const uint32_t* g32,
-                                                      const uint64_t* w64, const uint32_t* w32, const uint64_t* gs64, const uint32_t* gs32, uint64_t rep_pad, uint64_t n_reps, const uint64_t* part,
+                                                      const uint64_t* w64, const uint32_t* w32, uint32_t wa64, uint32_t wa32, const uint64_t* gs64, const uint32_t* gs32, uint64_t rep_pad, uint64_t n_reps, const uint64_t* part,
                                                       uint64_t* hist) {
   const DevHeader* h = reinterpret_cast<const DevHeader*>(tables);
   const uint32_t comp = blockIdx.y;
@@ -345,7 +360,7 @@ __global__ void __launch_bounds__(256) qk_hist_kernel(const uint8_t* tables, con
   const uint64_t w_c = (hi_c - lo_c) / QK_HIST_BINS + 1, w_t = (hi_t - lo_t) / QK_HIST_BINS + 1;
   for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_reps; r += (uint64_t)gridDim.x * blockDim.x) {
     qk_comp_stats s;
-    qk_comp_stats_dev(c, reinterpret_cast<const DevVec*>(tables + h->off_vecs), comp, g64, g32, w64, w32, gs64, gs32, rep_pad, r, &s);
+    qk_comp_stats_dev(c, reinterpret_cast<const DevVec*>(tables + h->off_vecs), comp, g64, g32, w64, w32, wa64, wa32, gs64, gs32, rep_pad, r, &s);
     if (s.time_ns >= lo_t && s.time_ns <= hi_t) atomicAdd(&sh[0][(s.time_ns - lo_t) / w_t], 1ull);
     if (s.count >= lo_c && s.count <= hi_c) atomicAdd(&sh[1][(s.count - lo_c) / w_c], 1ull);
   }
@@ -490,7 +505,7 @@ int qk_batch_create(const qk_model* m, const qk_batch_config* cfg, qk_batch** ou
   b->phased = false;
   b->split = false;
   b->have_side = false;
-  int rc = qk_lower(m, b->log, false, &b->low);
+  int rc = qk_lower(m, b->log, 0, &b->low);
   if (rc) {
     delete b;
     return rc;
@@ -503,6 +518,7 @@ int qk_batch_create(const qk_model* m, const qk_batch_config* cfg, qk_batch** ou
   b->hbm = (cfg->flags & QK_BATCH_STATE_IN_HBM) != 0;
   bool group = (cfg->flags & QK_BATCH_STATE_LANE_GROUP) != 0;
   bool split = (cfg->flags & QK_BATCH_STATE_SPLIT) != 0;
+  bool qsplit = split && (cfg->flags & QK_BATCH_QUEUE_TWO_TIER) != 0;
   if (split && (b->hbm || group || (cfg->flags & QK_BATCH_STATE_ON_CHIP))) {
     qk_set_error("qk_batch_create: QK_BATCH_STATE_SPLIT excludes the other placement flags");
     delete b;
@@ -521,16 +537,24 @@ int qk_batch_create(const qk_model* m, const qk_batch_config* cfg, qk_batch** ou
       /* ... when the scheduler queue is long enough for the cooperative pop to matter (measured: the 96- and
        * 67-component networks gain 10-45 %, the 10- and 13-component vector / container models lose a factor of two
        * against operating on the L1/L2-cached HBM planes, profiles/README.md) */
-      const char* e = getenv("QK_AUTO_PLACEMENT"); /* "hbm" / "group": force the choice for models of this class */
+      /* (round 2, profiles/README.md) ... and both lose to the split placement -- one thread per replication, with only
+       * the scheduler queue and the stocks' words on chip and the component records read in place through L2: 2-3 times the
+       * HBM planes on the 96- and 67-component networks, 1.1-1.3 times on the 10- and 13-component vector / container
+       * models.  Lean models (feature set 0) with a long queue also move their keyed events off the chip (two-tier queue). */
+      const char* e = getenv("QK_AUTO_PLACEMENT"); /* "hbm" / "group" / "split" / "qsplit": force the choice */
       if (e && e[0] == 'h') b->hbm = true;
+      else if (e && e[0] == 'g') group = true;
+      else if (e && e[0] == 'q') split = qsplit = true;
       else if (e && e[0] == 's') split = true;
-      else if ((e && e[0] == 'g') || h.n_sched >= 32) group = true;
-      else b->hbm = true;
+      else {
+        split = true;
+        qsplit = h.features == 0 && h.n_sched >= 32;
+      }
     }
   }
   if (split) {
     /* lower again with the component records in the cold planes; what is staged is the scheduler queue and the stocks */
-    rc = qk_lower(m, b->log, true, &b->low);
+    rc = qk_lower(m, b->log, qsplit ? 2 : 1, &b->low);
     if (rc) {
       delete b;
       return rc;
@@ -580,7 +604,19 @@ int qk_batch_create(const qk_model* m, const qk_batch_config* cfg, qk_batch** ou
   if (group) {
     /* geometry chosen above */
   } else if (!b->hbm) {
-    if (nt == 0) nt = choose_nt(per_rep, b->table_bytes_padded, split ? 256u : max_thr, nullptr);
+    uint32_t thr_cap = max_thr;
+    if (split) {
+      /* the split kernels take their block size at run time and are compiled without a residency target: what the
+       * register file allows is read off the kernel itself */
+      cudaFuncAttributes fa;
+      CREATE_TRY(cudaFuncGetAttributes(&fa, (const void*)pick_kernel(b->log, false, 0, h.features, h.split)));
+      const uint32_t regs = ((uint32_t)(fa.numRegs > 0 ? fa.numRegs : 128) + 7u) & ~7u;
+      thr_cap = (65536u / regs) & ~31u;
+      /* two-tier queue: its working set (4 KB per resident replication) lives in L2 -- past 12 warps per SM the extra
+       * replications cost more in L2 misses than their warps hide (measured: 3 x 128 threads beat 3 x 160 and 2 x 256) */
+      if (qsplit && thr_cap > 384u) thr_cap = 384u;
+    }
+    if (nt == 0) nt = choose_nt(per_rep, b->table_bytes_padded, thr_cap, nullptr);
     const bool fits = nt != 0 && nt <= QK_MAX_NT && !(nt & 31) &&
                       (uint64_t)b->table_bytes_padded + (uint64_t)per_rep * nt <= 227u * 1024u - 64u;
     if (!fits) {
@@ -649,7 +685,7 @@ int qk_batch_create(const qk_model* m, const qk_batch_config* cfg, qk_batch** ou
   CREATE_TRY(cudaMemset(b->d_tapes, 0, sizeof(double*) * (h.n_dist ? h.n_dist : 1)));
   CREATE_TRY(cudaMemset(b->d_tape_len, 0, sizeof(uint64_t) * (h.n_dist ? h.n_dist : 1)));
   b->kernel = group ? (b->phased ? pick_phased_kernel(b->log, b->lanes, h.features) : pick_group_kernel(b->log, b->lanes, h.features))
-                    : pick_kernel(b->log, b->hbm, b->nt, h.features, b->split);
+                    : pick_kernel(b->log, b->hbm, b->nt, h.features, h.split);
   {
     /* the opt-in limit covers static + dynamic shared memory: the kernels keep an mbarrier (and little else) in static */
     cudaFuncAttributes fa;
@@ -977,7 +1013,7 @@ int qk_batch_comp_stats(qk_batch* b, uint64_t rep0, uint64_t n, uint32_t comp, q
   const uint64_t piece = b->scratch_bytes / sizeof(qk_comp_stats);
   for (uint64_t done = 0; done < n; done += piece) {
     const uint64_t k = std::min<uint64_t>(piece, n - done);
-    qk_comp_stats_kernel<<<(unsigned)((k + 255) / 256), 256, 0, b->stream>>>(b->d_tables, b->g64, b->g32, warm64(b), warm32(b), b->gs64, b->gs32,
+    qk_comp_stats_kernel<<<(unsigned)((k + 255) / 256), 256, 0, b->stream>>>(b->d_tables, b->g64, b->g32, warm64(b), warm32(b), aos64(b), aos32(b), b->gs64, b->gs32,
                                                                               b->rep_pad, rep0 + done, k, comp, d);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(out + done, d, k * sizeof(qk_comp_stats), cudaMemcpyDeviceToHost, b->stream));
@@ -996,7 +1032,7 @@ int qk_batch_reduce_partials_device(qk_batch* b, uint64_t* d_partials, uint32_t 
   qk_partials_clear_kernel<<<(n_words + 255) / 256, 256, 0, b->stream>>>(d_partials, n_words);
   CUDA_TRY(cudaGetLastError());
   dim3 grid(b->red_blocks, n_comp);
-  qk_reduce_kernel<<<grid, 256, 0, b->stream>>>(b->d_tables, b->g64, b->g32, warm64(b), warm32(b), b->gs64, b->gs32, b->rep_pad, b->cfg.n_reps,
+  qk_reduce_kernel<<<grid, 256, 0, b->stream>>>(b->d_tables, b->g64, b->g32, warm64(b), warm32(b), aos64(b), aos32(b), b->gs64, b->gs32, b->rep_pad, b->cfg.n_reps,
                                                 d_partials);
   CUDA_TRY(cudaGetLastError());
   return QK_OK;
@@ -1020,7 +1056,7 @@ int qk_batch_histograms_device(qk_batch* b, const uint64_t* d_partials, uint64_t
   CUDA_TRY(cudaSetDevice(b->cfg.device));
   CUDA_TRY(cudaMemsetAsync(d_hist, 0, sizeof(uint64_t) * 2 * QK_HIST_BINS * n_comp, b->stream));
   dim3 grid(b->red_blocks, n_comp);
-  qk_hist_kernel<<<grid, 256, 0, b->stream>>>(b->d_tables, b->g64, b->g32, warm64(b), warm32(b), b->gs64, b->gs32, b->rep_pad, b->cfg.n_reps,
+  qk_hist_kernel<<<grid, 256, 0, b->stream>>>(b->d_tables, b->g64, b->g32, warm64(b), warm32(b), aos64(b), aos32(b), b->gs64, b->gs32, b->rep_pad, b->cfg.n_reps,
                                               d_partials, d_hist);
   CUDA_TRY(cudaGetLastError());
   return QK_OK;
@@ -1193,7 +1229,7 @@ int qk_batch_read_vector(qk_batch* b, uint64_t rep, uint32_t comp, double* out3)
   const DevVec& v = b->low.vecs[b->low.comps[comp].vec_idx];
   out3[0] = out3[1] = out3[2] = 0.0;
   for (uint32_t k = 0; k < v.dim; ++k)
-    CUDA_TRY(cudaMemcpy(&out3[k], warm64(b) + (size_t)(v.o64_res + k) * b->rep_pad + rep, 8, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(&out3[k], warm64_at(b, v.o64_res + k, rep), 8, cudaMemcpyDeviceToHost));
   return QK_OK;
 }
 
@@ -1214,8 +1250,11 @@ int qk_batch_read_stock(qk_batch* b, uint64_t rep, uint32_t comp, uint32_t* item
   if (!items) return QK_OK;
   if (cap < cnt) return QK_ERR_BUFFER_TOO_SMALL;
   std::vector<uint32_t> ring(c.ring_cap);
-  CUDA_TRY(cudaMemcpy2D(ring.data(), 4, b->gc32 + (size_t)c.ocold32 * b->rep_pad + rep, b->rep_pad * 4, 4,
-                        c.ring_cap, cudaMemcpyDeviceToHost));
+  if (b->split)
+    CUDA_TRY(cudaMemcpy(ring.data(), cold32_at(b, c.ocold32, rep), 4u * c.ring_cap, cudaMemcpyDeviceToHost));
+  else
+    CUDA_TRY(cudaMemcpy2D(ring.data(), 4, b->gc32 + (size_t)c.ocold32 * b->rep_pad + rep, b->rep_pad * 4, 4,
+                          c.ring_cap, cudaMemcpyDeviceToHost));
   for (uint32_t i = 0; i < cnt; ++i) items[i] = ring[(head + i) % c.ring_cap];
   return QK_OK;
 }
@@ -1247,8 +1286,8 @@ int qk_batch_read_containers(qk_batch* b, uint64_t rep, uint32_t comp, uint32_t*
   } else if (c.kind == QK_DISCRETE_PARALLEL_PROCESS || c.kind == QK_CONTAINER_LOAD_PROCESS ||
              c.kind == QK_CONTAINER_UNLOAD_PROCESS) {
     uint32_t nprog = 0, cq = 0;
-    CUDA_TRY(fetch(warm32(b), b->rep_pad, c.o32 + PP32_NPROG, rep, &nprog));
-    CUDA_TRY(fetch(warm32(b), b->rep_pad, c.o32 + PP32_COMPLETE, rep, &cq));
+    CUDA_TRY(cudaMemcpy(&nprog, warm32_at(b, c.o32 + PP32_NPROG, rep), 4, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(&cq, warm32_at(b, c.o32 + PP32_COMPLETE, rep), 4, cudaMemcpyDeviceToHost));
     const uint32_t ring = c.ring_cap, item0 = c.o32 + PP32_BASE_COUNT;
     for (uint32_t i = 0; i < nprog; ++i) {
       item_slot.push_back(item0 + i);
@@ -1261,7 +1300,7 @@ int qk_batch_read_containers(qk_batch* b, uint64_t rep, uint32_t comp, uint32_t*
     }
   } else {
     uint32_t flags = 0;
-    CUDA_TRY(fetch(warm32(b), b->rep_pad, c.o32 + P32_FLAGS, rep, &flags));
+    CUDA_TRY(cudaMemcpy(&flags, warm32_at(b, c.o32 + P32_FLAGS, rep), 4, cudaMemcpyDeviceToHost));
     if (flags & PF_HAS_ITEM) {
       item_slot.push_back(c.o32 + P32_ITEM);
       pay_slot.push_back(c.ocold64);
@@ -1271,8 +1310,10 @@ int qk_batch_read_containers(qk_batch* b, uint64_t rep, uint32_t comp, uint32_t*
   if (!handles || !resources) return QK_OK;
   if (cap < item_slot.size()) return QK_ERR_BUFFER_TOO_SMALL;
   for (size_t i = 0; i < item_slot.size(); ++i) {
-    CUDA_TRY(fetch(item_cold ? b->gc32 : warm32(b), b->rep_pad, item_slot[i], rep, &handles[i]));
-    for (uint32_t k = 0; k < 3; ++k) CUDA_TRY(fetch(b->gc64, b->rep_pad, pay_slot[i] + k, rep, &resources[i * 3 + k]));
+    CUDA_TRY(cudaMemcpy(&handles[i], item_cold ? cold32_at(b, item_slot[i], rep) : warm32_at(b, item_slot[i], rep), 4,
+                        cudaMemcpyDeviceToHost));
+    for (uint32_t k = 0; k < 3; ++k)
+      CUDA_TRY(cudaMemcpy(&resources[i * 3 + k], cold64_at(b, pay_slot[i] + k, rep), 8, cudaMemcpyDeviceToHost));
   }
   return QK_OK;
 }

@@ -246,10 +246,13 @@ typedef struct {
   uint32_t off_cinit; /* uint64_t cinit[n_initial][3]: resource bits of the initial containers (NONE sentinel) */
   uint32_t features; /* 0 = every process-like component is SIMPLE and nothing is scheduled externally ; 1 = general ;
                         2 = general + container family (vector_container.rs) */
-  uint32_t split;    /* 1: component records (everything but the fire slots, the stocks' hot words and the seq counters)
+  uint32_t n_hot, off_hot_rank; /* placement 2: entries of the hot fire array (stocks) ; u16 hot_rank[n_hot]: index -> rank */
+  uint32_t cfire0, busy32;      /* placement 2: first cold64 slot of the process-like fire array (by rank, padded to a
+                                   multiple of four) ; first hot32 slot of the busy mask (bit = rank) */
+  uint32_t split;    /* placement. 1: component records (everything but the fire slots, the stocks' hot words and the seq counters)
                         were allocated in the COLD planes: DevComp.o64 / o32, o64_dm, o64_nextdur, o64_ttnpe,
                         o32_next_item, DevDist.draw_slot, DevVec.o64_res / o64_low / o64_last / o32_qty are cold-plane slot
-                        numbers (the kernels' W64 / W32 accessors) */
+                        numbers (the kernels' W64 / W32 accessors).  2: as 1, and the scheduler queue is two-tier (qk_lower) */
 } DevHeader;
 
 /* ---- lane-group kernel geometry (qk_group.cuh): R replications per block, G lanes each ----------------------------

@@ -87,6 +87,11 @@ struct Ctx {
   uint32_t log_cnt;
   uint32_t key0, key1, rep_lo, rep_hi;
   uint32_t npend; /* consumed pre-drawn durations waiting for the REFILL phase */
+  /* two-tier scheduler queue (QK_SM_QSPLIT): first cold64 slot of the process-like fire array, first hot32 slot of the busy
+   * mask, and the cached minimum over that array by (time, rank) -- exact while kvalid */
+  uint32_t cfire0, busy32, kidx;
+  uint64_t kbest;
+  bool kvalid;
   uint64_t rep_local;
   const double* const* tapes;
   const uint64_t* tape_len;
@@ -121,21 +126,30 @@ __device__ __forceinline__ auto qk_ix(uint32_t slot, uint32_t stride) {
  * slots, except under the SPLIT placement (SM == QK_SM_SPLIT, DevHeader.split), where the lowering allocated them in the
  * cold planes so that only the scheduler queue and the stocks' state words occupy shared memory */
 #define QK_SM_SPLIT (-2)
+/* ... and QSPLIT: the split placement with the two-tier scheduler queue (qk_lower, placement 2): the hot fire array holds
+ * the stocks' slots only, the keyed events of the process-like components live in a cold array by rank */
+#define QK_SM_QSPLIT (-3)
+#define qk_is_split(sm) ((sm) == QK_SM_SPLIT || (sm) == QK_SM_QSPLIT)
 template <int SM>
 __device__ __forceinline__ uint64_t& qk_w64(const Ctx& cx, uint32_t slot) {
-  if constexpr (SM == QK_SM_SPLIT) return cx.gc64[(uint64_t)slot * cx.rep_pad];
+  if constexpr (qk_is_split(SM)) return cx.gc64[slot];
   else return qk_p64<SM>(cx)[qk_ix<SM>(slot, cx.stride)];
 }
 template <int SM>
 __device__ __forceinline__ uint32_t& qk_w32(const Ctx& cx, uint32_t slot) {
-  if constexpr (SM == QK_SM_SPLIT) return cx.gc32[(uint64_t)slot * cx.rep_pad];
+  if constexpr (qk_is_split(SM)) return cx.gc32[slot];
   else return qk_p32<SM>(cx)[qk_ix<SM>(slot, SM < 0 ? cx.stride32 : cx.stride)];
 }
 #define W64(slot) (qk_w64<SM>(cx, (uint32_t)(slot)))
 #define W32(slot) (qk_w32<SM>(cx, (uint32_t)(slot)))
 /* cold state: always global memory, whatever the placement of the hot planes */
-#define C64(slot) (cx.gc64[(uint64_t)(uint32_t)(slot) * cx.rep_pad])
-#define C32(slot) (cx.gc32[(uint64_t)(uint32_t)(slot) * cx.rep_pad])
+/* layout: [slot][replication] like the hot planes -- except under the split placements, where the cold planes hold the
+ * component records and are laid out [replication][slot] (DevHeader.split): the handlers of a warp work on 32 different
+ * components, so a 32-byte sector of a [slot][replication] plane would carry one useful word, while a replication's own
+ * record -- countdown, previous-check time, pre-drawn duration / flags, item, draw counter -- is two sectors here, and
+ * its keyed-event array (two-tier queue) one contiguous run */
+#define C64(slot) (cx.gc64[qk_is_split(SM) ? (uint64_t)(uint32_t)(slot) : (uint64_t)(uint32_t)(slot) * cx.rep_pad])
+#define C32(slot) (cx.gc32[qk_is_split(SM) ? (uint64_t)(uint32_t)(slot) : (uint64_t)(uint32_t)(slot) * cx.rep_pad])
 /* statistics accumulators: fire-and-forget RED atomics on the HBM planes (see qk_internal.h) */
 #ifdef QK_EXPERIMENT_NO_STATS /* perf experiment only: results are wrong */
 #define QK_ST64_ADD(comp, k, v) ((void)0)
@@ -296,16 +310,19 @@ __device__ __forceinline__ uint64_t qk_sample_duration_code(Ctx& cx, uint32_t di
 /* does the next update_state(comp) possibly start a process whose pre-drawn duration is still missing? */
 template <int SM>
 __device__ __forceinline__ bool qk_needs_refill_now(Ctx& cx, uint32_t comp) {
-  const DevHotB b = QK_HOT_B(comp); /* stocks never appear in a call list */
+  /* stocks never appear in a call list, but a BasicEnvironment does (the init list), and its row has no DevHotB: only
+   * the single-server discrete kinds pre-draw their process time */
+  const DevHotA a = QK_HOT_A(comp);
+  if (a.kind < QK_DISCRETE_PROCESS || a.kind > QK_DISCRETE_SINK) return false;
+  const DevHotB b = QK_HOT_B(comp);
   if (b.o64_nextdur == 0xFFFF) return false;
-  if constexpr (SM == QK_SM_SPLIT) {
+  if constexpr (qk_is_split(SM)) {
     /* the component record is in global memory: ask the pending mask (a hot word) instead -- its bit is set exactly while
      * the slot holds QK_DUR_EMPTY -- and do not look at the countdown at all.  Refilling a little early only changes WHEN
      * a variate is drawn, never which one (every distribution instance has its own counter / tape position) */
     return ((S32(cx.pf32 + (b.pf_idx >> 5)) >> (b.pf_idx & 31)) & 1u) != 0;
   }
   if (W64(b.o64_nextdur) != QK_DUR_EMPTY) return false;
-  const DevHotA a = QK_HOT_A(comp);
   const uint32_t flags = W32(a.o32 + P32_FLAGS);
   if (!(flags & PF_HAS_ITEM)) return true;
   return W64(a.o64 + P64_LEFT) <= cx.now - W64(a.o64 + P64_PREV); /* finishes in this call, may restart */
@@ -327,6 +344,42 @@ __device__ __forceinline__ void qk_refill(Ctx& cx) {
     }
   }
   cx.npend = 0;
+}
+
+/* ---- the fire slot of a process-like component (its pending keyed event, NeXosim's queue entry behind
+ * cx.schedule_keyed_event, discrete.rs:549,556), by rank.  One hot slot per component, or -- two-tier queue -- a cold slot
+ * plus a busy bit, with the cached minimum kept exact: every write goes through these three functions. */
+template <int SM>
+__device__ __forceinline__ bool qk_fire_busy(Ctx& cx, uint32_t idx) {
+  return ((S32(cx.busy32 + (idx >> 5)) >> (idx & 31)) & 1u) != 0;
+}
+template <int SM>
+__device__ __forceinline__ uint64_t qk_fire_get(Ctx& cx, uint32_t idx) {
+  if constexpr (SM == QK_SM_QSPLIT) return qk_fire_busy<SM>(cx, idx) ? C64(cx.cfire0 + idx) : QK_TIME_NONE;
+  else return S64(G64_FIRE0 + idx);
+}
+template <int SM>
+__device__ __forceinline__ void qk_fire_set(Ctx& cx, uint32_t idx, uint64_t t) { /* t != NONE */
+  if constexpr (SM == QK_SM_QSPLIT) {
+    C64(cx.cfire0 + idx) = t;
+    S32(cx.busy32 + (idx >> 5)) |= 1u << (idx & 31);
+    if (cx.kvalid && (t < cx.kbest || (t == cx.kbest && idx < cx.kidx))) {
+      cx.kbest = t;
+      cx.kidx = idx;
+    }
+  } else {
+    S64(G64_FIRE0 + idx) = t;
+  }
+}
+template <int SM>
+__device__ __forceinline__ void qk_fire_clear(Ctx& cx, uint32_t idx) {
+  if constexpr (SM == QK_SM_QSPLIT) {
+    C64(cx.cfire0 + idx) = QK_TIME_NONE; /* (the scan reads the array, not the mask) */
+    S32(cx.busy32 + (idx >> 5)) &= ~(1u << (idx & 31));
+    if (cx.kvalid && idx == cx.kidx) cx.kvalid = false; /* the minimum is gone: the next pop scans the cold array */
+  } else {
+    S64(G64_FIRE0 + idx) = QK_TIME_NONE;
+  }
 }
 
 /* ---- DiscreteStock (discrete.rs:158-252) ------------------------------------------------------------------ */
@@ -437,7 +490,7 @@ __device__ __forceinline__ bool qk_stock_add(Ctx& cx, uint32_t sidx, uint32_t it
 #define QK_RM_FAULT 2u
 template <bool LOG, int SM>
 __device__ __forceinline__ uint32_t qk_stock_remove(Ctx& cx, uint32_t sidx, uint64_t src, uint32_t* item_out,
-                                                    uint64_t* pay_out = nullptr) {
+                                                    uint64_t* pay_out = nullptr, const uint32_t* head_item = nullptr) {
   const DevHotA c = QK_HOT_A(sidx);
   const DevHotSB sb = QK_HOT_SB(sidx);
   const uint32_t hc = S32(c.o32 + S32_HC);
@@ -454,6 +507,8 @@ __device__ __forceinline__ uint32_t qk_stock_remove(Ctx& cx, uint32_t sidx, uint
     if (LOG && SM != 0) {
       qk_async_wait();
       item = S32(c.o32 + S32_HEADITEM);
+    } else if (head_item) {
+      item = *head_item; /* requested ahead of the call (qk_prefetch_record) */
     } else {
       item = C32(c.olog64 + head);
     }
@@ -571,9 +626,8 @@ __device__ __forceinline__ bool qk_post(Ctx& cx, const DevHotA& c, uint64_t ttnp
       return true;
     }
     const uint64_t next = cx.now + ttnpe;
-    const uint32_t fire = G64_FIRE0 + c.fire_idx;
-    if (next < S64(fire)) { /* NONE is the largest u64 */
-      S64(fire) = next;
+    if (next < qk_fire_get<SM>(cx, c.fire_idx)) { /* NONE is the largest u64 */
+      qk_fire_set<SM>(cx, c.fire_idx, next);
       if (LOG && !LEAN) C64(c.olog64 + PL64_SCHED_SRC) = src;
     }
   }
@@ -584,9 +638,12 @@ __device__ __forceinline__ bool qk_post(Ctx& cx, const DevHotA& c, uint64_t ttnp
  * event has not fired yet it stays queued (Q3) -> move it to the stale mask (it fires at `now`, in rank order) */
 template <bool LOG, int SM, bool LEAN = false>
 __device__ __forceinline__ void qk_pre(Ctx& cx, const DevHotA& c, uint32_t comp) {
-  const uint32_t fire = G64_FIRE0 + c.fire_idx;
-  if (S64(fire) <= cx.now) {
-    S64(fire) = QK_TIME_NONE;
+  if constexpr (SM == QK_SM_QSPLIT) {
+    /* nothing pending, or (cached minimum) nothing of any component due yet: no need to fetch the slot */
+    if (!qk_fire_busy<SM>(cx, c.fire_idx) || (cx.kvalid && cx.kbest > cx.now)) return;
+  }
+  if (qk_fire_get<SM>(cx, c.fire_idx) <= cx.now) {
+    qk_fire_clear<SM>(cx, c.fire_idx);
     S32(G32_STALE0 + (c.fire_idx >> 5)) |= 1u << (c.fire_idx & 31);
     if (LOG)
       C64(c.olog64 + PL64_STALE_SRC) =
@@ -625,7 +682,7 @@ __device__ __forceinline__ uint32_t qk_dm_quick(Ctx& cx, const DevSubQ& q, uint3
                                                 uint64_t* dt_out) {
   const DevHotA a = QK_HOT_A(comp);
   const uint32_t flags = W32(a.o32 + P32_FLAGS);
-  const uint64_t fire = S64(q.fire_slot);
+  const uint64_t fire = SM == QK_SM_QSPLIT ? qk_fire_get<SM>(cx, q.fire_slot) : S64(q.fire_slot);
   if (flags & ~PF_HAS_ITEM) return 0u; /* a mode in TimeUntilFix (or environment-stopped) */
   if (!(flags & PF_HAS_ITEM)) {
     if (fire != QK_TIME_NONE) return 0u;
@@ -688,7 +745,17 @@ __device__ __forceinline__ bool qk_try_quick(Ctx& cx, uint32_t ptr, uint64_t src
    * neighbour words are only fetched when the callee turns out to be idle: there a load is a memory transaction; the
    * logging kernels do the same because they have no registers to hold the two words: measured.) */
   constexpr bool EAGER = SM != 0 && !LOG;
-  const uint64_t fire = S64(q.fire_slot);
+  uint64_t fire;
+  if constexpr (SM == QK_SM_QSPLIT) {
+    /* two-tier queue: q.fire_slot is the callee's rank.  Busy (bit set) and, by the cached minimum, nothing of ANY
+     * component due yet: busy and not due without fetching the slot; only at a timestamp tie, or with the cache
+     * invalid, the slot itself is read */
+    if (!qk_fire_busy<SM>(cx, q.fire_slot)) fire = QK_TIME_NONE;
+    else if (cx.kvalid && cx.kbest > cx.now) fire = cx.kbest; /* some time > now: all the code below asks */
+    else fire = C64(cx.cfire0 + q.fire_slot);
+  } else {
+    fire = S64(q.fire_slot);
+  }
   uint32_t uw = 0, dw = 0;
   if constexpr (EAGER) {
     uw = S32(q.up_hc);
@@ -697,8 +764,10 @@ __device__ __forceinline__ bool qk_try_quick(Ctx& cx, uint32_t ptr, uint64_t src
   if (fire != QK_TIME_NONE) {
 #ifdef QK_HOST_EMUL
     const DevHotA c = QK_HOT_A(cx.subs[ptr]);
-    if (fire > cx.now && (!(W32(c.o32 + P32_FLAGS) & PF_HAS_ITEM) ||
-                          W64(c.o64 + P64_PREV) + W64(c.o64 + P64_LEFT) != fire))
+    const uint64_t fx = SM == QK_SM_QSPLIT ? C64(cx.cfire0 + q.fire_slot) : fire; /* the slot itself */
+    if (SM == QK_SM_QSPLIT && (fx > cx.now) != (fire > cx.now)) cx.status = 97; /* the cached minimum lied */
+    if (fx > cx.now && (!(W32(c.o32 + P32_FLAGS) & PF_HAS_ITEM) ||
+                        W64(c.o64 + P64_PREV) + W64(c.o64 + P64_LEFT) != fx))
       cx.status = 98; /* invariant check, CPU test build only */
 #endif
     return fire > cx.now; /* busy and not due: nothing to do ; due (<= now): pre_update_state drops the handle (Q3) */
@@ -726,14 +795,69 @@ __device__ __forceinline__ bool qk_try_quick(Ctx& cx, uint32_t ptr, uint64_t src
   return true;
 }
 
+/* ---- component record of a single-server discrete component, requested ahead of its update_state ------------------
+ * With the records in global memory (split placements, HBM planes) a finish-and-restart was a chain of dependent trips to
+ * L2 / DRAM -- flags and countdown, then the item, then the pre-drawn duration, then the head of the upstream ring -- 40 %
+ * of the split kernel's stall samples.  All of it is known by address once the lane knows which component its next call
+ * is for, so the event loop asks for everything at once, BEFORE the REFILL phase (whose own trip for the draw counters
+ * then overlaps), and the handler finds the values in registers.  Nothing but the REFILL phase runs in between, and that
+ * writes pre-drawn durations only: an EMPTY one is fetched again. */
+struct QkPre {
+  uint32_t comp, flags, item, idx, up_item;
+  uint64_t left, prev, dur;
+  bool has, has_up;
+};
+template <int SM>
+__device__ __forceinline__ void qk_prefetch_record(Ctx& cx, uint32_t comp, QkPre& pre) {
+  const DevHotA c = QK_HOT_A(comp);
+  if (c.kind < QK_DISCRETE_PROCESS || c.kind > QK_DISCRETE_SINK) return;
+  const DevHotB cb = QK_HOT_B(comp);
+  pre.comp = comp;
+  pre.has = true;
+  pre.flags = W32(c.o32 + P32_FLAGS);
+  pre.left = W64(c.o64 + P64_LEFT);
+  pre.prev = W64(c.o64 + P64_PREV);
+  pre.item = W32(c.o32 + P32_ITEM);
+  if (cb.o64_nextdur != 0xFFFF) pre.dur = W64(cb.o64_nextdur);
+  if (c.kind == QK_DISCRETE_SOURCE) pre.idx = W32(QK_HOT_C(comp).o32_next_item);
+  /* the item it would withdraw: the head of the upstream ring, if there is one now (a ring that is empty now can only
+   * receive its head from this very call -- a process whose downstream is its upstream -- and is then read in place) */
+  if (c.kind != QK_DISCRETE_SOURCE && cb.up_hc != QK_HC_NONE) {
+    const uint32_t hc = S32(cb.up_hc);
+    if (QK_HC_CNT(hc) != 0) {
+      pre.has_up = true;
+      pre.up_item = C32(QK_HOT_A((uint32_t)cx.comps[comp].up).olog64 + QK_HC_HEAD(hc));
+    }
+  }
+}
+
 /* ---- DiscreteProcess / DiscreteSource / DiscreteSink update_state, one code path ----------------------------- */
 template <bool LOG, int SM, int FT>
-__device__ __forceinline__ bool qk_update_single(Ctx& cx, const DevHotA& c, uint32_t comp, uint64_t src) {
+__device__ __forceinline__ bool qk_update_single(Ctx& cx, const DevHotA& c, uint32_t comp, uint64_t src,
+                                                 const QkPre* pre = nullptr) {
   const DevHotB cb = QK_HOT_B(comp);
   const uint32_t kind = c.kind;
-  uint32_t flags = W32(c.o32 + P32_FLAGS);
-  uint64_t left = W64(c.o64 + P64_LEFT);
-  const uint64_t dt = cx.now - W64(c.o64 + P64_PREV);
+  /* component record in global memory (split placements, HBM planes): the event loop has requested it ahead of the call
+   * (qk_prefetch_record); a caller without a prefetch gets the same loads here, side by side */
+  constexpr bool REC_GLOBAL = qk_is_split(SM) || SM == 0;
+  QkPre mine;
+  mine.has = false;
+  mine.has_up = false;
+  mine.dur = 0;
+  mine.idx = 0;
+  if constexpr (REC_GLOBAL) {
+    if (pre && pre->has && pre->comp == comp) {
+      mine = *pre;
+      if (cb.o64_nextdur != 0xFFFF && mine.dur == QK_DUR_EMPTY) mine.dur = W64(cb.o64_nextdur); /* refilled since */
+    } else {
+      qk_prefetch_record<SM>(cx, comp, mine);
+    }
+  }
+  uint32_t flags = REC_GLOBAL ? mine.flags : W32(c.o32 + P32_FLAGS);
+  uint64_t left = REC_GLOBAL ? mine.left : W64(c.o64 + P64_LEFT);
+  const uint64_t dt = cx.now - (REC_GLOBAL ? mine.prev : W64(c.o64 + P64_PREV));
+  const uint32_t pre_item = mine.item, pre_idx = mine.idx;
+  const uint64_t pre_dur = mine.dur;
   uint64_t ttnpe = QK_TIME_NONE;
   /* Vector3ContainerProcess / Source / Sink (core.rs:550-553): the item carries a resource, kept at cold64 `opay` */
   const bool ctr = FT >= 2 && (c.flags & DC_CONTAINER) != 0;
@@ -748,7 +872,7 @@ __device__ __forceinline__ bool qk_update_single(Ctx& cx, const DevHotA& c, uint
       left -= (dt < left ? dt : left); /* saturating_sub */
       if (left == 0) {
         flags &= ~PF_HAS_ITEM;
-        const uint32_t item = W32(c.o32 + P32_ITEM);
+        const uint32_t item = REC_GLOBAL ? pre_item : W32(c.o32 + P32_ITEM);
         src = qk_log<LOG, SM>(cx, c, comp, src, QK_LOG_PROCESS_FINISH, 0, item);
         if (ctr) {
           pay[0] = C64(opay);
@@ -783,7 +907,8 @@ __device__ __forceinline__ bool qk_update_single(Ctx& cx, const DevHotA& c, uint
       uint32_t item;
       if (need_us) {
         src = qk_log<LOG, SM>(cx, c, comp, src, QK_LOG_WITHDRAW_REQUEST, 0, 0);
-        const uint32_t rc = qk_stock_remove<LOG, SM>(cx, (uint32_t)cx.comps[comp].up, src, &item, ctr ? pay : nullptr);
+        const uint32_t rc = qk_stock_remove<LOG, SM>(cx, (uint32_t)cx.comps[comp].up, src, &item, ctr ? pay : nullptr,
+                                                     REC_GLOBAL && mine.has_up ? &mine.up_item : nullptr);
         if (rc & QK_RM_FAULT) return true;
         got = (rc & QK_RM_GOT) != 0;
       }
@@ -793,7 +918,7 @@ __device__ __forceinline__ bool qk_update_single(Ctx& cx, const DevHotA& c, uint
         const DevHotC cc = QK_HOT_C(comp);
         uint64_t d;
         if (cb.o64_nextdur != 0xFFFF) {
-          d = W64(cb.o64_nextdur);
+          d = REC_GLOBAL ? pre_dur : W64(cb.o64_nextdur);
           W64(cb.o64_nextdur) = QK_DUR_EMPTY;
           S32(cx.pf32 + (cb.pf_idx >> 5)) |= 1u << (cb.pf_idx & 31);
           cx.npend += 1;
@@ -801,7 +926,7 @@ __device__ __forceinline__ bool qk_update_single(Ctx& cx, const DevHotA& c, uint
           d = ((uint64_t)cc.const_dur_hi << 32) | cc.const_dur_lo;
         }
         if (!need_us) { /* ItemFactory::create_item discrete.rs:680-686 */
-          const uint32_t idx = W32(cc.o32_next_item);
+          const uint32_t idx = REC_GLOBAL ? pre_idx : W32(cc.o32_next_item);
           if (idx > 0x3FFFFFFu) {
             cx.status = QK_REP_ITEM_INDEX_OVERFLOW;
             return true;
@@ -1057,11 +1182,11 @@ __device__ __forceinline__ void qk_update_multi(Ctx& cx, const DevComp* c, uint3
 /* Process::update_state (core.rs:370-376) */
 /* returns true when the replication has faulted (cx.status) */
 template <bool LOG, int SM, int FT>
-__device__ __forceinline__ bool qk_update_state(Ctx& cx, uint32_t comp, uint64_t src) {
+__device__ __forceinline__ bool qk_update_state(Ctx& cx, uint32_t comp, uint64_t src, const QkPre* pre = nullptr) {
   const DevHotA a = QK_HOT_A(comp);
   if (FT == 0 || (a.kind >= QK_DISCRETE_PROCESS && a.kind <= QK_DISCRETE_SINK)) {
     qk_pre<LOG, SM, FT == 0>(cx, a, comp);
-    return qk_update_single<LOG, SM, FT>(cx, a, comp, src);
+    return qk_update_single<LOG, SM, FT>(cx, a, comp, src, pre);
   }
   if constexpr (FT != 0) {
     const DevComp* c = &cx.comps[comp];
@@ -1105,7 +1230,8 @@ constexpr int qk_lb_threads(int sm) { return sm > 0 ? sm : QK_MAX_NT; }
 constexpr int qk_lb_resident(int ft, bool log) { return ft == 0 ? (log ? QK_LEAN_THREADS_LOG : QK_LEAN_THREADS) : 512; }
 constexpr int qk_lb_blocks(int sm, int ft, bool log) {
   /* split placement: shared memory holds at most ~240 replications per SM, so registers are not what limits residency */
-  return sm == QK_SM_SPLIT ? 1 : sm > 0 ? (qk_lb_resident(ft, log) / sm > 0 ? qk_lb_resident(ft, log) / sm : 1) : (ft == 0 ? 3 : 2);
+  /* ... but with the two-tier queue 500-600 replications of a lean model fit: two blocks of 256 */
+  return sm == QK_SM_QSPLIT ? (ft == 0 ? 2 : 1) : sm == QK_SM_SPLIT ? 1 : sm > 0 ? (qk_lb_resident(ft, log) / sm > 0 ? qk_lb_resident(ft, log) / sm : 1) : (ft == 0 ? 3 : 2);
 }
 /* FT = feature set of the model: 0 = only SIMPLE single-server discrete components and stocks (no delay modes, no
  * environment, no scheduled events, no parallel or vector components): the handlers for everything else are
@@ -1157,8 +1283,13 @@ __global__ void __launch_bounds__(qk_lb_threads(SM), qk_lb_blocks(SM, FT, LOG)) 
   cx.rep_local = rep_local;
   cx.gs64 = P.gs64 + rep_local;
   cx.gs32 = P.gs32 + rep_local;
-  cx.gc64 = P.gc64 + rep_local;
-  cx.gc32 = P.gc32 + rep_local;
+  if constexpr (qk_is_split(SM)) { /* cold planes [replication][slot] */
+    cx.gc64 = P.gc64 + rep_local * P.n64c;
+    cx.gc32 = P.gc32 + rep_local * P.n32c;
+  } else {
+    cx.gc64 = P.gc64 + rep_local;
+    cx.gc32 = P.gc32 + rep_local;
+  }
   cx.rep_pad = (uint32_t)P.rep_pad;
   cx.key0 = (uint32_t)P.seed;
   cx.key1 = (uint32_t)(P.seed >> 32);
@@ -1170,17 +1301,29 @@ __global__ void __launch_bounds__(qk_lb_threads(SM), qk_lb_blocks(SM, FT, LOG)) 
   cx.log_base = LOG ? P.log + 2 * (size_t)rep_local * P.log_cap : nullptr;
   cx.status = 0;
   cx.npend = 0;
+  cx.cfire0 = cx.hdr->cfire0;
+  cx.busy32 = cx.hdr->busy32;
+  cx.kbest = QK_TIME_NONE;
+  cx.kidx = 0;
+  cx.kvalid = false; /* two-tier queue: the first pop of a launch scans the cold fire array */
   const uint32_t n_comp = cx.hdr->n_comp, n_sched = cx.hdr->n_sched, n_ext = cx.hdr->n_ext;
   const uint32_t n_stale_words = cx.hdr->n_stale_words;
   const uint32_t n_sched_pad = (n_sched + 3u) & ~3u;
+  /* entries of the hot fire array: every schedulable component, or (two-tier queue) the stocks */
+  const uint32_t n_hot_pad = SM == QK_SM_QSPLIT ? ((cx.hdr->n_hot + 3u) & ~3u) : n_sched_pad;
+  const uint16_t* const hot_rank =
+      reinterpret_cast<const uint16_t*>(reinterpret_cast<const uint8_t*>(cx.hdr) + cx.hdr->off_hot_rank);
+  (void)hot_rank;
 
   if (P.do_init) {
     /* fresh replication: zero state, no pending events, stocks hold their initial items */
     for (uint32_t s = 0; s < P.n64; ++s) S64(s) = 0;
     for (uint32_t s = 0; s < P.n32; ++s) S32(s) = 0;
-    for (uint32_t i = 0; i < n_sched_pad; ++i) S64(G64_FIRE0 + i) = QK_TIME_NONE; /* incl. the padding slots */
+    for (uint32_t i = 0; i < n_hot_pad; ++i) S64(G64_FIRE0 + i) = QK_TIME_NONE; /* incl. the padding slots */
     for (uint32_t s = 0; s < P.n64c; ++s) C64(s) = 0;
     for (uint32_t s = 0; s < P.n32c; ++s) C32(s) = 0;
+    if constexpr (SM == QK_SM_QSPLIT)
+      for (uint32_t i = 0; i < n_sched_pad; ++i) C64(cx.cfire0 + i) = QK_TIME_NONE;
     cx.now = P.t0;
     cx.log_cnt = 0;
     for (uint32_t s = 0; s < n_comp * ST_PER_COMP; ++s) {
@@ -1325,6 +1468,60 @@ __global__ void __launch_bounds__(qk_lb_threads(SM), qk_lb_blocks(SM, FT, LOG)) 
         /* fire[] is padded with NONE to a multiple of four slots (lowering): groups of four independent loads and a
          * two-level tournament instead of one long dependent chain of 64-bit compares.  Strict '<' everywhere keeps
          * the LOWEST index among equal times, i.e. registration-rank order. */
+        if constexpr (SM == QK_SM_QSPLIT) {
+          /* two-tier queue.  Keyed events: the cached minimum over the cold array, re-established by a scan (independent,
+           * coalesced global loads) only after the minimum itself was popped or dropped. */
+          if (!cx.kvalid) {
+            uint64_t kb = QK_TIME_NONE;
+            uint32_t ki = 0;
+            for (uint32_t i = 0; i < n_sched_pad; i += 4) {
+              const uint64_t t0 = C64(cx.cfire0 + i), t1 = C64(cx.cfire0 + i + 1);
+              const uint64_t t2 = C64(cx.cfire0 + i + 2), t3 = C64(cx.cfire0 + i + 3);
+              const bool p01 = t1 < t0, p23 = t3 < t2;
+              const uint64_t a = p01 ? t1 : t0, b = p23 ? t3 : t2;
+              const uint32_t ai = p01 ? i + 1 : i, bj = p23 ? i + 3 : i + 2;
+              const bool pab = b < a;
+              const uint64_t m = pab ? b : a;
+              if (m < kb) {
+                kb = m;
+                ki = pab ? bj : ai;
+              }
+            }
+            cx.kbest = kb;
+            cx.kidx = ki;
+            cx.kvalid = true;
+          }
+          /* the stocks' pending emit_change events: the hot array, in rank order */
+          uint64_t sb = QK_TIME_NONE;
+          uint32_t sj = 0;
+          for (uint32_t i = 0; i < n_hot_pad; i += 4) {
+            const uint64_t t0 = S64(G64_FIRE0 + i), t1 = S64(G64_FIRE0 + i + 1);
+            const uint64_t t2 = S64(G64_FIRE0 + i + 2), t3 = S64(G64_FIRE0 + i + 3);
+            const bool p01 = t1 < t0, p23 = t3 < t2;
+            const uint64_t a = p01 ? t1 : t0, b = p23 ? t3 : t2;
+            const uint32_t ai = p01 ? i + 1 : i, bj = p23 ? i + 3 : i + 2;
+            const bool pab = b < a;
+            const uint64_t m = pab ? b : a;
+            if (m < sb) {
+              sb = m;
+              sj = pab ? bj : ai;
+            }
+          }
+          /* min over (time, rank) of the two tiers; an external event (rank 0) keeps winning ties */
+          uint64_t m = cx.kbest;
+          uint32_t mi = cx.kidx;
+          if (sb != QK_TIME_NONE) {
+            const uint32_t sr = hot_rank[sj];
+            if (sb < m || (sb == m && sr < mi)) {
+              m = sb;
+              mi = sr;
+            }
+          }
+          if (m < best) {
+            best = m;
+            bi = (int)mi;
+          }
+        } else {
         for (uint32_t i = 0; i < n_sched_pad; i += 4) {
           const uint64_t t0 = S64(G64_FIRE0 + i), t1 = S64(G64_FIRE0 + i + 1);
           const uint64_t t2 = S64(G64_FIRE0 + i + 2), t3 = S64(G64_FIRE0 + i + 3);
@@ -1337,6 +1534,7 @@ __global__ void __launch_bounds__(qk_lb_threads(SM), qk_lb_blocks(SM, FT, LOG)) 
             best = m;
             bi = (int)(pab ? bj : ai);
           }
+        }
         }
         bool stale = false;
         uint32_t stale_word = 0, stale_mask = 0;
@@ -1426,7 +1624,7 @@ __global__ void __launch_bounds__(qk_lb_threads(SM), qk_lb_blocks(SM, FT, LOG)) 
                 if (LOG)
                   src = FT == 0 ? (((uint64_t)comp << 32) | (uint32_t)(S32(a.olog32 + L32_SEQ) - 1u))
                                 : C64(a.olog64 + PL64_SCHED_SRC);
-                S64(G64_FIRE0 + bi) = QK_TIME_NONE;
+                qk_fire_clear<SM>(cx, (uint32_t)bi);
                 keyed = true;
               }
               rem = 1;
@@ -1443,6 +1641,14 @@ __global__ void __launch_bounds__(qk_lb_threads(SM), qk_lb_blocks(SM, FT, LOG)) 
      * the few lanes that start a process need a variate on a given trip.  So starts consume a pre-drawn duration,
      * and the sampler runs as its own phase -- for all lanes with consumed slots at once -- when enough lanes are
      * waiting, or when some lane's next call could start a process whose slot is still empty. */
+    QkPre pre;
+    pre.has = false;
+    pre.has_up = false;
+    pre.dur = 0;
+    pre.idx = 0;
+    if constexpr (qk_is_split(SM) || SM == 0) {
+      if (rem != 0) qk_prefetch_record<SM>(cx, cx.subs[ptr], pre); /* the loads travel while the REFILL phase runs */
+    }
     {
       const bool must = rem != 0 && cx.npend != 0 && qk_needs_refill_now<SM>(cx, cx.subs[ptr]);
       const uint32_t waiting = QK_BALLOT(cx.npend != 0);
@@ -1455,7 +1661,7 @@ __global__ void __launch_bounds__(qk_lb_threads(SM), qk_lb_blocks(SM, FT, LOG)) 
       const uint32_t p = cx.subs[ptr];
       ptr += 1;
       rem -= 1;
-      const bool fault = qk_update_state<LOG, SM, FT>(cx, p, src);
+      const bool fault = qk_update_state<LOG, SM, FT>(cx, p, src, &pre);
       keyed = false;
       if (fault) {
         rem = 0;
@@ -1512,12 +1718,14 @@ __device__ __forceinline__ uint64_t qk_left_at_clock(uint32_t flags, uint64_t le
  * component records live in (the hot planes, or the cold ones under the split placement: DevHeader.split) */
 __device__ __forceinline__ void qk_comp_stats_dev(const DevComp* c, const DevVec* vecs, uint32_t comp, const uint64_t* g64,
                                                   const uint32_t* g32, const uint64_t* w64, const uint32_t* w32,
+                                                  uint32_t w_aos64, uint32_t w_aos32,
                                                   const uint64_t* gs64, const uint32_t* gs32,
                                                   uint64_t rep_pad, uint64_t rep, qk_comp_stats* o) {
+  /* w_aos64 / w_aos32: 0 = the record planes are [slot][replication] ; else [replication][slot] with that many slots */
 #define G64(slot) g64[(size_t)(slot)*rep_pad + rep]
 #define G32(slot) g32[(size_t)(slot)*rep_pad + rep]
-#define WG64(slot) w64[(size_t)(slot)*rep_pad + rep]
-#define WG32(slot) w32[(size_t)(slot)*rep_pad + rep]
+#define WG64(slot) w64[w_aos64 ? (size_t)rep * w_aos64 + (slot) : (size_t)(slot)*rep_pad + rep]
+#define WG32(slot) w32[w_aos32 ? (size_t)rep * w_aos32 + (slot) : (size_t)(slot)*rep_pad + rep]
 #define GS64(k) gs64[(size_t)(comp * ST_PER_COMP + (k)) * rep_pad + rep]
 #define GS32(k) gs32[(size_t)(comp * ST_PER_COMP + (k)) * rep_pad + rep]
   const uint64_t now = G64(G64_NOW);

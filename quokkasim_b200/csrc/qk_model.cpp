@@ -508,7 +508,7 @@ int qk_model_n_dists(const qk_model* m, uint32_t* out) {
 int qk_model_state_bytes(const qk_model* m, int with_log, uint32_t* out) {
   if (!m || !out) return QK_ERR_INVALID_ARG;
   QkLowered l;
-  int rc = qk_lower(m, with_log != 0, false, &l);
+  int rc = qk_lower(m, with_log != 0, 0, &l);
   if (rc) return rc;
   *out = l.hdr.n64 * 8 + l.hdr.n32 * 4;
   return QK_OK;
@@ -540,7 +540,9 @@ static uint64_t host_duration_code(double secs) {
   return (uint64_t)q;
 }
 
-int qk_lower(const qk_model* m, bool log, bool split, QkLowered* out) {
+int qk_lower(const qk_model* m, bool log, int placement, QkLowered* out) {
+  const bool split = placement != 0;   /* component records in the cold planes */
+  const bool qsplit = placement == 2;  /* ... and the process-like fire slots too (two-tier scheduler queue) */
   const size_t nc = m->comps.size();
   if (nc == 0) {
     qk_set_error("qk_lower: model has no components");
@@ -588,6 +590,27 @@ int qk_lower(const qk_model* m, bool log, bool split, QkLowered* out) {
   uint32_t n64 = G64_FIRE0 + ((n_sched + 3u) & ~3u); /* fire[] padded to a multiple of four (scheduler scan) */
   const uint32_t pf32 = G32_STALE0 + n_stale_words;
   uint32_t n32 = pf32 + n_pf_words;
+  /* two-tier scheduler queue (placement 2): the hot fire array holds the STOCKS' slots only (their emit_change events
+   * fire one nanosecond after they are scheduled: they are the next action almost every time one is pending); the keyed
+   * events of the process-like components live in a cold array indexed by rank, summarised on chip by a cached minimum
+   * (kernel registers) and a busy mask (hot words after the prefetch mask).  A stock's fire_idx is then its index in
+   * the hot array; hot_rank[] maps it back to the rank. */
+  std::vector<uint16_t> hot_rank;
+  uint32_t cfire0 = 0, busy32 = 0;
+  if (qsplit) {
+    for (uint32_t r = 0; r < n_sched; ++r) {
+      const uint32_t k = m->comps[sched[r]].d.kind;
+      if (is_item_stock(k) || k == QK_VECTOR_STOCK) {
+        dc[sched[r]].fire_idx = (uint16_t)hot_rank.size();
+        hot_rank.push_back((uint16_t)r);
+      }
+    }
+    n64 = G64_FIRE0 + (((uint32_t)hot_rank.size() + 3u) & ~3u);
+    cfire0 = n64c;
+    n64c += (n_sched + 3u) & ~3u;
+    busy32 = n32;
+    n32 += n_stale_words;
+  }
   /* split placement (qk_batch_create, QK_BATCH_STATE_SPLIT): only what the scheduler pop and the quick path read stays in
    * the hot planes -- the fire slots, the stocks' head|count and pending-emit words, the seq counters -- and every
    * component record (countdowns, flags, items, pre-drawn durations, draw counters, resources) is allocated in the
@@ -876,7 +899,10 @@ int qk_lower(const qk_model* m, bool log, bool split, QkLowered* out) {
   h.init_off = init_off;
   h.n_init = n_init;
   h.log_enabled = log ? 1 : 0;
-  h.split = split ? 1 : 0;
+  h.split = (uint32_t)placement;
+  h.n_hot = (uint32_t)hot_rank.size();
+  h.cfire0 = cfire0;
+  h.busy32 = busy32;
   uint32_t off = align8((uint32_t)sizeof(DevHeader));
   h.off_comps = off;
   off = align8(off + (uint32_t)(nc * sizeof(DevComp)));
@@ -892,6 +918,8 @@ int qk_lower(const qk_model* m, bool log, bool split, QkLowered* out) {
   off = align8(off + (uint32_t)(sched.size() * sizeof(uint16_t)));
   h.off_pf = off;
   off = align8(off + (uint32_t)(pf_comp.size() * sizeof(uint16_t)));
+  h.off_hot_rank = off;
+  off = align8(off + (uint32_t)(hot_rank.size() * sizeof(uint16_t)));
   h.n_vec = (uint32_t)vecs.size();
   h.off_vecs = off;
   off = align8(off + (uint32_t)(vecs.size() * sizeof(DevVec)));
@@ -953,7 +981,7 @@ int qk_lower(const qk_model* m, bool log, bool split, QkLowered* out) {
     const bool dm_quick = single_k && d.n_dm > 0 && d.env < 0 && !(d.flags & DC_CONTAINER);
     if (!(q.a.flags & DC_SIMPLE) && !dm_quick) continue; /* flags == 0: always the full handler */
     s.flags = dm_quick ? SQ_DM : SQ_QUICK;
-    s.fire_slot = (uint16_t)(G64_FIRE0 + d.fire_idx);
+    s.fire_slot = qsplit ? d.fire_idx : (uint16_t)(G64_FIRE0 + d.fire_idx); /* two-tier queue: the rank itself */
     if (d.kind == QK_DISCRETE_SOURCE) s.flags |= SQ_US_FORCED | (1u << SQ_US_SHIFT);
     else if (d.up < 0) s.flags |= SQ_US_FORCED | (3u << SQ_US_SHIFT);
     else s.up_hc = q.b.up_hc;
@@ -1021,6 +1049,7 @@ int qk_lower(const qk_model* m, bool log, bool split, QkLowered* out) {
   memcpy(out->blob.data() + h.off_subs, subs.data(), subs.size() * sizeof(uint16_t));
   if (!sched.empty()) memcpy(out->blob.data() + h.off_sched, sched.data(), sched.size() * sizeof(uint16_t));
   if (!pf_comp.empty()) memcpy(out->blob.data() + h.off_pf, pf_comp.data(), pf_comp.size() * sizeof(uint16_t));
+  if (!hot_rank.empty()) memcpy(out->blob.data() + h.off_hot_rank, hot_rank.data(), hot_rank.size() * sizeof(uint16_t));
   if (!vecs.empty()) memcpy(out->blob.data() + h.off_vecs, vecs.data(), vecs.size() * sizeof(DevVec));
   out->hdr = h;
   out->vecs = vecs;

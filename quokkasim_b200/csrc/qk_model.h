@@ -45,8 +45,9 @@ struct QkLowered {
 
 void qk_set_error(const char* fmt, ...);
 int qk_is_process_like(uint32_t kind);
-/* lowers the model for the given logging mode and state placement (split: component records in the cold planes, see
- * qk_lower); returns QK_OK or an error */
-int qk_lower(const qk_model* m, bool log, bool split, QkLowered* out);
+/* lowers the model for the given logging mode and state placement (0: everything in the hot planes ; 1: component
+ * records in the cold planes ; 2: ... and the keyed events of the process-like components too, see qk_lower); returns
+ * QK_OK or an error */
+int qk_lower(const qk_model* m, bool log, int placement, QkLowered* out);
 
 #endif

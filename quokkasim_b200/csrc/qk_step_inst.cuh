@@ -24,6 +24,7 @@ static StepKernel qk_pick_step(uint32_t nt) {
     case 224: return qk_step_kernel<LOG, 224, FT>;
     case 256: return qk_step_kernel<LOG, 256, FT>;
     case 0xFFFFFFFEu: return qk_step_kernel<LOG, QK_SM_SPLIT, FT>; /* split placement, run-time block size */
+    case 0xFFFFFFFDu: return qk_step_kernel<LOG, QK_SM_QSPLIT, FT>; /* ... with the two-tier scheduler queue */
     default: return qk_step_kernel<LOG, -1, FT>;
   }
 }

@@ -142,6 +142,7 @@ static int run(qk_batch* b, uint32_t do_init, uint64_t t0, uint64_t t_until, uin
     qk_emul_bid = (uint32_t)r;
     const bool hbm = (b->cfg.flags & QK_BATCH_STATE_IN_HBM) != 0;
     const bool split = (b->cfg.flags & QK_BATCH_STATE_SPLIT) != 0;
+    const bool qsplit = split && (b->cfg.flags & QK_BATCH_QUEUE_TWO_TIER) != 0;
     /* the product picks FT = 0 only for on-chip state; here both state placements run both feature sets so the
      * CPU suite covers the lean kernel on every simple model */
     const uint32_t ft = b->low.hdr.features;
@@ -153,10 +154,12 @@ static int run(qk_batch* b, uint32_t do_init, uint64_t t0, uint64_t t_until, uin
   } while (0)
     if (b->log) {
       if (hbm) QK_EMUL_RUN(true, 0);
+      else if (qsplit) QK_EMUL_RUN(true, QK_SM_QSPLIT);
       else if (split) QK_EMUL_RUN(true, QK_SM_SPLIT);
       else QK_EMUL_RUN(true, -1);
     } else {
       if (hbm) QK_EMUL_RUN(false, 0);
+      else if (qsplit) QK_EMUL_RUN(false, QK_SM_QSPLIT);
       else if (split) QK_EMUL_RUN(false, QK_SM_SPLIT);
       else QK_EMUL_RUN(false, -1);
     }
@@ -173,7 +176,8 @@ int qk_batch_create(const qk_model* m, const qk_batch_config* cfg, qk_batch** ou
   qk_batch* b = new qk_batch();
   b->cfg = *cfg;
   b->log = cfg->log_capacity != 0;
-  int rc = qk_lower(m, b->log, (cfg->flags & QK_BATCH_STATE_SPLIT) != 0, &b->low);
+  int rc = qk_lower(m, b->log,
+                    (cfg->flags & QK_BATCH_STATE_SPLIT) ? ((cfg->flags & QK_BATCH_QUEUE_TWO_TIER) ? 2 : 1) : 0, &b->low);
   if (rc) {
     delete b;
     return rc;
@@ -335,6 +339,7 @@ int qk_batch_comp_stats(qk_batch* b, uint64_t rep0, uint64_t n, uint32_t comp, q
   for (uint64_t i = 0; i < n; ++i)
     qk_comp_stats_dev(&b->low.comps[comp], b->low.vecs.data(), comp, b->g64.data(), b->g32.data(),
                       b->low.hdr.split ? b->gc64.data() : b->g64.data(), b->low.hdr.split ? b->gc32.data() : b->g32.data(),
+                      b->low.hdr.split ? b->low.hdr.n64c : 0u, b->low.hdr.split ? b->low.hdr.n32c : 0u,
                       b->gs64.data(), b->gs32.data(), b->rep_pad, rep0 + i, &out[i]);
   return QK_OK;
 }
@@ -467,7 +472,8 @@ int qk_batch_read_vector(qk_batch* b, uint64_t rep, uint32_t comp, double* out3)
     return QK_ERR_INVALID_ARG;
   const DevVec& v = b->low.vecs[b->low.comps[comp].vec_idx];
   out3[0] = out3[1] = out3[2] = 0.0;
-  for (uint32_t k = 0; k < v.dim; ++k) memcpy(&out3[k], &(b->low.hdr.split ? b->gc64 : b->g64)[(size_t)(v.o64_res + k) * b->rep_pad + rep], 8);
+  for (uint32_t k = 0; k < v.dim; ++k) memcpy(&out3[k], b->low.hdr.split ? &b->gc64[(size_t)rep * b->low.hdr.n64c + v.o64_res + k]
+                                                                             : &b->g64[(size_t)(v.o64_res + k) * b->rep_pad + rep], 8);
   return QK_OK;
 }
 
@@ -481,7 +487,8 @@ int qk_batch_read_stock(qk_batch* b, uint64_t rep, uint32_t comp, uint32_t* item
   if (!items) return QK_OK;
   if (cap < cnt) return QK_ERR_BUFFER_TOO_SMALL;
   for (uint32_t i = 0; i < cnt; ++i)
-    items[i] = b->gc32[(size_t)(c.ocold32 + (head + i) % c.ring_cap) * b->rep_pad + rep];
+    items[i] = b->low.hdr.split ? b->gc32[(size_t)rep * b->low.hdr.n32c + c.ocold32 + (head + i) % c.ring_cap]
+                                : b->gc32[(size_t)(c.ocold32 + (head + i) % c.ring_cap) * b->rep_pad + rep];
   return QK_OK;
 }
 
@@ -491,9 +498,14 @@ int qk_batch_read_containers(qk_batch* b, uint64_t rep, uint32_t comp, uint32_t*
     return QK_ERR_INVALID_ARG;
   const DevComp& c = b->low.comps[comp];
   auto h32 = [&](uint32_t slot) { return b->g32[(size_t)slot * b->rep_pad + rep]; };
-  auto w32 = [&](uint32_t slot) { return (b->low.hdr.split ? b->gc32 : b->g32)[(size_t)slot * b->rep_pad + rep]; };
-  auto c32 = [&](uint32_t slot) { return b->gc32[(size_t)slot * b->rep_pad + rep]; };
-  auto c64 = [&](uint32_t slot) { return b->gc64[(size_t)slot * b->rep_pad + rep]; };
+  const bool aos = b->low.hdr.split != 0; /* cold planes [replication][slot] */
+  auto c32 = [&](uint32_t slot) {
+    return aos ? b->gc32[(size_t)rep * b->low.hdr.n32c + slot] : b->gc32[(size_t)slot * b->rep_pad + rep];
+  };
+  auto c64 = [&](uint32_t slot) {
+    return aos ? b->gc64[(size_t)rep * b->low.hdr.n64c + slot] : b->gc64[(size_t)slot * b->rep_pad + rep];
+  };
+  auto w32 = [&](uint32_t slot) { return aos ? c32(slot) : b->g32[(size_t)slot * b->rep_pad + rep]; };
   std::vector<uint32_t> hs, ps;
   if (c.kind == QK_DISCRETE_STOCK) {
     const uint32_t hc = h32(c.o32 + S32_HC), head = QK_HC_HEAD(hc), cnt = QK_HC_CNT(hc);

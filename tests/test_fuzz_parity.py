@@ -169,6 +169,10 @@ def test_random_models_match_the_oracle_split_placement(emul_lib, seed):
     _run(emul_lib, seed, 2, flags=16)
     if seed < 712:
         _run_vector(emul_lib, seed, 2, flags=16)
+    # ... with the two-tier scheduler queue
+    _run(emul_lib, seed, 2, flags=16 | 32)
+    if seed < 712:
+        _run_vector(emul_lib, seed, 2, flags=16 | 32)
 
 
 def test_random_models_are_mostly_comparable(emul_lib):
@@ -296,8 +300,10 @@ def test_random_models_match_the_oracle_lane_groups_on_gpu(gpu_lib, seed):
 @pytest.mark.parametrize("seed", range(800, 812))
 def test_random_models_match_the_oracle_split_placement_on_gpu(gpu_lib, seed):
     _run(gpu_lib, seed, 96, flags=16)
+    _run(gpu_lib, seed, 96, flags=16 | 32)
     if seed < 804:
         _run_vector(gpu_lib, seed, 96, flags=16)
+        _run_vector(gpu_lib, seed, 96, flags=16 | 32)
 
 
 @pytest.mark.gpu

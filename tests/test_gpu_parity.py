@@ -491,11 +491,12 @@ def test_phased_kernel_matches_the_oracle(gpu_lib, lanes):
     _check(gpu_lib, H.container_haulage(), 128, n_events=6000, sample=[0, 127], log_capacity=65536, flags=f)
 
 
+@pytest.mark.parametrize("f", [16, 16 | 32])
 @pytest.mark.parametrize("tpb", [0, 64, 128])
-def test_split_placement_matches_the_oracle(gpu_lib, tpb):
+def test_split_placement_matches_the_oracle(gpu_lib, tpb, f):
     """QK_BATCH_STATE_SPLIT: the scheduler queue and the stocks' state words staged in shared memory, the component
-    records in global memory -- every model family, in one launch and across launches (state round trips)"""
-    f = 16
+    records in global memory -- every model family; with QK_BATCH_QUEUE_TWO_TIER the keyed events of the process-like
+    components leave the chip too (cached minimum + busy mask)"""
     kw = dict(flags=f, threads_per_block=tpb)
     _check(gpu_lib, H.haulage(n_src=8, per_queue=8), 301, n_events=20000, sample=[0, 150, 300], log_capacity=131072, **kw)
     _check(gpu_lib, H.serial_line(n_proc=32), 170, n_events=30000, sample=[0, 169], log_capacity=131072, **kw)
@@ -508,7 +509,8 @@ def test_split_placement_matches_the_oracle(gpu_lib, tpb):
 
 def test_split_placement_round_trips_and_agrees_with_the_other_placements(gpu_lib):
     blobs = []
-    for flags, how in ((16, "one"), (16, "pieces"), (16, "sliced"), (_gflags(8), "one"), (1, "one")):
+    for flags, how in ((16, "one"), (16, "pieces"), (16, "sliced"), (48, "one"), (48, "pieces"), (48, "sliced"),
+                       (_gflags(8), "one"), (1, "one")):
         m = H.haulage(n_src=3, per_queue=4)
         sim = m.sim(gpu_lib, 1000, base_seed=21, flags=flags, log_capacity=256)
         if how == "one":
