@@ -138,7 +138,8 @@ static StepKernel pick_kernel(bool log, bool hbm, uint32_t nt, uint32_t features
 }
 
 /* max_thr: resident threads per SM the register allocation of the kernel variant allows (its launch bounds) */
-static uint32_t choose_nt(uint32_t per_rep_bytes, uint32_t table_bytes, uint32_t max_thr, uint32_t* threads_per_sm) {
+static uint32_t choose_nt(uint32_t per_rep_bytes, uint32_t table_bytes, uint32_t max_thr, uint32_t* threads_per_sm,
+                          uint32_t min_nt = 64) {
   uint32_t best_nt = 0, best_thr = 0;
   for (uint32_t nt = 256; nt >= 32; nt -= 32) {
     const uint64_t bytes = (uint64_t)table_bytes + (uint64_t)per_rep_bytes * nt;
@@ -155,7 +156,7 @@ static uint32_t choose_nt(uint32_t per_rep_bytes, uint32_t table_bytes, uint32_t
   /* among block sizes within 12% of the best residency prefer the smallest (>= 64): a block holds its shared memory
    * until its slowest warp finishes, so small blocks recycle capacity sooner (measured on discrete_queue: 8 x 64
    * threads per SM beats 3 x 192 although the latter holds two more warps) */
-  for (uint32_t nt = 64; nt < best_nt; nt += 32) {
+  for (uint32_t nt = min_nt; nt < best_nt; nt += 32) {
     const uint64_t bytes = (uint64_t)table_bytes + (uint64_t)per_rep_bytes * nt;
     uint32_t bps = (uint32_t)((227u * 1024u) / (bytes + 1024u));
     if (bps > 32) bps = 32;
@@ -616,7 +617,9 @@ int qk_batch_create(const qk_model* m, const qk_batch_config* cfg, qk_batch** ou
        * replications cost more in L2 misses than their warps hide (measured: 3 x 128 threads beat 3 x 160 and 2 x 256) */
       if (qsplit && thr_cap > 384u) thr_cap = 384u;
     }
-    if (nt == 0) nt = choose_nt(per_rep, b->table_bytes_padded, thr_cap, nullptr);
+    /* (two-tier queue, measured on the 96-component network: 3 x 128 and 2 x 192 threads 4.2e9 events/s, 4 x 96 3.8e9,
+     * 5 x 64 3.7e9 -- every block carries its own 22 KB copy of the tables) */
+    if (nt == 0) nt = choose_nt(per_rep, b->table_bytes_padded, thr_cap, nullptr, qsplit ? 128u : 64u);
     const bool fits = nt != 0 && nt <= QK_MAX_NT && !(nt & 31) &&
                       (uint64_t)b->table_bytes_padded + (uint64_t)per_rep * nt <= 227u * 1024u - 64u;
     if (!fits) {

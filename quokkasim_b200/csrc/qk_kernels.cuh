@@ -89,7 +89,7 @@ struct Ctx {
   uint32_t npend; /* consumed pre-drawn durations waiting for the REFILL phase */
   /* two-tier scheduler queue (QK_SM_QSPLIT): first cold64 slot of the process-like fire array, first hot32 slot of the busy
    * mask, and the cached minimum over that array by (time, rank) -- exact while kvalid */
-  uint32_t cfire0, busy32, kidx;
+  uint32_t cfire0, busy32, emask32, kidx;
   uint64_t kbest;
   bool kvalid;
   uint64_t rep_local;
@@ -130,6 +130,9 @@ __device__ __forceinline__ auto qk_ix(uint32_t slot, uint32_t stride) {
  * the stocks' slots only, the keyed events of the process-like components live in a cold array by rank */
 #define QK_SM_QSPLIT (-3)
 #define qk_is_split(sm) ((sm) == QK_SM_SPLIT || (sm) == QK_SM_QSPLIT)
+#define qk_is_two_tier(sm) ((sm) == QK_SM_QSPLIT)
+/* keyed-event slot of rank idx under the two-tier queue (cold plane) */
+#define QK_CFIRE(idx) C64(cx.cfire0 + (idx))
 template <int SM>
 __device__ __forceinline__ uint64_t& qk_w64(const Ctx& cx, uint32_t slot) {
   if constexpr (qk_is_split(SM)) return cx.gc64[slot];
@@ -355,13 +358,13 @@ __device__ __forceinline__ bool qk_fire_busy(Ctx& cx, uint32_t idx) {
 }
 template <int SM>
 __device__ __forceinline__ uint64_t qk_fire_get(Ctx& cx, uint32_t idx) {
-  if constexpr (SM == QK_SM_QSPLIT) return qk_fire_busy<SM>(cx, idx) ? C64(cx.cfire0 + idx) : QK_TIME_NONE;
+  if constexpr (qk_is_two_tier(SM)) return qk_fire_busy<SM>(cx, idx) ? QK_CFIRE(idx) : QK_TIME_NONE;
   else return S64(G64_FIRE0 + idx);
 }
 template <int SM>
 __device__ __forceinline__ void qk_fire_set(Ctx& cx, uint32_t idx, uint64_t t) { /* t != NONE */
-  if constexpr (SM == QK_SM_QSPLIT) {
-    C64(cx.cfire0 + idx) = t;
+  if constexpr (qk_is_two_tier(SM)) {
+    QK_CFIRE(idx) = t;
     S32(cx.busy32 + (idx >> 5)) |= 1u << (idx & 31);
     if (cx.kvalid && (t < cx.kbest || (t == cx.kbest && idx < cx.kidx))) {
       cx.kbest = t;
@@ -373,8 +376,8 @@ __device__ __forceinline__ void qk_fire_set(Ctx& cx, uint32_t idx, uint64_t t) {
 }
 template <int SM>
 __device__ __forceinline__ void qk_fire_clear(Ctx& cx, uint32_t idx) {
-  if constexpr (SM == QK_SM_QSPLIT) {
-    C64(cx.cfire0 + idx) = QK_TIME_NONE; /* (the scan reads the array, not the mask) */
+  if constexpr (qk_is_two_tier(SM)) {
+    QK_CFIRE(idx) = QK_TIME_NONE; /* (the scan reads the array, not the mask) */
     S32(cx.busy32 + (idx >> 5)) &= ~(1u << (idx & 31));
     if (cx.kvalid && idx == cx.kidx) cx.kvalid = false; /* the minimum is gone: the next pop scans the cold array */
   } else {
@@ -403,6 +406,7 @@ __device__ __forceinline__ bool qk_emit_push(Ctx& cx, const DevHotA& c, uint32_t
   const uint64_t T = cx.now + 1;
   if (n == 0) {
     S64(fire) = T;
+    if constexpr (qk_is_two_tier(SM)) S32(cx.emask32 + (c.fire_idx >> 5)) |= 1u << (c.fire_idx & 31); /* pending */
     split = 1;
     head = 0;
   } else if (S64(fire) == T) {
@@ -440,6 +444,7 @@ __device__ __forceinline__ uint32_t qk_emit_pop(Ctx& cx, const DevHotA& c, uint3
   if (LOG && HOT && n != 0) S32(c.o32 + S32_EMITSRC) = C32(oemit + head); /* the next one moves up (rare) */
   if (n == 0) {
     S64(fire) = QK_TIME_NONE;
+    if constexpr (qk_is_two_tier(SM)) S32(cx.emask32 + (c.fire_idx >> 5)) &= ~(1u << (c.fire_idx & 31));
   } else if (split == 0) {
     S64(fire) = S64(fire) + 1;
     split = n;
@@ -638,7 +643,7 @@ __device__ __forceinline__ bool qk_post(Ctx& cx, const DevHotA& c, uint64_t ttnp
  * event has not fired yet it stays queued (Q3) -> move it to the stale mask (it fires at `now`, in rank order) */
 template <bool LOG, int SM, bool LEAN = false>
 __device__ __forceinline__ void qk_pre(Ctx& cx, const DevHotA& c, uint32_t comp) {
-  if constexpr (SM == QK_SM_QSPLIT) {
+  if constexpr (qk_is_two_tier(SM)) {
     /* nothing pending, or (cached minimum) nothing of any component due yet: no need to fetch the slot */
     if (!qk_fire_busy<SM>(cx, c.fire_idx) || (cx.kvalid && cx.kbest > cx.now)) return;
   }
@@ -682,7 +687,7 @@ __device__ __forceinline__ uint32_t qk_dm_quick(Ctx& cx, const DevSubQ& q, uint3
                                                 uint64_t* dt_out) {
   const DevHotA a = QK_HOT_A(comp);
   const uint32_t flags = W32(a.o32 + P32_FLAGS);
-  const uint64_t fire = SM == QK_SM_QSPLIT ? qk_fire_get<SM>(cx, q.fire_slot) : S64(q.fire_slot);
+  const uint64_t fire = qk_is_two_tier(SM) ? qk_fire_get<SM>(cx, q.fire_slot) : S64(q.fire_slot);
   if (flags & ~PF_HAS_ITEM) return 0u; /* a mode in TimeUntilFix (or environment-stopped) */
   if (!(flags & PF_HAS_ITEM)) {
     if (fire != QK_TIME_NONE) return 0u;
@@ -746,13 +751,13 @@ __device__ __forceinline__ bool qk_try_quick(Ctx& cx, uint32_t ptr, uint64_t src
    * logging kernels do the same because they have no registers to hold the two words: measured.) */
   constexpr bool EAGER = SM != 0 && !LOG;
   uint64_t fire;
-  if constexpr (SM == QK_SM_QSPLIT) {
+  if constexpr (qk_is_two_tier(SM)) {
     /* two-tier queue: q.fire_slot is the callee's rank.  Busy (bit set) and, by the cached minimum, nothing of ANY
      * component due yet: busy and not due without fetching the slot; only at a timestamp tie, or with the cache
      * invalid, the slot itself is read */
     if (!qk_fire_busy<SM>(cx, q.fire_slot)) fire = QK_TIME_NONE;
     else if (cx.kvalid && cx.kbest > cx.now) fire = cx.kbest; /* some time > now: all the code below asks */
-    else fire = C64(cx.cfire0 + q.fire_slot);
+    else fire = QK_CFIRE(q.fire_slot);
   } else {
     fire = S64(q.fire_slot);
   }
@@ -764,8 +769,8 @@ __device__ __forceinline__ bool qk_try_quick(Ctx& cx, uint32_t ptr, uint64_t src
   if (fire != QK_TIME_NONE) {
 #ifdef QK_HOST_EMUL
     const DevHotA c = QK_HOT_A(cx.subs[ptr]);
-    const uint64_t fx = SM == QK_SM_QSPLIT ? C64(cx.cfire0 + q.fire_slot) : fire; /* the slot itself */
-    if (SM == QK_SM_QSPLIT && (fx > cx.now) != (fire > cx.now)) cx.status = 97; /* the cached minimum lied */
+    const uint64_t fx = qk_is_two_tier(SM) ? QK_CFIRE(q.fire_slot) : fire; /* the slot itself */
+    if (qk_is_two_tier(SM) && (fx > cx.now) != (fire > cx.now)) cx.status = 97; /* the cached minimum lied */
     if (fx > cx.now && (!(W32(c.o32 + P32_FLAGS) & PF_HAS_ITEM) ||
                         W64(c.o64 + P64_PREV) + W64(c.o64 + P64_LEFT) != fx))
       cx.status = 98; /* invariant check, CPU test build only */
@@ -1231,7 +1236,7 @@ constexpr int qk_lb_resident(int ft, bool log) { return ft == 0 ? (log ? QK_LEAN
 constexpr int qk_lb_blocks(int sm, int ft, bool log) {
   /* split placement: shared memory holds at most ~240 replications per SM, so registers are not what limits residency */
   /* ... but with the two-tier queue 500-600 replications of a lean model fit: two blocks of 256 */
-  return sm == QK_SM_QSPLIT ? (ft == 0 ? 2 : 1) : sm == QK_SM_SPLIT ? 1 : sm > 0 ? (qk_lb_resident(ft, log) / sm > 0 ? qk_lb_resident(ft, log) / sm : 1) : (ft == 0 ? 3 : 2);
+  return sm == QK_SM_QSPLIT ? (ft == 0 ? 2 : 1) : qk_is_split(sm) ? 1 : sm > 0 ? (qk_lb_resident(ft, log) / sm > 0 ? qk_lb_resident(ft, log) / sm : 1) : (ft == 0 ? 3 : 2);
 }
 /* FT = feature set of the model: 0 = only SIMPLE single-server discrete components and stocks (no delay modes, no
  * environment, no scheduled events, no parallel or vector components): the handlers for everything else are
@@ -1303,6 +1308,7 @@ __global__ void __launch_bounds__(qk_lb_threads(SM), qk_lb_blocks(SM, FT, LOG)) 
   cx.npend = 0;
   cx.cfire0 = cx.hdr->cfire0;
   cx.busy32 = cx.hdr->busy32;
+  cx.emask32 = cx.hdr->emask32;
   cx.kbest = QK_TIME_NONE;
   cx.kidx = 0;
   cx.kvalid = false; /* two-tier queue: the first pop of a launch scans the cold fire array */
@@ -1310,7 +1316,7 @@ __global__ void __launch_bounds__(qk_lb_threads(SM), qk_lb_blocks(SM, FT, LOG)) 
   const uint32_t n_stale_words = cx.hdr->n_stale_words;
   const uint32_t n_sched_pad = (n_sched + 3u) & ~3u;
   /* entries of the hot fire array: every schedulable component, or (two-tier queue) the stocks */
-  const uint32_t n_hot_pad = SM == QK_SM_QSPLIT ? ((cx.hdr->n_hot + 3u) & ~3u) : n_sched_pad;
+  const uint32_t n_hot_pad = qk_is_two_tier(SM) ? ((cx.hdr->n_hot + 3u) & ~3u) : n_sched_pad;
   const uint16_t* const hot_rank =
       reinterpret_cast<const uint16_t*>(reinterpret_cast<const uint8_t*>(cx.hdr) + cx.hdr->off_hot_rank);
   (void)hot_rank;
@@ -1322,8 +1328,8 @@ __global__ void __launch_bounds__(qk_lb_threads(SM), qk_lb_blocks(SM, FT, LOG)) 
     for (uint32_t i = 0; i < n_hot_pad; ++i) S64(G64_FIRE0 + i) = QK_TIME_NONE; /* incl. the padding slots */
     for (uint32_t s = 0; s < P.n64c; ++s) C64(s) = 0;
     for (uint32_t s = 0; s < P.n32c; ++s) C32(s) = 0;
-    if constexpr (SM == QK_SM_QSPLIT)
-      for (uint32_t i = 0; i < n_sched_pad; ++i) C64(cx.cfire0 + i) = QK_TIME_NONE;
+    if constexpr (qk_is_two_tier(SM))
+      for (uint32_t i = 0; i < n_sched_pad; ++i) QK_CFIRE(i) = QK_TIME_NONE;
     cx.now = P.t0;
     cx.log_cnt = 0;
     for (uint32_t s = 0; s < n_comp * ST_PER_COMP; ++s) {
@@ -1468,15 +1474,15 @@ __global__ void __launch_bounds__(qk_lb_threads(SM), qk_lb_blocks(SM, FT, LOG)) 
         /* fire[] is padded with NONE to a multiple of four slots (lowering): groups of four independent loads and a
          * two-level tournament instead of one long dependent chain of 64-bit compares.  Strict '<' everywhere keeps
          * the LOWEST index among equal times, i.e. registration-rank order. */
-        if constexpr (SM == QK_SM_QSPLIT) {
+        if constexpr (qk_is_two_tier(SM)) {
           /* two-tier queue.  Keyed events: the cached minimum over the cold array, re-established by a scan (independent,
            * coalesced global loads) only after the minimum itself was popped or dropped. */
           if (!cx.kvalid) {
             uint64_t kb = QK_TIME_NONE;
             uint32_t ki = 0;
             for (uint32_t i = 0; i < n_sched_pad; i += 4) {
-              const uint64_t t0 = C64(cx.cfire0 + i), t1 = C64(cx.cfire0 + i + 1);
-              const uint64_t t2 = C64(cx.cfire0 + i + 2), t3 = C64(cx.cfire0 + i + 3);
+              const uint64_t t0 = QK_CFIRE(i), t1 = QK_CFIRE(i + 1);
+              const uint64_t t2 = QK_CFIRE(i + 2), t3 = QK_CFIRE(i + 3);
               const bool p01 = t1 < t0, p23 = t3 < t2;
               const uint64_t a = p01 ? t1 : t0, b = p23 ? t3 : t2;
               const uint32_t ai = p01 ? i + 1 : i, bj = p23 ? i + 3 : i + 2;
@@ -1492,19 +1498,19 @@ __global__ void __launch_bounds__(qk_lb_threads(SM), qk_lb_blocks(SM, FT, LOG)) 
             cx.kvalid = true;
           }
           /* the stocks' pending emit_change events: the hot array, in rank order */
+          /* (one or two are pending at a time: the pending mask names them, ascending = rank order) */
           uint64_t sb = QK_TIME_NONE;
           uint32_t sj = 0;
-          for (uint32_t i = 0; i < n_hot_pad; i += 4) {
-            const uint64_t t0 = S64(G64_FIRE0 + i), t1 = S64(G64_FIRE0 + i + 1);
-            const uint64_t t2 = S64(G64_FIRE0 + i + 2), t3 = S64(G64_FIRE0 + i + 3);
-            const bool p01 = t1 < t0, p23 = t3 < t2;
-            const uint64_t a = p01 ? t1 : t0, b = p23 ? t3 : t2;
-            const uint32_t ai = p01 ? i + 1 : i, bj = p23 ? i + 3 : i + 2;
-            const bool pab = b < a;
-            const uint64_t m = pab ? b : a;
-            if (m < sb) {
-              sb = m;
-              sj = pab ? bj : ai;
+          for (uint32_t w = 0; w * 32u < n_hot_pad; ++w) {
+            uint32_t em = S32(cx.emask32 + w);
+            while (em) {
+              const uint32_t j = w * 32u + (uint32_t)__ffs((int)em) - 1u;
+              em &= em - 1;
+              const uint64_t t = S64(G64_FIRE0 + j);
+              if (t < sb) {
+                sb = t;
+                sj = j;
+              }
             }
           }
           /* min over (time, rank) of the two tiers; an external event (rank 0) keeps winning ties */

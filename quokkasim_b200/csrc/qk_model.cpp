@@ -596,7 +596,7 @@ int qk_lower(const qk_model* m, bool log, int placement, QkLowered* out) {
    * (kernel registers) and a busy mask (hot words after the prefetch mask).  A stock's fire_idx is then its index in
    * the hot array; hot_rank[] maps it back to the rank. */
   std::vector<uint16_t> hot_rank;
-  uint32_t cfire0 = 0, busy32 = 0;
+  uint32_t cfire0 = 0, busy32 = 0, emask32 = 0;
   if (qsplit) {
     for (uint32_t r = 0; r < n_sched; ++r) {
       const uint32_t k = m->comps[sched[r]].d.kind;
@@ -610,6 +610,8 @@ int qk_lower(const qk_model* m, bool log, int placement, QkLowered* out) {
     n64c += (n_sched + 3u) & ~3u;
     busy32 = n32;
     n32 += n_stale_words;
+    emask32 = n32; /* bit j: hot fire entry j holds a pending emit_change */
+    n32 += ((uint32_t)hot_rank.size() + 31u) / 32u;
   }
   /* split placement (qk_batch_create, QK_BATCH_STATE_SPLIT): only what the scheduler pop and the quick path read stays in
    * the hot planes -- the fire slots, the stocks' head|count and pending-emit words, the seq counters -- and every
@@ -903,6 +905,7 @@ int qk_lower(const qk_model* m, bool log, int placement, QkLowered* out) {
   h.n_hot = (uint32_t)hot_rank.size();
   h.cfire0 = cfire0;
   h.busy32 = busy32;
+  h.emask32 = emask32;
   uint32_t off = align8((uint32_t)sizeof(DevHeader));
   h.off_comps = off;
   off = align8(off + (uint32_t)(nc * sizeof(DevComp)));

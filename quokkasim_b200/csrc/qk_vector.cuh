@@ -115,6 +115,7 @@ __device__ __forceinline__ void qk_vemit_push(Ctx& cx, const DevComp* c, uint32_
   const uint64_t T = cx.now + 1;
   if (n == 0) {
     S64(fire) = T;
+    if constexpr (qk_is_two_tier(SM)) S32(cx.emask32 + (c->fire_idx >> 5)) |= 1u << (c->fire_idx & 31); /* pending */
     split = 1;
     head = 0;
   } else if (S64(fire) == T) {

@@ -55,6 +55,14 @@ pub struct qk_component_desc {
     pub initial_env_state: u32,
 }
 
+/// qk_batch_config.flags (quokka_b200.h): 0 lets the library choose the state placement
+pub const QK_BATCH_STATE_IN_HBM: u32 = 1;
+pub const QK_BATCH_STATE_ON_CHIP: u32 = 2;
+pub const QK_BATCH_STATE_LANE_GROUP: u32 = 4;
+pub const QK_BATCH_GROUP_PHASED: u32 = 8;
+pub const QK_BATCH_STATE_SPLIT: u32 = 16;
+pub const QK_BATCH_QUEUE_TWO_TIER: u32 = 32;
+
 #[repr(C)]
 #[derive(Clone, Copy, Debug)]
 pub struct qk_batch_config {
