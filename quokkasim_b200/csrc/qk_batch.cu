@@ -615,7 +615,10 @@ int qk_batch_create(const qk_model* m, const qk_batch_config* cfg, qk_batch** ou
       thr_cap = (65536u / regs) & ~31u;
       /* two-tier queue: its working set (4 KB per resident replication) lives in L2 -- past 12 warps per SM the extra
        * replications cost more in L2 misses than their warps hide (measured: 3 x 128 threads beat 3 x 160 and 2 x 256) */
-      if (qsplit && thr_cap > 384u) thr_cap = 384u;
+      uint32_t qcap = 384u;
+      if (const char* e = getenv("QK_QSPLIT_THREADS")) /* experiments */
+        if (atoi(e) >= 32) qcap = (uint32_t)atoi(e) & ~31u;
+      if (qsplit && thr_cap > qcap) thr_cap = qcap;
     }
     /* (two-tier queue, measured on the 96-component network: 3 x 128 and 2 x 192 threads 4.2e9 events/s, 4 x 96 3.8e9,
      * 5 x 64 3.7e9 -- every block carries its own 22 KB copy of the tables) */

@@ -247,6 +247,7 @@ typedef struct {
   uint32_t features; /* 0 = every process-like component is SIMPLE and nothing is scheduled externally ; 1 = general ;
                         2 = general + container family (vector_container.rs) */
   uint32_t n_hot, off_hot_rank; /* placement 2: entries of the hot fire array (stocks) ; u16 hot_rank[n_hot]: index -> rank */
+  uint32_t gshift, n_groups, gmin64, gidx32, gdirty32; /* placement 2: group minima of the cold fire array (qk_lower) */
   uint32_t emask32;             /* placement 2: first hot32 slot of the pending-emit mask (bit = index in the hot fire array) */
   uint32_t cfire0, busy32;      /* placement 2: first cold64 slot of the process-like fire array (by rank, padded to a
                                    multiple of four) ; first hot32 slot of the busy mask (bit = rank) */

@@ -90,6 +90,7 @@ struct Ctx {
   /* two-tier scheduler queue (QK_SM_QSPLIT): first cold64 slot of the process-like fire array, first hot32 slot of the busy
    * mask, and the cached minimum over that array by (time, rank) -- exact while kvalid */
   uint32_t cfire0, busy32, emask32, kidx;
+  uint32_t gshift, n_groups, gmin64, gidx32, gdirty32; /* group minima of the cold fire array (DevHeader) */
   uint64_t kbest;
   bool kvalid;
   uint64_t rep_local;
@@ -366,6 +367,14 @@ __device__ __forceinline__ void qk_fire_set(Ctx& cx, uint32_t idx, uint64_t t) {
   if constexpr (qk_is_two_tier(SM)) {
     QK_CFIRE(idx) = t;
     S32(cx.busy32 + (idx >> 5)) |= 1u << (idx & 31);
+    const uint32_t g = idx >> cx.gshift;
+    if (!((S32(cx.gdirty32) >> g) & 1u)) { /* (a dirty group is re-scanned before it is used: it will see this write) */
+      const uint64_t gt = S64(cx.gmin64 + g);
+      if (t < gt || (t == gt && idx < S32(cx.gidx32 + g))) {
+        S64(cx.gmin64 + g) = t;
+        S32(cx.gidx32 + g) = idx;
+      }
+    }
     if (cx.kvalid && (t < cx.kbest || (t == cx.kbest && idx < cx.kidx))) {
       cx.kbest = t;
       cx.kidx = idx;
@@ -379,7 +388,9 @@ __device__ __forceinline__ void qk_fire_clear(Ctx& cx, uint32_t idx) {
   if constexpr (qk_is_two_tier(SM)) {
     QK_CFIRE(idx) = QK_TIME_NONE; /* (the scan reads the array, not the mask) */
     S32(cx.busy32 + (idx >> 5)) &= ~(1u << (idx & 31));
-    if (cx.kvalid && idx == cx.kidx) cx.kvalid = false; /* the minimum is gone: the next pop scans the cold array */
+    const uint32_t g = idx >> cx.gshift;
+    if (S64(cx.gmin64 + g) != QK_TIME_NONE && S32(cx.gidx32 + g) == idx) S32(cx.gdirty32) |= 1u << g; /* its group's minimum */
+    if (cx.kvalid && idx == cx.kidx) cx.kvalid = false; /* the minimum is gone: the next pop re-scans the dirty groups */
   } else {
     S64(G64_FIRE0 + idx) = QK_TIME_NONE;
   }
@@ -684,10 +695,24 @@ __device__ __forceinline__ void qk_pre(Ctx& cx, const DevHotA& c, uint32_t comp)
  * qk_dm_apply.  Reads only. */
 template <int SM>
 __device__ __forceinline__ uint32_t qk_dm_quick(Ctx& cx, const DevSubQ& q, uint32_t comp, uint64_t now, uint32_t* reason,
-                                                uint64_t* dt_out) {
+                                                uint64_t* dt_out, uint64_t* left_out = nullptr, uint64_t* dm0_out = nullptr) {
   const DevHotA a = QK_HOT_A(comp);
   const uint32_t flags = W32(a.o32 + P32_FLAGS);
   const uint64_t fire = qk_is_two_tier(SM) ? qk_fire_get<SM>(cx, q.fire_slot) : S64(q.fire_slot);
+  /* record in global memory (split placements, HBM planes): the countdown pair and the smallest until-delay countdown are
+   * requested together with the flags -- one trip to L2 for the whole test instead of three dependent ones (38 % of the
+   * split kernel's stall samples on the 67-component line sat on these lines) */
+  constexpr bool EAGER_REC = qk_is_split(SM) || SM == 0;
+  uint64_t e_prev = 0, e_left = 0, e_mindm = QK_TIME_NONE;
+  if constexpr (EAGER_REC) {
+    e_prev = W64(a.o64 + P64_PREV);
+    e_left = W64(a.o64 + P64_LEFT);
+    const DevHotB eb = QK_HOT_B(comp);
+    for (uint32_t k = 0; k < a.n_dm; ++k) {
+      const uint64_t d = W64(eb.o64_dm + k);
+      e_mindm = d < e_mindm ? d : e_mindm;
+    }
+  }
   if (flags & ~PF_HAS_ITEM) return 0u; /* a mode in TimeUntilFix (or environment-stopped) */
   if (!(flags & PF_HAS_ITEM)) {
     if (fire != QK_TIME_NONE) return 0u;
@@ -701,21 +726,30 @@ __device__ __forceinline__ uint32_t qk_dm_quick(Ctx& cx, const DevSubQ& q, uint3
     return 1u;
   }
   if (a.kind == QK_DISCRETE_SINK || fire == QK_TIME_NONE || fire <= now) return 0u;
-  const uint64_t prev = W64(a.o64 + P64_PREV), left = W64(a.o64 + P64_LEFT);
+  const uint64_t prev = EAGER_REC ? e_prev : W64(a.o64 + P64_PREV), left = EAGER_REC ? e_left : W64(a.o64 + P64_LEFT);
   if (prev + left < fire) return 0u; /* post_update_state would move the keyed event */
   const uint64_t dt = now - prev;
-  const DevHotB b = QK_HOT_B(comp);
-  for (uint32_t k = 0; k < a.n_dm; ++k)
-    if (W64(b.o64_dm + k) <= dt) return 0u; /* a breakdown starts in this call */
+  if constexpr (EAGER_REC) {
+    if (e_mindm <= dt) return 0u; /* a breakdown starts in this call */
+    if (left_out) *left_out = left; /* what qk_dm_apply is about to rewrite: it need not fetch them again */
+    if (dm0_out) *dm0_out = e_mindm;
+  } else {
+    const DevHotB b = QK_HOT_B(comp);
+    for (uint32_t k = 0; k < a.n_dm; ++k)
+      if (W64(b.o64_dm + k) <= dt) return 0u; /* a breakdown starts in this call */
+  }
   *dt_out = dt;
   return 2u;
 }
 template <int SM>
-__device__ __forceinline__ void qk_dm_apply(Ctx& cx, uint32_t comp, uint64_t now, uint64_t dt) {
+__device__ __forceinline__ void qk_dm_apply(Ctx& cx, uint32_t comp, uint64_t now, uint64_t dt,
+                                            const uint64_t* left_known = nullptr, const uint64_t* dm0_known = nullptr) {
   const DevHotA a = QK_HOT_A(comp);
   const DevHotB b = QK_HOT_B(comp);
-  for (uint32_t k = 0; k < a.n_dm; ++k) W64(b.o64_dm + k) -= dt;
-  W64(a.o64 + P64_LEFT) -= dt;
+  if (dm0_known && a.n_dm == 1) W64(b.o64_dm) = *dm0_known - dt; /* (one mode: its countdown is the minimum just tested) */
+  else for (uint32_t k = 0; k < a.n_dm; ++k) W64(b.o64_dm + k) -= dt;
+  if (left_known) W64(a.o64 + P64_LEFT) = *left_known - dt;
+  else W64(a.o64 + P64_LEFT) -= dt;
   W64(a.o64 + P64_PREV) = now;
 #ifdef QK_HOST_EMUL
   qk_emul_count(0); /* the CPU suite checks that its delay-mode models actually take this path */
@@ -735,10 +769,12 @@ __device__ __forceinline__ bool qk_try_quick(Ctx& cx, uint32_t ptr, uint64_t src
     const uint32_t comp = cx.subs[ptr];
     uint32_t reason = 0;
     uint64_t dt = 0;
-    const uint32_t code = qk_dm_quick<SM>(cx, q, comp, cx.now, &reason, &dt);
+    uint64_t left_k = 0, dm0_k = 0;
+    constexpr bool KNOWN = qk_is_split(SM) || SM == 0; /* qk_dm_quick fetched them */
+    const uint32_t code = qk_dm_quick<SM>(cx, q, comp, cx.now, &reason, &dt, &left_k, &dm0_k);
     if (code == 0u) return false;
     if (code == 2u)
-      qk_dm_apply<SM>(cx, comp, cx.now, dt);
+      qk_dm_apply<SM>(cx, comp, cx.now, dt, KNOWN ? &left_k : nullptr, KNOWN ? &dm0_k : nullptr);
     else if (LOG)
       qk_log<LOG, SM>(cx, QK_HOT_A(comp), comp, src, QK_LOG_PROCESS_NONSTART, reason, 0);
 #ifdef QK_HOST_EMUL
@@ -758,6 +794,9 @@ __device__ __forceinline__ bool qk_try_quick(Ctx& cx, uint32_t ptr, uint64_t src
     if (!qk_fire_busy<SM>(cx, q.fire_slot)) fire = QK_TIME_NONE;
     else if (cx.kvalid && cx.kbest > cx.now) fire = cx.kbest; /* some time > now: all the code below asks */
     else fire = QK_CFIRE(q.fire_slot);
+#ifdef QK_HOST_EMUL
+    if (qk_fire_busy<SM>(cx, q.fire_slot)) qk_emul_count((cx.kvalid && cx.kbest > cx.now) ? 2 : 3);
+#endif
   } else {
     fire = S64(q.fire_slot);
   }
@@ -1309,6 +1348,11 @@ __global__ void __launch_bounds__(qk_lb_threads(SM), qk_lb_blocks(SM, FT, LOG)) 
   cx.cfire0 = cx.hdr->cfire0;
   cx.busy32 = cx.hdr->busy32;
   cx.emask32 = cx.hdr->emask32;
+  cx.gshift = cx.hdr->gshift;
+  cx.n_groups = cx.hdr->n_groups;
+  cx.gmin64 = cx.hdr->gmin64;
+  cx.gidx32 = cx.hdr->gidx32;
+  cx.gdirty32 = cx.hdr->gdirty32;
   cx.kbest = QK_TIME_NONE;
   cx.kidx = 0;
   cx.kvalid = false; /* two-tier queue: the first pop of a launch scans the cold fire array */
@@ -1328,8 +1372,10 @@ __global__ void __launch_bounds__(qk_lb_threads(SM), qk_lb_blocks(SM, FT, LOG)) 
     for (uint32_t i = 0; i < n_hot_pad; ++i) S64(G64_FIRE0 + i) = QK_TIME_NONE; /* incl. the padding slots */
     for (uint32_t s = 0; s < P.n64c; ++s) C64(s) = 0;
     for (uint32_t s = 0; s < P.n32c; ++s) C32(s) = 0;
-    if constexpr (qk_is_two_tier(SM))
+    if constexpr (qk_is_two_tier(SM)) {
       for (uint32_t i = 0; i < n_sched_pad; ++i) QK_CFIRE(i) = QK_TIME_NONE;
+      for (uint32_t g = 0; g < cx.n_groups; ++g) S64(cx.gmin64 + g) = QK_TIME_NONE;
+    }
     cx.now = P.t0;
     cx.log_cnt = 0;
     for (uint32_t s = 0; s < n_comp * ST_PER_COMP; ++s) {
@@ -1478,19 +1524,42 @@ __global__ void __launch_bounds__(qk_lb_threads(SM), qk_lb_blocks(SM, FT, LOG)) 
           /* two-tier queue.  Keyed events: the cached minimum over the cold array, re-established by a scan (independent,
            * coalesced global loads) only after the minimum itself was popped or dropped. */
           if (!cx.kvalid) {
+            /* groups whose minimum fired or was dropped: fetch that group of the cold array (2^gshift consecutive ranks,
+             * one contiguous run of the replication's record) and re-establish its minimum */
+            uint32_t dm = S32(cx.gdirty32);
+            while (dm) {
+              const uint32_t g = (uint32_t)__ffs((int)dm) - 1u;
+              dm &= dm - 1;
+              const uint32_t lo = g << cx.gshift;
+              uint32_t hi = lo + (1u << cx.gshift);
+              if (hi > n_sched_pad) hi = n_sched_pad;
+              uint64_t gb = QK_TIME_NONE;
+              uint32_t gi = 0;
+              for (uint32_t i = lo; i < hi; i += 4) {
+                const uint64_t t0 = QK_CFIRE(i), t1 = QK_CFIRE(i + 1);
+                const uint64_t t2 = QK_CFIRE(i + 2), t3 = QK_CFIRE(i + 3);
+                const bool p01 = t1 < t0, p23 = t3 < t2;
+                const uint64_t a = p01 ? t1 : t0, b = p23 ? t3 : t2;
+                const uint32_t ai = p01 ? i + 1 : i, bj = p23 ? i + 3 : i + 2;
+                const bool pab = b < a;
+                const uint64_t m = pab ? b : a;
+                if (m < gb) {
+                  gb = m;
+                  gi = pab ? bj : ai;
+                }
+              }
+              S64(cx.gmin64 + g) = gb;
+              S32(cx.gidx32 + g) = gi;
+            }
+            S32(cx.gdirty32) = 0;
+            /* the overall minimum: the group minima, ascending = rank order (strict '<' keeps the lowest rank) */
             uint64_t kb = QK_TIME_NONE;
             uint32_t ki = 0;
-            for (uint32_t i = 0; i < n_sched_pad; i += 4) {
-              const uint64_t t0 = QK_CFIRE(i), t1 = QK_CFIRE(i + 1);
-              const uint64_t t2 = QK_CFIRE(i + 2), t3 = QK_CFIRE(i + 3);
-              const bool p01 = t1 < t0, p23 = t3 < t2;
-              const uint64_t a = p01 ? t1 : t0, b = p23 ? t3 : t2;
-              const uint32_t ai = p01 ? i + 1 : i, bj = p23 ? i + 3 : i + 2;
-              const bool pab = b < a;
-              const uint64_t m = pab ? b : a;
-              if (m < kb) {
-                kb = m;
-                ki = pab ? bj : ai;
+            for (uint32_t g = 0; g < cx.n_groups; ++g) {
+              const uint64_t t = S64(cx.gmin64 + g);
+              if (t < kb) {
+                kb = t;
+                ki = S32(cx.gidx32 + g);
               }
             }
             cx.kbest = kb;

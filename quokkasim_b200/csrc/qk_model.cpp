@@ -596,7 +596,7 @@ int qk_lower(const qk_model* m, bool log, int placement, QkLowered* out) {
    * (kernel registers) and a busy mask (hot words after the prefetch mask).  A stock's fire_idx is then its index in
    * the hot array; hot_rank[] maps it back to the rank. */
   std::vector<uint16_t> hot_rank;
-  uint32_t cfire0 = 0, busy32 = 0, emask32 = 0;
+  uint32_t cfire0 = 0, busy32 = 0, emask32 = 0, gshift = 0, n_groups = 0, gmin64 = 0, gidx32 = 0, gdirty32 = 0;
   if (qsplit) {
     for (uint32_t r = 0; r < n_sched; ++r) {
       const uint32_t k = m->comps[sched[r]].d.kind;
@@ -612,6 +612,18 @@ int qk_lower(const qk_model* m, bool log, int placement, QkLowered* out) {
     n32 += n_stale_words;
     emask32 = n32; /* bit j: hot fire entry j holds a pending emit_change */
     n32 += ((uint32_t)hot_rank.size() + 31u) / 32u;
+    /* group minima of the cold array: ranks in groups of 2^gshift (16, or more when there are over 512 ranks: the dirty
+     * mask is one word), each with its minimum (time: hot64 ; rank: hot32) kept exact on chip, so that re-establishing the
+     * overall minimum after a keyed event fired fetches ONE group of the cold array instead of all of it */
+    gshift = 4;
+    while (((n_sched + (1u << gshift) - 1u) >> gshift) > 32u) ++gshift;
+    n_groups = (n_sched + (1u << gshift) - 1u) >> gshift;
+    if (n_groups == 0) n_groups = 1;
+    gmin64 = n64;
+    n64 += n_groups;
+    gidx32 = n32;
+    n32 += n_groups;
+    gdirty32 = n32++;
   }
   /* split placement (qk_batch_create, QK_BATCH_STATE_SPLIT): only what the scheduler pop and the quick path read stays in
    * the hot planes -- the fire slots, the stocks' head|count and pending-emit words, the seq counters -- and every
@@ -906,6 +918,11 @@ int qk_lower(const qk_model* m, bool log, int placement, QkLowered* out) {
   h.cfire0 = cfire0;
   h.busy32 = busy32;
   h.emask32 = emask32;
+  h.gshift = gshift;
+  h.n_groups = n_groups;
+  h.gmin64 = gmin64;
+  h.gidx32 = gidx32;
+  h.gdirty32 = gdirty32;
   uint32_t off = align8((uint32_t)sizeof(DevHeader));
   h.off_comps = off;
   off = align8(off + (uint32_t)(nc * sizeof(DevComp)));

@@ -118,7 +118,7 @@ for f in sorted(os.listdir(EV)):
     txt += "\nwarp stall samples (share of all samples)\n"
     for v, h in sorted(stalls, reverse=True)[:10]:
         txt += "  %-28s %5.1f %%\n" % (h, 100 * v / tot)
-    mk = re.search(r"qk_step_kernel<(\d), (-?\d+), (\d)>", kname)
+    mk = re.search(r"qk_step_kernel<(?:\(bool\))?(\d), (?:\(int\))?(-?\d+), (?:\(int\))?(\d)>", kname)
     if mk:
         sm = int(mk.group(2))
         mangled = "_Z14qk_step_kernelILb%sELi%sELi%sEEv7KParams" % (mk.group(1), ("n%d" % -sm) if sm < 0 else str(sm),
@@ -138,7 +138,7 @@ for l in sass.split("\n"):
     m = re.search(r"Function : (\S+)", l)
     if m:
         cur = m.group(1)
-        counts[cur] = {"UBLKCP": 0, "SYNCS": 0, "LDGSTS": 0, "REDUX": 0, "RED": 0}
+        counts[cur] = {"UBLKCP": 0, "SYNCS": 0, "LDGSTS": 0, "REDUX": 0, "REDG": 0}
         continue
     if cur:
         for k in counts[cur]:
@@ -147,10 +147,10 @@ for l in sass.split("\n"):
 with open(os.path.join(PR, TAG + "_sass_bulk_copies.txt"), "w") as out:
     out.write("cuobjdump -sass quokkasim_b200/libquokka_b200.so (sha256 %s): instruction counts per kernel\n" % lib_sha)
     out.write("UBLKCP = cp.async.bulk (TMA engine) ; SYNCS = mbarrier operations ; LDGSTS = cp.async (per-thread) ; "
-              "REDUX = warp reduction ; RED = fire-and-forget atomics\n\n")
+              "REDUX = warp reduction ; REDG = fire-and-forget atomics (statistics planes)\n\n")
     for k in sorted(counts):
         if "qk_step_kernel" in k or "qk_group_kernel" in k or "qk_phased_kernel" in k:
             c = counts[k]
-            out.write("%-60s UBLKCP %3d  SYNCS %3d  LDGSTS %3d  REDUX %3d  RED %3d\n" % (
-                k, c["UBLKCP"], c["SYNCS"], c["LDGSTS"], c["REDUX"], c["RED"]))
+            out.write("%-60s UBLKCP %3d  SYNCS %3d  LDGSTS %3d  REDUX %3d  REDG %3d\n" % (
+                k, c["UBLKCP"], c["SYNCS"], c["LDGSTS"], c["REDUX"], c["REDG"]))
 print("profiles/ updated:", sorted(f for f in os.listdir(PR) if f.startswith(TAG)))

@@ -73,8 +73,10 @@ def text(f, l):
 
 
 print("total warp instructions %.4e, samples %d" % (tw, ts))
-for name, agg in (("by kernel-level line (%s)" % outer_file, outer), ("by innermost line", inner)):
+for name, agg, col in (("by kernel-level line (%s), most instructions first" % outer_file, outer, 0),
+                       ("by innermost line, most instructions first", inner, 0),
+                       ("by innermost line, most stall samples first", inner, 2)):
     print("==== " + name)
-    for k, v in sorted(agg.items(), key=lambda x: -x[1][0])[:top]:
+    for k, v in sorted(agg.items(), key=lambda x: -x[1][col])[:top]:
         print("%-16s %4d  inst %5.2f%%  samp %5.2f%%  lanes %4.1f | %s"
               % (k[0], k[1], 100 * v[0] / tw, 100 * v[2] / max(ts, 1), v[1] / v[0] if v[0] else 0, text(*k)))

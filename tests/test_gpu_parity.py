@@ -278,13 +278,17 @@ def test_state_placement_does_not_change_results(gpu_lib):
         blobs.append(blob)
         sim.close()
     assert blobs[0] == blobs[1]
-    # the default picks by residency: the 7-component line is staged on chip one thread per replication, the
-    # 96-component network gets a lane group per replication (state still on chip)
+    # the default picks by residency: the 7-component line is staged on chip whole, one thread per replication; of the
+    # 96-component network only the stocks' part of the scheduler queue is (split placement, two-tier queue: about 400 B per
+    # replication instead of 3,924); the 67-component line with breakdowns keeps its whole queue on chip (split)
     a = H.discrete_queue().sim(gpu_lib, 64)
     b = H.haulage(n_src=8, per_queue=8).sim(gpu_lib, 64)
-    ia, ib = a.info(), b.info()
-    assert ia["state_in_hbm"] == 0 and ia["lanes_per_replication"] == 1
-    assert ib["state_in_hbm"] == 0 and ib["lanes_per_replication"] == 8
+    c = H.serial_line(n_proc=32).sim(gpu_lib, 64)
+    ia, ib, ic = a.info(), b.info(), c.info()
+    assert ia["state_in_hbm"] == 0 and ia["lanes_per_replication"] == 1 and ia["state_split"] == 0
+    assert ib["state_in_hbm"] == 0 and ib["lanes_per_replication"] == 1 and ib["state_split"] == 1
+    assert ib["state_bytes_per_rep"] < 500 < ic["state_bytes_per_rep"] < 1000 and ic["state_split"] == 1
+    c.close()
     a.close()
     b.close()
 
