@@ -207,6 +207,16 @@ def lib_sha256(path=None):
     return h.hexdigest()
 
 
+def lib_build_id(path=None):
+    """What the library was built FROM (sha256 over csrc/, the public header and the compiler flags, compiled into the
+    library: quokkasim_b200/build.py).  Two builds of the same sources have the same id although the files differ in a
+    few dozen bytes of linker bookkeeping, which is why the ncu traffic record is keyed by it and not by the file hash."""
+    from quokkasim_b200 import _capi
+    from quokkasim_b200 import build as qbuild
+
+    return qbuild.built_id(path or _capi.DEFAULT_LIB)
+
+
 def median(xs):
     xs = sorted(xs)
     return xs[len(xs) // 2] if len(xs) % 2 else 0.5 * (xs[len(xs) // 2 - 1] + xs[len(xs) // 2])
@@ -385,13 +395,13 @@ def run_ours(args):
         step_kernel_ms = k_ms * launches_per_step
         achieved = alg_bytes_step / (step_kernel_ms * 1e-3) / 1e9
         # dram__bytes_read.sum + dram__bytes_write.sum of ONE step, from the committed ncu capture of this exact
-        # workload shape AND this exact build (sha256 of libquokka_b200.so); null otherwise
+        # workload shape AND this exact build (the source id compiled into libquokka_b200.so); null otherwise
         traffic = None
         try:
             tr = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
             rec = tr.get(args.workload, {}).get(args.log)
             if (rec and rec["replications"] == reps_gpu and rec["events"] == n_events
-                    and rec.get("lib_sha256") == lib_sha256(args.lib)):
+                    and rec.get("lib_build_id") == lib_build_id(args.lib)):
                 traffic = rec["dram_bytes_per_step"]
         except Exception:
             pass
@@ -415,7 +425,8 @@ def run_ours(args):
                          "algorithmic_bytes_per_step": alg_bytes_step,
                          "bytes_per_event": alg_bytes_step / ev_gpu,
                          "state_bytes_per_replication": state_bytes, "events_per_residency_K": n_events // residencies,
-                         "launches_per_step": launches_per_step, "lib_sha256": lib_sha256(args.lib)},
+                         "launches_per_step": launches_per_step, "lib_sha256": lib_sha256(args.lib),
+                         "lib_build_id": lib_build_id(args.lib)},
             "faulted_replications": int(ev_total[2].item()),
             "per_gpu_events_per_s": value / world,
             "placement": {"state": "hbm" if info["state_in_hbm"] else (

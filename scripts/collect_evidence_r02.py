@@ -28,6 +28,10 @@ def sha(path):
 
 
 lib_sha = sha(LIB)
+sys.path.insert(0, ROOT)
+from quokkasim_b200 import build as qbuild  # noqa: E402
+
+lib_id = qbuild.built_id(LIB)
 for f in sorted(os.listdir(EV)):
     if (f.startswith("bench_") or f.startswith("sweep_")) and f.endswith(".json") and os.path.getsize(os.path.join(EV, f)):
         shutil.copy(os.path.join(EV, f), os.path.join(PR, "%s_%s" % (TAG, f)))
@@ -75,7 +79,7 @@ for wl in shape:
             continue
         kname = rws[1][h.index("Kernel Name")]
         traffic.setdefault(wl, {})[lg] = {
-            "replications": shape[wl][0], "events": shape[wl][1], "lib_sha256": lib_sha, "kernel": kname,
+            "replications": shape[wl][0], "events": shape[wl][1], "lib_sha256": lib_sha, "lib_build_id": lib_id, "kernel": kname,
             "dram_bytes_per_step": m["dram__bytes_read.sum"] + m["dram__bytes_write.sum"],
             "dram_bytes_read": m["dram__bytes_read.sum"], "dram_bytes_write": m["dram__bytes_write.sum"],
             "kernel_ns_under_ncu": m.get("gpu__time_duration.sum"),

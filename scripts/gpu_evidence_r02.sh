@@ -24,6 +24,9 @@ run bench_c5_haulage_off --workload haulage --log off --no-cpu-baseline
 run bench_c4_serial_line_off --workload serial_line --log off --steps 2 --warmup 3 --e2e-steps 2 --no-lockstep-probe
 run bench_c4_serial_line_ring --workload serial_line --steps 1 --warmup 1 --e2e-steps 1 --no-lockstep-probe --no-cpu-baseline
 run bench_container_haulage_ring --workload container_haulage --no-cpu-baseline
+# ---- what ONE of eight GPUs does under strong scaling of C2 (1,048,576 / 8 replications: 1.38 waves of blocks)
+run bench_c2_ring_eighth --reps 131072 --no-cpu-baseline --no-lockstep-probe
+run bench_c2_off_eighth --reps 131072 --log off --no-cpu-baseline --no-lockstep-probe
 # ---- C5 replication sweep (1 GPU; 2,000 events per replication keep the large points short), statistics only and ring
 for n in 1024 16384 262144 4194304; do
   run sweep_c5_off_$n --workload haulage --reps $n --events 2000 --log off --no-cpu-baseline --no-lockstep-probe --e2e-steps 1 --steps 2
