@@ -462,7 +462,9 @@ def main():
     ap.add_argument("--workload", default="discrete_queue", choices=sorted(WORKLOADS))
     ap.add_argument("--reps", type=int, default=0, help="replications per GPU (default: the workload's)")
     ap.add_argument("--events", type=int, default=0, help="events per replication (default: the workload's)")
-    ap.add_argument("--log", default="ring", choices=["ring", "off"])
+    # (--logging: the same switch under a name torchrun's own parser does not claim: it rejects "--log" as ambiguous
+    # with its --log-dir even after the script name)
+    ap.add_argument("--log", "--logging", dest="log", default="ring", choices=["ring", "off"])
     ap.add_argument("--log-capacity", type=int, default=64)
     ap.add_argument("--threads-per-block", type=int, default=0)
     ap.add_argument("--state", default="auto", choices=["auto", "hbm", "chip", "group", "phased", "split", "qsplit"],

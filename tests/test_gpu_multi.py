@@ -144,7 +144,8 @@ def test_cpp_example_runs_the_job_on_every_gpu_without_python(gpu_lib, tmp_path)
     for g in sorted({1, _n_gpus()}):
         o = subprocess.check_output([exe, "--replications", "30001", "--events", "2000", "--gpus", str(g)], text=True)
         assert "gpus %d " % g in o
-        outs.append([ln for ln in o.splitlines() if not ln.startswith("step ")])
+        # (libnccl prints its version banner to stdout when NCCL_DEBUG asks for it)
+        outs.append([ln for ln in o.splitlines() if not ln.startswith("step ") and not ln.startswith("NCCL version")])
     assert all(x == outs[0] for x in outs) and any(ln.startswith("Sink: sum_count = ") for ln in outs[0])
     one = H.discrete_queue().sim(gpu_lib, 30001, base_seed=1234)
     one.step_events(2000)
