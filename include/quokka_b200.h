@@ -278,6 +278,15 @@ int qk_model_set_logged(qk_model*, uint32_t comp, int enabled);
  * with_max_capacity, with_initial_resource); VectorSource: init = source_vector; other kinds: dim only */
 int qk_model_set_vector(qk_model*, uint32_t comp, uint32_t dim, double low_capacity, double max_capacity,
                         const double* init);
+/* user-defined resource types (quokkasim_examples/src/bin/iron_ore.rs:21-96: `IronOre`, five f64 fields,
+ * `total() = fe + other_elements`): dim in 1..QK_VEC_MAX_DIM fields; ResourceTotal sums the fields named by
+ * total_mask (bit k = field k) in field order; ResourceAdd is field-wise; ResourceRemove(q) takes the proportion
+ * q / total() of EVERY field.  init[dim].  (dim 1 = f64, dim 3 with mask 7 = Vector3: the call above.)  Components
+ * connect only when dim and mask agree.  In the log a vector of more than three fields takes ceil(dim / 3)
+ * continuation records: QK_LOG_VEC_DATA with index byte = vector index + 8 * chunk. */
+#define QK_VEC_MAX_DIM 8
+int qk_model_set_vector_n(qk_model*, uint32_t comp, uint32_t dim, uint32_t total_mask, double low_capacity,
+                          double max_capacity, const double* init);
 /* VectorCombiner<M> / VectorSplitter<N>: number of ports (1..5) and split_ratios (vector.rs:756, 1056) */
 int qk_model_set_ports(qk_model*, uint32_t comp, uint32_t n_ports, const double* split_ratios);
 /* create_scheduled_event!(SetLowCapacity(v)) on an F64Stock (core.rs:1382-1386): setter + add(0.) at t */
@@ -398,6 +407,8 @@ int qk_batch_read_log(qk_batch*, uint64_t rep, qk_log_record* buf, uint64_t cap,
 int qk_batch_read_logs(qk_batch*, uint64_t rep0, uint64_t n, qk_log_record* buf, uint32_t* kept, uint64_t* total);
 /* resource of a vector stock / in-flight vector of a vector process-like component (3 doubles) */
 int qk_batch_read_vector(qk_batch*, uint64_t rep, uint32_t comp, double* out3);
+/* ... of any resource type: out[cap >= dim], *dim_out = the number of fields (qk_model_set_vector_n) */
+int qk_batch_read_vector_n(qk_batch*, uint64_t rep, uint32_t comp, double* out, uint32_t cap, uint32_t* dim_out);
 /* discrete stock contents in FIFO order */
 int qk_batch_read_stock(qk_batch*, uint64_t rep, uint32_t comp, uint32_t* items, uint64_t cap, uint64_t* n_out);
 /* containers held by a container stock (FIFO order) or by a container process-like component (in progress first, then

@@ -36,7 +36,7 @@ def lower_to_oracle(model):
                 dist_ids.setdefault(id(q), []).append(did)
         if hasattr(c, "vector_rows"):
             dim, low, maxc, init = c.vector_rows()
-            om.set_vector(i, dim, low, maxc, init)
+            om.set_vector(i, dim, low, maxc, init, getattr(c, "total_mask", None))
             if getattr(c, "n_ports", None):
                 om.set_splits(i, list(c.split_ratios))
         if hasattr(c, "process_time_distr"):

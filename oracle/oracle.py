@@ -78,6 +78,8 @@ def lib():
         "orc_model_schedule_env": (C.c_int, [vp, u64, u32, u32]),
         "orc_model_n_dists": (C.c_int, [vp]),
         "orc_model_set_vector": (C.c_int, [vp, u32, u32, dbl, dbl, P(dbl)]),
+        "orc_model_set_vector_n": (C.c_int, [vp, u32, u32, u32, dbl, dbl, P(dbl)]),
+        "orc_sim_vector_resource_n": (C.c_int, [vp, u32, P(dbl), u32]),
         "orc_model_set_splits": (C.c_int, [vp, u32, u32, P(dbl)]),
         "orc_model_schedule_low_capacity": (C.c_int, [vp, u64, u32, dbl]),
         "orc_model_schedule_process_quantity": (C.c_int, [vp, u64, u32, vp]),
@@ -164,9 +166,13 @@ class OracleModel:
     def n_dists(self):
         return self.L.orc_model_n_dists(self.h)
 
-    def set_vector(self, comp, dim, low, maxc, init):
-        arr = (C.c_double * 3)(*([float(x) for x in init] + [0.0] * (3 - len(init))))
-        if self.L.orc_model_set_vector(self.h, comp, dim, low, maxc, arr) != 0:
+    def set_vector(self, comp, dim, low, maxc, init, total_mask=None):
+        arr = (C.c_double * 8)(*([float(x) for x in init] + [0.0] * (8 - len(init))))
+        if total_mask is None:
+            rc = self.L.orc_model_set_vector(self.h, comp, dim, low, maxc, arr)
+        else:
+            rc = self.L.orc_model_set_vector_n(self.h, comp, dim, total_mask, low, maxc, arr)
+        if rc != 0:
             raise RuntimeError("orc_model_set_vector failed")
 
     def set_splits(self, comp, ratios):
@@ -271,6 +277,11 @@ class OracleSim:
         out = (C.c_double * 3)()
         self.L.orc_sim_vector_resource(self.h, comp, out)
         return list(out)
+
+    def vector_resource_n(self, comp):
+        out = (C.c_double * 8)()
+        n = self.L.orc_sim_vector_resource_n(self.h, comp, out, 8)
+        return list(out[:n])
 
     def containers(self, comp):
         h = np.zeros(4096, dtype=np.uint32)

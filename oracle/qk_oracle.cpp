@@ -262,7 +262,8 @@ struct CompDef {
   /* vector */
   uint32_t dim;
   double vlow, vmax;
-  double vinit[3];
+  double vinit[8];
+  uint32_t tmask; /* fields counted by ResourceTotal (set_vector_n) */
   int ups[5], downs[5];
   uint32_t n_ports;
   double ratios[5];
@@ -281,7 +282,8 @@ struct CompDef {
       ups[i] = downs[i] = -1;
       ratios[i] = 0;
     }
-    vinit[0] = vinit[1] = vinit[2] = 0;
+    for (int k = 0; k < 8; ++k) vinit[k] = 0;
+    tmask = 7;
   }
 };
 
@@ -362,8 +364,8 @@ struct Comp {
   /* environment */
   uint32_t env_state;
   /* vector components (vector.rs): stock resource / process in-flight vector; combiner keeps M vectors */
-  double vres[3];
-  std::vector<std::array<double, 3> > parts;
+  double vres[8];
+  std::vector<std::array<double, 8> > parts;
   double vlow; /* low_capacity is mutable at run time (SetLowCapacity, core.rs:1382-1386) */
   int qty_dist; /* process_quantity_distr is too (SetProcessQuantity, core.rs:1387-1391): -1 = the model's */
   bool ttnde_some;
@@ -376,7 +378,7 @@ struct Comp {
         sched_time(0), sched_key(0), next_event_index(0), previous_check_time(0), next_item_index(0), env_state(0),
         vlow(0), qty_dist(-1), ttnde_some(false), ttnde(0), area_last_t(0) {
     std::memset(&st, 0, sizeof(st));
-    vres[0] = vres[1] = vres[2] = 0;
+    for (int k = 0; k < 8; ++k) vres[k] = 0;
   }
 };
 
@@ -1025,7 +1027,7 @@ struct orc_sim {
           c[i].dm[k].dur = dur_from(secs);
         }
         if (d.kind == ORC_VECTOR_STOCK) {
-          for (int k = 0; k < 3; ++k) c[i].vres[k] = d.vinit[k];
+          for (int k = 0; k < 8; ++k) c[i].vres[k] = d.vinit[k];
           c[i].vlow = d.vlow;
           c[i].area_last_t = t0;
         }

@@ -178,6 +178,10 @@ int orc_model_schedule_env(orc_model*, uint64_t t_ns, uint32_t env, uint32_t sta
 int orc_model_n_dists(const orc_model*);
 /* vector components (fp64) */
 int orc_model_set_vector(orc_model*, uint32_t comp, uint32_t dim, double low, double max, const double* init);
+/* user-defined resource (quokkasim_examples/src/bin/iron_ore.rs:21-96): dim <= 8 fields, ResourceTotal sums the fields
+ * named by total_mask in field order, ResourceRemove is proportional over every field */
+int orc_model_set_vector_n(orc_model*, uint32_t comp, uint32_t dim, uint32_t total_mask, double low, double max,
+                           const double* init);
 int orc_model_set_splits(orc_model*, uint32_t comp, uint32_t n, const double* ratios);
 int orc_model_schedule_low_capacity(orc_model*, uint64_t t_ns, uint32_t stock, double value);
 int orc_model_schedule_process_quantity(orc_model*, uint64_t t_ns, uint32_t process, const orc_dist* d);
@@ -206,6 +210,7 @@ int orc_sim_comp_stats(orc_sim*, uint32_t comp, orc_comp_stats* out);
 uint64_t orc_sim_stock_items(const orc_sim*, uint32_t comp, uint32_t* buf, uint64_t cap);
 /* vector stock contents */
 int orc_sim_vector_resource(const orc_sim*, uint32_t comp, double* out3);
+int orc_sim_vector_resource_n(const orc_sim*, uint32_t comp, double* out, uint32_t cap); /* returns dim */
 uint64_t orc_sim_draws(const orc_sim*, uint32_t dist_id);
 /* containers held by a container stock (FIFO order) or a container process-like component (in progress, then
  * complete): handles [cap], resources [cap][3] (first double = ORC_CONTAINER_NONE_BITS for None); returns count */

@@ -16,6 +16,7 @@ from ._capi import QkError  # noqa: F401
 from .api import VectorProcessLogger, VectorStockLogger  # noqa: F401
 from .vector_api import (  # noqa: F401
     Vector3, VectorCombiner, VectorProcess, VectorSink, VectorSource, VectorSplitter, VectorStock,
+    define_resource, define_vector_variants,
 )
 
 from .api import ContainerProcessLogger, ContainerStockLogger  # noqa: F401

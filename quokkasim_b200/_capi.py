@@ -42,7 +42,7 @@ STATUS_NAMES = {
 EXPORTED_SYMBOLS = [
     "qk_abi_version", "qk_build_id", "qk_model_create", "qk_model_destroy", "qk_model_add_component", "qk_model_set_dist",
     "qk_model_add_delay_mode", "qk_model_connect", "qk_model_set_logged", "qk_model_schedule_env_state",
-    "qk_model_set_vector", "qk_model_set_ports", "qk_model_schedule_low_capacity", "qk_model_schedule_process_quantity", "qk_batch_read_vector",
+    "qk_model_set_vector", "qk_model_set_vector_n", "qk_batch_read_vector_n", "qk_model_set_ports", "qk_model_schedule_low_capacity", "qk_model_schedule_process_quantity", "qk_batch_read_vector",
     "qk_model_n_components", "qk_model_n_dists", "qk_model_state_bytes", "qk_batch_create", "qk_batch_destroy",
     "qk_batch_info_get",
     "qk_batch_set_tape", "qk_batch_init", "qk_batch_step_until", "qk_batch_step_events", "qk_batch_step_events_chunked", "qk_batch_step_events_sliced",
@@ -165,6 +165,8 @@ def load_library(path=None):
         "qk_model_schedule_low_capacity": (C.c_int, [vp, u64, u32, C.c_double]),
         "qk_model_schedule_process_quantity": (C.c_int, [vp, u64, u32, P(DistDesc), P(u32)]),
         "qk_batch_read_vector": (C.c_int, [vp, u64, u32, P(C.c_double)]),
+        "qk_model_set_vector_n": (C.c_int, [vp, u32, u32, u32, C.c_double, C.c_double, P(C.c_double)]),
+        "qk_batch_read_vector_n": (C.c_int, [vp, u64, u32, P(C.c_double), u32, P(u32)]),
         "qk_model_n_components": (C.c_int, [vp, P(u32)]),
         "qk_model_n_dists": (C.c_int, [vp, P(u32)]),
         "qk_model_state_bytes": (C.c_int, [vp, C.c_int, P(u32)]),

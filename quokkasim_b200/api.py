@@ -563,10 +563,10 @@ class ComponentLogger:
     def __str__(self):
         return self.variant
 
-    def write_csv(self, directory, sim, replication=0):
+    def write_csv(self, directory, sim, replication=0, record_map=None, header=None):
         from .csvlog import write_csv
 
-        return write_csv(self, directory, sim, replication)
+        return write_csv(self, directory, sim, replication, record_map, header)
 
 
 for _v in ComponentLogger._VARIANTS:
@@ -757,8 +757,11 @@ class BatchedSimulation:
                 if c.dim is None:
                     raise TypeError("vector component %r was never wrapped in a ComponentModel variant" % c.element_name)
                 dim, low, maxc, init = c.vector_rows()
-                arr = (C.c_double * 3)(*(list(init) + [0.0] * (3 - len(init))))
-                capi.check(L, L.qk_model_set_vector(self._model, c._id, dim, low, maxc, arr))
+                arr = (C.c_double * 8)(*(list(init) + [0.0] * (8 - len(init))))
+                if getattr(c, "total_mask", None) is None:
+                    capi.check(L, L.qk_model_set_vector(self._model, c._id, dim, low, maxc, arr))
+                else:  # a user-defined resource type (vector_api.define_resource)
+                    capi.check(L, L.qk_model_set_vector_n(self._model, c._id, dim, c.total_mask, low, maxc, arr))
                 if getattr(c, "n_ports", None):
                     ratios = (C.c_double * 5)(*(list(c.split_ratios) + [0.0] * (5 - len(c.split_ratios))))
                     capi.check(L, L.qk_model_set_ports(self._model, c._id, c.n_ports, ratios))
@@ -948,6 +951,14 @@ class BatchedSimulation:
         capi.check(self.L, self.L.qk_batch_read_vector(self._batch, replication, self._cid(component), out))
         return list(out)
 
+    def read_resource(self, component, replication):
+        """... of any resource type: one double per field (a user-defined resource: all of its fields)."""
+        self._materialize()
+        out, dim = (C.c_double * 8)(), C.c_uint32()
+        capi.check(self.L, self.L.qk_batch_read_vector_n(self._batch, replication, self._cid(component), out, 8,
+                                                         C.byref(dim)))
+        return list(out[: dim.value])
+
     def read_stock(self, component, replication):
         self._materialize()
         n = C.c_uint64()
@@ -1031,3 +1042,4 @@ Vector3Container, Vector3ContainerFactory = _ca.Vector3Container, _ca.Vector3Con
 ContainerLoadingProcess, ContainerUnloadingProcess = _ca.ContainerLoadingProcess, _ca.ContainerUnloadingProcess
 Vector3, VectorStock, VectorProcess, VectorSource = _va.Vector3, _va.VectorStock, _va.VectorProcess, _va.VectorSource
 VectorSink, VectorCombiner, VectorSplitter = _va.VectorSink, _va.VectorCombiner, _va.VectorSplitter
+define_resource, define_vector_variants = _va.define_resource, _va.define_vector_variants

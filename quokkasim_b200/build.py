@@ -13,7 +13,7 @@ LIB = os.path.join(_HERE, "libquokka_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
 SOURCES = ["qk_model.cpp", "qk_batch.cu", "qk_multi.cu", "qk_step_l0f0.cu", "qk_step_l0f1.cu", "qk_step_l1f0.cu", "qk_step_l1f1.cu",
-           "qk_step_l0f2.cu", "qk_step_l1f2.cu", "qk_group_l0f0.cu", "qk_group_l0f1.cu", "qk_group_l0f2.cu",
+           "qk_step_l0f2.cu", "qk_step_l1f2.cu", "qk_step_l0f3.cu", "qk_step_l1f3.cu", "qk_group_l0f0.cu", "qk_group_l0f1.cu", "qk_group_l0f2.cu",
            "qk_group_l1f0.cu", "qk_group_l1f1.cu", "qk_group_l1f2.cu"]
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

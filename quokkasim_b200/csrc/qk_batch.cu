@@ -106,6 +106,8 @@ StepKernel qk_pick_step_l1f0(uint32_t nt);
 StepKernel qk_pick_step_l1f1(uint32_t nt);
 StepKernel qk_pick_step_l0f2(uint32_t nt);
 StepKernel qk_pick_step_l1f2(uint32_t nt);
+StepKernel qk_pick_step_l0f3(uint32_t nt);
+StepKernel qk_pick_step_l1f3(uint32_t nt);
 /* ... the lane-group kernels in qk_group_l{0,1}f{0,1,2}.cu */
 StepKernel qk_pick_group_l0f0(uint32_t g);
 StepKernel qk_pick_group_l0f1(uint32_t g);
@@ -132,6 +134,7 @@ static StepKernel pick_group_kernel(bool log, uint32_t g, uint32_t features) {
 static uint32_t group_max_threads(uint32_t g) { return g <= 4 ? 256u : (g == 8 ? 512u : 768u); } /* qk_group_max_threads */
 static StepKernel pick_kernel(bool log, bool hbm, uint32_t nt, uint32_t features, uint32_t split = 0) {
   const uint32_t key = split == 2 ? 0xFFFFFFFDu : (split ? 0xFFFFFFFEu : (hbm ? 0u : nt));
+  if (features == 3) return log ? qk_pick_step_l1f3(key) : qk_pick_step_l0f3(key);
   if (features >= 2) return log ? qk_pick_step_l1f2(key) : qk_pick_step_l0f2(key);
   if (log) return features ? qk_pick_step_l1f1(key) : qk_pick_step_l1f0(key);
   return features ? qk_pick_step_l0f1(key) : qk_pick_step_l0f0(key);
@@ -520,6 +523,11 @@ int qk_batch_create(const qk_model* m, const qk_batch_config* cfg, qk_batch** ou
   bool group = (cfg->flags & QK_BATCH_STATE_LANE_GROUP) != 0;
   bool split = (cfg->flags & QK_BATCH_STATE_SPLIT) != 0;
   bool qsplit = split && (cfg->flags & QK_BATCH_QUEUE_TWO_TIER) != 0;
+  if (group && h.features == 3) {
+    qk_set_error("qk_batch_create: the lane-group kernels do not carry user-defined vector resources (feature set 3)");
+    delete b;
+    return QK_ERR_INVALID_ARG;
+  }
   if (split && (b->hbm || group || (cfg->flags & QK_BATCH_STATE_ON_CHIP))) {
     qk_set_error("qk_batch_create: QK_BATCH_STATE_SPLIT excludes the other placement flags");
     delete b;
@@ -1234,8 +1242,26 @@ int qk_batch_read_vector(qk_batch* b, uint64_t rep, uint32_t comp, double* out3)
   CUDA_TRY(cudaStreamSynchronize(b->stream));
   const DevVec& v = b->low.vecs[b->low.comps[comp].vec_idx];
   out3[0] = out3[1] = out3[2] = 0.0;
-  for (uint32_t k = 0; k < v.dim; ++k)
+  for (uint32_t k = 0; k < v.dim && k < 3; ++k)
     CUDA_TRY(cudaMemcpy(&out3[k], warm64_at(b, v.o64_res + k, rep), 8, cudaMemcpyDeviceToHost));
+  return QK_OK;
+}
+
+int qk_batch_read_vector_n(qk_batch* b, uint64_t rep, uint32_t comp, double* out, uint32_t cap, uint32_t* dim_out) {
+  int rc = check_range(b, rep, 1);
+  if (rc) return rc;
+  if (comp >= b->low.hdr.n_comp || b->low.comps[comp].kind < QK_VECTOR_STOCK ||
+      b->low.comps[comp].kind > QK_VECTOR_SPLITTER || !out) {
+    qk_set_error("qk_batch_read_vector_n: component %u is not a vector component", comp);
+    return QK_ERR_INVALID_ARG;
+  }
+  const DevVec& v = b->low.vecs[b->low.comps[comp].vec_idx];
+  if (dim_out) *dim_out = v.dim;
+  if (cap < v.dim) return QK_ERR_BUFFER_TOO_SMALL;
+  CUDA_TRY(cudaSetDevice(b->cfg.device));
+  CUDA_TRY(cudaStreamSynchronize(b->stream));
+  for (uint32_t k = 0; k < v.dim; ++k)
+    CUDA_TRY(cudaMemcpy(&out[k], warm64_at(b, v.o64_res + k, rep), 8, cudaMemcpyDeviceToHost));
   return QK_OK;
 }
 

@@ -208,10 +208,11 @@ typedef struct {
   double value;
 } DevExt; /* 32 bytes */
 
-/* extra description of a vector component (vector.rs); resource type f64 (dim 1) or Vector3 (dim 3) */
+/* extra description of a vector component (vector.rs); resource type f64 (dim 1), Vector3 (dim 3) or a user-defined
+ * struct of up to QK_VEC_MAX_DIM fields (feature set 3) */
 typedef struct {
   double vmax;      /* VectorStock.max_capacity */
-  double vinit[3];  /* VectorStock initial resource / VectorSource.source_vector */
+  double vinit[QK_VEC_MAX_DIM]; /* VectorStock initial resource / VectorSource.source_vector */
   double ratios[5]; /* VectorSplitter.split_ratios */
   int16_t ups[5];   /* VectorCombiner upstream stocks by port */
   int16_t downs[5]; /* VectorSplitter downstream stocks by port */
@@ -223,8 +224,9 @@ typedef struct {
   double vlow;       /* VectorStock.low_capacity at t0 */
   uint16_t o32_qty;  /* F64Process that a SetProcessQuantity event targets: plane32 slot holding the distribution instance
                         process_quantity_distr currently is (0xFFFF: it never changes, dist_qty) */
-  uint16_t pad[3];
-} DevVec; /* 120 bytes */
+  uint16_t tmask;    /* fields ResourceTotal counts (bit k = field k; Vector3: 7) */
+  uint16_t pad[2];
+} DevVec; /* 160 bytes */
 
 /* header of the table blob (all offsets in bytes from the blob start, 8-byte aligned) */
 typedef struct {
@@ -245,7 +247,8 @@ typedef struct {
   uint32_t off_ccap;  /* double ccap[64 + n_initial]: container capacity by source ordinal, then by initial-item index */
   uint32_t off_cinit; /* uint64_t cinit[n_initial][3]: resource bits of the initial containers (NONE sentinel) */
   uint32_t features; /* 0 = every process-like component is SIMPLE and nothing is scheduled externally ; 1 = general ;
-                        2 = general + container family (vector_container.rs) */
+                        2 = general + container family (vector_container.rs) ; 3 = general + user-defined vector
+                        resources of up to QK_VEC_MAX_DIM fields (no containers) */
   uint32_t n_hot, off_hot_rank; /* placement 2: entries of the hot fire array (stocks) ; u16 hot_rank[n_hot]: index -> rank */
   uint32_t gshift, n_groups, gmin64, gidx32, gdirty32; /* placement 2: group minima of the cold fire array (qk_lower) */
   uint32_t emask32;             /* placement 2: first hot32 slot of the pending-emit mask (bit = index in the hot fire array) */

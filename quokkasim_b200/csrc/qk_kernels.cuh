@@ -27,6 +27,9 @@
 #define QK_KERNELS_CUH
 #include "qk_device.cuh"
 
+/* fields a vector resource may have in the kernels of feature set FT (qk_vector.cuh) */
+template <int FT> struct QkVd { static constexpr int v = FT == 3 ? QK_VEC_MAX_DIM : 3; };
+#define qk_vd(ft) (QkVd<(ft)>::v)
 #define QK_D2U(d) ((uint64_t)__double_as_longlong(d))
 #define QK_U2D(u) (__longlong_as_double((long long)(u)))
 
@@ -904,7 +907,7 @@ __device__ __forceinline__ bool qk_update_single(Ctx& cx, const DevHotA& c, uint
   const uint64_t pre_dur = mine.dur;
   uint64_t ttnpe = QK_TIME_NONE;
   /* Vector3ContainerProcess / Source / Sink (core.rs:550-553): the item carries a resource, kept at cold64 `opay` */
-  const bool ctr = FT >= 2 && (c.flags & DC_CONTAINER) != 0;
+  const bool ctr = FT == 2 && (c.flags & DC_CONTAINER) != 0;
   const uint32_t opay = ctr ? cx.comps[comp].ocold64 : 0u;
   uint64_t pay[3];
   {
@@ -1048,9 +1051,9 @@ __device__ __forceinline__ void qk_update_multi(Ctx& cx, const DevComp* c, uint3
   const DevHotB hb = QK_HOT_B(comp);
   const uint32_t kind = c->kind;
   /* the container family is compiled in only for models that have it (feature set 2) */
-  const bool ctr = FT >= 2 && (c->flags & DC_CONTAINER) != 0;
-  const bool is_load = FT >= 2 && kind == QK_CONTAINER_LOAD_PROCESS;
-  const bool is_unload = FT >= 2 && kind == QK_CONTAINER_UNLOAD_PROCESS;
+  const bool ctr = FT == 2 && (c->flags & DC_CONTAINER) != 0;
+  const bool is_load = FT == 2 && kind == QK_CONTAINER_LOAD_PROCESS;
+  const bool is_unload = FT == 2 && kind == QK_CONTAINER_UNLOAD_PROCESS;
   uint32_t flags = W32(c->o32 + PP32_FLAGS);
   const uint64_t dt = cx.now - W64(c->o64 + PP64_PREV);
   const uint32_t cap = c->ring_cap;
@@ -1244,7 +1247,7 @@ __device__ __forceinline__ bool qk_update_state(Ctx& cx, uint32_t comp, uint64_t
       if (LOG && src == SRC_INIT && a.kind != QK_VECTOR_PROCESS)
         src = ((uint64_t)comp << 32) | S32(a.olog32 + L32_SEQ);
       qk_pre<LOG, SM>(cx, a, comp);
-      qk_update_vector<LOG, SM>(cx, c, comp, src);
+      qk_update_vector<LOG, SM, qk_vd(FT)>(cx, c, comp, src);
       return cx.status != 0;
     }
     qk_pre<LOG, SM>(cx, a, comp);
@@ -1398,7 +1401,7 @@ __global__ void __launch_bounds__(qk_lb_threads(SM), qk_lb_blocks(SM, FT, LOG)) 
           /* with_initial_resource: the count rides in DevComp.dist_time (unused for stocks) */
           const uint32_t n_init = c->dist_time;
           for (uint32_t k = 0; k < n_init; ++k) C32(c->ocold32 + k) = (63u << 26) | (initial_base + k);
-          if (FT >= 2 && (c->flags & DC_CONTAINER)) { /* with_initial_resource(ItemDeque<Vector3Container>) */
+          if (FT == 2 && (c->flags & DC_CONTAINER)) { /* with_initial_resource(ItemDeque<Vector3Container>) */
             const uint64_t* cinit = reinterpret_cast<const uint64_t*>(smem + cx.hdr->off_cinit) + 3u * initial_base;
             for (uint32_t k = 0; k < 3u * n_init; ++k) C64(c->ocold64 + k) = cinit[k];
           }
@@ -1411,7 +1414,7 @@ __global__ void __launch_bounds__(qk_lb_threads(SM), qk_lb_blocks(SM, FT, LOG)) 
           W32(c->o32 + E32_STATE) = c->low; /* initial state rides in `low` */
         } else if (c->kind == QK_VECTOR_STOCK) {
           const DevVec* v = &cx.vecs[c->vec_idx];
-          qk_vstore<SM>(cx, v->o64_res, v->dim, v->vinit);
+          qk_vstore<SM, qk_vd(FT)>(cx, v->o64_res, v->dim, v->vinit);
           W64(v->o64_low) = QK_D2U(v->vlow);
           W64(v->o64_last) = P.t0;
         } else if (FT != 0 && c->kind == QK_VECTOR_PROCESS && cx.vecs[c->vec_idx].o32_qty != 0xFFFF) {
@@ -1642,8 +1645,10 @@ __global__ void __launch_bounds__(qk_lb_threads(SM), qk_lb_blocks(SM, FT, LOG)) 
             if (e->type == 1) {
               /* SetLowCapacity on an F64Stock: with_low_capacity_inplace, then add((0., SCH_000000)) (core.rs:1382-1386) */
               W64(cx.vecs[cx.comps[target].vec_idx].o64_low) = QK_D2U(e->value);
-              const double zero[3] = {0.0, 0.0, 0.0};
-              qk_vstock_add<LOG, SM>(cx, target, zero, SRC_SCH);
+              double zero[qk_vd(FT)];
+#pragma unroll
+              for (int k = 0; k < qk_vd(FT); ++k) zero[k] = 0.0;
+              qk_vstock_add<LOG, SM, qk_vd(FT)>(cx, target, zero, SRC_SCH);
               if (cx.status) done = true;
             } else if (e->type == 2) {
               /* SetProcessQuantity on an F64Process: with_process_quantity_distr_inplace(instance), then
@@ -1808,12 +1813,9 @@ __device__ __forceinline__ void qk_comp_stats_dev(const DevComp* c, const DevVec
   o->faux = 0.0;
   if (c->kind == QK_VECTOR_STOCK) {
     const DevVec* v = &vecs[c->vec_idx];
-    double r[3] = {QK_U2D(WG64(v->o64_res)), 0.0, 0.0};
-    if (v->dim == 3) {
-      r[1] = QK_U2D(WG64(v->o64_res + 1));
-      r[2] = QK_U2D(WG64(v->o64_res + 2));
-    }
-    const double total = qk_vtotal(r, v->dim);
+    double r[QK_VEC_MAX_DIM];
+    for (uint32_t k = 0; k < QK_VEC_MAX_DIM; ++k) r[k] = k < v->dim ? QK_U2D(WG64(v->o64_res + k)) : 0.0;
+    const double total = qk_vtotaln<QK_VEC_MAX_DIM>(r, v->dim, v->tmask);
     o->count = GS32(ST32_COUNT);
     o->time_ns = 0;
     o->aux = 0;
@@ -1824,17 +1826,14 @@ __device__ __forceinline__ void qk_comp_stats_dev(const DevComp* c, const DevVec
     const DevVec* v = &vecs[c->vec_idx];
     const uint32_t flags = WG32(c->o32 + P32_FLAGS);
     const bool has = flags & PF_HAS_ITEM;
-    double r[3] = {QK_U2D(WG64(v->o64_res)), 0.0, 0.0};
-    if (v->dim == 3) {
-      r[1] = QK_U2D(WG64(v->o64_res + 1));
-      r[2] = QK_U2D(WG64(v->o64_res + 2));
-    }
+    double r[QK_VEC_MAX_DIM];
+    for (uint32_t k = 0; k < QK_VEC_MAX_DIM; ++k) r[k] = k < v->dim ? QK_U2D(WG64(v->o64_res + k)) : 0.0;
     o->count = GS32(ST32_COUNT);
     o->time_ns = GS64(ST64_TIME) - (has ? qk_left_at_clock(flags, WG64(c->o64 + P64_LEFT), now - WG64(c->o64 + P64_PREV)) : 0);
     o->aux = GS64(ST64_DELAY);
     o->level = has ? 1 : 0;
     o->fvalue = QK_U2D(GS64(ST64_FQ));
-    o->faux = !has ? 0.0 : (c->kind == QK_VECTOR_COMBINER ? QK_U2D(WG64(v->o64_res + v->dim)) : qk_vtotal(r, v->dim));
+    o->faux = !has ? 0.0 : (c->kind == QK_VECTOR_COMBINER ? QK_U2D(WG64(v->o64_res + v->dim)) : qk_vtotaln<QK_VEC_MAX_DIM>(r, v->dim, v->tmask));
   } else if (c->kind == QK_DISCRETE_STOCK) {
     const uint32_t cnt = QK_HC_CNT(G32(c->o32 + S32_HC));
     o->count = GS32(ST32_COUNT);

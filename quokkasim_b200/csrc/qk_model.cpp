@@ -134,7 +134,8 @@ int qk_model_add_component(qk_model* m, const qk_component_desc* d, uint32_t* ou
   }
   c.n_ports = (d->kind == QK_VECTOR_COMBINER || d->kind == QK_VECTOR_SPLITTER) ? 1 : 0;
   c.vlow = c.vmax = 0.0; /* VectorStock defaults (vector.rs:70-71) */
-  for (int k = 0; k < 3; ++k) c.vinit[k] = 0.0;
+  for (int k = 0; k < QK_VEC_MAX_DIM; ++k) c.vinit[k] = 0.0;
+  c.tmask = 1;
   for (int k = 0; k < 5; ++k) {
     c.ratios[k] = 0.0;
     c.ups[k] = c.downs[k] = -1;
@@ -277,7 +278,7 @@ int qk_model_connect(qk_model* m, uint32_t a, uint32_t b, int32_t port_n) {
     A.down = (int)b;
     return QK_OK;
   }
-  if (ka == QK_VECTOR_STOCK && A.dim == 3 && kb == QK_CONTAINER_LOAD_PROCESS) { /* core.rs:960-965 */
+  if (ka == QK_VECTOR_STOCK && A.dim == 3 && A.tmask == 7u && kb == QK_CONTAINER_LOAD_PROCESS) { /* core.rs:960-965 */
     if (B.ups[0] >= 0) {
       qk_set_error("qk_model_connect: load process %u already has an upstream resource stock", b);
       return QK_ERR_PORT_IN_USE;
@@ -286,7 +287,7 @@ int qk_model_connect(qk_model* m, uint32_t a, uint32_t b, int32_t port_n) {
     B.ups[0] = (int)a;
     return QK_OK;
   }
-  if (kb == QK_VECTOR_STOCK && B.dim == 3 && ka == QK_CONTAINER_UNLOAD_PROCESS) { /* core.rs:990-995 */
+  if (kb == QK_VECTOR_STOCK && B.dim == 3 && B.tmask == 7u && ka == QK_CONTAINER_UNLOAD_PROCESS) { /* core.rs:990-995 */
     if (A.downs[0] >= 0) {
       qk_set_error("qk_model_connect: unload process %u already has a downstream resource stock", a);
       return QK_ERR_PORT_IN_USE;
@@ -307,7 +308,7 @@ int qk_model_connect(qk_model* m, uint32_t a, uint32_t b, int32_t port_n) {
     return QK_OK;
   }
   /* vector arms (core.rs:572-616 for f64, same shape for Vector3; combiner/splitter arms need Some(n)) */
-  if (ka == QK_VECTOR_STOCK && A.dim == B.dim) {
+  if (ka == QK_VECTOR_STOCK && A.dim == B.dim && A.tmask == B.tmask) {
     if (kb == QK_VECTOR_PROCESS || kb == QK_VECTOR_SINK || kb == QK_VECTOR_SPLITTER) {
       if (B.up >= 0) {
         qk_set_error("qk_model_connect: component %u already has an upstream stock", b);
@@ -327,7 +328,7 @@ int qk_model_connect(qk_model* m, uint32_t a, uint32_t b, int32_t port_n) {
       return QK_OK;
     }
   }
-  if (kb == QK_VECTOR_STOCK && A.dim == B.dim) {
+  if (kb == QK_VECTOR_STOCK && A.dim == B.dim && A.tmask == B.tmask) {
     if (ka == QK_VECTOR_PROCESS || ka == QK_VECTOR_SOURCE || ka == QK_VECTOR_COMBINER) {
       if (A.down >= 0) {
         qk_set_error("qk_model_connect: component %u already has a downstream stock", a);
@@ -380,17 +381,33 @@ int qk_model_schedule_env_state(qk_model* m, uint64_t t_ns, uint32_t env, uint32
   return QK_OK;
 }
 
-int qk_model_set_vector(qk_model* m, uint32_t comp, uint32_t dim, double low, double max, const double* init) {
-  if (!m || comp >= m->comps.size() || !is_vector_kind(m->comps[comp].d.kind) || !(dim == 1 || dim == 3)) {
-    qk_set_error("qk_model_set_vector: component %u is not a vector component or dim %u is not 1 or 3", comp, dim);
+int qk_model_set_vector_n(qk_model* m, uint32_t comp, uint32_t dim, uint32_t total_mask, double low, double max,
+                          const double* init) {
+  if (!m || comp >= m->comps.size() || !is_vector_kind(m->comps[comp].d.kind) || dim < 1 || dim > QK_VEC_MAX_DIM) {
+    qk_set_error("qk_model_set_vector_n: component %u is not a vector component or dim %u is not in 1..%d", comp, dim,
+                 QK_VEC_MAX_DIM);
+    return QK_ERR_INVALID_ARG;
+  }
+  if (dim == 1) total_mask = 1; /* f64: the total is the value */
+  if (total_mask == 0 || (total_mask >> dim) != 0) {
+    qk_set_error("qk_model_set_vector_n: total mask 0x%x names no field, or a field beyond dim %u", total_mask, dim);
     return QK_ERR_INVALID_ARG;
   }
   QkHostComp& c = m->comps[comp];
   c.dim = dim;
+  c.tmask = total_mask;
   c.vlow = low;
   c.vmax = max;
-  for (uint32_t k = 0; k < 3; ++k) c.vinit[k] = (init && k < dim) ? init[k] : 0.0;
+  for (uint32_t k = 0; k < QK_VEC_MAX_DIM; ++k) c.vinit[k] = (init && k < dim) ? init[k] : 0.0;
   return QK_OK;
+}
+
+int qk_model_set_vector(qk_model* m, uint32_t comp, uint32_t dim, double low, double max, const double* init) {
+  if (!(dim == 1 || dim == 3)) {
+    qk_set_error("qk_model_set_vector: component %u is not a vector component or dim %u is not 1 or 3", comp, dim);
+    return QK_ERR_INVALID_ARG;
+  }
+  return qk_model_set_vector_n(m, comp, dim, dim == 1 ? 1u : 7u, low, max, init);
 }
 
 int qk_model_set_ports(qk_model* m, uint32_t comp, uint32_t n_ports, const double* ratios) {
@@ -732,6 +749,7 @@ int qk_lower(const qk_model* m, bool log, int placement, QkLowered* out) {
           DevVec v;
           memset(&v, 0, sizeof(v));
           v.dim = 3;
+          v.tmask = 7;
           for (int k = 0; k < 3; ++k) v.vinit[k] = c.csplit[k]; /* create_component_split */
           v.vmax = c.ccapacity;
           for (int k = 0; k < 5; ++k) v.ups[k] = v.downs[k] = -1;
@@ -758,6 +776,7 @@ int qk_lower(const qk_model* m, bool log, int placement, QkLowered* out) {
         DevVec v;
         memset(&v, 0, sizeof(v));
         v.dim = 3;
+        v.tmask = 7;
         for (int k = 0; k < 5; ++k) {
           v.ups[k] = (int16_t)c.ups[k];     /* Load: ups[0] = the Vector3Stock it withdraws resource from */
           v.downs[k] = (int16_t)c.downs[k]; /* Unload: downs[0] = the Vector3Stock it pushes resource to */
@@ -794,7 +813,8 @@ int qk_lower(const qk_model* m, bool log, int placement, QkLowered* out) {
       v.dim = (uint16_t)c.dim;
       v.vmax = c.vmax;
       v.vlow = c.vlow;
-      for (int k = 0; k < 3; ++k) v.vinit[k] = c.vinit[k];
+      v.tmask = (uint16_t)c.tmask;
+      for (int k = 0; k < QK_VEC_MAX_DIM; ++k) v.vinit[k] = c.vinit[k];
       for (int k = 0; k < 5; ++k) v.ups[k] = v.downs[k] = -1;
       d.o64 = (uint16_t)w64;
       v.o64_res = (uint16_t)w64;
@@ -821,7 +841,8 @@ int qk_lower(const qk_model* m, bool log, int placement, QkLowered* out) {
       memset(&v, 0, sizeof(v));
       v.dim = (uint16_t)c.dim;
       v.n_ports = (uint16_t)c.n_ports;
-      for (int k = 0; k < 3; ++k) v.vinit[k] = c.vinit[k];
+      v.tmask = (uint16_t)c.tmask;
+      for (int k = 0; k < QK_VEC_MAX_DIM; ++k) v.vinit[k] = c.vinit[k];
       for (int k = 0; k < 5; ++k) {
         v.ratios[k] = c.ratios[k];
         v.ups[k] = (int16_t)c.ups[k];
@@ -1045,6 +1066,17 @@ int qk_lower(const qk_model* m, bool log, int placement, QkLowered* out) {
     }
   }
   const bool any_ctr = std::any_of(dc.begin(), dc.end(), [](const DevComp& d) { return (d.flags & DC_CONTAINER) != 0; });
+  /* a vector resource that is neither f64 nor Vector3 (user-defined: more fields, or a total over a subset) */
+  const bool any_wide = std::any_of(m->comps.begin(), m->comps.end(), [](const QkHostComp& c) {
+    return is_vector_kind(c.d.kind) && !((c.dim == 1) || (c.dim == 3 && c.tmask == 7u));
+  });
+  if (any_wide) {
+    if (any_ctr) {
+      qk_set_error("user-defined vector resources and the Vector3 container family cannot share one model");
+      return QK_ERR_INVALID_ARG;
+    }
+    h.features = 3;
+  }
   if (any_ctr) {
     h.features = 2;
     h.off_ccap = off;

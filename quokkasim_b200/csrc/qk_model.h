@@ -17,7 +17,8 @@ struct QkHostComp {
   uint32_t initial_base;
   /* vector components */
   uint32_t dim, n_ports;
-  double vlow, vmax, vinit[3], ratios[5];
+  double vlow, vmax, vinit[QK_VEC_MAX_DIM], ratios[5];
+  uint32_t tmask; /* fields counted by the resource's total (qk_model_set_vector_n) */
   int ups[5], downs[5];
   /* container family: factory of a container source; initial contents of a container stock */
   int dist_cqty; /* create_quantity_distr instance or -1 (None) */

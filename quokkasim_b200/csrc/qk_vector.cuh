@@ -1,6 +1,8 @@
 /*
  * qk_vector.cuh -- continuous (vector) components on the device: VectorStock, VectorProcess, VectorSource,
- * VectorSink, VectorCombiner<M>, VectorSplitter<N> for f64 (dim 1) and Vector3 (dim 3) resources.
+ * VectorSink, VectorCombiner<M>, VectorSplitter<N> for f64 (dim 1) and Vector3 (dim 3) resources, and -- in the
+ * feature-set-3 kernels, VD = QK_VEC_MAX_DIM -- for user-defined resources of up to eight fields whose total counts a
+ * subset of them (quokkasim_examples/src/bin/iron_ore.rs:21-96).
  * Included by qk_kernels.cuh (uses its Ctx / S64 / S32 / qk_log / qk_post machinery).
  *
  * Replaces, for the batched path (paths relative to /root/reference/quokkasim/src):
@@ -42,19 +44,64 @@ __device__ __forceinline__ void qk_log_vec(Ctx& cx, const DevComp* c, uint32_t c
 __device__ __forceinline__ double qk_vtotal(const double* v, uint32_t dim) {
   return dim == 1 ? v[0] : __dadd_rn(__dadd_rn(v[0], v[1]), v[2]); /* core.rs:96-100: left-to-right sum */
 }
-
-template <int SM>
-__device__ __forceinline__ void qk_vload(Ctx& cx, uint32_t slot, uint32_t dim, double* v) {
-  v[0] = QK_U2D(W64(slot));
-  v[1] = dim == 3 ? QK_U2D(W64(slot + 1)) : 0.0;
-  v[2] = dim == 3 ? QK_U2D(W64(slot + 2)) : 0.0;
+/* ResourceTotal of a resource of up to VD fields: f64 and Vector3 as above (VD == 3: nothing else exists in those
+ * kernels); a user-defined resource sums the fields its total mask names, in field order (iron_ore.rs:75-79) */
+template <int VD>
+__device__ __forceinline__ double qk_vtotaln(const double* v, uint32_t dim, uint32_t mask) {
+  if constexpr (VD == 3) {
+    return qk_vtotal(v, dim);
+  } else {
+    if (dim == 1) return v[0];
+    double t = 0.0;
+    bool first = true;
+#pragma unroll
+    for (int k = 0; k < VD; ++k)
+      if ((uint32_t)k < dim && ((mask >> k) & 1u)) {
+        t = first ? v[k] : __dadd_rn(t, v[k]);
+        first = false;
+      }
+    return t;
+  }
 }
-template <int SM>
+
+/* fields beyond dim read as 0 */
+template <int SM, int VD = 3>
+__device__ __forceinline__ void qk_vload(Ctx& cx, uint32_t slot, uint32_t dim, double* v) {
+  if constexpr (VD == 3) {
+    v[0] = QK_U2D(W64(slot));
+    v[1] = dim == 3 ? QK_U2D(W64(slot + 1)) : 0.0;
+    v[2] = dim == 3 ? QK_U2D(W64(slot + 2)) : 0.0;
+  } else {
+#pragma unroll
+    for (int k = 0; k < VD; ++k) v[k] = (uint32_t)k < dim ? QK_U2D(W64(slot + k)) : 0.0;
+  }
+}
+template <int SM, int VD = 3>
 __device__ __forceinline__ void qk_vstore(Ctx& cx, uint32_t slot, uint32_t dim, const double* v) {
-  W64(slot) = QK_D2U(v[0]);
-  if (dim == 3) {
-    W64(slot + 1) = QK_D2U(v[1]);
-    W64(slot + 2) = QK_D2U(v[2]);
+  if constexpr (VD == 3) {
+    W64(slot) = QK_D2U(v[0]);
+    if (dim == 3) {
+      W64(slot + 1) = QK_D2U(v[1]);
+      W64(slot + 2) = QK_D2U(v[2]);
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < VD; ++k)
+      if ((uint32_t)k < dim) W64(slot + k) = QK_D2U(v[k]);
+  }
+}
+/* the continuation records of one vector: one per three fields, index + 8 * chunk in the record's index byte */
+template <bool LOG, int SM, int VD>
+__device__ __forceinline__ void qk_log_vecn(Ctx& cx, const DevComp* c, uint32_t comp, uint64_t id, uint32_t idx,
+                                            const double* v, uint32_t dim) {
+  if constexpr (VD == 3) {
+    qk_log_vec<LOG, SM>(cx, c, comp, id, idx, v[0], v[1], v[2]);
+  } else {
+#pragma unroll
+    for (int ch = 0; 3 * ch < VD; ++ch)
+      if ((uint32_t)(3 * ch) < dim)
+        qk_log_vec<LOG, SM>(cx, c, comp, id, idx + 8u * ch, v[3 * ch], 3 * ch + 1 < VD ? v[3 * ch + 1] : 0.0,
+                            3 * ch + 2 < VD ? v[3 * ch + 2] : 0.0);
   }
 }
 
@@ -90,20 +137,43 @@ __device__ __forceinline__ void qk_vremove(double* self, double q, uint32_t dim,
     self[k] = r.self[k];
   }
 }
+/* ... and of a user-defined resource: proportional over EVERY field, the proportion taken of the masked total
+ * (iron_ore.rs:52-73) */
+template <int VD>
+__device__ __forceinline__ void qk_vremoven(double* self, double q, uint32_t dim, uint32_t mask, double* out) {
+  if constexpr (VD == 3) {
+    qk_vremove(self, q, dim, out);
+  } else {
+    if (dim == 1) {
+      self[0] = __dsub_rn(self[0], q);
+      out[0] = q;
+#pragma unroll
+      for (int k = 1; k < VD; ++k) out[k] = 0.0;
+      return;
+    }
+    const double ps = __ddiv_rn(q, qk_vtotaln<VD>(self, dim, mask));
+    const double pr = __dsub_rn(1.0, ps);
+#pragma unroll
+    for (int k = 0; k < VD; ++k) {
+      out[k] = (uint32_t)k < dim ? __dmul_rn(self[k], ps) : 0.0;
+      if ((uint32_t)k < dim) self[k] = __dmul_rn(self[k], pr);
+    }
+  }
+}
 
 /* VectorStock::get_state (vector.rs:89-99): Full if max - occ <= 0, else Empty if occ < low, else Normal */
 __device__ __forceinline__ uint32_t qk_vcat(double occ, double low, double vmax) {
   return __dsub_rn(vmax, occ) <= 0.0 ? 2u : (occ < low ? 0u : 1u);
 }
 
-template <int SM>
+template <int SM, int VD = 3>
 __device__ __forceinline__ uint32_t qk_vstock_cat_of(Ctx& cx, int sidx) {
   if (sidx < 0) return 3u;
   const DevComp* c = &cx.comps[sidx];
   const DevVec* v = &cx.vecs[c->vec_idx];
-  double r[3];
-  qk_vload<SM>(cx, v->o64_res, v->dim, r);
-  return qk_vcat(qk_vtotal(r, v->dim), QK_U2D(W64(v->o64_low)), v->vmax);
+  double r[VD];
+  qk_vload<SM, VD>(cx, v->o64_res, v->dim, r);
+  return qk_vcat(qk_vtotaln<VD>(r, v->dim, v->tmask), QK_U2D(W64(v->o64_low)), v->vmax);
 }
 
 /* cx.schedule_event(now + 1ns, emit_change, (state, id)) -- the emit carries the state computed NOW */
@@ -144,46 +214,52 @@ __device__ __forceinline__ void qk_vstock_area(Ctx& cx, uint32_t sidx, const Dev
 }
 
 /* Stock::add (core.rs:177-183; vector.rs:110-135) */
-template <bool LOG, int SM>
+template <bool LOG, int SM, int VD = 3>
 __device__ __forceinline__ void qk_vstock_add(Ctx& cx, uint32_t sidx, const double* add, uint64_t src) {
   const DevComp* c = &cx.comps[sidx];
   const DevHotA ha = QK_HOT_A(sidx);
   const DevVec* v = &cx.vecs[c->vec_idx];
   const uint32_t dim = v->dim;
-  double r[3];
-  qk_vload<SM>(cx, v->o64_res, dim, r);
+  double r[VD];
+  qk_vload<SM, VD>(cx, v->o64_res, dim, r);
   const double low = QK_U2D(W64(v->o64_low));
-  const double before = qk_vtotal(r, dim);
+  const double before = qk_vtotaln<VD>(r, dim, v->tmask);
   const uint32_t prev = qk_vcat(before, low, v->vmax);
   qk_vstock_area<SM>(cx, sidx, v, before);
-  for (uint32_t k = 0; k < dim; ++k) r[k] = __dadd_rn(r[k], add[k]);
-  qk_vstore<SM>(cx, v->o64_res, dim, r);
+  if constexpr (VD == 3) {
+    for (uint32_t k = 0; k < dim; ++k) r[k] = __dadd_rn(r[k], add[k]);
+  } else {
+#pragma unroll
+    for (int k = 0; k < VD; ++k)
+      if ((uint32_t)k < dim) r[k] = __dadd_rn(r[k], add[k]);
+  }
+  qk_vstore<SM, VD>(cx, v->o64_res, dim, r);
   QK_ST32_ADD(sidx, ST32_COUNT, 1u);
-  const double after = qk_vtotal(r, dim);
+  const double after = qk_vtotaln<VD>(r, dim, v->tmask);
   const uint64_t id = qk_log<LOG, SM>(cx, ha, sidx, src, QK_LOG_VSTOCK_ADD, 0, QK_D2U(after));
-  qk_log_vec<LOG, SM>(cx, c, sidx, id, 0, add[0], add[1], add[2]);
+  qk_log_vecn<LOG, SM, VD>(cx, c, sidx, id, 0, add, dim);
   const uint32_t cur = qk_vcat(after, low, v->vmax);
   if (prev != cur) qk_vemit_push<LOG, SM>(cx, c, (uint32_t)id, cur, after);
 }
 
 /* Stock::remove (core.rs:197-204; vector.rs:137-165) */
-template <bool LOG, int SM>
+template <bool LOG, int SM, int VD = 3>
 __device__ __forceinline__ void qk_vstock_remove(Ctx& cx, uint32_t sidx, double q, uint64_t src, double* out) {
   const DevComp* c = &cx.comps[sidx];
   const DevHotA ha = QK_HOT_A(sidx);
   const DevVec* v = &cx.vecs[c->vec_idx];
   const uint32_t dim = v->dim;
-  double r[3];
-  qk_vload<SM>(cx, v->o64_res, dim, r);
+  double r[VD];
+  qk_vload<SM, VD>(cx, v->o64_res, dim, r);
   const double low = QK_U2D(W64(v->o64_low));
-  const double before = qk_vtotal(r, dim);
+  const double before = qk_vtotaln<VD>(r, dim, v->tmask);
   const uint32_t prev = qk_vcat(before, low, v->vmax);
   qk_vstock_area<SM>(cx, sidx, v, before);
-  qk_vremove(r, q, dim, out);
-  qk_vstore<SM>(cx, v->o64_res, dim, r);
-  const double after = qk_vtotal(r, dim);
+  qk_vremoven<VD>(r, q, dim, v->tmask, out);
+  qk_vstore<SM, VD>(cx, v->o64_res, dim, r);
+  const double after = qk_vtotaln<VD>(r, dim, v->tmask);
   const uint64_t id = qk_log<LOG, SM>(cx, ha, sidx, src, QK_LOG_VSTOCK_REMOVE, 0, QK_D2U(after));
-  qk_log_vec<LOG, SM>(cx, c, sidx, id, 0, out[0], out[1], out[2]);
+  qk_log_vecn<LOG, SM, VD>(cx, c, sidx, id, 0, out, dim);
   const uint32_t cur = qk_vcat(after, low, v->vmax);
   if (prev != cur) qk_vemit_push<LOG, SM>(cx, c, (uint32_t)id, cur, after);
 }
@@ -201,7 +277,7 @@ __device__ __forceinline__ uint64_t qk_dm_next_event(Ctx& cx, const DevComp* c, 
 }
 
 /* update_state_impl + post_update_state of the five vector process-like components */
-template <bool LOG, int SM>
+template <bool LOG, int SM, int VD = 3>
 __device__ __forceinline__ void qk_update_vector(Ctx& cx, const DevComp* c, uint32_t comp, uint64_t src) {
   const DevHotA ha = QK_HOT_A(comp);
   const DevHotB hb = QK_HOT_B(comp);
@@ -220,41 +296,45 @@ __device__ __forceinline__ void qk_update_vector(Ctx& cx, const DevComp* c, uint
       left -= (dt < left ? dt : left);
       if (left == 0) {
         flags &= ~PF_HAS_ITEM;
-        double r[3];
-        qk_vload<SM>(cx, v->o64_res, dim, r);
+        double r[VD];
+        qk_vload<SM, VD>(cx, v->o64_res, dim, r);
         QK_ST32_ADD(comp, ST32_COUNT, 1u);
         if (kind == QK_VECTOR_COMBINER) {
           /* the running total and quantity were accumulated at CombineStart in the reference's order */
           const double quantity = QK_U2D(W64(v->o64_res + dim));
           src = qk_log<LOG, SM>(cx, ha, comp, src, QK_LOG_VPROC_COMBINE_SUCCESS, 0, QK_D2U(quantity));
-          qk_log_vec<LOG, SM>(cx, c, comp, src, 0, r[0], r[1], r[2]);
+          qk_log_vecn<LOG, SM, VD>(cx, c, comp, src, 0, r, dim);
           qk_red_addf64(&cx.gs64[(size_t)(comp * ST_PER_COMP + ST64_FQ) * cx.rep_pad], quantity);
-          if (c->down >= 0) qk_vstock_add<LOG, SM>(cx, (uint32_t)c->down, r, src);
+          if (c->down >= 0) qk_vstock_add<LOG, SM, VD>(cx, (uint32_t)c->down, r, src);
         } else if (kind == QK_VECTOR_SPLITTER) {
-          const double total = qk_vtotal(r, dim);
-          double parts[5][3];
+          const double total = qk_vtotaln<VD>(r, dim, v->tmask);
+          double parts[5][VD];
           for (uint32_t i = 0; i < v->n_ports; ++i) { /* vector.rs:1152-1155: remove on a fresh clone */
-            double clone[3] = {r[0], r[1], r[2]};
-            qk_vremove(clone, __dmul_rn(total, v->ratios[i]), dim, parts[i]);
+            double clone[VD];
+#pragma unroll
+            for (int k = 0; k < VD; ++k) clone[k] = r[k];
+            qk_vremoven<VD>(clone, __dmul_rn(total, v->ratios[i]), dim, v->tmask, parts[i]);
           }
           src = qk_log<LOG, SM>(cx, ha, comp, src, QK_LOG_VPROC_SPLIT_SUCCESS, 0, QK_D2U(total));
-          for (uint32_t i = 0; i < v->n_ports; ++i) qk_log_vec<LOG, SM>(cx, c, comp, src, i, parts[i][0], parts[i][1], parts[i][2]);
+          for (uint32_t i = 0; i < v->n_ports; ++i) qk_log_vecn<LOG, SM, VD>(cx, c, comp, src, i, parts[i], dim);
           qk_red_addf64(&cx.gs64[(size_t)(comp * ST_PER_COMP + ST64_FQ) * cx.rep_pad], total);
           for (uint32_t i = 0; i < v->n_ports; ++i)
             if (v->downs[i] >= 0) {
-              qk_vstock_add<LOG, SM>(cx, (uint32_t)v->downs[i], parts[i], src);
+              qk_vstock_add<LOG, SM, VD>(cx, (uint32_t)v->downs[i], parts[i], src);
               if (cx.status) return;
             }
         } else {
-          const double quantity = qk_vtotal(r, dim);
+          const double quantity = qk_vtotaln<VD>(r, dim, v->tmask);
           src = qk_log<LOG, SM>(cx, ha, comp, src, QK_LOG_VPROC_SUCCESS, 0, QK_D2U(quantity));
-          qk_log_vec<LOG, SM>(cx, c, comp, src, 0, r[0], r[1], r[2]);
+          qk_log_vecn<LOG, SM, VD>(cx, c, comp, src, 0, r, dim);
           qk_red_addf64(&cx.gs64[(size_t)(comp * ST_PER_COMP + ST64_FQ) * cx.rep_pad], quantity);
-          if (kind != QK_VECTOR_SINK && c->down >= 0) qk_vstock_add<LOG, SM>(cx, (uint32_t)c->down, r, src);
+          if (kind != QK_VECTOR_SINK && c->down >= 0) qk_vstock_add<LOG, SM, VD>(cx, (uint32_t)c->down, r, src);
         }
         if (cx.status) return;
-        const double zero[3] = {0.0, 0.0, 0.0};
-        qk_vstore<SM>(cx, v->o64_res, dim, zero);
+        double zero[VD];
+#pragma unroll
+        for (int k = 0; k < VD; ++k) zero[k] = 0.0;
+        qk_vstore<SM, VD>(cx, v->o64_res, dim, zero);
         if (kind == QK_VECTOR_COMBINER) W64(v->o64_res + dim) = 0;
       }
     }
@@ -276,43 +356,43 @@ __device__ __forceinline__ void qk_update_vector(Ctx& cx, const DevComp* c, uint
     bool ok = false;
     uint32_t fail = 0;
     if (kind == QK_VECTOR_PROCESS) {
-      const uint32_t us = qk_vstock_cat_of<SM>(cx, c->up), ds = qk_vstock_cat_of<SM>(cx, c->down);
+      const uint32_t us = qk_vstock_cat_of<SM, VD>(cx, c->up), ds = qk_vstock_cat_of<SM, VD>(cx, c->down);
       if ((us == 1u || us == 2u) && (ds == 0u || ds == 1u)) ok = true;
       else if (us == 0u) fail = QK_REASON_UPSTREAM_EMPTY;
       else if (us == 3u) fail = QK_REASON_UPSTREAM_NOT_CONNECTED;
       else if (ds == 3u) fail = QK_REASON_DOWNSTREAM_NOT_CONNECTED;
       else fail = QK_REASON_DOWNSTREAM_FULL;
     } else if (kind == QK_VECTOR_SOURCE) {
-      const uint32_t ds = qk_vstock_cat_of<SM>(cx, c->down);
+      const uint32_t ds = qk_vstock_cat_of<SM, VD>(cx, c->down);
       if (ds == 2u) fail = QK_REASON_DOWNSTREAM_FULL;
       else if (ds == 3u) fail = QK_REASON_DOWNSTREAM_NOT_CONNECTED;
       else ok = true;
     } else if (kind == QK_VECTOR_SINK) {
-      const uint32_t us = qk_vstock_cat_of<SM>(cx, c->up);
+      const uint32_t us = qk_vstock_cat_of<SM, VD>(cx, c->up);
       if (us == 1u || us == 2u) ok = true;
       else if (us == 0u) fail = QK_REASON_UPSTREAM_EMPTY;
       else fail = QK_REASON_UPSTREAM_NOT_CONNECTED;
     } else if (kind == QK_VECTOR_COMBINER) {
       int all_us = 1; /* Some(true) / 0 Some(false) / -1 None (vector.rs:899-914) */
       for (uint32_t i = 0; i < v->n_ports; ++i) {
-        const uint32_t us = qk_vstock_cat_of<SM>(cx, v->ups[i]);
+        const uint32_t us = qk_vstock_cat_of<SM, VD>(cx, v->ups[i]);
         if (us == 3u) {
           all_us = -1;
           break;
         }
         if (!(us == 1u || us == 2u)) all_us = 0;
       }
-      const uint32_t ds = qk_vstock_cat_of<SM>(cx, c->down);
+      const uint32_t ds = qk_vstock_cat_of<SM, VD>(cx, c->down);
       if (all_us == 1 && (ds == 0u || ds == 1u)) ok = true;
       else if (all_us == 0) fail = QK_REASON_AN_UPSTREAM_EMPTY;
       else if (all_us == -1) fail = QK_REASON_NO_UPSTREAMS;
       else if (ds == 3u) fail = QK_REASON_DOWNSTREAM_NOT_CONNECTED;
       else fail = QK_REASON_DOWNSTREAM_FULL;
     } else { /* splitter (vector.rs:1200-1245) */
-      const uint32_t us = qk_vstock_cat_of<SM>(cx, c->up);
+      const uint32_t us = qk_vstock_cat_of<SM, VD>(cx, c->up);
       bool all_ds = true;
       for (uint32_t i = 0; i < v->n_ports; ++i) {
-        const uint32_t ds = qk_vstock_cat_of<SM>(cx, v->downs[i]);
+        const uint32_t ds = qk_vstock_cat_of<SM, VD>(cx, v->downs[i]);
         if (!(ds == 1u || ds == 0u)) all_ds = false;
       }
       if ((us == 2u || us == 1u) && all_ds) ok = true;
@@ -324,28 +404,29 @@ __device__ __forceinline__ void qk_update_vector(Ctx& cx, const DevComp* c, uint
       /* process_quantity_distr: the model's, or the instance the latest SetProcessQuantity event brought (core.rs:1387-1391) */
       const double q = qk_sample<SM>(cx, v->o32_qty != 0xFFFF ? W32(v->o32_qty) : (uint32_t)v->dist_qty);
       if (cx.status) return;
-      double got[5][3];
+      double got[5][VD];
       uint32_t ngot = 1, start_kind = QK_LOG_VPROC_START;
       if (kind == QK_VECTOR_SOURCE) {
-        const double st = qk_vtotal(v->vinit, dim);
+        const double st = qk_vtotaln<VD>(v->vinit, dim, v->tmask);
         if (!(st > 0.0)) {
           cx.status = QK_REP_SOURCE_VECTOR; /* panic!("Source vector has total 0 or negative") vector.rs:1490 */
           return;
         }
         const double factor = __ddiv_rn(q, st);
-        for (uint32_t k = 0; k < 3; ++k) got[0][k] = k < dim ? __dmul_rn(v->vinit[k], factor) : 0.0;
+#pragma unroll
+        for (int k = 0; k < VD; ++k) got[0][k] = (uint32_t)k < dim ? __dmul_rn(v->vinit[k], factor) : 0.0;
       } else {
         src = qk_log<LOG, SM>(cx, ha, comp, src, QK_LOG_WITHDRAW_REQUEST, 0, 0);
         if (kind == QK_VECTOR_COMBINER) {
           start_kind = QK_LOG_VPROC_COMBINE_START;
           ngot = v->n_ports;
           for (uint32_t i = 0; i < ngot; ++i) { /* the full quantity from EACH upstream (quirk Q7) */
-            qk_vstock_remove<LOG, SM>(cx, (uint32_t)v->ups[i], q, src, got[i]);
+            qk_vstock_remove<LOG, SM, VD>(cx, (uint32_t)v->ups[i], q, src, got[i]);
             if (cx.status) return;
           }
         } else {
           if (kind == QK_VECTOR_SPLITTER) start_kind = QK_LOG_VPROC_SPLIT_START;
-          qk_vstock_remove<LOG, SM>(cx, (uint32_t)c->up, q, src, got[0]);
+          qk_vstock_remove<LOG, SM, VD>(cx, (uint32_t)c->up, q, src, got[0]);
           if (cx.status) return;
         }
       }
@@ -355,19 +436,21 @@ __device__ __forceinline__ void qk_update_vector(Ctx& cx, const DevComp* c, uint
       flags |= PF_HAS_ITEM;
       QK_ST64_ADD(comp, ST64_TIME, d);
       if (kind == QK_VECTOR_COMBINER) {
-        double total[3] = {0.0, 0.0, 0.0};
+        double total[VD];
+#pragma unroll
+        for (int k = 0; k < VD; ++k) total[k] = 0.0;
         double qsum = 0.0;
         for (uint32_t i = 0; i < ngot; ++i) {
           for (uint32_t k = 0; k < dim; ++k) total[k] = __dadd_rn(total[k], got[i][k]);
-          qsum = __dadd_rn(qsum, qk_vtotal(got[i], dim));
+          qsum = __dadd_rn(qsum, qk_vtotaln<VD>(got[i], dim, v->tmask));
         }
-        qk_vstore<SM>(cx, v->o64_res, dim, total);
+        qk_vstore<SM, VD>(cx, v->o64_res, dim, total);
         W64(v->o64_res + dim) = QK_D2U(qsum);
       } else {
-        qk_vstore<SM>(cx, v->o64_res, dim, got[0]);
+        qk_vstore<SM, VD>(cx, v->o64_res, dim, got[0]);
       }
       const uint64_t id = qk_log<LOG, SM>(cx, ha, comp, src, start_kind, 0, QK_D2U(q));
-      for (uint32_t i = 0; i < ngot; ++i) qk_log_vec<LOG, SM>(cx, c, comp, id, i, got[i][0], got[i][1], got[i][2]);
+      for (uint32_t i = 0; i < ngot; ++i) qk_log_vecn<LOG, SM, VD>(cx, c, comp, id, i, got[i], dim);
       if (kind != QK_VECTOR_SINK) src = id; /* VectorSink drops the returned id (vector.rs:1747) */
       ttnpe = d;
     } else {

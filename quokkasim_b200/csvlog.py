@@ -179,8 +179,9 @@ class LogDecoder:
         return self.variants[comp].startswith("Vector3Container")
 
     def is_vector(self, comp):
-        v = self.variants[comp]
-        return v.startswith(("F64", "Vector3")) and not v.startswith("Vector3Container")
+        from . import vector_api
+
+        return self.variants[comp] in vector_api.VECTOR_VARIANTS
 
     def item_json(self, comp, handle, rec_vecs):
         """serde_json::to_string(item): a String item, or a Vector3Container (vector_container.rs:113-124)"""
@@ -202,12 +203,22 @@ class LogDecoder:
         return '{"id":%s,"resource":%s,"capacity":%s}' % (json_string(name), res, _json_f64(capacity))
 
     def vector_json(self, comp, v3):
-        if self.components[comp].dim == 1:
+        c = self.components[comp]
+        if c.dim == 1:
             return ryu_f64(v3[0])
-        return '{"x":%s,"y":%s,"z":%s}' % tuple(ryu_f64(x) for x in v3)
+        rt = getattr(c, "resource_type", None)
+        if rt is not None:  # #[derive(Serialize)] on the user's struct: its fields by name, in declaration order
+            return "{" + ",".join('"%s":%s' % (f, ryu_f64(x)) for f, x in zip(rt.FIELDS, v3)) + "}"
+        return '{"x":%s,"y":%s,"z":%s}' % tuple(ryu_f64(x) for x in v3[:3])
 
     def vector_total(self, comp, v3):
-        return v3[0] if self.components[comp].dim == 1 else (v3[0] + v3[1]) + v3[2]
+        c = self.components[comp]
+        if c.dim == 1:
+            return v3[0]
+        rt = getattr(c, "resource_type", None)
+        if rt is not None:
+            return rt(*v3[: c.dim]).total()
+        return (v3[0] + v3[1]) + v3[2]
 
     @staticmethod
     def _f64(bits):
@@ -220,8 +231,8 @@ class LogDecoder:
                 struct.unpack_from("<d", raw, 24)[0])
 
     # -- rows -------------------------------------------------------------------------------------------
-    def rows(self, records):
-        """yield (component id, [fields...]) for every main record, continuation records folded in."""
+    def _grouped(self, records):
+        """yield (main record, kind, vectors, raw words): every main record with its continuation records folded in."""
         i, n = 0, len(records)
         while i < n:
             r = records[i]
@@ -232,11 +243,67 @@ class LogDecoder:
             vecs, raws = [], []
             while i < n and int(records[i]["kind"]) == capi.LOG_VEC_DATA and int(records[i]["comp"]) == int(r["comp"]) \
                     and int(records[i]["seq"]) == int(r["seq"]):
-                vecs.append(self._vec_of(records[i]))
+                chunk = int(records[i]["reason"]) >> 3  # resources of more than three fields: index + 8 * chunk
+                if chunk == 0:
+                    vecs.append(self._vec_of(records[i]))
+                elif vecs:
+                    vecs[int(records[i]["reason"]) & 7] += self._vec_of(records[i])
                 q = struct.unpack("<QQQQ", records[i].tobytes())
-                raws.append((q[0], q[2], q[3]))  # the three fp64 words as raw bits (container None sentinel)
+                if chunk == 0:
+                    raws.append((q[0], q[2], q[3]))  # the three fp64 words as raw bits (container None sentinel)
                 i += 1
+            yield r, kind, vecs, raws
+
+    def rows(self, records):
+        """yield (component id, [fields...]) for every main record, continuation records folded in."""
+        for r, kind, vecs, raws in self._grouped(records):
             yield int(r["comp"]), self._row(r, kind, vecs, raws)
+
+    def vector_events(self, records):
+        """yield (component id, dict) for the records of the continuous components, typed like the reference's
+        VectorStockLog<T> / VectorProcessLog<T> (vector.rs:190-209, 543-592): what a user's own log struct is built
+        from when the logger is connected with `map_connect_sink(|c| c.clone().into(), ..)` (iron_ore.rs:143-155,
+        316-324).  `vector` / `vectors` are instances of the component's resource type (float, Vector3 or the class
+        made by define_resource)."""
+        from . import vector_api
+
+        for r, kind, vecs, _ in self._grouped(records):
+            comp = int(r["comp"])
+            if not self.is_vector(comp):
+                continue
+            c = self.components[comp]
+            rt = getattr(c, "resource_type", None)
+
+            def typed(v, c=c, rt=rt):
+                return v[0] if c.dim == 1 else (rt(*v[: c.dim]) if rt is not None else vector_api.Vector3(v[:3]))
+
+            ev = {"time": chrono_utc(int(r["time_ns"])), "event_id": self.event_id(comp, int(r["seq"])),
+                  "source_event_id": self.event_id(int(r["src_comp"]), int(r["src_seq"])),
+                  "element_name": c.element_name, "element_type": c.element_type}
+            reason, scalar = int(r["reason"]), self._f64(int(r["payload"]))
+            if kind in (capi.LOG_VSTOCK_ADD, capi.LOG_VSTOCK_REMOVE):
+                ev.update(log_type="Add" if kind == capi.LOG_VSTOCK_ADD else "Remove", balance=scalar,
+                          vector=typed(vecs[0]))
+            elif kind == capi.LOG_VSTOCK_STATE_CHANGE:
+                ev.update(log_type="StateChange", new_state=_STATE[reason])
+            elif kind in (capi.LOG_VPROC_START, capi.LOG_VPROC_COMBINE_START, capi.LOG_VPROC_SPLIT_START,
+                          capi.LOG_VPROC_SUCCESS, capi.LOG_VPROC_COMBINE_SUCCESS, capi.LOG_VPROC_SPLIT_SUCCESS):
+                names = {capi.LOG_VPROC_START: "ProcessStart", capi.LOG_VPROC_SUCCESS: "ProcessSuccess",
+                         capi.LOG_VPROC_COMBINE_START: "CombineStart", capi.LOG_VPROC_COMBINE_SUCCESS: "CombineSuccess",
+                         capi.LOG_VPROC_SPLIT_START: "SplitStart", capi.LOG_VPROC_SPLIT_SUCCESS: "SplitSuccess"}
+                ev.update(event_type=names[kind], quantity=scalar, vectors=[typed(v) for v in vecs])
+            elif kind == capi.LOG_VPROC_FAILURE:
+                ev.update(event_type="ProcessFailure", reason=_REASONS.get(reason))
+            elif kind == capi.LOG_WITHDRAW_REQUEST:
+                ev.update(event_type="WithdrawRequest")
+            elif kind in (capi.LOG_DELAY_START, capi.LOG_DELAY_END):
+                ev.update(event_type="DelayStart" if kind == capi.LOG_DELAY_START else "DelayEnd",
+                          reason=c.delay_modes[int(r["payload"])].name)
+            else:
+                simple = {capi.LOG_PROCESS_CONTINUE: "ProcessContinue", capi.LOG_PROCESS_NONSTART: "ProcessNonStart",
+                          capi.LOG_PROCESS_STOPPED: "ProcessStopped"}
+                ev.update(event_type=simple.get(kind, "Unknown"), reason=_REASONS.get(reason))
+            yield comp, ev
 
     def _row(self, r, kind, vecs, raws=()):
         comp = int(r["comp"])
@@ -311,8 +378,10 @@ HEADERS["ContainerStockLogger"] = HEADERS["DiscreteStockLogger"]
 HEADERS["ContainerProcessLogger"] = HEADERS["DiscreteProcessLogger"]
 
 
-def csv_text(component_logger, sim, replication=0):
-    """The CSV file content `logger.write_csv(dir)` would produce for one replication."""
+def csv_text(component_logger, sim, replication=0, record_map=None, header=None):
+    """The CSV file content `logger.write_csv(dir)` would produce for one replication.  `record_map` + `header`: a
+    user-defined logger (iron_ore.rs:98-256) -- record_map(event) turns the typed event of vector_events() into the
+    fields of the user's own log struct, `header` names them."""
     logger = component_logger.logger
     records, total = sim.read_log(replication)
     if total > len(records):
@@ -321,18 +390,23 @@ def csv_text(component_logger, sim, replication=0):
     members = set(id(c) for c in logger.components)
     dec = LogDecoder(sim)
     lines = []
-    for comp, fields in dec.rows(records):
-        if id(sim.components[comp]) in members:
-            lines.append(",".join(csv_field(f) for f in fields))
+    if record_map is not None:
+        for comp, ev in dec.vector_events(records):
+            if id(sim.components[comp]) in members:
+                lines.append(",".join(csv_field(f) for f in record_map(ev)))
+    else:
+        for comp, fields in dec.rows(records):
+            if id(sim.components[comp]) in members:
+                lines.append(",".join(csv_field(f) for f in fields))
     # csv::Writer with has_headers(true) writes the header with the first record only: an empty log is an empty file
     if not lines:
         return ""
-    return HEADERS[type(logger).__name__] + "\n" + "\n".join(lines) + "\n"
+    return (header if record_map is not None else HEADERS[type(logger).__name__]) + "\n" + "\n".join(lines) + "\n"
 
 
-def write_csv(component_logger, directory, sim, replication=0):
+def write_csv(component_logger, directory, sim, replication=0, record_map=None, header=None):
     """Logger::write_csv (core.rs:388-401): File::create("{dir}/{name}.csv")."""
     path = os.path.join(directory, "%s.csv" % component_logger.logger.get_name())
     with open(path, "w", newline="") as f:
-        f.write(csv_text(component_logger, sim, replication))
+        f.write(csv_text(component_logger, sim, replication, record_map, header))
     return path

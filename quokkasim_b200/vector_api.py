@@ -23,8 +23,70 @@ class Vector3:
         return "Vector3(%r)" % (self.values,)
 
 
+MAX_DIM = 8  # QK_VEC_MAX_DIM
+
+
+class _Resource:
+    """Base of the user-defined resource types made by define_resource()."""
+
+    NAME = None
+    FIELDS = ()
+    TOTAL_MASK = 0
+
+    def __init__(self, *args, **kw):
+        if args and kw:
+            raise TypeError("%s takes its fields by position or by name, not both" % self.NAME)
+        if kw:
+            unknown = set(kw) - set(self.FIELDS)
+            if unknown:
+                raise TypeError("%s has no field %s" % (self.NAME, sorted(unknown)[0]))
+            args = [kw.get(f, 0.0) for f in self.FIELDS]  # ..Default::default()
+        if not args:
+            args = [0.0] * len(self.FIELDS)
+        if len(args) != len(self.FIELDS):
+            raise TypeError("%s has %d fields" % (self.NAME, len(self.FIELDS)))
+        self.values = [float(x) for x in args]
+
+    @classmethod
+    def default(cls):
+        return cls()
+
+    def total(self):
+        t = None
+        for k, v in enumerate(self.values):  # the counted fields, left to right
+            if (self.TOTAL_MASK >> k) & 1:
+                t = v if t is None else t + v
+        return t
+
+    def __getattr__(self, name):
+        fields = type(self).FIELDS
+        if name in fields:
+            return self.values[fields.index(name)]
+        raise AttributeError(name)
+
+    def __repr__(self):
+        return "%s(%s)" % (self.NAME, ", ".join("%s=%r" % fv for fv in zip(self.FIELDS, self.values)))
+
+
+def define_resource(name, fields, total=None):
+    """A user-defined resource type: what `struct IronOre { fe, other_elements, magnetite, hematite, limonite }` with its
+    ResourceAdd / ResourceRemove / ResourceTotal / ResourceMultiply impls is in the reference
+    (quokkasim_examples/src/bin/iron_ore.rs:21-96).  `fields`: up to 8 f64 field names; `total`: the fields
+    ResourceTotal sums, in field order (default: all).  Add is field-wise, remove(q) takes q / total() of every field."""
+    fields = tuple(fields)
+    if not 1 <= len(fields) <= MAX_DIM or len(set(fields)) != len(fields):
+        raise TypeError("a resource has 1..%d distinct fields" % MAX_DIM)
+    counted = fields if total is None else tuple(total)
+    if not counted or any(f not in fields for f in counted):
+        raise TypeError("total= names fields of the resource")
+    mask = 0
+    for f in counted:
+        mask |= 1 << fields.index(f)
+    return type(name, (_Resource,), {"NAME": name, "FIELDS": fields, "TOTAL_MASK": mask})
+
+
 def _as_list(resource):
-    if isinstance(resource, Vector3):
+    if isinstance(resource, (Vector3, _Resource)):
         return list(resource.values)
     return [float(resource)]
 
@@ -41,6 +103,8 @@ class VectorStock(_Component):
         self.max_capacity = 0.0
         self.resource = None  # f64 0.0 or Vector3::default(), decided by the ComponentModel variant
         self.dim = None
+        self.total_mask = None  # user-defined resources only (define_resource)
+        self.resource_type = None
 
     def with_low_capacity(self, v):
         self.low_capacity = float(v)
@@ -69,6 +133,8 @@ class _VectorProcessLike(_ProcessLike):
     def __init__(self):
         super().__init__()
         self.dim = None
+        self.total_mask = None
+        self.resource_type = None
 
     def vector_rows(self):
         return self.dim, 0.0, 0.0, [0.0] * self.dim
@@ -156,10 +222,56 @@ for _prefix, _dim in (("F64", 1), ("Vector3", 3)):
         VECTOR_VARIANTS["%sSplitter%d" % (_prefix, _n)] = (VectorSplitter, _dim, _n)
 
 
+RESOURCE_OF = {}  # variant -> resource class, for the variants made by define_vector_variants
+PREFIXES = ["F64", "Vector3"]
+PREFIX_OF = {v: ("F64" if v.startswith("F64") else "Vector3") for v in VECTOR_VARIANTS}
+
+
+def define_vector_variants(prefix, resource_cls):
+    """The ComponentModel / ComponentLogger variants a user adds to define_model_enums! for an own resource type, with the
+    connection arms of `impl CustomComponentConnection` (iron_ore.rs:272-306): `<prefix>Stock`, `<prefix>Process`,
+    `<prefix>Source`, `<prefix>Sink`, `<prefix>Combiner1..5`, `<prefix>Splitter1..5`, `<prefix>StockLogger`,
+    `<prefix>ProcessLogger`.  They connect among themselves like the built-in vector variants (core.rs:572-883)."""
+    from . import api
+
+    if not (isinstance(resource_cls, type) and issubclass(resource_cls, _Resource)):
+        raise TypeError("define_vector_variants takes a class made by define_resource")
+    if prefix in PREFIXES or any((prefix + k) in api.ComponentModel._VARIANTS for k in ("Stock", "Process", "Source", "Sink")):
+        raise ValueError("variant prefix %r collides with an existing one" % prefix)
+    PREFIXES.append(prefix)
+    dim = len(resource_cls.FIELDS)
+    names = [(prefix + "Stock", VectorStock, None), (prefix + "Process", VectorProcess, None),
+             (prefix + "Source", VectorSource, None), (prefix + "Sink", VectorSink, None)]
+    for n in range(1, 6):
+        names.append(("%sCombiner%d" % (prefix, n), VectorCombiner, n))
+        names.append(("%sSplitter%d" % (prefix, n), VectorSplitter, n))
+    for v, cls, ports in names:
+        VECTOR_VARIANTS[v] = (cls, dim, ports)
+        PREFIX_OF[v] = prefix
+        RESOURCE_OF[v] = resource_cls
+        api.ComponentModel._VARIANTS[v] = cls
+        setattr(api.ComponentModel, v, api._variant_ctor(v))
+    api.VectorStockLogger.ACCEPTS = api.VectorStockLogger.ACCEPTS + (prefix + "Stock",)
+    api.VectorProcessLogger.ACCEPTS = api.VectorProcessLogger.ACCEPTS + tuple(v for v, _, _ in names[1:])
+    for v, lcls in ((prefix + "StockLogger", api.VectorStockLogger), (prefix + "ProcessLogger", api.VectorProcessLogger)):
+        api.ComponentLogger._VARIANTS[v] = lcls
+        setattr(api.ComponentLogger, v, staticmethod(lambda logger, _v=v: api.ComponentLogger(_v, logger)))
+    return resource_cls
+
+
 def bind_variant(variant, component):
-    """What the enum variant's type parameters fix in Rust: resource type (f64 / Vector3) and port count."""
+    """What the enum variant's type parameters fix in Rust: resource type (f64 / Vector3 / a user's struct) and port
+    count."""
     cls, dim, ports = VECTOR_VARIANTS[variant]
     component.dim = dim
+    rcls = RESOURCE_OF.get(variant)
+    if rcls is not None:
+        component.total_mask = rcls.TOTAL_MASK
+        component.resource_type = rcls
+        for what in ("resource", "source_vector"):
+            r = getattr(component, what, None)
+            if r is not None and not isinstance(r, rcls):
+                raise TypeError("%s carries %s resources" % (variant, rcls.NAME))
     if ports is not None:
         component.n_ports = ports
         if component.split_ratios is None:
@@ -177,9 +289,8 @@ def bind_variant(variant, component):
 def connection_ok(va, vb, n):
     """The vector arms of connect_components (core.rs:572-883): same resource type on both sides; Stock -> CombinerM
     and SplitterN -> Stock take Some(n)."""
-    for prefix in ("F64", "Vector3"):
-        if not (va.startswith(prefix) and vb.startswith(prefix)):
-            continue
+    prefix = PREFIX_OF.get(va)
+    if prefix is not None and PREFIX_OF.get(vb) == prefix:
         a, b = va[len(prefix):], vb[len(prefix):]
         if a == "Stock" and b in ("Process", "Sink"):
             return True

@@ -2,6 +2,12 @@
 rebuilt with the mirrored builder API.  Used by bench.py and by the tests (no oracle involvement here).
 """
 from . import api as qk
+from . import vector_api as _va
+
+# quokkasim_examples/src/bin/iron_ore.rs:21-96 -- a user-defined resource: five masses, total() = fe + other_elements --
+# and the ComponentModel / ComponentLogger variants its define_model_enums! block declares (:258-270)
+IronOre = qk.define_vector_variants("IronOre", qk.define_resource(
+    "IronOre", ("fe", "other_elements", "magnetite", "hematite", "limonite"), total=("fe", "other_elements")))
 
 
 class Model:
@@ -43,13 +49,13 @@ def _log_all(m):
     pl = qk.ComponentLogger.StringProcessLogger(qk.DiscreteProcessLogger.new("ProcessLogger"))
     el = qk.ComponentLogger.BasicEnvironmentLogger(qk.BasicEnvironmentLogger.new("EnvLogger"))
     vsl = {p: qk.ComponentLogger(p + "StockLogger", qk.VectorStockLogger.new(p + "StockLogger"))
-           for p in ("F64", "Vector3")}
+           for p in _va.PREFIXES}
     vpl = {p: qk.ComponentLogger(p + "ProcessLogger", qk.VectorProcessLogger.new(p + "ProcessLogger"))
-           for p in ("F64", "Vector3")}
+           for p in _va.PREFIXES}
     csl = qk.ComponentLogger.Vector3ContainerStockLogger(qk.ContainerStockLogger.new("ContainerStockLogger"))
     cpl = qk.ComponentLogger.Vector3ContainerProcessLogger(qk.ContainerProcessLogger.new("ContainerProcessLogger"))
     for c in m.components:
-        prefix = "F64" if c.variant.startswith("F64") else ("Vector3" if c.variant.startswith("Vector3") else None)
+        prefix = _va.PREFIX_OF.get(c.variant)
         if c.variant.startswith("Vector3Container"):
             if c.variant == "Vector3ContainerStock":
                 qk.connect_logger(csl, c)
@@ -354,6 +360,33 @@ def material_blending():
     return m
 
 
+def iron_ore():
+    """quokkasim_examples/src/bin/iron_ore.rs:308-372: IronOreStock -> IronOreProcess -> IronOreStock, quantity
+    Uniform(2, 8) from DistributionFactory(123456789), 10 s per batch; the example steps until 300 s."""
+    m = Model()
+    df = qk.DistributionFactory.new(123456789)
+    qd = df.create(qk.DistributionConfig.Uniform(2.0, 8.0))
+    m.random_dists.append(qd)
+    s1 = qk.ComponentModel.IronOreStock(
+        qk.VectorStock.new().with_name("MyStock1").with_code("SP1").with_type("IronOreStock")
+        .with_initial_resource(IronOre(fe=60.0, other_elements=40.0, magnetite=10.0, hematite=5.0, limonite=15.0))
+        .with_low_capacity(10.0).with_max_capacity(100.0), qk.Mailbox.new())
+    p1 = qk.ComponentModel.IronOreProcess(
+        qk.VectorProcess.new().with_name("MyProcess1").with_code("P1").with_name("IronOreProcess")
+        .with_process_quantity_distr(qd).with_process_time_distr(qk.Distribution.Constant(10.0)), qk.Mailbox.new())
+    s2 = qk.ComponentModel.IronOreStock(
+        qk.VectorStock.new().with_name("MyStock2").with_code("SP2").with_type("IronOreStock")
+        .with_initial_resource(IronOre(fe=3.0, other_elements=2.0, magnetite=0.5, hematite=0.25, limonite=0.75))
+        .with_low_capacity(10.0).with_max_capacity(100.0), qk.Mailbox.new())
+    qk.connect_components(s1, p1)
+    qk.connect_components(p1, s2)
+    for x in (s1, p1, s2):
+        m.reg(x)
+    _log_all(m)
+    m.mass = {"vector_stocks": [s1, s2], "vector_procs": [p1]}
+    return m
+
+
 def scheduled_event_f64():
     """quokkasim_examples/src/bin/scheduled_event.rs in spirit: F64 Stock -> Process -> Stock with
     SetLowCapacity(10) on the first stock at 60 s."""
@@ -427,8 +460,11 @@ def vector_flow(dim=3, random=True, breakdowns=True, env_events=True, sink_delay
     modes (transport.rs) and an environment stop/resume (delay_testing.rs)."""
     m = Model()
     df = qk.DistributionFactory(base_seed=555, next_seed=0)
-    P = "Vector3" if dim == 3 else "F64"
-    V = (lambda v: qk.Vector3(v)) if dim == 3 else (lambda v: float(sum(v)))
+    P = {1: "F64", 3: "Vector3", 5: "IronOre"}[dim]
+    if dim == 5:  # the same topology carrying the user-defined resource of iron_ore.rs (two of five fields counted)
+        V = lambda v: IronOre(v[0], v[1] + v[2], 0.5 * v[0], 0.25 * v[1], 0.125 * v[2] + 0.0625)  # noqa: E731
+    else:
+        V = (lambda v: qk.Vector3(v)) if dim == 3 else (lambda v: float(sum(v)))
 
     def dist(lo, hi):
         if not random:

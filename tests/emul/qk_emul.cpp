@@ -148,7 +148,8 @@ static int run(qk_batch* b, uint32_t do_init, uint64_t t0, uint64_t t_until, uin
     const uint32_t ft = b->low.hdr.features;
 #define QK_EMUL_RUN(L, S)                         \
   do {                                            \
-    if (ft >= 2) qk_step_kernel<L, S, 2>(P);      \
+    if (ft == 3) qk_step_kernel<L, S, 3>(P);      \
+    else if (ft == 2) qk_step_kernel<L, S, 2>(P); \
     else if (ft == 1) qk_step_kernel<L, S, 1>(P); \
     else qk_step_kernel<L, S, 0>(P);              \
   } while (0)
@@ -472,8 +473,20 @@ int qk_batch_read_vector(qk_batch* b, uint64_t rep, uint32_t comp, double* out3)
     return QK_ERR_INVALID_ARG;
   const DevVec& v = b->low.vecs[b->low.comps[comp].vec_idx];
   out3[0] = out3[1] = out3[2] = 0.0;
-  for (uint32_t k = 0; k < v.dim; ++k) memcpy(&out3[k], b->low.hdr.split ? &b->gc64[(size_t)rep * b->low.hdr.n64c + v.o64_res + k]
+  for (uint32_t k = 0; k < v.dim && k < 3; ++k) memcpy(&out3[k], b->low.hdr.split ? &b->gc64[(size_t)rep * b->low.hdr.n64c + v.o64_res + k]
                                                                              : &b->g64[(size_t)(v.o64_res + k) * b->rep_pad + rep], 8);
+  return QK_OK;
+}
+
+int qk_batch_read_vector_n(qk_batch* b, uint64_t rep, uint32_t comp, double* out, uint32_t cap, uint32_t* dim_out) {
+  if (!b || rep >= b->cfg.n_reps || comp >= b->low.hdr.n_comp || b->low.comps[comp].kind < QK_VECTOR_STOCK ||
+      b->low.comps[comp].kind > QK_VECTOR_SPLITTER || !out)
+    return QK_ERR_INVALID_ARG;
+  const DevVec& v = b->low.vecs[b->low.comps[comp].vec_idx];
+  if (dim_out) *dim_out = v.dim;
+  if (cap < v.dim) return QK_ERR_BUFFER_TOO_SMALL;
+  for (uint32_t k = 0; k < v.dim; ++k) memcpy(&out[k], b->low.hdr.split ? &b->gc64[(size_t)rep * b->low.hdr.n64c + v.o64_res + k]
+                                                                            : &b->g64[(size_t)(v.o64_res + k) * b->rep_pad + rep], 8);
   return QK_OK;
 }
 

@@ -11,11 +11,12 @@ from quokkasim_b200 import _capi as capi
 
 from quokkasim_b200.workloads import (Model, assembly_line, car_workshop, discrete_queue, haulage,  # noqa: F401
                                       material_blending, scheduled_event_f64, scheduled_process_quantity,
-                                      serial_line, source_sink, vector_flow,
+                                      serial_line, source_sink, vector_flow, iron_ore, IronOre,
                                       transport, delay_testing, the_example, container_haulage, container_open)
 
 
 from oracle.lowering import lower_to_oracle  # noqa: F401,E402
+from quokkasim_b200.vector_api import VECTOR_VARIANTS as _VECTOR_VARIANTS  # noqa: E402
 
 
 def make_tapes(model, n_reps, length, seed, lo=0.5, hi=9.5, dist_scale=None):
@@ -89,7 +90,7 @@ def assert_rep_parity(sim, osim, model, rep_local_idx, check_log=True):
                 assert int(gs["count"]) == int(os_["n_b"]), "cproc %d n_finish %d vs %d" % (ci, gs["count"], os_["n_b"])
                 assert int(gs["time_ns"]) == int(os_["t_a_ns"]), "cproc %d busy %d vs %d" % (ci, gs["time_ns"], os_["t_a_ns"])
                 assert int(gs["aux"]) == int(os_["t_b_ns"]), "cproc %d delay ns" % ci
-        elif cm.variant.startswith(("F64", "Vector3")):
+        elif cm.variant in _VECTOR_VARIANTS:
             # continuous components: fp64 values are compared BIT-exactly (same operation order, no FMA); the
             # north_star tolerance would be 1e-9 relative
             assert float(gs["fvalue"]).hex() == float(os_["fvalue"]).hex(), "comp %d fvalue %r vs %r" % (
@@ -98,14 +99,14 @@ def assert_rep_parity(sim, osim, model, rep_local_idx, check_log=True):
                 ci, gs["faux"], os_["faux"])
             if cm.variant.endswith("Stock"):
                 assert int(gs["count"]) == int(os_["n_a"]), "vstock %d adds" % ci
-                got, want = sim.read_vector(ci, rep_local_idx), osim.vector_resource(ci)
+                got, want = sim.read_resource(ci, rep_local_idx), osim.vector_resource_n(ci)
                 assert [x.hex() for x in got] == [x.hex() for x in want], "vstock %d resource %r vs %r" % (ci, got, want)
             else:
                 assert int(gs["count"]) == int(os_["n_b"]), "vproc %d successes" % ci
                 assert int(gs["time_ns"]) == int(os_["t_a_ns"]), "vproc %d busy" % ci
                 assert int(gs["aux"]) == int(os_["t_b_ns"]), "vproc %d delay ns" % ci
                 if "Combiner" not in cm.variant:
-                    got, want = sim.read_vector(ci, rep_local_idx), osim.vector_resource(ci)
+                    got, want = sim.read_resource(ci, rep_local_idx), osim.vector_resource_n(ci)
                     assert [x.hex() for x in got] == [x.hex() for x in want], "vproc %d in-flight" % ci
         elif cm.variant == "StringStock":
             items = osim.stock_items(ci)

@@ -248,3 +248,48 @@ def test_container_abi_argument_checks():
     capi.check(L, L.qk_model_state_bytes(m, 1, C.byref(n)))
     assert n.value > 0
     L.qk_model_destroy(m)
+
+
+def test_user_defined_resource_abi_argument_checks():
+    """qk_model_set_vector_n (iron_ore.rs: IronOre, five fields, total over two): dim 1..8, a total mask inside dim;
+    components connect only when field count and mask agree; the Python mirror types the variants."""
+    L = capi.load_library()
+    m = C.c_void_p()
+    capi.check(L, L.qk_model_create(C.byref(m)))
+
+    def add(kind):
+        d = capi.ComponentDesc()
+        d.kind = kind
+        out = C.c_uint32()
+        capi.check(L, L.qk_model_add_component(m, C.byref(d), C.byref(out)))
+        return out.value
+
+    init = (C.c_double * 8)(60, 40, 10, 5, 15, 0, 0, 0)
+    ore, proc, v3, other = add(capi.VECTOR_STOCK), add(capi.VECTOR_PROCESS), add(capi.VECTOR_STOCK), add(capi.VECTOR_STOCK)
+    assert L.qk_model_set_vector_n(m, ore, 9, 3, 10.0, 100.0, init) == -1  # more than QK_VEC_MAX_DIM fields
+    assert L.qk_model_set_vector_n(m, ore, 0, 1, 10.0, 100.0, init) == -1
+    assert L.qk_model_set_vector_n(m, ore, 5, 0, 10.0, 100.0, init) == -1  # a total over no field
+    assert L.qk_model_set_vector_n(m, ore, 5, 0x23, 10.0, 100.0, init) == -1  # ... over a field beyond dim
+    capi.check(L, L.qk_model_set_vector_n(m, ore, 5, 3, 10.0, 100.0, init))
+    capi.check(L, L.qk_model_set_vector_n(m, proc, 5, 3, 0.0, 0.0, None))
+    capi.check(L, L.qk_model_set_vector(m, v3, 3, 0.0, 10.0, init))
+    capi.check(L, L.qk_model_set_vector_n(m, other, 5, 7, 10.0, 100.0, init))  # same fields, another total
+    capi.check(L, L.qk_model_connect(m, ore, proc, -1))
+    assert L.qk_model_connect(m, proc, v3, -1) == -2
+    assert L.qk_model_connect(m, proc, other, -1) == -2
+    L.qk_model_destroy(m)
+
+    import quokkasim_b200 as qk
+    from quokkasim_b200.workloads import IronOre
+
+    assert IronOre(fe=60.0, other_elements=40.0, magnetite=10.0).total() == 100.0 and IronOre.TOTAL_MASK == 3
+    with pytest.raises(TypeError):
+        qk.ComponentModel.IronOreStock(qk.VectorStock.new().with_initial_resource(qk.Vector3([1, 2, 3])), qk.Mailbox.new())
+    a = qk.ComponentModel.IronOreStock(qk.VectorStock.new(), qk.Mailbox.new())
+    b = qk.ComponentModel.Vector3Process(qk.VectorProcess.new(), qk.Mailbox.new())
+    with pytest.raises(qk.api.ComponentConnectionError):
+        qk.connect_components(a, b)
+    with pytest.raises(ValueError):
+        qk.define_vector_variants("IronOre", IronOre)  # the variants exist already (workloads.py)
+    with pytest.raises(TypeError):
+        qk.define_resource("TooWide", ["f%d" % i for i in range(9)])

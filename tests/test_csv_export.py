@@ -206,3 +206,52 @@ def test_combiner_and_splitter_failures_are_process_failure_rows(emul_lib):
                        "At least one upstream is empty")
     assert rows[2] == "1970-01-01 00:00:00 UTC,SPL_000000,SPL_000000,Splitter,VectorSplitter,ProcessFailure,,,,Upstream is empty"
     sim.close()
+
+
+def _check_iron_ore_example(lib, tmp_path):
+    """examples/iron_ore.py = iron_ore.rs: the user's flat log structs over a five-field resource.  The removed vector
+    of the first batch is re-derived here from the logged quantity with the reference's own arithmetic
+    (iron_ore.rs:52-73: proportion of the masked total, every field scaled)."""
+    import csv
+    import sys
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "examples"))
+    import iron_ore
+
+    sim = iron_ore.main(4, str(tmp_path), lib=lib)
+    sim.close()
+    with open(os.path.join(str(tmp_path), "IronOreProcessLogger.csv")) as f:
+        prows = list(csv.reader(f))
+    with open(os.path.join(str(tmp_path), "IronOreStockLogger.csv")) as f:
+        srows = list(csv.reader(f))
+    assert prows[0] == iron_ore.PROCESS_HEADER.split(",") and srows[0] == iron_ore.STOCK_HEADER.split(",")
+    assert prows[1][:6] == ["1970-01-01 00:00:00 UTC", "P1_000000", "INIT_000000", "IronOreProcess", "VectorProcess",
+                            "WithdrawRequest"]
+    assert prows[2][5] == "ProcessStart" and prows[3][5] == "ProcessSuccess" and prows[3][0] == "1970-01-01 00:00:10 UTC"
+    q = float(prows[2][6])  # the sampled process quantity, Uniform(2, 8)
+    assert 2.0 <= q < 8.0
+    s1 = [60.0, 40.0, 10.0, 5.0, 15.0]
+    p = q / (s1[0] + s1[1])
+    removed = [x * p for x in s1]
+    left = [x * (1.0 - p) for x in s1]
+    r = srows[1]
+    assert r[:6] == ["1970-01-01 00:00:00 UTC", "SP1_000000", "P1_000000", "MyStock1", "IronOreStock", "Remove"]
+    assert r[6] == "" and r[7] == csvlog.ryu_f64(left[0] + left[1]) and r[8] == csvlog.ryu_f64(removed[0] + removed[1])
+    assert r[9:] == [csvlog.ryu_f64(x) for x in (removed[0], removed[1], removed[0] / (removed[0] + removed[1]),
+                                                 removed[2], removed[3], removed[4])]
+    assert prows[2][7:13] == r[9:]
+    assert srows[2][5:7] == ["StateChange", "Normal"] and srows[2][0] == "1970-01-01 00:00:00.000000001 UTC"
+    add = srows[3]
+    assert add[1:6] == ["SP2_000000", "P1_000002", "MyStock2", "IronOreStock", "Add"]
+    assert add[7] == csvlog.ryu_f64((3.0 + removed[0]) + (2.0 + removed[1])) and add[9:] == r[9:]
+    # every replication has its own Philox stream: the CSV of another replication differs in the quantities only
+    assert len(srows) > 20 and all(len(x) == 15 for x in srows) and all(len(x) == 14 for x in prows)
+
+
+def test_user_defined_resource_flat_csv(emul_lib, tmp_path):
+    _check_iron_ore_example(emul_lib, tmp_path)
+
+
+@pytest.mark.gpu
+def test_user_defined_resource_flat_csv_on_gpu(gpu_lib, tmp_path):
+    _check_iron_ore_example(gpu_lib, tmp_path)

@@ -229,6 +229,30 @@ def test_vector_examples(gpu_lib):
     _check(gpu_lib, H.scheduled_event_f64(), 32, t_until=120 * S, sample=[0, 31], log_capacity=2048)
 
 
+def test_user_defined_resource_iron_ore(gpu_lib):
+    """iron_ore.rs (five-field resource, total over two fields; qk_model_set_vector_n, feature-set-3 kernels): the example
+    itself until 300 s under native streams and a tape, in every state placement; then the C3 topology carrying that
+    resource through source, process with breakdowns, combiner, splitter, sink -- records and every field of every stock
+    bit for bit, and the masses conserved field by field"""
+    _check(gpu_lib, H.iron_ore(), 64, t_until=300 * S, sample=[0, 31, 63], log_capacity=2048)
+    _check(gpu_lib, H.iron_ore(), 64, t_until=300 * S, tape_len=64, sample=[0, 63], log_capacity=2048)
+    for flags in (1, 16):  # HBM planes ; split placement
+        _check(gpu_lib, H.iron_ore(), 64, t_until=300 * S, sample=[0, 63], log_capacity=2048, flags=flags)
+    _check(gpu_lib, H.vector_flow(5), 512, n_events=6000, sample=[0, 129, 511], log_capacity=65536)
+    _check(gpu_lib, H.vector_flow(5), 64, n_events=2500, tape_len=2500, sample=[0, 63], log_capacity=65536, flags=16)
+    m = H.iron_ore()
+    sim = m.sim(gpu_lib, 4096, base_seed=9)
+    sim.step_until(300 * S)
+    init = [63.0, 42.0, 10.5, 5.25, 15.75]
+    for r in (0, 1000, 4095):
+        tot = [0.0] * 5
+        for c in m.components:
+            for k, x in enumerate(sim.read_resource(c.component._id, r)):
+                tot[k] += x
+        assert all(abs(t - i) <= 1e-9 * i for t, i in zip(tot, init)), (r, tot)
+    sim.close()
+
+
 @pytest.mark.parametrize("dim", [1, 3])
 def test_vector_flow_native(gpu_lib, dim):
     """config C3 topology with native Philox streams, breakdowns and an environment stop/resume"""

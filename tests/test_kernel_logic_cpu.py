@@ -189,6 +189,22 @@ def test_vector_scheduled_low_capacity(emul_lib):
     _check(emul_lib, H.scheduled_event_f64(), 2, t_until=120 * S, log_capacity=2048)
 
 
+def test_user_defined_resource_iron_ore_example(emul_lib):
+    """iron_ore.rs: a five-field resource whose total counts two fields (feature set 3, qk_model_set_vector_n):
+    IronOreStock -> IronOreProcess -> IronOreStock until 300 s, native streams and a tape"""
+    _check(emul_lib, H.iron_ore(), 3, t_until=300 * S, log_capacity=2048)
+    _check(emul_lib, H.iron_ore(), 2, t_until=300 * S, tape_len=64, log_capacity=2048)
+    for flags in (1, 16):
+        _check(emul_lib, H.iron_ore(), 2, t_until=300 * S, log_capacity=2048, flags=flags)
+
+
+def test_user_defined_resource_flow(emul_lib):
+    """the C3 topology (source, process with breakdowns, combiner, splitter with feedback, sink, environment) carrying
+    the IronOre resource: every vector code path at five fields"""
+    _check(emul_lib, H.vector_flow(5), 3, n_events=4000, log_capacity=65536)
+    _check(emul_lib, H.vector_flow(5), 2, n_events=2500, tape_len=2500, log_capacity=65536, flags=16)
+
+
 @pytest.mark.parametrize("dim", [1, 3])
 def test_vector_flow_native(emul_lib, dim):
     """config C3 topology: random quantities and times, two breakdown modes, environment stop/resume"""
