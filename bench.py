@@ -46,6 +46,7 @@ WORKLOADS = {
     "serial_line": ("serial_line", {"n_proc": 32}, 100000, 1000000),               # C4
     "haulage": ("haulage", {"n_src": 8, "per_queue": 8}, 262144, 10000),           # C5 (one point of the sweep)
     "container_haulage": ("container_haulage", {"n_trucks": 8, "loaders": 2}, 262144, 10000),  # row f3
+    "iron_ore_flow": ("vector_flow", {"dim": 5}, 262144, 10000),  # row f3: C3's topology carrying iron_ore.rs's resource
 }
 
 

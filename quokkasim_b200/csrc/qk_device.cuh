@@ -95,8 +95,16 @@ __device__ __forceinline__ void qk_bulk_store(void* gdst, const void* smem_src, 
                "r"((uint32_t)__cvta_generic_to_shared(smem_src)), "r"(bytes)
                : "memory");
 }
+/* before the block exits: the stores must have READ their shared-memory source (the block's shared memory is handed to
+ * the next block the moment this one retires); that they have reached global memory is what the end of the grid
+ * guarantees, and waiting for it here kept every block resident for one more trip to L2 -- at one event per launch the
+ * kernel's rate is resident blocks / block lifetime (profiles/README.md R2.5) */
 __device__ __forceinline__ void qk_bulk_store_wait() {
+#ifdef QK_STORE_WAIT_FULL
   asm volatile("cp.async.bulk.commit_group;\n\tcp.async.bulk.wait_group 0;" ::: "memory");
+#else
+  asm volatile("cp.async.bulk.commit_group;\n\tcp.async.bulk.wait_group.read 0;" ::: "memory");
+#endif
 }
 /* writes made through the generic proxy (ordinary STS) become visible to the asynchronous proxy (bulk stores) */
 __device__ __forceinline__ void qk_fence_async_proxy() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }

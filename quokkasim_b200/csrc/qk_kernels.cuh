@@ -1288,13 +1288,47 @@ __global__ void __launch_bounds__(qk_lb_threads(SM), qk_lb_blocks(SM, FT, LOG)) 
   uint8_t* const smem = qk_smem;
   const uint32_t tid = QK_TID, nt = SM > 0 ? (uint32_t)SM : QK_NT;
 
-  /* model tables -> shared memory (read with data-dependent component indices afterwards) */
-  {
+  /* model tables -> shared memory (read with data-dependent component indices afterwards).  A launch that stages the
+   * block's hot planes (every launch but the init sweep of an on-chip placement) brings the tables in by the same
+   * bulk asynchronous copies, on the same mbarrier: the requests for tables and state leave together and the block
+   * waits once -- as LDG/STS + __syncthreads in front of the staging the table copy was a dependent trip to L2 of its
+   * own, 10 % of the stall samples of a one-event launch (profiles/README.md R2.3) */
+#if !defined(QK_HOST_EMUL) && !defined(QK_TABLES_BY_LDG)
+  constexpr bool BULK_PROLOGUE = SM != 0;
+  __shared__ __align__(8) uint64_t stage_bar;
+#else
+  constexpr bool BULK_PROLOGUE = false;
+#endif
+  if (!(BULK_PROLOGUE && !P.do_init)) {
     const uint4* srcp = reinterpret_cast<const uint4*>(P.tables);
     uint4* dstp = reinterpret_cast<uint4*>(smem);
     for (uint32_t i = tid; i < P.table_bytes / 16; i += nt) dstp[i] = srcp[i];
+    __syncthreads();
   }
-  __syncthreads();
+#if !defined(QK_HOST_EMUL) && !defined(QK_TABLES_BY_LDG)
+  else {
+    const uint64_t block_rep0 = (uint64_t)(P.tile0 + QK_BID) * nt;
+    if (tid == 0) {
+      qk_mbar_init(&stage_bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+      qk_mbar_expect_tx(&stage_bar, P.table_bytes + (P.n64 * 8u + P.n32 * 4u) * nt);
+      qk_bulk_load(smem, P.tables, P.table_bytes, &stage_bar);
+    }
+    uint64_t* const row64 = reinterpret_cast<uint64_t*>(qk_smem) + P.table_bytes / 8;
+    uint32_t* const row32 = reinterpret_cast<uint32_t*>(qk_smem) + (P.table_bytes + P.n64 * nt * 8) / 4;
+    for (uint32_t s = tid; s < P.n64 + P.n32; s += nt) {
+      if (s < P.n64)
+        qk_bulk_load(row64 + (size_t)s * nt, P.g64 + (size_t)s * P.rep_pad + block_rep0, nt * 8u, &stage_bar);
+      else
+        qk_bulk_load(row32 + (size_t)(s - P.n64) * nt, P.g32 + (size_t)(s - P.n64) * P.rep_pad + block_rep0, nt * 4u,
+                     &stage_bar);
+    }
+    qk_mbar_wait(&stage_bar, 0);
+  }
+#endif
 
   Ctx cx;
   cx.hdr = reinterpret_cast<const DevHeader*>(smem);
@@ -1431,7 +1465,9 @@ __global__ void __launch_bounds__(qk_lb_threads(SM), qk_lb_blocks(SM, FT, LOG)) 
        * rows in flight at once, completing on an mbarrier.  With few events per launch this load IS the kernel: as
        * dependent LDG/STS pairs it ran at 44 % of the HBM roofline, as one 4/8-byte cp.async (LDGSTS) per thread and slot
        * at 50-55 % (profiles/README.md). */
-#ifndef QK_HOST_EMUL
+#if !defined(QK_HOST_EMUL) && !defined(QK_TABLES_BY_LDG)
+      /* (done at the top of the kernel, together with the tables) */
+#elif !defined(QK_HOST_EMUL)
       __shared__ __align__(8) uint64_t stage_bar;
       const uint64_t block_rep0 = (uint64_t)(P.tile0 + QK_BID) * nt;
       if (tid == 0) {
