@@ -7,6 +7,7 @@
  * Replaces SimInit::init + Simulation::step_until for the batched path
  * (/root/reference/quokkasim_examples/src/bin/discrete_queue.rs:109-111).
  */
+#include <cuda.h> /* CUtensorMap and the enums of cuTensorMapEncodeTiled (types only: the entry point is asked of the runtime) */
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -37,6 +38,8 @@ struct qk_batch {
   bool log;
   bool hbm; /* state operated on in place in HBM instead of staged in shared memory */
   uint32_t nt, grid, smem_bytes, table_bytes_padded;
+  bool use_tma;       /* hot planes staged by TMA tensor copies (make_tensor_maps) */
+  QkTmap tm64, tm32;
   uint64_t rep_pad;
   uint64_t* g64;
   uint32_t* g32;
@@ -146,7 +149,7 @@ static uint32_t choose_nt(uint32_t per_rep_bytes, uint32_t table_bytes, uint32_t
   uint32_t best_nt = 0, best_thr = 0;
   for (uint32_t nt = 256; nt >= 32; nt -= 32) {
     const uint64_t bytes = (uint64_t)table_bytes + (uint64_t)per_rep_bytes * nt;
-    if (bytes > 227u * 1024u - 64u) continue; /* 64 B: the kernels' static shared memory (an mbarrier) */
+    if (bytes > 227u * 1024u - 256u) continue; /* 256 B: the kernels' static shared memory (an mbarrier) and the 128-byte alignment of the dynamic part */
     uint32_t bps = (uint32_t)((227u * 1024u) / (bytes + 1024u));
     if (bps > 32) bps = 32;
     uint32_t thr = bps * nt;
@@ -179,6 +182,45 @@ struct QkSlice {
   uint32_t tile0, n_tiles; /* n_tiles == 0: every tile of the batch */
   cudaStream_t stream;
 };
+
+/* Tensor maps of the hot planes for the step kernel's staging: plane = 2-D array [n_slots][rep_pad] of 8- / 4-byte
+ * elements, box = n_slots x nt (one block's replications of every slot), dense in shared memory.  Returns false where
+ * the tile form does not apply (more than 256 slots or threads, rows not 16-byte multiples, no driver entry point):
+ * the kernel then moves the rows one bulk copy each, as before. */
+static bool make_tensor_maps(qk_batch* b) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static_assert(sizeof(QkTmap) == sizeof(CUtensorMap), "QkTmap mirrors CUtensorMap");
+  const DevHeader& h = b->low.hdr;
+  if (getenv("QK_NO_TMA")) return false; /* experiments: A/B against the per-row bulk copies */
+  if (h.n64 == 0 || h.n64 > 256 || h.n32 > 256 || b->nt > 256 || (b->nt & 31u) || b->rep_pad >= (1ull << 31) ||
+      (b->table_bytes_padded & 127u))
+    return false;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn ||
+      q != cudaDriverEntryPointSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  const EncodeFn encode = reinterpret_cast<EncodeFn>(fn);
+  const cuuint32_t estr[2] = {1, 1};
+  for (int k = 0; k < 2; ++k) {
+    const uint32_t rows = k == 0 ? h.n64 : h.n32, esz = k == 0 ? 8u : 4u;
+    if (rows == 0) continue;
+    const cuuint64_t gdim[2] = {b->rep_pad, rows};
+    const cuuint64_t gstr[1] = {b->rep_pad * esz};
+    const cuuint32_t box[2] = {b->nt, rows};
+    CUtensorMap tm;
+    const CUresult rc = encode(&tm, k == 0 ? CU_TENSOR_MAP_DATA_TYPE_UINT64 : CU_TENSOR_MAP_DATA_TYPE_UINT32, 2,
+                               k == 0 ? (void*)b->g64 : (void*)b->g32, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) return false;
+    memcpy(k == 0 ? &b->tm64 : &b->tm32, &tm, sizeof(tm));
+  }
+  return true;
+}
 
 static int launch_step(qk_batch* b, uint32_t do_init, uint64_t t0, uint64_t t_until, uint64_t budget,
                        bool record_begin = true, bool record_end = true, const QkSlice* slice = nullptr) {
@@ -214,6 +256,11 @@ static int launch_step(qk_batch* b, uint32_t do_init, uint64_t t0, uint64_t t_un
   P.grp_stride32 = b->grp_stride32;
   P.grp_bar_off = b->grp_bar_off;
   P.grp_x64 = b->grp_x64;
+  P.use_tma = b->use_tma ? 1u : 0u;
+  if (b->use_tma) {
+    P.tm64 = b->tm64;
+    P.tm32 = b->tm32;
+  }
   cudaStream_t stream = b->stream;
   if (slice && slice->n_tiles) {
     P.tile0 = slice->tile0;
@@ -508,6 +555,7 @@ int qk_batch_create(const qk_model* m, const qk_batch_config* cfg, qk_batch** ou
   b->grp_reps = b->grp_stride64 = b->grp_stride32 = b->grp_bar_off = b->grp_x64 = 0;
   b->phased = false;
   b->split = false;
+  b->use_tma = false;
   b->have_side = false;
   int rc = qk_lower(m, b->log, 0, &b->low);
   if (rc) {
@@ -515,7 +563,7 @@ int qk_batch_create(const qk_model* m, const qk_batch_config* cfg, qk_batch** ou
     return rc;
   }
   const DevHeader& h = b->low.hdr; /* (a reference: a second lowering below is seen through it) */
-  b->table_bytes_padded = (h.total_bytes + 15u) & ~15u;
+  b->table_bytes_padded = (h.total_bytes + 127u) & ~127u;
   uint32_t per_rep = h.n64 * 8 + h.n32 * 4;
   uint32_t nt = cfg->threads_per_block;
   const uint32_t max_thr = (uint32_t)qk_lb_resident((int)h.features, b->log); /* the kernel variant's launch bounds */
@@ -569,7 +617,7 @@ int qk_batch_create(const qk_model* m, const qk_batch_config* cfg, qk_batch** ou
       return rc;
     }
     b->split = true;
-    b->table_bytes_padded = (h.total_bytes + 15u) & ~15u;
+    b->table_bytes_padded = (h.total_bytes + 127u) & ~127u;
     per_rep = h.n64 * 8 + h.n32 * 4;
   }
   bool phased = group && (cfg->flags & QK_BATCH_GROUP_PHASED) != 0;
@@ -582,10 +630,10 @@ int qk_batch_create(const qk_model* m, const qk_batch_config* cfg, qk_batch** ou
     if (G == 0) G = 8;
     QkGroupGeom geo;
     /* per-block budget: the SM's 228 KB over the blocks, less the 1 KB the system reserves per block and the static part */
-    const uint32_t budget = phased ? (228u * 1024u) / phased_blocks - 1024u - 64u : 227u * 1024u - 64u;
+    const uint32_t budget = phased ? (228u * 1024u) / phased_blocks - 1024u - 256u : 227u * 1024u - 256u;
     const bool ok = (G == 4 || G == 8 || G == 16) &&
                     qk_group_geometry(G, 32u, h.n64, h.n32, phased ? 2u : 0u, phased ? 6u : 0u, b->table_bytes_padded,
-                                      group_max_threads(G), budget < 227u * 1024u - 64u ? budget : 227u * 1024u - 64u,
+                                      group_max_threads(G), budget < 227u * 1024u - 256u ? budget : 227u * 1024u - 256u,
                                       1024u, 4u, &geo) != 0 &&
                     geo.reps >= 8;
     if (!ok) {
@@ -632,7 +680,7 @@ int qk_batch_create(const qk_model* m, const qk_batch_config* cfg, qk_batch** ou
      * 5 x 64 3.7e9 -- every block carries its own 22 KB copy of the tables) */
     if (nt == 0) nt = choose_nt(per_rep, b->table_bytes_padded, thr_cap, nullptr, qsplit ? 128u : 64u);
     const bool fits = nt != 0 && nt <= QK_MAX_NT && !(nt & 31) &&
-                      (uint64_t)b->table_bytes_padded + (uint64_t)per_rep * nt <= 227u * 1024u - 64u;
+                      (uint64_t)b->table_bytes_padded + (uint64_t)per_rep * nt <= 227u * 1024u - 256u;
     if (!fits) {
       if ((cfg->flags & QK_BATCH_STATE_ON_CHIP) || split) {
         qk_set_error("qk_batch_create: model needs %u B of on-chip state per replication (+%u B tables); "
@@ -686,6 +734,7 @@ int qk_batch_create(const qk_model* m, const qk_batch_config* cfg, qk_batch** ou
   CREATE_TRY(cudaMallocAsync(&b->gc32, (size_t)(h.n32c ? h.n32c : 1) * b->rep_pad * 4, b->stream));
   if (b->log) CREATE_TRY(cudaMallocAsync(&b->d_log, (size_t)b->rep_pad * cfg->log_capacity * 32, b->stream));
   CREATE_TRY(cudaStreamSynchronize(b->stream)); /* allocation failures of the pool surface here at the latest */
+  b->use_tma = !b->hbm && !group && make_tensor_maps(b);
   CREATE_TRY(cudaMalloc(&b->d_tables, b->table_bytes_padded));
   {
     std::vector<uint8_t> padded(b->table_bytes_padded, 0);

@@ -21,7 +21,7 @@
 #else
 #include <cuda_runtime.h>
 /* file-scope dynamic shared memory: every device function sees a pointer whose address space is known */
-extern __shared__ __align__(16) uint8_t qk_smem[];
+extern __shared__ __align__(128) uint8_t qk_smem[]; /* 128: destination of TMA tensor copies */
 #define QK_TID threadIdx.x
 #define QK_NT blockDim.x
 #define QK_BID blockIdx.x
@@ -87,6 +87,21 @@ __device__ __forceinline__ void qk_bulk_load(void* smem_dst, const void* gsrc, u
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                    (uint32_t)__cvta_generic_to_shared(smem_dst)),
                "l"(gsrc), "r"(bytes), "r"((uint32_t)__cvta_generic_to_shared(bar))
+               : "memory");
+}
+/* 2-D tile of a state plane ([slot][replication], tensor map made by qk_batch_create) -> shared memory: ONE instruction
+ * of the TMA engine moves the block's rows of EVERY slot (box = n_slots x block size, dense, no swizzle: exactly the
+ * [slot][thread] layout the kernel works on); smem_dst 128-byte aligned; completes on the mbarrier */
+__device__ __forceinline__ void qk_tma_load_2d(void* smem_dst, const void* tmap, uint32_t c0, uint32_t c1, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                   (uint32_t)__cvta_generic_to_shared(smem_dst)),
+               "l"(tmap), "r"(c0), "r"(c1), "r"((uint32_t)__cvta_generic_to_shared(bar))
+               : "memory");
+}
+/* ... and back */
+__device__ __forceinline__ void qk_tma_store_2d(const void* tmap, uint32_t c0, uint32_t c1, const void* smem_src) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(tmap), "r"(c0),
+               "r"(c1), "r"((uint32_t)__cvta_generic_to_shared(smem_src))
                : "memory");
 }
 /* shared -> global */

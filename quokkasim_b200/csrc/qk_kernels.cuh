@@ -33,6 +33,11 @@ template <int FT> struct QkVd { static constexpr int v = FT == 3 ? QK_VEC_MAX_DI
 #define QK_D2U(d) ((uint64_t)__double_as_longlong(d))
 #define QK_U2D(u) (__longlong_as_double((long long)(u)))
 
+/* a CUtensorMap (128 opaque bytes, 64-byte aligned) without <cuda.h>: the host emulation compiles this file too */
+struct alignas(64) QkTmap {
+  uint64_t opaque[16];
+};
+
 struct KParams {
   uint64_t* g64; /* [n64][rep_pad] */
   uint32_t* g32; /* [n32][rep_pad] */
@@ -58,6 +63,10 @@ struct KParams {
    * byte offset of the mbarrier */
   uint32_t grp_reps, grp_stride64, grp_stride32, grp_bar_off;
   uint32_t grp_x64; /* extra 64-bit rows after the state rows (the phased kernel's loop state); the 32-bit rows follow */
+  /* staging by TMA tensor copies (qk_step_kernel, on-chip and split placements): tensor maps of the two hot planes as
+   * 2-D arrays [slot][replication] with a box of (all slots) x (one block's replications) */
+  uint32_t use_tma;
+  QkTmap tm64, tm32;
 };
 
 struct Ctx {
@@ -1313,13 +1322,20 @@ __global__ void __launch_bounds__(qk_lb_threads(SM), qk_lb_blocks(SM, FT, LOG)) 
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    uint64_t* const row64 = reinterpret_cast<uint64_t*>(qk_smem) + P.table_bytes / 8;
+    uint32_t* const row32 = reinterpret_cast<uint32_t*>(qk_smem) + (P.table_bytes + P.n64 * nt * 8) / 4;
     if (tid == 0) {
       qk_mbar_expect_tx(&stage_bar, P.table_bytes + (P.n64 * 8u + P.n32 * 4u) * nt);
       qk_bulk_load(smem, P.tables, P.table_bytes, &stage_bar);
+      if (P.use_tma) {
+        /* the block's rows of every slot as ONE 2-D tile per plane (UTMALDG): two instructions instead of one bulk copy
+         * per slot row, each of which the compiler has to issue lane by lane (its operands are uniform registers) --
+         * a third of the instructions of a one-event launch */
+        qk_tma_load_2d(row64, &P.tm64, (uint32_t)block_rep0, 0u, &stage_bar);
+        if (P.n32) qk_tma_load_2d(row32, &P.tm32, (uint32_t)block_rep0, 0u, &stage_bar);
+      }
     }
-    uint64_t* const row64 = reinterpret_cast<uint64_t*>(qk_smem) + P.table_bytes / 8;
-    uint32_t* const row32 = reinterpret_cast<uint32_t*>(qk_smem) + (P.table_bytes + P.n64 * nt * 8) / 4;
-    for (uint32_t s = tid; s < P.n64 + P.n32; s += nt) {
+    for (uint32_t s = P.use_tma ? P.n64 + P.n32 : tid; s < P.n64 + P.n32; s += nt) {
       if (s < P.n64)
         qk_bulk_load(row64 + (size_t)s * nt, P.g64 + (size_t)s * P.rep_pad + block_rep0, nt * 8u, &stage_bar);
       else
@@ -1804,7 +1820,12 @@ __global__ void __launch_bounds__(qk_lb_threads(SM), qk_lb_blocks(SM, FT, LOG)) 
       uint64_t* const row64 = reinterpret_cast<uint64_t*>(qk_smem) + P.table_bytes / 8;
       uint32_t* const row32 = reinterpret_cast<uint32_t*>(qk_smem) + (P.table_bytes + P.n64 * nt * 8) / 4;
       bool stored = false;
-      for (uint32_t s = tid; s < P.n64 + P.n32; s += nt) {
+      if (P.use_tma && tid == 0) { /* one tile per plane (UTMASTG) */
+        qk_tma_store_2d(&P.tm64, (uint32_t)block_rep0, 0u, row64);
+        if (P.n32) qk_tma_store_2d(&P.tm32, (uint32_t)block_rep0, 0u, row32);
+        stored = true;
+      }
+      for (uint32_t s = P.use_tma ? P.n64 + P.n32 : tid; s < P.n64 + P.n32; s += nt) {
         if (s < P.n64)
           qk_bulk_store(P.g64 + (size_t)s * P.rep_pad + block_rep0, row64 + (size_t)s * nt, nt * 8u);
         else
