@@ -142,7 +142,7 @@ for l in sass.split("\n"):
     m = re.search(r"Function : (\S+)", l)
     if m:
         cur = m.group(1)
-        counts[cur] = {"UBLKCP": 0, "SYNCS": 0, "LDGSTS": 0, "REDUX": 0, "REDG": 0}
+        counts[cur] = {"UTMALDG": 0, "UTMASTG": 0, "UBLKCP": 0, "SYNCS": 0, "LDGSTS": 0, "REDUX": 0, "REDG": 0}
         continue
     if cur:
         for k in counts[cur]:
@@ -150,11 +150,12 @@ for l in sass.split("\n"):
                 counts[cur][k] += 1
 with open(os.path.join(PR, TAG + "_sass_bulk_copies.txt"), "w") as out:
     out.write("cuobjdump -sass quokkasim_b200/libquokka_b200.so (sha256 %s): instruction counts per kernel\n" % lib_sha)
-    out.write("UBLKCP = cp.async.bulk (TMA engine) ; SYNCS = mbarrier operations ; LDGSTS = cp.async (per-thread) ; "
-              "REDUX = warp reduction ; REDG = fire-and-forget atomics (statistics planes)\n\n")
+    out.write("UTMALDG / UTMASTG = cp.async.bulk.tensor.2d (TMA tile of a state plane: every slot x the block's replications) ; "
+              "UBLKCP = cp.async.bulk (TMA engine, one row / the model tables) ; SYNCS = mbarrier operations ; "
+              "LDGSTS = cp.async (per-thread) ; REDUX = warp reduction ; REDG = fire-and-forget atomics (statistics planes)\n\n")
     for k in sorted(counts):
         if "qk_step_kernel" in k or "qk_group_kernel" in k or "qk_phased_kernel" in k:
             c = counts[k]
-            out.write("%-60s UBLKCP %3d  SYNCS %3d  LDGSTS %3d  REDUX %3d  REDG %3d\n" % (
-                k, c["UBLKCP"], c["SYNCS"], c["LDGSTS"], c["REDUX"], c["REDG"]))
+            out.write("%-60s UTMALDG %2d  UTMASTG %2d  UBLKCP %3d  SYNCS %3d  LDGSTS %3d  REDUX %3d  REDG %3d\n" % (
+                k, c["UTMALDG"], c["UTMASTG"], c["UBLKCP"], c["SYNCS"], c["LDGSTS"], c["REDUX"], c["REDG"]))
 print("profiles/ updated:", sorted(f for f in os.listdir(PR) if f.startswith(TAG)))
