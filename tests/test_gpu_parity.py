@@ -317,6 +317,37 @@ def test_state_placement_does_not_change_results(gpu_lib):
     b.close()
 
 
+def test_tma_tile_staging_equals_row_copies(gpu_lib, monkeypatch):
+    """The step kernel stages a block's hot planes as one 2-D TMA tile per plane (tensor maps made by qk_batch_create);
+    QK_NO_TMA=1 makes the same library move them one bulk copy per slot row.  Same state, statistics and logs, bit for
+    bit, across many launches (every launch stages in and out), in the on-chip and the split placements, with block
+    sizes from 32 to 256 and a replication count that leaves the last block partly empty."""
+    cases = [(H.discrete_queue, {}, 0, 0), (H.discrete_queue, {}, 0, 32), (H.discrete_queue, {}, 0, 256),
+             (lambda: H.haulage(n_src=3, per_queue=4), {}, 16, 0), (lambda: H.vector_flow(3), {}, 16, 0),
+             (lambda: H.vector_flow(5), {}, 0, 0), (lambda: H.serial_line(n_proc=8), {}, 48, 0)]
+    for build, kw, flags, nt in cases:
+        blobs = []
+        for no_tma in (False, True):
+            if no_tma:
+                monkeypatch.setenv("QK_NO_TMA", "1")
+            else:
+                monkeypatch.delenv("QK_NO_TMA", raising=False)
+            m = build()
+            sim = m.sim(gpu_lib, 1000, base_seed=33, flags=flags, log_capacity=256, threads_per_block=nt)
+            sim.step_events_chunked(600, 7)  # 86 launches
+            sim.step_events(900)
+            st, now, ev = sim.status()
+            assert (ev == 1500).all() or (st != 0).any()
+            blob = st.tobytes() + now.tobytes() + ev.tobytes()
+            blob += b"".join(sim.comp_stats(ci).tobytes() for ci in range(len(m.components)))
+            for r in (0, 511, 999):
+                blob += sim.read_log(r)[0].tobytes()
+            blobs.append(blob)
+            sim.close()
+        monkeypatch.delenv("QK_NO_TMA", raising=False)
+        assert blobs[0] == blobs[1], (build, flags, nt)
+
+
 # ------------------------------------------------------------------------------------- lane-group kernel (qk_group.cuh)
 def _gflags(lanes, phased=False):
     # QK_BATCH_STATE_LANE_GROUP [| QK_BATCH_GROUP_PHASED] | lanes_per_replication << 8 (api.py convention)
