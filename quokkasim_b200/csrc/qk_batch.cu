@@ -14,6 +14,7 @@
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
+#include <mutex>
 #include <vector>
 
 #include "qk_step_inst.cuh"
@@ -71,6 +72,8 @@ struct qk_batch {
   size_t scratch_bytes;
   uint8_t* h_pinned;
   size_t pinned_bytes;
+  uint8_t* d_arena; /* ONE device allocation behind d_tables, d_tapes, d_tape_len, d_part, d_hist and d_scratch */
+  size_t arena_bytes;
   uint32_t grp_reps, grp_stride64, grp_stride32, grp_bar_off, grp_x64; /* lane-group kernel geometry (qk_group.cuh) */
   bool phased;
   bool split; /* QK_BATCH_STATE_SPLIT: component records live in the cold planes (DevHeader.split) */
@@ -481,6 +484,45 @@ static cudaError_t fetch(const uint64_t* plane, uint64_t rep_pad, uint32_t slot,
 /* ============================================ C ABI ============================================ */
 extern "C" {
 
+/* The small things a batch needs next to its planes -- model tables, tape table, reduction partials, read-back scratch,
+ * and a page-locked host buffer -- are ONE device arena and one pinned buffer, and a destroyed batch leaves them in a
+ * small per-process cache instead of giving them back to the driver: cudaMalloc, cudaFree and above all cudaHostAlloc
+ * are device-wide (and, with one process per GPU, machine-wide) synchronisations of 0.1-1 ms each, which a user who
+ * builds one batch after another paid on every batch (end to end at 8 GPUs: 8 ms of `create` on a 66 ms step). */
+struct QkSmall {
+  int device;
+  uint8_t* d_arena;
+  size_t arena_bytes;
+  uint8_t* h_pinned;
+  size_t pinned_bytes;
+};
+static std::mutex g_small_mu;
+static std::vector<QkSmall> g_small;
+enum { QK_SMALL_CACHE_MAX = 16 };
+
+static bool small_take(int device, size_t arena_bytes, size_t pinned_bytes, QkSmall* out) {
+  std::lock_guard<std::mutex> lk(g_small_mu);
+  for (size_t i = 0; i < g_small.size(); ++i)
+    if (g_small[i].device == device && g_small[i].arena_bytes >= arena_bytes && g_small[i].pinned_bytes >= pinned_bytes) {
+      *out = g_small[i];
+      g_small.erase(g_small.begin() + (long)i);
+      return true;
+    }
+  return false;
+}
+static void small_give(const QkSmall& e) {
+  {
+    std::lock_guard<std::mutex> lk(g_small_mu);
+    if (g_small.size() < QK_SMALL_CACHE_MAX) {
+      g_small.push_back(e);
+      return;
+    }
+  }
+  cudaFree(e.d_arena);
+  cudaFreeHost(e.h_pinned);
+}
+static size_t align256(size_t x) { return (x + 255u) & ~(size_t)255u; }
+
 /* inside qk_batch_create, once `b` exists: a failed CUDA call (typically cudaMalloc on a batch that does not fit the
  * GPU) releases what was allocated so far */
 #define CREATE_TRY(expr)                                                                         \
@@ -548,6 +590,8 @@ int qk_batch_create(const qk_model* m, const qk_batch_config* cfg, qk_batch** ou
   b->d_scratch = nullptr;
   b->h_pinned = nullptr;
   b->scratch_bytes = b->pinned_bytes = 0;
+  b->d_arena = nullptr;
+  b->arena_bytes = 0;
   b->n_sm = 148;
   b->wave_blocks = 0;
   b->lanes = 1;
@@ -735,18 +779,41 @@ int qk_batch_create(const qk_model* m, const qk_batch_config* cfg, qk_batch** ou
   if (b->log) CREATE_TRY(cudaMallocAsync(&b->d_log, (size_t)b->rep_pad * cfg->log_capacity * 32, b->stream));
   CREATE_TRY(cudaStreamSynchronize(b->stream)); /* allocation failures of the pool surface here at the latest */
   b->use_tma = !b->hbm && !group && make_tensor_maps(b);
-  CREATE_TRY(cudaMalloc(&b->d_tables, b->table_bytes_padded));
   {
-    std::vector<uint8_t> padded(b->table_bytes_padded, 0);
-    memcpy(padded.data(), b->low.blob.data(), b->low.blob.size());
-    CREATE_TRY(cudaMemcpy(b->d_tables, padded.data(), padded.size(), cudaMemcpyHostToDevice));
+    /* the arena: tables | tape pointers | tape lengths | partials | histograms | scratch, 256-byte aligned pieces */
+    const size_t n_dist = h.n_dist ? h.n_dist : 1;
+    b->scratch_bytes = std::max<size_t>(1u << 20, (size_t)h.n_comp * (QK_PARTIAL_WORDS + 2 * QK_HIST_BINS) * 8);
+    b->pinned_bytes = b->scratch_bytes;
+    const size_t o_tables = 0, o_tapes = o_tables + align256(b->table_bytes_padded);
+    const size_t o_len = o_tapes + align256(sizeof(double*) * n_dist), o_part = o_len + align256(sizeof(uint64_t) * n_dist);
+    const size_t o_hist = o_part + align256(sizeof(uint64_t) * QK_PARTIAL_WORDS * h.n_comp);
+    const size_t o_scratch = o_hist + align256(sizeof(uint64_t) * 2 * QK_HIST_BINS * h.n_comp);
+    const size_t need = o_scratch + align256(b->scratch_bytes);
+    QkSmall e;
+    if (small_take(cfg->device, need, b->pinned_bytes, &e)) {
+      b->d_arena = e.d_arena;
+      b->arena_bytes = e.arena_bytes;
+      b->h_pinned = e.h_pinned;
+      b->pinned_bytes = e.pinned_bytes;
+    } else {
+      CREATE_TRY(cudaMalloc(&b->d_arena, need));
+      b->arena_bytes = need;
+      CREATE_TRY(cudaHostAlloc(&b->h_pinned, b->pinned_bytes, cudaHostAllocDefault));
+    }
+    b->d_tables = b->d_arena + o_tables;
+    b->d_tapes = reinterpret_cast<const double**>(b->d_arena + o_tapes);
+    b->d_tape_len = reinterpret_cast<uint64_t*>(b->d_arena + o_len);
+    b->d_part = reinterpret_cast<uint64_t*>(b->d_arena + o_part);
+    b->d_hist = reinterpret_cast<uint64_t*>(b->d_arena + o_hist);
+    b->d_scratch = b->d_arena + o_scratch;
+    /* tables (zero-padded to the 128-byte multiple the kernels copy) and an empty tape table, in stream order: the
+     * launches that read them follow on the same stream.  (The source is pageable: the copy is staged before the call
+     * returns.) */
+    CREATE_TRY(cudaMemsetAsync(b->d_arena, 0, o_part, b->stream));
+    CREATE_TRY(cudaMemcpyAsync(b->d_tables, b->low.blob.data(), b->low.blob.size(), cudaMemcpyHostToDevice, b->stream));
   }
   b->h_tapes.assign(h.n_dist, nullptr);
   b->h_tape_len.assign(h.n_dist, 0);
-  CREATE_TRY(cudaMalloc(&b->d_tapes, sizeof(double*) * (h.n_dist ? h.n_dist : 1)));
-  CREATE_TRY(cudaMalloc(&b->d_tape_len, sizeof(uint64_t) * (h.n_dist ? h.n_dist : 1)));
-  CREATE_TRY(cudaMemset(b->d_tapes, 0, sizeof(double*) * (h.n_dist ? h.n_dist : 1)));
-  CREATE_TRY(cudaMemset(b->d_tape_len, 0, sizeof(uint64_t) * (h.n_dist ? h.n_dist : 1)));
   b->kernel = group ? (b->phased ? pick_phased_kernel(b->log, b->lanes, h.features) : pick_group_kernel(b->log, b->lanes, h.features))
                     : pick_kernel(b->log, b->hbm, b->nt, h.features, h.split);
   {
@@ -770,12 +837,6 @@ int qk_batch_create(const qk_model* m, const qk_batch_config* cfg, qk_batch** ou
     b->wave_blocks = (uint32_t)(sms * nb);
   }
   b->red_blocks = b->n_sm * 4;
-  CREATE_TRY(cudaMalloc(&b->d_part, sizeof(uint64_t) * QK_PARTIAL_WORDS * h.n_comp));
-  CREATE_TRY(cudaMalloc(&b->d_hist, sizeof(uint64_t) * 2 * QK_HIST_BINS * h.n_comp));
-  b->scratch_bytes = std::max<size_t>(1u << 20, (size_t)h.n_comp * (QK_PARTIAL_WORDS + 2 * QK_HIST_BINS) * 8);
-  CREATE_TRY(cudaMalloc(&b->d_scratch, b->scratch_bytes));
-  b->pinned_bytes = b->scratch_bytes;
-  CREATE_TRY(cudaHostAlloc(&b->h_pinned, b->pinned_bytes, cudaHostAllocDefault));
   *out = b;
   return QK_OK;
 }
@@ -816,10 +877,7 @@ void qk_batch_destroy(qk_batch* b) {
       if (p) cudaFreeAsync(p, b->stream);
     cudaStreamSynchronize(b->stream);
   }
-  cudaFree(b->d_tables);
   for (size_t i = 0; i < b->h_tapes.size(); ++i) cudaFree(b->h_tapes[i]);
-  cudaFree(b->d_tapes);
-  cudaFree(b->d_tape_len);
   if (b->have_side) {
     for (int i = 0; i < QK_SLICE_PARTS - 1; ++i) {
       cudaStreamDestroy(b->side[i]);
@@ -827,10 +885,13 @@ void qk_batch_destroy(qk_batch* b) {
     }
     cudaEventDestroy(b->ev_fork);
   }
-  cudaFree(b->d_part);
-  cudaFree(b->d_hist);
-  cudaFree(b->d_scratch);
-  if (b->h_pinned) cudaFreeHost(b->h_pinned);
+  if (b->d_arena && b->h_pinned) { /* (the stream was synchronised above: nothing in flight touches them) */
+    QkSmall e = {b->cfg.device, b->d_arena, b->arena_bytes, b->h_pinned, b->pinned_bytes};
+    small_give(e);
+  } else {
+    if (b->d_arena) cudaFree(b->d_arena);
+    if (b->h_pinned) cudaFreeHost(b->h_pinned);
+  }
   if (b->ev0) cudaEventDestroy(b->ev0);
   if (b->ev1) cudaEventDestroy(b->ev1);
   if (b->own_stream) cudaStreamDestroy(b->stream);
