@@ -187,15 +187,37 @@ def test_random_models_match_the_oracle_on_gpu(gpu_lib, seed):
 
 
 # ------------------------------------------------------------------------------------------ continuous family
-def random_vector_model(seed):
+# user-defined resources (iron_ore.rs): 2 to 8 fields, totals over a subset of them -- feature set 3 of the kernels
+_WIDE = []
+for _name, _n, _counted in (("FzPair", 2, (1,)), ("FzTri", 3, (0, 1)), ("FzQuad", 4, (0, 2)), ("FzOre", 5, (0, 1)),
+                            ("FzSept", 7, (0, 1, 2, 3, 4, 5, 6)), ("FzOct", 8, (0, 2, 4, 5, 7))):
+    _fields = ["f%d" % k for k in range(_n)]
+    _WIDE.append(qk.define_vector_variants(_name, qk.define_resource(_name, _fields, total=[_fields[k] for k in _counted])))
+
+
+def random_vector_model(seed, wide=False):
     """A random chain of the continuous components: Source -> stocks -> Process / Combiner2 / Splitter2 -> Sink, f64 or
-    Vector3, random capacities around the flow so that Full / Empty flips happen, breakdown modes, environment."""
+    Vector3 (wide: a user-defined resource of 2..8 fields whose total counts some of them), random capacities around the
+    flow so that Full / Empty flips happen, breakdown modes, environment."""
     rng = random.Random(10_000 + seed)
     m = Model()
     df = qk.DistributionFactory(base_seed=77 + seed, next_seed=0)
     dim = rng.choice([1, 3])
     P = "Vector3" if dim == 3 else "F64"
     V = (lambda v: qk.Vector3(v)) if dim == 3 else (lambda v: float(sum(v)))
+    if wide:
+        R = _WIDE[seed % len(_WIDE)]
+        P = R.NAME
+        n = len(R.FIELDS)
+        counted = [k for k in range(n) if (R.TOTAL_MASK >> k) & 1]
+
+        def V(v, R=R, n=n, counted=counted):  # noqa: E306
+            # the three numbers of the plain generator go to the counted fields (so capacities mean what they meant),
+            # the others carry their own quantities along
+            vals = [0.25 * (k + 1) * v[k % 3] for k in range(n)]
+            for j, k in enumerate(counted):
+                vals[k] = v[j % 3] if j < 3 else 0.125 * v[j % 3]
+            return R(*vals)
 
     def dist(a):
         k = rng.choice(["const", "uniform", "uniform", "tri"])
@@ -265,8 +287,8 @@ def random_vector_model(seed):
     return m
 
 
-def _run_vector(lib, seed, n_reps, flags=0):
-    m = random_vector_model(seed)
+def _run_vector(lib, seed, n_reps, flags=0, wide=False):
+    m = random_vector_model(seed, wide)
     om, dist_ids = H.lower_to_oracle(m)
     sim = m.sim(lib, n_reps, base_seed=seed, log_capacity=32768, flags=flags)
     sim.step_until(90 * 10**9)
@@ -281,6 +303,12 @@ def _run_vector(lib, seed, n_reps, flags=0):
 @pytest.mark.parametrize("seed", range(24))
 def test_random_vector_models_match_the_oracle(emul_lib, seed):
     _run_vector(emul_lib, seed, 2, flags=seed % 2)
+
+
+@pytest.mark.parametrize("seed", range(600, 624))
+def test_random_user_defined_resource_models_match_the_oracle(emul_lib, seed):
+    """feature set 3 (qk_model_set_vector_n): on-chip, HBM-plane and split placements"""
+    _run_vector(emul_lib, seed, 2, flags=(0, 1, 16)[seed % 3], wide=True)
 
 
 @pytest.mark.parametrize("seed", range(400, 408))
