@@ -1,4 +1,5 @@
-//! `extern "C"` declarations for include/quokka_b200.h (ABI version 1).  Plain-old-data only.
+//! `extern "C"` declarations for include/quokka_b200.h (ABI version 2): every entry point of the header, plain old data
+//! only.  Never compiled in the image this was written in (no Rust toolchain): kept in step with the header by hand.
 #![allow(non_camel_case_types, dead_code)]
 use core::ffi::{c_char, c_void};
 
@@ -103,11 +104,94 @@ pub struct qk_comp_stats {
     pub faux: f64,
 }
 
+pub const QK_HIST_BINS: usize = 32;
+/// whole-batch (or, after qk_multi_stats, whole-job) reduction of qk_comp_stats over the replications
+#[repr(C)]
+#[derive(Clone, Copy, Debug)]
+pub struct qk_comp_summary {
+    pub sum_count: u64,
+    pub sum_time_lo: u64,
+    pub sum_time_hi: u64,
+    pub sum_level: u64,
+    pub min_count: u64,
+    pub max_count: u64,
+    pub min_time: u64,
+    pub max_time: u64,
+    pub sumsq_time: f64,
+    pub sumsq_count: f64,
+    pub hist_time: [u64; QK_HIST_BINS],
+    pub hist_count: [u64; QK_HIST_BINS],
+    pub hist_lo_time: u64,
+    pub hist_hi_time: u64,
+    pub hist_lo_count: u64,
+    pub hist_hi_count: u64,
+    pub sumsq_time_ns2: [u64; 3],
+    pub sumsq_count_lo: u64,
+    pub sumsq_count_hi: u64,
+    pub sumsq_level: u64,
+}
+
+/// words of the packed partials that cross GPUs (qk_batch_reduce_partials*)
+pub const QK_PARTIAL_WORDS: usize = 20;
+
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
+pub struct qk_batch_summary {
+    pub n_reps: u64,
+    pub n_events: u64,
+    pub n_faulted: u64,
+    pub n_log_records: u64,
+    pub min_now_ns: u64,
+    pub max_now_ns: u64,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
+pub struct qk_batch_info {
+    pub threads_per_block: u32,
+    pub grid_blocks: u32,
+    pub shared_bytes_per_block: u32,
+    pub table_bytes: u32,
+    pub slots64: u32,
+    pub slots32: u32,
+    pub state_bytes_per_rep: u32,
+    pub resident_blocks_per_sm: u32,
+    pub state_in_hbm: u32,
+    pub cold_bytes_per_rep: u32,
+    pub replications_padded: u64,
+    pub state_bytes_total: u64,
+    pub log_bytes_total: u64,
+    pub lanes_per_replication: u32,
+    pub wave_blocks: u32,
+    pub last_step_chunks: u32,
+    pub state_split: u32,
+}
+
+/// one job on several GPUs of one box: `devices` null / `n_devices` 0 = every visible device
+#[repr(C)]
+#[derive(Clone, Copy, Debug)]
+pub struct qk_multi_config {
+    pub n_reps: u64,
+    pub rep_offset: u64,
+    pub base_seed: u64,
+    pub devices: *const i32,
+    pub n_devices: u32,
+    pub log_capacity: u32,
+    pub threads_per_block: u32,
+    pub flags: u32,
+    pub lanes_per_replication: u32,
+}
+
+/// fields a user-defined resource may have (qk_model_set_vector_n)
+pub const QK_VEC_MAX_DIM: usize = 8;
+
 pub enum qk_model {}
 pub enum qk_batch {}
+pub enum qk_multi {}
 
 extern "C" {
     pub fn qk_abi_version() -> i32;
+    pub fn qk_build_id() -> *const c_char;
     pub fn qk_last_error() -> *const c_char;
 
     pub fn qk_model_create(out: *mut *mut qk_model) -> i32;
@@ -123,11 +207,19 @@ extern "C" {
         out_until_fix: *mut u32,
     ) -> i32;
     pub fn qk_model_set_vector(m: *mut qk_model, comp: u32, dim: u32, low: f64, max: f64, init3: *const f64) -> i32;
+    /// user-defined resource types (iron_ore.rs:21-96): `dim` <= QK_VEC_MAX_DIM f64 fields, `total()` sums the fields of
+    /// `total_mask` in field order, `remove(q)` takes q / total() of every field; `init[dim]`
+    pub fn qk_model_set_vector_n(m: *mut qk_model, comp: u32, dim: u32, total_mask: u32, low: f64, max: f64, init: *const f64) -> i32;
     pub fn qk_model_set_ports(m: *mut qk_model, comp: u32, n_ports: u32, ratios5: *const f64) -> i32;
     pub fn qk_model_connect(m: *mut qk_model, a: u32, b: u32, port_n: i32) -> i32;
     pub fn qk_model_set_logged(m: *mut qk_model, comp: u32, enabled: i32) -> i32;
     pub fn qk_model_schedule_env_state(m: *mut qk_model, t_ns: u64, env: u32, state: u32) -> i32;
     pub fn qk_model_schedule_low_capacity(m: *mut qk_model, t_ns: u64, stock: u32, value: f64) -> i32;
+    /// create_scheduled_event!(SetProcessQuantity(cfg)) on an F64Process (core.rs:1387-1391)
+    pub fn qk_model_schedule_process_quantity(m: *mut qk_model, t_ns: u64, process: u32, dist: *const qk_dist_desc, out_dist_id: *mut u32) -> i32;
+    pub fn qk_model_n_components(m: *const qk_model, out: *mut u32) -> i32;
+    pub fn qk_model_n_dists(m: *const qk_model, out: *mut u32) -> i32;
+    pub fn qk_model_state_bytes(m: *const qk_model, with_log: i32, out_bytes: *mut u32) -> i32;
     /// Vector3ContainerFactory (vector_container.rs:126-156); `create_quantity` null = None
     pub fn qk_model_set_container_factory(
         m: *mut qk_model,
@@ -148,12 +240,37 @@ extern "C" {
     ) -> i32;
 
     pub fn qk_batch_create(m: *const qk_model, cfg: *const qk_batch_config, out: *mut *mut qk_batch) -> i32;
+    pub fn qk_batch_info_get(b: *mut qk_batch, out: *mut qk_batch_info) -> i32;
     pub fn qk_batch_destroy(b: *mut qk_batch);
     pub fn qk_batch_set_tape(b: *mut qk_batch, dist_id: u32, values: *const f64, per_rep_len: u64) -> i32;
     pub fn qk_batch_init(b: *mut qk_batch, t0_ns: u64) -> i32;
     pub fn qk_batch_step_until(b: *mut qk_batch, t_ns: u64) -> i32;
     pub fn qk_batch_step_events(b: *mut qk_batch, n_events: u64) -> i32;
+    pub fn qk_batch_step_events_chunked(b: *mut qk_batch, n_events: u64, chunk: u64) -> i32;
+    pub fn qk_batch_step_events_sliced(b: *mut qk_batch, n_events: u64, n_chunks: u32) -> i32;
     pub fn qk_batch_synchronize(b: *mut qk_batch) -> i32;
+    pub fn qk_batch_summary_get(b: *mut qk_batch, out: *mut qk_batch_summary) -> i32;
+    pub fn qk_batch_reduce_stats(b: *mut qk_batch, out: *mut qk_comp_summary, n_comp: u32) -> i32;
+    pub fn qk_batch_reduce_partials(b: *mut qk_batch, partials: *mut u64, n_comp: u32) -> i32;
+    pub fn qk_batch_reduce_partials_device(b: *mut qk_batch, d_partials: *mut u64, n_comp: u32) -> i32;
+    pub fn qk_batch_combine_partials_device(b: *mut qk_batch, d_parts: *const u64, n_parts: u32, d_out: *mut u64, n_comp: u32) -> i32;
+    pub fn qk_batch_histograms_device(b: *mut qk_batch, d_partials: *const u64, d_hist: *mut u64, n_comp: u32) -> i32;
+    pub fn qk_batch_read_logs(b: *mut qk_batch, rep0: u64, n: u64, buf: *mut qk_log_record, kept: *mut u32, total: *mut u64) -> i32;
+    pub fn qk_batch_read_vector_n(b: *mut qk_batch, rep: u64, comp: u32, out: *mut f64, cap: u32, dim_out: *mut u32) -> i32;
+    pub fn qk_batch_last_step_ms(b: *mut qk_batch, ms: *mut f32, n_launches: *mut u32) -> i32;
+
+    // one job on every GPU of the box: shards by contiguous replication range, NCCL only inside qk_multi_stats
+    pub fn qk_multi_create(m: *const qk_model, cfg: *const qk_multi_config, out: *mut *mut qk_multi) -> i32;
+    pub fn qk_multi_destroy(j: *mut qk_multi);
+    pub fn qk_multi_n_shards(j: *mut qk_multi, n: *mut u32) -> i32;
+    pub fn qk_multi_shard(j: *mut qk_multi, i: u32, batch: *mut *mut qk_batch, rep0: *mut u64, n_reps: *mut u64, device: *mut i32) -> i32;
+    pub fn qk_multi_set_tape(j: *mut qk_multi, dist_id: u32, values: *const f64, per_rep_len: u64) -> i32;
+    pub fn qk_multi_init(j: *mut qk_multi, t0_ns: u64) -> i32;
+    pub fn qk_multi_step_until(j: *mut qk_multi, t_ns: u64) -> i32;
+    pub fn qk_multi_step_events(j: *mut qk_multi, n_events: u64) -> i32;
+    pub fn qk_multi_synchronize(j: *mut qk_multi) -> i32;
+    pub fn qk_multi_last_step_ms(j: *mut qk_multi, ms_max: *mut f32) -> i32;
+    pub fn qk_multi_stats(j: *mut qk_multi, out: *mut qk_comp_summary, n_comp: u32, total: *mut qk_batch_summary) -> i32;
     pub fn qk_batch_read_status(b: *mut qk_batch, rep0: u64, n: u64, status: *mut u32, now_ns: *mut u64, n_events: *mut u64) -> i32;
     pub fn qk_batch_comp_stats(b: *mut qk_batch, rep0: u64, n: u64, comp: u32, out: *mut qk_comp_stats) -> i32;
     pub fn qk_batch_read_log(b: *mut qk_batch, rep: u64, buf: *mut qk_log_record, cap: u64, n_out: *mut u64, n_total: *mut u64) -> i32;

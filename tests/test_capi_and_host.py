@@ -293,3 +293,27 @@ def test_user_defined_resource_abi_argument_checks():
         qk.define_vector_variants("IronOre", IronOre)  # the variants exist already (workloads.py)
     with pytest.raises(TypeError):
         qk.define_resource("TooWide", ["f%d" % i for i in range(9)])
+
+
+def test_rust_ffi_declares_every_entry_point_of_the_header():
+    """rust_shim/src/ffi.rs is kept in step with include/quokka_b200.h by hand (no Rust toolchain in this image): same
+    set of entry points, same number of parameters each."""
+    import re
+
+    root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+    header = open(os.path.join(root, "include", "quokka_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    rust = open(os.path.join(root, "rust_shim", "src", "ffi.rs")).read()
+    rust = re.sub(r"//[^\n]*", "", rust)
+    c_fns = {m.group(1): m.group(2) for m in re.finditer(r"^(?:int|void|const char\*)\s+(qk_\w+)\(([^;]*?)\);", header,
+                                                         re.M | re.S)}
+    r_fns = {m.group(1): m.group(2) for m in re.finditer(r"pub fn (qk_\w+)\(([^;]*?)\)\s*(?:->[^;]*)?;", rust, re.S)}
+    assert set(c_fns) == set(r_fns), (sorted(set(c_fns) - set(r_fns)), sorted(set(r_fns) - set(c_fns)))
+
+    def arity(params):
+        p = params.strip()
+        return 0 if p in ("", "void") else len([x for x in p.split(",") if x.strip()])
+
+    for name in c_fns:
+        assert arity(c_fns[name]) == arity(r_fns[name]), name
+    assert len(c_fns) == len(capi.EXPORTED_SYMBOLS)
