@@ -307,8 +307,8 @@ def test_random_vector_models_match_the_oracle(emul_lib, seed):
 
 @pytest.mark.parametrize("seed", range(600, 624))
 def test_random_user_defined_resource_models_match_the_oracle(emul_lib, seed):
-    """feature set 3 (qk_model_set_vector_n): on-chip, HBM-plane and split placements"""
-    _run_vector(emul_lib, seed, 2, flags=(0, 1, 16)[seed % 3], wide=True)
+    """feature set 3 (qk_model_set_vector_n): on-chip, HBM-plane, split and two-tier placements"""
+    _run_vector(emul_lib, seed, 2, flags=(0, 1, 16, 48)[seed % 4], wide=True)
 
 
 @pytest.mark.parametrize("seed", range(400, 408))
