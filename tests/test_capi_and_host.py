@@ -317,3 +317,36 @@ def test_rust_ffi_declares_every_entry_point_of_the_header():
     for name in c_fns:
         assert arity(c_fns[name]) == arity(r_fns[name]), name
     assert len(c_fns) == len(capi.EXPORTED_SYMBOLS)
+
+
+def test_c_example_of_a_user_defined_resource_runs_on_the_kernel_emulation(emul_lib, tmp_path):
+    """examples/iron_ore.c (strict C99 over the C ABI: qk_model_set_vector_n, qk_batch_read_vector_n) linked against the
+    host build of the kernel source (tests/emul exports the same ABI) agrees to the last bit with the Python host
+    running the same model, and links against the product library as well."""
+    import subprocess
+
+    import helpers as H
+    from quokkasim_b200 import _capi
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = os.path.join(root, "examples", "iron_ore.c")
+    flags = ["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I" + os.path.join(root, "include"), src]
+    exe = str(tmp_path / "iron_ore_emul")
+    libdir, libname = os.path.dirname(emul_lib), os.path.basename(emul_lib)
+    subprocess.check_call(flags + ["-o", exe, "-L" + libdir, "-l:" + libname, "-Wl,-rpath," + libdir])
+    out = subprocess.check_output([exe, "8"], text=True).strip().split("\n")
+    pdir, pname = os.path.dirname(_capi.DEFAULT_LIB), os.path.basename(_capi.DEFAULT_LIB)
+    subprocess.check_call(flags + ["-o", str(tmp_path / "iron_ore_gpu"), "-L" + pdir, "-l:" + pname, "-Wl,-rpath," + pdir])
+
+    m = H.iron_ore()
+    sim = m.sim(emul_lib, 8, base_seed=123456789)
+    sim.step_until(300 * 10**9)
+    s2, p1 = m.by_name["MyStock2"].component._id, m.by_name["IronOreProcess"].component._id
+    ore = sim.read_resource(s2, 0)
+    moved = int(sim.comp_stats(p1, 0, 1)[0]["count"])
+    want = ("replication 0: %d batches moved, MyStock2 = {fe %.17g, other_elements %.17g, magnetite %.17g, hematite %.17g, "
+            "limonite %.17g} (5 fields), fe%% %.6f" % ((moved,) + tuple(ore) + (100.0 * ore[0] / (ore[0] + ore[1]),)))
+    assert out[0] == want, (out[0], want)
+    mean = sum(sum(sim.read_resource(s2, r)[:2]) for r in range(8)) / 8.0
+    assert out[1] == "mean of 8 replications: MyStock2 total %.6f" % mean
+    sim.close()
